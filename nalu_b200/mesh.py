@@ -1,0 +1,208 @@
+"""Flat-array Hex8 mesh substrate: generators, perturbation, partitioning.
+
+The reference reads its meshes through STK-IO / Ioss; the hot path only ever sees, per
+rank, node ids (`naluGlobalId`), node ownership, element->node connectivity and nodal /
+element fields.  This module produces exactly those arrays.
+
+  * `generated_box`   -- Ioss `generated:NxMxK` convention (unit-spaced nodes, id
+                         1+i+(N+1)j+(N+1)(M+1)k, Exodus Hex8 node order; confirmed by
+                         unit_tests/UnitTestTpetra.C:97-98 "elem 1 nodes: 1 2 4 3 5 6 8 7").
+  * `perturb_coords_lcg` -- unit_tests/UnitTestUtils.C:37-72 `perturb_coord_hex_8`.
+  * `partition_slabs` -- z-slab element decomposition (Ioss default for generated meshes,
+                         unit_tests/UnitTestUtils.C:30-35), shared nodes owned by the lowest
+                         sharing rank (STK rule, visible in unit_tests/UnitTestTpetra.C:149-156).
+  * `periodic_box`    -- periodic in x,y,z by id aliasing: a subject node keeps its own
+                         coordinates but adopts its monarch's id (src/PeriodicManager.C:698-724).
+"""
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+@dataclass
+class BoxInfo:
+    """Logical structure of a generated box (local to one rank): node (i,j,k) has local
+    index i + (nx+1)*j + (nx+1)*(ny+1)*k; element (i,j,k) has local index i + nx*j + nx*ny*k."""
+    nx: int
+    ny: int
+    nz: int
+    k0: int = 0          # global z-index of this rank's first element layer
+    nz_global: int = 0
+
+
+@dataclass
+class HexMesh:
+    coords: np.ndarray          # [nNode,3] f64
+    node_gid: np.ndarray        # [nNode] int64, 1-based naluGlobalId (aliases allowed: periodic)
+    node_owner: np.ndarray      # [nNode] int32
+    elem_nodes: np.ndarray      # [nElem,8] int32 local node indices, Exodus Hex8 order
+    rank: int = 0
+    nranks: int = 1
+    box: Optional[BoxInfo] = None
+    elem_gid: Optional[np.ndarray] = None
+
+    @property
+    def n_nodes(self):
+        return int(self.node_gid.size)
+
+    @property
+    def n_elems(self):
+        return int(self.elem_nodes.shape[0])
+
+
+def _box_conn(nx, ny, nz):
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    # element order: i fastest, then j, then k
+    i = i.transpose(2, 1, 0).ravel()
+    j = j.transpose(2, 1, 0).ravel()
+    k = k.transpose(2, 1, 0).ravel()
+    sx, sy = nx + 1, (nx + 1) * (ny + 1)
+    n0 = i + sx * j + sy * k
+    conn = np.stack([n0, n0 + 1, n0 + 1 + sx, n0 + sx,
+                     n0 + sy, n0 + 1 + sy, n0 + 1 + sx + sy, n0 + sx + sy], axis=1)
+    return conn.astype(np.int32)
+
+
+def _box_coords(nx, ny, nz, k0=0):
+    x = np.arange(nx + 1, dtype=np.float64)
+    y = np.arange(ny + 1, dtype=np.float64)
+    z = np.arange(k0, k0 + nz + 1, dtype=np.float64)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    return np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+
+def generated_box(nx, ny, nz) -> HexMesh:
+    """Ioss `generated:nx x ny x nz` on one rank."""
+    nn = (nx + 1) * (ny + 1) * (nz + 1)
+    return HexMesh(coords=_box_coords(nx, ny, nz),
+                   node_gid=np.arange(1, nn + 1, dtype=np.int64),
+                   node_owner=np.zeros(nn, dtype=np.int32),
+                   elem_nodes=_box_conn(nx, ny, nz),
+                   box=BoxInfo(nx, ny, nz, 0, nz),
+                   elem_gid=np.arange(1, nx * ny * nz + 1, dtype=np.int64))
+
+
+def slab_ranges(nz, nranks):
+    """Element-layer ranges [k0,k1) per rank: as even as possible, extra layers to low ranks."""
+    base, rem = divmod(nz, nranks)
+    out, k = [], 0
+    for r in range(nranks):
+        n = base + (1 if r < rem else 0)
+        out.append((k, k + n))
+        k += n
+    return out
+
+
+def generated_box_rank(nx, ny, nz, rank, nranks) -> HexMesh:
+    """Rank-local piece of `generated:nx x ny x nz` under the z-slab decomposition, built
+    directly (no global mesh is materialised: 256^3 on 8 ranks must not need 17M-node globals)."""
+    k0, k1 = slab_ranges(nz, nranks)[rank]
+    lz = k1 - k0
+    assert lz > 0, "more ranks than element layers"
+    sxy = (nx + 1) * (ny + 1)
+    nn = sxy * (lz + 1)
+    gid = np.arange(1, nn + 1, dtype=np.int64) + sxy * k0
+    owner = np.full(nn, rank, dtype=np.int32)
+    if rank > 0:
+        owner[:sxy] = rank - 1  # bottom plane shared with (and owned by) the lower rank
+    eg = np.arange(1, nx * ny * lz + 1, dtype=np.int64) + nx * ny * k0
+    return HexMesh(coords=_box_coords(nx, ny, lz, k0), node_gid=gid, node_owner=owner,
+                   elem_nodes=_box_conn(nx, ny, lz), rank=rank, nranks=nranks,
+                   box=BoxInfo(nx, ny, lz, k0, nz), elem_gid=eg)
+
+
+def partition_slabs(mesh: HexMesh, nranks: int):
+    """Split a one-rank generated box into z-slab rank meshes (general path: works from the
+    arrays, keeps whatever coordinates the mesh carries)."""
+    assert mesh.box is not None
+    nx, ny, nz = mesh.box.nx, mesh.box.ny, mesh.box.nz
+    sxy = (nx + 1) * (ny + 1)
+    out = []
+    for r, (k0, k1) in enumerate(slab_ranges(nz, nranks)):
+        lo, hi = sxy * k0, sxy * (k1 + 1)
+        m = generated_box_rank(nx, ny, nz, r, nranks)
+        m.coords = mesh.coords[lo:hi].copy()
+        out.append(m)
+    return out
+
+
+def partition_elements(mesh: HexMesh, elem_rank: np.ndarray, nranks: int):
+    """General element partition of an arbitrary one-rank Hex8 mesh: rank r gets the elements
+    with elem_rank==r and the closure of their nodes (ascending gid); a shared node is owned by
+    the lowest rank that touches it."""
+    ne = mesh.n_elems
+    node_min_rank = np.full(mesh.n_nodes, nranks, dtype=np.int32)
+    np.minimum.at(node_min_rank, mesh.elem_nodes.ravel(), np.repeat(elem_rank.astype(np.int32), 8))
+    out = []
+    for r in range(nranks):
+        es = np.nonzero(elem_rank == r)[0]
+        conn = mesh.elem_nodes[es]
+        nodes = np.unique(conn.ravel())
+        nodes = nodes[np.argsort(mesh.node_gid[nodes], kind="stable")]
+        g2l = np.full(mesh.n_nodes, -1, dtype=np.int32)
+        g2l[nodes] = np.arange(nodes.size, dtype=np.int32)
+        out.append(HexMesh(coords=mesh.coords[nodes].copy(), node_gid=mesh.node_gid[nodes].copy(),
+                           node_owner=node_min_rank[nodes].copy(), elem_nodes=g2l[conn],
+                           rank=r, nranks=nranks, box=None,
+                           elem_gid=(mesh.elem_gid[es].copy() if mesh.elem_gid is not None else es + 1)))
+    assert ne == sum(m.n_elems for m in out)
+    return out
+
+
+def periodic_box(nx, ny, nz) -> HexMesh:
+    """Box periodic in all three directions: nodes on the +x/+y/+z faces are subjects whose
+    naluGlobalId is their monarch's; they keep their own coordinates (so geometry is sane) and
+    must carry copies of the monarch's field values."""
+    m = generated_box(nx, ny, nz)
+    sx, sy = nx + 1, (nx + 1) * (ny + 1)
+    idx = np.arange(m.n_nodes)
+    i, j, k = idx % sx, (idx // sx) % (ny + 1), idx // sy
+    mi, mj, mk = i % nx, j % ny, k % nz
+    monarch = mi + sx * mj + sy * mk
+    m.node_gid = m.node_gid[monarch].copy()
+    m.box = None  # aliasing breaks the lexicographic id structure the box fast path relies on
+    m.periodic_monarch = monarch.astype(np.int32)
+    return m
+
+
+_LCG_A, _LCG_C, _LCG_M = 1103515245, 12345, 2147483647
+
+
+def lcg_stream(seed: int, n: int) -> np.ndarray:
+    """n values of the reference's LCG (unit_tests/UnitTestUtils.C:41-54) in [-1,1)."""
+    out = np.empty(n, dtype=np.float64)
+    prev = int(seed)
+    for t in range(n):
+        prev = (_LCG_A * prev + _LCG_C) % _LCG_M
+        out[t] = 2.0 * (prev / float(_LCG_M)) - 1.0
+    return out
+
+
+def perturb_coords_lcg(mesh: HexMesh, amplitude=0.125, seed=None):
+    """perturb_coord_hex_8: three LCG draws per locally-owned node, nodes in ascending id,
+    seed = rank+1.  Pure-Python loop: meant for the small fixture meshes."""
+    seed = mesh.rank + 1 if seed is None else seed
+    owned = np.nonzero(mesh.node_owner == mesh.rank)[0]
+    owned = owned[np.argsort(mesh.node_gid[owned], kind="stable")]
+    r = lcg_stream(seed, 3 * owned.size).reshape(-1, 3)
+    mesh.coords[owned] += amplitude * r
+    return mesh
+
+
+def perturb_coords_hash(mesh: HexMesh, amplitude=0.125):
+    """Deterministic, rank-independent perturbation keyed on the node id (vectorised): every
+    rank that holds a node computes the same displacement, so no owned->shared copy is needed.
+    Used for the large synthetic boxes, where the serial LCG stream would take minutes."""
+    g = mesh.node_gid.astype(np.uint64)
+    out = np.empty((g.size, 3))
+    for d in range(3):
+        x = (g * np.uint64(3) + np.uint64(d) + np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+        x ^= x >> np.uint64(30)
+        x = (x * np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+        x ^= x >> np.uint64(27)
+        x = (x * np.uint64(0x94D049BB133111EB)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+        x ^= x >> np.uint64(31)
+        out[:, d] = (x >> np.uint64(11)).astype(np.float64) * (2.0 / float(1 << 53)) - 1.0
+    mesh.coords += amplitude * out
+    return mesh

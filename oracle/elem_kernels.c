@@ -1,0 +1,505 @@
+/*
+ * elem_kernels.c -- oracle restatement of the element Kernel::execute bodies and of
+ * the per-element part of AssembleElemSolverAlgorithm::execute.
+ * TEST INFRASTRUCTURE ONLY (see nalu_oracle.h).  Scalar, reference loop order.
+ */
+#include "nalu_oracle.h"
+#include <string.h>
+
+/* what ScratchViews + MasterElementViews hold for one element
+ * (include/ScratchViews.h:85-108,630-683) -- only the views the path uses */
+typedef struct {
+  double coords[8][3];
+  double scs_areav[12][3];
+  double dndx[12][8][3];
+  double dndx_shifted[12][8][3];
+  double deriv[12][8][3];
+  double scv_volume[8];
+  int have_areav, have_dndx, have_dndx_shifted, have_scv_volume;
+} me_views;
+
+/* gather_elem_node_field (src/ScratchViews.C:16-88): 8 nodes x d contiguous doubles */
+static void gather(const double *field, int d, const int32_t *nodes, double *out)
+{
+  for (int n = 0; n < 8; ++n)
+    for (int j = 0; j < d; ++j) out[n * d + j] = field[(size_t)nodes[n] * d + j];
+}
+
+/* Kernel ctor: get_scs_shape_fn_data / get_scv_shape_fn_data (include/kernel/Kernel.h:26-56).
+ * The reference fills these tables once per kernel object; cache them the same way. */
+static double g_scs_shape[2][12][8];
+static double g_scv_shape[2][8][8];
+static volatile int g_tables_ready = 0;
+static void init_tables(void)
+{
+  if (g_tables_ready) return;
+  for (int s = 0; s < 2; ++s) {
+    double loc[36], locv[24];
+    orc_hex8_scs_intg_loc(s, loc);
+    orc_hex8_shape_fcn(12, loc, &g_scs_shape[s][0][0]);
+    orc_hex8_scv_intg_loc(s, locv);
+    orc_hex8_shape_fcn(8, locv, &g_scv_shape[s][0][0]);
+  }
+  g_tables_ready = 1;
+}
+static void scs_shape(int shifted, double shp[12][8])
+{
+  memcpy(shp, g_scs_shape[shifted ? 1 : 0], sizeof(double) * 96);
+}
+static void scv_shape(int shifted, double shp[8][8])
+{
+  memcpy(shp, g_scv_shape[shifted ? 1 : 0], sizeof(double) * 64);
+}
+
+/* ---- src/kernel/MomentumAdvDiffElemKernel.C:70-186 ---- */
+static void momentum_adv_diff(const orc_kernel_desc *k, const int32_t *nodes, int64_t e,
+                              const me_views *me, double *lhs, double *rhs)
+{
+  const int n = 24;
+  double v_uNp1[8][3], v_viscosity[8];
+  const double *v_mdot = k->massFlowRate + 12 * e;
+  gather(k->velocity, 3, nodes, &v_uNp1[0][0]);
+  gather(k->viscosity, 1, nodes, v_viscosity);
+  double v_shape_function_[12][8], v_adv_shape_function_[12][8];
+  scs_shape(0, v_shape_function_);
+  scs_shape(k->skewSymmetric, v_adv_shape_function_);
+  const double(*v_dndx)[8][3] = k->shiftedGradOp ? me->dndx_shifted : me->dndx;
+  const int *lrscv = orc_hex8_lrscv();
+  double w_uIp[3];
+
+  for (int ip = 0; ip < 12; ++ip) {
+    const int il = lrscv[2 * ip];
+    const int ir = lrscv[2 * ip + 1];
+    const int ilNdim = il * 3;
+    const int irNdim = ir * 3;
+    const double tmdot = v_mdot[ip];
+
+    double muIp = 0.0;
+    double divU = 0.0;
+    for (int i = 0; i < 3; ++i) w_uIp[i] = 0.0;
+
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      const double rAdv = v_adv_shape_function_[ip][ic];
+      muIp += r * v_viscosity[ic];
+      for (int j = 0; j < 3; ++j) {
+        const double uj = v_uNp1[ic][j];
+        w_uIp[j] += rAdv * uj;
+        divU += uj * v_dndx[ip][ic][j];
+      }
+    }
+
+    for (int i = 0; i < 3; ++i) {
+      const double uiIp = w_uIp[i];
+      const double aflux = tmdot * uiIp;
+      const double divUstress = 2.0 / 3.0 * muIp * divU * me->scs_areav[ip][i] * k->includeDivU;
+      const int indexL = ilNdim + i;
+      const int indexR = irNdim + i;
+      rhs[indexL] -= aflux + divUstress;
+      rhs[indexR] += aflux + divUstress;
+    }
+
+    for (int ic = 0; ic < 8; ++ic) {
+      const int icNdim = ic * 3;
+      const double lhsfacAdv = v_adv_shape_function_[ip][ic] * tmdot;
+
+      for (int i = 0; i < 3; ++i) {
+        const int indexL = ilNdim + i;
+        const int indexR = irNdim + i;
+
+        lhs[indexL * n + icNdim + i] += lhsfacAdv;
+        lhs[indexR * n + icNdim + i] -= lhsfacAdv;
+
+        double lhs_riC_i = 0.0;
+        for (int j = 0; j < 3; ++j) {
+          const double axj = me->scs_areav[ip][j];
+          const double uj = v_uNp1[ic][j];
+
+          const double lhsfacDiff_i = -muIp * v_dndx[ip][ic][j] * axj;
+          lhs_riC_i += lhsfacDiff_i;
+
+          const double lhsfacDiff_j = -muIp * v_dndx[ip][ic][i] * axj;
+          lhs[indexL * n + icNdim + j] += lhsfacDiff_j;
+          lhs[indexR * n + icNdim + j] -= lhsfacDiff_j;
+          rhs[indexL] -= lhsfacDiff_j * uj;
+          rhs[indexR] += lhsfacDiff_j * uj;
+        }
+
+        lhs[indexL * n + icNdim + i] += lhs_riC_i;
+        lhs[indexR * n + icNdim + i] -= lhs_riC_i;
+        const double ui = v_uNp1[ic][i];
+        rhs[indexL] -= lhs_riC_i * ui;
+        rhs[indexR] += lhs_riC_i * ui;
+      }
+    }
+  }
+}
+
+/* ---- src/kernel/ContinuityAdvElemKernel.C:86-148 (+ setup :78-84) ---- */
+static void continuity_adv(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
+                           double *lhs, double *rhs)
+{
+  const int n = 8;
+  const double projTimeScale_ = k->dt / k->gamma1;
+  double v_densityNp1[8], v_pressure[8], v_velocity[8][3], v_Gpdx[8][3];
+  gather(k->density, 1, nodes, v_densityNp1);
+  gather(k->pressure, 1, nodes, v_pressure);
+  gather(k->velocity, 3, nodes, &v_velocity[0][0]);
+  gather(k->Gpdx, 3, nodes, &v_Gpdx[0][0]);
+  double v_shape_function_[12][8];
+  scs_shape(k->shiftMdot, v_shape_function_);
+  const double(*v_dndx)[8][3] = k->shiftPoisson ? me->dndx_shifted : me->dndx;
+  const double(*v_dndx_lhs)[8][3] =
+      (k->shiftPoisson || k->reducedSensitivities) ? me->dndx_shifted : me->dndx;
+  const int *lrscv = orc_hex8_lrscv();
+  double w_rho_uIp[3], w_Gpdx_Ip[3], w_dpdxIp[3];
+
+  for (int ip = 0; ip < 12; ++ip) {
+    const int il = lrscv[2 * ip];
+    const int ir = lrscv[2 * ip + 1];
+
+    for (int j = 0; j < 3; ++j) {
+      w_rho_uIp[j] = 0.0;
+      w_Gpdx_Ip[j] = 0.0;
+      w_dpdxIp[j] = 0.0;
+    }
+
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      const double nodalPressure = v_pressure[ic];
+      const double nodalRho = v_densityNp1[ic];
+
+      double lhsfac = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        w_Gpdx_Ip[j] += r * v_Gpdx[ic][j];
+        w_rho_uIp[j] += r * nodalRho * v_velocity[ic][j];
+        w_dpdxIp[j] += v_dndx[ip][ic][j] * nodalPressure;
+        lhsfac += -v_dndx_lhs[ip][ic][j] * me->scs_areav[ip][j];
+      }
+
+      lhs[il * n + ic] += lhsfac;
+      lhs[ir * n + ic] -= lhsfac;
+    }
+
+    double mdot = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      mdot += (w_rho_uIp[j] - projTimeScale_ * (w_dpdxIp[j] - w_Gpdx_Ip[j])) * me->scs_areav[ip][j];
+    }
+
+    rhs[il] -= mdot / projTimeScale_;
+    rhs[ir] += mdot / projTimeScale_;
+  }
+}
+
+/* ---- src/kernel/ScalarAdvDiffElemKernel.C:69-127 ---- */
+static void scalar_adv_diff(const orc_kernel_desc *k, const int32_t *nodes, int64_t e,
+                            const me_views *me, double *lhs, double *rhs)
+{
+  const int n = 8;
+  double v_scalarQ[8], v_diffFluxCoeff[8];
+  const double *v_mdot = k->massFlowRate + 12 * e;
+  gather(k->scalarQ, 1, nodes, v_scalarQ);
+  gather(k->viscosity, 1, nodes, v_diffFluxCoeff);
+  double v_shape_function_[12][8], v_adv_shape_function_[12][8];
+  scs_shape(0, v_shape_function_);
+  scs_shape(k->skewSymmetric, v_adv_shape_function_);
+  const double(*v_dndx)[8][3] = k->shiftedGradOp ? me->dndx_shifted : me->dndx;
+  const int *lrscv = orc_hex8_lrscv();
+
+  for (int ip = 0; ip < 12; ++ip) {
+    const int il = lrscv[2 * ip];
+    const int ir = lrscv[2 * ip + 1];
+    const double tmdot = v_mdot[ip];
+
+    double diffFluxCoeffIp = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      diffFluxCoeffIp += r * v_diffFluxCoeff[ic];
+    }
+
+    double qAdv = 0.0;
+    double qDiff = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double lhsfacAdv = v_adv_shape_function_[ip][ic] * tmdot;
+      qAdv += lhsfacAdv * v_scalarQ[ic];
+
+      double lhsfacDiff = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        lhsfacDiff += -diffFluxCoeffIp * v_dndx[ip][ic][j] * me->scs_areav[ip][j];
+      }
+      qDiff += lhsfacDiff * v_scalarQ[ic];
+
+      lhs[il * n + ic] += lhsfacAdv + lhsfacDiff;
+      lhs[ir * n + ic] -= lhsfacAdv + lhsfacDiff;
+    }
+
+    rhs[il] -= qAdv + qDiff;
+    rhs[ir] += qAdv + qDiff;
+  }
+}
+
+/* ---- src/kernel/ScalarDiffElemKernel.C:64-110 ---- */
+static void scalar_diff(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
+                        double *lhs, double *rhs)
+{
+  const int n = 8;
+  double v_scalarQ[8], v_diffFluxCoeff[8];
+  gather(k->scalarQ, 1, nodes, v_scalarQ);
+  gather(k->viscosity, 1, nodes, v_diffFluxCoeff);
+  double v_shape_function_[12][8];
+  scs_shape(0, v_shape_function_);
+  const double(*v_dndx)[8][3] = k->shiftedGradOp ? me->dndx_shifted : me->dndx;
+  const int *lrscv = orc_hex8_lrscv();
+
+  for (int ip = 0; ip < 12; ++ip) {
+    const int il = lrscv[2 * ip];
+    const int ir = lrscv[2 * ip + 1];
+
+    double diffFluxCoeffIp = 0.0;
+    for (int ic = 0; ic < 8; ++ic) diffFluxCoeffIp += v_shape_function_[ip][ic] * v_diffFluxCoeff[ic];
+
+    double qDiff = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      double lhsfacDiff = 0.0;
+      for (int j = 0; j < 3; ++j) lhsfacDiff += -diffFluxCoeffIp * v_dndx[ip][ic][j] * me->scs_areav[ip][j];
+      qDiff += lhsfacDiff * v_scalarQ[ic];
+      lhs[il * n + ic] += lhsfacDiff;
+      lhs[ir * n + ic] -= lhsfacDiff;
+    }
+    rhs[il] -= qDiff;
+    rhs[ir] += qDiff;
+  }
+}
+
+/* ---- src/kernel/MomentumMassElemKernel.C:98-171 (+ setup :88-96) ---- */
+static void momentum_mass(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
+                          double *lhs, double *rhs)
+{
+  const int n = 24;
+  double v_densityNm1[8], v_densityN[8], v_densityNp1[8];
+  double v_velocityNm1[8][3], v_velocityN[8][3], v_velocityNp1[8][3], v_Gpdx[8][3];
+  gather(k->densityNm1, 1, nodes, v_densityNm1);
+  gather(k->densityN, 1, nodes, v_densityN);
+  gather(k->density, 1, nodes, v_densityNp1);
+  gather(k->velocityNm1, 3, nodes, &v_velocityNm1[0][0]);
+  gather(k->velocityN, 3, nodes, &v_velocityN[0][0]);
+  gather(k->velocity, 3, nodes, &v_velocityNp1[0][0]);
+  gather(k->Gpdx, 3, nodes, &v_Gpdx[0][0]);
+  double v_shape_function_[8][8];
+  scv_shape(k->lumpedMass, v_shape_function_);
+  const int *ipNodeMap_ = orc_hex8_scv_ip_node_map();
+  const double gamma1_ = k->gamma1, gamma2_ = k->gamma2, gamma3_ = k->gamma3, dt_ = k->dt;
+  double w_uNm1[3], w_uN[3], w_uNp1[3], w_Gjp[3];
+
+  for (int ip = 0; ip < 8; ++ip) {
+    const int nearestNode = ipNodeMap_[ip];
+
+    double rhoNm1 = 0.0, rhoN = 0.0, rhoNp1 = 0.0;
+    for (int j = 0; j < 3; j++) {
+      w_uNm1[j] = 0.0;
+      w_uN[j] = 0.0;
+      w_uNp1[j] = 0.0;
+      w_Gjp[j] = 0.0;
+    }
+
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      rhoNm1 += r * v_densityNm1[ic];
+      rhoN += r * v_densityN[ic];
+      rhoNp1 += r * v_densityNp1[ic];
+      for (int j = 0; j < 3; j++) {
+        w_uNm1[j] += r * v_velocityNm1[ic][j];
+        w_uN[j] += r * v_velocityN[ic][j];
+        w_uNp1[j] += r * v_velocityNp1[ic][j];
+        w_Gjp[j] += r * v_Gpdx[ic][j];
+      }
+    }
+
+    const double scV = me->scv_volume[ip];
+    const int nnNdim = nearestNode * 3;
+    const double densFac = rhoNp1 * k->densFac + k->om_densFac;
+    for (int j = 0; j < 3; ++j) {
+      rhs[nnNdim + j] += -(gamma1_ * rhoNp1 * w_uNp1[j] + gamma2_ * rhoN * w_uN[j] +
+                           gamma3_ * rhoNm1 * w_uNm1[j]) *
+                             scV / dt_ -
+                         w_Gjp[j] * scV * densFac;
+    }
+
+    for (int ic = 0; ic < 8; ++ic) {
+      const int icNdim = ic * 3;
+      const double r = v_shape_function_[ip][ic];
+      const double lhsfac = r * gamma1_ * rhoNp1 * scV / dt_;
+      for (int j = 0; j < 3; ++j) {
+        const int indexNN = nnNdim + j;
+        lhs[indexNN * n + icNdim + j] += lhsfac;
+      }
+    }
+  }
+}
+
+/* ---- src/kernel/ContinuityMassElemKernel.C:82-119 ---- */
+static void continuity_mass(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
+                            double *lhs, double *rhs)
+{
+  (void)lhs;
+  const double gamma1_ = k->gamma1, gamma2_ = k->gamma2, gamma3_ = k->gamma3, dt_ = k->dt;
+  const double projTimeScale = dt_ / gamma1_;
+  double v_densityNm1[8], v_densityN[8], v_densityNp1[8];
+  gather(k->densityNm1, 1, nodes, v_densityNm1);
+  gather(k->densityN, 1, nodes, v_densityN);
+  gather(k->density, 1, nodes, v_densityNp1);
+  double v_shape_function_[8][8];
+  scv_shape(k->lumpedMass, v_shape_function_);
+  const int *ipNodeMap_ = orc_hex8_scv_ip_node_map();
+
+  for (int ip = 0; ip < 8; ++ip) {
+    const int nearestNode = ipNodeMap_[ip];
+    double rhoNm1 = 0.0, rhoN = 0.0, rhoNp1 = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      rhoNm1 += r * v_densityNm1[ic];
+      rhoN += r * v_densityN[ic];
+      rhoNp1 += r * v_densityNp1[ic];
+    }
+    const double scV = me->scv_volume[ip];
+    rhs[nearestNode] += -(gamma1_ * rhoNp1 + gamma2_ * rhoN + gamma3_ * rhoNm1) * scV / dt_ / projTimeScale;
+  }
+}
+
+/* ---- src/kernel/ScalarMassElemKernel.C:96-156 ---- */
+static void scalar_mass(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
+                        double *lhs, double *rhs)
+{
+  const int n = 8;
+  const double gamma1_ = k->gamma1, gamma2_ = k->gamma2, gamma3_ = k->gamma3, dt_ = k->dt;
+  double v_qNm1[8], v_qN[8], v_qNp1[8], v_rhoNm1[8], v_rhoN[8], v_rhoNp1[8];
+  gather(k->scalarQNm1, 1, nodes, v_qNm1);
+  gather(k->scalarQN, 1, nodes, v_qN);
+  gather(k->scalarQ, 1, nodes, v_qNp1);
+  gather(k->densityNm1, 1, nodes, v_rhoNm1);
+  gather(k->densityN, 1, nodes, v_rhoN);
+  gather(k->density, 1, nodes, v_rhoNp1);
+  double v_shape_function_[8][8];
+  scv_shape(k->lumpedMass, v_shape_function_);
+  const int *ipNodeMap_ = orc_hex8_scv_ip_node_map();
+
+  for (int ip = 0; ip < 8; ++ip) {
+    const int nearestNode = ipNodeMap_[ip];
+    double qNm1Scv = 0.0, qNScv = 0.0, qNp1Scv = 0.0;
+    double rhoNm1Scv = 0.0, rhoNScv = 0.0, rhoNp1Scv = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      qNm1Scv += r * v_qNm1[ic];
+      qNScv += r * v_qN[ic];
+      qNp1Scv += r * v_qNp1[ic];
+      rhoNm1Scv += r * v_rhoNm1[ic];
+      rhoNScv += r * v_rhoN[ic];
+      rhoNp1Scv += r * v_rhoNp1[ic];
+    }
+    const double scV = me->scv_volume[ip];
+    rhs[nearestNode] +=
+        -(gamma1_ * rhoNp1Scv * qNp1Scv + gamma2_ * rhoNScv * qNScv + gamma3_ * rhoNm1Scv * qNm1Scv) * scV / dt_;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      const double lhsfac = r * gamma1_ * rhoNp1Scv * scV / dt_;
+      lhs[nearestNode * n + ic] += lhsfac;
+    }
+  }
+}
+
+/* which ME quantities each kernel registers in its constructor */
+static void me_needs(const orc_kernel_desc *k, int *areav, int *dndx, int *dndxs, int *scv)
+{
+  switch (k->kind) {
+  case ORC_MOMENTUM_ADV_DIFF: /* MomentumAdvDiffElemKernel.C:58-63 */
+  case ORC_SCALAR_ADV_DIFF:   /* ScalarAdvDiffElemKernel.C:57-62   */
+  case ORC_SCALAR_DIFF:
+    *areav = 1;
+    if (k->shiftedGradOp) *dndxs = 1; else *dndx = 1;
+    break;
+  case ORC_CONTINUITY_ADV: /* ContinuityAdvElemKernel.C:59-65 */
+    *areav = 1;
+    if (!k->shiftPoisson || !k->reducedSensitivities) *dndx = 1;
+    if (k->shiftPoisson || k->reducedSensitivities) *dndxs = 1;
+    break;
+  case ORC_MOMENTUM_MASS:
+  case ORC_CONTINUITY_MASS:
+  case ORC_SCALAR_MASS:
+    *scv = 1;
+    break;
+  default:
+    break;
+  }
+}
+
+/* src/AssembleElemSolverAlgorithm.C:74-100 + include/AssembleElemSolverAlgorithm.h:52-105
+ * + fill_master_element_views_new_me (include/ScratchViews.h:476-582), one element */
+void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
+                         const int32_t *elemNodes, int64_t elemIndex, double *lhs, double *rhs)
+{
+  const int rhsSize = 8 * numDof;
+  init_tables();
+  me_views me;
+  memset(&me, 0, sizeof(me));
+  int areav = 0, dndx = 0, dndxs = 0, scv = 0;
+  const double *coordField = NULL;
+  for (int i = 0; i < nk; ++i) {
+    me_needs(&kernels[i], &areav, &dndx, &dndxs, &scv);
+    if (kernels[i].coordinates) coordField = kernels[i].coordinates;
+  }
+  if (coordField) {
+    gather(coordField, 3, elemNodes, &me.coords[0][0]);
+    if (areav) orc_hex8_scs_areav(&me.coords[0][0], &me.scs_areav[0][0]);
+    if (dndx) orc_hex8_scs_grad_op(0, &me.coords[0][0], &me.dndx[0][0][0], &me.deriv[0][0][0]);
+    if (dndxs) orc_hex8_scs_grad_op(1, &me.coords[0][0], &me.dndx_shifted[0][0][0], &me.deriv[0][0][0]);
+    if (scv) orc_hex8_scv_volume(&me.coords[0][0], me.scv_volume);
+  }
+
+  /* set_zero(simdrhs), set_zero(simdlhs) */
+  for (int i = 0; i < rhsSize; ++i) rhs[i] = 0.0;
+  for (int i = 0; i < rhsSize * rhsSize; ++i) lhs[i] = 0.0;
+
+  for (int i = 0; i < nk; ++i) {
+    const orc_kernel_desc *k = &kernels[i];
+    switch (k->kind) {
+    case ORC_MOMENTUM_ADV_DIFF: momentum_adv_diff(k, elemNodes, elemIndex, &me, lhs, rhs); break;
+    case ORC_CONTINUITY_ADV: continuity_adv(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_SCALAR_ADV_DIFF: scalar_adv_diff(k, elemNodes, elemIndex, &me, lhs, rhs); break;
+    case ORC_SCALAR_DIFF: scalar_diff(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_MOMENTUM_MASS: momentum_mass(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_CONTINUITY_MASS: continuity_mass(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_SCALAR_MASS: scalar_mass(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_TEST_FIXED_BLOCK: /* unit_tests/UnitTestTpetra.C:125-139: lhs(i,j) = elemVals[i][j] */
+      for (int q = 0; q < rhsSize * rhsSize; ++q) lhs[q] = k->fixedBlock[q];
+      break;
+    default: break;
+    }
+  }
+}
+
+/* unit_tests/kernels/UnitTestKernelUtils.C:547-628 */
+void orc_calc_mass_flow_rate_scs(int64_t nElem, const int32_t *elemNodes, const double *coords,
+                                 const double *density, const double *velocity, double *mdot)
+{
+  double v_shape_function[12][8];
+  init_tables();
+  scs_shape(0, v_shape_function);
+  for (int64_t e = 0; e < nElem; ++e) {
+    const int32_t *nodes = elemNodes + 8 * e;
+    double c[8][3], v_densityNp1[8], v_velocityNp1[8][3], v_scs_areav[12][3];
+    gather(coords, 3, nodes, &c[0][0]);
+    gather(density, 1, nodes, v_densityNp1);
+    gather(velocity, 3, nodes, &v_velocityNp1[0][0]);
+    orc_hex8_scs_areav(&c[0][0], &v_scs_areav[0][0]);
+    for (int ip = 0; ip < 12; ++ip) {
+      double rhoU[3] = {0.0, 0.0, 0.0};
+      for (int ic = 0; ic < 8; ++ic) {
+        const double r = v_shape_function[ip][ic];
+        for (int j = 0; j < 3; ++j) rhoU[j] += r * v_densityNp1[ic] * v_velocityNp1[ic][j];
+      }
+      double tmdot = 0.0;
+      for (int j = 0; j < 3; j++) tmdot += rhoU[j] * v_scs_areav[ip][j];
+      mdot[12 * e + ip] = tmdot;
+    }
+  }
+}

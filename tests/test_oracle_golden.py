@@ -1,0 +1,149 @@
+"""Pin the CPU oracle against every golden vector the reference's unit tests hold for the
+Hex8 element-assembly path (tests/golden/*.json, extracted verbatim from the reference by
+tests/golden/make_golden.py).  Tolerance 1e-15 abs, as in the reference
+(unit_tests/kernels/UnitTestKernelUtils.h:158-205), except where the reference says otherwise."""
+import numpy as np
+import pytest
+
+import oracle
+from nalu_b200 import mesh
+from golden_io import load_golden, tab
+from nalu_fixtures import LowMachFixture, MixtureFractionFixture
+
+TOL = 1.0e-15
+
+# unit_tests/UnitTestUtils.C:361-372 create_one_perturbed_element(HEXAHEDRON_8): test INPUT
+PERTURBED_HEX8 = np.array([
+    [-0.453578, -0.327867, -0.321027], [0.673626, -0.438218, -0.557809],
+    [0.398767, 0.278356, -0.613672], [-0.511167, 0.656084, -0.510011],
+    [-0.553608, -0.331961, 0.418698], [0.574086, -0.565879, 0.728578],
+    [0.320175, 0.685044, 0.486804], [-0.349545, 0.510239, 0.58944]])
+
+
+def test_momentum_advdiff_gold():
+    g = load_golden("momentum_advdiff")
+    fx = LowMachFixture()
+    fx.calc_mdot(oracle)
+    keep = []
+    d = oracle.make_desc("momentum_adv_diff", keep, coordinates=fx.coords, velocity=fx.velocity,
+                         viscosity=fx.viscosity, massFlowRate=fx.mdot, includeDivU=0.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], 3, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(rhs, tab(g, "hex8_golds::advection_diffusion::rhs"), rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::advection_diffusion::lhs"), rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("variant", ["default", "reduced_sens", "shifted"])
+def test_continuity_adv_gold(variant):
+    g = load_golden("continuity_adv")
+    fx = LowMachFixture()
+    keep = []
+    opts = dict(default=dict(), reduced_sens=dict(reducedSensitivities=1), shifted=dict(shiftPoisson=1))[variant]
+    d = oracle.make_desc("continuity_adv", keep, coordinates=fx.coords, velocity=fx.velocity,
+                         density=fx.density, pressure=fx.pressure, Gpdx=fx.dpdx, dt=1.0, gamma1=1.0, **opts)
+    lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+    ns = "advection_default" if variant == "default" else "advection_reduced_sensitivities"
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=TOL)
+
+
+def test_scalar_advdiff_gold_perturbed():
+    g = load_golden("scalar_advdiff")
+    fx = MixtureFractionFixture(perturb=True)
+    fx.calc_mdot(oracle)
+    keep = []
+    d = oracle.make_desc("scalar_adv_diff", keep, coordinates=fx.coords, scalarQ=fx.mixFraction,
+                         viscosity=fx.viscosity, massFlowRate=fx.mdot)
+    lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(rhs, tab(g, "hex8_golds::advection_diffusion::rhs"), rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::advection_diffusion::lhs"), rtol=0, atol=TOL)
+
+
+def test_scalar_diff_gold():
+    # HeatCondKernelHex8Mesh: thermal conductivity 1.0 (UnitTestKernelUtils.h:446-478)
+    g = load_golden("scalar_diff")
+    fx = LowMachFixture()
+    keep = []
+    temperature = np.cos(fx.coords[:, 0])  # rhs is not checked by the reference test
+    d = oracle.make_desc("scalar_diff", keep, coordinates=fx.coords, scalarQ=temperature,
+                         viscosity=np.ones(8))
+    lhs, _ = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::heatcond::cvfem_diff::lhs"), rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("lumped", [False, True])
+def test_momentum_mass_gold(lumped):
+    g = load_golden("momentum_mass")
+    fx = LowMachFixture()
+    keep = []
+    d = oracle.make_desc("momentum_mass", keep, coordinates=fx.coords, velocity=fx.velocity,
+                         velocityN=fx.velocityN, velocityNm1=fx.velocityN, density=fx.density,
+                         densityN=fx.densityN, densityNm1=fx.densityN, Gpdx=fx.dpdx,
+                         lumpedMass=int(lumped), dt=0.1, gamma1=1.0, gamma2=-1.0, gamma3=0.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], 3, fx.mesh.elem_nodes[0])
+    if not lumped:
+        np.testing.assert_allclose(rhs, tab(g, "hex8_golds::momentum_time_derivative::rhs"), rtol=0, atol=TOL)
+        np.testing.assert_allclose(lhs, tab(g, "hex8_golds::momentum_time_derivative::lhs"), rtol=0, atol=TOL)
+    else:
+        np.testing.assert_allclose(rhs, tab(g, "hex8_golds::momentum_time_derivative_lumped::rhs"), rtol=0, atol=TOL)
+        # UnitTestMomentumMassElem.C:222-232: lumped lhs is 1.25 on the diagonal, 0 elsewhere
+        np.testing.assert_allclose(lhs, 1.25 * np.eye(24), rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("lumped", [False, True])
+def test_continuity_mass_gold(lumped):
+    # unit_tests/kernels/UnitTestContinuityMassElem.C:14-97: rhs == -12.5, lhs == 0
+    fx = LowMachFixture()
+    keep = []
+    d = oracle.make_desc("continuity_mass", keep, coordinates=fx.coords, density=fx.density,
+                         densityN=fx.densityN, densityNm1=fx.densityN, lumpedMass=int(lumped),
+                         dt=0.1, gamma1=1.0, gamma2=-1.0, gamma3=0.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(rhs, -12.5, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=TOL)
+
+
+def test_scv_grad_op_gold_perturbed():
+    # unit_tests/UnitTestKokkosME.C + UnitTestKokkosMEGold.h:13-79, tol 1e-10 (UnitTestUtils.h:67)
+    g = load_golden("kokkos_me_gold")
+    c = PERTURBED_HEX8
+    gop, _, nbad = oracle.scv_grad_op(c, shifted=False)
+    assert nbad == 0
+    np.testing.assert_allclose(gop.ravel(), tab(g, "kokkos_me_gold::hex8_scv_grad_op"), rtol=0, atol=1e-10)
+    gops, _, _ = oracle.scv_grad_op(c, shifted=True)
+    np.testing.assert_allclose(gops.ravel(), tab(g, "kokkos_me_gold::hex8_scv_shifted_grad_op"), rtol=0, atol=1e-10)
+
+
+def test_scv_volumes_unit_cube_and_affine_map():
+    # unit_tests/UnitTestHexSCVDeterminant.C:62-135
+    m = mesh.generated_box(1, 1, 1)
+    c = m.coords[m.elem_nodes[0]]
+    np.testing.assert_allclose(oracle.scv_volume(c), 0.125, rtol=0, atol=1e-15)
+    rng = np.random.default_rng(7)
+    Q = np.eye(3) + 0.3 * rng.standard_normal((3, 3))
+    if np.linalg.det(Q) < 0:
+        Q[:, 0] *= -1
+    assert abs(oracle.hex_volume_grandy(c @ Q.T) - np.linalg.det(Q)) < 1e-13
+    np.testing.assert_allclose(oracle.scv_volume(c @ Q.T).sum(), np.linalg.det(Q), rtol=1e-13)
+
+
+def test_shape_functions_partition_of_unity_and_lumping():
+    for shifted in (False, True):
+        assert np.allclose(oracle.scs_shape_fcn(shifted).sum(axis=1), 1.0, atol=1e-15)
+    # shifted SCV shape functions are the identity (lumped mass), Hex8CVFEM.C:99-107
+    np.testing.assert_allclose(oracle.scv_shape_fcn(True), np.eye(8), rtol=0, atol=0)
+
+
+def test_scs_areav_closed_surface_and_unit_cube():
+    m = mesh.generated_box(1, 1, 1)
+    c = m.coords[m.elem_nodes[0]]
+    a = oracle.scs_areav(c)
+    # each SCS of the unit cube has area 1/4 along its edge direction
+    np.testing.assert_allclose(np.abs(a).sum(axis=1), 0.25, atol=1e-15)
+    lr = [0, 1, 1, 2, 2, 3, 0, 3, 4, 5, 5, 6, 6, 7, 4, 7, 0, 4, 1, 5, 2, 6, 3, 7]
+    for ip in range(12):
+        edge = c[lr[2 * ip + 1]] - c[lr[2 * ip]]
+        assert a[ip] @ edge > 0  # area vector points from left to right node
+
+
+def test_lcg_matches_python_stream():
+    np.testing.assert_array_equal(oracle.lcg_sequence(1, 24), mesh.lcg_stream(1, 24))
