@@ -1,0 +1,248 @@
+/*
+ * nalu_b200.h -- C ABI of the B200-native Hex8 CVFEM element-assembly path.
+ *
+ * One shared library (nalu_b200/libnalu_b200.so) exports exactly these entry points.
+ * Plain pointers and sizes only; no C++/torch types; every function returns an int status
+ * (NALU_B200_OK == 0) and never throws across the boundary.  Device pointers are plain
+ * CUDA device addresses (cudaMalloc, torch.Tensor.data_ptr(), ...); the caller owns every
+ * buffer.  `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ * asynchronous on that stream unless stated otherwise.
+ *
+ * What each entry point replaces in the reference (paths relative to the Nalu tree):
+ *
+ *   nalu_b200_graph_*         TpetraLinearSystem::beginLinearSystemConstruction /
+ *                             buildElemToNodeGraph / finalizeLinearSystem
+ *                             (src/TpetraLinearSystem.C:190-327, 392-420, 1257-1353) and
+ *                             LocalGraphArrays (include/LinearSolver.h:54-120)
+ *   nalu_b200_zero_system     TpetraLinearSystem::zeroSystem (src/TpetraLinearSystem.C:1355-1372)
+ *   nalu_b200_assemble_elem   AssembleElemSolverAlgorithm::execute: gather, master-element
+ *                             views, every registered Kernel::execute, apply_coeff ->
+ *                             TpetraLinearSystem::sumInto
+ *                             (src/AssembleElemSolverAlgorithm.C:74-100,
+ *                              include/AssembleElemSolverAlgorithm.h:52-105,
+ *                              src/ScratchViews.C:408-509, src/kernel/ *ElemKernel.C,
+ *                              src/SolverAlgorithm.C:57-68, src/TpetraLinearSystem.C:1376-1522)
+ *   nalu_b200_assemble_node_mass  AssembleNodeSolverAlgorithm::execute with the
+ *                             {Momentum,Continuity,Scalar}MassBDF2NodeSuppAlg
+ *                             (src/AssembleNodeSolverAlgorithm.C:57-111,
+ *                              src/MomentumMassBDF2NodeSuppAlg.C:80-103)
+ *   nalu_b200_halo_*          TpetraLinearSystem::loadComplete: Export(ADD) of the
+ *                             shared-not-owned rows into the owners' rows
+ *                             (src/TpetraLinearSystem.C:1757-1778)
+ *   nalu_b200_mdot_scs        the mass_flow_rate_scs producer used by the reference's tests
+ *                             (unit_tests/kernels/UnitTestKernelUtils.C:547-628)
+ */
+#ifndef NALU_B200_H
+#define NALU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  NALU_B200_OK = 0,
+  NALU_B200_ERR_ARG = 1,       /* bad argument / unsupported combination            */
+  NALU_B200_ERR_CUDA = 2,      /* a CUDA call failed (see nalu_b200_last_error())   */
+  NALU_B200_ERR_NO_DEVICE = 3, /* no CUDA device: this path has no CPU fallback     */
+  NALU_B200_ERR_STATE = 4,     /* call sequence violated (e.g. finalize before begin)*/
+  NALU_B200_ERR_GEOMETRY = 5   /* non-positive Jacobian determinant detected        */
+};
+
+const char *nalu_b200_last_error(void);
+int nalu_b200_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t nalu_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Kernel descriptors: what the reference's Kernel constructors + setup() capture.       */
+/* ------------------------------------------------------------------------------------ */
+enum nalu_b200_kernel_kind {
+  NALU_K_MOMENTUM_ADV_DIFF = 0, /* src/kernel/MomentumAdvDiffElemKernel.C:70-186 */
+  NALU_K_CONTINUITY_ADV = 1,    /* src/kernel/ContinuityAdvElemKernel.C:86-148   */
+  NALU_K_SCALAR_ADV_DIFF = 2,   /* src/kernel/ScalarAdvDiffElemKernel.C:69-127   */
+  NALU_K_MOMENTUM_MASS = 3,     /* src/kernel/MomentumMassElemKernel.C:98-171    */
+  NALU_K_CONTINUITY_MASS = 4,   /* src/kernel/ContinuityMassElemKernel.C:82-119  */
+  NALU_K_SCALAR_MASS = 5,       /* src/kernel/ScalarMassElemKernel.C:96-156      */
+  NALU_K_SCALAR_DIFF = 6,       /* src/kernel/ScalarDiffElemKernel.C:64-110      */
+  NALU_K_TEST_FIXED_BLOCK = 7,  /* unit_tests/UnitTestTpetra.C:116-144 TestKernel */
+  NALU_K_COUNT = 8
+};
+
+/* option bits (SolutionOptions fields the kernels read) */
+enum {
+  NALU_OPT_SHIFTED_GRAD_OP = 1 << 0, /* get_shifted_grad_op(dofName)                       */
+  NALU_OPT_SKEW_SYMMETRIC = 1 << 1,  /* get_skew_symmetric(dofName): shifted adv shape fn   */
+  NALU_OPT_LUMPED_MASS = 1 << 2,     /* mass kernels: shifted SCV shape fn                  */
+  NALU_OPT_SHIFT_MDOT = 1 << 3,      /* cvfemShiftMdot_                                     */
+  NALU_OPT_SHIFT_POISSON = 1 << 4,   /* get_shifted_grad_op("pressure")                     */
+  NALU_OPT_REDUCED_SENS = 1 << 5     /* cvfemReducedSensPoisson_                            */
+};
+
+/* nodal-field slots of a descriptor; every field is [nNodes][ncomp] doubles, ncomp
+ * contiguous per node (the layout of an STK nodal field), device memory */
+enum nalu_b200_field_slot {
+  NALU_F_COORDINATES = 0, /* 3 */
+  NALU_F_VELOCITY = 1,    /* 3  velocity NP1 (velocity_rtm for continuity with mesh motion) */
+  NALU_F_VELOCITY_N = 2,  /* 3 */
+  NALU_F_VELOCITY_NM1 = 3,/* 3 */
+  NALU_F_VISCOSITY = 4,   /* 1  viscosity / diffFluxCoeff */
+  NALU_F_DENSITY = 5,     /* 1  density NP1 */
+  NALU_F_DENSITY_N = 6,   /* 1 */
+  NALU_F_DENSITY_NM1 = 7, /* 1 */
+  NALU_F_PRESSURE = 8,    /* 1 */
+  NALU_F_DPDX = 9,        /* 3 */
+  NALU_F_SCALARQ = 10,    /* 1  scalarQ NP1 */
+  NALU_F_SCALARQ_N = 11,  /* 1 */
+  NALU_F_SCALARQ_NM1 = 12,/* 1 */
+  NALU_F_DUAL_VOLUME = 13,/* 1  dual_nodal_volume (node mass algorithms only) */
+  NALU_F_COUNT = 16
+};
+
+typedef struct nalu_b200_kernel_desc {
+  int32_t kind;    /* nalu_b200_kernel_kind */
+  int32_t options; /* NALU_OPT_* bits */
+  double include_divu;          /* SolutionOptions::includeDivU_                     */
+  double dens_fac, om_dens_fac; /* balancedForce_ ? (1,0) : (0,1)                    */
+  double dt, gamma1, gamma2, gamma3; /* Kernel::setup(TimeIntegrator)                */
+  const double *nodal[NALU_F_COUNT]; /* device pointers, NULL when unused            */
+  const double *mass_flow_rate;      /* device [nElem][12], mass_flow_rate_scs       */
+  const double *fixed_block;         /* device [rhsSize*rhsSize], NALU_K_TEST_FIXED_BLOCK */
+} nalu_b200_kernel_desc;
+
+/* ------------------------------------------------------------------------------------ */
+/* Graph: DOF numbering + CSR graph, built once per mesh.                                */
+/* ------------------------------------------------------------------------------------ */
+typedef struct nalu_b200_graph nalu_b200_graph; /* opaque, host + device resident */
+
+/* Local mesh of this rank (host pointers, copied): nodes carry the 1-based naluGlobalId
+ * (periodic subjects alias their monarch's id) and the owning rank; all elements are
+ * locally owned.  box_n{x,y,z} > 0 declares that the nodes are the lexicographic
+ * (x fastest) numbering of an nx*ny*nz-element structured block with Ioss `generated:`
+ * connectivity, which enables the tiled write-once kernel; pass 0,0,0 otherwise. */
+int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof,
+                           int32_t n_nodes, const int64_t *node_gid, const int32_t *node_owner,
+                           int64_t n_elems, const int32_t *elem_nodes,
+                           int32_t box_nx, int32_t box_ny, int32_t box_nz);
+void nalu_b200_graph_destroy(nalu_b200_graph *g);
+
+/* Neighbour handshake (TpetraLinearSystem.C:678-738,924-952).  After create(), for every
+ * rank p != rank: query the byte size of the message for p, fetch it, exchange the messages
+ * with whatever transport the host has (MPI, torch.distributed, ...), and hand the received
+ * ones back.  Single-rank jobs skip straight to finalize. */
+int nalu_b200_graph_send_size(const nalu_b200_graph *g, int32_t dest_rank, int64_t *nbytes);
+int nalu_b200_graph_send_data(const nalu_b200_graph *g, int32_t dest_rank, void *buf);
+int nalu_b200_graph_recv_data(nalu_b200_graph *g, int32_t src_rank, const void *buf, int64_t nbytes);
+/* builds the owned and shared-not-owned CSR graphs, uploads them and the scatter maps */
+int nalu_b200_graph_finalize(nalu_b200_graph *g);
+/* same graph construction without touching a device: lets host-only tools (and the CPU test
+ * suite) inspect the graph; such a graph cannot be assembled into */
+int nalu_b200_graph_finalize_host_only(nalu_b200_graph *g);
+
+typedef struct nalu_b200_graph_info {
+  int32_t num_dof;
+  int32_t n_owned_rows, n_shared_rows; /* dof rows: maxOwnedRowId_, numSharedNotOwned*numDof */
+  int32_t n_cols;                      /* size of the column map (totalColsMap_)              */
+  int64_t nnz_owned, nnz_shared;
+  int64_t n_elems;
+  int32_t n_nodes;
+  int32_t is_box;
+} nalu_b200_graph_info;
+int nalu_b200_graph_get_info(const nalu_b200_graph *g, nalu_b200_graph_info *info);
+
+/* Host copies for parity checks / hand-off (caller-allocated; `shared` selects the
+ * shared-not-owned graph).  rowptr is size_t like the reference's (n_rows+1 entries,
+ * starting at 0 for each graph), colidx is int32 local column ids. */
+int nalu_b200_graph_copy_rowptr(const nalu_b200_graph *g, int shared, uint64_t *rowptr);
+int nalu_b200_graph_copy_colidx(const nalu_b200_graph *g, int shared, int32_t *colidx);
+int nalu_b200_graph_copy_row_gids(const nalu_b200_graph *g, int shared, int64_t *gids);
+int nalu_b200_graph_copy_col_gids(const nalu_b200_graph *g, int64_t *gids);
+/* entityToLID_ / entityToColLID_ for the local nodes */
+int nalu_b200_graph_copy_node_lids(const nalu_b200_graph *g, int32_t *row_lid, int32_t *col_lid);
+/* device-resident graph arrays (for a device solver): owned graph */
+int nalu_b200_graph_device_ptrs(const nalu_b200_graph *g, int shared, const uint64_t **d_rowptr,
+                                const int32_t **d_colidx);
+
+/* ------------------------------------------------------------------------------------ */
+/* Matrix / RHS storage.  `values` holds nnz_owned + nnz_shared doubles (owned CSR values */
+/* first, shared-not-owned after), `rhs` holds n_owned_rows + n_shared_rows doubles.      */
+/* ------------------------------------------------------------------------------------ */
+int nalu_b200_zero_system(const nalu_b200_graph *g, double *d_values, double *d_rhs, void *stream);
+
+enum {
+  NALU_ASSEMBLE_AUTO = 0,    /* tiled write-once kernel when the mesh is a box and the kernel
+                                list is supported by it, else the general kernel            */
+  NALU_ASSEMBLE_GENERAL = 1, /* any Hex8 mesh, any kernel list: accumulates (sumInto) into a
+                                zeroed or partially assembled system                        */
+  NALU_ASSEMBLE_BOX = 2      /* force the tiled kernel (error if unsupported)               */
+};
+/* AssembleElemSolverAlgorithm::execute for all locally-owned elements.
+ * `overwrite` != 0 tells the tiled kernel that the system holds no earlier contributions,
+ * so it may store instead of add (zero_system is then unnecessary for the matrix values and
+ * RHS rows it covers).  The general kernel always adds. */
+int nalu_b200_assemble_elem(const nalu_b200_graph *g, const nalu_b200_kernel_desc *kernels,
+                            int32_t n_kernels, double *d_values, double *d_rhs, int32_t mode,
+                            int32_t overwrite, void *stream);
+/* which kernel family the last nalu_b200_assemble_elem call used: 1 general, 2 box */
+int nalu_b200_last_assemble_mode(void);
+/* synchronises, then reports (and clears) the device flag raised when an element had a
+ * non-positive Jacobian determinant -- the reference asserts on this in debug builds
+ * (include/master_element/MasterElementFunctions.h:91-94) */
+int nalu_b200_geometry_errors(const nalu_b200_graph *g, int32_t *flag);
+
+/* AssembleNodeSolverAlgorithm::execute with the mass BDF2/backward-Euler node algorithms;
+ * `k` uses kind NALU_K_{MOMENTUM,CONTINUITY,SCALAR}_MASS and NALU_F_DUAL_VOLUME. */
+int nalu_b200_assemble_node_mass(const nalu_b200_graph *g, const nalu_b200_kernel_desc *k,
+                                 double *d_values, double *d_rhs, void *stream);
+
+/* calc_mass_flow_rate_scs: d_mdot[nElem][12] from coordinates, density, velocity */
+int nalu_b200_mdot_scs(const nalu_b200_graph *g, const double *d_coords, const double *d_density,
+                       const double *d_velocity, double *d_mdot, void *stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* loadComplete: shared-not-owned rows -> owners, ADD.                                   */
+/* ------------------------------------------------------------------------------------ */
+/* Per neighbour the exchange is a flat array of doubles: for each of my shared-not-owned
+ * dof rows owned by `peer` (ascending gid) its CSR values followed, after all rows, by the
+ * rows' RHS entries.  The owner adds them through a map built during the graph handshake. */
+int nalu_b200_halo_num_peers(const nalu_b200_graph *g, int32_t *n_send_peers, int32_t *n_recv_peers);
+int nalu_b200_halo_send_peer(const nalu_b200_graph *g, int32_t i, int32_t *peer_rank, int64_t *n_doubles);
+int nalu_b200_halo_recv_peer(const nalu_b200_graph *g, int32_t i, int32_t *peer_rank, int64_t *n_doubles);
+/* pack my shared rows for send-peer i into d_buf (contiguous copy: the shared rows of one
+ * owner are contiguous in `values` except for the RHS tail) */
+int nalu_b200_halo_pack(const nalu_b200_graph *g, int32_t i, const double *d_values,
+                        const double *d_rhs, double *d_buf, void *stream);
+/* owner side: add the doubles received from recv-peer i (device buffer, which may be a
+ * peer-GPU pointer mapped through CUDA IPC / P2P: the kernel then reads straight across
+ * NVLink) into my owned rows */
+int nalu_b200_halo_unpack_add(const nalu_b200_graph *g, int32_t i, const double *d_buf,
+                              double *d_values, double *d_rhs, void *stream);
+/* owner side, fused: read recv-peer i's shared rows directly out of the peer's arrays and add
+ * them -- no pack, no staging buffer.  d_peer_values / d_peer_rhs are peer device pointers to the
+ * START OF THE PEER'S SHARED-NOT-OWNED BLOCK (its values + nnz_owned, its rhs + n_owned_rows) */
+int nalu_b200_halo_pull_add(const nalu_b200_graph *g, int32_t i, const double *d_peer_values,
+                            const double *d_peer_rhs, double *d_values, double *d_rhs,
+                            void *stream);
+/* the handshake also tells each owner where recv-peer i's rows start inside the peer's
+ * values / rhs arrays (element offsets), needed by halo_pull_add */
+int nalu_b200_halo_peer_offsets(const nalu_b200_graph *g, int32_t i, int64_t *values_offset,
+                                int64_t *rhs_offset);
+
+/* CUDA IPC helpers so that separate processes (one per GPU) can map each other's buffers */
+int nalu_b200_ipc_get_handle(const void *d_ptr, void *handle64 /* 64 bytes */);
+int nalu_b200_ipc_open_handle(const void *handle64, void **d_ptr);
+int nalu_b200_ipc_close(void *d_ptr);
+
+/* device memory helpers (the C++ host layer owns its CSR storage through these) */
+int nalu_b200_malloc(void **d_ptr, size_t nbytes);
+int nalu_b200_free(void *d_ptr);
+int nalu_b200_memcpy_h2d(void *d_dst, const void *h_src, size_t nbytes, void *stream);
+int nalu_b200_memcpy_d2h(void *h_dst, const void *d_src, size_t nbytes, void *stream);
+int nalu_b200_stream_sync(void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NALU_B200_H */

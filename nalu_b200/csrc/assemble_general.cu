@@ -1,0 +1,264 @@
+// assemble_general.cu -- general Hex8 element assembly: any connectivity, any kernel list.
+//
+// One warp per element (grid-stride), element lhs/rhs in the warp's shared-memory scratch
+// (general_elem.cuh), then the sumInto step: every lhs entry goes straight to its CSR slot
+// through the per-element slot map built with the graph, as a double atomicAdd -- the
+// device analogue of TpetraLinearSystem::sumInto's sorted row merge
+// (src/TpetraLinearSystem.C:1376-1522), with the sort and the linear column search replaced
+// by the precomputed map.  This is the fallback for unstructured meshes and for kernel lists
+// the tiled kernel (assemble_box.cu) does not cover; it always accumulates.
+#include "general_elem.cuh"
+#include "internal.h"
+
+namespace nalu_b200 {
+
+struct GeneralParams {
+  long long n_elems;
+  const int *elem_nodes;
+  const int *node_row;
+  const long long *browptr;
+  const unsigned char *elem_slot;
+  double *values;
+  double *rhs;
+  int *err;
+  int nk;
+  nalu_b200_kernel_desc k[kMaxKernels];
+};
+
+constexpr int kWarpsPerCta = 4;
+
+template <int NDOF>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) assemble_general_kernel(const __grid_constant__ GeneralParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ElemScratch<NDOF> *all = reinterpret_cast<ElemScratch<NDOF> *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ElemScratch<NDOF> &ws = all[warp];
+  constexpr int R = 8 * NDOF;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerCta + warp;
+  const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+
+  MeNeeds need = {0, 0, 0, 0};
+  const double *coord_field = nullptr;
+  for (int i = 0; i < p.nk; ++i) {
+    me_needs_of(p.k[i], need);
+    if (p.k[i].nodal[NALU_F_COORDINATES]) coord_field = p.k[i].nodal[NALU_F_COORDINATES];
+  }
+
+  for (long long e = warp0; e < p.n_elems; e += nwarps) {
+    if (lane < 8) {
+      const int node = p.elem_nodes[e * 8 + lane];
+      const int rn = p.node_row[node];
+      const long long b0 = p.browptr[rn], b1 = p.browptr[rn + 1];
+      ws.nodes[lane] = node;
+      ws.rownode[lane] = rn;
+      ws.rownb[lane] = (int)(b1 - b0);
+      ws.rowbase[lane] = (long long)NDOF * NDOF * b0;
+      if (coord_field) {
+        ws.coords[lane][0] = coord_field[(size_t)node * 3 + 0];
+        ws.coords[lane][1] = coord_field[(size_t)node * 3 + 1];
+        ws.coords[lane][2] = coord_field[(size_t)node * 3 + 2];
+      }
+    }
+    if (lane == 0) ws.bad_det = 0;
+    for (int q = lane; q < R * R; q += 32) ws.lhs[q] = 0.0; // set_zero(simdlhs)
+    if (lane < R) ws.rhs[lane] = 0.0;                        // set_zero(simdrhs)
+    __syncwarp();
+    stage_geometry(lane, ws, need);
+    __syncwarp();
+    for (int i = 0; i < p.nk; ++i) {
+      const nalu_b200_kernel_desc &k = p.k[i];
+      stage_gather(lane, ws, k);
+      __syncwarp();
+      stage_ip(lane, ws, k, e);
+      __syncwarp();
+      stage_lhs(lane, ws, k);
+      stage_rhs(lane, ws, k);
+      __syncwarp();
+    }
+    if (lane == 0 && ws.bad_det) atomicExch(p.err, 1);
+    // sumInto: lhs[r][c] -> values[rowbase(k) + i*nb*NDOF + slot(k,ic)*NDOF + j]
+    const unsigned char *slots = p.elem_slot + e * 64;
+    for (int q = lane; q < R * R; q += 32) {
+      const double v = ws.lhs[q];
+      if (v == 0.0) continue;
+      const int r = q / R, c = q - r * R;
+      const int kn = r / NDOF, i = r - kn * NDOF;
+      const int ic = c / NDOF, j = c - ic * NDOF;
+      const int slot = slots[kn * 8 + ic];
+      const long long pos = ws.rowbase[kn] + (long long)i * ws.rownb[kn] * NDOF + slot * NDOF + j;
+      atomicAdd(p.values + pos, v);
+    }
+    if (lane < R) {
+      const double v = ws.rhs[lane];
+      if (v != 0.0) atomicAdd(p.rhs + (long long)ws.rownode[lane / NDOF] * NDOF + lane % NDOF, v);
+    }
+    __syncwarp();
+  }
+}
+
+int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
+                            double *d_rhs, cudaStream_t stream)
+{
+  if (nk < 1 || nk > kMaxKernels) {
+    set_error("assemble_elem: between 1 and 8 kernels per algorithm");
+    return NALU_B200_ERR_ARG;
+  }
+  GeneralParams p;
+  p.n_elems = g.n_elems;
+  p.elem_nodes = g.d_elem_nodes;
+  p.node_row = g.d_node_row;
+  p.browptr = (const long long *)g.d_browptr;
+  p.elem_slot = g.d_elem_slot;
+  p.values = d_values;
+  p.rhs = d_rhs;
+  p.err = g.d_err;
+  p.nk = nk;
+  bool need_coords = false;
+  for (int i = 0; i < nk; ++i) {
+    p.k[i] = kernels[i];
+    const int kind = kernels[i].kind;
+    if (kind < 0 || kind >= NALU_K_COUNT) {
+      set_error("assemble_elem: unknown kernel kind");
+      return NALU_B200_ERR_ARG;
+    }
+    const bool vec = kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_MASS;
+    if (kind != NALU_K_TEST_FIXED_BLOCK) {
+      need_coords = true;
+      if ((vec && g.ndof != 3) || (!vec && g.ndof != 1)) {
+        set_error("assemble_elem: kernel kind does not match the linear system's numDof");
+        return NALU_B200_ERR_ARG;
+      }
+      if (!kernels[i].nodal[NALU_F_COORDINATES]) {
+        set_error("assemble_elem: coordinates field missing (add_coordinates_field must precede master element calls)");
+        return NALU_B200_ERR_ARG;
+      }
+    }
+  }
+  (void)need_coords;
+  if (g.n_elems == 0) return NALU_B200_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (g.ndof == 3) {
+    const size_t smem = sizeof(ElemScratch<3>) * kWarpsPerCta;
+    NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = (g.n_elems + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ctas > (long long)sms * 16) ctas = (long long)sms * 16;
+    assemble_general_kernel<3><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+  } else if (g.ndof == 1) {
+    const size_t smem = sizeof(ElemScratch<1>) * kWarpsPerCta;
+    NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = (g.n_elems + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ctas > (long long)sms * 16) ctas = (long long)sms * 16;
+    assemble_general_kernel<1><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+  } else {
+    set_error("assemble_elem: numDof must be 1 or 3");
+    return NALU_B200_ERR_ARG;
+  }
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+// ---- node mass algorithms ----------------------------------------------------------------
+// AssembleNodeSolverAlgorithm::execute (src/AssembleNodeSolverAlgorithm.C:57-111) with
+// {Momentum,Continuity,Scalar}MassBDF2NodeSuppAlg::node_execute; one thread per local node,
+// locally-owned nodes only; the 1-node sumInto targets the diagonal block of the node's row.
+__global__ void node_mass_kernel(int n_nodes, int n_owned_nodes, int ndof, const int *node_row,
+                                 const long long *browptr, const int *bcol, nalu_b200_kernel_desc k,
+                                 double *values, double *rhs)
+{
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_nodes) return;
+  const int rn = node_row[node];
+  if (rn >= n_owned_nodes) return; // not locally owned
+  const long long b0 = browptr[rn], b1 = browptr[rn + 1];
+  // diagonal block: column rn (binary search, rows are sorted)
+  long long lo = b0, hi = b1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (bcol[mid] < rn) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= b1 || bcol[lo] != rn) return;
+  const int slot = (int)(lo - b0), nb = (int)(b1 - b0);
+  const double dualVolume = k.nodal[NALU_F_DUAL_VOLUME][node];
+  const double rhoNm1 = k.nodal[NALU_F_DENSITY_NM1][node], rhoN = k.nodal[NALU_F_DENSITY_N][node],
+               rhoNp1 = k.nodal[NALU_F_DENSITY][node];
+  const long long base = (long long)ndof * ndof * b0;
+  if (k.kind == NALU_K_MOMENTUM_MASS) {
+    const double lhsfac = k.gamma1 * rhoNp1 * dualVolume / k.dt;
+    for (int i = 0; i < 3; ++i) {
+      const double uNm1 = k.nodal[NALU_F_VELOCITY_NM1][(size_t)node * 3 + i], uN = k.nodal[NALU_F_VELOCITY_N][(size_t)node * 3 + i],
+                   uNp1 = k.nodal[NALU_F_VELOCITY][(size_t)node * 3 + i], dpdx = k.nodal[NALU_F_DPDX][(size_t)node * 3 + i];
+      const double r = -(k.gamma1 * rhoNp1 * uNp1 + k.gamma2 * rhoN * uN + k.gamma3 * rhoNm1 * uNm1) * dualVolume / k.dt -
+                       dpdx * dualVolume;
+      atomicAdd(rhs + (long long)rn * 3 + i, r);
+      atomicAdd(values + base + (long long)i * nb * 3 + slot * 3 + i, lhsfac);
+    }
+  } else if (k.kind == NALU_K_CONTINUITY_MASS) {
+    const double tau = k.dt / k.gamma1;
+    atomicAdd(rhs + rn, -(k.gamma1 * rhoNp1 + k.gamma2 * rhoN + k.gamma3 * rhoNm1) * dualVolume / k.dt / tau);
+  } else {
+    const double qNm1 = k.nodal[NALU_F_SCALARQ_NM1][node], qN = k.nodal[NALU_F_SCALARQ_N][node], qNp1 = k.nodal[NALU_F_SCALARQ][node];
+    atomicAdd(rhs + rn, -(k.gamma1 * rhoNp1 * qNp1 + k.gamma2 * qN * rhoN + k.gamma3 * qNm1 * rhoNm1) * dualVolume / k.dt);
+    atomicAdd(values + base + slot, k.gamma1 * rhoNp1 * dualVolume / k.dt);
+  }
+}
+
+int launch_node_mass(const Graph &g, const nalu_b200_kernel_desc &k, double *d_values, double *d_rhs, cudaStream_t stream)
+{
+  const bool vec = k.kind == NALU_K_MOMENTUM_MASS;
+  if (!(k.kind == NALU_K_MOMENTUM_MASS || k.kind == NALU_K_CONTINUITY_MASS || k.kind == NALU_K_SCALAR_MASS) ||
+      (vec ? g.ndof != 3 : g.ndof != 1) || !k.nodal[NALU_F_DUAL_VOLUME]) {
+    set_error("assemble_node_mass: needs a mass kernel kind matching numDof and the dual_nodal_volume field");
+    return NALU_B200_ERR_ARG;
+  }
+  if (g.n_nodes == 0) return NALU_B200_OK;
+  node_mass_kernel<<<(g.n_nodes + 255) / 256, 256, 0, stream>>>(g.n_nodes, g.n_owned_nodes, g.ndof, g.d_node_row,
+                                                               (const long long *)g.d_browptr, g.d_bcol, k, d_values, d_rhs);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+// ---- mass_flow_rate_scs producer (unit_tests/kernels/UnitTestKernelUtils.C:547-628) --------
+__global__ void mdot_kernel(long long n_elems, const int *elem_nodes, const double *coords, const double *density,
+                            const double *velocity, double *mdot)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = t / 12;
+  const int ip = (int)(t - e * 12);
+  if (e >= n_elems) return;
+  double c[8][3], ru[8][3];
+  for (int n = 0; n < 8; ++n) {
+    const int node = elem_nodes[e * 8 + n];
+    const double rho = density[node];
+    for (int d = 0; d < 3; ++d) {
+      c[n][d] = coords[(size_t)node * 3 + d];
+      ru[n][d] = rho * velocity[(size_t)node * 3 + d];
+    }
+  }
+  double a[3], s1, s2, s3;
+  hex8::scs_areav_ip(c, ip, a);
+  hex8::scs_intg_loc(ip, 0.25, s1, s2, s3);
+  double rhoU[3] = {0, 0, 0};
+  for (int n = 0; n < 8; ++n) {
+    const double r = hex8::shape_fcn(n, s1, s2, s3);
+    for (int d = 0; d < 3; ++d) rhoU[d] += r * ru[n][d];
+  }
+  mdot[e * 12 + ip] = rhoU[0] * a[0] + rhoU[1] * a[1] + rhoU[2] * a[2];
+}
+
+int launch_mdot(const Graph &g, const double *coords, const double *density, const double *velocity, double *mdot,
+                cudaStream_t stream)
+{
+  if (g.n_elems == 0) return NALU_B200_OK;
+  const long long nt = g.n_elems * 12;
+  mdot_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, stream>>>(g.n_elems, g.d_elem_nodes, coords, density, velocity, mdot);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+} // namespace nalu_b200

@@ -1,0 +1,362 @@
+// general_elem.cuh -- one Hex8 element through every registered kernel, warp-cooperatively.
+//
+// This is the general (any mesh, any kernel list) form of what the reference does per SIMD
+// lane in AssembleElemSolverAlgorithm::execute (src/AssembleElemSolverAlgorithm.C:74-100):
+// gather, master-element views, zero lhs/rhs, run each Kernel::execute in registration
+// order, hand lhs/rhs to sumInto.  One warp owns one element; the element's lhs/rhs and
+// master-element views live in that warp's shared-memory scratch.  Work is split into
+// stages separated by warp barriers; inside a stage each lane writes only locations it owns
+// (an integration point, a matrix column, or a matrix row), so no atomics are needed on
+// shared memory.  The stage functions take the lane as an argument so that the very same
+// code is executed lane-by-lane on the CPU by tests/cpu_harness (no GPU needed to check the
+// arithmetic against the oracle).
+#pragma once
+#include "../../include/nalu_b200.h"
+#include "hex8_dev.cuh"
+
+namespace nalu_b200 {
+
+struct MeNeeds {
+  int areav, dndx, dndx_shifted, scv_volume;
+};
+
+// which master-element views the kernel constructors request
+// (e.g. src/kernel/MomentumAdvDiffElemKernel.C:58-63, ContinuityAdvElemKernel.C:59-65)
+__host__ __device__ inline void me_needs_of(const nalu_b200_kernel_desc &k, MeNeeds &m)
+{
+  switch (k.kind) {
+  case NALU_K_MOMENTUM_ADV_DIFF:
+  case NALU_K_SCALAR_ADV_DIFF:
+  case NALU_K_SCALAR_DIFF:
+    m.areav = 1;
+    if (k.options & NALU_OPT_SHIFTED_GRAD_OP) m.dndx_shifted = 1; else m.dndx = 1;
+    break;
+  case NALU_K_CONTINUITY_ADV: {
+    const bool sp = k.options & NALU_OPT_SHIFT_POISSON, rs = k.options & NALU_OPT_REDUCED_SENS;
+    m.areav = 1;
+    if (!sp || !rs) m.dndx = 1;
+    if (sp || rs) m.dndx_shifted = 1;
+    break;
+  }
+  case NALU_K_MOMENTUM_MASS:
+  case NALU_K_CONTINUITY_MASS:
+  case NALU_K_SCALAR_MASS:
+    m.scv_volume = 1;
+    break;
+  default:
+    break;
+  }
+}
+
+// per-warp scratch (doubles unless noted)
+template <int NDOF>
+struct ElemScratch {
+  static constexpr int R = 8 * NDOF;
+  double coords[8][3];
+  double areav[12][3];
+  double dndx[12][8][3];
+  double dndxs[12][8][3];
+  double scv[8];
+  double fld[8][16];  // gathered nodal fields of the kernel currently running
+  double ipd[12][8];  // per-integration-point results passed between stages
+  double rhs[R];
+  double lhs[R * R];
+  long long rowbase[8]; // values offset of dof-row 0 of each element node's row
+  int rownb[8];         // blocks in that row
+  int rownode[8];
+  int nodes[8];
+  int bad_det;
+};
+
+// ---- stage: geometry --------------------------------------------------------------------
+template <int NDOF>
+__host__ __device__ inline void stage_geometry(int lane, ElemScratch<NDOF> &ws, const MeNeeds &need)
+{
+  if (lane < 12) {
+    const int ip = lane;
+    if (need.areav) hex8::scs_areav_ip(ws.coords, ip, ws.areav[ip]);
+    double s1, s2, s3;
+    if (need.dndx) {
+      hex8::scs_intg_loc(ip, 0.25, s1, s2, s3);
+      const double det = hex8::grad_op_ip(ws.coords, s1, s2, s3, ws.dndx[ip]);
+      if (!(det > 0.0)) ws.bad_det = 1;
+    }
+    if (need.dndx_shifted) {
+      hex8::scs_intg_loc(ip, 0.5, s1, s2, s3);
+      const double det = hex8::grad_op_ip(ws.coords, s1, s2, s3, ws.dndxs[ip]);
+      if (!(det > 0.0)) ws.bad_det = 1;
+    }
+  } else if (lane >= 16 && lane < 24 && need.scv_volume) {
+    ws.scv[lane - 16] = hex8::scv_volume_ip(ws.coords, lane - 16);
+  }
+}
+
+// ---- field gather: slot list per kernel kind ---------------------------------------------
+// fld[n][..] layout per kind (component offsets)
+enum { F_U = 0, F_MU = 3, F_RHO = 4, F_P = 5, F_GP = 6, F_Q = 9 };             // SCS kernels
+enum { M_UNP1 = 0, M_UN = 3, M_UNM1 = 6, M_GP = 9, M_RNP1 = 12, M_RN = 13, M_RNM1 = 14 }; // momentum mass
+enum { S_QNP1 = 0, S_QN = 1, S_QNM1 = 2, S_RNP1 = 3, S_RN = 4, S_RNM1 = 5 };  // scalar / continuity mass
+
+__host__ __device__ inline void gather_one(double *dst, const double *field, int ncomp, int node)
+{
+  for (int j = 0; j < ncomp; ++j) dst[j] = field[(size_t)node * ncomp + j];
+}
+
+template <int NDOF>
+__host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, const nalu_b200_kernel_desc &k)
+{
+  if (lane >= 8) return;
+  const int n = lane, node = ws.nodes[n];
+  double *f = ws.fld[n];
+  switch (k.kind) {
+  case NALU_K_MOMENTUM_ADV_DIFF:
+    gather_one(f + F_U, k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + F_MU, k.nodal[NALU_F_VISCOSITY], 1, node);
+    break;
+  case NALU_K_CONTINUITY_ADV:
+    gather_one(f + F_U, k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + F_RHO, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + F_P, k.nodal[NALU_F_PRESSURE], 1, node);
+    gather_one(f + F_GP, k.nodal[NALU_F_DPDX], 3, node);
+    break;
+  case NALU_K_SCALAR_ADV_DIFF:
+  case NALU_K_SCALAR_DIFF:
+    gather_one(f + F_Q, k.nodal[NALU_F_SCALARQ], 1, node);
+    gather_one(f + F_MU, k.nodal[NALU_F_VISCOSITY], 1, node);
+    break;
+  case NALU_K_MOMENTUM_MASS:
+    gather_one(f + M_UNP1, k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + M_UN, k.nodal[NALU_F_VELOCITY_N], 3, node);
+    gather_one(f + M_UNM1, k.nodal[NALU_F_VELOCITY_NM1], 3, node);
+    gather_one(f + M_GP, k.nodal[NALU_F_DPDX], 3, node);
+    gather_one(f + M_RNP1, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + M_RN, k.nodal[NALU_F_DENSITY_N], 1, node);
+    gather_one(f + M_RNM1, k.nodal[NALU_F_DENSITY_NM1], 1, node);
+    break;
+  case NALU_K_SCALAR_MASS:
+    gather_one(f + S_QNP1, k.nodal[NALU_F_SCALARQ], 1, node);
+    gather_one(f + S_QN, k.nodal[NALU_F_SCALARQ_N], 1, node);
+    gather_one(f + S_QNM1, k.nodal[NALU_F_SCALARQ_NM1], 1, node);
+    // fallthrough: densities
+  case NALU_K_CONTINUITY_MASS:
+    gather_one(f + S_RNP1, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + S_RN, k.nodal[NALU_F_DENSITY_N], 1, node);
+    gather_one(f + S_RNM1, k.nodal[NALU_F_DENSITY_NM1], 1, node);
+    break;
+  default:
+    break;
+  }
+}
+
+// ---- stage A: per integration point quantities (lane = ip) --------------------------------
+template <int NDOF>
+__host__ __device__ inline void stage_ip(int lane, ElemScratch<NDOF> &ws, const nalu_b200_kernel_desc &k,
+                                         long long elem)
+{
+  const int kind = k.kind;
+  if (kind == NALU_K_MOMENTUM_MASS || kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS ||
+      kind == NALU_K_TEST_FIXED_BLOCK)
+    return;
+  if (lane >= 12) return;
+  const int ip = lane;
+  double s1, s2, s3;
+  hex8::scs_intg_loc(ip, 0.25, s1, s2, s3);
+  const double (*A) = ws.areav[ip];
+
+  if (kind == NALU_K_MOMENTUM_ADV_DIFF) {
+    // MomentumAdvDiffElemKernel.C:102-136 and the rhs part of :138-184
+    const double (*g)[3] = (k.options & NALU_OPT_SHIFTED_GRAD_OP) ? ws.dndxs[ip] : ws.dndx[ip];
+    double a1 = s1, a2 = s2, a3 = s3; // advection shape function location
+    if (k.options & NALU_OPT_SKEW_SYMMETRIC) hex8::scs_intg_loc(ip, 0.5, a1, a2, a3);
+    const double tmdot = k.mass_flow_rate[elem * 12 + ip];
+    double mu = 0.0, divU = 0.0, u[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, s1, s2, s3), ra = hex8::shape_fcn(ic, a1, a2, a3);
+      mu += r * ws.fld[ic][F_MU];
+      for (int j = 0; j < 3; ++j) {
+        u[j] += ra * ws.fld[ic][F_U + j];
+        divU += ws.fld[ic][F_U + j] * g[ic][j];
+      }
+    }
+    double flux[3];
+    for (int i = 0; i < 3; ++i) flux[i] = tmdot * u[i] + 2.0 / 3.0 * mu * divU * A[i] * k.include_divu;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double *uc = &ws.fld[ic][F_U];
+      const double gA = g[ic][0] * A[0] + g[ic][1] * A[1] + g[ic][2] * A[2];
+      const double uA = uc[0] * A[0] + uc[1] * A[1] + uc[2] * A[2];
+      for (int i = 0; i < 3; ++i) flux[i] += -mu * (g[ic][i] * uA + gA * uc[i]);
+    }
+    ws.ipd[ip][0] = mu;
+    ws.ipd[ip][1] = flux[0];
+    ws.ipd[ip][2] = flux[1];
+    ws.ipd[ip][3] = flux[2];
+    ws.ipd[ip][4] = tmdot;
+  } else if (kind == NALU_K_CONTINUITY_ADV) {
+    // ContinuityAdvElemKernel.C:110-147
+    const bool sp = k.options & NALU_OPT_SHIFT_POISSON;
+    const double (*g)[3] = sp ? ws.dndxs[ip] : ws.dndx[ip];
+    double m1 = s1, m2 = s2, m3 = s3;
+    if (k.options & NALU_OPT_SHIFT_MDOT) hex8::scs_intg_loc(ip, 0.5, m1, m2, m3);
+    const double tau = k.dt / k.gamma1;
+    double rhoU[3] = {0, 0, 0}, Gp[3] = {0, 0, 0}, dpdx[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, m1, m2, m3);
+      const double p = ws.fld[ic][F_P], rho = ws.fld[ic][F_RHO];
+      for (int j = 0; j < 3; ++j) {
+        Gp[j] += r * ws.fld[ic][F_GP + j];
+        rhoU[j] += r * rho * ws.fld[ic][F_U + j];
+        dpdx[j] += g[ic][j] * p;
+      }
+    }
+    double mdot = 0.0;
+    for (int j = 0; j < 3; ++j) mdot += (rhoU[j] - tau * (dpdx[j] - Gp[j])) * A[j];
+    ws.ipd[ip][0] = mdot / tau;
+  } else { // NALU_K_SCALAR_ADV_DIFF, NALU_K_SCALAR_DIFF
+    // ScalarAdvDiffElemKernel.C:83-125, ScalarDiffElemKernel.C:80-108
+    const double (*g)[3] = (k.options & NALU_OPT_SHIFTED_GRAD_OP) ? ws.dndxs[ip] : ws.dndx[ip];
+    const bool adv = kind == NALU_K_SCALAR_ADV_DIFF;
+    double a1 = s1, a2 = s2, a3 = s3;
+    if (k.options & NALU_OPT_SKEW_SYMMETRIC) hex8::scs_intg_loc(ip, 0.5, a1, a2, a3);
+    const double tmdot = adv ? k.mass_flow_rate[elem * 12 + ip] : 0.0;
+    double gam = 0.0;
+    for (int ic = 0; ic < 8; ++ic) gam += hex8::shape_fcn(ic, s1, s2, s3) * ws.fld[ic][F_MU];
+    double q = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double fadv = hex8::shape_fcn(ic, a1, a2, a3) * tmdot;
+      const double fdiff = -gam * (g[ic][0] * A[0] + g[ic][1] * A[1] + g[ic][2] * A[2]);
+      q += (fadv + fdiff) * ws.fld[ic][F_Q];
+    }
+    ws.ipd[ip][0] = gam;
+    ws.ipd[ip][1] = q;
+    ws.ipd[ip][4] = tmdot;
+  }
+}
+
+// ---- stage B: lhs, one lane per matrix column (SCS kernels) or per SCV node (mass) -----------
+template <int NDOF>
+__host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const nalu_b200_kernel_desc &k)
+{
+  constexpr int R = ElemScratch<NDOF>::R;
+  const int kind = k.kind;
+  if (kind == NALU_K_MOMENTUM_ADV_DIFF) {
+    if (NDOF != 3 || lane >= 24) return;
+    const int ic = lane / 3, j = lane % 3;
+    const bool sh = k.options & NALU_OPT_SHIFTED_GRAD_OP;
+    for (int ip = 0; ip < 12; ++ip) {
+      const int L = hex8::scs_left(ip), Rn = hex8::scs_right(ip);
+      double a1, a2, a3;
+      hex8::scs_intg_loc(ip, (k.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25, a1, a2, a3);
+      const double *g = sh ? ws.dndxs[ip][ic] : ws.dndx[ip][ic];
+      const double *A = ws.areav[ip];
+      const double mu = ws.ipd[ip][0];
+      const double lhsfacAdv = hex8::shape_fcn(ic, a1, a2, a3) * ws.ipd[ip][4];
+      const double diag = lhsfacAdv - mu * (g[0] * A[0] + g[1] * A[1] + g[2] * A[2]);
+      for (int i = 0; i < 3; ++i) {
+        double v = -mu * g[i] * A[j];
+        if (i == j) v += diag;
+        ws.lhs[(L * 3 + i) * R + lane] += v;
+        ws.lhs[(Rn * 3 + i) * R + lane] -= v;
+      }
+    }
+  } else if (kind == NALU_K_CONTINUITY_ADV || kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF) {
+    if (NDOF != 1 || lane >= 8) return;
+    const int ic = lane;
+    for (int ip = 0; ip < 12; ++ip) {
+      const int L = hex8::scs_left(ip), Rn = hex8::scs_right(ip);
+      const double *A = ws.areav[ip];
+      double v;
+      if (kind == NALU_K_CONTINUITY_ADV) {
+        const bool shl = (k.options & NALU_OPT_SHIFT_POISSON) || (k.options & NALU_OPT_REDUCED_SENS);
+        const double *g = shl ? ws.dndxs[ip][ic] : ws.dndx[ip][ic];
+        v = -(g[0] * A[0] + g[1] * A[1] + g[2] * A[2]);
+      } else {
+        const double *g = (k.options & NALU_OPT_SHIFTED_GRAD_OP) ? ws.dndxs[ip][ic] : ws.dndx[ip][ic];
+        double a1, a2, a3;
+        hex8::scs_intg_loc(ip, (k.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25, a1, a2, a3);
+        v = hex8::shape_fcn(ic, a1, a2, a3) * ws.ipd[ip][4] -
+            ws.ipd[ip][0] * (g[0] * A[0] + g[1] * A[1] + g[2] * A[2]);
+      }
+      ws.lhs[L * R + ic] += v;
+      ws.lhs[Rn * R + ic] -= v;
+    }
+  } else if (kind == NALU_K_MOMENTUM_MASS) {
+    // MomentumMassElemKernel.C:119-170; lane = SCV ip = nearest node
+    if (NDOF != 3 || lane >= 8) return;
+    const int ip = lane;
+    double s1, s2, s3;
+    hex8::scv_intg_loc(ip, (k.options & NALU_OPT_LUMPED_MASS) ? 0.5 : 0.25, s1, s2, s3);
+    double rNm1 = 0, rN = 0, rNp1 = 0, uNm1[3] = {0, 0, 0}, uN[3] = {0, 0, 0}, uNp1[3] = {0, 0, 0}, Gp[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, s1, s2, s3);
+      const double *f = ws.fld[ic];
+      rNm1 += r * f[M_RNM1];
+      rN += r * f[M_RN];
+      rNp1 += r * f[M_RNP1];
+      for (int j = 0; j < 3; ++j) {
+        uNm1[j] += r * f[M_UNM1 + j];
+        uN[j] += r * f[M_UN + j];
+        uNp1[j] += r * f[M_UNP1 + j];
+        Gp[j] += r * f[M_GP + j];
+      }
+    }
+    const double scV = ws.scv[ip];
+    const double densFac = rNp1 * k.dens_fac + k.om_dens_fac;
+    for (int j = 0; j < 3; ++j)
+      ws.rhs[ip * 3 + j] += -(k.gamma1 * rNp1 * uNp1[j] + k.gamma2 * rN * uN[j] + k.gamma3 * rNm1 * uNm1[j]) * scV / k.dt -
+                            Gp[j] * scV * densFac;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double lhsfac = hex8::shape_fcn(ic, s1, s2, s3) * k.gamma1 * rNp1 * scV / k.dt;
+      for (int j = 0; j < 3; ++j) ws.lhs[(ip * 3 + j) * R + ic * 3 + j] += lhsfac;
+    }
+  } else if (kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS) {
+    // ContinuityMassElemKernel.C:98-117, ScalarMassElemKernel.C:117-154
+    if (NDOF != 1 || lane >= 8) return;
+    const int ip = lane;
+    double s1, s2, s3;
+    hex8::scv_intg_loc(ip, (k.options & NALU_OPT_LUMPED_MASS) ? 0.5 : 0.25, s1, s2, s3);
+    double q[3] = {0, 0, 0}, rho[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, s1, s2, s3);
+      const double *f = ws.fld[ic];
+      for (int t = 0; t < 3; ++t) {
+        rho[t] += r * f[S_RNP1 + t];
+        if (kind == NALU_K_SCALAR_MASS) q[t] += r * f[S_QNP1 + t];
+      }
+    }
+    const double scV = ws.scv[ip];
+    if (kind == NALU_K_CONTINUITY_MASS) {
+      const double tau = k.dt / k.gamma1;
+      ws.rhs[ip] += -(k.gamma1 * rho[0] + k.gamma2 * rho[1] + k.gamma3 * rho[2]) * scV / k.dt / tau;
+    } else {
+      ws.rhs[ip] += -(k.gamma1 * rho[0] * q[0] + k.gamma2 * rho[1] * q[1] + k.gamma3 * rho[2] * q[2]) * scV / k.dt;
+      for (int ic = 0; ic < 8; ++ic)
+        ws.lhs[ip * R + ic] += hex8::shape_fcn(ic, s1, s2, s3) * k.gamma1 * rho[0] * scV / k.dt;
+    }
+  } else if (kind == NALU_K_TEST_FIXED_BLOCK) {
+    // unit_tests/UnitTestTpetra.C:125-139: lhs(i,j) = elemVals[i][j] (assignment, not +=)
+    for (int q = lane; q < R * R; q += 32) ws.lhs[q] = k.fixed_block[q];
+  }
+}
+
+// ---- stage C: rhs of the SCS kernels, one lane per matrix row -----------------------------
+template <int NDOF>
+__host__ __device__ inline void stage_rhs(int lane, ElemScratch<NDOF> &ws, const nalu_b200_kernel_desc &k)
+{
+  constexpr int R = ElemScratch<NDOF>::R;
+  const int kind = k.kind;
+  if (lane >= R) return;
+  int col;
+  if (kind == NALU_K_MOMENTUM_ADV_DIFF) col = 1 + lane % 3;
+  else if (kind == NALU_K_CONTINUITY_ADV) col = 0;
+  else if (kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF) col = 1;
+  else return;
+  const int node = lane / NDOF;
+  double acc = 0.0;
+  for (int ip = 0; ip < 12; ++ip) {
+    if (hex8::scs_left(ip) == node) acc -= ws.ipd[ip][col];
+    else if (hex8::scs_right(ip) == node) acc += ws.ipd[ip][col];
+  }
+  ws.rhs[lane] += acc;
+}
+
+} // namespace nalu_b200

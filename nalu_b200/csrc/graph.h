@@ -1,0 +1,97 @@
+// graph.h -- internal representation behind the opaque nalu_b200_graph handle.
+//
+// Replaces TpetraLinearSystem's DOF numbering and CSR graph construction
+// (src/TpetraLinearSystem.C:190-327, 392-420, 1257-1353 of the reference) with a sort-based
+// node-block builder: the reference grows per-row std::vectors and does sorted inserts of
+// every (row, col) pair; here each row node gathers the nodes of its incident elements once,
+// sorts, uniques, and the dof-level rowptr/colidx are expanded on the device.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace nalu_b200 {
+
+struct HaloPeer {
+  int32_t rank = -1;
+  int64_t n_value_doubles = 0; // CSR values exchanged with this peer
+  int64_t n_rhs_doubles = 0;
+  // send side: my shared row nodes owned by `rank` (indices into the shared row-node list)
+  std::vector<int32_t> send_nodes;
+  int32_t *d_send_nodes = nullptr;
+  int64_t *d_send_node_packed_off = nullptr; // [n_send_nodes+1] offsets (doubles) in the packed buffer
+  // recv side: one entry per (peer row node, block)
+  int64_t n_segments = 0;
+  int64_t *d_src_packed = nullptr;  // offset of the (i=0) ndof-segment in the packed buffer
+  int64_t *d_src_inplace = nullptr; // same, relative to the start of the peer's shared values
+  int32_t *d_src_stride = nullptr;  // doubles between dof rows on the source side
+  int64_t *d_dst = nullptr;         // offset of the (i=0) segment in my values
+  int32_t *d_dst_stride = nullptr;
+  int64_t n_rhs_nodes = 0;
+  int64_t *d_rhs_src_inplace = nullptr; // per node: offset in the peer's shared rhs
+  int64_t *d_rhs_dst = nullptr;         // per node: offset in my rhs
+  int64_t peer_values_off = 0, peer_rhs_off = 0; // first row of this peer pair inside peer's shared block
+  // host staging of the maps above (uploaded by graph_upload, then released)
+  std::vector<int64_t> h_send_node_packed_off;
+  std::vector<int64_t> h_src_packed, h_src_inplace, h_dst, h_rhs_src_inplace, h_rhs_dst;
+  std::vector<int32_t> h_src_stride, h_dst_stride;
+};
+
+struct Graph {
+  int32_t rank = 0, nranks = 1, ndof = 1;
+  int32_t n_nodes = 0;
+  int64_t n_elems = 0;
+  int32_t box[3] = {0, 0, 0};
+  std::vector<int64_t> gid;
+  std::vector<int32_t> owner;
+  std::vector<int32_t> elem_nodes;
+
+  // numbering: row nodes = unique owned ids (ascending) then unique shared-not-owned ids
+  int32_t n_owned_nodes = 0, n_shared_nodes = 0;
+  std::vector<int32_t> node_row;     // [n_nodes] local node -> row node
+  std::vector<int64_t> row_node_gid; // [n_owned+n_shared]
+  std::vector<int32_t> shared_owner; // [n_shared]
+
+  // local adjacency (row node -> sorted unique row nodes), before the handshake
+  std::vector<int64_t> adj_ptr;
+  std::vector<int32_t> adj;
+
+  // handshake
+  std::vector<std::vector<int64_t>> send_msg, recv_msg;
+  std::vector<char> recv_have;
+  bool finalized = false;
+
+  // column map: [owned row nodes][shared row nodes][remote nodes sorted by (owner,gid)]
+  std::vector<int64_t> remote_gid;
+  std::vector<int32_t> remote_owner;
+
+  // final node-block graph; owned rows [0,n_owned), shared rows after
+  std::vector<int64_t> browptr; // [n_row_nodes+1]
+  std::vector<int32_t> bcol;    // block column = column LID / ndof
+  int64_t nblk_owned = 0, nblk_shared = 0;
+
+  // device
+  int32_t *d_elem_nodes = nullptr; // [n_elems][8]
+  int32_t *d_node_row = nullptr;   // [n_nodes]
+  int64_t *d_browptr = nullptr;    // [n_row_nodes+1]
+  int32_t *d_bcol = nullptr;
+  uint8_t *d_elem_slot = nullptr;  // [n_elems][8][8]
+  uint8_t *d_node_slot27 = nullptr; // box only: [n_nodes][27] slot of lattice neighbour (dz,dy,dx)
+  uint64_t *d_rowptr_owned = nullptr, *d_rowptr_shared = nullptr;
+  int32_t *d_colidx_owned = nullptr, *d_colidx_shared = nullptr;
+  int32_t *d_err = nullptr; // device error flag (negative Jacobians)
+
+  std::vector<HaloPeer> send_peers, recv_peers;
+
+  int64_t nnz_owned() const { return nblk_owned * ndof * ndof; }
+  int64_t nnz_shared() const { return nblk_shared * ndof * ndof; }
+  int32_t n_row_nodes() const { return n_owned_nodes + n_shared_nodes; }
+};
+
+// host-side phases (graph.cpp)
+int graph_number_and_adjacency(Graph &g, std::string &err);
+int graph_build_send_messages(Graph &g, std::string &err);
+int graph_finalize_host(Graph &g, std::vector<uint8_t> &elem_slot, std::vector<uint8_t> &node_slot27,
+                        std::string &err);
+
+} // namespace nalu_b200

@@ -1,0 +1,44 @@
+// internal.h -- glue shared by the translation units of libnalu_b200.so
+#pragma once
+#include "../../include/nalu_b200.h"
+#include "graph.h"
+#include <cuda_runtime.h>
+#include <string>
+
+struct nalu_b200_graph {
+  nalu_b200::Graph g;
+};
+
+namespace nalu_b200 {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+void set_last_mode(int m);
+
+#define NALU_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t _e = (call);                                                   \
+    if (_e != cudaSuccess) return ::nalu_b200::cuda_fail(_e, #call);           \
+  } while (0)
+
+// assemble_general.cu
+int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
+                            double *d_rhs, cudaStream_t stream);
+int launch_node_mass(const Graph &g, const nalu_b200_kernel_desc &k, double *d_values, double *d_rhs,
+                     cudaStream_t stream);
+int launch_mdot(const Graph &g, const double *coords, const double *density, const double *velocity,
+                double *mdot, cudaStream_t stream);
+// assemble_box.cu
+bool box_supported(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk);
+int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
+                        double *d_rhs, int overwrite, cudaStream_t stream);
+// halo.cu
+int launch_halo_pack(const Graph &g, const HaloPeer &p, const double *d_values, const double *d_rhs,
+                     double *d_buf, cudaStream_t stream);
+int launch_halo_add(const Graph &g, const HaloPeer &p, const double *src_values, const double *src_rhs,
+                    bool inplace, double *d_values, double *d_rhs, cudaStream_t stream);
+
+constexpr int kMaxKernels = 8;
+
+} // namespace nalu_b200

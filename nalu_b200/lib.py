@@ -1,0 +1,88 @@
+"""ctypes binding of libnalu_b200.so -- the C ABI declared in include/nalu_b200.h.
+
+This is the only door into the product's compute path.  If the library is missing it is
+built in-tree (nvcc, sm_100a); if that fails the import fails loudly: there is no CPU
+fallback for the assembly path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+OK = 0
+ERR_NO_DEVICE = 3
+
+K = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3, continuity_mass=4,
+         scalar_mass=5, scalar_diff=6, test_fixed_block=7)
+OPT = dict(shifted_grad_op=1, skew_symmetric=2, lumped_mass=4, shift_mdot=8, shift_poisson=16, reduced_sens=32)
+F = dict(coordinates=0, velocity=1, velocity_n=2, velocity_nm1=3, viscosity=4, density=5, density_n=6,
+         density_nm1=7, pressure=8, dpdx=9, scalarq=10, scalarq_n=11, scalarq_nm1=12, dual_volume=13)
+F_COUNT = 16
+MODE = dict(auto=0, general=1, box=2)
+
+
+class KernelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("options", C.c_int32), ("include_divu", C.c_double),
+                ("dens_fac", C.c_double), ("om_dens_fac", C.c_double), ("dt", C.c_double),
+                ("gamma1", C.c_double), ("gamma2", C.c_double), ("gamma3", C.c_double),
+                ("nodal", C.c_void_p * F_COUNT), ("mass_flow_rate", C.c_void_p), ("fixed_block", C.c_void_p)]
+
+
+class GraphInfo(C.Structure):
+    _fields_ = [("num_dof", C.c_int32), ("n_owned_rows", C.c_int32), ("n_shared_rows", C.c_int32),
+                ("n_cols", C.c_int32), ("nnz_owned", C.c_int64), ("nnz_shared", C.c_int64),
+                ("n_elems", C.c_int64), ("n_nodes", C.c_int32), ("is_box", C.c_int32)]
+
+
+# every symbol include/nalu_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "nalu_b200_last_error", "nalu_b200_version", "nalu_b200_launch_count", "nalu_b200_graph_create",
+    "nalu_b200_graph_destroy", "nalu_b200_graph_send_size", "nalu_b200_graph_send_data",
+    "nalu_b200_graph_recv_data", "nalu_b200_graph_finalize", "nalu_b200_graph_finalize_host_only",
+    "nalu_b200_graph_get_info", "nalu_b200_graph_copy_rowptr", "nalu_b200_graph_copy_colidx",
+    "nalu_b200_graph_copy_row_gids", "nalu_b200_graph_copy_col_gids", "nalu_b200_graph_copy_node_lids",
+    "nalu_b200_graph_device_ptrs", "nalu_b200_zero_system", "nalu_b200_assemble_elem",
+    "nalu_b200_last_assemble_mode", "nalu_b200_geometry_errors", "nalu_b200_assemble_node_mass",
+    "nalu_b200_mdot_scs", "nalu_b200_halo_num_peers", "nalu_b200_halo_send_peer", "nalu_b200_halo_recv_peer",
+    "nalu_b200_halo_pack", "nalu_b200_halo_unpack_add", "nalu_b200_halo_pull_add",
+    "nalu_b200_halo_peer_offsets", "nalu_b200_ipc_get_handle", "nalu_b200_ipc_open_handle",
+    "nalu_b200_ipc_close", "nalu_b200_malloc", "nalu_b200_free", "nalu_b200_memcpy_h2d",
+    "nalu_b200_memcpy_d2h", "nalu_b200_stream_sync",
+]
+
+
+class NaluB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = _build.OUT
+        if not os.path.exists(so):
+            so = _build.build()
+        L = C.CDLL(so)
+        L.nalu_b200_last_error.restype = C.c_char_p
+        L.nalu_b200_launch_count.restype = C.c_int64
+        L.nalu_b200_graph_destroy.restype = None
+        _LIB = L
+    return _LIB
+
+
+def check(rc, what=""):
+    if rc != OK:
+        msg = lib().nalu_b200_last_error().decode()
+        raise NaluB200Error(f"{what} failed (status {rc}): {msg}")
+
+
+def ptr(a):
+    """void* of a numpy array or torch tensor (device or host)."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
