@@ -1,0 +1,373 @@
+"""CUDA parity tests (run on the B200 box): the product path, called through the C ABI, against
+(1) the reference's golden vectors and (2) the CPU oracle on the same seeded inputs.
+Bar: CSR graph bit-exact (tests/test_graph.py), LHS/RHS values within 1e-12 relative (FP64)."""
+import numpy as np
+import pytest
+
+import oracle
+from golden_io import load_golden, tab
+from nalu_fixtures import LowMachFixture, MixtureFractionFixture
+from parity_util import State, oracle_desc, perturbed_box, product_desc, rel_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1.0e-12  # north_star: FP64 values within 1e-12 relative of the reference
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required: the assembly path has no CPU fallback")
+    return "cuda"
+
+
+def _linsys(m, ndof, **kw):
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    return DeviceCsrLinearSystem(m, ndof, **kw).allocate(_cuda())
+
+
+def _one_element_lhs_rhs(ls, ndof):
+    """TestLinearSystem::sumInto capture (unit_tests/UnitTestLinearSystem.h:40-61): rebuild the
+    element lhs/rhs from the assembled one-element CSR."""
+    rp, ci = ls.rowptr(), ls.colidx()
+    v = ls.owned_values().cpu().numpy()
+    n = 8 * ndof
+    A = np.zeros((n, n))
+    for r in range(n):
+        A[r, ci[int(rp[r]):int(rp[r + 1])]] = v[int(rp[r]):int(rp[r + 1])]
+    rl, cl = ls.node_lids()
+    en = ls.mesh.elem_nodes[0]
+    rows = np.concatenate([rl[en[k]] + np.arange(ndof) for k in range(8)])
+    return A[np.ix_(rows, rows)], ls.owned_rhs().cpu().numpy()[rows]
+
+
+def _dev_fields(fx, dev):
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
+    return t
+
+
+def test_momentum_advdiff_golden():
+    g = load_golden("momentum_advdiff")
+    fx = LowMachFixture()
+    fx.calc_mdot(oracle)
+    dev = _cuda()
+    t = _dev_fields(fx, dev)
+    ls = _linsys(fx.mesh, 3)
+    ls.zero_system()
+    d = ls.make_desc("momentum_adv_diff", fields=dict(coordinates=t(fx.coords), velocity=t(fx.velocity),
+                                                      viscosity=t(fx.viscosity)),
+                     mass_flow_rate=t(fx.mdot), include_divu=0.0)
+    ls.assemble_elem([d])
+    lhs, rhs = _one_element_lhs_rhs(ls, 3)
+    np.testing.assert_allclose(rhs, tab(g, "hex8_golds::advection_diffusion::rhs"), rtol=0, atol=2e-15)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::advection_diffusion::lhs"), rtol=0, atol=2e-15)
+    assert ls.geometry_errors() == 0
+
+
+@pytest.mark.parametrize("variant", ["default", "reduced_sens", "shifted"])
+def test_continuity_adv_golden(variant):
+    g = load_golden("continuity_adv")
+    fx = LowMachFixture()
+    dev = _cuda()
+    t = _dev_fields(fx, dev)
+    ls = _linsys(fx.mesh, 1)
+    ls.zero_system()
+    opts = dict(default=(), reduced_sens=("reduced_sens",), shifted=("shift_poisson",))[variant]
+    d = ls.make_desc("continuity_adv", options=opts, dt=1.0, gamma1=1.0,
+                     fields=dict(coordinates=t(fx.coords), velocity=t(fx.velocity), density=t(fx.density),
+                                 pressure=t(fx.pressure), dpdx=t(fx.dpdx)))
+    ls.assemble_elem([d])
+    lhs, rhs = _one_element_lhs_rhs(ls, 1)
+    ns = "advection_default" if variant == "default" else "advection_reduced_sensitivities"
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=2e-15)
+    np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=2e-15)
+
+
+def test_scalar_advdiff_golden_perturbed():
+    g = load_golden("scalar_advdiff")
+    fx = MixtureFractionFixture(perturb=True)
+    dev = _cuda()
+    t = _dev_fields(fx, dev)
+    ls = _linsys(fx.mesh, 1)
+    ls.zero_system()
+    # mass_flow_rate_scs computed on the device too (calc_mass_flow_rate_scs)
+    mdot = ls.mdot_scs(t(fx.coords), t(fx.density), t(fx.velocity))
+    np.testing.assert_allclose(mdot.cpu().numpy(), fx.calc_mdot(oracle), rtol=0, atol=1e-18 + 1e-14 * np.abs(fx.mdot).max())
+    d = ls.make_desc("scalar_adv_diff", fields=dict(coordinates=t(fx.coords), scalarq=t(fx.mixFraction),
+                                                    viscosity=t(fx.viscosity)), mass_flow_rate=mdot)
+    ls.assemble_elem([d])
+    lhs, rhs = _one_element_lhs_rhs(ls, 1)
+    np.testing.assert_allclose(rhs, tab(g, "hex8_golds::advection_diffusion::rhs"), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::advection_diffusion::lhs"), rtol=0, atol=1e-15)
+
+
+def test_scalar_diff_golden():
+    g = load_golden("scalar_diff")
+    fx = LowMachFixture()
+    dev = _cuda()
+    t = _dev_fields(fx, dev)
+    ls = _linsys(fx.mesh, 1)
+    ls.zero_system()
+    d = ls.make_desc("scalar_diff", fields=dict(coordinates=t(fx.coords), scalarq=t(np.cos(fx.coords[:, 0])),
+                                                viscosity=t(np.ones(8))))
+    ls.assemble_elem([d])
+    lhs, _ = _one_element_lhs_rhs(ls, 1)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::heatcond::cvfem_diff::lhs"), rtol=0, atol=2e-15)
+
+
+@pytest.mark.parametrize("lumped", [False, True])
+def test_momentum_mass_golden(lumped):
+    g = load_golden("momentum_mass")
+    fx = LowMachFixture()
+    dev = _cuda()
+    t = _dev_fields(fx, dev)
+    ls = _linsys(fx.mesh, 3)
+    ls.zero_system()
+    d = ls.make_desc("momentum_mass", options=(("lumped_mass",) if lumped else ()), dt=0.1, gamma1=1.0, gamma2=-1.0,
+                     gamma3=0.0,
+                     fields=dict(coordinates=t(fx.coords), velocity=t(fx.velocity), velocity_n=t(fx.velocityN),
+                                 velocity_nm1=t(fx.velocityN), density=t(fx.density), density_n=t(fx.densityN),
+                                 density_nm1=t(fx.densityN), dpdx=t(fx.dpdx)))
+    ls.assemble_elem([d])
+    lhs, rhs = _one_element_lhs_rhs(ls, 3)
+    if lumped:
+        np.testing.assert_allclose(rhs, tab(g, "hex8_golds::momentum_time_derivative_lumped::rhs"), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(lhs, 1.25 * np.eye(24), rtol=0, atol=1e-14)
+    else:
+        np.testing.assert_allclose(rhs, tab(g, "hex8_golds::momentum_time_derivative::rhs"), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(lhs, tab(g, "hex8_golds::momentum_time_derivative::lhs"), rtol=0, atol=1e-14)
+
+
+def test_continuity_mass_golden():
+    fx = LowMachFixture()
+    dev = _cuda()
+    t = _dev_fields(fx, dev)
+    ls = _linsys(fx.mesh, 1)
+    ls.zero_system()
+    d = ls.make_desc("continuity_mass", dt=0.1, gamma1=1.0, gamma2=-1.0, gamma3=0.0,
+                     fields=dict(coordinates=t(fx.coords), density=t(fx.density), density_n=t(fx.densityN),
+                                 density_nm1=t(fx.densityN)))
+    ls.assemble_elem([d])
+    lhs, rhs = _one_element_lhs_rhs(ls, 1)
+    np.testing.assert_allclose(rhs, -12.5, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-system parity against the oracle
+# ---------------------------------------------------------------------------------------------
+CASES = {
+    "momentum": (3, [("momentum_adv_diff", (), dict(include_divu=1.0))]),
+    "momentum_nodivu": (3, [("momentum_adv_diff", (), dict(include_divu=0.0))]),
+    "momentum_shifted_skew": (3, [("momentum_adv_diff", ("shifted_grad_op", "skew_symmetric"), dict(include_divu=1.0))]),
+    "momentum_mass+advdiff": (3, [("momentum_mass", ("lumped_mass",), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
+                                  ("momentum_adv_diff", (), dict(include_divu=1.0))]),
+    "momentum_consistent_mass": (3, [("momentum_mass", (), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5, dens_fac=1.0, om_dens_fac=0.0))]),
+    "continuity": (1, [("continuity_adv", (), dict(dt=0.05, gamma1=1.5))]),
+    "continuity_reduced_shiftmdot": (1, [("continuity_adv", ("reduced_sens", "shift_mdot"), dict(dt=0.05, gamma1=1.5))]),
+    "continuity_mass+adv": (1, [("continuity_mass", ("lumped_mass",), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
+                                ("continuity_adv", ("shift_poisson",), dict(dt=0.05, gamma1=1.5))]),
+    "scalar": (1, [("scalar_adv_diff", (), {})]),
+    "scalar_mass+advdiff": (1, [("scalar_mass", (), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
+                                ("scalar_adv_diff", ("skew_symmetric",), {})]),
+    "scalar_diff": (1, [("scalar_diff", ("shifted_grad_op",), {})]),
+}
+
+
+def _compare_system(ls, orc, rank=0, tol=RTOL):
+    v = ls.owned_values().cpu().numpy()
+    r = ls.owned_rhs().cpu().numpy()
+    ov, orr = orc.values(rank), orc.rhs(rank)
+    scale = max(np.abs(ov).max(), 1e-300)
+    ev = rel_err(v, ov, 1e-3 * scale)
+    er = rel_err(r, orr, 1e-3 * max(np.abs(orr).max(), 1e-300))
+    assert ev < tol, f"values rel err {ev:.3e}"
+    assert er < tol, f"rhs rel err {er:.3e}"
+    if ls.n_shared_rows:
+        sv = ls.shared_values().cpu().numpy()
+        assert rel_err(sv, orc.values(rank, True), 1e-3 * scale) < tol
+    return ev, er
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("mode", ["general", "auto"])
+def test_system_parity_vs_oracle(case, mode):
+    ndof, klist = CASES[case]
+    m = perturbed_box(9, 7, 6)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], ndof)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, k, o, keep, **s) for k, o, s in klist])
+    ls = _linsys(m, ndof)
+    ls.zero_system()
+    used = ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode=mode, overwrite=True)
+    assert used in (1, 2)
+    _compare_system(ls, orc)
+    assert ls.geometry_errors() == 0
+
+
+def test_system_parity_64cubed_scalar():
+    """BASELINE config 2 size (64^3 = 262144 Hex8), scalar adv-diff, full comparison with the oracle."""
+    m = perturbed_box(64, 64, 64)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 1)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, "scalar_adv_diff", (), keep)])
+    ls = _linsys(m, 1)
+    ls.zero_system()
+    ls.assemble_elem([product_desc(ls, dev, "scalar_adv_diff")], overwrite=True)
+    _compare_system(ls, orc)
+
+
+def test_system_parity_40cubed_momentum():
+    m = perturbed_box(40, 40, 40)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 3)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, "momentum_adv_diff", (), keep, include_divu=1.0)])
+    ls = _linsys(m, 3)
+    ls.zero_system()
+    ls.assemble_elem([product_desc(ls, dev, "momentum_adv_diff", include_divu=1.0)], overwrite=True)
+    _compare_system(ls, orc)
+
+
+def test_periodic_box_scalar_parity():
+    from nalu_b200 import mesh as M
+    m = M.periodic_box(6, 5, 4)
+    M.perturb_coords_hash(m, 0.1)
+    st = State(m)
+    # subjects carry their monarch's field values
+    for k in st.names():
+        if k != "coordinates":
+            setattr(st, k, getattr(st, k)[m.periodic_monarch])
+    st.mdot = oracle.calc_mass_flow_rate_scs(m.elem_nodes, st.coordinates, st.density, st.velocity)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 1)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, "scalar_adv_diff", (), keep)])
+    ls = _linsys(m, 1)
+    ls.zero_system()
+    ls.assemble_elem([product_desc(ls, dev, "scalar_adv_diff")])
+    _compare_system(ls, orc)
+
+
+@pytest.mark.parametrize("kind,ndof", [("momentum_mass", 3), ("continuity_mass", 1), ("scalar_mass", 1)])
+def test_node_mass_algorithms(kind, ndof):
+    m = perturbed_box(5, 4, 3)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    sc = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    orc = oracle.LinSys([m], ndof)
+    keep = []
+    orc.assemble_node_mass(0, oracle_desc(st, kind, (), keep, **sc), st.dual_volume)
+    ls = _linsys(m, ndof)
+    ls.zero_system()
+    ls.assemble_node_mass(product_desc(ls, dev, kind, **sc))
+    _compare_system(ls, orc)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-rank: graph handshake + shared-not-owned rows + loadComplete, ranks simulated on one GPU
+# ---------------------------------------------------------------------------------------------
+def _build_ranks(parts, ndof):
+    from test_graph import build_product_systems  # CPU helper: routes the handshake in-process
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    host = build_product_systems(parts, ndof)
+    sends = {p.mesh.rank: p.handshake_send for p in host}
+    out = []
+    for m in parts:
+        ex = lambda send, r=m.rank: {src: sends[src][r] for src in sends if r in sends[src]}
+        out.append(DeviceCsrLinearSystem(m, ndof, exchange=ex).allocate(_cuda()))
+    return out
+
+
+@pytest.mark.parametrize("nranks,transport", [(2, "packed"), (2, "pull"), (3, "packed"), (3, "pull")])
+def test_tpetra_two_hex_and_slabs_load_complete(nranks, transport):
+    """UnitTestTpetra.C `basic` at np=2 (1x1x2) and a 3-slab variant: fixed element block, shared rows
+    exported to the owner with ADD; values looked up by global ids as in verify_matrix_for_2_hex8_mesh."""
+    from nalu_b200 import mesh as M
+    g = load_golden("tpetra_2elem")
+    elemVals = tab(g, "elemVals")
+    full = M.generated_box(1, 1, 2) if nranks == 2 else M.generated_box(2, 2, 6)
+    parts = M.partition_slabs(full, nranks)
+    systems = _build_ranks(parts, 1)
+    blk = torch.as_tensor(elemVals, device="cuda").contiguous()
+    for ls in systems:
+        ls.zero_system()
+        ls.assemble_elem([ls.make_desc("test_fixed_block", fixed_block=blk)])
+    torch.cuda.synchronize()
+    # loadComplete
+    for ls in systems:
+        send, recv = ls.halo_peers()
+        for i, (peer, n) in enumerate(recv):
+            src = systems[peer]
+            if transport == "packed":
+                ssend, _ = src.halo_peers()
+                j = [q for q, (pr, _) in enumerate(ssend) if pr == ls.mesh.rank][0]
+                buf = torch.empty(ssend[j][1], dtype=torch.float64, device="cuda")
+                assert ssend[j][1] == n
+                src.halo_pack(j, buf)
+                ls.halo_unpack_add(i, buf)
+            else:
+                ls.halo_pull_add(i, src.shared_values().data_ptr(), src.shared_rhs().data_ptr())
+    torch.cuda.synchronize()
+    # oracle for the same job
+    orc = oracle.LinSys(parts, 1)
+    keep = []
+    d = oracle.make_desc("test_fixed_block", keep, fixedBlock=elemVals)
+    for r in range(nranks):
+        orc.assemble_elem(r, [d])
+    orc.load_complete()
+    for r, ls in enumerate(systems):
+        np.testing.assert_allclose(ls.owned_values().cpu().numpy(), orc.values(r), rtol=0, atol=1e-13)
+        np.testing.assert_allclose(ls.owned_rhs().cpu().numpy(), orc.rhs(r), rtol=0, atol=1e-13)
+    if nranks == 2:
+        lhsVals = tab(g, "lhsVals")
+        for ls in systems:
+            rp, ci, v, rg, cg = ls.rowptr(), ls.colidx(), ls.owned_values().cpu().numpy(), ls.row_gids(), ls.col_gids()
+            for row in range(ls.n_owned_rows):
+                for j in range(int(rp[row]), int(rp[row + 1])):
+                    assert abs(lhsVals[rg[row] - 1][cg[ci[j]] - 1] - v[j]) < 1e-9
+
+
+@pytest.mark.parametrize("ndof,kind", [(3, "momentum_adv_diff"), (1, "continuity_adv")])
+def test_np4_physics_parity_after_load_complete(ndof, kind):
+    from nalu_b200 import mesh as M
+    full = perturbed_box(6, 5, 9)
+    parts = M.partition_slabs(full, 4)
+    systems = _build_ranks(parts, ndof)
+    orc = oracle.LinSys(parts, ndof)
+    keep = []
+    sc = dict(include_divu=1.0) if ndof == 3 else dict(dt=0.05, gamma1=1.5)
+    for r, (m, ls) in enumerate(zip(parts, systems)):
+        st = State(m)
+        dev = st.to_device("cuda")
+        orc.assemble_elem(r, [oracle_desc(st, kind, (), keep, **sc)])
+        ls.zero_system()
+        ls.assemble_elem([product_desc(ls, dev, kind, **sc)], overwrite=True)
+    torch.cuda.synchronize()
+    for ls in systems:
+        _, recv = ls.halo_peers()
+        for i, (peer, n) in enumerate(recv):
+            ls.halo_pull_add(i, systems[peer].shared_values().data_ptr(), systems[peer].shared_rhs().data_ptr())
+    torch.cuda.synchronize()
+    orc.load_complete()
+    for r, ls in enumerate(systems):
+        _compare_system(ls, orc, rank=r)
+
+
+def test_missing_device_pointer_is_an_error():
+    from nalu_b200.lib import NaluB200Error
+    m = perturbed_box(2, 2, 2)
+    ls = _linsys(m, 3)
+    d = ls.make_desc("momentum_adv_diff")  # no coordinates
+    with pytest.raises(NaluB200Error):
+        ls.assemble_elem([d])
+    ls1 = _linsys(m, 1)
+    st = State(m)
+    dev = st.to_device("cuda")
+    with pytest.raises(NaluB200Error):
+        ls1.assemble_elem([product_desc(ls1, dev, "momentum_adv_diff")])  # numDof mismatch
