@@ -1,11 +1,200 @@
-// assemble_box.cu -- tiled write-once assembly for structured Hex8 blocks (placeholder until
-// the tiled kernel lands: reports "unsupported" so AUTO mode uses the general kernel).
+// assemble_box.cu -- launch side of the tiled write-once assembly (see box_tile.cuh).
+//
+// Grid: one CTA per (node tile, z chunk).  Per node plane a CTA runs
+//   phase 1 (ip data of the element layer above the plane)  -> sync
+//   lower octants (layer below)                              -> sync (that layer's buffer becomes the
+//                                                               row staging area)
+//   upper octants, block flush, rhs                           -> sync
+//   coalesced copy of the finished rows to HBM               -> sync
+// Two CTAs are resident per SM (6x4 node tile, 192 threads, ~101 KB shared memory) so that one
+// CTA's copy/phase-1 overlaps the other's FP64-bound phase 2.
+#include "box_tile.cuh"
 #include "internal.h"
+
+#include <cstdlib>
+
 namespace nalu_b200 {
-bool box_supported(const Graph &, const nalu_b200_kernel_desc *, int) { return false; }
-int launch_assemble_box(const Graph &, const nalu_b200_kernel_desc *, int, double *, double *, int, cudaStream_t)
+
+using box::BoxParams;
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_kernel(const __grid_constant__ BoxParams P)
 {
-  set_error("tiled kernel not built");
-  return NALU_B200_ERR_ARG;
+  extern __shared__ __align__(16) double sm[];
+  double *const tab = sm + 2 * C::LBUF;
+  const int tid = threadIdx.x;
+  const int ntile = P.tiles_x * P.tiles_y;
+  const int tile = blockIdx.x % ntile, zc = blockIdx.x / ntile;
+  const int x0 = (tile % P.tiles_x) * C::TBX, y0 = (tile / P.tiles_x) * C::TBY;
+  const int zs = zc * P.z_chunk;
+  const int ze = (zs + P.z_chunk < P.NZ) ? zs + P.z_chunk : P.NZ;
+  const bool divu = P.include_divu != 0.0;
+
+  for (int i = tid; i < 192; i += C::NT) box::build_table_entry<C>(i, P.options, tab);
+
+  box::NodeCtx N;
+  {
+    const int nl = tid >> 3;
+    N.cls = tid & 7;
+    N.lx = nl % C::TBX;
+    N.ly = nl / C::TBX;
+    N.x = x0 + N.lx;
+    N.y = y0 + N.ly;
+    N.active = N.x < P.NX && N.y < P.NY;
+  }
+  if (zs >= 1)
+    for (int it = tid; it < C::NITEM; it += C::NT) box::phase1_item<C>(P, it, x0, y0, zs - 1, sm + ((zs - 1) & 1) * C::LBUF);
+
+  for (int z = zs; z < ze; ++z) {
+    if (z < P.nz)
+      for (int it = tid; it < C::NITEM; it += C::NT) box::phase1_item<C>(P, it, x0, y0, z, sm + (z & 1) * C::LBUF);
+    __syncthreads();
+    const double *lower = sm + ((z + 1) & 1) * C::LBUF;
+    const double *upper = sm + (z & 1) * C::LBUF;
+    double *stg = sm + ((z + 1) & 1) * C::LBUF;
+    box::P2State S;
+    box::p2_zero(S);
+    S.rr[0] = S.rr[1] = S.rr[2] = 0.0;
+    N.z = z;
+    int ncov = 0;
+    if (N.active) {
+      N.n = N.x + (long long)P.NX * (N.y + (long long)P.NY * z);
+      N.row = P.node_row[N.n];
+      const long long b0 = P.browptr[N.row];
+      N.nb = (int)(P.browptr[N.row + 1] - b0);
+      N.rowbase = 9 * b0;
+      ncov = ((N.x > 0) + 1 + (N.x < P.NX - 1)) * ((N.y > 0) + 1 + (N.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
+      box::p2_pass<C, 0>(P, N, S, lower, tab, divu);
+    }
+    __syncthreads(); // every thread is done with the lower layer: its buffer is now the staging area
+    if (N.active && N.nb != ncov) {
+      // row also holds columns no local element touches (remote columns announced by the ranks
+      // sharing this node): they must read zero
+      double *row = stg + (N.lx + C::TBX * N.ly) * C::SROW;
+      for (int q = N.cls; q < N.nb * 9; q += 8) row[q] = 0.0;
+    }
+    __syncwarp();
+    if (N.active) {
+      if (N.cls & 4) {
+        box::p2_flush<C>(P, N, S, -1, stg);
+        box::p2_zero(S);
+      }
+      box::p2_pass<C, 1>(P, N, S, upper, tab, divu);
+      box::p2_flush<C>(P, N, S, (N.cls & 4) ? 1 : 0, stg);
+    }
+    // rhs: sum the 8 class partials of the node
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double v = S.rr[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      S.rr[i] = v;
+    }
+    if (N.active && N.cls < 3) {
+      double *r = P.rhs + (long long)N.row * 3 + N.cls;
+      const double v = N.cls == 0 ? S.rr[0] : (N.cls == 1 ? S.rr[1] : S.rr[2]);
+      *r = P.overwrite ? v : *r + v;
+    }
+    __syncthreads();
+    // finished rows -> HBM, one warp per node, 256 B per store instruction
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int nl = warp; nl < C::NNODE; nl += C::NT / 32) {
+        const int lx = nl % C::TBX, ly = nl / C::TBX;
+        const int x = x0 + lx, y = y0 + ly;
+        if (x >= P.NX || y >= P.NY) continue;
+        const long long n = x + (long long)P.NX * (y + (long long)P.NY * z);
+        const int r = P.node_row[n];
+        const long long b0 = P.browptr[r];
+        const int len = (int)(P.browptr[r + 1] - b0) * 9;
+        double *dst = P.values + 9 * b0;
+        const double *src = stg + nl * C::SROW;
+        if (P.overwrite)
+          for (int q = lane; q < len; q += 32) dst[q] = src[q];
+        else
+          for (int q = lane; q < len; q += 32) dst[q] += src[q];
+      }
+    }
+    __syncthreads();
+  }
 }
+
+bool box_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+{
+  if (g.box[0] <= 0 || !g.d_node_slot27 || g.ndof != 3 || nk != 1) return false;
+  if (k[0].kind != NALU_K_MOMENTUM_ADV_DIFF) return false;
+  if (!k[0].nodal[NALU_F_COORDINATES] || !k[0].nodal[NALU_F_VELOCITY] || !k[0].nodal[NALU_F_VISCOSITY] ||
+      !k[0].mass_flow_rate)
+    return false;
+  return true;
+}
+
+template <class C>
+static int launch_cfg(const Graph &g, BoxParams &P, cudaStream_t stream)
+{
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  P.tiles_x = (P.NX + C::TBX - 1) / C::TBX;
+  P.tiles_y = (P.NY + C::TBY - 1) / C::TBY;
+  const long long ntile = (long long)P.tiles_x * P.tiles_y;
+  // z chunks: enough CTAs for ~16 waves, but at least 16 planes per chunk (each chunk recomputes
+  // one element layer)
+  const int occ = C::NT <= 256 ? 2 : 1;
+  long long want = ((long long)sms * occ * 16 + ntile - 1) / ntile;
+  int zchunks = (int)(want < 1 ? 1 : want);
+  int zc = (P.NZ + zchunks - 1) / zchunks;
+  if (zc < 16) zc = 16;
+  if (const char *e = getenv("NALU_BOX_ZCHUNK")) {
+    const int v = atoi(e);
+    if (v > 0) zc = v;
+  }
+  if (zc > P.NZ) zc = P.NZ;
+  P.z_chunk = zc;
+  zchunks = (P.NZ + zc - 1) / zc;
+  const size_t smem = sizeof(double) * C::SMEM_DOUBLES;
+  NALU_CUDA(cudaFuncSetAttribute(assemble_box_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long ctas = ntile * zchunks;
+  if (ctas > 0x7fffffffLL) {
+    set_error("assemble_box: grid too large");
+    return NALU_B200_ERR_ARG;
+  }
+  assemble_box_kernel<C><<<(unsigned)ctas, C::NT, smem, stream>>>(P);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs,
+                        int overwrite, cudaStream_t stream)
+{
+  if (!box_supported(g, k, nk)) {
+    set_error("assemble_box: unsupported mesh / kernel list");
+    return NALU_B200_ERR_ARG;
+  }
+  if (g.n_elems == 0) return NALU_B200_OK;
+  BoxParams P;
+  P.nx = g.box[0]; P.ny = g.box[1]; P.nz = g.box[2];
+  P.NX = P.nx + 1; P.NY = P.ny + 1; P.NZ = P.nz + 1;
+  P.coords = k[0].nodal[NALU_F_COORDINATES];
+  P.vel = k[0].nodal[NALU_F_VELOCITY];
+  P.visc = k[0].nodal[NALU_F_VISCOSITY];
+  P.mdot = k[0].mass_flow_rate;
+  P.node_row = g.d_node_row;
+  P.browptr = (const long long *)g.d_browptr;
+  P.slot27 = g.d_node_slot27;
+  P.values = d_values;
+  P.rhs = d_rhs;
+  P.err = g.d_err;
+  P.include_divu = k[0].include_divu;
+  P.options = k[0].options;
+  P.overwrite = overwrite;
+  int tile = 0;
+  if (const char *e = getenv("NALU_BOX_TILE")) tile = atoi(e);
+  if (tile == 84) return launch_cfg<box::Cfg<8, 4>>(g, P, stream);
+  if (tile == 86) return launch_cfg<box::Cfg<8, 6>>(g, P, stream);
+  return launch_cfg<box::Cfg<6, 4>>(g, P, stream);
+}
+
 } // namespace nalu_b200

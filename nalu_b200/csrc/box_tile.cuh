@@ -1,0 +1,379 @@
+// box_tile.cuh -- tiled, write-once MomentumAdvDiff assembly for structured Hex8 blocks.
+//
+// What is computed is what AssembleElemSolverAlgorithm::execute + MomentumAdvDiffElemKernel::execute
+// + TpetraLinearSystem::sumInto produce (src/AssembleElemSolverAlgorithm.C:74-100,
+// src/kernel/MomentumAdvDiffElemKernel.C:70-186, src/TpetraLinearSystem.C:1457-1522); how it is
+// computed is turned inside out so that every CSR value is written exactly once, already summed:
+//
+//   * a CTA owns a TBX x TBY column of NODES and sweeps it along z; each node row is owned by
+//     8 threads ("classes" (a,b,c) in {0,1}^3: the thread owns the column nodes whose offset from
+//     the row node is (+-a, +-b, +-c), so every one of the 8 elements around the node hands each
+//     class exactly one column node -> all 8 threads do identical work, 24 (element, ip, column)
+//     triples per node plane);
+//   * phase 1 evaluates, once per element layer, the per-integration-point data the rows need:
+//     G' = -mu_ip adj(J)/det(J)   (so that -mu dN_ic/dx = G' dN_ic/dxi), the SCS area vector A,
+//     the mass flow rate and the div(u) stress scalar -- 14 doubles per ip in shared memory.
+//     The trilinear map is expanded in its 8 coefficient vectors, which makes the Jacobian at an
+//     SCS ip 5 vector FMAs and the area vector one cross product (the reference subdivides the hex
+//     into 27 points and recomputes a derivative table per element, Hex8CVFEM.C:24-70,547-581);
+//   * phase 2 accumulates the 3x3 blocks  sum_{e,ip} +-( (G' dN_ic) (x) A + (N_ic mdot + (G' dN_ic).A) I )
+//     in registers (the L and R rows of an ip differ only in sign, MomentumAdvDiffElemKernel.C:152-183),
+//     lays the finished row out in shared memory exactly as the CSR stores it and streams it to HBM
+//     with full-width coalesced stores;
+//   * rhs = -(assembled row) . u - divU stress: algebraically what the reference accumulates entry by
+//     entry (rhs -= lhsfac*u, :171-182) because the advection lhs and aflux share one shape function.
+//
+// Every phase is a plain function of the thread index so that tests/cpu_harness can execute the
+// kernel thread by thread on the CPU (no GPU in the development container).
+#pragma once
+#include "../../include/nalu_b200.h"
+#include "hex8_dev.cuh"
+
+namespace nalu_b200 {
+namespace box {
+
+struct BoxParams {
+  int nx, ny, nz;    // elements of the local block
+  int NX, NY, NZ;    // nodes
+  int z_chunk;       // node planes per CTA
+  int tiles_x, tiles_y;
+  const double *coords; // [nNodes][3]
+  const double *vel;    // [nNodes][3]
+  const double *visc;   // [nNodes]
+  const double *mdot;   // [nElem][12]
+  const int *node_row;
+  const long long *browptr;
+  const unsigned char *slot27;
+  double *values;
+  double *rhs;
+  int *err;
+  double include_divu;
+  int options;
+  int overwrite;
+};
+
+template <int TBX_, int TBY_>
+struct Cfg {
+  static constexpr int TBX = TBX_, TBY = TBY_;
+  static constexpr int NNODE = TBX * TBY;
+  static constexpr int NT = NNODE * 8;
+  static constexpr int ELX = TBX + 1, ELY = TBY + 1, NEL = ELX * ELY;
+  static constexpr int IPD = 14;            // doubles per ip: G'[9], A[3], mdot, w
+  static constexpr int ES = 12 * IPD + 2;   // element stride (doubles); +2 spreads the 16-byte bank groups
+  static constexpr int SROW = 248;          // staging row stride (doubles) >= 27*9
+  static constexpr int LBUF = (NEL * ES > NNODE * SROW) ? NEL * ES : NNODE * SROW;
+  static constexpr int TAB = 8 * 3 * 2 * 8 * 2; // [octant][edge dir][half][class][2]
+  static constexpr int SMEM_DOUBLES = 2 * LBUF + TAB;
+  static constexpr int NITEM = NEL * 3;     // phase-1 work items: (element, edge direction)
+};
+
+// ---- small integer helpers on the Hex8 numbering (Hex8CVFEM.C:264-276, 396-412) -------------
+__host__ __device__ __forceinline__ int node_of_bits(int bx, int by, int bz) { return bz * 4 + by * 2 + (bx ^ by); }
+__host__ __device__ __forceinline__ int bit_x(int n) { return (n ^ (n >> 1)) & 1; }
+__host__ __device__ __forceinline__ int bit_y(int n) { return (n >> 1) & 1; }
+__host__ __device__ __forceinline__ int bit_z(int n) { return (n >> 2) & 1; }
+// the SCS ip on the edge that leaves node k in direction dir (0 x, 1 y, 2 z)
+__host__ __device__ __forceinline__ int ip_of(int k, int dir)
+{
+  const int bz = bit_z(k);
+  if (dir == 0) return bit_y(k) ? (bz ? 6 : 2) : (bz ? 4 : 0);
+  if (dir == 1) return bit_x(k) ? (bz ? 5 : 1) : (bz ? 7 : 3);
+  return 8 + (k & 3);
+}
+
+// ---- phase 2 constant table -------------------------------------------------------------------
+// For octant s (bits: 1 = +x, 2 = +y, 4 = +z: the element lies on that side of the row node),
+// edge direction pp and class cls: parametric derivative of the class's column node at the ip, in
+// the ip's local axis order (t,u,v) = (pp, pp+1, pp+2), and the advection shape function value.
+template <class C>
+__host__ __device__ inline void build_table_entry(int idx, int options, double *tab)
+{
+  const int cls = idx & 7, pp = (idx >> 3) % 3, s = idx / 24;
+  const int sxp = s & 1, syp = (s >> 1) & 1, szp = (s >> 2) & 1;
+  // row node sits at the corner of the element opposite to the octant direction
+  const int k = node_of_bits(!sxp, !syp, !szp);
+  const int a = cls & 1, b = (cls >> 1) & 1, c = (cls >> 2) & 1;
+  const int ic = node_of_bits(a ? sxp : !sxp, b ? syp : !syp, c ? szp : !szp);
+  const int ip = ip_of(k, pp);
+  double s1, s2, s3, d[3];
+  hex8::scs_intg_loc(ip, (options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25, s1, s2, s3);
+  hex8::shape_deriv(ic, s1, s2, s3, d);
+  hex8::scs_intg_loc(ip, (options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25, s1, s2, s3);
+  const double nadv = hex8::shape_fcn(ic, s1, s2, s3);
+  double *t0 = tab + ((s * 3 + pp) * 2 + 0) * 16 + cls * 2;
+  double *t1 = tab + ((s * 3 + pp) * 2 + 1) * 16 + cls * 2;
+  t0[0] = d[pp];
+  t0[1] = d[(pp + 1) % 3];
+  t1[0] = d[(pp + 2) % 3];
+  t1[1] = nadv;
+}
+
+// ---- phase 1: integration-point data of one (element, edge direction) item ---------------------
+// Local axes (t,u,v) = (g, g+1, g+2) mod 3; local node m has bits (b0,b1,b2) along (t,u,v).
+template <class C>
+__host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0, int y0, int ez, double *buf)
+{
+  const int g = item / C::NEL, el = item - g * C::NEL;
+  const int elx = el % C::ELX, ely = el / C::ELX;
+  const int ex = x0 - 1 + elx, ey = y0 - 1 + ely;
+  if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) return;
+  const int st[3] = {1, P.NX, P.NX * P.NY};
+  const int s_t = st[g], s_u = st[(g + 1) % 3], s_v = st[(g + 2) % 3];
+  const long long n000 = ex + (long long)P.NX * (ey + (long long)P.NY * ez);
+  const bool divu = P.include_divu != 0.0;
+
+  // butterfly: C[mask] = sum_m prod_{axis in mask} sign_axis(m) f_m   (mask bits: 1 = t, 2 = u, 4 = v)
+  double X[3][8], M[8], U[3][8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const long long n = n000 + (m & 1) * s_t + ((m >> 1) & 1) * s_u + ((m >> 2) & 1) * s_v;
+    X[0][m] = P.coords[n * 3 + 0];
+    X[1][m] = P.coords[n * 3 + 1];
+    X[2][m] = P.coords[n * 3 + 2];
+    M[m] = P.visc[n];
+    if (divu) {
+      U[0][m] = P.vel[n * 3 + 0];
+      U[1][m] = P.vel[n * 3 + 1];
+      U[2][m] = P.vel[n * 3 + 2];
+    }
+  }
+  auto butterfly = [](double *f) {
+#pragma unroll
+    for (int h = 1; h < 8; h <<= 1)
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+        if (!(m & h)) {
+          const double lo = f[m], hi = f[m | h];
+          f[m] = hi + lo;
+          f[m | h] = hi - lo;
+        }
+  };
+  butterfly(X[0]);
+  butterfly(X[1]);
+  butterfly(X[2]);
+  butterfly(M);
+  if (divu) {
+    butterfly(U[0]);
+    butterfly(U[1]);
+    butterfly(U[2]);
+  }
+  enum { T = 1, Uu = 2, V = 4, TU = 3, TV = 5, UV = 6, TUV = 7 };
+  // area vector of the facet through the t = 0 plane, pointing along +t:
+  //   A = Cu x Cv / 64 + Cuv x (sig2 Cv - sig1 Cu) / 128
+  double base[3];
+  base[0] = (X[1][Uu] * X[2][V] - X[2][Uu] * X[1][V]) * (1.0 / 64.0);
+  base[1] = (X[2][Uu] * X[0][V] - X[0][Uu] * X[2][V]) * (1.0 / 64.0);
+  base[2] = (X[0][Uu] * X[1][V] - X[1][Uu] * X[0][V]) * (1.0 / 64.0);
+  const double q = (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
+  const long long e = ex + (long long)P.nx * (ey + (long long)P.ny * ez);
+  // original-axis bit positions of the local axes
+  const int at = g, au = (g + 1) % 3, av = (g + 2) % 3;
+
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const int b1 = f & 1, b2 = f >> 1;
+    const double sg1 = b1 ? 1.0 : -1.0, sg2 = b2 ? 1.0 : -1.0;
+    // which ip: the edge along t at (u,v) side (b1,b2); take its node with bit_t = 0
+    int ob[3];
+    ob[at] = 0;
+    ob[au] = b1;
+    ob[av] = b2;
+    const int k0 = node_of_bits(ob[0], ob[1], ob[2]);
+    const int ip = ip_of(k0, g);
+    const double orient = (hex8::scs_left(ip) == k0) ? 1.0 : -1.0;
+
+    double J[3][3]; // J[i][j] = d x_i / d xi_j, local axis order
+    const double c1 = 0.5 * q * sg1, c2 = 0.5 * q * sg2, c12 = q * q * sg1 * sg2;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      J[i][0] = 0.25 * X[i][T] + c1 * X[i][TU] + c2 * X[i][TV] + c12 * X[i][TUV];
+      J[i][1] = 0.25 * X[i][Uu] + c2 * X[i][UV];
+      J[i][2] = 0.25 * X[i][V] + c1 * X[i][UV];
+    }
+    double adj[3][3];
+    adj[0][0] = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+    adj[0][1] = J[1][2] * J[2][0] - J[2][2] * J[1][0];
+    adj[0][2] = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+    adj[1][0] = J[0][2] * J[2][1] - J[2][2] * J[0][1];
+    adj[1][1] = J[0][0] * J[2][2] - J[2][0] * J[0][2];
+    adj[1][2] = J[0][1] * J[2][0] - J[2][1] * J[0][0];
+    adj[2][0] = J[0][1] * J[1][2] - J[1][1] * J[0][2];
+    adj[2][1] = J[0][2] * J[1][0] - J[1][2] * J[0][0];
+    adj[2][2] = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+    const double det = J[0][0] * adj[0][0] + J[1][0] * adj[1][0] + J[2][0] * adj[2][0];
+    if (!(det > 0.0)) *P.err = 1; // MasterElementFunctions.h:91-94 asserts this in debug builds
+    const double inv = 1.0 / det;
+    // mu at the (never shifted) ip location, MomentumAdvDiffElemKernel.C:107-110
+    const double mu = 0.125 * M[0] + 0.0625 * (sg1 * M[Uu] + sg2 * M[V]) + 0.03125 * sg1 * sg2 * M[UV];
+    const double fac = -mu * inv;
+
+    double *o = buf + el * C::ES + ip * C::IPD;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) o[i * 3 + j] = fac * adj[i][j];
+    // area vector
+    double W[3], A[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) W[i] = sg2 * X[i][V] - sg1 * X[i][Uu];
+    A[0] = base[0] + (X[1][UV] * W[2] - X[2][UV] * W[1]) * (1.0 / 128.0);
+    A[1] = base[1] + (X[2][UV] * W[0] - X[0][UV] * W[2]) * (1.0 / 128.0);
+    A[2] = base[2] + (X[0][UV] * W[1] - X[1][UV] * W[0]) * (1.0 / 128.0);
+    o[9] = orient * A[0];
+    o[10] = orient * A[1];
+    o[11] = orient * A[2];
+    o[12] = P.mdot[e * 12 + ip];
+    double w = 0.0;
+    if (divu) {
+      // divU = sum_i sum_j (adj[i][j]/det) d u_i / d xi_j   (u_j dN/dx_j summed, :111-114)
+      double dv = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double d0 = 0.25 * U[i][T] + c1 * U[i][TU] + c2 * U[i][TV] + c12 * U[i][TUV];
+        const double d1 = 0.25 * U[i][Uu] + c2 * U[i][UV];
+        const double d2 = 0.25 * U[i][V] + c1 * U[i][UV];
+        dv += adj[i][0] * d0 + adj[i][1] * d1 + adj[i][2] * d2;
+      }
+      w = 2.0 / 3.0 * mu * (dv * inv) * P.include_divu;
+    }
+    o[13] = w;
+  }
+}
+
+// ---- phase 2 per-thread state ---------------------------------------------------------------------
+struct P2State {
+  double acc[4][9]; // 3x3 blocks per (sx,sy) quadrant, row-major [i][j]
+  double D[4];      // diagonal part of each block
+  double rr[3];     // rhs partial of this thread
+};
+
+struct NodeCtx {
+  int active;        // node inside the domain
+  int x, y, z;
+  int lx, ly;        // position in the tile
+  long long n;       // lattice node index
+  long long rowbase; // values offset of the node's first dof row
+  int nb;            // blocks in the row
+  int row;           // row node index (rhs offset / 3)
+  int cls;
+};
+
+__host__ __device__ inline void p2_zero(P2State &S)
+{
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) S.acc[q][t] = 0.0;
+    S.D[q] = 0.0;
+  }
+}
+
+// one z-half (SZP = 0: elements below the node plane, 1: above) of the 8 octants
+template <class C, int SZP>
+__host__ __device__ inline void p2_pass(const BoxParams &P, const NodeCtx &N, P2State &S, const double *buf,
+                                        const double *tab, bool divu)
+{
+  const int ez = N.z - 1 + SZP;
+  if (ez < 0 || ez >= P.nz) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int sxp = q & 1, syp = q >> 1;
+    const int ex = N.x - 1 + sxp, ey = N.y - 1 + syp;
+    if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) continue;
+    const int s = q + 4 * SZP;
+    const int k = node_of_bits(!sxp, !syp, !SZP);
+    const double *eb = buf + ((N.lx + sxp) + C::ELX * (N.ly + syp)) * C::ES;
+#pragma unroll
+    for (int pp = 0; pp < 3; ++pp) {
+      const int ip = ip_of(k, pp);
+      const bool isL = hex8::scs_left(ip) == k;
+      const double *o = eb + ip * C::IPD;
+      const double *t0 = tab + ((s * 3 + pp) * 2 + 0) * 16 + N.cls * 2;
+      const double *t1 = tab + ((s * 3 + pp) * 2 + 1) * 16 + N.cls * 2;
+      const double d0 = t0[0], d1 = t0[1], d2 = t1[0], nadv = t1[1];
+      double h[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) h[i] = o[i * 3 + 0] * d0 + o[i * 3 + 1] * d1 + o[i * 3 + 2] * d2;
+      const double A0 = o[9], A1 = o[10], A2 = o[11];
+      const double dsum = h[0] * A0 + h[1] * A1 + h[2] * A2 + nadv * o[12];
+      if (isL) {
+        S.D[q] += dsum;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          S.acc[q][i * 3 + 0] += h[i] * A0;
+          S.acc[q][i * 3 + 1] += h[i] * A1;
+          S.acc[q][i * 3 + 2] += h[i] * A2;
+        }
+      } else {
+        S.D[q] -= dsum;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          S.acc[q][i * 3 + 0] -= h[i] * A0;
+          S.acc[q][i * 3 + 1] -= h[i] * A1;
+          S.acc[q][i * 3 + 2] -= h[i] * A2;
+        }
+      }
+      if (divu && N.cls == 0) {
+        // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135); the centre class meets every
+        // (element, ip) next to the node exactly once
+        const double w = isL ? o[13] : -o[13];
+        S.rr[0] -= w * A0;
+        S.rr[1] -= w * A1;
+        S.rr[2] -= w * A2;
+      }
+    }
+  }
+}
+
+// fold the quadrant accumulators of the axes the class does not distinguish, then write the
+// finished blocks into the staging row (CSR layout) and take their share of rhs = -row . u
+template <class C>
+__host__ __device__ inline void p2_flush(const BoxParams &P, const NodeCtx &N, P2State &S, int dz, double *stg)
+{
+  const int a = N.cls & 1, b = (N.cls >> 1) & 1;
+  if (!a) {
+#pragma unroll
+    for (int sy = 0; sy < 2; ++sy) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) S.acc[sy * 2][t] += S.acc[sy * 2 + 1][t];
+      S.D[sy * 2] += S.D[sy * 2 + 1];
+    }
+  }
+  if (!b) {
+#pragma unroll
+    for (int sx = 0; sx < 2; ++sx) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) S.acc[sx][t] += S.acc[2 + sx][t];
+      S.D[sx] += S.D[2 + sx];
+    }
+  }
+  const unsigned char *slots = P.slot27 + N.n * 27;
+  double *row = stg + (N.lx + C::TBX * N.ly) * C::SROW;
+  const int rs = N.nb * 3; // doubles per dof row
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int sxp = q & 1, syp = q >> 1;
+    if ((!a && sxp) || (!b && syp)) continue;
+    const int dx = a ? (sxp ? 1 : -1) : 0, dy = b ? (syp ? 1 : -1) : 0;
+    const int cx = N.x + dx, cy = N.y + dy, cz = N.z + dz;
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= P.NX || cy >= P.NY || cz >= P.NZ) continue;
+    const int slot = slots[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+    const long long nc = N.n + dx + (long long)P.NX * (dy + (long long)P.NY * dz);
+    const double u0 = P.vel[nc * 3 + 0], u1 = P.vel[nc * 3 + 1], u2 = P.vel[nc * 3 + 2];
+    double *bp = row + slot * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double v0 = S.acc[q][i * 3 + 0], v1 = S.acc[q][i * 3 + 1], v2 = S.acc[q][i * 3 + 2];
+      if (i == 0) v0 += S.D[q];
+      if (i == 1) v1 += S.D[q];
+      if (i == 2) v2 += S.D[q];
+      bp[i * rs + 0] = v0;
+      bp[i * rs + 1] = v1;
+      bp[i * rs + 2] = v2;
+      S.rr[i] -= v0 * u0 + v1 * u1 + v2 * u2;
+    }
+  }
+}
+
+} // namespace box
+} // namespace nalu_b200
