@@ -21,7 +21,12 @@ template <class C>
 __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_kernel(const __grid_constant__ BoxParams P)
 {
   extern __shared__ __align__(16) double sm[];
-  double *const tab = sm + 2 * C::LBUF;
+  double *const tab = sm + C::OFF_TAB;
+  double *const ring = sm + C::OFF_RING;
+  double *const mdb = sm + C::OFF_MD;
+  long long *const s_rb = reinterpret_cast<long long *>(sm + C::OFF_RB);
+  int *const s_len = reinterpret_cast<int *>(sm + C::OFF_LEN);
+  constexpr int PLN = C::RN * C::NF;
   const int tid = threadIdx.x;
   const int ntile = P.tiles_x * P.tiles_y;
   const int tile = blockIdx.x % ntile, zc = blockIdx.x / ntile;
@@ -29,40 +34,81 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
   const int zs = zc * P.z_chunk;
   const int ze = (zs + P.z_chunk < P.NZ) ? zs + P.z_chunk : P.NZ;
   const bool divu = P.include_divu != 0.0;
-
-  for (int i = tid; i < 192; i += C::NT) box::build_table_entry<C>(i, P.options, tab);
+  const long long plane_nodes = (long long)P.NX * P.NY;
 
   box::NodeCtx N;
-  {
-    const int nl = tid >> 3;
-    N.cls = tid & 7;
-    N.lx = nl % C::TBX;
-    N.ly = nl / C::TBX;
-    N.x = x0 + N.lx;
-    N.y = y0 + N.ly;
-    N.active = N.x < P.NX && N.y < P.NY;
+  const int nl = tid >> 3;
+  N.cls = tid & 7;
+  N.lx = nl % C::TBX;
+  N.ly = nl / C::TBX;
+  N.x = x0 + N.lx;
+  N.y = y0 + N.ly;
+  N.active = N.x < P.NX && N.y < P.NY;
+  const int dz_fin = (N.cls & 4) ? 1 : 0;
+
+  double regP[C::NPL], regM[C::NML];
+  // ---- prologue: table, node planes zs-1..zs+1, the layer below the first plane, first node ctx
+  for (int i = tid; i < 192; i += C::NT) box::build_table_entry<C>(i, P.options, tab);
+  for (int pl = zs - 1; pl <= zs + 1; ++pl) {
+    box::plane_load<C>(P, tid, x0, y0, pl, regP);
+    box::plane_store<C>(tid, regP, ring + ((pl + 3) % 3) * PLN);
   }
+  box::mdot_load<C>(P, tid, x0, y0, zs - 1, regM);
+  box::mdot_store<C>(tid, regM, mdb);
+  __syncthreads();
   if (zs >= 1)
-    for (int it = tid; it < C::NITEM; it += C::NT) box::phase1_item<C>(P, it, x0, y0, zs - 1, sm + ((zs - 1) & 1) * C::LBUF);
+    for (int it = tid; it < C::NITEM; it += C::NT)
+      box::phase1_item<C>(P, it, x0, y0, ring + ((zs - 1) % 3) * PLN, ring + (zs % 3) * PLN, mdb, sm + ((zs - 1) & 1) * C::LBUF);
+  __syncthreads();
+  box::mdot_load<C>(P, tid, x0, y0, zs, regM);
+  box::mdot_store<C>(tid, regM, mdb);
+  N.n = N.x + (long long)P.NX * (N.y + (long long)P.NY * zs);
+  N.row = 0; N.nb = 0; N.rowbase = 0; N.slots_mid = N.slots_fin = 0xFFFFFFFFu;
+  if (N.active) {
+    N.row = P.node_row[N.n];
+    const long long b0 = P.browptr[N.row];
+    N.nb = (int)(P.browptr[N.row + 1] - b0);
+    N.rowbase = 9 * b0;
+    N.slots_mid = box::load_slots(P.slot27 + N.n * 27, N.cls, -1);
+    N.slots_fin = box::load_slots(P.slot27 + N.n * 27, N.cls, dz_fin);
+  }
+  __syncthreads();
 
   for (int z = zs; z < ze; ++z) {
+    const bool more = z + 1 < ze;
+    // loads for the next plane / layer, parked in registers
+    box::plane_load<C>(P, tid, x0, y0, z + 2, regP);
+    box::mdot_load<C>(P, tid, x0, y0, z + 1, regM);
+    int row_n = 0;
+    if (N.active && more) row_n = P.node_row[N.n + plane_nodes];
+    const double *pl_m = ring + ((z + 2) % 3) * PLN; // plane z-1
+    const double *pl_0 = ring + (z % 3) * PLN;
+    const double *pl_p = ring + ((z + 1) % 3) * PLN;
     if (z < P.nz)
-      for (int it = tid; it < C::NITEM; it += C::NT) box::phase1_item<C>(P, it, x0, y0, z, sm + (z & 1) * C::LBUF);
+      for (int it = tid; it < C::NITEM; it += C::NT) box::phase1_item<C>(P, it, x0, y0, pl_0, pl_p, mdb, sm + (z & 1) * C::LBUF);
     __syncthreads();
+    box::mdot_store<C>(tid, regM, mdb);
     const double *lower = sm + ((z + 1) & 1) * C::LBUF;
     const double *upper = sm + (z & 1) * C::LBUF;
     double *stg = sm + ((z + 1) & 1) * C::LBUF;
+    if (N.cls == 0) {
+      s_rb[nl] = N.rowbase;
+      s_len[nl] = N.active ? N.nb * 9 : 0;
+    }
+    long long b0_n = 0, b1_n = 0;
+    unsigned sm_n = 0xFFFFFFFFu, sf_n = 0xFFFFFFFFu;
+    if (N.active && more) {
+      b0_n = P.browptr[row_n];
+      b1_n = P.browptr[row_n + 1];
+      const unsigned char *sl = P.slot27 + (N.n + plane_nodes) * 27;
+      sm_n = box::load_slots(sl, N.cls, -1);
+      sf_n = box::load_slots(sl, N.cls, dz_fin);
+    }
     box::P2State S;
-    box::p2_zero(S);
-    S.rr[0] = S.rr[1] = S.rr[2] = 0.0;
+    box::p2_begin(S);
     N.z = z;
     int ncov = 0;
     if (N.active) {
-      N.n = N.x + (long long)P.NX * (N.y + (long long)P.NY * z);
-      N.row = P.node_row[N.n];
-      const long long b0 = P.browptr[N.row];
-      N.nb = (int)(P.browptr[N.row + 1] - b0);
-      N.rowbase = 9 * b0;
       ncov = ((N.x > 0) + 1 + (N.x < P.NX - 1)) * ((N.y > 0) + 1 + (N.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
       box::p2_pass<C, 0>(P, N, S, lower, tab, divu);
     }
@@ -70,22 +116,22 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     if (N.active && N.nb != ncov) {
       // row also holds columns no local element touches (remote columns announced by the ranks
       // sharing this node): they must read zero
-      double *row = stg + (N.lx + C::TBX * N.ly) * C::SROW;
+      double *row = stg + nl * C::SROW;
       for (int q = N.cls; q < N.nb * 9; q += 8) row[q] = 0.0;
     }
     __syncwarp();
     if (N.active) {
       if (N.cls & 4) {
-        box::p2_flush<C>(P, N, S, -1, stg);
+        box::p2_flush<C>(N, S, N.slots_mid, pl_m, stg);
         box::p2_zero(S);
       }
       box::p2_pass<C, 1>(P, N, S, upper, tab, divu);
-      box::p2_flush<C>(P, N, S, (N.cls & 4) ? 1 : 0, stg);
+      box::p2_flush<C>(N, S, N.slots_fin, dz_fin ? pl_p : pl_0, stg);
     }
-    // rhs: sum the 8 class partials of the node
+    // rhs: sum the 8 class partials of the node (classes 0..2 also carry the divU stress components)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double v = S.rr[i];
+      double v = S.rr[i] + (N.cls == i ? S.dv : 0.0);
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -97,26 +143,37 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
       *r = P.overwrite ? v : *r + v;
     }
     __syncthreads();
+    box::plane_store<C>(tid, regP, ring + ((z + 2) % 3) * PLN); // plane z-1 is no longer needed
     // finished rows -> HBM, one warp per node, 256 B per store instruction
     {
       const int warp = tid >> 5, lane = tid & 31;
-      for (int nl = warp; nl < C::NNODE; nl += C::NT / 32) {
-        const int lx = nl % C::TBX, ly = nl / C::TBX;
-        const int x = x0 + lx, y = y0 + ly;
-        if (x >= P.NX || y >= P.NY) continue;
-        const long long n = x + (long long)P.NX * (y + (long long)P.NY * z);
-        const int r = P.node_row[n];
-        const long long b0 = P.browptr[r];
-        const int len = (int)(P.browptr[r + 1] - b0) * 9;
-        double *dst = P.values + 9 * b0;
-        const double *src = stg + nl * C::SROW;
-        if (P.overwrite)
-          for (int q = lane; q < len; q += 32) dst[q] = src[q];
-        else
-          for (int q = lane; q < len; q += 32) dst[q] += src[q];
+      for (int m = warp; m < C::NNODE; m += C::NT / 32) {
+        const int len = s_len[m];
+        double *dst = P.values + s_rb[m];
+        const double *src = stg + m * C::SROW;
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (lane + 32 * k < len) v[k] = src[lane + 32 * k];
+        if (P.overwrite) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (lane + 32 * k < len) dst[lane + 32 * k] = v[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (lane + 32 * k < len) dst[lane + 32 * k] += v[k];
+        }
       }
     }
     __syncthreads();
+    // rotate the node context
+    N.n += plane_nodes;
+    N.row = row_n;
+    N.nb = (int)(b1_n - b0_n);
+    N.rowbase = 9 * b0_n;
+    N.slots_mid = sm_n;
+    N.slots_fin = sf_n;
   }
 }
 

@@ -63,7 +63,16 @@ struct Cfg {
   static constexpr int SROW = 248;          // staging row stride (doubles) >= 27*9
   static constexpr int LBUF = (NEL * ES > NNODE * SROW) ? NEL * ES : NNODE * SROW;
   static constexpr int TAB = 8 * 3 * 2 * 8 * 2; // [octant][edge dir][half][class][2]
-  static constexpr int SMEM_DOUBLES = 2 * LBUF + TAB;
+  static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY; // node neighbourhood of the tile
+  static constexpr int NF = 7;              // staged nodal doubles: x[3], mu, u[3]
+  static constexpr int RING = 3 * RN * NF;  // three node planes
+  static constexpr int MDB = NEL * 12;      // mass flow rates of one element layer
+  static constexpr int NPL = (RN * NF + NT - 1) / NT;  // per-thread loads to stage one node plane
+  static constexpr int NML = (MDB + NT - 1) / NT;      // per-thread loads to stage one mdot layer
+  // doubles: two layer buffers, table, nodal ring, mdot layer, row base (as 8-byte ints) and row length
+  static constexpr int OFF_TAB = 2 * LBUF, OFF_RING = OFF_TAB + TAB, OFF_MD = OFF_RING + RING,
+                       OFF_RB = OFF_MD + MDB, OFF_LEN = OFF_RB + NNODE;
+  static constexpr int SMEM_DOUBLES = OFF_LEN + (NNODE + 1) / 2;
   static constexpr int NITEM = NEL * 3;     // phase-1 work items: (element, edge direction)
 };
 
@@ -108,33 +117,89 @@ __host__ __device__ inline void build_table_entry(int idx, int options, double *
   t1[1] = nadv;
 }
 
+// ---- staging of nodal fields / mass flow rates (global -> registers -> shared) ---------------------
+// Slot k of thread tid covers flat index tid + k*NT of the [RN][NF] plane image; the loads are
+// issued one plane ahead of their use and parked in registers so their latency is off the path.
+template <class C>
+__host__ __device__ inline void plane_load(const BoxParams &P, int tid, int x0, int y0, int zp, double (&reg)[C::NPL])
+{
+#pragma unroll
+  for (int k = 0; k < C::NPL; ++k) {
+    const int idx = tid + k * C::NT;
+    reg[k] = 0.0;
+    if (idx >= C::RN * C::NF || zp < 0 || zp >= P.NZ) continue;
+    const int rn = idx / C::NF, f = idx - rn * C::NF;
+    const int x = x0 - 1 + rn % C::RNX, y = y0 - 1 + rn / C::RNX;
+    if (x < 0 || y < 0 || x >= P.NX || y >= P.NY) continue;
+    const long long n = x + (long long)P.NX * (y + (long long)P.NY * zp);
+    reg[k] = f < 3 ? P.coords[n * 3 + f] : (f == 3 ? P.visc[n] : P.vel[n * 3 + (f - 4)]);
+  }
+}
+template <class C>
+__host__ __device__ inline void plane_store(int tid, const double (&reg)[C::NPL], double *ring_plane)
+{
+#pragma unroll
+  for (int k = 0; k < C::NPL; ++k) {
+    const int idx = tid + k * C::NT;
+    if (idx < C::RN * C::NF) ring_plane[idx] = reg[k];
+  }
+}
+template <class C>
+__host__ __device__ inline void mdot_load(const BoxParams &P, int tid, int x0, int y0, int ez, double (&reg)[C::NML])
+{
+#pragma unroll
+  for (int k = 0; k < C::NML; ++k) {
+    const int idx = tid + k * C::NT;
+    reg[k] = 0.0;
+    if (idx >= C::MDB || ez < 0 || ez >= P.nz) continue;
+    const int el = idx / 12, ip = idx - el * 12;
+    const int ex = x0 - 1 + el % C::ELX, ey = y0 - 1 + el / C::ELX;
+    if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) continue;
+    reg[k] = P.mdot[(ex + (long long)P.nx * (ey + (long long)P.ny * ez)) * 12 + ip];
+  }
+}
+template <class C>
+__host__ __device__ inline void mdot_store(int tid, const double (&reg)[C::NML], double *mdb)
+{
+#pragma unroll
+  for (int k = 0; k < C::NML; ++k) {
+    const int idx = tid + k * C::NT;
+    if (idx < C::MDB) mdb[idx] = reg[k];
+  }
+}
+
 // ---- phase 1: integration-point data of one (element, edge direction) item ---------------------
 // Local axes (t,u,v) = (g, g+1, g+2) mod 3; local node m has bits (b0,b1,b2) along (t,u,v).
+// pl0 / pl1: staged node planes below / above the element layer; mdb: the layer's mass flow rates
 template <class C>
-__host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0, int y0, int ez, double *buf)
+__host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0, int y0, const double *pl0,
+                                            const double *pl1, const double *mdb, double *buf)
 {
   const int g = item / C::NEL, el = item - g * C::NEL;
   const int elx = el % C::ELX, ely = el / C::ELX;
   const int ex = x0 - 1 + elx, ey = y0 - 1 + ely;
   if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) return;
-  const int st[3] = {1, P.NX, P.NX * P.NY};
-  const int s_t = st[g], s_u = st[(g + 1) % 3], s_v = st[(g + 2) % 3];
-  const long long n000 = ex + (long long)P.NX * (ey + (long long)P.NY * ez);
+  // strides of the local axes (t,u,v) in the staged image: x -> NF, y -> RNX*NF, z -> other plane
+  const int sx = C::NF, sy = C::RNX * C::NF;
+  const int s_t = g == 0 ? sx : (g == 1 ? sy : 0), s_u = g == 0 ? sy : (g == 1 ? 0 : sx),
+            s_v = g == 0 ? 0 : (g == 1 ? sx : sy);
+  const int zbit = g == 0 ? 4 : (g == 1 ? 2 : 1); // which local bit is the z axis
+  const int n000 = (elx + C::RNX * ely) * C::NF;
   const bool divu = P.include_divu != 0.0;
 
   // butterfly: C[mask] = sum_m prod_{axis in mask} sign_axis(m) f_m   (mask bits: 1 = t, 2 = u, 4 = v)
   double X[3][8], M[8], U[3][8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    const long long n = n000 + (m & 1) * s_t + ((m >> 1) & 1) * s_u + ((m >> 2) & 1) * s_v;
-    X[0][m] = P.coords[n * 3 + 0];
-    X[1][m] = P.coords[n * 3 + 1];
-    X[2][m] = P.coords[n * 3 + 2];
-    M[m] = P.visc[n];
+    const double *nd = ((m & zbit) ? pl1 : pl0) + n000 + (m & 1) * s_t + ((m >> 1) & 1) * s_u + ((m >> 2) & 1) * s_v;
+    X[0][m] = nd[0];
+    X[1][m] = nd[1];
+    X[2][m] = nd[2];
+    M[m] = nd[3];
     if (divu) {
-      U[0][m] = P.vel[n * 3 + 0];
-      U[1][m] = P.vel[n * 3 + 1];
-      U[2][m] = P.vel[n * 3 + 2];
+      U[0][m] = nd[4];
+      U[1][m] = nd[5];
+      U[2][m] = nd[6];
     }
   }
   auto butterfly = [](double *f) {
@@ -165,7 +230,6 @@ __host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0
   base[1] = (X[2][Uu] * X[0][V] - X[0][Uu] * X[2][V]) * (1.0 / 64.0);
   base[2] = (X[0][Uu] * X[1][V] - X[1][Uu] * X[0][V]) * (1.0 / 64.0);
   const double q = (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
-  const long long e = ex + (long long)P.nx * (ey + (long long)P.ny * ez);
   // original-axis bit positions of the local axes
   const int at = g, au = (g + 1) % 3, av = (g + 2) % 3;
 
@@ -222,7 +286,7 @@ __host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0
     o[9] = orient * A[0];
     o[10] = orient * A[1];
     o[11] = orient * A[2];
-    o[12] = P.mdot[e * 12 + ip];
+    o[12] = mdb[el * 12 + ip];
     double w = 0.0;
     if (divu) {
       // divU = sum_i sum_j (adj[i][j]/det) d u_i / d xi_j   (u_j dN/dx_j summed, :111-114)
@@ -245,6 +309,7 @@ struct P2State {
   double acc[4][9]; // 3x3 blocks per (sx,sy) quadrant, row-major [i][j]
   double D[4];      // diagonal part of each block
   double rr[3];     // rhs partial of this thread
+  double dv;        // divU stress component carried by classes 0..2
 };
 
 struct NodeCtx {
@@ -256,7 +321,26 @@ struct NodeCtx {
   int nb;            // blocks in the row
   int row;           // row node index (rhs offset / 3)
   int cls;
+  unsigned slots_mid, slots_fin; // CSR block slot (0xFF: no such neighbour) of the 4 quadrant blocks
 };
+
+// CSR slots of the blocks this class flushes: byte q = quadrant (sx,sy) -> offset (a sx, b sy, dz)
+__host__ __device__ inline unsigned load_slots(const unsigned char *slots, int cls, int dz)
+{
+  const int a = cls & 1, b = (cls >> 1) & 1;
+  unsigned r = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int sxp = q & 1, syp = q >> 1;
+    unsigned v = 0xFF;
+    if (!((!a && sxp) || (!b && syp))) {
+      const int dx = a ? (sxp ? 1 : -1) : 0, dy = b ? (syp ? 1 : -1) : 0;
+      v = slots[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+    }
+    r |= v << (8 * q);
+  }
+  return r;
+}
 
 __host__ __device__ inline void p2_zero(P2State &S)
 {
@@ -266,6 +350,12 @@ __host__ __device__ inline void p2_zero(P2State &S)
     for (int t = 0; t < 9; ++t) S.acc[q][t] = 0.0;
     S.D[q] = 0.0;
   }
+}
+__host__ __device__ inline void p2_begin(P2State &S)
+{
+  p2_zero(S);
+  S.rr[0] = S.rr[1] = S.rr[2] = 0.0;
+  S.dv = 0.0;
 }
 
 // one z-half (SZP = 0: elements below the node plane, 1: above) of the 8 octants
@@ -313,22 +403,22 @@ __host__ __device__ inline void p2_pass(const BoxParams &P, const NodeCtx &N, P2
           S.acc[q][i * 3 + 2] -= h[i] * A2;
         }
       }
-      if (divu && N.cls == 0) {
-        // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135); the centre class meets every
-        // (element, ip) next to the node exactly once
-        const double w = isL ? o[13] : -o[13];
-        S.rr[0] -= w * A0;
-        S.rr[1] -= w * A1;
-        S.rr[2] -= w * A2;
+      if (divu) {
+        // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135).  Every class meets each (element, ip)
+        // next to the node exactly once; classes 0,1,2 each carry one component of w A (the other
+        // classes' copies are discarded in p2_rhs_partial)
+        const double Asel = N.cls == 0 ? A0 : (N.cls == 1 ? A1 : A2);
+        if (isL) S.dv -= o[13] * Asel; else S.dv += o[13] * Asel;
       }
     }
   }
 }
 
 // fold the quadrant accumulators of the axes the class does not distinguish, then write the
-// finished blocks into the staging row (CSR layout) and take their share of rhs = -row . u
+// finished blocks into the staging row (CSR layout) and take their share of rhs = -row . u.
+// `slots`: packed CSR slots of the 4 quadrant blocks; `uplane`: staged node plane of the column nodes
 template <class C>
-__host__ __device__ inline void p2_flush(const BoxParams &P, const NodeCtx &N, P2State &S, int dz, double *stg)
+__host__ __device__ inline void p2_flush(const NodeCtx &N, P2State &S, unsigned slots, const double *uplane, double *stg)
 {
   const int a = N.cls & 1, b = (N.cls >> 1) & 1;
   if (!a) {
@@ -347,19 +437,17 @@ __host__ __device__ inline void p2_flush(const BoxParams &P, const NodeCtx &N, P
       S.D[sx] += S.D[2 + sx];
     }
   }
-  const unsigned char *slots = P.slot27 + N.n * 27;
   double *row = stg + (N.lx + C::TBX * N.ly) * C::SROW;
   const int rs = N.nb * 3; // doubles per dof row
+  const double *uc = uplane + ((N.lx + 1) + C::RNX * (N.ly + 1)) * C::NF + 4;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int sxp = q & 1, syp = q >> 1;
-    if ((!a && sxp) || (!b && syp)) continue;
+    const unsigned slot = (slots >> (8 * q)) & 0xFF;
+    if (slot == 0xFF) continue; // block not owned by this class, or no such neighbour node
     const int dx = a ? (sxp ? 1 : -1) : 0, dy = b ? (syp ? 1 : -1) : 0;
-    const int cx = N.x + dx, cy = N.y + dy, cz = N.z + dz;
-    if (cx < 0 || cy < 0 || cz < 0 || cx >= P.NX || cy >= P.NY || cz >= P.NZ) continue;
-    const int slot = slots[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
-    const long long nc = N.n + dx + (long long)P.NX * (dy + (long long)P.NY * dz);
-    const double u0 = P.vel[nc * 3 + 0], u1 = P.vel[nc * 3 + 1], u2 = P.vel[nc * 3 + 2];
+    const double *u = uc + (dx + C::RNX * dy) * C::NF;
+    const double u0 = u[0], u1 = u[1], u2 = u[2];
     double *bp = row + slot * 3;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {

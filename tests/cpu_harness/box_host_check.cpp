@@ -85,84 +85,149 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
   P.tiles_y = (P.NY + C::TBY - 1) / C::TBY;
   P.z_chunk = z_chunk;
   const int zchunks = (P.NZ + z_chunk - 1) / z_chunk;
+  constexpr int PLN = C::RN * C::NF;
+  constexpr int NT = C::NT;
   std::vector<double> sm(C::SMEM_DOUBLES);
-  std::vector<box::P2State> S(C::NT);
-  std::vector<box::NodeCtx> N(C::NT);
-  std::vector<int> ncov(C::NT);
+  std::vector<box::P2State> S(NT);
+  std::vector<box::NodeCtx> N(NT);
+  std::vector<int> ncov(NT), row_n(NT);
+  std::vector<long long> b0_n(NT), b1_n(NT);
+  std::vector<unsigned> sm_n(NT), sf_n(NT);
+  struct Regs { double p[C::NPL]; double m[C::NML]; };
+  std::vector<Regs> R(NT);
   const bool divu = P.include_divu != 0.0;
+  const long long plane_nodes = (long long)P.NX * P.NY;
   for (int cta = 0; cta < P.tiles_x * P.tiles_y * zchunks; ++cta) {
     for (auto &v : sm) v = NAN; // uninitialised shared memory must never be consumed
-    double *tab = sm.data() + 2 * C::LBUF;
+    double *tab = sm.data() + C::OFF_TAB, *ring = sm.data() + C::OFF_RING, *mdb = sm.data() + C::OFF_MD;
+    long long *s_rb = reinterpret_cast<long long *>(sm.data() + C::OFF_RB);
+    int *s_len = reinterpret_cast<int *>(sm.data() + C::OFF_LEN);
     const int ntile = P.tiles_x * P.tiles_y;
     const int tile = cta % ntile, zc = cta / ntile;
     const int x0 = (tile % P.tiles_x) * C::TBX, y0 = (tile / P.tiles_x) * C::TBY;
     const int zs = zc * P.z_chunk;
     const int ze = (zs + P.z_chunk < P.NZ) ? zs + P.z_chunk : P.NZ;
     for (int i = 0; i < 192; ++i) box::build_table_entry<C>(i, P.options, tab);
-    for (int tid = 0; tid < C::NT; ++tid) {
-      const int nl = tid >> 3;
-      N[tid].cls = tid & 7;
-      N[tid].lx = nl % C::TBX;
-      N[tid].ly = nl / C::TBX;
-      N[tid].x = x0 + N[tid].lx;
-      N[tid].y = y0 + N[tid].ly;
-      N[tid].active = N[tid].x < P.NX && N[tid].y < P.NY;
+    for (int pl = zs - 1; pl <= zs + 1; ++pl)
+      for (int tid = 0; tid < NT; ++tid) {
+        box::plane_load<C>(P, tid, x0, y0, pl, R[tid].p);
+        box::plane_store<C>(tid, R[tid].p, ring + ((pl + 3) % 3) * PLN);
+      }
+    for (int tid = 0; tid < NT; ++tid) {
+      box::mdot_load<C>(P, tid, x0, y0, zs - 1, R[tid].m);
+      box::mdot_store<C>(tid, R[tid].m, mdb);
     }
     if (zs >= 1)
-      for (int it = 0; it < C::NITEM; ++it) box::phase1_item<C>(P, it, x0, y0, zs - 1, sm.data() + ((zs - 1) & 1) * C::LBUF);
+      for (int it = 0; it < C::NITEM; ++it)
+        box::phase1_item<C>(P, it, x0, y0, ring + ((zs - 1) % 3) * PLN, ring + (zs % 3) * PLN, mdb,
+                            sm.data() + ((zs - 1) & 1) * C::LBUF);
+    for (int tid = 0; tid < NT; ++tid) {
+      box::mdot_load<C>(P, tid, x0, y0, zs, R[tid].m);
+      box::mdot_store<C>(tid, R[tid].m, mdb);
+      box::NodeCtx &n = N[tid];
+      const int nl = tid >> 3;
+      n.cls = tid & 7;
+      n.lx = nl % C::TBX;
+      n.ly = nl / C::TBX;
+      n.x = x0 + n.lx;
+      n.y = y0 + n.ly;
+      n.active = n.x < P.NX && n.y < P.NY;
+      n.n = n.x + (long long)P.NX * (n.y + (long long)P.NY * zs);
+      n.row = 0; n.nb = 0; n.rowbase = 0; n.slots_mid = n.slots_fin = 0xFFFFFFFFu;
+      if (n.active) {
+        n.row = P.node_row[n.n];
+        const long long b0 = P.browptr[n.row];
+        n.nb = (int)(P.browptr[n.row + 1] - b0);
+        n.rowbase = 9 * b0;
+        n.slots_mid = box::load_slots(P.slot27 + n.n * 27, n.cls, -1);
+        n.slots_fin = box::load_slots(P.slot27 + n.n * 27, n.cls, (n.cls & 4) ? 1 : 0);
+      }
+    }
     for (int z = zs; z < ze; ++z) {
+      const bool more = z + 1 < ze;
+      for (int tid = 0; tid < NT; ++tid) {
+        box::plane_load<C>(P, tid, x0, y0, z + 2, R[tid].p);
+        box::mdot_load<C>(P, tid, x0, y0, z + 1, R[tid].m);
+        row_n[tid] = (N[tid].active && more) ? P.node_row[N[tid].n + plane_nodes] : 0;
+      }
+      const double *pl_m = ring + ((z + 2) % 3) * PLN, *pl_0 = ring + (z % 3) * PLN, *pl_p = ring + ((z + 1) % 3) * PLN;
       if (z < P.nz)
-        for (int it = 0; it < C::NITEM; ++it) box::phase1_item<C>(P, it, x0, y0, z, sm.data() + (z & 1) * C::LBUF);
+        for (int it = 0; it < C::NITEM; ++it) box::phase1_item<C>(P, it, x0, y0, pl_0, pl_p, mdb, sm.data() + (z & 1) * C::LBUF);
+      // ---- barrier S1
       const double *lower = sm.data() + ((z + 1) & 1) * C::LBUF;
       const double *upper = sm.data() + (z & 1) * C::LBUF;
       double *stg = sm.data() + ((z + 1) & 1) * C::LBUF;
-      for (int tid = 0; tid < C::NT; ++tid) {
-        box::p2_zero(S[tid]);
-        S[tid].rr[0] = S[tid].rr[1] = S[tid].rr[2] = 0.0;
+      for (int tid = 0; tid < NT; ++tid) {
+        box::mdot_store<C>(tid, R[tid].m, mdb);
         box::NodeCtx &n = N[tid];
+        const int nl = tid >> 3;
+        if (n.cls == 0) {
+          s_rb[nl] = n.rowbase;
+          s_len[nl] = n.active ? n.nb * 9 : 0;
+        }
+        b0_n[tid] = b1_n[tid] = 0;
+        sm_n[tid] = sf_n[tid] = 0xFFFFFFFFu;
+        if (n.active && more) {
+          b0_n[tid] = P.browptr[row_n[tid]];
+          b1_n[tid] = P.browptr[row_n[tid] + 1];
+          const unsigned char *sl = P.slot27 + (n.n + plane_nodes) * 27;
+          sm_n[tid] = box::load_slots(sl, n.cls, -1);
+          sf_n[tid] = box::load_slots(sl, n.cls, (n.cls & 4) ? 1 : 0);
+        }
+        box::p2_begin(S[tid]);
         n.z = z;
         if (n.active) {
-          n.n = n.x + (long long)P.NX * (n.y + (long long)P.NY * z);
-          n.row = P.node_row[n.n];
-          const long long b0 = P.browptr[n.row];
-          n.nb = (int)(P.browptr[n.row + 1] - b0);
-          n.rowbase = 9 * b0;
           ncov[tid] = ((n.x > 0) + 1 + (n.x < P.NX - 1)) * ((n.y > 0) + 1 + (n.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
           box::p2_pass<C, 0>(P, n, S[tid], lower, tab, divu);
         }
       }
-      // barrier: the lower layer's buffer becomes the staging area
+      // ---- barrier S2: the lower layer's buffer becomes the staging area
       for (int q = 0; q < C::LBUF; ++q) stg[q] = NAN;
-      for (int tid = 0; tid < C::NT; ++tid) {
+      for (int tid = 0; tid < NT; ++tid) {
         box::NodeCtx &n = N[tid];
         if (n.active && n.nb != ncov[tid]) {
-          double *row = stg + (n.lx + C::TBX * n.ly) * C::SROW;
+          double *row = stg + (tid >> 3) * C::SROW;
           for (int q = n.cls; q < n.nb * 9; q += 8) row[q] = 0.0;
         }
       }
-      for (int tid = 0; tid < C::NT; ++tid) {
+      for (int tid = 0; tid < NT; ++tid) {
         box::NodeCtx &n = N[tid];
         if (!n.active) continue;
+        const int dz_fin = (n.cls & 4) ? 1 : 0;
         if (n.cls & 4) {
-          box::p2_flush<C>(P, n, S[tid], -1, stg);
+          box::p2_flush<C>(n, S[tid], n.slots_mid, pl_m, stg);
           box::p2_zero(S[tid]);
         }
         box::p2_pass<C, 1>(P, n, S[tid], upper, tab, divu);
-        box::p2_flush<C>(P, n, S[tid], (n.cls & 4) ? 1 : 0, stg);
+        box::p2_flush<C>(n, S[tid], n.slots_fin, dz_fin ? pl_p : pl_0, stg);
       }
       for (int nl = 0; nl < C::NNODE; ++nl) {
         const box::NodeCtx &n = N[nl * 8];
         if (!n.active) continue;
         for (int i = 0; i < 3; ++i) {
           double v = 0;
-          for (int c = 0; c < 8; ++c) v += S[nl * 8 + c].rr[i];
+          for (int c = 0; c < 8; ++c) v += S[nl * 8 + c].rr[i] + (c == i ? S[nl * 8 + c].dv : 0.0);
           double *r = P.rhs + (long long)n.row * 3 + i;
           *r = P.overwrite ? v : *r + v;
         }
-        const int len = n.nb * 9;
-        double *dst = P.values + n.rowbase;
-        const double *src = stg + nl * C::SROW;
+      }
+      // ---- barrier S3
+      for (int tid = 0; tid < NT; ++tid) box::plane_store<C>(tid, R[tid].p, ring + ((z + 2) % 3) * PLN);
+      for (int m = 0; m < C::NNODE; ++m) {
+        const int len = s_len[m];
+        double *dst = P.values + s_rb[m];
+        const double *src = stg + m * C::SROW;
         for (int q = 0; q < len; ++q) dst[q] = P.overwrite ? src[q] : dst[q] + src[q];
+      }
+      // ---- barrier S4
+      for (int tid = 0; tid < NT; ++tid) {
+        box::NodeCtx &n = N[tid];
+        n.n += plane_nodes;
+        n.row = row_n[tid];
+        n.nb = (int)(b1_n[tid] - b0_n[tid]);
+        n.rowbase = 9 * b0_n[tid];
+        n.slots_mid = sm_n[tid];
+        n.slots_fin = sf_n[tid];
       }
     }
   }
