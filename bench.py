@@ -187,7 +187,7 @@ def run_ours(args):
     d = {k: torch.as_tensor(np.ascontiguousarray(v), device=dev) for k, v in h.items()}
     d_rho = torch.as_tensor(rho, device=dev)
     mdot = ls.mdot_scs(d["coordinates"], d_rho, d["velocity"])
-    desc = ls.make_desc("momentum_adv_diff", fields=d, mass_flow_rate=mdot, include_divu=1.0)
+    desc = ls.make_desc("momentum_adv_diff", fields=d, mass_flow_rate=mdot, include_divu=args.divu)
 
     mode = args.mode
     probe = ls.assemble_elem([desc], mode=mode, overwrite=True)  # also a first warm-up
@@ -314,7 +314,7 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"hex8_box_{n}x{n}x{n * world}_momentum_advdiff_assembly",
-                           "elements_per_gpu": n_elems_rank, "kernels": ["MomentumAdvDiffElemKernel(includeDivU=1)"],
+                           "elements_per_gpu": n_elems_rank, "kernels": [f"MomentumAdvDiffElemKernel(includeDivU={args.divu:g})"],
                            "partition": f"z-slabs x{world}", "halo": "nccl p2p pack/unpack-add" if world > 1 else "none",
                            "l2_policy": "working set (>=36 GB CSR per GPU at n=256) exceeds the 126 MB L2",
                            "assemble_kernel": roofline["kernel"], "graph_build_s": t_graph},
@@ -335,6 +335,7 @@ def main():
                     help="elements per box edge per GPU")
     ap.add_argument("--mode", default="auto", choices=["auto", "general", "box"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--divu", type=float, default=1.0, help="SolutionOptions::includeDivU_ (reference default 0; 1 is the costlier variant)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,12 +38,7 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
 
   box::NodeCtx N;
   const int nl = tid >> 3;
-  N.cls = tid & 7;
-  N.lx = nl % C::TBX;
-  N.ly = nl / C::TBX;
-  N.x = x0 + N.lx;
-  N.y = y0 + N.ly;
-  N.active = N.x < P.NX && N.y < P.NY;
+  box::node_ctx_init<C>(P, N, tid, x0, y0);
   const int dz_fin = (N.cls & 4) ? 1 : 0;
 
   double regP[C::NPL], regM[C::NML];
@@ -110,7 +105,7 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     int ncov = 0;
     if (N.active) {
       ncov = ((N.x > 0) + 1 + (N.x < P.NX - 1)) * ((N.y > 0) + 1 + (N.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
-      box::p2_pass<C, 0>(P, N, S, lower, tab, divu);
+      box::p2_pass<C, 0>(P, N, S, lower, tab + 2 * N.cls, divu);
     }
     __syncthreads(); // every thread is done with the lower layer: its buffer is now the staging area
     if (N.active && N.nb != ncov) {
@@ -125,7 +120,7 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
         box::p2_flush<C>(N, S, N.slots_mid, pl_m, stg);
         box::p2_zero(S);
       }
-      box::p2_pass<C, 1>(P, N, S, upper, tab, divu);
+      box::p2_pass<C, 1>(P, N, S, upper, tab + 2 * N.cls, divu);
       box::p2_flush<C>(N, S, N.slots_fin, dz_fin ? pl_p : pl_0, stg);
     }
     // rhs: sum the 8 class partials of the node (classes 0..2 also carry the divU stress components)

@@ -73,7 +73,10 @@ struct Cfg {
   static constexpr int OFF_TAB = 2 * LBUF, OFF_RING = OFF_TAB + TAB, OFF_MD = OFF_RING + RING,
                        OFF_RB = OFF_MD + MDB, OFF_LEN = OFF_RB + NNODE;
   static constexpr int SMEM_DOUBLES = OFF_LEN + (NNODE + 1) / 2;
-  static constexpr int NITEM = NEL * 3;     // phase-1 work items: (element, edge direction)
+  // phase-1 work items: (element, edge direction), split once more in two when that still fits one
+  // round of the CTA's threads
+  static constexpr bool SPLIT = NEL * 6 <= NT;
+  static constexpr int NITEM = NEL * 3 * (SPLIT ? 2 : 1);
 };
 
 // ---- small integer helpers on the Hex8 numbering (Hex8CVFEM.C:264-276, 396-412) -------------
@@ -168,14 +171,32 @@ __host__ __device__ inline void mdot_store(int tid, const double (&reg)[C::NML],
   }
 }
 
-// ---- phase 1: integration-point data of one (element, edge direction) item ---------------------
+// ---- phase 1: integration-point data of one (element, edge direction[, half]) item -------------
 // Local axes (t,u,v) = (g, g+1, g+2) mod 3; local node m has bits (b0,b1,b2) along (t,u,v).
-// pl0 / pl1: staged node planes below / above the element layer; mdb: the layer's mass flow rates
+// pl0 / pl1: staged node planes below / above the element layer; mdb: the layer's mass flow rates.
+// An item covers the 4 ips of one edge direction, or (C::SPLIT) the 2 of them on one v side so that
+// every warp of a large tile has phase-1 work.
+__host__ __device__ __forceinline__ void butterfly8(double *f)
+{
+#pragma unroll
+  for (int h = 1; h < 8; h <<= 1)
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      if (!(m & h)) {
+        const double lo = f[m], hi = f[m | h];
+        f[m] = hi + lo;
+        f[m | h] = hi - lo;
+      }
+}
+
 template <class C>
 __host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0, int y0, const double *pl0,
                                             const double *pl1, const double *mdb, double *buf)
 {
-  const int g = item / C::NEL, el = item - g * C::NEL;
+  constexpr int NH = C::SPLIT ? 2 : 1, NIP = 4 / NH;
+  const int half = C::SPLIT ? (item & 1) : 0;
+  const int ge = item / NH;
+  const int g = ge / C::NEL, el = ge - g * C::NEL;
   const int elx = el % C::ELX, ely = el / C::ELX;
   const int ex = x0 - 1 + elx, ey = y0 - 1 + ely;
   if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) return;
@@ -186,121 +207,121 @@ __host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0
   const int zbit = g == 0 ? 4 : (g == 1 ? 2 : 1); // which local bit is the z axis
   const int n000 = (elx + C::RNX * ely) * C::NF;
   const bool divu = P.include_divu != 0.0;
+  enum { T = 1, Uu = 2, V = 4, TU = 3, TV = 5, UV = 6, TUV = 7 };
+  const double q = (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
+  // original-axis bit positions of the local axes
+  const int at = g, au = (g + 1) % 3, av = (g + 2) % 3;
+  double *const oe = buf + el * C::ES;
+  int ipn[NIP];
 
-  // butterfly: C[mask] = sum_m prod_{axis in mask} sign_axis(m) f_m   (mask bits: 1 = t, 2 = u, 4 = v)
-  double X[3][8], M[8], U[3][8];
+  { // ---- geometry: G' = -mu adj(J)/det, area vector
+    // butterfly: C[mask] = sum_m prod_{axis in mask} sign_axis(m) f_m   (mask bits: 1 = t, 2 = u, 4 = v)
+    double X[3][8], M[8];
 #pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    const double *nd = ((m & zbit) ? pl1 : pl0) + n000 + (m & 1) * s_t + ((m >> 1) & 1) * s_u + ((m >> 2) & 1) * s_v;
-    X[0][m] = nd[0];
-    X[1][m] = nd[1];
-    X[2][m] = nd[2];
-    M[m] = nd[3];
-    if (divu) {
+    for (int m = 0; m < 8; ++m) {
+      const double *nd = ((m & zbit) ? pl1 : pl0) + n000 + (m & 1) * s_t + ((m >> 1) & 1) * s_u + ((m >> 2) & 1) * s_v;
+      X[0][m] = nd[0];
+      X[1][m] = nd[1];
+      X[2][m] = nd[2];
+      M[m] = nd[3];
+    }
+    butterfly8(X[0]);
+    butterfly8(X[1]);
+    butterfly8(X[2]);
+    butterfly8(M);
+    // area vector of the facet through the t = 0 plane, pointing along +t:
+    //   A = Cu x Cv / 64 + Cuv x (sig2 Cv - sig1 Cu) / 128
+    double base[3];
+    base[0] = (X[1][Uu] * X[2][V] - X[2][Uu] * X[1][V]) * (1.0 / 64.0);
+    base[1] = (X[2][Uu] * X[0][V] - X[0][Uu] * X[2][V]) * (1.0 / 64.0);
+    base[2] = (X[0][Uu] * X[1][V] - X[1][Uu] * X[0][V]) * (1.0 / 64.0);
+#pragma unroll
+    for (int ff = 0; ff < NIP; ++ff) {
+      const int b1 = ff & 1, b2 = C::SPLIT ? half : (ff >> 1);
+      const double sg1 = b1 ? 1.0 : -1.0, sg2 = b2 ? 1.0 : -1.0;
+      // which ip: the edge along t at (u,v) side (b1,b2); take its node with bit_t = 0
+      const int obx = at == 0 ? 0 : (au == 0 ? b1 : b2), oby = at == 1 ? 0 : (au == 1 ? b1 : b2),
+                obz = at == 2 ? 0 : (au == 2 ? b1 : b2);
+      (void)av;
+      const int k0 = node_of_bits(obx, oby, obz);
+      const int ip = ip_of(k0, g);
+      ipn[ff] = ip;
+      const double orient = (hex8::scs_left(ip) == k0) ? 1.0 : -1.0;
+
+      double J[3][3]; // J[i][j] = d x_i / d xi_j, local axis order
+      const double c1 = 0.5 * q * sg1, c2 = 0.5 * q * sg2, c12 = q * q * sg1 * sg2;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        J[i][0] = 0.25 * X[i][T] + c1 * X[i][TU] + c2 * X[i][TV] + c12 * X[i][TUV];
+        J[i][1] = 0.25 * X[i][Uu] + c2 * X[i][UV];
+        J[i][2] = 0.25 * X[i][V] + c1 * X[i][UV];
+      }
+      double adj[3][3];
+      adj[0][0] = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+      adj[0][1] = J[1][2] * J[2][0] - J[2][2] * J[1][0];
+      adj[0][2] = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+      adj[1][0] = J[0][2] * J[2][1] - J[2][2] * J[0][1];
+      adj[1][1] = J[0][0] * J[2][2] - J[2][0] * J[0][2];
+      adj[1][2] = J[0][1] * J[2][0] - J[2][1] * J[0][0];
+      adj[2][0] = J[0][1] * J[1][2] - J[1][1] * J[0][2];
+      adj[2][1] = J[0][2] * J[1][0] - J[1][2] * J[0][0];
+      adj[2][2] = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+      const double det = J[0][0] * adj[0][0] + J[1][0] * adj[1][0] + J[2][0] * adj[2][0];
+      if (!(det > 0.0)) *P.err = 1; // MasterElementFunctions.h:91-94 asserts this in debug builds
+      const double inv = 1.0 / det;
+      // mu at the (never shifted) ip location, MomentumAdvDiffElemKernel.C:107-110
+      const double mu = 0.125 * M[0] + 0.0625 * (sg1 * M[Uu] + sg2 * M[V]) + 0.03125 * sg1 * sg2 * M[UV];
+      const double fac = -mu * inv;
+
+      double *o = oe + ip * C::IPD;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[i * 3 + j] = fac * adj[i][j];
+      double W[3], A[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) W[i] = sg2 * X[i][V] - sg1 * X[i][Uu];
+      A[0] = base[0] + (X[1][UV] * W[2] - X[2][UV] * W[1]) * (1.0 / 128.0);
+      A[1] = base[1] + (X[2][UV] * W[0] - X[0][UV] * W[2]) * (1.0 / 128.0);
+      A[2] = base[2] + (X[0][UV] * W[1] - X[1][UV] * W[0]) * (1.0 / 128.0);
+      o[9] = orient * A[0];
+      o[10] = orient * A[1];
+      o[11] = orient * A[2];
+      o[12] = mdb[el * 12 + ip];
+      if (!divu) o[13] = 0.0;
+    }
+  }
+  if (divu) {
+    // ---- divU stress scalar w = 2/3 mu divU includeDivU (:111-114,:127), with
+    //   mu divU = mu sum_ij (adj_ij/det) d u_i/d xi_j = - sum_ij G'_ij d u_i/d xi_j   (G' read back)
+    double U[3][8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const double *nd = ((m & zbit) ? pl1 : pl0) + n000 + (m & 1) * s_t + ((m >> 1) & 1) * s_u + ((m >> 2) & 1) * s_v;
       U[0][m] = nd[4];
       U[1][m] = nd[5];
       U[2][m] = nd[6];
     }
-  }
-  auto butterfly = [](double *f) {
+    butterfly8(U[0]);
+    butterfly8(U[1]);
+    butterfly8(U[2]);
+    const double wf = -2.0 / 3.0 * P.include_divu;
 #pragma unroll
-    for (int h = 1; h < 8; h <<= 1)
-#pragma unroll
-      for (int m = 0; m < 8; ++m)
-        if (!(m & h)) {
-          const double lo = f[m], hi = f[m | h];
-          f[m] = hi + lo;
-          f[m | h] = hi - lo;
-        }
-  };
-  butterfly(X[0]);
-  butterfly(X[1]);
-  butterfly(X[2]);
-  butterfly(M);
-  if (divu) {
-    butterfly(U[0]);
-    butterfly(U[1]);
-    butterfly(U[2]);
-  }
-  enum { T = 1, Uu = 2, V = 4, TU = 3, TV = 5, UV = 6, TUV = 7 };
-  // area vector of the facet through the t = 0 plane, pointing along +t:
-  //   A = Cu x Cv / 64 + Cuv x (sig2 Cv - sig1 Cu) / 128
-  double base[3];
-  base[0] = (X[1][Uu] * X[2][V] - X[2][Uu] * X[1][V]) * (1.0 / 64.0);
-  base[1] = (X[2][Uu] * X[0][V] - X[0][Uu] * X[2][V]) * (1.0 / 64.0);
-  base[2] = (X[0][Uu] * X[1][V] - X[1][Uu] * X[0][V]) * (1.0 / 64.0);
-  const double q = (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
-  // original-axis bit positions of the local axes
-  const int at = g, au = (g + 1) % 3, av = (g + 2) % 3;
-
-#pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    const int b1 = f & 1, b2 = f >> 1;
-    const double sg1 = b1 ? 1.0 : -1.0, sg2 = b2 ? 1.0 : -1.0;
-    // which ip: the edge along t at (u,v) side (b1,b2); take its node with bit_t = 0
-    int ob[3];
-    ob[at] = 0;
-    ob[au] = b1;
-    ob[av] = b2;
-    const int k0 = node_of_bits(ob[0], ob[1], ob[2]);
-    const int ip = ip_of(k0, g);
-    const double orient = (hex8::scs_left(ip) == k0) ? 1.0 : -1.0;
-
-    double J[3][3]; // J[i][j] = d x_i / d xi_j, local axis order
-    const double c1 = 0.5 * q * sg1, c2 = 0.5 * q * sg2, c12 = q * q * sg1 * sg2;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      J[i][0] = 0.25 * X[i][T] + c1 * X[i][TU] + c2 * X[i][TV] + c12 * X[i][TUV];
-      J[i][1] = 0.25 * X[i][Uu] + c2 * X[i][UV];
-      J[i][2] = 0.25 * X[i][V] + c1 * X[i][UV];
-    }
-    double adj[3][3];
-    adj[0][0] = J[1][1] * J[2][2] - J[2][1] * J[1][2];
-    adj[0][1] = J[1][2] * J[2][0] - J[2][2] * J[1][0];
-    adj[0][2] = J[1][0] * J[2][1] - J[2][0] * J[1][1];
-    adj[1][0] = J[0][2] * J[2][1] - J[2][2] * J[0][1];
-    adj[1][1] = J[0][0] * J[2][2] - J[2][0] * J[0][2];
-    adj[1][2] = J[0][1] * J[2][0] - J[2][1] * J[0][0];
-    adj[2][0] = J[0][1] * J[1][2] - J[1][1] * J[0][2];
-    adj[2][1] = J[0][2] * J[1][0] - J[1][2] * J[0][0];
-    adj[2][2] = J[0][0] * J[1][1] - J[1][0] * J[0][1];
-    const double det = J[0][0] * adj[0][0] + J[1][0] * adj[1][0] + J[2][0] * adj[2][0];
-    if (!(det > 0.0)) *P.err = 1; // MasterElementFunctions.h:91-94 asserts this in debug builds
-    const double inv = 1.0 / det;
-    // mu at the (never shifted) ip location, MomentumAdvDiffElemKernel.C:107-110
-    const double mu = 0.125 * M[0] + 0.0625 * (sg1 * M[Uu] + sg2 * M[V]) + 0.03125 * sg1 * sg2 * M[UV];
-    const double fac = -mu * inv;
-
-    double *o = buf + el * C::ES + ip * C::IPD;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) o[i * 3 + j] = fac * adj[i][j];
-    // area vector
-    double W[3], A[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) W[i] = sg2 * X[i][V] - sg1 * X[i][Uu];
-    A[0] = base[0] + (X[1][UV] * W[2] - X[2][UV] * W[1]) * (1.0 / 128.0);
-    A[1] = base[1] + (X[2][UV] * W[0] - X[0][UV] * W[2]) * (1.0 / 128.0);
-    A[2] = base[2] + (X[0][UV] * W[1] - X[1][UV] * W[0]) * (1.0 / 128.0);
-    o[9] = orient * A[0];
-    o[10] = orient * A[1];
-    o[11] = orient * A[2];
-    o[12] = mdb[el * 12 + ip];
-    double w = 0.0;
-    if (divu) {
-      // divU = sum_i sum_j (adj[i][j]/det) d u_i / d xi_j   (u_j dN/dx_j summed, :111-114)
+    for (int ff = 0; ff < NIP; ++ff) {
+      const int b1 = ff & 1, b2 = C::SPLIT ? half : (ff >> 1);
+      const double sg1 = b1 ? 1.0 : -1.0, sg2 = b2 ? 1.0 : -1.0;
+      const double c1 = 0.5 * q * sg1, c2 = 0.5 * q * sg2, c12 = q * q * sg1 * sg2;
+      double *o = oe + ipn[ff] * C::IPD;
       double dv = 0.0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const double d0 = 0.25 * U[i][T] + c1 * U[i][TU] + c2 * U[i][TV] + c12 * U[i][TUV];
         const double d1 = 0.25 * U[i][Uu] + c2 * U[i][UV];
         const double d2 = 0.25 * U[i][V] + c1 * U[i][UV];
-        dv += adj[i][0] * d0 + adj[i][1] * d1 + adj[i][2] * d2;
+        dv += o[i * 3 + 0] * d0 + o[i * 3 + 1] * d1 + o[i * 3 + 2] * d2;
       }
-      w = 2.0 / 3.0 * mu * (dv * inv) * P.include_divu;
+      o[13] = wf * dv;
     }
-    o[13] = w;
   }
 }
 
@@ -322,7 +343,27 @@ struct NodeCtx {
   int row;           // row node index (rhs offset / 3)
   int cls;
   unsigned slots_mid, slots_fin; // CSR block slot (0xFF: no such neighbour) of the 4 quadrant blocks
+  int vmask;         // bit q: the (sx,sy) quadrant q holds an element column
+  int eoff;          // offset of element (lx,ly) of the layer tile in a layer buffer
 };
+
+template <class C>
+__host__ __device__ inline void node_ctx_init(const BoxParams &P, NodeCtx &N, int tid, int x0, int y0)
+{
+  const int nl = tid >> 3;
+  N.cls = tid & 7;
+  N.lx = nl % C::TBX;
+  N.ly = nl / C::TBX;
+  N.x = x0 + N.lx;
+  N.y = y0 + N.ly;
+  N.active = N.x < P.NX && N.y < P.NY;
+  N.vmask = 0;
+  for (int q = 0; q < 4; ++q) {
+    const int ex = N.x - 1 + (q & 1), ey = N.y - 1 + (q >> 1);
+    if (ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny) N.vmask |= 1 << q;
+  }
+  N.eoff = (N.lx + C::ELX * N.ly) * C::ES;
+}
 
 // CSR slots of the blocks this class flushes: byte q = quadrant (sx,sy) -> offset (a sx, b sy, dz)
 __host__ __device__ inline unsigned load_slots(const unsigned char *slots, int cls, int dz)
@@ -358,28 +399,29 @@ __host__ __device__ inline void p2_begin(P2State &S)
   S.dv = 0.0;
 }
 
-// one z-half (SZP = 0: elements below the node plane, 1: above) of the 8 octants
+// one z-half (SZP = 0: elements below the node plane, 1: above) of the 8 octants.
+// tabc = table + 2*cls; buf = that layer's ip data
 template <class C, int SZP>
 __host__ __device__ inline void p2_pass(const BoxParams &P, const NodeCtx &N, P2State &S, const double *buf,
-                                        const double *tab, bool divu)
+                                        const double *tabc, bool divu)
 {
   const int ez = N.z - 1 + SZP;
   if (ez < 0 || ez >= P.nz) return;
+  const double *ebase = buf + N.eoff;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int sxp = q & 1, syp = q >> 1;
-    const int ex = N.x - 1 + sxp, ey = N.y - 1 + syp;
-    if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) continue;
+    if (!(N.vmask & (1 << q))) continue; // no element in this quadrant (domain boundary)
     const int s = q + 4 * SZP;
     const int k = node_of_bits(!sxp, !syp, !SZP);
-    const double *eb = buf + ((N.lx + sxp) + C::ELX * (N.ly + syp)) * C::ES;
+    const double *eb = ebase + (sxp + C::ELX * syp) * C::ES;
 #pragma unroll
     for (int pp = 0; pp < 3; ++pp) {
       const int ip = ip_of(k, pp);
       const bool isL = hex8::scs_left(ip) == k;
       const double *o = eb + ip * C::IPD;
-      const double *t0 = tab + ((s * 3 + pp) * 2 + 0) * 16 + N.cls * 2;
-      const double *t1 = tab + ((s * 3 + pp) * 2 + 1) * 16 + N.cls * 2;
+      const double *t0 = tabc + ((s * 3 + pp) * 2 + 0) * 16;
+      const double *t1 = tabc + ((s * 3 + pp) * 2 + 1) * 16;
       const double d0 = t0[0], d1 = t0[1], d2 = t1[0], nadv = t1[1];
       double h[3];
 #pragma unroll

@@ -125,13 +125,7 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
       box::mdot_load<C>(P, tid, x0, y0, zs, R[tid].m);
       box::mdot_store<C>(tid, R[tid].m, mdb);
       box::NodeCtx &n = N[tid];
-      const int nl = tid >> 3;
-      n.cls = tid & 7;
-      n.lx = nl % C::TBX;
-      n.ly = nl / C::TBX;
-      n.x = x0 + n.lx;
-      n.y = y0 + n.ly;
-      n.active = n.x < P.NX && n.y < P.NY;
+      box::node_ctx_init<C>(P, n, tid, x0, y0);
       n.n = n.x + (long long)P.NX * (n.y + (long long)P.NY * zs);
       n.row = 0; n.nb = 0; n.rowbase = 0; n.slots_mid = n.slots_fin = 0xFFFFFFFFu;
       if (n.active) {
@@ -178,7 +172,7 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
         n.z = z;
         if (n.active) {
           ncov[tid] = ((n.x > 0) + 1 + (n.x < P.NX - 1)) * ((n.y > 0) + 1 + (n.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
-          box::p2_pass<C, 0>(P, n, S[tid], lower, tab, divu);
+          box::p2_pass<C, 0>(P, n, S[tid], lower, tab + 2 * n.cls, divu);
         }
       }
       // ---- barrier S2: the lower layer's buffer becomes the staging area
@@ -198,7 +192,7 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
           box::p2_flush<C>(n, S[tid], n.slots_mid, pl_m, stg);
           box::p2_zero(S[tid]);
         }
-        box::p2_pass<C, 1>(P, n, S[tid], upper, tab, divu);
+        box::p2_pass<C, 1>(P, n, S[tid], upper, tab + 2 * n.cls, divu);
         box::p2_flush<C>(n, S[tid], n.slots_fin, dz_fin ? pl_p : pl_0, stg);
       }
       for (int nl = 0; nl < C::NNODE; ++nl) {
