@@ -22,6 +22,8 @@
  *                              include/AssembleElemSolverAlgorithm.h:52-105,
  *                              src/ScratchViews.C:408-509, src/kernel/ *ElemKernel.C,
  *                              src/SolverAlgorithm.C:57-68, src/TpetraLinearSystem.C:1376-1522)
+ *   nalu_b200_sum_into        TpetraLinearSystem::sumInto for host callers
+ *                             (src/TpetraLinearSystem.C:1457-1522)
  *   nalu_b200_assemble_node_mass  AssembleNodeSolverAlgorithm::execute with the
  *                             {Momentum,Continuity,Scalar}MassBDF2NodeSuppAlg
  *                             (src/AssembleNodeSolverAlgorithm.C:57-111,
@@ -191,6 +193,14 @@ int nalu_b200_last_assemble_mode(void);
  * non-positive Jacobian determinant -- the reference asserts on this in debug builds
  * (include/master_element/MasterElementFunctions.h:91-94) */
 int nalu_b200_geometry_errors(const nalu_b200_graph *g, int32_t *flag);
+
+/* TpetraLinearSystem::sumInto for host callers (src/TpetraLinearSystem.C:1457-1522; node algorithms,
+ * boundary conditions): `nodes` are local node indices, `rhs` [n] and `lhs` [n][n] row-major with
+ * n = n_entities*num_dof, all HOST pointers (copied to the device on `stream`).  Columns absent from
+ * a row are skipped, like the reference (:1397,1439-1451).  The element algorithm never calls this:
+ * it scatters in bulk inside nalu_b200_assemble_elem. */
+int nalu_b200_sum_into(const nalu_b200_graph *g, int32_t n_entities, const int32_t *nodes, const double *rhs,
+                       const double *lhs, double *d_values, double *d_rhs, void *stream);
 
 /* AssembleNodeSolverAlgorithm::execute with the mass BDF2/backward-Euler node algorithms;
  * `k` uses kind NALU_K_{MOMENTUM,CONTINUITY,SCALAR}_MASS and NALU_F_DUAL_VOLUME. */

@@ -222,6 +222,60 @@ int launch_node_mass(const Graph &g, const nalu_b200_kernel_desc &k, double *d_v
   return NALU_B200_OK;
 }
 
+// ---- sumInto for host callers (src/TpetraLinearSystem.C:1457-1522) ---------------------------------
+// One thread per lhs entry; the column search the reference does by walking the sorted row is a
+// binary search over the row's block columns; absent columns are skipped like the reference does.
+__global__ void sum_into_kernel(int n_entities, int ndof, const int *nodes, const double *rhs, const double *lhs,
+                                const int *node_row, const long long *browptr, const int *bcol, double *values, double *grhs)
+{
+  const int n = n_entities * ndof;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * n) return;
+  const int r = t / n, c = t - r * n;
+  const int rn = node_row[nodes[r / ndof]], i = r % ndof;
+  const int cn = node_row[nodes[c / ndof]], j = c % ndof;
+  const long long b0 = browptr[rn], b1 = browptr[rn + 1];
+  long long lo = b0, hi = b1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (bcol[mid] < cn) lo = mid + 1; else hi = mid;
+  }
+  if (lo < b1 && bcol[lo] == cn) {
+    const long long nb = b1 - b0;
+    atomicAdd(values + (long long)ndof * ndof * b0 + (long long)i * nb * ndof + (lo - b0) * ndof + j, lhs[t]);
+  }
+  if (c == 0) atomicAdd(grhs + (long long)rn * ndof + i, rhs[r]);
+}
+
+int launch_sum_into(const Graph &g, int n_entities, const int *h_nodes, const double *h_rhs, const double *h_lhs,
+                    double *d_values, double *d_rhs, cudaStream_t stream)
+{
+  if (n_entities <= 0) return NALU_B200_OK;
+  for (int e = 0; e < n_entities; ++e)
+    if (h_nodes[e] < 0 || h_nodes[e] >= g.n_nodes) {
+      set_error("sum_into: node index out of range");
+      return NALU_B200_ERR_ARG;
+    }
+  const int n = n_entities * g.ndof;
+  const size_t bytes_nodes = (size_t(n_entities) * sizeof(int) + 7) & ~size_t(7);
+  const size_t bytes = bytes_nodes + (size_t(n) + size_t(n) * n) * sizeof(double);
+  char *d = nullptr;
+  NALU_CUDA(cudaMallocAsync((void **)&d, bytes, stream));
+  NALU_CUDA(cudaMemcpyAsync(d, h_nodes, size_t(n_entities) * sizeof(int), cudaMemcpyHostToDevice, stream));
+  NALU_CUDA(cudaMemcpyAsync(d + bytes_nodes, h_rhs, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, stream));
+  NALU_CUDA(cudaMemcpyAsync(d + bytes_nodes + size_t(n) * sizeof(double), h_lhs, size_t(n) * n * sizeof(double),
+                            cudaMemcpyHostToDevice, stream));
+  sum_into_kernel<<<(n * n + 127) / 128, 128, 0, stream>>>(n_entities, g.ndof, (const int *)d, (const double *)(d + bytes_nodes),
+                                                         (const double *)(d + bytes_nodes + size_t(n) * sizeof(double)), g.d_node_row,
+                                                         (const long long *)g.d_browptr, g.d_bcol, d_values, d_rhs);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  NALU_CUDA(cudaFreeAsync(d, stream));
+  // the host buffers may be reused by the caller as soon as we return
+  NALU_CUDA(cudaStreamSynchronize(stream));
+  return NALU_B200_OK;
+}
+
 // ---- mass_flow_rate_scs producer (unit_tests/kernels/UnitTestKernelUtils.C:547-628) --------
 __global__ void mdot_kernel(long long n_elems, const int *elem_nodes, const double *coords, const double *density,
                             const double *velocity, double *mdot)

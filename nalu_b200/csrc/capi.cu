@@ -404,6 +404,13 @@ int nalu_b200_assemble_node_mass(const nalu_b200_graph *h, const nalu_b200_kerne
   return launch_node_mass(h->g, *k, d_values, d_rhs, (cudaStream_t)stream);
 }
 
+int nalu_b200_sum_into(const nalu_b200_graph *h, int32_t n_entities, const int32_t *nodes, const double *rhs, const double *lhs,
+                       double *d_values, double *d_rhs, void *stream)
+{
+  if (!h || !nodes || !rhs || !lhs || !d_values || !d_rhs || !h->g.d_browptr) return NALU_B200_ERR_STATE;
+  return launch_sum_into(h->g, n_entities, nodes, rhs, lhs, d_values, d_rhs, (cudaStream_t)stream);
+}
+
 int nalu_b200_mdot_scs(const nalu_b200_graph *h, const double *d_coords, const double *d_density, const double *d_velocity,
                        double *d_mdot, void *stream)
 {

@@ -1,0 +1,58 @@
+// MasterElement.h -- the master-element objects the kernels' constructors query
+// (include/master_element/MasterElement.h, MasterElementFactory.h; Hex8CVFEM.C:75-108,255-345,832-847).
+// Only the constant tables live on the host (lrscv, ipNodeMap, shape functions at the integration
+// points); the geometric operators (determinant, grad_op, ...) run inside the CUDA kernels
+// (nalu_b200/csrc/hex8_dev.cuh, box_tile.cuh) and asking the host object for them throws, like the
+// reference's unimplemented MasterElement virtuals (include/master_element/MasterElement.h:56-272).
+#pragma once
+#include "../stk_shim.h"
+#include <stdexcept>
+
+namespace sierra {
+namespace nalu {
+
+class MasterElement {
+public:
+  virtual ~MasterElement() {}
+  virtual const int *adjacentNodes() { throw std::runtime_error("adjacentNodes not implemented"); }
+  virtual const int *ipNodeMap(int /*ordinal*/ = 0) { throw std::runtime_error("ipNodeMap not implemented"); }
+  virtual void shape_fcn(double *) { throw std::runtime_error("shape_fcn not implemented"); }
+  virtual void shifted_shape_fcn(double *) { throw std::runtime_error("shifted_shape_fcn not implemented"); }
+  virtual void determinant(const int, const double *, double *, double *)
+  {
+    throw std::runtime_error("determinant: geometric operators run on the device on this path");
+  }
+  virtual void grad_op(const int, const double *, double *, double *, double *, double *)
+  {
+    throw std::runtime_error("grad_op: geometric operators run on the device on this path");
+  }
+  int nDim_ = 3, nodesPerElement_ = 0, numIntPoints_ = 0;
+};
+
+class HexSCS : public MasterElement {
+public:
+  HexSCS();
+  const int *adjacentNodes() override { return lrscv_; }
+  void shape_fcn(double *shpfc) override;         // [12][8], intgLoc_
+  void shifted_shape_fcn(double *shpfc) override; // [12][8], intgLocShift_
+private:
+  int lrscv_[24];
+};
+
+class HexSCV : public MasterElement {
+public:
+  HexSCV();
+  const int *ipNodeMap(int = 0) override { return ipNodeMap_; }
+  void shape_fcn(double *shpfc) override;         // [8][8]
+  void shifted_shape_fcn(double *shpfc) override; // identity: lumping
+private:
+  int ipNodeMap_[8];
+};
+
+struct MasterElementRepo {
+  static MasterElement *get_surface_master_element(const stk::topology &theTopo);
+  static MasterElement *get_volume_master_element(const stk::topology &theTopo);
+};
+
+} // namespace nalu
+} // namespace sierra

@@ -1,0 +1,915 @@
+// host.cpp -- host side of the drop-in boundary: the reference's registration API lowered onto the C ABI.
+#include "../include/AssembleElemSolverAlgorithm.h"
+#include "../include/kernel/ContinuityAdvElemKernel.h"
+#include "../include/kernel/MassElemKernels.h"
+#include "../include/kernel/MomentumAdvDiffElemKernel.h"
+#include "../include/kernel/ScalarAdvDiffElemKernel.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+void check(int rc, const char *what)
+{
+  if (rc != NALU_B200_OK)
+    throw std::runtime_error(std::string(what) + " failed (status " + std::to_string(rc) + "): " + nalu_b200_last_error());
+}
+} // namespace
+
+// ================================================================================================
+// stk shim
+// ================================================================================================
+namespace stk {
+namespace mesh {
+
+void FieldBase::release_device()
+{
+  if (dev_ && dev_owned_) nalu_b200_free(dev_);
+  dev_ = nullptr;
+  dev_owned_ = false;
+}
+
+void FieldBase::sync_to_device()
+{
+  if (!dev_) {
+    void *p = nullptr;
+    check(nalu_b200_malloc(&p, host_.size() * sizeof(double)), "field device allocation");
+    dev_ = static_cast<double *>(p);
+    dev_owned_ = true;
+    host_dirty_ = true;
+  }
+  if (host_dirty_ && dev_owned_) {
+    check(nalu_b200_memcpy_h2d(dev_, host_.data(), host_.size() * sizeof(double), nullptr), "field host->device copy");
+    check(nalu_b200_stream_sync(nullptr), "stream sync");
+  }
+  host_dirty_ = false;
+}
+
+const double *FieldBase::device_data()
+{
+  sync_to_device();
+  return dev_;
+}
+
+void BulkData::fill_generated_mesh(int nx, int ny, int nzg, Part &block, const std::string &coords_name)
+{
+  // z-slab decomposition: extra layers to the low ranks; a shared plane is owned by the lower rank
+  const int base = nzg / nranks_, rem = nzg % nranks_;
+  int k0 = 0;
+  for (int r = 0; r < rank_; ++r) k0 += base + (r < rem ? 1 : 0);
+  const int lz = base + (rank_ < rem ? 1 : 0);
+  STK_ThrowRequireMsg(lz > 0, "generated mesh: more ranks than element layers");
+  const int NX = nx + 1, NY = ny + 1, NZ = lz + 1;
+  const int64_t sxy = int64_t(NX) * NY;
+  node_gid_.clear(); node_owner_.clear(); conn_.clear();
+  for (int z = 0; z < NZ; ++z)
+    for (int y = 0; y < NY; ++y)
+      for (int x = 0; x < NX; ++x) {
+        node_gid_.push_back(1 + x + int64_t(NX) * y + sxy * (z + k0));
+        node_owner_.push_back((rank_ > 0 && z == 0) ? rank_ - 1 : rank_);
+      }
+  for (int k = 0; k < lz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) {
+        const int32_t n0 = i + NX * (j + NY * k), s = int32_t(sxy);
+        const int32_t c[8] = {n0, n0 + 1, n0 + 1 + NX, n0 + NX, n0 + s, n0 + 1 + s, n0 + 1 + NX + s, n0 + NX + s};
+        conn_.insert(conn_.end(), c, c + 8);
+      }
+  elem_gid0_ = 1 + int64_t(nx) * ny * k0;
+  box_[0] = nx; box_[1] = ny; box_[2] = lz;
+  block_ = &block;
+  for (FieldBase *f : meta_.fields_)
+    f->set_num_entities(f->entity_rank() == topology::NODE_RANK ? num_nodes() : num_elems());
+  if (Field<double> *c = meta_.get_field<double>(topology::NODE_RANK, coords_name)) {
+    STK_ThrowRequireMsg(c->max_size() == 3, "coordinates field must have 3 scalars per node");
+    double *x = c->host_data();
+    size_t n = 0;
+    for (int z = 0; z < NZ; ++z)
+      for (int y = 0; y < NY; ++y)
+        for (int xx = 0; xx < NX; ++xx, ++n) {
+          x[3 * n + 0] = xx;
+          x[3 * n + 1] = y;
+          x[3 * n + 2] = z + k0;
+        }
+    c->modify_on_host();
+  }
+}
+
+Entity BulkData::get_entity(EntityRank rank, int64_t id) const
+{
+  Entity e;
+  e.rank = rank;
+  if (rank == topology::NODE_RANK) {
+    auto it = std::lower_bound(node_gid_.begin(), node_gid_.end(), id);
+    e.index = (it != node_gid_.end() && *it == id) ? int64_t(it - node_gid_.begin()) : -1;
+  } else {
+    e.index = id - elem_gid0_;
+    if (e.index < 0 || e.index >= int64_t(num_elems())) e.index = -1;
+  }
+  return e;
+}
+
+} // namespace mesh
+} // namespace stk
+
+namespace sierra {
+namespace nalu {
+
+// ================================================================================================
+// ElemDataRequests (src/ElemDataRequests.C:13-102)
+// ================================================================================================
+void ElemDataRequests::add_gathered_nodal_field(const stk::mesh::FieldBase &field, unsigned scalarsPerNode)
+{
+  STK_ThrowRequireMsg(field.entity_rank() == stk::topology::NODE_RANK,
+                      "ElemDataRequests ERROR, add_gathered_nodal_field called with field "
+                          << field.name() << " which has entity-rank==" << field.entity_rank()
+                          << " but is expected to have rank==NODE_RANK");
+  FieldInfo fieldInfo(&field, scalarsPerNode);
+  auto iter = fields.find(fieldInfo);
+  if (iter == fields.end())
+    fields.insert(fieldInfo);
+  else
+    STK_ThrowRequireMsg(iter->scalarsDim1 == scalarsPerNode,
+                        "ElemDataRequests ERROR, gathered-nodal-field " << field.name() << " requested with scalarsPerNode=="
+                                                                       << scalarsPerNode
+                                                                       << ", but previously requested with scalarsPerNode=="
+                                                                       << iter->scalarsDim1);
+}
+void ElemDataRequests::add_gathered_nodal_field(const stk::mesh::FieldBase &field, unsigned d1, unsigned d2)
+{
+  STK_ThrowRequireMsg(field.entity_rank() == stk::topology::NODE_RANK,
+                      "ElemDataRequests ERROR, add_gathered_nodal_field called with field "
+                          << field.name() << " which has entity-rank==" << field.entity_rank()
+                          << " but is expected to have rank==NODE_RANK");
+  FieldInfo fieldInfo(&field, d1, d2);
+  auto iter = fields.find(fieldInfo);
+  if (iter == fields.end())
+    fields.insert(fieldInfo);
+  else
+    STK_ThrowRequireMsg(iter->scalarsDim1 == d1 && iter->scalarsDim2 == d2,
+                        "ElemDataRequests ERROR, gathered-nodal-field " << field.name() << " requested with tensorDim1==" << d1
+                                                                       << ",tensorDim2==" << d2 << ", but previously requested with tensorDim1=="
+                                                                       << iter->scalarsDim1 << ",tensorDim2==" << iter->scalarsDim2);
+}
+void ElemDataRequests::add_ip_field(const stk::mesh::FieldBase &field, unsigned scalarsPerElement)
+{
+  FieldInfo fieldInfo(&field, scalarsPerElement);
+  auto iter = fields.find(fieldInfo);
+  if (iter == fields.end())
+    fields.insert(fieldInfo);
+  else
+    STK_ThrowRequireMsg(iter->scalarsDim1 == scalarsPerElement,
+                        "ElemDataRequests ERROR, ip-field " << field.name() << " requested with scalarsPerElement==" << scalarsPerElement
+                                                           << ", but previously requested with scalarsPerElement==" << iter->scalarsDim1);
+}
+void ElemDataRequests::add_face_field(const stk::mesh::FieldBase &field, unsigned scalarsPerFace)
+{
+  STK_ThrowRequireMsg(field.entity_rank() == stk::topology::FACE_RANK || field.entity_rank() == stk::topology::EDGE_RANK,
+                      "ElemDataRequests ERROR, add_face_field called with field " << field.name() << " which has entity-rank=="
+                                                                                 << field.entity_rank());
+  add_ip_field(field, scalarsPerFace);
+}
+void ElemDataRequests::add_element_field(const stk::mesh::FieldBase &field, unsigned scalarsPerElement)
+{
+  STK_ThrowRequireMsg(field.entity_rank() == stk::topology::ELEM_RANK,
+                      "ElemDataRequests ERROR, add_element_field called with field "
+                          << field.name() << " which has entity-rank==" << field.entity_rank()
+                          << " but is expected to have rank==ELEM_RANK");
+  add_ip_field(field, scalarsPerElement);
+}
+void ElemDataRequests::add_ip_field(const stk::mesh::FieldBase &field, unsigned d1, unsigned d2)
+{
+  FieldInfo fieldInfo(&field, d1, d2);
+  auto iter = fields.find(fieldInfo);
+  if (iter == fields.end())
+    fields.insert(fieldInfo);
+  else
+    STK_ThrowRequireMsg(iter->scalarsDim1 == d1 && iter->scalarsDim2 == d2,
+                        "ElemDataRequests ERROR, ip-field " << field.name() << " requested with different tensor dimensions");
+}
+void ElemDataRequests::add_element_field(const stk::mesh::FieldBase &field, unsigned d1, unsigned d2)
+{
+  STK_ThrowRequireMsg(field.entity_rank() == stk::topology::ELEM_RANK,
+                      "ElemDataRequests ERROR, add_element_field called with field " << field.name() << " of the wrong rank");
+  add_ip_field(field, d1, d2);
+}
+void ElemDataRequests::add_coordinates_field(const stk::mesh::FieldBase &field, unsigned scalarsPerNode, COORDS_TYPES cType)
+{
+  coordsFields_[cType] = &field;
+  add_gathered_nodal_field(field, scalarsPerNode);
+}
+
+// ================================================================================================
+// Master elements: constant tables (Hex8CVFEM.C:75-108,255-345; MasterElementWork.F:2344-2402)
+// ================================================================================================
+namespace {
+double sgx(int n) { return ((n ^ (n >> 1)) & 1) ? 1.0 : -1.0; }
+double sgy(int n) { return ((n >> 1) & 1) ? 1.0 : -1.0; }
+double sgz(int n) { return ((n >> 2) & 1) ? 1.0 : -1.0; }
+void hex_shape(const double *loc, int npts, double *shp)
+{
+  for (int p = 0; p < npts; ++p)
+    for (int n = 0; n < 8; ++n)
+      shp[p * 8 + n] = (0.5 + sgx(n) * loc[3 * p]) * (0.5 + sgy(n) * loc[3 * p + 1]) * (0.5 + sgz(n) * loc[3 * p + 2]);
+}
+const int kLrscv[24] = {0, 1, 1, 2, 2, 3, 0, 3, 4, 5, 5, 6, 6, 7, 4, 7, 0, 4, 1, 5, 2, 6, 3, 7};
+void scs_loc(double q, double *loc)
+{
+  for (int ip = 0; ip < 12; ++ip) {
+    const int L = kLrscv[2 * ip], R = kLrscv[2 * ip + 1];
+    // the ip sits on the facet through the midpoint of edge (L,R): average of the two nodes' signs, scaled
+    loc[3 * ip + 0] = q * (sgx(L) + sgx(R)) * 0.5;
+    loc[3 * ip + 1] = q * (sgy(L) + sgy(R)) * 0.5;
+    loc[3 * ip + 2] = q * (sgz(L) + sgz(R)) * 0.5;
+  }
+}
+void scv_loc(double q, double *loc)
+{
+  for (int ip = 0; ip < 8; ++ip) {
+    loc[3 * ip + 0] = q * sgx(ip);
+    loc[3 * ip + 1] = q * sgy(ip);
+    loc[3 * ip + 2] = q * sgz(ip);
+  }
+}
+} // namespace
+
+HexSCS::HexSCS()
+{
+  nodesPerElement_ = 8;
+  numIntPoints_ = 12;
+  std::memcpy(lrscv_, kLrscv, sizeof(kLrscv));
+}
+void HexSCS::shape_fcn(double *shpfc)
+{
+  double loc[36];
+  scs_loc(0.25, loc);
+  hex_shape(loc, 12, shpfc);
+}
+void HexSCS::shifted_shape_fcn(double *shpfc)
+{
+  double loc[36];
+  scs_loc(0.5, loc);
+  hex_shape(loc, 12, shpfc);
+}
+HexSCV::HexSCV()
+{
+  nodesPerElement_ = 8;
+  numIntPoints_ = 8;
+  for (int i = 0; i < 8; ++i) ipNodeMap_[i] = i;
+}
+void HexSCV::shape_fcn(double *shpfc)
+{
+  double loc[24];
+  scv_loc(0.25, loc);
+  hex_shape(loc, 8, shpfc);
+}
+void HexSCV::shifted_shape_fcn(double *shpfc)
+{
+  double loc[24];
+  scv_loc(0.5, loc);
+  hex_shape(loc, 8, shpfc);
+}
+MasterElement *MasterElementRepo::get_surface_master_element(const stk::topology &theTopo)
+{
+  static HexSCS scs;
+  if (theTopo.t_ != stk::topology::HEX_8) throw std::runtime_error("only Hex8 master elements are on this path");
+  return &scs;
+}
+MasterElement *MasterElementRepo::get_volume_master_element(const stk::topology &theTopo)
+{
+  static HexSCV scv;
+  if (theTopo.t_ != stk::topology::HEX_8) throw std::runtime_error("only Hex8 master elements are on this path");
+  return &scv;
+}
+
+// ================================================================================================
+// Kernels
+// ================================================================================================
+void Kernel::clear(nalu_b200_kernel_desc &d)
+{
+  std::memset(&d, 0, sizeof(d));
+  d.om_dens_fac = 1.0;
+  d.dt = 1.0;
+  d.gamma1 = 1.0;
+  d.gamma2 = -1.0;
+}
+void Kernel::bind(nalu_b200_kernel_desc &d, int slot, stk::mesh::FieldBase *f)
+{
+  if (!f) throw std::runtime_error("kernel field not found in MetaData");
+  d.nodal[slot] = f->device_data();
+}
+
+template <typename AlgTraits>
+MomentumAdvDiffElemKernel<AlgTraits>::MomentumAdvDiffElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                               VectorFieldType *velocity, ScalarFieldType *viscosity,
+                                                               ElemDataRequests &dataPreReqs)
+    : Kernel(), viscosity_(viscosity),
+      lrscv_(MasterElementRepo::get_surface_master_element(AlgTraits::topo_)->adjacentNodes()),
+      includeDivU_(solnOpts.includeDivU_), shiftedGradOp_(solnOpts.get_shifted_grad_op(velocity->name()))
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  velocityNp1_ = &(velocity->field_of_state(stk::mesh::StateNP1));
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  massFlowRate_ = metaData.get_field<double>(stk::topology::ELEMENT_RANK, "mass_flow_rate_scs");
+  STK_ThrowRequireMsg(coordinates_ && massFlowRate_, "MomentumAdvDiffElemKernel: coordinates / mass_flow_rate_scs not registered");
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(AlgTraits::topo_);
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shape_fcn(ptr); }, v_shape_function_);
+  skewSymmetric_ = solnOpts.get_skew_symmetric(velocity->name());
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { skewSymmetric_ ? meSCS->shifted_shape_fcn(ptr) : meSCS->shape_fcn(ptr); },
+                                   v_adv_shape_function_);
+  dataPreReqs.add_cvfem_surface_me(meSCS);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*velocityNp1_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*viscosity_, 1);
+  dataPreReqs.add_element_field(*massFlowRate_, AlgTraits::numScsIp_);
+  dataPreReqs.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_GRAD_OP : SCS_GRAD_OP, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+bool MomentumAdvDiffElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_MOMENTUM_ADV_DIFF;
+  d.options = (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0) | (skewSymmetric_ ? NALU_OPT_SKEW_SYMMETRIC : 0);
+  d.include_divu = includeDivU_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityNp1_);
+  bind(d, NALU_F_VISCOSITY, viscosity_);
+  d.mass_flow_rate = massFlowRate_->device_data();
+  return true;
+}
+
+template <typename AlgTraits>
+ContinuityAdvElemKernel<AlgTraits>::ContinuityAdvElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                           ElemDataRequests &dataPreReqs)
+    : Kernel(), meshMotion_(solnOpts.does_mesh_move()), shiftMdot_(solnOpts.cvfemShiftMdot_),
+      shiftPoisson_(solnOpts.get_shifted_grad_op("pressure")), reducedSensitivities_(solnOpts.cvfemReducedSensPoisson_),
+      lrscv_(MasterElementRepo::get_surface_master_element(AlgTraits::topo_)->adjacentNodes())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  const std::string velocity_name = meshMotion_ ? "velocity_rtm" : "velocity";
+  velocityRTM_ = metaData.get_field<double>(stk::topology::NODE_RANK, velocity_name);
+  Gpdx_ = metaData.get_field<double>(stk::topology::NODE_RANK, "dpdx");
+  pressure_ = metaData.get_field<double>(stk::topology::NODE_RANK, "pressure");
+  ScalarFieldType *density = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  STK_ThrowRequireMsg(velocityRTM_ && Gpdx_ && pressure_ && density, "ContinuityAdvElemKernel: required fields not registered");
+  densityNp1_ = &(density->field_of_state(stk::mesh::StateNP1));
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(AlgTraits::topo_);
+  dataPreReqs.add_cvfem_surface_me(meSCS);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*velocityRTM_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*pressure_, 1);
+  dataPreReqs.add_gathered_nodal_field(*Gpdx_, AlgTraits::nDim_);
+  dataPreReqs.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  if (!shiftPoisson_ || !reducedSensitivities_) dataPreReqs.add_master_element_call(SCS_GRAD_OP, CURRENT_COORDINATES);
+  if (shiftPoisson_ || reducedSensitivities_) dataPreReqs.add_master_element_call(SCS_SHIFTED_GRAD_OP, CURRENT_COORDINATES);
+  if (shiftMdot_)
+    get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shifted_shape_fcn(ptr); }, v_shape_function_);
+  else
+    get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shape_fcn(ptr); }, v_shape_function_);
+}
+template <typename AlgTraits>
+void ContinuityAdvElemKernel<AlgTraits>::setup(const TimeIntegrator &timeIntegrator)
+{
+  dt_ = timeIntegrator.get_time_step();
+  gamma1_ = timeIntegrator.get_gamma1();
+  projTimeScale_ = dt_ / gamma1_;
+}
+template <typename AlgTraits>
+bool ContinuityAdvElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_CONTINUITY_ADV;
+  d.options = (shiftMdot_ ? NALU_OPT_SHIFT_MDOT : 0) | (shiftPoisson_ ? NALU_OPT_SHIFT_POISSON : 0) |
+              (reducedSensitivities_ ? NALU_OPT_REDUCED_SENS : 0);
+  d.dt = dt_;
+  d.gamma1 = gamma1_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityRTM_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_PRESSURE, pressure_);
+  bind(d, NALU_F_DPDX, Gpdx_);
+  return true;
+}
+
+template <typename AlgTraits>
+ScalarAdvDiffElemKernel<AlgTraits>::ScalarAdvDiffElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                           ScalarFieldType *scalarQ, ScalarFieldType *diffFluxCoeff,
+                                                           ElemDataRequests &dataPreReqs)
+    : Kernel(), scalarQ_(scalarQ), diffFluxCoeff_(diffFluxCoeff),
+      lrscv_(MasterElementRepo::get_surface_master_element(AlgTraits::topo_)->adjacentNodes()),
+      shiftedGradOp_(solnOpts.get_shifted_grad_op(scalarQ->name()))
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  massFlowRate_ = metaData.get_field<double>(stk::topology::ELEMENT_RANK, "mass_flow_rate_scs");
+  STK_ThrowRequireMsg(coordinates_ && massFlowRate_, "ScalarAdvDiffElemKernel: coordinates / mass_flow_rate_scs not registered");
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(AlgTraits::topo_);
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shape_fcn(ptr); }, v_shape_function_);
+  skewSymmetric_ = solnOpts.get_skew_symmetric(scalarQ->name());
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { skewSymmetric_ ? meSCS->shifted_shape_fcn(ptr) : meSCS->shape_fcn(ptr); },
+                                   v_adv_shape_function_);
+  dataPreReqs.add_cvfem_surface_me(meSCS);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*scalarQ_, 1);
+  dataPreReqs.add_gathered_nodal_field(*diffFluxCoeff_, 1);
+  dataPreReqs.add_element_field(*massFlowRate_, AlgTraits::numScsIp_);
+  dataPreReqs.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_GRAD_OP : SCS_GRAD_OP, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+bool ScalarAdvDiffElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_SCALAR_ADV_DIFF;
+  d.options = (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0) | (skewSymmetric_ ? NALU_OPT_SKEW_SYMMETRIC : 0);
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_SCALARQ, scalarQ_);
+  bind(d, NALU_F_VISCOSITY, diffFluxCoeff_);
+  d.mass_flow_rate = massFlowRate_->device_data();
+  return true;
+}
+
+template <typename AlgTraits>
+ScalarDiffElemKernel<AlgTraits>::ScalarDiffElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                     ScalarFieldType *scalarQ, ScalarFieldType *diffFluxCoeff,
+                                                     ElemDataRequests &dataPreReqs)
+    : Kernel(), scalarQ_(scalarQ), diffFluxCoeff_(diffFluxCoeff),
+      lrscv_(MasterElementRepo::get_surface_master_element(AlgTraits::topo_)->adjacentNodes()),
+      shiftedGradOp_(solnOpts.get_shifted_grad_op(scalarQ_->name()))
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(coordinates_, "ScalarDiffElemKernel: coordinates not registered");
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(AlgTraits::topo_);
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shape_fcn(ptr); }, v_shape_function_);
+  dataPreReqs.add_cvfem_surface_me(meSCS);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*scalarQ_, 1);
+  dataPreReqs.add_gathered_nodal_field(*diffFluxCoeff_, 1);
+  dataPreReqs.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_GRAD_OP : SCS_GRAD_OP, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+bool ScalarDiffElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_SCALAR_DIFF;
+  d.options = shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_SCALARQ, scalarQ_);
+  bind(d, NALU_F_VISCOSITY, diffFluxCoeff_);
+  return true;
+}
+
+namespace {
+// StateN / StateNM1 selection of the mass kernels (src/kernel/MomentumMassElemKernel.C:46-56): with two
+// states NM1 aliases N
+template <typename F>
+void pick_states(F *f, F *&nm1, F *&n, F *&np1)
+{
+  n = &(f->field_of_state(stk::mesh::StateN));
+  np1 = &(f->field_of_state(stk::mesh::StateNP1));
+  nm1 = f->number_of_states() == 2 ? n : &(f->field_of_state(stk::mesh::StateNM1));
+}
+} // namespace
+
+template <typename AlgTraits>
+MomentumMassElemKernel<AlgTraits>::MomentumMassElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                         ElemDataRequests &dataPreReqs, const bool lumpedMass)
+    : Kernel(), lumpedMass_(lumpedMass), densFac_(solnOpts.balancedForce_ ? 1.0 : 0.0),
+      om_densFac_(solnOpts.balancedForce_ ? 0.0 : 1.0),
+      ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  VectorFieldType *velocity = metaData.get_field<double>(stk::topology::NODE_RANK, "velocity");
+  ScalarFieldType *density = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  STK_ThrowRequireMsg(velocity && density, "MomentumMassElemKernel: velocity / density not registered");
+  STK_ThrowRequireMsg(velocity->number_of_states() >= 2 && density->number_of_states() >= 2,
+                      "MomentumMassElemKernel: velocity and density need at least two states");
+  pick_states(velocity, velocityNm1_, velocityN_, velocityNp1_);
+  pick_states(density, densityNm1_, densityN_, densityNp1_);
+  Gjp_ = metaData.get_field<double>(stk::topology::NODE_RANK, "dpdx");
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(Gjp_ && coordinates_, "MomentumMassElemKernel: dpdx / coordinates not registered");
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(AlgTraits::topo_);
+  if (lumpedMass_)
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shifted_shape_fcn(ptr); }, v_shape_function_);
+  else
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shape_fcn(ptr); }, v_shape_function_);
+  dataPreReqs.add_cvfem_volume_me(meSCV);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*densityNm1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityN_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*velocityNm1_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*velocityN_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*velocityNp1_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*Gjp_, AlgTraits::nDim_);
+  dataPreReqs.add_master_element_call(SCV_VOLUME, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+void MomentumMassElemKernel<AlgTraits>::setup(const TimeIntegrator &ti)
+{
+  dt_ = ti.get_time_step();
+  gamma1_ = ti.get_gamma1();
+  gamma2_ = ti.get_gamma2();
+  gamma3_ = ti.get_gamma3();
+}
+template <typename AlgTraits>
+bool MomentumMassElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_MOMENTUM_MASS;
+  d.options = lumpedMass_ ? NALU_OPT_LUMPED_MASS : 0;
+  d.dens_fac = densFac_;
+  d.om_dens_fac = om_densFac_;
+  d.dt = dt_; d.gamma1 = gamma1_; d.gamma2 = gamma2_; d.gamma3 = gamma3_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityNp1_);
+  bind(d, NALU_F_VELOCITY_N, velocityN_);
+  bind(d, NALU_F_VELOCITY_NM1, velocityNm1_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_DENSITY_N, densityN_);
+  bind(d, NALU_F_DENSITY_NM1, densityNm1_);
+  bind(d, NALU_F_DPDX, Gjp_);
+  return true;
+}
+
+template <typename AlgTraits>
+ContinuityMassElemKernel<AlgTraits>::ContinuityMassElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                             ElemDataRequests &dataPreReqs, const bool lumpedMass)
+    : Kernel(), lumpedMass_(lumpedMass), ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  ScalarFieldType *density = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  STK_ThrowRequireMsg(density && density->number_of_states() >= 2, "ContinuityMassElemKernel: density needs at least two states");
+  pick_states(density, densityNm1_, densityN_, densityNp1_);
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(coordinates_, "ContinuityMassElemKernel: coordinates not registered");
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(AlgTraits::topo_);
+  if (lumpedMass_)
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shifted_shape_fcn(ptr); }, v_shape_function_);
+  else
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shape_fcn(ptr); }, v_shape_function_);
+  dataPreReqs.add_cvfem_volume_me(meSCV);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*densityNm1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityN_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1_, 1);
+  dataPreReqs.add_master_element_call(SCV_VOLUME, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+void ContinuityMassElemKernel<AlgTraits>::setup(const TimeIntegrator &ti)
+{
+  dt_ = ti.get_time_step();
+  gamma1_ = ti.get_gamma1();
+  gamma2_ = ti.get_gamma2();
+  gamma3_ = ti.get_gamma3();
+}
+template <typename AlgTraits>
+bool ContinuityMassElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_CONTINUITY_MASS;
+  d.options = lumpedMass_ ? NALU_OPT_LUMPED_MASS : 0;
+  d.dt = dt_; d.gamma1 = gamma1_; d.gamma2 = gamma2_; d.gamma3 = gamma3_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_DENSITY_N, densityN_);
+  bind(d, NALU_F_DENSITY_NM1, densityNm1_);
+  return true;
+}
+
+template <typename AlgTraits>
+ScalarMassElemKernel<AlgTraits>::ScalarMassElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                     ScalarFieldType *scalarQ, ElemDataRequests &dataPreReqs, const bool lumpedMass)
+    : Kernel(), lumpedMass_(lumpedMass), ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  STK_ThrowRequireMsg(scalarQ->number_of_states() >= 2, "ScalarMassElemKernel: scalarQ needs at least two states");
+  pick_states(scalarQ, scalarQNm1_, scalarQN_, scalarQNp1_);
+  ScalarFieldType *density = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  STK_ThrowRequireMsg(density && density->number_of_states() >= 2, "ScalarMassElemKernel: density needs at least two states");
+  pick_states(density, densityNm1_, densityN_, densityNp1_);
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(coordinates_, "ScalarMassElemKernel: coordinates not registered");
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(AlgTraits::topo_);
+  if (lumpedMass_)
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shifted_shape_fcn(ptr); }, v_shape_function_);
+  else
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shape_fcn(ptr); }, v_shape_function_);
+  dataPreReqs.add_cvfem_volume_me(meSCV);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*scalarQNm1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*scalarQN_, 1);
+  dataPreReqs.add_gathered_nodal_field(*scalarQNp1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityNm1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityN_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1_, 1);
+  dataPreReqs.add_master_element_call(SCV_VOLUME, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+void ScalarMassElemKernel<AlgTraits>::setup(const TimeIntegrator &ti)
+{
+  dt_ = ti.get_time_step();
+  gamma1_ = ti.get_gamma1();
+  gamma2_ = ti.get_gamma2();
+  gamma3_ = ti.get_gamma3();
+}
+template <typename AlgTraits>
+bool ScalarMassElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_SCALAR_MASS;
+  d.options = lumpedMass_ ? NALU_OPT_LUMPED_MASS : 0;
+  d.dt = dt_; d.gamma1 = gamma1_; d.gamma2 = gamma2_; d.gamma3 = gamma3_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_SCALARQ, scalarQNp1_);
+  bind(d, NALU_F_SCALARQ_N, scalarQN_);
+  bind(d, NALU_F_SCALARQ_NM1, scalarQNm1_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_DENSITY_N, densityN_);
+  bind(d, NALU_F_DENSITY_NM1, densityNm1_);
+  return true;
+}
+
+NALU_B200_DECLARE_KERNEL(MomentumAdvDiffElemKernel)
+NALU_B200_DECLARE_KERNEL(ContinuityAdvElemKernel)
+NALU_B200_DECLARE_KERNEL(ScalarAdvDiffElemKernel)
+NALU_B200_DECLARE_KERNEL(ScalarDiffElemKernel)
+NALU_B200_DECLARE_KERNEL(MomentumMassElemKernel)
+NALU_B200_DECLARE_KERNEL(ContinuityMassElemKernel)
+NALU_B200_DECLARE_KERNEL(ScalarMassElemKernel)
+
+// ================================================================================================
+// Algorithms
+// ================================================================================================
+Algorithm::~Algorithm()
+{
+  for (Kernel *k : activeKernels_) delete k;
+}
+EquationSystem::~EquationSystem() { delete linsys_; }
+
+AssembleElemSolverAlgorithm::AssembleElemSolverAlgorithm(Realm &realm, stk::mesh::Part *part, EquationSystem *eqSystem,
+                                                         stk::mesh::EntityRank entityRank, unsigned nodesPerEntity,
+                                                         bool interleaveMEViews)
+    : SolverAlgorithm(realm, part, eqSystem), entityRank_(entityRank), nodesPerEntity_(nodesPerEntity),
+      rhsSize_(nodesPerEntity * eqSystem->linsys_->numDof()), interleaveMEViews_(interleaveMEViews)
+{
+}
+void AssembleElemSolverAlgorithm::initialize_connectivity() { eqSystem_->linsys_->buildElemToNodeGraph(partVec_); }
+
+void AssembleElemSolverAlgorithm::execute()
+{
+  // set any data
+  for (Kernel *k : activeKernels_) k->setup(*realm_.timeIntegrator_);
+  DeviceCsrLinearSystem *ls = dynamic_cast<DeviceCsrLinearSystem *>(eqSystem_->linsys_);
+  if (!ls) throw std::runtime_error("AssembleElemSolverAlgorithm: the device path needs a DeviceCsrLinearSystem");
+  STK_ThrowRequireMsg(nodesPerEntity_ == 8 && entityRank_ == stk::topology::ELEM_RANK,
+                      "AssembleElemSolverAlgorithm expected nodesPerEntity_ = 8 (Hex8), got " << nodesPerEntity_);
+  std::vector<nalu_b200_kernel_desc> descs(activeKernels_.size());
+  for (size_t i = 0; i < activeKernels_.size(); ++i)
+    if (!activeKernels_[i]->device_descriptor(descs[i]))
+      throw std::runtime_error(std::string("kernel ") + activeKernels_[i]->name() + " has no device form; this path has no CPU fallback");
+  if (descs.empty()) return;
+  ls->assembleElemDevice(descs.data(), int(descs.size()), firstAlgorithmAfterZero_);
+}
+
+AssembleNodeSolverAlgorithm::AssembleNodeSolverAlgorithm(Realm &realm, stk::mesh::Part *part, EquationSystem *eqSystem)
+    : SolverAlgorithm(realm, part, eqSystem)
+{
+}
+void AssembleNodeSolverAlgorithm::initialize_connectivity() { eqSystem_->linsys_->buildNodeGraph(partVec_); }
+void AssembleNodeSolverAlgorithm::execute()
+{
+  DeviceCsrLinearSystem *ls = dynamic_cast<DeviceCsrLinearSystem *>(eqSystem_->linsys_);
+  if (!ls) throw std::runtime_error("AssembleNodeSolverAlgorithm: the device path needs a DeviceCsrLinearSystem");
+  const stk::mesh::MetaData &meta = realm_.meta_data();
+  const TimeIntegrator &ti = *realm_.timeIntegrator_;
+  nalu_b200_kernel_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.kind = massKind_;
+  d.om_dens_fac = 1.0;
+  d.dt = ti.get_time_step(); d.gamma1 = ti.get_gamma1(); d.gamma2 = ti.get_gamma2(); d.gamma3 = ti.get_gamma3();
+  auto get = [&](const char *name) {
+    stk::mesh::Field<double> *f = meta.get_field<double>(stk::topology::NODE_RANK, name);
+    if (!f) throw std::runtime_error(std::string("node mass algorithm: field ") + name + " not registered");
+    return f;
+  };
+  auto states = [&](stk::mesh::Field<double> *f, int np1, int n, int nm1) {
+    stk::mesh::Field<double> *a, *b, *c;
+    pick_states(f, a, b, c);
+    d.nodal[np1] = c->device_data();
+    d.nodal[n] = b->device_data();
+    d.nodal[nm1] = a->device_data();
+  };
+  states(get("density"), NALU_F_DENSITY, NALU_F_DENSITY_N, NALU_F_DENSITY_NM1);
+  d.nodal[NALU_F_DUAL_VOLUME] = get("dual_nodal_volume")->device_data();
+  if (massKind_ == NALU_K_MOMENTUM_MASS) {
+    states(get("velocity"), NALU_F_VELOCITY, NALU_F_VELOCITY_N, NALU_F_VELOCITY_NM1);
+    d.nodal[NALU_F_DPDX] = get("dpdx")->device_data();
+  } else if (massKind_ == NALU_K_SCALAR_MASS) {
+    if (!scalarQ_) throw std::runtime_error("scalar node mass algorithm: scalarQ_ not set");
+    states(static_cast<stk::mesh::Field<double> *>(scalarQ_), NALU_F_SCALARQ, NALU_F_SCALARQ_N, NALU_F_SCALARQ_NM1);
+  }
+  check(nalu_b200_assemble_node_mass(ls->graph(), &d, ls->deviceValues(), ls->deviceRhs(), nullptr), "assemble_node_mass");
+}
+
+// ================================================================================================
+// LinearSystem
+// ================================================================================================
+LinearSystem::LinearSystem(Realm &realm, const unsigned numDof, EquationSystem *eqSys, LinearSolver *linearSolver)
+    : realm_(realm), eqSys_(eqSys), inConstruction_(false), numDof_(numDof), eqSysName_(eqSys ? eqSys->name_ : ""),
+      linearSolver_(linearSolver)
+{
+}
+LinearSystem *LinearSystem::create(Realm &realm, const unsigned numDof, EquationSystem *eqSys, LinearSolver *linearSolver)
+{
+  // src/LinearSystem.C:85-97 switches on the solver type; this build has exactly one
+  return new DeviceCsrLinearSystem(realm, numDof, eqSys, linearSolver);
+}
+
+DeviceCsrLinearSystem::DeviceCsrLinearSystem(Realm &realm, const unsigned numDof, EquationSystem *eqSys, LinearSolver *linearSolver)
+    : LinearSystem(realm, numDof, eqSys, linearSolver)
+{
+  STK_ThrowRequireMsg(numDof == 1 || numDof == 3, "DeviceCsrLinearSystem: numDof must be 1 or 3");
+}
+DeviceCsrLinearSystem::~DeviceCsrLinearSystem()
+{
+  if (d_values_) nalu_b200_free(d_values_);
+  if (d_rhs_) nalu_b200_free(d_rhs_);
+  for (double *p : sendBufs_) nalu_b200_free(p);
+  for (double *p : recvBufs_) nalu_b200_free(p);
+  if (graph_) nalu_b200_graph_destroy(graph_);
+}
+void DeviceCsrLinearSystem::unsupported(const char *what) const
+{
+  throw std::runtime_error(std::string("DeviceCsrLinearSystem::") + what + " is outside the element-assembly path");
+}
+void DeviceCsrLinearSystem::beginLinearSystemConstruction()
+{
+  if (inConstruction_) return;
+  inConstruction_ = true;
+}
+void DeviceCsrLinearSystem::buildNodeGraph(const stk::mesh::PartVector &)
+{
+  beginLinearSystemConstruction(); // every node is connected to itself by any element graph; nothing to add
+}
+void DeviceCsrLinearSystem::buildElemToNodeGraph(const stk::mesh::PartVector &)
+{
+  beginLinearSystemConstruction();
+  elemGraphRequested_ = true;
+}
+void DeviceCsrLinearSystem::finalizeLinearSystem()
+{
+  STK_ThrowRequireMsg(inConstruction_, "finalizeLinearSystem called before any build*Graph");
+  STK_ThrowRequireMsg(elemGraphRequested_, "DeviceCsrLinearSystem needs buildElemToNodeGraph (node-only graphs are not on this path)");
+  STK_ThrowRequireMsg(!graph_, "finalizeLinearSystem called twice");
+  inConstruction_ = false;
+  stk::mesh::BulkData &bulk = realm_.bulk_data();
+  const int *box = bulk.box();
+  check(nalu_b200_graph_create(&graph_, bulk.parallel_rank(), bulk.parallel_size(), int(numDof_), int(bulk.num_nodes()),
+                               bulk.node_ids().data(), bulk.node_owners().data(), int64_t(bulk.num_elems()),
+                               bulk.connectivity().data(), box[0], box[1], box[2]),
+        "graph_create");
+  if (bulk.parallel_size() > 1) {
+    STK_ThrowRequireMsg(bool(transport_.exchange_graph), "multi-rank DeviceCsrLinearSystem needs a HaloTransport (setTransport)");
+    std::map<int, std::vector<int64_t>> send;
+    for (int p = 0; p < bulk.parallel_size(); ++p) {
+      if (p == bulk.parallel_rank()) continue;
+      int64_t nbytes = 0;
+      check(nalu_b200_graph_send_size(graph_, p, &nbytes), "graph_send_size");
+      if (!nbytes) continue;
+      std::vector<int64_t> buf(size_t(nbytes / 8));
+      check(nalu_b200_graph_send_data(graph_, p, buf.data()), "graph_send_data");
+      send[p] = std::move(buf);
+    }
+    for (auto &kv : transport_.exchange_graph(send))
+      check(nalu_b200_graph_recv_data(graph_, kv.first, kv.second.data(), int64_t(kv.second.size() * 8)), "graph_recv_data");
+  }
+  check(nalu_b200_graph_finalize(graph_), "graph_finalize");
+  check(nalu_b200_graph_get_info(graph_, &info_), "graph_get_info");
+  void *p = nullptr;
+  check(nalu_b200_malloc(&p, size_t(info_.nnz_owned + info_.nnz_shared) * sizeof(double)), "values allocation");
+  d_values_ = static_cast<double *>(p);
+  check(nalu_b200_malloc(&p, size_t(info_.n_owned_rows + info_.n_shared_rows) * sizeof(double)), "rhs allocation");
+  d_rhs_ = static_cast<double *>(p);
+  node_row_lid_.resize(bulk.num_nodes());
+  check(nalu_b200_graph_copy_node_lids(graph_, node_row_lid_.data(), nullptr), "copy_node_lids");
+  zeroSystem();
+}
+void DeviceCsrLinearSystem::zeroSystem() { check(nalu_b200_zero_system(graph_, d_values_, d_rhs_, nullptr), "zero_system"); }
+
+void DeviceCsrLinearSystem::assembleElemDevice(const nalu_b200_kernel_desc *descs, int n, bool overwrite)
+{
+  check(nalu_b200_assemble_elem(graph_, descs, n, d_values_, d_rhs_, NALU_ASSEMBLE_AUTO, overwrite ? 1 : 0, nullptr), "assemble_elem");
+  last_family_ = nalu_b200_last_assemble_mode();
+}
+
+int DeviceCsrLinearSystem::entityToLID(stk::mesh::Entity node) const { return node_row_lid_[size_t(node.index)]; }
+
+void DeviceCsrLinearSystem::sumInto(unsigned numEntities, const stk::mesh::Entity *entities, const double *rhs, const double *lhs,
+                                    int *, int *, const char *)
+{
+  std::vector<int32_t> nodes(numEntities);
+  for (unsigned i = 0; i < numEntities; ++i) nodes[i] = int32_t(entities[i].index);
+  check(nalu_b200_sum_into(graph_, int(numEntities), nodes.data(), rhs, lhs, d_values_, d_rhs_, nullptr), "sum_into");
+}
+void DeviceCsrLinearSystem::sumInto(const std::vector<stk::mesh::Entity> &sym_meshobj, std::vector<int> &, std::vector<double> &,
+                                    const std::vector<double> &rhs, const std::vector<double> &lhs, const char *tag)
+{
+  sumInto(unsigned(sym_meshobj.size()), sym_meshobj.data(), rhs.data(), lhs.data(), nullptr, nullptr, tag);
+}
+
+void DeviceCsrLinearSystem::loadComplete()
+{
+  int32_t ns = 0, nr = 0;
+  check(nalu_b200_halo_num_peers(graph_, &ns, &nr), "halo_num_peers");
+  if (ns == 0 && nr == 0) return;
+  STK_ThrowRequireMsg(bool(transport_.exchange_rows), "loadComplete on more than one rank needs a HaloTransport");
+  std::vector<int> sp(ns), rp(nr);
+  std::vector<int64_t> sc(ns), rc(nr);
+  for (int i = 0; i < ns; ++i) check(nalu_b200_halo_send_peer(graph_, i, &sp[i], &sc[i]), "halo_send_peer");
+  for (int i = 0; i < nr; ++i) check(nalu_b200_halo_recv_peer(graph_, i, &rp[i], &rc[i]), "halo_recv_peer");
+  if (sendBufs_.empty() && recvBufs_.empty()) {
+    for (int i = 0; i < ns; ++i) {
+      void *p = nullptr;
+      check(nalu_b200_malloc(&p, size_t(sc[i]) * 8), "halo buffer");
+      sendBufs_.push_back(static_cast<double *>(p));
+    }
+    for (int i = 0; i < nr; ++i) {
+      void *p = nullptr;
+      check(nalu_b200_malloc(&p, size_t(rc[i]) * 8), "halo buffer");
+      recvBufs_.push_back(static_cast<double *>(p));
+    }
+  }
+  for (int i = 0; i < ns; ++i) check(nalu_b200_halo_pack(graph_, i, d_values_, d_rhs_, sendBufs_[i], nullptr), "halo_pack");
+  check(nalu_b200_stream_sync(nullptr), "stream sync");
+  transport_.exchange_rows(sp, sendBufs_, sc, rp, recvBufs_, rc);
+  for (int i = 0; i < nr; ++i) check(nalu_b200_halo_unpack_add(graph_, i, recvBufs_[i], d_values_, d_rhs_, nullptr), "halo_unpack_add");
+}
+
+std::vector<uint64_t> DeviceCsrLinearSystem::ownedRowPtr() const
+{
+  std::vector<uint64_t> v(size_t(info_.n_owned_rows) + 1);
+  check(nalu_b200_graph_copy_rowptr(graph_, 0, v.data()), "copy_rowptr");
+  return v;
+}
+std::vector<int32_t> DeviceCsrLinearSystem::ownedColIdx() const
+{
+  std::vector<int32_t> v(size_t(info_.nnz_owned));
+  check(nalu_b200_graph_copy_colidx(graph_, 0, v.data()), "copy_colidx");
+  return v;
+}
+std::vector<int64_t> DeviceCsrLinearSystem::ownedRowGids() const
+{
+  std::vector<int64_t> v(size_t(info_.n_owned_rows));
+  check(nalu_b200_graph_copy_row_gids(graph_, 0, v.data()), "copy_row_gids");
+  return v;
+}
+std::vector<int64_t> DeviceCsrLinearSystem::colGids() const
+{
+  std::vector<int64_t> v(size_t(info_.n_cols));
+  check(nalu_b200_graph_copy_col_gids(graph_, v.data()), "copy_col_gids");
+  return v;
+}
+std::vector<double> DeviceCsrLinearSystem::ownedValues() const
+{
+  std::vector<double> v(size_t(info_.nnz_owned));
+  check(nalu_b200_memcpy_d2h(v.data(), d_values_, v.size() * 8, nullptr), "values device->host");
+  check(nalu_b200_stream_sync(nullptr), "stream sync");
+  return v;
+}
+std::vector<double> DeviceCsrLinearSystem::ownedRhs() const
+{
+  std::vector<double> v(size_t(info_.n_owned_rows));
+  check(nalu_b200_memcpy_d2h(v.data(), d_rhs_, v.size() * 8, nullptr), "rhs device->host");
+  check(nalu_b200_stream_sync(nullptr), "stream sync");
+  return v;
+}
+void DeviceCsrLinearSystem::writeToFile(const char *filename, bool)
+{
+  // MatrixMarket coordinate format with global ids, like Tpetra::MatrixMarket::Writer output of the owned matrix
+  const auto rp = ownedRowPtr();
+  const auto ci = ownedColIdx();
+  const auto rg = ownedRowGids();
+  const auto cg = colGids();
+  const auto v = ownedValues();
+  FILE *f = std::fopen(filename, "w");
+  if (!f) throw std::runtime_error(std::string("writeToFile: cannot open ") + filename);
+  std::fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n");
+  int64_t maxg = 0;
+  for (int64_t g : cg) maxg = std::max(maxg, g);
+  std::fprintf(f, "%lld %lld %zu\n", (long long)maxg, (long long)maxg, v.size());
+  for (size_t r = 0; r + 1 < rp.size(); ++r)
+    for (uint64_t q = rp[r]; q < rp[r + 1]; ++q)
+      std::fprintf(f, "%lld %lld %.17g\n", (long long)rg[r], (long long)cg[size_t(ci[q])], v[q]);
+  std::fclose(f);
+}
+
+} // namespace nalu
+} // namespace sierra

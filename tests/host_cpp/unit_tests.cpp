@@ -1,0 +1,545 @@
+// C++ unit tests of the host API, written the way the reference's own kernel / linear-system unit tests
+// are (unit_tests/kernels/UnitTestMomentumAdvDiffElem.C:274-305, UnitTestContinuityAdvElem.C,
+// UnitTestScalarAdvDiffElem.C, UnitTestMomentumMassElem.C, UnitTestTpetra.C:86-203,
+// UnitTestKokkosViews.C): build a generated Hex8 mesh and the fixture's analytic fields, make the
+// helper objects (realm, equation system, linear system, AssembleElemSolverAlgorithm), construct the
+// kernel with the reference's constructor arguments, push it into activeKernels_, execute(), compare the
+// captured lhs/rhs with the reference's golden tables.
+//
+//   unit_tests <golden_dir> cpu     registration / error-convention tests, no device needed
+//   unit_tests <golden_dir> gpu     everything (runs the CUDA path through the C ABI)
+#include "AssembleElemSolverAlgorithm.h"
+#include "kernel/ContinuityAdvElemKernel.h"
+#include "kernel/KernelBuilder.h"
+#include "kernel/MassElemKernels.h"
+#include "kernel/MomentumAdvDiffElemKernel.h"
+#include "kernel/ScalarAdvDiffElemKernel.h"
+
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <memory>
+
+using namespace sierra::nalu;
+
+static int g_failures = 0, g_checks = 0;
+#define EXPECT_TRUE(c)                                                                   \
+  do {                                                                                   \
+    ++g_checks;                                                                          \
+    if (!(c)) {                                                                          \
+      ++g_failures;                                                                      \
+      std::printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #c);                       \
+    }                                                                                    \
+  } while (0)
+#define EXPECT_NEAR(a, b, tol)                                                           \
+  do {                                                                                   \
+    ++g_checks;                                                                          \
+    if (!(std::fabs((a) - (b)) <= (tol))) {                                              \
+      ++g_failures;                                                                      \
+      std::printf("  FAILED %s:%d: |%.17g - %.17g| > %g\n", __FILE__, __LINE__, (double)(a), (double)(b), (double)(tol)); \
+    }                                                                                    \
+  } while (0)
+#define EXPECT_THROW(stmt)                                                               \
+  do {                                                                                   \
+    ++g_checks;                                                                          \
+    bool thrown = false;                                                                 \
+    try { stmt; } catch (const std::exception &) { thrown = true; }                      \
+    if (!thrown) { ++g_failures; std::printf("  FAILED %s:%d: no throw: %s\n", __FILE__, __LINE__, #stmt); } \
+  } while (0)
+
+static std::string g_golden;
+struct Table { std::vector<int> dims; std::vector<double> v; };
+static Table gold(const std::string &file, const std::string &name)
+{
+  std::ifstream f(g_golden + "/" + file + "__" + name + ".txt");
+  if (!f) throw std::runtime_error("missing golden table " + file + " " + name);
+  Table t;
+  int nd; f >> nd;
+  t.dims.resize(nd);
+  size_t n = 1;
+  for (int &d : t.dims) { f >> d; n *= d; }
+  t.v.resize(n);
+  for (double &x : t.v) f >> x;
+  return t;
+}
+
+namespace unit_test_utils {
+const double pi = std::acos(-1.0), a = 0.3;
+
+// unit_tests/UnitTestUtils.C:37-72 perturb_coord_hex_8: three LCG draws per node, ascending id
+void perturb_coord_hex_8(stk::mesh::BulkData &bulk, stk::mesh::Field<double> &coords, double scale = 0.125)
+{
+  uint32_t prev = bulk.parallel_rank() + 1;
+  auto lcg = [&]() {
+    prev = (uint32_t)(((uint64_t)1103515245u * prev + 12345u) % 2147483647u);
+    return 2.0 * ((double)prev / 2147483647.0) - 1.0;
+  };
+  for (size_t n = 0; n < bulk.num_nodes(); ++n)
+    for (int d = 0; d < 3; ++d) coords.host_data()[3 * n + d] += scale * lcg();
+  coords.modify_on_host();
+}
+
+// unit_tests/kernels/UnitTestKernelUtils.h:217-352 (LowMachKernelHex8Mesh / MomentumKernelHex8Mesh)
+struct LowMachKernelHex8Mesh {
+  LowMachKernelHex8Mesh(int nx = 1, int ny = 1, int nz = 1) : meta_(3), bulk_(std::make_shared<stk::mesh::BulkData>(meta_))
+  {
+    part_ = &meta_.declare_part_with_topology("block_1", stk::topology::HEX_8);
+    partVec_ = {part_};
+    coordinates_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "coordinates");
+    velocity_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "velocity", 2);
+    dpdx_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dpdx", 2);
+    density_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "density", 2);
+    pressure_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "pressure", 2);
+    viscosity_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "viscosity");
+    scalarQ_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "scalarQ", 2);
+    diffFluxCoeff_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "diffFluxCoeff");
+    dualNodalVolume_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dual_nodal_volume");
+    massFlowRate_ = &meta_.declare_field<double>(stk::topology::ELEM_RANK, "mass_flow_rate_scs");
+    stk::mesh::put_field_on_mesh(*coordinates_, *part_, 3);
+    stk::mesh::put_field_on_mesh(*velocity_, *part_, 3);
+    stk::mesh::put_field_on_mesh(*dpdx_, *part_, 3);
+    stk::mesh::put_field_on_mesh(*density_, *part_, 1);
+    stk::mesh::put_field_on_mesh(*pressure_, *part_, 1);
+    stk::mesh::put_field_on_mesh(*viscosity_, *part_, 1);
+    stk::mesh::put_field_on_mesh(*scalarQ_, *part_, 1);
+    stk::mesh::put_field_on_mesh(*diffFluxCoeff_, *part_, 1);
+    stk::mesh::put_field_on_mesh(*dualNodalVolume_, *part_, 1);
+    stk::mesh::put_field_on_mesh(*massFlowRate_, *part_, 12);
+    bulk_->fill_generated_mesh(nx, ny, nz, *part_);
+  }
+  // steady Taylor vortex etc. (unit_tests/kernels/UnitTestKernelUtils.C:23-274); only StateNP1 is filled
+  void fill_mesh_and_init_fields(bool doPerturb = false)
+  {
+    if (doPerturb) perturb_coord_hex_8(*bulk_, *coordinates_);
+    const double *x = coordinates_->host_data();
+    for (size_t n = 0; n < bulk_->num_nodes(); ++n) {
+      const double X = x[3 * n], Y = x[3 * n + 1];
+      double *u = velocity_->host_data() + 3 * n;
+      u[0] = -std::cos(a * pi * X) * std::sin(a * pi * Y);
+      u[1] = +std::sin(a * pi * X) * std::cos(a * pi * Y);
+      u[2] = 0.0;
+      pressure_->host_data()[n] = -0.25 * (std::cos(2 * a * pi * X) + std::cos(2 * a * pi * Y));
+      double *g = dpdx_->host_data() + 3 * n;
+      g[0] = 0.5 * a * pi * std::sin(2 * a * pi * X);
+      g[1] = 0.5 * a * pi * std::sin(2 * a * pi * Y);
+      g[2] = 0.0;
+      density_->host_data()[n] = 1.0;
+      viscosity_->host_data()[n] = 0.1;
+    }
+    for (auto *f : {velocity_, pressure_, dpdx_, density_, viscosity_}) f->modify_on_host();
+  }
+  stk::mesh::MetaData meta_;
+  std::shared_ptr<stk::mesh::BulkData> bulk_;
+  stk::mesh::Part *part_;
+  stk::mesh::PartVector partVec_;
+  SolutionOptions solnOpts_;
+  VectorFieldType *coordinates_, *velocity_, *dpdx_;
+  ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_;
+  GenericFieldType *massFlowRate_;
+};
+
+// unit_tests/UnitTestHelperObjects.h:16-54
+struct HelperObjects {
+  HelperObjects(std::shared_ptr<stk::mesh::BulkData> bulk, stk::topology topo, int numDof, stk::mesh::Part *part)
+      : eqSystem(realm, "eq")
+  {
+    realm.bulkData_ = bulk;
+    linsys = dynamic_cast<DeviceCsrLinearSystem *>(LinearSystem::create(realm, numDof, &eqSystem, nullptr));
+    eqSystem.linsys_ = linsys;
+    assembleElemSolverAlg = new AssembleElemSolverAlgorithm(realm, part, &eqSystem, topo.rank(), topo.num_nodes(), false);
+  }
+  ~HelperObjects()
+  {
+    assembleElemSolverAlg->activeKernels_.clear(); // the tests own their kernels, like the reference's
+    delete assembleElemSolverAlg;
+  }
+  /** initialize_connectivity + finalize + zero: what EquationSystem::initialize does before the first assembly */
+  void build_system()
+  {
+    assembleElemSolverAlg->initialize_connectivity();
+    linsys->finalizeLinearSystem();
+    linsys->zeroSystem();
+  }
+  /** what TestLinearSystem::sumInto captures in the reference (unit_tests/UnitTestLinearSystem.h:40-61): the
+   *  element lhs/rhs, here rebuilt from the assembled one-element CSR */
+  void element_lhs_rhs(std::vector<double> &lhs, std::vector<double> &rhs)
+  {
+    const int ndof = linsys->numDof(), n = 8 * ndof;
+    const auto rp = linsys->ownedRowPtr();
+    const auto ci = linsys->ownedColIdx();
+    const auto v = linsys->ownedValues();
+    const auto r = linsys->ownedRhs();
+    const int32_t *en = realm.bulk_data().begin_nodes(stk::mesh::Entity{stk::topology::ELEM_RANK, 0});
+    std::vector<int> rows;
+    for (int k = 0; k < 8; ++k)
+      for (int d = 0; d < ndof; ++d) rows.push_back(linsys->entityToLID(stk::mesh::Entity{stk::topology::NODE_RANK, en[k]}) + d);
+    lhs.assign(size_t(n) * n, 0.0);
+    rhs.resize(n);
+    for (int i = 0; i < n; ++i) {
+      rhs[i] = r[rows[i]];
+      for (uint64_t q = rp[rows[i]]; q < rp[rows[i] + 1]; ++q)
+        for (int j = 0; j < n; ++j)
+          if (ci[q] == rows[j]) lhs[size_t(i) * n + j] = v[q];
+    }
+  }
+  Realm realm;
+  EquationSystem eqSystem;
+  DeviceCsrLinearSystem *linsys;
+  AssembleElemSolverAlgorithm *assembleElemSolverAlg;
+};
+
+void expect_all_near(const std::vector<double> &calc, const Table &gold, double tol = 1.0e-15)
+{
+  EXPECT_TRUE(calc.size() == gold.v.size());
+  for (size_t i = 0; i < calc.size() && i < gold.v.size(); ++i) EXPECT_NEAR(calc[i], gold.v[i], tol);
+}
+
+// calc_mass_flow_rate_scs (unit_tests/kernels/UnitTestKernelUtils.C:547-628), on the device
+void calc_mass_flow_rate_scs(HelperObjects &h, LowMachKernelHex8Mesh &fx)
+{
+  void *d = nullptr;
+  const size_t n = fx.bulk_->num_elems() * 12;
+  if (nalu_b200_malloc(&d, n * 8) != 0) throw std::runtime_error("malloc");
+  if (nalu_b200_mdot_scs(h.linsys->graph(), fx.coordinates_->device_data(), fx.density_->device_data(), fx.velocity_->device_data(),
+                         (double *)d, nullptr) != 0)
+    throw std::runtime_error(nalu_b200_last_error());
+  nalu_b200_memcpy_d2h(fx.massFlowRate_->host_data(), d, n * 8, nullptr);
+  nalu_b200_stream_sync(nullptr);
+  nalu_b200_free(d);
+  fx.massFlowRate_->modify_on_host();
+}
+} // namespace unit_test_utils
+
+using unit_test_utils::HelperObjects;
+using unit_test_utils::LowMachKernelHex8Mesh;
+
+// ---------------------------------------------------------------------------------------------------
+// CPU-only: registration and error conventions
+// ---------------------------------------------------------------------------------------------------
+static void test_elem_data_requests()
+{
+  std::printf("ElemDataRequests: registration order and conflicting sizes (include/ElemDataRequests.h:89-101, src/ElemDataRequests.C:21-27)\n");
+  LowMachKernelHex8Mesh fx;
+  ElemDataRequests req;
+  EXPECT_THROW(req.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES)); // coordinates must come first
+  req.add_coordinates_field(*fx.coordinates_, 3, CURRENT_COORDINATES);
+  req.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  req.add_gathered_nodal_field(*fx.velocity_, 3);
+  req.add_gathered_nodal_field(*fx.velocity_, 3); // same size twice is fine
+  EXPECT_THROW(req.add_gathered_nodal_field(*fx.velocity_, 1));
+  EXPECT_THROW(req.add_gathered_nodal_field(*fx.massFlowRate_, 12)); // element field through the nodal door
+  EXPECT_THROW(req.add_element_field(*fx.velocity_, 3));
+  req.add_element_field(*fx.massFlowRate_, 12);
+  EXPECT_TRUE(req.get_fields().size() == 3);
+  EXPECT_TRUE(req.get_data_enums(CURRENT_COORDINATES).count(SCS_AREAV) == 1);
+  EXPECT_THROW(req.get_coordinates_field(MODEL_COORDINATES));
+}
+
+static void test_kernel_registration()
+{
+  std::printf("Kernel constructors register what the reference's do (src/kernel/*ElemKernel.C ctors)\n");
+  LowMachKernelHex8Mesh fx;
+  {
+    ElemDataRequests req;
+    MomentumAdvDiffElemKernel<AlgTraitsHex8> k(*fx.bulk_, fx.solnOpts_, fx.velocity_, fx.viscosity_, req);
+    EXPECT_TRUE(req.get_fields().size() == 4); // coordinates, velocity, viscosity, mass_flow_rate_scs
+    EXPECT_TRUE(req.get_data_enums(CURRENT_COORDINATES) == (std::set<ELEM_DATA_NEEDED>{SCS_AREAV, SCS_GRAD_OP}));
+    EXPECT_TRUE(req.get_cvfem_surface_me() != nullptr && req.get_cvfem_volume_me() == nullptr);
+    EXPECT_NEAR(k.v_shape_function_[0][0], 0.28125, 0.0); // (1/2)(3/4)(3/4): ip 0 sits next to nodes 0,1
+  }
+  {
+    SolutionOptions so;
+    so.shiftedGradOpMap_["velocity"] = true;
+    ElemDataRequests req;
+    MomentumAdvDiffElemKernel<AlgTraitsHex8> k(*fx.bulk_, so, fx.velocity_, fx.viscosity_, req);
+    EXPECT_TRUE(req.get_data_enums(CURRENT_COORDINATES) == (std::set<ELEM_DATA_NEEDED>{SCS_AREAV, SCS_SHIFTED_GRAD_OP}));
+  }
+  {
+    SolutionOptions so;
+    so.cvfemReducedSensPoisson_ = true;
+    ElemDataRequests req;
+    ContinuityAdvElemKernel<AlgTraitsHex8> k(*fx.bulk_, so, req);
+    EXPECT_TRUE(req.get_fields().size() == 5);
+    EXPECT_TRUE(req.get_data_enums(CURRENT_COORDINATES) == (std::set<ELEM_DATA_NEEDED>{SCS_AREAV, SCS_GRAD_OP, SCS_SHIFTED_GRAD_OP}));
+  }
+  {
+    ElemDataRequests req;
+    MomentumMassElemKernel<AlgTraitsHex8> k(*fx.bulk_, fx.solnOpts_, req, true);
+    // density N/NP1, velocity N/NP1 (NM1 aliases N with two states), dpdx, coordinates
+    EXPECT_TRUE(req.get_fields().size() == 6);
+    EXPECT_TRUE(req.get_data_enums(CURRENT_COORDINATES) == (std::set<ELEM_DATA_NEEDED>{SCV_VOLUME}));
+    EXPECT_NEAR(k.v_shape_function_[3][3], 1.0, 0.0); // lumped: shifted SCV shape functions are the identity
+    EXPECT_NEAR(k.v_shape_function_[3][4], 0.0, 0.0);
+  }
+  {
+    // shared requests: two kernels on one algorithm take the union; a size conflict throws
+    ElemDataRequests req;
+    MomentumMassElemKernel<AlgTraitsHex8> m(*fx.bulk_, fx.solnOpts_, req, false);
+    MomentumAdvDiffElemKernel<AlgTraitsHex8> k(*fx.bulk_, fx.solnOpts_, fx.velocity_, fx.viscosity_, req);
+    EXPECT_TRUE(req.get_fields().size() == 8);
+    EXPECT_TRUE(req.get_data_enums(CURRENT_COORDINATES) == (std::set<ELEM_DATA_NEEDED>{SCS_AREAV, SCS_GRAD_OP, SCV_VOLUME}));
+  }
+  {
+    // KernelBuilder: name-gated creation in call order (include/kernel/KernelBuilder.h:170-191)
+    ElemSrcTermsMap terms;
+    terms["momentum"] = {"advection_diffusion", "lumped_momentum_time_derivative"};
+    std::vector<Kernel *> kernels;
+    ElemDataRequests req;
+    const stk::topology topo = stk::topology::HEX_8;
+    bool made = build_topo_kernel_if_requested<MomentumMassElemKernel>(topo, terms, "momentum", kernels, "momentum_time_derivative",
+                                                                        *fx.bulk_, fx.solnOpts_, req, false);
+    EXPECT_TRUE(!made);
+    made = build_topo_kernel_if_requested<MomentumMassElemKernel>(topo, terms, "momentum", kernels, "lumped_momentum_time_derivative",
+                                                                   *fx.bulk_, fx.solnOpts_, req, true);
+    EXPECT_TRUE(made);
+    made = build_topo_kernel_if_requested<MomentumAdvDiffElemKernel>(topo, terms, "momentum", kernels, "advection_diffusion", *fx.bulk_,
+                                                                      fx.solnOpts_, fx.velocity_, fx.viscosity_, req);
+    EXPECT_TRUE(made && kernels.size() == 2);
+    EXPECT_TRUE(std::string(kernels[0]->name()) == "MomentumMassElemKernel"); // source order, not YAML order
+    EXPECT_THROW(build_topo_kernel<MomentumAdvDiffElemKernel>(stk::topology(stk::topology::HEX_27), *fx.bulk_, fx.solnOpts_, fx.velocity_,
+                                                               fx.viscosity_, req));
+    for (Kernel *k : kernels) delete k;
+  }
+  {
+    MasterElement *scs = MasterElementRepo::get_surface_master_element(stk::topology::HEX_8);
+    const int lr[24] = {0, 1, 1, 2, 2, 3, 0, 3, 4, 5, 5, 6, 6, 7, 4, 7, 0, 4, 1, 5, 2, 6, 3, 7};
+    for (int i = 0; i < 24; ++i) EXPECT_TRUE(scs->adjacentNodes()[i] == lr[i]);
+    double shp[96];
+    scs->shifted_shape_fcn(shp); // edge midpoints: 1/2 on the two edge nodes
+    EXPECT_NEAR(shp[0], 0.5, 0.0);
+    EXPECT_NEAR(shp[1], 0.5, 0.0);
+    EXPECT_NEAR(shp[2], 0.0, 0.0);
+    EXPECT_THROW(scs->determinant(1, nullptr, nullptr, nullptr));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GPU: golden kernel tests
+// ---------------------------------------------------------------------------------------------------
+static void test_momentum_advection_diffusion()
+{
+  std::printf("MomentumKernelHex8Mesh.advection_diffusion (unit_tests/kernels/UnitTestMomentumAdvDiffElem.C:274-305)\n");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  fx.solnOpts_.includeDivU_ = 0.0;
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+  helperObjs.build_system();
+  unit_test_utils::calc_mass_flow_rate_scs(helperObjs, fx);
+  std::unique_ptr<Kernel> kernel(new MomentumAdvDiffElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_, fx.velocity_, fx.viscosity_,
+                                                                              helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  EXPECT_TRUE(lhs.size() == 24u * 24u && rhs.size() == 24u);
+  unit_test_utils::expect_all_near(rhs, gold("momentum_advdiff", "hex8_golds::advection_diffusion::rhs"), 2e-15);
+  unit_test_utils::expect_all_near(lhs, gold("momentum_advdiff", "hex8_golds::advection_diffusion::lhs"), 2e-15);
+}
+
+static void test_continuity_advection(const char *variant)
+{
+  std::printf("ContinuityKernelHex8Mesh.%s (unit_tests/kernels/UnitTestContinuityAdvElem.C:59-170)\n", variant);
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  const std::string v(variant);
+  fx.solnOpts_.cvfemShiftMdot_ = false;
+  fx.solnOpts_.shiftedGradOpMap_["pressure"] = v == "advection_reduced_shift_cvfem_poisson";
+  fx.solnOpts_.cvfemReducedSensPoisson_ = v == "advection_reduced_sens_cvfem_poisson";
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 1, fx.partVec_[0]);
+  helperObjs.build_system();
+  helperObjs.realm.timeIntegrator_->timeStepN_ = 1.0;
+  helperObjs.realm.timeIntegrator_->gamma1_ = 1.0;
+  std::unique_ptr<Kernel> kernel(
+      new ContinuityAdvElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_, helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  const std::string ns = v == "advection_default" ? "advection_default" : "advection_reduced_sensitivities";
+  unit_test_utils::expect_all_near(rhs, gold("continuity_adv", "hex8_golds::" + ns + "::rhs"), 2e-15);
+  unit_test_utils::expect_all_near(lhs, gold("continuity_adv", "hex8_golds::" + ns + "::lhs"), 2e-15);
+}
+
+static void test_momentum_mass(bool lumped)
+{
+  std::printf("MomentumKernelHex8Mesh.%s (unit_tests/kernels/UnitTestMomentumMassElem.C:144-215)\n",
+              lumped ? "momentum_time_derivative_lumped" : "momentum_time_derivative");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+  helperObjs.build_system();
+  TimeIntegrator &ti = *helperObjs.realm.timeIntegrator_;
+  ti.timeStepN_ = 0.1; ti.timeStepNm1_ = 0.1; ti.gamma1_ = 1.0; ti.gamma2_ = -1.0; ti.gamma3_ = 0.0;
+  std::unique_ptr<Kernel> kernel(new MomentumMassElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
+                                                                           helperObjs.assembleElemSolverAlg->dataNeededByKernels_, lumped));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  if (lumped) {
+    unit_test_utils::expect_all_near(rhs, gold("momentum_mass", "hex8_golds::momentum_time_derivative_lumped::rhs"), 1e-14);
+    for (int i = 0; i < 24; ++i)
+      for (int j = 0; j < 24; ++j) EXPECT_NEAR(lhs[i * 24 + j], i == j ? 1.25 : 0.0, 1e-14);
+  } else {
+    unit_test_utils::expect_all_near(rhs, gold("momentum_mass", "hex8_golds::momentum_time_derivative::rhs"), 1e-14);
+    unit_test_utils::expect_all_near(lhs, gold("momentum_mass", "hex8_golds::momentum_time_derivative::lhs"), 1e-14);
+  }
+}
+
+static void test_scalar_diff()
+{
+  std::printf("HeatCondKernelHex8Mesh.cvfem_diff (unit_tests/kernels/UnitTestScalarDiffElem.C:30-58)\n");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  for (size_t n = 0; n < fx.bulk_->num_nodes(); ++n) {
+    fx.scalarQ_->host_data()[n] = std::cos(fx.coordinates_->host_data()[3 * n]);
+    fx.diffFluxCoeff_->host_data()[n] = 1.0;
+  }
+  fx.scalarQ_->modify_on_host();
+  fx.diffFluxCoeff_->modify_on_host();
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 1, fx.partVec_[0]);
+  helperObjs.build_system();
+  std::unique_ptr<Kernel> kernel(new ScalarDiffElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_, fx.scalarQ_, fx.diffFluxCoeff_,
+                                                                         helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  unit_test_utils::expect_all_near(lhs, gold("scalar_diff", "hex8_golds::heatcond::cvfem_diff::lhs"), 2e-15);
+}
+
+// unit_tests/UnitTestTpetra.C:86-203: 1x1x2 mesh, a TestKernel writing a fixed 8x8 block, row lengths and the
+// assembled values looked up by global ids; plus sumInto for a host caller and the two-kernel accumulation order
+static void test_tpetra_basic()
+{
+  std::printf("Tpetra.basic, np=1 (unit_tests/UnitTestTpetra.C:86-203)\n");
+  struct TestKernel : public Kernel {
+    const double *block;
+    explicit TestKernel(const double *b) : block(b) {}
+    bool device_descriptor(nalu_b200_kernel_desc &d) override
+    {
+      clear(d);
+      d.kind = NALU_K_TEST_FIXED_BLOCK;
+      d.fixed_block = block;
+      return true;
+    }
+  };
+  LowMachKernelHex8Mesh fx(1, 1, 2);
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 1, fx.partVec_[0]);
+  helperObjs.build_system();
+  EXPECT_TRUE(helperObjs.linsys->numOwnedRows() == 12);
+  EXPECT_TRUE(helperObjs.linsys->numSharedNotOwnedRows() == 0);
+  const auto rp = helperObjs.linsys->ownedRowPtr();
+  const int lens[12] = {8, 8, 8, 8, 12, 12, 12, 12, 8, 8, 8, 8};
+  for (int r = 0; r < 12; ++r) EXPECT_TRUE(int(rp[r + 1] - rp[r]) == lens[r]);
+  const Table elemVals = gold("tpetra_2elem", "elemVals"), lhsVals = gold("tpetra_2elem", "lhsVals");
+  void *dblk = nullptr;
+  nalu_b200_malloc(&dblk, 64 * 8);
+  nalu_b200_memcpy_h2d(dblk, elemVals.v.data(), 64 * 8, nullptr);
+  TestKernel *tk = new TestKernel((const double *)dblk);
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(tk);
+  helperObjs.assembleElemSolverAlg->execute();
+  helperObjs.linsys->loadComplete();
+  const auto ci = helperObjs.linsys->ownedColIdx();
+  const auto v = helperObjs.linsys->ownedValues();
+  const auto rg = helperObjs.linsys->ownedRowGids();
+  const auto cg = helperObjs.linsys->colGids();
+  for (int r = 0; r < 12; ++r)
+    for (uint64_t q = rp[r]; q < rp[r + 1]; ++q) EXPECT_NEAR(lhsVals.v[size_t(rg[r] - 1) * 12 + size_t(cg[ci[q]] - 1)], v[q], 1e-14);
+  // sumInto from a host caller (one node, like AssembleNodeSolverAlgorithm does)
+  stk::mesh::Entity node = fx.bulk_->get_entity(stk::topology::NODE_RANK, 5);
+  std::vector<int> ids;
+  std::vector<double> vals, rhs1 = {2.5}, lhs1 = {7.0};
+  helperObjs.linsys->sumInto(std::vector<stk::mesh::Entity>{node}, ids, vals, rhs1, lhs1, "unit test");
+  const auto v2 = helperObjs.linsys->ownedValues();
+  const auto r2 = helperObjs.linsys->ownedRhs();
+  const int lid = helperObjs.linsys->entityToLID(node);
+  EXPECT_NEAR(r2[lid], 2.5, 1e-14);
+  for (uint64_t q = rp[lid]; q < rp[lid + 1]; ++q) EXPECT_NEAR(v2[q] - v[q], ci[q] == lid ? 7.0 : 0.0, 1e-14);
+  delete tk;
+  nalu_b200_free(dblk);
+}
+
+// UnitTestSimdMomentum-style smoke on generated:20x20x20 with two kernels on one algorithm: the fused launch must
+// equal the sum of the two kernels run alone (accumulation into one zeroed lhs/rhs,
+// src/AssembleElemSolverAlgorithm.C:86-91), and the big mesh takes the tiled kernel when it can
+static void test_two_kernels_one_algorithm()
+{
+  std::printf("Hex8Mesh 20x20x20: mass + advection_diffusion on one algorithm (unit_tests/UnitTestSimdMomentum.C:16-63)\n");
+  auto run = [](bool mass, bool advdiff, std::vector<double> &values, std::vector<double> &rhs, int &family) {
+    LowMachKernelHex8Mesh fx(20, 20, 20);
+    fx.fill_mesh_and_init_fields(true);
+    fx.solnOpts_.includeDivU_ = 1.0;
+    HelperObjects h(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+    h.build_system();
+    h.realm.timeIntegrator_->timeStepN_ = 0.05;
+    unit_test_utils::calc_mass_flow_rate_scs(h, fx);
+    std::vector<std::unique_ptr<Kernel>> own;
+    auto &req = h.assembleElemSolverAlg->dataNeededByKernels_;
+    if (mass) own.emplace_back(new MomentumMassElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_, req, true));
+    if (advdiff) own.emplace_back(new MomentumAdvDiffElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_, fx.velocity_, fx.viscosity_, req));
+    for (auto &k : own) h.assembleElemSolverAlg->activeKernels_.push_back(k.get());
+    h.assembleElemSolverAlg->execute();
+    values = h.linsys->ownedValues();
+    rhs = h.linsys->ownedRhs();
+    family = h.linsys->lastAssembleKernelFamily();
+  };
+  std::vector<double> vb, rb, vm, rm, va, ra;
+  int fb, fm, fa;
+  run(true, true, vb, rb, fb);
+  run(true, false, vm, rm, fm);
+  run(false, true, va, ra, fa);
+  EXPECT_TRUE(fa == 2); // advection-diffusion alone on a generated box: tiled write-once kernel
+  EXPECT_TRUE(fb == 1 && fm == 1);
+  double scale = 0, err = 0;
+  for (size_t i = 0; i < vb.size(); ++i) {
+    scale = std::fmax(scale, std::fabs(vb[i]));
+    err = std::fmax(err, std::fabs(vb[i] - vm[i] - va[i]));
+  }
+  EXPECT_TRUE(err <= 1e-12 * scale);
+  double rs = 0, re = 0;
+  for (size_t i = 0; i < rb.size(); ++i) {
+    rs = std::fmax(rs, std::fabs(rb[i]));
+    re = std::fmax(re, std::fabs(rb[i] - rm[i] - ra[i]));
+  }
+  EXPECT_TRUE(re <= 1e-12 * rs);
+}
+
+int main(int argc, char **argv)
+{
+  if (argc < 3) {
+    std::printf("usage: unit_tests <golden_dir> cpu|gpu\n");
+    return 2;
+  }
+  g_golden = argv[1];
+  const bool gpu = std::string(argv[2]) == "gpu";
+  try {
+    test_elem_data_requests();
+    test_kernel_registration();
+    if (gpu) {
+      test_momentum_advection_diffusion();
+      test_continuity_advection("advection_default");
+      test_continuity_advection("advection_reduced_sens_cvfem_poisson");
+      test_continuity_advection("advection_reduced_shift_cvfem_poisson");
+      test_momentum_mass(false);
+      test_momentum_mass(true);
+      test_scalar_diff();
+      test_tpetra_basic();
+      test_two_kernels_one_algorithm();
+    } else {
+      // no device: building a system must fail loudly, never fall back
+      LowMachKernelHex8Mesh fx;
+      HelperObjects h(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+      bool threw = false;
+      try { h.build_system(); } catch (const std::exception &e) { threw = true; std::printf("no-device error (expected): %s\n", e.what()); }
+      EXPECT_TRUE(threw);
+    }
+  } catch (const std::exception &e) {
+    std::printf("UNCAUGHT: %s\n", e.what());
+    return 1;
+  }
+  std::printf("%d checks, %d failures\n", g_checks, g_failures);
+  return g_failures ? 1 : 0;
+}
