@@ -171,13 +171,21 @@ def run_ours(args):
     m = mesh.generated_box_rank(n, n, n * world, rank, world)
     mesh.perturb_coords_hash(m, 0.12)
 
-    def exchange(send):
-        # neighbour handshake over torch.distributed (object lists are fine: once per mesh)
-        allsend = [None] * world
-        dist.all_gather_object(allsend, {k: v for k, v in send.items()})
-        return {src: allsend[src][rank] for src in range(world) if allsend[src] and rank in allsend[src]}
-
-    ls = DeviceCsrLinearSystem(m, 3, exchange=exchange if world > 1 else None).allocate(dev)
+    from nalu_b200 import dist as nd
+    halo = args.halo if world > 1 else "none"
+    ls = DeviceCsrLinearSystem(m, 3, exchange=nd.make_exchange(rank, world) if world > 1 else None)
+    ls.allocate(dev, raw=(halo == "pull"))
+    windows = None
+    if halo == "pull":
+        try:
+            windows = nd.PeerWindows(ls, rank, world)
+        except Exception as e:  # CUDA IPC unavailable in this container: say so and use NCCL
+            sys.stderr.write(f"[rank {rank}] peer windows unavailable ({e}); falling back to NCCL send/recv\n")
+            halo = "nccl"
+        flag = torch.tensor([1 if halo == "pull" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            halo, windows = "nccl", None
     t_graph = time.perf_counter() - t0
 
     # ---- state: host (pinned) + device ----------------------------------------------------------
@@ -199,6 +207,16 @@ def run_ours(args):
             ls.zero_system()   # the general kernel accumulates: zeroSystem is part of its step
         ls.assemble_elem([desc], mode=mode, overwrite=overwrite)
         if world > 1:
+            load_complete()
+
+    def load_complete():
+        if windows is not None:
+            # owners read the sharers' rows straight across NVLink; the barrier orders "my neighbour finished
+            # assembling" before "I pull its rows", a second one keeps it from re-assembling under my reads
+            windows.load_complete(lambda: (torch.cuda.synchronize(), dist.barrier()))
+            torch.cuda.synchronize()
+            dist.barrier()
+        else:
             ls.load_complete_nccl()
 
     def barrier():
@@ -227,7 +245,7 @@ def run_ours(args):
         ls.assemble_elem([desc], mode=mode, overwrite=overwrite)
         asm_ev[i][1].record()
         if world > 1:
-            ls.load_complete_nccl()
+            load_complete()
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -304,6 +322,9 @@ def run_ours(args):
              "finite": bool(torch.isfinite(vals).all()) and bool(torch.isfinite(ls.rhs).all()),
              "geometry_errors": ls.geometry_errors()}
 
+    if world > 1:
+        props["multi_rank_selfcheck"] = multi_rank_selfcheck(rank, world, dev, halo)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=2, warmup=1)
@@ -315,7 +336,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"hex8_box_{n}x{n}x{n * world}_momentum_advdiff_assembly",
                            "elements_per_gpu": n_elems_rank, "kernels": [f"MomentumAdvDiffElemKernel(includeDivU={args.divu:g})"],
-                           "partition": f"z-slabs x{world}", "halo": "nccl p2p pack/unpack-add" if world > 1 else "none",
+                           "partition": f"z-slabs x{world}", "halo": {"nccl": "pack kernel -> NCCL send/recv -> unpack-add kernel", "pull": "owner kernel reads peer rows over NVLink (CUDA IPC), no pack/staging", "none": "none"}[halo],
                            "l2_policy": "working set (>=36 GB CSR per GPU at n=256) exceeds the 126 MB L2",
                            "assemble_kernel": roofline["kernel"], "graph_build_s": t_graph},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
@@ -323,6 +344,60 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_rank_selfcheck(rank, world, dev, halo, n=10):
+    """Distributed assembly + loadComplete over the real transport against a single-rank assembly of the same
+    global box (done redundantly by every rank): owned rows must agree entry by entry, matched by global ids.
+    Returns the largest relative difference over all ranks."""
+    import scipy.sparse as sp
+    import torch
+    import torch.distributed as dist
+    from nalu_b200 import dist as nd
+    from nalu_b200 import fields, mesh
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+
+    def assemble(m, exchange, raw):
+        mesh.perturb_coords_hash(m, 0.12)
+        ls = DeviceCsrLinearSystem(m, 3, exchange=exchange).allocate(dev, raw=raw)
+        c = m.coords
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+        d = {"coordinates": t(c), "velocity": t(fields.velocity(c)), "viscosity": t(fields.smooth_viscosity(c))}
+        mdot = ls.mdot_scs(d["coordinates"], t(fields.smooth_density(c)), d["velocity"])
+        ls.assemble_elem([ls.make_desc("momentum_adv_diff", fields=d, mass_flow_rate=mdot, include_divu=1.0)], overwrite=True)
+        return ls
+
+    def to_global(ls):
+        rp, ci = ls.rowptr().astype(np.int64), ls.colidx()
+        cg, rg = ls.col_gids(), ls.row_gids()
+        v = ls.owned_values().cpu().numpy()
+        ncol = int(3 * (n + 1) * (n + 1) * (n * world + 1)) + 1
+        rows = np.repeat(rg, np.diff(rp))
+        return sp.csr_matrix((v, (rows, cg[ci])), shape=(ncol, ncol)), ls.owned_rhs().cpu().numpy(), rg
+
+    part = assemble(mesh.generated_box_rank(n, n, n * world, rank, world), nd.make_exchange(rank, world), halo == "pull")
+    if halo == "pull":
+        w = nd.PeerWindows(part, rank, world)
+        w.load_complete(lambda: (torch.cuda.synchronize(), dist.barrier()))
+        torch.cuda.synchronize()
+        dist.barrier()
+        w.close()
+    else:
+        part.load_complete_nccl()
+    torch.cuda.synchronize()
+    full = assemble(mesh.generated_box(n, n, n * world), None, False)
+    A, b, rg = to_global(part)
+    Af, bf, rgf = to_global(full)
+    sel = np.zeros(A.shape[0], dtype=bool)
+    sel[rg] = True
+    D = (A - Af.multiply(sp.csr_matrix(sel[:, None].astype(np.float64)))).tocsr()
+    err = abs(D).max() / abs(Af).max() if D.nnz else 0.0
+    bfull = np.zeros(A.shape[0])
+    bfull[rgf] = bf
+    errb = np.abs(b - bfull[rg]).max() / np.abs(bf).max()
+    e = torch.tensor([max(float(err), float(errb))], dtype=torch.float64, device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    return float(e.item())
 
 
 def main():
@@ -335,6 +410,7 @@ def main():
                     help="elements per box edge per GPU")
     ap.add_argument("--mode", default="auto", choices=["auto", "general", "box"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "pull"], help="loadComplete transport at N>1")
     ap.add_argument("--divu", type=float, default=1.0, help="SolutionOptions::includeDivU_ (reference default 0; 1 is the costlier variant)")
     args = ap.parse_args()
     if args.impl == "reference":

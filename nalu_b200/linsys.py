@@ -120,12 +120,34 @@ class DeviceCsrLinearSystem:
         return rp.value, ci.value
 
     # ---- storage -----------------------------------------------------------------------------
-    def allocate(self, device="cuda"):
+    def allocate(self, device="cuda", raw=False):
+        """values / rhs storage.  raw=True takes the memory straight from cudaMalloc (through the C ABI)
+        instead of torch's caching allocator, so that a CUDA-IPC handle of the tensor maps exactly this
+        buffer in a peer process (dist.PeerWindows)."""
         import torch
         self.device = torch.device(device)
-        self.values = torch.empty(self.nnz_owned + self.nnz_shared, dtype=torch.float64, device=self.device)
-        self.rhs = torch.empty(self.n_owned_rows + self.n_shared_rows, dtype=torch.float64, device=self.device)
+        nv, nr = self.nnz_owned + self.nnz_shared, self.n_owned_rows + self.n_shared_rows
+        if raw:
+            self._raw = []
+            self.values = self._raw_tensor(nv)
+            self.rhs = self._raw_tensor(nr)
+        else:
+            self.values = torch.empty(nv, dtype=torch.float64, device=self.device)
+            self.rhs = torch.empty(nr, dtype=torch.float64, device=self.device)
         return self
+
+    def _raw_tensor(self, n):
+        import torch
+        p = C.c_void_p()
+        check(self.L.nalu_b200_malloc(C.byref(p), C.c_size_t(max(n, 1) * 8)), "malloc")
+
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p.value, False), "version": 3}
+        t = torch.as_tensor(m, device=self.device)
+        self._raw.append((p, m))
+        return t
 
     def _stream(self):
         import torch
