@@ -6,8 +6,7 @@
 //                                                               row staging area)
 //   upper octants, block flush, rhs                           -> sync
 //   coalesced copy of the finished rows to HBM               -> sync
-// Two CTAs are resident per SM (6x4 node tile, 192 threads, ~101 KB shared memory) so that one
-// CTA's copy/phase-1 overlaps the other's FP64-bound phase 2.
+// Default tile: 8x4 nodes, 16 threads per node = 512 threads (16 warps), one CTA per SM.
 #include "box_tile.cuh"
 #include "internal.h"
 
@@ -18,12 +17,13 @@ namespace nalu_b200 {
 using box::BoxParams;
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_kernel(const __grid_constant__ BoxParams P)
+__global__ void __launch_bounds__(C::NT, (C::NT <= 288 ? 2 : 1)) assemble_box_kernel(const __grid_constant__ BoxParams P)
 {
   extern __shared__ __align__(16) double sm[];
   double *const tab = sm + C::OFF_TAB;
   double *const ring = sm + C::OFF_RING;
   double *const mdb = sm + C::OFF_MD;
+  double *const park = sm + C::OFF_PARK;
   long long *const s_rb = reinterpret_cast<long long *>(sm + C::OFF_RB);
   int *const s_len = reinterpret_cast<int *>(sm + C::OFF_LEN);
   constexpr int PLN = C::RN * C::NF;
@@ -37,12 +37,12 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
   const long long plane_nodes = (long long)P.NX * P.NY;
 
   box::NodeCtx N;
-  const int nl = tid >> 3;
   box::node_ctx_init<C>(P, N, tid, x0, y0);
+  const int sub = tid % C::TPN;
   const int dz_fin = (N.cls & 4) ? 1 : 0;
 
   double regP[C::NPL], regM[C::NML];
-  // ---- prologue: table, node planes zs-1..zs+1, the layer below the first plane, first node ctx
+  // ---- prologue: table, node planes zs-1..zs+1, the layer below the first plane, first row context
   for (int i = tid; i < 192; i += C::NT) box::build_table_entry<C>(i, P.options, tab);
   for (int pl = zs - 1; pl <= zs + 1; ++pl) {
     box::plane_load<C>(P, tid, x0, y0, pl, regP);
@@ -58,14 +58,13 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
   box::mdot_load<C>(P, tid, x0, y0, zs, regM);
   box::mdot_store<C>(tid, regM, mdb);
   N.n = N.x + (long long)P.NX * (N.y + (long long)P.NY * zs);
-  N.row = 0; N.nb = 0; N.rowbase = 0; N.slots_mid = N.slots_fin = 0xFFFFFFFFu;
+  N.row = 0; N.nb = 0; N.rowbase = 0; N.slots = 0xFFFFFFFFu;
   if (N.active) {
     N.row = P.node_row[N.n];
     const long long b0 = P.browptr[N.row];
     N.nb = (int)(P.browptr[N.row + 1] - b0);
     N.rowbase = 9 * b0;
-    N.slots_mid = box::load_slots(P.slot27 + N.n * 27, N.cls, -1);
-    N.slots_fin = box::load_slots(P.slot27 + N.n * 27, N.cls, dz_fin);
+    N.slots = P.slotpack[N.n * 16 + sub];
   }
   __syncthreads();
 
@@ -75,7 +74,11 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     box::plane_load<C>(P, tid, x0, y0, z + 2, regP);
     box::mdot_load<C>(P, tid, x0, y0, z + 1, regM);
     int row_n = 0;
-    if (N.active && more) row_n = P.node_row[N.n + plane_nodes];
+    unsigned slots_n = 0xFFFFFFFFu;
+    if (N.active && more) {
+      row_n = P.node_row[N.n + plane_nodes];
+      slots_n = P.slotpack[(N.n + plane_nodes) * 16 + sub];
+    }
     const double *pl_m = ring + ((z + 2) % 3) * PLN; // plane z-1
     const double *pl_0 = ring + (z % 3) * PLN;
     const double *pl_p = ring + ((z + 1) % 3) * PLN;
@@ -86,18 +89,14 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     const double *lower = sm + ((z + 1) & 1) * C::LBUF;
     const double *upper = sm + (z & 1) * C::LBUF;
     double *stg = sm + ((z + 1) & 1) * C::LBUF;
-    if (N.cls == 0) {
-      s_rb[nl] = N.rowbase;
-      s_len[nl] = N.active ? N.nb * 9 : 0;
+    if (sub == 0) {
+      s_rb[N.nl] = N.rowbase;
+      s_len[N.nl] = N.active ? N.nb * 9 : 0;
     }
     long long b0_n = 0, b1_n = 0;
-    unsigned sm_n = 0xFFFFFFFFu, sf_n = 0xFFFFFFFFu;
     if (N.active && more) {
       b0_n = P.browptr[row_n];
       b1_n = P.browptr[row_n + 1];
-      const unsigned char *sl = P.slot27 + (N.n + plane_nodes) * 27;
-      sm_n = box::load_slots(sl, N.cls, -1);
-      sf_n = box::load_slots(sl, N.cls, dz_fin);
     }
     box::P2State S;
     box::p2_begin(S);
@@ -105,36 +104,38 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     int ncov = 0;
     if (N.active) {
       ncov = ((N.x > 0) + 1 + (N.x < P.NX - 1)) * ((N.y > 0) + 1 + (N.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
-      box::p2_pass<C, 0>(P, N, S, lower, tab + 2 * N.cls, divu);
+      box::p2_pass<C, 0>(P, N, S, lower, tab, divu);
     }
     __syncthreads(); // every thread is done with the lower layer: its buffer is now the staging area
     if (N.active && N.nb != ncov) {
       // row also holds columns no local element touches (remote columns announced by the ranks
       // sharing this node): they must read zero
-      double *row = stg + nl * C::SROW;
-      for (int q = N.cls; q < N.nb * 9; q += 8) row[q] = 0.0;
+      double *row = stg + N.nl * C::SROW;
+      for (int q = sub; q < N.nb * 9; q += C::TPN) row[q] = 0.0;
     }
+    const bool on_mid = N.active && (N.cls & 4);
+    box::p2_flush_a<C>(N, S, on_mid, park);
     __syncwarp();
-    if (N.active) {
-      if (N.cls & 4) {
-        box::p2_flush<C>(N, S, N.slots_mid, pl_m, stg);
-        box::p2_zero(S);
-      }
-      box::p2_pass<C, 1>(P, N, S, upper, tab + 2 * N.cls, divu);
-      box::p2_flush<C>(N, S, N.slots_fin, dz_fin ? pl_p : pl_0, stg);
-    }
-    // rhs: sum the 8 class partials of the node (classes 0..2 also carry the divU stress components)
+    box::p2_flush_b<C>(N, S, on_mid, 0, pl_m, stg, park);
+    if (on_mid) box::p2_zero(S);
+    __syncwarp();
+    if (N.active) box::p2_pass<C, 1>(P, N, S, upper, tab, divu);
+    box::p2_flush_a<C>(N, S, N.active, park);
+    __syncwarp();
+    box::p2_flush_b<C>(N, S, N.active, 1, dz_fin ? pl_p : pl_0, stg, park);
+    // rhs: sum the 16 partials of the node (classes 0..2 also carry the divU stress components)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       double v = S.rr[i] + (N.cls == i ? S.dv : 0.0);
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
       S.rr[i] = v;
     }
-    if (N.active && N.cls < 3) {
-      double *r = P.rhs + (long long)N.row * 3 + N.cls;
-      const double v = N.cls == 0 ? S.rr[0] : (N.cls == 1 ? S.rr[1] : S.rr[2]);
+    if (N.active && sub < 3) {
+      double *r = P.rhs + (long long)N.row * 3 + sub;
+      const double v = sub == 0 ? S.rr[0] : (sub == 1 ? S.rr[1] : S.rr[2]);
       *r = P.overwrite ? v : *r + v;
     }
     __syncthreads();
@@ -162,19 +163,18 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
       }
     }
     __syncthreads();
-    // rotate the node context
+    // rotate the row context
     N.n += plane_nodes;
     N.row = row_n;
     N.nb = (int)(b1_n - b0_n);
     N.rowbase = 9 * b0_n;
-    N.slots_mid = sm_n;
-    N.slots_fin = sf_n;
+    N.slots = slots_n;
   }
 }
 
 bool box_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
 {
-  if (g.box[0] <= 0 || !g.d_node_slot27 || g.ndof != 3 || nk != 1) return false;
+  if (g.box[0] <= 0 || !g.d_node_slot27 || !g.d_node_slotpack || g.ndof != 3 || nk != 1) return false;
   if (k[0].kind != NALU_K_MOMENTUM_ADV_DIFF) return false;
   if (!k[0].nodal[NALU_F_COORDINATES] || !k[0].nodal[NALU_F_VELOCITY] || !k[0].nodal[NALU_F_VISCOSITY] ||
       !k[0].mass_flow_rate)
@@ -193,7 +193,7 @@ static int launch_cfg(const Graph &g, BoxParams &P, cudaStream_t stream)
   const long long ntile = (long long)P.tiles_x * P.tiles_y;
   // z chunks: enough CTAs for ~16 waves, but at least 16 planes per chunk (each chunk recomputes
   // one element layer)
-  const int occ = C::NT <= 256 ? 2 : 1;
+  const int occ = C::NT <= 288 ? 2 : 1;
   long long want = ((long long)sms * occ * 16 + ntile - 1) / ntile;
   int zchunks = (int)(want < 1 ? 1 : want);
   int zc = (P.NZ + zchunks - 1) / zchunks;
@@ -236,6 +236,7 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   P.node_row = g.d_node_row;
   P.browptr = (const long long *)g.d_browptr;
   P.slot27 = g.d_node_slot27;
+  P.slotpack = g.d_node_slotpack;
   P.values = d_values;
   P.rhs = d_rhs;
   P.err = g.d_err;
@@ -244,9 +245,9 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   P.overwrite = overwrite;
   int tile = 0;
   if (const char *e = getenv("NALU_BOX_TILE")) tile = atoi(e);
-  if (tile == 84) return launch_cfg<box::Cfg<8, 4>>(g, P, stream);
-  if (tile == 86) return launch_cfg<box::Cfg<8, 6>>(g, P, stream);
-  return launch_cfg<box::Cfg<6, 4>>(g, P, stream);
+  if (tile == 63) return launch_cfg<box::Cfg<6, 3>>(g, P, stream); // 288 threads, 2 CTAs / SM
+  if (tile == 64) return launch_cfg<box::Cfg<6, 4>>(g, P, stream); // 384 threads, 1 CTA / SM
+  return launch_cfg<box::Cfg<8, 4>>(g, P, stream);                  // 512 threads, 1 CTA / SM
 }
 
 } // namespace nalu_b200

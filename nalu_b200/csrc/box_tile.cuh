@@ -6,10 +6,11 @@
 // computed is turned inside out so that every CSR value is written exactly once, already summed:
 //
 //   * a CTA owns a TBX x TBY column of NODES and sweeps it along z; each node row is owned by
-//     8 threads ("classes" (a,b,c) in {0,1}^3: the thread owns the column nodes whose offset from
-//     the row node is (+-a, +-b, +-c), so every one of the 8 elements around the node hands each
-//     class exactly one column node -> all 8 threads do identical work, 24 (element, ip, column)
-//     triples per node plane);
+//     16 threads: 8 "classes" (a,b,c) in {0,1}^3 -- the class owns the column nodes whose offset
+//     from the row node is (+-a, +-b, +-c), so every one of the 8 elements around the node hands each
+//     class exactly one column node -- times 2 "halves" H that split the class's 4 (x,y) quadrants
+//     along the axis the class distinguishes (x if a, else y).  All 16 threads do identical work
+//     (12 (element, ip, column) triples per node plane) with 2 block accumulators each;
 //   * phase 1 evaluates, once per element layer, the per-integration-point data the rows need:
 //     G' = -mu_ip adj(J)/det(J)   (so that -mu dN_ic/dx = G' dN_ic/dxi), the SCS area vector A,
 //     the mass flow rate and the div(u) stress scalar -- 14 doubles per ip in shared memory.
@@ -43,7 +44,8 @@ struct BoxParams {
   const double *mdot;   // [nElem][12]
   const int *node_row;
   const long long *browptr;
-  const unsigned char *slot27;
+  const unsigned char *slot27; // [nNodes][27] CSR slot of each lattice neighbour (host emulation / table build)
+  const unsigned *slotpack;    // [nNodes][16] slot_pack() of every thread of the node
   double *values;
   double *rhs;
   int *err;
@@ -56,22 +58,25 @@ template <int TBX_, int TBY_>
 struct Cfg {
   static constexpr int TBX = TBX_, TBY = TBY_;
   static constexpr int NNODE = TBX * TBY;
-  static constexpr int NT = NNODE * 8;
+  static constexpr int TPN = 16;            // threads per node row
+  static constexpr int NT = NNODE * TPN;
   static constexpr int ELX = TBX + 1, ELY = TBY + 1, NEL = ELX * ELY;
   static constexpr int IPD = 14;            // doubles per ip: G'[9], A[3], mdot, w
   static constexpr int ES = 12 * IPD + 2;   // element stride (doubles); +2 spreads the 16-byte bank groups
   static constexpr int SROW = 248;          // staging row stride (doubles) >= 27*9
   static constexpr int LBUF = (NEL * ES > NNODE * SROW) ? NEL * ES : NNODE * SROW;
-  static constexpr int TAB = 8 * 3 * 2 * 8 * 2; // [octant][edge dir][half][class][2]
+  static constexpr int TABE = 6;            // d0,d1,d2 (ip-local axes), N_adv, sign, pad -- all pre-multiplied by the L/R sign
+  static constexpr int TAB = 8 * 3 * 8 * TABE; // [octant][edge dir][class][TABE]
   static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY; // node neighbourhood of the tile
   static constexpr int NF = 7;              // staged nodal doubles: x[3], mu, u[3]
   static constexpr int RING = 3 * RN * NF;  // three node planes
   static constexpr int MDB = NEL * 12;      // mass flow rates of one element layer
   static constexpr int NPL = (RN * NF + NT - 1) / NT;  // per-thread loads to stage one node plane
   static constexpr int NML = (MDB + NT - 1) / NT;      // per-thread loads to stage one mdot layer
-  // doubles: two layer buffers, table, nodal ring, mdot layer, row base (as 8-byte ints) and row length
+  // doubles: two layer buffers, table, nodal ring, mdot layer, parked half blocks, row base (8-byte ints), row length
+  static constexpr int PARK = NNODE * 2 * 9; // half blocks of the two centre-column classes
   static constexpr int OFF_TAB = 2 * LBUF, OFF_RING = OFF_TAB + TAB, OFF_MD = OFF_RING + RING,
-                       OFF_RB = OFF_MD + MDB, OFF_LEN = OFF_RB + NNODE;
+                       OFF_PARK = OFF_MD + MDB, OFF_RB = OFF_PARK + PARK, OFF_LEN = OFF_RB + NNODE;
   static constexpr int SMEM_DOUBLES = OFF_LEN + (NNODE + 1) / 2;
   // phase-1 work items: (element, edge direction), split once more in two when that still fits one
   // round of the CTA's threads
@@ -107,17 +112,20 @@ __host__ __device__ inline void build_table_entry(int idx, int options, double *
   const int a = cls & 1, b = (cls >> 1) & 1, c = (cls >> 2) & 1;
   const int ic = node_of_bits(a ? sxp : !sxp, b ? syp : !syp, c ? szp : !szp);
   const int ip = ip_of(k, pp);
+  // rows L and R of an ip receive +X and -X (MomentumAdvDiffElemKernel.C:152-183): fold the sign here
+  const double sg = hex8::scs_left(ip) == k ? 1.0 : -1.0;
   double s1, s2, s3, d[3];
   hex8::scs_intg_loc(ip, (options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25, s1, s2, s3);
   hex8::shape_deriv(ic, s1, s2, s3, d);
   hex8::scs_intg_loc(ip, (options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25, s1, s2, s3);
   const double nadv = hex8::shape_fcn(ic, s1, s2, s3);
-  double *t0 = tab + ((s * 3 + pp) * 2 + 0) * 16 + cls * 2;
-  double *t1 = tab + ((s * 3 + pp) * 2 + 1) * 16 + cls * 2;
-  t0[0] = d[pp];
-  t0[1] = d[(pp + 1) % 3];
-  t1[0] = d[(pp + 2) % 3];
-  t1[1] = nadv;
+  double *t = tab + ((s * 3 + pp) * 8 + cls) * C::TABE;
+  t[0] = sg * d[pp];
+  t[1] = sg * d[(pp + 1) % 3];
+  t[2] = sg * d[(pp + 2) % 3];
+  t[3] = sg * nadv;
+  t[4] = sg;
+  t[5] = 0.0;
 }
 
 // ---- staging of nodal fields / mass flow rates (global -> registers -> shared) ---------------------
@@ -327,66 +335,111 @@ __host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0
 
 // ---- phase 2 per-thread state ---------------------------------------------------------------------
 struct P2State {
-  double acc[4][9]; // 3x3 blocks per (sx,sy) quadrant, row-major [i][j]
-  double D[4];      // diagonal part of each block
+  double acc[2][9]; // 3x3 blocks of the thread's two quadrants, row-major [i][j]
+  double D[2];      // diagonal part of each block
   double rr[3];     // rhs partial of this thread
   double dv;        // divU stress component carried by classes 0..2
 };
 
+// Per-thread constants and the per-plane row context.  sub = tid % 16 = cls + 8 H.
 struct NodeCtx {
   int active;        // node inside the domain
   int x, y, z;
-  int lx, ly;        // position in the tile
+  int lx, ly, nl;    // position in the tile
   long long n;       // lattice node index
   long long rowbase; // values offset of the node's first dof row
   int nb;            // blocks in the row
   int row;           // row node index (rhs offset / 3)
-  int cls;
-  unsigned slots_mid, slots_fin; // CSR block slot (0xFF: no such neighbour) of the 4 quadrant blocks
-  int vmask;         // bit q: the (sx,sy) quadrant q holds an element column
-  int eoff;          // offset of element (lx,ly) of the layer tile in a layer buffer
+  int cls, H;
+  int q[2];          // (x,y) quadrant handled by accumulator 0 / 1: bit 0 = +x side, bit 1 = +y side
+  int valid[2];      // that quadrant holds an element column
+  int eoff[2];       // its element's offset in a layer buffer
+  int toff[2];       // its table offset (octants of the lower layer; + 4*3*8*TABE for the upper layer)
+  int ipo[2][3];     // ip*IPD of the x-, y-, z-edge ip next to the row node, lower layer (x,y: -4*IPD above)
+  int fold;          // the two accumulators belong to one block
+  int pair;          // ... which the H = 0 and H = 1 threads share (class a = b = 0)
+  int nblk;          // blocks this thread finishes per flush (pair: H = 0 finishes it)
+  int uoff[2];       // offset of the block's column node in a staged node plane (velocity at +4)
+  unsigned slots;    // CSR block slots: byte 0,1 = mid flush (dz = -1), byte 2,3 = final flush
 };
+
+// offsets (dx,dy) of the block finished from accumulator j by thread (cls, H)
+__host__ __device__ inline void block_offset(int cls, int H, int j, int &dx, int &dy)
+{
+  const int a = cls & 1, b = (cls >> 1) & 1;
+  if (a) {
+    dx = H ? 1 : -1;
+    dy = b ? (j ? 1 : -1) : 0;
+  } else {
+    dx = 0;
+    dy = b ? (H ? 1 : -1) : 0;
+  }
+}
+
+// CSR slots of the (up to two) blocks a thread finishes in the mid and final flush, from the node's
+// 27-neighbour slot row (0xFF: no such neighbour / no such block)
+__host__ __device__ inline unsigned slot_pack(const unsigned char *s27, int sub)
+{
+  const int cls = sub & 7, H = sub >> 3;
+  const int a = cls & 1, b = (cls >> 1) & 1, c = (cls >> 2) & 1;
+  const int fold = a ? !b : 1, pair = !a && !b;
+  const int nblk = fold ? 1 : 2;
+  unsigned r = 0;
+  for (int f = 0; f < 2; ++f) {      // 0: mid flush (dz = -1, classes with c only), 1: final flush
+    const int dz = f == 0 ? -1 : (c ? 1 : 0);
+    for (int j = 0; j < 2; ++j) {
+      unsigned v = 0xFF;
+      if (j < nblk && !(pair && H == 1) && (f == 1 || c)) {
+        int dx, dy;
+        block_offset(cls, H, j, dx, dy);
+        v = s27[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+      }
+      r |= v << (8 * (2 * f + j));
+    }
+  }
+  return r;
+}
 
 template <class C>
 __host__ __device__ inline void node_ctx_init(const BoxParams &P, NodeCtx &N, int tid, int x0, int y0)
 {
-  const int nl = tid >> 3;
-  N.cls = tid & 7;
-  N.lx = nl % C::TBX;
-  N.ly = nl / C::TBX;
+  N.nl = tid / C::TPN;
+  const int sub = tid % C::TPN;
+  N.cls = sub & 7;
+  N.H = sub >> 3;
+  N.lx = N.nl % C::TBX;
+  N.ly = N.nl / C::TBX;
   N.x = x0 + N.lx;
   N.y = y0 + N.ly;
   N.active = N.x < P.NX && N.y < P.NY;
-  N.vmask = 0;
-  for (int q = 0; q < 4; ++q) {
-    const int ex = N.x - 1 + (q & 1), ey = N.y - 1 + (q >> 1);
-    if (ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny) N.vmask |= 1 << q;
-  }
-  N.eoff = (N.lx + C::ELX * N.ly) * C::ES;
-}
-
-// CSR slots of the blocks this class flushes: byte q = quadrant (sx,sy) -> offset (a sx, b sy, dz)
-__host__ __device__ inline unsigned load_slots(const unsigned char *slots, int cls, int dz)
-{
-  const int a = cls & 1, b = (cls >> 1) & 1;
-  unsigned r = 0;
+  const int a = N.cls & 1, b = (N.cls >> 1) & 1;
+  N.fold = a ? !b : 1;
+  N.pair = !a && !b;
+  N.nblk = N.fold ? 1 : 2;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int sxp = q & 1, syp = q >> 1;
-    unsigned v = 0xFF;
-    if (!((!a && sxp) || (!b && syp))) {
-      const int dx = a ? (sxp ? 1 : -1) : 0, dy = b ? (syp ? 1 : -1) : 0;
-      v = slots[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
-    }
-    r |= v << (8 * q);
+  for (int j = 0; j < 2; ++j) {
+    // classes that distinguish x split their quadrants by x (H = sx, j = sy); the others by y
+    const int sxp = (a || !b) ? N.H : j, syp = (a || !b) ? j : N.H;
+    N.q[j] = sxp + 2 * syp;
+    const int ex = N.x - 1 + sxp, ey = N.y - 1 + syp;
+    N.valid[j] = N.active && ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny;
+    N.eoff[j] = ((N.lx + sxp) + C::ELX * (N.ly + syp)) * C::ES;
+    N.toff[j] = (N.q[j] * 3 * 8 + N.cls) * C::TABE;
+    // ips next to the row node in the element BELOW the plane (row node = top corner, bz = 1)
+    const int k = node_of_bits(!sxp, !syp, 1);
+    N.ipo[j][0] = ip_of(k, 0) * C::IPD;
+    N.ipo[j][1] = ip_of(k, 1) * C::IPD;
+    N.ipo[j][2] = ip_of(k, 2) * C::IPD;
+    int dx, dy;
+    block_offset(N.cls, N.H, j, dx, dy);
+    N.uoff[j] = ((N.lx + 1 + dx) + C::RNX * (N.ly + 1 + dy)) * C::NF + 4;
   }
-  return r;
 }
 
 __host__ __device__ inline void p2_zero(P2State &S)
 {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) S.acc[q][t] = 0.0;
     S.D[q] = 0.0;
@@ -399,104 +452,95 @@ __host__ __device__ inline void p2_begin(P2State &S)
   S.dv = 0.0;
 }
 
-// one z-half (SZP = 0: elements below the node plane, 1: above) of the 8 octants.
-// tabc = table + 2*cls; buf = that layer's ip data
+// one z-half (SZP = 0: elements below the node plane, 1: above): the thread's two quadrants, 3 ips each.
+// The x-/y-edge ips next to the row node lie on the element's top face below the plane (ip 4..7) and on
+// its bottom face above it (ip 0..3): 4 ips = 4*IPD doubles earlier; the z-edge ip is the same.
 template <class C, int SZP>
 __host__ __device__ inline void p2_pass(const BoxParams &P, const NodeCtx &N, P2State &S, const double *buf,
-                                        const double *tabc, bool divu)
+                                        const double *tab, bool divu)
 {
   const int ez = N.z - 1 + SZP;
   if (ez < 0 || ez >= P.nz) return;
-  const double *ebase = buf + N.eoff;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int sxp = q & 1, syp = q >> 1;
-    if (!(N.vmask & (1 << q))) continue; // no element in this quadrant (domain boundary)
-    const int s = q + 4 * SZP;
-    const int k = node_of_bits(!sxp, !syp, !SZP);
-    const double *eb = ebase + (sxp + C::ELX * syp) * C::ES;
+  for (int j = 0; j < 2; ++j) {
+    if (!N.valid[j]) continue; // no element in this quadrant (domain boundary / node outside the domain)
+    const double *eb = buf + N.eoff[j];
+    const double *tb = tab + N.toff[j] + SZP * (4 * 3 * 8 * C::TABE);
 #pragma unroll
     for (int pp = 0; pp < 3; ++pp) {
-      const int ip = ip_of(k, pp);
-      const bool isL = hex8::scs_left(ip) == k;
-      const double *o = eb + ip * C::IPD;
-      const double *t0 = tabc + ((s * 3 + pp) * 2 + 0) * 16;
-      const double *t1 = tabc + ((s * 3 + pp) * 2 + 1) * 16;
-      const double d0 = t0[0], d1 = t0[1], d2 = t1[0], nadv = t1[1];
-      double h[3];
+      const double *o = eb + N.ipo[j][pp] - ((SZP && pp < 2) ? 4 * C::IPD : 0);
+      const double *t = tb + pp * (8 * C::TABE);
+      const double d0 = t[0], d1 = t[1], d2 = t[2], nadv = t[3];
+      double h[3]; // signed: +-(-mu dN_ic/dx)
 #pragma unroll
       for (int i = 0; i < 3; ++i) h[i] = o[i * 3 + 0] * d0 + o[i * 3 + 1] * d1 + o[i * 3 + 2] * d2;
       const double A0 = o[9], A1 = o[10], A2 = o[11];
-      const double dsum = h[0] * A0 + h[1] * A1 + h[2] * A2 + nadv * o[12];
-      if (isL) {
-        S.D[q] += dsum;
+      S.D[j] += h[0] * A0 + h[1] * A1 + h[2] * A2 + nadv * o[12];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          S.acc[q][i * 3 + 0] += h[i] * A0;
-          S.acc[q][i * 3 + 1] += h[i] * A1;
-          S.acc[q][i * 3 + 2] += h[i] * A2;
-        }
-      } else {
-        S.D[q] -= dsum;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          S.acc[q][i * 3 + 0] -= h[i] * A0;
-          S.acc[q][i * 3 + 1] -= h[i] * A1;
-          S.acc[q][i * 3 + 2] -= h[i] * A2;
-        }
+      for (int i = 0; i < 3; ++i) {
+        S.acc[j][i * 3 + 0] += h[i] * A0;
+        S.acc[j][i * 3 + 1] += h[i] * A1;
+        S.acc[j][i * 3 + 2] += h[i] * A2;
       }
       if (divu) {
         // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135).  Every class meets each (element, ip)
-        // next to the node exactly once; classes 0,1,2 each carry one component of w A (the other
-        // classes' copies are discarded in p2_rhs_partial)
-        const double Asel = N.cls == 0 ? A0 : (N.cls == 1 ? A1 : A2);
-        if (isL) S.dv -= o[13] * Asel; else S.dv += o[13] * Asel;
+        // next to the node exactly once (over its two halves); classes 0,1,2 each carry one component
+        // of w A, the other classes' sums are dropped when the partials are combined
+        S.dv -= t[4] * o[13] * o[9 + (N.cls < 3 ? N.cls : 0)];
       }
     }
   }
 }
 
-// fold the quadrant accumulators of the axes the class does not distinguish, then write the
-// finished blocks into the staging row (CSR layout) and take their share of rhs = -row . u.
-// `slots`: packed CSR slots of the 4 quadrant blocks; `uplane`: staged node plane of the column nodes
+// Finish the blocks of one flush (mid: dz = -1, classes with c; final: dz = c ? +1 : 0), in two steps
+// with a warp barrier between them; every thread of the warp calls both (`on` = takes part).
+// Step a: fold the two accumulators when they belong to one block; the H = 1 thread of the centre-column
+// classes (a = b = 0) parks its half of the shared block in shared memory.
 template <class C>
-__host__ __device__ inline void p2_flush(const NodeCtx &N, P2State &S, unsigned slots, const double *uplane, double *stg)
+__host__ __device__ inline void p2_flush_a(const NodeCtx &N, P2State &S, bool on, double *parkbase)
 {
-  const int a = N.cls & 1, b = (N.cls >> 1) & 1;
-  if (!a) {
+  if (!on) return;
+  if (N.fold) {
 #pragma unroll
-    for (int sy = 0; sy < 2; ++sy) {
-#pragma unroll
-      for (int t = 0; t < 9; ++t) S.acc[sy * 2][t] += S.acc[sy * 2 + 1][t];
-      S.D[sy * 2] += S.D[sy * 2 + 1];
-    }
+    for (int t = 0; t < 9; ++t) S.acc[0][t] += S.acc[1][t];
+    S.D[0] += S.D[1];
   }
-  if (!b) {
+  if (N.pair && N.H == 1) {
+    double *park = parkbase + (N.nl * 2 + (N.cls >> 2)) * 9;
 #pragma unroll
-    for (int sx = 0; sx < 2; ++sx) {
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) S.acc[sx][t] += S.acc[2 + sx][t];
-      S.D[sx] += S.D[2 + sx];
-    }
+      for (int j = 0; j < 3; ++j) park[i * 3 + j] = S.acc[0][i * 3 + j] + (i == j ? S.D[0] : 0.0);
   }
-  double *row = stg + (N.lx + C::TBX * N.ly) * C::SROW;
+}
+// Step b: write the finished blocks into the staging row (CSR layout) and take their share of
+// rhs = -row . u.  `half` selects the mid (0) / final (1) slot bytes; `uplane` = staged plane of the column nodes.
+template <class C>
+__host__ __device__ inline void p2_flush_b(const NodeCtx &N, P2State &S, bool on, int half, const double *uplane,
+                                           double *stg, const double *parkbase)
+{
+  if (!on) return;
+  double *row = stg + N.nl * C::SROW;
+  const double *park = parkbase + (N.nl * 2 + (N.cls >> 2)) * 9;
   const int rs = N.nb * 3; // doubles per dof row
-  const double *uc = uplane + ((N.lx + 1) + C::RNX * (N.ly + 1)) * C::NF + 4;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int sxp = q & 1, syp = q >> 1;
-    const unsigned slot = (slots >> (8 * q)) & 0xFF;
-    if (slot == 0xFF) continue; // block not owned by this class, or no such neighbour node
-    const int dx = a ? (sxp ? 1 : -1) : 0, dy = b ? (syp ? 1 : -1) : 0;
-    const double *u = uc + (dx + C::RNX * dy) * C::NF;
+  for (int j = 0; j < 2; ++j) {
+    const unsigned slot = (N.slots >> (8 * (2 * half + j))) & 0xFF;
+    if (slot == 0xFF) continue; // not a block this thread finishes, or no such neighbour node
+    const double *u = uplane + N.uoff[j];
     const double u0 = u[0], u1 = u[1], u2 = u[2];
     double *bp = row + slot * 3;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double v0 = S.acc[q][i * 3 + 0], v1 = S.acc[q][i * 3 + 1], v2 = S.acc[q][i * 3 + 2];
-      if (i == 0) v0 += S.D[q];
-      if (i == 1) v1 += S.D[q];
-      if (i == 2) v2 += S.D[q];
+      double v0 = S.acc[j][i * 3 + 0], v1 = S.acc[j][i * 3 + 1], v2 = S.acc[j][i * 3 + 2];
+      if (i == 0) v0 += S.D[j];
+      if (i == 1) v1 += S.D[j];
+      if (i == 2) v2 += S.D[j];
+      if (N.pair) {
+        v0 += park[i * 3 + 0];
+        v1 += park[i * 3 + 1];
+        v2 += park[i * 3 + 2];
+      }
       bp[i * rs + 0] = v0;
       bp[i * rs + 1] = v1;
       bp[i * rs + 2] = v2;
