@@ -6,7 +6,7 @@
 //                                                               row staging area)
 //   upper octants, block flush, rhs                           -> sync
 //   coalesced copy of the finished rows to HBM               -> sync
-// Default tile: 8x4 nodes, 16 threads per node = 512 threads (16 warps), one CTA per SM.
+// Default tile: 6x4 nodes, 8 threads per node = 192 threads, two CTAs per SM.
 #include "box_tile.cuh"
 #include "internal.h"
 
@@ -17,7 +17,7 @@ namespace nalu_b200 {
 using box::BoxParams;
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, (C::NT <= 288 ? 2 : 1)) assemble_box_kernel(const __grid_constant__ BoxParams P)
+__global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_kernel(const __grid_constant__ BoxParams P)
 {
   extern __shared__ __align__(16) double sm[];
   double *const tab = sm + C::OFF_TAB;
@@ -39,7 +39,6 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 288 ? 2 : 1)) assemble_box_ke
   box::NodeCtx N;
   box::node_ctx_init<C>(P, N, tid, x0, y0);
   const int sub = tid % C::TPN;
-  const int dz_fin = (N.cls & 4) ? 1 : 0;
 
   double regP[C::NPL], regM[C::NML];
   // ---- prologue: table, node planes zs-1..zs+1, the layer below the first plane, first row context
@@ -58,13 +57,15 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 288 ? 2 : 1)) assemble_box_ke
   box::mdot_load<C>(P, tid, x0, y0, zs, regM);
   box::mdot_store<C>(tid, regM, mdb);
   N.n = N.x + (long long)P.NX * (N.y + (long long)P.NY * zs);
-  N.row = 0; N.nb = 0; N.rowbase = 0; N.slots = 0xFFFFFFFFu;
+  N.row = 0; N.nb = 0; N.rowbase = 0; N.slots_mid = N.slots_fin = 0xFFFFFFFFu;
   if (N.active) {
     N.row = P.node_row[N.n];
     const long long b0 = P.browptr[N.row];
     N.nb = (int)(P.browptr[N.row + 1] - b0);
     N.rowbase = 9 * b0;
-    N.slots = P.slotpack[N.n * 16 + sub];
+    const uint2 sp = reinterpret_cast<const uint2 *>(P.slotpack)[N.n * 8 + sub];
+    N.slots_mid = sp.x;
+    N.slots_fin = sp.y;
   }
   __syncthreads();
 
@@ -74,10 +75,10 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 288 ? 2 : 1)) assemble_box_ke
     box::plane_load<C>(P, tid, x0, y0, z + 2, regP);
     box::mdot_load<C>(P, tid, x0, y0, z + 1, regM);
     int row_n = 0;
-    unsigned slots_n = 0xFFFFFFFFu;
+    uint2 slots_n = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     if (N.active && more) {
       row_n = P.node_row[N.n + plane_nodes];
-      slots_n = P.slotpack[(N.n + plane_nodes) * 16 + sub];
+      slots_n = reinterpret_cast<const uint2 *>(P.slotpack)[(N.n + plane_nodes) * 8 + sub];
     }
     const double *pl_m = ring + ((z + 2) % 3) * PLN; // plane z-1
     const double *pl_0 = ring + (z % 3) * PLN;
@@ -113,24 +114,26 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 288 ? 2 : 1)) assemble_box_ke
       double *row = stg + N.nl * C::SROW;
       for (int q = sub; q < N.nb * 9; q += C::TPN) row[q] = 0.0;
     }
-    const bool on_mid = N.active && (N.cls & 4);
-    box::p2_flush_a<C>(N, S, on_mid, park);
+    // mid flush: the dz = -1 blocks (classes with c = 1) are complete
+    box::p2_flush_a<C, 1>(N, S, N.active, park);
     __syncwarp();
-    box::p2_flush_b<C>(N, S, on_mid, 0, pl_m, stg, park);
-    if (on_mid) box::p2_zero(S);
+    box::p2_flush_b<C, 1>(N, S, N.active, N.slots_mid, pl_m, stg, park);
+    box::p2_zero<1>(S);
     __syncwarp();
     if (N.active) box::p2_pass<C, 1>(P, N, S, upper, tab, divu);
-    box::p2_flush_a<C>(N, S, N.active, park);
+    // final flush: dz = 0 (c = 0) and dz = +1 (c = 1)
+    box::p2_flush_a<C, 0>(N, S, N.active, park);
+    box::p2_flush_a<C, 1>(N, S, N.active, park);
     __syncwarp();
-    box::p2_flush_b<C>(N, S, N.active, 1, dz_fin ? pl_p : pl_0, stg, park);
-    // rhs: sum the 16 partials of the node (classes 0..2 also carry the divU stress components)
+    box::p2_flush_b<C, 0>(N, S, N.active, N.slots_fin, pl_0, stg, park);
+    box::p2_flush_b<C, 1>(N, S, N.active, N.slots_fin >> 16, pl_p, stg, park);
+    // rhs: sum the 8 partials of the node ((a,b) != (1,1) threads also carry the divU stress components)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double v = S.rr[i] + (N.cls == i ? S.dv : 0.0);
+      double v = S.rr[i] + (N.ab == i ? S.dv : 0.0);
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
       S.rr[i] = v;
     }
     if (N.active && sub < 3) {
@@ -168,7 +171,8 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 288 ? 2 : 1)) assemble_box_ke
     N.row = row_n;
     N.nb = (int)(b1_n - b0_n);
     N.rowbase = 9 * b0_n;
-    N.slots = slots_n;
+    N.slots_mid = slots_n.x;
+    N.slots_fin = slots_n.y;
   }
 }
 
@@ -193,7 +197,7 @@ static int launch_cfg(const Graph &g, BoxParams &P, cudaStream_t stream)
   const long long ntile = (long long)P.tiles_x * P.tiles_y;
   // z chunks: enough CTAs for ~16 waves, but at least 16 planes per chunk (each chunk recomputes
   // one element layer)
-  const int occ = C::NT <= 288 ? 2 : 1;
+  const int occ = C::NT <= 256 ? 2 : 1;
   long long want = ((long long)sms * occ * 16 + ntile - 1) / ntile;
   int zchunks = (int)(want < 1 ? 1 : want);
   int zc = (P.NZ + zchunks - 1) / zchunks;
@@ -245,9 +249,9 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   P.overwrite = overwrite;
   int tile = 0;
   if (const char *e = getenv("NALU_BOX_TILE")) tile = atoi(e);
-  if (tile == 63) return launch_cfg<box::Cfg<6, 3>>(g, P, stream); // 288 threads, 2 CTAs / SM
-  if (tile == 64) return launch_cfg<box::Cfg<6, 4>>(g, P, stream); // 384 threads, 1 CTA / SM
-  return launch_cfg<box::Cfg<8, 4>>(g, P, stream);                  // 512 threads, 1 CTA / SM
+  if (tile == 84) return launch_cfg<box::Cfg<8, 4>>(g, P, stream); // 256 threads
+  if (tile == 86) return launch_cfg<box::Cfg<8, 6>>(g, P, stream); // 384 threads, 1 CTA / SM
+  return launch_cfg<box::Cfg<6, 4>>(g, P, stream);                  // 192 threads, 2 CTAs / SM
 }
 
 } // namespace nalu_b200

@@ -6,11 +6,12 @@
 // computed is turned inside out so that every CSR value is written exactly once, already summed:
 //
 //   * a CTA owns a TBX x TBY column of NODES and sweeps it along z; each node row is owned by
-//     16 threads: 8 "classes" (a,b,c) in {0,1}^3 -- the class owns the column nodes whose offset
-//     from the row node is (+-a, +-b, +-c), so every one of the 8 elements around the node hands each
-//     class exactly one column node -- times 2 "halves" H that split the class's 4 (x,y) quadrants
-//     along the axis the class distinguishes (x if a, else y).  All 16 threads do identical work
-//     (12 (element, ip, column) triples per node plane) with 2 block accumulators each;
+//     8 threads.  Column nodes fall into 8 "classes" (a,b,c) in {0,1}^3 -- the class holds the column
+//     nodes whose offset from the row node is (+-a, +-b, +-c), so every one of the 8 elements around
+//     the node hands each class exactly one column node.  A thread owns the class pair (a,b,0),(a,b,1)
+//     on one half H of the 4 (x,y) quadrants (split along x if a, else along y): per loaded integration
+//     point it serves two column nodes, and all 8 threads do identical work (24 (element, ip, column)
+//     triples per node plane) with 4 block accumulators each;
 //   * phase 1 evaluates, once per element layer, the per-integration-point data the rows need:
 //     G' = -mu_ip adj(J)/det(J)   (so that -mu dN_ic/dx = G' dN_ic/dxi), the SCS area vector A,
 //     the mass flow rate and the div(u) stress scalar -- 14 doubles per ip in shared memory.
@@ -45,7 +46,7 @@ struct BoxParams {
   const int *node_row;
   const long long *browptr;
   const unsigned char *slot27; // [nNodes][27] CSR slot of each lattice neighbour (host emulation / table build)
-  const unsigned *slotpack;    // [nNodes][16] slot_pack() of every thread of the node
+  const unsigned *slotpack;    // [nNodes][8][2] slot_pack(.., w = 0, 1) of every thread of the node
   double *values;
   double *rhs;
   int *err;
@@ -58,7 +59,7 @@ template <int TBX_, int TBY_>
 struct Cfg {
   static constexpr int TBX = TBX_, TBY = TBY_;
   static constexpr int NNODE = TBX * TBY;
-  static constexpr int TPN = 16;            // threads per node row
+  static constexpr int TPN = 8;             // threads per node row
   static constexpr int NT = NNODE * TPN;
   static constexpr int ELX = TBX + 1, ELY = TBY + 1, NEL = ELX * ELY;
   static constexpr int IPD = 14;            // doubles per ip: G'[9], A[3], mdot, w
@@ -335,13 +336,13 @@ __host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0
 
 // ---- phase 2 per-thread state ---------------------------------------------------------------------
 struct P2State {
-  double acc[2][9]; // 3x3 blocks of the thread's two quadrants, row-major [i][j]
-  double D[2];      // diagonal part of each block
-  double rr[3];     // rhs partial of this thread
-  double dv;        // divU stress component carried by classes 0..2
+  double acc[2][2][9]; // [cc][quadrant slot] 3x3 blocks, row-major [i][j]; cc = c bit of the class
+  double D[2][2];      // diagonal part of each block
+  double rr[3];        // rhs partial of this thread
+  double dv;           // divU stress component carried by the (a,b) != (1,1) threads
 };
 
-// Per-thread constants and the per-plane row context.  sub = tid % 16 = cls + 8 H.
+// Per-thread constants and the per-plane row context.  sub = tid % 8 = ab + 4 H, ab = a + 2 b.
 struct NodeCtx {
   int active;        // node inside the domain
   int x, y, z;
@@ -350,23 +351,22 @@ struct NodeCtx {
   long long rowbase; // values offset of the node's first dof row
   int nb;            // blocks in the row
   int row;           // row node index (rhs offset / 3)
-  int cls, H;
-  int q[2];          // (x,y) quadrant handled by accumulator 0 / 1: bit 0 = +x side, bit 1 = +y side
-  int valid[2];      // that quadrant holds an element column
+  int ab, H;
+  int valid[2];      // quadrant slot j holds an element column
   int eoff[2];       // its element's offset in a layer buffer
-  int toff[2];       // its table offset (octants of the lower layer; + 4*3*8*TABE for the upper layer)
+  int toff[2];       // its table offset for class (a,b,0), lower layer (+4*TABE: c = 1; +96*TABE: upper layer)
   int ipo[2][3];     // ip*IPD of the x-, y-, z-edge ip next to the row node, lower layer (x,y: -4*IPD above)
-  int fold;          // the two accumulators belong to one block
-  int pair;          // ... which the H = 0 and H = 1 threads share (class a = b = 0)
-  int nblk;          // blocks this thread finishes per flush (pair: H = 0 finishes it)
+  int fold;          // the two quadrant slots belong to one block
+  int pair;          // ... which the H = 0 and H = 1 threads share (a = b = 0)
   int uoff[2];       // offset of the block's column node in a staged node plane (velocity at +4)
-  unsigned slots;    // CSR block slots: byte 0,1 = mid flush (dz = -1), byte 2,3 = final flush
+  unsigned slots_mid; // CSR block slots (0xFF: none): byte j = slot of block j, dz = -1 (class c = 1)
+  unsigned slots_fin; // byte j: dz = 0 (class c = 0); byte 2+j: dz = +1 (class c = 1)
 };
 
-// offsets (dx,dy) of the block finished from accumulator j by thread (cls, H)
-__host__ __device__ inline void block_offset(int cls, int H, int j, int &dx, int &dy)
+// offsets (dx,dy) of the block finished from quadrant slot j by thread (ab, H)
+__host__ __device__ inline void block_offset(int ab, int H, int j, int &dx, int &dy)
 {
-  const int a = cls & 1, b = (cls >> 1) & 1;
+  const int a = ab & 1, b = (ab >> 1) & 1;
   if (a) {
     dx = H ? 1 : -1;
     dy = b ? (j ? 1 : -1) : 0;
@@ -376,25 +376,25 @@ __host__ __device__ inline void block_offset(int cls, int H, int j, int &dx, int
   }
 }
 
-// CSR slots of the (up to two) blocks a thread finishes in the mid and final flush, from the node's
-// 27-neighbour slot row (0xFF: no such neighbour / no such block)
-__host__ __device__ inline unsigned slot_pack(const unsigned char *s27, int sub)
+// CSR slots of the blocks a thread finishes, from the node's 27-neighbour slot row (0xFF: no such
+// neighbour / not a block of this thread): w = 0 -> slots_mid, w = 1 -> slots_fin
+__host__ __device__ inline unsigned slot_pack(const unsigned char *s27, int sub, int w)
 {
-  const int cls = sub & 7, H = sub >> 3;
-  const int a = cls & 1, b = (cls >> 1) & 1, c = (cls >> 2) & 1;
+  const int ab = sub & 3, H = sub >> 2;
+  const int a = ab & 1, b = (ab >> 1) & 1;
   const int fold = a ? !b : 1, pair = !a && !b;
   const int nblk = fold ? 1 : 2;
   unsigned r = 0;
-  for (int f = 0; f < 2; ++f) {      // 0: mid flush (dz = -1, classes with c only), 1: final flush
-    const int dz = f == 0 ? -1 : (c ? 1 : 0);
+  for (int g = 0; g < 2; ++g) { // w = 0: g = 0 only (dz = -1); w = 1: g = 0 -> dz = 0, g = 1 -> dz = +1
+    const int dz = w == 0 ? -1 : g;
     for (int j = 0; j < 2; ++j) {
       unsigned v = 0xFF;
-      if (j < nblk && !(pair && H == 1) && (f == 1 || c)) {
+      if (j < nblk && !(pair && H == 1) && !(w == 0 && g == 1)) {
         int dx, dy;
-        block_offset(cls, H, j, dx, dy);
+        block_offset(ab, H, j, dx, dy);
         v = s27[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
       }
-      r |= v << (8 * (2 * f + j));
+      r |= v << (8 * (2 * g + j));
     }
   }
   return r;
@@ -405,56 +405,58 @@ __host__ __device__ inline void node_ctx_init(const BoxParams &P, NodeCtx &N, in
 {
   N.nl = tid / C::TPN;
   const int sub = tid % C::TPN;
-  N.cls = sub & 7;
-  N.H = sub >> 3;
+  N.ab = sub & 3;
+  N.H = sub >> 2;
   N.lx = N.nl % C::TBX;
   N.ly = N.nl / C::TBX;
   N.x = x0 + N.lx;
   N.y = y0 + N.ly;
   N.active = N.x < P.NX && N.y < P.NY;
-  const int a = N.cls & 1, b = (N.cls >> 1) & 1;
+  const int a = N.ab & 1, b = (N.ab >> 1) & 1;
   N.fold = a ? !b : 1;
   N.pair = !a && !b;
-  N.nblk = N.fold ? 1 : 2;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    // classes that distinguish x split their quadrants by x (H = sx, j = sy); the others by y
+    // threads that distinguish x split their quadrants by x (H = sx, j = sy); the others by y
     const int sxp = (a || !b) ? N.H : j, syp = (a || !b) ? j : N.H;
-    N.q[j] = sxp + 2 * syp;
+    const int q = sxp + 2 * syp;
     const int ex = N.x - 1 + sxp, ey = N.y - 1 + syp;
     N.valid[j] = N.active && ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny;
     N.eoff[j] = ((N.lx + sxp) + C::ELX * (N.ly + syp)) * C::ES;
-    N.toff[j] = (N.q[j] * 3 * 8 + N.cls) * C::TABE;
-    // ips next to the row node in the element BELOW the plane (row node = top corner, bz = 1)
+    N.toff[j] = (q * 3 * 8 + N.ab) * C::TABE;
+    // ips next to the row node in the element BELOW the plane (row node = a top corner, bz = 1)
     const int k = node_of_bits(!sxp, !syp, 1);
     N.ipo[j][0] = ip_of(k, 0) * C::IPD;
     N.ipo[j][1] = ip_of(k, 1) * C::IPD;
     N.ipo[j][2] = ip_of(k, 2) * C::IPD;
     int dx, dy;
-    block_offset(N.cls, N.H, j, dx, dy);
+    block_offset(N.ab, N.H, j, dx, dy);
     N.uoff[j] = ((N.lx + 1 + dx) + C::RNX * (N.ly + 1 + dy)) * C::NF + 4;
   }
 }
 
+template <int CC>
 __host__ __device__ inline void p2_zero(P2State &S)
 {
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int j = 0; j < 2; ++j) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) S.acc[q][t] = 0.0;
-    S.D[q] = 0.0;
+    for (int t = 0; t < 9; ++t) S.acc[CC][j][t] = 0.0;
+    S.D[CC][j] = 0.0;
   }
 }
 __host__ __device__ inline void p2_begin(P2State &S)
 {
-  p2_zero(S);
+  p2_zero<0>(S);
+  p2_zero<1>(S);
   S.rr[0] = S.rr[1] = S.rr[2] = 0.0;
   S.dv = 0.0;
 }
 
-// one z-half (SZP = 0: elements below the node plane, 1: above): the thread's two quadrants, 3 ips each.
-// The x-/y-edge ips next to the row node lie on the element's top face below the plane (ip 4..7) and on
-// its bottom face above it (ip 0..3): 4 ips = 4*IPD doubles earlier; the z-edge ip is the same.
+// one z-half (SZP = 0: elements below the node plane, 1: above): the thread's two quadrants, 3 ips each,
+// two column nodes (c = 0, 1) per ip.  The x-/y-edge ips next to the row node lie on the element's top
+// face below the plane (ip 4..7) and on its bottom face above it (ip 0..3): 4*IPD doubles earlier; the
+// z-edge ip is the same.
 template <class C, int SZP>
 __host__ __device__ inline void p2_pass(const BoxParams &P, const NodeCtx &N, P2State &S, const double *buf,
                                         const double *tab, bool divu)
@@ -469,73 +471,75 @@ __host__ __device__ inline void p2_pass(const BoxParams &P, const NodeCtx &N, P2
 #pragma unroll
     for (int pp = 0; pp < 3; ++pp) {
       const double *o = eb + N.ipo[j][pp] - ((SZP && pp < 2) ? 4 * C::IPD : 0);
-      const double *t = tb + pp * (8 * C::TABE);
-      const double d0 = t[0], d1 = t[1], d2 = t[2], nadv = t[3];
-      double h[3]; // signed: +-(-mu dN_ic/dx)
+      const double G00 = o[0], G01 = o[1], G02 = o[2], G10 = o[3], G11 = o[4], G12 = o[5], G20 = o[6], G21 = o[7],
+                   G22 = o[8];
+      const double A0 = o[9], A1 = o[10], A2 = o[11], md = o[12];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) h[i] = o[i * 3 + 0] * d0 + o[i * 3 + 1] * d1 + o[i * 3 + 2] * d2;
-      const double A0 = o[9], A1 = o[10], A2 = o[11];
-      S.D[j] += h[0] * A0 + h[1] * A1 + h[2] * A2 + nadv * o[12];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        S.acc[j][i * 3 + 0] += h[i] * A0;
-        S.acc[j][i * 3 + 1] += h[i] * A1;
-        S.acc[j][i * 3 + 2] += h[i] * A2;
+      for (int cc = 0; cc < 2; ++cc) {
+        const double *t = tb + pp * (8 * C::TABE) + cc * (4 * C::TABE);
+        const double d0 = t[0], d1 = t[1], d2 = t[2], nadv = t[3];
+        // signed: +-(-mu dN_ic/dx)
+        const double h0 = G00 * d0 + G01 * d1 + G02 * d2;
+        const double h1 = G10 * d0 + G11 * d1 + G12 * d2;
+        const double h2 = G20 * d0 + G21 * d1 + G22 * d2;
+        S.D[cc][j] += h0 * A0 + h1 * A1 + h2 * A2 + nadv * md;
+        S.acc[cc][j][0] += h0 * A0; S.acc[cc][j][1] += h0 * A1; S.acc[cc][j][2] += h0 * A2;
+        S.acc[cc][j][3] += h1 * A0; S.acc[cc][j][4] += h1 * A1; S.acc[cc][j][5] += h1 * A2;
+        S.acc[cc][j][6] += h2 * A0; S.acc[cc][j][7] += h2 * A1; S.acc[cc][j][8] += h2 * A2;
       }
       if (divu) {
-        // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135).  Every class meets each (element, ip)
-        // next to the node exactly once (over its two halves); classes 0,1,2 each carry one component
-        // of w A, the other classes' sums are dropped when the partials are combined
-        S.dv -= t[4] * o[13] * o[9 + (N.cls < 3 ? N.cls : 0)];
+        // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135).  Every (a,b) thread pair (H = 0, 1) meets
+        // each (element, ip) next to the node exactly once; (a,b) = (0,0),(1,0),(0,1) each carry one
+        // component of w A, the (1,1) threads' sums are dropped when the partials are combined
+        S.dv -= tb[pp * (8 * C::TABE) + 4] * o[13] * o[9 + (N.ab < 3 ? N.ab : 0)];
       }
     }
   }
 }
 
-// Finish the blocks of one flush (mid: dz = -1, classes with c; final: dz = c ? +1 : 0), in two steps
-// with a warp barrier between them; every thread of the warp calls both (`on` = takes part).
-// Step a: fold the two accumulators when they belong to one block; the H = 1 thread of the centre-column
-// classes (a = b = 0) parks its half of the shared block in shared memory.
-template <class C>
+// Finish the blocks of class c = CC, in two steps with a warp barrier between them; every thread of the
+// warp calls both (`on` = takes part).  Step a: fold the two quadrant slots when they belong to one
+// block; the H = 1 thread of the centre-column classes (a = b = 0) parks its half of the shared block.
+template <class C, int CC>
 __host__ __device__ inline void p2_flush_a(const NodeCtx &N, P2State &S, bool on, double *parkbase)
 {
   if (!on) return;
   if (N.fold) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) S.acc[0][t] += S.acc[1][t];
-    S.D[0] += S.D[1];
+    for (int t = 0; t < 9; ++t) S.acc[CC][0][t] += S.acc[CC][1][t];
+    S.D[CC][0] += S.D[CC][1];
   }
   if (N.pair && N.H == 1) {
-    double *park = parkbase + (N.nl * 2 + (N.cls >> 2)) * 9;
+    double *park = parkbase + (N.nl * 2 + CC) * 9;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) park[i * 3 + j] = S.acc[0][i * 3 + j] + (i == j ? S.D[0] : 0.0);
+      for (int j = 0; j < 3; ++j) park[i * 3 + j] = S.acc[CC][0][i * 3 + j] + (i == j ? S.D[CC][0] : 0.0);
   }
 }
 // Step b: write the finished blocks into the staging row (CSR layout) and take their share of
-// rhs = -row . u.  `half` selects the mid (0) / final (1) slot bytes; `uplane` = staged plane of the column nodes.
-template <class C>
-__host__ __device__ inline void p2_flush_b(const NodeCtx &N, P2State &S, bool on, int half, const double *uplane,
+// rhs = -row . u.  `slots`: byte j = CSR slot of block j; `uplane` = staged plane of the column nodes.
+template <class C, int CC>
+__host__ __device__ inline void p2_flush_b(const NodeCtx &N, P2State &S, bool on, unsigned slots, const double *uplane,
                                            double *stg, const double *parkbase)
 {
   if (!on) return;
   double *row = stg + N.nl * C::SROW;
-  const double *park = parkbase + (N.nl * 2 + (N.cls >> 2)) * 9;
+  const double *park = parkbase + (N.nl * 2 + CC) * 9;
   const int rs = N.nb * 3; // doubles per dof row
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const unsigned slot = (N.slots >> (8 * (2 * half + j))) & 0xFF;
+    const unsigned slot = (slots >> (8 * j)) & 0xFF;
     if (slot == 0xFF) continue; // not a block this thread finishes, or no such neighbour node
     const double *u = uplane + N.uoff[j];
     const double u0 = u[0], u1 = u[1], u2 = u[2];
     double *bp = row + slot * 3;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double v0 = S.acc[j][i * 3 + 0], v1 = S.acc[j][i * 3 + 1], v2 = S.acc[j][i * 3 + 2];
-      if (i == 0) v0 += S.D[j];
-      if (i == 1) v1 += S.D[j];
-      if (i == 2) v2 += S.D[j];
+      double v0 = S.acc[CC][j][i * 3 + 0], v1 = S.acc[CC][j][i * 3 + 1], v2 = S.acc[CC][j][i * 3 + 2];
+      if (i == 0) v0 += S.D[CC][j];
+      if (i == 1) v1 += S.D[CC][j];
+      if (i == 2) v2 += S.D[CC][j];
       if (N.pair) {
         v0 += park[i * 3 + 0];
         v1 += park[i * 3 + 1];

@@ -100,7 +100,9 @@ static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const s
     std::vector<uint32_t> pack(size_t(g.n_nodes) * 16);
 #pragma omp parallel for schedule(static)
     for (int64_t n = 0; n < g.n_nodes; ++n)
-      for (int sub = 0; sub < 16; ++sub) pack[size_t(n) * 16 + sub] = box::slot_pack(&node_slot27[size_t(n) * 27], sub);
+      for (int sub = 0; sub < 8; ++sub)
+        for (int w = 0; w < 2; ++w)
+          pack[size_t(n) * 16 + sub * 2 + w] = box::slot_pack(&node_slot27[size_t(n) * 27], sub, w);
     if ((rc = upload(&g.d_node_slotpack, pack))) return rc;
   }
   NALU_CUDA(cudaMalloc((void **)&g.d_err, sizeof(int)));

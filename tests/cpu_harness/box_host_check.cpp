@@ -92,7 +92,7 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
   std::vector<box::NodeCtx> N(NT);
   std::vector<int> ncov(NT), row_n(NT);
   std::vector<long long> b0_n(NT), b1_n(NT);
-  std::vector<unsigned> slots_n(NT);
+  std::vector<unsigned> slots_n0(NT), slots_n1(NT);
   struct Regs { double p[C::NPL]; double m[C::NML]; };
   std::vector<Regs> R(NT);
   const bool divu = P.include_divu != 0.0;
@@ -128,13 +128,14 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
       box::NodeCtx &n = N[tid];
       box::node_ctx_init<C>(P, n, tid, x0, y0);
       n.n = n.x + (long long)P.NX * (n.y + (long long)P.NY * zs);
-      n.row = 0; n.nb = 0; n.rowbase = 0; n.slots = 0xFFFFFFFFu;
+      n.row = 0; n.nb = 0; n.rowbase = 0; n.slots_mid = n.slots_fin = 0xFFFFFFFFu;
       if (n.active) {
         n.row = P.node_row[n.n];
         const long long b0 = P.browptr[n.row];
         n.nb = (int)(P.browptr[n.row + 1] - b0);
         n.rowbase = 9 * b0;
-        n.slots = box::slot_pack(P.slot27 + n.n * 27, tid % C::TPN);
+        n.slots_mid = box::slot_pack(P.slot27 + n.n * 27, tid % C::TPN, 0);
+        n.slots_fin = box::slot_pack(P.slot27 + n.n * 27, tid % C::TPN, 1);
       }
     }
     for (int z = zs; z < ze; ++z) {
@@ -143,10 +144,11 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
         box::plane_load<C>(P, tid, x0, y0, z + 2, R[tid].p);
         box::mdot_load<C>(P, tid, x0, y0, z + 1, R[tid].m);
         row_n[tid] = 0;
-        slots_n[tid] = 0xFFFFFFFFu;
+        slots_n0[tid] = slots_n1[tid] = 0xFFFFFFFFu;
         if (N[tid].active && more) {
           row_n[tid] = P.node_row[N[tid].n + plane_nodes];
-          slots_n[tid] = box::slot_pack(P.slot27 + (N[tid].n + plane_nodes) * 27, tid % C::TPN);
+          slots_n0[tid] = box::slot_pack(P.slot27 + (N[tid].n + plane_nodes) * 27, tid % C::TPN, 0);
+          slots_n1[tid] = box::slot_pack(P.slot27 + (N[tid].n + plane_nodes) * 27, tid % C::TPN, 1);
         }
       }
       const double *pl_m = ring + ((z + 2) % 3) * PLN, *pl_0 = ring + (z % 3) * PLN, *pl_p = ring + ((z + 1) % 3) * PLN;
@@ -185,24 +187,28 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
         }
       }
       // mid flush: step a for every thread, warp barrier, step b
-      for (int tid = 0; tid < NT; ++tid) box::p2_flush_a<C>(N[tid], S[tid], N[tid].active && (N[tid].cls & 4), park);
+      for (int tid = 0; tid < NT; ++tid) box::p2_flush_a<C, 1>(N[tid], S[tid], N[tid].active, park);
       for (int tid = 0; tid < NT; ++tid) {
-        const bool on = N[tid].active && (N[tid].cls & 4);
-        box::p2_flush_b<C>(N[tid], S[tid], on, 0, pl_m, stg, park);
-        if (on) box::p2_zero(S[tid]);
+        box::p2_flush_b<C, 1>(N[tid], S[tid], N[tid].active, N[tid].slots_mid, pl_m, stg, park);
+        box::p2_zero<1>(S[tid]);
       }
       for (int q = 0; q < C::PARK; ++q) park[q] = NAN;
       for (int tid = 0; tid < NT; ++tid)
         if (N[tid].active) box::p2_pass<C, 1>(P, N[tid], S[tid], upper, tab, divu);
-      for (int tid = 0; tid < NT; ++tid) box::p2_flush_a<C>(N[tid], S[tid], N[tid].active, park);
-      for (int tid = 0; tid < NT; ++tid)
-        box::p2_flush_b<C>(N[tid], S[tid], N[tid].active, 1, (N[tid].cls & 4) ? pl_p : pl_0, stg, park);
+      for (int tid = 0; tid < NT; ++tid) {
+        box::p2_flush_a<C, 0>(N[tid], S[tid], N[tid].active, park);
+        box::p2_flush_a<C, 1>(N[tid], S[tid], N[tid].active, park);
+      }
+      for (int tid = 0; tid < NT; ++tid) {
+        box::p2_flush_b<C, 0>(N[tid], S[tid], N[tid].active, N[tid].slots_fin, pl_0, stg, park);
+        box::p2_flush_b<C, 1>(N[tid], S[tid], N[tid].active, N[tid].slots_fin >> 16, pl_p, stg, park);
+      }
       for (int nl = 0; nl < C::NNODE; ++nl) {
         const box::NodeCtx &n = N[nl * C::TPN];
         if (!n.active) continue;
         for (int i = 0; i < 3; ++i) {
           double v = 0;
-          for (int c = 0; c < C::TPN; ++c) v += S[nl * C::TPN + c].rr[i] + ((c & 7) == i ? S[nl * C::TPN + c].dv : 0.0);
+          for (int c = 0; c < C::TPN; ++c) v += S[nl * C::TPN + c].rr[i] + ((c & 3) == i ? S[nl * C::TPN + c].dv : 0.0);
           double *r = P.rhs + (long long)n.row * 3 + i;
           *r = P.overwrite ? v : *r + v;
         }
@@ -222,7 +228,8 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
         n.row = row_n[tid];
         n.nb = (int)(b1_n[tid] - b0_n[tid]);
         n.rowbase = 9 * b0_n[tid];
-        n.slots = slots_n[tid];
+        n.slots_mid = slots_n0[tid];
+        n.slots_fin = slots_n1[tid];
       }
     }
   }
@@ -347,8 +354,8 @@ int main()
   for (const Case &c : cases) {
     const double e64 = run_case<box::Cfg<6, 4>>(c.nx, c.ny, c.nz, c.R, c.zc, c.opt, c.divu, c.ow);
     const double e84 = run_case<box::Cfg<8, 4>>(c.nx, c.ny, c.nz, c.R, c.zc, c.opt, c.divu, c.ow);
-    const double e86 = run_case<box::Cfg<6, 3>>(c.nx, c.ny, c.nz, c.R, c.zc, c.opt, c.divu, c.ow);
-    printf("box %dx%dx%d ranks %d zchunk %d opt %d divu %.0f overwrite %d: relerr 6x4 %.3e  8x4 %.3e  6x3 %.3e\n", c.nx,
+    const double e86 = run_case<box::Cfg<8, 6>>(c.nx, c.ny, c.nz, c.R, c.zc, c.opt, c.divu, c.ow);
+    printf("box %dx%dx%d ranks %d zchunk %d opt %d divu %.0f overwrite %d: relerr 6x4 %.3e  8x4 %.3e  8x6 %.3e\n", c.nx,
            c.ny, c.nz, c.R, c.zc, c.opt, c.divu, c.ow, e64, e84, e86);
     worst = fmax(worst, fmax(e64, fmax(e84, e86)));
   }

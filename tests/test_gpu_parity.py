@@ -380,7 +380,7 @@ def test_missing_device_pointer_is_an_error():
 # ---------------------------------------------------------------------------------------------
 # tiled write-once kernel (assemble_box.cu): tile shapes, z chunking, overwrite semantics, determinism
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tile", ["63", "64", "84"])
+@pytest.mark.parametrize("tile", ["64", "84", "86"])
 @pytest.mark.parametrize("zchunk", ["1", "3", "0"])
 def test_box_kernel_tiles_and_chunks(tile, zchunk, monkeypatch):
     monkeypatch.setenv("NALU_BOX_TILE", tile)
