@@ -6,7 +6,8 @@
 //                                                               row staging area)
 //   upper octants, block flush, rhs                           -> sync
 //   coalesced copy of the finished rows to HBM               -> sync
-// Default tile: 6x4 nodes, 8 threads per node = 192 threads, two CTAs per SM.
+// Two CTAs are resident per SM (6x4 node tile, 192 threads, ~101 KB shared memory) so that one
+// CTA's copy/phase-1 overlaps the other's FP64-bound phase 2.
 #include "box_tile.cuh"
 #include "internal.h"
 
@@ -23,7 +24,6 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
   double *const tab = sm + C::OFF_TAB;
   double *const ring = sm + C::OFF_RING;
   double *const mdb = sm + C::OFF_MD;
-  double *const park = sm + C::OFF_PARK;
   long long *const s_rb = reinterpret_cast<long long *>(sm + C::OFF_RB);
   int *const s_len = reinterpret_cast<int *>(sm + C::OFF_LEN);
   constexpr int PLN = C::RN * C::NF;
@@ -37,11 +37,12 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
   const long long plane_nodes = (long long)P.NX * P.NY;
 
   box::NodeCtx N;
+  const int nl = tid >> 3;
   box::node_ctx_init<C>(P, N, tid, x0, y0);
-  const int sub = tid % C::TPN;
+  const int dz_fin = (N.cls & 4) ? 1 : 0;
 
   double regP[C::NPL], regM[C::NML];
-  // ---- prologue: table, node planes zs-1..zs+1, the layer below the first plane, first row context
+  // ---- prologue: table, node planes zs-1..zs+1, the layer below the first plane, first node ctx
   for (int i = tid; i < 192; i += C::NT) box::build_table_entry<C>(i, P.options, tab);
   for (int pl = zs - 1; pl <= zs + 1; ++pl) {
     box::plane_load<C>(P, tid, x0, y0, pl, regP);
@@ -63,9 +64,8 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     const long long b0 = P.browptr[N.row];
     N.nb = (int)(P.browptr[N.row + 1] - b0);
     N.rowbase = 9 * b0;
-    const uint2 sp = reinterpret_cast<const uint2 *>(P.slotpack)[N.n * 8 + sub];
-    N.slots_mid = sp.x;
-    N.slots_fin = sp.y;
+    N.slots_mid = box::load_slots(P.slot27 + N.n * 27, N.cls, -1);
+    N.slots_fin = box::load_slots(P.slot27 + N.n * 27, N.cls, dz_fin);
   }
   __syncthreads();
 
@@ -75,11 +75,7 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     box::plane_load<C>(P, tid, x0, y0, z + 2, regP);
     box::mdot_load<C>(P, tid, x0, y0, z + 1, regM);
     int row_n = 0;
-    uint2 slots_n = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-    if (N.active && more) {
-      row_n = P.node_row[N.n + plane_nodes];
-      slots_n = reinterpret_cast<const uint2 *>(P.slotpack)[(N.n + plane_nodes) * 8 + sub];
-    }
+    if (N.active && more) row_n = P.node_row[N.n + plane_nodes];
     const double *pl_m = ring + ((z + 2) % 3) * PLN; // plane z-1
     const double *pl_0 = ring + (z % 3) * PLN;
     const double *pl_p = ring + ((z + 1) % 3) * PLN;
@@ -90,14 +86,18 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     const double *lower = sm + ((z + 1) & 1) * C::LBUF;
     const double *upper = sm + (z & 1) * C::LBUF;
     double *stg = sm + ((z + 1) & 1) * C::LBUF;
-    if (sub == 0) {
-      s_rb[N.nl] = N.rowbase;
-      s_len[N.nl] = N.active ? N.nb * 9 : 0;
+    if (N.cls == 0) {
+      s_rb[nl] = N.rowbase;
+      s_len[nl] = N.active ? N.nb * 9 : 0;
     }
     long long b0_n = 0, b1_n = 0;
+    unsigned sm_n = 0xFFFFFFFFu, sf_n = 0xFFFFFFFFu;
     if (N.active && more) {
       b0_n = P.browptr[row_n];
       b1_n = P.browptr[row_n + 1];
+      const unsigned char *sl = P.slot27 + (N.n + plane_nodes) * 27;
+      sm_n = box::load_slots(sl, N.cls, -1);
+      sf_n = box::load_slots(sl, N.cls, dz_fin);
     }
     box::P2State S;
     box::p2_begin(S);
@@ -105,40 +105,36 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
     int ncov = 0;
     if (N.active) {
       ncov = ((N.x > 0) + 1 + (N.x < P.NX - 1)) * ((N.y > 0) + 1 + (N.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
-      box::p2_pass<C, 0>(P, N, S, lower, tab, divu);
+      box::p2_pass<C, 0>(P, N, S, lower, tab + 2 * N.cls, divu);
     }
     __syncthreads(); // every thread is done with the lower layer: its buffer is now the staging area
     if (N.active && N.nb != ncov) {
       // row also holds columns no local element touches (remote columns announced by the ranks
       // sharing this node): they must read zero
-      double *row = stg + N.nl * C::SROW;
-      for (int q = sub; q < N.nb * 9; q += C::TPN) row[q] = 0.0;
+      double *row = stg + nl * C::SROW;
+      for (int q = N.cls; q < N.nb * 9; q += 8) row[q] = 0.0;
     }
-    // mid flush: the dz = -1 blocks (classes with c = 1) are complete
-    box::p2_flush_a<C, 1>(N, S, N.active, park);
     __syncwarp();
-    box::p2_flush_b<C, 1>(N, S, N.active, N.slots_mid, pl_m, stg, park);
-    box::p2_zero<1>(S);
-    __syncwarp();
-    if (N.active) box::p2_pass<C, 1>(P, N, S, upper, tab, divu);
-    // final flush: dz = 0 (c = 0) and dz = +1 (c = 1)
-    box::p2_flush_a<C, 0>(N, S, N.active, park);
-    box::p2_flush_a<C, 1>(N, S, N.active, park);
-    __syncwarp();
-    box::p2_flush_b<C, 0>(N, S, N.active, N.slots_fin, pl_0, stg, park);
-    box::p2_flush_b<C, 1>(N, S, N.active, N.slots_fin >> 16, pl_p, stg, park);
-    // rhs: sum the 8 partials of the node ((a,b) != (1,1) threads also carry the divU stress components)
+    if (N.active) {
+      if (N.cls & 4) {
+        box::p2_flush<C>(N, S, N.slots_mid, pl_m, stg);
+        box::p2_zero(S);
+      }
+      box::p2_pass<C, 1>(P, N, S, upper, tab + 2 * N.cls, divu);
+      box::p2_flush<C>(N, S, N.slots_fin, dz_fin ? pl_p : pl_0, stg);
+    }
+    // rhs: sum the 8 class partials of the node (classes 0..2 also carry the divU stress components)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double v = S.rr[i] + (N.ab == i ? S.dv : 0.0);
+      double v = S.rr[i] + (N.cls == i ? S.dv : 0.0);
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       S.rr[i] = v;
     }
-    if (N.active && sub < 3) {
-      double *r = P.rhs + (long long)N.row * 3 + sub;
-      const double v = sub == 0 ? S.rr[0] : (sub == 1 ? S.rr[1] : S.rr[2]);
+    if (N.active && N.cls < 3) {
+      double *r = P.rhs + (long long)N.row * 3 + N.cls;
+      const double v = N.cls == 0 ? S.rr[0] : (N.cls == 1 ? S.rr[1] : S.rr[2]);
       *r = P.overwrite ? v : *r + v;
     }
     __syncthreads();
@@ -166,19 +162,19 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 256 ? 2 : 1)) assemble_box_ke
       }
     }
     __syncthreads();
-    // rotate the row context
+    // rotate the node context
     N.n += plane_nodes;
     N.row = row_n;
     N.nb = (int)(b1_n - b0_n);
     N.rowbase = 9 * b0_n;
-    N.slots_mid = slots_n.x;
-    N.slots_fin = slots_n.y;
+    N.slots_mid = sm_n;
+    N.slots_fin = sf_n;
   }
 }
 
 bool box_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
 {
-  if (g.box[0] <= 0 || !g.d_node_slot27 || !g.d_node_slotpack || g.ndof != 3 || nk != 1) return false;
+  if (g.box[0] <= 0 || !g.d_node_slot27 || g.ndof != 3 || nk != 1) return false;
   if (k[0].kind != NALU_K_MOMENTUM_ADV_DIFF) return false;
   if (!k[0].nodal[NALU_F_COORDINATES] || !k[0].nodal[NALU_F_VELOCITY] || !k[0].nodal[NALU_F_VISCOSITY] ||
       !k[0].mass_flow_rate)
@@ -240,7 +236,6 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   P.node_row = g.d_node_row;
   P.browptr = (const long long *)g.d_browptr;
   P.slot27 = g.d_node_slot27;
-  P.slotpack = g.d_node_slotpack;
   P.values = d_values;
   P.rhs = d_rhs;
   P.err = g.d_err;
@@ -249,9 +244,9 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   P.overwrite = overwrite;
   int tile = 0;
   if (const char *e = getenv("NALU_BOX_TILE")) tile = atoi(e);
-  if (tile == 84) return launch_cfg<box::Cfg<8, 4>>(g, P, stream); // 256 threads
-  if (tile == 86) return launch_cfg<box::Cfg<8, 6>>(g, P, stream); // 384 threads, 1 CTA / SM
-  return launch_cfg<box::Cfg<6, 4>>(g, P, stream);                  // 192 threads, 2 CTAs / SM
+  if (tile == 84) return launch_cfg<box::Cfg<8, 4>>(g, P, stream);
+  if (tile == 86) return launch_cfg<box::Cfg<8, 6>>(g, P, stream);
+  return launch_cfg<box::Cfg<6, 4>>(g, P, stream);
 }
 
 } // namespace nalu_b200

@@ -6,12 +6,10 @@
 // computed is turned inside out so that every CSR value is written exactly once, already summed:
 //
 //   * a CTA owns a TBX x TBY column of NODES and sweeps it along z; each node row is owned by
-//     8 threads.  Column nodes fall into 8 "classes" (a,b,c) in {0,1}^3 -- the class holds the column
-//     nodes whose offset from the row node is (+-a, +-b, +-c), so every one of the 8 elements around
-//     the node hands each class exactly one column node.  A thread owns the class pair (a,b,0),(a,b,1)
-//     on one half H of the 4 (x,y) quadrants (split along x if a, else along y): per loaded integration
-//     point it serves two column nodes, and all 8 threads do identical work (24 (element, ip, column)
-//     triples per node plane) with 4 block accumulators each;
+//     8 threads ("classes" (a,b,c) in {0,1}^3: the thread owns the column nodes whose offset from
+//     the row node is (+-a, +-b, +-c), so every one of the 8 elements around the node hands each
+//     class exactly one column node -> all 8 threads do identical work, 24 (element, ip, column)
+//     triples per node plane);
 //   * phase 1 evaluates, once per element layer, the per-integration-point data the rows need:
 //     G' = -mu_ip adj(J)/det(J)   (so that -mu dN_ic/dx = G' dN_ic/dxi), the SCS area vector A,
 //     the mass flow rate and the div(u) stress scalar -- 14 doubles per ip in shared memory.
@@ -45,8 +43,7 @@ struct BoxParams {
   const double *mdot;   // [nElem][12]
   const int *node_row;
   const long long *browptr;
-  const unsigned char *slot27; // [nNodes][27] CSR slot of each lattice neighbour (host emulation / table build)
-  const unsigned *slotpack;    // [nNodes][8][2] slot_pack(.., w = 0, 1) of every thread of the node
+  const unsigned char *slot27;
   double *values;
   double *rhs;
   int *err;
@@ -59,25 +56,22 @@ template <int TBX_, int TBY_>
 struct Cfg {
   static constexpr int TBX = TBX_, TBY = TBY_;
   static constexpr int NNODE = TBX * TBY;
-  static constexpr int TPN = 8;             // threads per node row
-  static constexpr int NT = NNODE * TPN;
+  static constexpr int NT = NNODE * 8;
   static constexpr int ELX = TBX + 1, ELY = TBY + 1, NEL = ELX * ELY;
   static constexpr int IPD = 14;            // doubles per ip: G'[9], A[3], mdot, w
   static constexpr int ES = 12 * IPD + 2;   // element stride (doubles); +2 spreads the 16-byte bank groups
   static constexpr int SROW = 248;          // staging row stride (doubles) >= 27*9
   static constexpr int LBUF = (NEL * ES > NNODE * SROW) ? NEL * ES : NNODE * SROW;
-  static constexpr int TABE = 6;            // d0,d1,d2 (ip-local axes), N_adv, sign, pad -- all pre-multiplied by the L/R sign
-  static constexpr int TAB = 8 * 3 * 8 * TABE; // [octant][edge dir][class][TABE]
+  static constexpr int TAB = 8 * 3 * 2 * 8 * 2; // [octant][edge dir][half][class][2]
   static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY; // node neighbourhood of the tile
   static constexpr int NF = 7;              // staged nodal doubles: x[3], mu, u[3]
   static constexpr int RING = 3 * RN * NF;  // three node planes
   static constexpr int MDB = NEL * 12;      // mass flow rates of one element layer
   static constexpr int NPL = (RN * NF + NT - 1) / NT;  // per-thread loads to stage one node plane
   static constexpr int NML = (MDB + NT - 1) / NT;      // per-thread loads to stage one mdot layer
-  // doubles: two layer buffers, table, nodal ring, mdot layer, parked half blocks, row base (8-byte ints), row length
-  static constexpr int PARK = NNODE * 2 * 9; // half blocks of the two centre-column classes
+  // doubles: two layer buffers, table, nodal ring, mdot layer, row base (as 8-byte ints) and row length
   static constexpr int OFF_TAB = 2 * LBUF, OFF_RING = OFF_TAB + TAB, OFF_MD = OFF_RING + RING,
-                       OFF_PARK = OFF_MD + MDB, OFF_RB = OFF_PARK + PARK, OFF_LEN = OFF_RB + NNODE;
+                       OFF_RB = OFF_MD + MDB, OFF_LEN = OFF_RB + NNODE;
   static constexpr int SMEM_DOUBLES = OFF_LEN + (NNODE + 1) / 2;
   // phase-1 work items: (element, edge direction), split once more in two when that still fits one
   // round of the CTA's threads
@@ -113,20 +107,17 @@ __host__ __device__ inline void build_table_entry(int idx, int options, double *
   const int a = cls & 1, b = (cls >> 1) & 1, c = (cls >> 2) & 1;
   const int ic = node_of_bits(a ? sxp : !sxp, b ? syp : !syp, c ? szp : !szp);
   const int ip = ip_of(k, pp);
-  // rows L and R of an ip receive +X and -X (MomentumAdvDiffElemKernel.C:152-183): fold the sign here
-  const double sg = hex8::scs_left(ip) == k ? 1.0 : -1.0;
   double s1, s2, s3, d[3];
   hex8::scs_intg_loc(ip, (options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25, s1, s2, s3);
   hex8::shape_deriv(ic, s1, s2, s3, d);
   hex8::scs_intg_loc(ip, (options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25, s1, s2, s3);
   const double nadv = hex8::shape_fcn(ic, s1, s2, s3);
-  double *t = tab + ((s * 3 + pp) * 8 + cls) * C::TABE;
-  t[0] = sg * d[pp];
-  t[1] = sg * d[(pp + 1) % 3];
-  t[2] = sg * d[(pp + 2) % 3];
-  t[3] = sg * nadv;
-  t[4] = sg;
-  t[5] = 0.0;
+  double *t0 = tab + ((s * 3 + pp) * 2 + 0) * 16 + cls * 2;
+  double *t1 = tab + ((s * 3 + pp) * 2 + 1) * 16 + cls * 2;
+  t0[0] = d[pp];
+  t0[1] = d[(pp + 1) % 3];
+  t1[0] = d[(pp + 2) % 3];
+  t1[1] = nadv;
 }
 
 // ---- staging of nodal fields / mass flow rates (global -> registers -> shared) ---------------------
@@ -336,215 +327,176 @@ __host__ __device__ inline void phase1_item(const BoxParams &P, int item, int x0
 
 // ---- phase 2 per-thread state ---------------------------------------------------------------------
 struct P2State {
-  double acc[2][2][9]; // [cc][quadrant slot] 3x3 blocks, row-major [i][j]; cc = c bit of the class
-  double D[2][2];      // diagonal part of each block
-  double rr[3];        // rhs partial of this thread
-  double dv;           // divU stress component carried by the (a,b) != (1,1) threads
+  double acc[4][9]; // 3x3 blocks per (sx,sy) quadrant, row-major [i][j]
+  double D[4];      // diagonal part of each block
+  double rr[3];     // rhs partial of this thread
+  double dv;        // divU stress component carried by classes 0..2
 };
 
-// Per-thread constants and the per-plane row context.  sub = tid % 8 = ab + 4 H, ab = a + 2 b.
 struct NodeCtx {
   int active;        // node inside the domain
   int x, y, z;
-  int lx, ly, nl;    // position in the tile
+  int lx, ly;        // position in the tile
   long long n;       // lattice node index
   long long rowbase; // values offset of the node's first dof row
   int nb;            // blocks in the row
   int row;           // row node index (rhs offset / 3)
-  int ab, H;
-  int valid[2];      // quadrant slot j holds an element column
-  int eoff[2];       // its element's offset in a layer buffer
-  int toff[2];       // its table offset for class (a,b,0), lower layer (+4*TABE: c = 1; +96*TABE: upper layer)
-  int ipo[2][3];     // ip*IPD of the x-, y-, z-edge ip next to the row node, lower layer (x,y: -4*IPD above)
-  int fold;          // the two quadrant slots belong to one block
-  int pair;          // ... which the H = 0 and H = 1 threads share (a = b = 0)
-  int uoff[2];       // offset of the block's column node in a staged node plane (velocity at +4)
-  unsigned slots_mid; // CSR block slots (0xFF: none): byte j = slot of block j, dz = -1 (class c = 1)
-  unsigned slots_fin; // byte j: dz = 0 (class c = 0); byte 2+j: dz = +1 (class c = 1)
+  int cls;
+  unsigned slots_mid, slots_fin; // CSR block slot (0xFF: no such neighbour) of the 4 quadrant blocks
+  int vmask;         // bit q: the (sx,sy) quadrant q holds an element column
+  int eoff;          // offset of element (lx,ly) of the layer tile in a layer buffer
 };
-
-// offsets (dx,dy) of the block finished from quadrant slot j by thread (ab, H)
-__host__ __device__ inline void block_offset(int ab, int H, int j, int &dx, int &dy)
-{
-  const int a = ab & 1, b = (ab >> 1) & 1;
-  if (a) {
-    dx = H ? 1 : -1;
-    dy = b ? (j ? 1 : -1) : 0;
-  } else {
-    dx = 0;
-    dy = b ? (H ? 1 : -1) : 0;
-  }
-}
-
-// CSR slots of the blocks a thread finishes, from the node's 27-neighbour slot row (0xFF: no such
-// neighbour / not a block of this thread): w = 0 -> slots_mid, w = 1 -> slots_fin
-__host__ __device__ inline unsigned slot_pack(const unsigned char *s27, int sub, int w)
-{
-  const int ab = sub & 3, H = sub >> 2;
-  const int a = ab & 1, b = (ab >> 1) & 1;
-  const int fold = a ? !b : 1, pair = !a && !b;
-  const int nblk = fold ? 1 : 2;
-  unsigned r = 0;
-  for (int g = 0; g < 2; ++g) { // w = 0: g = 0 only (dz = -1); w = 1: g = 0 -> dz = 0, g = 1 -> dz = +1
-    const int dz = w == 0 ? -1 : g;
-    for (int j = 0; j < 2; ++j) {
-      unsigned v = 0xFF;
-      if (j < nblk && !(pair && H == 1) && !(w == 0 && g == 1)) {
-        int dx, dy;
-        block_offset(ab, H, j, dx, dy);
-        v = s27[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
-      }
-      r |= v << (8 * (2 * g + j));
-    }
-  }
-  return r;
-}
 
 template <class C>
 __host__ __device__ inline void node_ctx_init(const BoxParams &P, NodeCtx &N, int tid, int x0, int y0)
 {
-  N.nl = tid / C::TPN;
-  const int sub = tid % C::TPN;
-  N.ab = sub & 3;
-  N.H = sub >> 2;
-  N.lx = N.nl % C::TBX;
-  N.ly = N.nl / C::TBX;
+  const int nl = tid >> 3;
+  N.cls = tid & 7;
+  N.lx = nl % C::TBX;
+  N.ly = nl / C::TBX;
   N.x = x0 + N.lx;
   N.y = y0 + N.ly;
   N.active = N.x < P.NX && N.y < P.NY;
-  const int a = N.ab & 1, b = (N.ab >> 1) & 1;
-  N.fold = a ? !b : 1;
-  N.pair = !a && !b;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    // threads that distinguish x split their quadrants by x (H = sx, j = sy); the others by y
-    const int sxp = (a || !b) ? N.H : j, syp = (a || !b) ? j : N.H;
-    const int q = sxp + 2 * syp;
-    const int ex = N.x - 1 + sxp, ey = N.y - 1 + syp;
-    N.valid[j] = N.active && ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny;
-    N.eoff[j] = ((N.lx + sxp) + C::ELX * (N.ly + syp)) * C::ES;
-    N.toff[j] = (q * 3 * 8 + N.ab) * C::TABE;
-    // ips next to the row node in the element BELOW the plane (row node = a top corner, bz = 1)
-    const int k = node_of_bits(!sxp, !syp, 1);
-    N.ipo[j][0] = ip_of(k, 0) * C::IPD;
-    N.ipo[j][1] = ip_of(k, 1) * C::IPD;
-    N.ipo[j][2] = ip_of(k, 2) * C::IPD;
-    int dx, dy;
-    block_offset(N.ab, N.H, j, dx, dy);
-    N.uoff[j] = ((N.lx + 1 + dx) + C::RNX * (N.ly + 1 + dy)) * C::NF + 4;
+  N.vmask = 0;
+  for (int q = 0; q < 4; ++q) {
+    const int ex = N.x - 1 + (q & 1), ey = N.y - 1 + (q >> 1);
+    if (ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny) N.vmask |= 1 << q;
   }
+  N.eoff = (N.lx + C::ELX * N.ly) * C::ES;
 }
 
-template <int CC>
+// CSR slots of the blocks this class flushes: byte q = quadrant (sx,sy) -> offset (a sx, b sy, dz)
+__host__ __device__ inline unsigned load_slots(const unsigned char *slots, int cls, int dz)
+{
+  const int a = cls & 1, b = (cls >> 1) & 1;
+  unsigned r = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int sxp = q & 1, syp = q >> 1;
+    unsigned v = 0xFF;
+    if (!((!a && sxp) || (!b && syp))) {
+      const int dx = a ? (sxp ? 1 : -1) : 0, dy = b ? (syp ? 1 : -1) : 0;
+      v = slots[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+    }
+    r |= v << (8 * q);
+  }
+  return r;
+}
+
 __host__ __device__ inline void p2_zero(P2State &S)
 {
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int q = 0; q < 4; ++q) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) S.acc[CC][j][t] = 0.0;
-    S.D[CC][j] = 0.0;
+    for (int t = 0; t < 9; ++t) S.acc[q][t] = 0.0;
+    S.D[q] = 0.0;
   }
 }
 __host__ __device__ inline void p2_begin(P2State &S)
 {
-  p2_zero<0>(S);
-  p2_zero<1>(S);
+  p2_zero(S);
   S.rr[0] = S.rr[1] = S.rr[2] = 0.0;
   S.dv = 0.0;
 }
 
-// one z-half (SZP = 0: elements below the node plane, 1: above): the thread's two quadrants, 3 ips each,
-// two column nodes (c = 0, 1) per ip.  The x-/y-edge ips next to the row node lie on the element's top
-// face below the plane (ip 4..7) and on its bottom face above it (ip 0..3): 4*IPD doubles earlier; the
-// z-edge ip is the same.
+// one z-half (SZP = 0: elements below the node plane, 1: above) of the 8 octants.
+// tabc = table + 2*cls; buf = that layer's ip data
 template <class C, int SZP>
 __host__ __device__ inline void p2_pass(const BoxParams &P, const NodeCtx &N, P2State &S, const double *buf,
-                                        const double *tab, bool divu)
+                                        const double *tabc, bool divu)
 {
   const int ez = N.z - 1 + SZP;
   if (ez < 0 || ez >= P.nz) return;
+  const double *ebase = buf + N.eoff;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    if (!N.valid[j]) continue; // no element in this quadrant (domain boundary / node outside the domain)
-    const double *eb = buf + N.eoff[j];
-    const double *tb = tab + N.toff[j] + SZP * (4 * 3 * 8 * C::TABE);
+  for (int q = 0; q < 4; ++q) {
+    const int sxp = q & 1, syp = q >> 1;
+    if (!(N.vmask & (1 << q))) continue; // no element in this quadrant (domain boundary)
+    const int s = q + 4 * SZP;
+    const int k = node_of_bits(!sxp, !syp, !SZP);
+    const double *eb = ebase + (sxp + C::ELX * syp) * C::ES;
 #pragma unroll
     for (int pp = 0; pp < 3; ++pp) {
-      const double *o = eb + N.ipo[j][pp] - ((SZP && pp < 2) ? 4 * C::IPD : 0);
-      const double G00 = o[0], G01 = o[1], G02 = o[2], G10 = o[3], G11 = o[4], G12 = o[5], G20 = o[6], G21 = o[7],
-                   G22 = o[8];
-      const double A0 = o[9], A1 = o[10], A2 = o[11], md = o[12];
+      const int ip = ip_of(k, pp);
+      const bool isL = hex8::scs_left(ip) == k;
+      const double *o = eb + ip * C::IPD;
+      const double *t0 = tabc + ((s * 3 + pp) * 2 + 0) * 16;
+      const double *t1 = tabc + ((s * 3 + pp) * 2 + 1) * 16;
+      const double d0 = t0[0], d1 = t0[1], d2 = t1[0], nadv = t1[1];
+      double h[3];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const double *t = tb + pp * (8 * C::TABE) + cc * (4 * C::TABE);
-        const double d0 = t[0], d1 = t[1], d2 = t[2], nadv = t[3];
-        // signed: +-(-mu dN_ic/dx)
-        const double h0 = G00 * d0 + G01 * d1 + G02 * d2;
-        const double h1 = G10 * d0 + G11 * d1 + G12 * d2;
-        const double h2 = G20 * d0 + G21 * d1 + G22 * d2;
-        S.D[cc][j] += h0 * A0 + h1 * A1 + h2 * A2 + nadv * md;
-        S.acc[cc][j][0] += h0 * A0; S.acc[cc][j][1] += h0 * A1; S.acc[cc][j][2] += h0 * A2;
-        S.acc[cc][j][3] += h1 * A0; S.acc[cc][j][4] += h1 * A1; S.acc[cc][j][5] += h1 * A2;
-        S.acc[cc][j][6] += h2 * A0; S.acc[cc][j][7] += h2 * A1; S.acc[cc][j][8] += h2 * A2;
+      for (int i = 0; i < 3; ++i) h[i] = o[i * 3 + 0] * d0 + o[i * 3 + 1] * d1 + o[i * 3 + 2] * d2;
+      const double A0 = o[9], A1 = o[10], A2 = o[11];
+      const double dsum = h[0] * A0 + h[1] * A1 + h[2] * A2 + nadv * o[12];
+      if (isL) {
+        S.D[q] += dsum;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          S.acc[q][i * 3 + 0] += h[i] * A0;
+          S.acc[q][i * 3 + 1] += h[i] * A1;
+          S.acc[q][i * 3 + 2] += h[i] * A2;
+        }
+      } else {
+        S.D[q] -= dsum;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          S.acc[q][i * 3 + 0] -= h[i] * A0;
+          S.acc[q][i * 3 + 1] -= h[i] * A1;
+          S.acc[q][i * 3 + 2] -= h[i] * A2;
+        }
       }
       if (divu) {
-        // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135).  Every (a,b) thread pair (H = 0, 1) meets
-        // each (element, ip) next to the node exactly once; (a,b) = (0,0),(1,0),(0,1) each carry one
-        // component of w A, the (1,1) threads' sums are dropped when the partials are combined
-        S.dv -= tb[pp * (8 * C::TABE) + 4] * o[13] * o[9 + (N.ab < 3 ? N.ab : 0)];
+        // rhs(L) -= divUstress, rhs(R) += divUstress (:127-135).  Every class meets each (element, ip)
+        // next to the node exactly once; classes 0,1,2 each carry one component of w A (the other
+        // classes' copies are dropped when the partials are combined)
+        const double Asel = o[9 + (N.cls < 3 ? N.cls : 0)];
+        if (isL) S.dv -= o[13] * Asel; else S.dv += o[13] * Asel;
       }
     }
   }
 }
 
-// Finish the blocks of class c = CC, in two steps with a warp barrier between them; every thread of the
-// warp calls both (`on` = takes part).  Step a: fold the two quadrant slots when they belong to one
-// block; the H = 1 thread of the centre-column classes (a = b = 0) parks its half of the shared block.
-template <class C, int CC>
-__host__ __device__ inline void p2_flush_a(const NodeCtx &N, P2State &S, bool on, double *parkbase)
+// fold the quadrant accumulators of the axes the class does not distinguish, then write the
+// finished blocks into the staging row (CSR layout) and take their share of rhs = -row . u.
+// `slots`: packed CSR slots of the 4 quadrant blocks; `uplane`: staged node plane of the column nodes
+template <class C>
+__host__ __device__ inline void p2_flush(const NodeCtx &N, P2State &S, unsigned slots, const double *uplane, double *stg)
 {
-  if (!on) return;
-  if (N.fold) {
+  const int a = N.cls & 1, b = (N.cls >> 1) & 1;
+  if (!a) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) S.acc[CC][0][t] += S.acc[CC][1][t];
-    S.D[CC][0] += S.D[CC][1];
+    for (int sy = 0; sy < 2; ++sy) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) S.acc[sy * 2][t] += S.acc[sy * 2 + 1][t];
+      S.D[sy * 2] += S.D[sy * 2 + 1];
+    }
   }
-  if (N.pair && N.H == 1) {
-    double *park = parkbase + (N.nl * 2 + CC) * 9;
+  if (!b) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int sx = 0; sx < 2; ++sx) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) park[i * 3 + j] = S.acc[CC][0][i * 3 + j] + (i == j ? S.D[CC][0] : 0.0);
+      for (int t = 0; t < 9; ++t) S.acc[sx][t] += S.acc[2 + sx][t];
+      S.D[sx] += S.D[2 + sx];
+    }
   }
-}
-// Step b: write the finished blocks into the staging row (CSR layout) and take their share of
-// rhs = -row . u.  `slots`: byte j = CSR slot of block j; `uplane` = staged plane of the column nodes.
-template <class C, int CC>
-__host__ __device__ inline void p2_flush_b(const NodeCtx &N, P2State &S, bool on, unsigned slots, const double *uplane,
-                                           double *stg, const double *parkbase)
-{
-  if (!on) return;
-  double *row = stg + N.nl * C::SROW;
-  const double *park = parkbase + (N.nl * 2 + CC) * 9;
+  double *row = stg + (N.lx + C::TBX * N.ly) * C::SROW;
   const int rs = N.nb * 3; // doubles per dof row
+  const double *uc = uplane + ((N.lx + 1) + C::RNX * (N.ly + 1)) * C::NF + 4;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const unsigned slot = (slots >> (8 * j)) & 0xFF;
-    if (slot == 0xFF) continue; // not a block this thread finishes, or no such neighbour node
-    const double *u = uplane + N.uoff[j];
+  for (int q = 0; q < 4; ++q) {
+    const int sxp = q & 1, syp = q >> 1;
+    const unsigned slot = (slots >> (8 * q)) & 0xFF;
+    if (slot == 0xFF) continue; // block not owned by this class, or no such neighbour node
+    const int dx = a ? (sxp ? 1 : -1) : 0, dy = b ? (syp ? 1 : -1) : 0;
+    const double *u = uc + (dx + C::RNX * dy) * C::NF;
     const double u0 = u[0], u1 = u[1], u2 = u[2];
     double *bp = row + slot * 3;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double v0 = S.acc[CC][j][i * 3 + 0], v1 = S.acc[CC][j][i * 3 + 1], v2 = S.acc[CC][j][i * 3 + 2];
-      if (i == 0) v0 += S.D[CC][j];
-      if (i == 1) v1 += S.D[CC][j];
-      if (i == 2) v2 += S.D[CC][j];
-      if (N.pair) {
-        v0 += park[i * 3 + 0];
-        v1 += park[i * 3 + 1];
-        v2 += park[i * 3 + 2];
-      }
+      double v0 = S.acc[q][i * 3 + 0], v1 = S.acc[q][i * 3 + 1], v2 = S.acc[q][i * 3 + 2];
+      if (i == 0) v0 += S.D[q];
+      if (i == 1) v1 += S.D[q];
+      if (i == 2) v2 += S.D[q];
       bp[i * rs + 0] = v0;
       bp[i * rs + 1] = v1;
       bp[i * rs + 2] = v2;

@@ -1,6 +1,5 @@
 // capi.cu -- the extern "C" boundary declared in include/nalu_b200.h.
 #include "internal.h"
-#include "box_tile.cuh"
 
 #include <atomic>
 #include <cstring>
@@ -77,7 +76,7 @@ static void free_graph_device(Graph &g)
     if (p) cudaFree(p);
     p = nullptr;
   };
-  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_slotpack);
+  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27);
   F(g.d_rowptr_owned); F(g.d_rowptr_shared); F(g.d_colidx_owned); F(g.d_colidx_shared); F(g.d_err);
   for (auto *peers : {&g.send_peers, &g.recv_peers})
     for (HaloPeer &p : *peers) {
@@ -95,16 +94,6 @@ static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const s
   if ((rc = upload(&g.d_bcol, g.bcol))) return rc;
   if ((rc = upload(&g.d_elem_slot, elem_slot))) return rc;
   if ((rc = upload(&g.d_node_slot27, node_slot27))) return rc;
-  if (!node_slot27.empty()) {
-    // per-thread packed slots of the tiled kernel (box_tile.cuh: slot_pack)
-    std::vector<uint32_t> pack(size_t(g.n_nodes) * 16);
-#pragma omp parallel for schedule(static)
-    for (int64_t n = 0; n < g.n_nodes; ++n)
-      for (int sub = 0; sub < 8; ++sub)
-        for (int w = 0; w < 2; ++w)
-          pack[size_t(n) * 16 + sub * 2 + w] = box::slot_pack(&node_slot27[size_t(n) * 27], sub, w);
-    if ((rc = upload(&g.d_node_slotpack, pack))) return rc;
-  }
   NALU_CUDA(cudaMalloc((void **)&g.d_err, sizeof(int)));
   NALU_CUDA(cudaMemset(g.d_err, 0, sizeof(int)));
   const int nown = g.n_owned_nodes, nrow = g.n_row_nodes(), ndof = g.ndof;

@@ -77,7 +77,6 @@ struct Graph {
   int32_t *d_bcol = nullptr;
   uint8_t *d_elem_slot = nullptr;  // [n_elems][8][8]
   uint8_t *d_node_slot27 = nullptr; // box only: [n_nodes][27] slot of lattice neighbour (dz,dy,dx)
-  uint32_t *d_node_slotpack = nullptr; // box only: [n_nodes][8][2] packed slots per thread of the tiled kernel
   uint64_t *d_rowptr_owned = nullptr, *d_rowptr_shared = nullptr;
   int32_t *d_colidx_owned = nullptr, *d_colidx_shared = nullptr;
   int32_t *d_err = nullptr; // device error flag (negative Jacobians)

@@ -92,7 +92,7 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
   std::vector<box::NodeCtx> N(NT);
   std::vector<int> ncov(NT), row_n(NT);
   std::vector<long long> b0_n(NT), b1_n(NT);
-  std::vector<unsigned> slots_n0(NT), slots_n1(NT);
+  std::vector<unsigned> sm_n(NT), sf_n(NT);
   struct Regs { double p[C::NPL]; double m[C::NML]; };
   std::vector<Regs> R(NT);
   const bool divu = P.include_divu != 0.0;
@@ -100,7 +100,6 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
   for (int cta = 0; cta < P.tiles_x * P.tiles_y * zchunks; ++cta) {
     for (auto &v : sm) v = NAN; // uninitialised shared memory must never be consumed
     double *tab = sm.data() + C::OFF_TAB, *ring = sm.data() + C::OFF_RING, *mdb = sm.data() + C::OFF_MD;
-    double *park = sm.data() + C::OFF_PARK;
     long long *s_rb = reinterpret_cast<long long *>(sm.data() + C::OFF_RB);
     int *s_len = reinterpret_cast<int *>(sm.data() + C::OFF_LEN);
     const int ntile = P.tiles_x * P.tiles_y;
@@ -134,8 +133,8 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
         const long long b0 = P.browptr[n.row];
         n.nb = (int)(P.browptr[n.row + 1] - b0);
         n.rowbase = 9 * b0;
-        n.slots_mid = box::slot_pack(P.slot27 + n.n * 27, tid % C::TPN, 0);
-        n.slots_fin = box::slot_pack(P.slot27 + n.n * 27, tid % C::TPN, 1);
+        n.slots_mid = box::load_slots(P.slot27 + n.n * 27, n.cls, -1);
+        n.slots_fin = box::load_slots(P.slot27 + n.n * 27, n.cls, (n.cls & 4) ? 1 : 0);
       }
     }
     for (int z = zs; z < ze; ++z) {
@@ -143,13 +142,7 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
       for (int tid = 0; tid < NT; ++tid) {
         box::plane_load<C>(P, tid, x0, y0, z + 2, R[tid].p);
         box::mdot_load<C>(P, tid, x0, y0, z + 1, R[tid].m);
-        row_n[tid] = 0;
-        slots_n0[tid] = slots_n1[tid] = 0xFFFFFFFFu;
-        if (N[tid].active && more) {
-          row_n[tid] = P.node_row[N[tid].n + plane_nodes];
-          slots_n0[tid] = box::slot_pack(P.slot27 + (N[tid].n + plane_nodes) * 27, tid % C::TPN, 0);
-          slots_n1[tid] = box::slot_pack(P.slot27 + (N[tid].n + plane_nodes) * 27, tid % C::TPN, 1);
-        }
+        row_n[tid] = (N[tid].active && more) ? P.node_row[N[tid].n + plane_nodes] : 0;
       }
       const double *pl_m = ring + ((z + 2) % 3) * PLN, *pl_0 = ring + (z % 3) * PLN, *pl_p = ring + ((z + 1) % 3) * PLN;
       if (z < P.nz)
@@ -161,20 +154,25 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
       for (int tid = 0; tid < NT; ++tid) {
         box::mdot_store<C>(tid, R[tid].m, mdb);
         box::NodeCtx &n = N[tid];
-        if (tid % C::TPN == 0) {
-          s_rb[n.nl] = n.rowbase;
-          s_len[n.nl] = n.active ? n.nb * 9 : 0;
+        const int nl = tid >> 3;
+        if (n.cls == 0) {
+          s_rb[nl] = n.rowbase;
+          s_len[nl] = n.active ? n.nb * 9 : 0;
         }
         b0_n[tid] = b1_n[tid] = 0;
+        sm_n[tid] = sf_n[tid] = 0xFFFFFFFFu;
         if (n.active && more) {
           b0_n[tid] = P.browptr[row_n[tid]];
           b1_n[tid] = P.browptr[row_n[tid] + 1];
+          const unsigned char *sl = P.slot27 + (n.n + plane_nodes) * 27;
+          sm_n[tid] = box::load_slots(sl, n.cls, -1);
+          sf_n[tid] = box::load_slots(sl, n.cls, (n.cls & 4) ? 1 : 0);
         }
         box::p2_begin(S[tid]);
         n.z = z;
         if (n.active) {
           ncov[tid] = ((n.x > 0) + 1 + (n.x < P.NX - 1)) * ((n.y > 0) + 1 + (n.y < P.NY - 1)) * ((z > 0) + 1 + (z < P.NZ - 1));
-          box::p2_pass<C, 0>(P, n, S[tid], lower, tab, divu);
+          box::p2_pass<C, 0>(P, n, S[tid], lower, tab + 2 * n.cls, divu);
         }
       }
       // ---- barrier S2: the lower layer's buffer becomes the staging area
@@ -182,33 +180,27 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
       for (int tid = 0; tid < NT; ++tid) {
         box::NodeCtx &n = N[tid];
         if (n.active && n.nb != ncov[tid]) {
-          double *row = stg + n.nl * C::SROW;
-          for (int q = tid % C::TPN; q < n.nb * 9; q += C::TPN) row[q] = 0.0;
+          double *row = stg + (tid >> 3) * C::SROW;
+          for (int q = n.cls; q < n.nb * 9; q += 8) row[q] = 0.0;
         }
       }
-      // mid flush: step a for every thread, warp barrier, step b
-      for (int tid = 0; tid < NT; ++tid) box::p2_flush_a<C, 1>(N[tid], S[tid], N[tid].active, park);
       for (int tid = 0; tid < NT; ++tid) {
-        box::p2_flush_b<C, 1>(N[tid], S[tid], N[tid].active, N[tid].slots_mid, pl_m, stg, park);
-        box::p2_zero<1>(S[tid]);
-      }
-      for (int q = 0; q < C::PARK; ++q) park[q] = NAN;
-      for (int tid = 0; tid < NT; ++tid)
-        if (N[tid].active) box::p2_pass<C, 1>(P, N[tid], S[tid], upper, tab, divu);
-      for (int tid = 0; tid < NT; ++tid) {
-        box::p2_flush_a<C, 0>(N[tid], S[tid], N[tid].active, park);
-        box::p2_flush_a<C, 1>(N[tid], S[tid], N[tid].active, park);
-      }
-      for (int tid = 0; tid < NT; ++tid) {
-        box::p2_flush_b<C, 0>(N[tid], S[tid], N[tid].active, N[tid].slots_fin, pl_0, stg, park);
-        box::p2_flush_b<C, 1>(N[tid], S[tid], N[tid].active, N[tid].slots_fin >> 16, pl_p, stg, park);
+        box::NodeCtx &n = N[tid];
+        if (!n.active) continue;
+        const int dz_fin = (n.cls & 4) ? 1 : 0;
+        if (n.cls & 4) {
+          box::p2_flush<C>(n, S[tid], n.slots_mid, pl_m, stg);
+          box::p2_zero(S[tid]);
+        }
+        box::p2_pass<C, 1>(P, n, S[tid], upper, tab + 2 * n.cls, divu);
+        box::p2_flush<C>(n, S[tid], n.slots_fin, dz_fin ? pl_p : pl_0, stg);
       }
       for (int nl = 0; nl < C::NNODE; ++nl) {
-        const box::NodeCtx &n = N[nl * C::TPN];
+        const box::NodeCtx &n = N[nl * 8];
         if (!n.active) continue;
         for (int i = 0; i < 3; ++i) {
           double v = 0;
-          for (int c = 0; c < C::TPN; ++c) v += S[nl * C::TPN + c].rr[i] + ((c & 3) == i ? S[nl * C::TPN + c].dv : 0.0);
+          for (int c = 0; c < 8; ++c) v += S[nl * 8 + c].rr[i] + (c == i ? S[nl * 8 + c].dv : 0.0);
           double *r = P.rhs + (long long)n.row * 3 + i;
           *r = P.overwrite ? v : *r + v;
         }
@@ -228,8 +220,8 @@ static void emulate(const BoxParams &P0, int z_chunk, double *values, double *rh
         n.row = row_n[tid];
         n.nb = (int)(b1_n[tid] - b0_n[tid]);
         n.rowbase = 9 * b0_n[tid];
-        n.slots_mid = slots_n0[tid];
-        n.slots_fin = slots_n1[tid];
+        n.slots_mid = sm_n[tid];
+        n.slots_fin = sf_n[tid];
       }
     }
   }
