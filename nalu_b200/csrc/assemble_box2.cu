@@ -1,0 +1,226 @@
+// assemble_box2.cu -- launch side of the column-pair tiled assembly (see box2_tile.cuh).
+//
+// Grid: one CTA (256 threads = 8 class warps x 32 nodes) per (8x4 node tile, z chunk), two CTAs per SM.
+// Per node plane z a CTA runs
+//   A  lower octants (face ips TF(z-1), z-edge ips ZE(z-1)): dz=-1 group -> S1, dz=0 partial -> S0
+//   B  bulk copy of S1 to HBM  ||  phase 1a: BF(z), ZE(z)
+//   C  upper octants: dz=0 completed in S0, dz=+1 group -> S1, rhs partials
+//   D  bulk copy of S0, S1, rhs  ||  phase 1b: TF(z)  ||  metadata / field prefetch of the next plane
+// with one CTA barrier between consecutive phases.
+#include "box2_tile.cuh"
+#include "internal.h"
+
+#include <cstdint>
+#include <cstdlib>
+
+namespace nalu_b200 {
+
+using box::BoxParams;
+using C = box2::Cfg;
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(double *dst, const double *src, int bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"((unsigned)__cvta_generic_to_shared(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_add(double *dst, const double *src, int bytes)
+{
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst),
+               "r"((unsigned)__cvta_generic_to_shared(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// dof row i of dz group g of one node: staging -> values.  The staging offset carries the parity of
+// the destination, so the 16-byte aligned middle goes out as one bulk copy and at most one double
+// at either end as a plain store.
+template <bool BULK>
+__device__ __forceinline__ void copy_run(const box2::Meta &M, int node, int i, int g, const double *S, double *values,
+                                         int overwrite)
+{
+  const box2::Run r = box2::run_of(M, node, i, g);
+  if (r.L == 0) return;
+  const double *src = S + r.soff;
+  double *dst = values + r.G;
+  if (BULK) {
+    int L = r.L;
+    if (r.G & 1) {
+      *dst = overwrite ? *src : *dst + *src;
+      ++dst; ++src; --L;
+    }
+    if (L & 1) {
+      --L;
+      dst[L] = overwrite ? src[L] : dst[L] + src[L];
+    }
+    if (L) {
+      if (overwrite) bulk_store(dst, src, L * 8);
+      else bulk_add(dst, src, L * 8);
+    }
+  } else {
+    for (int k = 0; k < r.L; ++k) dst[k] = overwrite ? src[k] : dst[k] + src[k];
+  }
+}
+
+// phase 1 over one item list.  kind 0: prologue (top face + z edges of the layer below the first
+// plane), 1: phase 1a (bottom face + z edges), 2: phase 1b (top face).  One out-of-line body for
+// the three call sites keeps the kernel inside the instruction cache.
+__device__ __noinline__ void p1_phase(const BoxParams &P, int kind, int x0, int y0, const double *pl0, const double *pl1,
+                                      const double *mdb, double *F, double *ZE)
+{
+  const int n = kind == 2 ? C::NP1B : C::NP1A;
+  for (int it = threadIdx.x; it < n; it += C::NT) {
+    const int k = it / C::NEL, el = it - k * C::NEL;
+    const int g = k < 2 ? k : 2;
+    const int side = k < 2 ? (kind == 1 ? 0 : 1) : k - 2;
+    box2::p1_item(P, el, g, side, x0, y0, pl0, pl1, mdb, F, ZE);
+  }
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_constant__ BoxParams P)
+{
+  extern __shared__ __align__(16) double sm[];
+  double *const F = sm + C::OFF_F, *const ZE = sm + C::OFF_ZE, *const S0 = sm + C::OFF_S0, *const S1 = sm + C::OFF_S1;
+  double *const ring = sm + C::OFF_RING, *const mdb = sm + C::OFF_MD, *const rp = sm + C::OFF_RP;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntile = P.tiles_x * P.tiles_y;
+  const int tile = blockIdx.x % ntile, zc = blockIdx.x / ntile;
+  const int x0 = (tile % P.tiles_x) * C::TBX, y0 = (tile / P.tiles_x) * C::TBY;
+  const int zs = zc * P.z_chunk;
+  const int ze = (zs + P.z_chunk < P.NZ) ? zs + P.z_chunk : P.NZ;
+
+  box2::T2 N;
+  box2::t2_init(P, N, lane, x0, y0);
+  box2::ClsK Q;
+  double f23;
+  {
+    box2::P2K K;
+    box2::p2k_init(K, P.options, P.include_divu);
+    box2::cls_init(Q, K, warp);
+    f23 = K.f23;
+  }
+
+  box2::StageIdx SI;
+  box2::stage_init(P, SI, tid, x0, y0);
+  double regP[C::NPL], regM[C::NML];
+  // ---- prologue: node planes zs-1, zs; the face/z-edge ips of the layer below the first plane
+#pragma unroll 1
+  for (int pl = zs - 1; pl <= zs; ++pl) {
+    box2::plane_fetch(P, SI, pl, regP);
+    box::plane_store<C>(tid, regP, ring + ((pl + 3) % 3) * C::PLN);
+  }
+  box2::mdot_fetch(P, SI, zs - 1, regM);
+  box::mdot_store<C>(tid, regM, mdb);
+  if (warp < 3) box2::meta_load(P, box2::meta_at(sm, zs & 1), lane, warp, x0, y0, zs);
+  __syncthreads();
+  if (zs >= 1) p1_phase(P, 0, x0, y0, ring + ((zs - 1) % 3) * C::PLN, ring + (zs % 3) * C::PLN, mdb, F, ZE);
+  box2::plane_fetch(P, SI, zs + 1, regP);
+  box2::mdot_fetch(P, SI, zs, regM);
+  __syncthreads();
+
+  // One iteration = one z half of a plane (H = 0: elements below, H = 1: above) followed by the
+  // work that overlaps it; every piece of code appears once (instruction-cache footprint).
+  for (int hs = 2 * zs; hs < 2 * ze; ++hs) {
+    const int z = hs >> 1, H = hs & 1;
+    const box2::Meta M = box2::meta_at(sm, z & 1);
+    const bool lower = z >= 1, upper = z < P.nz;
+    // ---- A (H = 0) / C (H = 1)
+    if (!H) {
+      box::plane_store<C>(tid, regP, ring + ((z + 1) % 3) * C::PLN);
+      box::mdot_store<C>(tid, regM, mdb);
+      N.rr[0] = N.rr[1] = N.rr[2] = 0.0;
+    }
+    if (H ? upper : lower) box2::p2_half(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, lower);
+    if (H) {
+      rp[(warp * C::NNODE + lane) * 3 + 0] = N.rr[0];
+      rp[(warp * C::NNODE + lane) * 3 + 1] = N.rr[1];
+      rp[(warp * C::NNODE + lane) * 3 + 2] = N.rr[2];
+    }
+    if (BULK) fence_async_smem();
+    __syncthreads();
+    // ---- B (H = 0): dz=-1 group out, phase 1a / D (H = 1): dz=0,+1 groups and rhs out, phase 1b,
+    //      metadata and field prefetch of the next plane
+    if (H) {
+      box2::plane_fetch(P, SI, z + 2, regP);
+      box2::mdot_fetch(P, SI, z + 1, regM);
+    }
+    {
+      // warps 0-2: dof rows of the first group of this half, warps 3-5: of the second (H = 1 only)
+      const int wi = warp < 3 ? warp : warp - 3;
+      const int g = H ? (warp < 3 ? 1 : 2) : 0;
+      const bool doit = warp < (H ? 6 : 3) && (g == 0 ? lower : (g == 2 ? upper : true));
+      if (doit) {
+        copy_run<BULK>(M, lane, wi, g, g == 1 ? S0 : S1, P.values, P.overwrite);
+        if (BULK) bulk_commit();
+        if (g == 1 && P.overwrite) box2::zero_uncovered(M, lane, wi, P.values);
+      }
+    }
+    if (H && tid >= C::NT - 3 * C::NNODE) {
+      // rhs: sum the class partials; thread -> (node, dof) so that an x line of nodes is one run
+      const int t = tid - (C::NT - 3 * C::NNODE);
+      const int node = t / 3, i = t - node * 3;
+      if (M.cnt[node * 4 + 1]) {
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < C::NCLS; ++c) v += rp[(c * C::NNODE + node) * 3 + i];
+        double *r = P.rhs + (long long)M.row[node] * 3 + i;
+        *r = P.overwrite ? v : *r + v;
+      }
+    }
+    if (upper) p1_phase(P, H ? 2 : 1, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, F, ZE);
+    if (H && z + 1 < ze && warp >= 3 && warp < 6)
+      box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), lane, warp - 3, x0, y0, z + 1);
+    if (BULK) bulk_wait_read();
+    __syncthreads();
+  }
+}
+
+template <bool BULK>
+static int launch2(BoxParams &P, cudaStream_t stream)
+{
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  P.tiles_x = (P.NX + C::TBX - 1) / C::TBX;
+  P.tiles_y = (P.NY + C::TBY - 1) / C::TBY;
+  const long long ntile = (long long)P.tiles_x * P.tiles_y;
+  // z chunks: enough CTAs for ~12 waves of 2 CTAs per SM, but at least 16 planes per chunk (each chunk
+  // recomputes one element layer in its prologue)
+  long long want = ((long long)sms * 2 * 12 + ntile - 1) / ntile;
+  int zchunks = (int)(want < 1 ? 1 : want);
+  int zc = (P.NZ + zchunks - 1) / zchunks;
+  if (zc < 16) zc = 16;
+  if (const char *e = getenv("NALU_BOX_ZCHUNK")) {
+    const int v = atoi(e);
+    if (v > 0) zc = v;
+  }
+  if (zc > P.NZ) zc = P.NZ;
+  P.z_chunk = zc;
+  zchunks = (P.NZ + zc - 1) / zc;
+  const size_t smem = sizeof(double) * C::SMEM_DOUBLES;
+  NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<BULK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  const long long ctas = ntile * zchunks;
+  if (ctas > 0x7fffffffLL) {
+    set_error("assemble_box2: grid too large");
+    return NALU_B200_ERR_ARG;
+  }
+  assemble_box2_kernel<BULK><<<(unsigned)ctas, C::NT, smem, stream>>>(P);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+int launch_assemble_box2(BoxParams &P, cudaStream_t stream)
+{
+  // the bulk copies need 16-byte aligned destinations: staging parity is matched to the offset in
+  // `values`, so the base pointer itself must be aligned (cudaMalloc gives 256 bytes)
+  bool bulk = ((uintptr_t)P.values & 15) == 0;
+  if (const char *e = getenv("NALU_BOX_BULK")) bulk = bulk && atoi(e) != 0;
+  return bulk ? launch2<true>(P, stream) : launch2<false>(P, stream);
+}
+
+} // namespace nalu_b200

@@ -35,6 +35,9 @@ int launch_mdot(const Graph &g, const double *coords, const double *density, con
 bool box_supported(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk);
 int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
                         double *d_rhs, int overwrite, cudaStream_t stream);
+// assemble_box2.cu
+namespace box { struct BoxParams; }
+int launch_assemble_box2(box::BoxParams &P, cudaStream_t stream);
 // halo.cu
 int launch_halo_pack(const Graph &g, const HaloPeer &p, const double *d_values, const double *d_rhs,
                      double *d_buf, cudaStream_t stream);

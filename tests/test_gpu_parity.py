@@ -378,12 +378,16 @@ def test_missing_device_pointer_is_an_error():
 
 
 # ---------------------------------------------------------------------------------------------
-# tiled write-once kernel (assemble_box.cu): tile shapes, z chunking, overwrite semantics, determinism
+# tiled write-once kernels (assemble_box2.cu, assemble_box.cu): tile shapes, z chunking, overwrite semantics, determinism
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tile", ["64", "84", "86"])
+@pytest.mark.parametrize("tile", ["0", "0-plain-copy", "64", "84", "86"])
 @pytest.mark.parametrize("zchunk", ["1", "3", "0"])
 def test_box_kernel_tiles_and_chunks(tile, zchunk, monkeypatch):
-    monkeypatch.setenv("NALU_BOX_TILE", tile)
+    # "0": the column-pair kernel (assemble_box2.cu, default) with cp.async.bulk row streaming,
+    # "0-plain-copy": the same with plain stores; "64"/"84"/"86": first-generation class kernel
+    monkeypatch.setenv("NALU_BOX_TILE", tile.split("-")[0])
+    if tile == "0-plain-copy":
+        monkeypatch.setenv("NALU_BOX_BULK", "0")
     if zchunk != "0":
         monkeypatch.setenv("NALU_BOX_ZCHUNK", zchunk)
     m = perturbed_box(13, 9, 7)
