@@ -242,6 +242,7 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   P.include_divu = k[0].include_divu;
   P.options = k[0].options;
   P.overwrite = overwrite;
+  P.trace = nullptr;
   int tile = 0;
   if (const char *e = getenv("NALU_BOX_TILE")) tile = atoi(e);
   // default: the column-pair kernel (assemble_box2.cu); NALU_BOX_TILE selects the first-generation

@@ -11,6 +11,7 @@
 #include "internal.h"
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 namespace nalu_b200 {
@@ -64,11 +65,40 @@ __device__ __forceinline__ void copy_run(const box2::Meta &M, int node, int i, i
   }
 }
 
+// Cooperative variant: one warp per run, lane k moves double k (27 lanes busy, one 216-byte run per
+// instruction pair).  Runs [r0, r0 + n) of the phase's run list; run r -> group g0 + r / 96, dof row
+// (r % 96) / 32, node r % 32.
+__device__ __forceinline__ void copy_runs_warp(const box2::Meta &M, int warp, int lane, int nk, int g0, const double *S0,
+                                               const double *S1, double *values, int overwrite)
+{
+  // warp w takes runs w, w + 8, ...; batches of four: all descriptors, then all staging loads, then
+  // all stores, so that the descriptor -> data -> store chains of the four runs overlap
+  for (int k0 = 0; k0 < nk; k0 += 4) {
+    box2::Run run[4];
+    const double *src[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = warp + C::NCLS * (k0 + u);
+      const int g = g0 + r / 96, rr = r % 96;
+      run[u] = box2::run_of(M, rr & 31, rr >> 5, g);
+      src[u] = (g == 1 ? S0 : S1) + run[u].soff;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = lane < run[u].L ? src[u][lane] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (lane < run[u].L) {
+        double *dst = values + run[u].G + lane;
+        *dst = overwrite ? v[u] : *dst + v[u];
+      }
+  }
+}
+
 // phase 1 over one item list.  kind 0: prologue (top face + z edges of the layer below the first
-// plane), 1: phase 1a (bottom face + z edges), 2: phase 1b (top face).  One out-of-line body for
-// the three call sites keeps the kernel inside the instruction cache.
-__device__ __noinline__ void p1_phase(const BoxParams &P, int kind, int x0, int y0, const double *pl0, const double *pl1,
-                                      const double *mdb, double *F, double *ZE)
+// plane), 1: phase 1a (bottom face + z edges), 2: phase 1b (top face).
+__device__ __forceinline__ void p1_phase(const BoxParams &P, int kind, int x0, int y0, const double *pl0, const double *pl1,
+                                         const double *mdb, double *F, double *ZE)
 {
   const int n = kind == 2 ? C::NP1B : C::NP1A;
   for (int it = threadIdx.x; it < n; it += C::NT) {
@@ -78,6 +108,21 @@ __device__ __noinline__ void p1_phase(const BoxParams &P, int kind, int x0, int 
     box2::p1_item(P, el, g, side, x0, y0, pl0, pl1, mdb, F, ZE);
   }
 }
+// out-of-line copy for the prologue (runs once per CTA; keeps the second copy of phase 1 out of the loop's
+// register allocation)
+__device__ __noinline__ void p1_prologue(const BoxParams &P, int x0, int y0, const double *pl0, const double *pl1,
+                                         const double *mdb, double *F, double *ZE)
+{
+  p1_phase(P, 0, x0, y0, pl0, pl1, mdb, F, ZE);
+}
+
+// profiling aid: warp w of CTA `TRACE_CTA` stamps the clock at phase boundaries
+#define TRACE_CTA 1500
+#define TRACE(slot)                                                                                   \
+  do {                                                                                                \
+    if (P.trace && blockIdx.x == TRACE_CTA && lane == 0 && hs < 2 * zs + 16)                           \
+      P.trace[((hs - 2 * zs) * 8 + warp) * 8 + (slot)] = clock64();                                    \
+  } while (0)
 
 template <bool BULK>
 __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_constant__ BoxParams P)
@@ -94,15 +139,20 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
 
   box2::T2 N;
   box2::t2_init(P, N, lane, x0, y0);
-  box2::ClsK Q;
-  double f23;
-  {
+  // class constants live in shared memory (12 doubles per class warp) and are fetched at the head of
+  // every phase 2 pass, so that they do not occupy registers during phase 1
+  double *const qk = sm + C::OFF_QK + warp * 12;
+  if (lane == 0) {
     box2::P2K K;
+    box2::ClsK Q;
     box2::p2k_init(K, P.options, P.include_divu);
     box2::cls_init(Q, K, warp);
-    f23 = K.f23;
+    box2::cls_store(Q, qk);
   }
+  const double f23 = 2.0 / 3.0 * P.include_divu;
 
+  // records of elements outside the domain are never written: they must read zero (phase 2 does not test)
+  for (int i = tid; i < 2 * C::NEL * C::ES; i += C::NT) sm[C::OFF_F + i] = 0.0;
   box2::StageIdx SI;
   box2::stage_init(P, SI, tid, x0, y0);
   double regP[C::NPL], regM[C::NML];
@@ -116,7 +166,7 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
   box::mdot_store<C>(tid, regM, mdb);
   if (warp < 3) box2::meta_load(P, box2::meta_at(sm, zs & 1), lane, warp, x0, y0, zs);
   __syncthreads();
-  if (zs >= 1) p1_phase(P, 0, x0, y0, ring + ((zs - 1) % 3) * C::PLN, ring + (zs % 3) * C::PLN, mdb, F, ZE);
+  if (zs >= 1) p1_prologue(P, x0, y0, ring + ((zs - 1) % 3) * C::PLN, ring + (zs % 3) * C::PLN, mdb, F, ZE);
   box2::plane_fetch(P, SI, zs + 1, regP);
   box2::mdot_fetch(P, SI, zs, regM);
   __syncthreads();
@@ -128,36 +178,49 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
     const box2::Meta M = box2::meta_at(sm, z & 1);
     const bool lower = z >= 1, upper = z < P.nz;
     // ---- A (H = 0) / C (H = 1)
+    TRACE(0);
     if (!H) {
       box::plane_store<C>(tid, regP, ring + ((z + 1) % 3) * C::PLN);
       box::mdot_store<C>(tid, regM, mdb);
       N.rr[0] = N.rr[1] = N.rr[2] = 0.0;
     }
-    if (H ? upper : lower) box2::p2_half(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, lower);
+    if (H ? upper : lower) {
+      box2::ClsK Q;
+      box2::cls_fetch(Q, qk, warp);
+      box2::p2_half(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, lower);
+    }
     if (H) {
       rp[(warp * C::NNODE + lane) * 3 + 0] = N.rr[0];
       rp[(warp * C::NNODE + lane) * 3 + 1] = N.rr[1];
       rp[(warp * C::NNODE + lane) * 3 + 2] = N.rr[2];
     }
     if (BULK) fence_async_smem();
+    TRACE(1);
     __syncthreads();
+    TRACE(2);
     // ---- B (H = 0): dz=-1 group out, phase 1a / D (H = 1): dz=0,+1 groups and rhs out, phase 1b,
     //      metadata and field prefetch of the next plane
     if (H) {
       box2::plane_fetch(P, SI, z + 2, regP);
       box2::mdot_fetch(P, SI, z + 1, regM);
     }
-    {
-      // warps 0-2: dof rows of the first group of this half, warps 3-5: of the second (H = 1 only)
-      const int wi = warp < 3 ? warp : warp - 3;
-      const int g = H ? (warp < 3 ? 1 : 2) : 0;
-      const bool doit = warp < (H ? 6 : 3) && (g == 0 ? lower : (g == 2 ? upper : true));
+    if (BULK) {
+      // the run list of this half (H = 0: 96 runs of the dz=-1 group; H = 1: 96 of dz=0, then 96 of
+      // dz=+1) spread over all 8 warps: the per-lane bulk issue serialises inside a warp
+      const int per = H ? 24 : 12;
+      const int r = warp * per + lane;
+      const int g = H ? 1 + r / 96 : 0, rr = r % 96;
+      const bool doit = lane < per && (g == 0 ? lower : (g == 2 ? upper : true));
       if (doit) {
-        copy_run<BULK>(M, lane, wi, g, g == 1 ? S0 : S1, P.values, P.overwrite);
-        if (BULK) bulk_commit();
-        if (g == 1 && P.overwrite) box2::zero_uncovered(M, lane, wi, P.values);
+        copy_run<BULK>(M, rr & 31, rr >> 5, g, g == 1 ? S0 : S1, P.values, P.overwrite);
+        bulk_commit();
       }
+    } else {
+      // run list of this half: H = 0: the 96 runs of the dz=-1 group; H = 1: 96 runs of dz=0, then 96 of dz=+1
+      const int nrun = H ? (upper ? 192 : 96) : (lower ? 96 : 0);
+      copy_runs_warp(M, warp, lane, nrun / C::NCLS, H ? 1 : 0, S0, S1, P.values, P.overwrite);
     }
+    if (H && warp < 3 && P.overwrite) box2::zero_uncovered(M, lane, warp, P.values);
     if (H && tid >= C::NT - 3 * C::NNODE) {
       // rhs: sum the class partials; thread -> (node, dof) so that an x line of nodes is one run
       const int t = tid - (C::NT - 3 * C::NNODE);
@@ -170,11 +233,15 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
         *r = P.overwrite ? v : *r + v;
       }
     }
+    TRACE(3);
     if (upper) p1_phase(P, H ? 2 : 1, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, F, ZE);
-    if (H && z + 1 < ze && warp >= 3 && warp < 6)
-      box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), lane, warp - 3, x0, y0, z + 1);
+    // metadata of the next plane: warps 5-7 have little phase 1a work
+    if (!H && z + 1 < ze && warp >= 5) box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), lane, warp - 5, x0, y0, z + 1);
+    TRACE(4);
     if (BULK) bulk_wait_read();
+    TRACE(5);
     __syncthreads();
+    TRACE(6);
   }
 }
 
@@ -208,9 +275,28 @@ static int launch2(BoxParams &P, cudaStream_t stream)
     set_error("assemble_box2: grid too large");
     return NALU_B200_ERR_ARG;
   }
+  static long long *d_trace = nullptr;
+  const bool trace = getenv("NALU_BOX_TRACE") != nullptr;
+  if (trace && !d_trace) NALU_CUDA(cudaMalloc(&d_trace, 16 * 8 * 8 * sizeof(long long)));
+  P.trace = trace ? d_trace : nullptr;
+  if (trace) NALU_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 8 * 8 * sizeof(long long), stream));
   assemble_box2_kernel<BULK><<<(unsigned)ctas, C::NT, smem, stream>>>(P);
   count_launch();
   NALU_CUDA(cudaGetLastError());
+  if (trace) {
+    static long long h[16 * 8 * 8];
+    NALU_CUDA(cudaStreamSynchronize(stream));
+    NALU_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+    if (FILE *f = fopen(getenv("NALU_BOX_TRACE"), "w")) {
+      for (int hs = 0; hs < 16; ++hs)
+        for (int w = 0; w < 8; ++w) {
+          fprintf(f, "%d %d", hs, w);
+          for (int k = 0; k < 7; ++k) fprintf(f, " %lld", h[(hs * 8 + w) * 8 + k] ? h[(hs * 8 + w) * 8 + k] - h[0] : -1LL);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
   return NALU_B200_OK;
 }
 

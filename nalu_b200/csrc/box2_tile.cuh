@@ -58,7 +58,8 @@ struct Cfg {
   static constexpr int META_RB = 0, META_NB = NNODE, META_ROW = META_NB + NNODE / 2, META_SLOT = META_ROW + NNODE / 2,
                        META_GP = META_SLOT + NNODE * 28 / 8, META_CNT = META_GP + NNODE * 8 / 8,
                        META = META_CNT + NNODE * 4 / 8;
-  static constexpr int SMEM_DOUBLES = OFF_META + 2 * META;
+  static constexpr int OFF_QK = OFF_META + 2 * META;  // class constants: [NCLS][12]
+  static constexpr int SMEM_DOUBLES = OFF_QK + NCLS * 12;
 };
 
 struct Meta {
@@ -284,6 +285,30 @@ __host__ __device__ inline void cls_init(ClsK &Q, const P2K &K, int cls)
   }
 }
 
+__host__ __device__ inline void cls_store(const ClsK &Q, double *qk)
+{
+#pragma unroll
+  for (int pp = 0; pp < 3; ++pp) {
+    qk[pp] = Q.c0[pp];
+    qk[3 + pp] = Q.c1[pp];
+    qk[6 + pp] = Q.c2[pp];
+    qk[9 + pp] = Q.cn[pp];
+  }
+}
+__host__ __device__ inline void cls_fetch(ClsK &Q, const double *qk, int cls)
+{
+  Q.a = cls & 1;
+  Q.b = (cls >> 1) & 1;
+  Q.c = (cls >> 2) & 1;
+#pragma unroll
+  for (int pp = 0; pp < 3; ++pp) {
+    Q.c0[pp] = qk[pp];
+    Q.c1[pp] = qk[3 + pp];
+    Q.c2[pp] = qk[6 + pp];
+    Q.cn[pp] = qk[9 + pp];
+  }
+}
+
 // one integration point: acc += (tau h) (x) A, dm += tau N mdot
 __host__ __device__ __forceinline__ void p2_ip(const double *rec, double c0, double c1, double c2, double cn,
                                                double (&acc)[9], double &dm)
@@ -370,45 +395,63 @@ __host__ __device__ __forceinline__ void p2_flush(T2 &N, const Meta &M, const Cl
   }
 }
 
-// one z half (H = 0 below / 1 above the plane) of the node's octants.  Quadrants that fold into the
-// same column node are visited back to back so that one 3x3 accumulator is live: the visiting order
-// and the flush points are functions of the (warp-uniform) class.
-__host__ __device__ inline void p2_half(T2 &N, const Meta &M, const ClsK &Q, double f23, int H, int z, const double *F,
-                                        const double *ZE, const double *ring, double *S0, double *S1, bool has_lower)
+// the three ips of one quadrant (SX,SY: the element lies on the +x / +y side of the row node); the
+// outward signs tau_x, tau_y are compile-time, tau_z comes in through z1, z2, zn
+template <int SX, int SY>
+__host__ __device__ __forceinline__ void p2_quad(const T2 &N, const ClsK &Q, const double *eF, const double *eZ, double z1,
+                                                 double z2, double zn, double (&acc)[9], double &dm)
 {
   using C = Cfg;
-  if (!N.active) return;
+  // no test for quadrants outside the domain: their records are zero (never written by phase 1 after
+  // the prologue cleared F / ZE), so they contribute exact zeros
+  constexpr int eo = (SX + C::ELX * SY) * C::ES;
+  // the row node is corner (!sx, !sy, !H) of the element; its three ips (Hex8CVFEM.C:264-276)
+  constexpr int fx = SY ? 0 : 2;               // x edge of the face: ip & 3
+  constexpr int fy = SX ? 3 : 1;               // y edge
+  constexpr int fz = (SY ? 0 : 2) + (SX ^ SY); // z edge above/below bottom node (k & 3)
+  p2_ip(eF + eo + fx * C::IPD, Q.c0[0], SX ? Q.c1[0] : -Q.c1[0], SX ? Q.c2[0] : -Q.c2[0], SX ? Q.cn[0] : -Q.cn[0], acc, dm);
+  p2_ip(eF + eo + fy * C::IPD, Q.c0[1], SY ? Q.c1[1] : -Q.c1[1], SY ? Q.c2[1] : -Q.c2[1], SY ? Q.cn[1] : -Q.cn[1], acc, dm);
+  p2_ip(eZ + eo + fz * C::IPD, Q.c0[2], z1, z2, zn, acc, dm);
+}
+
+// one z half (H = 0 below / 1 above the plane) of the node's octants.  Quadrants that fold into the
+// same column node are visited back to back so that one 3x3 accumulator is live; the flush points
+// are a function of the (warp-uniform) class: (a,b) = (1,1): every quadrant is its own column;
+// (0,1): pairs differing in sx fold; (1,0): pairs differing in sy fold (SWAP: visit sy fastest);
+// (0,0): all four fold.
+template <bool SWAP>
+__host__ __device__ inline void p2_half_t(T2 &N, const Meta &M, const ClsK &Q, double f23, int H, int z, const double *F,
+                                          const double *ZE, const double *ring, double *S0, double *S1, bool has_lower)
+{
+  using C = Cfg;
   const double *eF = F + (N.lx + C::ELX * N.ly) * C::ES;
   const double *eZ = ZE + (N.lx + C::ELX * N.ly) * C::ES;
-  // (a,b) = (1,1): every quadrant is its own column; (0,1): pairs differing in sx fold; (1,0): pairs
-  // differing in sy fold (visit sy fastest); (0,0): all four fold
-  const unsigned flushmask = (Q.a & Q.b) ? 0xFu : ((Q.a | Q.b) ? 0xAu : 0x8u);
-  const bool swap = Q.a && !Q.b;
+  const unsigned fm = (Q.a & Q.b) ? 0xFu : ((Q.a | Q.b) ? 0xAu : 0x8u);
   // z-edge ips: tau_z = +1 for the elements above the plane
   const double z1 = flip_if(Q.c1[2], !H), z2 = flip_if(Q.c2[2], !H), zn = flip_if(Q.cn[2], !H);
   double acc[9], dm = 0.0;
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.0;
-#pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
-    const int sx = swap ? (j >> 1) : (j & 1), sy = swap ? (j & 1) : (j >> 1);
-    if (N.vmask & (1 << (sx + 2 * sy))) { // else: no element in this quadrant (domain boundary)
-      const int eo = (sx + C::ELX * sy) * C::ES;
-      // the row node is corner (!sx, !sy, !H) of the element; its three ips (Hex8CVFEM.C:264-276)
-      const int fx = sy ? 0 : 2;               // x edge of the face: ip & 3
-      const int fy = sx ? 3 : 1;               // y edge
-      const int fz = (sy ? 0 : 2) + (sx ^ sy); // z edge above/below bottom node (k & 3)
-      p2_ip(eF + eo + fx * C::IPD, Q.c0[0], flip_if(Q.c1[0], !sx), flip_if(Q.c2[0], !sx), flip_if(Q.cn[0], !sx), acc, dm);
-      p2_ip(eF + eo + fy * C::IPD, Q.c0[1], flip_if(Q.c1[1], !sy), flip_if(Q.c2[1], !sy), flip_if(Q.cn[1], !sy), acc, dm);
-      p2_ip(eZ + eo + fz * C::IPD, Q.c0[2], z1, z2, zn, acc, dm);
-    }
-    if ((flushmask >> j) & 1) {
-      p2_flush(N, M, Q, H, sx, sy, z, ring, S0, S1, acc, dm, f23, has_lower);
-#pragma unroll
-      for (int t = 0; t < 9; ++t) acc[t] = 0.0;
-      dm = 0.0;
-    }
+#define NALU_P2_STEP(J, SX, SY)                                                        \
+  p2_quad<SX, SY>(N, Q, eF, eZ, z1, z2, zn, acc, dm);                                  \
+  if (fm & (1u << J)) {                                                                \
+    p2_flush(N, M, Q, H, SX, SY, z, ring, S0, S1, acc, dm, f23, has_lower);            \
+    _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[t] = 0.0;                        \
+    dm = 0.0;                                                                          \
   }
+  NALU_P2_STEP(0, 0, 0)
+  NALU_P2_STEP(1, (SWAP ? 0 : 1), (SWAP ? 1 : 0))
+  NALU_P2_STEP(2, (SWAP ? 1 : 0), (SWAP ? 0 : 1))
+  NALU_P2_STEP(3, 1, 1)
+#undef NALU_P2_STEP
+}
+
+__host__ __device__ inline void p2_half(T2 &N, const Meta &M, const ClsK &Q, double f23, int H, int z, const double *F,
+                                        const double *ZE, const double *ring, double *S0, double *S1, bool has_lower)
+{
+  // nodes outside the domain run the same code on zero records; their flushes see slot 0xFF
+  if (Q.a && !Q.b) p2_half_t<true>(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, has_lower);
+  else p2_half_t<false>(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, has_lower);
 }
 
 // ---- node metadata of plane z: thread (node, g) reads the 9 slots of dz group g ------------------

@@ -50,6 +50,7 @@ struct BoxParams {
   double include_divu;
   int options;
   int overwrite;
+  long long *trace; // profiling aid (NALU_BOX_TRACE): per-warp clock stamps of one CTA, else null
 };
 
 template <int TBX_, int TBY_>

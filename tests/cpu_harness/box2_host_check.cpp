@@ -129,6 +129,7 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
   for (int c = 0; c < C::NCLS; ++c) box2::cls_init(Q[c], K, c);
   for (int cta = 0; cta < P.tiles_x * P.tiles_y * zchunks; ++cta) {
     for (int i = 0; i < C::SMEM_DOUBLES; ++i) sm[i] = NAN; // uninitialised shared memory must never be consumed
+    for (int i = 0; i < 2 * C::NEL * C::ES; ++i) sm[C::OFF_F + i] = 0.0; // kernel prologue: records outside the domain read zero
     double *F = sm + C::OFF_F, *ZE = sm + C::OFF_ZE, *S0 = sm + C::OFF_S0, *S1 = sm + C::OFF_S1;
     double *ring = sm + C::OFF_RING, *mdb = sm + C::OFF_MD, *rp = sm + C::OFF_RP;
     const int ntile = P.tiles_x * P.tiles_y;
@@ -179,13 +180,14 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
       // ---- barrier; B
       for (int tid = 0; tid < 96; ++tid)
         if (lower) copy_run_host(M, tid & 31, tid >> 5, 0, S1, P.values, P.overwrite, bulk);
-      for (int i = 0; i < C::NEL * C::ES; ++i) F[i] = ZE[i] = NAN; // dead: phase 1a rewrites what phase C reads
       for (int i = 0; i < C::NNODE * C::SNODE; ++i) S1[i] = NAN;
       if (upper)
         for (int it = 0; it < C::NP1A; ++it) {
           const int k = it / C::NEL, el = it - k * C::NEL;
           box2::p1_item(P, el, k < 2 ? k : 2, k < 2 ? 0 : k - 2, x0, y0, pl_0, pl_p, mdb, F, ZE);
         }
+      if (z + 1 < ze)
+        for (int tid = 0; tid < 96; ++tid) box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), tid & 31, tid >> 5, x0, y0, z + 1);
       // ---- barrier; C
       for (int tid = 0; tid < NT; ++tid) {
         box2::T2 &n = N[tid];
@@ -210,15 +212,12 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
           *r = P.overwrite ? v : *r + v;
         }
       }
-      for (int i = 0; i < C::NEL * C::ES; ++i) F[i] = NAN; // phase 1b rewrites the face ips
       for (int i = 0; i < C::NNODE * C::SNODE; ++i) S0[i] = S1[i] = NAN;
       if (upper)
         for (int it = 0; it < C::NP1B; ++it) {
           const int k = it / C::NEL, el = it - k * C::NEL;
           box2::p1_item(P, el, k, 1, x0, y0, pl_0, pl_p, mdb, F, ZE);
         }
-      if (z + 1 < ze)
-        for (int tid = 0; tid < 96; ++tid) box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), tid & 31, tid >> 5, x0, y0, z + 1);
       // ---- barrier
     }
   }
