@@ -309,11 +309,13 @@ __host__ __device__ inline void cls_fetch(ClsK &Q, const double *qk, int cls)
   }
 }
 
-// one integration point: acc += (tau h) (x) A, dm += tau N mdot
-__host__ __device__ __forceinline__ void p2_ip(const double *rec, double c0, double c1, double c2, double cn,
-                                               double (&acc)[9], double &dm)
-{
+// one integration point: acc += (tau h) (x) A, dm += tau N mdot.  Load and arithmetic are separate
+// so that the caller can keep the next record in flight while this one is consumed.
+struct Rec {
   double o[14];
+};
+__host__ __device__ __forceinline__ void rec_load(Rec &R, const double *rec)
+{
 #ifdef __CUDA_ARCH__
   const double2 *r2 = reinterpret_cast<const double2 *>(rec);
 #else
@@ -321,9 +323,14 @@ __host__ __device__ __forceinline__ void p2_ip(const double *rec, double c0, dou
 #endif
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
-    o[2 * k] = r2[k].x;
-    o[2 * k + 1] = r2[k].y;
+    R.o[2 * k] = r2[k].x;
+    R.o[2 * k + 1] = r2[k].y;
   }
+}
+__host__ __device__ __forceinline__ void rec_apply(const Rec &R, double c0, double c1, double c2, double cn,
+                                                   double (&acc)[9], double &dm)
+{
+  const double *o = R.o;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const double h = o[i * 3 + 0] * c0 + o[i * 3 + 1] * c1 + o[i * 3 + 2] * c2;
@@ -395,30 +402,35 @@ __host__ __device__ __forceinline__ void p2_flush(T2 &N, const Meta &M, const Cl
   }
 }
 
-// the three ips of one quadrant (SX,SY: the element lies on the +x / +y side of the row node); the
-// outward signs tau_x, tau_y are compile-time, tau_z comes in through z1, z2, zn
-template <int SX, int SY>
-__host__ __device__ __forceinline__ void p2_quad(const T2 &N, const ClsK &Q, const double *eF, const double *eZ, double z1,
-                                                 double z2, double zn, double (&acc)[9], double &dm)
+// record k (0..2: x edge, y edge, z edge ip) of quadrant (SX,SY: the element lies on the +x / +y side
+// of the row node).  The row node is corner (!sx, !sy, !H) of the element (Hex8CVFEM.C:264-276).
+template <int SX, int SY, int K>
+__host__ __device__ __forceinline__ const double *rec_addr(const double *eF, const double *eZ)
 {
   using C = Cfg;
-  // no test for quadrants outside the domain: their records are zero (never written by phase 1 after
-  // the prologue cleared F / ZE), so they contribute exact zeros
   constexpr int eo = (SX + C::ELX * SY) * C::ES;
-  // the row node is corner (!sx, !sy, !H) of the element; its three ips (Hex8CVFEM.C:264-276)
   constexpr int fx = SY ? 0 : 2;               // x edge of the face: ip & 3
   constexpr int fy = SX ? 3 : 1;               // y edge
   constexpr int fz = (SY ? 0 : 2) + (SX ^ SY); // z edge above/below bottom node (k & 3)
-  p2_ip(eF + eo + fx * C::IPD, Q.c0[0], SX ? Q.c1[0] : -Q.c1[0], SX ? Q.c2[0] : -Q.c2[0], SX ? Q.cn[0] : -Q.cn[0], acc, dm);
-  p2_ip(eF + eo + fy * C::IPD, Q.c0[1], SY ? Q.c1[1] : -Q.c1[1], SY ? Q.c2[1] : -Q.c2[1], SY ? Q.cn[1] : -Q.cn[1], acc, dm);
-  p2_ip(eZ + eo + fz * C::IPD, Q.c0[2], z1, z2, zn, acc, dm);
+  return K == 0 ? eF + eo + fx * C::IPD : (K == 1 ? eF + eo + fy * C::IPD : eZ + eo + fz * C::IPD);
+}
+// the outward signs tau_x, tau_y are compile-time, tau_z comes in through z1, z2, zn
+template <int SX, int SY, int K>
+__host__ __device__ __forceinline__ void rec_use(const Rec &R, const ClsK &Q, double z1, double z2, double zn,
+                                                 double (&acc)[9], double &dm)
+{
+  if (K == 0) rec_apply(R, Q.c0[0], SX ? Q.c1[0] : -Q.c1[0], SX ? Q.c2[0] : -Q.c2[0], SX ? Q.cn[0] : -Q.cn[0], acc, dm);
+  else if (K == 1) rec_apply(R, Q.c0[1], SY ? Q.c1[1] : -Q.c1[1], SY ? Q.c2[1] : -Q.c2[1], SY ? Q.cn[1] : -Q.cn[1], acc, dm);
+  else rec_apply(R, Q.c0[2], z1, z2, zn, acc, dm);
 }
 
 // one z half (H = 0 below / 1 above the plane) of the node's octants.  Quadrants that fold into the
 // same column node are visited back to back so that one 3x3 accumulator is live; the flush points
 // are a function of the (warp-uniform) class: (a,b) = (1,1): every quadrant is its own column;
 // (0,1): pairs differing in sx fold; (1,0): pairs differing in sy fold (SWAP: visit sy fastest);
-// (0,0): all four fold.
+// (0,0): all four fold.  No test for quadrants / nodes outside the domain: their records are zero
+// (never written by phase 1 after the prologue cleared F / ZE) and their flushes see slot 0xFF.
+// The 12 records are double-buffered in registers: record k+1 is loaded before record k is used.
 template <bool SWAP>
 __host__ __device__ inline void p2_half_t(T2 &N, const Meta &M, const ClsK &Q, double f23, int H, int z, const double *F,
                                           const double *ZE, const double *ring, double *S0, double *S1, bool has_lower)
@@ -432,18 +444,27 @@ __host__ __device__ inline void p2_half_t(T2 &N, const Meta &M, const ClsK &Q, d
   double acc[9], dm = 0.0;
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.0;
-#define NALU_P2_STEP(J, SX, SY)                                                        \
-  p2_quad<SX, SY>(N, Q, eF, eZ, z1, z2, zn, acc, dm);                                  \
-  if (fm & (1u << J)) {                                                                \
-    p2_flush(N, M, Q, H, SX, SY, z, ring, S0, S1, acc, dm, f23, has_lower);            \
-    _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[t] = 0.0;                        \
-    dm = 0.0;                                                                          \
-  }
-  NALU_P2_STEP(0, 0, 0)
-  NALU_P2_STEP(1, (SWAP ? 0 : 1), (SWAP ? 1 : 0))
-  NALU_P2_STEP(2, (SWAP ? 1 : 0), (SWAP ? 0 : 1))
-  NALU_P2_STEP(3, 1, 1)
-#undef NALU_P2_STEP
+  constexpr int X1 = SWAP ? 0 : 1, Y1 = SWAP ? 1 : 0, X2 = SWAP ? 1 : 0, Y2 = SWAP ? 0 : 1;
+  Rec RA, RB;
+  rec_load(RA, rec_addr<0, 0, 0>(eF, eZ));
+#define NALU_P2_QUAD(J, SX, SY, NX_, NY_, LAST)                                                   \
+  rec_load(RB, rec_addr<SX, SY, 1>(eF, eZ));                                                      \
+  rec_use<SX, SY, 0>(RA, Q, z1, z2, zn, acc, dm);                                                 \
+  rec_load(RA, rec_addr<SX, SY, 2>(eF, eZ));                                                      \
+  rec_use<SX, SY, 1>(RB, Q, z1, z2, zn, acc, dm);                                                 \
+  if (!LAST) rec_load(RB, rec_addr<NX_, NY_, 0>(eF, eZ));                                         \
+  rec_use<SX, SY, 2>(RA, Q, z1, z2, zn, acc, dm);                                                 \
+  if (fm & (1u << J)) {                                                                           \
+    p2_flush(N, M, Q, H, SX, SY, z, ring, S0, S1, acc, dm, f23, has_lower);                       \
+    _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[t] = 0.0;                                   \
+    dm = 0.0;                                                                                     \
+  }                                                                                               \
+  if (!LAST) RA = RB;
+  NALU_P2_QUAD(0, 0, 0, X1, Y1, false)
+  NALU_P2_QUAD(1, X1, Y1, X2, Y2, false)
+  NALU_P2_QUAD(2, X2, Y2, 1, 1, false)
+  NALU_P2_QUAD(3, 1, 1, 1, 1, true)
+#undef NALU_P2_QUAD
 }
 
 __host__ __device__ inline void p2_half(T2 &N, const Meta &M, const ClsK &Q, double f23, int H, int z, const double *F,
