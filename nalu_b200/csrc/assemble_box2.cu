@@ -1,6 +1,6 @@
 // assemble_box2.cu -- launch side of the column-pair tiled assembly (see box2_tile.cuh).
 //
-// Grid: one CTA (256 threads = 8 class warps x 32 nodes) per (8x4 node tile, z chunk), two CTAs per SM.
+// Grid: one CTA (128 threads = 4 class warps x 32 nodes, two column nodes per thread) per (8x4 node tile, z chunk), two CTAs per SM.
 // Per node plane z a CTA runs
 //   A  lower octants (face ips TF(z-1), z-edge ips ZE(z-1)): dz=-1 group -> S1, dz=0 partial -> S0
 //   B  bulk copy of S1 to HBM  ||  phase 1a: BF(z), ZE(z)
@@ -76,7 +76,7 @@ __device__ __forceinline__ void copy_runs_warp(const box2::Meta &M, int warp, in
   for (int k0 = 0; k0 < nk; k0 += 4) {
     box2::Run run[4];
     const double *src[4];
-    double v[4];
+    double v[4], w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = warp + C::NCLS * (k0 + u);
@@ -85,13 +85,16 @@ __device__ __forceinline__ void copy_runs_warp(const box2::Meta &M, int warp, in
       src[u] = (g == 1 ? S0 : S1) + run[u].soff;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = lane < run[u].L ? src[u][lane] : 0.0;
+    for (int u = 0; u < 4; ++u) {
+      v[u] = lane < run[u].L ? src[u][lane] : 0.0;
+      w[u] = lane + 32 < run[u].L ? src[u][lane + 32] : 0.0; // merged dz=0 / dz=+1 runs are 54 long
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (lane < run[u].L) {
-        double *dst = values + run[u].G + lane;
-        *dst = overwrite ? v[u] : *dst + v[u];
-      }
+    for (int u = 0; u < 4; ++u) {
+      double *dst = values + run[u].G + lane;
+      if (lane < run[u].L) *dst = overwrite ? v[u] : *dst + v[u];
+      if (lane + 32 < run[u].L) dst[32] = overwrite ? w[u] : dst[32] + w[u];
+    }
   }
 }
 
@@ -128,7 +131,7 @@ template <bool BULK>
 __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_constant__ BoxParams P)
 {
   extern __shared__ __align__(16) double sm[];
-  double *const F = sm + C::OFF_F, *const ZE = sm + C::OFF_ZE, *const S0 = sm + C::OFF_S0, *const S1 = sm + C::OFF_S1;
+  double *const F = sm + C::OFF_F, *const ZE = sm + C::OFF_ZE, *const S0 = sm + C::OFF_S, *const S1 = sm + C::OFF_S;
   double *const ring = sm + C::OFF_RING, *const mdb = sm + C::OFF_MD, *const rp = sm + C::OFF_RP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntile = P.tiles_x * P.tiles_y;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
   box2::t2_init(P, N, lane, x0, y0);
   // class constants live in shared memory (12 doubles per class warp) and are fetched at the head of
   // every phase 2 pass, so that they do not occupy registers during phase 1
-  double *const qk = sm + C::OFF_QK + warp * 12;
+  double *const qk = sm + C::OFF_QK + warp * 24;
   if (lane == 0) {
     box2::P2K K;
     box2::ClsK Q;
@@ -153,22 +156,19 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
 
   // records of elements outside the domain are never written: they must read zero (phase 2 does not test)
   for (int i = tid; i < 2 * C::NEL * C::ES; i += C::NT) sm[C::OFF_F + i] = 0.0;
-  box2::StageIdx SI;
-  box2::stage_init(P, SI, tid, x0, y0);
-  double regP[C::NPL], regM[C::NML];
   // ---- prologue: node planes zs-1, zs; the face/z-edge ips of the layer below the first plane
-#pragma unroll 1
-  for (int pl = zs - 1; pl <= zs; ++pl) {
-    box2::plane_fetch(P, SI, pl, regP);
-    box::plane_store<C>(tid, regP, ring + ((pl + 3) % 3) * C::PLN);
-  }
-  box2::mdot_fetch(P, SI, zs - 1, regM);
-  box::mdot_store<C>(tid, regM, mdb);
-  if (warp < 3) box2::meta_load(P, box2::meta_at(sm, zs & 1), lane, warp, x0, y0, zs);
+  box2::stage_plane(P, ring + ((zs + 2) % 3) * C::PLN, tid, x0, y0, zs - 1);
+  box2::stage_plane(P, ring + (zs % 3) * C::PLN, tid, x0, y0, zs);
+  box2::stage_mdot(P, mdb, tid, x0, y0, zs - 1);
+  if (warp == C::NCLS - 1) box2::meta_load(P, box2::meta_at(sm, zs & 1), lane, x0, y0, zs);
+  box2::stage_wait();
   __syncthreads();
   if (zs >= 1) p1_prologue(P, x0, y0, ring + ((zs - 1) % 3) * C::PLN, ring + (zs % 3) * C::PLN, mdb, F, ZE);
-  box2::plane_fetch(P, SI, zs + 1, regP);
-  box2::mdot_fetch(P, SI, zs, regM);
+  // the last warp (least phase 1 work) owns the node metadata; the row index is fetched one phase ahead
+  const bool meta_warp = warp == C::NCLS - 1;
+  int row_next = meta_warp ? box2::meta_row(P, lane, x0, y0, zs + 1) : -1;
+  // first pass of the loop expects node plane zs+1 already in flight (see phase D below)
+  box2::stage_plane(P, ring + ((zs + 1) % 3) * C::PLN, tid, x0, y0, zs + 1);
   __syncthreads();
 
   // One iteration = one z half of a plane (H = 0: elements below, H = 1: above) followed by the
@@ -180,47 +180,55 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
     // ---- A (H = 0) / C (H = 1)
     TRACE(0);
     if (!H) {
-      box::plane_store<C>(tid, regP, ring + ((z + 1) % 3) * C::PLN);
-      box::mdot_store<C>(tid, regM, mdb);
+      // the mass flow rates of layer z land while the lower octants are processed (node plane z+1 has
+      // been in flight since phase D of the previous plane)
+      box2::stage_mdot(P, mdb, tid, x0, y0, z);
       N.rr[0] = N.rr[1] = N.rr[2] = 0.0;
     }
-    if (H ? upper : lower) {
+    if ((H ? upper : lower) && !(P.options & (1 << 18))) {
       box2::ClsK Q;
       box2::cls_fetch(Q, qk, warp);
-      box2::p2_half(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, lower);
+      box2::p2_half(N, sm, Q, f23, H, z, lower);
     }
     if (H) {
       rp[(warp * C::NNODE + lane) * 3 + 0] = N.rr[0];
       rp[(warp * C::NNODE + lane) * 3 + 1] = N.rr[1];
       rp[(warp * C::NNODE + lane) * 3 + 2] = N.rr[2];
     }
+    if (!H) box2::stage_wait();
     if (BULK) fence_async_smem();
     TRACE(1);
     __syncthreads();
     TRACE(2);
     // ---- B (H = 0): dz=-1 group out, phase 1a / D (H = 1): dz=0,+1 groups and rhs out, phase 1b,
     //      metadata and field prefetch of the next plane
+    box2::MetaRaw MR;
+    const bool do_meta = !H && z + 1 < ze && meta_warp;
+    if (do_meta) box2::meta_fetch(P, MR, lane, x0, y0, z + 1, row_next);
     if (H) {
-      box2::plane_fetch(P, SI, z + 2, regP);
-      box2::mdot_fetch(P, SI, z + 1, regM);
+      // node plane z+2 -> the ring slot of plane z-1 (dead since phase A); row indices of plane z+2
+      box2::stage_plane(P, ring + ((z + 2) % 3) * C::PLN, tid, x0, y0, z + 2);
+      if (meta_warp) row_next = box2::meta_row(P, lane, x0, y0, z + 2);
     }
-    if (BULK) {
+    if (P.options & (1 << 16)) {
+    } else if (BULK) {
       // the run list of this half (H = 0: 96 runs of the dz=-1 group; H = 1: 96 of dz=0, then 96 of
       // dz=+1) spread over all 8 warps: the per-lane bulk issue serialises inside a warp
-      const int per = H ? 24 : 12;
-      const int r = warp * per + lane;
-      const int g = H ? 1 + r / 96 : 0, rr = r % 96;
-      const bool doit = lane < per && (g == 0 ? lower : (g == 2 ? upper : true));
-      if (doit) {
-        copy_run<BULK>(M, rr & 31, rr >> 5, g, g == 1 ? S0 : S1, P.values, P.overwrite);
-        bulk_commit();
+      const int per = (H ? 192 : 96) / C::NCLS;
+#pragma unroll 1
+      for (int l = lane; l < per; l += 32) {
+        // H = 1: every warp takes 24 runs of dz=0 (which carry dz=+1 along when merged) and 24 of dz=+1
+        const int g = H ? 1 + l / 24 : 0, rr = warp * 24 + l % 24;
+        if (g == 0 ? lower : (g == 2 ? upper : true))
+          copy_run<BULK>(M, rr & 31, rr >> 5, g, g == 1 ? S0 : S1, P.values, P.overwrite);
       }
+      bulk_commit();
     } else {
       // run list of this half: H = 0: the 96 runs of the dz=-1 group; H = 1: 96 runs of dz=0, then 96 of dz=+1
       const int nrun = H ? (upper ? 192 : 96) : (lower ? 96 : 0);
       copy_runs_warp(M, warp, lane, nrun / C::NCLS, H ? 1 : 0, S0, S1, P.values, P.overwrite);
     }
-    if (H && warp < 3 && P.overwrite) box2::zero_uncovered(M, lane, warp, P.values);
+    if (H && tid < 3 * C::NNODE && P.overwrite) box2::zero_uncovered(M, lane, warp, P.values);
     if (H && tid >= C::NT - 3 * C::NNODE) {
       // rhs: sum the class partials; thread -> (node, dof) so that an x line of nodes is one run
       const int t = tid - (C::NT - 3 * C::NNODE);
@@ -234,9 +242,8 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
       }
     }
     TRACE(3);
-    if (upper) p1_phase(P, H ? 2 : 1, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, F, ZE);
-    // metadata of the next plane: warps 5-7 have little phase 1a work
-    if (!H && z + 1 < ze && warp >= 5) box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), lane, warp - 5, x0, y0, z + 1);
+    if (upper && !(P.options & (1 << 17))) p1_phase(P, H ? 2 : 1, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, F, ZE);
+    if (do_meta) box2::meta_store(P, box2::meta_at(sm, (z + 1) & 1), MR, lane);
     TRACE(4);
     if (BULK) bulk_wait_read();
     TRACE(5);
@@ -267,7 +274,8 @@ static int launch2(BoxParams &P, cudaStream_t stream)
   if (zc > P.NZ) zc = P.NZ;
   P.z_chunk = zc;
   zchunks = (P.NZ + zc - 1) / zc;
-  const size_t smem = sizeof(double) * C::SMEM_DOUBLES;
+  size_t smem = sizeof(double) * C::SMEM_DOUBLES;
+  if (getenv("NALU_BOX_ONE_CTA")) smem = 120 * 1024; // profiling aid: one CTA per SM
   NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<BULK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const long long ctas = ntile * zchunks;
@@ -304,6 +312,7 @@ int launch_assemble_box2(BoxParams &P, cudaStream_t stream)
 {
   // the bulk copies need 16-byte aligned destinations: staging parity is matched to the offset in
   // `values`, so the base pointer itself must be aligned (cudaMalloc gives 256 bytes)
+  if (const char *e = getenv("NALU_BOX_ABLATE")) P.options |= atoi(e) << 16; // profiling aid: skip copy (1) / phase 1 (2) / phase 2 (4)
   bool bulk = ((uintptr_t)P.values & 15) == 0;
   if (const char *e = getenv("NALU_BOX_BULK")) bulk = bulk && atoi(e) != 0;
   return bulk ? launch2<true>(P, stream) : launch2<false>(P, stream);

@@ -39,27 +39,30 @@ using box::ip_of;
 using box::node_of_bits;
 
 struct Cfg {
-  static constexpr int TBX = 8, TBY = 4, NNODE = TBX * TBY, NCLS = 8, NT = NCLS * NNODE;
+  static constexpr int TBX = 8, TBY = 4, NNODE = TBX * TBY, NCLS = 4, NT = NCLS * NNODE;
   static constexpr int ELX = TBX + 1, ELY = TBY + 1, NEL = ELX * ELY;
   static constexpr int IPD = 14;          // doubles per ip record: G~[9], A[3], mdot, pad
   static constexpr int ES = 4 * IPD + 2;  // element stride; ES/2 odd: the 8 lanes of an LDS.128 phase hit 8 bank groups
   static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY, NF = 7, PLN = RN * NF;
   static constexpr int MDB = NEL * 12;
   static constexpr int NPL = (PLN + NT - 1) / NT, NML = (MDB + NT - 1) / NT;
-  static constexpr int SROWP = 28;             // staging pitch of a dof row of one dz group (27 + parity slack)
-  static constexpr int SNODE = 3 * SROWP + 1;  // odd: conflict-free 64-bit stores across the nodes of a warp
+  // staging of one node: 3 dof rows x [parity pad | dz=0 group (27) | dz=-1 or dz=+1 group (27)]; the two
+  // parts are adjacent like in the CSR row, so that dz=0 and dz=+1 leave as ONE 54-double run
+  static constexpr int SROWP = 56;
+  static constexpr int SNODE = 3 * SROWP + 1;  // odd: spreads the nodes of a warp over the banks
   static constexpr int NP1A = 4 * NEL, NP1B = 2 * NEL;
   // shared-memory map (doubles)
-  static constexpr int OFF_F = 0, OFF_ZE = OFF_F + NEL * ES, OFF_S0 = OFF_ZE + NEL * ES, OFF_S1 = OFF_S0 + NNODE * SNODE,
-                       OFF_RING = OFF_S1 + NNODE * SNODE, OFF_MD = OFF_RING + 3 * PLN, OFF_RP = OFF_MD + MDB,
+  static constexpr int OFF_F = 0, OFF_ZE = OFF_F + NEL * ES, OFF_S = OFF_ZE + NEL * ES,
+                       OFF_RING = OFF_S + NNODE * SNODE, OFF_MD = OFF_RING + 3 * PLN, OFF_RP = OFF_MD + MDB,
                        OFF_META = OFF_RP + NCLS * NNODE * 3;
   // node metadata of one plane: rowbase int64[NNODE]; nb int[NNODE], row int[NNODE];
-  // slots uint8[NNODE][28]; gp uint16[NNODE][4] (group start | parity bits << 8); cnt uint8[NNODE][4]
+  // slots uint8[NNODE][28]; gp uint16[NNODE][4]: [g] = first slot of dz group g | its staging offset << 8,
+  // [3] = parity bits of the three dof rows | merged flag << 3; cnt uint8[NNODE][4]: columns of group g
   static constexpr int META_RB = 0, META_NB = NNODE, META_ROW = META_NB + NNODE / 2, META_SLOT = META_ROW + NNODE / 2,
                        META_GP = META_SLOT + NNODE * 28 / 8, META_CNT = META_GP + NNODE * 8 / 8,
                        META = META_CNT + NNODE * 4 / 8;
-  static constexpr int OFF_QK = OFF_META + 2 * META;  // class constants: [NCLS][12]
-  static constexpr int SMEM_DOUBLES = OFF_QK + NCLS * 12;
+  static constexpr int OFF_QK = OFF_META + 2 * META;  // class constants: [NCLS][24]
+  static constexpr int SMEM_DOUBLES = OFF_QK + NCLS * 24;
 };
 
 struct Meta {
@@ -82,58 +85,53 @@ __host__ __device__ inline Meta meta_at(double *sm, int buf)
   return M;
 }
 
-// ---- staging of nodal fields / mass flow rates (global -> registers -> shared) ---------------------
-// Slot k of thread tid covers flat index tid + k*NT of the [RN][NF] plane image (box::plane_store)
-// and of the [NEL][12] mass-flow image (box::mdot_store).  What does not depend on z is folded once
-// into a packed index: pk = (x + NX y) * 8 + field, mk = (ex + nx ey) * 12 + ip, -1 = outside.
-struct StageIdx {
-  int pk[Cfg::NPL];
-  int mk[Cfg::NML];
-};
-__host__ __device__ inline void stage_init(const BoxParams &P, StageIdx &S, int tid, int x0, int y0)
+// ---- staging of nodal fields / mass flow rates: global -> shared with cp.async (no registers) ------
+// plane image [RN][NF] = (x, y, z, mu, u, v, w) of the tile's node neighbourhood at node plane zp;
+// mass-flow image [NEL][12] of element layer ez.  Entries outside the mesh read zero (cp.async
+// with source size 0).  The caller waits (stage_wait) and passes a CTA barrier before use.
+__host__ __device__ __forceinline__ void copy8_or_zero(double *dst, const double *src, bool valid)
+{
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(valid ? 8 : 0)
+               : "memory");
+#else
+  *dst = valid ? *src : 0.0;
+#endif
+}
+__host__ __device__ __forceinline__ void stage_wait()
+{
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+__host__ __device__ inline void stage_plane(const BoxParams &P, double *ring_plane, int tid, int x0, int y0, int zp)
 {
   using C = Cfg;
-#pragma unroll
-  for (int k = 0; k < C::NPL; ++k) {
-    const int idx = tid + k * C::NT;
-    S.pk[k] = -1;
-    if (idx >= C::PLN) continue;
+  const long long pn = (long long)P.NX * P.NY;
+  const bool zin = zp >= 0 && zp < P.NZ;
+#pragma unroll 1
+  for (int idx = tid; idx < C::PLN; idx += C::NT) {
     const int rn = idx / C::NF, f = idx - rn * C::NF;
     const int x = x0 - 1 + rn % C::RNX, y = y0 - 1 + rn / C::RNX;
-    if (x < 0 || y < 0 || x >= P.NX || y >= P.NY) continue;
-    S.pk[k] = (x + P.NX * y) * 8 + f;
+    const bool valid = zin && x >= 0 && y >= 0 && x < P.NX && y < P.NY;
+    const long long n = valid ? x + (long long)P.NX * y + pn * zp : 0;
+    const double *src = f < 3 ? P.coords + n * 3 + f : (f == 3 ? P.visc + n : P.vel + n * 3 + (f - 4));
+    copy8_or_zero(ring_plane + idx, src, valid);
   }
-#pragma unroll
-  for (int k = 0; k < C::NML; ++k) {
-    const int idx = tid + k * C::NT;
-    S.mk[k] = -1;
-    if (idx >= C::MDB) continue;
+}
+__host__ __device__ inline void stage_mdot(const BoxParams &P, double *mdb, int tid, int x0, int y0, int ez)
+{
+  using C = Cfg;
+  const long long ln = (long long)P.nx * P.ny;
+  const bool zin = ez >= 0 && ez < P.nz;
+#pragma unroll 1
+  for (int idx = tid; idx < C::MDB; idx += C::NT) {
     const int el = idx / 12, ip = idx - el * 12;
     const int ex = x0 - 1 + el % C::ELX, ey = y0 - 1 + el / C::ELX;
-    if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) continue;
-    S.mk[k] = (ex + P.nx * ey) * 12 + ip;
-  }
-}
-__host__ __device__ inline void plane_fetch(const BoxParams &P, const StageIdx &S, int zp, double (&reg)[Cfg::NPL])
-{
-  const long long pn = (long long)P.NX * P.NY;
-#pragma unroll
-  for (int k = 0; k < Cfg::NPL; ++k) {
-    reg[k] = 0.0;
-    if (S.pk[k] < 0 || zp < 0 || zp >= P.NZ) continue;
-    const long long n = (S.pk[k] >> 3) + pn * zp;
-    const int f = S.pk[k] & 7;
-    reg[k] = f < 3 ? P.coords[n * 3 + f] : (f == 3 ? P.visc[n] : P.vel[n * 3 + (f - 4)]);
-  }
-}
-__host__ __device__ inline void mdot_fetch(const BoxParams &P, const StageIdx &S, int ez, double (&reg)[Cfg::NML])
-{
-  const long long ln = (long long)P.nx * P.ny * 12;
-#pragma unroll
-  for (int k = 0; k < Cfg::NML; ++k) {
-    reg[k] = 0.0;
-    if (S.mk[k] < 0 || ez < 0 || ez >= P.nz) continue;
-    reg[k] = P.mdot[S.mk[k] + ln * ez];
+    const bool valid = zin && ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny;
+    const long long e = valid ? ex + (long long)P.nx * ey + ln * ez : 0;
+    copy8_or_zero(mdb + idx, P.mdot + e * 12 + ip, valid);
   }
 }
 
@@ -260,53 +258,59 @@ struct D2 {
   double x, y;
 };
 
-// per-class constants (class = (a,b,c): the column node differs from the row node along x / y / z).
-// For the ip on the row's edge along axis pp, with local axes (t,u,v) = (pp, pp+1, pp+2):
-//   tau d_t = c0[pp],  tau d_u = tau c1[pp],  tau d_v = tau c2[pp],  tau N_adv = tau cn[pp]
-// where tau is the outward sign of the face for the row node.  Classes are data, not code: all
-// warps run one instruction stream (the instruction cache does not hold per-class variants).
+// per-class constants.  Class (a,b): the thread's two column nodes differ from the row node along
+// x iff a, along y iff b, and along z iff c (c = 0: the column in the row's plane, c = 1: the one in
+// the neighbouring plane).  For the ip on the row's edge along axis pp, local axes (t,u,v) =
+// (pp, pp+1, pp+2):  tau d_t = c0[c][pp],  tau d_u = tau c1[c][pp],  tau d_v = tau c2[c][pp],
+// tau N_adv = tau cn[c][pp], where tau is the outward sign of the face for the row node.
+// Classes are data, not code: all warps run one instruction stream (per-class instruction streams
+// overflow the instruction cache: measured 43 % no-instruction stalls).
 struct ClsK {
-  double c0[3], c1[3], c2[3], cn[3];
-  int a, b, c;
+  double c0[2][3], c1[2][3], c2[2][3], cn[2][3];
+  int a, b;
 };
 __host__ __device__ inline void cls_init(ClsK &Q, const P2K &K, int cls)
 {
   Q.a = cls & 1;
   Q.b = (cls >> 1) & 1;
-  Q.c = (cls >> 2) & 1;
-  const int rho[3] = {Q.a, Q.b, Q.c};
 #pragma unroll
-  for (int pp = 0; pp < 3; ++pp) {
-    const int rt = rho[pp], ru = rho[(pp + 1) % 3], rv = rho[(pp + 2) % 3];
-    Q.c0[pp] = rt ? K.kt[ru + rv] : -K.kt[ru + rv];
-    Q.c1[pp] = ru ? -K.kh[rv] : K.kh[rv];
-    Q.c2[pp] = rv ? -K.kh[ru] : K.kh[ru];
-    Q.cn[pp] = K.kn[ru + rv];
+  for (int c = 0; c < 2; ++c) {
+    const int rho[3] = {Q.a, Q.b, c};
+#pragma unroll
+    for (int pp = 0; pp < 3; ++pp) {
+      const int rt = rho[pp], ru = rho[(pp + 1) % 3], rv = rho[(pp + 2) % 3];
+      Q.c0[c][pp] = rt ? K.kt[ru + rv] : -K.kt[ru + rv];
+      Q.c1[c][pp] = ru ? -K.kh[rv] : K.kh[rv];
+      Q.c2[c][pp] = rv ? -K.kh[ru] : K.kh[ru];
+      Q.cn[c][pp] = K.kn[ru + rv];
+    }
   }
 }
-
 __host__ __device__ inline void cls_store(const ClsK &Q, double *qk)
 {
 #pragma unroll
-  for (int pp = 0; pp < 3; ++pp) {
-    qk[pp] = Q.c0[pp];
-    qk[3 + pp] = Q.c1[pp];
-    qk[6 + pp] = Q.c2[pp];
-    qk[9 + pp] = Q.cn[pp];
-  }
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int pp = 0; pp < 3; ++pp) {
+      qk[c * 12 + pp] = Q.c0[c][pp];
+      qk[c * 12 + 3 + pp] = Q.c1[c][pp];
+      qk[c * 12 + 6 + pp] = Q.c2[c][pp];
+      qk[c * 12 + 9 + pp] = Q.cn[c][pp];
+    }
 }
 __host__ __device__ inline void cls_fetch(ClsK &Q, const double *qk, int cls)
 {
   Q.a = cls & 1;
   Q.b = (cls >> 1) & 1;
-  Q.c = (cls >> 2) & 1;
 #pragma unroll
-  for (int pp = 0; pp < 3; ++pp) {
-    Q.c0[pp] = qk[pp];
-    Q.c1[pp] = qk[3 + pp];
-    Q.c2[pp] = qk[6 + pp];
-    Q.cn[pp] = qk[9 + pp];
-  }
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int pp = 0; pp < 3; ++pp) {
+      Q.c0[c][pp] = qk[c * 12 + pp];
+      Q.c1[c][pp] = qk[c * 12 + 3 + pp];
+      Q.c2[c][pp] = qk[c * 12 + 6 + pp];
+      Q.cn[c][pp] = qk[c * 12 + 9 + pp];
+    }
 }
 
 // one integration point: acc += (tau h) (x) A, dm += tau N mdot.  Load and arithmetic are separate
@@ -327,18 +331,23 @@ __host__ __device__ __forceinline__ void rec_load(Rec &R, const double *rec)
     R.o[2 * k + 1] = r2[k].y;
   }
 }
+// NEG: the outward sign tau of the face is -1 (applies to the u, v derivative terms and to mdot;
+// tau d_t is sign-free, see ClsK).  Written so that the sign is an operand modifier of the FMA.
+template <bool NEG>
 __host__ __device__ __forceinline__ void rec_apply(const Rec &R, double c0, double c1, double c2, double cn,
                                                    double (&acc)[9], double &dm)
 {
   const double *o = R.o;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double h = o[i * 3 + 0] * c0 + o[i * 3 + 1] * c1 + o[i * 3 + 2] * c2;
+    const double w = o[i * 3 + 1] * c1 + o[i * 3 + 2] * c2;
+    const double h = NEG ? o[i * 3 + 0] * c0 - w : o[i * 3 + 0] * c0 + w;
     acc[i * 3 + 0] += h * o[9];
     acc[i * 3 + 1] += h * o[10];
     acc[i * 3 + 2] += h * o[11];
   }
-  dm += cn * o[12];
+  if (NEG) dm -= cn * o[12];
+  else dm += cn * o[12];
 }
 
 struct T2 {
@@ -362,43 +371,48 @@ __host__ __device__ inline void t2_init(const BoxParams &P, T2 &N, int lane, int
   }
 }
 
-// finished block of one (sx,sy) group -> staging; rhs share.  H = 0: elements below the plane
-// (class c = 1 fills the dz = -1 group, c = 0 the first half of dz = 0), H = 1: above (c = 1 ->
-// dz = +1, c = 0 completes dz = 0 on top of the partial left in the staging row when `has_lower`).
-__host__ __device__ __forceinline__ void p2_flush(T2 &N, const Meta &M, const ClsK &Q, int H, int sx, int sy, int z,
-                                                  const double *ring, double *S0, double *S1, const double (&acc)[9],
-                                                  double dm, double f23, bool has_lower)
+// finished blocks of one (sx,sy) group -> staging; rhs share.  H = 0: elements below the plane
+// (column c = 1 fills the dz = -1 group in S1, c = 0 the first half of dz = 0 in S0), H = 1: above
+// (c = 1 -> dz = +1, c = 0 completes dz = 0 on top of the partial left in S0 when `has_lower`).
+// (An out-of-line version costs ~100 warp instructions per node in call overhead: measured.)
+__host__ __device__ __forceinline__ void p2_flush(T2 &N, double *sm, const ClsK &Q, int H, int sx, int sy, int z,
+                                                  const double (&acc)[2][9], const double (&dm)[2], double f23,
+                                                  bool has_lower)
 {
   using C = Cfg;
+  const Meta M = meta_at(sm, z & 1);
   const int dx = Q.a ? (sx ? 1 : -1) : 0, dy = Q.b ? (sy ? 1 : -1) : 0;
-  const int dz = Q.c ? (H ? 1 : -1) : 0;
-  const int g = dz + 1;
-  const unsigned slot = M.slot[N.node * 28 + g * 9 + (dy + 1) * 3 + (dx + 1)];
-  if (slot == 0xFF) return; // no such neighbour
-  const unsigned gp = M.gp[N.node * 4 + g];
-  const unsigned gs = gp & 0xFF, pb = gp >> 8;
-  const double *u = ring + ((z + dz + 3) % 3) * C::PLN + ((N.lx + 1 + dx) + C::RNX * (N.ly + 1 + dy)) * C::NF + 4;
-  const double u0 = u[0], u1 = u[1], u2 = u[2];
-  const double D = dm + (acc[0] + acc[4] + acc[8]);
-  double *Sb = (Q.c ? S1 : S0) + N.node * C::SNODE + (slot - gs) * 3;
-  const bool add = !Q.c && H && has_lower;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    double v0 = acc[i * 3 + 0], v1 = acc[i * 3 + 1], v2 = acc[i * 3 + 2];
-    if (i == 0) v0 += D;
-    if (i == 1) v1 += D;
-    if (i == 2) v2 += D;
-    N.rr[i] -= v0 * u0 + v1 * u1 + v2 * u2;
-    N.rr[i] += f23 * (acc[0 + i] * u0 + acc[3 + i] * u1 + acc[6 + i] * u2);
-    double *d = Sb + i * C::SROWP + ((pb >> i) & 1);
-    if (add) {
-      v0 += d[0];
-      v1 += d[1];
-      v2 += d[2];
+  for (int c = 0; c < 2; ++c) {
+    const int dz = c ? (H ? 1 : -1) : 0;
+    const int g = dz + 1;
+    const unsigned slot = M.slot[N.node * 28 + g * 9 + (dy + 1) * 3 + (dx + 1)];
+    if (slot == 0xFF) continue; // no such neighbour
+    const unsigned gp = M.gp[N.node * 4 + g], pb = M.gp[N.node * 4 + 3];
+    const unsigned gs = gp & 0xFF, gbase = gp >> 8;
+    const double *u = sm + C::OFF_RING + ((z + dz + 3) % 3) * C::PLN + ((N.lx + 1 + dx) + C::RNX * (N.ly + 1 + dy)) * C::NF + 4;
+    const double u0 = u[0], u1 = u[1], u2 = u[2];
+    const double D = dm[c] + (acc[c][0] + acc[c][4] + acc[c][8]);
+    double *Sb = sm + C::OFF_S + N.node * C::SNODE + gbase + (slot - gs) * 3;
+    const bool add = c == 0 && H && has_lower;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double v0 = acc[c][i * 3 + 0], v1 = acc[c][i * 3 + 1], v2 = acc[c][i * 3 + 2];
+      if (i == 0) v0 += D;
+      if (i == 1) v1 += D;
+      if (i == 2) v2 += D;
+      N.rr[i] -= v0 * u0 + v1 * u1 + v2 * u2;
+      N.rr[i] += f23 * (acc[c][0 + i] * u0 + acc[c][3 + i] * u1 + acc[c][6 + i] * u2);
+      double *d = Sb + i * C::SROWP + ((pb >> i) & 1);
+      if (add) {
+        v0 += d[0];
+        v1 += d[1];
+        v2 += d[2];
+      }
+      d[0] = v0;
+      d[1] = v1;
+      d[2] = v2;
     }
-    d[0] = v0;
-    d[1] = v1;
-    d[2] = v2;
   }
 }
 
@@ -414,14 +428,18 @@ __host__ __device__ __forceinline__ const double *rec_addr(const double *eF, con
   constexpr int fz = (SY ? 0 : 2) + (SX ^ SY); // z edge above/below bottom node (k & 3)
   return K == 0 ? eF + eo + fx * C::IPD : (K == 1 ? eF + eo + fy * C::IPD : eZ + eo + fz * C::IPD);
 }
-// the outward signs tau_x, tau_y are compile-time, tau_z comes in through z1, z2, zn
+// the outward signs tau_x, tau_y are compile-time, tau_z comes in through z1, z2, zn; one record feeds
+// both column nodes of the thread
 template <int SX, int SY, int K>
-__host__ __device__ __forceinline__ void rec_use(const Rec &R, const ClsK &Q, double z1, double z2, double zn,
-                                                 double (&acc)[9], double &dm)
+__host__ __device__ __forceinline__ void rec_use(const Rec &R, const ClsK &Q, const double (&z1)[2], const double (&z2)[2],
+                                                 const double (&zn)[2], double (&acc)[2][9], double (&dm)[2])
 {
-  if (K == 0) rec_apply(R, Q.c0[0], SX ? Q.c1[0] : -Q.c1[0], SX ? Q.c2[0] : -Q.c2[0], SX ? Q.cn[0] : -Q.cn[0], acc, dm);
-  else if (K == 1) rec_apply(R, Q.c0[1], SY ? Q.c1[1] : -Q.c1[1], SY ? Q.c2[1] : -Q.c2[1], SY ? Q.cn[1] : -Q.cn[1], acc, dm);
-  else rec_apply(R, Q.c0[2], z1, z2, zn, acc, dm);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if (K == 0) rec_apply<!SX>(R, Q.c0[c][0], Q.c1[c][0], Q.c2[c][0], Q.cn[c][0], acc[c], dm[c]);
+    else if (K == 1) rec_apply<!SY>(R, Q.c0[c][1], Q.c1[c][1], Q.c2[c][1], Q.cn[c][1], acc[c], dm[c]);
+    else rec_apply<false>(R, Q.c0[c][2], z1[c], z2[c], zn[c], acc[c], dm[c]);
+  }
 }
 
 // one z half (H = 0 below / 1 above the plane) of the node's octants.  Quadrants that fold into the
@@ -432,18 +450,24 @@ __host__ __device__ __forceinline__ void rec_use(const Rec &R, const ClsK &Q, do
 // (never written by phase 1 after the prologue cleared F / ZE) and their flushes see slot 0xFF.
 // The 12 records are double-buffered in registers: record k+1 is loaded before record k is used.
 template <bool SWAP>
-__host__ __device__ inline void p2_half_t(T2 &N, const Meta &M, const ClsK &Q, double f23, int H, int z, const double *F,
-                                          const double *ZE, const double *ring, double *S0, double *S1, bool has_lower)
+__host__ __device__ inline void p2_half_t(T2 &N, double *sm, const ClsK &Q, double f23, int H, int z, bool has_lower)
 {
   using C = Cfg;
-  const double *eF = F + (N.lx + C::ELX * N.ly) * C::ES;
-  const double *eZ = ZE + (N.lx + C::ELX * N.ly) * C::ES;
+  const double *eF = sm + C::OFF_F + (N.lx + C::ELX * N.ly) * C::ES;
+  const double *eZ = sm + C::OFF_ZE + (N.lx + C::ELX * N.ly) * C::ES;
   const unsigned fm = (Q.a & Q.b) ? 0xFu : ((Q.a | Q.b) ? 0xAu : 0x8u);
   // z-edge ips: tau_z = +1 for the elements above the plane
-  const double z1 = flip_if(Q.c1[2], !H), z2 = flip_if(Q.c2[2], !H), zn = flip_if(Q.cn[2], !H);
-  double acc[9], dm = 0.0;
+  double z1[2], z2[2], zn[2];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.0;
+  for (int c = 0; c < 2; ++c) {
+    z1[c] = flip_if(Q.c1[c][2], !H);
+    z2[c] = flip_if(Q.c2[c][2], !H);
+    zn[c] = flip_if(Q.cn[c][2], !H);
+  }
+  double acc[2][9], dm[2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[0][t] = acc[1][t] = 0.0;
+  dm[0] = dm[1] = 0.0;
   constexpr int X1 = SWAP ? 0 : 1, Y1 = SWAP ? 1 : 0, X2 = SWAP ? 1 : 0, Y2 = SWAP ? 0 : 1;
   Rec RA, RB;
   rec_load(RA, rec_addr<0, 0, 0>(eF, eZ));
@@ -455,9 +479,9 @@ __host__ __device__ inline void p2_half_t(T2 &N, const Meta &M, const ClsK &Q, d
   if (!LAST) rec_load(RB, rec_addr<NX_, NY_, 0>(eF, eZ));                                         \
   rec_use<SX, SY, 2>(RA, Q, z1, z2, zn, acc, dm);                                                 \
   if (fm & (1u << J)) {                                                                           \
-    p2_flush(N, M, Q, H, SX, SY, z, ring, S0, S1, acc, dm, f23, has_lower);                       \
-    _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[t] = 0.0;                                   \
-    dm = 0.0;                                                                                     \
+    p2_flush(N, sm, Q, H, SX, SY, z, acc, dm, f23, has_lower);                                    \
+    _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[0][t] = acc[1][t] = 0.0;                    \
+    dm[0] = dm[1] = 0.0;                                                                          \
   }                                                                                               \
   if (!LAST) RA = RB;
   NALU_P2_QUAD(0, 0, 0, X1, Y1, false)
@@ -467,58 +491,100 @@ __host__ __device__ inline void p2_half_t(T2 &N, const Meta &M, const ClsK &Q, d
 #undef NALU_P2_QUAD
 }
 
-__host__ __device__ inline void p2_half(T2 &N, const Meta &M, const ClsK &Q, double f23, int H, int z, const double *F,
-                                        const double *ZE, const double *ring, double *S0, double *S1, bool has_lower)
+__host__ __device__ inline void p2_half(T2 &N, double *sm, const ClsK &Q, double f23, int H, int z, bool has_lower)
 {
   // nodes outside the domain run the same code on zero records; their flushes see slot 0xFF
-  if (Q.a && !Q.b) p2_half_t<true>(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, has_lower);
-  else p2_half_t<false>(N, M, Q, f23, H, z, F, ZE, ring, S0, S1, has_lower);
+  if (Q.a && !Q.b) p2_half_t<true>(N, sm, Q, f23, H, z, has_lower);
+  else p2_half_t<false>(N, sm, Q, f23, H, z, has_lower);
 }
 
 // ---- node metadata of plane z: thread (node, g) reads the 9 slots of dz group g ------------------
-__host__ __device__ inline void meta_load(const BoxParams &P, const Meta &M, int node, int g, int x0, int y0, int z)
+// One thread per node.  Split in three so that the two dependent global loads (node_row -> browptr)
+// and the slot bytes are in flight while other work runs: meta_row one phase ahead, meta_fetch
+// before phase 1a, meta_store after.
+struct MetaRaw {
+  unsigned s[27];
+  long long b0, b1;
+  int row;
+};
+__host__ __device__ inline int meta_row(const BoxParams &P, int node, int x0, int y0, int z)
 {
   using C = Cfg;
   const int x = x0 + node % C::TBX, y = y0 + node / C::TBX;
-  unsigned mn = 255, mx = 0, cnt = 0;
-  long long rowbase = 0;
-  int nb = 0, row = 0;
-  if (x < P.NX && y < P.NY && z < P.NZ) {
-    const long long n = x + (long long)P.NX * (y + (long long)P.NY * z);
-    const unsigned char *sl = P.slot27 + n * 27 + g * 9;
+  if (!(x < P.NX && y < P.NY && z < P.NZ)) return -1;
+  return P.node_row[x + (long long)P.NX * (y + (long long)P.NY * z)];
+}
+__host__ __device__ inline void meta_fetch(const BoxParams &P, MetaRaw &R, int node, int x0, int y0, int z, int row)
+{
+  using C = Cfg;
+  R.row = row;
+  R.b0 = R.b1 = 0;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) R.s[k] = 0xFF;
+  if (row < 0) return;
+  const int x = x0 + node % C::TBX, y = y0 + node / C::TBX;
+  const long long n = x + (long long)P.NX * (y + (long long)P.NY * z);
+  const unsigned char *sl = P.slot27 + n * 27;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) R.s[k] = sl[k];
+  R.b0 = P.browptr[row];
+  R.b1 = P.browptr[row + 1];
+}
+__host__ __device__ inline void meta_store(const BoxParams &P, const Meta &M, const MetaRaw &R, int node)
+{
+  using C = Cfg;
+  unsigned mn[3], cnt[3];
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    unsigned lo = 255, hi = 0, c = 0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const unsigned s = sl[k];
+      const unsigned s = R.s[g * 9 + k];
       M.slot[node * 28 + g * 9 + k] = (unsigned char)s;
       if (s != 0xFF) {
-        mn = s < mn ? s : mn;
-        mx = s > mx ? s : mx;
-        ++cnt;
+        lo = s < lo ? s : lo;
+        hi = s > hi ? s : hi;
+        ++c;
       }
     }
-    if (cnt && mx - mn + 1 != cnt) *P.err = 2; // the columns of a dz group must be contiguous in the row
-    row = P.node_row[n];
-    const long long b0 = P.browptr[row];
-    nb = (int)(P.browptr[row + 1] - b0);
-    rowbase = 9 * b0;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) M.slot[node * 28 + g * 9 + k] = 0xFF;
+    if (c && hi - lo + 1 != c) *P.err = 2; // the columns of a dz group must be contiguous in the row
+    mn[g] = c ? lo : 0;
+    cnt[g] = c;
   }
-  if (!cnt) mn = 0;
+  const int nb = (int)(R.b1 - R.b0);
+  const long long rowbase = 9 * R.b0;
+  // parity of dof row i: staging offset of the dz=0 group = 16-byte phase of its place in `values`
   unsigned pb = 0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const long long G = rowbase + ((long long)i * nb + mn) * 3;
-    pb |= (unsigned)((G ^ node) & 1) << i;
+  for (int i = 0; i < 3; ++i) pb |= (unsigned)((rowbase + ((long long)i * nb + mn[1]) * 3 + node) & 1) << i;
+  // the dz=-1 / dz=+1 group sits right behind the dz=0 group (as in the row); one more double if its
+  // own 16-byte phase demands it (only when the groups are not neighbours in the row)
+  unsigned base[3], fix2 = 0;
+  base[1] = 0;
+#pragma unroll
+  for (int g = 0; g < 3; g += 2) {
+    const unsigned b = cnt[1] * 3;
+    const unsigned fix = (unsigned)((node + (pb & 1) + b + rowbase + (long long)mn[g] * 3) & 1);
+    base[g] = b + fix;
+    if (g == 2) fix2 = fix;
   }
-  M.gp[node * 4 + g] = (unsigned short)(mn | (pb << 8));
-  M.cnt[node * 4 + g] = (unsigned char)cnt;
-  if (g == 0) {
-    M.rowbase[node] = rowbase;
-    M.nb[node] = nb;
-    M.row[node] = row;
+  const unsigned merged = cnt[2] && cnt[1] && mn[2] == mn[1] + cnt[1] && !fix2;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    M.gp[node * 4 + g] = (unsigned short)(mn[g] | (base[g] << 8));
+    M.cnt[node * 4 + g] = (unsigned char)cnt[g];
   }
+  M.gp[node * 4 + 3] = (unsigned short)(pb | (merged << 3));
+  M.rowbase[node] = rowbase;
+  M.nb[node] = nb;
+  M.row[node] = R.row < 0 ? 0 : R.row;
+  (void)C::SROWP;
+}
+__host__ __device__ inline void meta_load(const BoxParams &P, const Meta &M, int node, int x0, int y0, int z)
+{
+  MetaRaw R;
+  meta_fetch(P, R, node, x0, y0, z, meta_row(P, node, x0, y0, z));
+  meta_store(P, M, R, node);
 }
 
 // ---- copy-out of dof row i of dz group g of one node: where it lives -------------------------------
@@ -531,10 +597,13 @@ __host__ __device__ inline Run run_of(const Meta &M, int node, int i, int g)
 {
   using C = Cfg;
   Run r;
-  const unsigned gp = M.gp[node * 4 + g];
+  const unsigned gp = M.gp[node * 4 + g], nf = M.gp[node * 4 + 3];
+  const bool merged = (nf >> 3) & 1;
   r.L = 3 * M.cnt[node * 4 + g];
+  if (merged && g == 1) r.L += 3 * M.cnt[node * 4 + 2]; // dz=0 and dz=+1 leave as one run
+  if (merged && g == 2) r.L = 0;
   r.G = M.rowbase[node] + ((long long)i * M.nb[node] + (gp & 0xFF)) * 3;
-  r.soff = node * C::SNODE + i * C::SROWP + ((gp >> (8 + i)) & 1);
+  r.soff = node * C::SNODE + i * C::SROWP + ((nf >> i) & 1) + (gp >> 8);
   return r;
 }
 

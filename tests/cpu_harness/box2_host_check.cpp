@@ -120,9 +120,7 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
   double *sm = nullptr;
   if (posix_memalign((void **)&sm, 16, sizeof(double) * C::SMEM_DOUBLES)) abort();
   std::vector<box2::T2> N(NT);
-  struct Regs { double p[C::NPL]; double m[C::NML]; };
-  std::vector<Regs> R(NT);
-  std::vector<box2::StageIdx> SI(NT);
+
   box2::P2K K;
   box2::p2k_init(K, P.options, P.include_divu);
   box2::ClsK Q[C::NCLS];
@@ -130,7 +128,7 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
   for (int cta = 0; cta < P.tiles_x * P.tiles_y * zchunks; ++cta) {
     for (int i = 0; i < C::SMEM_DOUBLES; ++i) sm[i] = NAN; // uninitialised shared memory must never be consumed
     for (int i = 0; i < 2 * C::NEL * C::ES; ++i) sm[C::OFF_F + i] = 0.0; // kernel prologue: records outside the domain read zero
-    double *F = sm + C::OFF_F, *ZE = sm + C::OFF_ZE, *S0 = sm + C::OFF_S0, *S1 = sm + C::OFF_S1;
+    double *F = sm + C::OFF_F, *ZE = sm + C::OFF_ZE, *S0 = sm + C::OFF_S, *S1 = sm + C::OFF_S;
     double *ring = sm + C::OFF_RING, *mdb = sm + C::OFF_MD, *rp = sm + C::OFF_RP;
     const int ntile = P.tiles_x * P.tiles_y;
     const int tile = cta % ntile, zc = cta / ntile;
@@ -139,17 +137,12 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
     const int ze = (zs + P.z_chunk < P.NZ) ? zs + P.z_chunk : P.NZ;
     for (int tid = 0; tid < NT; ++tid) {
       box2::t2_init(P, N[tid], tid & 31, x0, y0);
-      box2::stage_init(P, SI[tid], tid, x0, y0);
     }
-    for (int pl = zs - 1; pl <= zs; ++pl)
-      for (int tid = 0; tid < NT; ++tid) {
-        box2::plane_fetch(P, SI[tid], pl, R[tid].p);
-        box::plane_store<C>(tid, R[tid].p, ring + ((pl + 3) % 3) * C::PLN);
-      }
     for (int tid = 0; tid < NT; ++tid) {
-      box2::mdot_fetch(P, SI[tid], zs - 1, R[tid].m);
-      box::mdot_store<C>(tid, R[tid].m, mdb);
-      if ((tid >> 5) < 3) box2::meta_load(P, box2::meta_at(sm, zs & 1), tid & 31, tid >> 5, x0, y0, zs);
+      box2::stage_plane(P, ring + ((zs + 2) % 3) * C::PLN, tid, x0, y0, zs - 1);
+      box2::stage_plane(P, ring + (zs % 3) * C::PLN, tid, x0, y0, zs);
+      box2::stage_mdot(P, mdb, tid, x0, y0, zs - 1);
+      if ((tid >> 5) == 0) box2::meta_load(P, box2::meta_at(sm, zs & 1), tid & 31, x0, y0, zs);
     }
     // ---- barrier
     if (zs >= 1)
@@ -158,47 +151,37 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
         box2::p1_item(P, el, k < 2 ? k : 2, k < 2 ? 1 : k - 2, x0, y0, ring + ((zs - 1) % 3) * C::PLN,
                       ring + (zs % 3) * C::PLN, mdb, F, ZE);
       }
-    for (int tid = 0; tid < NT; ++tid) {
-      box2::plane_fetch(P, SI[tid], zs + 1, R[tid].p);
-      box2::mdot_fetch(P, SI[tid], zs, R[tid].m);
-    }
+    for (int tid = 0; tid < NT; ++tid) box2::stage_plane(P, ring + ((zs + 1) % 3) * C::PLN, tid, x0, y0, zs + 1);
     // ---- barrier
     for (int z = zs; z < ze; ++z) {
       const box2::Meta M = box2::meta_at(sm, z & 1);
       const double *pl_0 = ring + (z % 3) * C::PLN, *pl_p = ring + ((z + 1) % 3) * C::PLN;
       const bool lower = z >= 1, upper = z < P.nz;
       // ---- A
-      for (int tid = 0; tid < NT; ++tid) {
-        box::plane_store<C>(tid, R[tid].p, ring + ((z + 1) % 3) * C::PLN);
-        box::mdot_store<C>(tid, R[tid].m, mdb);
-      }
+      for (int tid = 0; tid < NT; ++tid) box2::stage_mdot(P, mdb, tid, x0, y0, z);
       for (int tid = 0; tid < NT; ++tid) {
         box2::T2 &n = N[tid];
         n.rr[0] = n.rr[1] = n.rr[2] = 0.0;
-        if (lower) box2::p2_half(n, M, Q[tid >> 5], K.f23, 0, z, F, ZE, ring, S0, S1, false);
+        if (lower) box2::p2_half(n, sm, Q[tid >> 5], K.f23, 0, z, false);
       }
       // ---- barrier; B
       for (int tid = 0; tid < 96; ++tid)
         if (lower) copy_run_host(M, tid & 31, tid >> 5, 0, S1, P.values, P.overwrite, bulk);
-      for (int i = 0; i < C::NNODE * C::SNODE; ++i) S1[i] = NAN;
       if (upper)
         for (int it = 0; it < C::NP1A; ++it) {
           const int k = it / C::NEL, el = it - k * C::NEL;
           box2::p1_item(P, el, k < 2 ? k : 2, k < 2 ? 0 : k - 2, x0, y0, pl_0, pl_p, mdb, F, ZE);
         }
       if (z + 1 < ze)
-        for (int tid = 0; tid < 96; ++tid) box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), tid & 31, tid >> 5, x0, y0, z + 1);
+        for (int tid = 0; tid < 32; ++tid) box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), tid, x0, y0, z + 1);
       // ---- barrier; C
       for (int tid = 0; tid < NT; ++tid) {
         box2::T2 &n = N[tid];
-        if (upper) box2::p2_half(n, M, Q[tid >> 5], K.f23, 1, z, F, ZE, ring, S0, S1, lower);
+        if (upper) box2::p2_half(n, sm, Q[tid >> 5], K.f23, 1, z, lower);
         for (int i = 0; i < 3; ++i) rp[((tid >> 5) * C::NNODE + (tid & 31)) * 3 + i] = n.rr[i];
       }
       // ---- barrier; D
-      for (int tid = 0; tid < NT; ++tid) {
-        box2::plane_fetch(P, SI[tid], z + 2, R[tid].p);
-        box2::mdot_fetch(P, SI[tid], z + 1, R[tid].m);
-      }
+      for (int tid = 0; tid < NT; ++tid) box2::stage_plane(P, ring + ((z + 2) % 3) * C::PLN, tid, x0, y0, z + 2);
       for (int tid = 0; tid < 96; ++tid) {
         const int lane = tid & 31, warp = tid >> 5;
         copy_run_host(M, lane, warp, 1, S0, P.values, P.overwrite, bulk);
@@ -212,7 +195,7 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
           *r = P.overwrite ? v : *r + v;
         }
       }
-      for (int i = 0; i < C::NNODE * C::SNODE; ++i) S0[i] = S1[i] = NAN;
+      for (int i = 0; i < C::NNODE * C::SNODE; ++i) S0[i] = NAN;
       if (upper)
         for (int it = 0; it < C::NP1B; ++it) {
           const int k = it / C::NEL, el = it - k * C::NEL;

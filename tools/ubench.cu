@@ -93,6 +93,25 @@ __global__ void k_bulk(double *dst, int bytes, int nrun, int iters, long long *c
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+// issue cost: `nw` warps, every lane issues `nops` bulk copies back to back (waterfall per warp instruction),
+// clock per warp-level issue loop; no wait inside the timed region
+__global__ void k_bulk_issue(double *dst, int bytes, int nops, long long *cyc)
+{
+  extern __shared__ __align__(128) double s[];
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) s[i] = i;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const unsigned src = (unsigned)__cvta_generic_to_shared(s) + (threadIdx.x & 63) * 512;
+  char *g = (char *)dst + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 512;
+  long long t0 = clock64();
+  for (int i = 0; i < nops; ++i)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(src), "r"(bytes) : "memory");
+  long long t1 = clock64();
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 int main()
 {
   int sms = 0;
@@ -153,6 +172,14 @@ int main()
     printf(",\n \"bulk_%dB_x%d\": {\"GBps\": %.1f, \"Mops_per_s_per_sm\": %.2f, \"cyc_per_round\": %.1f}", bytes, nrun,
            ops * bytes / (ms * 1e-3) / 1e9, ops / (ms * 1e-3) / 1e6 / sms, (double)h / iters);
   }
+  for (int nw = 1; nw <= 4; nw *= 4)
+    for (int bytes = 208; bytes <= 432; bytes += 224) {
+      CK(cudaFuncSetAttribute(k_bulk_issue, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      k_bulk_issue<<<sms, 32 * nw, 65536>>>(out, bytes, 8, cyc);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+      printf(",\n \"bulk_issue_%dB_w%d_cyc_per_lane_op\": %.1f", bytes, nw, (double)h / (8.0 * 32));
+    }
   printf("}\n");
   return 0;
 }
