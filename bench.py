@@ -269,7 +269,8 @@ def run_ours(args):
     bytes_alg = algorithmic_bytes(m.n_nodes, n_elems_rank, nnz, 3, nodal_comps=7, elem_comps=12)
     achieved = bytes_alg / (asm_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "assemble_box" if overwrite else "assemble_general",
+                "traffic": None, "peak_source": peak_src, "kernel": (("assemble_box2" if os.environ.get("NALU_BOX_TILE", "0") == "0" else "assemble_box") if overwrite
+                           else "assemble_general"),
                 "algorithmic_bytes_per_launch": bytes_alg, "bytes_per_element": bytes_alg / n_elems_rank,
                 "kernel_ms": asm_ms}
     tf = os.path.join(ROOT, "profiles", "traffic.json")

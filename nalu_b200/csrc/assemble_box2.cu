@@ -186,6 +186,10 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
       N.rr[0] = N.rr[1] = N.rr[2] = 0.0;
     }
     if ((H ? upper : lower) && !(P.options & (1 << 18))) {
+      // profiling aid: 9 stamps inside the pass for half-steps 4 and 5 of the traced CTA
+      N.trace = (P.trace && blockIdx.x == TRACE_CTA && lane == 0 && (hs == 2 * zs + 4 || hs == 2 * zs + 5))
+                    ? P.trace + 16 * 8 * 8 + ((hs - 2 * zs - 4) * 4 + warp) * 16
+                    : nullptr;
       box2::ClsK Q;
       box2::cls_fetch(Q, qk, warp);
       box2::p2_half(N, sm, Q, f23, H, z, lower);
@@ -214,13 +218,22 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
     } else if (BULK) {
       // the run list of this half (H = 0: 96 runs of the dz=-1 group; H = 1: 96 of dz=0, then 96 of
       // dz=+1) spread over all 8 warps: the per-lane bulk issue serialises inside a warp
-      const int per = (H ? 192 : 96) / C::NCLS;
+      if (H) {
+        // every warp takes 24 runs of dz=0 (which carry dz=+1 along when merged) and 24 of dz=+1
 #pragma unroll 1
-      for (int l = lane; l < per; l += 32) {
-        // H = 1: every warp takes 24 runs of dz=0 (which carry dz=+1 along when merged) and 24 of dz=+1
-        const int g = H ? 1 + l / 24 : 0, rr = warp * 24 + l % 24;
-        if (g == 0 ? lower : (g == 2 ? upper : true))
-          copy_run<BULK>(M, rr & 31, rr >> 5, g, g == 1 ? S0 : S1, P.values, P.overwrite);
+        for (int l = lane; l < 48; l += 32) {
+          const int g = 1 + l / 24, rr = warp * 24 + l % 24;
+          if (g == 2 ? upper : true) copy_run<BULK>(M, rr & 31, rr >> 5, g, S0, P.values, P.overwrite);
+        }
+      } else if (lower) {
+        // the 96 runs of dz=-1, shared out against the phase 1a load (180 items on 128 threads: warp 0
+        // has two items per lane, warp 1 two on 20 lanes): 0 / 8 / 44 / 44 runs
+        const int first = warp < 2 ? 0 : 8 + (warp - 2) * 44, cnt = warp == 0 ? 0 : (warp == 1 ? 8 : 44);
+#pragma unroll 1
+        for (int l = lane; l < cnt; l += 32) {
+          const int rr = first + l;
+          copy_run<BULK>(M, rr & 31, rr >> 5, 0, S0, P.values, P.overwrite);
+        }
       }
       bulk_commit();
     } else {
@@ -285,14 +298,14 @@ static int launch2(BoxParams &P, cudaStream_t stream)
   }
   static long long *d_trace = nullptr;
   const bool trace = getenv("NALU_BOX_TRACE") != nullptr;
-  if (trace && !d_trace) NALU_CUDA(cudaMalloc(&d_trace, 16 * 8 * 8 * sizeof(long long)));
+  if (trace && !d_trace) NALU_CUDA(cudaMalloc(&d_trace, (16 * 8 * 8 + 128) * sizeof(long long)));
   P.trace = trace ? d_trace : nullptr;
-  if (trace) NALU_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 8 * 8 * sizeof(long long), stream));
+  if (trace) NALU_CUDA(cudaMemsetAsync(d_trace, 0, (16 * 8 * 8 + 128) * sizeof(long long), stream));
   assemble_box2_kernel<BULK><<<(unsigned)ctas, C::NT, smem, stream>>>(P);
   count_launch();
   NALU_CUDA(cudaGetLastError());
   if (trace) {
-    static long long h[16 * 8 * 8];
+    static long long h[16 * 8 * 8 + 128];
     NALU_CUDA(cudaStreamSynchronize(stream));
     NALU_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
     if (FILE *f = fopen(getenv("NALU_BOX_TRACE"), "w")) {
@@ -302,6 +315,12 @@ static int launch2(BoxParams &P, cudaStream_t stream)
           for (int k = 0; k < 7; ++k) fprintf(f, " %lld", h[(hs * 8 + w) * 8 + k] ? h[(hs * 8 + w) * 8 + k] - h[0] : -1LL);
           fprintf(f, "\n");
         }
+      for (int k = 0; k < 8; ++k) {
+        fprintf(f, "p2 half %d warp %d:", k / 4, k % 4);
+        const long long *t = h + 16 * 8 * 8 + k * 16;
+        for (int j = 1; j < 9; ++j) fprintf(f, " %lld", t[j] && t[j - 1] ? t[j] - t[j - 1] : -1LL);
+        fprintf(f, "\n");
+      }
       fclose(f);
     }
   }

@@ -2,23 +2,30 @@
 // Hex8 blocks ("column-pair" kernel).  Same contract as box_tile.cuh (what
 // AssembleElemSolverAlgorithm::execute + MomentumAdvDiffElemKernel::execute +
 // TpetraLinearSystem::sumInto produce: src/AssembleElemSolverAlgorithm.C:74-100,
-// src/kernel/MomentumAdvDiffElemKernel.C:70-186, src/TpetraLinearSystem.C:1457-1522), new
-// work decomposition, chosen from the measured machine balance (tools/ubench.cu: one LDS.128 per
-// clock per SM whatever the address pattern, DFMA needs 4 independent instructions in flight per
-// scheduler, 208-byte cp.async.bulk stores sustain ~6 TB/s):
+// src/kernel/MomentumAdvDiffElemKernel.C:70-186, src/TpetraLinearSystem.C:1457-1522), new work
+// decomposition, driven by what was measured on the B200 (shared-memory
+// wavefronts, instruction-cache footprint, per-warp latency, cost of a bulk-copy issue):
 //
-//   * a CTA owns an 8 x 4 column of nodes and sweeps z; a node row is served by 8 threads, one
-//     per WARP-UNIFORM class (a,b,c) in {0,1}^3: the thread owns the column nodes at offset
-//     (+-a, +-b, +-c) and reads an integration-point record with 7 x LDS.128; the shape-function
-//     constants of a class are 12 per-thread registers (classes are data, not code: per-class
-//     instruction streams overflow the instruction cache -- measured 43 % no-instruction stalls),
-//     the only other sign is the outward direction tau of the face with respect to the row node;
+//   * a CTA owns an 8 x 4 column of nodes and sweeps z; a node row is served by 4 threads, one
+//     per WARP-UNIFORM class (a,b) in {0,1}^2: the thread owns the column nodes at offset
+//     (+-a, +-b, *) and computes, for every integration point it visits, BOTH the column in the
+//     row's plane (c = 0) and the one in the neighbouring plane (c = 1) from one 7 x LDS.128 read
+//     (half the shared-memory traffic of one column per thread).  The shape-function constants of
+//     a class are per-thread registers fetched from shared memory (classes are data, not code:
+//     per-class instruction streams overflow the instruction cache -- measured 43 % no-instruction
+//     stalls); the outward signs tau_x, tau_y of a face are compile-time (quadrants are unrolled)
+//     and applied as FMA operand modifiers;
 //   * only 8 of an element's 12 integration points are resident at a time: the 4 z-edge points
 //     (used by the node plane below and the one above) and the 4 points of one face (bottom face
 //     for the rows below the layer, top face for the rows above it) -- phase 1 runs twice per plane;
-//   * finished 3x3 blocks go to a staging image of ONE dz group of the row (9 columns, 27 doubles
-//     per dof row) which is streamed to HBM by cp.async.bulk (one 208-byte copy per dof row and
-//     group); the dz = 0 group is completed in two halves (elements below / above the plane);
+//     records of elements outside the domain are zero, so phase 2 carries no boundary tests;
+//   * finished 3x3 blocks go to a staging image of the row's dz = 0 group followed by its dz = -1
+//     (lower half) or dz = +1 (upper half) group, laid out like the CSR row and phase-aligned with
+//     it modulo 16 bytes, and leave through cp.async.bulk: one 27-double run per dof row for dz = -1,
+//     one 54-double run for dz = 0 and dz = +1 together;
+//   * nodal fields and mass flow rates are staged with cp.async one phase ahead, node metadata
+//     (row offsets, the 27 column slots) with loads split across phases: no global-memory latency
+//     sits on a phase's critical path;
 //   * the div(u) stress needs no integration-point scalar: with acc = sum tau h (x) A accumulated for
 //     the viscous block anyway, rhs_i -= 2/3 mu divU A_i  ==  rhs_i += 2/3 sum_c sum_j acc_c[j][i] u_cj
 //     (MomentumAdvDiffElemKernel.C:105-136 uses the same dndx and mu for divU and the viscous lhs).
@@ -45,7 +52,6 @@ struct Cfg {
   static constexpr int ES = 4 * IPD + 2;  // element stride; ES/2 odd: the 8 lanes of an LDS.128 phase hit 8 bank groups
   static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY, NF = 7, PLN = RN * NF;
   static constexpr int MDB = NEL * 12;
-  static constexpr int NPL = (PLN + NT - 1) / NT, NML = (MDB + NT - 1) / NT;
   // staging of one node: 3 dof rows x [parity pad | dz=0 group (27) | dz=-1 or dz=+1 group (27)]; the two
   // parts are adjacent like in the CSR row, so that dz=0 and dz=+1 leave as ONE 54-double run
   static constexpr int SROWP = 56;
@@ -354,7 +360,13 @@ struct T2 {
   int lx, ly, node;
   int active, vmask;
   double rr[3];
+  long long *trace; // profiling aid: clock stamps inside phase 2 (null unless NALU_BOX_TRACE)
 };
+#ifdef __CUDA_ARCH__
+#define NALU_T2_STAMP(N) do { if ((N).trace) *(N).trace++ = clock64(); } while (0)
+#else
+#define NALU_T2_STAMP(N) do { } while (0)
+#endif
 
 __host__ __device__ inline void t2_init(const BoxParams &P, T2 &N, int lane, int x0, int y0)
 {
@@ -364,6 +376,7 @@ __host__ __device__ inline void t2_init(const BoxParams &P, T2 &N, int lane, int
   N.ly = lane / C::TBX;
   const int x = x0 + N.lx, y = y0 + N.ly;
   N.active = x < P.NX && y < P.NY;
+  N.trace = nullptr;
   N.vmask = 0;
   for (int q = 0; q < 4; ++q) {
     const int ex = x - 1 + (q & 1), ey = y - 1 + (q >> 1);
@@ -371,30 +384,64 @@ __host__ __device__ inline void t2_init(const BoxParams &P, T2 &N, int lane, int
   }
 }
 
-// finished blocks of one (sx,sy) group -> staging; rhs share.  H = 0: elements below the plane
-// (column c = 1 fills the dz = -1 group in S1, c = 0 the first half of dz = 0 in S0), H = 1: above
-// (c = 1 -> dz = +1, c = 0 completes dz = 0 on top of the partial left in S0 when `has_lower`).
-// (An out-of-line version costs ~100 warp instructions per node in call overhead: measured.)
-__host__ __device__ __forceinline__ void p2_flush(T2 &N, double *sm, const ClsK &Q, int H, int sx, int sy, int z,
-                                                  const double (&acc)[2][9], const double (&dm)[2], double f23,
-                                                  bool has_lower)
+// ---- flush of the finished blocks of one (sx,sy) group -> staging; rhs share ------------------------
+// H = 0: elements below the plane (column c = 1 fills the dz = -1 group, c = 0 the first half of
+// dz = 0), H = 1: above (c = 1 -> dz = +1, c = 0 completes dz = 0 on top of the partial left in the
+// staging row when `has_lower`).  Split in three so that no shared-memory latency sits between the
+// last FMA of a block and its stores (the dependent slot -> offset -> operand chain was measured at
+// 600-1700 cycles per flush): flush_prep (start of the pass: slot bytes -> staging offsets),
+// flush_fetch (start of the quadrant: u of the column nodes, partial of the dz = 0 block),
+// flush_commit (arithmetic and stores only).
+struct FlushPrep {
+  int s[2];   // staging offset of the (i = 0) row of the block of column c, < 0: no such neighbour
+  int uo[2];  // offset of the column node's velocity in the ring
+};
+struct FlushOps {
+  double u[2][3];
+  double part[9];
+};
+__host__ __device__ __forceinline__ void flush_prep(FlushPrep &F, const T2 &N, const Meta &M, const ClsK &Q, int H, int sx,
+                                                    int sy, int z, unsigned gp0, unsigned gp1)
 {
   using C = Cfg;
-  const Meta M = meta_at(sm, z & 1);
   const int dx = Q.a ? (sx ? 1 : -1) : 0, dy = Q.b ? (sy ? 1 : -1) : 0;
+  const int idx = (dy + 1) * 3 + (dx + 1);
+  const int g1 = H ? 2 : 0;
+  const unsigned slot0 = M.slot[N.node * 28 + 9 + idx], slot1 = M.slot[N.node * 28 + g1 * 9 + idx];
+  F.s[0] = slot0 == 0xFF ? -1 : (int)(N.node * C::SNODE + (gp0 >> 8) + (slot0 - (gp0 & 0xFF)) * 3);
+  F.s[1] = slot1 == 0xFF ? -1 : (int)(N.node * C::SNODE + (gp1 >> 8) + (slot1 - (gp1 & 0xFF)) * 3);
+  const int uo = ((N.lx + 1 + dx) + C::RNX * (N.ly + 1 + dy)) * C::NF + 4;
+  F.uo[0] = C::OFF_RING + (z % 3) * C::PLN + uo;
+  F.uo[1] = C::OFF_RING + ((z + (H ? 1 : 2)) % 3) * C::PLN + uo;
+}
+__host__ __device__ __forceinline__ void flush_fetch(FlushOps &O, const FlushPrep &F, const double *sm, unsigned pb, bool add)
+{
+  using C = Cfg;
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) O.u[c][j] = sm[F.uo[c] + j];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) O.part[t] = 0.0;
+  if (add && F.s[0] >= 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double *d = sm + C::OFF_S + F.s[0] + i * C::SROWP + ((pb >> i) & 1);
+      O.part[i * 3 + 0] = d[0];
+      O.part[i * 3 + 1] = d[1];
+      O.part[i * 3 + 2] = d[2];
+    }
+  }
+}
+__host__ __device__ __forceinline__ void flush_commit(T2 &N, double *sm, const FlushPrep &F, const FlushOps &O, unsigned pb,
+                                                      const double (&acc)[2][9], const double (&dm)[2], double f23)
+{
+  using C = Cfg;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const int dz = c ? (H ? 1 : -1) : 0;
-    const int g = dz + 1;
-    const unsigned slot = M.slot[N.node * 28 + g * 9 + (dy + 1) * 3 + (dx + 1)];
-    if (slot == 0xFF) continue; // no such neighbour
-    const unsigned gp = M.gp[N.node * 4 + g], pb = M.gp[N.node * 4 + 3];
-    const unsigned gs = gp & 0xFF, gbase = gp >> 8;
-    const double *u = sm + C::OFF_RING + ((z + dz + 3) % 3) * C::PLN + ((N.lx + 1 + dx) + C::RNX * (N.ly + 1 + dy)) * C::NF + 4;
-    const double u0 = u[0], u1 = u[1], u2 = u[2];
+    if (F.s[c] < 0) continue; // no such neighbour
+    const double u0 = O.u[c][0], u1 = O.u[c][1], u2 = O.u[c][2];
     const double D = dm[c] + (acc[c][0] + acc[c][4] + acc[c][8]);
-    double *Sb = sm + C::OFF_S + N.node * C::SNODE + gbase + (slot - gs) * 3;
-    const bool add = c == 0 && H && has_lower;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       double v0 = acc[c][i * 3 + 0], v1 = acc[c][i * 3 + 1], v2 = acc[c][i * 3 + 2];
@@ -403,11 +450,11 @@ __host__ __device__ __forceinline__ void p2_flush(T2 &N, double *sm, const ClsK 
       if (i == 2) v2 += D;
       N.rr[i] -= v0 * u0 + v1 * u1 + v2 * u2;
       N.rr[i] += f23 * (acc[c][0 + i] * u0 + acc[c][3 + i] * u1 + acc[c][6 + i] * u2);
-      double *d = Sb + i * C::SROWP + ((pb >> i) & 1);
-      if (add) {
-        v0 += d[0];
-        v1 += d[1];
-        v2 += d[2];
+      double *d = sm + C::OFF_S + F.s[c] + i * C::SROWP + ((pb >> i) & 1);
+      if (c == 0) { // the partial of the lower half (zero when there is none)
+        v0 += O.part[i * 3 + 0];
+        v1 += O.part[i * 3 + 1];
+        v2 += O.part[i * 3 + 2];
       }
       d[0] = v0;
       d[1] = v1;
@@ -469,20 +516,34 @@ __host__ __device__ inline void p2_half_t(T2 &N, double *sm, const ClsK &Q, doub
   for (int t = 0; t < 9; ++t) acc[0][t] = acc[1][t] = 0.0;
   dm[0] = dm[1] = 0.0;
   constexpr int X1 = SWAP ? 0 : 1, Y1 = SWAP ? 1 : 0, X2 = SWAP ? 1 : 0, Y2 = SWAP ? 0 : 1;
+  // staging offsets and velocity addresses of the (up to) four flushes of this pass
+  const Meta M = meta_at(sm, z & 1);
+  const unsigned gp0 = M.gp[N.node * 4 + 1], gp1 = M.gp[N.node * 4 + (H ? 2 : 0)], pb = M.gp[N.node * 4 + 3];
+  const bool add = H && has_lower;
+  FlushPrep FP0, FP1, FP2, FP3;
+  flush_prep(FP0, N, M, Q, H, 0, 0, z, gp0, gp1);
+  flush_prep(FP1, N, M, Q, H, X1, Y1, z, gp0, gp1);
+  flush_prep(FP2, N, M, Q, H, X2, Y2, z, gp0, gp1);
+  flush_prep(FP3, N, M, Q, H, 1, 1, z, gp0, gp1);
+  FlushOps FO;
   Rec RA, RB;
+  NALU_T2_STAMP(N);
   rec_load(RA, rec_addr<0, 0, 0>(eF, eZ));
 #define NALU_P2_QUAD(J, SX, SY, NX_, NY_, LAST)                                                   \
+  if (fm & (1u << J)) flush_fetch(FO, FP##J, sm, pb, add);                                        \
   rec_load(RB, rec_addr<SX, SY, 1>(eF, eZ));                                                      \
   rec_use<SX, SY, 0>(RA, Q, z1, z2, zn, acc, dm);                                                 \
   rec_load(RA, rec_addr<SX, SY, 2>(eF, eZ));                                                      \
   rec_use<SX, SY, 1>(RB, Q, z1, z2, zn, acc, dm);                                                 \
   if (!LAST) rec_load(RB, rec_addr<NX_, NY_, 0>(eF, eZ));                                         \
   rec_use<SX, SY, 2>(RA, Q, z1, z2, zn, acc, dm);                                                 \
+  NALU_T2_STAMP(N);                                                                               \
   if (fm & (1u << J)) {                                                                           \
-    p2_flush(N, sm, Q, H, SX, SY, z, acc, dm, f23, has_lower);                                    \
+    flush_commit(N, sm, FP##J, FO, pb, acc, dm, f23);                                             \
     _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[0][t] = acc[1][t] = 0.0;                    \
     dm[0] = dm[1] = 0.0;                                                                          \
   }                                                                                               \
+  NALU_T2_STAMP(N);                                                                               \
   if (!LAST) RA = RB;
   NALU_P2_QUAD(0, 0, 0, X1, Y1, false)
   NALU_P2_QUAD(1, X1, Y1, X2, Y2, false)
