@@ -247,7 +247,11 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   if (const char *e = getenv("NALU_BOX_TILE")) tile = atoi(e);
   // default: the column-pair kernel (assemble_box2.cu); NALU_BOX_TILE selects the first-generation
   // class kernel of this file (kept for cross-checks and A/B measurements)
-  if (tile == 0) return launch_assemble_box2(P, stream);
+  if (tile == 0) {
+    if (const char *e = getenv("NALU_BOX_KERNEL"))
+      if (atoi(e) == 3) return launch_assemble_box3(P, stream);
+    return launch_assemble_box2(P, stream);
+  }
   if (tile == 84) return launch_cfg<box::Cfg<8, 4>>(g, P, stream);
   if (tile == 86) return launch_cfg<box::Cfg<8, 6>>(g, P, stream);
   return launch_cfg<box::Cfg<6, 4>>(g, P, stream);

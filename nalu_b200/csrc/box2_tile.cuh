@@ -572,7 +572,7 @@ __host__ __device__ inline int meta_row(const BoxParams &P, int node, int x0, in
 {
   using C = Cfg;
   const int x = x0 + node % C::TBX, y = y0 + node / C::TBX;
-  if (!(x < P.NX && y < P.NY && z < P.NZ)) return -1;
+  if (!(x < P.NX && y < P.NY && z >= 0 && z < P.NZ)) return -1;
   return P.node_row[x + (long long)P.NX * (y + (long long)P.NY * z)];
 }
 __host__ __device__ inline void meta_fetch(const BoxParams &P, MetaRaw &R, int node, int x0, int y0, int z, int row)

@@ -416,6 +416,32 @@ def test_box_kernel_tiles_and_chunks(tile, zchunk, monkeypatch):
     assert ls.geometry_errors() == 0
 
 
+@pytest.mark.parametrize("zchunk", ["2", "0"])
+def test_box3_warp_specialised_kernel(zchunk, monkeypatch):
+    """assemble_box3.cu (experimental warp-specialised pipeline, NALU_BOX_KERNEL=3): same contract."""
+    monkeypatch.setenv("NALU_BOX_KERNEL", "3")
+    monkeypatch.setenv("NALU_BOX_TILE", "0")
+    if zchunk != "0":
+        monkeypatch.setenv("NALU_BOX_ZCHUNK", zchunk)
+    m = perturbed_box(13, 9, 7)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 3)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, "momentum_adv_diff", ("shifted_grad_op",), keep, include_divu=1.0)])
+    ls = _linsys(m, 3)
+    ls.values.fill_(float("nan"))
+    ls.rhs.fill_(float("nan"))
+    d = product_desc(ls, dev, "momentum_adv_diff", ("shifted_grad_op",), include_divu=1.0)
+    assert ls.assemble_elem([d], mode="box", overwrite=True) == 2
+    _compare_system(ls, orc)
+    v1, r1 = ls.values.clone(), ls.rhs.clone()
+    ls.assemble_elem([d], mode="box", overwrite=False)
+    torch.testing.assert_close(ls.values, 2 * v1, rtol=1e-15, atol=0)
+    torch.testing.assert_close(ls.rhs, 2 * r1, rtol=1e-15, atol=0)
+    assert ls.geometry_errors() == 0
+
+
 def test_box_kernel_matches_general_kernel_96cubed():
     """Beyond oracle-sized meshes: the two CUDA kernel families (atomic sumInto vs tiled write-once)
     are independent implementations; they must agree on a mesh too large for the CPU oracle."""
