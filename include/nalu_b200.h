@@ -187,6 +187,16 @@ enum {
 int nalu_b200_assemble_elem(const nalu_b200_graph *g, const nalu_b200_kernel_desc *kernels,
                             int32_t n_kernels, double *d_values, double *d_rhs, int32_t mode,
                             int32_t overwrite, void *stream);
+/* The same for the rows of node planes [z_begin, z_end) of a structured block only (tiled kernel;
+ * error if the mesh / kernel list is not supported by it).  The reference's execute() loops over
+ * element buckets (src/AssembleElemSolverAlgorithm.C:74-100) and any partition of that loop is a
+ * valid schedule; here the partition is by ROW plane, each row being written once by exactly one
+ * launch, so that a caller can overlap the host->device copy of the fields of the next planes with
+ * the assembly of the current ones.  Needs the nodal fields of planes z_begin-1 .. z_end and the
+ * element field of layers z_begin-1 .. z_end-1 to be valid at launch. */
+int nalu_b200_assemble_elem_zrange(const nalu_b200_graph *g, const nalu_b200_kernel_desc *kernels,
+                                   int32_t n_kernels, double *d_values, double *d_rhs, int32_t overwrite,
+                                   int32_t z_begin, int32_t z_end, void *stream);
 /* which kernel family the last nalu_b200_assemble_elem call used: 1 general, 2 box */
 int nalu_b200_last_assemble_mode(void);
 /* synchronises, then reports (and clears) the device flag raised when an element had a

@@ -219,7 +219,7 @@ static int launch_cfg(const Graph &g, BoxParams &P, cudaStream_t stream)
 }
 
 int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs,
-                        int overwrite, cudaStream_t stream)
+                        int overwrite, cudaStream_t stream, int z_begin, int z_end)
 {
   if (!box_supported(g, k, nk)) {
     set_error("assemble_box: unsupported mesh / kernel list");
@@ -243,6 +243,18 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   P.options = k[0].options;
   P.overwrite = overwrite;
   P.trace = nullptr;
+  P.z_first = 0;
+  P.z_last = P.NZ;
+  if (z_begin >= 0) {
+    // a range of node planes: only the column-pair kernel takes one
+    if (z_begin >= z_end || z_end > P.NZ) {
+      set_error("assemble_box: bad node-plane range");
+      return NALU_B200_ERR_ARG;
+    }
+    P.z_first = z_begin;
+    P.z_last = z_end;
+    return launch_assemble_box2(P, stream);
+  }
   int tile = 0;
   if (const char *e = getenv("NALU_BOX_TILE")) tile = atoi(e);
   // default: the column-pair kernel (assemble_box2.cu); NALU_BOX_TILE selects the first-generation

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
   const int ntile = P.tiles_x * P.tiles_y;
   const int tile = blockIdx.x % ntile, zc = blockIdx.x / ntile;
   const int x0 = (tile % P.tiles_x) * C::TBX, y0 = (tile / P.tiles_x) * C::TBY;
-  const int zs = zc * P.z_chunk;
-  const int ze = (zs + P.z_chunk < P.NZ) ? zs + P.z_chunk : P.NZ;
+  const int zs = P.z_first + zc * P.z_chunk;
+  const int ze = (zs + P.z_chunk < P.z_last) ? zs + P.z_chunk : P.z_last;
 
   box2::T2 N;
   box2::t2_init(P, N, lane, x0, y0);
@@ -278,15 +278,16 @@ static int launch2(BoxParams &P, cudaStream_t stream)
   // recomputes one element layer in its prologue)
   long long want = ((long long)sms * 2 * 12 + ntile - 1) / ntile;
   int zchunks = (int)(want < 1 ? 1 : want);
-  int zc = (P.NZ + zchunks - 1) / zchunks;
+  const int nplanes = P.z_last - P.z_first;
+  int zc = (nplanes + zchunks - 1) / zchunks;
   if (zc < 16) zc = 16;
   if (const char *e = getenv("NALU_BOX_ZCHUNK")) {
     const int v = atoi(e);
     if (v > 0) zc = v;
   }
-  if (zc > P.NZ) zc = P.NZ;
+  if (zc > nplanes) zc = nplanes;
   P.z_chunk = zc;
-  zchunks = (P.NZ + zc - 1) / zc;
+  zchunks = (nplanes + zc - 1) / zc;
   size_t smem = sizeof(double) * C::SMEM_DOUBLES;
   if (getenv("NALU_BOX_ONE_CTA")) smem = 120 * 1024; // profiling aid: one CTA per SM
   NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

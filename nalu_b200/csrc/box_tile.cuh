@@ -50,6 +50,7 @@ struct BoxParams {
   double include_divu;
   int options;
   int overwrite;
+  int z_first, z_last; // node planes [z_first, z_last) this launch assembles (column-pair kernel; default all)
   long long *trace; // profiling aid (NALU_BOX_TRACE): per-warp clock stamps of one CTA, else null
 };
 

@@ -388,6 +388,30 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   return launch_assemble_general(g, kernels, nk, d_values, d_rhs, s);
 }
 
+int nalu_b200_assemble_elem_zrange(const nalu_b200_graph *h, const nalu_b200_kernel_desc *kernels, int32_t nk,
+                                   double *d_values, double *d_rhs, int32_t overwrite, int32_t z_begin, int32_t z_end,
+                                   void *stream)
+{
+  if (!h || !kernels || !d_values || !d_rhs) {
+    set_error("assemble_elem_zrange: null argument");
+    return NALU_B200_ERR_ARG;
+  }
+  if (!h->g.d_browptr) {
+    set_error("assemble_elem_zrange: graph not finalized on a device");
+    return NALU_B200_ERR_STATE;
+  }
+  if (!box_supported(h->g, kernels, nk)) {
+    set_error("assemble_elem_zrange: tiled kernel does not support this mesh / kernel list");
+    return NALU_B200_ERR_ARG;
+  }
+  if (z_begin < 0) {
+    set_error("assemble_elem_zrange: bad node-plane range");
+    return NALU_B200_ERR_ARG;
+  }
+  set_last_mode(2);
+  return launch_assemble_box(h->g, kernels, nk, d_values, d_rhs, overwrite, (cudaStream_t)stream, z_begin, z_end);
+}
+
 int nalu_b200_geometry_errors(const nalu_b200_graph *h, int32_t *flag)
 {
   if (!h || !flag || !h->g.d_err) return NALU_B200_ERR_STATE;

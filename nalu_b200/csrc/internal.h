@@ -34,7 +34,7 @@ int launch_mdot(const Graph &g, const double *coords, const double *density, con
 // assemble_box.cu
 bool box_supported(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk);
 int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
-                        double *d_rhs, int overwrite, cudaStream_t stream);
+                        double *d_rhs, int overwrite, cudaStream_t stream, int z_begin = -1, int z_end = -1);
 // assemble_box2.cu
 namespace box { struct BoxParams; }
 int launch_assemble_box2(box::BoxParams &P, cudaStream_t stream);

@@ -45,7 +45,7 @@ SYMBOLS = [
     "nalu_b200_graph_recv_data", "nalu_b200_graph_finalize", "nalu_b200_graph_finalize_host_only",
     "nalu_b200_graph_get_info", "nalu_b200_graph_copy_rowptr", "nalu_b200_graph_copy_colidx",
     "nalu_b200_graph_copy_row_gids", "nalu_b200_graph_copy_col_gids", "nalu_b200_graph_copy_node_lids",
-    "nalu_b200_graph_device_ptrs", "nalu_b200_zero_system", "nalu_b200_assemble_elem",
+    "nalu_b200_graph_device_ptrs", "nalu_b200_zero_system", "nalu_b200_assemble_elem", "nalu_b200_assemble_elem_zrange",
     "nalu_b200_last_assemble_mode", "nalu_b200_geometry_errors", "nalu_b200_sum_into", "nalu_b200_assemble_node_mass",
     "nalu_b200_mdot_scs", "nalu_b200_halo_num_peers", "nalu_b200_halo_send_peer", "nalu_b200_halo_recv_peer",
     "nalu_b200_halo_pack", "nalu_b200_halo_unpack_add", "nalu_b200_halo_pull_add",

@@ -193,6 +193,13 @@ class DeviceCsrLinearSystem:
                                              int(overwrite), self._stream()), "assemble_elem")
         return self.L.nalu_b200_last_assemble_mode()
 
+    def assemble_elem_zrange(self, descs, z_begin, z_end, overwrite=True, stream=None):
+        """Rows of node planes [z_begin, z_end) of a structured block (tiled kernel only)."""
+        arr = (KernelDesc * len(descs))(*descs)
+        st = self._stream() if stream is None else C.c_void_p(stream)
+        check(self.L.nalu_b200_assemble_elem_zrange(self.h, arr, len(descs), ptr(self.values), ptr(self.rhs),
+                                                    int(overwrite), int(z_begin), int(z_end), st), "assemble_elem_zrange")
+
     def assemble_node_mass(self, desc):
         check(self.L.nalu_b200_assemble_node_mass(self.h, C.byref(desc), ptr(self.values), ptr(self.rhs),
                                                   self._stream()), "assemble_node_mass")

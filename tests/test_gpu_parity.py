@@ -442,6 +442,28 @@ def test_box3_warp_specialised_kernel(zchunk, monkeypatch):
     assert ls.geometry_errors() == 0
 
 
+def test_box_kernel_zrange_pieces_equal_one_launch():
+    """nalu_b200_assemble_elem_zrange: the rows of consecutive node-plane ranges, assembled by separate
+    launches, are bit-identical to one launch over the block (each row is written by exactly one launch)."""
+    m = perturbed_box(11, 10, 37)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    ls = _linsys(m, 3)
+    d = product_desc(ls, dev, "momentum_adv_diff", ("skew_symmetric",), include_divu=1.0)
+    ls.values.fill_(float("nan"))
+    ls.rhs.fill_(float("nan"))
+    assert ls.assemble_elem([d], mode="box", overwrite=True) == 2
+    v1, r1 = ls.values.clone(), ls.rhs.clone()
+    ls.values.fill_(float("nan"))
+    ls.rhs.fill_(float("nan"))
+    for z0, z1 in ((0, 1), (1, 17), (17, 20), (20, 38)):
+        ls.assemble_elem_zrange([d], z0, z1, overwrite=True)
+    assert torch.equal(v1, ls.values) and torch.equal(r1, ls.rhs)
+    with pytest.raises(Exception):
+        ls.assemble_elem_zrange([d], 5, 39, overwrite=True)
+    assert ls.geometry_errors() == 0
+
+
 def test_box_kernel_matches_general_kernel_96cubed():
     """Beyond oracle-sized meshes: the two CUDA kernel families (atomic sumInto vs tiled write-once)
     are independent implementations; they must agree on a mesh too large for the CPU oracle."""
