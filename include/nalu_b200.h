@@ -70,7 +70,9 @@ enum nalu_b200_kernel_kind {
   NALU_K_SCALAR_MASS = 5,       /* src/kernel/ScalarMassElemKernel.C:96-156      */
   NALU_K_SCALAR_DIFF = 6,       /* src/kernel/ScalarDiffElemKernel.C:64-110      */
   NALU_K_TEST_FIXED_BLOCK = 7,  /* unit_tests/UnitTestTpetra.C:116-144 TestKernel */
-  NALU_K_COUNT = 8
+  NALU_K_MOMENTUM_BUOYANCY_SRC = 8,            /* src/kernel/MomentumBuoyancySrcElemKernel.C:61-90           */
+  NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC = 9, /* src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C:66-94 */
+  NALU_K_COUNT = 10
 };
 
 /* option bits (SolutionOptions fields the kernels read) */
@@ -100,6 +102,7 @@ enum nalu_b200_field_slot {
   NALU_F_SCALARQ_N = 11,  /* 1 */
   NALU_F_SCALARQ_NM1 = 12,/* 1 */
   NALU_F_DUAL_VOLUME = 13,/* 1  dual_nodal_volume (node mass algorithms only) */
+  NALU_F_TEMPERATURE = 14,/* 1  temperature NP1 (Boussinesq buoyancy) */
   NALU_F_COUNT = 16
 };
 
@@ -112,6 +115,10 @@ typedef struct nalu_b200_kernel_desc {
   const double *nodal[NALU_F_COUNT]; /* device pointers, NULL when unused            */
   const double *mass_flow_rate;      /* device [nElem][12], mass_flow_rate_scs       */
   const double *fixed_block;         /* device [rhsSize*rhsSize], NALU_K_TEST_FIXED_BLOCK */
+  /* buoyancy source kernels: SolutionOptions::gravity_, referenceDensity_, referenceTemperature_,
+   * thermalExpansionCoeff_ (src/kernel/MomentumBuoyancySrcElemKernel.C:31-41) */
+  double gravity[3];
+  double rho_ref, t_ref, beta;
 } nalu_b200_kernel_desc;
 
 /* ------------------------------------------------------------------------------------ */

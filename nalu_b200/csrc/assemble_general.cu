@@ -122,7 +122,8 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
       set_error("assemble_elem: unknown kernel kind");
       return NALU_B200_ERR_ARG;
     }
-    const bool vec = kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_MASS;
+    const bool vec = kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_MASS ||
+                     kind == NALU_K_MOMENTUM_BUOYANCY_SRC || kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC;
     if (kind != NALU_K_TEST_FIXED_BLOCK) {
       need_coords = true;
       if ((vec && g.ndof != 3) || (!vec && g.ndof != 1)) {

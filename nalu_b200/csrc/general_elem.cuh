@@ -41,6 +41,8 @@ __host__ __device__ inline void me_needs_of(const nalu_b200_kernel_desc &k, MeNe
   case NALU_K_MOMENTUM_MASS:
   case NALU_K_CONTINUITY_MASS:
   case NALU_K_SCALAR_MASS:
+  case NALU_K_MOMENTUM_BUOYANCY_SRC:            // MomentumBuoyancySrcElemKernel.C:50-53
+  case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC: // MomentumBuoyancyBoussinesqSrcElemKernel.C:52-58
     m.scv_volume = 1;
     break;
   default:
@@ -96,6 +98,7 @@ __host__ __device__ inline void stage_geometry(int lane, ElemScratch<NDOF> &ws, 
 enum { F_U = 0, F_MU = 3, F_RHO = 4, F_P = 5, F_GP = 6, F_Q = 9 };             // SCS kernels
 enum { M_UNP1 = 0, M_UN = 3, M_UNM1 = 6, M_GP = 9, M_RNP1 = 12, M_RN = 13, M_RNM1 = 14 }; // momentum mass
 enum { S_QNP1 = 0, S_QN = 1, S_QNM1 = 2, S_RNP1 = 3, S_RN = 4, S_RNM1 = 5 };  // scalar / continuity mass
+enum { B_S = 0 };                                                              // buoyancy: density or temperature
 
 __host__ __device__ inline void gather_one(double *dst, const double *field, int ncomp, int node)
 {
@@ -143,6 +146,12 @@ __host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, co
     gather_one(f + S_RN, k.nodal[NALU_F_DENSITY_N], 1, node);
     gather_one(f + S_RNM1, k.nodal[NALU_F_DENSITY_NM1], 1, node);
     break;
+  case NALU_K_MOMENTUM_BUOYANCY_SRC:
+    gather_one(f + B_S, k.nodal[NALU_F_DENSITY], 1, node);
+    break;
+  case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC:
+    gather_one(f + B_S, k.nodal[NALU_F_TEMPERATURE], 1, node);
+    break;
   default:
     break;
   }
@@ -155,7 +164,8 @@ __host__ __device__ inline void stage_ip(int lane, ElemScratch<NDOF> &ws, const 
 {
   const int kind = k.kind;
   if (kind == NALU_K_MOMENTUM_MASS || kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS ||
-      kind == NALU_K_TEST_FIXED_BLOCK)
+      kind == NALU_K_TEST_FIXED_BLOCK || kind == NALU_K_MOMENTUM_BUOYANCY_SRC ||
+      kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC)
     return;
   if (lane >= 12) return;
   const int ip = lane;
@@ -308,6 +318,19 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
       const double lhsfac = hex8::shape_fcn(ic, s1, s2, s3) * k.gamma1 * rNp1 * scV / k.dt;
       for (int j = 0; j < 3; ++j) ws.lhs[(ip * 3 + j) * R + ic * 3 + j] += lhsfac;
     }
+  } else if (kind == NALU_K_MOMENTUM_BUOYANCY_SRC || kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC) {
+    // MomentumBuoyancySrcElemKernel.C:69-86, MomentumBuoyancyBoussinesqSrcElemKernel.C:74-91; lane = SCV ip =
+    // nearest node; the (never shifted) SCV shape function; no lhs
+    if (NDOF != 3 || lane >= 8) return;
+    const int ip = lane;
+    double s1, s2, s3;
+    hex8::scv_intg_loc(ip, 0.25, s1, s2, s3);
+    double sIp = 0.0;
+    for (int ic = 0; ic < 8; ++ic) sIp += hex8::shape_fcn(ic, s1, s2, s3) * ws.fld[ic][B_S];
+    const double scV = ws.scv[ip];
+    const double fac = kind == NALU_K_MOMENTUM_BUOYANCY_SRC ? (sIp - k.rho_ref) * scV
+                                                             : -k.rho_ref * k.beta * (sIp - k.t_ref) * scV;
+    for (int j = 0; j < 3; ++j) ws.rhs[ip * 3 + j] += fac * k.gravity[j];
   } else if (kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS) {
     // ContinuityMassElemKernel.C:98-117, ScalarMassElemKernel.C:117-154
     if (NDOF != 1 || lane >= 8) return;

@@ -3,6 +3,7 @@
 #include "../include/kernel/ContinuityAdvElemKernel.h"
 #include "../include/kernel/MassElemKernels.h"
 #include "../include/kernel/MomentumAdvDiffElemKernel.h"
+#include "../include/kernel/MomentumBuoyancySrcElemKernel.h"
 #include "../include/kernel/ScalarAdvDiffElemKernel.h"
 
 #include <algorithm>
@@ -637,6 +638,79 @@ bool ScalarMassElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d
   return true;
 }
 
+// ---- src/kernel/MomentumBuoyancySrcElemKernel.C:26-54 / MomentumBuoyancyBoussinesqSrcElemKernel.C:26-59
+template <typename AlgTraits>
+MomentumBuoyancySrcElemKernel<AlgTraits>::MomentumBuoyancySrcElemKernel(const stk::mesh::BulkData &bulkData,
+                                                                       const SolutionOptions &solnOpts,
+                                                                       ElemDataRequests &dataPreReqs)
+    : Kernel(), rhoRef_(solnOpts.referenceDensity_),
+      ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  ScalarFieldType *density = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  STK_ThrowRequireMsg(density, "MomentumBuoyancySrcElemKernel: density not registered");
+  densityNp1_ = &(density->field_of_state(stk::mesh::StateNP1));
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(coordinates_, "MomentumBuoyancySrcElemKernel: coordinates not registered");
+  const std::array<double, 3> g = solnOpts.get_gravity_vector();
+  for (int i = 0; i < AlgTraits::nDim_; ++i) gravity_[i] = g[i];
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(AlgTraits::topo_);
+  get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shape_fcn(ptr); }, v_shape_function_);
+  dataPreReqs.add_cvfem_volume_me(meSCV);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1_, 1);
+  dataPreReqs.add_master_element_call(SCV_VOLUME, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+bool MomentumBuoyancySrcElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_MOMENTUM_BUOYANCY_SRC;
+  d.rho_ref = rhoRef_;
+  for (int i = 0; i < 3; ++i) d.gravity[i] = gravity_[i];
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  return true;
+}
+
+template <typename AlgTraits>
+MomentumBuoyancyBoussinesqSrcElemKernel<AlgTraits>::MomentumBuoyancyBoussinesqSrcElemKernel(
+    const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts, ElemDataRequests &dataPreReqs)
+    : Kernel(), rhoRef_(solnOpts.referenceDensity_), tRef_(solnOpts.referenceTemperature_),
+      beta_(solnOpts.thermalExpansionCoeff_),
+      ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  ScalarFieldType *temperature = metaData.get_field<double>(stk::topology::NODE_RANK, "temperature");
+  STK_ThrowRequireMsg(temperature, "MomentumBuoyancyBoussinesqSrcElemKernel: temperature not registered");
+  temperatureNp1_ = &(temperature->field_of_state(stk::mesh::StateNP1));
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(coordinates_, "MomentumBuoyancyBoussinesqSrcElemKernel: coordinates not registered");
+  const std::array<double, 3> g = solnOpts.get_gravity_vector();
+  for (int i = 0; i < AlgTraits::nDim_; ++i) gravity_[i] = g[i];
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(AlgTraits::topo_);
+  get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shape_fcn(ptr); }, v_shape_function_);
+  dataPreReqs.add_cvfem_volume_me(meSCV);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*temperatureNp1_, 1);
+  dataPreReqs.add_master_element_call(SCV_VOLUME, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+bool MomentumBuoyancyBoussinesqSrcElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC;
+  d.rho_ref = rhoRef_;
+  d.t_ref = tRef_;
+  d.beta = beta_;
+  for (int i = 0; i < 3; ++i) d.gravity[i] = gravity_[i];
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_TEMPERATURE, temperatureNp1_);
+  return true;
+}
+
+NALU_B200_DECLARE_KERNEL(MomentumBuoyancySrcElemKernel)
+NALU_B200_DECLARE_KERNEL(MomentumBuoyancyBoussinesqSrcElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumAdvDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(ContinuityAdvElemKernel)
 NALU_B200_DECLARE_KERNEL(ScalarAdvDiffElemKernel)

@@ -173,6 +173,11 @@ class DeviceCsrLinearSystem:
         d.gamma1 = scalars.get("gamma1", 1.0)
         d.gamma2 = scalars.get("gamma2", -1.0)
         d.gamma3 = scalars.get("gamma3", 0.0)
+        g = scalars.get("gravity", (0.0, 0.0, 0.0))
+        d.gravity[0], d.gravity[1], d.gravity[2] = float(g[0]), float(g[1]), float(g[2])
+        d.rho_ref = scalars.get("rho_ref", 0.0)
+        d.t_ref = scalars.get("t_ref", 0.0)
+        d.beta = scalars.get("beta", 0.0)
         for name, t in (fields or {}).items():
             if t is None:
                 continue

@@ -366,6 +366,31 @@ static void continuity_mass(const orc_kernel_desc *k, const int32_t *nodes, cons
   }
 }
 
+/* ---- src/kernel/MomentumBuoyancySrcElemKernel.C:61-90 and
+ *      src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C:66-94 ---- */
+static void momentum_buoyancy(const orc_kernel_desc *k, int boussinesq, const int32_t *nodes, const me_views *me,
+                              double *lhs, double *rhs)
+{
+  (void)lhs; /* No LHS contributions */
+  double v_s[8];
+  gather(boussinesq ? k->temperature : k->density, 1, nodes, v_s);
+  double v_shape_function_[8][8];
+  scv_shape(0, v_shape_function_); /* meSCV->shape_fcn: never shifted (ctor :43 / :50) */
+  const int *ipNodeMap_ = orc_hex8_scv_ip_node_map();
+  for (int ip = 0; ip < 8; ++ip) {
+    const int nearestNode = ipNodeMap_[ip];
+    double sIp = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      sIp += r * v_s[ic];
+    }
+    const double scV = me->scv_volume[ip];
+    const int nnNdim = nearestNode * 3;
+    const double fac = boussinesq ? -k->rhoRef * k->beta * (sIp - k->tRef) * scV : (sIp - k->rhoRef) * scV;
+    for (int j = 0; j < 3; ++j) rhs[nnNdim + j] += fac * k->gravity[j];
+  }
+}
+
 /* ---- src/kernel/ScalarMassElemKernel.C:96-156 ---- */
 static void scalar_mass(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
                         double *lhs, double *rhs)
@@ -425,6 +450,8 @@ static void me_needs(const orc_kernel_desc *k, int *areav, int *dndx, int *dndxs
   case ORC_MOMENTUM_MASS:
   case ORC_CONTINUITY_MASS:
   case ORC_SCALAR_MASS:
+  case ORC_MOMENTUM_BUOYANCY_SRC:
+  case ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC:
     *scv = 1;
     break;
   default:
@@ -469,6 +496,8 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     case ORC_MOMENTUM_MASS: momentum_mass(k, elemNodes, &me, lhs, rhs); break;
     case ORC_CONTINUITY_MASS: continuity_mass(k, elemNodes, &me, lhs, rhs); break;
     case ORC_SCALAR_MASS: scalar_mass(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_MOMENTUM_BUOYANCY_SRC: momentum_buoyancy(k, 0, elemNodes, &me, lhs, rhs); break;
+    case ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC: momentum_buoyancy(k, 1, elemNodes, &me, lhs, rhs); break;
     case ORC_TEST_FIXED_BLOCK: /* unit_tests/UnitTestTpetra.C:125-139: lhs(i,j) = elemVals[i][j] */
       for (int q = 0; q < rhsSize * rhsSize; ++q) lhs[q] = k->fixedBlock[q];
       break;

@@ -68,7 +68,9 @@ enum orc_kernel_kind {
   ORC_CONTINUITY_MASS = 4,   /* src/kernel/ContinuityMassElemKernel.C  */
   ORC_SCALAR_MASS = 5,       /* src/kernel/ScalarMassElemKernel.C      */
   ORC_SCALAR_DIFF = 6,       /* src/kernel/ScalarDiffElemKernel.C      */
-  ORC_TEST_FIXED_BLOCK = 7   /* unit_tests/UnitTestTpetra.C:116-144 TestKernel */
+  ORC_TEST_FIXED_BLOCK = 7,  /* unit_tests/UnitTestTpetra.C:116-144 TestKernel */
+  ORC_MOMENTUM_BUOYANCY_SRC = 8,            /* src/kernel/MomentumBuoyancySrcElemKernel.C           */
+  ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC = 9  /* src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C */
 };
 
 /* what the kernel constructors/ setup() capture (options + time integrator) */
@@ -101,6 +103,10 @@ typedef struct orc_kernel_desc {
   /* element fields */
   const double *massFlowRate; /* [nElem][12] mass_flow_rate_scs */
   const double *fixedBlock;   /* ORC_TEST_FIXED_BLOCK: rhsSize*rhsSize values written (not added) */
+  /* buoyancy sources: solnOpts.gravity_, referenceDensity_, referenceTemperature_, thermalExpansionCoeff_ */
+  const double *temperature;  /* [1]  temperatureNp1 */
+  double gravity[3];
+  double rhoRef, tRef, beta;
 } orc_kernel_desc;
 
 /* One element through the registered kernels, exactly as

@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 KIND = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3,
-            continuity_mass=4, scalar_mass=5, scalar_diff=6, test_fixed_block=7)
+            continuity_mass=4, scalar_mass=5, scalar_diff=6, test_fixed_block=7, momentum_buoyancy_src=8,
+            momentum_buoyancy_boussinesq_src=9)
 
 
 def build(force=False):
@@ -45,12 +46,13 @@ class KernelDesc(C.Structure):
                 ("dt", C.c_double), ("gamma1", C.c_double), ("gamma2", C.c_double), ("gamma3", C.c_double)] + \
                [(n, C.c_void_p) for n in ("coordinates", "velocity", "velocityN", "velocityNm1", "viscosity",
                                           "density", "densityN", "densityNm1", "pressure", "Gpdx", "scalarQ",
-                                          "scalarQN", "scalarQNm1", "massFlowRate", "fixedBlock")]
+                                          "scalarQN", "scalarQNm1", "massFlowRate", "fixedBlock", "temperature")] + \
+               [("gravity", C.c_double * 3), ("rhoRef", C.c_double), ("tRef", C.c_double), ("beta", C.c_double)]
 
 
 _PTR_FIELDS = ("coordinates", "velocity", "velocityN", "velocityNm1", "viscosity", "density", "densityN",
                "densityNm1", "pressure", "Gpdx", "scalarQ", "scalarQN", "scalarQNm1", "massFlowRate",
-               "fixedBlock")
+               "fixedBlock", "temperature")
 
 
 def _f64(a):
@@ -74,6 +76,9 @@ def make_desc(kind, keep, **kw):
             arr = _f64(v)
             keep.append(arr)
             setattr(d, k, arr.ctypes.data)
+        elif k == "gravity":
+            for j in range(3):
+                d.gravity[j] = float(v[j])
         else:
             setattr(d, k, v)
     return d

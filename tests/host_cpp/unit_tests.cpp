@@ -13,6 +13,7 @@
 #include "kernel/KernelBuilder.h"
 #include "kernel/MassElemKernels.h"
 #include "kernel/MomentumAdvDiffElemKernel.h"
+#include "kernel/MomentumBuoyancySrcElemKernel.h"
 #include "kernel/ScalarAdvDiffElemKernel.h"
 
 #include <cmath>
@@ -21,6 +22,7 @@
 #include <functional>
 #include <iostream>
 #include <memory>
+#include <random>
 
 using namespace sierra::nalu;
 
@@ -96,6 +98,7 @@ struct LowMachKernelHex8Mesh {
     scalarQ_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "scalarQ", 2);
     diffFluxCoeff_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "diffFluxCoeff");
     dualNodalVolume_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dual_nodal_volume");
+    temperature_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "temperature"); // UnitTestKernelUtils.h:330-350
     massFlowRate_ = &meta_.declare_field<double>(stk::topology::ELEM_RANK, "mass_flow_rate_scs");
     stk::mesh::put_field_on_mesh(*coordinates_, *part_, 3);
     stk::mesh::put_field_on_mesh(*velocity_, *part_, 3);
@@ -106,6 +109,7 @@ struct LowMachKernelHex8Mesh {
     stk::mesh::put_field_on_mesh(*scalarQ_, *part_, 1);
     stk::mesh::put_field_on_mesh(*diffFluxCoeff_, *part_, 1);
     stk::mesh::put_field_on_mesh(*dualNodalVolume_, *part_, 1);
+    stk::mesh::put_field_on_mesh(*temperature_, *part_, 1);
     stk::mesh::put_field_on_mesh(*massFlowRate_, *part_, 12);
     bulk_->fill_generated_mesh(nx, ny, nz, *part_);
   }
@@ -127,8 +131,9 @@ struct LowMachKernelHex8Mesh {
       g[2] = 0.0;
       density_->host_data()[n] = 1.0;
       viscosity_->host_data()[n] = 0.1;
+      temperature_->host_data()[n] = 300.0; // stk::mesh::field_fill(300.0, *temperature_), :350
     }
-    for (auto *f : {velocity_, pressure_, dpdx_, density_, viscosity_}) f->modify_on_host();
+    for (auto *f : {velocity_, pressure_, dpdx_, density_, viscosity_, temperature_}) f->modify_on_host();
   }
   stk::mesh::MetaData meta_;
   std::shared_ptr<stk::mesh::BulkData> bulk_;
@@ -136,7 +141,7 @@ struct LowMachKernelHex8Mesh {
   stk::mesh::PartVector partVec_;
   SolutionOptions solnOpts_;
   VectorFieldType *coordinates_, *velocity_, *dpdx_;
-  ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_;
+  ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_, *temperature_;
   GenericFieldType *massFlowRate_;
 };
 
@@ -388,6 +393,44 @@ static void test_momentum_mass(bool lumped)
   }
 }
 
+static void test_momentum_buoyancy(bool boussinesq)
+{
+  std::printf("MomentumKernelHex8Mesh.%s (unit_tests/kernels/UnitTestMomentumBuoyancy%sSrcElem.C)\n",
+              boussinesq ? "buoyancy_boussinesq" : "buoyancy", boussinesq ? "Boussinesq" : "");
+  std::mt19937 rng;
+  rng.seed(0); // fixed seed
+  std::uniform_real_distribution<double> ref_densities(0.8, 1.3);
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  fx.solnOpts_.gravity_[2] = -9.81;
+  fx.solnOpts_.referenceDensity_ = ref_densities(rng);
+  fx.solnOpts_.referenceTemperature_ = 298;
+  fx.solnOpts_.thermalExpansionCoeff_ = 1.0;
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+  helperObjs.build_system();
+  std::unique_ptr<Kernel> kernel;
+  if (boussinesq)
+    kernel.reset(new MomentumBuoyancyBoussinesqSrcElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
+                                                                            helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  else
+    kernel.reset(new MomentumBuoyancySrcElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
+                                                                  helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  EXPECT_TRUE(rhs.size() == 24u && lhs.size() == 576u);
+  std::vector<double> rhsExact(24, 0.0);
+  for (size_t i = 2; i < 24; i += 3)
+    rhsExact[i] = boussinesq ? -0.125 * fx.solnOpts_.gravity_[2] * fx.solnOpts_.referenceDensity_ * 1.0 * (300.0 - 298.0)
+                             : 0.125 * fx.solnOpts_.gravity_[2] * (1.0 - fx.solnOpts_.referenceDensity_);
+  Table exact;
+  exact.dims = {24};
+  exact.v = rhsExact;
+  unit_test_utils::expect_all_near(rhs, exact, 4e-15);
+  for (double v : lhs) EXPECT_TRUE(v == 0.0);
+}
+
 static void test_scalar_diff()
 {
   std::printf("HeatCondKernelHex8Mesh.cvfem_diff (unit_tests/kernels/UnitTestScalarDiffElem.C:30-58)\n");
@@ -525,6 +568,8 @@ int main(int argc, char **argv)
       test_continuity_advection("advection_reduced_shift_cvfem_poisson");
       test_momentum_mass(false);
       test_momentum_mass(true);
+      test_momentum_buoyancy(false);
+      test_momentum_buoyancy(true);
       test_scalar_diff();
       test_tpetra_basic();
       test_two_kernels_one_algorithm();

@@ -154,6 +154,57 @@ def test_continuity_mass_golden():
     np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("boussinesq", [False, True])
+def test_momentum_buoyancy_golden(boussinesq):
+    """unit_tests/kernels/UnitTestMomentumBuoyancySrcElem.C:16-59, ...BoussinesqSrcElem.C:16-66, through the
+    CUDA path; then on a perturbed box with a varying density / temperature against the oracle."""
+    from test_oracle_golden import reference_density_of_the_reference_tests
+    rho_ref = reference_density_of_the_reference_tests()
+    fx = LowMachFixture()
+    dev = _cuda()
+    t = _dev_fields(fx, dev)
+    ls = _linsys(fx.mesh, 3)
+    ls.zero_system()
+    if boussinesq:
+        d = ls.make_desc("momentum_buoyancy_boussinesq_src", gravity=(0.0, 0.0, -9.81), rho_ref=rho_ref, t_ref=298.0,
+                         beta=1.0, fields=dict(coordinates=t(fx.coords), temperature=t(np.full(fx.mesh.n_nodes, 300.0))))
+        exact_z = -0.125 * -9.81 * rho_ref * (300.0 - 298.0)
+    else:
+        d = ls.make_desc("momentum_buoyancy_src", gravity=(0.0, 0.0, -9.81), rho_ref=rho_ref,
+                         fields=dict(coordinates=t(fx.coords), density=t(fx.density)))
+        exact_z = 0.125 * -9.81 * (1.0 - rho_ref)
+    ls.assemble_elem([d])
+    lhs, rhs = _one_element_lhs_rhs(ls, 3)
+    exact = np.zeros(24)
+    exact[2::3] = exact_z
+    np.testing.assert_allclose(rhs, exact, rtol=0, atol=4e-15)
+    np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=0)
+
+    # perturbed 7x5x4 box, all three gravity components, varying field: vs the oracle
+    m = perturbed_box(7, 5, 4)
+    c = m.coords
+    s = 1.0 + 0.3 * np.sin(0.7 * c[:, 0]) * np.cos(0.4 * c[:, 1] + 0.2 * c[:, 2])
+    g = (0.3, -1.7, -9.81)
+    keep = []
+    orc = oracle.LinSys([m], 3)
+    if boussinesq:
+        od = oracle.make_desc("momentum_buoyancy_boussinesq_src", keep, coordinates=c, temperature=300.0 * s, gravity=g,
+                              rhoRef=1.1, tRef=298.0, beta=3.4e-3)
+    else:
+        od = oracle.make_desc("momentum_buoyancy_src", keep, coordinates=c, density=s, gravity=g, rhoRef=1.1)
+    orc.assemble_elem(0, [od])
+    ls = _linsys(m, 3)
+    ls.zero_system()
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    if boussinesq:
+        d = ls.make_desc("momentum_buoyancy_boussinesq_src", gravity=g, rho_ref=1.1, t_ref=298.0, beta=3.4e-3,
+                         fields=dict(coordinates=tt(c), temperature=tt(300.0 * s)))
+    else:
+        d = ls.make_desc("momentum_buoyancy_src", gravity=g, rho_ref=1.1, fields=dict(coordinates=tt(c), density=tt(s)))
+    assert ls.assemble_elem([d]) == 1
+    _compare_system(ls, orc)
+
+
 # ---------------------------------------------------------------------------------------------
 # whole-system parity against the oracle
 # ---------------------------------------------------------------------------------------------

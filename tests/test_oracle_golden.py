@@ -102,6 +102,46 @@ def test_continuity_mass_gold(lumped):
     np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=TOL)
 
 
+def reference_density_of_the_reference_tests():
+    """std::mt19937 seeded with 0 through std::uniform_real_distribution<double>(0.8, 1.3)
+    (unit_tests/kernels/UnitTestMomentumBuoyancySrcElem.C:18-31): libstdc++ draws two 32-bit words,
+    (g0 + g1 2^32) / 2^64.  tests/golden/make_golden.py checks the value against a compiled C++ draw."""
+    bg = np.random.MT19937()
+    bg._legacy_seeding(0)
+    g0, g1 = (float(x) for x in bg.random_raw(2))
+    return 0.8 + 0.5 * ((g0 + g1 * 4294967296.0) / 18446744073709551616.0)
+
+
+def test_momentum_buoyancy_gold():
+    # unit_tests/kernels/UnitTestMomentumBuoyancySrcElem.C:16-59: rhs_z = 0.125 g_z (1 - rhoRef), lhs == 0
+    rho_ref = reference_density_of_the_reference_tests()
+    assert abs(rho_ref - 1.0964223082583413) < 1e-16
+    fx = LowMachFixture()
+    keep = []
+    d = oracle.make_desc("momentum_buoyancy_src", keep, coordinates=fx.coords, density=fx.density,
+                         gravity=(0.0, 0.0, -9.81), rhoRef=rho_ref)
+    lhs, rhs = oracle.element_lhs_rhs([d], 3, fx.mesh.elem_nodes[0])
+    exact = np.zeros(24)
+    exact[2::3] = 0.125 * -9.81 * (1.0 - rho_ref)
+    np.testing.assert_allclose(rhs, exact, rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=0)
+
+
+def test_momentum_buoyancy_boussinesq_gold():
+    # unit_tests/kernels/UnitTestMomentumBuoyancyBoussinesqSrcElem.C:16-66: T = 300, Tref = 298, beta = 1
+    rho_ref = reference_density_of_the_reference_tests()
+    fx = LowMachFixture()
+    keep = []
+    d = oracle.make_desc("momentum_buoyancy_boussinesq_src", keep, coordinates=fx.coords,
+                         temperature=np.full(fx.mesh.n_nodes, 300.0), gravity=(0.0, 0.0, -9.81), rhoRef=rho_ref,
+                         tRef=298.0, beta=1.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], 3, fx.mesh.elem_nodes[0])
+    exact = np.zeros(24)
+    exact[2::3] = -0.125 * -9.81 * rho_ref * 1.0 * (300.0 - 298.0)
+    np.testing.assert_allclose(rhs, exact, rtol=0, atol=4 * TOL)  # |rhs| ~ 2.7: two ulps
+    np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=0)
+
+
 def test_scv_grad_op_gold_perturbed():
     # unit_tests/UnitTestKokkosME.C + UnitTestKokkosMEGold.h:13-79, tol 1e-10 (UnitTestUtils.h:67)
     g = load_golden("kokkos_me_gold")
