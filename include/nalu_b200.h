@@ -72,7 +72,9 @@ enum nalu_b200_kernel_kind {
   NALU_K_TEST_FIXED_BLOCK = 7,  /* unit_tests/UnitTestTpetra.C:116-144 TestKernel */
   NALU_K_MOMENTUM_BUOYANCY_SRC = 8,            /* src/kernel/MomentumBuoyancySrcElemKernel.C:61-90           */
   NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC = 9, /* src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C:66-94 */
-  NALU_K_COUNT = 10
+  NALU_K_TKE_SST_SRC = 10, /* src/kernel/TurbKineticEnergySSTSrcElemKernel.C:95-174       */
+  NALU_K_SDR_SST_SRC = 11, /* src/kernel/SpecificDissipationRateSSTSrcElemKernel.C:100-204 */
+  NALU_K_COUNT = 12
 };
 
 /* option bits (SolutionOptions fields the kernels read) */
@@ -103,7 +105,11 @@ enum nalu_b200_field_slot {
   NALU_F_SCALARQ_NM1 = 12,/* 1 */
   NALU_F_DUAL_VOLUME = 13,/* 1  dual_nodal_volume (node mass algorithms only) */
   NALU_F_TEMPERATURE = 14,/* 1  temperature NP1 (Boussinesq buoyancy) */
-  NALU_F_COUNT = 16
+  NALU_F_TKE = 15,        /* 1  turbulent_ke NP1 */
+  NALU_F_SDR = 16,        /* 1  specific_dissipation_rate NP1 */
+  NALU_F_TVISC = 17,      /* 1  turbulent_viscosity */
+  NALU_F_FONE_BLEND = 18, /* 1  sst_f_one_blending */
+  NALU_F_COUNT = 24
 };
 
 typedef struct nalu_b200_kernel_desc {
@@ -119,7 +125,11 @@ typedef struct nalu_b200_kernel_desc {
    * thermalExpansionCoeff_ (src/kernel/MomentumBuoyancySrcElemKernel.C:31-41) */
   double gravity[3];
   double rho_ref, t_ref, beta;
+  /* SST source kernels: SolutionOptions::get_turb_model_constant (src/SolutionOptions.C:742-770) */
+  double turb[8]; /* NALU_TM_* */
 } nalu_b200_kernel_desc;
+enum { NALU_TM_BETA_STAR = 0, NALU_TM_TKE_PROD_LIMIT_RATIO = 1, NALU_TM_SIGMA_W_TWO = 2, NALU_TM_BETA_ONE = 3,
+       NALU_TM_BETA_TWO = 4, NALU_TM_GAMMA_ONE = 5, NALU_TM_GAMMA_TWO = 6 };
 
 /* ------------------------------------------------------------------------------------ */
 /* Graph: DOF numbering + CSR graph, built once per mesh.                                */

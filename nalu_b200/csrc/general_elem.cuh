@@ -17,7 +17,7 @@
 namespace nalu_b200 {
 
 struct MeNeeds {
-  int areav, dndx, dndx_shifted, scv_volume;
+  int areav, dndx, dndx_shifted, scv_volume, dndx_scv, dndx_scv_shifted;
 };
 
 // which master-element views the kernel constructors request
@@ -45,6 +45,11 @@ __host__ __device__ inline void me_needs_of(const nalu_b200_kernel_desc &k, MeNe
   case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC: // MomentumBuoyancyBoussinesqSrcElemKernel.C:52-58
     m.scv_volume = 1;
     break;
+  case NALU_K_TKE_SST_SRC: // TurbKineticEnergySSTSrcElemKernel.C:84-89
+  case NALU_K_SDR_SST_SRC: // SpecificDissipationRateSSTSrcElemKernel.C:91-96
+    m.scv_volume = 1;
+    if (k.options & NALU_OPT_SHIFTED_GRAD_OP) m.dndx_scv_shifted = 1; else m.dndx_scv = 1;
+    break;
   default:
     break;
   }
@@ -59,6 +64,7 @@ struct ElemScratch {
   double dndx[12][8][3];
   double dndxs[12][8][3];
   double scv[8];
+  double dndx_scv[8][8][3]; // SCV (shifted) grad op, HexSCV::grad_op / shifted_grad_op (Hex8CVFEM.C:182-190,221-229)
   double fld[8][16];  // gathered nodal fields of the kernel currently running
   double ipd[12][8];  // per-integration-point results passed between stages
   double rhs[R];
@@ -90,6 +96,12 @@ __host__ __device__ inline void stage_geometry(int lane, ElemScratch<NDOF> &ws, 
     }
   } else if (lane >= 16 && lane < 24 && need.scv_volume) {
     ws.scv[lane - 16] = hex8::scv_volume_ip(ws.coords, lane - 16);
+  } else if (lane >= 24 && (need.dndx_scv || need.dndx_scv_shifted)) {
+    const int ip = lane - 24;
+    double s1, s2, s3;
+    hex8::scv_intg_loc(ip, need.dndx_scv_shifted ? 0.5 : 0.25, s1, s2, s3);
+    const double det = hex8::grad_op_ip(ws.coords, s1, s2, s3, ws.dndx_scv[ip]);
+    if (!(det > 0.0)) ws.bad_det = 1;
   }
 }
 
@@ -98,7 +110,8 @@ __host__ __device__ inline void stage_geometry(int lane, ElemScratch<NDOF> &ws, 
 enum { F_U = 0, F_MU = 3, F_RHO = 4, F_P = 5, F_GP = 6, F_Q = 9 };             // SCS kernels
 enum { M_UNP1 = 0, M_UN = 3, M_UNM1 = 6, M_GP = 9, M_RNP1 = 12, M_RN = 13, M_RNM1 = 14 }; // momentum mass
 enum { S_QNP1 = 0, S_QN = 1, S_QNM1 = 2, S_RNP1 = 3, S_RN = 4, S_RNM1 = 5 };  // scalar / continuity mass
-enum { B_S = 0 };                                                              // buoyancy: density or temperature
+enum { B_S = 0 };
+enum { T_U = 0, T_RHO = 3, T_K = 4, T_W = 5, T_NUT = 6, T_F1 = 7 };           // SST sources                                                              // buoyancy: density or temperature
 
 __host__ __device__ inline void gather_one(double *dst, const double *field, int ncomp, int node)
 {
@@ -149,6 +162,16 @@ __host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, co
   case NALU_K_MOMENTUM_BUOYANCY_SRC:
     gather_one(f + B_S, k.nodal[NALU_F_DENSITY], 1, node);
     break;
+  case NALU_K_SDR_SST_SRC:
+    gather_one(f + T_F1, k.nodal[NALU_F_FONE_BLEND], 1, node);
+    // fallthrough
+  case NALU_K_TKE_SST_SRC:
+    gather_one(f + T_U, k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + T_RHO, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + T_K, k.nodal[NALU_F_TKE], 1, node);
+    gather_one(f + T_W, k.nodal[NALU_F_SDR], 1, node);
+    gather_one(f + T_NUT, k.nodal[NALU_F_TVISC], 1, node);
+    break;
   case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC:
     gather_one(f + B_S, k.nodal[NALU_F_TEMPERATURE], 1, node);
     break;
@@ -165,7 +188,7 @@ __host__ __device__ inline void stage_ip(int lane, ElemScratch<NDOF> &ws, const 
   const int kind = k.kind;
   if (kind == NALU_K_MOMENTUM_MASS || kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS ||
       kind == NALU_K_TEST_FIXED_BLOCK || kind == NALU_K_MOMENTUM_BUOYANCY_SRC ||
-      kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC)
+      kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC || kind == NALU_K_TKE_SST_SRC || kind == NALU_K_SDR_SST_SRC)
     return;
   if (lane >= 12) return;
   const int ip = lane;
@@ -331,6 +354,56 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
     const double fac = kind == NALU_K_MOMENTUM_BUOYANCY_SRC ? (sIp - k.rho_ref) * scV
                                                              : -k.rho_ref * k.beta * (sIp - k.t_ref) * scV;
     for (int j = 0; j < 3; ++j) ws.rhs[ip * 3 + j] += fac * k.gravity[j];
+  } else if (kind == NALU_K_TKE_SST_SRC || kind == NALU_K_SDR_SST_SRC) {
+    // TurbKineticEnergySSTSrcElemKernel.C:120-172, SpecificDissipationRateSSTSrcElemKernel.C:128-202;
+    // lane = SCV ip = nearest node
+    if (NDOF != 1 || lane >= 8) return;
+    const int ip = lane;
+    double s1, s2, s3;
+    hex8::scv_intg_loc(ip, (k.options & NALU_OPT_LUMPED_MASS) ? 0.5 : 0.25, s1, s2, s3);
+    double rho = 0, tke = 0, sdr = 0, tvisc = 0, f1 = 0, dudx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, dkdx[3] = {0, 0, 0},
+           dwdx[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, s1, s2, s3);
+      const double *f = ws.fld[ic];
+      rho += r * f[T_RHO];
+      tke += r * f[T_K];
+      sdr += r * f[T_W];
+      tvisc += r * f[T_NUT];
+      f1 += r * f[T_F1];
+      const double *g = ws.dndx_scv[ip][ic];
+      for (int i = 0; i < 3; ++i) {
+        dkdx[i] += g[i] * f[T_K];
+        dwdx[i] += g[i] * f[T_W];
+        for (int j = 0; j < 3; ++j) dudx[i][j] += g[j] * f[T_U + i];
+      }
+    }
+    double Pk = 0.0, crossDiff = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      crossDiff += dkdx[i] * dwdx[i];
+      for (int j = 0; j < 3; ++j) Pk += dudx[i][j] * (dudx[i][j] + dudx[j][i]);
+    }
+    Pk *= tvisc;
+    const double betaStar = k.turb[NALU_TM_BETA_STAR], limit = k.turb[NALU_TM_TKE_PROD_LIMIT_RATIO];
+    const double scV = ws.scv[ip];
+    const double Dk = betaStar * rho * sdr * tke;
+    Pk = fmin(Pk, limit * Dk);
+    double lhsfac;
+    if (kind == NALU_K_TKE_SST_SRC) {
+      ws.rhs[ip] += (Pk - Dk) * scV;
+      lhsfac = betaStar * rho * sdr * scV;
+    } else {
+      const double om = 1.0 - f1;
+      const double beta = f1 * k.turb[NALU_TM_BETA_ONE] + om * k.turb[NALU_TM_BETA_TWO];
+      const double gamma = f1 * k.turb[NALU_TM_GAMMA_ONE] + om * k.turb[NALU_TM_GAMMA_TWO];
+      const double sigmaD = 2.0 * om * k.turb[NALU_TM_SIGMA_W_TWO];
+      const double Pw = gamma * rho * Pk / fmax(tvisc, 1.0e-16);
+      const double Dw = beta * rho * sdr * sdr;
+      const double Sw = sigmaD * rho * crossDiff / sdr;
+      ws.rhs[ip] += (Pw - Dw + Sw) * scV;
+      lhsfac = (2.0 * beta * rho * sdr + fmax(Sw / sdr, 0.0)) * scV;
+    }
+    for (int ic = 0; ic < 8; ++ic) ws.lhs[ip * R + ic] += hex8::shape_fcn(ic, s1, s2, s3) * lhsfac;
   } else if (kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS) {
     // ContinuityMassElemKernel.C:98-117, ScalarMassElemKernel.C:117-154
     if (NDOF != 1 || lane >= 8) return;

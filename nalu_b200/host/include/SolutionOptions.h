@@ -3,10 +3,18 @@
 #pragma once
 #include <array>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <vector>
 namespace sierra {
 namespace nalu {
+// include/Enums.h:156-208 (the members this path reads)
+enum TurbulenceModel { LAMINAR = 0, KSGS = 1, SMAGORINSKY = 2, WALE = 3, SST = 4, SST_DES = 5, KEPS = 6, LRKSGS = 7 };
+enum TurbulenceModelConstant {
+  TM_cMu = 0, TM_kappa = 1, TM_cDESke = 2, TM_cDESkw = 3, TM_tkeProdLimitRatio = 4, TM_cmuEps = 5, TM_cEps = 6,
+  TM_betaStar = 7, TM_aOne = 8, TM_betaOne = 9, TM_betaTwo = 10, TM_gammaOne = 11, TM_gammaTwo = 12,
+  TM_sigmaKOne = 13, TM_sigmaKTwo = 14, TM_sigmaWOne = 15, TM_sigmaWTwo = 16, TM_END = 27
+};
 class SolutionOptions {
 public:
   double includeDivU_ = 0.0;                // src/SolutionOptions.C:49
@@ -17,6 +25,33 @@ public:
   // thermalExpansionCoeff_; get_gravity_vector pads to three components)
   std::vector<double> gravity_ = std::vector<double>(3, 0.0);
   double referenceDensity_ = 0.0, referenceTemperature_ = 298.0, thermalExpansionCoeff_ = 1.0;
+  // src/SolutionOptions.C:742-770 (values of the constants the SST source kernels read), :824-832
+  TurbulenceModel turbulenceModel_ = LAMINAR;
+  std::map<TurbulenceModelConstant, double> turbModelConstantMap_;
+  void initialize_turbulence_constants()
+  {
+    turbModelConstantMap_[TM_cMu] = 0.09;
+    turbModelConstantMap_[TM_kappa] = 0.41;
+    turbModelConstantMap_[TM_cDESke] = 0.61;
+    turbModelConstantMap_[TM_cDESkw] = 0.78;
+    turbModelConstantMap_[TM_tkeProdLimitRatio] = (turbulenceModel_ == SST || turbulenceModel_ == SST_DES) ? 10.0 : 500.0;
+    turbModelConstantMap_[TM_betaStar] = 0.09;
+    turbModelConstantMap_[TM_aOne] = 0.31;
+    turbModelConstantMap_[TM_betaOne] = 0.075;
+    turbModelConstantMap_[TM_betaTwo] = 0.0828;
+    turbModelConstantMap_[TM_gammaOne] = 5.0 / 9.0;
+    turbModelConstantMap_[TM_gammaTwo] = 0.44;
+    turbModelConstantMap_[TM_sigmaKOne] = 0.85;
+    turbModelConstantMap_[TM_sigmaKTwo] = 1.0;
+    turbModelConstantMap_[TM_sigmaWOne] = 0.50;
+    turbModelConstantMap_[TM_sigmaWTwo] = 0.856;
+  }
+  double get_turb_model_constant(TurbulenceModelConstant turbModelEnum) const
+  {
+    auto it = turbModelConstantMap_.find(turbModelEnum);
+    if (it == turbModelConstantMap_.end()) throw std::runtime_error("unknown (not initialized) turbulence model constant");
+    return it->second;
+  }
   std::array<double, 3> get_gravity_vector() const
   {
     std::array<double, 3> g{{0.0, 0.0, 0.0}};

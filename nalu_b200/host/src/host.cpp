@@ -4,6 +4,7 @@
 #include "../include/kernel/MassElemKernels.h"
 #include "../include/kernel/MomentumAdvDiffElemKernel.h"
 #include "../include/kernel/MomentumBuoyancySrcElemKernel.h"
+#include "../include/kernel/SSTSrcElemKernels.h"
 #include "../include/kernel/ScalarAdvDiffElemKernel.h"
 
 #include <algorithm>
@@ -709,6 +710,116 @@ bool MomentumBuoyancyBoussinesqSrcElemKernel<AlgTraits>::device_descriptor(nalu_
   return true;
 }
 
+// ---- src/kernel/TurbKineticEnergySSTSrcElemKernel.C:28-90, SpecificDissipationRateSSTSrcElemKernel.C:26-97
+namespace {
+template <typename AlgTraits, typename K>
+void sst_common_registrations(K &k, const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                              ElemDataRequests &dataPreReqs, bool lumpedMass, bool shiftedGradOp, ScalarFieldType *&tkeNp1,
+                              ScalarFieldType *&sdrNp1, ScalarFieldType *&densityNp1, VectorFieldType *&velocityNp1,
+                              ScalarFieldType *&tvisc, VectorFieldType *&coordinates, ScalarFieldType **fOneBlend)
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  ScalarFieldType *tke = metaData.get_field<double>(stk::topology::NODE_RANK, "turbulent_ke");
+  ScalarFieldType *sdr = metaData.get_field<double>(stk::topology::NODE_RANK, "specific_dissipation_rate");
+  ScalarFieldType *density = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  VectorFieldType *velocity = metaData.get_field<double>(stk::topology::NODE_RANK, "velocity");
+  tvisc = metaData.get_field<double>(stk::topology::NODE_RANK, "turbulent_viscosity");
+  coordinates = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(tke && sdr && density && velocity && tvisc && coordinates, "SST source kernel: field not registered");
+  tkeNp1 = &tke->field_of_state(stk::mesh::StateNP1);
+  sdrNp1 = &sdr->field_of_state(stk::mesh::StateNP1);
+  densityNp1 = &density->field_of_state(stk::mesh::StateNP1);
+  velocityNp1 = &velocity->field_of_state(stk::mesh::StateNP1);
+  if (fOneBlend) {
+    *fOneBlend = metaData.get_field<double>(stk::topology::NODE_RANK, "sst_f_one_blending");
+    STK_ThrowRequireMsg(*fOneBlend, "SST source kernel: sst_f_one_blending not registered");
+  }
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(AlgTraits::topo_);
+  if (lumpedMass)
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shifted_shape_fcn(ptr); }, k.v_shape_function_);
+  else
+    get_scv_shape_fn_data<AlgTraits>([&](double *ptr) { meSCV->shape_fcn(ptr); }, k.v_shape_function_);
+  dataPreReqs.add_cvfem_volume_me(meSCV);
+  dataPreReqs.add_coordinates_field(*coordinates, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*tkeNp1, 1);
+  dataPreReqs.add_gathered_nodal_field(*sdrNp1, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1, 1);
+  dataPreReqs.add_gathered_nodal_field(*velocityNp1, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*tvisc, 1);
+  if (fOneBlend) dataPreReqs.add_gathered_nodal_field(**fOneBlend, 1);
+  dataPreReqs.add_master_element_call(SCV_VOLUME, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(shiftedGradOp ? SCV_SHIFTED_GRAD_OP : SCV_GRAD_OP, CURRENT_COORDINATES);
+}
+} // namespace
+
+template <typename AlgTraits>
+TurbKineticEnergySSTSrcElemKernel<AlgTraits>::TurbKineticEnergySSTSrcElemKernel(const stk::mesh::BulkData &bulkData,
+                                                                               const SolutionOptions &solnOpts,
+                                                                               ElemDataRequests &dataPreReqs,
+                                                                               const bool lumpedMass)
+    : Kernel(), lumpedMass_(lumpedMass), shiftedGradOp_(solnOpts.get_shifted_grad_op("velocity")),
+      betaStar_(solnOpts.get_turb_model_constant(TM_betaStar)),
+      tkeProdLimitRatio_(solnOpts.get_turb_model_constant(TM_tkeProdLimitRatio)),
+      ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  sst_common_registrations<AlgTraits>(*this, bulkData, solnOpts, dataPreReqs, lumpedMass_, shiftedGradOp_, tkeNp1_, sdrNp1_,
+                                      densityNp1_, velocityNp1_, tvisc_, coordinates_, nullptr);
+}
+template <typename AlgTraits>
+bool TurbKineticEnergySSTSrcElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_TKE_SST_SRC;
+  d.options = (lumpedMass_ ? NALU_OPT_LUMPED_MASS : 0) | (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0);
+  d.turb[NALU_TM_BETA_STAR] = betaStar_;
+  d.turb[NALU_TM_TKE_PROD_LIMIT_RATIO] = tkeProdLimitRatio_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityNp1_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_TKE, tkeNp1_);
+  bind(d, NALU_F_SDR, sdrNp1_);
+  bind(d, NALU_F_TVISC, tvisc_);
+  return true;
+}
+
+template <typename AlgTraits>
+SpecificDissipationRateSSTSrcElemKernel<AlgTraits>::SpecificDissipationRateSSTSrcElemKernel(
+    const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts, ElemDataRequests &dataPreReqs, const bool lumpedMass)
+    : Kernel(), lumpedMass_(lumpedMass), shiftedGradOp_(solnOpts.get_shifted_grad_op("velocity")),
+      betaStar_(solnOpts.get_turb_model_constant(TM_betaStar)), sigmaWTwo_(solnOpts.get_turb_model_constant(TM_sigmaWTwo)),
+      betaOne_(solnOpts.get_turb_model_constant(TM_betaOne)), betaTwo_(solnOpts.get_turb_model_constant(TM_betaTwo)),
+      gammaOne_(solnOpts.get_turb_model_constant(TM_gammaOne)), gammaTwo_(solnOpts.get_turb_model_constant(TM_gammaTwo)),
+      tkeProdLimitRatio_(solnOpts.get_turb_model_constant(TM_tkeProdLimitRatio)),
+      ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  sst_common_registrations<AlgTraits>(*this, bulkData, solnOpts, dataPreReqs, lumpedMass_, shiftedGradOp_, tkeNp1_, sdrNp1_,
+                                      densityNp1_, velocityNp1_, tvisc_, coordinates_, &fOneBlend_);
+}
+template <typename AlgTraits>
+bool SpecificDissipationRateSSTSrcElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_SDR_SST_SRC;
+  d.options = (lumpedMass_ ? NALU_OPT_LUMPED_MASS : 0) | (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0);
+  d.turb[NALU_TM_BETA_STAR] = betaStar_;
+  d.turb[NALU_TM_TKE_PROD_LIMIT_RATIO] = tkeProdLimitRatio_;
+  d.turb[NALU_TM_SIGMA_W_TWO] = sigmaWTwo_;
+  d.turb[NALU_TM_BETA_ONE] = betaOne_;
+  d.turb[NALU_TM_BETA_TWO] = betaTwo_;
+  d.turb[NALU_TM_GAMMA_ONE] = gammaOne_;
+  d.turb[NALU_TM_GAMMA_TWO] = gammaTwo_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityNp1_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_TKE, tkeNp1_);
+  bind(d, NALU_F_SDR, sdrNp1_);
+  bind(d, NALU_F_TVISC, tvisc_);
+  bind(d, NALU_F_FONE_BLEND, fOneBlend_);
+  return true;
+}
+
+NALU_B200_DECLARE_KERNEL(TurbKineticEnergySSTSrcElemKernel)
+NALU_B200_DECLARE_KERNEL(SpecificDissipationRateSSTSrcElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumBuoyancySrcElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumBuoyancyBoussinesqSrcElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumAdvDiffElemKernel)

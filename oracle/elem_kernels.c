@@ -4,6 +4,7 @@
  * TEST INFRASTRUCTURE ONLY (see nalu_oracle.h).  Scalar, reference loop order.
  */
 #include "nalu_oracle.h"
+#include <math.h>
 #include <string.h>
 
 /* what ScratchViews + MasterElementViews hold for one element
@@ -15,6 +16,7 @@ typedef struct {
   double dndx_shifted[12][8][3];
   double deriv[12][8][3];
   double scv_volume[8];
+  double dndx_scv[8][8][3]; /* dndx_scv or dndx_scv_shifted, whichever the SST kernels requested */
   int have_areav, have_dndx, have_dndx_shifted, have_scv_volume;
 } me_views;
 
@@ -391,6 +393,77 @@ static void momentum_buoyancy(const orc_kernel_desc *k, int boussinesq, const in
   }
 }
 
+/* ---- src/kernel/TurbKineticEnergySSTSrcElemKernel.C:95-174 (sdr_kernel = 0) and
+ *      src/kernel/SpecificDissipationRateSSTSrcElemKernel.C:100-204 (sdr_kernel = 1) ---- */
+static void sst_src(const orc_kernel_desc *k, int sdr_kernel, const int32_t *nodes, const me_views *me, double *lhs,
+                    double *rhs)
+{
+  double v_tkeNp1[8], v_sdrNp1[8], v_densityNp1[8], v_velocityNp1[8][3], v_tvisc[8], v_fOneBlend[8];
+  gather(k->tke, 1, nodes, v_tkeNp1);
+  gather(k->sdr, 1, nodes, v_sdrNp1);
+  gather(k->density, 1, nodes, v_densityNp1);
+  gather(k->velocity, 3, nodes, &v_velocityNp1[0][0]);
+  gather(k->tvisc, 1, nodes, v_tvisc);
+  if (sdr_kernel) gather(k->fOneBlend, 1, nodes, v_fOneBlend);
+  double v_shape_function_[8][8];
+  scv_shape(k->lumpedMass, v_shape_function_);
+  const int *ipNodeMap_ = orc_hex8_scv_ip_node_map();
+  const double betaStar_ = k->betaStar, tkeProdLimitRatio_ = k->tkeProdLimitRatio;
+
+  for (int ip = 0; ip < 8; ++ip) {
+    const int nearestNode = ipNodeMap_[ip];
+    const double scV = me->scv_volume[ip];
+    double rho = 0.0, tke = 0.0, sdr = 0.0, tvisc = 0.0, fOneBlend = 0.0;
+    double w_dudx[3][3], w_dkdx[3], w_dwdx[3];
+    for (int i = 0; i < 3; ++i) {
+      w_dkdx[i] = 0.0;
+      w_dwdx[i] = 0.0;
+      for (int j = 0; j < 3; ++j) w_dudx[i][j] = 0.0;
+    }
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      rho += r * v_densityNp1[ic];
+      tke += r * v_tkeNp1[ic];
+      sdr += r * v_sdrNp1[ic];
+      tvisc += r * v_tvisc[ic];
+      if (sdr_kernel) fOneBlend += r * v_fOneBlend[ic];
+      for (int i = 0; i < 3; ++i) {
+        const double dni = me->dndx_scv[ip][ic][i];
+        const double ui = v_velocityNp1[ic][i];
+        w_dkdx[i] += dni * v_tkeNp1[ic];
+        w_dwdx[i] += dni * v_sdrNp1[ic];
+        for (int j = 0; j < 3; ++j) w_dudx[i][j] += me->dndx_scv[ip][ic][j] * ui;
+      }
+    }
+    double Pk = 0.0, crossDiff = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      crossDiff += w_dkdx[i] * w_dwdx[i];
+      for (int j = 0; j < 3; ++j) Pk += w_dudx[i][j] * (w_dudx[i][j] + w_dudx[j][i]);
+    }
+    Pk *= tvisc;
+    if (!sdr_kernel) {
+      const double tkeFac = betaStar_ * rho * sdr;
+      const double Dk = tkeFac * tke;
+      Pk = fmin(Pk, tkeProdLimitRatio_ * Dk);
+      rhs[nearestNode] += (Pk - Dk) * scV;
+      for (int ic = 0; ic < 8; ++ic) lhs[nearestNode * 8 + ic] += v_shape_function_[ip][ic] * tkeFac * scV;
+    } else {
+      const double Dk = betaStar_ * rho * sdr * tke;
+      Pk = fmin(Pk, tkeProdLimitRatio_ * Dk);
+      const double om_fOneBlend = 1.0 - fOneBlend;
+      const double beta = fOneBlend * k->betaOne + om_fOneBlend * k->betaTwo;
+      const double gamma = fOneBlend * k->gammaOne + om_fOneBlend * k->gammaTwo;
+      const double sigmaD = 2.0 * om_fOneBlend * k->sigmaWTwo;
+      const double Pw = gamma * rho * Pk / fmax(tvisc, 1.0e-16);
+      const double Dw = beta * rho * sdr * sdr;
+      const double Sw = sigmaD * rho * crossDiff / sdr;
+      rhs[nearestNode] += (Pw - Dw + Sw) * scV;
+      for (int ic = 0; ic < 8; ++ic)
+        lhs[nearestNode * 8 + ic] += v_shape_function_[ip][ic] * (2.0 * beta * rho * sdr + fmax(Sw / sdr, 0.0)) * scV;
+    }
+  }
+}
+
 /* ---- src/kernel/ScalarMassElemKernel.C:96-156 ---- */
 static void scalar_mass(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
                         double *lhs, double *rhs)
@@ -480,6 +553,12 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     if (dndx) orc_hex8_scs_grad_op(0, &me.coords[0][0], &me.dndx[0][0][0], &me.deriv[0][0][0]);
     if (dndxs) orc_hex8_scs_grad_op(1, &me.coords[0][0], &me.dndx_shifted[0][0][0], &me.deriv[0][0][0]);
     if (scv) orc_hex8_scv_volume(&me.coords[0][0], me.scv_volume);
+    for (int i = 0; i < nk; ++i)
+      if (kernels[i].kind == ORC_TKE_SST_SRC || kernels[i].kind == ORC_SDR_SST_SRC) {
+        /* SCV_GRAD_OP or SCV_SHIFTED_GRAD_OP (TurbKineticEnergySSTSrcElemKernel.C:84-89) */
+        orc_hex8_scv_volume(&me.coords[0][0], me.scv_volume);
+        orc_hex8_scv_grad_op(kernels[i].shiftedGradOp, &me.coords[0][0], &me.dndx_scv[0][0][0], NULL);
+      }
   }
 
   /* set_zero(simdrhs), set_zero(simdlhs) */
@@ -498,6 +577,8 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     case ORC_SCALAR_MASS: scalar_mass(k, elemNodes, &me, lhs, rhs); break;
     case ORC_MOMENTUM_BUOYANCY_SRC: momentum_buoyancy(k, 0, elemNodes, &me, lhs, rhs); break;
     case ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC: momentum_buoyancy(k, 1, elemNodes, &me, lhs, rhs); break;
+    case ORC_TKE_SST_SRC: sst_src(k, 0, elemNodes, &me, lhs, rhs); break;
+    case ORC_SDR_SST_SRC: sst_src(k, 1, elemNodes, &me, lhs, rhs); break;
     case ORC_TEST_FIXED_BLOCK: /* unit_tests/UnitTestTpetra.C:125-139: lhs(i,j) = elemVals[i][j] */
       for (int q = 0; q < rhsSize * rhsSize; ++q) lhs[q] = k->fixedBlock[q];
       break;

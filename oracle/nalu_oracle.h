@@ -70,7 +70,9 @@ enum orc_kernel_kind {
   ORC_SCALAR_DIFF = 6,       /* src/kernel/ScalarDiffElemKernel.C      */
   ORC_TEST_FIXED_BLOCK = 7,  /* unit_tests/UnitTestTpetra.C:116-144 TestKernel */
   ORC_MOMENTUM_BUOYANCY_SRC = 8,            /* src/kernel/MomentumBuoyancySrcElemKernel.C           */
-  ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC = 9  /* src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C */
+  ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC = 9, /* src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C */
+  ORC_TKE_SST_SRC = 10,                     /* src/kernel/TurbKineticEnergySSTSrcElemKernel.C       */
+  ORC_SDR_SST_SRC = 11                      /* src/kernel/SpecificDissipationRateSSTSrcElemKernel.C */
 };
 
 /* what the kernel constructors/ setup() capture (options + time integrator) */
@@ -107,6 +109,9 @@ typedef struct orc_kernel_desc {
   const double *temperature;  /* [1]  temperatureNp1 */
   double gravity[3];
   double rhoRef, tRef, beta;
+  /* SST sources */
+  const double *tke, *sdr, *tvisc, *fOneBlend; /* [1] each */
+  double betaStar, tkeProdLimitRatio, sigmaWTwo, betaOne, betaTwo, gammaOne, gammaTwo; /* get_turb_model_constant */
 } orc_kernel_desc;
 
 /* One element through the registered kernels, exactly as

@@ -10,7 +10,7 @@ _LIB = None
 
 KIND = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3,
             continuity_mass=4, scalar_mass=5, scalar_diff=6, test_fixed_block=7, momentum_buoyancy_src=8,
-            momentum_buoyancy_boussinesq_src=9)
+            momentum_buoyancy_boussinesq_src=9, tke_sst_src=10, sdr_sst_src=11)
 
 
 def build(force=False):
@@ -47,12 +47,15 @@ class KernelDesc(C.Structure):
                [(n, C.c_void_p) for n in ("coordinates", "velocity", "velocityN", "velocityNm1", "viscosity",
                                           "density", "densityN", "densityNm1", "pressure", "Gpdx", "scalarQ",
                                           "scalarQN", "scalarQNm1", "massFlowRate", "fixedBlock", "temperature")] + \
-               [("gravity", C.c_double * 3), ("rhoRef", C.c_double), ("tRef", C.c_double), ("beta", C.c_double)]
+               [("gravity", C.c_double * 3), ("rhoRef", C.c_double), ("tRef", C.c_double), ("beta", C.c_double)] + \
+               [(n, C.c_void_p) for n in ("tke", "sdr", "tvisc", "fOneBlend")] + \
+               [(n, C.c_double) for n in ("betaStar", "tkeProdLimitRatio", "sigmaWTwo", "betaOne", "betaTwo",
+                                          "gammaOne", "gammaTwo")]
 
 
 _PTR_FIELDS = ("coordinates", "velocity", "velocityN", "velocityNm1", "viscosity", "density", "densityN",
                "densityNm1", "pressure", "Gpdx", "scalarQ", "scalarQN", "scalarQNm1", "massFlowRate",
-               "fixedBlock", "temperature")
+               "fixedBlock", "temperature", "tke", "sdr", "tvisc", "fOneBlend")
 
 
 def _f64(a):

@@ -19,6 +19,7 @@ Sources (relative to /root/reference):
   unit_tests/kernels/UnitTestMomentumMassElem.C:17-140      momentum mass consistent / lumped
   unit_tests/UnitTestKokkosMEGold.h:13-79                   SCV grad-op tables (perturbed element)
   unit_tests/UnitTestTpetra.C:86-114                        2-element assembled matrix
+  unit_tests/kernels/UnitTestSSTSrcElem.C:17-176            SST tke / tke-DES / sdr source lhs/rhs
 """
 import json
 import os
@@ -108,6 +109,7 @@ def main():
         "momentum_mass": "kernels/UnitTestMomentumMassElem.C",
         "kokkos_me_gold": "UnitTestKokkosMEGold.h",
         "tpetra_2elem": "UnitTestTpetra.C",
+        "sst_src": "kernels/UnitTestSSTSrcElem.C",
     }
     for key, rel in files.items():
         tabs = parse_tables(os.path.join(REF, rel))

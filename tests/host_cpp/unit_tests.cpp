@@ -14,6 +14,7 @@
 #include "kernel/MassElemKernels.h"
 #include "kernel/MomentumAdvDiffElemKernel.h"
 #include "kernel/MomentumBuoyancySrcElemKernel.h"
+#include "kernel/SSTSrcElemKernels.h"
 #include "kernel/ScalarAdvDiffElemKernel.h"
 
 #include <cmath>
@@ -99,6 +100,11 @@ struct LowMachKernelHex8Mesh {
     diffFluxCoeff_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "diffFluxCoeff");
     dualNodalVolume_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dual_nodal_volume");
     temperature_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "temperature"); // UnitTestKernelUtils.h:330-350
+    // SSTKernelHex8Mesh (UnitTestKernelUtils.h:362-405)
+    tke_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "turbulent_ke");
+    sdr_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "specific_dissipation_rate");
+    tvisc_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "turbulent_viscosity");
+    fOneBlend_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "sst_f_one_blending");
     massFlowRate_ = &meta_.declare_field<double>(stk::topology::ELEM_RANK, "mass_flow_rate_scs");
     stk::mesh::put_field_on_mesh(*coordinates_, *part_, 3);
     stk::mesh::put_field_on_mesh(*velocity_, *part_, 3);
@@ -110,6 +116,7 @@ struct LowMachKernelHex8Mesh {
     stk::mesh::put_field_on_mesh(*diffFluxCoeff_, *part_, 1);
     stk::mesh::put_field_on_mesh(*dualNodalVolume_, *part_, 1);
     stk::mesh::put_field_on_mesh(*temperature_, *part_, 1);
+    for (auto *f : {tke_, sdr_, tvisc_, fOneBlend_}) stk::mesh::put_field_on_mesh(*f, *part_, 1);
     stk::mesh::put_field_on_mesh(*massFlowRate_, *part_, 12);
     bulk_->fill_generated_mesh(nx, ny, nz, *part_);
   }
@@ -135,13 +142,28 @@ struct LowMachKernelHex8Mesh {
     }
     for (auto *f : {velocity_, pressure_, dpdx_, density_, viscosity_, temperature_}) f->modify_on_host();
   }
+  // SSTKernelHex8Mesh::fill_mesh_and_init_fields (UnitTestKernelUtils.h:385-398) on top of the above:
+  // tvisc = 0.3 and the TrigFieldFunction density / tke / sdr / f-one-blending (UnitTestKernelUtils.C:93-220)
+  void fill_sst_fields()
+  {
+    const double *x = coordinates_->host_data();
+    for (size_t n = 0; n < bulk_->num_nodes(); ++n) {
+      const double X = x[3 * n], Y = x[3 * n + 1], Z = x[3 * n + 2];
+      tvisc_->host_data()[n] = 0.3;
+      density_->host_data()[n] = std::cos(a * pi * X) * std::cos(a * pi * Y) * std::cos(a * pi * Z);
+      tke_->host_data()[n] = 2.0 + std::cos(a * pi * X) * std::sin(a * pi * Y) * std::cos(a * pi * Z);
+      sdr_->host_data()[n] = 2.0 + std::cos(a * pi * X) * std::sin(a * pi * Y) * std::sin(a * pi * Z);
+      fOneBlend_->host_data()[n] = std::sin(a * pi * X) * std::cos(a * pi * Y) * std::sin(a * pi * Z);
+    }
+    for (auto *f : {density_, tke_, sdr_, tvisc_, fOneBlend_}) f->modify_on_host();
+  }
   stk::mesh::MetaData meta_;
   std::shared_ptr<stk::mesh::BulkData> bulk_;
   stk::mesh::Part *part_;
   stk::mesh::PartVector partVec_;
   SolutionOptions solnOpts_;
   VectorFieldType *coordinates_, *velocity_, *dpdx_;
-  ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_, *temperature_;
+  ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_, *temperature_, *tke_, *sdr_, *tvisc_, *fOneBlend_;
   GenericFieldType *massFlowRate_;
 };
 
@@ -431,6 +453,33 @@ static void test_momentum_buoyancy(bool boussinesq)
   for (double v : lhs) EXPECT_TRUE(v == 0.0);
 }
 
+static void test_sst_src(bool sdr)
+{
+  std::printf("SSTKernelHex8Mesh.%s (unit_tests/kernels/UnitTestSSTSrcElem.C:%s)\n",
+              sdr ? "specificdissipationratesstsrcelem" : "turbkineticenergysstsrcelem", sdr ? "259-297" : "179-217");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  fx.fill_sst_fields();
+  fx.solnOpts_.initialize_turbulence_constants();
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 1, fx.partVec_[0]);
+  helperObjs.build_system();
+  std::unique_ptr<Kernel> kernel;
+  if (sdr)
+    kernel.reset(new SpecificDissipationRateSSTSrcElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
+                                                                            helperObjs.assembleElemSolverAlg->dataNeededByKernels_, false));
+  else
+    kernel.reset(new TurbKineticEnergySSTSrcElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
+                                                                      helperObjs.assembleElemSolverAlg->dataNeededByKernels_, false));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  EXPECT_TRUE(rhs.size() == 8u && lhs.size() == 64u);
+  const std::string ns = sdr ? "SpecificDissipationRateSSTSrcElemKernel" : "TurbKineticEnergySSTSrcElemKernel";
+  unit_test_utils::expect_all_near(rhs, gold("sst_src", "hex8_golds::" + ns + "::rhs"), 2e-15);
+  unit_test_utils::expect_all_near(lhs, gold("sst_src", "hex8_golds::" + ns + "::lhs"), 2e-15);
+}
+
 static void test_scalar_diff()
 {
   std::printf("HeatCondKernelHex8Mesh.cvfem_diff (unit_tests/kernels/UnitTestScalarDiffElem.C:30-58)\n");
@@ -570,6 +619,8 @@ int main(int argc, char **argv)
       test_momentum_mass(true);
       test_momentum_buoyancy(false);
       test_momentum_buoyancy(true);
+      test_sst_src(false);
+      test_sst_src(true);
       test_scalar_diff();
       test_tpetra_basic();
       test_two_kernels_one_algorithm();

@@ -52,3 +52,26 @@ class MixtureFractionFixture:
     def calc_mdot(self, oracle):
         self.mdot = oracle.calc_mass_flow_rate_scs(self.mesh.elem_nodes, self.coords, self.density, self.velocity)
         return self.mdot
+
+
+class SSTFixture(LowMachFixture):
+    """SSTKernelHex8Mesh (unit_tests/kernels/UnitTestKernelUtils.h:362-405): the low-Mach fields, then
+    tvisc = 0.3 and the trigonometric density / tke / sdr / f-one-blending fields of
+    TrigFieldFunction (unit_tests/kernels/UnitTestKernelUtils.C:93-220, a = 0.3)."""
+
+    def __init__(self, perturb=False):
+        super().__init__(perturb=perturb)
+        c = self.coords
+        a = 0.3 * np.pi
+        x, y, z = c[:, 0], c[:, 1], c[:, 2]
+        n = self.mesh.n_nodes
+        self.tvisc = np.full(n, 0.3)
+        self.density = np.cos(a * x) * np.cos(a * y) * np.cos(a * z)
+        self.tke = 2.0 + np.cos(a * x) * np.sin(a * y) * np.cos(a * z)
+        self.sdr = 2.0 + np.cos(a * x) * np.sin(a * y) * np.sin(a * z)
+        self.fOneBlend = np.sin(a * x) * np.cos(a * y) * np.sin(a * z)
+
+    # SolutionOptions::initialize_turbulence_constants with turbulenceModel_ == LAMINAR (the tests never set it):
+    # src/SolutionOptions.C:742-770
+    TURB = dict(betaStar=0.09, tkeProdLimitRatio=500.0, sigmaWTwo=0.856, betaOne=0.075, betaTwo=0.0828,
+                gammaOne=5.0 / 9.0, gammaTwo=0.44)

@@ -205,6 +205,47 @@ def test_momentum_buoyancy_golden(boussinesq):
     _compare_system(ls, orc)
 
 
+@pytest.mark.parametrize("kind,ns", [("tke_sst_src", "TurbKineticEnergySSTSrcElemKernel"),
+                                     ("sdr_sst_src", "SpecificDissipationRateSSTSrcElemKernel")])
+def test_sst_src_golden(kind, ns):
+    """unit_tests/kernels/UnitTestSSTSrcElem.C:179-217, 259-297 through the CUDA path; then a perturbed box with
+    the shifted SCV grad-op and lumped shape functions against the oracle."""
+    from nalu_b200 import fields
+    from nalu_fixtures import SSTFixture
+    g = load_golden("sst_src")
+    fx = SSTFixture()
+    dev = _cuda()
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    turb = dict(beta_star=0.09, tke_prod_limit_ratio=500.0, sigma_w_two=0.856, beta_one=0.075, beta_two=0.0828,
+                gamma_one=5.0 / 9.0, gamma_two=0.44)
+    ls = _linsys(fx.mesh, 1)
+    ls.zero_system()
+    f = dict(coordinates=tt(fx.coords), velocity=tt(fx.velocity), density=tt(fx.density), tke=tt(fx.tke), sdr=tt(fx.sdr),
+             tvisc=tt(fx.tvisc), f_one_blend=tt(fx.fOneBlend))
+    ls.assemble_elem([ls.make_desc(kind, fields=f, turb=turb)])
+    lhs, rhs = _one_element_lhs_rhs(ls, 1)
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=2e-15)
+    np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=2e-15)
+
+    m = perturbed_box(6, 5, 4)
+    c = m.coords
+    a = 0.3 * np.pi
+    x, y, z = c[:, 0], c[:, 1], c[:, 2]
+    fld = dict(velocity=fields.velocity(c), density=1.0 + 0.2 * np.cos(a * x) * np.cos(a * y),
+               tke=2.0 + np.cos(a * x) * np.sin(a * y) * np.cos(a * z), sdr=2.0 + np.cos(a * x) * np.sin(a * y) * np.sin(a * z),
+               tvisc=0.3 + 0.1 * np.sin(a * z), fOneBlend=0.5 + 0.4 * np.sin(a * x) * np.cos(a * y))
+    keep = []
+    orc = oracle.LinSys([m], 1)
+    orc.assemble_elem(0, [oracle.make_desc(kind, keep, coordinates=c, shiftedGradOp=1, lumpedMass=1, **fld,
+                                           **SSTFixture.TURB)])
+    ls = _linsys(m, 1)
+    ls.zero_system()
+    f = dict(coordinates=tt(c), velocity=tt(fld["velocity"]), density=tt(fld["density"]), tke=tt(fld["tke"]),
+             sdr=tt(fld["sdr"]), tvisc=tt(fld["tvisc"]), f_one_blend=tt(fld["fOneBlend"]))
+    assert ls.assemble_elem([ls.make_desc(kind, fields=f, options=("shifted_grad_op", "lumped_mass"), turb=turb)]) == 1
+    _compare_system(ls, orc)
+
+
 # ---------------------------------------------------------------------------------------------
 # whole-system parity against the oracle
 # ---------------------------------------------------------------------------------------------

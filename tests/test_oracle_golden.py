@@ -8,7 +8,7 @@ import pytest
 import oracle
 from nalu_b200 import mesh
 from golden_io import load_golden, tab
-from nalu_fixtures import LowMachFixture, MixtureFractionFixture
+from nalu_fixtures import LowMachFixture, MixtureFractionFixture, SSTFixture
 
 TOL = 1.0e-15
 
@@ -140,6 +140,20 @@ def test_momentum_buoyancy_boussinesq_gold():
     exact[2::3] = -0.125 * -9.81 * rho_ref * 1.0 * (300.0 - 298.0)
     np.testing.assert_allclose(rhs, exact, rtol=0, atol=4 * TOL)  # |rhs| ~ 2.7: two ulps
     np.testing.assert_allclose(lhs, 0.0, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("kind,ns", [("tke_sst_src", "TurbKineticEnergySSTSrcElemKernel"),
+                                     ("sdr_sst_src", "SpecificDissipationRateSSTSrcElemKernel")])
+def test_sst_src_gold(kind, ns):
+    # unit_tests/kernels/UnitTestSSTSrcElem.C:179-217, 259-297 (lumpedMass = false)
+    g = load_golden("sst_src")
+    fx = SSTFixture()
+    keep = []
+    d = oracle.make_desc(kind, keep, coordinates=fx.coords, velocity=fx.velocity, density=fx.density, tke=fx.tke,
+                         sdr=fx.sdr, tvisc=fx.tvisc, fOneBlend=fx.fOneBlend, **SSTFixture.TURB)
+    lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=TOL)
 
 
 def test_scv_grad_op_gold_perturbed():
