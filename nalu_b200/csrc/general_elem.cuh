@@ -11,6 +11,7 @@
 // code is executed lane-by-lane on the CPU by tests/cpu_harness (no GPU needed to check the
 // arithmetic against the oracle).
 #pragma once
+#include <cmath>
 #include "../../include/nalu_b200.h"
 #include "hex8_dev.cuh"
 
