@@ -98,6 +98,33 @@ __device__ __forceinline__ void copy_runs_warp(const box2::Meta &M, int warp, in
   }
 }
 
+// Descriptor variant (the default): one warp per run, lane k moves double k; the run descriptors of the plane
+// were stored by build_run_desc at the head of phase A, so a run costs a broadcast descriptor load, one staging
+// load and one predicated store, eight independent runs in flight per warp.  No bulk-copy issue: a
+// cp.async.bulk occupies its warp for 58 (idle SM) to 250 (inside this kernel) cycles whatever its size, and a
+// plane has 192 of them (profiles/r2u_phase_trace.txt: 9.8 k of a plane's 31 k cycles).
+template <int NB>
+__device__ __forceinline__ void copy_runs_desc(const double *sm, int first, int n, int lane, double *values, int overwrite)
+{
+  const int4 *rd = reinterpret_cast<const int4 *>(sm + C::OFF_RD);
+  const double *S = sm + C::OFF_S;
+#pragma unroll 1
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    int4 d[NB];
+    double v[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) d[u] = rd[first + k0 + u];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) v[u] = S[d[u].z + lane];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const long long G = (long long)(((unsigned long long)(unsigned)d[u].y << 32) | (unsigned)d[u].x);
+      double *dst = values + G + lane;
+      if (lane < d[u].w) *dst = overwrite ? v[u] : *dst + v[u];
+    }
+  }
+}
+
 // phase 1 over one item list.  kind 0: prologue (top face + z edges of the layer below the first
 // plane), 1: phase 1a (bottom face + z edges), 2: phase 1b (top face).
 __device__ __forceinline__ void p1_phase(const BoxParams &P, int kind, int x0, int y0, const double *pl0, const double *pl1,
@@ -127,7 +154,8 @@ __device__ __noinline__ void p1_prologue(const BoxParams &P, int x0, int y0, con
       P.trace[((hs - 2 * zs) * 8 + warp) * 8 + (slot)] = clock64();                                    \
   } while (0)
 
-template <bool BULK>
+// MODE 0: cooperative copy-out with in-loop run_of, 1: cp.async.bulk, 2: descriptor copy-out
+template <int MODE>
 __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_constant__ BoxParams P)
 {
   extern __shared__ __align__(16) double sm[];
@@ -139,6 +167,7 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
   const int x0 = (tile % P.tiles_x) * C::TBX, y0 = (tile / P.tiles_x) * C::TBY;
   const int zs = P.z_first + zc * P.z_chunk;
   const int ze = (zs + P.z_chunk < P.z_last) ? zs + P.z_chunk : P.z_last;
+  constexpr bool BULK = MODE == 1;
 
   box2::T2 N;
   box2::t2_init(P, N, lane, x0, y0);
@@ -184,6 +213,7 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
       // been in flight since phase D of the previous plane)
       box2::stage_mdot(P, mdb, tid, x0, y0, z);
       N.rr[0] = N.rr[1] = N.rr[2] = 0.0;
+      if (MODE == 2) box2::build_run_desc(M, sm, tid);
     }
     if ((H ? upper : lower) && !(P.options & (1 << 18))) {
       // profiling aid: 9 stamps inside the pass for half-steps 4 and 5 of the traced CTA
@@ -215,6 +245,12 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
       if (meta_warp) row_next = box2::meta_row(P, lane, x0, y0, z + 2);
     }
     if (P.options & (1 << 16)) {
+    } else if (MODE == 2) {
+      // H = 0: the 96 runs of dz=-1; H = 1: the 96 of dz=0 and the 96 of dz=+1; 24 / 48 per warp
+      if (H) copy_runs_desc<8>(sm, 3 * C::NNODE + warp * (upper ? 48 : 24), upper ? 48 : 24, lane, P.values, P.overwrite);
+      // (an uneven 0 / 8 / 44 / 44 split against the phase 1a load measured 1 % slower: the stores drain at a
+      // rate set by the memory system, not by the issuing warp)
+      else if (lower) copy_runs_desc<8>(sm, warp * 24, 24, lane, P.values, P.overwrite);
     } else if (BULK) {
       // the run list of this half (H = 0: 96 runs of the dz=-1 group; H = 1: 96 of dz=0, then 96 of
       // dz=+1) spread over all 8 warps: the per-lane bulk issue serialises inside a warp
@@ -265,7 +301,7 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
   }
 }
 
-template <bool BULK>
+template <int MODE>
 static int launch2(BoxParams &P, cudaStream_t stream)
 {
   int dev = 0, sms = 148;
@@ -290,8 +326,8 @@ static int launch2(BoxParams &P, cudaStream_t stream)
   zchunks = (nplanes + zc - 1) / zc;
   size_t smem = sizeof(double) * C::SMEM_DOUBLES;
   if (getenv("NALU_BOX_ONE_CTA")) smem = 120 * 1024; // profiling aid: one CTA per SM
-  NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<BULK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NALU_CUDA(cudaFuncSetAttribute(assemble_box2_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const long long ctas = ntile * zchunks;
   if (ctas > 0x7fffffffLL) {
     set_error("assemble_box2: grid too large");
@@ -302,14 +338,16 @@ static int launch2(BoxParams &P, cudaStream_t stream)
   if (trace && !d_trace) NALU_CUDA(cudaMalloc(&d_trace, (16 * 8 * 8 + 128) * sizeof(long long)));
   P.trace = trace ? d_trace : nullptr;
   if (trace) NALU_CUDA(cudaMemsetAsync(d_trace, 0, (16 * 8 * 8 + 128) * sizeof(long long), stream));
-  assemble_box2_kernel<BULK><<<(unsigned)ctas, C::NT, smem, stream>>>(P);
+  assemble_box2_kernel<MODE><<<(unsigned)ctas, C::NT, smem, stream>>>(P);
   count_launch();
   NALU_CUDA(cudaGetLastError());
   if (trace) {
     static long long h[16 * 8 * 8 + 128];
     NALU_CUDA(cudaStreamSynchronize(stream));
     NALU_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
-    if (FILE *f = fopen(getenv("NALU_BOX_TRACE"), "w")) {
+    bool any = false; // launches without the traced CTA (small z ranges) leave the file alone
+    for (int k = 0; k < 16 * 8 * 8 && !any; ++k) any = h[k] != 0;
+    if (FILE *f = any ? fopen(getenv("NALU_BOX_TRACE"), "w") : nullptr) {
       for (int hs = 0; hs < 16; ++hs)
         for (int w = 0; w < 8; ++w) {
           fprintf(f, "%d %d", hs, w);
@@ -333,9 +371,12 @@ int launch_assemble_box2(BoxParams &P, cudaStream_t stream)
   // the bulk copies need 16-byte aligned destinations: staging parity is matched to the offset in
   // `values`, so the base pointer itself must be aligned (cudaMalloc gives 256 bytes)
   if (const char *e = getenv("NALU_BOX_ABLATE")) P.options |= atoi(e) << 16; // profiling aid: skip copy (1) / phase 1 (2) / phase 2 (4)
-  bool bulk = ((uintptr_t)P.values & 15) == 0;
-  if (const char *e = getenv("NALU_BOX_BULK")) bulk = bulk && atoi(e) != 0;
-  return bulk ? launch2<true>(P, stream) : launch2<false>(P, stream);
+  // copy-out: 2 = run descriptors + plain stores (default), 1 = cp.async.bulk (needs a 16-byte aligned
+  // `values`), 0 = first cooperative variant; NALU_BOX_BULK selects for A/B runs
+  int mode = 2;
+  if (const char *e = getenv("NALU_BOX_BULK")) mode = atoi(e);
+  if (mode == 1 && ((uintptr_t)P.values & 15) != 0) mode = 2;
+  return mode == 1 ? launch2<1>(P, stream) : (mode == 0 ? launch2<0>(P, stream) : launch2<2>(P, stream));
 }
 
 } // namespace nalu_b200

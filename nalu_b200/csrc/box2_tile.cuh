@@ -68,7 +68,10 @@ struct Cfg {
                        META_GP = META_SLOT + NNODE * 28 / 8, META_CNT = META_GP + NNODE * 8 / 8,
                        META = META_CNT + NNODE * 4 / 8;
   static constexpr int OFF_QK = OFF_META + 2 * META;  // class constants: [NCLS][24]
-  static constexpr int SMEM_DOUBLES = OFF_QK + NCLS * 24;
+  // run descriptors of one plane (descriptor copy-out): [3 dz groups][3 dof rows][NNODE] x {int64 first double in
+  // `values`, int32 staging offset, int32 doubles}
+  static constexpr int NRUN = 9 * NNODE, OFF_RD = OFF_QK + NCLS * 24;
+  static constexpr int SMEM_DOUBLES = OFF_RD + 2 * NRUN;
 };
 
 struct Meta {
@@ -666,6 +669,28 @@ __host__ __device__ inline Run run_of(const Meta &M, int node, int i, int g)
   r.G = M.rowbase[node] + ((long long)i * M.nb[node] + (gp & 0xFF)) * 3;
   r.soff = node * C::SNODE + i * C::SROWP + ((nf >> i) & 1) + (gp >> 8);
   return r;
+}
+
+// descriptor copy-out: the (never merged, <= 27 doubles) run of dz group g of dof row i of a node, stored once
+// per plane so that the copy loop is descriptor load -> staging load -> store with no index arithmetic
+struct RunDesc {
+  long long G;
+  int soff, L;
+};
+__host__ __device__ inline void build_run_desc(const Meta &M, double *sm, int tid)
+{
+  using C = Cfg;
+  RunDesc *rd = reinterpret_cast<RunDesc *>(sm + C::OFF_RD);
+  for (int idx = tid; idx < C::NRUN; idx += C::NT) {
+    const int g = idx / (3 * C::NNODE), rr = idx - g * 3 * C::NNODE;
+    const int i = rr / C::NNODE, node = rr - i * C::NNODE;
+    const unsigned gp = M.gp[node * 4 + g], nf = M.gp[node * 4 + 3];
+    RunDesc d;
+    d.L = 3 * M.cnt[node * 4 + g];
+    d.G = M.rowbase[node] + ((long long)i * M.nb[node] + (gp & 0xFF)) * 3;
+    d.soff = node * C::SNODE + i * C::SROWP + ((nf >> i) & 1) + (gp >> 8);
+    rd[idx] = d;
+  }
 }
 
 // columns of the row that no local element touches (remote columns announced by the ranks sharing
