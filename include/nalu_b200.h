@@ -74,7 +74,9 @@ enum nalu_b200_kernel_kind {
   NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC = 9, /* src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C:66-94 */
   NALU_K_TKE_SST_SRC = 10, /* src/kernel/TurbKineticEnergySSTSrcElemKernel.C:95-174       */
   NALU_K_SDR_SST_SRC = 11, /* src/kernel/SpecificDissipationRateSSTSrcElemKernel.C:100-204 */
-  NALU_K_COUNT = 12
+  NALU_K_SCALAR_UPW_ADV_DIFF = 12,   /* src/kernel/ScalarUpwAdvDiffElemKernel.C:110-256   */
+  NALU_K_MOMENTUM_UPW_ADV_DIFF = 13, /* src/kernel/MomentumUpwAdvDiffElemKernel.C:108-311 */
+  NALU_K_COUNT = 14
 };
 
 /* option bits (SolutionOptions fields the kernels read) */
@@ -84,7 +86,9 @@ enum {
   NALU_OPT_LUMPED_MASS = 1 << 2,     /* mass kernels: shifted SCV shape fn                  */
   NALU_OPT_SHIFT_MDOT = 1 << 3,      /* cvfemShiftMdot_                                     */
   NALU_OPT_SHIFT_POISSON = 1 << 4,   /* get_shifted_grad_op("pressure")                     */
-  NALU_OPT_REDUCED_SENS = 1 << 5     /* cvfemReducedSensPoisson_                            */
+  NALU_OPT_REDUCED_SENS = 1 << 5,    /* cvfemReducedSensPoisson_                            */
+  NALU_OPT_USE_LIMITER = 1 << 6,     /* primitive_uses_limiter(dofName): van Leer limiter   */
+  NALU_OPT_PECLET_TANH = 1 << 7      /* get_tanh_functional_form(dofName) != "classic"      */
 };
 
 /* nodal-field slots of a descriptor; every field is [nNodes][ncomp] doubles, ncomp
@@ -109,6 +113,9 @@ enum nalu_b200_field_slot {
   NALU_F_SDR = 16,        /* 1  specific_dissipation_rate NP1 */
   NALU_F_TVISC = 17,      /* 1  turbulent_viscosity */
   NALU_F_FONE_BLEND = 18, /* 1  sst_f_one_blending */
+  NALU_F_GJQ = 19,        /* 3  projected nodal gradient of scalarQ (upwind kernels) */
+  NALU_F_GJU = 20,        /* 9  dudx: Gju(node,i,j) at [3*i+j] (upwind kernels) */
+  NALU_F_VELOCITY_RTM = 21, /* 3  velocity_rtm of the upwind kernels when the mesh moves; NULL: NALU_F_VELOCITY */
   NALU_F_COUNT = 24
 };
 
@@ -127,7 +134,13 @@ typedef struct nalu_b200_kernel_desc {
   double rho_ref, t_ref, beta;
   /* SST source kernels: SolutionOptions::get_turb_model_constant (src/SolutionOptions.C:742-770) */
   double turb[8]; /* NALU_TM_* */
+  /* upwind adv-diff kernels: SolutionOptions::get_alpha_factor / get_alpha_upw_factor / get_upw_factor and the
+   * Peclet function EquationSystem::create_peclet_function builds (include/EquationSystem.h:306-325):
+   * classic A = 5 with Realm::get_hybrid_factor, or tanh with get_tanh_trans / get_tanh_width */
+  double upw[8]; /* NALU_UPW_* */
 } nalu_b200_kernel_desc;
+enum { NALU_UPW_ALPHA = 0, NALU_UPW_ALPHA_UPW = 1, NALU_UPW_HO_UPWIND = 2, NALU_UPW_HYBRID_FACTOR = 3,
+       NALU_UPW_TANH_TRANS = 4, NALU_UPW_TANH_WIDTH = 5 };
 enum { NALU_TM_BETA_STAR = 0, NALU_TM_TKE_PROD_LIMIT_RATIO = 1, NALU_TM_SIGMA_W_TWO = 2, NALU_TM_BETA_ONE = 3,
        NALU_TM_BETA_TWO = 4, NALU_TM_GAMMA_ONE = 5, NALU_TM_GAMMA_TWO = 6 };
 

@@ -123,7 +123,8 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
       return NALU_B200_ERR_ARG;
     }
     const bool vec = kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_MASS ||
-                     kind == NALU_K_MOMENTUM_BUOYANCY_SRC || kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC;
+                     kind == NALU_K_MOMENTUM_BUOYANCY_SRC || kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC ||
+                     kind == NALU_K_MOMENTUM_UPW_ADV_DIFF;
     if (kind != NALU_K_TEST_FIXED_BLOCK) {
       need_coords = true;
       if ((vec && g.ndof != 3) || (!vec && g.ndof != 1)) {

@@ -29,6 +29,8 @@ __host__ __device__ inline void me_needs_of(const nalu_b200_kernel_desc &k, MeNe
   case NALU_K_MOMENTUM_ADV_DIFF:
   case NALU_K_SCALAR_ADV_DIFF:
   case NALU_K_SCALAR_DIFF:
+  case NALU_K_SCALAR_UPW_ADV_DIFF:   // ScalarUpwAdvDiffElemKernel.C:82-89
+  case NALU_K_MOMENTUM_UPW_ADV_DIFF: // MomentumUpwAdvDiffElemKernel.C:82-89
     m.areav = 1;
     if (k.options & NALU_OPT_SHIFTED_GRAD_OP) m.dndx_shifted = 1; else m.dndx = 1;
     break;
@@ -66,7 +68,7 @@ struct ElemScratch {
   double dndxs[12][8][3];
   double scv[8];
   double dndx_scv[8][8][3]; // SCV (shifted) grad op, HexSCV::grad_op / shifted_grad_op (Hex8CVFEM.C:182-190,221-229)
-  double fld[8][16];  // gathered nodal fields of the kernel currently running
+  double fld[8][20];  // gathered nodal fields of the kernel currently running
   double ipd[12][8];  // per-integration-point results passed between stages
   double rhs[R];
   double lhs[R * R];
@@ -109,6 +111,7 @@ __host__ __device__ inline void stage_geometry(int lane, ElemScratch<NDOF> &ws, 
 // ---- field gather: slot list per kernel kind ---------------------------------------------
 // fld[n][..] layout per kind (component offsets)
 enum { F_U = 0, F_MU = 3, F_RHO = 4, F_P = 5, F_GP = 6, F_Q = 9 };             // SCS kernels
+enum { F_GJU = 5, F_RTM = 14 };                                                // momentum upwind: dudx[9], velocity_rtm[3]
 enum { M_UNP1 = 0, M_UN = 3, M_UNM1 = 6, M_GP = 9, M_RNP1 = 12, M_RN = 13, M_RNM1 = 14 }; // momentum mass
 enum { S_QNP1 = 0, S_QN = 1, S_QNM1 = 2, S_RNP1 = 3, S_RN = 4, S_RNM1 = 5 };  // scalar / continuity mass
 enum { B_S = 0 };
@@ -140,6 +143,20 @@ __host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, co
   case NALU_K_SCALAR_DIFF:
     gather_one(f + F_Q, k.nodal[NALU_F_SCALARQ], 1, node);
     gather_one(f + F_MU, k.nodal[NALU_F_VISCOSITY], 1, node);
+    break;
+  case NALU_K_SCALAR_UPW_ADV_DIFF: // ScalarUpwAdvDiffElemKernel.C:74-81; Gjq sits in the dpdx slot
+    gather_one(f + F_U, k.nodal[NALU_F_VELOCITY_RTM] ? k.nodal[NALU_F_VELOCITY_RTM] : k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + F_GP, k.nodal[NALU_F_GJQ], 3, node);
+    gather_one(f + F_Q, k.nodal[NALU_F_SCALARQ], 1, node);
+    gather_one(f + F_RHO, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + F_MU, k.nodal[NALU_F_VISCOSITY], 1, node);
+    break;
+  case NALU_K_MOMENTUM_UPW_ADV_DIFF: // MomentumUpwAdvDiffElemKernel.C:74-81
+    gather_one(f + F_U, k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + F_MU, k.nodal[NALU_F_VISCOSITY], 1, node);
+    gather_one(f + F_RHO, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + F_GJU, k.nodal[NALU_F_GJU], 9, node);
+    gather_one(f + F_RTM, k.nodal[NALU_F_VELOCITY_RTM] ? k.nodal[NALU_F_VELOCITY_RTM] : k.nodal[NALU_F_VELOCITY], 3, node);
     break;
   case NALU_K_MOMENTUM_MASS:
     gather_one(f + M_UNP1, k.nodal[NALU_F_VELOCITY], 3, node);
@@ -179,6 +196,47 @@ __host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, co
   default:
     break;
   }
+}
+
+// ---- upwind kernels: Peclet function and limiter --------------------------------------------
+// ClassicPecletFunction (A = 5) / TanhFunction, src/PecletFunction.C:67-71,98-101
+__host__ __device__ inline double peclet_function(const nalu_b200_kernel_desc &k, double x)
+{
+  if (k.options & NALU_OPT_PECLET_TANH) return 0.50 * (1.0 + tanh((x - k.upw[NALU_UPW_TANH_TRANS]) / k.upw[NALU_UPW_TANH_WIDTH]));
+  const double m = k.upw[NALU_UPW_HYBRID_FACTOR] * x;
+  return m * m / (5.0 + m * m);
+}
+// ScalarUpwAdvDiffElemKernel.C:258-266
+__host__ __device__ inline double van_leer(double dqm, double dqp)
+{
+  return (2.0 * (dqm * dqp + fabs(dqm * dqp))) / ((dqm + dqp) * (dqm + dqp) + 1.0e-16);
+}
+// what both upwind kernels derive per integration point from the edge (il, ir): the Peclet blending factor and
+// the operator-sensitivity factors (ScalarUpwAdvDiffElemKernel.C:151-163,208-223)
+struct UpwIp {
+  double pecfac, adv_eff, aL, aR;
+};
+template <int NDOF>
+__host__ __device__ inline void upw_edge(const ElemScratch<NDOF> &ws, const nalu_b200_kernel_desc &k, int il, int ir,
+                                         const double *uL, const double *uR, double tmdot, UpwIp &U)
+{
+  const double diffIp = 0.5 * (ws.fld[il][F_MU] / ws.fld[il][F_RHO] + ws.fld[ir][F_MU] / ws.fld[ir][F_RHO]);
+  double udotx = 0.0;
+  for (int j = 0; j < 3; ++j) udotx += 0.5 * (uL[j] + uR[j]) * (ws.coords[ir][j] - ws.coords[il][j]);
+  U.pecfac = peclet_function(k, fabs(udotx) / (diffIp + 1.0e-16));
+  const double om_pecfac = 1.0 - U.pecfac, alpha = k.upw[NALU_UPW_ALPHA], alphaUpw = k.upw[NALU_UPW_ALPHA_UPW];
+  U.adv_eff = tmdot * (U.pecfac * (1.0 - alphaUpw) + om_pecfac * (1.0 - alpha));
+  U.aL = 0.5 * (tmdot + fabs(tmdot)) * U.pecfac * alphaUpw + 0.5 * alpha * om_pecfac * tmdot;
+  U.aR = 0.5 * (tmdot - fabs(tmdot)) * U.pecfac * alphaUpw + 0.5 * alpha * om_pecfac * tmdot;
+}
+// blended advected value: pecfac * upwind + (1 - pecfac) * generalized central (:186-198)
+__host__ __device__ inline double upw_blend(const nalu_b200_kernel_desc &k, double pecfac, double tmdot, double qIp,
+                                            double qIpL, double qIpR)
+{
+  const double alpha = k.upw[NALU_UPW_ALPHA], alphaUpw = k.upw[NALU_UPW_ALPHA_UPW];
+  const double qUpwind = tmdot > 0 ? alphaUpw * qIpL + (1.0 - alphaUpw) * qIp : alphaUpw * qIpR + (1.0 - alphaUpw) * qIp;
+  const double qHatL = alpha * qIpL + (1.0 - alpha) * qIp, qHatR = alpha * qIpR + (1.0 - alpha) * qIp;
+  return pecfac * qUpwind + (1.0 - pecfac) * (0.5 * (qHatL + qHatR));
 }
 
 // ---- stage A: per integration point quantities (lane = ip) --------------------------------
@@ -225,6 +283,92 @@ __host__ __device__ inline void stage_ip(int lane, ElemScratch<NDOF> &ws, const 
     ws.ipd[ip][2] = flux[1];
     ws.ipd[ip][3] = flux[2];
     ws.ipd[ip][4] = tmdot;
+  } else if (kind == NALU_K_MOMENTUM_UPW_ADV_DIFF) {
+    // MomentumUpwAdvDiffElemKernel.C:140-311: the rhs flux of the point; the lhs factors for stage B
+    const double (*g)[3] = (k.options & NALU_OPT_SHIFTED_GRAD_OP) ? ws.dndxs[ip] : ws.dndx[ip];
+    double a1 = s1, a2 = s2, a3 = s3;
+    if (k.options & NALU_OPT_SKEW_SYMMETRIC) hex8::scs_intg_loc(ip, 0.5, a1, a2, a3);
+    const int il = hex8::scs_left(ip), ir = hex8::scs_right(ip);
+    const double tmdot = k.mass_flow_rate[elem * 12 + ip];
+    double mu = 0.0, divU = 0.0, u[3] = {0, 0, 0}, xip[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, s1, s2, s3), ra = hex8::shape_fcn(ic, a1, a2, a3);
+      mu += r * ws.fld[ic][F_MU];
+      for (int j = 0; j < 3; ++j) {
+        u[j] += ra * ws.fld[ic][F_U + j];
+        xip[j] += ra * ws.coords[ic][j];
+        divU += ws.fld[ic][F_U + j] * g[ic][j];
+      }
+    }
+    UpwIp U;
+    upw_edge(ws, k, il, ir, &ws.fld[il][F_RTM], &ws.fld[ir][F_RTM], tmdot, U);
+    double flux[3];
+    for (int i = 0; i < 3; ++i) {
+      double duL = 0.0, duR = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        duL += (xip[j] - ws.coords[il][j]) * ws.fld[il][F_GJU + 3 * i + j];
+        duR += (ws.coords[ir][j] - xip[j]) * ws.fld[ir][F_GJU + 3 * i + j];
+      }
+      double limL = 1.0, limR = 1.0;
+      if (k.options & NALU_OPT_USE_LIMITER) {
+        const double dq = ws.fld[ir][F_U + i] - ws.fld[il][F_U + i];
+        limL = van_leer(2.0 * 2.0 * duL - dq, dq);
+        limR = van_leer(2.0 * 2.0 * duR - dq, dq);
+      }
+      const double uL = ws.fld[il][F_U + i] + duL * k.upw[NALU_UPW_HO_UPWIND] * limL;
+      const double uR = ws.fld[ir][F_U + i] - duR * k.upw[NALU_UPW_HO_UPWIND] * limR;
+      flux[i] = tmdot * upw_blend(k, U.pecfac, tmdot, u[i], uL, uR) + 2.0 / 3.0 * mu * divU * A[i] * k.include_divu;
+    }
+    for (int ic = 0; ic < 8; ++ic) {
+      const double *uc = &ws.fld[ic][F_U];
+      const double gA = g[ic][0] * A[0] + g[ic][1] * A[1] + g[ic][2] * A[2];
+      const double uA = uc[0] * A[0] + uc[1] * A[1] + uc[2] * A[2];
+      for (int i = 0; i < 3; ++i) flux[i] += -mu * (g[ic][i] * uA + gA * uc[i]);
+    }
+    ws.ipd[ip][0] = mu;
+    ws.ipd[ip][1] = flux[0];
+    ws.ipd[ip][2] = flux[1];
+    ws.ipd[ip][3] = flux[2];
+    ws.ipd[ip][4] = U.adv_eff;
+    ws.ipd[ip][5] = U.aL;
+    ws.ipd[ip][6] = U.aR;
+  } else if (kind == NALU_K_SCALAR_UPW_ADV_DIFF) {
+    // ScalarUpwAdvDiffElemKernel.C:132-252
+    const double (*g)[3] = (k.options & NALU_OPT_SHIFTED_GRAD_OP) ? ws.dndxs[ip] : ws.dndx[ip];
+    double a1 = s1, a2 = s2, a3 = s3;
+    if (k.options & NALU_OPT_SKEW_SYMMETRIC) hex8::scs_intg_loc(ip, 0.5, a1, a2, a3);
+    const int il = hex8::scs_left(ip), ir = hex8::scs_right(ip);
+    const double tmdot = k.mass_flow_rate[elem * 12 + ip];
+    double qIp = 0.0, gam = 0.0, xip[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, s1, s2, s3), ra = hex8::shape_fcn(ic, a1, a2, a3);
+      qIp += ra * ws.fld[ic][F_Q];
+      gam += r * ws.fld[ic][F_MU];
+      for (int j = 0; j < 3; ++j) xip[j] += ra * ws.coords[ic][j];
+    }
+    UpwIp U;
+    upw_edge(ws, k, il, ir, &ws.fld[il][F_U], &ws.fld[ir][F_U], tmdot, U);
+    double dqL = 0.0, dqR = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      dqL += (xip[j] - ws.coords[il][j]) * ws.fld[il][F_GP + j];
+      dqR += (ws.coords[ir][j] - xip[j]) * ws.fld[ir][F_GP + j];
+    }
+    double limL = 1.0, limR = 1.0;
+    if (k.options & NALU_OPT_USE_LIMITER) {
+      const double dq = ws.fld[ir][F_Q] - ws.fld[il][F_Q];
+      limL = van_leer(2.0 * 2.0 * dqL - dq, dq);
+      limR = van_leer(2.0 * 2.0 * dqR - dq, dq);
+    }
+    const double qL = ws.fld[il][F_Q] + dqL * k.upw[NALU_UPW_HO_UPWIND] * limL;
+    const double qR = ws.fld[ir][F_Q] - dqR * k.upw[NALU_UPW_HO_UPWIND] * limR;
+    double q = tmdot * upw_blend(k, U.pecfac, tmdot, qIp, qL, qR);
+    for (int ic = 0; ic < 8; ++ic)
+      q += -gam * (g[ic][0] * A[0] + g[ic][1] * A[1] + g[ic][2] * A[2]) * ws.fld[ic][F_Q];
+    ws.ipd[ip][0] = gam;
+    ws.ipd[ip][1] = q;
+    ws.ipd[ip][4] = U.adv_eff;
+    ws.ipd[ip][5] = U.aL;
+    ws.ipd[ip][6] = U.aR;
   } else if (kind == NALU_K_CONTINUITY_ADV) {
     // ContinuityAdvElemKernel.C:110-147
     const bool sp = k.options & NALU_OPT_SHIFT_POISSON;
@@ -272,9 +416,10 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
 {
   constexpr int R = ElemScratch<NDOF>::R;
   const int kind = k.kind;
-  if (kind == NALU_K_MOMENTUM_ADV_DIFF) {
+  if (kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_UPW_ADV_DIFF) {
     if (NDOF != 3 || lane >= 24) return;
     const int ic = lane / 3, j = lane % 3;
+    const bool upw = kind == NALU_K_MOMENTUM_UPW_ADV_DIFF;
     const bool sh = k.options & NALU_OPT_SHIFTED_GRAD_OP;
     for (int ip = 0; ip < 12; ++ip) {
       const int L = hex8::scs_left(ip), Rn = hex8::scs_right(ip);
@@ -283,7 +428,11 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
       const double *g = sh ? ws.dndxs[ip][ic] : ws.dndx[ip][ic];
       const double *A = ws.areav[ip];
       const double mu = ws.ipd[ip][0];
-      const double lhsfacAdv = hex8::shape_fcn(ic, a1, a2, a3) * ws.ipd[ip][4];
+      // ipd[4]: mdot, or mdot (pecfac (1 - alphaUpw) + (1 - pecfac)(1 - alpha)) for the upwind kernel, whose left /
+      // right node columns also take alhsfacL / alhsfacR on the diagonal of the block (:246-255)
+      double lhsfacAdv = hex8::shape_fcn(ic, a1, a2, a3) * ws.ipd[ip][4];
+      if (upw && ic == L) lhsfacAdv += ws.ipd[ip][5];
+      if (upw && ic == Rn) lhsfacAdv += ws.ipd[ip][6];
       const double diag = lhsfacAdv - mu * (g[0] * A[0] + g[1] * A[1] + g[2] * A[2]);
       for (int i = 0; i < 3; ++i) {
         double v = -mu * g[i] * A[j];
@@ -292,7 +441,8 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
         ws.lhs[(Rn * 3 + i) * R + lane] -= v;
       }
     }
-  } else if (kind == NALU_K_CONTINUITY_ADV || kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF) {
+  } else if (kind == NALU_K_CONTINUITY_ADV || kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF ||
+             kind == NALU_K_SCALAR_UPW_ADV_DIFF) {
     if (NDOF != 1 || lane >= 8) return;
     const int ic = lane;
     for (int ip = 0; ip < 12; ++ip) {
@@ -309,6 +459,10 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
         hex8::scs_intg_loc(ip, (k.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25, a1, a2, a3);
         v = hex8::shape_fcn(ic, a1, a2, a3) * ws.ipd[ip][4] -
             ws.ipd[ip][0] * (g[0] * A[0] + g[1] * A[1] + g[2] * A[2]);
+        if (kind == NALU_K_SCALAR_UPW_ADV_DIFF) { // ScalarUpwAdvDiffElemKernel.C:208-223
+          if (ic == L) v += ws.ipd[ip][5];
+          if (ic == Rn) v += ws.ipd[ip][6];
+        }
       }
       ws.lhs[L * R + ic] += v;
       ws.lhs[Rn * R + ic] -= v;
@@ -443,9 +597,9 @@ __host__ __device__ inline void stage_rhs(int lane, ElemScratch<NDOF> &ws, const
   const int kind = k.kind;
   if (lane >= R) return;
   int col;
-  if (kind == NALU_K_MOMENTUM_ADV_DIFF) col = 1 + lane % 3;
+  if (kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_UPW_ADV_DIFF) col = 1 + lane % 3;
   else if (kind == NALU_K_CONTINUITY_ADV) col = 0;
-  else if (kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF) col = 1;
+  else if (kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF || kind == NALU_K_SCALAR_UPW_ADV_DIFF) col = 1;
   else return;
   const int node = lane / NDOF;
   double acc = 0.0;

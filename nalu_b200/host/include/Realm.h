@@ -21,6 +21,15 @@ public:
     delete solutionOptions_;
     delete timeIntegrator_;
   }
+  // src/Realm.C:4231-4241,4416-4458
+  double get_hybrid_factor(const std::string dofName) { return SolutionOptions::lookup(solutionOptions_->hybridMap_, dofName, solutionOptions_->hybridDefault_); }
+  std::string get_tanh_functional_form(const std::string dofName)
+  {
+    auto it = solutionOptions_->tanhFormMap_.find(dofName);
+    return it == solutionOptions_->tanhFormMap_.end() ? solutionOptions_->tanhFormDefault_ : it->second;
+  }
+  double get_tanh_trans(const std::string dofName) { return SolutionOptions::lookup(solutionOptions_->tanhTransMap_, dofName, solutionOptions_->tanhTransDefault_); }
+  double get_tanh_width(const std::string dofName) { return SolutionOptions::lookup(solutionOptions_->tanhWidthMap_, dofName, solutionOptions_->tanhWidthDefault_); }
   stk::mesh::BulkData &bulk_data() { return *bulkData_; }
   stk::mesh::MetaData &meta_data() { return bulkData_->mesh_meta_data(); }
   std::shared_ptr<stk::mesh::BulkData> bulkData_;

@@ -58,6 +58,27 @@ public:
     for (size_t i = 0; i < gravity_.size() && i < 3; ++i) g[i] = gravity_[i];
     return g;
   }
+  // upwind / Peclet blending (defaults src/SolutionOptions.C:32-44; accessors :776-821; the hybrid / tanh
+  // accessors live on Realm in the reference, src/Realm.C:4231-4458, and read these maps)
+  double hybridDefault_ = 0.0, alphaDefault_ = 0.0, alphaUpwDefault_ = 1.0, upwDefault_ = 1.0;
+  std::string tanhFormDefault_ = "classic";
+  double tanhTransDefault_ = 2.0, tanhWidthDefault_ = 4.0;
+  std::map<std::string, double> hybridMap_, alphaMap_, alphaUpwMap_, upwMap_, tanhTransMap_, tanhWidthMap_;
+  std::map<std::string, bool> limiterMap_;
+  std::map<std::string, std::string> tanhFormMap_;
+  static double lookup(const std::map<std::string, double> &m, const std::string &dofName, double dflt)
+  {
+    auto it = m.find(dofName);
+    return it == m.end() ? dflt : it->second;
+  }
+  double get_alpha_factor(const std::string &dofName) const { return lookup(alphaMap_, dofName, alphaDefault_); }
+  double get_alpha_upw_factor(const std::string &dofName) const { return lookup(alphaUpwMap_, dofName, alphaUpwDefault_); }
+  double get_upw_factor(const std::string &dofName) const { return lookup(upwMap_, dofName, upwDefault_); }
+  bool primitive_uses_limiter(const std::string &dofName) const
+  {
+    auto it = limiterMap_.find(dofName);
+    return it == limiterMap_.end() ? false : it->second;
+  }
   bool meshMotion_ = false, meshDeformation_ = false, externalMeshDeformation_ = false;
   std::map<std::string, bool> shiftedGradOpMap_, skewSymmetricMap_;
   bool does_mesh_move() const { return meshMotion_ || meshDeformation_ || externalMeshDeformation_; }

@@ -6,6 +6,7 @@
 #include "../include/kernel/MomentumBuoyancySrcElemKernel.h"
 #include "../include/kernel/SSTSrcElemKernels.h"
 #include "../include/kernel/ScalarAdvDiffElemKernel.h"
+#include "../include/kernel/UpwAdvDiffElemKernels.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -818,7 +819,166 @@ bool SpecificDissipationRateSSTSrcElemKernel<AlgTraits>::device_descriptor(nalu_
   return true;
 }
 
+// ---- upwind adv-diff kernels --------------------------------------------------------------------
+namespace {
+// EquationSystem::create_peclet_function (include/EquationSystem.h:306-325), captured as data
+PecletFunctionSpec make_peclet_spec(EquationSystem *eqSystem, const std::string &dofName)
+{
+  STK_ThrowRequireMsg(eqSystem, "upwind kernel: an EquationSystem is needed to create the Peclet function");
+  PecletFunctionSpec p;
+  Realm &realm = eqSystem->realm_;
+  if ("classic" == realm.get_tanh_functional_form(dofName)) {
+    p.tanh_form = false;
+    p.hybridFactor = realm.get_hybrid_factor(dofName);
+  } else {
+    p.tanh_form = true;
+    p.c1 = realm.get_tanh_trans(dofName);
+    p.c2 = realm.get_tanh_width(dofName);
+  }
+  return p;
+}
+void upw_fill(nalu_b200_kernel_desc &d, const PecletFunctionSpec &p, double alpha, double alphaUpw, double hoUpwind, bool useLimiter)
+{
+  d.upw[NALU_UPW_ALPHA] = alpha;
+  d.upw[NALU_UPW_ALPHA_UPW] = alphaUpw;
+  d.upw[NALU_UPW_HO_UPWIND] = hoUpwind;
+  d.upw[NALU_UPW_HYBRID_FACTOR] = p.hybridFactor;
+  d.upw[NALU_UPW_TANH_TRANS] = p.c1;
+  d.upw[NALU_UPW_TANH_WIDTH] = p.c2;
+  if (useLimiter) d.options |= NALU_OPT_USE_LIMITER;
+  if (p.tanh_form) d.options |= NALU_OPT_PECLET_TANH;
+}
+} // namespace
+
+template <typename AlgTraits>
+ScalarUpwAdvDiffElemKernel<AlgTraits>::ScalarUpwAdvDiffElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                                 EquationSystem *eqSystem, ScalarFieldType *scalarQ,
+                                                                 VectorFieldType *Gjq, ScalarFieldType *diffFluxCoeff,
+                                                                 ElemDataRequests &dataPreReqs)
+    : Kernel(), solnOpts_(solnOpts), scalarQ_(scalarQ), Gjq_(Gjq), diffFluxCoeff_(diffFluxCoeff),
+      lrscv_(MasterElementRepo::get_surface_master_element(AlgTraits::topo_)->adjacentNodes()), dofName_(scalarQ->name()),
+      alpha_(solnOpts.get_alpha_factor(dofName_)), alphaUpw_(solnOpts.get_alpha_upw_factor(dofName_)),
+      hoUpwind_(solnOpts.get_upw_factor(dofName_)), useLimiter_(solnOpts.primitive_uses_limiter(dofName_)),
+      om_alpha_(1.0 - alpha_), om_alphaUpw_(1.0 - alphaUpw_), shiftedGradOp_(solnOpts.get_shifted_grad_op(scalarQ->name())),
+      pecletFunction_(make_peclet_spec(eqSystem, dofName_))
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  massFlowRate_ = metaData.get_field<double>(stk::topology::ELEMENT_RANK, "mass_flow_rate_scs");
+  density_ = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  velocityRTM_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.does_mesh_move() ? "velocity_rtm" : "velocity");
+  STK_ThrowRequireMsg(coordinates_ && massFlowRate_ && density_ && velocityRTM_ && Gjq_,
+                      "ScalarUpwAdvDiffElemKernel: required fields not registered");
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(AlgTraits::topo_);
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shape_fcn(ptr); }, v_shape_function_);
+  skewSymmetric_ = solnOpts.get_skew_symmetric(scalarQ->name());
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { skewSymmetric_ ? meSCS->shifted_shape_fcn(ptr) : meSCS->shape_fcn(ptr); },
+                                   v_adv_shape_function_);
+  dataPreReqs.add_cvfem_surface_me(meSCS);
+  dataPreReqs.add_gathered_nodal_field(*velocityRTM_, AlgTraits::nDim_);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*Gjq_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*scalarQ_, 1);
+  dataPreReqs.add_gathered_nodal_field(*density_, 1);
+  dataPreReqs.add_gathered_nodal_field(*diffFluxCoeff_, 1);
+  dataPreReqs.add_element_field(*massFlowRate_, AlgTraits::numScsIp_);
+  dataPreReqs.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_GRAD_OP : SCS_GRAD_OP, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+void ScalarUpwAdvDiffElemKernel<AlgTraits>::setup(const TimeIntegrator &)
+{
+  alpha_ = solnOpts_.get_alpha_factor(dofName_);
+  alphaUpw_ = solnOpts_.get_alpha_upw_factor(dofName_);
+  hoUpwind_ = solnOpts_.get_upw_factor(dofName_);
+  useLimiter_ = solnOpts_.primitive_uses_limiter(dofName_);
+  om_alpha_ = 1.0 - alpha_;
+  om_alphaUpw_ = 1.0 - alphaUpw_;
+}
+template <typename AlgTraits>
+bool ScalarUpwAdvDiffElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_SCALAR_UPW_ADV_DIFF;
+  d.options = (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0) | (skewSymmetric_ ? NALU_OPT_SKEW_SYMMETRIC : 0);
+  upw_fill(d, pecletFunction_, alpha_, alphaUpw_, hoUpwind_, useLimiter_);
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityRTM_);
+  bind(d, NALU_F_GJQ, Gjq_);
+  bind(d, NALU_F_SCALARQ, scalarQ_);
+  bind(d, NALU_F_DENSITY, density_);
+  bind(d, NALU_F_VISCOSITY, diffFluxCoeff_);
+  d.mass_flow_rate = massFlowRate_->device_data();
+  return true;
+}
+
+template <typename AlgTraits>
+MomentumUpwAdvDiffElemKernel<AlgTraits>::MomentumUpwAdvDiffElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                                     EquationSystem *eqSystem, VectorFieldType *velocity,
+                                                                     ScalarFieldType *viscosity, GenericFieldType *Gju,
+                                                                     ElemDataRequests &dataPreReqs)
+    : Kernel(), solnOpts_(solnOpts), viscosity_(viscosity), Gju_(Gju),
+      lrscv_(MasterElementRepo::get_surface_master_element(AlgTraits::topo_)->adjacentNodes()), dofName_(velocity->name()),
+      alpha_(solnOpts.get_alpha_factor(dofName_)), alphaUpw_(solnOpts.get_alpha_upw_factor(dofName_)),
+      hoUpwind_(solnOpts.get_upw_factor(dofName_)), useLimiter_(solnOpts.primitive_uses_limiter(dofName_)),
+      om_alpha_(1.0 - alpha_), om_alphaUpw_(1.0 - alphaUpw_), includeDivU_(solnOpts.includeDivU_),
+      shiftedGradOp_(solnOpts.get_shifted_grad_op(velocity->name())), pecletFunction_(make_peclet_spec(eqSystem, dofName_))
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  velocityRTM_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.does_mesh_move() ? "velocity_rtm" : "velocity");
+  velocityNp1_ = &(velocity->field_of_state(stk::mesh::StateNP1));
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  density_ = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  massFlowRate_ = metaData.get_field<double>(stk::topology::ELEMENT_RANK, "mass_flow_rate_scs");
+  STK_ThrowRequireMsg(coordinates_ && massFlowRate_ && density_ && velocityRTM_ && Gju_,
+                      "MomentumUpwAdvDiffElemKernel: required fields not registered");
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(AlgTraits::topo_);
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shape_fcn(ptr); }, v_shape_function_);
+  skewSymmetric_ = solnOpts.get_skew_symmetric(velocity->name());
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { skewSymmetric_ ? meSCS->shifted_shape_fcn(ptr) : meSCS->shape_fcn(ptr); },
+                                   v_adv_shape_function_);
+  dataPreReqs.add_cvfem_surface_me(meSCS);
+  dataPreReqs.add_gathered_nodal_field(*Gju_, AlgTraits::nDim_, AlgTraits::nDim_);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*velocityRTM_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*velocityNp1_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*density_, 1);
+  dataPreReqs.add_gathered_nodal_field(*viscosity_, 1);
+  dataPreReqs.add_element_field(*massFlowRate_, AlgTraits::numScsIp_);
+  dataPreReqs.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_GRAD_OP : SCS_GRAD_OP, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+void MomentumUpwAdvDiffElemKernel<AlgTraits>::setup(const TimeIntegrator &)
+{
+  alpha_ = solnOpts_.get_alpha_factor(dofName_);
+  alphaUpw_ = solnOpts_.get_alpha_upw_factor(dofName_);
+  hoUpwind_ = solnOpts_.get_upw_factor(dofName_);
+  useLimiter_ = solnOpts_.primitive_uses_limiter(dofName_);
+  om_alpha_ = 1.0 - alpha_;
+  om_alphaUpw_ = 1.0 - alphaUpw_;
+}
+template <typename AlgTraits>
+bool MomentumUpwAdvDiffElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_MOMENTUM_UPW_ADV_DIFF;
+  d.options = (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0) | (skewSymmetric_ ? NALU_OPT_SKEW_SYMMETRIC : 0);
+  d.include_divu = includeDivU_;
+  upw_fill(d, pecletFunction_, alpha_, alphaUpw_, hoUpwind_, useLimiter_);
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityNp1_);
+  if (velocityRTM_ != velocityNp1_) bind(d, NALU_F_VELOCITY_RTM, velocityRTM_);
+  bind(d, NALU_F_VISCOSITY, viscosity_);
+  bind(d, NALU_F_DENSITY, density_);
+  bind(d, NALU_F_GJU, Gju_);
+  d.mass_flow_rate = massFlowRate_->device_data();
+  return true;
+}
+
 NALU_B200_DECLARE_KERNEL(TurbKineticEnergySSTSrcElemKernel)
+NALU_B200_DECLARE_KERNEL(ScalarUpwAdvDiffElemKernel)
+NALU_B200_DECLARE_KERNEL(MomentumUpwAdvDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(SpecificDissipationRateSSTSrcElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumBuoyancySrcElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumBuoyancyBoussinesqSrcElemKernel)

@@ -180,6 +180,8 @@ class DeviceCsrLinearSystem:
         d.beta = scalars.get("beta", 0.0)
         for name, v in (scalars.get("turb") or {}).items():
             d.turb[_lib.TM[name]] = float(v)
+        for name, v in (scalars.get("upw") or {}).items():
+            d.upw[_lib.UPW[name]] = float(v)
         for name, t in (fields or {}).items():
             if t is None:
                 continue

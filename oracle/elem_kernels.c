@@ -505,6 +505,277 @@ static void scalar_mass(const orc_kernel_desc *k, const int32_t *nodes, const me
   }
 }
 
+/* ---- src/PecletFunction.C:67-71 (classic), :98-101 (tanh); built by EquationSystem::create_peclet_function
+ *      (include/EquationSystem.h:306-325).  No reference unit test pins these two kernels: the restatement is
+ *      anchored by its reduction to the golden tables of the central kernels (alpha = 0, hybridFactor = 0 makes
+ *      pecfac = 0 and every upwind term vanish, tests/test_oracle_golden.py) -- the upwind / limiter branches
+ *      themselves are PARITY-UNPINNED restatements. ---- */
+static double peclet_function(const orc_kernel_desc *k, double x)
+{
+  if (k->pecletTanh) return 0.50 * (1.0 + tanh((x - k->tanhTrans) / k->tanhWidth));
+  const double modPeclet = k->hybridFactor * x;
+  return modPeclet * modPeclet / (5.0 + modPeclet * modPeclet);
+}
+/* ScalarUpwAdvDiffElemKernel.C:258-266 == MomentumUpwAdvDiffElemKernel.C:314-322 */
+static double van_leer(double dqm, double dqp)
+{
+  const double small_ = 1.0e-16;
+  return (2.0 * (dqm * dqp + fabs(dqm * dqp))) / ((dqm + dqp) * (dqm + dqp) + small_);
+}
+
+/* ---- src/kernel/ScalarUpwAdvDiffElemKernel.C:110-256 ---- */
+static void scalar_upw_adv_diff(const orc_kernel_desc *k, const int32_t *nodes, int64_t e,
+                                const me_views *me, double *lhs, double *rhs)
+{
+  const int n = 8;
+  const double small_ = 1.0e-16;
+  const double alpha_ = k->alpha, alphaUpw_ = k->alphaUpw, hoUpwind_ = k->hoUpwind;
+  const double om_alpha_ = 1.0 - alpha_, om_alphaUpw_ = 1.0 - alphaUpw_;
+  double v_velocityRTM[8][3], v_Gjq[8][3], v_scalarQ[8], v_density[8], v_diffFluxCoeff[8];
+  const double(*v_coordinates)[3] = me->coords;
+  const double *v_mdot = k->massFlowRate + 12 * e;
+  gather(k->velocityRTM ? k->velocityRTM : k->velocity, 3, nodes, &v_velocityRTM[0][0]);
+  gather(k->Gjq, 3, nodes, &v_Gjq[0][0]);
+  gather(k->scalarQ, 1, nodes, v_scalarQ);
+  gather(k->density, 1, nodes, v_density);
+  gather(k->viscosity, 1, nodes, v_diffFluxCoeff);
+  double v_shape_function_[12][8], v_adv_shape_function_[12][8];
+  scs_shape(0, v_shape_function_);
+  scs_shape(k->skewSymmetric, v_adv_shape_function_);
+  const double(*v_dndx)[8][3] = k->shiftedGradOp ? me->dndx_shifted : me->dndx;
+  const int *lrscv = orc_hex8_lrscv();
+  double w_coordIp[3];
+
+  for (int ip = 0; ip < 12; ++ip) {
+    const int il = lrscv[2 * ip];
+    const int ir = lrscv[2 * ip + 1];
+    const double tmdot = v_mdot[ip];
+    for (int j = 0; j < 3; ++j) w_coordIp[j] = 0.0;
+
+    double qIp = 0.0;
+    double diffFluxCoeffIp = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      const double rAdv = v_adv_shape_function_[ip][ic];
+      qIp += rAdv * v_scalarQ[ic];
+      diffFluxCoeffIp += r * v_diffFluxCoeff[ic];
+      for (int i = 0; i < 3; ++i) w_coordIp[i] += rAdv * v_coordinates[ic][i];
+    }
+
+    /* Peclet factor; along the edge */
+    const double diffIp = 0.5 * (v_diffFluxCoeff[il] / v_density[il] + v_diffFluxCoeff[ir] / v_density[ir]);
+    double udotx = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      const double dxj = v_coordinates[ir][j] - v_coordinates[il][j];
+      const double uj = 0.5 * (v_velocityRTM[il][j] + v_velocityRTM[ir][j]);
+      udotx += uj * dxj;
+    }
+    const double tmp = fabs(udotx) / (diffIp + small_);
+    const double pecfac = peclet_function(k, tmp);
+    const double om_pecfac = 1.0 - pecfac;
+
+    /* left and right extrapolation */
+    double dqL = 0.0;
+    double dqR = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      const double dxjL = w_coordIp[j] - v_coordinates[il][j];
+      const double dxjR = v_coordinates[ir][j] - w_coordIp[j];
+      dqL += dxjL * v_Gjq[il][j];
+      dqR += dxjR * v_Gjq[ir][j];
+    }
+
+    double limitL = 1.0;
+    double limitR = 1.0;
+    if (k->useLimiter) {
+      const double dq = v_scalarQ[ir] - v_scalarQ[il];
+      const double dqMl = 2.0 * 2.0 * dqL - dq;
+      const double dqMr = 2.0 * 2.0 * dqR - dq;
+      limitL = van_leer(dqMl, dq);
+      limitR = van_leer(dqMr, dq);
+    }
+
+    const double qIpL = v_scalarQ[il] + dqL * hoUpwind_ * limitL;
+    const double qIpR = v_scalarQ[ir] - dqR * hoUpwind_ * limitR;
+
+    const double qUpwind = tmdot > 0 ? alphaUpw_ * qIpL + om_alphaUpw_ * qIp : alphaUpw_ * qIpR + om_alphaUpw_ * qIp;
+
+    const double qHatL = alpha_ * qIpL + om_alpha_ * qIp;
+    const double qHatR = alpha_ * qIpR + om_alpha_ * qIp;
+    const double qCds = 0.5 * (qHatL + qHatR);
+
+    const double aflux = tmdot * (pecfac * qUpwind + om_pecfac * qCds);
+
+    rhs[il] -= aflux;
+    rhs[ir] += aflux;
+
+    const double alhsfacL = 0.5 * (tmdot + fabs(tmdot)) * pecfac * alphaUpw_ + 0.5 * alpha_ * om_pecfac * tmdot;
+    lhs[il * n + il] += alhsfacL;
+    lhs[ir * n + il] -= alhsfacL;
+
+    const double alhsfacR = 0.5 * (tmdot - fabs(tmdot)) * pecfac * alphaUpw_ + 0.5 * alpha_ * om_pecfac * tmdot;
+    lhs[ir * n + ir] -= alhsfacR;
+    lhs[il * n + ir] += alhsfacR;
+
+    double qDiff = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double lhsfacAdv = v_adv_shape_function_[ip][ic] * tmdot * (pecfac * om_alphaUpw_ + om_pecfac * om_alpha_);
+      lhs[il * n + ic] += lhsfacAdv;
+      lhs[ir * n + ic] -= lhsfacAdv;
+
+      double lhsfacDiff = 0.0;
+      for (int j = 0; j < 3; ++j) lhsfacDiff += -diffFluxCoeffIp * v_dndx[ip][ic][j] * me->scs_areav[ip][j];
+      qDiff += lhsfacDiff * v_scalarQ[ic];
+
+      lhs[il * n + ic] += lhsfacDiff;
+      lhs[ir * n + ic] -= lhsfacDiff;
+    }
+
+    rhs[il] -= qDiff;
+    rhs[ir] += qDiff;
+  }
+}
+
+/* ---- src/kernel/MomentumUpwAdvDiffElemKernel.C:108-311 ---- */
+static void momentum_upw_adv_diff(const orc_kernel_desc *k, const int32_t *nodes, int64_t e,
+                                  const me_views *me, double *lhs, double *rhs)
+{
+  const int n = 24;
+  const double small_ = 1.0e-16;
+  const double alpha_ = k->alpha, alphaUpw_ = k->alphaUpw, hoUpwind_ = k->hoUpwind;
+  const double om_alpha_ = 1.0 - alpha_, om_alphaUpw_ = 1.0 - alphaUpw_;
+  double w_uIp[3], w_uIpL[3], w_uIpR[3], w_coordIp[3], w_duL[3], w_duR[3], w_limitL[3], w_limitR[3];
+  for (int i = 0; i < 3; ++i) {
+    w_limitL[i] = 1.0;
+    w_limitR[i] = 1.0;
+  }
+  double v_Gju[8][3][3], v_uNp1[8][3], v_density[8], v_viscosity[8], v_velocityRTM[8][3];
+  const double(*v_coordinates)[3] = me->coords;
+  const double *v_mdot = k->massFlowRate + 12 * e;
+  gather(k->Gju, 9, nodes, &v_Gju[0][0][0]);
+  gather(k->velocity, 3, nodes, &v_uNp1[0][0]);
+  gather(k->density, 1, nodes, v_density);
+  gather(k->viscosity, 1, nodes, v_viscosity);
+  gather(k->velocityRTM ? k->velocityRTM : k->velocity, 3, nodes, &v_velocityRTM[0][0]);
+  double v_shape_function_[12][8], v_adv_shape_function_[12][8];
+  scs_shape(0, v_shape_function_);
+  scs_shape(k->skewSymmetric, v_adv_shape_function_);
+  const double(*v_dndx)[8][3] = k->shiftedGradOp ? me->dndx_shifted : me->dndx;
+  const int *lrscv = orc_hex8_lrscv();
+
+  for (int ip = 0; ip < 12; ++ip) {
+    const int il = lrscv[2 * ip];
+    const int ir = lrscv[2 * ip + 1];
+    const int ilNdim = il * 3;
+    const int irNdim = ir * 3;
+    const double tmdot = v_mdot[ip];
+
+    double muIp = 0.0;
+    double divU = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      w_uIp[i] = 0.0;
+      w_coordIp[i] = 0.0;
+    }
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      const double rAdv = v_adv_shape_function_[ip][ic];
+      muIp += r * v_viscosity[ic];
+      for (int j = 0; j < 3; ++j) {
+        const double uj = v_uNp1[ic][j];
+        w_uIp[j] += rAdv * uj;
+        w_coordIp[j] += rAdv * v_coordinates[ic][j];
+        divU += uj * v_dndx[ip][ic][j];
+      }
+    }
+
+    double udotx = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      const double dxi = v_coordinates[ir][i] - v_coordinates[il][i];
+      const double ui = 0.5 * (v_velocityRTM[il][i] + v_velocityRTM[ir][i]);
+      udotx += ui * dxi;
+      w_duL[i] = 0.0;
+      w_duR[i] = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        const double dxjL = w_coordIp[j] - v_coordinates[il][j];
+        const double dxjR = v_coordinates[ir][j] - w_coordIp[j];
+        w_duL[i] += dxjL * v_Gju[il][i][j];
+        w_duR[i] += dxjR * v_Gju[ir][i][j];
+      }
+    }
+
+    const double diffIp = 0.5 * (v_viscosity[il] / v_density[il] + v_viscosity[ir] / v_density[ir]);
+    const double pecFuncArg = fabs(udotx) / (diffIp + small_);
+    const double pecfac = peclet_function(k, pecFuncArg);
+    const double om_pecfac = 1.0 - pecfac;
+
+    if (k->useLimiter) {
+      for (int i = 0; i < 3; ++i) {
+        const double dq = v_uNp1[ir][i] - v_uNp1[il][i];
+        const double dqMl = 2.0 * 2.0 * w_duL[i] - dq;
+        const double dqMr = 2.0 * 2.0 * w_duR[i] - dq;
+        w_limitL[i] = van_leer(dqMl, dq);
+        w_limitR[i] = van_leer(dqMr, dq);
+      }
+    }
+
+    for (int i = 0; i < 3; ++i) {
+      w_uIpL[i] = v_uNp1[il][i] + w_duL[i] * hoUpwind_ * w_limitL[i];
+      w_uIpR[i] = v_uNp1[ir][i] - w_duR[i] * hoUpwind_ * w_limitR[i];
+    }
+
+    for (int i = 0; i < 3; ++i) {
+      const double uiIp = w_uIp[i];
+      const double uiUpwind =
+          tmdot > 0 ? alphaUpw_ * w_uIpL[i] + om_alphaUpw_ * uiIp : alphaUpw_ * w_uIpR[i] + om_alphaUpw_ * uiIp;
+      const double uiHatL = alpha_ * w_uIpL[i] + om_alpha_ * uiIp;
+      const double uiHatR = alpha_ * w_uIpR[i] + om_alpha_ * uiIp;
+      const double uiCds = 0.5 * (uiHatL + uiHatR);
+      const double aflux = tmdot * (pecfac * uiUpwind + om_pecfac * uiCds);
+      const double divUstress = 2.0 / 3.0 * muIp * divU * me->scs_areav[ip][i] * k->includeDivU;
+      const int indexL = ilNdim + i;
+      const int indexR = irNdim + i;
+      rhs[indexL] -= aflux + divUstress;
+      rhs[indexR] += aflux + divUstress;
+
+      const double alhsfacL = 0.5 * (tmdot + fabs(tmdot)) * pecfac * alphaUpw_ + 0.5 * alpha_ * om_pecfac * tmdot;
+      lhs[indexL * n + indexL] += alhsfacL;
+      lhs[indexR * n + indexL] -= alhsfacL;
+
+      const double alhsfacR = 0.5 * (tmdot - fabs(tmdot)) * pecfac * alphaUpw_ + 0.5 * alpha_ * om_pecfac * tmdot;
+      lhs[indexR * n + indexR] -= alhsfacR;
+      lhs[indexL * n + indexR] += alhsfacR;
+    }
+
+    for (int ic = 0; ic < 8; ++ic) {
+      const int icNdim = ic * 3;
+      const double lhsfacAdv = v_adv_shape_function_[ip][ic] * tmdot * (pecfac * om_alphaUpw_ + om_pecfac * om_alpha_);
+      for (int i = 0; i < 3; ++i) {
+        const int indexL = ilNdim + i;
+        const int indexR = irNdim + i;
+        lhs[indexL * n + icNdim + i] += lhsfacAdv;
+        lhs[indexR * n + icNdim + i] -= lhsfacAdv;
+
+        double lhs_riC_i = 0.0;
+        for (int j = 0; j < 3; ++j) {
+          const double axj = me->scs_areav[ip][j];
+          const double uj = v_uNp1[ic][j];
+          const double lhsfacDiff_i = -muIp * v_dndx[ip][ic][j] * axj;
+          lhs_riC_i += lhsfacDiff_i;
+          const double lhsfacDiff_j = -muIp * v_dndx[ip][ic][i] * axj;
+          lhs[indexL * n + icNdim + j] += lhsfacDiff_j;
+          lhs[indexR * n + icNdim + j] -= lhsfacDiff_j;
+          rhs[indexL] -= lhsfacDiff_j * uj;
+          rhs[indexR] += lhsfacDiff_j * uj;
+        }
+        lhs[indexL * n + icNdim + i] += lhs_riC_i;
+        lhs[indexR * n + icNdim + i] -= lhs_riC_i;
+        const double ui = v_uNp1[ic][i];
+        rhs[indexL] -= lhs_riC_i * ui;
+        rhs[indexR] += lhs_riC_i * ui;
+      }
+    }
+  }
+}
+
 /* which ME quantities each kernel registers in its constructor */
 static void me_needs(const orc_kernel_desc *k, int *areav, int *dndx, int *dndxs, int *scv)
 {
@@ -512,6 +783,8 @@ static void me_needs(const orc_kernel_desc *k, int *areav, int *dndx, int *dndxs
   case ORC_MOMENTUM_ADV_DIFF: /* MomentumAdvDiffElemKernel.C:58-63 */
   case ORC_SCALAR_ADV_DIFF:   /* ScalarAdvDiffElemKernel.C:57-62   */
   case ORC_SCALAR_DIFF:
+  case ORC_SCALAR_UPW_ADV_DIFF:   /* ScalarUpwAdvDiffElemKernel.C:82-89   */
+  case ORC_MOMENTUM_UPW_ADV_DIFF: /* MomentumUpwAdvDiffElemKernel.C:82-89 */
     *areav = 1;
     if (k->shiftedGradOp) *dndxs = 1; else *dndx = 1;
     break;
@@ -572,6 +845,8 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     case ORC_CONTINUITY_ADV: continuity_adv(k, elemNodes, &me, lhs, rhs); break;
     case ORC_SCALAR_ADV_DIFF: scalar_adv_diff(k, elemNodes, elemIndex, &me, lhs, rhs); break;
     case ORC_SCALAR_DIFF: scalar_diff(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_SCALAR_UPW_ADV_DIFF: scalar_upw_adv_diff(k, elemNodes, elemIndex, &me, lhs, rhs); break;
+    case ORC_MOMENTUM_UPW_ADV_DIFF: momentum_upw_adv_diff(k, elemNodes, elemIndex, &me, lhs, rhs); break;
     case ORC_MOMENTUM_MASS: momentum_mass(k, elemNodes, &me, lhs, rhs); break;
     case ORC_CONTINUITY_MASS: continuity_mass(k, elemNodes, &me, lhs, rhs); break;
     case ORC_SCALAR_MASS: scalar_mass(k, elemNodes, &me, lhs, rhs); break;

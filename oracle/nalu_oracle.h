@@ -72,7 +72,9 @@ enum orc_kernel_kind {
   ORC_MOMENTUM_BUOYANCY_SRC = 8,            /* src/kernel/MomentumBuoyancySrcElemKernel.C           */
   ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC = 9, /* src/kernel/MomentumBuoyancyBoussinesqSrcElemKernel.C */
   ORC_TKE_SST_SRC = 10,                     /* src/kernel/TurbKineticEnergySSTSrcElemKernel.C       */
-  ORC_SDR_SST_SRC = 11                      /* src/kernel/SpecificDissipationRateSSTSrcElemKernel.C */
+  ORC_SDR_SST_SRC = 11,                     /* src/kernel/SpecificDissipationRateSSTSrcElemKernel.C */
+  ORC_SCALAR_UPW_ADV_DIFF = 12,             /* src/kernel/ScalarUpwAdvDiffElemKernel.C              */
+  ORC_MOMENTUM_UPW_ADV_DIFF = 13            /* src/kernel/MomentumUpwAdvDiffElemKernel.C            */
 };
 
 /* what the kernel constructors/ setup() capture (options + time integrator) */
@@ -112,6 +114,14 @@ typedef struct orc_kernel_desc {
   /* SST sources */
   const double *tke, *sdr, *tvisc, *fOneBlend; /* [1] each */
   double betaStar, tkeProdLimitRatio, sigmaWTwo, betaOne, betaTwo, gammaOne, gammaTwo; /* get_turb_model_constant */
+  /* upwind adv-diff kernels (ScalarUpwAdvDiffElemKernel.C:28-90, MomentumUpwAdvDiffElemKernel.C:28-90) */
+  const double *Gjq;         /* [3]  projected nodal gradient of scalarQ              */
+  const double *Gju;         /* [9]  dudx, Gju(node,i,j) at [3*i+j]                   */
+  const double *velocityRTM; /* [3]  velocity_rtm when the mesh moves; NULL: velocity */
+  double alpha, alphaUpw, hoUpwind; /* get_alpha_factor / get_alpha_upw_factor / get_upw_factor */
+  int useLimiter;                   /* primitive_uses_limiter                          */
+  int pecletTanh;                   /* 0: ClassicPecletFunction(A=5, hybridFactor), 1: TanhFunction(c1, c2) */
+  double hybridFactor, tanhTrans, tanhWidth; /* EquationSystem.h:306-325                */
 } orc_kernel_desc;
 
 /* One element through the registered kernels, exactly as

@@ -10,7 +10,8 @@ _LIB = None
 
 KIND = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3,
             continuity_mass=4, scalar_mass=5, scalar_diff=6, test_fixed_block=7, momentum_buoyancy_src=8,
-            momentum_buoyancy_boussinesq_src=9, tke_sst_src=10, sdr_sst_src=11)
+            momentum_buoyancy_boussinesq_src=9, tke_sst_src=10, sdr_sst_src=11, scalar_upw_adv_diff=12,
+            momentum_upw_adv_diff=13)
 
 
 def build(force=False):
@@ -50,12 +51,16 @@ class KernelDesc(C.Structure):
                [("gravity", C.c_double * 3), ("rhoRef", C.c_double), ("tRef", C.c_double), ("beta", C.c_double)] + \
                [(n, C.c_void_p) for n in ("tke", "sdr", "tvisc", "fOneBlend")] + \
                [(n, C.c_double) for n in ("betaStar", "tkeProdLimitRatio", "sigmaWTwo", "betaOne", "betaTwo",
-                                          "gammaOne", "gammaTwo")]
+                                          "gammaOne", "gammaTwo")] + \
+               [(n, C.c_void_p) for n in ("Gjq", "Gju", "velocityRTM")] + \
+               [(n, C.c_double) for n in ("alpha", "alphaUpw", "hoUpwind")] + \
+               [("useLimiter", C.c_int), ("pecletTanh", C.c_int)] + \
+               [(n, C.c_double) for n in ("hybridFactor", "tanhTrans", "tanhWidth")]
 
 
 _PTR_FIELDS = ("coordinates", "velocity", "velocityN", "velocityNm1", "viscosity", "density", "densityN",
                "densityNm1", "pressure", "Gpdx", "scalarQ", "scalarQN", "scalarQNm1", "massFlowRate",
-               "fixedBlock", "temperature", "tke", "sdr", "tvisc", "fOneBlend")
+               "fixedBlock", "temperature", "tke", "sdr", "tvisc", "fOneBlend", "Gjq", "Gju", "velocityRTM")
 
 
 def _f64(a):

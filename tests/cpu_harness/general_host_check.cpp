@@ -74,6 +74,47 @@ int main()
     }
     for (int i = 0; i < 12; ++i) mdot[i] = frand();
 
+    // upwind adv-diff kernels: shifted grad-op / skew-symmetric / limiter x classic or tanh Peclet function
+    for (int kind = NALU_K_SCALAR_UPW_ADV_DIFF; kind <= NALU_K_MOMENTUM_UPW_ADV_DIFF; ++kind) {
+      for (int opt = 0; opt < 8; ++opt) {
+        static double gjq[NN * 3], gju[NN * 9], rtm[NN * 3];
+        for (int n = 0; n < NN * 3; ++n) { gjq[n] = frand(); rtm[n] = frand(); }
+        for (int n = 0; n < NN * 9; ++n) gju[n] = frand();
+        nalu_b200_kernel_desc k;
+        orc_kernel_desc o;
+        memset(&k, 0, sizeof(k));
+        memset(&o, 0, sizeof(o));
+        k.kind = kind; o.kind = kind;
+        k.include_divu = o.includeDivU = (opt & 1) ? 1.0 : 0.0;
+        int options = 0;
+        if (opt & 1) { options |= NALU_OPT_SHIFTED_GRAD_OP; o.shiftedGradOp = 1; }
+        if (opt & 2) { options |= NALU_OPT_SKEW_SYMMETRIC; o.skewSymmetric = 1; }
+        if (opt & 4) { options |= NALU_OPT_USE_LIMITER; o.useLimiter = 1; }
+        if (trial & 1) { options |= NALU_OPT_PECLET_TANH; o.pecletTanh = 1; }
+        k.options = options;
+        k.upw[NALU_UPW_ALPHA] = o.alpha = 0.1 * (trial % 3);
+        k.upw[NALU_UPW_ALPHA_UPW] = o.alphaUpw = 1.0 - 0.25 * (trial % 2);
+        k.upw[NALU_UPW_HO_UPWIND] = o.hoUpwind = (opt & 2) ? 1.0 : 0.5;
+        k.upw[NALU_UPW_HYBRID_FACTOR] = o.hybridFactor = 0.7;
+        k.upw[NALU_UPW_TANH_TRANS] = o.tanhTrans = 2.0;
+        k.upw[NALU_UPW_TANH_WIDTH] = o.tanhWidth = 4.0;
+        k.nodal[NALU_F_COORDINATES] = o.coordinates = coords;
+        k.nodal[NALU_F_VELOCITY] = o.velocity = vel;
+        k.nodal[NALU_F_VISCOSITY] = o.viscosity = visc;
+        k.nodal[NALU_F_DENSITY] = o.density = rho;
+        k.nodal[NALU_F_SCALARQ] = o.scalarQ = q;
+        k.nodal[NALU_F_GJQ] = o.Gjq = gjq;
+        k.nodal[NALU_F_GJU] = o.Gju = gju;
+        if (opt & 4) k.nodal[NALU_F_VELOCITY_RTM] = o.velocityRTM = rtm; // mesh motion: separate velocity_rtm
+        k.mass_flow_rate = o.massFlowRate = mdot;
+        std::vector<nalu_b200_kernel_desc> ks{k};
+        std::vector<orc_kernel_desc> os{o};
+        const double e = kind == NALU_K_MOMENTUM_UPW_ADV_DIFF ? run_case<3>(ks, os, nodes, coords) : run_case<1>(ks, os, nodes, coords);
+        if (e > 1e-13) { printf("FAIL upw kind %d opt %d trial %d relerr %.3e\n", kind, opt, trial, e); return 1; }
+        worst = fmax(worst, e);
+      }
+    }
+
     for (int kind = 0; kind < 7; ++kind) {
       for (int opt = 0; opt < 4; ++opt) {
         nalu_b200_kernel_desc k;

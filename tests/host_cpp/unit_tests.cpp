@@ -16,6 +16,7 @@
 #include "kernel/MomentumBuoyancySrcElemKernel.h"
 #include "kernel/SSTSrcElemKernels.h"
 #include "kernel/ScalarAdvDiffElemKernel.h"
+#include "kernel/UpwAdvDiffElemKernels.h"
 
 #include <cmath>
 #include <cstdio>
@@ -105,6 +106,9 @@ struct LowMachKernelHex8Mesh {
     sdr_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "specific_dissipation_rate");
     tvisc_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "turbulent_viscosity");
     fOneBlend_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "sst_f_one_blending");
+    // projected nodal gradients of the upwind kernels (dqdx / dudx in the reference's equation systems)
+    dqdx_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dqdx");
+    dudx_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dudx");
     massFlowRate_ = &meta_.declare_field<double>(stk::topology::ELEM_RANK, "mass_flow_rate_scs");
     stk::mesh::put_field_on_mesh(*coordinates_, *part_, 3);
     stk::mesh::put_field_on_mesh(*velocity_, *part_, 3);
@@ -117,6 +121,8 @@ struct LowMachKernelHex8Mesh {
     stk::mesh::put_field_on_mesh(*dualNodalVolume_, *part_, 1);
     stk::mesh::put_field_on_mesh(*temperature_, *part_, 1);
     for (auto *f : {tke_, sdr_, tvisc_, fOneBlend_}) stk::mesh::put_field_on_mesh(*f, *part_, 1);
+    stk::mesh::put_field_on_mesh(*dqdx_, *part_, 3);
+    stk::mesh::put_field_on_mesh(*dudx_, *part_, 9);
     stk::mesh::put_field_on_mesh(*massFlowRate_, *part_, 12);
     bulk_->fill_generated_mesh(nx, ny, nz, *part_);
   }
@@ -162,7 +168,8 @@ struct LowMachKernelHex8Mesh {
   stk::mesh::Part *part_;
   stk::mesh::PartVector partVec_;
   SolutionOptions solnOpts_;
-  VectorFieldType *coordinates_, *velocity_, *dpdx_;
+  VectorFieldType *coordinates_, *velocity_, *dpdx_, *dqdx_;
+  GenericFieldType *dudx_;
   ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_, *temperature_, *tke_, *sdr_, *tvisc_, *fOneBlend_;
   GenericFieldType *massFlowRate_;
 };
@@ -480,6 +487,81 @@ static void test_sst_src(bool sdr)
   unit_test_utils::expect_all_near(lhs, gold("sst_src", "hex8_golds::" + ns + "::lhs"), 2e-15);
 }
 
+// The reference has no unit test for the upwind kernels.  With the SolutionOptions defaults (alpha = 0, hybrid factor
+// 0 -> classic Peclet function = 0, src/SolutionOptions.C:32-44) every upwind term vanishes, so the kernel must
+// reproduce the golden table of MomentumAdvDiffElemKernel whatever the limiter / upwind settings are.
+static void test_momentum_upw_defaults_reproduce_central_gold()
+{
+  std::printf("MomentumUpwAdvDiffElemKernel, default blending == MomentumKernelHex8Mesh.advection_diffusion gold\n");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  fx.solnOpts_.includeDivU_ = 0.0;
+  fx.solnOpts_.limiterMap_["velocity"] = true;
+  for (size_t n = 0; n < 9 * fx.bulk_->num_nodes(); ++n) fx.dudx_->host_data()[n] = 0.1 * std::sin(1.0 + n);
+  fx.dudx_->modify_on_host();
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+  helperObjs.build_system();
+  unit_test_utils::calc_mass_flow_rate_scs(helperObjs, fx);
+  std::unique_ptr<Kernel> kernel(new MomentumUpwAdvDiffElemKernel<AlgTraitsHex8>(
+      *fx.bulk_, fx.solnOpts_, &helperObjs.eqSystem, fx.velocity_, fx.viscosity_, fx.dudx_,
+      helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  EXPECT_TRUE(lhs.size() == 24u * 24u && rhs.size() == 24u);
+  unit_test_utils::expect_all_near(rhs, gold("momentum_advdiff", "hex8_golds::advection_diffusion::rhs"), 2e-15);
+  unit_test_utils::expect_all_near(lhs, gold("momentum_advdiff", "hex8_golds::advection_diffusion::lhs"), 2e-15);
+}
+
+// upwind blending switched on (hybrid factor 1, limiter): structure the reference's loop guarantees -- every ip adds
+// +v to the left row and -v to the right row, so lhs columns and the rhs sum to zero over the element; and
+// setup() must pick up option changes made after construction (ScalarUpwAdvDiffElemKernel.C:96-108)
+static void test_scalar_upw_blending()
+{
+  std::printf("ScalarUpwAdvDiffElemKernel, upwind blending: conservation structure, setup() re-reads the options\n");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields(true);
+  const double *x = fx.coordinates_->host_data();
+  for (size_t n = 0; n < fx.bulk_->num_nodes(); ++n) {
+    fx.scalarQ_->host_data()[n] = std::cos(x[3 * n]) * std::sin(0.5 + x[3 * n + 1]) + 0.2 * x[3 * n + 2];
+    fx.diffFluxCoeff_->host_data()[n] = 1.0e-3;
+    for (int j = 0; j < 3; ++j) fx.dqdx_->host_data()[3 * n + j] = 0.3 * std::cos(1.0 + j + x[3 * n + j]);
+  }
+  for (stk::mesh::FieldBase *f : {(stk::mesh::FieldBase *)fx.scalarQ_, (stk::mesh::FieldBase *)fx.diffFluxCoeff_, (stk::mesh::FieldBase *)fx.dqdx_})
+    f->modify_on_host();
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 1, fx.partVec_[0]);
+  helperObjs.realm.solutionOptions_->hybridMap_["scalarQ"] = 1.0;
+  fx.solnOpts_.limiterMap_["scalarQ"] = true;
+  helperObjs.build_system();
+  unit_test_utils::calc_mass_flow_rate_scs(helperObjs, fx);
+  std::unique_ptr<Kernel> kernel(new ScalarUpwAdvDiffElemKernel<AlgTraitsHex8>(
+      *fx.bulk_, fx.solnOpts_, &helperObjs.eqSystem, fx.scalarQ_, fx.dqdx_, fx.diffFluxCoeff_,
+      helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  EXPECT_TRUE(lhs.size() == 64u && rhs.size() == 8u);
+  double scale = 0, rs = 0;
+  for (double v : lhs) scale = std::fmax(scale, std::fabs(v));
+  for (int c = 0; c < 8; ++c) {
+    double s = 0;
+    for (int r = 0; r < 8; ++r) s += lhs[r * 8 + c];
+    EXPECT_TRUE(std::fabs(s) <= 1e-14 * scale);
+  }
+  for (double v : rhs) rs += v;
+  EXPECT_TRUE(std::fabs(rs) <= 1e-14);
+  // the upwind operator is not the central one
+  nalu_b200_kernel_desc d;
+  kernel->device_descriptor(d);
+  EXPECT_TRUE(d.kind == NALU_K_SCALAR_UPW_ADV_DIFF && (d.options & NALU_OPT_USE_LIMITER) && d.upw[NALU_UPW_HYBRID_FACTOR] == 1.0);
+  fx.solnOpts_.alphaUpwMap_["scalarQ"] = 0.5;
+  kernel->setup(*helperObjs.realm.timeIntegrator_);
+  kernel->device_descriptor(d);
+  EXPECT_TRUE(d.upw[NALU_UPW_ALPHA_UPW] == 0.5);
+}
+
 static void test_scalar_diff()
 {
   std::printf("HeatCondKernelHex8Mesh.cvfem_diff (unit_tests/kernels/UnitTestScalarDiffElem.C:30-58)\n");
@@ -622,6 +704,8 @@ int main(int argc, char **argv)
       test_sst_src(false);
       test_sst_src(true);
       test_scalar_diff();
+      test_momentum_upw_defaults_reproduce_central_gold();
+      test_scalar_upw_blending();
       test_tpetra_basic();
       test_two_kernels_one_algorithm();
     } else {

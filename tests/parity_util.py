@@ -28,12 +28,16 @@ class State:
         self.scalarq_n = 0.97 * self.scalarq
         self.scalarq_nm1 = 0.93 * self.scalarq
         self.dual_volume = np.full(n, 1.0) + 0.1 * np.cos(c[:, 0])
+        # projected nodal gradients of the upwind kernels (any smooth field does: they are inputs)
+        a = 0.3 * np.pi
+        self.gjq = np.stack([np.cos(a * c[:, j] + 0.1 * j) * (0.2 + 0.05 * j) for j in range(3)], axis=1)
+        self.gju = np.stack([np.sin(a * c[:, j % 3] + 0.2 * j) * (0.3 + 0.02 * j) for j in range(9)], axis=1)
         self.mdot = oracle.calc_mass_flow_rate_scs(m.elem_nodes, c, self.density, self.velocity)
         del rng
 
     def names(self):
         return ["coordinates", "velocity", "velocity_n", "velocity_nm1", "viscosity", "density", "density_n",
-                "density_nm1", "pressure", "dpdx", "scalarq", "scalarq_n", "scalarq_nm1", "dual_volume"]
+                "density_nm1", "pressure", "dpdx", "scalarq", "scalarq_n", "scalarq_nm1", "dual_volume", "gjq", "gju"]
 
     def to_device(self, device="cuda"):
         import torch
@@ -46,9 +50,12 @@ class State:
 _ORC_FIELD = dict(coordinates="coordinates", velocity="velocity", velocity_n="velocityN", velocity_nm1="velocityNm1",
                   viscosity="viscosity", density="density", density_n="densityN", density_nm1="densityNm1",
                   pressure="pressure", dpdx="Gpdx", scalarq="scalarQ", scalarq_n="scalarQN",
-                  scalarq_nm1="scalarQNm1")
+                  scalarq_nm1="scalarQNm1", gjq="Gjq", gju="Gju")
 _ORC_OPT = dict(shifted_grad_op="shiftedGradOp", skew_symmetric="skewSymmetric", lumped_mass="lumpedMass",
-                shift_mdot="shiftMdot", shift_poisson="shiftPoisson", reduced_sens="reducedSensitivities")
+                shift_mdot="shiftMdot", shift_poisson="shiftPoisson", reduced_sens="reducedSensitivities",
+                use_limiter="useLimiter", peclet_tanh="pecletTanh")
+_ORC_UPW = dict(alpha="alpha", alpha_upw="alphaUpw", ho_upwind="hoUpwind", hybrid_factor="hybridFactor",
+                tanh_trans="tanhTrans", tanh_width="tanhWidth")
 _ORC_SCALAR = dict(include_divu="includeDivU", dens_fac="densFac", om_dens_fac="om_densFac", dt="dt",
                    gamma1="gamma1", gamma2="gamma2", gamma3="gamma3")
 
@@ -60,7 +67,11 @@ def oracle_desc(st, kind, options=(), keep=None, fixed_block=None, **scalars):
     for o in options:
         kw[_ORC_OPT[o]] = 1
     for k, v in scalars.items():
-        kw[_ORC_SCALAR[k]] = v
+        if k == "upw":
+            for kk, vv in v.items():
+                kw[_ORC_UPW[kk]] = vv
+        else:
+            kw[_ORC_SCALAR[k]] = v
     if fixed_block is not None:
         kw["fixedBlock"] = fixed_block
     d = oracle.make_desc(kind, keep, **kw)

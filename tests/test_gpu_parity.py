@@ -264,6 +264,18 @@ CASES = {
     "scalar_mass+advdiff": (1, [("scalar_mass", (), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
                                 ("scalar_adv_diff", ("skew_symmetric",), {})]),
     "scalar_diff": (1, [("scalar_diff", ("shifted_grad_op",), {})]),
+    # upwind adv-diff kernels (BASELINE configs 1 and 4): classic Peclet blending, limiter, tanh blending
+    "scalar_upw": (1, [("scalar_upw_adv_diff", ("use_limiter",),
+                        dict(upw=dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, hybrid_factor=1.0)))]),
+    "scalar_mass+upw_tanh": (1, [("scalar_mass", ("lumped_mass",), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
+                                 ("scalar_upw_adv_diff", ("peclet_tanh", "skew_symmetric"),
+                                  dict(upw=dict(alpha=0.1, alpha_upw=0.75, ho_upwind=0.5, tanh_trans=2.0, tanh_width=4.0)))]),
+    "momentum_upw": (3, [("momentum_upw_adv_diff", ("use_limiter",),
+                          dict(include_divu=1.0, upw=dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, hybrid_factor=1.0)))]),
+    "momentum_mass+upw_tanh+buoyancy-free": (3, [
+        ("momentum_mass", ("lumped_mass",), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
+        ("momentum_upw_adv_diff", ("peclet_tanh", "shifted_grad_op"),
+         dict(include_divu=0.0, upw=dict(alpha=0.1, alpha_upw=0.75, ho_upwind=0.5, tanh_trans=2.0, tanh_width=4.0)))]),
 }
 
 

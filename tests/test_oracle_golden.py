@@ -201,3 +201,79 @@ def test_scs_areav_closed_surface_and_unit_cube():
 
 def test_lcg_matches_python_stream():
     np.testing.assert_array_equal(oracle.lcg_sequence(1, 24), mesh.lcg_stream(1, 24))
+
+
+# ---- upwind adv-diff kernels (ScalarUpwAdvDiffElemKernel.C, MomentumUpwAdvDiffElemKernel.C) ---------------
+# The reference has no unit test for them.  Anchors: (1) alpha = 0 and hybridFactor = 0 give pecfac = 0, every
+# upwind term vanishes and the kernels must reproduce the golden tables of the central kernels; (2) with
+# pecfac = 1, alphaUpw = 1, hoUpwind = 0 the advective flux is first-order upwind, restated here in numpy.
+def _grad_like(c, ncomp):
+    a = 0.3 * np.pi
+    return np.stack([np.cos(a * c[:, j % 3] + 0.1 * j) * (1.0 + 0.05 * j) for j in range(ncomp)], axis=1)
+
+
+def test_scalar_upw_reduces_to_central_gold():
+    g = load_golden("scalar_advdiff")
+    fx = MixtureFractionFixture(perturb=True)
+    fx.calc_mdot(oracle)
+    keep = []
+    d = oracle.make_desc("scalar_upw_adv_diff", keep, coordinates=fx.coords, scalarQ=fx.mixFraction,
+                         viscosity=fx.viscosity, density=fx.density, velocity=fx.velocity, Gjq=_grad_like(fx.coords, 3),
+                         massFlowRate=fx.mdot, alpha=0.0, alphaUpw=1.0, hoUpwind=1.0, useLimiter=1, hybridFactor=0.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(rhs, tab(g, "hex8_golds::advection_diffusion::rhs"), rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::advection_diffusion::lhs"), rtol=0, atol=TOL)
+
+
+def test_momentum_upw_reduces_to_central_gold():
+    g = load_golden("momentum_advdiff")
+    fx = LowMachFixture()
+    fx.calc_mdot(oracle)
+    keep = []
+    d = oracle.make_desc("momentum_upw_adv_diff", keep, coordinates=fx.coords, velocity=fx.velocity,
+                         viscosity=fx.viscosity, density=fx.density, Gju=_grad_like(fx.coords, 9), massFlowRate=fx.mdot,
+                         includeDivU=0.0, alpha=0.0, alphaUpw=1.0, hoUpwind=1.0, useLimiter=1, hybridFactor=0.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], 3, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(rhs, tab(g, "hex8_golds::advection_diffusion::rhs"), rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::advection_diffusion::lhs"), rtol=0, atol=TOL)
+
+
+LRSCV = [(0, 1), (1, 2), (2, 3), (0, 3), (4, 5), (5, 6), (6, 7), (4, 7), (0, 4), (1, 5), (2, 6), (3, 7)]  # Hex8CVFEM.C:264-276
+
+
+@pytest.mark.parametrize("ndof", [1, 3])
+def test_upw_first_order_upwind_limit(ndof):
+    """pecfac = 1 (tanh function far above its transition), alphaUpw = 1, hoUpwind = 0:
+    aflux = mdot * q(upwind node); lhs gets (mdot + |mdot|)/2 on the left column, (mdot - |mdot|)/2 on the right."""
+    fx = MixtureFractionFixture(perturb=True)
+    mdot = fx.calc_mdot(oracle)[0] * np.array([1, -1, 1, -1, 1, 1, -1, -1, 1, -1, -1, 1.0])  # both signs
+    mdot = mdot[None, :].copy()
+    keep = []
+    common = dict(coordinates=fx.coords, viscosity=fx.viscosity, density=fx.density, velocity=fx.velocity,
+                  massFlowRate=mdot, alpha=0.0, alphaUpw=1.0, hoUpwind=0.0, pecletTanh=1, tanhTrans=-1.0e3, tanhWidth=1.0)
+    if ndof == 1:
+        q = fx.mixFraction[:, None]
+        d = oracle.make_desc("scalar_upw_adv_diff", keep, scalarQ=fx.mixFraction, Gjq=_grad_like(fx.coords, 3), **common)
+        dd = oracle.make_desc("scalar_diff", keep, coordinates=fx.coords, scalarQ=fx.mixFraction, viscosity=fx.viscosity)
+    else:
+        q = fx.velocity
+        d = oracle.make_desc("momentum_upw_adv_diff", keep, Gju=_grad_like(fx.coords, 9), includeDivU=1.0, **common)
+        dd = oracle.make_desc("momentum_adv_diff", keep, coordinates=fx.coords, velocity=fx.velocity, viscosity=fx.viscosity,
+                              massFlowRate=np.zeros((1, 12)), includeDivU=1.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], ndof, fx.mesh.elem_nodes[0])
+    lhs_d, rhs_d = oracle.element_lhs_rhs([dd], ndof, fx.mesh.elem_nodes[0])
+    n = 8 * ndof
+    q = q[fx.mesh.elem_nodes[0]]  # element-local node order
+    elhs, erhs = lhs_d.reshape(n, n).copy(), rhs_d.copy()
+    for ip, (il, ir) in enumerate(LRSCV):
+        m = mdot[0, ip]
+        up = il if m > 0 else ir
+        for i in range(ndof):
+            L, R = il * ndof + i, ir * ndof + i
+            erhs[L] -= m * q[up, i]
+            erhs[R] += m * q[up, i]
+            elhs[L, L] += 0.5 * (m + abs(m)); elhs[R, L] -= 0.5 * (m + abs(m))
+            elhs[R, R] -= 0.5 * (m - abs(m)); elhs[L, R] += 0.5 * (m - abs(m))
+    scale = np.abs(elhs).max()
+    np.testing.assert_allclose(lhs.reshape(n, n), elhs, rtol=0, atol=1e-14 * scale)
+    np.testing.assert_allclose(rhs, erhs, rtol=0, atol=1e-14 * max(1.0, np.abs(erhs).max()))
