@@ -247,6 +247,21 @@ int nalu_b200_sum_into(const nalu_b200_graph *g, int32_t n_entities, const int32
 int nalu_b200_assemble_node_mass(const nalu_b200_graph *g, const nalu_b200_kernel_desc *k,
                                  double *d_values, double *d_rhs, void *stream);
 
+/* TpetraLinearSystem::applyDirichletBCs (src/TpetraLinearSystem.C:1579-1653): for every listed local node and
+ * dof d in [begin_pos, end_pos) the CSR row is replaced by the identity row (locally-owned rows; a
+ * shared-not-owned row is cleared, its owner holds the 1) and the residual by bc - solution (0 for a
+ * shared-not-owned row).  d_nodes: device [n_nodes] local node ids (the nodes the reference's selector picks:
+ * owned or shared, on the BC parts, with the solution field); d_solution / d_bc_values: device nodal fields
+ * [nNodes][numDof].  Call after the assembly, before nalu_b200 loadComplete -- the order of
+ * EquationSystem::assemble_and_solve (src/EquationSystem.C:271-283). */
+int nalu_b200_apply_dirichlet_bcs(const nalu_b200_graph *g, int32_t n_nodes, const int32_t *d_nodes,
+                                  const double *d_solution, const double *d_bc_values, int32_t begin_pos,
+                                  int32_t end_pos, double *d_values, double *d_rhs, void *stream);
+/* TpetraLinearSystem::resetRows (src/TpetraLinearSystem.C:1706-1755): rows of the listed nodes, dofs
+ * [begin_pos, end_pos): every entry (diagonal included) and the residual become 0. */
+int nalu_b200_reset_rows(const nalu_b200_graph *g, int32_t n_nodes, const int32_t *d_nodes, int32_t begin_pos,
+                         int32_t end_pos, double *d_values, double *d_rhs, void *stream);
+
 /* calc_mass_flow_rate_scs: d_mdot[nElem][12] from coordinates, density, velocity */
 int nalu_b200_mdot_scs(const nalu_b200_graph *g, const double *d_coords, const double *d_density,
                        const double *d_velocity, double *d_mdot, void *stream);

@@ -278,6 +278,57 @@ int launch_sum_into(const Graph &g, int n_entities, const int *h_nodes, const do
   return NALU_B200_OK;
 }
 
+// ---- applyDirichletBCs / resetRows (src/TpetraLinearSystem.C:1579-1653,1706-1755) ---------------------
+// One warp per (listed node, dof row d in [beginPos, endPos)): the whole CSR row is overwritten -- 1 on the
+// diagonal of a locally-owned row, 0 elsewhere (a shared-not-owned row is cleared completely, its owner
+// holds the 1) -- and the residual entry becomes bc - solution (owned), 0 (shared-not-owned), or 0 for
+// resetRows.  solution / bc_values are nodal fields [nNodes][numDof] indexed by the local node id.
+__global__ void row_fixup_kernel(int n_list, int begin_pos, int end_pos, int ndof, int n_owned_nodes, const int *list,
+                                 const int *node_row, const long long *browptr, const int *bcol, const double *solution,
+                                 const double *bc_values, int dirichlet, double *values, double *rhs)
+{
+  const int nd = end_pos - begin_pos;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)n_list * nd) return;
+  const int node = list[w / nd], d = begin_pos + (int)(w % nd);
+  const int rn = node_row[node];
+  const bool owned = rn < n_owned_nodes;
+  const long long b0 = browptr[rn], b1 = browptr[rn + 1];
+  const int nb = (int)(b1 - b0);
+  int diag = -1;
+  if (dirichlet && owned) { // column of the row's own node: the block graph row is sorted
+    long long lo = b0, hi = b1;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (bcol[mid] < rn) lo = mid + 1; else hi = mid;
+    }
+    if (lo < b1 && bcol[lo] == rn) diag = (int)(lo - b0) * ndof + d;
+  }
+  double *row = values + (long long)ndof * ndof * b0 + (long long)d * nb * ndof;
+  for (int e = lane; e < nb * ndof; e += 32) row[e] = e == diag ? 1.0 : 0.0;
+  if (lane == 0)
+    rhs[(long long)rn * ndof + d] =
+        (dirichlet && owned) ? bc_values[(long long)node * ndof + d] - solution[(long long)node * ndof + d] : 0.0;
+}
+
+int launch_row_fixup(const Graph &g, int n_list, const int *d_list, int begin_pos, int end_pos, const double *d_solution,
+                     const double *d_bc_values, int dirichlet, double *d_values, double *d_rhs, cudaStream_t stream)
+{
+  if (begin_pos < 0 || end_pos > g.ndof || begin_pos > end_pos) {
+    set_error("applyDirichletBCs / resetRows: [beginPos, endPos) outside the system's dofs");
+    return NALU_B200_ERR_ARG;
+  }
+  const long long warps = (long long)n_list * (end_pos - begin_pos);
+  if (warps <= 0) return NALU_B200_OK;
+  row_fixup_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(n_list, begin_pos, end_pos, g.ndof, g.n_owned_nodes, d_list,
+                                                                           g.d_node_row, (const long long *)g.d_browptr, g.d_bcol,
+                                                                           d_solution, d_bc_values, dirichlet, d_values, d_rhs);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
 // ---- mass_flow_rate_scs producer (unit_tests/kernels/UnitTestKernelUtils.C:547-628) --------
 __global__ void mdot_kernel(long long n_elems, const int *elem_nodes, const double *coords, const double *density,
                             const double *velocity, double *mdot)

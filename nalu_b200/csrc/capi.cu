@@ -435,6 +435,24 @@ int nalu_b200_sum_into(const nalu_b200_graph *h, int32_t n_entities, const int32
   return launch_sum_into(h->g, n_entities, nodes, rhs, lhs, d_values, d_rhs, (cudaStream_t)stream);
 }
 
+int nalu_b200_apply_dirichlet_bcs(const nalu_b200_graph *h, int32_t n_nodes, const int32_t *d_nodes, const double *d_solution,
+                                  const double *d_bc_values, int32_t begin_pos, int32_t end_pos, double *d_values, double *d_rhs,
+                                  void *stream)
+{
+  if (!h || !d_values || !d_rhs || !h->g.d_browptr) return NALU_B200_ERR_STATE;
+  if (n_nodes > 0 && (!d_nodes || !d_solution || !d_bc_values)) return NALU_B200_ERR_ARG;
+  return launch_row_fixup(h->g, n_nodes, d_nodes, begin_pos, end_pos, d_solution, d_bc_values, 1, d_values, d_rhs,
+                          (cudaStream_t)stream);
+}
+
+int nalu_b200_reset_rows(const nalu_b200_graph *h, int32_t n_nodes, const int32_t *d_nodes, int32_t begin_pos, int32_t end_pos,
+                         double *d_values, double *d_rhs, void *stream)
+{
+  if (!h || !d_values || !d_rhs || !h->g.d_browptr) return NALU_B200_ERR_STATE;
+  if (n_nodes > 0 && !d_nodes) return NALU_B200_ERR_ARG;
+  return launch_row_fixup(h->g, n_nodes, d_nodes, begin_pos, end_pos, nullptr, nullptr, 0, d_values, d_rhs, (cudaStream_t)stream);
+}
+
 int nalu_b200_mdot_scs(const nalu_b200_graph *h, const double *d_coords, const double *d_density, const double *d_velocity,
                        double *d_mdot, void *stream)
 {

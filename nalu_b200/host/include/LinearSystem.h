@@ -99,10 +99,10 @@ public:
   void sumInto(const std::vector<stk::mesh::Entity> &sym_meshobj, std::vector<int> &scratchIds,
                std::vector<double> &scratchVals, const std::vector<double> &rhs, const std::vector<double> &lhs,
                const char *trace_tag = 0) override;                         // :1524-1577
-  void applyDirichletBCs(stk::mesh::FieldBase *, stk::mesh::FieldBase *, const stk::mesh::PartVector &, const unsigned,
-                         const unsigned) override { unsupported("applyDirichletBCs (SURVEY 8f-2: next)"); }
+  void applyDirichletBCs(stk::mesh::FieldBase *solutionField, stk::mesh::FieldBase *bcValuesField,
+                         const stk::mesh::PartVector &parts, const unsigned beginPos, const unsigned endPos) override; // :1579-1653
   void prepareConstraints(const unsigned, const unsigned) override { unsupported("prepareConstraints"); }
-  void resetRows(std::vector<stk::mesh::Entity>, const unsigned, const unsigned) override { unsupported("resetRows"); }
+  void resetRows(std::vector<stk::mesh::Entity> nodeList, const unsigned beginPos, const unsigned endPos) override; // :1706-1755
   int solve(stk::mesh::FieldBase *) override { unsupported("solve (the linear solver is a consumer of this path)"); return 1; }
   void loadComplete() override;                                             // :1757-1778
   void writeToFile(const char *filename, bool useOwned = true) override;   // MatrixMarket coordinate file

@@ -57,9 +57,20 @@ public:
   Part(const std::string &name, topology t) : name_(name), topo_(t) {}
   const std::string &name() const { return name_; }
   stk::topology topology() const { return topo_; }
+  // A node-set / side-set part (what the boundary-condition parts of an Exodus mesh are): the local node
+  // indices it holds.  A part without an explicit list (an element block) holds every node of the mesh.
+  void set_nodes(const std::vector<int32_t> &local_nodes)
+  {
+    nodes_ = local_nodes;
+    explicit_nodes_ = true;
+  }
+  bool has_explicit_nodes() const { return explicit_nodes_; }
+  const std::vector<int32_t> &nodes() const { return nodes_; }
 private:
   std::string name_;
   stk::topology topo_;
+  std::vector<int32_t> nodes_;
+  bool explicit_nodes_ = false;
 };
 typedef std::vector<Part *> PartVector;
 

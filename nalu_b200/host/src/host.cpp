@@ -1170,6 +1170,56 @@ void DeviceCsrLinearSystem::sumInto(const std::vector<stk::mesh::Entity> &sym_me
   sumInto(unsigned(sym_meshobj.size()), sym_meshobj.data(), rhs.data(), lhs.data(), nullptr, nullptr, tag);
 }
 
+// TpetraLinearSystem::applyDirichletBCs (src/TpetraLinearSystem.C:1579-1653).  The selector of the reference --
+// (locally owned | globally shared) & union(parts) & has the solution field & active -- is, on the flat mesh,
+// the union of the parts' node lists; rows and residual entries are rewritten on the device.
+void DeviceCsrLinearSystem::applyDirichletBCs(stk::mesh::FieldBase *solutionField, stk::mesh::FieldBase *bcValuesField,
+                                              const stk::mesh::PartVector &parts, const unsigned beginPos, const unsigned endPos)
+{
+  STK_ThrowRequireMsg(solutionField && bcValuesField, "applyDirichletBCs: solution / bc fields required");
+  STK_ThrowRequireMsg(solutionField->max_size() == numDof_ && bcValuesField->max_size() == numDof_,
+                      "applyDirichletBCs: fieldSize == numDof_ (TpetraLinearSystem.C:1603)");
+  const size_t nNodes = realm_.bulk_data().num_nodes();
+  std::vector<char> in(nNodes, 0);
+  for (const stk::mesh::Part *p : parts) {
+    if (!p->has_explicit_nodes()) std::fill(in.begin(), in.end(), 1);
+    else
+      for (int32_t n : p->nodes()) {
+        STK_ThrowRequireMsg(n >= 0 && size_t(n) < nNodes, "applyDirichletBCs: part node out of range");
+        in[size_t(n)] = 1;
+      }
+  }
+  std::vector<int32_t> nodes;
+  for (size_t n = 0; n < nNodes; ++n)
+    if (in[n]) nodes.push_back(int32_t(n));
+  if (nodes.empty()) return;
+  void *d_nodes = nullptr;
+  check(nalu_b200_malloc(&d_nodes, nodes.size() * sizeof(int32_t)), "applyDirichletBCs node list");
+  check(nalu_b200_memcpy_h2d(d_nodes, nodes.data(), nodes.size() * sizeof(int32_t), nullptr), "applyDirichletBCs node list copy");
+  const int rc = nalu_b200_apply_dirichlet_bcs(graph_, int32_t(nodes.size()), static_cast<const int32_t *>(d_nodes),
+                                               solutionField->device_data(), bcValuesField->device_data(), int32_t(beginPos),
+                                               int32_t(endPos), d_values_, d_rhs_, nullptr);
+  nalu_b200_stream_sync(nullptr);
+  nalu_b200_free(d_nodes);
+  check(rc, "apply_dirichlet_bcs");
+}
+
+// TpetraLinearSystem::resetRows (src/TpetraLinearSystem.C:1706-1755)
+void DeviceCsrLinearSystem::resetRows(std::vector<stk::mesh::Entity> nodeList, const unsigned beginPos, const unsigned endPos)
+{
+  if (nodeList.empty()) return;
+  std::vector<int32_t> nodes(nodeList.size());
+  for (size_t i = 0; i < nodeList.size(); ++i) nodes[i] = int32_t(nodeList[i].index);
+  void *d_nodes = nullptr;
+  check(nalu_b200_malloc(&d_nodes, nodes.size() * sizeof(int32_t)), "resetRows node list");
+  check(nalu_b200_memcpy_h2d(d_nodes, nodes.data(), nodes.size() * sizeof(int32_t), nullptr), "resetRows node list copy");
+  const int rc = nalu_b200_reset_rows(graph_, int32_t(nodes.size()), static_cast<const int32_t *>(d_nodes), int32_t(beginPos),
+                                      int32_t(endPos), d_values_, d_rhs_, nullptr);
+  nalu_b200_stream_sync(nullptr);
+  nalu_b200_free(d_nodes);
+  check(rc, "reset_rows");
+}
+
 void DeviceCsrLinearSystem::loadComplete()
 {
   int32_t ns = 0, nr = 0;

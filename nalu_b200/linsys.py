@@ -213,6 +213,17 @@ class DeviceCsrLinearSystem:
         check(self.L.nalu_b200_assemble_node_mass(self.h, C.byref(desc), ptr(self.values), ptr(self.rhs),
                                                   self._stream()), "assemble_node_mass")
 
+    def apply_dirichlet_bcs(self, nodes, solution, bc_values, begin_pos, end_pos):
+        """LinearSystem::applyDirichletBCs; nodes: int32 device tensor of local node ids."""
+        check(self.L.nalu_b200_apply_dirichlet_bcs(self.h, int(nodes.numel()), ptr(nodes), ptr(solution), ptr(bc_values),
+                                                   int(begin_pos), int(end_pos), ptr(self.values), ptr(self.rhs),
+                                                   self._stream()), "apply_dirichlet_bcs")
+
+    def reset_rows(self, nodes, begin_pos, end_pos):
+        """LinearSystem::resetRows."""
+        check(self.L.nalu_b200_reset_rows(self.h, int(nodes.numel()), ptr(nodes), int(begin_pos), int(end_pos),
+                                          ptr(self.values), ptr(self.rhs), self._stream()), "reset_rows")
+
     def mdot_scs(self, coords, density, velocity, out=None):
         import torch
         if out is None:

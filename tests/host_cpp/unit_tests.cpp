@@ -562,6 +562,65 @@ static void test_scalar_upw_blending()
   EXPECT_TRUE(d.upw[NALU_UPW_ALPHA_UPW] == 0.5);
 }
 
+// LinearSystem::applyDirichletBCs / resetRows (src/TpetraLinearSystem.C:1579-1653,1706-1755) after an assembly:
+// identity rows + (bc - solution) residuals on a node-set part, zero rows on a node list, every other row untouched
+static void test_dirichlet_and_reset_rows()
+{
+  std::printf("DeviceCsrLinearSystem::applyDirichletBCs / resetRows\n");
+  LowMachKernelHex8Mesh fx(3, 3, 3);
+  fx.fill_mesh_and_init_fields(true);
+  fx.solnOpts_.includeDivU_ = 1.0;
+  HelperObjects h(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+  h.build_system();
+  unit_test_utils::calc_mass_flow_rate_scs(h, fx);
+  std::unique_ptr<Kernel> kernel(new MomentumAdvDiffElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_, fx.velocity_, fx.viscosity_,
+                                                                              h.assembleElemSolverAlg->dataNeededByKernels_));
+  h.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  h.assembleElemSolverAlg->execute();
+  const std::vector<double> v0 = h.linsys->ownedValues(), r0 = h.linsys->ownedRhs();
+  const std::vector<uint64_t> rp = h.linsys->ownedRowPtr();
+  const std::vector<int32_t> ci = h.linsys->ownedColIdx();
+  // a wall: the nodes of the first node plane (ids 1..16 of generated:3x3x3), given as a node-set part
+  stk::mesh::Part &wall = fx.meta_.declare_part_with_topology("surface_1", stk::topology::NODE);
+  std::vector<int32_t> wallNodes;
+  for (int n = 0; n < 16; ++n) wallNodes.push_back(n);
+  wall.set_nodes(wallNodes);
+  VectorFieldType &bc = fx.meta_.declare_field<double>(stk::topology::NODE_RANK, "velocity_bc");
+  stk::mesh::put_field_on_mesh(bc, *fx.part_, 3);
+  bc.set_num_entities(fx.bulk_->num_nodes());
+  for (size_t n = 0; n < 3 * fx.bulk_->num_nodes(); ++n) bc.host_data()[n] = 0.25 + 0.01 * n;
+  bc.modify_on_host();
+  h.linsys->applyDirichletBCs(fx.velocity_, &bc, {&wall}, 0, 3);
+  std::vector<stk::mesh::Entity> resetList;
+  for (int n : {20, 37, 63}) {
+    stk::mesh::Entity e;
+    e.rank = stk::topology::NODE_RANK;
+    e.index = n;
+    resetList.push_back(e);
+  }
+  h.linsys->resetRows(resetList, 1, 2);
+  const std::vector<double> v1 = h.linsys->ownedValues(), r1 = h.linsys->ownedRhs();
+  const double *u = fx.velocity_->host_data();
+  int bad = 0, ones = 0;
+  for (int node = 0; node < int(fx.bulk_->num_nodes()); ++node) {
+    const int lid0 = h.linsys->entityToLID({stk::topology::NODE_RANK, node});
+    for (int d = 0; d < 3; ++d) {
+      const int row = lid0 + d;
+      const bool dir = node < 16, rst = (node == 20 || node == 37 || node == 63) && d == 1;
+      for (uint64_t j = rp[row]; j < rp[row + 1]; ++j) {
+        const double want = dir ? (ci[j] == row ? 1.0 : 0.0) : (rst ? 0.0 : v0[j]);
+        if (v1[j] != want) ++bad;
+        if (dir && ci[j] == row) ++ones;
+      }
+      const double rw = dir ? bc.host_data()[3 * node + d] - u[3 * node + d] : (rst ? 0.0 : r0[row]);
+      if (r1[row] != rw) ++bad;
+    }
+  }
+  EXPECT_TRUE(bad == 0);
+  EXPECT_TRUE(ones == 48);
+  EXPECT_THROW(h.linsys->applyDirichletBCs(fx.velocity_, &bc, {&wall}, 0, 4));
+}
+
 static void test_scalar_diff()
 {
   std::printf("HeatCondKernelHex8Mesh.cvfem_diff (unit_tests/kernels/UnitTestScalarDiffElem.C:30-58)\n");
@@ -706,6 +765,7 @@ int main(int argc, char **argv)
       test_scalar_diff();
       test_momentum_upw_defaults_reproduce_central_gold();
       test_scalar_upw_blending();
+      test_dirichlet_and_reset_rows();
       test_tpetra_basic();
       test_two_kernels_one_algorithm();
     } else {

@@ -584,3 +584,56 @@ def test_box_kernel_matches_general_kernel_96cubed():
     assert float((ls.values - vg).abs().max()) / scale < 1e-12
     assert float((ls.rhs - rg).abs().max()) / float(rg.abs().max()) < 1e-12
     assert ls.geometry_errors() == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# applyDirichletBCs / resetRows (src/TpetraLinearSystem.C:1579-1653,1706-1755)
+# ---------------------------------------------------------------------------------------------
+def _row_fixup_expected(ls, m, v, r, nodes, ndof, begin, end, sol=None, bc=None):
+    """numpy restatement of the two reference loops on this rank's owned + shared CSR."""
+    rowptr = np.concatenate([ls.rowptr(), ls.rowptr()[-1] + ls.rowptr(shared=True)[1:]]) if ls.n_shared_rows else ls.rowptr()
+    colidx = np.concatenate([ls.colidx(), ls.colidx(shared=True)]) if ls.n_shared_rows else ls.colidx()
+    row_lid, _ = ls.node_lids()
+    n_owned = ls.n_owned_rows
+    v, r = v.copy(), r.copy()
+    for node in nodes:
+        for d in range(begin, end):
+            lid = int(row_lid[node]) + d
+            owned = lid < n_owned
+            b, e = int(rowptr[lid]), int(rowptr[lid + 1])
+            v[b:e] = np.where((colidx[b:e] == lid) & owned & (sol is not None), 1.0, 0.0)
+            r[lid] = (bc[node, d] - sol[node, d]) if (owned and sol is not None) else 0.0
+    return v, r
+
+
+@pytest.mark.parametrize("ndof", [1, 3])
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_dirichlet_and_reset_rows(ndof, nranks):
+    from nalu_b200 import mesh as M
+    meshes = M.partition_slabs(perturbed_box(6, 5, 4), nranks)
+    systems = _build_ranks(meshes, ndof)
+    for rank, (m, ls) in enumerate(zip(meshes, systems)):
+        dev = _cuda()
+        g = torch.Generator().manual_seed(5 + rank)
+        nnz = ls.values.numel()
+        ls.values.copy_(torch.rand(nnz, generator=g, dtype=torch.float64).to(dev) + 0.5)
+        ls.rhs.copy_(torch.rand(ls.rhs.numel(), generator=g, dtype=torch.float64).to(dev) + 0.5)
+        v0, r0 = ls.values.cpu().numpy(), ls.rhs.cpu().numpy()
+        # the nodes of the x = 0 face (owned and shared alike, like the reference's selector)
+        x0 = m.coords[:, 0].min()
+        nodes = np.nonzero(np.abs(m.coords[:, 0] - x0) < 0.3)[0].astype(np.int32)
+        sol = np.cos(m.coords[:, :1] + np.arange(ndof)[None, :])
+        bc = 2.0 + np.sin(m.coords[:, 1:2] + np.arange(ndof)[None, :])
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+        begin, end = (0, 1) if ndof == 1 else (1, 3)
+        ls.apply_dirichlet_bcs(t(nodes), t(sol), t(bc), begin, end)
+        ev, er = _row_fixup_expected(ls, m, v0, r0, nodes, ndof, begin, end, sol, bc)
+        np.testing.assert_array_equal(ls.values.cpu().numpy(), ev)
+        np.testing.assert_array_equal(ls.rhs.cpu().numpy(), er)
+        assert (ev == 1.0).sum() > 0
+        # resetRows on a few other nodes
+        others = np.setdiff1d(np.arange(m.n_nodes, dtype=np.int32), nodes)[::7].astype(np.int32)
+        ls.reset_rows(t(others), 0, ndof)
+        ev2, er2 = _row_fixup_expected(ls, m, ev, er, others, ndof, 0, ndof)
+        np.testing.assert_array_equal(ls.values.cpu().numpy(), ev2)
+        np.testing.assert_array_equal(ls.rhs.cpu().numpy(), er2)
