@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" boundary declared in include/nalu_b200.h.
 #include "internal.h"
+#include <cstdlib>
 
 #include <atomic>
 #include <cstring>
@@ -368,6 +369,12 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   const Graph &g = h->g;
   cudaStream_t s = (cudaStream_t)stream;
   bool use_box = false;
+  // the one-dof tiled kernel (ContinuityAdvElemKernel on a structured block); NALU_CONT_BOX=0 keeps the general kernel
+  static const bool cont_tiled = !(getenv("NALU_CONT_BOX") && atoi(getenv("NALU_CONT_BOX")) == 0);
+  if (mode != NALU_ASSEMBLE_GENERAL && cont_tiled && cont_box_supported(g, kernels, nk)) {
+    set_last_mode(2);
+    return launch_assemble_cont_box(g, kernels, nk, d_values, d_rhs, overwrite, s);
+  }
   if (mode == NALU_ASSEMBLE_BOX) {
     if (!box_supported(g, kernels, nk)) {
       set_error("assemble_elem: tiled kernel does not support this mesh / kernel list");

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Continuity assembly (ContinuityAdvElemKernel) on an n^3 box: tiled write-once kernel vs the general
+(atomic) kernel, device-resident inputs, CUDA events.  usage: bench_continuity.py [n] [steps]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nalu_b200 import fields, mesh  # noqa: E402
+from nalu_b200.linsys import DeviceCsrLinearSystem  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+dev = torch.device("cuda", 0)
+m = mesh.generated_box(n, n, n)
+mesh.perturb_coords_hash(m, 0.12)
+c = m.coords
+t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+f = dict(coordinates=t(c), velocity=t(fields.velocity(c)), density=t(fields.smooth_density(c)),
+         pressure=t(fields.pressure(c)), dpdx=t(fields.dpdx(c)))
+ls = DeviceCsrLinearSystem(m, 1).allocate(dev)
+desc = ls.make_desc("continuity_adv", fields=f, dt=0.05, gamma1=1.5)
+out = {"n": n, "elements": m.n_elems}
+ref = None
+for mode in ("general", "auto"):
+    ow = mode == "auto"
+
+    def step():
+        if not ow:
+            ls.zero_system()
+        return ls.assemble_elem([desc], mode=mode, overwrite=ow)
+
+    for _ in range(3):
+        fam = step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    v, r = ls.owned_values().clone(), ls.owned_rhs().clone()
+    if ref is None:
+        ref = (v, r)
+    else:
+        out["tiled_vs_general_values_relerr"] = float((v - ref[0]).abs().max() / ref[0].abs().max())
+        out["tiled_vs_general_rhs_relerr"] = float((r - ref[1]).abs().max() / ref[1].abs().max())
+    nnz = ls.nnz_owned
+    bytes_alg = 8 * 11 * m.n_nodes + 32 * m.n_elems + 8 * nnz + 8 * m.n_nodes
+    out[mode] = {"kernel_family": fam, "ms": ms, "Melem_per_s": m.n_elems / ms / 1e3, "GBps_algorithmic": bytes_alg / ms / 1e6,
+                 "bytes_per_element": bytes_alg / m.n_elems}
+out["geometry_errors"] = ls.geometry_errors()
+print(json.dumps(out))
