@@ -375,6 +375,10 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
     set_last_mode(2);
     return launch_assemble_cont_box(g, kernels, nk, d_values, d_rhs, overwrite, s);
   }
+  if (mode != NALU_ASSEMBLE_GENERAL && cont_tiled && scalar_box_supported(g, kernels, nk)) {
+    set_last_mode(2);
+    return launch_assemble_scalar_box(g, kernels, nk, d_values, d_rhs, overwrite, s);
+  }
   if (mode == NALU_ASSEMBLE_BOX) {
     if (!box_supported(g, kernels, nk)) {
       set_error("assemble_elem: tiled kernel does not support this mesh / kernel list");

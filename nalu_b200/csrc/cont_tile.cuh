@@ -252,7 +252,8 @@ __host__ __device__ __forceinline__ void p2_layer(const double *sm, int lx, int 
 }
 
 // ---- the finished row of node (x, y, z) -> CSR ---------------------------------------------------------------
-__host__ __device__ inline void write_row(const ContParams &P, int x, int y, int z, const double (&acc)[27], double r)
+template <class Params>
+__host__ __device__ inline void write_row(const Params &P, int x, int y, int z, const double (&acc)[27], double r)
 {
   const long long n = x + (long long)P.NX * (y + (long long)P.NY * z);
   const int row = P.node_row[n];

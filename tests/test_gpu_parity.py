@@ -637,3 +637,74 @@ def test_dirichlet_and_reset_rows(ndof, nranks):
         ev2, er2 = _row_fixup_expected(ls, m, ev, er, others, ndof, 0, ndof)
         np.testing.assert_array_equal(ls.values.cpu().numpy(), ev2)
         np.testing.assert_array_equal(ls.rhs.cpu().numpy(), er2)
+
+
+# ---------------------------------------------------------------------------------------------
+# tiled write-once continuity kernel (assemble_cont_box.cu)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("zchunk", [0, 1, 5])
+@pytest.mark.parametrize("options", [(), ("shift_mdot",), ("reduced_sens",), ("shift_poisson", "reduced_sens")])
+def test_cont_box_kernel_options_and_chunks(options, zchunk, monkeypatch):
+    if zchunk:
+        monkeypatch.setenv("NALU_BOX_ZCHUNK", str(zchunk))
+    m = perturbed_box(33, 16, 9)  # more than two tiles in x and y, partial tiles at the far sides
+    st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 1)
+    keep = []
+    sc = dict(dt=0.05, gamma1=1.5)
+    orc.assemble_elem(0, [oracle_desc(st, "continuity_adv", options, keep, **sc)])
+    ls = _linsys(m, 1)
+    ls.values.fill_(float("nan"))  # overwrite mode: every entry must be written
+    ls.rhs.fill_(float("nan"))
+    assert ls.assemble_elem([product_desc(ls, dev, "continuity_adv", options, **sc)], mode="auto", overwrite=True) == 2
+    _compare_system(ls, orc)
+    assert ls.geometry_errors() == 0
+    # accumulate mode (sumInto semantics) on top of the overwritten system: twice the values
+    v1, r1 = ls.owned_values().clone(), ls.owned_rhs().clone()
+    assert ls.assemble_elem([product_desc(ls, dev, "continuity_adv", options, **sc)], mode="auto", overwrite=False) == 2
+    assert torch.equal(ls.owned_values(), 2 * v1) and torch.equal(ls.owned_rhs(), 2 * r1)
+    # bit-reproducible run to run
+    ls.assemble_elem([product_desc(ls, dev, "continuity_adv", options, **sc)], mode="auto", overwrite=True)
+    assert torch.equal(ls.owned_values(), v1) and torch.equal(ls.owned_rhs(), r1)
+
+
+def test_cont_box_matches_general_kernel_96cubed():
+    m = perturbed_box(96, 96, 96)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    sc = dict(dt=0.05, gamma1=1.5)
+    ls = _linsys(m, 1)
+    ls.zero_system()
+    assert ls.assemble_elem([product_desc(ls, dev, "continuity_adv", **sc)], mode="general") == 1
+    v0, r0 = ls.owned_values().clone(), ls.owned_rhs().clone()
+    assert ls.assemble_elem([product_desc(ls, dev, "continuity_adv", **sc)], mode="auto", overwrite=True) == 2
+    assert float((ls.owned_values() - v0).abs().max() / v0.abs().max()) < 1e-13
+    assert float((ls.owned_rhs() - r0).abs().max() / r0.abs().max()) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# tiled write-once scalar adv-diff / diffusion kernel (assemble_scalar_box.cu)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("zchunk", [0, 3])
+@pytest.mark.parametrize("kind,options", [("scalar_adv_diff", ()), ("scalar_adv_diff", ("skew_symmetric",)),
+                                          ("scalar_adv_diff", ("shifted_grad_op", "skew_symmetric")),
+                                          ("scalar_diff", ()), ("scalar_diff", ("shifted_grad_op",))])
+def test_scalar_box_kernel_options_and_chunks(kind, options, zchunk, monkeypatch):
+    if zchunk:
+        monkeypatch.setenv("NALU_BOX_ZCHUNK", str(zchunk))
+    m = perturbed_box(33, 16, 9)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 1)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, kind, options, keep)])
+    ls = _linsys(m, 1)
+    ls.values.fill_(float("nan"))
+    ls.rhs.fill_(float("nan"))
+    assert ls.assemble_elem([product_desc(ls, dev, kind, options)], mode="auto", overwrite=True) == 2
+    _compare_system(ls, orc)
+    assert ls.geometry_errors() == 0
+    v1, r1 = ls.owned_values().clone(), ls.owned_rhs().clone()
+    assert ls.assemble_elem([product_desc(ls, dev, kind, options)], mode="auto", overwrite=False) == 2
+    assert torch.equal(ls.owned_values(), 2 * v1) and torch.equal(ls.owned_rhs(), 2 * r1)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Continuity assembly (ContinuityAdvElemKernel) on an n^3 box: tiled write-once kernel vs the general
-(atomic) kernel, device-resident inputs, CUDA events.  usage: bench_continuity.py [n] [steps]"""
+"""One-dof assembly (ContinuityAdvElemKernel or ScalarAdvDiffElemKernel) on an n^3 box: tiled write-once kernel vs
+the general (atomic) kernel, device-resident inputs, CUDA events.
+usage: bench_continuity.py [n] [steps] [continuity_adv|scalar_adv_diff]"""
 import json
 import os
 import sys
@@ -14,6 +15,7 @@ from nalu_b200.linsys import DeviceCsrLinearSystem  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+kind = sys.argv[3] if len(sys.argv) > 3 else "continuity_adv"
 dev = torch.device("cuda", 0)
 m = mesh.generated_box(n, n, n)
 mesh.perturb_coords_hash(m, 0.12)
@@ -22,8 +24,15 @@ t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
 f = dict(coordinates=t(c), velocity=t(fields.velocity(c)), density=t(fields.smooth_density(c)),
          pressure=t(fields.pressure(c)), dpdx=t(fields.dpdx(c)))
 ls = DeviceCsrLinearSystem(m, 1).allocate(dev)
-desc = ls.make_desc("continuity_adv", fields=f, dt=0.05, gamma1=1.5)
-out = {"n": n, "elements": m.n_elems}
+if kind == "continuity_adv":
+    desc = ls.make_desc("continuity_adv", fields=f, dt=0.05, gamma1=1.5)
+    nodal_comps, elem_comps = 11, 0
+else:
+    f = dict(coordinates=f["coordinates"], scalarq=t(fields.mixture_fraction(c, 1.0, 0.37)), viscosity=t(fields.smooth_viscosity(c)))
+    mdot = DeviceCsrLinearSystem.mdot_scs(ls, f["coordinates"], t(fields.smooth_density(c)), t(fields.velocity(c)))
+    desc = ls.make_desc("scalar_adv_diff", fields=f, mass_flow_rate=mdot)
+    nodal_comps, elem_comps = 5, 12
+out = {"n": n, "elements": m.n_elems, "kind": kind}
 ref = None
 for mode in ("general", "auto"):
     ow = mode == "auto"
@@ -50,7 +59,7 @@ for mode in ("general", "auto"):
         out["tiled_vs_general_values_relerr"] = float((v - ref[0]).abs().max() / ref[0].abs().max())
         out["tiled_vs_general_rhs_relerr"] = float((r - ref[1]).abs().max() / ref[1].abs().max())
     nnz = ls.nnz_owned
-    bytes_alg = 8 * 11 * m.n_nodes + 32 * m.n_elems + 8 * nnz + 8 * m.n_nodes
+    bytes_alg = 8 * nodal_comps * m.n_nodes + (32 + 8 * elem_comps) * m.n_elems + 8 * nnz + 8 * m.n_nodes
     out[mode] = {"kernel_family": fam, "ms": ms, "Melem_per_s": m.n_elems / ms / 1e3, "GBps_algorithmic": bytes_alg / ms / 1e6,
                  "bytes_per_element": bytes_alg / m.n_elems}
 out["geometry_errors"] = ls.geometry_errors()
