@@ -253,6 +253,8 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
     }
     P.z_first = z_begin;
     P.z_last = z_end;
+    if (const char *e = getenv("NALU_BOX_KERNEL"))
+      if (atoi(e) == 4) return launch_assemble_box4(P, stream);
     return launch_assemble_box2(P, stream);
   }
   int tile = 0;
@@ -262,6 +264,8 @@ int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, 
   if (tile == 0) {
     if (const char *e = getenv("NALU_BOX_KERNEL"))
       if (atoi(e) == 3) return launch_assemble_box3(P, stream);
+    if (const char *e = getenv("NALU_BOX_KERNEL"))
+      if (atoi(e) == 4) return launch_assemble_box4(P, stream);
     return launch_assemble_box2(P, stream);
   }
   if (tile == 84) return launch_cfg<box::Cfg<8, 4>>(g, P, stream);

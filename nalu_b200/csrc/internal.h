@@ -48,6 +48,7 @@ namespace box { struct BoxParams; }
 int launch_assemble_box2(box::BoxParams &P, cudaStream_t stream);
 // assemble_box3.cu (experimental warp-specialised variant, NALU_BOX_KERNEL=3)
 int launch_assemble_box3(box::BoxParams &P, cudaStream_t stream);
+int launch_assemble_box4(box::BoxParams &P, cudaStream_t stream);
 // halo.cu
 int launch_halo_pack(const Graph &g, const HaloPeer &p, const double *d_values, const double *d_rhs,
                      double *d_buf, cudaStream_t stream);

@@ -708,3 +708,32 @@ def test_scalar_box_kernel_options_and_chunks(kind, options, zchunk, monkeypatch
     v1, r1 = ls.owned_values().clone(), ls.owned_rhs().clone()
     assert ls.assemble_elem([product_desc(ls, dev, kind, options)], mode="auto", overwrite=False) == 2
     assert torch.equal(ls.owned_values(), 2 * v1) and torch.equal(ls.owned_rhs(), 2 * r1)
+
+
+@pytest.mark.parametrize("zchunk", ["2", "0"])
+@pytest.mark.parametrize("options,divu", [((), 1.0), (("shifted_grad_op", "skew_symmetric"), 1.0), (("skew_symmetric",), 0.0)])
+def test_box4_row_thread_kernel(options, divu, zchunk, monkeypatch):
+    """assemble_box4.cu (row-thread phase 2, NALU_BOX_KERNEL=4): same contract as the column-pair kernel."""
+    monkeypatch.setenv("NALU_BOX_KERNEL", "4")
+    monkeypatch.setenv("NALU_BOX_TILE", "0")
+    if zchunk != "0":
+        monkeypatch.setenv("NALU_BOX_ZCHUNK", zchunk)
+    m = perturbed_box(19, 9, 7)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 3)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, "momentum_adv_diff", options, keep, include_divu=divu)])
+    ls = _linsys(m, 3)
+    ls.values.fill_(float("nan"))
+    ls.rhs.fill_(float("nan"))
+    d = product_desc(ls, dev, "momentum_adv_diff", options, include_divu=divu)
+    assert ls.assemble_elem([d], mode="box", overwrite=True) == 2
+    _compare_system(ls, orc)
+    assert ls.geometry_errors() == 0
+    v1, r1 = ls.values.clone(), ls.rhs.clone()
+    ls.assemble_elem([d], mode="box", overwrite=False)
+    torch.testing.assert_close(ls.values, 2 * v1, rtol=1e-15, atol=0)
+    torch.testing.assert_close(ls.rhs, 2 * r1, rtol=1e-15, atol=0)
+    ls.assemble_elem([d], mode="box", overwrite=True)
+    assert torch.equal(ls.values, v1) and torch.equal(ls.rhs, r1)  # bit-reproducible
