@@ -36,6 +36,24 @@ __device__ __noinline__ void p1_prologue4(const BoxParams &P, int x0, int y0, co
   p1_phase4(P, 0, x0, y0, pl0, pl1, mdb, F, ZE);
 }
 
+// the 32 staged runs of the warp's slice -> CSR: one run (<= 27 contiguous doubles) per warp instruction
+__device__ __forceinline__ void copy_staged_warp(const BoxParams &P, double *sm, const box4::Row &N, const box4::RunW &run, int lane)
+{
+  const double *S = box4::warp_slice(sm, N);
+  __syncwarp();
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const long long G = __shfl_sync(0xffffffffu, run.G, r);
+    const int L = __shfl_sync(0xffffffffu, run.L, r);
+    const double v = S[r * 27 + lane];
+    if (lane < L) {
+      double *d = P.values + G + lane;
+      *d = P.overwrite ? v : *d + v;
+    }
+  }
+  __syncwarp();
+}
+
 // profiling aid (NALU_BOX_TRACE): warp w of CTA 1500 stamps the clock at phase boundaries, format of assemble_box2.cu
 #define TRACE4(hs, slot)                                                                      \
   do {                                                                                        \
@@ -63,6 +81,7 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box4_kernel(const __grid_co
   box2::P2K Kc;
   box2::p2k_init(Kc, P.options, P.include_divu);
   const bool rowthread = warp < 3;
+  const bool direct = (P.options & (1 << 20)) == 0; // NALU_BOX_ABLATE=16: warp-staged coalesced output (measured slower)
 
   for (int i = tid; i < 2 * C::NEL * C::ES; i += C::NT) sm[C::OFF_F + i] = 0.0;
   box2::stage_plane(P, ring + ((zs + 2) % 3) * C::PLN, tid, x0, y0, zs - 1);
@@ -108,7 +127,8 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box4_kernel(const __grid_co
     if (rowthread) {
       if (lower) {
         box4::finalize_row<0>(sm, N, acc, rr, Kc.f23, z);
-        box4::store_group(P, M, N, 0, 9, acc);
+        if (direct) box4::store_group(P, M, N, 0, 9, acc);
+        else copy_staged_warp(P, sm, N, box4::stage_group(sm, M, N, 0, 9, acc), lane);
       } else {
 #pragma unroll
         for (int c = 0; c < 9; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
@@ -149,8 +169,14 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box4_kernel(const __grid_co
       // the exchange carries only the upper half's share; the lower half's (diagonal term included) waits in the park
       if (upper) box4::finalize_row<1>(sm, N, acc, rr, Kc.f23, z);
       box4::unpark_add(sm, N, acc, rr);
-      box4::store_group(P, M, N, 1, 0, acc);
-      if (upper) box4::store_group(P, M, N, 2, 9, acc);
+      if (direct) {
+        box4::store_group(P, M, N, 1, 0, acc);
+        if (upper) box4::store_group(P, M, N, 2, 9, acc);
+      } else {
+        __syncwarp(); // every lane has read its parked share before the slice becomes the staging area
+        copy_staged_warp(P, sm, N, box4::stage_group(sm, M, N, 1, 0, acc), lane);
+        if (upper) copy_staged_warp(P, sm, N, box4::stage_group(sm, M, N, 2, 9, acc), lane);
+      }
       if (P.overwrite) box2::zero_uncovered(M, lane, warp, P.values);
       if (M.cnt[lane * 4 + 1]) {
         double *r = P.rhs + (long long)M.row[lane] * 3 + warp;
@@ -194,6 +220,7 @@ int launch_assemble_box4(BoxParams &P, cudaStream_t stream)
     set_error("assemble_box4: grid too large");
     return NALU_B200_ERR_ARG;
   }
+  if (const char *e = getenv("NALU_BOX_ABLATE")) P.options |= atoi(e) << 16;
   static long long *d_trace = nullptr;
   const bool trace = getenv("NALU_BOX_TRACE") != nullptr;
   constexpr int TN = 16 * 8 * 8;

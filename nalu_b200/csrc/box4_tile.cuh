@@ -198,6 +198,35 @@ __host__ __device__ __forceinline__ void store_group(const BoxParams &P, const M
   }
 }
 
+// ---- coalesced output: the group is first laid out like the CSR run in the warp's own park slice (the slice is
+// private to the warp of dof row i, so only warp-level synchronisation is needed), then streamed out one run per
+// warp instruction (assemble_box4.cu, copy_staged_warp).  A register write-out (store_group) costs 243 sector
+// requests per node -- lanes are 1 944 bytes apart -- and the LSU takes about one per clock.
+struct RunW {
+  long long G; // first double of the run in `values`
+  int L;       // doubles
+};
+__host__ __device__ __forceinline__ double *warp_slice(double *sm, const Row &N) { return sm + OFF_PARK + N.i * PARKN * C::NNODE; }
+__host__ __device__ __forceinline__ RunW stage_group(double *sm, const Meta &M, const Row &N, int g, int c9,
+                                                     const double (&acc)[18][3])
+{
+  double *S = warp_slice(sm, N) + N.node * 27;
+  const unsigned s0 = M.gp[N.node * 4 + g] & 0xFF;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const unsigned s = M.slot[N.node * 28 + g * 9 + k];
+    if (s == 0xFF) continue;
+    double *d = S + (s - s0) * 3;
+    d[0] = acc[c9 + k][0];
+    d[1] = acc[c9 + k][1];
+    d[2] = acc[c9 + k][2];
+  }
+  RunW r;
+  r.L = 3 * M.cnt[N.node * 4 + g];
+  r.G = M.rowbase[N.node] + ((long long)N.i * M.nb[N.node] + s0) * 3;
+  return r;
+}
+
 __host__ __device__ __forceinline__ void park(double *sm, const Row &N, const double (&acc)[18][3], double rr)
 {
   double *p = sm + OFF_PARK + N.i * PARKN * C::NNODE + N.node;

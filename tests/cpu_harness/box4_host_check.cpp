@@ -79,7 +79,19 @@ static RankMesh make_rank(int nx, int ny, int nzg, int rank, int nranks)
 using C2 = box2::Cfg;
 
 static int g_align_fail = 0;
-static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *rhs, bool)
+// copy_staged_warp of assemble_box4.cu
+static void copy_staged_host(const BoxParams &P, double *sm, const box4::Row &N, const box4::RunW (&runs)[32])
+{
+  const double *S = box4::warp_slice(sm, N);
+  for (int r = 0; r < 32; ++r)
+    for (int lane = 0; lane < 32; ++lane)
+      if (lane < runs[r].L) {
+        double *d = P.values + runs[r].G + lane;
+        *d = P.overwrite ? S[r * 27 + lane] : *d + S[r * 27 + lane];
+      }
+}
+
+static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *rhs, bool bulk)
 {
   using C = C2;
   BoxParams P = P0;
@@ -147,15 +159,20 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
         }
       }
       // ---- barrier; A2 + B
-      for (int tid = 0; tid < 96; ++tid) {
-        Th &t = T[tid];
-        if (lower) {
-          box4::finalize_row<0>(sm, t.N, t.acc, t.rr, K.f23, z);
-          box4::store_group(P, M, t.N, 0, 9, t.acc);
-        } else {
-          for (int c = 0; c < 9; ++c) t.acc[c][0] = t.acc[c][1] = t.acc[c][2] = 0.0;
+      for (int w = 0; w < 3; ++w) {
+        box4::RunW runs[32];
+        for (int tid = 32 * w; tid < 32 * w + 32; ++tid) {
+          Th &t = T[tid];
+          if (lower) {
+            box4::finalize_row<0>(sm, t.N, t.acc, t.rr, K.f23, z);
+            if (bulk) runs[tid & 31] = box4::stage_group(sm, M, t.N, 0, 9, t.acc);
+            else box4::store_group(P, M, t.N, 0, 9, t.acc);
+          } else {
+            for (int c = 0; c < 9; ++c) t.acc[c][0] = t.acc[c][1] = t.acc[c][2] = 0.0;
+          }
         }
-        box4::park(sm, t.N, t.acc, t.rr);
+        if (lower && bulk) copy_staged_host(P, sm, T[32 * w].N, runs);
+        for (int tid = 32 * w; tid < 32 * w + 32; ++tid) box4::park(sm, T[tid].N, T[tid].acc, T[tid].rr);
       }
       if (upper)
         for (int it = 0; it < C::NP1A; ++it) {
@@ -182,13 +199,30 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
       }
       // ---- barrier; C2 + D
       for (int tid = 0; tid < NT; ++tid) box2::stage_plane(P, ring + ((z + 2) % 3) * C::PLN, tid, x0, y0, z + 2);
+      for (int w = 0; w < 3; ++w) {
+        box4::RunW runs[32];
+        for (int tid = 32 * w; tid < 32 * w + 32; ++tid) {
+          Th &t = T[tid];
+          if (upper) box4::finalize_row<1>(sm, t.N, t.acc, t.rr, K.f23, z);
+          box4::unpark_add(sm, t.N, t.acc, t.rr);
+          if (!bulk) {
+            box4::store_group(P, M, t.N, 1, 0, t.acc);
+            if (upper) box4::store_group(P, M, t.N, 2, 9, t.acc);
+          }
+        }
+        if (bulk) {
+          for (int k = 0; k < box4::PARKN * C::NNODE; ++k) box4::warp_slice(sm, T[32 * w].N)[k] = NAN;
+          for (int tid = 32 * w; tid < 32 * w + 32; ++tid) runs[tid & 31] = box4::stage_group(sm, M, T[tid].N, 1, 0, T[tid].acc);
+          copy_staged_host(P, sm, T[32 * w].N, runs);
+          if (upper) {
+            for (int tid = 32 * w; tid < 32 * w + 32; ++tid) runs[tid & 31] = box4::stage_group(sm, M, T[tid].N, 2, 9, T[tid].acc);
+            copy_staged_host(P, sm, T[32 * w].N, runs);
+          }
+        }
+      }
       for (int tid = 0; tid < 96; ++tid) {
         Th &t = T[tid];
         const int lane = tid & 31, warp = tid >> 5;
-        if (upper) box4::finalize_row<1>(sm, t.N, t.acc, t.rr, K.f23, z);
-        box4::unpark_add(sm, t.N, t.acc, t.rr);
-        box4::store_group(P, M, t.N, 1, 0, t.acc);
-        if (upper) box4::store_group(P, M, t.N, 2, 9, t.acc);
         if (P.overwrite) box2::zero_uncovered(M, lane, warp, P.values);
         if (M.cnt[lane * 4 + 1]) {
           double *r = P.rhs + (long long)M.row[lane] * 3 + warp;
