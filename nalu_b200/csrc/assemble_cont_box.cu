@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(CC::NT, 2) assemble_cont_box_kernel(const __gr
   for (int ez = zs - 1; ez < ze; ++ez) {
     // plane ez+2 lands while phase 1 and phase 2 of this layer run (its slot held plane ez-1, dead)
     cont::stage_plane(P, ring + ((ez + 2 + 3) % 3) * CC::PLN, tid, x0, y0, ez + 2);
-    cont::p1_element(P, sm, tid, x0, y0, ez, ring + ((ez + 3) % 3) * CC::PLN, ring + ((ez + 1 + 3) % 3) * CC::PLN);
+    cont::p1_element_c(P, sm, tid, x0, y0, ez, ring + ((ez + 3) % 3) * CC::PLN, ring + ((ez + 1 + 3) % 3) * CC::PLN);
     __syncthreads();
     if (in_tile) cont::p2_layer<SH>(sm, lx, ly, accA, rA, accB, rB);
     if (active && ez >= zs) cont::write_row(P, x0 + lx, y0 + ly, ez, accA, rA);

@@ -174,6 +174,14 @@ __host__ __device__ inline void p1_item(const BoxParams &P, int el, int g, int s
     X[2][m] = nd[2];
     M[m] = nd[3];
   }
+  // coordinates relative to the item's first node: only difference coefficients are used below, and differences
+  // of partial sums of large coordinates would cost |x|/h ulps
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double o = X[i][0];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) X[i][m] -= o;
+  }
   butterfly8(X[0]);
   butterfly8(X[1]);
   butterfly8(X[2]);

@@ -202,6 +202,203 @@ __host__ __device__ inline void p1_element(const ContParams &P, double *sm, int 
   }
 }
 
+// ---- coefficient form of phase 1 ---------------------------------------------------------------------------------
+// A trilinear field is f(xi) = sum_m F[m] prod_{a in m} xi_a / 2^(3-|m|) with the Walsh-Hadamard coefficients
+// F[m] = sum_n (prod_{a in m} sigma_na) f_n (m: bit 0 = x, 1 = y, 2 = z).  At the SCS point of the edge along t
+// (local axes (t,u,v) cyclic) on the sides (su, sv): xi_t = 0, xi_u = su q, xi_v = sv q, hence
+//   f = F0/8 + Fu xi_u/4 + Fv xi_v/4 + Fuv xi_u xi_v/2
+//   df/dxi_t = Ft/4 + Ftu xi_u/2 + Ftv xi_v/2 + Ftuv xi_u xi_v,  df/dxi_u = Fu/4 + Fuv xi_v/2,  df/dxi_v = Fv/4 + Fuv xi_u/2
+// and the facet's area vector along +t is Xu x Xv/64 + Xuv x (sv Xv - su Xu)/128: the vector area of the closed
+// quadrilateral (edge midpoint, two face centroids, element centroid) the reference triangulates
+// (Hex8CVFEM.C:547-581, Hex8GeometryFunctions.h:30-76) -- 5 vector FMAs for the Jacobian and one cross product for
+// the area instead of four 8-node interpolations and a 72-FMA Jacobian per point.
+struct Coef {
+  double X[3][8]; // coordinates
+};
+__host__ __device__ __forceinline__ void gather_bits(const double *pl0, const double *pl1, int n000, int f, double (&g)[8])
+{
+  using C = Cfg;
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+    g[m] = ((m & 4) ? pl1 : pl0)[n000 + ((m & 1) + C::RNX * ((m >> 1) & 1)) * C::NF + f];
+}
+__host__ __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3])
+{
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+// geometry of the point (T, SU, SV): area vector along +t, and at location q the vector b~ with
+// b~[k] = (d xi_k / d x) . A (k = 0 t, 1 u, 2 v).  Returns det J.
+template <int T, int SU, int SV>
+__host__ __device__ __forceinline__ void area_plus_t(const double (&X)[3][8], double (&A)[3])
+{
+  constexpr int t = 1 << T, u = 1 << ((T + 1) % 3), v = 1 << ((T + 2) % 3);
+  (void)t;
+  constexpr double su = SU ? 1.0 : -1.0, sv = SV ? 1.0 : -1.0;
+  double xu[3], xv[3], xuv[3], w[3], c1[3], c2[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    xu[i] = X[i][u];
+    xv[i] = X[i][v];
+    xuv[i] = X[i][u | v];
+    w[i] = sv * xv[i] - su * xu[i];
+  }
+  cross3(xu, xv, c1);
+  cross3(xuv, w, c2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) A[i] = c1[i] * (1.0 / 64.0) + c2[i] * (1.0 / 128.0);
+}
+template <int T, int SU, int SV>
+__host__ __device__ __forceinline__ double grad_dot_area_c(const double (&X)[3][8], double q, const double (&A)[3], double (&b)[3])
+{
+  constexpr int t = 1 << T, u = 1 << ((T + 1) % 3), v = 1 << ((T + 2) % 3);
+  const double xu_ = (SU ? q : -q), xv_ = (SV ? q : -q);
+  double ct[3], cu[3], cv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    ct[i] = 0.25 * X[i][t] + (0.5 * xu_) * X[i][t | u] + (0.5 * xv_) * X[i][t | v] + (xu_ * xv_) * X[i][t | u | v];
+    cu[i] = 0.25 * X[i][u] + (0.5 * xv_) * X[i][u | v];
+    cv[i] = 0.25 * X[i][v] + (0.5 * xu_) * X[i][u | v];
+  }
+  double n_t[3], n_u[3], n_v[3];
+  cross3(cu, cv, n_t); // det * grad xi_t
+  cross3(cv, ct, n_u);
+  cross3(ct, cu, n_v);
+  const double det = ct[0] * n_t[0] + ct[1] * n_t[1] + ct[2] * n_t[2];
+  const double inv = 1.0 / det;
+  b[0] = (n_t[0] * A[0] + n_t[1] * A[1] + n_t[2] * A[2]) * inv;
+  b[1] = (n_u[0] * A[0] + n_u[1] * A[1] + n_u[2] * A[2]) * inv;
+  b[2] = (n_v[0] * A[0] + n_v[1] * A[1] + n_v[2] * A[2]) * inv;
+  return det;
+}
+// value and parametric gradient (t,u,v order) of a field given by its coefficients, at location q of the point
+template <int T, int SU, int SV>
+__host__ __device__ __forceinline__ double value_c(const double (&F)[8], double q)
+{
+  constexpr int u = 1 << ((T + 1) % 3), v = 1 << ((T + 2) % 3);
+  const double xu_ = (SU ? q : -q), xv_ = (SV ? q : -q);
+  return 0.125 * F[0] + (0.25 * xu_) * F[u] + (0.25 * xv_) * F[v] + (0.5 * xu_ * xv_) * F[u | v];
+}
+template <int T, int SU, int SV>
+__host__ __device__ __forceinline__ void grad_c(const double (&F)[8], double q, double (&d)[3])
+{
+  constexpr int t = 1 << T, u = 1 << ((T + 1) % 3), v = 1 << ((T + 2) % 3);
+  const double xu_ = (SU ? q : -q), xv_ = (SV ? q : -q);
+  d[0] = 0.25 * F[t] + (0.5 * xu_) * F[t | u] + (0.5 * xv_) * F[t | v] + (xu_ * xv_) * F[t | u | v];
+  d[1] = 0.25 * F[u] + (0.5 * xv_) * F[u | v];
+  d[2] = 0.25 * F[v] + (0.5 * xu_) * F[u | v];
+}
+// the integration point (its index, and the sign that turns the +t area vector into the reference's left -> right one)
+template <int T, int SU, int SV>
+__host__ __device__ __forceinline__ int point_index(double &orient)
+{
+  constexpr int U = (T + 1) % 3, V = (T + 2) % 3;
+  int bits[3];
+  bits[T] = 0;
+  bits[U] = SU;
+  bits[V] = SV;
+  const int k0 = node_of_bits(bits[0], bits[1], bits[2]); // the node of the edge with bit_t = 0
+  const int ip = ip_of(k0, T);
+  orient = hex8::scs_left(ip) == k0 ? 1.0 : -1.0;
+  return ip;
+}
+
+struct ContElem {
+  double X[3][8], Pc[8], W[3][8];
+  double ql, qr, qm, tau;
+  bool two; // the rhs grad-op sits at another location than the lhs one
+};
+template <int T, int SU, int SV>
+__host__ __device__ __forceinline__ void p1_point_c(const ContParams &P, const ContElem &E, double *rec)
+{
+  constexpr int U = (T + 1) % 3, V = (T + 2) % 3;
+  double orient;
+  const int ip = point_index<T, SU, SV>(orient);
+  double A[3], bl[3], br[3];
+  area_plus_t<T, SU, SV>(E.X, A);
+  A[0] *= orient;
+  A[1] *= orient;
+  A[2] *= orient;
+  const double det = grad_dot_area_c<T, SU, SV>(E.X, E.ql, A, bl);
+  if (!(det > 0.0)) *P.err = 1; // MasterElementFunctions.h:91-94
+  if (E.two) {
+    const double det2 = grad_dot_area_c<T, SU, SV>(E.X, E.qr, A, br);
+    if (!(det2 > 0.0)) *P.err = 1;
+  } else {
+    br[0] = bl[0];
+    br[1] = bl[1];
+    br[2] = bl[2];
+  }
+  double dp[3];
+  grad_c<T, SU, SV>(E.Pc, E.qr, dp);
+  const double dpdxA = dp[0] * br[0] + dp[1] * br[1] + dp[2] * br[2];
+  const double w0 = value_c<T, SU, SV>(E.W[0], E.qm), w1 = value_c<T, SU, SV>(E.W[1], E.qm), w2 = value_c<T, SU, SV>(E.W[2], E.qm);
+  const double mdot = w0 * A[0] + w1 * A[1] + w2 * A[2] - E.tau * dpdxA;
+  rec[ip * 4 + T] = -bl[0];
+  rec[ip * 4 + U] = -bl[1];
+  rec[ip * 4 + V] = -bl[2];
+  rec[ip * 4 + 3] = mdot / E.tau;
+}
+template <int T>
+__host__ __device__ __forceinline__ void p1_edge_dir_c(const ContParams &P, const ContElem &E, double *rec)
+{
+  p1_point_c<T, 0, 0>(P, E, rec);
+  p1_point_c<T, 1, 0>(P, E, rec);
+  p1_point_c<T, 0, 1>(P, E, rec);
+  p1_point_c<T, 1, 1>(P, E, rec);
+}
+__host__ __device__ inline void p1_element_c(const ContParams &P, double *sm, int el, int x0, int y0, int ez, const double *pl0,
+                                             const double *pl1)
+{
+  using C = Cfg;
+  const int elx = el % C::ELX, ely = el / C::ELX;
+  const int ex = x0 - 1 + elx, ey = y0 - 1 + ely;
+  double *rec = sm + C::OFF_REC + el * C::ES;
+  if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny || ez < 0 || ez >= P.nz) {
+#pragma unroll
+    for (int i = 0; i < 48; ++i) rec[i] = 0.0;
+    return;
+  }
+  const int n000 = (elx + C::RNX * ely) * C::NF;
+  ContElem E;
+  double u[3][8], rho[8], gp[3][8];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gather_bits(pl0, pl1, n000, i, E.X[i]);
+    gather_bits(pl0, pl1, n000, 4 + i, u[i]);
+    gather_bits(pl0, pl1, n000, 8 + i, gp[i]);
+  }
+  gather_bits(pl0, pl1, n000, 3, E.Pc);
+  gather_bits(pl0, pl1, n000, 7, rho);
+  // coordinates relative to the element's first node: the coefficients used are differences, and differences of
+  // partial sums of large coordinates would cost |x|/h ulps
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double o = E.X[i][0];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) E.X[i][m] -= o;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) E.W[i][m] = rho[m] * u[i][m] + P.tau * gp[i][m]; // rho u + tau Gp
+    box::butterfly8(E.X[i]);
+    box::butterfly8(E.W[i]);
+  }
+  box::butterfly8(E.Pc);
+  const bool sp = (P.options & NALU_OPT_SHIFT_POISSON) != 0;
+  const bool sl = sp || (P.options & NALU_OPT_REDUCED_SENS) != 0; // v_dndx_lhs, ContinuityAdvElemKernel.C:107-108
+  E.ql = sl ? 0.5 : 0.25;
+  E.qr = sp ? 0.5 : 0.25;
+  E.qm = (P.options & NALU_OPT_SHIFT_MDOT) ? 0.5 : 0.25;
+  E.tau = P.tau;
+  E.two = sl != sp;
+  p1_edge_dir_c<0>(P, E, rec);
+  p1_edge_dir_c<1>(P, E, rec);
+  p1_edge_dir_c<2>(P, E, rec);
+}
+
 // ---- phase 2: thread = node (lx, ly) of the tile -----------------------------------------------------------
 // accA / rA: row of the node in plane ez (below the layer), accB / rB: row of the node in plane ez+1.
 // acc index = (dz+1)*9 + (dy+1)*3 + (dx+1) of the column node relative to the row node (the order of

@@ -128,6 +128,87 @@ __host__ __device__ inline void p1_element(const ScalarParams &P, double *sm, in
   }
 }
 
+// ---- phase 1 in coefficient form (cont_tile.cuh: Walsh-Hadamard coefficients of the trilinear fields) -----------
+struct ScalElem {
+  double X[3][8], Q[8], G[8];
+  double qg, qa;
+  const double *md;
+};
+template <int T, int SU, int SV>
+__host__ __device__ __forceinline__ void p1_point_c(const ScalarParams &P, const ScalElem &E, double *rec)
+{
+  using C = Cfg;
+  constexpr int U = (T + 1) % 3, V = (T + 2) % 3;
+  double orient;
+  const int ip = cont::point_index<T, SU, SV>(orient);
+  double A[3], b[3];
+  cont::area_plus_t<T, SU, SV>(E.X, A);
+  A[0] *= orient;
+  A[1] *= orient;
+  A[2] *= orient;
+  const double det = cont::grad_dot_area_c<T, SU, SV>(E.X, E.qg, A, b);
+  if (!(det > 0.0)) *P.err = 1; // MasterElementFunctions.h:91-94
+  double dq[3];
+  cont::grad_c<T, SU, SV>(E.Q, E.qg, dq);
+  const double gam = cont::value_c<T, SU, SV>(E.G, 0.25);  // diffFluxCoeffIp: never shifted
+  const double qip = cont::value_c<T, SU, SV>(E.Q, E.qa);  // advection shape function
+  const double tmdot = E.md ? E.md[ip] : 0.0;
+  const double b0 = -gam * b[0], b1 = -gam * b[1], b2 = -gam * b[2];
+  rec[ip * C::RD + T] = b0;
+  rec[ip * C::RD + U] = b1;
+  rec[ip * C::RD + V] = b2;
+  rec[ip * C::RD + 3] = tmdot;
+  rec[ip * C::RD + 4] = tmdot * qip + (b0 * dq[0] + b1 * dq[1] + b2 * dq[2]);
+  rec[ip * C::RD + 5] = 0.0;
+}
+template <int T>
+__host__ __device__ __forceinline__ void p1_edge_dir_c(const ScalarParams &P, const ScalElem &E, double *rec)
+{
+  p1_point_c<T, 0, 0>(P, E, rec);
+  p1_point_c<T, 1, 0>(P, E, rec);
+  p1_point_c<T, 0, 1>(P, E, rec);
+  p1_point_c<T, 1, 1>(P, E, rec);
+}
+__host__ __device__ inline void p1_element_c(const ScalarParams &P, double *sm, int el, int x0, int y0, int ez, const double *pl0,
+                                             const double *pl1)
+{
+  using C = Cfg;
+  const int elx = el % C::ELX, ely = el / C::ELX;
+  const int ex = x0 - 1 + elx, ey = y0 - 1 + ely;
+  double *rec = sm + C::OFF_REC + el * C::ES;
+  if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny || ez < 0 || ez >= P.nz) {
+#pragma unroll
+    for (int i = 0; i < 12 * C::RD; ++i) rec[i] = 0.0;
+    return;
+  }
+  const int n000 = (elx + C::RNX * ely) * C::NF;
+  ScalElem E;
+  E.md = P.mdot ? P.mdot + 12 * (ex + (long long)P.nx * (ey + (long long)P.ny * ez)) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      E.X[i][m] = ((m & 4) ? pl1 : pl0)[n000 + ((m & 1) + C::RNX * ((m >> 1) & 1)) * C::NF + i];
+    const double o = E.X[i][0]; // relative to the element's first node (see cont_tile.cuh)
+#pragma unroll
+    for (int m = 0; m < 8; ++m) E.X[i][m] -= o;
+    box::butterfly8(E.X[i]);
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const double *nd = ((m & 4) ? pl1 : pl0) + n000 + ((m & 1) + C::RNX * ((m >> 1) & 1)) * C::NF;
+    E.Q[m] = nd[3];
+    E.G[m] = nd[4];
+  }
+  box::butterfly8(E.Q);
+  box::butterfly8(E.G);
+  E.qg = (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
+  E.qa = (P.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25;
+  p1_edge_dir_c<0>(P, E, rec);
+  p1_edge_dir_c<1>(P, E, rec);
+  p1_edge_dir_c<2>(P, E, rec);
+}
+
 // ---- phase 2: thread = node (lx, ly) of the tile (see cont_tile.cuh) ----------------------------------------
 // SH: shifted grad-op, SK: skew-symmetric (shifted advection shape function)
 template <bool SH, bool SK, int SX, int SY, int DIR, int LVL>

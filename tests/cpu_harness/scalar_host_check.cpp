@@ -112,7 +112,7 @@ static void emulate(const ScalarParams &P0, int z_chunk)
     for (int ez = zs - 1; ez < ze; ++ez) {
       for (int tid = 0; tid < CC::NT; ++tid) {
         scal::stage_plane(P, ring + ((ez + 2 + 3) % 3) * CC::PLN, tid, x0, y0, ez + 2);
-        scal::p1_element(P, sm, tid, x0, y0, ez, ring + ((ez + 3) % 3) * CC::PLN, ring + ((ez + 1 + 3) % 3) * CC::PLN);
+        scal::p1_element_c(P, sm, tid, x0, y0, ez, ring + ((ez + 3) % 3) * CC::PLN, ring + ((ez + 1 + 3) % 3) * CC::PLN);
       }
       // ---- barrier
       for (int tid = 0; tid < CC::NT; ++tid) {
