@@ -227,7 +227,8 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *g, const nalu_b200_kernel_des
 int nalu_b200_assemble_elem_zrange(const nalu_b200_graph *g, const nalu_b200_kernel_desc *kernels,
                                    int32_t n_kernels, double *d_values, double *d_rhs, int32_t overwrite,
                                    int32_t z_begin, int32_t z_end, void *stream);
-/* which kernel family the last nalu_b200_assemble_elem call used: 1 general, 2 box */
+/* which kernel family the last nalu_b200_assemble_elem call used: 1 general (atomic scatter), 2 tiled write-once,
+ * 3 tiled write-once for one kernel of the list + general for the others */
 int nalu_b200_last_assemble_mode(void);
 /* synchronises, then reports (and clears) the device flag raised when an element had a
  * non-positive Jacobian determinant -- the reference asserts on this in debug builds

@@ -163,6 +163,86 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
   return NALU_B200_OK;
 }
 
+// ---- lumped mass kernels on their own: thread = (element, sub-control volume) -------------------------------------
+// MomentumMassElemKernel / ContinuityMassElemKernel / ScalarMassElemKernel with the lumped (shifted) shape function
+// (src/kernel/MomentumMassElemKernel.C:119-170, ContinuityMassElemKernel.C:98-117, ScalarMassElemKernel.C:117-154):
+// the shape function is 1 at the SCV's own node and 0 elsewhere, so the element contributes the SCV volume times
+// nodal quantities to the diagonal entry and the residual of that node -- 6 (momentum) or 2 atomics per SCV instead of
+// a 24 x 24 scratch block per element.  Used for the lumped mass kernels of a list whose adv-diff kernel went through
+// a tiled kernel (capi.cu).
+__global__ void __launch_bounds__(256) scv_lumped_mass_kernel(long long n_elems, int ndof, const int *elem_nodes, const int *node_row,
+                                                              const long long *browptr, const unsigned char *elem_slot,
+                                                              nalu_b200_kernel_desc k, double *values, double *rhs)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = t >> 3;
+  const int ip = (int)(t & 7);
+  if (e >= n_elems) return;
+  double c[8][3];
+  const double *X = k.nodal[NALU_F_COORDINATES];
+  for (int n = 0; n < 8; ++n) {
+    const int nd = elem_nodes[e * 8 + n];
+    c[n][0] = X[(size_t)nd * 3 + 0];
+    c[n][1] = X[(size_t)nd * 3 + 1];
+    c[n][2] = X[(size_t)nd * 3 + 2];
+  }
+  const double scV = hex8::scv_volume_ip(c, ip);
+  const int node = elem_nodes[e * 8 + ip];
+  const int rn = node_row[node];
+  const long long b0 = browptr[rn];
+  const int nb = (int)(browptr[rn + 1] - b0), slot = elem_slot[e * 64 + ip * 8 + ip];
+  const double rNp1 = k.nodal[NALU_F_DENSITY][node], rN = k.nodal[NALU_F_DENSITY_N][node], rNm1 = k.nodal[NALU_F_DENSITY_NM1][node];
+  if (k.kind == NALU_K_MOMENTUM_MASS) {
+    const double densFac = rNp1 * k.dens_fac + k.om_dens_fac;
+    const double lhsfac = k.gamma1 * rNp1 * scV / k.dt;
+    for (int j = 0; j < 3; ++j) {
+      const double uNp1 = k.nodal[NALU_F_VELOCITY][(size_t)node * 3 + j], uN = k.nodal[NALU_F_VELOCITY_N][(size_t)node * 3 + j],
+                   uNm1 = k.nodal[NALU_F_VELOCITY_NM1][(size_t)node * 3 + j], Gp = k.nodal[NALU_F_DPDX][(size_t)node * 3 + j];
+      atomicAdd(rhs + (long long)rn * 3 + j,
+                -(k.gamma1 * rNp1 * uNp1 + k.gamma2 * rN * uN + k.gamma3 * rNm1 * uNm1) * scV / k.dt - Gp * scV * densFac);
+      atomicAdd(values + 9 * b0 + (long long)j * nb * 3 + slot * 3 + j, lhsfac);
+    }
+  } else if (k.kind == NALU_K_CONTINUITY_MASS) {
+    const double tau = k.dt / k.gamma1;
+    atomicAdd(rhs + rn, -(k.gamma1 * rNp1 + k.gamma2 * rN + k.gamma3 * rNm1) * scV / k.dt / tau);
+  } else {
+    const double qNp1 = k.nodal[NALU_F_SCALARQ][node], qN = k.nodal[NALU_F_SCALARQ_N][node], qNm1 = k.nodal[NALU_F_SCALARQ_NM1][node];
+    atomicAdd(rhs + rn, -(k.gamma1 * rNp1 * qNp1 + k.gamma2 * rN * qN + k.gamma3 * rNm1 * qNm1) * scV / k.dt);
+    atomicAdd(values + b0 + slot, k.gamma1 * rNp1 * scV / k.dt);
+  }
+  (void)ndof;
+}
+
+bool scv_lumped_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+{
+  if (!g.d_elem_slot || nk < 1) return false;
+  for (int i = 0; i < nk; ++i) {
+    const int kind = k[i].kind;
+    const bool mass = kind == NALU_K_MOMENTUM_MASS || kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS;
+    if (!mass || !(k[i].options & NALU_OPT_LUMPED_MASS) || !k[i].nodal[NALU_F_COORDINATES]) return false;
+    if ((kind == NALU_K_MOMENTUM_MASS) != (g.ndof == 3)) return false;
+  }
+  return true;
+}
+
+int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs, cudaStream_t stream)
+{
+  if (!scv_lumped_supported(g, k, nk)) {
+    set_error("scv_lumped: unsupported kernel list");
+    return NALU_B200_ERR_ARG;
+  }
+  if (g.n_elems == 0) return NALU_B200_OK;
+  const long long threads = g.n_elems * 8;
+  for (int i = 0; i < nk; ++i) {
+    scv_lumped_mass_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(g.n_elems, g.ndof, g.d_elem_nodes, g.d_node_row,
+                                                                                 (const long long *)g.d_browptr, g.d_elem_slot, k[i],
+                                                                                 d_values, d_rhs);
+    count_launch();
+  }
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
 // ---- node mass algorithms ----------------------------------------------------------------
 // AssembleNodeSolverAlgorithm::execute (src/AssembleNodeSolverAlgorithm.C:57-111) with
 // {Momentum,Continuity,Scalar}MassBDF2NodeSuppAlg::node_execute; one thread per local node,

@@ -368,6 +368,33 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   }
   const Graph &g = h->g;
   cudaStream_t s = (cudaStream_t)stream;
+  // A list with one kernel the tiled write-once kernels know plus others (e.g. [MomentumMass(lumped), MomentumAdvDiff],
+  // the momentum list of the low-Mach equation system, src/LowMachEquationSystem.C:1304-1398): the tiled kernel
+  // takes its kernel first (it may overwrite), the others accumulate on top through the general kernel -- the sum the
+  // reference forms in one scratch lhs/rhs (src/AssembleElemSolverAlgorithm.C:86-91), in another order.
+  static const bool split_lists = !(getenv("NALU_SPLIT_LISTS") && atoi(getenv("NALU_SPLIT_LISTS")) == 0);
+  if (mode == NALU_ASSEMBLE_AUTO && nk > 1 && nk <= kMaxKernels && split_lists) {
+    int t = -1;
+    for (int i = 0; i < nk && t < 0; ++i)
+      if (kernels[i].kind != NALU_K_TEST_FIXED_BLOCK &&
+          (box_supported(g, kernels + i, 1) || cont_box_supported(g, kernels + i, 1) || scalar_box_supported(g, kernels + i, 1)))
+        t = i;
+    bool fixed = false; // TestKernel assigns its block (unit_tests/UnitTestTpetra.C:125-139): order matters, no split
+    for (int i = 0; i < nk; ++i) fixed = fixed || kernels[i].kind == NALU_K_TEST_FIXED_BLOCK;
+    if (t >= 0 && !fixed) {
+      int rc = nalu_b200_assemble_elem(h, kernels + t, 1, d_values, d_rhs, NALU_ASSEMBLE_AUTO, overwrite, stream);
+      if (rc != NALU_B200_OK) return rc;
+      nalu_b200_kernel_desc rest[kMaxKernels];
+      int nr = 0;
+      for (int i = 0; i < nk; ++i)
+        if (i != t) rest[nr++] = kernels[i];
+      // lumped mass kernels need no element scratch: one thread per sub-control volume
+      rc = scv_lumped_supported(g, rest, nr) ? launch_scv_lumped(g, rest, nr, d_values, d_rhs, s)
+                                             : launch_assemble_general(g, rest, nr, d_values, d_rhs, s);
+      set_last_mode(3);
+      return rc;
+    }
+  }
   bool use_box = false;
   // the one-dof tiled kernel (ContinuityAdvElemKernel on a structured block); NALU_CONT_BOX=0 keeps the general kernel
   static const bool cont_tiled = !(getenv("NALU_CONT_BOX") && atoi(getenv("NALU_CONT_BOX")) == 0);

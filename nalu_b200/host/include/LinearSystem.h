@@ -124,7 +124,7 @@ public:
   std::vector<double> ownedRhs() const;
   double *deviceValues() const { return d_values_; }
   double *deviceRhs() const { return d_rhs_; }
-  int lastAssembleKernelFamily() const { return last_family_; } // 1 general (atomic), 2 tiled write-once
+  int lastAssembleKernelFamily() const { return last_family_; } // 1 general (atomic), 2 tiled write-once, 3 tiled + general
   int entityToLID(stk::mesh::Entity node) const;
 
 private:
