@@ -119,28 +119,54 @@ __host__ __device__ inline void stage_plane(const BoxParams &P, double *ring_pla
   using C = Cfg;
   const long long pn = (long long)P.NX * P.NY;
   const bool zin = zp >= 0 && zp < P.NZ;
-#pragma unroll 1
-  for (int idx = tid; idx < C::PLN; idx += C::NT) {
-    const int rn = idx / C::NF, f = idx - rn * C::NF;
+  // one node per thread: the index arithmetic is paid once per node, not once per double
+  if (tid < C::RN) {
+    const int rn = tid;
     const int x = x0 - 1 + rn % C::RNX, y = y0 - 1 + rn / C::RNX;
     const bool valid = zin && x >= 0 && y >= 0 && x < P.NX && y < P.NY;
     const long long n = valid ? x + (long long)P.NX * y + pn * zp : 0;
-    const double *src = f < 3 ? P.coords + n * 3 + f : (f == 3 ? P.visc + n : P.vel + n * 3 + (f - 4));
-    copy8_or_zero(ring_plane + idx, src, valid);
+    double *d = ring_plane + rn * C::NF;
+    const double *xc = P.coords + n * 3, *u = P.vel + n * 3;
+    copy8_or_zero(d + 0, xc + 0, valid);
+    copy8_or_zero(d + 1, xc + 1, valid);
+    copy8_or_zero(d + 2, xc + 2, valid);
+    copy8_or_zero(d + 3, P.visc + n, valid);
+    copy8_or_zero(d + 4, u + 0, valid);
+    copy8_or_zero(d + 5, u + 1, valid);
+    copy8_or_zero(d + 6, u + 2, valid);
   }
+}
+// 16 bytes at a time: the 12 mass flow rates of an element are 96 contiguous, 16-byte aligned bytes on both sides
+__host__ __device__ __forceinline__ void copy16_or_zero(double *dst, const double *src, bool valid)
+{
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(valid ? 16 : 0)
+               : "memory");
+#else
+  dst[0] = valid ? src[0] : 0.0;
+  dst[1] = valid ? src[1] : 0.0;
+#endif
 }
 __host__ __device__ inline void stage_mdot(const BoxParams &P, double *mdb, int tid, int x0, int y0, int ez)
 {
   using C = Cfg;
   const long long ln = (long long)P.nx * P.ny;
   const bool zin = ez >= 0 && ez < P.nz;
+  const bool wide = (((unsigned long long)P.mdot) & 15) == 0; // uniform
 #pragma unroll 1
-  for (int idx = tid; idx < C::MDB; idx += C::NT) {
-    const int el = idx / 12, ip = idx - el * 12;
+  for (int idx = tid; idx < C::NEL * 6; idx += C::NT) {
+    const int el = idx / 6, pr = idx - el * 6;
     const int ex = x0 - 1 + el % C::ELX, ey = y0 - 1 + el / C::ELX;
     const bool valid = zin && ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny;
     const long long e = valid ? ex + (long long)P.nx * ey + ln * ez : 0;
-    copy8_or_zero(mdb + idx, P.mdot + e * 12 + ip, valid);
+    const double *src = P.mdot + e * 12 + 2 * pr;
+    double *dst = mdb + el * 12 + 2 * pr;
+    if (wide) copy16_or_zero(dst, src, valid);
+    else {
+      copy8_or_zero(dst, src, valid);
+      copy8_or_zero(dst + 1, src + 1, valid);
+    }
   }
 }
 

@@ -86,15 +86,25 @@ __host__ __device__ inline void stage_plane(const ContParams &P, double *ring_pl
   using C = Cfg;
   const long long pn = (long long)P.NX * P.NY;
   const bool zin = zp >= 0 && zp < P.NZ;
+  // one node per thread and round: the index arithmetic is paid once per node, not once per double
 #pragma unroll 1
-  for (int idx = tid; idx < C::PLN; idx += C::NT) {
-    const int rn = idx / C::NF, f = idx - rn * C::NF;
+  for (int rn = tid; rn < C::RN; rn += C::NT) {
     const int x = x0 - 1 + rn % C::RNX, y = y0 - 1 + rn / C::RNX;
     const bool valid = zin && x >= 0 && y >= 0 && x < P.NX && y < P.NY;
     const long long n = valid ? x + (long long)P.NX * y + pn * zp : 0;
-    const double *src = f < 3 ? P.coords + n * 3 + f
-                              : (f == 3 ? P.p + n : (f < 7 ? P.vel + n * 3 + (f - 4) : (f == 7 ? P.rho + n : P.gp + n * 3 + (f - 8))));
-    copy8_or_zero(ring_plane + idx, src, valid);
+    double *d = ring_plane + rn * C::NF;
+    const double *xc = P.coords + n * 3, *u = P.vel + n * 3, *g = P.gp + n * 3;
+    copy8_or_zero(d + 0, xc + 0, valid);
+    copy8_or_zero(d + 1, xc + 1, valid);
+    copy8_or_zero(d + 2, xc + 2, valid);
+    copy8_or_zero(d + 3, P.p + n, valid);
+    copy8_or_zero(d + 4, u + 0, valid);
+    copy8_or_zero(d + 5, u + 1, valid);
+    copy8_or_zero(d + 6, u + 2, valid);
+    copy8_or_zero(d + 7, P.rho + n, valid);
+    copy8_or_zero(d + 8, g + 0, valid);
+    copy8_or_zero(d + 9, g + 1, valid);
+    copy8_or_zero(d + 10, g + 2, valid);
   }
 }
 
