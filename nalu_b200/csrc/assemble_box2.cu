@@ -118,8 +118,7 @@ __device__ __forceinline__ void copy_runs_desc(const double *sm, int first, int 
     for (int u = 0; u < NB; ++u) v[u] = S[d[u].z + lane];
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
-      const long long G = (long long)(((unsigned long long)(unsigned)d[u].y << 32) | (unsigned)d[u].x);
-      double *dst = values + G + lane;
+      double *dst = reinterpret_cast<double *>(((unsigned long long)(unsigned)d[u].y << 32) | (unsigned)d[u].x) + lane;
       if (lane < d[u].w) *dst = overwrite ? v[u] : *dst + v[u];
     }
   }
@@ -213,7 +212,7 @@ __global__ void __launch_bounds__(C::NT, 2) assemble_box2_kernel(const __grid_co
       // been in flight since phase D of the previous plane)
       box2::stage_mdot(P, mdb, tid, x0, y0, z);
       N.rr[0] = N.rr[1] = N.rr[2] = 0.0;
-      if (MODE == 2) box2::build_run_desc(M, sm, tid);
+      if (MODE == 2) box2::build_run_desc(M, sm, tid, P.values);
     }
     if ((H ? upper : lower) && !(P.options & (1 << 18))) {
       // profiling aid: 9 stamps inside the pass for half-steps 4 and 5 of the traced CTA

@@ -566,7 +566,9 @@ __host__ __device__ inline void p2_half_t(T2 &N, double *sm, const ClsK &Q, doub
   Rec RA, RB;
   NALU_T2_STAMP(N);
   rec_load(RA, rec_addr<0, 0, 0>(eF, eZ));
-#define NALU_P2_QUAD(J, SX, SY, NX_, NY_, LAST)                                                   \
+  // the record buffers swap roles from quadrant to quadrant (three records each: A, B, A then B, A, B): the
+  // first record of the next quadrant is loaded into the buffer the next quadrant starts with, no copy
+#define NALU_P2_QUAD(J, SX, SY, NX_, NY_, LAST, RA, RB)                                           \
   if (fm & (1u << J)) flush_fetch(FO, FP##J, sm, pb, add);                                        \
   rec_load(RB, rec_addr<SX, SY, 1>(eF, eZ));                                                      \
   rec_use<SX, SY, 0>(RA, Q, z1, z2, zn, acc, dm);                                                 \
@@ -580,12 +582,11 @@ __host__ __device__ inline void p2_half_t(T2 &N, double *sm, const ClsK &Q, doub
     _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[0][t] = acc[1][t] = 0.0;                    \
     dm[0] = dm[1] = 0.0;                                                                          \
   }                                                                                               \
-  NALU_T2_STAMP(N);                                                                               \
-  if (!LAST) RA = RB;
-  NALU_P2_QUAD(0, 0, 0, X1, Y1, false)
-  NALU_P2_QUAD(1, X1, Y1, X2, Y2, false)
-  NALU_P2_QUAD(2, X2, Y2, 1, 1, false)
-  NALU_P2_QUAD(3, 1, 1, 1, 1, true)
+  NALU_T2_STAMP(N);
+  NALU_P2_QUAD(0, 0, 0, X1, Y1, false, RA, RB)
+  NALU_P2_QUAD(1, X1, Y1, X2, Y2, false, RB, RA)
+  NALU_P2_QUAD(2, X2, Y2, 1, 1, false, RA, RB)
+  NALU_P2_QUAD(3, 1, 1, 1, 1, true, RB, RA)
 #undef NALU_P2_QUAD
 }
 
@@ -708,10 +709,10 @@ __host__ __device__ inline Run run_of(const Meta &M, int node, int i, int g)
 // descriptor copy-out: the (never merged, <= 27 doubles) run of dz group g of dof row i of a node, stored once
 // per plane so that the copy loop is descriptor load -> staging load -> store with no index arithmetic
 struct RunDesc {
-  long long G;
+  double *dst; // first double of the run in `values` (the address itself: nothing left to compute in the copy loop)
   int soff, L;
 };
-__host__ __device__ inline void build_run_desc(const Meta &M, double *sm, int tid)
+__host__ __device__ inline void build_run_desc(const Meta &M, double *sm, int tid, double *values)
 {
   using C = Cfg;
   RunDesc *rd = reinterpret_cast<RunDesc *>(sm + C::OFF_RD);
@@ -721,7 +722,7 @@ __host__ __device__ inline void build_run_desc(const Meta &M, double *sm, int ti
     const unsigned gp = M.gp[node * 4 + g], nf = M.gp[node * 4 + 3];
     RunDesc d;
     d.L = 3 * M.cnt[node * 4 + g];
-    d.G = M.rowbase[node] + ((long long)i * M.nb[node] + (gp & 0xFF)) * 3;
+    d.dst = values + (M.rowbase[node] + ((long long)i * M.nb[node] + (gp & 0xFF)) * 3);
     d.soff = node * C::SNODE + i * C::SROWP + ((nf >> i) & 1) + (gp >> 8);
     rd[idx] = d;
   }
