@@ -248,6 +248,13 @@ int nalu_b200_sum_into(const nalu_b200_graph *g, int32_t n_entities, const int32
 int nalu_b200_assemble_node_mass(const nalu_b200_graph *g, const nalu_b200_kernel_desc *k,
                                  double *d_values, double *d_rhs, void *stream);
 
+/* ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254): the producer of the element field
+ * mass_flow_rate_scs [nElem][12] the adv-diff kernels read, mdot_ip = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip
+ * with projTimeScale = dt / gamma1; options: NALU_OPT_SHIFT_MDOT (shifted shape function), NALU_OPT_SHIFT_POISSON
+ * (shifted grad-op).  With it the field never leaves the device between two assemblies. */
+int nalu_b200_compute_mdot_elem(const nalu_b200_graph *g, const double *d_coords, const double *d_density,
+                                const double *d_velocity, const double *d_pressure, const double *d_gpdx,
+                                double proj_time_scale, int32_t options, double *d_mdot, void *stream);
 /* TpetraLinearSystem::applyDirichletBCs (src/TpetraLinearSystem.C:1579-1653): for every listed local node and
  * dof d in [begin_pos, end_pos) the CSR row is replaced by the identity row (locally-owned rows; a
  * shared-not-owned row is cleared, its owner holds the 1) and the residual by bc - solution (0 for a

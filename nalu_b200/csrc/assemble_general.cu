@@ -437,6 +437,56 @@ __global__ void mdot_kernel(long long n_elems, const int *elem_nodes, const doub
   mdot[e * 12 + ip] = rhoU[0] * a[0] + rhoU[1] * a[1] + rhoU[2] * a[2];
 }
 
+// ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254): the producer of mass_flow_rate_scs in a
+// time step, mdot_ip = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip; one thread per (element, point)
+__global__ void compute_mdot_kernel(long long n_elems, const int *elem_nodes, const double *coords, const double *density,
+                                    const double *velocity, const double *pressure, const double *gpdx, double tau,
+                                    int shift_mdot, int shift_poisson, double *mdot, int *err)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = t / 12;
+  const int ip = (int)(t - e * 12);
+  if (e >= n_elems) return;
+  double c[8][3], w[8][3], pn[8];
+  for (int n = 0; n < 8; ++n) {
+    const int node = elem_nodes[e * 8 + n];
+    const double rho = density[node];
+    pn[n] = pressure[node];
+    for (int d = 0; d < 3; ++d) {
+      c[n][d] = coords[(size_t)node * 3 + d];
+      w[n][d] = rho * velocity[(size_t)node * 3 + d] + tau * gpdx[(size_t)node * 3 + d]; // interpolated with one shape function
+    }
+  }
+  double a[3], s1, s2, s3, dndx[8][3];
+  hex8::scs_areav_ip(c, ip, a);
+  hex8::scs_intg_loc(ip, shift_poisson ? 0.5 : 0.25, s1, s2, s3);
+  const double det = hex8::grad_op_ip(c, s1, s2, s3, dndx);
+  if (!(det > 0.0)) *err = 1;
+  hex8::scs_intg_loc(ip, shift_mdot ? 0.5 : 0.25, s1, s2, s3);
+  double wip[3] = {0, 0, 0}, dpdx[3] = {0, 0, 0};
+  for (int n = 0; n < 8; ++n) {
+    const double r = hex8::shape_fcn(n, s1, s2, s3);
+    for (int d = 0; d < 3; ++d) {
+      wip[d] += r * w[n][d];
+      dpdx[d] += dndx[n][d] * pn[n];
+    }
+  }
+  mdot[e * 12 + ip] = (wip[0] - tau * dpdx[0]) * a[0] + (wip[1] - tau * dpdx[1]) * a[1] + (wip[2] - tau * dpdx[2]) * a[2];
+}
+
+int launch_compute_mdot(const Graph &g, const double *coords, const double *density, const double *velocity, const double *pressure,
+                        const double *gpdx, double tau, int options, double *mdot, cudaStream_t stream)
+{
+  if (g.n_elems == 0) return NALU_B200_OK;
+  const long long nt = g.n_elems * 12;
+  compute_mdot_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, stream>>>(g.n_elems, g.d_elem_nodes, coords, density, velocity, pressure,
+                                                                       gpdx, tau, (options & NALU_OPT_SHIFT_MDOT) != 0,
+                                                                       (options & NALU_OPT_SHIFT_POISSON) != 0, mdot, g.d_err);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
 int launch_mdot(const Graph &g, const double *coords, const double *density, const double *velocity, double *mdot,
                 cudaStream_t stream)
 {

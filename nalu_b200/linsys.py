@@ -213,6 +213,18 @@ class DeviceCsrLinearSystem:
         check(self.L.nalu_b200_assemble_node_mass(self.h, C.byref(desc), ptr(self.values), ptr(self.rhs),
                                                   self._stream()), "assemble_node_mass")
 
+    def compute_mdot_elem(self, coords, density, velocity, pressure, dpdx, proj_time_scale, options=(), out=None):
+        """ComputeMdotElemAlgorithm::execute: mass_flow_rate_scs of every locally-owned element."""
+        import torch
+        if out is None:
+            out = torch.empty((self.mesh.n_elems, 12), dtype=torch.float64, device=coords.device)
+        opt = 0
+        for o in options:
+            opt |= OPT[o]
+        check(self.L.nalu_b200_compute_mdot_elem(self.h, ptr(coords), ptr(density), ptr(velocity), ptr(pressure), ptr(dpdx),
+                                                 C.c_double(proj_time_scale), opt, ptr(out), self._stream()), "compute_mdot_elem")
+        return out
+
     def apply_dirichlet_bcs(self, nodes, solution, bc_values, begin_pos, end_pos):
         """LinearSystem::applyDirichletBCs; nodes: int32 device tensor of local node ids."""
         check(self.L.nalu_b200_apply_dirichlet_bcs(self.h, int(nodes.numel()), ptr(nodes), ptr(solution), ptr(bc_values),

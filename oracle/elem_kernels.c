@@ -888,3 +888,45 @@ void orc_calc_mass_flow_rate_scs(int64_t nElem, const int32_t *elemNodes, const 
     }
   }
 }
+
+/* src/ComputeMdotElemAlgorithm.C:85-254: mass_flow_rate_scs of every locally-owned element,
+ * mdot_ip = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip; shape function shifted when
+ * shiftMdot (:153-156), grad-op shifted when shiftPoisson (:190-193).  No reference unit test holds a table
+ * for it; the formula is the one ContinuityAdvElemKernel.C:135-147 evaluates, so it is pinned through the
+ * continuity golds (tests/test_oracle_golden.py::test_compute_mdot_elem_matches_continuity_gold). */
+void orc_compute_mdot_elem(int64_t nElem, const int32_t *elemNodes, const double *coords, const double *density,
+                           const double *velocity, const double *pressure, const double *Gpdx, double projTimeScale,
+                           int shiftMdot, int shiftPoisson, double *mdot)
+{
+  double p_shape_function[12][8];
+  init_tables();
+  scs_shape(shiftMdot, p_shape_function);
+  for (int64_t e = 0; e < nElem; ++e) {
+    const int32_t *nodes = elemNodes + 8 * e;
+    double p_coordinates[8][3], p_density[8], p_pressure[8], p_vrtm[8][3], p_Gpdx[8][3];
+    double p_scs_areav[12][3], p_dndx[12][8][3], deriv[12][8][3];
+    gather(coords, 3, nodes, &p_coordinates[0][0]);
+    gather(density, 1, nodes, p_density);
+    gather(pressure, 1, nodes, p_pressure);
+    gather(velocity, 3, nodes, &p_vrtm[0][0]);
+    gather(Gpdx, 3, nodes, &p_Gpdx[0][0]);
+    orc_hex8_scs_areav(&p_coordinates[0][0], &p_scs_areav[0][0]);
+    orc_hex8_scs_grad_op(shiftPoisson, &p_coordinates[0][0], &p_dndx[0][0][0], &deriv[0][0][0]);
+    for (int ip = 0; ip < 12; ++ip) {
+      double p_rho_uIp[3] = {0.0, 0.0, 0.0}, p_GpdxIp[3] = {0.0, 0.0, 0.0}, p_dpdxIp[3] = {0.0, 0.0, 0.0};
+      for (int ic = 0; ic < 8; ++ic) {
+        const double r = p_shape_function[ip][ic];
+        const double nodalPressure = p_pressure[ic];
+        const double nodalRho = p_density[ic];
+        for (int j = 0; j < 3; ++j) {
+          p_GpdxIp[j] += r * p_Gpdx[ic][j];
+          p_rho_uIp[j] += r * nodalRho * p_vrtm[ic][j];
+          p_dpdxIp[j] += p_dndx[ip][ic][j] * nodalPressure;
+        }
+      }
+      double tmdot = 0.0;
+      for (int j = 0; j < 3; ++j) tmdot += (p_rho_uIp[j] - projTimeScale * (p_dpdxIp[j] - p_GpdxIp[j])) * p_scs_areav[ip][j];
+      mdot[12 * e + ip] = tmdot;
+    }
+  }
+}

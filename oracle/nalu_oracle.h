@@ -136,6 +136,11 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
 void orc_calc_mass_flow_rate_scs(int64_t nElem, const int32_t *elemNodes, const double *coords,
                                  const double *density, const double *velocity, double *mdot);
 
+/* src/ComputeMdotElemAlgorithm.C:85-254 */
+void orc_compute_mdot_elem(int64_t nElem, const int32_t *elemNodes, const double *coords, const double *density,
+                           const double *velocity, const double *pressure, const double *Gpdx, double projTimeScale,
+                           int shiftMdot, int shiftPoisson, double *mdot);
+
 /* ------------------------------------------------------------------ */
 /* Linear system: graph, sumInto, loadComplete (src/TpetraLinearSystem.C)*/
 /* ------------------------------------------------------------------ */

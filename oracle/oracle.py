@@ -174,6 +174,17 @@ def calc_mass_flow_rate_scs(elem_nodes, coords, density, velocity):
     return mdot
 
 
+def compute_mdot_elem(elem_nodes, coords, density, velocity, pressure, Gpdx, proj_time_scale, shift_mdot=False,
+                      shift_poisson=False):
+    """ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254)."""
+    en = np.ascontiguousarray(elem_nodes, dtype=np.int32).reshape(-1, 8)
+    mdot = np.zeros((en.shape[0], 12))
+    a = [_f64(x) for x in (coords, density, velocity, pressure, Gpdx)]
+    lib().orc_compute_mdot_elem(C.c_int64(en.shape[0]), _p(en), *[_p(x) for x in a], C.c_double(proj_time_scale),
+                                int(shift_mdot), int(shift_poisson), _p(mdot))
+    return mdot
+
+
 class LinSys:
     """All ranks of one simulated MPI job (orc_linsys)."""
 

@@ -277,3 +277,21 @@ def test_upw_first_order_upwind_limit(ndof):
     scale = np.abs(elhs).max()
     np.testing.assert_allclose(lhs.reshape(n, n), elhs, rtol=0, atol=1e-14 * scale)
     np.testing.assert_allclose(rhs, erhs, rtol=0, atol=1e-14 * max(1.0, np.abs(erhs).max()))
+
+
+@pytest.mark.parametrize("variant", ["default", "shifted"])
+def test_compute_mdot_elem_matches_continuity_gold(variant):
+    """ComputeMdotElemAlgorithm (src/ComputeMdotElemAlgorithm.C:85-254) evaluates the mass flow rate
+    ContinuityAdvElemKernel.C:135-147 forms: rhs(il) -= mdot/tau, rhs(ir) += mdot/tau must reproduce the reference's
+    continuity golds (unit_tests/kernels/UnitTestContinuityAdvElem.C, dt = gamma1 = 1)."""
+    g = load_golden("continuity_adv")
+    fx = LowMachFixture()
+    sp = variant == "shifted"
+    mdot = oracle.compute_mdot_elem(fx.mesh.elem_nodes, fx.coords, fx.density, fx.velocity, fx.pressure, fx.dpdx, 1.0,
+                                    shift_mdot=False, shift_poisson=sp)[0]
+    rhs = np.zeros(8)
+    for ip, (il, ir) in enumerate(LRSCV):
+        rhs[il] -= mdot[ip]
+        rhs[ir] += mdot[ip]
+    ns = "advection_default" if variant == "default" else "advection_reduced_sensitivities"
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=2e-15)
