@@ -248,6 +248,15 @@ int nalu_b200_sum_into(const nalu_b200_graph *g, int32_t n_entities, const int32
 int nalu_b200_assemble_node_mass(const nalu_b200_graph *g, const nalu_b200_kernel_desc *k,
                                  double *d_values, double *d_rhs, void *stream);
 
+/* AssembleNodalGradElemAlgorithm::execute / AssembleNodalGradUElemAlgorithm::execute
+ * (src/AssembleNodalGradElemAlgorithm.C:77-133, src/AssembleNodalGradUElemAlgorithm.C:120-195): interior Green-Gauss
+ * contributions of every locally-owned element to the projected nodal gradient -- dpdx, dqdx (ncomp = 1 -> [nNodes][3])
+ * or dudx (ncomp = 3 -> [nNodes][9], (i,j) at 3*i+j) -- the inputs of the continuity, upwind and mass kernels.
+ * d_grad is accumulated into (zero it first; boundary contributions and the parallel sum are the caller's, as in the
+ * reference); use_shifted: shifted shape function. */
+int nalu_b200_assemble_nodal_grad_elem(const nalu_b200_graph *g, const double *d_coords, const double *d_field,
+                                       int32_t ncomp, const double *d_dual_volume, int32_t use_shifted, double *d_grad,
+                                       void *stream);
 /* ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254): the producer of the element field
  * mass_flow_rate_scs [nElem][12] the adv-diff kernels read, mdot_ip = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip
  * with projTimeScale = dt / gamma1; options: NALU_OPT_SHIFT_MDOT (shifted shape function), NALU_OPT_SHIFT_POISSON

@@ -437,6 +437,58 @@ __global__ void mdot_kernel(long long n_elems, const int *elem_nodes, const doub
   mdot[e * 12 + ip] = rhoU[0] * a[0] + rhoU[1] * a[1] + rhoU[2] * a[2];
 }
 
+// AssembleNodalGradElemAlgorithm / AssembleNodalGradUElemAlgorithm (src/AssembleNodalGradElemAlgorithm.C:77-133,
+// src/AssembleNodalGradUElemAlgorithm.C:120-195): interior Green-Gauss contributions to the projected nodal gradient
+// (dpdx, dqdx, dudx: inputs of the continuity, upwind and mass kernels).  One thread per (element, point).
+template <int NCOMP>
+__global__ void nodal_grad_kernel(long long n_elems, const int *elem_nodes, const double *coords, const double *field,
+                                  const double *dual_volume, int use_shifted, double *grad)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = t / 12;
+  const int ip = (int)(t - e * 12);
+  if (e >= n_elems) return;
+  double c[8][3];
+  int nd[8];
+  for (int n = 0; n < 8; ++n) {
+    nd[n] = elem_nodes[e * 8 + n];
+    for (int d = 0; d < 3; ++d) c[n][d] = coords[(size_t)nd[n] * 3 + d];
+  }
+  double a[3], s1, s2, s3, q[NCOMP];
+  hex8::scs_areav_ip(c, ip, a);
+  hex8::scs_intg_loc(ip, use_shifted ? 0.5 : 0.25, s1, s2, s3);
+  for (int i = 0; i < NCOMP; ++i) q[i] = 0.0;
+  for (int n = 0; n < 8; ++n) {
+    const double r = hex8::shape_fcn(n, s1, s2, s3);
+    for (int i = 0; i < NCOMP; ++i) q[i] += r * field[(size_t)nd[n] * NCOMP + i];
+  }
+  const int nl = nd[hex8::scs_left(ip)], nr = nd[hex8::scs_right(ip)];
+  const double ivl = 1.0 / dual_volume[nl], ivr = 1.0 / dual_volume[nr];
+  for (int i = 0; i < NCOMP; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double fac = q[i] * a[j];
+      atomicAdd(grad + (size_t)nl * NCOMP * 3 + i * 3 + j, fac * ivl);
+      atomicAdd(grad + (size_t)nr * NCOMP * 3 + i * 3 + j, -fac * ivr);
+    }
+}
+
+int launch_nodal_grad(const Graph &g, const double *coords, const double *field, int ncomp, const double *dual_volume, int use_shifted,
+                      double *grad, cudaStream_t stream)
+{
+  if (ncomp != 1 && ncomp != 3) {
+    set_error("assemble_nodal_grad_elem: ncomp must be 1 (scalar) or 3 (vector)");
+    return NALU_B200_ERR_ARG;
+  }
+  if (g.n_elems == 0) return NALU_B200_OK;
+  const long long nt = g.n_elems * 12;
+  const unsigned nb = (unsigned)((nt + 127) / 128);
+  if (ncomp == 1) nodal_grad_kernel<1><<<nb, 128, 0, stream>>>(g.n_elems, g.d_elem_nodes, coords, field, dual_volume, use_shifted, grad);
+  else nodal_grad_kernel<3><<<nb, 128, 0, stream>>>(g.n_elems, g.d_elem_nodes, coords, field, dual_volume, use_shifted, grad);
+  count_launch();
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
 // ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254): the producer of mass_flow_rate_scs in a
 // time step, mdot_ip = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip; one thread per (element, point)
 __global__ void compute_mdot_kernel(long long n_elems, const int *elem_nodes, const double *coords, const double *density,

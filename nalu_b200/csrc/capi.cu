@@ -498,6 +498,13 @@ int nalu_b200_mdot_scs(const nalu_b200_graph *h, const double *d_coords, const d
   return launch_mdot(h->g, d_coords, d_density, d_velocity, d_mdot, (cudaStream_t)stream);
 }
 
+int nalu_b200_assemble_nodal_grad_elem(const nalu_b200_graph *h, const double *d_coords, const double *d_field, int32_t ncomp,
+                                       const double *d_dual_volume, int32_t use_shifted, double *d_grad, void *stream)
+{
+  if (!h || !d_coords || !d_field || !d_dual_volume || !d_grad || !h->g.d_elem_nodes) return NALU_B200_ERR_STATE;
+  return launch_nodal_grad(h->g, d_coords, d_field, ncomp, d_dual_volume, use_shifted, d_grad, (cudaStream_t)stream);
+}
+
 int nalu_b200_compute_mdot_elem(const nalu_b200_graph *h, const double *d_coords, const double *d_density, const double *d_velocity,
                                 const double *d_pressure, const double *d_gpdx, double proj_time_scale, int32_t options,
                                 double *d_mdot, void *stream)

@@ -35,6 +35,8 @@ int launch_assemble_scalar_box(const Graph &g, const nalu_b200_kernel_desc *k, i
                                int overwrite, cudaStream_t stream);
 bool scv_lumped_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
 int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs, cudaStream_t stream);
+int launch_nodal_grad(const Graph &g, const double *coords, const double *field, int ncomp, const double *dual_volume, int use_shifted,
+                      double *grad, cudaStream_t stream);
 int launch_compute_mdot(const Graph &g, const double *coords, const double *density, const double *velocity, const double *pressure,
                         const double *gpdx, double tau, int options, double *mdot, cudaStream_t stream);
 int launch_row_fixup(const Graph &g, int n_list, const int *d_list, int begin_pos, int end_pos, const double *d_solution,

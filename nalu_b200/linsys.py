@@ -213,6 +213,13 @@ class DeviceCsrLinearSystem:
         check(self.L.nalu_b200_assemble_node_mass(self.h, C.byref(desc), ptr(self.values), ptr(self.rhs),
                                                   self._stream()), "assemble_node_mass")
 
+    def assemble_nodal_grad_elem(self, coords, field, dual_volume, grad, use_shifted=False):
+        """AssembleNodalGrad(U)ElemAlgorithm::execute: interior contributions accumulated into `grad`."""
+        ncomp = 1 if field.dim() == 1 else int(field.shape[1])
+        check(self.L.nalu_b200_assemble_nodal_grad_elem(self.h, ptr(coords), ptr(field), ncomp, ptr(dual_volume), int(use_shifted),
+                                                        ptr(grad), self._stream()), "assemble_nodal_grad_elem")
+        return grad
+
     def compute_mdot_elem(self, coords, density, velocity, pressure, dpdx, proj_time_scale, options=(), out=None):
         """ComputeMdotElemAlgorithm::execute: mass_flow_rate_scs of every locally-owned element."""
         import torch

@@ -930,3 +930,42 @@ void orc_compute_mdot_elem(int64_t nElem, const int32_t *elemNodes, const double
     }
   }
 }
+
+/* src/AssembleNodalGradElemAlgorithm.C:77-133 (ncomp = 1: dqdx) and src/AssembleNodalGradUElemAlgorithm.C:120-195
+ * (ncomp = 3: dudx, row_gradQ = i*nDim): interior Green-Gauss contributions of every locally-owned element,
+ * grad(L, i*3+j) += q_i,ip areav_j / dualVolume_L,  grad(R, i*3+j) -= q_i,ip areav_j / dualVolume_R.
+ * `grad` is accumulated into (the reference zeroes it before the interior and boundary algorithms run). */
+void orc_assemble_nodal_grad_elem(int64_t nElem, const int32_t *elemNodes, const double *coords, const double *field,
+                                  int ncomp, const double *dualNodalVolume, int useShifted, double *grad)
+{
+  double p_shape_function[12][8];
+  init_tables();
+  scs_shape(useShifted, p_shape_function);
+  const int *lrscv = orc_hex8_lrscv();
+  for (int64_t e = 0; e < nElem; ++e) {
+    const int32_t *nodes = elemNodes + 8 * e;
+    double p_coordinates[8][3], p_dualVolume[8], p_q[8][3], p_scs_areav[12][3];
+    gather(coords, 3, nodes, &p_coordinates[0][0]);
+    gather(dualNodalVolume, 1, nodes, p_dualVolume);
+    for (int n = 0; n < 8; ++n)
+      for (int i = 0; i < ncomp; ++i) p_q[n][i] = field[(size_t)nodes[n] * ncomp + i];
+    orc_hex8_scs_areav(&p_coordinates[0][0], &p_scs_areav[0][0]);
+    for (int ip = 0; ip < 12; ++ip) {
+      const int il = lrscv[2 * ip];
+      const int ir = lrscv[2 * ip + 1];
+      double *gradQL = grad + (size_t)nodes[il] * ncomp * 3;
+      double *gradQR = grad + (size_t)nodes[ir] * ncomp * 3;
+      const double inv_volL = 1.0 / p_dualVolume[il];
+      const double inv_volR = 1.0 / p_dualVolume[ir];
+      for (int i = 0; i < ncomp; ++i) {
+        double qIp = 0.0;
+        for (int ic = 0; ic < 8; ++ic) qIp += p_shape_function[ip][ic] * p_q[ic][i];
+        for (int j = 0; j < 3; ++j) {
+          const double fac = qIp * p_scs_areav[ip][j];
+          gradQL[i * 3 + j] += fac * inv_volL;
+          gradQR[i * 3 + j] -= fac * inv_volR;
+        }
+      }
+    }
+  }
+}

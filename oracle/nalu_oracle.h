@@ -136,6 +136,9 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
 void orc_calc_mass_flow_rate_scs(int64_t nElem, const int32_t *elemNodes, const double *coords,
                                  const double *density, const double *velocity, double *mdot);
 
+/* src/AssembleNodalGradElemAlgorithm.C:77-133, src/AssembleNodalGradUElemAlgorithm.C:120-195 */
+void orc_assemble_nodal_grad_elem(int64_t nElem, const int32_t *elemNodes, const double *coords, const double *field,
+                                  int ncomp, const double *dualNodalVolume, int useShifted, double *grad);
 /* src/ComputeMdotElemAlgorithm.C:85-254 */
 void orc_compute_mdot_elem(int64_t nElem, const int32_t *elemNodes, const double *coords, const double *density,
                            const double *velocity, const double *pressure, const double *Gpdx, double projTimeScale,

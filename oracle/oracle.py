@@ -174,6 +174,19 @@ def calc_mass_flow_rate_scs(elem_nodes, coords, density, velocity):
     return mdot
 
 
+def assemble_nodal_grad_elem(elem_nodes, coords, field, dual_volume, use_shifted=False, grad=None):
+    """AssembleNodalGradElemAlgorithm / AssembleNodalGradUElemAlgorithm: interior Green-Gauss nodal gradient."""
+    en = np.ascontiguousarray(elem_nodes, dtype=np.int32).reshape(-1, 8)
+    f = _f64(field)
+    ncomp = 1 if f.ndim == 1 else f.shape[1]
+    n_nodes = f.shape[0]
+    if grad is None:
+        grad = np.zeros((n_nodes, 3 * ncomp))
+    c, v = _f64(coords), _f64(dual_volume)
+    lib().orc_assemble_nodal_grad_elem(C.c_int64(en.shape[0]), _p(en), _p(c), _p(f), int(ncomp), _p(v), int(use_shifted), _p(grad))
+    return grad
+
+
 def compute_mdot_elem(elem_nodes, coords, density, velocity, pressure, Gpdx, proj_time_scale, shift_mdot=False,
                       shift_poisson=False):
     """ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254)."""

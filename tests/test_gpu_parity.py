@@ -757,3 +757,17 @@ def test_compute_mdot_elem(options):
     scale = np.abs(ref).max()
     assert np.abs(got.cpu().numpy() - ref).max() <= 1e-13 * scale
     assert ls.geometry_errors() == 0
+
+
+@pytest.mark.parametrize("ncomp,shifted", [(1, False), (1, True), (3, False)])
+def test_assemble_nodal_grad_elem(ncomp, shifted):
+    m = perturbed_box(9, 7, 6)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    field = st.pressure if ncomp == 1 else st.velocity
+    ref = oracle.assemble_nodal_grad_elem(m.elem_nodes, st.coordinates, field, st.dual_volume, use_shifted=shifted)
+    ls = _linsys(m, 1)
+    grad = torch.zeros((m.n_nodes, 3 * ncomp), dtype=torch.float64, device=_cuda())
+    ls.assemble_nodal_grad_elem(dev["coordinates"], dev["pressure"] if ncomp == 1 else dev["velocity"], dev["dual_volume"], grad,
+                                use_shifted=shifted)
+    assert np.abs(grad.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()

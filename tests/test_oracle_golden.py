@@ -295,3 +295,19 @@ def test_compute_mdot_elem_matches_continuity_gold(variant):
         rhs[ir] += mdot[ip]
     ns = "advection_default" if variant == "default" else "advection_reduced_sensitivities"
     np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=2e-15)
+
+
+@pytest.mark.parametrize("ncomp", [1, 3])
+def test_nodal_grad_elem_is_exact_for_linear_fields(ncomp):
+    """AssembleNodalGrad(U)ElemAlgorithm: known answer -- on the (affine) generated box the interior Green-Gauss sum
+    over the closed dual-volume surface of an interior node returns the gradient of a linear field exactly
+    (dual nodal volume of an interior node of the unit lattice = 1)."""
+    m = mesh.generated_box(4, 3, 3)
+    c = m.coords
+    Gm = np.array([[0.3, -1.2, 0.7], [2.0, 0.1, -0.4], [-0.6, 0.9, 1.5]])[:ncomp]
+    f = c @ Gm.T + 0.25
+    field = f[:, 0] if ncomp == 1 else f
+    grad = oracle.assemble_nodal_grad_elem(m.elem_nodes, c, field, np.ones(m.n_nodes))
+    interior = np.all((c > 0.5) & (c < np.array([3.5, 2.5, 2.5])), axis=1)
+    assert interior.sum() == 3 * 2 * 2
+    np.testing.assert_allclose(grad[interior], np.tile(Gm.reshape(-1), (interior.sum(), 1)), rtol=0, atol=1e-13)
