@@ -71,6 +71,29 @@ __global__ void k_dfma(double *out, double a, double b, int iters, long long *cy
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+// store drain: every warp writes `nrun` runs of 27 doubles (216 bytes, lane k -> double k) back to back to its own
+// contiguous stretch of a buffer much larger than L2 -- what the copy-out of the tiled momentum kernel does.
+// `vec`: lanes 0..13 store a double2 instead (the 27th double is dropped; alignment of the run start permitting)
+__global__ void k_store_runs(double *dst, long long nrun, int vec, long long *cyc)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double *base = dst + ((long long)blockIdx.x * nw + warp) * nrun * 28; // 28: keeps the double2 variant 16-byte aligned
+  const double v = (double)lane;
+  long long t0 = clock64();
+  if (vec == 2) { // 27-double runs back to back, no holes: sectors shared by two runs are completed by the next run
+    for (long long r = 0; r < nrun; ++r)
+      if (lane < 27) base[r * 27 + lane] = v;
+  } else if (!vec) {
+    for (long long r = 0; r < nrun; ++r)
+      if (lane < 27) base[r * 28 + lane] = v;
+  } else {
+    for (long long r = 0; r < nrun; ++r)
+      if (lane < 14) reinterpret_cast<double2 *>(base + r * 28)[lane] = make_double2(v, v);
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 // every thread < nrun issues one bulk copy of `bytes` from its own smem run to its own global run
 __global__ void k_bulk(double *dst, int bytes, int nrun, int iters, long long *cyc)
 {
@@ -150,6 +173,31 @@ int main()
   RUN_DFMA(1, 1) RUN_DFMA(2, 1) RUN_DFMA(4, 1) RUN_DFMA(8, 1)
   RUN_DFMA(1, 4) RUN_DFMA(2, 4) RUN_DFMA(4, 4) RUN_DFMA(8, 4)
   RUN_DFMA(1, 8) RUN_DFMA(2, 8) RUN_DFMA(4, 8) RUN_DFMA(2, 16)
+  // ---- store drain to HBM (8 GB footprint >> L2), 2 CTAs per SM, 4 / 8 / 16 warps per CTA
+  {
+    double *big = nullptr;
+    const size_t bytes_total = (size_t)8 << 30;
+    CK(cudaMalloc(&big, bytes_total));
+    for (int vec = 0; vec < 3; ++vec)
+      for (int nw = 4; nw <= 16; nw *= 2) {
+        const long long nrun = (long long)(bytes_total / 8 / 28) / ((long long)sms * 2 * nw);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        k_store_runs<<<sms * 2, 32 * nw>>>(big, nrun / 8, vec, cyc);
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        k_store_runs<<<sms * 2, 32 * nw>>>(big, nrun, vec, cyc);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+        const double b = (double)sms * 2 * nw * nrun * (vec == 1 ? 224.0 : 216.0);
+        printf(",\n \"store_runs_%s_w%d\": {\"GBps\": %.1f, \"bytes_per_clk_per_sm\": %.2f, \"cyc_per_run_per_warp\": %.1f}",
+               vec == 1 ? "double2" : (vec == 2 ? "double_contig" : "double_holes"), nw, b / (ms * 1e-3) / 1e9, b / sms / ((double)h), (double)h / nrun);
+      }
+    CK(cudaFree(big));
+  }
   // ---- bulk stores
   const int sizes[5] = {208, 432, 1936, 15552, 208};
   const int nruns[5] = {96, 96, 32, 4, 32};
