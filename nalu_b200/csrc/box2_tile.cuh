@@ -248,7 +248,7 @@ __host__ __device__ inline void p1_item(const BoxParams &P, int el, int g, int s
     if (!(det > 0.0)) *P.err = 1; // MasterElementFunctions.h:91-94 asserts this in debug builds
     // mu at the (never shifted) ip location, MomentumAdvDiffElemKernel.C:107-110
     const double mu = 0.125 * M[0] + 0.0625 * (sg1 * M[Uu] + sg2 * M[V]) + 0.03125 * sg1 * sg2 * M[UV];
-    const double fac = -mu / det;
+    const double fac = -mu * (1.0 / det); // reciprocal + multiply: half the instructions of a full FP64 division
     const double fu = fac * sg1, fv = fac * sg2;
     double *o = (g == 2 ? ZE + el * C::ES + (ip - 8) * C::IPD : F + el * C::ES + (ip & 3) * C::IPD);
 #pragma unroll
