@@ -168,6 +168,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
     L = lib.lib()
+    lib.tune(box_kernel=args.box_kernel)
 
     # ---- mesh, graph (once per mesh; outside the timed region) ------------------------------
     t0 = time.perf_counter()
@@ -272,8 +273,7 @@ def run_ours(args):
     bytes_alg = algorithmic_bytes(m.n_nodes, n_elems_rank, nnz, 3, nodal_comps=7, elem_comps=12)
     achieved = bytes_alg / (asm_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": (("assemble_box2" if os.environ.get("NALU_BOX_TILE", "0") == "0" else "assemble_box") if overwrite
-                           else "assemble_general"),
+                "traffic": None, "peak_source": peak_src, "kernel": (f"assemble_box{args.box_kernel}" if overwrite else "assemble_general"),
                 "algorithmic_bytes_per_launch": bytes_alg, "bytes_per_element": bytes_alg / n_elems_rank,
                 "kernel_ms": asm_ms}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
@@ -364,7 +364,7 @@ def run_ours(args):
 
     serial_ms = time_e2e(e2e_step)
     fp_serial, rhs_serial = matrix_fingerprint(), rhs_host.clone()
-    use_pipe = overwrite and os.environ.get("NALU_BOX_TILE", "0") == "0" and nchunk > 1
+    use_pipe = overwrite and nchunk > 1
     e2e_ms = time_e2e(e2e_step_pipelined) if use_pipe else serial_ms
     if use_pipe:  # same system, whichever schedule
         assert torch.equal(fp_serial, matrix_fingerprint()) and torch.equal(rhs_serial, rhs_host), \
@@ -529,6 +529,8 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("NALU_BENCH_N", "256")),
                     help="elements per box edge per GPU")
     ap.add_argument("--mode", default="auto", choices=["auto", "general", "box"])
+    ap.add_argument("--box-kernel", type=int, default=5, choices=[5, 2],
+                    help="tiled momentum kernel: 5 row-thread (default), 2 column-pair (round-1 kernel, for A/B runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuity", action="store_true", help="skip the continuity pass reported beside the headline metric")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="node-plane ranges of the pipelined end-to-end step")

@@ -230,6 +230,15 @@ int nalu_b200_assemble_elem_zrange(const nalu_b200_graph *g, const nalu_b200_ker
 /* which kernel family the last nalu_b200_assemble_elem call used: 1 general (atomic scatter), 2 tiled write-once,
  * 3 tiled write-once for one kernel of the list + general for the others */
 int nalu_b200_last_assemble_mode(void);
+/* Launch-configuration knobs for A/B measurements and tests; none changes what is computed.  name / value:
+ *   "box_kernel"  5 row-thread tiled momentum kernel (default), 2 column-pair kernel
+ *   "box_zchunk"  node planes per CTA of the tiled kernels, 0 = automatic
+ *   "split_lists" 1 (default) a list with one tiled-capable kernel runs tiled + accumulate, 0 general kernel only
+ *   "cont_tiled"  1 (default) one-dof lists on structured blocks use the tiled kernels
+ * The initial values come from the environment variables NALU_BOX_KERNEL, NALU_BOX_ZCHUNK, NALU_SPLIT_LISTS,
+ * NALU_CONT_BOX, read once when the library is first used -- nothing on the launch path reads the environment.
+ * Returns NALU_B200_ERR_ARG for an unknown name. */
+int nalu_b200_tune(const char *name, int32_t value);
 /* synchronises, then reports (and clears) the device flag raised when an element had a
  * non-positive Jacobian determinant -- the reference asserts on this in debug builds
  * (include/master_element/MasterElementFunctions.h:91-94) */

@@ -84,10 +84,7 @@ static int launch_scalar(ScalarParams &P, cudaStream_t stream)
   int zchunks = (int)(want < 1 ? 1 : want);
   int zc = (nplanes + zchunks - 1) / zchunks;
   if (zc < 16) zc = 16;
-  if (const char *e = getenv("NALU_BOX_ZCHUNK")) {
-    const int v = atoi(e);
-    if (v > 0) zc = v;
-  }
+  if (tuning().box_zchunk > 0) zc = tuning().box_zchunk;
   if (zc > nplanes) zc = nplanes;
   P.z_chunk = zc;
   zchunks = (nplanes + zc - 1) / zc;

@@ -397,13 +397,7 @@ struct T2 {
   int lx, ly, node;
   int active, vmask;
   double rr[3];
-  long long *trace; // profiling aid: clock stamps inside phase 2 (null unless NALU_BOX_TRACE)
 };
-#ifdef __CUDA_ARCH__
-#define NALU_T2_STAMP(N) do { if ((N).trace) *(N).trace++ = clock64(); } while (0)
-#else
-#define NALU_T2_STAMP(N) do { } while (0)
-#endif
 
 __host__ __device__ inline void t2_init(const BoxParams &P, T2 &N, int lane, int x0, int y0)
 {
@@ -413,7 +407,6 @@ __host__ __device__ inline void t2_init(const BoxParams &P, T2 &N, int lane, int
   N.ly = lane / C::TBX;
   const int x = x0 + N.lx, y = y0 + N.ly;
   N.active = x < P.NX && y < P.NY;
-  N.trace = nullptr;
   N.vmask = 0;
   for (int q = 0; q < 4; ++q) {
     const int ex = x - 1 + (q & 1), ey = y - 1 + (q >> 1);
@@ -564,7 +557,6 @@ __host__ __device__ inline void p2_half_t(T2 &N, double *sm, const ClsK &Q, doub
   flush_prep(FP3, N, M, Q, H, 1, 1, z, gp0, gp1);
   FlushOps FO;
   Rec RA, RB;
-  NALU_T2_STAMP(N);
   rec_load(RA, rec_addr<0, 0, 0>(eF, eZ));
   // the record buffers swap roles from quadrant to quadrant (three records each: A, B, A then B, A, B): the
   // first record of the next quadrant is loaded into the buffer the next quadrant starts with, no copy
@@ -576,13 +568,11 @@ __host__ __device__ inline void p2_half_t(T2 &N, double *sm, const ClsK &Q, doub
   rec_use<SX, SY, 1>(RB, Q, z1, z2, zn, acc, dm);                                                 \
   if (!LAST) rec_load(RB, rec_addr<NX_, NY_, 0>(eF, eZ));                                         \
   rec_use<SX, SY, 2>(RA, Q, z1, z2, zn, acc, dm);                                                 \
-  NALU_T2_STAMP(N);                                                                               \
   if (fm & (1u << J)) {                                                                           \
     flush_commit(N, sm, FP##J, FO, pb, acc, dm, f23);                                             \
     _Pragma("unroll") for (int t = 0; t < 9; ++t) acc[0][t] = acc[1][t] = 0.0;                    \
     dm[0] = dm[1] = 0.0;                                                                          \
-  }                                                                                               \
-  NALU_T2_STAMP(N);
+  }
   NALU_P2_QUAD(0, 0, 0, X1, Y1, false, RA, RB)
   NALU_P2_QUAD(1, X1, Y1, X2, Y2, false, RB, RA)
   NALU_P2_QUAD(2, X2, Y2, 1, 1, false, RA, RB)

@@ -26,6 +26,19 @@ int cuda_fail(cudaError_t e, const char *what)
   return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? NALU_B200_ERR_NO_DEVICE : NALU_B200_ERR_CUDA;
 }
 void count_launch(int n) { g_launches += n; }
+static Tuning &tuning_rw()
+{
+  static Tuning t = [] {
+    Tuning v;
+    if (const char *e = getenv("NALU_BOX_KERNEL")) v.box_kernel = atoi(e) == 2 ? 2 : 5;
+    if (const char *e = getenv("NALU_BOX_ZCHUNK")) v.box_zchunk = atoi(e) > 0 ? atoi(e) : 0;
+    if (const char *e = getenv("NALU_SPLIT_LISTS")) v.split_lists = atoi(e) != 0;
+    if (const char *e = getenv("NALU_CONT_BOX")) v.cont_tiled = atoi(e) != 0;
+    return v;
+  }();
+  return t;
+}
+const Tuning &tuning() { return tuning_rw(); }
 void set_last_mode(int m) { g_last_mode = m; }
 
 template <typename T>
@@ -77,7 +90,7 @@ static void free_graph_device(Graph &g)
     if (p) cudaFree(p);
     p = nullptr;
   };
-  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27);
+  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_desc);
   F(g.d_rowptr_owned); F(g.d_rowptr_shared); F(g.d_colidx_owned); F(g.d_colidx_shared); F(g.d_err);
   for (auto *peers : {&g.send_peers, &g.recv_peers})
     for (HaloPeer &p : *peers) {
@@ -95,6 +108,8 @@ static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const s
   if ((rc = upload(&g.d_bcol, g.bcol))) return rc;
   if ((rc = upload(&g.d_elem_slot, elem_slot))) return rc;
   if ((rc = upload(&g.d_node_slot27, node_slot27))) return rc;
+  if ((rc = upload(&g.d_node_desc, g.node_desc))) return rc;
+  std::vector<uint64_t>().swap(g.node_desc);
   NALU_CUDA(cudaMalloc((void **)&g.d_err, sizeof(int)));
   NALU_CUDA(cudaMemset(g.d_err, 0, sizeof(int)));
   const int nown = g.n_owned_nodes, nrow = g.n_row_nodes(), ndof = g.ndof;
@@ -146,6 +161,21 @@ const char *nalu_b200_last_error(void)
 int nalu_b200_version(void) { return 100; }
 int64_t nalu_b200_launch_count(void) { return g_launches.load(); }
 int nalu_b200_last_assemble_mode(void) { return g_last_mode.load(); }
+int nalu_b200_tune(const char *name, int32_t value)
+{
+  if (!name) return NALU_B200_ERR_ARG;
+  Tuning &t = tuning_rw();
+  const std::string n(name);
+  if (n == "box_kernel") t.box_kernel = value == 2 ? 2 : 5;
+  else if (n == "box_zchunk") t.box_zchunk = value > 0 ? value : 0;
+  else if (n == "split_lists") t.split_lists = value != 0;
+  else if (n == "cont_tiled") t.cont_tiled = value != 0;
+  else {
+    set_error("tune: unknown knob " + n);
+    return NALU_B200_ERR_ARG;
+  }
+  return NALU_B200_OK;
+}
 
 int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof, int32_t n_nodes,
                            const int64_t *node_gid, const int32_t *node_owner, int64_t n_elems,
@@ -156,8 +186,9 @@ int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, 
     set_error("graph_create: bad argument (numDof must be 1 or 3)");
     return NALU_B200_ERR_ARG;
   }
+  nalu_b200_graph *h = nullptr;
   try {
-    nalu_b200_graph *h = new nalu_b200_graph();
+    h = new nalu_b200_graph();
     Graph &g = h->g;
     g.rank = rank; g.nranks = nranks; g.ndof = num_dof; g.n_nodes = n_nodes; g.n_elems = n_elems;
     g.box[0] = box_nx; g.box[1] = box_ny; g.box[2] = box_nz;
@@ -175,6 +206,7 @@ int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, 
     return NALU_B200_OK;
   } catch (const std::exception &e) {
     set_error(std::string("graph_create: ") + e.what());
+    delete h;
     return NALU_B200_ERR_ARG;
   }
 }
@@ -372,7 +404,7 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   // the momentum list of the low-Mach equation system, src/LowMachEquationSystem.C:1304-1398): the tiled kernel
   // takes its kernel first (it may overwrite), the others accumulate on top through the general kernel -- the sum the
   // reference forms in one scratch lhs/rhs (src/AssembleElemSolverAlgorithm.C:86-91), in another order.
-  static const bool split_lists = !(getenv("NALU_SPLIT_LISTS") && atoi(getenv("NALU_SPLIT_LISTS")) == 0);
+  const bool split_lists = tuning().split_lists;
   if (mode == NALU_ASSEMBLE_AUTO && nk > 1 && nk <= kMaxKernels && split_lists) {
     int t = -1;
     for (int i = 0; i < nk && t < 0; ++i)
@@ -397,7 +429,7 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   }
   bool use_box = false;
   // the one-dof tiled kernel (ContinuityAdvElemKernel on a structured block); NALU_CONT_BOX=0 keeps the general kernel
-  static const bool cont_tiled = !(getenv("NALU_CONT_BOX") && atoi(getenv("NALU_CONT_BOX")) == 0);
+  const bool cont_tiled = tuning().cont_tiled;
   if (mode != NALU_ASSEMBLE_GENERAL && cont_tiled && cont_box_supported(g, kernels, nk)) {
     set_last_mode(2);
     return launch_assemble_cont_box(g, kernels, nk, d_values, d_rhs, overwrite, s);

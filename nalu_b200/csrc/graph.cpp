@@ -322,6 +322,7 @@ int graph_finalize_host(Graph &g, std::vector<uint8_t> &elem_slot, std::vector<u
   }
   if (overflow) { err = "row with more than 254 node blocks (or missing connection)"; return 1; }
 
+  const int64_t d2 = int64_t(ndof) * ndof;
   // ---- box meshes: slot of each lattice neighbour ----------------------------------------
   node_slot27.clear();
   if (g.box[0] > 0) {
@@ -344,6 +345,36 @@ int graph_finalize_host(Graph &g, std::vector<uint8_t> &elem_slot, std::vector<u
             if (s >= 0) node_slot27[size_t(n) * 27 + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] = uint8_t(s);
           }
     }
+    // row descriptors of the tiled kernels.  They rely on one property of the column ordering: the columns of a row
+    // that share dz are contiguous in the row (true for every z-slab ownership: owned, shared and remote columns keep
+    // lattice order inside a plane).  A box declared with another ownership pattern (e.g. an x / y decomposition, where
+    // a node plane mixes owned and shared nodes) does not have it: the block then loses its box attribute and is
+    // assembled by the general kernel.
+    g.node_desc.assign(size_t(g.n_nodes) * 3, 0);
+    int scattered = 0;
+#pragma omp parallel for schedule(static) reduction(+ : scattered)
+    for (int64_t n = 0; n < g.n_nodes; ++n) {
+      const int32_t r = g.node_row[n];
+      const int64_t nb = g.browptr[r + 1] - g.browptr[r];
+      bool natural = nb == 27;
+      uint64_t w2 = 0;
+      for (int gq = 0; gq < 3; ++gq) {
+        unsigned lo = 255, hi = 0, c = 0;
+        for (int k = 0; k < 9; ++k) {
+          const unsigned v = node_slot27[size_t(n) * 27 + gq * 9 + k];
+          if (v == 0xFF) continue;
+          lo = v < lo ? v : lo;
+          hi = v > hi ? v : hi;
+          ++c;
+        }
+        if (c && hi - lo + 1 != c) ++scattered;
+        for (int k = 0; k < 9; ++k) natural = natural && node_slot27[size_t(n) * 27 + gq * 9 + k] == lo + k;
+        w2 |= uint64_t(c ? lo : 0) << (8 * gq) | uint64_t(c) << (24 + 8 * gq);
+      }
+      g.node_desc[size_t(n) * 3 + 0] = uint64_t(d2 * g.browptr[r]);
+      g.node_desc[size_t(n) * 3 + 1] = uint64_t(uint32_t(r)) | uint64_t(nb & 0xFF) << 32 | uint64_t(natural) << 40 | uint64_t(1) << 41;
+      g.node_desc[size_t(n) * 3 + 2] = w2;
+    }
     // the tiled kernel assumes Ioss `generated:` connectivity
     const int64_t nx = g.box[0], ny = g.box[1];
     int badconn = 0;
@@ -357,12 +388,16 @@ int graph_finalize_host(Graph &g, std::vector<uint8_t> &elem_slot, std::vector<u
         if (g.elem_nodes[e * 8 + q] != ref[q]) ++badconn;
     }
     if (badconn) { err = "box declared but connectivity is not the generated-box pattern"; return 1; }
+    if (scattered) {
+      g.box[0] = g.box[1] = g.box[2] = 0;
+      node_slot27.clear();
+      g.node_desc.clear();
+    }
   }
 
   // ---- halo maps: send side -------------------------------------------------------------
   g.send_peers.clear();
   g.recv_peers.clear();
-  const int64_t d2 = int64_t(ndof) * ndof;
   for (int p = 0; p < g.nranks; ++p) {
     if (g.send_msg[p].empty()) continue;
     HaloPeer hp;

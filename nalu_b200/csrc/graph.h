@@ -77,6 +77,11 @@ struct Graph {
   int32_t *d_bcol = nullptr;
   uint8_t *d_elem_slot = nullptr;  // [n_elems][8][8]
   uint8_t *d_node_slot27 = nullptr; // box only: [n_nodes][27] slot of lattice neighbour (dz,dy,dx)
+  // box only: [n_nodes][3] row descriptor of the tiled kernels: [0] first value of the node's rows (ndof^2 browptr[row]),
+  // [1] row | blocks << 32 | natural << 40 (all 27 lattice neighbours present, in lattice order) | 1 << 41,
+  // [2] bytes 0..2: first slot of the dz = -1, 0, +1 column group, bytes 3..5: columns in the group
+  std::vector<uint64_t> node_desc;
+  uint64_t *d_node_desc = nullptr;
   uint64_t *d_rowptr_owned = nullptr, *d_rowptr_shared = nullptr;
   int32_t *d_colidx_owned = nullptr, *d_colidx_shared = nullptr;
   int32_t *d_err = nullptr; // device error flag (negative Jacobians)

@@ -49,12 +49,12 @@ int launch_mdot(const Graph &g, const double *coords, const double *density, con
 bool box_supported(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk);
 int launch_assemble_box(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
                         double *d_rhs, int overwrite, cudaStream_t stream, int z_begin = -1, int z_end = -1);
-// assemble_box2.cu
+// assemble_box2.cu (column-pair kernel: option combinations the row-thread kernel does not take), assemble_box5.cu
+// (row-thread kernel, the default)
 namespace box { struct BoxParams; }
 int launch_assemble_box2(box::BoxParams &P, cudaStream_t stream);
-// assemble_box3.cu (experimental warp-specialised variant, NALU_BOX_KERNEL=3)
-int launch_assemble_box3(box::BoxParams &P, cudaStream_t stream);
-int launch_assemble_box4(box::BoxParams &P, cudaStream_t stream);
+bool box5_supported(const box::BoxParams &P);
+int launch_assemble_box5(box::BoxParams &P, cudaStream_t stream);
 // halo.cu
 int launch_halo_pack(const Graph &g, const HaloPeer &p, const double *d_values, const double *d_rhs,
                      double *d_buf, cudaStream_t stream);
@@ -62,5 +62,17 @@ int launch_halo_add(const Graph &g, const HaloPeer &p, const double *src_values,
                     bool inplace, double *d_values, double *d_rhs, cudaStream_t stream);
 
 constexpr int kMaxKernels = 8;
+
+// Tuning knobs for A/B measurements, read ONCE from the environment when the library is first used (never on the
+// launch path): NALU_BOX_KERNEL=2 column-pair kernel instead of the row-thread kernel, NALU_BOX_ZCHUNK=n node planes
+// per CTA, NALU_SPLIT_LISTS=0 multi-kernel lists through the general kernel only, NALU_CONT_BOX=0 one-dof lists through
+// the general kernel.  None of them changes what is computed.
+struct Tuning {
+  int box_kernel = 5;
+  int box_zchunk = 0;
+  bool split_lists = true;
+  bool cont_tiled = true;
+};
+const Tuning &tuning();
 
 } // namespace nalu_b200

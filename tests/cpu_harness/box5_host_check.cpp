@@ -1,13 +1,13 @@
-// CPU emulation of the row-thread tiled momentum kernel (nalu_b200/csrc/box4_tile.cuh compiled as plain
-// C++): the phases are executed thread by thread with the kernel's own control flow
-// (assemble_box4.cu), the CTA barriers being the boundaries between the loops, and the assembled
-// CSR values / rhs are compared with the oracle's literal restatement of the reference on the
-// same mesh and state.  Covers 1 rank and both ranks of a 2-slab decomposition (shared-not-owned
-// rows, remote columns), several tile shapes and z chunkings.  Test scaffolding.
+// CPU emulation of the row-thread tiled kernel (nalu_b200/csrc/box5_tile.cuh compiled as plain C++):
+// the phases are executed thread by thread with the kernel's own control flow (assemble_box5.cu), the
+// CTA barriers being the boundaries between the loops and the quad shuffles explicit array exchanges,
+// and the assembled CSR values / rhs are compared with the oracle's literal restatement of the
+// reference on the same mesh and state.  Covers 1-3 ranks of a z-slab decomposition (shared-not-owned
+// rows, remote columns), z chunkings, options, overwrite / accumulate.  Test scaffolding.
 #define __host__
 #define __device__
 #define __forceinline__ inline
-#include "../../nalu_b200/csrc/box4_tile.cuh"
+#include "../../nalu_b200/csrc/box5_tile.cuh"
 #include "../../nalu_b200/csrc/graph.h"
 #include "../../oracle/nalu_oracle.h"
 #include <cmath>
@@ -76,24 +76,85 @@ static RankMesh make_rank(int nx, int ny, int nzg, int rank, int nranks)
 }
 
 
-using C2 = box2::Cfg;
 
-static int g_align_fail = 0;
-// copy_staged_warp of assemble_box4.cu
-static void copy_staged_host(const BoxParams &P, double *sm, const box4::Row &N, const box4::RunW (&runs)[32])
+using C5 = box5::Cfg;
+
+// finalize of one dz group for all lanes of the CTA (the device does the exchange with quad shuffles)
+static void finalize_all(std::vector<box5::Thr> &N, double *sm, int slot, std::vector<double (*)[3]> &acc, double f23)
 {
-  const double *S = box4::warp_slice(sm, N);
-  for (int r = 0; r < 32; ++r)
-    for (int lane = 0; lane < 32; ++lane)
-      if (lane < runs[r].L) {
-        double *d = P.values + runs[r].G + lane;
-        *d = P.overwrite ? S[r * 27 + lane] : *d + S[r * 27 + lane];
-      }
+  const int NT = C5::NT;
+  std::vector<double> T(NT * 3, 0.0), D(NT * 9, 0.0);
+  for (int tid = 0; tid < NT; ++tid) {
+    double t[3] = {0, 0, 0};
+    if (f23 != 0.0) box5::fin_transposed(N[tid], sm, box5::vel_off(N[tid], slot), *(double(*)[9][3])acc[tid], t);
+    for (int k = 0; k < 3; ++k) T[tid * 3 + k] = t[k];
+    for (int c = 0; c < 9; ++c) D[tid * 9 + c] = acc[tid][c][0];
+  }
+  for (int tid = 0; tid < NT; ++tid) {
+    const int q = tid & ~3, i = N[tid].i;
+    double d[9];
+    for (int c = 0; c < 9; ++c) d[c] = D[(q | 3) * 9 + c];
+    const double t1 = T[(q | ((i + 2) % 3)) * 3 + 1], t2 = T[(q | ((i + 1) % 3)) * 3 + 2];
+    box5::fin_apply(N[tid], sm, box5::vel_off(N[tid], slot), *(double(*)[9][3])acc[tid], d, T[tid * 3], t1, t2, f23);
+  }
 }
 
-static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *rhs, bool bulk)
+// output of one dz group for all warps
+static void output_all(const BoxParams &P, std::vector<box5::Thr> &N, const box5::Meta &M, int g, double *sm,
+                       std::vector<double (*)[3]> &acc, int x0, int y0, int z)
 {
-  using C = C2;
+  for (int warp = 0; warp < 4; ++warp) {
+    double *scr = sm + C5::OFF_SCR + warp * C5::SCRW;
+    for (int k = 0; k < C5::SCRW; ++k) scr[k] = NAN;
+    const bool natural = box5::line_natural(M, warp);
+    const int n0 = C5::TBX * warp;
+    if (natural) {
+      for (int lane = 0; lane < 32; ++lane) box5::out_stage_natural(N[warp * 32 + lane], scr, *(double(*)[9][3])acc[warp * 32 + lane]);
+      double *base = P.values + M.rowbase(n0) + 3 * M.s0(n0, g);
+      for (int lane = 0; lane < 27; ++lane)
+        for (int r = 0; r < 24; ++r) {
+          double *dst = base + lane + (r / 3) * 243 + (r % 3) * 81;
+          const double v = scr[r * 27 + lane];
+          *dst = P.overwrite ? v : *dst + v;
+        }
+    } else {
+      long long G[32];
+      int L[32];
+      for (int lane = 0; lane < 32; ++lane) {
+        const box5::Thr &n = N[warp * 32 + lane];
+        G[lane] = 0; L[lane] = 0;
+        if (n.i < 3 && n.active) {
+          const unsigned char *sl = P.slot27 + 27 * ((x0 + n.lx) + (long long)P.NX * ((y0 + n.ly) + (long long)P.NY * z));
+          box5::out_stage_slots(n, M, sl, g, scr, *(double(*)[9][3])acc[warp * 32 + lane]);
+          G[lane] = box5::run_first(M, n.node, n.i, g);
+          L[lane] = 3 * M.cnt(n.node, g);
+        }
+      }
+      for (int r = 0; r < 24; ++r) {
+        const int src = (r / 3) * 4 + r % 3;
+        for (int lane = 0; lane < L[src]; ++lane) {
+          double *dst = P.values + G[src] + lane;
+          const double v = scr[r * 27 + lane];
+          *dst = P.overwrite ? v : *dst + v;
+        }
+      }
+    }
+  }
+}
+
+static void p1_phase(const BoxParams &P, bool do_face, int top, bool do_z, int x0, int y0, const double *pl0, const double *pl1,
+                     const double *mdb, double *rec)
+{
+  for (int tid = 0; tid < C5::NT; ++tid) {
+    if (tid < 64) {
+      if (do_face && tid < C5::NEL) box5::p1_face_unit(P, tid, top, x0, y0, pl0, pl1, mdb, rec);
+    } else if (do_z && tid - 64 < C5::NEL) box5::p1_z_unit(P, tid - 64, x0, y0, pl0, pl1, mdb, rec);
+  }
+}
+
+static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *rhs, bool)
+{
+  using C = C5;
   BoxParams P = P0;
   P.values = values;
   P.rhs = rhs;
@@ -106,135 +167,79 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
   constexpr int NT = C::NT;
   double *sm = nullptr;
   if (posix_memalign((void **)&sm, 16, sizeof(double) * C::SMEM_DOUBLES)) abort();
-  struct Th { box4::Row N; double acc[18][3], dm[18], rr; };
-  std::vector<Th> T(NT);
-  box2::P2K K;
-  box2::p2k_init(K, P.options, P.include_divu);
+  std::vector<box5::Thr> N(NT);
+  std::vector<double> acc2s(NT * 27);
+  std::vector<double (*)[3]> a1(NT), a2(NT);
+  box5::P2K K;
+  box5::p2k_init(K, P.options, P.include_divu);
   for (int cta = 0; cta < P.tiles_x * P.tiles_y * zchunks; ++cta) {
     for (int i = 0; i < C::SMEM_DOUBLES; ++i) sm[i] = NAN; // uninitialised shared memory must never be consumed
-    for (int i = 0; i < 2 * C::NEL * C::ES; ++i) sm[C::OFF_F + i] = 0.0;
-    double *F = sm + C::OFF_F, *ZE = sm + C::OFF_ZE;
-    double *ring = sm + C::OFF_RING, *mdb = sm + C::OFF_MD;
+    double *rec = sm + C::OFF_REC, *ring = sm + C::OFF_RING, *mdb = sm + C::OFF_MD;
+    for (int i = 0; i < C::NEL * C::ES; ++i) rec[i] = 0.0; // kernel prologue
     const int ntile = P.tiles_x * P.tiles_y;
     const int tile = cta % ntile, zc = cta / ntile;
     const int x0 = (tile % P.tiles_x) * C::TBX, y0 = (tile / P.tiles_x) * C::TBY;
-    const int zs = zc * P.z_chunk;
-    const int ze = (zs + P.z_chunk < P.NZ) ? zs + P.z_chunk : P.NZ;
+    const int zs = P.z_first + zc * P.z_chunk;
+    const int ze = (zs + P.z_chunk < P.z_last) ? zs + P.z_chunk : P.z_last;
     for (int tid = 0; tid < NT; ++tid) {
-      box4::Row &N = T[tid].N;
-      N.node = tid & 31; N.lx = N.node % C::TBX; N.ly = N.node / C::TBX; N.i = tid >> 5;
+      box5::thr_init(P, N[tid], tid, x0, y0);
+      a1[tid] = N[tid].acc1;
+      a2[tid] = (double(*)[3])(acc2s.data() + tid * 27);
     }
     for (int tid = 0; tid < NT; ++tid) {
-      box2::stage_plane(P, ring + ((zs + 2) % 3) * C::PLN, tid, x0, y0, zs - 1);
-      box2::stage_plane(P, ring + (zs % 3) * C::PLN, tid, x0, y0, zs);
-      box2::stage_mdot(P, mdb, tid, x0, y0, zs - 1);
-      if ((tid >> 5) == 3) box2::meta_load(P, box2::meta_at(sm, zs & 1), tid & 31, x0, y0, zs);
+      box5::stage_plane(P, ring + ((zs + 2) % 3) * C::PLN, tid, x0, y0, zs - 1);
+      box5::stage_plane(P, ring + (zs % 3) * C::PLN, tid, x0, y0, zs);
+      box5::stage_plane(P, ring + ((zs + 1) % 3) * C::PLN, tid, x0, y0, zs + 1);
+      box5::stage_mdot(P, mdb, tid, x0, y0, zs - 1);
+      if ((tid >> 5) == 3) box5::meta_load(P, sm, zs & 1, tid & 31, x0, y0, zs);
     }
     // ---- barrier
-    if (zs >= 1)
-      for (int it = 0; it < 4 * C::NEL; ++it) {
-        const int k = it / C::NEL, el = it - k * C::NEL;
-        box2::p1_item(P, el, k < 2 ? k : 2, k < 2 ? 1 : k - 2, x0, y0, ring + ((zs - 1) % 3) * C::PLN,
-                      ring + (zs % 3) * C::PLN, mdb, F, ZE);
-      }
-    for (int tid = 0; tid < NT; ++tid) box2::stage_plane(P, ring + ((zs + 1) % 3) * C::PLN, tid, x0, y0, zs + 1);
+    if (zs >= 1) p1_phase(P, true, 1, true, x0, y0, ring + ((zs - 1) % 3) * C::PLN, ring + (zs % 3) * C::PLN, mdb, rec);
     // ---- barrier
     for (int z = zs; z < ze; ++z) {
-      const box2::Meta M = box2::meta_at(sm, z & 1);
-      const double *pl_0 = ring + (z % 3) * C::PLN, *pl_p = ring + ((z + 1) % 3) * C::PLN;
+      const box5::Meta M = box5::meta_at(sm, z & 1);
       const bool lower = z >= 1, upper = z < P.nz;
-      // ---- A1
-      for (int tid = 0; tid < NT; ++tid) box2::stage_mdot(P, mdb, tid, x0, y0, z);
+      // ---- A
+      for (int tid = 0; tid < NT; ++tid) box5::stage_mdot(P, mdb, tid, x0, y0, z);
+      if (lower) {
+        for (int tid = 0; tid < NT; ++tid) {
+          for (int k = 0; k < 27; ++k) acc2s[tid * 27 + k] = 0.0;
+          box5::sweep_half(N[tid], sm, K, 0, N[tid].acc1, *(double(*)[9][3])a2[tid]);
+        }
+        finalize_all(N, sm, (z + 2) % 3, a2, K.f23);
+        output_all(P, N, M, 0, sm, a2, x0, y0, z);
+      }
+      // ---- barrier; B
+      if (upper) p1_phase(P, true, 0, true, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, rec);
+      // ---- barrier; C
       for (int tid = 0; tid < NT; ++tid) {
-        Th &t = T[tid];
-        t.rr = 0.0;
-        for (int c = 0; c < 18; ++c) t.acc[c][0] = t.acc[c][1] = t.acc[c][2] = t.dm[c] = 0.0;
-        if (!lower) continue;
-        if (t.N.i < 3) {
-          box4::half_rows<0>(sm, t.N, K, t.acc);
-          box4::exchange_put_row<0>(sm, t.N, t.acc, z);
-        } else {
-          box4::half_adv<0>(sm, t.N, K, t.dm);
-          box4::exchange_put_adv(sm, t.N, t.dm);
-        }
+        for (int k = 0; k < 27; ++k) acc2s[tid * 27 + k] = 0.0;
+        if (upper) box5::sweep_half(N[tid], sm, K, 1, N[tid].acc1, *(double(*)[9][3])a2[tid]);
       }
-      // ---- barrier; A2 + B
-      for (int w = 0; w < 3; ++w) {
-        box4::RunW runs[32];
-        for (int tid = 32 * w; tid < 32 * w + 32; ++tid) {
-          Th &t = T[tid];
-          if (lower) {
-            box4::finalize_row<0>(sm, t.N, t.acc, t.rr, K.f23, z);
-            if (bulk) runs[tid & 31] = box4::stage_group(sm, M, t.N, 0, 9, t.acc);
-            else box4::store_group(P, M, t.N, 0, 9, t.acc);
-          } else {
-            for (int c = 0; c < 9; ++c) t.acc[c][0] = t.acc[c][1] = t.acc[c][2] = 0.0;
-          }
-        }
-        if (lower && bulk) copy_staged_host(P, sm, T[32 * w].N, runs);
-        for (int tid = 32 * w; tid < 32 * w + 32; ++tid) box4::park(sm, T[tid].N, T[tid].acc, T[tid].rr);
+      finalize_all(N, sm, z % 3, a1, K.f23);
+      output_all(P, N, M, 1, sm, a1, x0, y0, z);
+      if (upper) {
+        finalize_all(N, sm, (z + 1) % 3, a2, K.f23);
+        output_all(P, N, M, 2, sm, a2, x0, y0, z);
       }
-      if (upper)
-        for (int it = 0; it < C::NP1A; ++it) {
-          const int k = it / C::NEL, el = it - k * C::NEL;
-          box2::p1_item(P, el, k < 2 ? k : 2, k < 2 ? 0 : k - 2, x0, y0, pl_0, pl_p, mdb, F, ZE);
+      for (int tid = 0; tid < NT; ++tid) {
+        box5::Thr &n = N[tid];
+        if (n.i < 3 && n.active) {
+          double *r = P.rhs + (long long)M.row(n.node) * 3 + n.i;
+          *r = P.overwrite ? n.rr : *r + n.rr;
+          if (P.overwrite && !box5::line_natural(M, n.ly)) box5::zero_uncovered(M, n.node, n.i, P.values);
         }
+        for (int c = 0; c < 9; ++c) n.acc1[c][0] = n.acc1[c][1] = n.acc1[c][2] = 0.0;
+        n.rr = 0.0;
+      }
+      // ---- barrier; D
+      if (upper && z + 1 < ze) p1_phase(P, true, 1, false, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, rec);
       if (z + 1 < ze)
-        for (int tid = 0; tid < 32; ++tid) box2::meta_load(P, box2::meta_at(sm, (z + 1) & 1), tid, x0, y0, z + 1);
-      // the exchange buffer is rewritten by C1: poison it so that stale reads show
-      for (int i = 0; i < 4 * 18 * C::NNODE + 9 * C::NNODE; ++i) sm[box4::OFF_EX + i] = NAN;
-      // ---- barrier; C1
-      for (int tid = 0; tid < NT; ++tid) {
-        Th &t = T[tid];
-        t.rr = 0.0;
-        for (int c = 0; c < 18; ++c) t.acc[c][0] = t.acc[c][1] = t.acc[c][2] = t.dm[c] = 0.0;
-        if (!upper) continue;
-        if (t.N.i < 3) {
-          box4::half_rows<1>(sm, t.N, K, t.acc);
-          box4::exchange_put_row<1>(sm, t.N, t.acc, z);
-        } else {
-          box4::half_adv<1>(sm, t.N, K, t.dm);
-          box4::exchange_put_adv(sm, t.N, t.dm);
+        for (int lane = 0; lane < 32; ++lane) {
+          box5::meta_load(P, sm, (z + 1) & 1, lane, x0, y0, z + 1);
+          box5::stage_plane(P, ring + ((z + 2) % 3) * C::PLN, lane, x0, y0, z + 2);
+          box5::stage_plane(P, ring + ((z + 2) % 3) * C::PLN, lane + 32, x0, y0, z + 2);
         }
-      }
-      // ---- barrier; C2 + D
-      for (int tid = 0; tid < NT; ++tid) box2::stage_plane(P, ring + ((z + 2) % 3) * C::PLN, tid, x0, y0, z + 2);
-      for (int w = 0; w < 3; ++w) {
-        box4::RunW runs[32];
-        for (int tid = 32 * w; tid < 32 * w + 32; ++tid) {
-          Th &t = T[tid];
-          if (upper) box4::finalize_row<1>(sm, t.N, t.acc, t.rr, K.f23, z);
-          box4::unpark_add(sm, t.N, t.acc, t.rr);
-          if (!bulk) {
-            box4::store_group(P, M, t.N, 1, 0, t.acc);
-            if (upper) box4::store_group(P, M, t.N, 2, 9, t.acc);
-          }
-        }
-        if (bulk) {
-          for (int k = 0; k < box4::PARKN * C::NNODE; ++k) box4::warp_slice(sm, T[32 * w].N)[k] = NAN;
-          for (int tid = 32 * w; tid < 32 * w + 32; ++tid) runs[tid & 31] = box4::stage_group(sm, M, T[tid].N, 1, 0, T[tid].acc);
-          copy_staged_host(P, sm, T[32 * w].N, runs);
-          if (upper) {
-            for (int tid = 32 * w; tid < 32 * w + 32; ++tid) runs[tid & 31] = box4::stage_group(sm, M, T[tid].N, 2, 9, T[tid].acc);
-            copy_staged_host(P, sm, T[32 * w].N, runs);
-          }
-        }
-      }
-      for (int tid = 0; tid < 96; ++tid) {
-        Th &t = T[tid];
-        const int lane = tid & 31, warp = tid >> 5;
-        if (P.overwrite) box2::zero_uncovered(M, lane, warp, P.values);
-        if (M.cnt[lane * 4 + 1]) {
-          double *r = P.rhs + (long long)M.row[lane] * 3 + warp;
-          *r = P.overwrite ? t.rr : *r + t.rr;
-        }
-      }
-      if (upper)
-        for (int it = 0; it < C::NP1B; ++it) {
-          const int k = it / C::NEL, el = it - k * C::NEL;
-          box2::p1_item(P, el, k, 1, x0, y0, pl_0, pl_p, mdb, F, ZE);
-        }
-      for (int i = 0; i < C::NNODE * 3 * box4::PARKN + 4 * 18 * C::NNODE + 9 * C::NNODE; ++i) sm[box4::OFF_PARK + i] = NAN;
       // ---- barrier
     }
   }
@@ -310,6 +315,7 @@ static double run_case(int nx, int ny, int nzg, int R, int z_chunk, int options,
     P.NX = nx + 1; P.NY = ny + 1; P.NZ = ms[r].nz + 1;
     P.coords = ms[r].coords.data(); P.vel = ms[r].vel.data(); P.visc = ms[r].visc.data(); P.mdot = ms[r].mdot.data();
     P.node_row = g.node_row.data(); P.browptr = bp.data(); P.slot27 = slot27[r].data();
+    P.node_desc = (const unsigned long long *)g.node_desc.data();
     int errflag = 0;
     P.err = &errflag;
     P.include_divu = include_divu; P.options = options; P.overwrite = overwrite;
@@ -358,18 +364,18 @@ int main()
   const Case cases[] = {
       {1, 1, 1, 1, 16, 0, 0.0, 1},  {2, 3, 2, 1, 16, 0, 1.0, 1},  {7, 5, 4, 1, 2, 0, 1.0, 1},
       {13, 9, 5, 1, 3, NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC, 1.0, 1},
-      {6, 4, 6, 2, 16, 0, 1.0, 1},  {9, 7, 5, 2, 2, NALU_OPT_SKEW_SYMMETRIC, 0.0, 0},
-      {5, 5, 7, 3, 1, NALU_OPT_SHIFTED_GRAD_OP, 1.0, 1}, {17, 8, 3, 1, 16, 0, 1.0, 0},
+      {6, 4, 6, 2, 16, 0, 1.0, 1},  {9, 7, 5, 2, 2, 0, 0.0, 0},
+      {5, 5, 7, 3, 1, NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC, 1.0, 1}, {17, 8, 3, 1, 16, 0, 1.0, 0},
+      {20, 6, 4, 1, 16, 0, 1.0, 1},
   };
   for (const Case &c : cases) {
     const double e0 = run_case(c.nx, c.ny, c.nz, c.R, c.zc, c.opt, c.divu, c.ow, false);
-    const double e1 = run_case(c.nx, c.ny, c.nz, c.R, c.zc, c.opt, c.divu, c.ow, true);
-    printf("box4 %dx%dx%d ranks %d zchunk %d opt %d divu %.0f overwrite %d: relerr plain %.3e  bulk %.3e\n", c.nx, c.ny,
-           c.nz, c.R, c.zc, c.opt, c.divu, c.ow, e0, e1);
-    worst = fmax(worst, fmax(e0, e1));
+    printf("box5 %dx%dx%d ranks %d zchunk %d opt %d divu %.0f overwrite %d: relerr %.3e\n", c.nx, c.ny, c.nz, c.R, c.zc, c.opt,
+           c.divu, c.ow, e0);
+    worst = fmax(worst, e0);
   }
-  printf("worst %.3e  bulk alignment failures %d\n", worst, g_align_fail);
-  if (!(worst < 1e-12) || g_align_fail) {
+  printf("worst %.3e\n", worst);
+  if (!(worst < 1e-12)) {
     printf("FAIL\n");
     return 1;
   }

@@ -16,6 +16,14 @@ RTOL = 1.0e-12  # north_star: FP64 values within 1e-12 relative of the reference
 FLOOR = 1.0e-2  # relative-error denominator floor, as a fraction of the largest |entry| (see _compare_system)
 
 
+@pytest.fixture
+def tune():
+    """nalu_b200_tune knobs, restored to their defaults after the test."""
+    from nalu_b200 import lib
+    yield lib.tune
+    lib.tune(box_kernel=5, box_zchunk=0, split_lists=1, cont_tiled=1)
+
+
 def _cuda():
     if not torch.cuda.is_available():
         pytest.fail("CUDA device required: the assembly path has no CPU fallback")
@@ -485,29 +493,27 @@ def test_missing_device_pointer_is_an_error():
 
 
 # ---------------------------------------------------------------------------------------------
-# tiled write-once kernels (assemble_box2.cu, assemble_box.cu): tile shapes, z chunking, overwrite semantics, determinism
+# tiled write-once momentum kernels (assemble_box5.cu, assemble_box2.cu): z chunking, options, overwrite semantics, determinism
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tile", ["0", "0-plain-copy", "64", "84", "86"])
-@pytest.mark.parametrize("zchunk", ["1", "3", "0"])
-def test_box_kernel_tiles_and_chunks(tile, zchunk, monkeypatch):
-    # "0": the column-pair kernel (assemble_box2.cu, default) with cp.async.bulk row streaming,
-    # "0-plain-copy": the same with plain stores; "64"/"84"/"86": first-generation class kernel
-    monkeypatch.setenv("NALU_BOX_TILE", tile.split("-")[0])
-    if tile == "0-plain-copy":
-        monkeypatch.setenv("NALU_BOX_BULK", "0")
-    if zchunk != "0":
-        monkeypatch.setenv("NALU_BOX_ZCHUNK", zchunk)
-    m = perturbed_box(13, 9, 7)
+@pytest.mark.parametrize("kernel", [5, 2])
+@pytest.mark.parametrize("zchunk", [1, 3, 0])
+@pytest.mark.parametrize("options,divu", [(("skew_symmetric",), 1.0), ((), 1.0), (("shifted_grad_op", "skew_symmetric"), 1.0),
+                                          (("shifted_grad_op",), 0.0)])
+def test_box_kernel_tiles_and_chunks(kernel, zchunk, options, divu, tune):
+    # kernel 5: row-thread kernel (assemble_box5.cu, the default); 2: column-pair kernel (assemble_box2.cu), which also
+    # serves the option combinations the row-thread kernel does not take (it is then selected whatever the knob says)
+    tune(box_kernel=kernel, box_zchunk=zchunk)
+    m = perturbed_box(19, 9, 7)
     st = State(m)
     dev = st.to_device(_cuda())
     orc = oracle.LinSys([m], 3)
     keep = []
-    orc.assemble_elem(0, [oracle_desc(st, "momentum_adv_diff", ("skew_symmetric",), keep, include_divu=1.0)])
+    orc.assemble_elem(0, [oracle_desc(st, "momentum_adv_diff", options, keep, include_divu=divu)])
     ls = _linsys(m, 3)
     # overwrite mode must not depend on what the arrays held: no zeroSystem, poison instead
     ls.values.fill_(float("nan"))
     ls.rhs.fill_(float("nan"))
-    d = product_desc(ls, dev, "momentum_adv_diff", ("skew_symmetric",), include_divu=1.0)
+    d = product_desc(ls, dev, "momentum_adv_diff", options, include_divu=divu)
     assert ls.assemble_elem([d], mode="box", overwrite=True) == 2
     _compare_system(ls, orc)
     v1, r1 = ls.values.clone(), ls.rhs.clone()
@@ -523,29 +529,24 @@ def test_box_kernel_tiles_and_chunks(tile, zchunk, monkeypatch):
     assert ls.geometry_errors() == 0
 
 
-@pytest.mark.parametrize("zchunk", ["2", "0"])
-def test_box3_warp_specialised_kernel(zchunk, monkeypatch):
-    """assemble_box3.cu (experimental warp-specialised pipeline, NALU_BOX_KERNEL=3): same contract."""
-    monkeypatch.setenv("NALU_BOX_KERNEL", "3")
-    monkeypatch.setenv("NALU_BOX_TILE", "0")
-    if zchunk != "0":
-        monkeypatch.setenv("NALU_BOX_ZCHUNK", zchunk)
-    m = perturbed_box(13, 9, 7)
+def test_row_thread_and_column_pair_kernels_agree_64cubed(tune):
+    """The two tiled momentum kernels on a block with many interior (natural) x lines and every kind of boundary line."""
+    m = perturbed_box(67, 37, 21)
     st = State(m)
     dev = st.to_device(_cuda())
-    orc = oracle.LinSys([m], 3)
-    keep = []
-    orc.assemble_elem(0, [oracle_desc(st, "momentum_adv_diff", ("shifted_grad_op",), keep, include_divu=1.0)])
     ls = _linsys(m, 3)
+    d = product_desc(ls, dev, "momentum_adv_diff", (), include_divu=1.0)
+    tune(box_kernel=2)
     ls.values.fill_(float("nan"))
     ls.rhs.fill_(float("nan"))
-    d = product_desc(ls, dev, "momentum_adv_diff", ("shifted_grad_op",), include_divu=1.0)
     assert ls.assemble_elem([d], mode="box", overwrite=True) == 2
-    _compare_system(ls, orc)
-    v1, r1 = ls.values.clone(), ls.rhs.clone()
-    ls.assemble_elem([d], mode="box", overwrite=False)
-    torch.testing.assert_close(ls.values, 2 * v1, rtol=1e-15, atol=0)
-    torch.testing.assert_close(ls.rhs, 2 * r1, rtol=1e-15, atol=0)
+    v2, r2 = ls.values.clone(), ls.rhs.clone()
+    tune(box_kernel=5)
+    ls.values.fill_(float("nan"))
+    ls.rhs.fill_(float("nan"))
+    assert ls.assemble_elem([d], mode="box", overwrite=True) == 2
+    assert float((ls.values - v2).abs().max() / v2.abs().max()) < 1e-14
+    assert float((ls.rhs - r2).abs().max() / r2.abs().max()) < 1e-13
     assert ls.geometry_errors() == 0
 
 
@@ -647,9 +648,8 @@ def test_dirichlet_and_reset_rows(ndof, nranks):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("zchunk", [0, 1, 5])
 @pytest.mark.parametrize("options", [(), ("shift_mdot",), ("reduced_sens",), ("shift_poisson", "reduced_sens")])
-def test_cont_box_kernel_options_and_chunks(options, zchunk, monkeypatch):
-    if zchunk:
-        monkeypatch.setenv("NALU_BOX_ZCHUNK", str(zchunk))
+def test_cont_box_kernel_options_and_chunks(options, zchunk, tune):
+    tune(box_zchunk=zchunk)
     m = perturbed_box(33, 16, 9)  # more than two tiles in x and y, partial tiles at the far sides
     st = State(m)
     dev = st.to_device(_cuda())
@@ -693,9 +693,8 @@ def test_cont_box_matches_general_kernel_96cubed():
 @pytest.mark.parametrize("kind,options", [("scalar_adv_diff", ()), ("scalar_adv_diff", ("skew_symmetric",)),
                                           ("scalar_adv_diff", ("shifted_grad_op", "skew_symmetric")),
                                           ("scalar_diff", ()), ("scalar_diff", ("shifted_grad_op",))])
-def test_scalar_box_kernel_options_and_chunks(kind, options, zchunk, monkeypatch):
-    if zchunk:
-        monkeypatch.setenv("NALU_BOX_ZCHUNK", str(zchunk))
+def test_scalar_box_kernel_options_and_chunks(kind, options, zchunk, tune):
+    tune(box_zchunk=zchunk)
     m = perturbed_box(33, 16, 9)
     st = State(m)
     dev = st.to_device(_cuda())
@@ -711,35 +710,6 @@ def test_scalar_box_kernel_options_and_chunks(kind, options, zchunk, monkeypatch
     v1, r1 = ls.owned_values().clone(), ls.owned_rhs().clone()
     assert ls.assemble_elem([product_desc(ls, dev, kind, options)], mode="auto", overwrite=False) == 2
     assert torch.equal(ls.owned_values(), 2 * v1) and torch.equal(ls.owned_rhs(), 2 * r1)
-
-
-@pytest.mark.parametrize("zchunk", ["2", "0"])
-@pytest.mark.parametrize("options,divu", [((), 1.0), (("shifted_grad_op", "skew_symmetric"), 1.0), (("skew_symmetric",), 0.0)])
-def test_box4_row_thread_kernel(options, divu, zchunk, monkeypatch):
-    """assemble_box4.cu (row-thread phase 2, NALU_BOX_KERNEL=4): same contract as the column-pair kernel."""
-    monkeypatch.setenv("NALU_BOX_KERNEL", "4")
-    monkeypatch.setenv("NALU_BOX_TILE", "0")
-    if zchunk != "0":
-        monkeypatch.setenv("NALU_BOX_ZCHUNK", zchunk)
-    m = perturbed_box(19, 9, 7)
-    st = State(m)
-    dev = st.to_device(_cuda())
-    orc = oracle.LinSys([m], 3)
-    keep = []
-    orc.assemble_elem(0, [oracle_desc(st, "momentum_adv_diff", options, keep, include_divu=divu)])
-    ls = _linsys(m, 3)
-    ls.values.fill_(float("nan"))
-    ls.rhs.fill_(float("nan"))
-    d = product_desc(ls, dev, "momentum_adv_diff", options, include_divu=divu)
-    assert ls.assemble_elem([d], mode="box", overwrite=True) == 2
-    _compare_system(ls, orc)
-    assert ls.geometry_errors() == 0
-    v1, r1 = ls.values.clone(), ls.rhs.clone()
-    ls.assemble_elem([d], mode="box", overwrite=False)
-    torch.testing.assert_close(ls.values, 2 * v1, rtol=1e-15, atol=0)
-    torch.testing.assert_close(ls.rhs, 2 * r1, rtol=1e-15, atol=0)
-    ls.assemble_elem([d], mode="box", overwrite=True)
-    assert torch.equal(ls.values, v1) and torch.equal(ls.rhs, r1)  # bit-reproducible
 
 
 @pytest.mark.parametrize("options", [(), ("shift_mdot",), ("shift_poisson",), ("shift_mdot", "shift_poisson")])
