@@ -4,9 +4,10 @@
 // two CTAs per SM.  Per node plane z a CTA runs
 //   A  lower half: the 4 elements below every node (top-face + z-edge points of layer z-1): dz=-1 group finished,
 //      written out; dz=0 group half done (stays in registers)
-//   B  phase 1a: bottom-face + z-edge points of layer z
+//   B  phase 1a: bottom-face + z-edge points of layer z (face units on warps 0-1, z units on warps 2-3)
 //   C  upper half: dz=0 and dz=+1 groups finished, written out; rhs
-//   D  phase 1b: top-face points of layer z  ||  metadata of plane z+1, field prefetch of plane z+2
+//   D  phase 1b: top-face points of layer z (x-edge pairs on warps 0-1, y-edge pairs on warps 2-3), metadata of plane
+//      z+1, field prefetch of plane z+2
 // with one CTA barrier between consecutive phases; inside A and C a warp synchronises only with itself.
 #include "box5_tile.cuh"
 #include "internal.h"
@@ -24,17 +25,20 @@ constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 
-// diagonal term + rhs share of one finished dz group (box5_tile.cuh, fin_*), quad exchange by shuffles
-__device__ __forceinline__ void finalize_group(box5::Thr &N, const double *sm, int uoff, double (&acc)[9][3], double f23, int lane)
+// diagonal term + rhs share of one finished dz group (box5_tile.cuh, fin_apply), quad exchange by shuffles
+__device__ __forceinline__ void finalize_group(const box5::Thr &N, const double *sm, int uoff, double (&acc)[9][3], double &rr,
+                                               double f23, int lane)
 {
-  double T[3] = {0.0, 0.0, 0.0};
-  if (f23 != 0.0) box5::fin_transposed(N, sm, uoff, acc, T);
-  double D[9];
+  double D[9], T[3];
 #pragma unroll
   for (int c = 0; c < 9; ++c) D[c] = shfl_d(acc[c][0], lane | 3);
-  const int q = lane & ~3;
-  const double t1 = shfl_d(T[1], q | ((N.i + 2) % 3)), t2 = shfl_d(T[2], q | ((N.i + 1) % 3));
-  box5::fin_apply(N, sm, uoff, acc, D, T[0], t1, t2, f23);
+  const double r = box5::fin_apply(N, sm, uoff, acc, D, T);
+  double t = 0.0;
+  if (f23 != 0.0) {
+    const int q = lane & ~3;
+    t = T[0] + shfl_d(T[1], q | ((N.i + 2) % 3)) + shfl_d(T[2], q | ((N.i + 1) % 3));
+  }
+  rr += f23 * t - r;
 }
 
 // the 24 runs (8 nodes x 3 dof rows) of dz group g of the warp's x line: registers -> warp scratch -> CSR
@@ -82,18 +86,6 @@ __device__ __forceinline__ void output_group(const box5::Thr &N, const box5::Met
   }
 }
 
-// phase 1: warps 0-1 take the face units (threads 0..44), warps 2-3 the z units (threads 64..108): no warp runs both
-__device__ __forceinline__ void p1_phase(const BoxParams &P, bool do_face, int top, bool do_z, int x0, int y0, const double *pl0,
-                                         const double *pl1, const double *mdb, double *rec)
-{
-  const int tid = threadIdx.x;
-  if (tid < 64) {
-    if (do_face && tid < C5::NEL) box5::p1_face_unit(P, tid, top, x0, y0, pl0, pl1, mdb, rec);
-  } else {
-    if (do_z && tid - 64 < C5::NEL) box5::p1_z_unit(P, tid - 64, x0, y0, pl0, pl1, mdb, rec);
-  }
-}
-
 template <bool OW>
 __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_constant__ BoxParams P)
 {
@@ -107,17 +99,18 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
   const int zs = P.z_first + zc * P.z_chunk;
   const int ze = (zs + P.z_chunk < P.z_last) ? zs + P.z_chunk : P.z_last;
 
-  box5::Thr N;
-  box5::thr_init(P, N, tid, x0, y0);
-  box5::P2K Kc;
-  box5::p2k_init(Kc, P.options, P.include_divu);
+  // what lives across phases: the dz=0 group between the two halves of a plane (across phase 1a), the rhs of dof row i.
+  // The accumulators are given their zeros right before the sweep, never after the output: a value that stays live
+  // across phase 1, even as zero, costs phase 1 its registers (measured: it ends up in local memory).
+  double acc1[9][3], rr = 0.0;
 
   // records of elements outside the domain are never written: they must read zero (phase 2 does not test)
   for (int i = tid; i < C5::NEL * C5::ES; i += C5::NT) rec[i] = 0.0;
-  // ---- prologue: node planes zs-1 .. zs+1, the top-face / z-edge points of the layer below the first plane
-  box5::stage_plane(P, ring + ((zs + 2) % 3) * C5::PLN, tid, x0, y0, zs - 1);
-  box5::stage_plane(P, ring + (zs % 3) * C5::PLN, tid, x0, y0, zs);
-  box5::stage_plane(P, ring + ((zs + 1) % 3) * C5::PLN, tid, x0, y0, zs + 1);
+  // ---- prologue: node planes zs-1 .. zs+1, the mass flow rates of the layer below the first plane
+  if (warp < 3) {
+    box5::stage_plane(P, ring + ((zs + 2 + warp) % 3) * C5::PLN, lane, x0, y0, zs - 1 + warp);
+    box5::stage_plane(P, ring + ((zs + 2 + warp) % 3) * C5::PLN, lane + 32, x0, y0, zs - 1 + warp);
+  }
   box5::stage_mdot(P, mdb, tid, x0, y0, zs - 1);
   if (warp == 3) box5::meta_load(P, sm, zs & 1, lane, x0, y0, zs);
   box5::stage_wait();
@@ -130,52 +123,65 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
   for (int hs = zs >= 1 ? 2 * zs - 1 : 2 * zs; hs < 2 * ze; ++hs) {
     const int z = hs >> 1, H = hs & 1;
     const bool lead = hs < 2 * zs;
-    const box5::Meta M = box5::meta_at(sm, z & 1);
     const bool lower = z >= 1, upper = z < P.nz;
     if (!lead) {
+      const box5::Thr N = box5::thr_make(P, tid, x0, y0);
+      const box5::Meta M = box5::meta_at(sm, z & 1);
       const bool act = H ? upper : lower;
-      // is the warp's x line stored back to back in lattice order?  (then the runs of a group sit at fixed offsets)
-      const bool natural = __all_sync(FULL, box5::node_in_natural_line(M, N.node));
-      const unsigned char *sl = P.slot27 + 27 * ((x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z));
       // ---- A (H = 0): dz=-1 group finished, dz=0 half done / C (H = 1): dz=0 and dz=+1 groups finished, rhs
-      if (!H) box5::stage_mdot(P, mdb, tid, x0, y0, z); // lands while the lower half is computed
+      if (!H) {
+        box5::stage_mdot(P, mdb, tid, x0, y0, z); // lands while the lower half is computed
+#pragma unroll
+        for (int c = 0; c < 9; ++c) acc1[c][0] = acc1[c][1] = acc1[c][2] = 0.0;
+      }
       double acc2[9][3];
 #pragma unroll
       for (int c = 0; c < 9; ++c) acc2[c][0] = acc2[c][1] = acc2[c][2] = 0.0;
-      if (act) box5::sweep_half(N, sm, Kc, H, N.acc1, acc2);
+      if (act) box5::sweep_half(N, sm, P, H, acc1, acc2);
+      // is the warp's x line stored back to back in lattice order?  (then the runs of a group sit at fixed offsets)
+      const bool natural = __all_sync(FULL, box5::node_in_natural_line(M, N.node));
+      const unsigned char *sl = P.slot27 + 27 * ((x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z));
       if (H) {
-        finalize_group(N, sm, box5::vel_off(N, z % 3), N.acc1, Kc.f23, lane);
-        output_group<OW>(N, M, sl, 1, natural, scr, N.acc1, P.values, lane);
+        finalize_group(N, sm, box5::vel_off(N, z % 3), acc1, rr, P.f23, lane);
+        output_group<OW>(N, M, sl, 1, natural, scr, acc1, P.values, lane);
       }
       if (act) {
-        finalize_group(N, sm, box5::vel_off(N, (z + (H ? 1 : 2)) % 3), acc2, Kc.f23, lane);
+        finalize_group(N, sm, box5::vel_off(N, (z + (H ? 1 : 2)) % 3), acc2, rr, P.f23, lane);
         output_group<OW>(N, M, sl, H ? 2 : 0, natural, scr, acc2, P.values, lane);
       }
       if (H) {
         if (N.i < 3 && N.active) {
           double *r = P.rhs + (long long)M.row(N.node) * 3 + N.i;
-          *r = OW ? N.rr : *r + N.rr;
-          if (OW && !natural) box5::zero_uncovered(M, N.node, N.i, P.values);
+          *r = OW ? rr : *r + rr;
+          if (OW && !M.natural(N.node)) box5::zero_uncovered(M, N.node, N.i, P.values);
         }
-#pragma unroll
-        for (int c = 0; c < 9; ++c) N.acc1[c][0] = N.acc1[c][1] = N.acc1[c][2] = 0.0;
-        N.rr = 0.0;
+        rr = 0.0;
       } else {
         box5::stage_wait();
       }
       __syncthreads();
     }
-    // ---- B (H = 0): phase 1a: bottom-face + z-edge points of layer z / D (H = 1): phase 1b: top-face points of
-    //      layer z (+ its z-edge points in the leading iteration), metadata of the next plane, field prefetch
-    if (upper && (!H || z + 1 < ze))
-      p1_phase(P, true, H, !H || lead, x0, y0, ring + (z % 3) * C5::PLN, ring + ((z + 1) % 3) * C5::PLN, mdb, rec);
-    if (H && z + 1 < ze && !lead) {
-      if (warp == 3) box5::meta_load(P, sm, (z + 1) & 1, lane, x0, y0, z + 1);
-      if (warp == 2) {
-        // node plane z+2 -> the ring slot of plane z-1 (dead since the dz=-1 group was finalized)
-        box5::stage_plane(P, ring + ((z + 2) % 3) * C5::PLN, lane, x0, y0, z + 2);
-        box5::stage_plane(P, ring + ((z + 2) % 3) * C5::PLN, lane + 32, x0, y0, z + 2);
+    // ---- B (H = 0) / leading iteration: phase 1a: the face units of layer z (bottom face; top face in the leading
+    //      iteration) on warps 0-1, its z units on warps 2-3: no warp runs both
+    //      D (H = 1): phase 1b: top-face points of layer z, x-edge pairs on warps 0-1, y-edge pairs on warps 2-3;
+    //      metadata of the next plane, field prefetch
+    if (upper) {
+      const double *pl0 = ring + (z % 3) * C5::PLN, *pl1 = ring + ((z + 1) % 3) * C5::PLN;
+      const int t = tid & 63;
+      if (!H || lead) {
+        if (tid < 64) {
+          if (t < C5::NEL) box5::p1_face_unit(P, t, lead ? 1 : 0, x0, y0, pl0, pl1, mdb, rec);
+        } else if (t < C5::NEL) box5::p1_z_unit(P, t, x0, y0, pl0, pl1, mdb, rec);
+      } else if (z + 1 < ze) {
+        if (tid < 64) {
+          if (t < C5::NEL) box5::p1_face_half<0>(P, t, 1, x0, y0, pl0, pl1, mdb, rec);
+        } else if (t < C5::NEL) box5::p1_face_half<1>(P, t, 1, x0, y0, pl0, pl1, mdb, rec);
       }
+    }
+    if (H && !lead && z + 1 < ze) {
+      if (warp == 3) box5::meta_load(P, sm, (z + 1) & 1, lane, x0, y0, z + 1);
+      // node plane z+2 -> the ring slot of plane z-1 (dead since the dz=-1 group was finalized)
+      if (warp == 1 || warp == 2) box5::stage_plane(P, ring + ((z + 2) % 3) * C5::PLN, lane + 32 * (warp - 1), x0, y0, z + 2);
     }
     __syncthreads();
   }
@@ -190,6 +196,7 @@ int launch_assemble_box5(BoxParams &P, cudaStream_t stream)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  box5::p2k_init(P);
   P.tiles_x = (P.NX + C5::TBX - 1) / C5::TBX;
   P.tiles_y = (P.NY + C5::TBY - 1) / C5::TBY;
   const long long ntile = (long long)P.tiles_x * P.tiles_y;

@@ -10,7 +10,9 @@
 //   * a CTA (128 threads) owns an 8 x 4 column of nodes and sweeps z; a warp owns one x line of 8 nodes, a node is
 //     served by a QUAD of lanes: lane i = 0..2 keeps dof row i of the node's blocks in registers, lane 3 keeps the
 //     diagonal term D_c = sum tau (N_c mdot + h_c . A) of every block (MomentumAdvDiffElemKernel.C:160-176);
-//     all four run ONE instruction stream: lane 3 reads the row B' = G~^T A -+ mdot/2 and the "area vector" (1,*,*);
+//     all four run ONE instruction stream: lane 3 reads the row B' = G~^T A -+ mdot/2 and the "area vector" (1,*,*).
+//     (A variant with two quads per node, one per column plane, 27 accumulators and 16 warps per SM was measured in
+//     round 2: both quads load the same records, the shared-memory pipe -- already 70 % busy -- saturates, no gain);
 //   * per (integration point, column node) a lane spends 6 FMAs: h = G~_i . (tau dN_c/dxi) (3), acc[c][.] += h A (3);
 //     all shape-function derivatives are compile-time signs times 7 run-time magnitudes, quadrants / points / columns
 //     are unrolled, the lower / upper z half differ in a run-time sign only (one copy of the code);
@@ -47,14 +49,17 @@ struct Cfg {
   // B_t + mdot/2, A[3] (along +t), 1.0
   static constexpr int REC = 17;
   static constexpr int ES = 8 * REC + 4; // element stride: 4 face points, 4 z-edge points; = 12 mod 16 (bank spread)
-  static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY, NF = 8, PLN = RN * NF; // x y z mu | u v w -
+  // staged node plane: geometry part [RN][6] = x y z mu - - (48-byte stride: the 16-byte loads of 8 consecutive
+  // elements cover all banks), velocity part [RN][3] (the quads of a warp read 24 consecutive doubles)
+  static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY, GEO = 6, VEL = 3, OFF_VEL = RN * GEO, PLN = RN * (GEO + VEL);
   static constexpr int SCRW = 24 * 27; // doubles of scratch per warp: 24 runs of 27
+  static constexpr int NWARP = NT / 32;
   static constexpr int MDB = NEL * 12;
-  // shared-memory map (doubles)
-  static constexpr int OFF_REC = 0, OFF_SCR = OFF_REC + NEL * ES, OFF_RING = OFF_SCR + 4 * SCRW, OFF_MD = OFF_RING + 3 * PLN,
-                       OFF_META = OFF_MD + MDB;
   // node metadata of one plane = the graph's row descriptors (graph.h, node_desc) of the tile's 32 nodes: [3][32] words
   static constexpr int META = 3 * NNODE;
+  // shared-memory map (doubles)
+  static constexpr int OFF_REC = 0, OFF_SCR = OFF_REC + NEL * ES, OFF_RING = OFF_SCR + NWARP * SCRW, OFF_MD = OFF_RING + 3 * PLN,
+                       OFF_META = OFF_MD + MDB;
   static constexpr int SMEM_DOUBLES = OFF_META + 2 * META;
 };
 static_assert(Cfg::ES % 16 == 12, "element stride must spread the quads of a warp over the banks");
@@ -115,30 +120,31 @@ __host__ __device__ inline void stage_plane(const BoxParams &P, double *ring_pla
   const int x = x0 - 1 + t % C::RNX, y = y0 - 1 + t / C::RNX;
   const bool valid = zp >= 0 && zp < P.NZ && x >= 0 && y >= 0 && x < P.NX && y < P.NY;
   const long long n = valid ? x + (long long)P.NX * y + pn * zp : 0;
-  double *d = ring_plane + t * C::NF;
+  double *d = ring_plane + t * C::GEO, *v = ring_plane + C::OFF_VEL + t * C::VEL;
   const double *xc = P.coords + n * 3, *u = P.vel + n * 3;
   copy8_or_zero(d + 0, xc + 0, valid);
   copy8_or_zero(d + 1, xc + 1, valid);
   copy8_or_zero(d + 2, xc + 2, valid);
   copy8_or_zero(d + 3, P.visc + n, valid);
-  copy8_or_zero(d + 4, u + 0, valid);
-  copy8_or_zero(d + 5, u + 1, valid);
-  copy8_or_zero(d + 6, u + 2, valid);
+  copy8_or_zero(v + 0, u + 0, valid);
+  copy8_or_zero(v + 1, u + 1, valid);
+  copy8_or_zero(v + 2, u + 2, valid);
 }
-// mass flow rates of element layer ez: [NEL][12]; `t` = 0..NT-1
+// mass flow rates of element layer ez: [NEL][12] as 270 16-byte copies; thread t makes copies t, t + NT, t + 2 NT
 __host__ __device__ inline void stage_mdot(const BoxParams &P, double *mdb, int t, int x0, int y0, int ez)
 {
   using C = Cfg;
-  const long long ln = (long long)P.nx * P.ny;
   const bool zin = ez >= 0 && ez < P.nz;
+  const double *layer = P.mdot + (zin ? (long long)P.nx * P.ny * ez * 12 : 0);
   const bool wide = (((unsigned long long)P.mdot) & 15) == 0; // uniform
-#pragma unroll 1
-  for (int idx = t; idx < C::NEL * 6; idx += C::NT) {
+#pragma unroll
+  for (int k = 0; k < (C::NEL * 6 + C::NT - 1) / C::NT; ++k) {
+    const int idx = t + k * C::NT;
+    if (idx >= C::NEL * 6) continue;
     const int el = idx / 6, pr = idx - el * 6;
     const int ex = x0 - 1 + el % C::ELX, ey = y0 - 1 + el / C::ELX;
     const bool valid = zin && ex >= 0 && ey >= 0 && ex < P.nx && ey < P.ny;
-    const long long e = valid ? ex + (long long)P.nx * ey + ln * ez : 0;
-    const double *src = P.mdot + e * 12 + 2 * pr;
+    const double *src = layer + (valid ? (ex + P.nx * ey) * 12 + 2 * pr : 0);
     double *dst = mdb + el * 12 + 2 * pr;
     if (wide) copy16_or_zero(dst, src, valid);
     else {
@@ -172,7 +178,7 @@ __host__ __device__ __forceinline__ void coef_load(Coef &C, const double *pl0, c
   using K = Cfg;
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    const double *nd = ((m & 4) ? pl1 : pl0) + ((elx + (m & 1)) + K::RNX * (ely + ((m >> 1) & 1))) * K::NF;
+    const double *nd = ((m & 4) ? pl1 : pl0) + ((elx + (m & 1)) + K::RNX * (ely + ((m >> 1) & 1))) * K::GEO;
     ld4(nd, C.X[0][m], C.X[1][m], C.X[2][m], C.M[m]);
   }
 #pragma unroll
@@ -273,11 +279,39 @@ __host__ __device__ inline void p1_face_unit(const BoxParams &P, int el, int top
   double bx[3], by[3];
   area_base<0>(C, bx);
   area_base<1>(C, by);
-  // T = 0: (u,v) = (y,z); T = 1: (u,v) = (z,x)
-  p1_point<0>(C, bx, -1.0, sz, q, md[0], o + 0 * K::REC, P.err);
-  p1_point<1>(C, by, sz, 1.0, q, md[1], o + 1 * K::REC, P.err);
-  p1_point<0>(C, bx, 1.0, sz, q, -md[2], o + 2 * K::REC, P.err);
-  p1_point<1>(C, by, sz, -1.0, q, md[3], o + 3 * K::REC, P.err);
+  // T = 0: (u,v) = (y,z); T = 1: (u,v) = (z,x).  A loop, not four inlined copies: phase 1 shares 128 registers per
+  // thread with the accumulate sweep's budget, and 16 resident warps hide the latency an unrolled version would
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    const double sg = s ? 1.0 : -1.0;
+    p1_point<0>(C, bx, sg, sz, q, s ? -md[2] : md[0], o + (2 * s) * K::REC, P.err);  // ip 0 (y-), ip 2 (y+, L -> R along -x)
+    p1_point<1>(C, by, sz, -sg, q, s ? md[3] : md[1], o + (1 + 2 * s) * K::REC, P.err); // ip 1 (x+), ip 3 (x-)
+  }
+}
+// half of a face unit: the 2 points of edge direction T (0: x edges = ips 0, 2; 1: y edges = ips 1, 3) of the bottom /
+// top face.  Phase 1b spreads these over four warps (one butterfly per 2 points, but half the critical path)
+template <int T>
+__host__ __device__ inline void p1_face_half(const BoxParams &P, int el, int top, int x0, int y0, const double *pl0, const double *pl1,
+                                             const double *mdb, double *rec)
+{
+  using K = Cfg;
+  const int elx = el % K::ELX, ely = el / K::ELX;
+  const int ex = x0 - 1 + elx, ey = y0 - 1 + ely;
+  if (ex < 0 || ey < 0 || ex >= P.nx || ey >= P.ny) return;
+  const double q = (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
+  Coef C;
+  coef_load(C, pl0, pl1, elx, ely);
+  const double sz = top ? 1.0 : -1.0;
+  const double *md = mdb + el * 12 + (top ? 4 : 0);
+  double *o = rec + el * K::ES;
+  double b[3];
+  area_base<T>(C, b);
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    const double sg = s ? 1.0 : -1.0;
+    if (T == 0) p1_point<0>(C, b, sg, sz, q, s ? -md[2] : md[0], o + (2 * s) * K::REC, P.err);   // ip 0 (y-), ip 2 (y+, L -> R along -x)
+    else p1_point<1>(C, b, sz, -sg, q, s ? md[3] : md[1], o + (1 + 2 * s) * K::REC, P.err);     // ip 1 (x+), ip 3 (x-)
+  }
 }
 // z unit: the 4 z-edge points (ip 8 + n above bottom node n) -> record slots 4..7
 __host__ __device__ inline void p1_z_unit(const BoxParams &P, int el, int x0, int y0, const double *pl0, const double *pl1,
@@ -295,28 +329,24 @@ __host__ __device__ inline void p1_z_unit(const BoxParams &P, int el, int x0, in
   double bz[3];
   area_base<2>(C, bz);
   // T = 2: (u,v) = (x,y); bottom nodes 0..3 = (x-,y-), (x+,y-), (x+,y+), (x-,y+)
-  p1_point<2>(C, bz, -1.0, -1.0, q, md[0], o + 0 * K::REC, P.err);
-  p1_point<2>(C, bz, 1.0, -1.0, q, md[1], o + 1 * K::REC, P.err);
-  p1_point<2>(C, bz, 1.0, 1.0, q, md[2], o + 2 * K::REC, P.err);
-  p1_point<2>(C, bz, -1.0, 1.0, q, md[3], o + 3 * K::REC, P.err);
+#pragma unroll 1
+  for (int n = 0; n < 4; ++n)
+    p1_point<2>(C, bz, (n == 1 || n == 2) ? 1.0 : -1.0, n >= 2 ? 1.0 : -1.0, q, md[n], o + n * K::REC, P.err);
 }
 
 // ---- phase 2 -----------------------------------------------------------------------------------------------------------
 // Run-time magnitudes of the shape-function derivatives.  In the frame of the row node an integration point sits at 0
 // along its edge and at distance q towards the row node on the two transverse axes; phi = 1/2 + q for a column on the
 // row's side of a transverse axis, 1/2 - q otherwise (Hex8CVFEM.C:24-70,318-345).
-struct P2K {
-  double kt[3]; // phi_u phi_v for 0, 1, 2 transverse axes on which the column differs from the row
-  double kh[2]; // 1/2 phi
-  double f23;   // 2/3 includeDivU
-};
-__host__ __device__ inline void p2k_init(P2K &K, int options, double include_divu)
+// kt[n] = phi_u phi_v for n = 0, 1, 2 transverse axes on which the column differs from the row; kh = 1/2 phi; f23 = 2/3
+// includeDivU.  They live in BoxParams (constant bank), filled by the launcher.
+__host__ __device__ inline void p2k_init(BoxParams &P)
 {
-  const double q = (options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
+  const double q = (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25;
   const double p0 = 0.5 + q, p1 = 0.5 - q;
-  K.kt[0] = p0 * p0; K.kt[1] = p0 * p1; K.kt[2] = p1 * p1;
-  K.kh[0] = 0.5 * p0; K.kh[1] = 0.5 * p1;
-  K.f23 = 2.0 / 3.0 * include_divu;
+  P.kt[0] = p0 * p0; P.kt[1] = p0 * p1; P.kt[2] = p1 * p1;
+  P.kh[0] = 0.5 * p0; P.kh[1] = 0.5 * p1;
+  P.f23 = 2.0 / 3.0 * P.include_divu;
 }
 // the advection shape function must sit at the same point as the gradient operator (N_c = |dN_c/dxi_t| / 2 is what
 // lets lane 3 fold N_c mdot into its row): both options on or both off
@@ -325,7 +355,7 @@ __host__ __device__ inline bool options_supported(int options)
   return ((options & NALU_OPT_SHIFTED_GRAD_OP) != 0) == ((options & NALU_OPT_SKEW_SYMMETRIC) != 0);
 }
 
-// per-thread state that lives across the phases of a plane
+// who a thread is: a pure function of its index, rebuilt at the head of every phase
 struct Thr {
   int lx, ly, i;       // node of the tile, lane role (0..2 dof row, 3 diagonal term)
   int node;            // lx + 8 ly
@@ -333,33 +363,28 @@ struct Thr {
   int active;          // node inside the domain
   // element (lx, ly) (= quadrant (0,0)) record base + lane offsets, in doubles from the start of shared memory
   int oG, oGp, oA[3];
-  double acc1[9][3];   // dz = 0 group (kept across phase 1a), rotated
-  double rr;           // rhs of dof row i
 };
-__host__ __device__ inline void thr_init(const BoxParams &P, Thr &N, int tid, int x0, int y0)
+__host__ __device__ __forceinline__ Thr thr_make(const BoxParams &P, int tid, int x0, int y0)
 {
   using C = Cfg;
+  Thr N;
   const int lane = tid & 31;
   N.ly = tid >> 5;
   N.lx = lane >> 2;
   N.i = lane & 3;
   N.node = N.lx + C::TBX * N.ly;
   const int r = N.i < 3 ? N.i : 0;
-  for (int k = 0; k < 3; ++k) N.rot[k] = (r + k) % 3;
+  N.rot[0] = r;
+  N.rot[1] = r == 2 ? 0 : r + 1;
+  N.rot[2] = r == 0 ? 2 : r - 1;
   N.active = (x0 + N.lx < P.NX) && (y0 + N.ly < P.NY);
   const int rec = C::OFF_REC + (N.lx + C::ELX * N.ly) * C::ES;
   N.oG = rec + (N.i < 3 ? 3 * N.i : 9);
   N.oGp = N.i < 3 ? N.oG : rec + 12;
-  if (N.i < 3) {
-    for (int k = 0; k < 3; ++k) N.oA[k] = rec + 13 + N.rot[k];
-  } else {
-    N.oA[0] = rec + 16; // 1.0: acc[c][0] of lane 3 accumulates D_c
-    N.oA[1] = rec + 13;
-    N.oA[2] = rec + 14;
-  }
-#pragma unroll
-  for (int c = 0; c < 9; ++c) N.acc1[c][0] = N.acc1[c][1] = N.acc1[c][2] = 0.0;
-  N.rr = 0.0;
+  N.oA[0] = N.i < 3 ? rec + 13 + N.rot[0] : rec + 16; // lane 3: 1.0, acc[c][0] accumulates D_c
+  N.oA[1] = N.i < 3 ? rec + 13 + N.rot[1] : rec + 13;
+  N.oA[2] = N.i < 3 ? rec + 13 + N.rot[2] : rec + 14;
+  return N;
 }
 
 // record slot of point K (0 x edge, 1 y edge, 2 z edge) of the row node in quadrant (SX,SY: the element lies on the
@@ -378,7 +403,7 @@ __host__ __device__ constexpr int rec_off()
 //   Gt: B_t + sigma_t mdot/2 for lane 3 -> the `far` copy for columns with sigma_t = +1
 template <int SX, int SY, int K>
 __host__ __device__ __forceinline__ void sweep_point(const double *pT0, const double *pT1, const double *pG, const double *pA0,
-                                                     const double *pA1, const double *pA2, const P2K &Kc, const double (&khz)[2],
+                                                     const double *pA1, const double *pA2, const BoxParams &Kc, const double (&khz)[2],
                                                      double (&acc1)[9][3], double (&acc2)[9][3])
 {
   constexpr int off = rec_off<SX, SY, K>();
@@ -419,7 +444,7 @@ __host__ __device__ __forceinline__ void sweep_point(const double *pT0, const do
 
 // one z half of the node's octants: H = 0 the 4 elements below the plane (acc2 = dz -1 group), H = 1 above (acc2 =
 // dz +1 group); acc1 = dz 0 group.  No test for elements / nodes outside the domain: their records are zero.
-__host__ __device__ __forceinline__ void sweep_half(const Thr &N, const double *sm, const P2K &Kc, int H, double (&acc1)[9][3],
+__host__ __device__ __forceinline__ void sweep_half(const Thr &N, const double *sm, const BoxParams &Kc, int H, double (&acc1)[9][3],
                                                     double (&acc2)[9][3])
 {
   const double *pG = sm + N.oG, *pGp = sm + N.oGp, *pA0 = sm + N.oA[0], *pA1 = sm + N.oA[1], *pA2 = sm + N.oA[2];
@@ -441,40 +466,31 @@ __host__ __device__ __forceinline__ void sweep_half(const Thr &N, const double *
 __host__ __device__ __forceinline__ int vel_off(const Thr &N, int slot)
 {
   using C = Cfg;
-  return C::OFF_RING + slot * C::PLN + ((N.lx + 1) + C::RNX * (N.ly + 1)) * C::NF + 4;
+  return C::OFF_RING + slot * C::PLN + C::OFF_VEL + ((N.lx + 1) + C::RNX * (N.ly + 1)) * C::VEL;
 }
-// what a lane publishes to its quad: lane 3: D[c] = acc[c][0]; lanes i < 3: T[k'] = sum_c acc[c][k'] u_c[i] (the
-// transposed div(u) terms: T[1] goes to dof row (i+1) mod 3, T[2] to (i+2) mod 3)
-__host__ __device__ __forceinline__ void fin_transposed(const Thr &N, const double *sm, int uoff, const double (&acc)[9][3],
-                                                        double (&T)[3])
-{
-  using C = Cfg;
-  T[0] = T[1] = T[2] = 0.0;
-  const double *pu = sm + uoff + N.rot[0];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) {
-    const double u = pu[((c % 3 - 1) + C::RNX * (c / 3 - 1)) * C::NF];
-    T[0] += acc[c][0] * u;
-    T[1] += acc[c][1] * u;
-    T[2] += acc[c][2] * u;
-  }
-}
-// D[c]: the quad's diagonal terms (from lane 3); Tin1 = T[1] of dof row (i+2) mod 3, Tin2 = T[2] of dof row (i+1) mod 3
-__host__ __device__ __forceinline__ void fin_apply(Thr &N, const double *sm, int uoff, double (&acc)[9][3], const double (&D)[9],
-                                                   double T0, double Tin1, double Tin2, double f23)
+// D[c]: the quad's diagonal terms (acc[c][0] of lane 3).  Adds them, takes the group's share of rhs_i = -(row . u) and
+// returns in T what the other dof rows need for the div(u) stress: T[k'] = sum_c acc[c][k'] u_c[i] before the diagonal
+// term (T[0] stays, T[1] goes to dof row (i+1) mod 3, T[2] to (i+2) mod 3).  Returns row . u.
+__host__ __device__ __forceinline__ double fin_apply(const Thr &N, const double *sm, int uoff, double (&acc)[9][3], const double (&D)[9],
+                                                     double (&T)[3])
 {
   using C = Cfg;
   const double *pu0 = sm + uoff + N.rot[0], *pu1 = sm + uoff + N.rot[1], *pu2 = sm + uoff + N.rot[2];
   double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  T[0] = T[1] = T[2] = 0.0;
 #pragma unroll
   for (int c = 0; c < 9; ++c) {
+    const int o = ((c % 3 - 1) + C::RNX * (c / 3 - 1)) * C::VEL;
+    const double u0 = pu0[o], u1 = pu1[o], u2 = pu2[o];
+    T[0] += acc[c][0] * u0;
+    T[1] += acc[c][1] * u0;
+    T[2] += acc[c][2] * u0;
     acc[c][0] += D[c];
-    const int o = ((c % 3 - 1) + C::RNX * (c / 3 - 1)) * C::NF;
-    r0 += acc[c][0] * pu0[o];
-    r1 += acc[c][1] * pu1[o];
-    r2 += acc[c][2] * pu2[o];
+    r0 += acc[c][0] * u0;
+    r1 += acc[c][1] * u1;
+    r2 += acc[c][2] * u2;
   }
-  N.rr += f23 * (T0 + Tin1 + Tin2) - (r0 + (r1 + r2));
+  return r0 + (r1 + r2);
 }
 
 // ---- output ------------------------------------------------------------------------------------------------------------

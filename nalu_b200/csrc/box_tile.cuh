@@ -26,7 +26,10 @@ struct BoxParams {
   double include_divu;
   int options;
   int overwrite;
-  int z_first, z_last; // node planes [z_first, z_last) this launch assembles (column-pair kernel; default all)
+  int z_first, z_last; // node planes [z_first, z_last) this launch assembles (default all)
+  // row-thread kernel: magnitudes of the shape-function derivatives (box5_tile.cuh, p2k_init), read by the FMAs
+  // straight from the constant bank the kernel parameters live in
+  double kt[3], kh[2], f23;
 };
 
 // ---- small integer helpers on the Hex8 numbering (Hex8CVFEM.C:264-276, 396-412) -------------

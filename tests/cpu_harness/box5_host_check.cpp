@@ -79,29 +79,39 @@ static RankMesh make_rank(int nx, int ny, int nzg, int rank, int nranks)
 
 using C5 = box5::Cfg;
 
-// finalize of one dz group for all lanes of the CTA (the device does the exchange with quad shuffles)
-static void finalize_all(std::vector<box5::Thr> &N, double *sm, int slot, std::vector<double (*)[3]> &acc, double f23)
+// a thread of the emulated CTA: who it is + what the kernel keeps in registers
+struct HThr : box5::Thr {
+  double acc1[9][3], acc2[9][3];
+  double rr;
+};
+static void zero9(double (&a)[9][3])
 {
-  const int NT = C5::NT;
-  std::vector<double> T(NT * 3, 0.0), D(NT * 9, 0.0);
-  for (int tid = 0; tid < NT; ++tid) {
-    double t[3] = {0, 0, 0};
-    if (f23 != 0.0) box5::fin_transposed(N[tid], sm, box5::vel_off(N[tid], slot), *(double(*)[9][3])acc[tid], t);
+  for (int c = 0; c < 9; ++c) a[c][0] = a[c][1] = a[c][2] = 0.0;
+}
+
+// finalize of one dz group (which = 1: acc1, 2: acc2) for all lanes (the device does the exchange with quad shuffles)
+static void finalize_all(std::vector<HThr> &N, double *sm, int slot, int which, double f23)
+{
+  std::vector<double> T(C5::NT * 3, 0.0), R(C5::NT, 0.0);
+  for (int tid = 0; tid < C5::NT; ++tid) {
+    double d[9], t[3];
+    const int q = tid & ~3;
+    double(&acc)[9][3] = which == 1 ? N[tid].acc1 : N[tid].acc2;
+    double(&acc3)[9][3] = which == 1 ? N[q | 3].acc1 : N[q | 3].acc2;
+    for (int c = 0; c < 9; ++c) d[c] = acc3[c][0]; // lane 3 comes last in its quad: its D is still untouched
+    R[tid] = box5::fin_apply(N[tid], sm, box5::vel_off(N[tid], slot), acc, d, t);
     for (int k = 0; k < 3; ++k) T[tid * 3 + k] = t[k];
-    for (int c = 0; c < 9; ++c) D[tid * 9 + c] = acc[tid][c][0];
   }
-  for (int tid = 0; tid < NT; ++tid) {
+  for (int tid = 0; tid < C5::NT; ++tid) {
     const int q = tid & ~3, i = N[tid].i;
-    double d[9];
-    for (int c = 0; c < 9; ++c) d[c] = D[(q | 3) * 9 + c];
-    const double t1 = T[(q | ((i + 2) % 3)) * 3 + 1], t2 = T[(q | ((i + 1) % 3)) * 3 + 2];
-    box5::fin_apply(N[tid], sm, box5::vel_off(N[tid], slot), *(double(*)[9][3])acc[tid], d, T[tid * 3], t1, t2, f23);
+    double t = 0.0;
+    if (f23 != 0.0) t = T[tid * 3] + T[(q | ((i + 2) % 3)) * 3 + 1] + T[(q | ((i + 1) % 3)) * 3 + 2];
+    N[tid].rr += f23 * t - R[tid];
   }
 }
 
-// output of one dz group for all warps
-static void output_all(const BoxParams &P, std::vector<box5::Thr> &N, const box5::Meta &M, int g, double *sm,
-                       std::vector<double (*)[3]> &acc, int x0, int y0, int z)
+static void output_all(const BoxParams &P, std::vector<HThr> &N, const box5::Meta &M, int g, double *sm, int which, int x0, int y0,
+                       int z)
 {
   for (int warp = 0; warp < 4; ++warp) {
     double *scr = sm + C5::OFF_SCR + warp * C5::SCRW;
@@ -109,7 +119,10 @@ static void output_all(const BoxParams &P, std::vector<box5::Thr> &N, const box5
     const bool natural = box5::line_natural(M, warp);
     const int n0 = C5::TBX * warp;
     if (natural) {
-      for (int lane = 0; lane < 32; ++lane) box5::out_stage_natural(N[warp * 32 + lane], scr, *(double(*)[9][3])acc[warp * 32 + lane]);
+      for (int lane = 0; lane < 32; ++lane) {
+        HThr &n = N[warp * 32 + lane];
+        box5::out_stage_natural(n, scr, which == 1 ? n.acc1 : n.acc2);
+      }
       double *base = P.values + M.rowbase(n0) + 3 * M.s0(n0, g);
       for (int lane = 0; lane < 27; ++lane)
         for (int r = 0; r < 24; ++r) {
@@ -121,11 +134,11 @@ static void output_all(const BoxParams &P, std::vector<box5::Thr> &N, const box5
       long long G[32];
       int L[32];
       for (int lane = 0; lane < 32; ++lane) {
-        const box5::Thr &n = N[warp * 32 + lane];
+        HThr &n = N[warp * 32 + lane];
         G[lane] = 0; L[lane] = 0;
         if (n.i < 3 && n.active) {
           const unsigned char *sl = P.slot27 + 27 * ((x0 + n.lx) + (long long)P.NX * ((y0 + n.ly) + (long long)P.NY * z));
-          box5::out_stage_slots(n, M, sl, g, scr, *(double(*)[9][3])acc[warp * 32 + lane]);
+          box5::out_stage_slots(n, M, sl, g, scr, which == 1 ? n.acc1 : n.acc2);
           G[lane] = box5::run_first(M, n.node, n.i, g);
           L[lane] = 3 * M.cnt(n.node, g);
         }
@@ -139,16 +152,6 @@ static void output_all(const BoxParams &P, std::vector<box5::Thr> &N, const box5
         }
       }
     }
-  }
-}
-
-static void p1_phase(const BoxParams &P, bool do_face, int top, bool do_z, int x0, int y0, const double *pl0, const double *pl1,
-                     const double *mdb, double *rec)
-{
-  for (int tid = 0; tid < C5::NT; ++tid) {
-    if (tid < 64) {
-      if (do_face && tid < C5::NEL) box5::p1_face_unit(P, tid, top, x0, y0, pl0, pl1, mdb, rec);
-    } else if (do_z && tid - 64 < C5::NEL) box5::p1_z_unit(P, tid - 64, x0, y0, pl0, pl1, mdb, rec);
   }
 }
 
@@ -167,11 +170,8 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
   constexpr int NT = C::NT;
   double *sm = nullptr;
   if (posix_memalign((void **)&sm, 16, sizeof(double) * C::SMEM_DOUBLES)) abort();
-  std::vector<box5::Thr> N(NT);
-  std::vector<double> acc2s(NT * 27);
-  std::vector<double (*)[3]> a1(NT), a2(NT);
-  box5::P2K K;
-  box5::p2k_init(K, P.options, P.include_divu);
+  std::vector<HThr> N(NT);
+  box5::p2k_init(P);
   for (int cta = 0; cta < P.tiles_x * P.tiles_y * zchunks; ++cta) {
     for (int i = 0; i < C::SMEM_DOUBLES; ++i) sm[i] = NAN; // uninitialised shared memory must never be consumed
     double *rec = sm + C::OFF_REC, *ring = sm + C::OFF_RING, *mdb = sm + C::OFF_MD;
@@ -182,59 +182,71 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
     const int zs = P.z_first + zc * P.z_chunk;
     const int ze = (zs + P.z_chunk < P.z_last) ? zs + P.z_chunk : P.z_last;
     for (int tid = 0; tid < NT; ++tid) {
-      box5::thr_init(P, N[tid], tid, x0, y0);
-      a1[tid] = N[tid].acc1;
-      a2[tid] = (double(*)[3])(acc2s.data() + tid * 27);
+      static_cast<box5::Thr &>(N[tid]) = box5::thr_make(P, tid, x0, y0);
+      for (int c = 0; c < 9; ++c) N[tid].acc1[c][0] = N[tid].acc1[c][1] = N[tid].acc1[c][2] = NAN;
+      N[tid].rr = 0.0;
     }
     for (int tid = 0; tid < NT; ++tid) {
-      box5::stage_plane(P, ring + ((zs + 2) % 3) * C::PLN, tid, x0, y0, zs - 1);
-      box5::stage_plane(P, ring + (zs % 3) * C::PLN, tid, x0, y0, zs);
-      box5::stage_plane(P, ring + ((zs + 1) % 3) * C::PLN, tid, x0, y0, zs + 1);
+      const int warp = tid >> 5, lane = tid & 31;
+      if (warp < 3) {
+        box5::stage_plane(P, ring + ((zs + 2 + warp) % 3) * C::PLN, lane, x0, y0, zs - 1 + warp);
+        box5::stage_plane(P, ring + ((zs + 2 + warp) % 3) * C::PLN, lane + 32, x0, y0, zs - 1 + warp);
+      }
       box5::stage_mdot(P, mdb, tid, x0, y0, zs - 1);
-      if ((tid >> 5) == 3) box5::meta_load(P, sm, zs & 1, tid & 31, x0, y0, zs);
+      if (warp == 3) box5::meta_load(P, sm, zs & 1, lane, x0, y0, zs);
     }
     // ---- barrier
-    if (zs >= 1) p1_phase(P, true, 1, true, x0, y0, ring + ((zs - 1) % 3) * C::PLN, ring + (zs % 3) * C::PLN, mdb, rec);
-    // ---- barrier
-    for (int z = zs; z < ze; ++z) {
+    for (int hs = zs >= 1 ? 2 * zs - 1 : 2 * zs; hs < 2 * ze; ++hs) {
+      const int z = hs >> 1, H = hs & 1;
+      const bool lead = hs < 2 * zs;
       const box5::Meta M = box5::meta_at(sm, z & 1);
       const bool lower = z >= 1, upper = z < P.nz;
-      // ---- A
-      for (int tid = 0; tid < NT; ++tid) box5::stage_mdot(P, mdb, tid, x0, y0, z);
-      if (lower) {
+      if (!lead) {
+        const bool act = H ? upper : lower;
         for (int tid = 0; tid < NT; ++tid) {
-          for (int k = 0; k < 27; ++k) acc2s[tid * 27 + k] = 0.0;
-          box5::sweep_half(N[tid], sm, K, 0, N[tid].acc1, *(double(*)[9][3])a2[tid]);
+          if (!H) {
+            box5::stage_mdot(P, mdb, tid, x0, y0, z);
+            zero9(N[tid].acc1);
+          }
+          zero9(N[tid].acc2);
+          if (act) box5::sweep_half(N[tid], sm, P, H, N[tid].acc1, N[tid].acc2);
         }
-        finalize_all(N, sm, (z + 2) % 3, a2, K.f23);
-        output_all(P, N, M, 0, sm, a2, x0, y0, z);
+        if (H) {
+          finalize_all(N, sm, z % 3, 1, P.f23);
+          output_all(P, N, M, 1, sm, 1, x0, y0, z);
+        }
+        if (act) {
+          finalize_all(N, sm, (z + (H ? 1 : 2)) % 3, 2, P.f23);
+          output_all(P, N, M, H ? 2 : 0, sm, 2, x0, y0, z);
+        }
+        if (H)
+          for (int tid = 0; tid < NT; ++tid) {
+            HThr &n = N[tid];
+            if (n.i < 3 && n.active) {
+              double *r = P.rhs + (long long)M.row(n.node) * 3 + n.i;
+              *r = P.overwrite ? n.rr : *r + n.rr;
+              if (P.overwrite && !M.natural(n.node)) box5::zero_uncovered(M, n.node, n.i, P.values);
+            }
+            n.rr = 0.0;
+            for (int c = 0; c < 9; ++c) n.acc1[c][0] = n.acc1[c][1] = n.acc1[c][2] = NAN; // dead until the next plane
+          }
+        // ---- barrier
       }
-      // ---- barrier; B
-      if (upper) p1_phase(P, true, 0, true, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, rec);
-      // ---- barrier; C
-      for (int tid = 0; tid < NT; ++tid) {
-        for (int k = 0; k < 27; ++k) acc2s[tid * 27 + k] = 0.0;
-        if (upper) box5::sweep_half(N[tid], sm, K, 1, N[tid].acc1, *(double(*)[9][3])a2[tid]);
-      }
-      finalize_all(N, sm, z % 3, a1, K.f23);
-      output_all(P, N, M, 1, sm, a1, x0, y0, z);
       if (upper) {
-        finalize_all(N, sm, (z + 1) % 3, a2, K.f23);
-        output_all(P, N, M, 2, sm, a2, x0, y0, z);
-      }
-      for (int tid = 0; tid < NT; ++tid) {
-        box5::Thr &n = N[tid];
-        if (n.i < 3 && n.active) {
-          double *r = P.rhs + (long long)M.row(n.node) * 3 + n.i;
-          *r = P.overwrite ? n.rr : *r + n.rr;
-          if (P.overwrite && !box5::line_natural(M, n.ly)) box5::zero_uncovered(M, n.node, n.i, P.values);
+        const double *pl0 = ring + (z % 3) * C::PLN, *pl1 = ring + ((z + 1) % 3) * C::PLN;
+        for (int tid = 0; tid < NT; ++tid) {
+          const int t = tid & 63;
+          if (t >= C::NEL) continue;
+          if (!H || lead) {
+            if (tid < 64) box5::p1_face_unit(P, t, lead ? 1 : 0, x0, y0, pl0, pl1, mdb, rec);
+            else box5::p1_z_unit(P, t, x0, y0, pl0, pl1, mdb, rec);
+          } else if (z + 1 < ze) {
+            if (tid < 64) box5::p1_face_half<0>(P, t, 1, x0, y0, pl0, pl1, mdb, rec);
+            else box5::p1_face_half<1>(P, t, 1, x0, y0, pl0, pl1, mdb, rec);
+          }
         }
-        for (int c = 0; c < 9; ++c) n.acc1[c][0] = n.acc1[c][1] = n.acc1[c][2] = 0.0;
-        n.rr = 0.0;
       }
-      // ---- barrier; D
-      if (upper && z + 1 < ze) p1_phase(P, true, 1, false, x0, y0, ring + (z % 3) * C::PLN, ring + ((z + 1) % 3) * C::PLN, mdb, rec);
-      if (z + 1 < ze)
+      if (H && !lead && z + 1 < ze)
         for (int lane = 0; lane < 32; ++lane) {
           box5::meta_load(P, sm, (z + 1) & 1, lane, x0, y0, z + 1);
           box5::stage_plane(P, ring + ((z + 2) % 3) * C::PLN, lane, x0, y0, z + 2);
