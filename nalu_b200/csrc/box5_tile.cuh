@@ -47,8 +47,13 @@ struct Cfg {
   static constexpr int ELX = TBX + 1, ELY = TBY + 1, NEL = ELX * ELY;
   // record of one integration point: G~[3][3] (rows = dof, columns = local axes t,u,v), B_t - mdot/2, B_u, B_v,
   // B_t + mdot/2, A[3] (along +t), 1.0
+  // Layout: field-major, [8 points: 4 face, 4 z-edge][17 fields][FS elements]: the threads of phase 1 (thread = element)
+  // write consecutive doubles; a 64-bit shared load is served half a warp at a time: the 16 lanes (4 consecutive
+  // elements x lanes i = 0..3 reading fields 3i + const) must hit 16 different 8-byte bank slots, i.e. 3 FS = 4 mod 16
   static constexpr int REC = 17;
-  static constexpr int ES = 8 * REC + 4; // element stride: 4 face points, 4 z-edge points; = 12 mod 16 (bank spread)
+  static constexpr int FS = 60;           // field stride >= NEL, = 12 mod 16
+  static constexpr int PS = REC * FS;     // point stride
+  static constexpr int RECSZ = 8 * PS;
   // staged node plane: geometry part [RN][6] = x y z mu - - (48-byte stride: the 16-byte loads of 8 consecutive
   // elements cover all banks), velocity part [RN][3] (the quads of a warp read 24 consecutive doubles)
   static constexpr int RNX = TBX + 2, RNY = TBY + 2, RN = RNX * RNY, GEO = 6, VEL = 3, OFF_VEL = RN * GEO, PLN = RN * (GEO + VEL);
@@ -58,11 +63,11 @@ struct Cfg {
   // node metadata of one plane = the graph's row descriptors (graph.h, node_desc) of the tile's 32 nodes: [3][32] words
   static constexpr int META = 3 * NNODE;
   // shared-memory map (doubles)
-  static constexpr int OFF_REC = 0, OFF_SCR = OFF_REC + NEL * ES, OFF_RING = OFF_SCR + NWARP * SCRW, OFF_MD = OFF_RING + 3 * PLN,
+  static constexpr int OFF_REC = 0, OFF_SCR = OFF_REC + RECSZ, OFF_RING = OFF_SCR + NWARP * SCRW, OFF_MD = OFF_RING + 3 * PLN,
                        OFF_META = OFF_MD + MDB;
   static constexpr int SMEM_DOUBLES = OFF_META + 2 * META;
 };
-static_assert(Cfg::ES % 16 == 12, "element stride must spread the quads of a warp over the banks");
+static_assert(Cfg::FS % 16 == 12 && Cfg::FS >= Cfg::NEL, "field stride must spread the quads of a warp over the banks");
 static_assert((Cfg::OFF_RING % 2) == 0 && (Cfg::OFF_MD % 2) == 0, "16-byte aligned staging areas");
 
 struct Meta {
@@ -247,18 +252,19 @@ __host__ __device__ __forceinline__ void p1_point(const Coef &C, const double (&
   double B[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) B[k] = G[0][k] * A[0] + G[1][k] * A[1] + G[2][k] * A[2];
+  constexpr int F = Cfg::FS;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) o[i * 3 + k] = G[i][k];
-  o[9] = B[0] - 0.5 * md;
-  o[10] = B[1];
-  o[11] = B[2];
-  o[12] = B[0] + 0.5 * md;
-  o[13] = A[0];
-  o[14] = A[1];
-  o[15] = A[2];
-  o[16] = 1.0;
+    for (int k = 0; k < 3; ++k) o[(i * 3 + k) * F] = G[i][k];
+  o[9 * F] = B[0] - 0.5 * md;
+  o[10 * F] = B[1];
+  o[11 * F] = B[2];
+  o[12 * F] = B[0] + 0.5 * md;
+  o[13 * F] = A[0];
+  o[14 * F] = A[1];
+  o[15 * F] = A[2];
+  o[16 * F] = 1.0;
 }
 // face unit: the 4 points of the bottom (top = 0) or top (top = 1) face of element `el` -> record slots 0..3
 // (slot = ip & 3: Hex8CVFEM.C:264-276: ip 0: x edge at y-, 1: y edge at x+, 2: x edge at y+ (L -> R runs along -x),
@@ -275,7 +281,7 @@ __host__ __device__ inline void p1_face_unit(const BoxParams &P, int el, int top
   coef_load(C, pl0, pl1, elx, ely);
   const double sz = top ? 1.0 : -1.0;
   const double *md = mdb + el * 12 + (top ? 4 : 0);
-  double *o = rec + el * K::ES;
+  double *o = rec + el;
   double bx[3], by[3];
   area_base<0>(C, bx);
   area_base<1>(C, by);
@@ -284,8 +290,8 @@ __host__ __device__ inline void p1_face_unit(const BoxParams &P, int el, int top
 #pragma unroll 1
   for (int s = 0; s < 2; ++s) {
     const double sg = s ? 1.0 : -1.0;
-    p1_point<0>(C, bx, sg, sz, q, s ? -md[2] : md[0], o + (2 * s) * K::REC, P.err);  // ip 0 (y-), ip 2 (y+, L -> R along -x)
-    p1_point<1>(C, by, sz, -sg, q, s ? md[3] : md[1], o + (1 + 2 * s) * K::REC, P.err); // ip 1 (x+), ip 3 (x-)
+    p1_point<0>(C, bx, sg, sz, q, s ? -md[2] : md[0], o + (2 * s) * K::PS, P.err);  // ip 0 (y-), ip 2 (y+, L -> R along -x)
+    p1_point<1>(C, by, sz, -sg, q, s ? md[3] : md[1], o + (1 + 2 * s) * K::PS, P.err); // ip 1 (x+), ip 3 (x-)
   }
 }
 // half of a face unit: the 2 points of edge direction T (0: x edges = ips 0, 2; 1: y edges = ips 1, 3) of the bottom /
@@ -303,14 +309,14 @@ __host__ __device__ inline void p1_face_half(const BoxParams &P, int el, int top
   coef_load(C, pl0, pl1, elx, ely);
   const double sz = top ? 1.0 : -1.0;
   const double *md = mdb + el * 12 + (top ? 4 : 0);
-  double *o = rec + el * K::ES;
+  double *o = rec + el;
   double b[3];
   area_base<T>(C, b);
 #pragma unroll 1
   for (int s = 0; s < 2; ++s) {
     const double sg = s ? 1.0 : -1.0;
-    if (T == 0) p1_point<0>(C, b, sg, sz, q, s ? -md[2] : md[0], o + (2 * s) * K::REC, P.err);   // ip 0 (y-), ip 2 (y+, L -> R along -x)
-    else p1_point<1>(C, b, sz, -sg, q, s ? md[3] : md[1], o + (1 + 2 * s) * K::REC, P.err);     // ip 1 (x+), ip 3 (x-)
+    if (T == 0) p1_point<0>(C, b, sg, sz, q, s ? -md[2] : md[0], o + (2 * s) * K::PS, P.err);   // ip 0 (y-), ip 2 (y+, L -> R along -x)
+    else p1_point<1>(C, b, sz, -sg, q, s ? md[3] : md[1], o + (1 + 2 * s) * K::PS, P.err);     // ip 1 (x+), ip 3 (x-)
   }
 }
 // z unit: the 4 z-edge points (ip 8 + n above bottom node n) -> record slots 4..7
@@ -325,13 +331,13 @@ __host__ __device__ inline void p1_z_unit(const BoxParams &P, int el, int x0, in
   Coef C;
   coef_load(C, pl0, pl1, elx, ely);
   const double *md = mdb + el * 12 + 8;
-  double *o = rec + el * K::ES + 4 * K::REC;
+  double *o = rec + el + 4 * K::PS;
   double bz[3];
   area_base<2>(C, bz);
   // T = 2: (u,v) = (x,y); bottom nodes 0..3 = (x-,y-), (x+,y-), (x+,y+), (x-,y+)
 #pragma unroll 1
   for (int n = 0; n < 4; ++n)
-    p1_point<2>(C, bz, (n == 1 || n == 2) ? 1.0 : -1.0, n >= 2 ? 1.0 : -1.0, q, md[n], o + n * K::REC, P.err);
+    p1_point<2>(C, bz, (n == 1 || n == 2) ? 1.0 : -1.0, n >= 2 ? 1.0 : -1.0, q, md[n], o + n * K::PS, P.err);
 }
 
 // ---- phase 2 -----------------------------------------------------------------------------------------------------------
@@ -378,12 +384,12 @@ __host__ __device__ __forceinline__ Thr thr_make(const BoxParams &P, int tid, in
   N.rot[1] = r == 2 ? 0 : r + 1;
   N.rot[2] = r == 0 ? 2 : r - 1;
   N.active = (x0 + N.lx < P.NX) && (y0 + N.ly < P.NY);
-  const int rec = C::OFF_REC + (N.lx + C::ELX * N.ly) * C::ES;
-  N.oG = rec + (N.i < 3 ? 3 * N.i : 9);
-  N.oGp = N.i < 3 ? N.oG : rec + 12;
-  N.oA[0] = N.i < 3 ? rec + 13 + N.rot[0] : rec + 16; // lane 3: 1.0, acc[c][0] accumulates D_c
-  N.oA[1] = N.i < 3 ? rec + 13 + N.rot[1] : rec + 13;
-  N.oA[2] = N.i < 3 ? rec + 13 + N.rot[2] : rec + 14;
+  const int rec = C::OFF_REC + (N.lx + C::ELX * N.ly);
+  N.oG = rec + 3 * N.i * C::FS;                           // lane 3: field 9 = B_t - mdot/2
+  N.oGp = N.i < 3 ? N.oG : rec + 12 * C::FS;
+  N.oA[0] = rec + (N.i < 3 ? 13 + N.rot[0] : 16) * C::FS; // lane 3: 1.0, acc[c][0] accumulates D_c
+  N.oA[1] = rec + (N.i < 3 ? 13 + N.rot[1] : 16) * C::FS; // lane 3: anything finite on a bank slot of its own
+  N.oA[2] = rec + (N.i < 3 ? 13 + N.rot[2] : 16) * C::FS;
   return N;
 }
 
@@ -392,8 +398,7 @@ __host__ __device__ __forceinline__ Thr thr_make(const BoxParams &P, int tid, in
 template <int SX, int SY, int K>
 __host__ __device__ constexpr int rec_off()
 {
-  return (SX + Cfg::ELX * SY) * Cfg::ES +
-         (K == 0 ? (SY ? 0 : 2) : (K == 1 ? (SX ? 3 : 1) : 4 + (SY ? 0 : 2) + (SX ^ SY))) * Cfg::REC;
+  return (SX + Cfg::ELX * SY) + (K == 0 ? (SY ? 0 : 2) : (K == 1 ? (SX ? 3 : 1) : 4 + (SY ? 0 : 2) + (SX ^ SY))) * Cfg::PS;
 }
 
 // one integration point into the 8 column nodes of its element.  sH = rho_z = +1 for the lower half (the row node is
@@ -407,7 +412,7 @@ __host__ __device__ __forceinline__ void sweep_point(const double *pT0, const do
                                                      double (&acc1)[9][3], double (&acc2)[9][3])
 {
   constexpr int off = rec_off<SX, SY, K>();
-  const double gt0 = pT0[off], gt1 = pT1[off], gu = pG[off + 1], gv = pG[off + 2];
+  const double gt0 = pT0[off], gt1 = pT1[off], gu = pG[off + Cfg::FS], gv = pG[off + 2 * Cfg::FS];
   const double a0 = pA0[off], a1 = pA1[off], a2 = pA2[off];
   constexpr int T = K, U = (K + 1) % 3, V = (K + 2) % 3;
   // compile-time part of rho along the natural axes (rho_z = sH is applied through khz)

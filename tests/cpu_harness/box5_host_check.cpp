@@ -175,7 +175,7 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
   for (int cta = 0; cta < P.tiles_x * P.tiles_y * zchunks; ++cta) {
     for (int i = 0; i < C::SMEM_DOUBLES; ++i) sm[i] = NAN; // uninitialised shared memory must never be consumed
     double *rec = sm + C::OFF_REC, *ring = sm + C::OFF_RING, *mdb = sm + C::OFF_MD;
-    for (int i = 0; i < C::NEL * C::ES; ++i) rec[i] = 0.0; // kernel prologue
+    for (int i = 0; i < C::RECSZ; ++i) rec[i] = 0.0; // kernel prologue
     const int ntile = P.tiles_x * P.tiles_y;
     const int tile = cta % ntile, zc = cta / ntile;
     const int x0 = (tile % P.tiles_x) * C::TBX, y0 = (tile / P.tiles_x) * C::TBY;
