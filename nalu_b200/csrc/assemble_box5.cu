@@ -200,9 +200,10 @@ int launch_assemble_box5(BoxParams &P, cudaStream_t stream)
   P.tiles_x = (P.NX + C5::TBX - 1) / C5::TBX;
   P.tiles_y = (P.NY + C5::TBY - 1) / C5::TBY;
   const long long ntile = (long long)P.tiles_x * P.tiles_y;
-  // z chunks: enough CTAs for ~12 waves of 2 CTAs per SM, but at least 16 planes per chunk (each chunk recomputes the
-  // top-face / z-edge points of one element layer in its prologue)
-  long long want = ((long long)sms * 2 * 12 + ntile - 1) / ntile;
+  // z chunks: enough CTAs for ~24 waves of 2 CTAs per SM (tail effect; measured at 256^3: 2 chunks 840, 4-6 chunks 851
+  // Melem/s), but at least 16 planes per chunk (each chunk recomputes the top-face / z-edge points of one element
+  // layer in its leading iteration)
+  long long want = ((long long)sms * 2 * 24 + ntile - 1) / ntile;
   int zchunks = (int)(want < 1 ? 1 : want);
   const int nplanes = P.z_last - P.z_first;
   int zc = (nplanes + zchunks - 1) / zchunks;
