@@ -9,6 +9,8 @@
 // the tiled kernel (assemble_box.cu) does not cover; it always accumulates.
 #include "general_elem.cuh"
 #include "internal.h"
+#include <initializer_list>
+#include <string>
 
 namespace nalu_b200 {
 
@@ -97,6 +99,54 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) assemble_general_kernel(con
   }
 }
 
+// the nodal / element fields each kernel kind dereferences (its add_gathered_nodal_field / add_element_field
+// registrations in the reference's constructors); a missing one is an argument error on the host, not an illegal
+// address on the device.  Returns the name of the first missing field, or null.
+const char *missing_field(const nalu_b200_kernel_desc &k)
+{
+  static const char *names[NALU_F_COUNT] = {"coordinates", "velocity", "velocity(N)", "velocity(NM1)", "viscosity", "density",
+                                            "density(N)", "density(NM1)", "pressure", "dpdx", "scalarQ", "scalarQ(N)",
+                                            "scalarQ(NM1)", "dual_nodal_volume", "temperature", "turbulent_ke",
+                                            "specific_dissipation_rate", "turbulent_viscosity", "sst_f_one_blending", "Gjq",
+                                            "dudx", "velocity_rtm", "", ""};
+  int need[12];
+  int n = 0;
+  bool mdot = false;
+  auto add = [&](std::initializer_list<int> l) { for (int f : l) need[n++] = f; };
+  switch (k.kind) {
+  case NALU_K_MOMENTUM_ADV_DIFF: add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_VISCOSITY}); mdot = true; break;
+  case NALU_K_CONTINUITY_ADV: add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_DENSITY, NALU_F_PRESSURE, NALU_F_DPDX}); break;
+  case NALU_K_SCALAR_ADV_DIFF: add({NALU_F_COORDINATES, NALU_F_SCALARQ, NALU_F_VISCOSITY}); mdot = true; break;
+  case NALU_K_SCALAR_DIFF: add({NALU_F_COORDINATES, NALU_F_SCALARQ, NALU_F_VISCOSITY}); break;
+  case NALU_K_SCALAR_UPW_ADV_DIFF:
+    add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_GJQ, NALU_F_SCALARQ, NALU_F_DENSITY, NALU_F_VISCOSITY}); mdot = true; break;
+  case NALU_K_MOMENTUM_UPW_ADV_DIFF:
+    add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_VISCOSITY, NALU_F_DENSITY, NALU_F_GJU}); mdot = true; break;
+  case NALU_K_MOMENTUM_MASS:
+    add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_VELOCITY_N, NALU_F_VELOCITY_NM1, NALU_F_DPDX, NALU_F_DENSITY, NALU_F_DENSITY_N,
+         NALU_F_DENSITY_NM1}); break;
+  case NALU_K_SCALAR_MASS:
+    add({NALU_F_COORDINATES, NALU_F_SCALARQ, NALU_F_SCALARQ_N, NALU_F_SCALARQ_NM1, NALU_F_DENSITY, NALU_F_DENSITY_N, NALU_F_DENSITY_NM1}); break;
+  case NALU_K_CONTINUITY_MASS: add({NALU_F_COORDINATES, NALU_F_DENSITY, NALU_F_DENSITY_N, NALU_F_DENSITY_NM1}); break;
+  case NALU_K_MOMENTUM_BUOYANCY_SRC: add({NALU_F_COORDINATES, NALU_F_DENSITY}); break;
+  case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC: add({NALU_F_COORDINATES, NALU_F_TEMPERATURE}); break;
+  case NALU_K_TKE_SST_SRC:
+  case NALU_K_SDR_SST_SRC:
+    add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_DENSITY, NALU_F_TKE, NALU_F_SDR, NALU_F_TVISC});
+    if (k.kind == NALU_K_SDR_SST_SRC) add({NALU_F_FONE_BLEND});
+    break;
+  case NALU_K_TEST_FIXED_BLOCK: return k.fixed_block ? nullptr : "fixed_block";
+  default: return "unknown kernel kind";
+  }
+  const bool upw = k.kind == NALU_K_SCALAR_UPW_ADV_DIFF || k.kind == NALU_K_MOMENTUM_UPW_ADV_DIFF;
+  for (int q = 0; q < n; ++q) {
+    if (need[q] == NALU_F_VELOCITY && upw && k.kind == NALU_K_SCALAR_UPW_ADV_DIFF && k.nodal[NALU_F_VELOCITY_RTM]) continue;
+    if (!k.nodal[need[q]]) return names[need[q]];
+  }
+  if (mdot && !k.mass_flow_rate) return "mass_flow_rate_scs";
+  return nullptr;
+}
+
 int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
                             double *d_rhs, cudaStream_t stream)
 {
@@ -135,6 +185,10 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
         set_error("assemble_elem: coordinates field missing (add_coordinates_field must precede master element calls)");
         return NALU_B200_ERR_ARG;
       }
+    }
+    if (const char *missing = missing_field(kernels[i])) {
+      set_error(std::string("assemble_elem: field missing for kernel ") + std::to_string(i) + ": " + missing);
+      return NALU_B200_ERR_ARG;
     }
   }
   (void)need_coords;
@@ -231,6 +285,11 @@ int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, do
     set_error("scv_lumped: unsupported kernel list");
     return NALU_B200_ERR_ARG;
   }
+  for (int i = 0; i < nk; ++i)
+    if (const char *missing = missing_field(k[i])) {
+      set_error(std::string("assemble_elem: field missing for a lumped mass kernel: ") + missing);
+      return NALU_B200_ERR_ARG;
+    }
   if (g.n_elems == 0) return NALU_B200_OK;
   const long long threads = g.n_elems * 8;
   for (int i = 0; i < nk; ++i) {
@@ -245,16 +304,16 @@ int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, do
 
 // ---- node mass algorithms ----------------------------------------------------------------
 // AssembleNodeSolverAlgorithm::execute (src/AssembleNodeSolverAlgorithm.C:57-111) with
-// {Momentum,Continuity,Scalar}MassBDF2NodeSuppAlg::node_execute; one thread per local node,
-// locally-owned nodes only; the 1-node sumInto targets the diagonal block of the node's row.
-__global__ void node_mass_kernel(int n_nodes, int n_owned_nodes, int ndof, const int *node_row,
-                                 const long long *browptr, const int *bcol, nalu_b200_kernel_desc k,
-                                 double *values, double *rhs)
+// {Momentum,Continuity,Scalar}MassBDF2NodeSuppAlg::node_execute; one thread per locally-owned ROW: the node visited is the
+// row's representative (periodic subjects, which alias their monarch's row, are excluded from the reference's selector), so
+// every row is touched by exactly one thread -- plain adds, no atomics.  The 1-node sumInto targets the diagonal block.
+__global__ void node_mass_kernel(int n_owned_nodes, int ndof, const int *row_rep, const long long *browptr, const int *bcol,
+                                 nalu_b200_kernel_desc k, double *values, double *rhs)
 {
-  const int node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= n_nodes) return;
-  const int rn = node_row[node];
-  if (rn >= n_owned_nodes) return; // not locally owned
+  const int rn = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rn >= n_owned_nodes) return;
+  const int node = row_rep[rn];
+  if (node < 0) return;
   const long long b0 = browptr[rn], b1 = browptr[rn + 1];
   // diagonal block: column rn (binary search, rows are sorted)
   long long lo = b0, hi = b1;
@@ -275,16 +334,16 @@ __global__ void node_mass_kernel(int n_nodes, int n_owned_nodes, int ndof, const
                    uNp1 = k.nodal[NALU_F_VELOCITY][(size_t)node * 3 + i], dpdx = k.nodal[NALU_F_DPDX][(size_t)node * 3 + i];
       const double r = -(k.gamma1 * rhoNp1 * uNp1 + k.gamma2 * rhoN * uN + k.gamma3 * rhoNm1 * uNm1) * dualVolume / k.dt -
                        dpdx * dualVolume;
-      atomicAdd(rhs + (long long)rn * 3 + i, r);
-      atomicAdd(values + base + (long long)i * nb * 3 + slot * 3 + i, lhsfac);
+      rhs[(long long)rn * 3 + i] += r;
+      values[base + (long long)i * nb * 3 + slot * 3 + i] += lhsfac;
     }
   } else if (k.kind == NALU_K_CONTINUITY_MASS) {
     const double tau = k.dt / k.gamma1;
-    atomicAdd(rhs + rn, -(k.gamma1 * rhoNp1 + k.gamma2 * rhoN + k.gamma3 * rhoNm1) * dualVolume / k.dt / tau);
+    rhs[rn] += -(k.gamma1 * rhoNp1 + k.gamma2 * rhoN + k.gamma3 * rhoNm1) * dualVolume / k.dt / tau;
   } else {
     const double qNm1 = k.nodal[NALU_F_SCALARQ_NM1][node], qN = k.nodal[NALU_F_SCALARQ_N][node], qNp1 = k.nodal[NALU_F_SCALARQ][node];
-    atomicAdd(rhs + rn, -(k.gamma1 * rhoNp1 * qNp1 + k.gamma2 * qN * rhoN + k.gamma3 * qNm1 * rhoNm1) * dualVolume / k.dt);
-    atomicAdd(values + base + slot, k.gamma1 * rhoNp1 * dualVolume / k.dt);
+    rhs[rn] += -(k.gamma1 * rhoNp1 * qNp1 + k.gamma2 * qN * rhoN + k.gamma3 * qNm1 * rhoNm1) * dualVolume / k.dt;
+    values[base + slot] += k.gamma1 * rhoNp1 * dualVolume / k.dt;
   }
 }
 
@@ -296,8 +355,12 @@ int launch_node_mass(const Graph &g, const nalu_b200_kernel_desc &k, double *d_v
     set_error("assemble_node_mass: needs a mass kernel kind matching numDof and the dual_nodal_volume field");
     return NALU_B200_ERR_ARG;
   }
-  if (g.n_nodes == 0) return NALU_B200_OK;
-  node_mass_kernel<<<(g.n_nodes + 255) / 256, 256, 0, stream>>>(g.n_nodes, g.n_owned_nodes, g.ndof, g.d_node_row,
+  if (const char *missing = missing_field(k)) {
+    set_error(std::string("assemble_node_mass: nodal field missing: ") + missing);
+    return NALU_B200_ERR_ARG;
+  }
+  if (g.n_owned_nodes == 0) return NALU_B200_OK;
+  node_mass_kernel<<<(g.n_owned_nodes + 255) / 256, 256, 0, stream>>>(g.n_owned_nodes, g.ndof, g.d_row_rep,
                                                                (const long long *)g.d_browptr, g.d_bcol, k, d_values, d_rhs);
   count_launch();
   NALU_CUDA(cudaGetLastError());

@@ -90,7 +90,7 @@ static void free_graph_device(Graph &g)
     if (p) cudaFree(p);
     p = nullptr;
   };
-  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_desc);
+  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_row_rep); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_desc);
   F(g.d_rowptr_owned); F(g.d_rowptr_shared); F(g.d_colidx_owned); F(g.d_colidx_shared); F(g.d_err);
   for (auto *peers : {&g.send_peers, &g.recv_peers})
     for (HaloPeer &p : *peers) {
@@ -104,6 +104,7 @@ static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const s
   int rc;
   if ((rc = upload(&g.d_elem_nodes, g.elem_nodes))) return rc;
   if ((rc = upload(&g.d_node_row, g.node_row))) return rc;
+  if ((rc = upload(&g.d_row_rep, g.row_rep))) return rc;
   if ((rc = upload(&g.d_browptr, g.browptr))) return rc;
   if ((rc = upload(&g.d_bcol, g.bcol))) return rc;
   if ((rc = upload(&g.d_elem_slot, elem_slot))) return rc;

@@ -96,6 +96,10 @@ int graph_number_and_adjacency(Graph &g, std::string &err)
     err = "a node id is owned by this rank on one alias and by another rank on another";
     return 1;
   }
+  // the node the reference's node algorithms visit for a row: periodic subjects are excluded from their selectors
+  // (src/AssembleNodeSolverAlgorithm.C:57-111), which leaves the monarch = the lowest local node of the id
+  g.row_rep.assign(nrow, -1);
+  for (int32_t n = nn - 1; n >= 0; --n) g.row_rep[g.node_row[n]] = n;
 
   // ---- element incidence per row node ------------------------------------------------
   const int64_t ne = g.n_elems;

@@ -49,6 +49,7 @@ struct Graph {
   // numbering: row nodes = unique owned ids (ascending) then unique shared-not-owned ids
   int32_t n_owned_nodes = 0, n_shared_nodes = 0;
   std::vector<int32_t> node_row;     // [n_nodes] local node -> row node
+  std::vector<int32_t> row_rep;      // [n_row_nodes] lowest local node of the row (several nodes alias a row on periodic meshes)
   std::vector<int64_t> row_node_gid; // [n_owned+n_shared]
   std::vector<int32_t> shared_owner; // [n_shared]
 
@@ -73,6 +74,7 @@ struct Graph {
   // device
   int32_t *d_elem_nodes = nullptr; // [n_elems][8]
   int32_t *d_node_row = nullptr;   // [n_nodes]
+  int32_t *d_row_rep = nullptr;    // [n_row_nodes]
   int64_t *d_browptr = nullptr;    // [n_row_nodes+1]
   int32_t *d_bcol = nullptr;
   uint8_t *d_elem_slot = nullptr;  // [n_elems][8][8]

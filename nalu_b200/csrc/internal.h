@@ -25,6 +25,7 @@ void set_last_mode(int m);
 // assemble_general.cu
 int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values,
                             double *d_rhs, cudaStream_t stream);
+const char *missing_field(const nalu_b200_kernel_desc &k);
 int launch_node_mass(const Graph &g, const nalu_b200_kernel_desc &k, double *d_values, double *d_rhs,
                      cudaStream_t stream);
 bool cont_box_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);

@@ -119,6 +119,21 @@ class DeviceCsrLinearSystem:
         check(self.L.nalu_b200_graph_device_ptrs(self.h, int(shared), C.byref(rp), C.byref(ci)), "device_ptrs")
         return rp.value, ci.value
 
+    def device_graph_tensors(self, shared=False):
+        """(rowptr int64[nRows+1], colidx int32[nnz]) as torch views of the device-resident graph (no copy)."""
+        import torch
+        rp, ci = self.device_graph(shared)
+        n = self.n_shared_rows if shared else self.n_owned_rows
+        nnz = self.nnz_shared if shared else self.nnz_owned
+
+        def view(addr, count, typestr):
+            class _Mem:
+                pass
+            m = _Mem()
+            m.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(addr), False), "version": 3}
+            return torch.as_tensor(m, device=self.device)
+        return view(rp, n + 1, "<i8"), view(ci, max(nnz, 1), "<i4")[:nnz]
+
     # ---- storage -----------------------------------------------------------------------------
     def allocate(self, device="cuda", raw=False):
         """values / rhs storage.  raw=True takes the memory straight from cudaMalloc (through the C ABI)

@@ -94,6 +94,23 @@ def rel_err(a, b, floor_scale):
     return float(np.max(np.abs(a - b) / denom)) if a.size else 0.0
 
 
+def rel_err_rows(a, b, rowptr, floor_frac):
+    """max over entries of |a-b| / max(|a|, |b|, floor_frac * max|row of b|): the per-row floor of SURVEY 8(d) -- an
+    entry that cancels to (near) zero is compared against the scale of ITS OWN row, not of the whole matrix."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.size == 0:
+        return 0.0
+    rp = np.asarray(rowptr, dtype=np.int64)
+    lens = np.diff(rp)
+    rowmax = np.zeros(lens.size)
+    nz = lens > 0
+    rowmax[nz] = np.maximum.reduceat(np.abs(b), rp[:-1][nz])
+    floor = np.repeat(floor_frac * rowmax, lens)
+    denom = np.maximum(np.maximum(np.abs(a), np.abs(b)), np.maximum(floor, 1e-300))
+    return float(np.max(np.abs(a - b) / denom))
+
+
 def perturbed_box(nx, ny, nz, amp=0.12):
     m = mesh.generated_box(nx, ny, nz)
     mesh.perturb_coords_hash(m, amp)
