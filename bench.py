@@ -4,11 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
 
-One "step" = one AssembleElemSolverAlgorithm::execute of MomentumAdvDiffElemKernel over all
-locally-owned Hex8 elements of a perturbed structured box (LHS + RHS computed AND scattered into
-the CSR), followed, when N > 1, by loadComplete (the shared-row halo sum).  Weak scaling: every
-GPU holds an n^3-element slab (n=256 by default: BASELINE config 3 at N=1; 8 x 256^3 = the 512^3
-element count of config 4 at N=8).  Prints ONE JSON line (rank 0).
+One "step" = one AssembleElemSolverAlgorithm::execute of the momentum kernel list of the low-Mach
+equation system, [MomentumMassElemKernel(lumped), MomentumAdvDiffElemKernel]
+(src/LowMachEquationSystem.C:1304-1398; BASELINE config 3), over all locally-owned Hex8 elements of a
+perturbed structured box (LHS + RHS computed AND scattered into the CSR), followed, when N > 1, by
+loadComplete (the shared-row halo sum).  --scaling weak (default): every GPU holds an n^3-element
+slab (n=256: BASELINE config 3 at N=1; 8 x 256^3 = the 512^3 element count of config 4 at N=8);
+--scaling strong: ONE n x n x n box cut into N z-slabs (config 3 "at 1/2/4/8 B200").  Prints ONE JSON
+line (rank 0).
 """
 import argparse
 import json
@@ -31,6 +34,42 @@ UNIT = "Melem/s"
 
 def algorithmic_bytes(n_nodes, n_elems, nnz, ndof, nodal_comps, elem_comps):
     return 8 * nodal_comps * n_nodes + 8 * elem_comps * n_elems + 32 * n_elems + 8 * nnz + 8 * ndof * n_nodes
+
+
+MASS = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5, dens_fac=0.0, om_dens_fac=1.0)
+
+
+def workload_fields(c):
+    """nodal state of the benchmark as analytic functions of the coordinates (host, numpy): any rank -- and the
+    sampled-row checker -- can recreate the fields of any node"""
+    from nalu_b200 import fields
+    vel, rho = fields.velocity(c), fields.smooth_density(c)
+    return {"coordinates": c, "velocity": vel, "viscosity": fields.smooth_viscosity(c), "density": rho,
+            "density_n": 0.98 * rho, "density_nm1": 0.95 * rho, "velocity_n": 0.9 * vel, "velocity_nm1": 0.8 * vel,
+            "dpdx": fields.dpdx(c), "pressure": fields.pressure(c)}
+
+
+def oracle_kernels(kernels, divu):
+    """kernel_fn of tests/sampled_parity.check_sampled_rows: the oracle's descriptors of the benchmark's kernel list"""
+    import oracle
+
+    def fn(sub, f):
+        keep = []
+        mdot = oracle.calc_mass_flow_rate_scs(sub.elem_nodes, f["coordinates"], f["density"], f["velocity"])
+        out = []
+        for k in kernels:
+            if k == "momentum_mass":
+                out.append(oracle.make_desc("momentum_mass", keep, coordinates=f["coordinates"], velocity=f["velocity"],
+                                            velocityN=f["velocity_n"], velocityNm1=f["velocity_nm1"], density=f["density"],
+                                            densityN=f["density_n"], densityNm1=f["density_nm1"], Gpdx=f["dpdx"], lumpedMass=1,
+                                            dt=MASS["dt"], gamma1=MASS["gamma1"], gamma2=MASS["gamma2"], gamma3=MASS["gamma3"],
+                                            densFac=MASS["dens_fac"], om_densFac=MASS["om_dens_fac"]))
+            else:
+                out.append(oracle.make_desc("momentum_adv_diff", keep, coordinates=f["coordinates"], velocity=f["velocity"],
+                                            viscosity=f["viscosity"], massFlowRate=mdot, includeDivU=divu))
+        fn.keep = keep
+        return out
+    return fn
 
 
 def load_peaks():
@@ -90,32 +129,28 @@ class ClockSampler:
 # reference arm / cpu_baseline: the oracle (literal restatement of the reference algorithm)
 # timed on the host cores, P slab partitions on P threads standing in for P MPI ranks
 # --------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, cores=None, nx=64, layers_per_rank=16):
+def cpu_reference_run(steps, warmup, kernels, divu, cores=None, nx=64, layers_per_rank=16):
     import oracle
-    from nalu_b200 import fields, mesh
+    from nalu_b200 import mesh
     P = cores or min(os.cpu_count() or 1, 64)
     parts = [mesh.generated_box_rank(nx, nx, layers_per_rank * P, r, P) for r in range(P)]
     for m in parts:
         mesh.perturb_coords_hash(m, 0.12)
     ls = oracle.LinSys(parts, 3)  # graph construction is outside the timed region, as for the GPU arm
-    keep = []
-    descs = []
+    fns, descs = [], []
     for m in parts:
-        c = m.coords
-        vel = fields.velocity(c)
-        rho = fields.smooth_density(c)
-        mdot = oracle.calc_mass_flow_rate_scs(m.elem_nodes, c, rho, vel)
-        descs.append(oracle.make_desc("momentum_adv_diff", keep, coordinates=c, velocity=vel,
-                                      viscosity=fields.smooth_viscosity(c), massFlowRate=mdot, includeDivU=1.0))
+        fn = oracle_kernels(kernels, divu)
+        descs.append(fn(m, workload_fields(m.coords)))
+        fns.append(fn)
     n_elems = sum(m.n_elems for m in parts)
 
     def one_step():
         ls.zero()
         t0 = time.perf_counter()
         if P == 1:
-            ls.assemble_elem(0, [descs[0]])
+            ls.assemble_elem(0, descs[0])
         else:
-            th = [threading.Thread(target=ls.assemble_elem, args=(r, [descs[r]])) for r in range(P)]
+            th = [threading.Thread(target=ls.assemble_elem, args=(r, descs[r])) for r in range(P)]
             for t in th:
                 t.start()
             for t in th:
@@ -128,20 +163,32 @@ def cpu_reference_run(steps, warmup, cores=None, nx=64, layers_per_rank=16):
     times = [one_step() for _ in range(steps)]
     t = float(np.mean(times))
     return {"value": n_elems / t / 1e6, "unit": UNIT, "cores": P, "kind": "port",
-            "sample": f"{nx}x{nx}x{layers_per_rank * P} Hex8 box in {P} z-slabs ({n_elems} elements), "
-                      f"momentum adv-diff + sumInto + export-add, {steps} steps, oracle C restatement -O3",
+            "sample": f"{nx}x{nx}x{layers_per_rank * P} Hex8 box in {P} z-slabs ({n_elems} elements; the GPU arm's workload is "
+                      f"the same kernel list on a larger box: same_config=false), kernels {kernels}, gather + kernels + sumInto "
+                      f"+ export-add, {steps} steps; oracle C restatement of the reference, scalar code (no SIMD across "
+                      "elements), gcc -O3 -march=x86-64-v3 -ffp-contract=off, one thread per slab",
             "ms_per_step": t * 1e3, "n_elems": n_elems}
+
+
+def kernel_names(args):
+    return ["momentum_mass", "momentum_adv_diff"] if args.kernels == "list" else ["momentum_adv_diff"]
+
+
+def kernel_labels(args):
+    adv = f"MomentumAdvDiffElemKernel(includeDivU={args.divu:g})"
+    return ["MomentumMassElemKernel(lumped)", adv] if args.kernels == "list" else [adv]
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(max(1, args.steps), max(1, min(args.warmup, 2)))
+    r = cpu_reference_run(max(1, args.steps), max(1, min(args.warmup, 2)), kernel_names(args), args.divu)
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "hex8_box_momentum_advdiff_assembly", "sample": r["sample"]},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "hex8_box_momentum_list_assembly" if args.kernels == "list" else "hex8_box_momentum_advdiff_assembly",
+                       "kernels": kernel_labels(args), "sample": r["sample"], "same_config": False},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -167,12 +214,14 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
+    strong = args.scaling == "strong"
+    nzg = n if strong else n * world   # element layers of the global box
     L = lib.lib()
     lib.tune(box_kernel=args.box_kernel)
 
     # ---- mesh, graph (once per mesh; outside the timed region) ------------------------------
     t0 = time.perf_counter()
-    m = mesh.generated_box_rank(n, n, n * world, rank, world)
+    m = mesh.generated_box_rank(n, n, nzg, rank, world)
     mesh.perturb_coords_hash(m, 0.12)
 
     from nalu_b200 import dist as nd
@@ -180,6 +229,8 @@ def run_ours(args):
     ls = DeviceCsrLinearSystem(m, 3, exchange=nd.make_exchange(rank, world) if world > 1 else None)
     ls.allocate(dev, raw=(halo == "pull"))
     windows = None
+    comm = nd.make_comm(rank, world) if halo == "capi" else None
+    halo_stream = torch.cuda.Stream(device=dev) if halo == "capi" else None
     if halo == "pull":
         try:
             windows = nd.PeerWindows(ls, rank, world)
@@ -193,33 +244,70 @@ def run_ours(args):
     t_graph = time.perf_counter() - t0
 
     # ---- state: host (pinned) + device ----------------------------------------------------------
-    c = m.coords
-    h = {"coordinates": c, "velocity": fields.velocity(c), "viscosity": fields.smooth_viscosity(c)}
-    rho = fields.smooth_density(c)
+    h = workload_fields(m.coords)
     d = {k: torch.as_tensor(np.ascontiguousarray(v), device=dev) for k, v in h.items()}
-    d_rho = torch.as_tensor(rho, device=dev)
-    mdot = ls.mdot_scs(d["coordinates"], d_rho, d["velocity"])
-    desc = ls.make_desc("momentum_adv_diff", fields=d, mass_flow_rate=mdot, include_divu=args.divu)
+    mdot = ls.mdot_scs(d["coordinates"], d["density"], d["velocity"])
+    adv_fields = {k: d[k] for k in ("coordinates", "velocity", "viscosity")}
+    mass_fields = {k: d[k] for k in ("coordinates", "velocity", "velocity_n", "velocity_nm1", "density", "density_n",
+                                     "density_nm1", "dpdx")}
+    desc_adv = ls.make_desc("momentum_adv_diff", fields=adv_fields, mass_flow_rate=mdot, include_divu=args.divu)
+    desc_mass = ls.make_desc("momentum_mass", fields=mass_fields, options=("lumped_mass",), **MASS)
+    descs = [desc_mass, desc_adv] if args.kernels == "list" else [desc_adv]
+    nodal_comps = 19 if args.kernels == "list" else 7   # doubles read per node: x3 u3 mu (+ u_n3 u_nm13 rho x3 dpdx3)
 
     mode = args.mode
-    probe = ls.assemble_elem([desc], mode=mode, overwrite=True)  # also a first warm-up
+    probe = ls.assemble_elem(descs, mode=mode, overwrite=True)  # also a first warm-up
     overwrite = probe == 2
-    send_peers, recv_peers = ls.halo_peers()
+    kernel_name = (f"assemble_box{args.box_kernel}" if probe == 2 else
+                   ("assemble_box + scv_lumped_mass (two launches)" if probe == 3 else "assemble_general"))
 
-    def step():
+    NZl = m.box.nz + 1
+    overlap = halo == "capi" and overwrite and NZl >= 4
+
+    def assemble(ev0=None, ev1=None):
+        """the assembly launches of one step; with the library's loadComplete the interface node planes (my shared plane
+        0, owned by the rank below; my top plane, which receives the rank above's rows) are assembled first and the
+        exchange runs on a second stream while the interior is assembled"""
         if not overwrite:
-            ls.zero_system()   # the general kernel accumulates: zeroSystem is part of its step
-        ls.assemble_elem([desc], mode=mode, overwrite=overwrite)
-        if world > 1:
+            ls.zero_system()   # kernels that accumulate: zeroSystem is part of their step
+        if ev0 is not None:
+            ev0.record()
+        if not overlap:
+            ls.assemble_elem(descs, mode=mode, overwrite=overwrite)
+            if ev1 is not None:
+                ev1.record()
+            return None
+        lo, hi = (1 if rank > 0 else 0), (NZl - 1 if rank < world - 1 else NZl)
+        if lo > 0:
+            ls.assemble_elem_zrange(descs, 0, lo, overwrite=True)
+        if hi < NZl:
+            ls.assemble_elem_zrange(descs, hi, NZl, overwrite=True)
+        cur = torch.cuda.current_stream(dev)
+        e1 = torch.cuda.Event()
+        e1.record(cur)
+        halo_stream.wait_event(e1)
+        ls.load_complete(comm, stream=halo_stream.cuda_stream)
+        e2 = torch.cuda.Event()
+        e2.record(halo_stream)
+        ls.assemble_elem_zrange(descs, lo, hi, overwrite=True)
+        if ev1 is not None:
+            ev1.record()
+        return e2
+
+    def step(ev0=None, ev1=None):
+        e2 = assemble(ev0, ev1)
+        if e2 is not None:
+            torch.cuda.current_stream(dev).wait_event(e2)
+        elif world > 1:
             load_complete()
 
     def load_complete():
-        if windows is not None:
-            # owners read the sharers' rows straight across NVLink; the barrier orders "my neighbour finished
-            # assembling" before "I pull its rows", a second one keeps it from re-assembling under my reads
+        if comm is not None:
+            ls.load_complete(comm)
+        elif windows is not None:
+            # owners read the sharers' rows straight across NVLink; the barriers inside order "my neighbour finished
+            # assembling" before "I pull its rows" and keep it from re-assembling under my reads
             windows.load_complete(lambda: (torch.cuda.synchronize(), dist.barrier()))
-            torch.cuda.synchronize()
-            dist.barrier()
         else:
             ls.load_complete_nccl()
 
@@ -243,13 +331,7 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         ev[i][0].record()
-        if not overwrite:
-            ls.zero_system()
-        asm_ev[i][0].record()
-        ls.assemble_elem([desc], mode=mode, overwrite=overwrite)
-        asm_ev[i][1].record()
-        if world > 1:
-            load_complete()
+        step(asm_ev[i][0], asm_ev[i][1])
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -264,28 +346,53 @@ def run_ours(args):
     step_ms = max(step_ms, 1e-9)
 
     n_elems_rank = m.n_elems
-    n_elems_total = n_elems_rank * world
+    n_elems_total = n * n * nzg
     value = n_elems_total / (step_ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (the assembly kernel), per launch ---------------------
     peak, peak_src = load_peaks()
     nnz = ls.nnz_owned + ls.nnz_shared
-    bytes_alg = algorithmic_bytes(m.n_nodes, n_elems_rank, nnz, 3, nodal_comps=7, elem_comps=12)
+    bytes_alg = algorithmic_bytes(m.n_nodes, n_elems_rank, nnz, 3, nodal_comps=nodal_comps, elem_comps=12)
     achieved = bytes_alg / (asm_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": (f"assemble_box{args.box_kernel}" if overwrite else "assemble_general"),
+                "traffic": None, "traffic_source": None, "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": bytes_alg, "bytes_per_element": bytes_alg / n_elems_rank,
-                "kernel_ms": asm_ms}
+                "kernel_ms": asm_ms, "exposed_halo_ms": step_ms - asm_ms if world > 1 else 0.0}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
         try:
             with open(tf) as f:
-                roofline["traffic"] = json.load(f).get(roofline["kernel"])
+                t = json.load(f).get(kernel_name)
+            if t is not None:
+                roofline["traffic"] = t
+                roofline["traffic_source"] = "static: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (profiles/traffic.json), not measured in this run"
         except Exception:
             pass
 
-    # ---- e2e: host buffers in, residual (RHS) + matrix checksum out, every step ------------------
-    pinned = {k: torch.as_tensor(np.ascontiguousarray(v)).pin_memory() for k, v in h.items()}
+    # ---- correctness of the timed result (outside the timed region) -----------------------------------------------
+    props = {"finite": bool(torch.isfinite(ls.owned_values()).all()) and bool(torch.isfinite(ls.owned_rhs()).all()),
+             "geometry_errors": ls.geometry_errors()}
+    if not args.no_oracle_check:
+        # sampled rows of THIS system (after loadComplete on several ranks) against the oracle: sub-boxes at the corners,
+        # edges, faces, interior and across the rank interfaces of the timed mesh (tests/sampled_parity.py)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import sampled_parity as sp
+        res = sp.check_sampled_rows(ls, m, nzg, workload_fields, oracle_kernels(kernel_names(args), args.divu), ndof=3, size=5,
+                                    n_random=16)
+        agg = torch.tensor([res["max_rel_err_values"], res["max_rel_err_rhs"], float(res["rows"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = agg.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            res["max_rel_err_values"], res["max_rel_err_rhs"], res["rows"] = float(mx[0]), float(mx[1]), int(agg[2])
+        res["tolerance"] = 1e-12
+        res["passed"] = bool(res["max_rel_err_values"] < 1e-12 and res["max_rel_err_rhs"] < 1e-12)
+        props["sampled_rows_vs_oracle"] = res
+
+    # ---- e2e: host buffers in, residual (RHS) out, every step ------------------------------------------------------
+    e2e_keys = ["coordinates", "velocity", "viscosity"] + (["velocity_n", "velocity_nm1", "density", "density_n", "density_nm1", "dpdx"]
+                                                          if args.kernels == "list" else [])
+    pinned = {k: torch.as_tensor(np.ascontiguousarray(h[k])).pin_memory() for k in e2e_keys}
     pinned["mdot"] = mdot.cpu().pin_memory()
     rhs_host = torch.empty(ls.n_owned_rows, dtype=torch.float64).pin_memory()
     h2d = sum(t.numel() * 8 for t in pinned.values())
@@ -293,7 +400,7 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_step():
-        for k in ("coordinates", "velocity", "viscosity"):
+        for k in e2e_keys:
             d[k].copy_(pinned[k], non_blocking=True)
         mdot.copy_(pinned["mdot"], non_blocking=True)
         step()
@@ -306,9 +413,10 @@ def run_ours(args):
 
     # The same step with the host->device copies of the next node planes overlapped with the assembly of
     # the current ones (nalu_b200_assemble_elem_zrange on the compute stream, copies on a second stream).
-    NZl = n + 1
+    lz = m.box.nz
+    NZl = lz + 1
     nxy_nodes, nxy_elems = (n + 1) * (n + 1), n * n
-    nchunk = max(1, min(args.e2e_chunks, n // 16))
+    nchunk = max(1, min(args.e2e_chunks, lz // 16))
     zb = [round(i * NZl / nchunk) for i in range(nchunk + 1)]
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)
@@ -321,11 +429,11 @@ def run_ours(args):
         for c in range(nchunk):
             z0, z1 = zb[c], zb[c + 1]
             p_hi = min(z1 + 1, NZl)        # node planes z0-1 .. z1
-            l_hi = min(z1, n)              # element layers z0-1 .. z1-1
+            l_hi = min(z1, lz)             # element layers z0-1 .. z1-1
             with torch.cuda.stream(copy_stream):
                 if p_hi > planes_done:
                     a, b = planes_done * nxy_nodes, p_hi * nxy_nodes
-                    for k in ("coordinates", "velocity", "viscosity"):
+                    for k in e2e_keys:
                         d[k][a:b].copy_(pinned[k][a:b], non_blocking=True)
                     planes_done = p_hi
                 if l_hi > layers_done:
@@ -335,7 +443,7 @@ def run_ours(args):
                 evc = torch.cuda.Event()
                 evc.record(copy_stream)
             cur.wait_event(evc)
-            ls.assemble_elem_zrange([desc], z0, z1, overwrite=True)
+            ls.assemble_elem_zrange(descs, z0, z1, overwrite=True)
             if world == 1:
                 # the residual rows of a finished range go home while the next range is assembled (full duplex)
                 evk = torch.cuda.Event()
@@ -373,151 +481,79 @@ def run_ours(args):
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "serial_ms_per_step": serial_ms,
            "schedule": (f"{nchunk} node-plane ranges: host->device copy of range c+1 overlaps the assembly of range c "
                         "(nalu_b200_assemble_elem_zrange)") if use_pipe else "copy everything, then assemble",
-           "note": "inputs (coords, velocity, viscosity, mdot) from pinned host memory every step; the RHS "
-                   "(nonlinear residual) is read back to the host; the CSR values stay device-resident for a "
-                   "device solver"}
+           "note": "every nodal field the kernel list gathers and the element field mass_flow_rate_scs come from pinned host "
+                   "memory every step; the RHS (nonlinear residual) is read back to the host; the CSR values stay "
+                   "device-resident for a device solver"}
 
-    # ---- size-independent correctness properties on the timed result --------------------------
-    vals = ls.owned_values()
-    sum_v, sum_abs = float(vals.sum()), float(vals.abs().sum())
-    props = {"sum_values_over_sum_abs": sum_v / sum_abs if sum_abs else None,
-             "finite": bool(torch.isfinite(vals).all()) and bool(torch.isfinite(ls.rhs).all()),
-             "geometry_errors": ls.geometry_errors()}
-
-    if world > 1:
-        props["multi_rank_selfcheck"] = multi_rank_selfcheck(rank, world, dev, halo)
-
-    # ---- the other pass of BASELINE config 3: continuity (ContinuityAdvElemKernel) on the same mesh, device-resident
-    # inputs, outside the timed region of the headline metric; reported beside it, not folded into `value`
-    continuity = None
-    if world == 1 and not args.no_continuity:
-        ls1 = DeviceCsrLinearSystem(m, 1).allocate(dev)
-        f1 = {"coordinates": d["coordinates"], "velocity": d["velocity"], "density": d_rho,
-              "pressure": torch.as_tensor(fields.pressure(c), device=dev), "dpdx": torch.as_tensor(np.ascontiguousarray(fields.dpdx(c)), device=dev)}
-        desc1 = ls1.make_desc("continuity_adv", fields=f1, dt=0.05, gamma1=1.5)
-        fam = 0
-        for _ in range(3):
-            fam = ls1.assemble_elem([desc1], mode=mode if mode != "box" else "auto", overwrite=True)
+    # ---- what explains the headline: the adv-diff kernel alone, the continuity pass of BASELINE config 3 (one rank,
+    # device-resident inputs, outside the timed region of the headline metric)
+    def time_launches(fn, reps=5):
+        for _ in range(2):
+            fn()
         torch.cuda.synchronize()
-        cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-        for a, b in cev:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
             a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    if world == 1 and not args.no_continuity:
+        if args.kernels == "list":
+            fam1 = ls.assemble_elem([desc_adv], mode=mode, overwrite=True)
+            s_ms = time_launches(lambda: ls.assemble_elem([desc_adv], mode=mode, overwrite=(fam1 == 2)))
+            s_bytes = algorithmic_bytes(m.n_nodes, n_elems_rank, nnz, 3, nodal_comps=7, elem_comps=12)
+            roofline["single_kernel"] = {"kernels": [f"MomentumAdvDiffElemKernel(includeDivU={args.divu:g})"], "value": n_elems_rank / s_ms / 1e3,
+                                         "unit": UNIT, "ms": s_ms, "bytes_per_element": s_bytes / n_elems_rank,
+                                         "frac": s_bytes / s_ms / 1e6 / peak, "list_over_single": s_ms / asm_ms}
+            if not args.no_oracle_check and fam1 == 2:
+                props["row_sum_identity_advdiff"] = sp.row_sum_identity(ls, m, mdot)
+        ls1 = DeviceCsrLinearSystem(m, 1).allocate(dev)
+        f1 = {k: d[k] for k in ("coordinates", "velocity", "density", "pressure", "dpdx")}
+        desc1 = ls1.make_desc("continuity_adv", fields=f1, dt=0.05, gamma1=1.5)
+        cmode = mode if mode != "box" else "auto"
+        fam = ls1.assemble_elem([desc1], mode=cmode, overwrite=True)
+
+        def cont():
             if fam != 2:
                 ls1.zero_system()
-            ls1.assemble_elem([desc1], mode=mode if mode != "box" else "auto", overwrite=(fam == 2))
-            b.record()
-        torch.cuda.synchronize()
-        c_ms = float(np.mean([a.elapsed_time(b) for a, b in cev]))
+            ls1.assemble_elem([desc1], mode=cmode, overwrite=(fam == 2))
+        c_ms = time_launches(cont)
         c_bytes = algorithmic_bytes(m.n_nodes, n_elems_rank, ls1.nnz_owned, 1, nodal_comps=11, elem_comps=0)
-        continuity = {"kernel": "assemble_cont_box" if fam == 2 else "assemble_general", "value": n_elems_rank / c_ms / 1e3,
-                      "unit": UNIT, "ms": c_ms, "bytes_per_element": c_bytes / n_elems_rank,
-                      "achieved_GBps": c_bytes / c_ms / 1e6, "frac_of_hbm": c_bytes / c_ms / 1e6 / peak, "bound": "fp64",
-                      "finite": bool(torch.isfinite(ls1.values).all()), "geometry_errors": ls1.geometry_errors(),
-                      "momentum_plus_continuity_two_passes": {"value": n_elems_rank / (asm_ms + c_ms) / 1e3, "unit": UNIT,
-                                                               "frac_of_hbm": (bytes_alg + c_bytes) / (asm_ms + c_ms) / 1e6 / peak}}
+        roofline["continuity"] = {"kernel": "assemble_cont_box" if fam == 2 else "assemble_general", "value": n_elems_rank / c_ms / 1e3,
+                                  "unit": UNIT, "ms": c_ms, "bytes_per_element": c_bytes / n_elems_rank,
+                                  "frac": c_bytes / c_ms / 1e6 / peak, "bound": "fp64 / instruction issue",
+                                  "finite": bool(torch.isfinite(ls1.values).all()), "geometry_errors": ls1.geometry_errors()}
+        roofline["momentum_plus_continuity"] = {"value": n_elems_rank / (asm_ms + c_ms) / 1e3, "unit": UNIT,
+                                                "frac": (bytes_alg + c_bytes) / (asm_ms + c_ms) / 1e6 / peak,
+                                                "note": "two passes (momentum list, then continuity), BASELINE config 3; target 0.60"}
         del ls1
-
-    # ---- the momentum kernel LIST of the low-Mach equation system (BASELINE config 3: lumped mass + adv-diff) through
-    # the public call: tiled write-once kernel for adv-diff, per-SCV kernel for the lumped mass on top
-    momentum_list = None
-    if world == 1 and not args.no_continuity and overwrite:
-        vel_h = h["velocity"]
-        fl = dict(d)
-        fl.update(velocity_n=torch.as_tensor(np.ascontiguousarray(0.9 * vel_h), device=dev),
-                  velocity_nm1=torch.as_tensor(np.ascontiguousarray(0.8 * vel_h), device=dev), density=d_rho,
-                  density_n=0.98 * d_rho, density_nm1=0.95 * d_rho,
-                  dpdx=torch.as_tensor(np.ascontiguousarray(fields.dpdx(c)), device=dev))
-        dl = [ls.make_desc("momentum_mass", fields=fl, options=("lumped_mass",), dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5), desc]
-        fam = 0
-        for _ in range(2):
-            fam = ls.assemble_elem(dl, mode="auto", overwrite=True)
-        torch.cuda.synchronize()
-        lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-        for a, b in lev:
-            a.record()
-            ls.assemble_elem(dl, mode="auto", overwrite=True)
-            b.record()
-        torch.cuda.synchronize()
-        l_ms = float(np.mean([a.elapsed_time(b) for a, b in lev]))
-        momentum_list = {"kernels": ["MomentumMassElemKernel(lumped)", f"MomentumAdvDiffElemKernel(includeDivU={args.divu:g})"],
-                         "kernel_family": fam, "value": n_elems_rank / l_ms / 1e3, "unit": UNIT, "ms": l_ms,
-                         "finite": bool(torch.isfinite(ls.values).all())}
-        ls.assemble_elem([desc], mode=mode, overwrite=True)  # leave the headline system in place
+        ls.assemble_elem(descs, mode=mode, overwrite=overwrite)  # leave the headline system in place
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=2, warmup=1)
+        r = cpu_reference_run(2, 1, kernel_names(args), args.divu)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
+        wl = "momentum_list" if args.kernels == "list" else "momentum_advdiff"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"hex8_box_{n}x{n}x{n * world}_momentum_advdiff_assembly",
-                           "elements_per_gpu": n_elems_rank, "kernels": [f"MomentumAdvDiffElemKernel(includeDivU={args.divu:g})"],
-                           "partition": f"z-slabs x{world}", "halo": {"nccl": "pack kernel -> NCCL send/recv -> unpack-add kernel", "pull": "owner kernel reads peer rows over NVLink (CUDA IPC), no pack/staging", "none": "none"}[halo],
+                "config": {"workload": f"hex8_box_{n}x{n}x{nzg}_{wl}_assembly",
+                           "elements_per_gpu": n_elems_rank, "kernels": kernel_labels(args),
+                           "partition": f"z-slabs x{world}",
+                           "halo": {"capi": "nalu_b200_load_complete: pack kernel -> ncclSend/ncclRecv -> unpack-add kernel on a second stream" + (", interface planes assembled first, exchange overlapped with the interior assembly" if overlap else ""),
+                                    "nccl": "pack kernel -> torch.distributed send/recv -> unpack-add kernel",
+                                    "pull": "owner kernel reads peer rows over NVLink (CUDA IPC), no pack/staging", "none": "none"}[halo],
                            "l2_policy": "working set (>=36 GB CSR per GPU at n=256) exceeds the 126 MB L2",
-                           "assemble_kernel": roofline["kernel"], "graph_build_s": t_graph},
+                           "assemble_kernel": kernel_name, "graph_build_s": t_graph},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "wall_ms_per_step": wall_ms, "checks": props, "continuity": continuity,
-                "momentum_list": momentum_list}
+                "clocks": clocks, "wall_ms_per_step": wall_ms, "checks": props}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def multi_rank_selfcheck(rank, world, dev, halo, n=10):
-    """Distributed assembly + loadComplete over the real transport against a single-rank assembly of the same
-    global box (done redundantly by every rank): owned rows must agree entry by entry, matched by global ids.
-    Returns the largest relative difference over all ranks."""
-    import scipy.sparse as sp
-    import torch
-    import torch.distributed as dist
-    from nalu_b200 import dist as nd
-    from nalu_b200 import fields, mesh
-    from nalu_b200.linsys import DeviceCsrLinearSystem
-
-    def assemble(m, exchange, raw):
-        mesh.perturb_coords_hash(m, 0.12)
-        ls = DeviceCsrLinearSystem(m, 3, exchange=exchange).allocate(dev, raw=raw)
-        c = m.coords
-        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
-        d = {"coordinates": t(c), "velocity": t(fields.velocity(c)), "viscosity": t(fields.smooth_viscosity(c))}
-        mdot = ls.mdot_scs(d["coordinates"], t(fields.smooth_density(c)), d["velocity"])
-        ls.assemble_elem([ls.make_desc("momentum_adv_diff", fields=d, mass_flow_rate=mdot, include_divu=1.0)], overwrite=True)
-        return ls
-
-    def to_global(ls):
-        rp, ci = ls.rowptr().astype(np.int64), ls.colidx()
-        cg, rg = ls.col_gids(), ls.row_gids()
-        v = ls.owned_values().cpu().numpy()
-        ncol = int(3 * (n + 1) * (n + 1) * (n * world + 1)) + 1
-        rows = np.repeat(rg, np.diff(rp))
-        return sp.csr_matrix((v, (rows, cg[ci])), shape=(ncol, ncol)), ls.owned_rhs().cpu().numpy(), rg
-
-    part = assemble(mesh.generated_box_rank(n, n, n * world, rank, world), nd.make_exchange(rank, world), halo == "pull")
-    if halo == "pull":
-        w = nd.PeerWindows(part, rank, world)
-        w.load_complete(lambda: (torch.cuda.synchronize(), dist.barrier()))
-        torch.cuda.synchronize()
-        dist.barrier()
-        w.close()
-    else:
-        part.load_complete_nccl()
-    torch.cuda.synchronize()
-    full = assemble(mesh.generated_box(n, n, n * world), None, False)
-    A, b, rg = to_global(part)
-    Af, bf, rgf = to_global(full)
-    sel = np.zeros(A.shape[0], dtype=bool)
-    sel[rg] = True
-    D = (A - Af.multiply(sp.csr_matrix(sel[:, None].astype(np.float64)))).tocsr()
-    err = abs(D).max() / abs(Af).max() if D.nnz else 0.0
-    bfull = np.zeros(A.shape[0])
-    bfull[rgf] = bf
-    errb = np.abs(b - bfull[rg]).max() / np.abs(bf).max()
-    e = torch.tensor([max(float(err), float(errb))], dtype=torch.float64, device=dev)
-    dist.all_reduce(e, op=dist.ReduceOp.MAX)
-    return float(e.item())
 
 
 def main():
@@ -531,10 +567,16 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "general", "box"])
     ap.add_argument("--box-kernel", type=int, default=5, choices=[5, 2],
                     help="tiled momentum kernel: 5 row-thread (default), 2 column-pair (round-1 kernel, for A/B runs)")
+    ap.add_argument("--kernels", default="list", choices=["list", "advdiff"],
+                    help="list: [MomentumMass(lumped), MomentumAdvDiff], the momentum list of the low-Mach system (default); advdiff: MomentumAdvDiff alone")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU holds an n^3 slab; strong: one n^3 box cut into --gpus z-slabs")
+    ap.add_argument("--no-oracle-check", action="store_true", help="skip the sampled-row comparison with the oracle after the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuity", action="store_true", help="skip the continuity pass reported beside the headline metric")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="node-plane ranges of the pipelined end-to-end step")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "pull"], help="loadComplete transport at N>1")
+    ap.add_argument("--halo", default="capi", choices=["capi", "nccl", "pull"],
+                    help="loadComplete transport at N>1: capi = nalu_b200_load_complete (library-owned NCCL communicator, overlapped)")
     ap.add_argument("--divu", type=float, default=1.0, help="SolutionOptions::includeDivU_ (reference default 0; 1 is the costlier variant)")
     args = ap.parse_args()
     if args.impl == "reference":

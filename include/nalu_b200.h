@@ -321,6 +321,20 @@ int nalu_b200_halo_pull_add(const nalu_b200_graph *g, int32_t i, const double *d
 int nalu_b200_halo_peer_offsets(const nalu_b200_graph *g, int32_t i, int64_t *values_offset,
                                 int64_t *rhs_offset);
 
+/* loadComplete inside the library (TpetraLinearSystem::loadComplete, src/TpetraLinearSystem.C:1757-1778: Export(ADD) of
+ * the shared-not-owned matrix and rhs rows to their owners): pack kernel -> ncclSend / ncclRecv per neighbour in one
+ * group -> unpack-add kernel, all enqueued on `stream`, exchange buffers persistent in the graph handle.  NCCL is bound
+ * at run time (dlopen of libnccl.so.2); the communicator is the library's own: rank 0 asks for a unique id (128 bytes),
+ * the caller distributes it (MPI_Bcast, torch.distributed, a file), every rank calls nalu_b200_comm_create.  To overlap
+ * the exchange with the assembly, assemble the interface node planes first (nalu_b200_assemble_elem_zrange), call this
+ * on a second stream that waits for them, and assemble the interior meanwhile.  A graph without neighbours returns OK
+ * at once (comm may be NULL). */
+typedef struct nalu_b200_comm nalu_b200_comm;
+int nalu_b200_comm_get_unique_id(void *id128);
+int nalu_b200_comm_create(nalu_b200_comm **comm, int32_t nranks, int32_t rank, const void *id128);
+void nalu_b200_comm_destroy(nalu_b200_comm *comm);
+int nalu_b200_load_complete(nalu_b200_graph *g, nalu_b200_comm *comm, double *d_values, double *d_rhs, void *stream);
+
 /* CUDA IPC helpers so that separate processes (one per GPU) can map each other's buffers */
 int nalu_b200_ipc_get_handle(const void *d_ptr, void *handle64 /* 64 bytes */);
 int nalu_b200_ipc_open_handle(const void *handle64, void **d_ptr);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnalu_b200.so")
 CU = ["capi.cu", "assemble_general.cu", "assemble_box.cu", "assemble_box2.cu", "assemble_box5.cu", "assemble_cont_box.cu", "assemble_scalar_box.cu", "halo.cu"]
-CPP = ["graph.cpp"]
+CPP = ["graph.cpp", "comm.cpp"]
 HDR = ["internal.h", "graph.h", "general_elem.cuh", "hex8_dev.cuh", "box_tile.cuh", "box2_tile.cuh", "box5_tile.cuh", "cont_tile.cuh", "scalar_tile.cuh", "../../include/nalu_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(log[-1])
             raise RuntimeError("nvcc failed on " + f)
         objs.append(obj)
-    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lcudart", "-lgomp"]
+    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lcudart", "-lgomp", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:

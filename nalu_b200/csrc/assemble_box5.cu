@@ -102,10 +102,12 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
   // what lives across phases: the dz=0 group between the two halves of a plane (across phase 1a), the rhs of dof row i.
   // The accumulators are given their zeros right before the sweep, never after the output: a value that stays live
   // across phase 1, even as zero, costs phase 1 its registers (measured: it ends up in local memory).
-  double acc1[9][3], rr = 0.0;
+  double acc1[9][3], rr = 0.0, vol = 0.0;
+  double *const scv = sm + C5::OFF_SCV;
 
   // records of elements outside the domain are never written: they must read zero (phase 2 does not test)
   for (int i = tid; i < C5::RECSZ; i += C5::NT) rec[i] = 0.0;
+  for (int i = tid; i < C5::NEL * 8; i += C5::NT) scv[i] = 0.0;
   // ---- prologue: node planes zs-1 .. zs+1, the mass flow rates of the layer below the first plane
   if (warp < 3) {
     box5::stage_plane(P, ring + ((zs + 2 + warp) % 3) * C5::PLN, lane, x0, y0, zs - 1 + warp);
@@ -138,11 +140,19 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
 #pragma unroll
       for (int c = 0; c < 9; ++c) acc2[c][0] = acc2[c][1] = acc2[c][2] = 0.0;
       if (act) box5::sweep_half(N, sm, P, H, acc1, acc2);
+      if (P.fuse_mass && act) vol += box5::dual_volume_half(N, sm, H);
       // is the warp's x line stored back to back in lattice order?  (then the runs of a group sit at fixed offsets)
       const bool natural = __all_sync(FULL, box5::node_in_natural_line(M, N.node));
       const unsigned char *sl = P.slot27 + 27 * ((x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z));
       if (H) {
         finalize_group(N, sm, box5::vel_off(N, z % 3), acc1, rr, P.f23, lane);
+        if (P.fuse_mass) {
+          // lumped mass: diagonal entries of the node's own block (column 4 of the dz=0 group; the diagonal is rotated
+          // index 0) and the residual, from the dual volume gathered over the two halves
+          if (N.i < 3 && N.active)
+            box5::lumped_mass_terms(P, (x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z), N.i, vol, acc1[4][0], rr);
+          vol = 0.0;
+        }
         output_group<OW>(N, M, sl, 1, natural, scr, acc1, P.values, lane);
       }
       if (act) {
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
       if (!H || lead) {
         if (tid < 64) {
           if (t < C5::NEL) box5::p1_face_unit(P, t, lead ? 1 : 0, x0, y0, pl0, pl1, mdb, rec);
-        } else if (t < C5::NEL) box5::p1_z_unit(P, t, x0, y0, pl0, pl1, mdb, rec);
+        } else if (t < C5::NEL) box5::p1_z_unit(P, t, x0, y0, pl0, pl1, mdb, rec, scv);
       } else if (z + 1 < ze) {
         if (tid < 64) {
           if (t < C5::NEL) box5::p1_face_half<0>(P, t, 1, x0, y0, pl0, pl1, mdb, rec);

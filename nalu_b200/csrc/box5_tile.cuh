@@ -62,10 +62,10 @@ struct Cfg {
   static constexpr int MDB = NEL * 12;
   // node metadata of one plane = the graph's row descriptors (graph.h, node_desc) of the tile's 32 nodes: [3][32] words
   static constexpr int META = 3 * NNODE;
-  // shared-memory map (doubles)
+  // shared-memory map (doubles); SCV: the 8 sub-control-volume volumes of every element of the layer (fused lumped mass)
   static constexpr int OFF_REC = 0, OFF_SCR = OFF_REC + RECSZ, OFF_RING = OFF_SCR + NWARP * SCRW, OFF_MD = OFF_RING + 3 * PLN,
-                       OFF_META = OFF_MD + MDB;
-  static constexpr int SMEM_DOUBLES = OFF_META + 2 * META;
+                       OFF_META = OFF_MD + MDB, OFF_SCV = OFF_META + 2 * META;
+  static constexpr int SMEM_DOUBLES = OFF_SCV + NEL * 8;
 };
 static_assert(Cfg::FS % 16 == 12 && Cfg::FS >= Cfg::NEL, "field stride must spread the quads of a warp over the banks");
 static_assert((Cfg::OFF_RING % 2) == 0 && (Cfg::OFF_MD % 2) == 0, "16-byte aligned staging areas");
@@ -266,6 +266,39 @@ __host__ __device__ __forceinline__ void p1_point(const Coef &C, const double (&
   o[15 * F] = A[2];
   o[16 * F] = 1.0;
 }
+// Volumes of the 8 sub-control volumes of an element (HexSCV::determinant, Hex8CVFEM.C:149-178; hex_volume_grandy,
+// Hex8GeometryFunctions.h:78-163), from the coefficient vectors.  The sub-hex of corner s = (s1,s2,s3) is the image of the
+// parametric octant xi_k = s_k/4 + eta_k/2, eta in [-1/2,1/2]^3; in eta the map is again trilinear,
+//   dx/d eta_k = (B_k + B_kl eta_l + B_km eta_m + C_klm eta_l eta_m) / 8,
+//   B_k = C_k + s_l C_kl/2 + s_m C_km/2 + s_l s_m C_klm/4,   B_kl = C_kl + s_m C_klm/2,
+// and the integral of its Jacobian determinant over the cube (what Grandy's 24-triangle formula evaluates exactly for
+// a hex with bilinear faces) keeps only the even monomials:
+//   V = [ det(B1,B2,B3) + ( det(B13,B23,B3) + det(B12,B2,B23) + det(B1,B12,B13) ) / 12 ] / 512.
+// out[n], n = Hex8 node index of the corner.
+__host__ __device__ __forceinline__ double det3(const double (&a)[3], const double (&b)[3], const double (&c)[3])
+{
+  return a[0] * (b[1] * c[2] - b[2] * c[1]) + a[1] * (b[2] * c[0] - b[0] * c[2]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+}
+__host__ __device__ inline void scv_volumes(const Coef &C, double *out)
+{
+#pragma unroll 1
+  for (int n = 0; n < 8; ++n) {
+    const double s1 = ((n ^ (n >> 1)) & 1) ? 1.0 : -1.0, s2 = ((n >> 1) & 1) ? 1.0 : -1.0, s3 = ((n >> 2) & 1) ? 1.0 : -1.0;
+    double B1[3], B2[3], B3[3], B12[3], B13[3], B23[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double c7 = C.X[i][7];
+      B1[i] = C.X[i][1] + 0.5 * (s2 * C.X[i][3] + s3 * C.X[i][5]) + 0.25 * s2 * s3 * c7;
+      B2[i] = C.X[i][2] + 0.5 * (s1 * C.X[i][3] + s3 * C.X[i][6]) + 0.25 * s1 * s3 * c7;
+      B3[i] = C.X[i][4] + 0.5 * (s1 * C.X[i][5] + s2 * C.X[i][6]) + 0.25 * s1 * s2 * c7;
+      B12[i] = C.X[i][3] + 0.5 * s3 * c7;
+      B13[i] = C.X[i][5] + 0.5 * s2 * c7;
+      B23[i] = C.X[i][6] + 0.5 * s1 * c7;
+    }
+    out[n] = (det3(B1, B2, B3) + (det3(B13, B23, B3) + det3(B12, B2, B23) + det3(B1, B12, B13)) * (1.0 / 12.0)) * (1.0 / 512.0);
+  }
+}
+
 // face unit: the 4 points of the bottom (top = 0) or top (top = 1) face of element `el` -> record slots 0..3
 // (slot = ip & 3: Hex8CVFEM.C:264-276: ip 0: x edge at y-, 1: y edge at x+, 2: x edge at y+ (L -> R runs along -x),
 // 3: y edge at x-)
@@ -321,7 +354,7 @@ __host__ __device__ inline void p1_face_half(const BoxParams &P, int el, int top
 }
 // z unit: the 4 z-edge points (ip 8 + n above bottom node n) -> record slots 4..7
 __host__ __device__ inline void p1_z_unit(const BoxParams &P, int el, int x0, int y0, const double *pl0, const double *pl1,
-                                          const double *mdb, double *rec)
+                                          const double *mdb, double *rec, double *scv)
 {
   using K = Cfg;
   const int elx = el % K::ELX, ely = el / K::ELX;
@@ -332,6 +365,7 @@ __host__ __device__ inline void p1_z_unit(const BoxParams &P, int el, int x0, in
   coef_load(C, pl0, pl1, elx, ely);
   const double *md = mdb + el * 12 + 8;
   double *o = rec + el + 4 * K::PS;
+  if (P.fuse_mass) scv_volumes(C, scv + el * 8);
   double bz[3];
   area_base<2>(C, bz);
   // T = 2: (u,v) = (x,y); bottom nodes 0..3 = (x-,y-), (x+,y-), (x+,y+), (x-,y+)
@@ -464,6 +498,27 @@ __host__ __device__ __forceinline__ void sweep_half(const Thr &N, const double *
   sweep_point<SX, SY, 2>(pZ0, pZ1, pG, pA0, pA1, pA2, Kc, khz, acc1, acc2);
   NALU_B5_Q(0, 0) NALU_B5_Q(1, 0) NALU_B5_Q(0, 1) NALU_B5_Q(1, 1)
 #undef NALU_B5_Q
+}
+
+// ---- fused lumped MomentumMassElemKernel (src/kernel/MomentumMassElemKernel.C:98-171) -----------------------------------
+// With the shifted (lumped) SCV shape function every sub-control volume talks to its own node only, so the 8 elements
+// around a node contribute (sum of their sub-control volumes at the node) x nodal quantities to the node's diagonal
+// entries and residual.  Share of one z half of the dual volume: the 4 elements of the half, corner (!SX, !SY, !H).
+__host__ __device__ __forceinline__ double dual_volume_half(const Thr &N, const double *sm, int H)
+{
+  using C = Cfg;
+  const double *s = sm + C::OFF_SCV + (N.lx + C::ELX * N.ly) * 8;
+  const int bz = H ? 0 : 4;
+  // node_of_bits(bx, by, bz) = bz*4 + by*2 + (bx ^ by): quadrant (SX,SY) sees the node as corner (!SX, !SY)
+  return (s[bz + 2] + s[8 + bz + 3]) + (s[C::ELX * 8 + bz + 1] + s[(C::ELX + 1) * 8 + bz + 0]);
+}
+// lane (node, i < 3): diagonal entry (i,i) of the node's own block and residual of dof row i
+__host__ __device__ __forceinline__ void lumped_mass_terms(const BoxParams &P, long long n, int i, double V, double &diag, double &rr)
+{
+  const double rp = P.rho_np1[n], rn = P.rho_n[n], rm = P.rho_nm1[n];
+  const double up = P.vel[n * 3 + i], un = P.vel_n[n * 3 + i], um = P.vel_nm1[n * 3 + i], gp = P.dpdx[n * 3 + i];
+  diag += P.g1_dt * rp * V;
+  rr += -(P.g1_dt * rp * up + P.g2_dt * rn * un + P.g3_dt * rm * um) * V - gp * V * (rp * P.dens_fac + P.om_dens_fac);
 }
 
 // ---- finalize of one dz group: diagonal term, rhs share ---------------------------------------------------------------

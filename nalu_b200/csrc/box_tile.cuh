@@ -30,6 +30,12 @@ struct BoxParams {
   // row-thread kernel: magnitudes of the shape-function derivatives (box5_tile.cuh, p2k_init), read by the FMAs
   // straight from the constant bank the kernel parameters live in
   double kt[3], kh[2], f23;
+  // fused lumped MomentumMassElemKernel (row-thread kernel only; fuse_mass = 0: adv-diff alone)
+  int fuse_mass;
+  const double *rho_np1, *rho_n, *rho_nm1; // [nNodes]
+  const double *vel_n, *vel_nm1, *dpdx;    // [nNodes][3]
+  double g1_dt, g2_dt, g3_dt;              // gamma / dt
+  double dens_fac, om_dens_fac;
 };
 
 // ---- small integer helpers on the Hex8 numbering (Hex8CVFEM.C:264-276, 396-412) -------------

@@ -95,7 +95,7 @@ static void free_graph_device(Graph &g)
   for (auto *peers : {&g.send_peers, &g.recv_peers})
     for (HaloPeer &p : *peers) {
       F(p.d_send_nodes); F(p.d_send_node_packed_off); F(p.d_src_packed); F(p.d_src_inplace); F(p.d_src_stride);
-      F(p.d_dst); F(p.d_dst_stride); F(p.d_rhs_src_inplace); F(p.d_rhs_dst);
+      F(p.d_dst); F(p.d_dst_stride); F(p.d_rhs_src_inplace); F(p.d_rhs_dst); F(p.d_buf);
     }
 }
 
@@ -406,7 +406,7 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   // takes its kernel first (it may overwrite), the others accumulate on top through the general kernel -- the sum the
   // reference forms in one scratch lhs/rhs (src/AssembleElemSolverAlgorithm.C:86-91), in another order.
   const bool split_lists = tuning().split_lists;
-  if (mode == NALU_ASSEMBLE_AUTO && nk > 1 && nk <= kMaxKernels && split_lists) {
+  if (mode == NALU_ASSEMBLE_AUTO && nk > 1 && nk <= kMaxKernels && split_lists && !box_supported(g, kernels, nk)) {
     int t = -1;
     for (int i = 0; i < nk && t < 0; ++i)
       if (kernels[i].kind != NALU_K_TEST_FIXED_BLOCK &&

@@ -31,6 +31,7 @@ struct HaloPeer {
   int64_t *d_rhs_src_inplace = nullptr; // per node: offset in the peer's shared rhs
   int64_t *d_rhs_dst = nullptr;         // per node: offset in my rhs
   int64_t peer_values_off = 0, peer_rhs_off = 0; // first row of this peer pair inside peer's shared block
+  double *d_buf = nullptr; // persistent exchange buffer of nalu_b200_load_complete (values, then rhs), allocated on first use
   // host staging of the maps above (uploaded by graph_upload, then released)
   std::vector<int64_t> h_send_node_packed_off;
   std::vector<int64_t> h_src_packed, h_src_inplace, h_dst, h_rhs_src_inplace, h_rhs_dst;

@@ -64,10 +64,13 @@ class PeerWindows:
                             pr.value + allh[peer]["roff"] + 8 * allh[peer]["n_owned_rows"])
 
     def load_complete(self, barrier):
-        """every rank's assembly must be finished (barrier) before its rows are pulled"""
+        """`barrier()` = synchronise this rank's stream, then barrier across ranks.  Every rank's assembly must be
+        finished before its rows are pulled, and no rank may start its next assembly (overwrite mode rewrites the
+        shared rows) or zeroSystem while an owner is still reading them over NVLink: barrier on both sides."""
         barrier()
         for i, (pv, pr) in self.ptrs.items():
             self.ls.halo_pull_add(i, pv, pr)
+        barrier()
 
     def close(self):
         for p in self.opened:
@@ -75,3 +78,24 @@ class PeerWindows:
         self.opened = []
 
 
+
+
+def make_comm(rank, world):
+    """The library's own NCCL communicator (nalu_b200_comm_create): rank 0's unique id travels over torch.distributed."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import lib as _lib
+    L = _lib.lib()
+    ident = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_char * 128)()
+        _lib.check(L.nalu_b200_comm_get_unique_id(buf), "comm_get_unique_id")
+        ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = ident.to(dev)
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().numpy().tobytes())
+    comm = C.c_void_p()
+    _lib.check(L.nalu_b200_comm_create(C.byref(comm), world, rank, raw), "comm_create")
+    return comm

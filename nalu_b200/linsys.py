@@ -312,6 +312,11 @@ class DeviceCsrLinearSystem:
                                              C.c_void_p(peer_shared_rhs_ptr), ptr(self.values), ptr(self.rhs),
                                              self._stream()), "halo_pull_add")
 
+    def load_complete(self, comm, stream=None):
+        """LinearSystem::loadComplete inside the library (nalu_b200_load_complete): `comm` from nalu_b200.dist.make_comm."""
+        st = self._stream() if stream is None else C.c_void_p(stream)
+        check(self.L.nalu_b200_load_complete(self.h, comm, ptr(self.values), ptr(self.rhs), st), "load_complete")
+
     def load_complete_nccl(self, group=None):
         """loadComplete over torch.distributed: pack -> batched isend/irecv -> unpack-add."""
         import torch

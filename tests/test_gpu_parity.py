@@ -326,8 +326,11 @@ def test_system_parity_vs_oracle(case, mode):
     used = ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode=mode, overwrite=True)
     assert used in (1, 2, 3)
     tiled = {"momentum_adv_diff", "continuity_adv", "scalar_adv_diff", "scalar_diff"}
-    if mode == "auto" and len(klist) > 1:  # a tiled-capable kernel plus others: tiled + general
-        assert used == (3 if any(k in tiled for k, _, _ in klist) else 1)
+    if mode == "auto" and len(klist) > 1:
+        # [lumped MomentumMass, MomentumAdvDiff]: one launch of the row-thread kernel (fused); another tiled-capable
+        # kernel plus others: tiled + accumulate; otherwise the general kernel
+        fused = case == "momentum_mass+advdiff"
+        assert used == (2 if fused else (3 if any(k in tiled for k, _, _ in klist) else 1))
     _compare_system(ls, orc)
     assert ls.geometry_errors() == 0
 
@@ -599,6 +602,37 @@ def test_box_kernel_tiles_and_chunks(kernel, zchunk, options, divu, tune):
     torch.testing.assert_close(ls.values, 2 * v1, rtol=1e-15, atol=0)
     torch.testing.assert_close(ls.rhs, 2 * r1, rtol=1e-15, atol=0)
     assert ls.geometry_errors() == 0
+
+
+@pytest.mark.parametrize("zchunk", [0, 2])
+@pytest.mark.parametrize("options,divu,order", [((), 1.0, 0), (("shifted_grad_op", "skew_symmetric"), 0.0, 1)])
+def test_fused_lumped_mass_list(options, divu, order, zchunk, tune):
+    """The momentum list of the low-Mach equation system, [MomentumMassElemKernel(lumped), MomentumAdvDiffElemKernel]
+    (src/LowMachEquationSystem.C:1304-1398), in ONE launch of the row-thread kernel: SCV volumes from the coefficient
+    form of the trilinear map, diagonal + residual terms added to the dz=0 group before it is written."""
+    tune(box_zchunk=zchunk)
+    m = perturbed_box(19, 9, 7)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    sc = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5, dens_fac=0.25, om_dens_fac=0.75)
+    klist = [("momentum_mass", ("lumped_mass",), sc), ("momentum_adv_diff", options, dict(include_divu=divu))]
+    if order:
+        klist.reverse()
+    orc = oracle.LinSys([m], 3)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, k, o, keep, **s) for k, o, s in klist])
+    ls = _linsys(m, 3)
+    ls.values.fill_(float("nan"))
+    ls.rhs.fill_(float("nan"))
+    descs = [product_desc(ls, dev, k, o, **s) for k, o, s in klist]
+    launches0 = ls.L.nalu_b200_launch_count()
+    assert ls.assemble_elem(descs, mode="auto", overwrite=True) == 2
+    assert ls.L.nalu_b200_launch_count() - launches0 == 1
+    _compare_system(ls, orc)
+    assert ls.geometry_errors() == 0
+    v1 = ls.values.clone()
+    ls.assemble_elem(descs, mode="auto", overwrite=True)
+    assert torch.equal(v1, ls.values)  # bit-reproducible
 
 
 def test_row_thread_and_column_pair_kernels_agree_64cubed(tune):
