@@ -390,19 +390,24 @@ def run_ours(args):
         props["sampled_rows_vs_oracle"] = res
 
     # ---- e2e: host buffers in, residual (RHS) out, every step ------------------------------------------------------
-    e2e_keys = ["coordinates", "velocity", "viscosity"] + (["velocity_n", "velocity_nm1", "density", "density_n", "density_nm1", "dpdx"]
-                                                          if args.kernels == "list" else [])
+    # every nodal field the step reads comes from the host; the element field mass_flow_rate_scs is produced on the device
+    # from them (ComputeMdotElemAlgorithm::execute, what a time step runs between the continuity solve and this assembly)
+    e2e_keys = ["coordinates", "velocity", "viscosity", "density", "pressure", "dpdx"] + \
+               (["velocity_n", "velocity_nm1", "density_n", "density_nm1"] if args.kernels == "list" else [])
     pinned = {k: torch.as_tensor(np.ascontiguousarray(h[k])).pin_memory() for k in e2e_keys}
-    pinned["mdot"] = mdot.cpu().pin_memory()
     rhs_host = torch.empty(ls.n_owned_rows, dtype=torch.float64).pin_memory()
     h2d = sum(t.numel() * 8 for t in pinned.values())
     d2h = rhs_host.numel() * 8
     e2e_steps = max(1, min(args.steps, 5))
+    tau = MASS["dt"] / MASS["gamma1"]
+
+    def produce_mdot(e_range=None):
+        ls.compute_mdot_elem(d["coordinates"], d["density"], d["velocity"], d["pressure"], d["dpdx"], tau, out=mdot, e_range=e_range)
 
     def e2e_step():
         for k in e2e_keys:
             d[k].copy_(pinned[k], non_blocking=True)
-        mdot.copy_(pinned["mdot"], non_blocking=True)
+        produce_mdot()
         step()
         rhs_host.copy_(ls.owned_rhs(), non_blocking=True)
         torch.cuda.synchronize()
@@ -436,13 +441,12 @@ def run_ours(args):
                     for k in e2e_keys:
                         d[k][a:b].copy_(pinned[k][a:b], non_blocking=True)
                     planes_done = p_hi
-                if l_hi > layers_done:
-                    a, b = layers_done * nxy_elems, l_hi * nxy_elems
-                    mdot[a:b].copy_(pinned["mdot"][a:b], non_blocking=True)
-                    layers_done = l_hi
                 evc = torch.cuda.Event()
                 evc.record(copy_stream)
             cur.wait_event(evc)
+            if l_hi > layers_done:
+                produce_mdot((layers_done * nxy_elems, l_hi * nxy_elems))
+                layers_done = l_hi
             ls.assemble_elem_zrange(descs, z0, z1, overwrite=True)
             if world == 1:
                 # the residual rows of a finished range go home while the next range is assembled (full duplex)
@@ -481,9 +485,10 @@ def run_ours(args):
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "serial_ms_per_step": serial_ms,
            "schedule": (f"{nchunk} node-plane ranges: host->device copy of range c+1 overlaps the assembly of range c "
                         "(nalu_b200_assemble_elem_zrange)") if use_pipe else "copy everything, then assemble",
-           "note": "every nodal field the kernel list gathers and the element field mass_flow_rate_scs come from pinned host "
-                   "memory every step; the RHS (nonlinear residual) is read back to the host; the CSR values stay "
-                   "device-resident for a device solver"}
+           "note": "every nodal field the step reads (coordinates, velocity states, viscosity, density states, pressure, dpdx) "
+                   "comes from pinned host memory every step; mass_flow_rate_scs is produced on the device from them "
+                   "(nalu_b200_compute_mdot_elem_range); the RHS (nonlinear residual) is read back to the host; the CSR "
+                   "values stay device-resident for a device solver"}
 
     # ---- what explains the headline: the adv-diff kernel alone, the continuity pass of BASELINE config 3 (one rank,
     # device-resident inputs, outside the timed region of the headline metric)

@@ -273,6 +273,12 @@ int nalu_b200_assemble_nodal_grad_elem(const nalu_b200_graph *g, const double *d
 int nalu_b200_compute_mdot_elem(const nalu_b200_graph *g, const double *d_coords, const double *d_density,
                                 const double *d_velocity, const double *d_pressure, const double *d_gpdx,
                                 double proj_time_scale, int32_t options, double *d_mdot, void *stream);
+/* the same for the elements [e_begin, e_end) only (a caller that streams the nodal fields onto the device produces the
+ * element field range by range, ahead of nalu_b200_assemble_elem_zrange) */
+int nalu_b200_compute_mdot_elem_range(const nalu_b200_graph *g, const double *d_coords, const double *d_density,
+                                      const double *d_velocity, const double *d_pressure, const double *d_gpdx,
+                                      double proj_time_scale, int32_t options, int64_t e_begin, int64_t e_end,
+                                      double *d_mdot, void *stream);
 /* TpetraLinearSystem::applyDirichletBCs (src/TpetraLinearSystem.C:1579-1653): for every listed local node and
  * dof d in [begin_pos, end_pos) the CSR row is replaced by the identity row (locally-owned rows; a
  * shared-not-owned row is cleared, its owner holds the 1) and the residual by bc - solution (0 for a

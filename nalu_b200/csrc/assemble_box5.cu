@@ -141,6 +141,9 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
       for (int c = 0; c < 9; ++c) acc2[c][0] = acc2[c][1] = acc2[c][2] = 0.0;
       if (act) box5::sweep_half(N, sm, P, H, acc1, acc2);
       if (P.fuse_mass && act) vol += box5::dual_volume_half(N, sm, H);
+      box5::MassNode mn;
+      const bool mass_lane = P.fuse_mass && H && N.i < 3 && N.active;
+      if (mass_lane) box5::mass_fetch(P, (x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z), N.i, mn);
       // is the warp's x line stored back to back in lattice order?  (then the runs of a group sit at fixed offsets)
       const bool natural = __all_sync(FULL, box5::node_in_natural_line(M, N.node));
       const unsigned char *sl = P.slot27 + 27 * ((x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z));
@@ -149,8 +152,7 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
         if (P.fuse_mass) {
           // lumped mass: diagonal entries of the node's own block (column 4 of the dz=0 group; the diagonal is rotated
           // index 0) and the residual, from the dual volume gathered over the two halves
-          if (N.i < 3 && N.active)
-            box5::lumped_mass_terms(P, (x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z), N.i, vol, acc1[4][0], rr);
+          if (mass_lane) box5::mass_apply(P, mn, vol, acc1[4][0], rr);
           vol = 0.0;
         }
         output_group<OW>(N, M, sl, 1, natural, scr, acc1, P.values, lane);
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
       const int t = tid & 63;
       if (!H || lead) {
         if (tid < 64) {
-          if (t < C5::NEL) box5::p1_face_unit(P, t, lead ? 1 : 0, x0, y0, pl0, pl1, mdb, rec);
+          if (t < C5::NEL) box5::p1_face_unit(P, t, lead ? 1 : 0, x0, y0, pl0, pl1, mdb, rec, scv);
         } else if (t < C5::NEL) box5::p1_z_unit(P, t, x0, y0, pl0, pl1, mdb, rec, scv);
       } else if (z + 1 < ze) {
         if (tid < 64) {

@@ -8,6 +8,7 @@
 // by the precomputed map.  This is the fallback for unstructured meshes and for kernel lists
 // the tiled kernel (assemble_box.cu) does not cover; it always accumulates.
 #include "general_elem.cuh"
+#include "box_tile.cuh"
 #include "internal.h"
 #include <initializer_list>
 #include <string>
@@ -553,50 +554,114 @@ int launch_nodal_grad(const Graph &g, const double *coords, const double *field,
 }
 
 // ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254): the producer of mass_flow_rate_scs in a
-// time step, mdot_ip = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip; one thread per (element, point)
-__global__ void compute_mdot_kernel(long long n_elems, const int *elem_nodes, const double *coords, const double *density,
+// time step, mdot_ip = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip.  One thread per element, all 12 points:
+// the trilinear fields (coordinates relative to the first node, w = rho u + tau Gp, p) are expanded once in their
+// Walsh-Hadamard coefficients (box_tile.cuh butterfly8); at a point on an edge along t (local axes t,u,v) the Jacobian
+// is 5 vector FMAs, the area vector one cross product (as in box5_tile.cuh p1_point), and
+//   dpdx . A = (adj^T A) . dp/dxi / det,   w_ip = W_0/8 + q_m (s_u W_u + s_v W_v)/4 + q_m^2 s_u s_v W_uv/2.
+// Elements [e0, e1): a caller that streams the nodal fields in (bench.py end-to-end step) produces the field range by range.
+template <int T>
+__device__ __forceinline__ double mdot_point(const double (&X)[3][8], const double (&W)[3][8], const double (&Pc)[8], double sgu,
+                                             double sgv, double qp, double qm, double tau, int *err)
+{
+  constexpr int mt = 1 << T, mu = 1 << ((T + 1) % 3), mv = 1 << ((T + 2) % 3);
+  const double c1 = 0.5 * qp * sgu, c2 = 0.5 * qp * sgv, c12 = qp * qp * sgu * sgv;
+  double J[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    J[i][0] = 0.25 * X[i][mt] + c1 * X[i][mt | mu] + c2 * X[i][mt | mv] + c12 * X[i][7];
+    J[i][1] = 0.25 * X[i][mu] + c2 * X[i][mu | mv];
+    J[i][2] = 0.25 * X[i][mv] + c1 * X[i][mu | mv];
+  }
+  double adj[3][3];
+  adj[0][0] = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+  adj[0][1] = J[1][2] * J[2][0] - J[2][2] * J[1][0];
+  adj[0][2] = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+  adj[1][0] = J[0][2] * J[2][1] - J[2][2] * J[0][1];
+  adj[1][1] = J[0][0] * J[2][2] - J[2][0] * J[0][2];
+  adj[1][2] = J[0][1] * J[2][0] - J[2][1] * J[0][0];
+  adj[2][0] = J[0][1] * J[1][2] - J[1][1] * J[0][2];
+  adj[2][1] = J[0][2] * J[1][0] - J[1][2] * J[0][0];
+  adj[2][2] = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+  const double det = J[0][0] * adj[0][0] + J[1][0] * adj[1][0] + J[2][0] * adj[2][0];
+  if (!(det > 0.0)) *err = 1;
+  // area vector along +t (geometry of the sub-control surface: never shifted)
+  double A[3], Wv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) Wv[i] = sgv * X[i][mv] - sgu * X[i][mu];
+  A[0] = (X[1][mu] * X[2][mv] - X[2][mu] * X[1][mv]) * (1.0 / 64.0) + (X[1][mu | mv] * Wv[2] - X[2][mu | mv] * Wv[1]) * (1.0 / 128.0);
+  A[1] = (X[2][mu] * X[0][mv] - X[0][mu] * X[2][mv]) * (1.0 / 64.0) + (X[2][mu | mv] * Wv[0] - X[0][mu | mv] * Wv[2]) * (1.0 / 128.0);
+  A[2] = (X[0][mu] * X[1][mv] - X[1][mu] * X[0][mv]) * (1.0 / 64.0) + (X[0][mu | mv] * Wv[1] - X[1][mu | mv] * Wv[0]) * (1.0 / 128.0);
+  // dp/dxi at the grad-op point, local axis order
+  const double pt = 0.25 * Pc[mt] + c1 * Pc[mt | mu] + c2 * Pc[mt | mv] + c12 * Pc[7];
+  const double pu = 0.25 * Pc[mu] + c2 * Pc[mu | mv], pv = 0.25 * Pc[mv] + c1 * Pc[mu | mv];
+  double gA = 0.0, wA = 0.0;
+  const double m1 = 0.25 * qm * sgu, m2 = 0.25 * qm * sgv, m12 = 0.5 * qm * qm * sgu * sgv;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    gA += (adj[j][0] * pt + adj[j][1] * pu + adj[j][2] * pv) * A[j];
+    wA += (0.125 * W[j][0] + m1 * W[j][mu] + m2 * W[j][mv] + m12 * W[j][mu | mv]) * A[j];
+  }
+  return wA - tau * gA / det;
+}
+
+__global__ void compute_mdot_kernel(long long e0, long long e1, const int *elem_nodes, const double *coords, const double *density,
                                     const double *velocity, const double *pressure, const double *gpdx, double tau,
                                     int shift_mdot, int shift_poisson, double *mdot, int *err)
 {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long e = t / 12;
-  const int ip = (int)(t - e * 12);
-  if (e >= n_elems) return;
-  double c[8][3], w[8][3], pn[8];
+  const long long e = e0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= e1) return;
+  double X[3][8], W[3][8], Pc[8];
+  // Hex8 node n -> lattice bits (x, y, z): box_tile.cuh bit_x / bit_y / bit_z; coefficient index m = x + 2 y + 4 z
+#pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int node = elem_nodes[e * 8 + n];
+    const int m = box::bit_x(n) + 2 * box::bit_y(n) + 4 * box::bit_z(n);
     const double rho = density[node];
-    pn[n] = pressure[node];
+    Pc[m] = pressure[node];
+#pragma unroll
     for (int d = 0; d < 3; ++d) {
-      c[n][d] = coords[(size_t)node * 3 + d];
-      w[n][d] = rho * velocity[(size_t)node * 3 + d] + tau * gpdx[(size_t)node * 3 + d]; // interpolated with one shape function
+      X[d][m] = coords[(size_t)node * 3 + d];
+      W[d][m] = rho * velocity[(size_t)node * 3 + d] + tau * gpdx[(size_t)node * 3 + d]; // interpolated with one shape function
     }
   }
-  double a[3], s1, s2, s3, dndx[8][3];
-  hex8::scs_areav_ip(c, ip, a);
-  hex8::scs_intg_loc(ip, shift_poisson ? 0.5 : 0.25, s1, s2, s3);
-  const double det = hex8::grad_op_ip(c, s1, s2, s3, dndx);
-  if (!(det > 0.0)) *err = 1;
-  hex8::scs_intg_loc(ip, shift_mdot ? 0.5 : 0.25, s1, s2, s3);
-  double wip[3] = {0, 0, 0}, dpdx[3] = {0, 0, 0};
-  for (int n = 0; n < 8; ++n) {
-    const double r = hex8::shape_fcn(n, s1, s2, s3);
-    for (int d = 0; d < 3; ++d) {
-      wip[d] += r * w[n][d];
-      dpdx[d] += dndx[n][d] * pn[n];
-    }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double o = X[d][0];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) X[d][m] -= o;
+    box::butterfly8(X[d]);
+    box::butterfly8(W[d]);
   }
-  mdot[e * 12 + ip] = (wip[0] - tau * dpdx[0]) * a[0] + (wip[1] - tau * dpdx[1]) * a[1] + (wip[2] - tau * dpdx[2]) * a[2];
+  box::butterfly8(Pc);
+  const double qp = shift_poisson ? 0.5 : 0.25, qm = shift_mdot ? 0.5 : 0.25;
+  double *o = mdot + e * 12;
+  // ip numbering and L -> R orientation: Hex8CVFEM.C:264-276 (ip 2 and 6 run along -x)
+#pragma unroll 1
+  for (int f = 0; f < 2; ++f) { // bottom / top face
+    const double sz = f ? 1.0 : -1.0;
+    o[4 * f + 0] = mdot_point<0>(X, W, Pc, -1.0, sz, qp, qm, tau, err);
+    o[4 * f + 1] = mdot_point<1>(X, W, Pc, sz, 1.0, qp, qm, tau, err);
+    o[4 * f + 2] = -mdot_point<0>(X, W, Pc, 1.0, sz, qp, qm, tau, err);
+    o[4 * f + 3] = mdot_point<1>(X, W, Pc, sz, -1.0, qp, qm, tau, err);
+  }
+#pragma unroll 1
+  for (int n = 0; n < 4; ++n)
+    o[8 + n] = mdot_point<2>(X, W, Pc, (n == 1 || n == 2) ? 1.0 : -1.0, n >= 2 ? 1.0 : -1.0, qp, qm, tau, err);
 }
 
 int launch_compute_mdot(const Graph &g, const double *coords, const double *density, const double *velocity, const double *pressure,
-                        const double *gpdx, double tau, int options, double *mdot, cudaStream_t stream)
+                        const double *gpdx, double tau, int options, double *mdot, cudaStream_t stream, long long e0, long long e1)
 {
-  if (g.n_elems == 0) return NALU_B200_OK;
-  const long long nt = g.n_elems * 12;
-  compute_mdot_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, stream>>>(g.n_elems, g.d_elem_nodes, coords, density, velocity, pressure,
-                                                                       gpdx, tau, (options & NALU_OPT_SHIFT_MDOT) != 0,
-                                                                       (options & NALU_OPT_SHIFT_POISSON) != 0, mdot, g.d_err);
+  if (e1 < 0) e1 = g.n_elems;
+  if (e0 < 0 || e0 > e1 || e1 > g.n_elems) {
+    set_error("compute_mdot_elem: bad element range");
+    return NALU_B200_ERR_ARG;
+  }
+  if (e1 == e0) return NALU_B200_OK;
+  compute_mdot_kernel<<<(unsigned)((e1 - e0 + 127) / 128), 128, 0, stream>>>(e0, e1, g.d_elem_nodes, coords, density, velocity, pressure,
+                                                                           gpdx, tau, (options & NALU_OPT_SHIFT_MDOT) != 0,
+                                                                           (options & NALU_OPT_SHIFT_POISSON) != 0, mdot, g.d_err);
   count_launch();
   NALU_CUDA(cudaGetLastError());
   return NALU_B200_OK;

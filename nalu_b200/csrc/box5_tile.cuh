@@ -274,15 +274,16 @@ __host__ __device__ __forceinline__ void p1_point(const Coef &C, const double (&
 // and the integral of its Jacobian determinant over the cube (what Grandy's 24-triangle formula evaluates exactly for
 // a hex with bilinear faces) keeps only the even monomials:
 //   V = [ det(B1,B2,B3) + ( det(B13,B23,B3) + det(B12,B2,B23) + det(B1,B12,B13) ) / 12 ] / 512.
-// out[n], n = Hex8 node index of the corner.
+// out[n], n = Hex8 node index of the corner; the four corners n0 .. n0+3 of the bottom (n0 = 0) or top (n0 = 4) face: the
+// face units of phase 1a take the bottom corners, the z units the top corners, so that the two kinds stay balanced.
 __host__ __device__ __forceinline__ double det3(const double (&a)[3], const double (&b)[3], const double (&c)[3])
 {
   return a[0] * (b[1] * c[2] - b[2] * c[1]) + a[1] * (b[2] * c[0] - b[0] * c[2]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
 }
-__host__ __device__ inline void scv_volumes(const Coef &C, double *out)
+__host__ __device__ inline void scv_volumes(const Coef &C, double *out, int n0)
 {
 #pragma unroll 1
-  for (int n = 0; n < 8; ++n) {
+  for (int n = n0; n < n0 + 4; ++n) {
     const double s1 = ((n ^ (n >> 1)) & 1) ? 1.0 : -1.0, s2 = ((n >> 1) & 1) ? 1.0 : -1.0, s3 = ((n >> 2) & 1) ? 1.0 : -1.0;
     double B1[3], B2[3], B3[3], B12[3], B13[3], B23[3];
 #pragma unroll
@@ -303,7 +304,7 @@ __host__ __device__ inline void scv_volumes(const Coef &C, double *out)
 // (slot = ip & 3: Hex8CVFEM.C:264-276: ip 0: x edge at y-, 1: y edge at x+, 2: x edge at y+ (L -> R runs along -x),
 // 3: y edge at x-)
 __host__ __device__ inline void p1_face_unit(const BoxParams &P, int el, int top, int x0, int y0, const double *pl0, const double *pl1,
-                                             const double *mdb, double *rec)
+                                             const double *mdb, double *rec, double *scv)
 {
   using K = Cfg;
   const int elx = el % K::ELX, ely = el / K::ELX;
@@ -315,6 +316,7 @@ __host__ __device__ inline void p1_face_unit(const BoxParams &P, int el, int top
   const double sz = top ? 1.0 : -1.0;
   const double *md = mdb + el * 12 + (top ? 4 : 0);
   double *o = rec + el;
+  if (P.fuse_mass && !top) scv_volumes(C, scv + el * 8, 0);
   double bx[3], by[3];
   area_base<0>(C, bx);
   area_base<1>(C, by);
@@ -365,7 +367,7 @@ __host__ __device__ inline void p1_z_unit(const BoxParams &P, int el, int x0, in
   coef_load(C, pl0, pl1, elx, ely);
   const double *md = mdb + el * 12 + 8;
   double *o = rec + el + 4 * K::PS;
-  if (P.fuse_mass) scv_volumes(C, scv + el * 8);
+  if (P.fuse_mass) scv_volumes(C, scv + el * 8, 4);
   double bz[3];
   area_base<2>(C, bz);
   // T = 2: (u,v) = (x,y); bottom nodes 0..3 = (x-,y-), (x+,y-), (x+,y+), (x-,y+)
@@ -512,13 +514,21 @@ __host__ __device__ __forceinline__ double dual_volume_half(const Thr &N, const 
   // node_of_bits(bx, by, bz) = bz*4 + by*2 + (bx ^ by): quadrant (SX,SY) sees the node as corner (!SX, !SY)
   return (s[bz + 2] + s[8 + bz + 3]) + (s[C::ELX * 8 + bz + 1] + s[(C::ELX + 1) * 8 + bz + 0]);
 }
-// lane (node, i < 3): diagonal entry (i,i) of the node's own block and residual of dof row i
-__host__ __device__ __forceinline__ void lumped_mass_terms(const BoxParams &P, long long n, int i, double V, double &diag, double &rr)
+// lane (node, i < 3): diagonal entry (i,i) of the node's own block and residual of dof row i.  The nodal values are
+// fetched (mass_fetch) right after the sweep and used (mass_apply) after the dz=0 group is finalized: the global-memory
+// latency hides under the finalize arithmetic.
+struct MassNode {
+  double rp, rn, rm, up, un, um, gp;
+};
+__host__ __device__ __forceinline__ void mass_fetch(const BoxParams &P, long long n, int i, MassNode &m)
 {
-  const double rp = P.rho_np1[n], rn = P.rho_n[n], rm = P.rho_nm1[n];
-  const double up = P.vel[n * 3 + i], un = P.vel_n[n * 3 + i], um = P.vel_nm1[n * 3 + i], gp = P.dpdx[n * 3 + i];
-  diag += P.g1_dt * rp * V;
-  rr += -(P.g1_dt * rp * up + P.g2_dt * rn * un + P.g3_dt * rm * um) * V - gp * V * (rp * P.dens_fac + P.om_dens_fac);
+  m.rp = P.rho_np1[n]; m.rn = P.rho_n[n]; m.rm = P.rho_nm1[n];
+  m.up = P.vel[n * 3 + i]; m.un = P.vel_n[n * 3 + i]; m.um = P.vel_nm1[n * 3 + i]; m.gp = P.dpdx[n * 3 + i];
+}
+__host__ __device__ __forceinline__ void mass_apply(const BoxParams &P, const MassNode &m, double V, double &diag, double &rr)
+{
+  diag += P.g1_dt * m.rp * V;
+  rr += -(P.g1_dt * m.rp * m.up + P.g2_dt * m.rn * m.un + P.g3_dt * m.rm * m.um) * V - m.gp * V * (m.rp * P.dens_fac + P.om_dens_fac);
 }
 
 // ---- finalize of one dz group: diagonal term, rhs share ---------------------------------------------------------------

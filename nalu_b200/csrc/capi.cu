@@ -547,6 +547,15 @@ int nalu_b200_compute_mdot_elem(const nalu_b200_graph *h, const double *d_coords
                              (cudaStream_t)stream);
 }
 
+int nalu_b200_compute_mdot_elem_range(const nalu_b200_graph *h, const double *d_coords, const double *d_density,
+                                      const double *d_velocity, const double *d_pressure, const double *d_gpdx, double proj_time_scale,
+                                      int32_t options, int64_t e_begin, int64_t e_end, double *d_mdot, void *stream)
+{
+  if (!h || !d_coords || !d_density || !d_velocity || !d_pressure || !d_gpdx || !d_mdot || !h->g.d_elem_nodes) return NALU_B200_ERR_STATE;
+  return launch_compute_mdot(h->g, d_coords, d_density, d_velocity, d_pressure, d_gpdx, proj_time_scale, options, d_mdot,
+                             (cudaStream_t)stream, e_begin, e_end);
+}
+
 int nalu_b200_halo_num_peers(const nalu_b200_graph *h, int32_t *ns, int32_t *nr)
 {
   if (!h || !h->g.finalized) return NALU_B200_ERR_STATE;

@@ -39,7 +39,8 @@ int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, do
 int launch_nodal_grad(const Graph &g, const double *coords, const double *field, int ncomp, const double *dual_volume, int use_shifted,
                       double *grad, cudaStream_t stream);
 int launch_compute_mdot(const Graph &g, const double *coords, const double *density, const double *velocity, const double *pressure,
-                        const double *gpdx, double tau, int options, double *mdot, cudaStream_t stream);
+                        const double *gpdx, double tau, int options, double *mdot, cudaStream_t stream, long long e0 = 0,
+                        long long e1 = -1);
 int launch_row_fixup(const Graph &g, int n_list, const int *d_list, int begin_pos, int end_pos, const double *d_solution,
                      const double *d_bc_values, int dirichlet, double *d_values, double *d_rhs, cudaStream_t stream);
 int launch_sum_into(const Graph &g, int n_entities, const int *h_nodes, const double *h_rhs, const double *h_lhs,

@@ -235,16 +235,18 @@ class DeviceCsrLinearSystem:
                                                         ptr(grad), self._stream()), "assemble_nodal_grad_elem")
         return grad
 
-    def compute_mdot_elem(self, coords, density, velocity, pressure, dpdx, proj_time_scale, options=(), out=None):
-        """ComputeMdotElemAlgorithm::execute: mass_flow_rate_scs of every locally-owned element."""
+    def compute_mdot_elem(self, coords, density, velocity, pressure, dpdx, proj_time_scale, options=(), out=None, e_range=None):
+        """ComputeMdotElemAlgorithm::execute: mass_flow_rate_scs of every locally-owned element (or of elements e_range)."""
         import torch
         if out is None:
             out = torch.empty((self.mesh.n_elems, 12), dtype=torch.float64, device=coords.device)
         opt = 0
         for o in options:
             opt |= OPT[o]
-        check(self.L.nalu_b200_compute_mdot_elem(self.h, ptr(coords), ptr(density), ptr(velocity), ptr(pressure), ptr(dpdx),
-                                                 C.c_double(proj_time_scale), opt, ptr(out), self._stream()), "compute_mdot_elem")
+        e0, e1 = e_range if e_range is not None else (0, self.mesh.n_elems)
+        check(self.L.nalu_b200_compute_mdot_elem_range(self.h, ptr(coords), ptr(density), ptr(velocity), ptr(pressure), ptr(dpdx),
+                                                       C.c_double(proj_time_scale), opt, C.c_int64(e0), C.c_int64(e1), ptr(out),
+                                                       self._stream()), "compute_mdot_elem")
         return out
 
     def apply_dirichlet_bcs(self, nodes, solution, bc_values, begin_pos, end_pos):

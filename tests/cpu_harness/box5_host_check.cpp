@@ -218,8 +218,11 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
           if (P.fuse_mass)
             for (int tid = 0; tid < NT; ++tid) {
               HThr &n = N[tid];
-              if (n.i < 3 && n.active)
-                box5::lumped_mass_terms(P, (x0 + n.lx) + (long long)P.NX * ((y0 + n.ly) + (long long)P.NY * z), n.i, n.vol, n.acc1[4][0], n.rr);
+              if (n.i < 3 && n.active) {
+                box5::MassNode mn;
+                box5::mass_fetch(P, (x0 + n.lx) + (long long)P.NX * ((y0 + n.ly) + (long long)P.NY * z), n.i, mn);
+                box5::mass_apply(P, mn, n.vol, n.acc1[4][0], n.rr);
+              }
               n.vol = 0.0;
             }
           output_all(P, N, M, 1, sm, 1, x0, y0, z);
@@ -247,7 +250,7 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
           const int t = tid & 63;
           if (t >= C::NEL) continue;
           if (!H || lead) {
-            if (tid < 64) box5::p1_face_unit(P, t, lead ? 1 : 0, x0, y0, pl0, pl1, mdb, rec);
+            if (tid < 64) box5::p1_face_unit(P, t, lead ? 1 : 0, x0, y0, pl0, pl1, mdb, rec, sm + C::OFF_SCV);
             else box5::p1_z_unit(P, t, x0, y0, pl0, pl1, mdb, rec, sm + C::OFF_SCV);
           } else if (z + 1 < ze) {
             if (tid < 64) box5::p1_face_half<0>(P, t, 1, x0, y0, pl0, pl1, mdb, rec);

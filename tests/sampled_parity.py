@@ -62,11 +62,14 @@ def make_subbox(nx, ny, nz, origin, size, amp):
     return sub, gid, complete
 
 
-def check_sampled_rows(ls, m, nz_global, field_fn, kernel_fn, ndof=3, size=5, n_random=16, row_floor=1e-2, amp=0.12, shift=True):
+def check_sampled_rows(ls, m, nz_global, field_fn, kernel_fn, ndof=3, size=5, n_random=16, row_floor=1e-2, amp=0.12, shift=True,
+                       sol_scale=1.0):
     """ls: DeviceCsrLinearSystem holding the assembled (and, on several ranks, loadComplete'd) system of rank mesh `m`, a
     z-slab of the global nx x ny x nz_global generated box.  field_fn(coords) -> {name: nodal array} recreates the nodal
     fields of any set of nodes; kernel_fn(sub_mesh, fields) -> list of oracle descriptors (keeps its arrays alive).
-    Relative error of an entry is taken against max(|a|, |b|, row_floor * max|row|).  The oracle sees every
+    Relative error of a matrix entry is taken against max(|a|, |b|, row_floor * max|row|); of a residual
+    entry against max(|a|, |b|, row_floor * sum|row| * sol_scale): the residual is -(row . u) - (time terms), every term of
+    the size of a row entry times the solution scale, the sum of them far smaller on smooth fields.  The oracle sees every
     sub-box in coordinates relative to its first node unless shift=False: the assembled system is translation invariant,
     the reference's rounding error is not (it differences absolute coordinates: |x|/h ulps)."""
     import torch
@@ -124,8 +127,7 @@ def check_sampled_rows(ls, m, nz_global, field_fn, kernel_fn, ndof=3, size=5, n_
                 x, y = ovals[o1], vals[o2]
                 scale = max(np.abs(x).max(), 1e-300)
                 worst_v = max(worst_v, float(np.max(np.abs(x - y) / np.maximum(np.maximum(np.abs(x), np.abs(y)), row_floor * scale))))
-                # rhs_i = -(row . u) + ...: its rounding error scales with the row, not with itself
-                rs = max(abs(orhs[r]), abs(prhs[t]), row_floor * row_floor * float(np.abs(x).sum()), 1e-300)
+                rs = max(abs(orhs[r]), abs(prhs[t]), row_floor * sol_scale * float(np.abs(x).sum()), 1e-300)
                 worst_r = max(worst_r, float(abs(orhs[r] - prhs[t]) / rs))
                 t += 1
                 nrows += 1
