@@ -193,6 +193,11 @@ int nalu_b200_graph_copy_row_gids(const nalu_b200_graph *g, int shared, int64_t 
 int nalu_b200_graph_copy_col_gids(const nalu_b200_graph *g, int64_t *gids);
 /* entityToLID_ / entityToColLID_ for the local nodes */
 int nalu_b200_graph_copy_node_lids(const nalu_b200_graph *g, int32_t *row_lid, int32_t *col_lid);
+/* Element colouring used by the general kernel's scatter (elements of one colour share no row node: a colour is summed
+ * into the CSR with plain read-modify-writes, colours in ascending order -- deterministic, no atomics).  n_colors = 0:
+ * the mesh has no colouring (an element touches one row through two of its nodes; atomic scatter).  color_of_elem
+ * (host, [n_elems]) may be NULL. */
+int nalu_b200_graph_copy_elem_colors(const nalu_b200_graph *g, int32_t *n_colors, int32_t *color_of_elem);
 /* device-resident graph arrays (for a device solver): owned graph */
 int nalu_b200_graph_device_ptrs(const nalu_b200_graph *g, int shared, const uint64_t **d_rowptr,
                                 const int32_t **d_colidx);

@@ -2,11 +2,14 @@
 //
 // One warp per element (grid-stride), element lhs/rhs in the warp's shared-memory scratch
 // (general_elem.cuh), then the sumInto step: every lhs entry goes straight to its CSR slot
-// through the per-element slot map built with the graph, as a double atomicAdd -- the
-// device analogue of TpetraLinearSystem::sumInto's sorted row merge
-// (src/TpetraLinearSystem.C:1376-1522), with the sort and the linear column search replaced
-// by the precomputed map.  This is the fallback for unstructured meshes and for kernel lists
-// the tiled kernel (assemble_box.cu) does not cover; it always accumulates.
+// through the per-element slot map built with the graph -- the device analogue of
+// TpetraLinearSystem::sumInto's sorted row merge (src/TpetraLinearSystem.C:1376-1522), with the sort
+// and the linear column search replaced by the precomputed map.  The elements are processed colour
+// by colour (graph.cpp: elements of one colour share no row node), one launch per colour, so the sum
+// is a plain read-modify-write in a fixed order: deterministic, no atomics.  (Meshes the colouring
+// gives up on -- an element touching one row twice -- fall back to atomicAdd.)  This is the path for
+// unstructured meshes, periodic aliasing and for kernel lists the tiled kernels do not cover; it
+// always accumulates.
 #include "general_elem.cuh"
 #include "box_tile.cuh"
 #include "internal.h"
@@ -16,7 +19,8 @@
 namespace nalu_b200 {
 
 struct GeneralParams {
-  long long n_elems;
+  long long n_elems;          // elements this launch processes
+  const int *elem_list;       // their ids (one colour), or null: 0 .. n_elems-1 with an atomic scatter
   const int *elem_nodes;
   const int *node_row;
   const long long *browptr;
@@ -48,7 +52,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) assemble_general_kernel(con
     if (p.k[i].nodal[NALU_F_COORDINATES]) coord_field = p.k[i].nodal[NALU_F_COORDINATES];
   }
 
-  for (long long e = warp0; e < p.n_elems; e += nwarps) {
+  for (long long t = warp0; t < p.n_elems; t += nwarps) {
+    const long long e = p.elem_list ? p.elem_list[t] : t;
     if (lane < 8) {
       const int node = p.elem_nodes[e * 8 + lane];
       const int rn = p.node_row[node];
@@ -82,19 +87,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) assemble_general_kernel(con
     if (lane == 0 && ws.bad_det) atomicExch(p.err, 1);
     // sumInto: lhs[r][c] -> values[rowbase(k) + i*nb*NDOF + slot(k,ic)*NDOF + j]
     const unsigned char *slots = p.elem_slot + e * 64;
-    for (int q = lane; q < R * R; q += 32) {
-      const double v = ws.lhs[q];
-      if (v == 0.0) continue;
+    auto slot_of = [&](int q) -> long long {
       const int r = q / R, c = q - r * R;
       const int kn = r / NDOF, i = r - kn * NDOF;
       const int ic = c / NDOF, j = c - ic * NDOF;
-      const int slot = slots[kn * 8 + ic];
-      const long long pos = ws.rowbase[kn] + (long long)i * ws.rownb[kn] * NDOF + slot * NDOF + j;
-      atomicAdd(p.values + pos, v);
+      return ws.rowbase[kn] + (long long)i * ws.rownb[kn] * NDOF + slots[kn * 8 + ic] * NDOF + j;
+    };
+    if (p.elem_list) {
+      // no other element of this colour touches these rows: plain read-modify-write, the loads of a batch issued
+      // together (the entries of one element are distinct, so nothing aliases inside a batch)
+      constexpr int NIT = (R * R + 31) / 32, B = NIT % 6 == 0 ? 6 : 2;
+#pragma unroll 1
+      for (int it = 0; it < NIT; it += B) {
+        double v[B], old[B];
+        long long pos[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+          const int q = lane + 32 * (it + u);
+          v[u] = q < R * R ? ws.lhs[q] : 0.0;
+          pos[u] = v[u] != 0.0 ? slot_of(q) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+          if (pos[u] >= 0) old[u] = p.values[pos[u]];
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+          if (pos[u] >= 0) p.values[pos[u]] = old[u] + v[u];
+      }
+    } else {
+      for (int q = lane; q < R * R; q += 32) {
+        const double v = ws.lhs[q];
+        if (v != 0.0) atomicAdd(p.values + slot_of(q), v);
+      }
     }
     if (lane < R) {
       const double v = ws.rhs[lane];
-      if (v != 0.0) atomicAdd(p.rhs + (long long)ws.rownode[lane / NDOF] * NDOF + lane % NDOF, v);
+      double *r = p.rhs + (long long)ws.rownode[lane / NDOF] * NDOF + lane % NDOF;
+      if (v != 0.0) {
+        if (p.elem_list) *r += v;
+        else atomicAdd(r, v);
+      }
     }
     __syncwarp();
   }
@@ -197,23 +229,26 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (g.ndof == 3) {
-    const size_t smem = sizeof(ElemScratch<3>) * kWarpsPerCta;
-    NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long ctas = (g.n_elems + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (ctas > (long long)sms * 16) ctas = (long long)sms * 16;
-    assemble_general_kernel<3><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
-  } else if (g.ndof == 1) {
-    const size_t smem = sizeof(ElemScratch<1>) * kWarpsPerCta;
-    NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long ctas = (g.n_elems + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (ctas > (long long)sms * 16) ctas = (long long)sms * 16;
-    assemble_general_kernel<1><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
-  } else {
+  if (g.ndof != 1 && g.ndof != 3) {
     set_error("assemble_elem: numDof must be 1 or 3");
     return NALU_B200_ERR_ARG;
   }
-  count_launch();
+  const size_t smem = (g.ndof == 3 ? sizeof(ElemScratch<3>) : sizeof(ElemScratch<1>)) * kWarpsPerCta;
+  if (g.ndof == 3) NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // one launch per (chunk, colour) group (same stream: the groups run in order), or a single atomic launch when there
+  // is no colouring
+  const long long ncolor = g.d_color_elems ? (long long)g.color_ptr.size() - 1 : 1;
+  for (long long c = 0; c < ncolor; ++c) {
+    p.elem_list = g.d_color_elems ? g.d_color_elems + g.color_ptr[c] : nullptr;
+    p.n_elems = g.d_color_elems ? g.color_ptr[c + 1] - g.color_ptr[c] : g.n_elems;
+    if (p.n_elems == 0) continue;
+    long long ctas = (p.n_elems + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ctas > (long long)sms * 16) ctas = (long long)sms * 16;
+    if (g.ndof == 3) assemble_general_kernel<3><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+    else assemble_general_kernel<1><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+    count_launch();
+  }
   NALU_CUDA(cudaGetLastError());
   return NALU_B200_OK;
 }
@@ -222,17 +257,23 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
 // MomentumMassElemKernel / ContinuityMassElemKernel / ScalarMassElemKernel with the lumped (shifted) shape function
 // (src/kernel/MomentumMassElemKernel.C:119-170, ContinuityMassElemKernel.C:98-117, ScalarMassElemKernel.C:117-154):
 // the shape function is 1 at the SCV's own node and 0 elsewhere, so the element contributes the SCV volume times
-// nodal quantities to the diagonal entry and the residual of that node -- 6 (momentum) or 2 atomics per SCV instead of
+// nodal quantities to the diagonal entry and the residual of that node -- 6 (momentum) or 2 adds per SCV instead of
 // a 24 x 24 scratch block per element.  Used for the lumped mass kernels of a list whose adv-diff kernel went through
-// a tiled kernel (capi.cu).
-__global__ void __launch_bounds__(256) scv_lumped_mass_kernel(long long n_elems, int ndof, const int *elem_nodes, const int *node_row,
-                                                              const long long *browptr, const unsigned char *elem_slot,
+// a tiled kernel (capi.cu).  Colour by colour like the general kernel (elem_list = the elements of one colour: plain adds
+// in a fixed order); without a colouring (elem_list null) the adds are atomic.
+#define NALU_ADD(ptr, val)                 \
+  do {                                     \
+    if (elem_list) *(ptr) += (val);        \
+    else atomicAdd((ptr), (val));          \
+  } while (0)
+__global__ void __launch_bounds__(256) scv_lumped_mass_kernel(long long n_elems, const int *elem_list, int ndof, const int *elem_nodes,
+                                                              const int *node_row, const long long *browptr, const unsigned char *elem_slot,
                                                               nalu_b200_kernel_desc k, double *values, double *rhs)
 {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long e = t >> 3;
   const int ip = (int)(t & 7);
-  if (e >= n_elems) return;
+  if ((t >> 3) >= n_elems) return;
+  const long long e = elem_list ? elem_list[t >> 3] : (t >> 3);
   double c[8][3];
   const double *X = k.nodal[NALU_F_COORDINATES];
   for (int n = 0; n < 8; ++n) {
@@ -253,20 +294,21 @@ __global__ void __launch_bounds__(256) scv_lumped_mass_kernel(long long n_elems,
     for (int j = 0; j < 3; ++j) {
       const double uNp1 = k.nodal[NALU_F_VELOCITY][(size_t)node * 3 + j], uN = k.nodal[NALU_F_VELOCITY_N][(size_t)node * 3 + j],
                    uNm1 = k.nodal[NALU_F_VELOCITY_NM1][(size_t)node * 3 + j], Gp = k.nodal[NALU_F_DPDX][(size_t)node * 3 + j];
-      atomicAdd(rhs + (long long)rn * 3 + j,
-                -(k.gamma1 * rNp1 * uNp1 + k.gamma2 * rN * uN + k.gamma3 * rNm1 * uNm1) * scV / k.dt - Gp * scV * densFac);
-      atomicAdd(values + 9 * b0 + (long long)j * nb * 3 + slot * 3 + j, lhsfac);
+      NALU_ADD(rhs + (long long)rn * 3 + j,
+               -(k.gamma1 * rNp1 * uNp1 + k.gamma2 * rN * uN + k.gamma3 * rNm1 * uNm1) * scV / k.dt - Gp * scV * densFac);
+      NALU_ADD(values + 9 * b0 + (long long)j * nb * 3 + slot * 3 + j, lhsfac);
     }
   } else if (k.kind == NALU_K_CONTINUITY_MASS) {
     const double tau = k.dt / k.gamma1;
-    atomicAdd(rhs + rn, -(k.gamma1 * rNp1 + k.gamma2 * rN + k.gamma3 * rNm1) * scV / k.dt / tau);
+    NALU_ADD(rhs + rn, -(k.gamma1 * rNp1 + k.gamma2 * rN + k.gamma3 * rNm1) * scV / k.dt / tau);
   } else {
     const double qNp1 = k.nodal[NALU_F_SCALARQ][node], qN = k.nodal[NALU_F_SCALARQ_N][node], qNm1 = k.nodal[NALU_F_SCALARQ_NM1][node];
-    atomicAdd(rhs + rn, -(k.gamma1 * rNp1 * qNp1 + k.gamma2 * rN * qN + k.gamma3 * rNm1 * qNm1) * scV / k.dt);
-    atomicAdd(values + b0 + slot, k.gamma1 * rNp1 * scV / k.dt);
+    NALU_ADD(rhs + rn, -(k.gamma1 * rNp1 * qNp1 + k.gamma2 * rN * qN + k.gamma3 * rNm1 * qNm1) * scV / k.dt);
+    NALU_ADD(values + b0 + slot, k.gamma1 * rNp1 * scV / k.dt);
   }
   (void)ndof;
 }
+#undef NALU_ADD
 
 bool scv_lumped_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
 {
@@ -292,13 +334,17 @@ int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, do
       return NALU_B200_ERR_ARG;
     }
   if (g.n_elems == 0) return NALU_B200_OK;
-  const long long threads = g.n_elems * 8;
-  for (int i = 0; i < nk; ++i) {
-    scv_lumped_mass_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(g.n_elems, g.ndof, g.d_elem_nodes, g.d_node_row,
+  const long long ncolor = g.d_color_elems ? (long long)g.color_ptr.size() - 1 : 1;
+  for (int i = 0; i < nk; ++i)
+    for (long long c = 0; c < ncolor; ++c) {
+      const int *list = g.d_color_elems ? g.d_color_elems + g.color_ptr[c] : nullptr;
+      const long long n = g.d_color_elems ? g.color_ptr[c + 1] - g.color_ptr[c] : g.n_elems;
+      if (n == 0) continue;
+      scv_lumped_mass_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, stream>>>(n, list, g.ndof, g.d_elem_nodes, g.d_node_row,
                                                                                  (const long long *)g.d_browptr, g.d_elem_slot, k[i],
                                                                                  d_values, d_rhs);
-    count_launch();
-  }
+      count_launch();
+    }
   NALU_CUDA(cudaGetLastError());
   return NALU_B200_OK;
 }

@@ -90,7 +90,7 @@ static void free_graph_device(Graph &g)
     if (p) cudaFree(p);
     p = nullptr;
   };
-  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_row_rep); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_desc);
+  F(g.d_elem_nodes); F(g.d_node_row); F(g.d_row_rep); F(g.d_color_elems); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_desc);
   F(g.d_rowptr_owned); F(g.d_rowptr_shared); F(g.d_colidx_owned); F(g.d_colidx_shared); F(g.d_err);
   for (auto *peers : {&g.send_peers, &g.recv_peers})
     for (HaloPeer &p : *peers) {
@@ -105,6 +105,7 @@ static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const s
   if ((rc = upload(&g.d_elem_nodes, g.elem_nodes))) return rc;
   if ((rc = upload(&g.d_node_row, g.node_row))) return rc;
   if ((rc = upload(&g.d_row_rep, g.row_rep))) return rc;
+  if ((rc = upload(&g.d_color_elems, g.color_elems))) return rc;
   if ((rc = upload(&g.d_browptr, g.browptr))) return rc;
   if ((rc = upload(&g.d_bcol, g.bcol))) return rc;
   if ((rc = upload(&g.d_elem_slot, elem_slot))) return rc;
@@ -367,6 +368,17 @@ int nalu_b200_graph_copy_node_lids(const nalu_b200_graph *h, int32_t *row_lid, i
     if (row_lid) row_lid[n] = g.node_row[n] * g.ndof;
     if (col_lid) col_lid[n] = g.node_row[n] * g.ndof; /* local nodes: column lid == row lid */
   }
+  return NALU_B200_OK;
+}
+
+int nalu_b200_graph_copy_elem_colors(const nalu_b200_graph *h, int32_t *n_colors, int32_t *color_of_elem)
+{
+  if (!h || !n_colors) return NALU_B200_ERR_ARG;
+  const Graph &g = h->g;
+  *n_colors = g.color_ptr.empty() ? 0 : g.n_colors;
+  if (color_of_elem && *n_colors)
+    for (size_t grp = 0; grp + 1 < g.color_ptr.size(); ++grp)
+      for (int64_t q = g.color_ptr[grp]; q < g.color_ptr[grp + 1]; ++q) color_of_elem[g.color_elems[size_t(q)]] = int32_t(grp % g.n_colors);
   return NALU_B200_OK;
 }
 

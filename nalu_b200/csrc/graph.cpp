@@ -124,6 +124,54 @@ int graph_number_and_adjacency(Graph &g, std::string &err)
       for (int k = 0; k < 8; ++k) inc[pos[erow[e * 8 + k]]++] = e;
   }
 
+  // ---- element colouring (greedy over the row-node incidence; parity of (i,j,k) on a generated box) ----------
+  g.color_elems.clear();
+  g.color_ptr.clear();
+  if (ne > 0 && ne < (int64_t(1) << 31)) {
+    std::vector<int8_t> color(size_t(ne), -1);
+    bool ok = true;
+    int ncolor = 0;
+    bool aliased = false; // an element that touches one row through two of its nodes races with itself
+#pragma omp parallel for schedule(static) reduction(|| : aliased)
+    for (int64_t e = 0; e < ne; ++e)
+      for (int a = 0; a < 8; ++a)
+        for (int b = a + 1; b < 8; ++b) aliased = aliased || erow[e * 8 + a] == erow[e * 8 + b];
+    if (aliased) ok = false;
+    if (ok && g.box[0] > 0 && nrow == nn) {
+      const int64_t nx = g.box[0], ny = g.box[1];
+#pragma omp parallel for schedule(static)
+      for (int64_t e = 0; e < ne; ++e) color[e] = int8_t(((e % nx) & 1) | ((((e / nx) % ny) & 1) << 1) | (((e / (nx * ny)) & 1) << 2));
+      ncolor = 8;
+    } else if (ok) {
+      for (int64_t e = 0; e < ne && ok; ++e) {
+        uint64_t used = 0;
+        for (int k = 0; k < 8; ++k) {
+          const int32_t r = erow[e * 8 + k];
+          for (int64_t p = inc_ptr[r]; p < inc_ptr[r + 1]; ++p) {
+            const int8_t c = color[inc[p]];
+            if (c >= 0) used |= uint64_t(1) << c;
+          }
+        }
+        if (~used == 0) { ok = false; break; }
+        const int c = __builtin_ctzll(~used);
+        color[e] = int8_t(c);
+        ncolor = std::max(ncolor, c + 1);
+      }
+    }
+    if (ok) {
+      // sort key = (chunk of consecutive element ids, colour): the general kernel runs one launch per (chunk, colour) in
+      // this order (graph.h, kColorChunk: one chunk today)
+      const int64_t nchunk = (ne + kColorChunk - 1) / kColorChunk;
+      g.n_colors = ncolor;
+      g.color_ptr.assign(size_t(nchunk * ncolor) + 1, 0);
+      for (int64_t e = 0; e < ne; ++e) ++g.color_ptr[(e / kColorChunk) * ncolor + color[e] + 1];
+      for (int64_t c = 0; c < nchunk * ncolor; ++c) g.color_ptr[c + 1] += g.color_ptr[c];
+      g.color_elems.resize(size_t(ne));
+      std::vector<int64_t> pos(g.color_ptr.begin(), g.color_ptr.end() - 1);
+      for (int64_t e = 0; e < ne; ++e) g.color_elems[pos[(e / kColorChunk) * ncolor + color[e]]++] = int32_t(e);
+    }
+  }
+
   // ---- adjacency: nodes of incident elements, sorted unique --------------------------
   const int nchunk = std::max(1, omp_get_max_threads() * 8);
   std::vector<std::vector<int32_t>> chunk_adj(nchunk);

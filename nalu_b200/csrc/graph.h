@@ -38,6 +38,12 @@ struct HaloPeer {
   std::vector<int32_t> h_src_stride, h_dst_stride;
 };
 
+// elements per chunk of the (chunk, colour) launch order of the general kernel.  Measured on B200 at 128^3 (momentum
+// adv-diff, general kernel): one chunk (8 launches, every colour streams the whole matrix) 60 Melem/s; 16 K-element chunks
+// (L2-resident rows, 512 small launches) 46 Melem/s -- the kernel is bound by its per-element latency, not by DRAM, so
+// the launches must stay large.  One chunk it is.
+constexpr int64_t kColorChunk = int64_t(1) << 40;
+
 struct Graph {
   int32_t rank = 0, nranks = 1, ndof = 1;
   int32_t n_nodes = 0;
@@ -53,6 +59,16 @@ struct Graph {
   std::vector<int32_t> row_rep;      // [n_row_nodes] lowest local node of the row (several nodes alias a row on periodic meshes)
   std::vector<int64_t> row_node_gid; // [n_owned+n_shared]
   std::vector<int32_t> shared_owner; // [n_shared]
+
+  // element colouring for the general kernel's scatter: elements of one colour share no row node, so a colour is summed
+  // into the CSR with plain read-modify-writes, colours in a fixed order (deterministic; no atomics).  color_elems =
+  // element ids sorted by (chunk of kColorChunk consecutive ids, colour), color_ptr[g] .. color_ptr[g+1] the elements of
+  // group g = chunk * n_colors + colour; empty: no colouring (an element touches one row twice, or more than 64
+  // colours) -> atomic scatter.
+  std::vector<int32_t> color_elems;
+  std::vector<int64_t> color_ptr;
+  int32_t n_colors = 0;
+  int32_t *d_color_elems = nullptr;
 
   // local adjacency (row node -> sorted unique row nodes), before the handshake
   std::vector<int64_t> adj_ptr;

@@ -113,6 +113,13 @@ class DeviceCsrLinearSystem:
         check(self.L.nalu_b200_graph_copy_node_lids(self.h, ptr(r), ptr(c)), "copy_node_lids")
         return r, c
 
+    def elem_colors(self):
+        """(number of colours, colour of every element) of the general kernel's scatter; (0, None) without a colouring."""
+        n = C.c_int32()
+        out = np.full(self.mesh.n_elems, -1, dtype=np.int32)
+        check(self.L.nalu_b200_graph_copy_elem_colors(self.h, C.byref(n), ptr(out)), "copy_elem_colors")
+        return n.value, (out if n.value else None)
+
     def device_graph(self, shared=False):
         """(rowptr, colidx) device addresses for a device-side consumer (solver)."""
         rp, ci = C.c_void_p(), C.c_void_p()

@@ -394,6 +394,39 @@ def test_periodic_box_scalar_parity(n):
     _compare_system(ls, orc)
 
 
+@pytest.mark.parametrize("kind", ["shuffled", "periodic", "box"])
+def test_general_kernel_is_deterministic(kind):
+    """The general kernel's scatter is colour by colour, not atomic: two assemblies of the same state are bit-identical
+    (unstructured connectivity, periodic aliasing, and a kernel list the tiled kernels do not take)."""
+    if kind == "periodic":
+        m, st = _periodic_state(9, 8, 7)
+    else:
+        m = perturbed_box(9, 8, 7)
+        if kind == "shuffled":
+            m.node_gid = (np.random.default_rng(1).permutation(m.n_nodes) + 1).astype(np.int64)
+            m.box = None
+        st = State(m)
+    dev = st.to_device(_cuda())
+    ls = _linsys(m, 3)
+    assert ls.elem_colors()[0] >= 8
+    descs = [product_desc(ls, dev, "momentum_mass", (), dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5),
+             product_desc(ls, dev, "momentum_upw_adv_diff", ("use_limiter",), include_divu=1.0,
+                          upw=dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, hybrid_factor=1.0))]
+    out = []
+    for _ in range(3):
+        ls.zero_system()
+        assert ls.assemble_elem(descs, mode="general") == 1
+        out.append((ls.values.clone(), ls.rhs.clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][0], out[2][0])
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][1], out[2][1])
+    orc = oracle.LinSys([m], 3)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, "momentum_mass", (), keep, dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5),
+                          oracle_desc(st, "momentum_upw_adv_diff", ("use_limiter",), keep, include_divu=1.0,
+                                      upw=dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, hybrid_factor=1.0))])
+    _compare_system(ls, orc)
+
+
 @pytest.mark.parametrize("kind,ndof", [("momentum_mass", 3), ("scalar_mass", 1)])
 def test_node_mass_algorithms_periodic(kind, ndof):
     """AssembleNodeSolverAlgorithm::execute excludes the periodic subject parts from its selector
@@ -424,23 +457,33 @@ def test_momentum_256cubed_sampled_rows_vs_oracle():
     n = 256
     m = perturbed_box(n, n, n)
     dev = _cuda()
-    c = m.coords
-    h = {"coordinates": c, "velocity": fields.velocity(c), "viscosity": fields.smooth_viscosity(c)}
+
+    def field_fn(c):
+        return {"coordinates": c, "velocity": fields.velocity(c), "viscosity": fields.smooth_viscosity(c),
+                "density": fields.smooth_density(c)}
+
+    def kernel_fn(sub, f):
+        keep = []
+        mdot = oracle.calc_mass_flow_rate_scs(sub.elem_nodes, f["coordinates"], f["density"], f["velocity"])
+        kernel_fn.keep = keep
+        return [oracle.make_desc("momentum_adv_diff", keep, coordinates=f["coordinates"], velocity=f["velocity"],
+                                 viscosity=f["viscosity"], massFlowRate=mdot, includeDivU=1.0)]
+
+    h = field_fn(m.coords)
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
     d = {k: t(v) for k, v in h.items()}
     ls = _linsys(m, 3)
-    mdot = ls.mdot_scs(d["coordinates"], t(fields.smooth_density(c)), d["velocity"])
+    mdot = ls.mdot_scs(d["coordinates"], d["density"], d["velocity"])
     ls.values.fill_(float("nan"))
     ls.rhs.fill_(float("nan"))
-    desc = ls.make_desc("momentum_adv_diff", fields=d, mass_flow_rate=mdot, include_divu=1.0)
+    desc = ls.make_desc("momentum_adv_diff", fields={k: d[k] for k in ("coordinates", "velocity", "viscosity")}, mass_flow_rate=mdot,
+                        include_divu=1.0)
     assert ls.assemble_elem([desc], mode="auto", overwrite=True) == 2
-    res = sp.check_sampled_rows(ls, m, h, mdot, [("momentum_adv_diff", dict(includeDivU=1.0))], ndof=3, size=5, n_random=24,
-                                row_floor=ROW_FLOOR)
+    res = sp.check_sampled_rows(ls, m, n, field_fn, kernel_fn, ndof=3, size=5, n_random=24, row_floor=ROW_FLOOR)
     assert res["rows"] >= 3 * 1000, res
     assert res["max_rel_err_values"] < RTOL and res["max_rel_err_rhs"] < RTOL, res
     # against the reference arithmetic in absolute coordinates (|x|/h up to 256): the reference's own rounding error shows
-    raw = sp.check_sampled_rows(ls, m, h, mdot, [("momentum_adv_diff", dict(includeDivU=1.0))], ndof=3, size=5, n_random=24,
-                                row_floor=ROW_FLOOR, shift=False)
+    raw = sp.check_sampled_rows(ls, m, n, field_fn, kernel_fn, ndof=3, size=5, n_random=24, row_floor=ROW_FLOOR, shift=False)
     assert raw["max_rel_err_values"] < 256 * RTOL and raw["max_rel_err_rhs"] < 256 * RTOL, raw
     print("256^3 sampled rows:", res, "unshifted oracle:", raw["max_rel_err_values"], raw["max_rel_err_rhs"])
     assert sp.row_sum_identity(ls, m, mdot) < 1e-11

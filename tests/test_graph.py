@@ -91,6 +91,36 @@ def test_periodic_box_graph_np1():
         assert set(np.diff(prod[0].rowptr()).astype(int)) == {27 * ndof}
 
 
+@pytest.mark.parametrize("kind", ["box", "shuffled", "periodic", "partition"])
+def test_element_colouring_is_conflict_free(kind):
+    """Elements of one colour share no ROW node (periodic aliases count as one row): the general kernel sums a colour
+    into the CSR without atomics."""
+    rng = np.random.default_rng(5)
+    if kind == "periodic":
+        meshes = [mesh.periodic_box(5, 4, 3)]
+    else:
+        full = mesh.generated_box(6, 5, 4)
+        if kind == "shuffled":
+            full.node_gid = (rng.permutation(full.n_nodes) + 1).astype(np.int64)
+            full.box = None
+        meshes = mesh.partition_elements(full, rng.integers(0, 3, full.n_elems), 3) if kind == "partition" else [full]
+    for p, m in zip(build_product_systems(meshes, 3), meshes):
+        ncol, col = p.elem_colors()
+        assert ncol >= 1
+        assert col.min() >= 0
+        rows, _ = p.node_lids()
+        er = rows[m.elem_nodes]                      # [nElem, 8] row of every element node
+        for c in range(ncol):
+            r = er[col == c].ravel()
+            assert np.unique(r).size == r.size, f"colour {c} touches a row twice"
+
+
+def test_tiny_periodic_box_has_no_colouring():
+    # 1 cell in x: an element reaches the same row through two of its nodes -> atomic fallback
+    p = build_product_systems([mesh.periodic_box(1, 3, 3)], 1)[0]
+    assert p.elem_colors()[0] == 0
+
+
 def test_row_lengths_of_a_box():
     # interior 27, face 18, edge 12, corner 8 node blocks (UnitTestTpetra.C:146-158 for 1x1x2)
     p = build_product_systems([mesh.generated_box(4, 4, 4)], 3)[0]
