@@ -9,6 +9,7 @@
 //   unit_tests <golden_dir> cpu     registration / error-convention tests, no device needed
 //   unit_tests <golden_dir> gpu     everything (runs the CUDA path through the C ABI)
 #include "AssembleElemSolverAlgorithm.h"
+#include "ScratchViews.h"
 #include "kernel/ContinuityAdvElemKernel.h"
 #include "kernel/KernelBuilder.h"
 #include "kernel/MassElemKernels.h"
@@ -269,6 +270,56 @@ static void test_elem_data_requests()
   EXPECT_TRUE(req.get_fields().size() == 3);
   EXPECT_TRUE(req.get_data_enums(CURRENT_COORDINATES).count(SCS_AREAV) == 1);
   EXPECT_THROW(req.get_coordinates_field(MODEL_COORDINATES));
+}
+
+// the reference's per-element scratch on the host: view shapes, lookup by field ordinal, gather, master-element views
+// (include/ScratchViews.h:111-175,584-704; src/ScratchViews.C:408-484; unit_tests/UnitTestScratchViews.C)
+static void test_scratch_views()
+{
+  std::printf("ScratchViews: shapes, gather and master-element views of one Hex8 element (include/ScratchViews.h:111-175)\n");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  ElemDataRequests req;
+  MomentumAdvDiffElemKernel<AlgTraitsHex8> k(*fx.bulk_, fx.solnOpts_, fx.velocity_, fx.viscosity_, req);
+  ScratchViews<double> sv(TeamHandleType(), *fx.bulk_, 8, req);
+  // coords 24 + velocity 24 + viscosity 8 + mdot 12 + areav 36 + dndx 288 + deriv 288 + det_j 12 = 692 doubles
+  EXPECT_TRUE(sv.total_bytes() == 692 * 8);
+  EXPECT_THROW(sv.get_scratch_view_1D(*fx.pressure_));              // not a pre-req field of this kernel
+  EXPECT_THROW(sv.get_scratch_view_1D(*fx.velocity_));              // registered as a vector
+  stk::mesh::Entity elem;
+  elem.rank = stk::topology::ELEM_RANK;
+  elem.index = 0;
+  fill_pre_req_data(req, *fx.bulk_, elem, sv);
+  auto &u = sv.get_scratch_view_2D(*fx.velocity_);
+  auto &mu = sv.get_scratch_view_1D(*fx.viscosity_);
+  EXPECT_TRUE(u.extent(0) == 8 && u.extent(1) == 3 && mu.extent(0) == 8);
+  const int32_t *nodes = fx.bulk_->begin_nodes(elem);
+  EXPECT_TRUE(sv.elemNodes == nodes);
+  double err = 0;
+  for (int n = 0; n < 8; ++n) {
+    err = std::fmax(err, std::fabs(mu(n) - fx.viscosity_->host_data()[nodes[n]]));
+    for (int d = 0; d < 3; ++d) err = std::fmax(err, std::fabs(u(n, d) - fx.velocity_->host_data()[nodes[n] * 3 + d]));
+  }
+  EXPECT_TRUE(err == 0.0);
+  // unit cube: every sub-control surface has area 1/4 along its edge, from the left to the right node
+  // (HexSCS::determinant, Hex8CVFEM.C:547-581); the gradient operator sums to zero over the nodes
+  auto &me = sv.get_me_views(CURRENT_COORDINATES);
+  HexSCS scs;
+  const int *lr = scs.adjacentNodes();
+  auto &x = sv.get_scratch_view_2D(*fx.coordinates_);
+  for (int ip = 0; ip < 12; ++ip) {
+    double dot = 0, a2 = 0, sum[3] = {0, 0, 0};
+    for (int d = 0; d < 3; ++d) {
+      dot += me.scs_areav(ip, d) * (x(lr[2 * ip + 1], d) - x(lr[2 * ip], d));
+      a2 += me.scs_areav(ip, d) * me.scs_areav(ip, d);
+      for (int n = 0; n < 8; ++n) sum[d] += me.dndx(ip, n, d);
+    }
+    EXPECT_NEAR(dot, 0.25, 1e-15);
+    EXPECT_NEAR(a2, 0.0625, 1e-15);
+    EXPECT_NEAR(std::fabs(sum[0]) + std::fabs(sum[1]) + std::fabs(sum[2]), 0.0, 1e-14);
+    EXPECT_NEAR(me.det_j(ip), 1.0, 1e-15);
+  }
+  EXPECT_THROW(sv.get_me_views(MODEL_COORDINATES));
 }
 
 static void test_kernel_registration()
@@ -751,6 +802,7 @@ int main(int argc, char **argv)
   try {
     test_elem_data_requests();
     test_kernel_registration();
+    test_scratch_views();
     if (gpu) {
       test_momentum_advection_diffusion();
       test_continuity_advection("advection_default");
