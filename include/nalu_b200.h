@@ -76,7 +76,9 @@ enum nalu_b200_kernel_kind {
   NALU_K_SDR_SST_SRC = 11, /* src/kernel/SpecificDissipationRateSSTSrcElemKernel.C:100-204 */
   NALU_K_SCALAR_UPW_ADV_DIFF = 12,   /* src/kernel/ScalarUpwAdvDiffElemKernel.C:110-256   */
   NALU_K_MOMENTUM_UPW_ADV_DIFF = 13, /* src/kernel/MomentumUpwAdvDiffElemKernel.C:108-311 */
-  NALU_K_COUNT = 14
+  NALU_K_TKE_SST_DES_SRC = 14, /* src/kernel/TurbKineticEnergySSTDESSrcElemKernel.C:106-198 */
+  NALU_K_TKE_KSGS_SRC = 15,    /* src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C:78-128    */
+  NALU_K_COUNT = 16
 };
 
 /* option bits (SolutionOptions fields the kernels read) */
@@ -116,7 +118,10 @@ enum nalu_b200_field_slot {
   NALU_F_GJQ = 19,        /* 3  projected nodal gradient of scalarQ (upwind kernels) */
   NALU_F_GJU = 20,        /* 9  dudx: Gju(node,i,j) at [3*i+j] (upwind kernels) */
   NALU_F_VELOCITY_RTM = 21, /* 3  velocity_rtm of the upwind kernels when the mesh moves; NULL: NALU_F_VELOCITY */
-  NALU_F_COUNT = 24
+  NALU_F_SST_MAX_LENGTH_SCALE = 22, /* 1  sst_max_length_scale (SST-DES source) */
+  NALU_F_C_EPSILON = 23,    /* 1  c_epsilon (Ksgs source) */
+  NALU_F_DSQRTK_DX_SQ = 24, /* 1  dsqrtk_dx_sq (Ksgs source; the reference binds the viscosity field when lrksgsfac = 0) */
+  NALU_F_COUNT = 26
 };
 
 typedef struct nalu_b200_kernel_desc {
@@ -133,7 +138,7 @@ typedef struct nalu_b200_kernel_desc {
   double gravity[3];
   double rho_ref, t_ref, beta;
   /* SST source kernels: SolutionOptions::get_turb_model_constant (src/SolutionOptions.C:742-770) */
-  double turb[8]; /* NALU_TM_* */
+  double turb[10]; /* NALU_TM_* */
   /* upwind adv-diff kernels: SolutionOptions::get_alpha_factor / get_alpha_upw_factor / get_upw_factor and the
    * Peclet function EquationSystem::create_peclet_function builds (include/EquationSystem.h:306-325):
    * classic A = 5 with Realm::get_hybrid_factor, or tanh with get_tanh_trans / get_tanh_width */
@@ -142,7 +147,8 @@ typedef struct nalu_b200_kernel_desc {
 enum { NALU_UPW_ALPHA = 0, NALU_UPW_ALPHA_UPW = 1, NALU_UPW_HO_UPWIND = 2, NALU_UPW_HYBRID_FACTOR = 3,
        NALU_UPW_TANH_TRANS = 4, NALU_UPW_TANH_WIDTH = 5 };
 enum { NALU_TM_BETA_STAR = 0, NALU_TM_TKE_PROD_LIMIT_RATIO = 1, NALU_TM_SIGMA_W_TWO = 2, NALU_TM_BETA_ONE = 3,
-       NALU_TM_BETA_TWO = 4, NALU_TM_GAMMA_ONE = 5, NALU_TM_GAMMA_TWO = 6 };
+       NALU_TM_BETA_TWO = 4, NALU_TM_GAMMA_ONE = 5, NALU_TM_GAMMA_TWO = 6, NALU_TM_CDES_KW = 7, NALU_TM_CDES_KE = 8,
+       NALU_TM_LRKSGS_FAC = 9 /* TurbKineticEnergyKsgsSrcElemKernel.C:54-57: 1 with the low-Reynolds correction, else 0 */ };
 
 /* ------------------------------------------------------------------------------------ */
 /* Graph: DOF numbering + CSR graph, built once per mesh.                                */

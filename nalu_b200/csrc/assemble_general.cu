@@ -141,7 +141,7 @@ const char *missing_field(const nalu_b200_kernel_desc &k)
                                             "density(N)", "density(NM1)", "pressure", "dpdx", "scalarQ", "scalarQ(N)",
                                             "scalarQ(NM1)", "dual_nodal_volume", "temperature", "turbulent_ke",
                                             "specific_dissipation_rate", "turbulent_viscosity", "sst_f_one_blending", "Gjq",
-                                            "dudx", "velocity_rtm", "", ""};
+                                            "dudx", "velocity_rtm", "sst_max_length_scale", "c_epsilon", "dsqrtk_dx_sq", ""};
   int need[12];
   int n = 0;
   bool mdot = false;
@@ -167,6 +167,14 @@ const char *missing_field(const nalu_b200_kernel_desc &k)
   case NALU_K_SDR_SST_SRC:
     add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_DENSITY, NALU_F_TKE, NALU_F_SDR, NALU_F_TVISC});
     if (k.kind == NALU_K_SDR_SST_SRC) add({NALU_F_FONE_BLEND});
+    break;
+  case NALU_K_TKE_SST_DES_SRC:
+    add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_DENSITY, NALU_F_TKE, NALU_F_SDR, NALU_F_TVISC, NALU_F_FONE_BLEND,
+         NALU_F_SST_MAX_LENGTH_SCALE});
+    break;
+  case NALU_K_TKE_KSGS_SRC:
+    add({NALU_F_COORDINATES, NALU_F_TKE, NALU_F_DENSITY, NALU_F_TVISC, NALU_F_DUAL_VOLUME, NALU_F_C_EPSILON, NALU_F_GJU,
+         NALU_F_VISCOSITY, NALU_F_DSQRTK_DX_SQ});
     break;
   case NALU_K_TEST_FIXED_BLOCK: return k.fixed_block ? nullptr : "fixed_block";
   default: return "unknown kernel kind";

@@ -46,10 +46,12 @@ __host__ __device__ inline void me_needs_of(const nalu_b200_kernel_desc &k, MeNe
   case NALU_K_SCALAR_MASS:
   case NALU_K_MOMENTUM_BUOYANCY_SRC:            // MomentumBuoyancySrcElemKernel.C:50-53
   case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC: // MomentumBuoyancyBoussinesqSrcElemKernel.C:52-58
+  case NALU_K_TKE_KSGS_SRC:                     // TurbKineticEnergyKsgsSrcElemKernel.C:64
     m.scv_volume = 1;
     break;
   case NALU_K_TKE_SST_SRC: // TurbKineticEnergySSTSrcElemKernel.C:84-89
   case NALU_K_SDR_SST_SRC: // SpecificDissipationRateSSTSrcElemKernel.C:91-96
+  case NALU_K_TKE_SST_DES_SRC: // TurbKineticEnergySSTDESSrcElemKernel.C:91-96
     m.scv_volume = 1;
     if (k.options & NALU_OPT_SHIFTED_GRAD_OP) m.dndx_scv_shifted = 1; else m.dndx_scv = 1;
     break;
@@ -115,7 +117,8 @@ enum { F_GJU = 5, F_RTM = 14 };                                                /
 enum { M_UNP1 = 0, M_UN = 3, M_UNM1 = 6, M_GP = 9, M_RNP1 = 12, M_RN = 13, M_RNM1 = 14 }; // momentum mass
 enum { S_QNP1 = 0, S_QN = 1, S_QNM1 = 2, S_RNP1 = 3, S_RN = 4, S_RNM1 = 5 };  // scalar / continuity mass
 enum { B_S = 0 };
-enum { T_U = 0, T_RHO = 3, T_K = 4, T_W = 5, T_NUT = 6, T_F1 = 7 };           // SST sources                                                              // buoyancy: density or temperature
+enum { T_U = 0, T_RHO = 3, T_K = 4, T_W = 5, T_NUT = 6, T_F1 = 7, T_LMAX = 8 }; // SST / SST-DES sources
+enum { G_K = 0, G_RHO = 1, G_NUT = 2, G_VOL = 3, G_CEPS = 4, G_MU = 5, G_DSQ = 6, G_DUDX = 7 }; // Ksgs source
 
 __host__ __device__ inline void gather_one(double *dst, const double *field, int ncomp, int node)
 {
@@ -180,6 +183,9 @@ __host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, co
   case NALU_K_MOMENTUM_BUOYANCY_SRC:
     gather_one(f + B_S, k.nodal[NALU_F_DENSITY], 1, node);
     break;
+  case NALU_K_TKE_SST_DES_SRC:
+    gather_one(f + T_LMAX, k.nodal[NALU_F_SST_MAX_LENGTH_SCALE], 1, node);
+    // fallthrough
   case NALU_K_SDR_SST_SRC:
     gather_one(f + T_F1, k.nodal[NALU_F_FONE_BLEND], 1, node);
     // fallthrough
@@ -192,6 +198,16 @@ __host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, co
     break;
   case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC:
     gather_one(f + B_S, k.nodal[NALU_F_TEMPERATURE], 1, node);
+    break;
+  case NALU_K_TKE_KSGS_SRC: // TurbKineticEnergyKsgsSrcElemKernel.C:62-72
+    gather_one(f + G_K, k.nodal[NALU_F_TKE], 1, node);
+    gather_one(f + G_RHO, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + G_NUT, k.nodal[NALU_F_TVISC], 1, node);
+    gather_one(f + G_VOL, k.nodal[NALU_F_DUAL_VOLUME], 1, node);
+    gather_one(f + G_CEPS, k.nodal[NALU_F_C_EPSILON], 1, node);
+    gather_one(f + G_MU, k.nodal[NALU_F_VISCOSITY], 1, node);
+    gather_one(f + G_DSQ, k.nodal[NALU_F_DSQRTK_DX_SQ], 1, node);
+    gather_one(f + G_DUDX, k.nodal[NALU_F_GJU], 9, node);
     break;
   default:
     break;
@@ -247,7 +263,8 @@ __host__ __device__ inline void stage_ip(int lane, ElemScratch<NDOF> &ws, const 
   const int kind = k.kind;
   if (kind == NALU_K_MOMENTUM_MASS || kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS ||
       kind == NALU_K_TEST_FIXED_BLOCK || kind == NALU_K_MOMENTUM_BUOYANCY_SRC ||
-      kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC || kind == NALU_K_TKE_SST_SRC || kind == NALU_K_SDR_SST_SRC)
+      kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC || kind == NALU_K_TKE_SST_SRC || kind == NALU_K_SDR_SST_SRC ||
+      kind == NALU_K_TKE_SST_DES_SRC || kind == NALU_K_TKE_KSGS_SRC)
     return;
   if (lane >= 12) return;
   const int ip = lane;
@@ -509,15 +526,15 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
     const double fac = kind == NALU_K_MOMENTUM_BUOYANCY_SRC ? (sIp - k.rho_ref) * scV
                                                              : -k.rho_ref * k.beta * (sIp - k.t_ref) * scV;
     for (int j = 0; j < 3; ++j) ws.rhs[ip * 3 + j] += fac * k.gravity[j];
-  } else if (kind == NALU_K_TKE_SST_SRC || kind == NALU_K_SDR_SST_SRC) {
-    // TurbKineticEnergySSTSrcElemKernel.C:120-172, SpecificDissipationRateSSTSrcElemKernel.C:128-202;
-    // lane = SCV ip = nearest node
+  } else if (kind == NALU_K_TKE_SST_SRC || kind == NALU_K_SDR_SST_SRC || kind == NALU_K_TKE_SST_DES_SRC) {
+    // TurbKineticEnergySSTSrcElemKernel.C:120-172, SpecificDissipationRateSSTSrcElemKernel.C:128-202,
+    // TurbKineticEnergySSTDESSrcElemKernel.C:131-196; lane = SCV ip = nearest node
     if (NDOF != 1 || lane >= 8) return;
     const int ip = lane;
     double s1, s2, s3;
     hex8::scv_intg_loc(ip, (k.options & NALU_OPT_LUMPED_MASS) ? 0.5 : 0.25, s1, s2, s3);
-    double rho = 0, tke = 0, sdr = 0, tvisc = 0, f1 = 0, dudx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, dkdx[3] = {0, 0, 0},
-           dwdx[3] = {0, 0, 0};
+    double rho = 0, tke = 0, sdr = 0, tvisc = 0, f1 = 0, lmax = 0, dudx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}},
+           dkdx[3] = {0, 0, 0}, dwdx[3] = {0, 0, 0};
     for (int ic = 0; ic < 8; ++ic) {
       const double r = hex8::shape_fcn(ic, s1, s2, s3);
       const double *f = ws.fld[ic];
@@ -526,6 +543,7 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
       sdr += r * f[T_W];
       tvisc += r * f[T_NUT];
       f1 += r * f[T_F1];
+      lmax += r * f[T_LMAX];
       const double *g = ws.dndx_scv[ip][ic];
       for (int i = 0; i < 3; ++i) {
         dkdx[i] += g[i] * f[T_K];
@@ -541,9 +559,23 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
     Pk *= tvisc;
     const double betaStar = k.turb[NALU_TM_BETA_STAR], limit = k.turb[NALU_TM_TKE_PROD_LIMIT_RATIO];
     const double scV = ws.scv[ip];
-    const double Dk = betaStar * rho * sdr * tke;
-    Pk = fmin(Pk, limit * Dk);
+    double Dk = betaStar * rho * sdr * tke;
     double lhsfac;
+    if (kind == NALU_K_TKE_SST_DES_SRC) {
+      // the DES length scale replaces k^(1/2) / (betaStar omega) where the grid resolves it (:165-178)
+      const double cDES = f1 * k.turb[NALU_TM_CDES_KW] + (1.0 - f1) * k.turb[NALU_TM_CDES_KE];
+      const double sqrtTke = sqrt(tke);
+      const double lSST = sqrtTke / betaStar / sdr;
+      const double lDES = fmax(1.0e-16, fmin(lSST, cDES * lmax));
+      const double tkeFac = rho * sqrtTke / lDES;
+      Dk = tkeFac * tke;
+      Pk = fmin(Pk, limit * Dk);
+      ws.rhs[ip] += (Pk - Dk) * scV;
+      lhsfac = tkeFac * scV;
+      for (int ic = 0; ic < 8; ++ic) ws.lhs[ip * R + ic] += hex8::shape_fcn(ic, s1, s2, s3) * lhsfac;
+      return;
+    }
+    Pk = fmin(Pk, limit * Dk);
     if (kind == NALU_K_TKE_SST_SRC) {
       ws.rhs[ip] += (Pk - Dk) * scV;
       lhsfac = betaStar * rho * sdr * scV;
@@ -559,6 +591,23 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
       lhsfac = (2.0 * beta * rho * sdr + fmax(Sw / sdr, 0.0)) * scV;
     }
     for (int ic = 0; ic < 8; ++ic) ws.lhs[ip * R + ic] += hex8::shape_fcn(ic, s1, s2, s3) * lhsfac;
+  } else if (kind == NALU_K_TKE_KSGS_SRC) {
+    // TurbKineticEnergyKsgsSrcElemKernel.C:90-126: everything evaluated at the nearest node, lumped diagonal
+    if (NDOF != 1 || lane >= 8) return;
+    const int ip = lane;
+    const double *f = ws.fld[ip];
+    const double *G = f + G_DUDX;
+    double Pk = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Pk += G[3 * i + j] * (G[3 * i + j] + G[3 * j + i]);
+    Pk *= f[G_NUT];
+    const double tke = f[G_K];
+    const double tkeFac = f[G_CEPS] * f[G_RHO] * sqrt(tke) / cbrt(f[G_VOL]);
+    const double Dk = tkeFac * tke + k.turb[NALU_TM_LRKSGS_FAC] * 2.0 * f[G_MU] * f[G_DSQ];
+    Pk = fmin(Pk, k.turb[NALU_TM_TKE_PROD_LIMIT_RATIO] * Dk);
+    const double scV = ws.scv[ip];
+    ws.rhs[ip] += (Pk - Dk) * scV;
+    ws.lhs[ip * R + ip] += 1.5 * tkeFac * scV;
   } else if (kind == NALU_K_CONTINUITY_MASS || kind == NALU_K_SCALAR_MASS) {
     // ContinuityMassElemKernel.C:98-117, ScalarMassElemKernel.C:117-154
     if (NDOF != 1 || lane >= 8) return;

@@ -819,6 +819,99 @@ bool SpecificDissipationRateSSTSrcElemKernel<AlgTraits>::device_descriptor(nalu_
   return true;
 }
 
+// ---- src/kernel/TurbKineticEnergySSTDESSrcElemKernel.C:27-99
+template <typename AlgTraits>
+TurbKineticEnergySSTDESSrcElemKernel<AlgTraits>::TurbKineticEnergySSTDESSrcElemKernel(const stk::mesh::BulkData &bulkData,
+                                                                                     const SolutionOptions &solnOpts,
+                                                                                     ElemDataRequests &dataPreReqs,
+                                                                                     const bool lumpedMass)
+    : Kernel(), lumpedMass_(lumpedMass), shiftedGradOp_(solnOpts.get_shifted_grad_op("velocity")),
+      betaStar_(solnOpts.get_turb_model_constant(TM_betaStar)),
+      tkeProdLimitRatio_(solnOpts.get_turb_model_constant(TM_tkeProdLimitRatio)),
+      cDESke_(solnOpts.get_turb_model_constant(TM_cDESke)), cDESkw_(solnOpts.get_turb_model_constant(TM_cDESkw)),
+      ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  sst_common_registrations<AlgTraits>(*this, bulkData, solnOpts, dataPreReqs, lumpedMass_, shiftedGradOp_, tkeNp1_, sdrNp1_,
+                                      densityNp1_, velocityNp1_, tvisc_, coordinates_, &fOneBlend_);
+  maxLengthScale_ = bulkData.mesh_meta_data().get_field<double>(stk::topology::NODE_RANK, "sst_max_length_scale");
+  STK_ThrowRequireMsg(maxLengthScale_, "SST-DES source kernel: sst_max_length_scale not registered");
+  dataPreReqs.add_gathered_nodal_field(*maxLengthScale_, 1);
+}
+template <typename AlgTraits>
+bool TurbKineticEnergySSTDESSrcElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_TKE_SST_DES_SRC;
+  d.options = (lumpedMass_ ? NALU_OPT_LUMPED_MASS : 0) | (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0);
+  d.turb[NALU_TM_BETA_STAR] = betaStar_;
+  d.turb[NALU_TM_TKE_PROD_LIMIT_RATIO] = tkeProdLimitRatio_;
+  d.turb[NALU_TM_CDES_KE] = cDESke_;
+  d.turb[NALU_TM_CDES_KW] = cDESkw_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_VELOCITY, velocityNp1_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_TKE, tkeNp1_);
+  bind(d, NALU_F_SDR, sdrNp1_);
+  bind(d, NALU_F_TVISC, tvisc_);
+  bind(d, NALU_F_FONE_BLEND, fOneBlend_);
+  bind(d, NALU_F_SST_MAX_LENGTH_SCALE, maxLengthScale_);
+  return true;
+}
+
+// ---- src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C:27-72
+template <typename AlgTraits>
+TurbKineticEnergyKsgsSrcElemKernel<AlgTraits>::TurbKineticEnergyKsgsSrcElemKernel(const stk::mesh::BulkData &bulkData,
+                                                                                 const SolutionOptions &solnOpts,
+                                                                                 ElemDataRequests &dataPreReqs, double lrksgsfac)
+    : Kernel(), lrksgsfac_(lrksgsfac), tkeProdLimitRatio_(solnOpts.get_turb_model_constant(TM_tkeProdLimitRatio)),
+      ipNodeMap_(MasterElementRepo::get_volume_master_element(AlgTraits::topo_)->ipNodeMap())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  auto scalar = [&](const char *n) { return metaData.get_field<double>(stk::topology::NODE_RANK, n); };
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  tkeNp1_ = scalar("turbulent_ke");
+  densityNp1_ = scalar("density");
+  tvisc_ = scalar("turbulent_viscosity");
+  dualNodalVolume_ = scalar("dual_nodal_volume");
+  cEps_ = scalar("c_epsilon");
+  Gju_ = metaData.get_field<double>(stk::topology::NODE_RANK, "dudx");
+  visc_ = scalar("viscosity");
+  // a field the low-Re form alone reads is bound to one that always exists otherwise (:51-55)
+  dsqrtkSq_ = lrksgsfac > 0.0 ? scalar("dsqrtk_dx_sq") : visc_;
+  STK_ThrowRequireMsg(coordinates_ && tkeNp1_ && densityNp1_ && tvisc_ && dualNodalVolume_ && cEps_ && Gju_ && visc_ && dsqrtkSq_,
+                      "Ksgs source kernel: field not registered");
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(AlgTraits::topo_);
+  dataPreReqs.add_cvfem_volume_me(meSCV);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*tkeNp1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*tvisc_, 1);
+  dataPreReqs.add_gathered_nodal_field(*dualNodalVolume_, 1);
+  dataPreReqs.add_gathered_nodal_field(*cEps_, 1);
+  dataPreReqs.add_gathered_nodal_field(*Gju_, AlgTraits::nDim_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*visc_, 1);
+  dataPreReqs.add_gathered_nodal_field(*dsqrtkSq_, 1);
+  dataPreReqs.add_master_element_call(SCV_VOLUME, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+bool TurbKineticEnergyKsgsSrcElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_TKE_KSGS_SRC;
+  d.turb[NALU_TM_TKE_PROD_LIMIT_RATIO] = tkeProdLimitRatio_;
+  d.turb[NALU_TM_LRKSGS_FAC] = lrksgsfac_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_TKE, tkeNp1_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_TVISC, tvisc_);
+  bind(d, NALU_F_DUAL_VOLUME, dualNodalVolume_);
+  bind(d, NALU_F_C_EPSILON, cEps_);
+  bind(d, NALU_F_GJU, Gju_);
+  bind(d, NALU_F_VISCOSITY, visc_);
+  bind(d, NALU_F_DSQRTK_DX_SQ, dsqrtkSq_);
+  return true;
+}
+
 // ---- upwind adv-diff kernels --------------------------------------------------------------------
 namespace {
 // EquationSystem::create_peclet_function (include/EquationSystem.h:306-325), captured as data
@@ -977,6 +1070,8 @@ bool MomentumUpwAdvDiffElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel
 }
 
 NALU_B200_DECLARE_KERNEL(TurbKineticEnergySSTSrcElemKernel)
+NALU_B200_DECLARE_KERNEL(TurbKineticEnergySSTDESSrcElemKernel)
+NALU_B200_DECLARE_KERNEL(TurbKineticEnergyKsgsSrcElemKernel)
 NALU_B200_DECLARE_KERNEL(ScalarUpwAdvDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumUpwAdvDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(SpecificDissipationRateSSTSrcElemKernel)

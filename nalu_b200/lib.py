@@ -19,13 +19,14 @@ ERR_NO_DEVICE = 3
 K = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3, continuity_mass=4,
          scalar_mass=5, scalar_diff=6, test_fixed_block=7, momentum_buoyancy_src=8,
          momentum_buoyancy_boussinesq_src=9, tke_sst_src=10, sdr_sst_src=11, scalar_upw_adv_diff=12,
-         momentum_upw_adv_diff=13)
+         momentum_upw_adv_diff=13, tke_sst_des_src=14, tke_ksgs_src=15)
 OPT = dict(shifted_grad_op=1, skew_symmetric=2, lumped_mass=4, shift_mdot=8, shift_poisson=16, reduced_sens=32,
            use_limiter=64, peclet_tanh=128)
 F = dict(coordinates=0, velocity=1, velocity_n=2, velocity_nm1=3, viscosity=4, density=5, density_n=6,
          density_nm1=7, pressure=8, dpdx=9, scalarq=10, scalarq_n=11, scalarq_nm1=12, dual_volume=13, temperature=14, tke=15, sdr=16,
-         tvisc=17, f_one_blend=18, gjq=19, gju=20, velocity_rtm=21)
-F_COUNT = 24
+         tvisc=17, f_one_blend=18, gjq=19, gju=20, velocity_rtm=21, sst_max_length_scale=22, c_epsilon=23,
+         dsqrtk_dx_sq=24)
+F_COUNT = 26
 MODE = dict(auto=0, general=1, box=2)
 
 
@@ -35,11 +36,12 @@ class KernelDesc(C.Structure):
                 ("gamma1", C.c_double), ("gamma2", C.c_double), ("gamma3", C.c_double),
                 ("nodal", C.c_void_p * F_COUNT), ("mass_flow_rate", C.c_void_p), ("fixed_block", C.c_void_p),
                 ("gravity", C.c_double * 3), ("rho_ref", C.c_double), ("t_ref", C.c_double), ("beta", C.c_double),
-                ("turb", C.c_double * 8), ("upw", C.c_double * 8)]
+                ("turb", C.c_double * 10), ("upw", C.c_double * 8)]
 
 
 UPW = dict(alpha=0, alpha_upw=1, ho_upwind=2, hybrid_factor=3, tanh_trans=4, tanh_width=5)
-TM = dict(beta_star=0, tke_prod_limit_ratio=1, sigma_w_two=2, beta_one=3, beta_two=4, gamma_one=5, gamma_two=6)
+TM = dict(beta_star=0, tke_prod_limit_ratio=1, sigma_w_two=2, beta_one=3, beta_two=4, gamma_one=5, gamma_two=6, cdes_kw=7, cdes_ke=8,
+          lrksgs_fac=9)
 
 
 class GraphInfo(C.Structure):

@@ -464,6 +464,88 @@ static void sst_src(const orc_kernel_desc *k, int sdr_kernel, const int32_t *nod
   }
 }
 
+/* ---- src/kernel/TurbKineticEnergySSTDESSrcElemKernel.C:106-198 ---- */
+static void sst_des_src(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me, double *lhs, double *rhs)
+{
+  double v_tkeNp1[8], v_sdrNp1[8], v_densityNp1[8], v_velocityNp1[8][3], v_tvisc[8], v_maxLengthScale[8], v_fOneBlend[8];
+  gather(k->tke, 1, nodes, v_tkeNp1);
+  gather(k->sdr, 1, nodes, v_sdrNp1);
+  gather(k->density, 1, nodes, v_densityNp1);
+  gather(k->velocity, 3, nodes, &v_velocityNp1[0][0]);
+  gather(k->tvisc, 1, nodes, v_tvisc);
+  gather(k->maxLengthScale, 1, nodes, v_maxLengthScale);
+  gather(k->fOneBlend, 1, nodes, v_fOneBlend);
+  double v_shape_function_[8][8];
+  scv_shape(k->lumpedMass, v_shape_function_);
+  const int *ipNodeMap_ = orc_hex8_scv_ip_node_map();
+  const double betaStar_ = k->betaStar, tkeProdLimitRatio_ = k->tkeProdLimitRatio, cDESkw_ = k->cDESkw, cDESke_ = k->cDESke;
+
+  for (int ip = 0; ip < 8; ++ip) {
+    const int nearestNode = ipNodeMap_[ip];
+    const double scV = me->scv_volume[ip];
+    double rho = 0.0, tke = 0.0, sdr = 0.0, tvisc = 0.0, maxLengthScale = 0.0, fOneBlend = 0.0;
+    double w_dudx[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) w_dudx[i][j] = 0.0;
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      rho += r * v_densityNp1[ic];
+      tke += r * v_tkeNp1[ic];
+      sdr += r * v_sdrNp1[ic];
+      tvisc += r * v_tvisc[ic];
+      maxLengthScale += r * v_maxLengthScale[ic];
+      fOneBlend += r * v_fOneBlend[ic];
+      for (int i = 0; i < 3; ++i) {
+        const double ui = v_velocityNp1[ic][i];
+        for (int j = 0; j < 3; ++j) w_dudx[i][j] += me->dndx_scv[ip][ic][j] * ui;
+      }
+    }
+    double Pk = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Pk += w_dudx[i][j] * (w_dudx[i][j] + w_dudx[j][i]);
+    Pk *= tvisc;
+    const double cDES = fOneBlend * cDESkw_ + (1.0 - fOneBlend) * cDESke_;
+    const double sqrtTke = sqrt(tke);
+    const double lSST = sqrtTke / betaStar_ / sdr;
+    const double lDES = fmax(1.0e-16, fmin(lSST, cDES * maxLengthScale));
+    const double tkeFac = rho * sqrtTke / lDES;
+    const double Dk = tkeFac * tke;
+    Pk = fmin(Pk, tkeProdLimitRatio_ * Dk);
+    rhs[nearestNode] += (Pk - Dk) * scV;
+    for (int ic = 0; ic < 8; ++ic) lhs[nearestNode * 8 + ic] += v_shape_function_[ip][ic] * tkeFac * scV;
+  }
+}
+
+/* ---- src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C:78-128: everything at the nearest node, lumped ---- */
+static void ksgs_src(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me, double *lhs, double *rhs)
+{
+  double v_tkeNp1[8], v_densityNp1[8], v_tvisc[8], v_dualNodalVolume[8], v_cEps[8], v_Gju[8][3][3], v_visc[8], v_dsqrtkSq[8];
+  gather(k->tke, 1, nodes, v_tkeNp1);
+  gather(k->density, 1, nodes, v_densityNp1);
+  gather(k->tvisc, 1, nodes, v_tvisc);
+  gather(k->dualNodalVolume, 1, nodes, v_dualNodalVolume);
+  gather(k->cEps, 1, nodes, v_cEps);
+  gather(k->Gju, 9, nodes, &v_Gju[0][0][0]);
+  gather(k->viscosity, 1, nodes, v_visc);
+  gather(k->dsqrtkSq, 1, nodes, v_dsqrtkSq);
+  const int *ipNodeMap_ = orc_hex8_scv_ip_node_map();
+  const double lrksgsfac_ = k->lrksgsfac, tkeProdLimitRatio_ = k->tkeProdLimitRatio;
+  for (int ip = 0; ip < 8; ++ip) {
+    const int nearestNode = ipNodeMap_[ip];
+    double Pk = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Pk += v_Gju[nearestNode][i][j] * (v_Gju[nearestNode][i][j] + v_Gju[nearestNode][j][i]);
+    Pk *= v_tvisc[nearestNode];
+    const double tke = v_tkeNp1[nearestNode];
+    const double tkeFac = v_cEps[nearestNode] * v_densityNp1[nearestNode] * sqrt(tke) / cbrt(v_dualNodalVolume[nearestNode]);
+    const double Dk = tkeFac * tke + lrksgsfac_ * 2.0 * v_visc[nearestNode] * v_dsqrtkSq[nearestNode];
+    Pk = fmin(Pk, tkeProdLimitRatio_ * Dk);
+    const double scvol = me->scv_volume[ip];
+    rhs[nearestNode] += (Pk - Dk) * scvol;
+    lhs[nearestNode * 8 + nearestNode] += 1.5 * tkeFac * scvol;
+  }
+}
+
 /* ---- src/kernel/ScalarMassElemKernel.C:96-156 ---- */
 static void scalar_mass(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
                         double *lhs, double *rhs)
@@ -798,6 +880,7 @@ static void me_needs(const orc_kernel_desc *k, int *areav, int *dndx, int *dndxs
   case ORC_SCALAR_MASS:
   case ORC_MOMENTUM_BUOYANCY_SRC:
   case ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC:
+  case ORC_TKE_KSGS_SRC: /* TurbKineticEnergyKsgsSrcElemKernel.C:64 */
     *scv = 1;
     break;
   default:
@@ -827,7 +910,7 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     if (dndxs) orc_hex8_scs_grad_op(1, &me.coords[0][0], &me.dndx_shifted[0][0][0], &me.deriv[0][0][0]);
     if (scv) orc_hex8_scv_volume(&me.coords[0][0], me.scv_volume);
     for (int i = 0; i < nk; ++i)
-      if (kernels[i].kind == ORC_TKE_SST_SRC || kernels[i].kind == ORC_SDR_SST_SRC) {
+      if (kernels[i].kind == ORC_TKE_SST_SRC || kernels[i].kind == ORC_SDR_SST_SRC || kernels[i].kind == ORC_TKE_SST_DES_SRC) {
         /* SCV_GRAD_OP or SCV_SHIFTED_GRAD_OP (TurbKineticEnergySSTSrcElemKernel.C:84-89) */
         orc_hex8_scv_volume(&me.coords[0][0], me.scv_volume);
         orc_hex8_scv_grad_op(kernels[i].shiftedGradOp, &me.coords[0][0], &me.dndx_scv[0][0][0], NULL);
@@ -854,6 +937,8 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     case ORC_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC: momentum_buoyancy(k, 1, elemNodes, &me, lhs, rhs); break;
     case ORC_TKE_SST_SRC: sst_src(k, 0, elemNodes, &me, lhs, rhs); break;
     case ORC_SDR_SST_SRC: sst_src(k, 1, elemNodes, &me, lhs, rhs); break;
+    case ORC_TKE_SST_DES_SRC: sst_des_src(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_TKE_KSGS_SRC: ksgs_src(k, elemNodes, &me, lhs, rhs); break;
     case ORC_TEST_FIXED_BLOCK: /* unit_tests/UnitTestTpetra.C:125-139: lhs(i,j) = elemVals[i][j] */
       for (int q = 0; q < rhsSize * rhsSize; ++q) lhs[q] = k->fixedBlock[q];
       break;

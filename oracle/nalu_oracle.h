@@ -74,7 +74,9 @@ enum orc_kernel_kind {
   ORC_TKE_SST_SRC = 10,                     /* src/kernel/TurbKineticEnergySSTSrcElemKernel.C       */
   ORC_SDR_SST_SRC = 11,                     /* src/kernel/SpecificDissipationRateSSTSrcElemKernel.C */
   ORC_SCALAR_UPW_ADV_DIFF = 12,             /* src/kernel/ScalarUpwAdvDiffElemKernel.C              */
-  ORC_MOMENTUM_UPW_ADV_DIFF = 13            /* src/kernel/MomentumUpwAdvDiffElemKernel.C            */
+  ORC_MOMENTUM_UPW_ADV_DIFF = 13,           /* src/kernel/MomentumUpwAdvDiffElemKernel.C            */
+  ORC_TKE_SST_DES_SRC = 14,                 /* src/kernel/TurbKineticEnergySSTDESSrcElemKernel.C    */
+  ORC_TKE_KSGS_SRC = 15                     /* src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C      */
 };
 
 /* what the kernel constructors/ setup() capture (options + time integrator) */
@@ -122,6 +124,12 @@ typedef struct orc_kernel_desc {
   int useLimiter;                   /* primitive_uses_limiter                          */
   int pecletTanh;                   /* 0: ClassicPecletFunction(A=5, hybridFactor), 1: TanhFunction(c1, c2) */
   double hybridFactor, tanhTrans, tanhWidth; /* EquationSystem.h:306-325                */
+  /* SST-DES / Ksgs sources */
+  const double *maxLengthScale; /* [1] sst_max_length_scale                                  */
+  const double *cEps;           /* [1] c_epsilon                                             */
+  const double *dsqrtkSq;       /* [1] dsqrtk_dx_sq (the viscosity field when lrksgsfac = 0) */
+  const double *dualNodalVolume;/* [1] dual_nodal_volume                                     */
+  double cDESke, cDESkw, lrksgsfac;
 } orc_kernel_desc;
 
 /* One element through the registered kernels, exactly as

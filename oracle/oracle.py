@@ -11,7 +11,7 @@ _LIB = None
 KIND = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3,
             continuity_mass=4, scalar_mass=5, scalar_diff=6, test_fixed_block=7, momentum_buoyancy_src=8,
             momentum_buoyancy_boussinesq_src=9, tke_sst_src=10, sdr_sst_src=11, scalar_upw_adv_diff=12,
-            momentum_upw_adv_diff=13)
+            momentum_upw_adv_diff=13, tke_sst_des_src=14, tke_ksgs_src=15)
 
 
 def build(force=False):
@@ -55,12 +55,15 @@ class KernelDesc(C.Structure):
                [(n, C.c_void_p) for n in ("Gjq", "Gju", "velocityRTM")] + \
                [(n, C.c_double) for n in ("alpha", "alphaUpw", "hoUpwind")] + \
                [("useLimiter", C.c_int), ("pecletTanh", C.c_int)] + \
-               [(n, C.c_double) for n in ("hybridFactor", "tanhTrans", "tanhWidth")]
+               [(n, C.c_double) for n in ("hybridFactor", "tanhTrans", "tanhWidth")] + \
+               [(n, C.c_void_p) for n in ("maxLengthScale", "cEps", "dsqrtkSq", "dualNodalVolume")] + \
+               [(n, C.c_double) for n in ("cDESke", "cDESkw", "lrksgsfac")]
 
 
 _PTR_FIELDS = ("coordinates", "velocity", "velocityN", "velocityNm1", "viscosity", "density", "densityN",
                "densityNm1", "pressure", "Gpdx", "scalarQ", "scalarQN", "scalarQNm1", "massFlowRate",
-               "fixedBlock", "temperature", "tke", "sdr", "tvisc", "fOneBlend", "Gjq", "Gju", "velocityRTM")
+               "fixedBlock", "temperature", "tke", "sdr", "tvisc", "fOneBlend", "Gjq", "Gju", "velocityRTM",
+               "maxLengthScale", "cEps", "dsqrtkSq", "dualNodalVolume")
 
 
 def _f64(a):

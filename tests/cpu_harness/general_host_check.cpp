@@ -115,6 +115,55 @@ int main()
       }
     }
 
+    // turbulence source kernels: SST tke / sdr, SST-DES tke, Ksgs tke; lumped x shifted grad-op
+    for (int kind : {NALU_K_TKE_SST_SRC, NALU_K_SDR_SST_SRC, NALU_K_TKE_SST_DES_SRC, NALU_K_TKE_KSGS_SRC}) {
+      for (int opt = 0; opt < 4; ++opt) {
+        static double tke[NN], sdr[NN], tvisc[NN], f1[NN], lmax[NN], ceps[NN], dsq[NN], dvol[NN], gju[NN * 9];
+        for (int n = 0; n < NN; ++n) {
+          tke[n] = 2.0 + frand(); sdr[n] = 2.0 + frand(); tvisc[n] = 0.3 + 0.2 * frand(); f1[n] = 0.5 + frand();
+          lmax[n] = 8.0 + 14.0 * frand(); ceps[n] = 0.845 + 0.1 * frand(); dsq[n] = 0.5 + frand(); dvol[n] = 1.0 + 0.5 * frand();
+          for (int j = 0; j < 9; ++j) gju[n * 9 + j] = (n & 1 ? 6.0 : 1.0) * frand();
+        }
+        nalu_b200_kernel_desc k;
+        orc_kernel_desc o;
+        memset(&k, 0, sizeof(k));
+        memset(&o, 0, sizeof(o));
+        k.kind = kind; o.kind = kind;
+        int options = 0;
+        if (opt & 1) { options |= NALU_OPT_SHIFTED_GRAD_OP; o.shiftedGradOp = 1; }
+        if (opt & 2) { options |= NALU_OPT_LUMPED_MASS; o.lumpedMass = 1; }
+        k.options = options;
+        k.turb[NALU_TM_BETA_STAR] = o.betaStar = 0.09;
+        k.turb[NALU_TM_TKE_PROD_LIMIT_RATIO] = o.tkeProdLimitRatio = (trial & 1) ? 0.5 : 10.0;
+        k.turb[NALU_TM_SIGMA_W_TWO] = o.sigmaWTwo = 0.856;
+        k.turb[NALU_TM_BETA_ONE] = o.betaOne = 0.075;
+        k.turb[NALU_TM_BETA_TWO] = o.betaTwo = 0.0828;
+        k.turb[NALU_TM_GAMMA_ONE] = o.gammaOne = 5.0 / 9.0;
+        k.turb[NALU_TM_GAMMA_TWO] = o.gammaTwo = 0.44;
+        k.turb[NALU_TM_CDES_KW] = o.cDESkw = 0.78;
+        k.turb[NALU_TM_CDES_KE] = o.cDESke = 0.61;
+        k.turb[NALU_TM_LRKSGS_FAC] = o.lrksgsfac = (opt & 1) ? 1.0 : 0.0;
+        k.nodal[NALU_F_COORDINATES] = o.coordinates = coords;
+        k.nodal[NALU_F_VELOCITY] = o.velocity = vel;
+        k.nodal[NALU_F_DENSITY] = o.density = rho;
+        k.nodal[NALU_F_VISCOSITY] = o.viscosity = visc;
+        k.nodal[NALU_F_TKE] = o.tke = tke;
+        k.nodal[NALU_F_SDR] = o.sdr = sdr;
+        k.nodal[NALU_F_TVISC] = o.tvisc = tvisc;
+        k.nodal[NALU_F_FONE_BLEND] = o.fOneBlend = f1;
+        k.nodal[NALU_F_SST_MAX_LENGTH_SCALE] = o.maxLengthScale = lmax;
+        k.nodal[NALU_F_C_EPSILON] = o.cEps = ceps;
+        k.nodal[NALU_F_DSQRTK_DX_SQ] = o.dsqrtkSq = dsq;
+        k.nodal[NALU_F_DUAL_VOLUME] = o.dualNodalVolume = dvol;
+        k.nodal[NALU_F_GJU] = o.Gju = gju;
+        std::vector<nalu_b200_kernel_desc> ks{k};
+        std::vector<orc_kernel_desc> os{o};
+        const double e = run_case<1>(ks, os, nodes, coords);
+        if (e > 1e-13) { printf("FAIL turbulence source kind %d opt %d trial %d relerr %.3e\n", kind, opt, trial, e); return 1; }
+        worst = fmax(worst, e);
+      }
+    }
+
     for (int kind = 0; kind < 7; ++kind) {
       for (int opt = 0; opt < 4; ++opt) {
         nalu_b200_kernel_desc k;

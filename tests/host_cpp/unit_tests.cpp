@@ -107,6 +107,7 @@ struct LowMachKernelHex8Mesh {
     sdr_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "specific_dissipation_rate");
     tvisc_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "turbulent_viscosity");
     fOneBlend_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "sst_f_one_blending");
+    maxLengthScale_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "sst_max_length_scale");
     // projected nodal gradients of the upwind kernels (dqdx / dudx in the reference's equation systems)
     dqdx_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dqdx");
     dudx_ = &meta_.declare_field<double>(stk::topology::NODE_RANK, "dudx");
@@ -121,7 +122,7 @@ struct LowMachKernelHex8Mesh {
     stk::mesh::put_field_on_mesh(*diffFluxCoeff_, *part_, 1);
     stk::mesh::put_field_on_mesh(*dualNodalVolume_, *part_, 1);
     stk::mesh::put_field_on_mesh(*temperature_, *part_, 1);
-    for (auto *f : {tke_, sdr_, tvisc_, fOneBlend_}) stk::mesh::put_field_on_mesh(*f, *part_, 1);
+    for (auto *f : {tke_, sdr_, tvisc_, fOneBlend_, maxLengthScale_}) stk::mesh::put_field_on_mesh(*f, *part_, 1);
     stk::mesh::put_field_on_mesh(*dqdx_, *part_, 3);
     stk::mesh::put_field_on_mesh(*dudx_, *part_, 9);
     stk::mesh::put_field_on_mesh(*massFlowRate_, *part_, 12);
@@ -161,8 +162,9 @@ struct LowMachKernelHex8Mesh {
       tke_->host_data()[n] = 2.0 + std::cos(a * pi * X) * std::sin(a * pi * Y) * std::cos(a * pi * Z);
       sdr_->host_data()[n] = 2.0 + std::cos(a * pi * X) * std::sin(a * pi * Y) * std::sin(a * pi * Z);
       fOneBlend_->host_data()[n] = std::sin(a * pi * X) * std::cos(a * pi * Y) * std::sin(a * pi * Z);
+      maxLengthScale_->host_data()[n] = 0.5; // stk::mesh::field_fill(0.5, *maxLengthScale_), :391
     }
-    for (auto *f : {density_, tke_, sdr_, tvisc_, fOneBlend_}) f->modify_on_host();
+    for (auto *f : {density_, tke_, sdr_, tvisc_, fOneBlend_, maxLengthScale_}) f->modify_on_host();
   }
   stk::mesh::MetaData meta_;
   std::shared_ptr<stk::mesh::BulkData> bulk_;
@@ -171,7 +173,7 @@ struct LowMachKernelHex8Mesh {
   SolutionOptions solnOpts_;
   VectorFieldType *coordinates_, *velocity_, *dpdx_, *dqdx_;
   GenericFieldType *dudx_;
-  ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_, *temperature_, *tke_, *sdr_, *tvisc_, *fOneBlend_;
+  ScalarFieldType *density_, *pressure_, *viscosity_, *scalarQ_, *diffFluxCoeff_, *dualNodalVolume_, *temperature_, *tke_, *sdr_, *tvisc_, *fOneBlend_, *maxLengthScale_;
   GenericFieldType *massFlowRate_;
 };
 
@@ -511,10 +513,12 @@ static void test_momentum_buoyancy(bool boussinesq)
   for (double v : lhs) EXPECT_TRUE(v == 0.0);
 }
 
-static void test_sst_src(bool sdr)
+static void test_sst_src(int which)
 {
+  const bool sdr = which == 1, des = which == 2;
   std::printf("SSTKernelHex8Mesh.%s (unit_tests/kernels/UnitTestSSTSrcElem.C:%s)\n",
-              sdr ? "specificdissipationratesstsrcelem" : "turbkineticenergysstsrcelem", sdr ? "259-297" : "179-217");
+              sdr ? "specificdissipationratesstsrcelem" : des ? "turbkineticenergysstdessrcelem" : "turbkineticenergysstsrcelem",
+              sdr ? "259-297" : des ? "219-257" : "179-217");
   LowMachKernelHex8Mesh fx;
   fx.fill_mesh_and_init_fields();
   fx.fill_sst_fields();
@@ -525,6 +529,9 @@ static void test_sst_src(bool sdr)
   if (sdr)
     kernel.reset(new SpecificDissipationRateSSTSrcElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
                                                                             helperObjs.assembleElemSolverAlg->dataNeededByKernels_, false));
+  else if (des)
+    kernel.reset(new TurbKineticEnergySSTDESSrcElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
+                                                                         helperObjs.assembleElemSolverAlg->dataNeededByKernels_, false));
   else
     kernel.reset(new TurbKineticEnergySSTSrcElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_,
                                                                       helperObjs.assembleElemSolverAlg->dataNeededByKernels_, false));
@@ -533,7 +540,8 @@ static void test_sst_src(bool sdr)
   std::vector<double> lhs, rhs;
   helperObjs.element_lhs_rhs(lhs, rhs);
   EXPECT_TRUE(rhs.size() == 8u && lhs.size() == 64u);
-  const std::string ns = sdr ? "SpecificDissipationRateSSTSrcElemKernel" : "TurbKineticEnergySSTSrcElemKernel";
+  const std::string ns = sdr ? "SpecificDissipationRateSSTSrcElemKernel"
+                             : des ? "TurbKineticEnergySSTDESSrcElemKernel" : "TurbKineticEnergySSTSrcElemKernel";
   unit_test_utils::expect_all_near(rhs, gold("sst_src", "hex8_golds::" + ns + "::rhs"), 2e-15);
   unit_test_utils::expect_all_near(lhs, gold("sst_src", "hex8_golds::" + ns + "::lhs"), 2e-15);
 }
@@ -812,8 +820,9 @@ int main(int argc, char **argv)
       test_momentum_mass(true);
       test_momentum_buoyancy(false);
       test_momentum_buoyancy(true);
-      test_sst_src(false);
-      test_sst_src(true);
+      test_sst_src(0);
+      test_sst_src(1);
+      test_sst_src(2);
       test_scalar_diff();
       test_momentum_upw_defaults_reproduce_central_gold();
       test_scalar_upw_blending();

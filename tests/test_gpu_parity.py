@@ -261,6 +261,89 @@ def test_sst_src_golden(kind, ns):
     _compare_system(ls, orc)
 
 
+def test_sst_des_src_golden():
+    """unit_tests/kernels/UnitTestSSTSrcElem.C:219-257 (sst_max_length_scale = 0.5) through the CUDA path; then a
+    perturbed box where both branches of the DES length-scale switch occur, against the oracle."""
+    from nalu_b200 import fields
+    from nalu_fixtures import SSTFixture
+    g = load_golden("sst_src")
+    fx = SSTFixture()
+    dev = _cuda()
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    turb = dict(beta_star=0.09, tke_prod_limit_ratio=500.0, cdes_ke=0.61, cdes_kw=0.78)
+    ls = _linsys(fx.mesh, 1)
+    ls.zero_system()
+    f = dict(coordinates=tt(fx.coords), velocity=tt(fx.velocity), density=tt(fx.density), tke=tt(fx.tke), sdr=tt(fx.sdr),
+             tvisc=tt(fx.tvisc), f_one_blend=tt(fx.fOneBlend), sst_max_length_scale=tt(np.full(fx.mesh.n_nodes, 0.5)))
+    ls.assemble_elem([ls.make_desc("tke_sst_des_src", fields=f, turb=turb)])
+    lhs, rhs = _one_element_lhs_rhs(ls, 1)
+    ns = "TurbKineticEnergySSTDESSrcElemKernel"
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=2e-15)
+    np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=2e-15)
+
+    m = perturbed_box(6, 5, 4)
+    c = m.coords
+    a = 0.3 * np.pi
+    x, y, z = c[:, 0], c[:, 1], c[:, 2]
+    fld = dict(velocity=fields.velocity(c), density=1.0 + 0.2 * np.cos(a * x) * np.cos(a * y),
+               tke=2.0 + np.cos(a * x) * np.sin(a * y) * np.cos(a * z), sdr=2.0 + np.cos(a * x) * np.sin(a * y) * np.sin(a * z),
+               tvisc=0.3 + 0.1 * np.sin(a * z), fOneBlend=0.5 + 0.4 * np.sin(a * x) * np.cos(a * y),
+               maxLengthScale=4.0 + 3.9 * np.sin(1.3 * x + 0.4 * z))  # l_SST ~ 3 .. 15: both sides of min()
+    lsst = np.sqrt(fld["tke"]) / 0.09 / fld["sdr"]
+    cdes = fld["fOneBlend"] * 0.78 + (1 - fld["fOneBlend"]) * 0.61
+    assert (lsst < cdes * fld["maxLengthScale"]).any() and (lsst > cdes * fld["maxLengthScale"]).any()
+    for opts, oopts in (((), {}), (("shifted_grad_op", "lumped_mass"), dict(shiftedGradOp=1, lumpedMass=1))):
+        keep = []
+        orc = oracle.LinSys([m], 1)
+        orc.assemble_elem(0, [oracle.make_desc("tke_sst_des_src", keep, coordinates=c, betaStar=0.09, tkeProdLimitRatio=10.0,
+                                               cDESke=0.61, cDESkw=0.78, **oopts, **fld)])
+        ls = _linsys(m, 1)
+        ls.zero_system()
+        f = dict(coordinates=tt(c), velocity=tt(fld["velocity"]), density=tt(fld["density"]), tke=tt(fld["tke"]),
+                 sdr=tt(fld["sdr"]), tvisc=tt(fld["tvisc"]), f_one_blend=tt(fld["fOneBlend"]),
+                 sst_max_length_scale=tt(fld["maxLengthScale"]))
+        assert ls.assemble_elem([ls.make_desc("tke_sst_des_src", fields=f, options=opts,
+                                              turb=dict(turb, tke_prod_limit_ratio=10.0))]) == 1
+        _compare_system(ls, orc)
+
+
+@pytest.mark.parametrize("lrksgsfac", [0.0, 1.0])
+def test_ksgs_src_vs_oracle(lrksgsfac):
+    """src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C:78-128 (no reference unit test; the oracle restatement is
+    checked against a closed form in tests/test_oracle_golden.py): perturbed box, the production limiter active on
+    part of the nodes, with and without the low-Reynolds term."""
+    dev = _cuda()
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    m = perturbed_box(6, 5, 4)
+    st = State(m)
+    c = m.coords
+    a = 0.3 * np.pi
+    x, y, z = c[:, 0], c[:, 1], c[:, 2]
+    tke = 2.0 + np.cos(a * x) * np.sin(a * y) * np.cos(a * z)
+    tvisc = 0.3 + 0.1 * np.sin(a * z)
+    ceps = 0.845 + 0.1 * np.cos(a * y)
+    dsq = 0.5 + 0.4 * np.sin(a * x + 0.3)
+    gju = st.gju * (1.0 + 8.0 * (x > 3.0))[:, None]  # production above the limit where x > 3
+    limit = 2.0
+    keep = []
+    orc = oracle.LinSys([m], 1)
+    orc.assemble_elem(0, [oracle.make_desc("tke_ksgs_src", keep, coordinates=c, density=st.density, tke=tke, tvisc=tvisc, Gju=gju,
+                                           viscosity=st.viscosity, cEps=ceps, dsqrtkSq=dsq if lrksgsfac else st.viscosity,
+                                           dualNodalVolume=st.dual_volume, lrksgsfac=lrksgsfac, tkeProdLimitRatio=limit)])
+    ls = _linsys(m, 1)
+    ls.zero_system()
+    f = dict(coordinates=tt(c), density=tt(st.density), tke=tt(tke), tvisc=tt(tvisc), gju=tt(gju), viscosity=tt(st.viscosity),
+             c_epsilon=tt(ceps), dsqrtk_dx_sq=tt(dsq if lrksgsfac else st.viscosity), dual_volume=tt(st.dual_volume))
+    d = ls.make_desc("tke_ksgs_src", fields=f, turb=dict(tke_prod_limit_ratio=limit, lrksgs_fac=lrksgsfac))
+    assert ls.assemble_elem([d]) == 1
+    _compare_system(ls, orc)
+    # a field the kernel gathers is an argument error when missing, not an illegal address
+    f2 = dict(f)
+    del f2["c_epsilon"]
+    with pytest.raises(RuntimeError, match="c_epsilon"):
+        ls.assemble_elem([ls.make_desc("tke_ksgs_src", fields=f2, turb=dict(tke_prod_limit_ratio=limit))])
+
+
 # ---------------------------------------------------------------------------------------------
 # whole-system parity against the oracle
 # ---------------------------------------------------------------------------------------------

@@ -156,6 +156,49 @@ def test_sst_src_gold(kind, ns):
     np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=TOL)
 
 
+def test_sst_des_src_gold():
+    # unit_tests/kernels/UnitTestSSTSrcElem.C:219-257: sst_max_length_scale = 0.5 (UnitTestKernelUtils.h:391),
+    # cDESke / cDESkw from SolutionOptions::initialize_turbulence_constants (src/SolutionOptions.C)
+    g = load_golden("sst_src")
+    fx = SSTFixture()
+    keep = []
+    d = oracle.make_desc("tke_sst_des_src", keep, coordinates=fx.coords, velocity=fx.velocity, density=fx.density,
+                         tke=fx.tke, sdr=fx.sdr, tvisc=fx.tvisc, fOneBlend=fx.fOneBlend,
+                         maxLengthScale=np.full(fx.mesh.n_nodes, 0.5), cDESke=0.61, cDESkw=0.78,
+                         betaStar=SSTFixture.TURB["betaStar"], tkeProdLimitRatio=SSTFixture.TURB["tkeProdLimitRatio"])
+    lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+    np.testing.assert_allclose(rhs, tab(g, "hex8_golds::TurbKineticEnergySSTDESSrcElemKernel::rhs"), rtol=0, atol=TOL)
+    np.testing.assert_allclose(lhs, tab(g, "hex8_golds::TurbKineticEnergySSTDESSrcElemKernel::lhs"), rtol=0, atol=TOL)
+
+
+def test_ksgs_src_unit_cube_closed_form():
+    # src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C:78-128 has no gold table in the reference's unit tests: on the unit
+    # cube every SCV is 1/8 and every quantity is the nearest node's, so each node's rhs / diagonal has a closed form
+    fx = SSTFixture()
+    n = fx.mesh.n_nodes
+    rng = np.random.default_rng(3)
+    gju = rng.standard_normal((n, 9))
+    ceps = np.full(n, 0.845)
+    dvol = 0.125 + 0.01 * rng.random(n)
+    visc = 0.02 + 0.01 * rng.random(n)
+    dsq = rng.random(n)
+    rho = 1.0 + 0.1 * rng.random(n)
+    for lrk, limit in ((0.0, 500.0), (1.0, 500.0), (1.0, 0.5)):
+        keep = []
+        d = oracle.make_desc("tke_ksgs_src", keep, coordinates=fx.coords, density=rho, tke=fx.tke, tvisc=fx.tvisc,
+                             Gju=gju, viscosity=visc, cEps=ceps, dsqrtkSq=dsq, dualNodalVolume=dvol, lrksgsfac=lrk,
+                             tkeProdLimitRatio=limit)
+        lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
+        nodes = fx.mesh.elem_nodes[0]
+        G = gju[nodes].reshape(8, 3, 3)
+        pk = fx.tvisc[nodes] * np.einsum("nij,nij->n", G, G + G.transpose(0, 2, 1))
+        fac = ceps[nodes] * rho[nodes] * np.sqrt(fx.tke[nodes]) / np.cbrt(dvol[nodes])
+        dk = fac * fx.tke[nodes] + lrk * 2.0 * visc[nodes] * dsq[nodes]
+        pk = np.minimum(pk, limit * dk)
+        np.testing.assert_allclose(rhs, (pk - dk) * 0.125, rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(lhs.reshape(8, 8), np.diag(1.5 * fac * 0.125), rtol=1e-13, atol=1e-15)
+
+
 def test_scv_grad_op_gold_perturbed():
     # unit_tests/UnitTestKokkosME.C + UnitTestKokkosMEGold.h:13-79, tol 1e-10 (UnitTestUtils.h:67)
     g = load_golden("kokkos_me_gold")
