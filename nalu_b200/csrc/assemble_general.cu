@@ -536,11 +536,14 @@ __global__ void mdot_kernel(long long n_elems, const int *elem_nodes, const doub
   const int ip = (int)(t - e * 12);
   if (e >= n_elems) return;
   double c[8][3], ru[8][3];
+  // coordinates relative to the element's first node: the area vector is translation invariant, its rounding error in
+  // absolute coordinates (|x|/h ulps) is not
+  const size_t n0 = (size_t)elem_nodes[e * 8] * 3;
   for (int n = 0; n < 8; ++n) {
     const int node = elem_nodes[e * 8 + n];
     const double rho = density[node];
     for (int d = 0; d < 3; ++d) {
-      c[n][d] = coords[(size_t)node * 3 + d];
+      c[n][d] = coords[(size_t)node * 3 + d] - coords[n0 + d];
       ru[n][d] = rho * velocity[(size_t)node * 3 + d];
     }
   }
