@@ -358,11 +358,14 @@ def run_ours(args):
                 "traffic": None, "traffic_source": None, "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": bytes_alg, "bytes_per_element": bytes_alg / n_elems_rank,
                 "kernel_ms": asm_ms, "exposed_halo_ms": step_ms - asm_ms if world > 1 else 0.0}
+    workload_name = f"hex8_box_{n}x{n}x{nzg}_{'momentum_list' if args.kernels == 'list' else 'momentum_advdiff'}_assembly"
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
         try:
             with open(tf) as f:
                 t = json.load(f).get(kernel_name)
+            if isinstance(t, dict):  # valid for the workload and per-rank element count it was captured on only
+                t = t["bytes"] if (t.get("workload") == workload_name and t.get("elements") == n_elems_rank) else None
             if t is not None:
                 roofline["traffic"] = t
                 roofline["traffic_source"] = "static: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (profiles/traffic.json), not measured in this run"
@@ -542,11 +545,10 @@ def run_ours(args):
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        wl = "momentum_list" if args.kernels == "list" else "momentum_advdiff"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"hex8_box_{n}x{n}x{nzg}_{wl}_assembly",
+                "config": {"workload": workload_name,
                            "elements_per_gpu": n_elems_rank, "kernels": kernel_labels(args),
                            "partition": f"z-slabs x{world}",
                            "halo": {"capi": "nalu_b200_load_complete: pack kernel -> ncclSend/ncclRecv -> unpack-add kernel on a second stream" + (", interface planes assembled first, exchange overlapped with the interior assembly" if overlap else ""),
