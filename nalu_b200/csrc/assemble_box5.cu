@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
 
   // records of elements outside the domain are never written: they must read zero (phase 2 does not test)
   for (int i = tid; i < C5::RECSZ; i += C5::NT) rec[i] = 0.0;
-  for (int i = tid; i < C5::NEL * 8; i += C5::NT) scv[i] = 0.0;
+  for (int i = tid; i < C5::NEL * 16; i += C5::NT) scv[i] = 0.0;
   // ---- prologue: node planes zs-1 .. zs+1, the mass flow rates of the layer below the first plane
   if (warp < 3) {
     box5::stage_plane(P, ring + ((zs + 2 + warp) % 3) * C5::PLN, lane, x0, y0, zs - 1 + warp);

@@ -62,10 +62,11 @@ struct Cfg {
   static constexpr int MDB = NEL * 12;
   // node metadata of one plane = the graph's row descriptors (graph.h, node_desc) of the tile's 32 nodes: [3][32] words
   static constexpr int META = 3 * NNODE;
-  // shared-memory map (doubles); SCV: the 8 sub-control-volume volumes of every element of the layer (fused lumped mass)
+  // shared-memory map (doubles); SCV: the 8 sub-control-volume volumes of every element of the layer, as two partial sums
+  // (fused lumped mass)
   static constexpr int OFF_REC = 0, OFF_SCR = OFF_REC + RECSZ, OFF_RING = OFF_SCR + NWARP * SCRW, OFF_MD = OFF_RING + 3 * PLN,
                        OFF_META = OFF_MD + MDB, OFF_SCV = OFF_META + 2 * META;
-  static constexpr int SMEM_DOUBLES = OFF_SCV + NEL * 8;
+  static constexpr int SMEM_DOUBLES = OFF_SCV + NEL * 16;
 };
 static_assert(Cfg::FS % 16 == 12 && Cfg::FS >= Cfg::NEL, "field stride must spread the quads of a warp over the banks");
 static_assert((Cfg::OFF_RING % 2) == 0 && (Cfg::OFF_MD % 2) == 0, "16-byte aligned staging areas");
@@ -273,31 +274,67 @@ __host__ __device__ __forceinline__ void p1_point(const Coef &C, const double (&
 //   B_k = C_k + s_l C_kl/2 + s_m C_km/2 + s_l s_m C_klm/4,   B_kl = C_kl + s_m C_klm/2,
 // and the integral of its Jacobian determinant over the cube (what Grandy's 24-triangle formula evaluates exactly for
 // a hex with bilinear faces) keeps only the even monomials:
-//   V = [ det(B1,B2,B3) + ( det(B13,B23,B3) + det(B12,B2,B23) + det(B1,B12,B13) ) / 12 ] / 512.
-// out[n], n = Hex8 node index of the corner; the four corners n0 .. n0+3 of the bottom (n0 = 0) or top (n0 = 4) face: the
-// face units of phase 1a take the bottom corners, the z units the top corners, so that the two kinds stay balanced.
-__host__ __device__ __forceinline__ double det3(const double (&a)[3], const double (&b)[3], const double (&c)[3])
+//   V(s) = [ det(B1,B2,B3) + ( det(B13,B23,B3) + det(B12,B2,B23) + det(B1,B12,B13) ) / 12 ] / 512.
+// As a function of the corner, V(s) = sum_mask w_mask prod_{k in mask} s_k (s_k^2 = 1), and expanding the determinants
+// leaves 29 triple products [abc] = C_a . (C_b x C_c) of the coefficient vectors (indices = axis masks 1 x, 2 y, 4 z):
+//   512 w0 =  [124] + ([135] - [236] + [456])/3          512 w4 = -[146]/2 - [157]/6 + [245]/2 + [267]/6
+//   512 w1 = ([125] + [134])/2 + ([457] - [237])/6       512 w5 = (-[147] - [156] + [345])/4 + [367]/12
+//   512 w2 = ([126] - [234])/2 + ([137] - [467])/6       512 w6 = ( [247] - [256] - [346])/4 - [357]/12
+//   512 w3 = ([127] + [136] - [235])/4 - [567]/12        512 w7 = -[356]/4
+// -- a third of the arithmetic of eight separate corner formulas.  The triple products are grouped by a shared cross
+// product and split into two parts of about equal cost: PART 0 (cross products 12, 13, 23, 45; the face units of phase
+// 1a) and PART 1 (67, 56, 47, 46, 57; the z units).  Each part synthesises its share of the 8 volumes
+// (out[part * 8 + Hex8 node of the corner]); the consumer adds the two.
+__host__ __device__ __forceinline__ void cross_c(const Coef &C, int a, int b, double (&p)[3])
 {
-  return a[0] * (b[1] * c[2] - b[2] * c[1]) + a[1] * (b[2] * c[0] - b[0] * c[2]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+  p[0] = C.X[1][a] * C.X[2][b] - C.X[2][a] * C.X[1][b];
+  p[1] = C.X[2][a] * C.X[0][b] - C.X[0][a] * C.X[2][b];
+  p[2] = C.X[0][a] * C.X[1][b] - C.X[1][a] * C.X[0][b];
 }
-__host__ __device__ inline void scv_volumes(const Coef &C, double *out, int n0)
+__host__ __device__ __forceinline__ double dot_c(const Coef &C, const double (&p)[3], int c)
 {
-#pragma unroll 1
-  for (int n = n0; n < n0 + 4; ++n) {
-    const double s1 = ((n ^ (n >> 1)) & 1) ? 1.0 : -1.0, s2 = ((n >> 1) & 1) ? 1.0 : -1.0, s3 = ((n >> 2) & 1) ? 1.0 : -1.0;
-    double B1[3], B2[3], B3[3], B12[3], B13[3], B23[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double c7 = C.X[i][7];
-      B1[i] = C.X[i][1] + 0.5 * (s2 * C.X[i][3] + s3 * C.X[i][5]) + 0.25 * s2 * s3 * c7;
-      B2[i] = C.X[i][2] + 0.5 * (s1 * C.X[i][3] + s3 * C.X[i][6]) + 0.25 * s1 * s3 * c7;
-      B3[i] = C.X[i][4] + 0.5 * (s1 * C.X[i][5] + s2 * C.X[i][6]) + 0.25 * s1 * s2 * c7;
-      B12[i] = C.X[i][3] + 0.5 * s3 * c7;
-      B13[i] = C.X[i][5] + 0.5 * s2 * c7;
-      B23[i] = C.X[i][6] + 0.5 * s1 * c7;
-    }
-    out[n] = (det3(B1, B2, B3) + (det3(B13, B23, B3) + det3(B12, B2, B23) + det3(B1, B12, B13)) * (1.0 / 12.0)) * (1.0 / 512.0);
+  return p[0] * C.X[0][c] + p[1] * C.X[1][c] + p[2] * C.X[2][c];
+}
+template <int PART>
+__host__ __device__ __forceinline__ void scv_volumes_part(const Coef &C, double *out)
+{
+  constexpr double h = 0.5, q = 0.25, t = 1.0 / 3.0, s = 1.0 / 6.0, w12 = 1.0 / 12.0;
+  double w[8], p[3];
+  if (PART == 0) {
+    cross_c(C, 1, 2, p);
+    w[0] = dot_c(C, p, 4); w[1] = h * dot_c(C, p, 5); w[2] = h * dot_c(C, p, 6); w[3] = q * dot_c(C, p, 7);
+    cross_c(C, 1, 3, p);
+    w[0] += t * dot_c(C, p, 5); w[1] += h * dot_c(C, p, 4); w[2] += s * dot_c(C, p, 7); w[3] += q * dot_c(C, p, 6);
+    cross_c(C, 2, 3, p);
+    w[0] -= t * dot_c(C, p, 6); w[1] -= s * dot_c(C, p, 7); w[2] -= h * dot_c(C, p, 4); w[3] -= q * dot_c(C, p, 5);
+    cross_c(C, 4, 5, p);
+    w[0] += t * dot_c(C, p, 6); w[1] += s * dot_c(C, p, 7); w[4] = h * dot_c(C, p, 2); w[5] = q * dot_c(C, p, 3);
+    w[6] = 0.0; w[7] = 0.0;
+  } else {
+    cross_c(C, 6, 7, p);
+    w[2] = -s * dot_c(C, p, 4); w[3] = -w12 * dot_c(C, p, 5); w[4] = s * dot_c(C, p, 2); w[5] = w12 * dot_c(C, p, 3);
+    cross_c(C, 5, 6, p);
+    w[5] -= q * dot_c(C, p, 1); w[6] = -q * dot_c(C, p, 2); w[7] = -q * dot_c(C, p, 3);
+    cross_c(C, 4, 7, p);
+    w[5] -= q * dot_c(C, p, 1); w[6] += q * dot_c(C, p, 2);
+    cross_c(C, 4, 6, p);
+    w[4] -= h * dot_c(C, p, 1); w[6] -= q * dot_c(C, p, 3);
+    cross_c(C, 5, 7, p);
+    w[4] -= s * dot_c(C, p, 1); w[6] -= w12 * dot_c(C, p, 3);
+    w[0] = 0.0; w[1] = 0.0;
   }
+  // synthesis: V[bits] = sum_mask w_mask prod s_k, s_k = +1 where bit k of `bits` is set
+#pragma unroll
+  for (int b = 1; b < 8; b <<= 1)
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      if (!(m & b)) {
+        const double lo = w[m], hi = w[m | b];
+        w[m] = lo - hi;
+        w[m | b] = lo + hi;
+      }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) out[PART * 8 + node_of_bits(m & 1, (m >> 1) & 1, m >> 2)] = w[m] * (1.0 / 512.0);
 }
 
 // face unit: the 4 points of the bottom (top = 0) or top (top = 1) face of element `el` -> record slots 0..3
@@ -316,7 +353,7 @@ __host__ __device__ inline void p1_face_unit(const BoxParams &P, int el, int top
   const double sz = top ? 1.0 : -1.0;
   const double *md = mdb + el * 12 + (top ? 4 : 0);
   double *o = rec + el;
-  if (P.fuse_mass && !top) scv_volumes(C, scv + el * 8, 0);
+  if (P.fuse_mass) scv_volumes_part<0>(C, scv + el * 16);
   double bx[3], by[3];
   area_base<0>(C, bx);
   area_base<1>(C, by);
@@ -367,7 +404,7 @@ __host__ __device__ inline void p1_z_unit(const BoxParams &P, int el, int x0, in
   coef_load(C, pl0, pl1, elx, ely);
   const double *md = mdb + el * 12 + 8;
   double *o = rec + el + 4 * K::PS;
-  if (P.fuse_mass) scv_volumes(C, scv + el * 8, 4);
+  if (P.fuse_mass) scv_volumes_part<1>(C, scv + el * 16);
   double bz[3];
   area_base<2>(C, bz);
   // T = 2: (u,v) = (x,y); bottom nodes 0..3 = (x-,y-), (x+,y-), (x+,y+), (x-,y+)
@@ -509,10 +546,12 @@ __host__ __device__ __forceinline__ void sweep_half(const Thr &N, const double *
 __host__ __device__ __forceinline__ double dual_volume_half(const Thr &N, const double *sm, int H)
 {
   using C = Cfg;
-  const double *s = sm + C::OFF_SCV + (N.lx + C::ELX * N.ly) * 8;
+  const double *s = sm + C::OFF_SCV + (N.lx + C::ELX * N.ly) * 16;
   const int bz = H ? 0 : 4;
-  // node_of_bits(bx, by, bz) = bz*4 + by*2 + (bx ^ by): quadrant (SX,SY) sees the node as corner (!SX, !SY)
-  return (s[bz + 2] + s[8 + bz + 3]) + (s[C::ELX * 8 + bz + 1] + s[(C::ELX + 1) * 8 + bz + 0]);
+  // node_of_bits(bx, by, bz) = bz*4 + by*2 + (bx ^ by): quadrant (SX,SY) sees the node as corner (!SX, !SY); every
+  // volume is stored as two partial sums (scv_volumes_part)
+  const double *e0 = s + bz + 2, *e1 = s + 16 + bz + 3, *e2 = s + C::ELX * 16 + bz + 1, *e3 = s + (C::ELX + 1) * 16 + bz;
+  return ((e0[0] + e0[8]) + (e1[0] + e1[8])) + ((e2[0] + e2[8]) + (e3[0] + e3[8]));
 }
 // lane (node, i < 3): diagonal entry (i,i) of the node's own block and residual of dof row i.  The nodal values are
 // fetched (mass_fetch) right after the sweep and used (mass_apply) after the dz=0 group is finalized: the global-memory

@@ -186,7 +186,7 @@ static void emulate2(const BoxParams &P0, int z_chunk, double *values, double *r
       for (int c = 0; c < 9; ++c) N[tid].acc1[c][0] = N[tid].acc1[c][1] = N[tid].acc1[c][2] = NAN;
       N[tid].rr = N[tid].vol = 0.0;
     }
-    for (int i = 0; i < C::NEL * 8; ++i) sm[C::OFF_SCV + i] = 0.0;
+    for (int i = 0; i < C::NEL * 16; ++i) sm[C::OFF_SCV + i] = 0.0;
     for (int tid = 0; tid < NT; ++tid) {
       const int warp = tid >> 5, lane = tid & 31;
       if (warp < 3) {

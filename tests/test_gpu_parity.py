@@ -1013,6 +1013,10 @@ def test_decomposed_exodus_mesh_parity_after_load_complete(ndof, kind):
     import os
     base = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "ether_conform_coarse_mks.g")
     parts = exodus.read_exodus_pieces(base, 4)
+    for m in parts:
+        # the deck is 7.5 cm across (mks units); the analytic test fields vary over O(1) lengths: rescale so that the
+        # residual is not a 1e-4 remainder of cancelling terms (the comparison floor is 1 % of the largest residual)
+        m.coords = m.coords * (10.0 / 0.075)
     systems = _build_ranks(parts, ndof)
     orc = oracle.LinSys(parts, ndof)
     keep = []
