@@ -139,11 +139,13 @@ __global__ void __launch_bounds__(C5::NT, 2) assemble_box5_kernel(const __grid_c
       double acc2[9][3];
 #pragma unroll
       for (int c = 0; c < 9; ++c) acc2[c][0] = acc2[c][1] = acc2[c][2] = 0.0;
+      const bool mass_lane = P.fuse_mass && H && N.i < 3 && N.active;
+      const long long gnode = (x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z);
+      if (mass_lane) box5::mass_prefetch(P, gnode, N.i);
       if (act) box5::sweep_half(N, sm, P, H, acc1, acc2);
       if (P.fuse_mass && act) vol += box5::dual_volume_half(N, sm, H);
       box5::MassNode mn;
-      const bool mass_lane = P.fuse_mass && H && N.i < 3 && N.active;
-      if (mass_lane) box5::mass_fetch(P, (x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z), N.i, mn);
+      if (mass_lane) box5::mass_fetch(P, gnode, N.i, mn);
       // is the warp's x line stored back to back in lattice order?  (then the runs of a group sit at fixed offsets)
       const bool natural = __all_sync(FULL, box5::node_in_natural_line(M, N.node));
       const unsigned char *sl = P.slot27 + 27 * ((x0 + N.lx) + (long long)P.NX * ((y0 + N.ly) + (long long)P.NY * z));

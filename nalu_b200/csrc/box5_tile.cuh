@@ -564,6 +564,21 @@ __host__ __device__ __forceinline__ void mass_fetch(const BoxParams &P, long lon
   m.rp = P.rho_np1[n]; m.rn = P.rho_n[n]; m.rm = P.rho_nm1[n];
   m.up = P.vel[n * 3 + i]; m.un = P.vel_n[n * 3 + i]; m.um = P.vel_nm1[n * 3 + i]; m.gp = P.dpdx[n * 3 + i];
 }
+// the same addresses, touched before the sweep so that mass_fetch finds them in L1 / L2 (no registers held meanwhile)
+__host__ __device__ __forceinline__ void mass_prefetch(const BoxParams &P, long long n, int i)
+{
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(P.rho_np1 + n));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(P.rho_n + n));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(P.rho_nm1 + n));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(P.vel + n * 3 + i));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(P.vel_n + n * 3 + i));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(P.vel_nm1 + n * 3 + i));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(P.dpdx + n * 3 + i));
+#else
+  (void)P; (void)n; (void)i;
+#endif
+}
 __host__ __device__ __forceinline__ void mass_apply(const BoxParams &P, const MassNode &m, double V, double &diag, double &rr)
 {
   diag += P.g1_dt * m.rp * V;
