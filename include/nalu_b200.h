@@ -78,7 +78,8 @@ enum nalu_b200_kernel_kind {
   NALU_K_MOMENTUM_UPW_ADV_DIFF = 13, /* src/kernel/MomentumUpwAdvDiffElemKernel.C:108-311 */
   NALU_K_TKE_SST_DES_SRC = 14, /* src/kernel/TurbKineticEnergySSTDESSrcElemKernel.C:106-198 */
   NALU_K_TKE_KSGS_SRC = 15,    /* src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C:78-128    */
-  NALU_K_COUNT = 16
+  NALU_K_MOMENTUM_NSO = 16,    /* src/nso/MomentumNSOElemKernel.C:127-310                   */
+  NALU_K_COUNT = 17
 };
 
 /* option bits (SolutionOptions fields the kernels read) */
@@ -143,6 +144,10 @@ typedef struct nalu_b200_kernel_desc {
    * Peclet function EquationSystem::create_peclet_function builds (include/EquationSystem.h:306-325):
    * classic A = 5 with Realm::get_hybrid_factor, or tanh with get_tanh_trans / get_tanh_width */
   double upw[8]; /* NALU_UPW_* */
+  /* MomentumNSOElemKernel constructor arguments fourthFac / altResFac (src/nso/MomentumNSOElemKernel.C:28-36): the
+   * kernel reads NALU_F_GJU, the three velocity and density states, NALU_F_VELOCITY_RTM (NULL: NALU_F_VELOCITY),
+   * NALU_F_VISCOSITY, NALU_F_PRESSURE, dt / gamma1..3, include_divu and NALU_OPT_SHIFTED_GRAD_OP */
+  double nso_fourth_fac, nso_alt_res_fac;
 } nalu_b200_kernel_desc;
 enum { NALU_UPW_ALPHA = 0, NALU_UPW_ALPHA_UPW = 1, NALU_UPW_HO_UPWIND = 2, NALU_UPW_HYBRID_FACTOR = 3,
        NALU_UPW_TANH_TRANS = 4, NALU_UPW_TANH_WIDTH = 5 };

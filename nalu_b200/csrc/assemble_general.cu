@@ -172,6 +172,10 @@ const char *missing_field(const nalu_b200_kernel_desc &k)
     add({NALU_F_COORDINATES, NALU_F_VELOCITY, NALU_F_DENSITY, NALU_F_TKE, NALU_F_SDR, NALU_F_TVISC, NALU_F_FONE_BLEND,
          NALU_F_SST_MAX_LENGTH_SCALE});
     break;
+  case NALU_K_MOMENTUM_NSO:
+    add({NALU_F_COORDINATES, NALU_F_GJU, NALU_F_VELOCITY, NALU_F_VELOCITY_N, NALU_F_VELOCITY_NM1, NALU_F_DENSITY, NALU_F_DENSITY_N,
+         NALU_F_DENSITY_NM1, NALU_F_VISCOSITY, NALU_F_PRESSURE});
+    break;
   case NALU_K_TKE_KSGS_SRC:
     add({NALU_F_COORDINATES, NALU_F_TKE, NALU_F_DENSITY, NALU_F_TVISC, NALU_F_DUAL_VOLUME, NALU_F_C_EPSILON, NALU_F_GJU,
          NALU_F_VISCOSITY, NALU_F_DSQRTK_DX_SQ});
@@ -215,7 +219,7 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
     }
     const bool vec = kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_MASS ||
                      kind == NALU_K_MOMENTUM_BUOYANCY_SRC || kind == NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC ||
-                     kind == NALU_K_MOMENTUM_UPW_ADV_DIFF;
+                     kind == NALU_K_MOMENTUM_UPW_ADV_DIFF || kind == NALU_K_MOMENTUM_NSO;
     if (kind != NALU_K_TEST_FIXED_BLOCK) {
       need_coords = true;
       if ((vec && g.ndof != 3) || (!vec && g.ndof != 1)) {

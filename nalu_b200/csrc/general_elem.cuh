@@ -18,7 +18,7 @@
 namespace nalu_b200 {
 
 struct MeNeeds {
-  int areav, dndx, dndx_shifted, scv_volume, dndx_scv, dndx_scv_shifted;
+  int areav, dndx, dndx_shifted, scv_volume, dndx_scv, dndx_scv_shifted, gij;
 };
 
 // which master-element views the kernel constructors request
@@ -32,6 +32,11 @@ __host__ __device__ inline void me_needs_of(const nalu_b200_kernel_desc &k, MeNe
   case NALU_K_SCALAR_UPW_ADV_DIFF:   // ScalarUpwAdvDiffElemKernel.C:82-89
   case NALU_K_MOMENTUM_UPW_ADV_DIFF: // MomentumUpwAdvDiffElemKernel.C:82-89
     m.areav = 1;
+    if (k.options & NALU_OPT_SHIFTED_GRAD_OP) m.dndx_shifted = 1; else m.dndx = 1;
+    break;
+  case NALU_K_MOMENTUM_NSO: // MomentumNSOElemKernel.C:98-104
+    m.areav = 1;
+    m.gij = 1;
     if (k.options & NALU_OPT_SHIFTED_GRAD_OP) m.dndx_shifted = 1; else m.dndx = 1;
     break;
   case NALU_K_CONTINUITY_ADV: {
@@ -81,6 +86,11 @@ struct ElemScratch {
   int bad_det;
 };
 
+// metric tensors of SCS point ip (NSO kernel): 12 doubles in the storage of the SCV grad-op
+template <int NDOF>
+__host__ __device__ __forceinline__ double *gij_of(ElemScratch<NDOF> &ws, int ip) { return &ws.dndx_scv[0][0][0] + 12 * ip; }
+using hex8::sym3;
+
 // ---- stage: geometry --------------------------------------------------------------------
 template <int NDOF>
 __host__ __device__ inline void stage_geometry(int lane, ElemScratch<NDOF> &ws, const MeNeeds &need)
@@ -98,6 +108,13 @@ __host__ __device__ inline void stage_geometry(int lane, ElemScratch<NDOF> &ws, 
       hex8::scs_intg_loc(ip, 0.5, s1, s2, s3);
       const double det = hex8::grad_op_ip(ws.coords, s1, s2, s3, ws.dndxs[ip]);
       if (!(det > 0.0)) ws.bad_det = 1;
+    }
+    if (need.gij) {
+      // HexSCS::gij (Hex8CVFEM.C:800-808: always the unshifted points) + generic_gij_3d (MasterElementFunctions.h:171-236):
+      // g^ij = J J^T, g_ij = its inverse; both symmetric: [0..5] upper 00 01 02 11 12 22, [6..11] lower.  A list with
+      // the NSO kernel has three dofs per node, the SCV grad-op (one-dof SST kernels) is never in it: its storage is free
+      hex8::scs_intg_loc(ip, 0.25, s1, s2, s3);
+      hex8::gij_ip(ws.coords, s1, s2, s3, gij_of(ws, ip));
     }
   } else if (lane >= 16 && lane < 24 && need.scv_volume) {
     ws.scv[lane - 16] = hex8::scv_volume_ip(ws.coords, lane - 16);
@@ -118,6 +135,7 @@ enum { M_UNP1 = 0, M_UN = 3, M_UNM1 = 6, M_GP = 9, M_RNP1 = 12, M_RN = 13, M_RNM
 enum { S_QNP1 = 0, S_QN = 1, S_QNM1 = 2, S_RNP1 = 3, S_RN = 4, S_RNM1 = 5 };  // scalar / continuity mass
 enum { B_S = 0 };
 enum { T_U = 0, T_RHO = 3, T_K = 4, T_W = 5, T_NUT = 6, T_F1 = 7, T_LMAX = 8 }; // SST / SST-DES sources
+enum { N_U = 0, N_RTM = 3, N_RHO = 6, N_MU = 7, N_P = 8, N_GJU = 9 }; // momentum NSO (the old states are read from global memory)
 enum { G_K = 0, G_RHO = 1, G_NUT = 2, G_VOL = 3, G_CEPS = 4, G_MU = 5, G_DSQ = 6, G_DUDX = 7 }; // Ksgs source
 
 __host__ __device__ inline void gather_one(double *dst, const double *field, int ncomp, int node)
@@ -199,6 +217,14 @@ __host__ __device__ inline void stage_gather(int lane, ElemScratch<NDOF> &ws, co
   case NALU_K_MOMENTUM_BUOYANCY_BOUSSINESQ_SRC:
     gather_one(f + B_S, k.nodal[NALU_F_TEMPERATURE], 1, node);
     break;
+  case NALU_K_MOMENTUM_NSO: // MomentumNSOElemKernel.C:82-95
+    gather_one(f + N_U, k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + N_RTM, k.nodal[NALU_F_VELOCITY_RTM] ? k.nodal[NALU_F_VELOCITY_RTM] : k.nodal[NALU_F_VELOCITY], 3, node);
+    gather_one(f + N_RHO, k.nodal[NALU_F_DENSITY], 1, node);
+    gather_one(f + N_MU, k.nodal[NALU_F_VISCOSITY], 1, node);
+    gather_one(f + N_P, k.nodal[NALU_F_PRESSURE], 1, node);
+    gather_one(f + N_GJU, k.nodal[NALU_F_GJU], 9, node);
+    break;
   case NALU_K_TKE_KSGS_SRC: // TurbKineticEnergyKsgsSrcElemKernel.C:62-72
     gather_one(f + G_K, k.nodal[NALU_F_TKE], 1, node);
     gather_one(f + G_RHO, k.nodal[NALU_F_DENSITY], 1, node);
@@ -272,7 +298,69 @@ __host__ __device__ inline void stage_ip(int lane, ElemScratch<NDOF> &ws, const 
   hex8::scs_intg_loc(ip, 0.25, s1, s2, s3);
   const double (*A) = ws.areav[ip];
 
-  if (kind == NALU_K_MOMENTUM_ADV_DIFF) {
+  if (kind == NALU_K_MOMENTUM_NSO) {
+    // MomentumNSOElemKernel.C:141-308: per point the three artificial viscosities nu_k and residuals -nu_k gijFac_k
+    const double (*g)[3] = (k.options & NALU_OPT_SHIFTED_GRAD_OP) ? ws.dndxs[ip] : ws.dndx[ip];
+    const double *G = gij_of(ws, ip);
+    const double *uN = k.nodal[NALU_F_VELOCITY_N], *uNm1 = k.nodal[NALU_F_VELOCITY_NM1];
+    const double *rN = k.nodal[NALU_F_DENSITY_N], *rNm1 = k.nodal[NALU_F_DENSITY_NM1];
+    double rhoNm1Scs = 0.0, rhoNScs = 0.0, rhoNp1Scs = 0.0, dFdxCont = 0.0, divU = 0.0, rhoVrtm[3] = {0, 0, 0}, dpdx[3] = {0, 0, 0};
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = hex8::shape_fcn(ic, s1, s2, s3);
+      const double *f = ws.fld[ic];
+      rhoNm1Scs += r * rNm1[ws.nodes[ic]];
+      rhoNScs += r * rN[ws.nodes[ic]];
+      rhoNp1Scs += r * f[N_RHO];
+      for (int j = 0; j < 3; ++j) {
+        rhoVrtm[j] += r * f[N_RHO] * f[N_RTM + j];
+        divU += r * f[N_GJU + 4 * j];
+        dFdxCont += f[N_RHO] * f[N_RTM + j] * g[ic][j];
+        dpdx[j] += f[N_P] * g[ic][j];
+      }
+    }
+    const double contRes = (k.gamma1 * rhoNp1Scs + k.gamma2 * rhoNScs + k.gamma3 * rhoNm1Scs) / k.dt + dFdxCont;
+    const double nonConservedForm = 0.0, Cupw = 0.1, small = 1.0e-16; // include/nso/MomentumNSOElemKernel.h:73-80
+    // g_j = sum_i g^ij A_i: fac(ic) = g . dN_ic/dx
+    double gA[3];
+    for (int j = 0; j < 3; ++j) gA[j] = sym3(G, 0, j) * A[0] + sym3(G, 1, j) * A[1] + sym3(G, 2, j) * A[2];
+    double rGr = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) rGr += rhoVrtm[i] * sym3(G + 6, i, j) * rhoVrtm[j];
+    const double nuFirstOrder = sqrt(rGr);
+    for (int kk = 0; kk < 3; ++kk) {
+      double dFdxkAdv = 0.0, dFdxkDiff = 0.0, ukNm1Scs = 0.0, ukNScs = 0.0, ukNp1Scs = 0.0, dukdx[3] = {0, 0, 0}, gijFac = 0.0;
+      for (int ic = 0; ic < 8; ++ic) {
+        const double r = hex8::shape_fcn(ic, s1, s2, s3);
+        const double *f = ws.fld[ic];
+        const double uk = f[N_U + kk];
+        ukNm1Scs += r * uNm1[(size_t)ws.nodes[ic] * 3 + kk];
+        ukNScs += r * uN[(size_t)ws.nodes[ic] * 3 + kk];
+        ukNp1Scs += r * uk;
+        double fac = 0.0, facG = 0.0;
+        for (int j = 0; j < 3; ++j) {
+          const double dnj = g[ic][j];
+          dukdx[j] += uk * dnj;
+          dFdxkAdv += f[N_RHO] * f[N_RTM + j] * uk * dnj;
+          dFdxkDiff += f[N_MU] * (f[N_GJU + 3 * kk + j] + f[N_GJU + 3 * j + kk] - (kk == j ? 2.0 / 3.0 * divU * k.include_divu : 0.0)) * dnj;
+          fac += gA[j] * dnj;
+          facG += gA[j] * f[N_GJU + 3 * kk + j];
+        }
+        gijFac += fac * uk - r * facG * k.nso_fourth_fac;
+      }
+      double residualAlt = dFdxkAdv - ukNp1Scs * dFdxCont;
+      for (int j = 0; j < 3; ++j) residualAlt -= rhoVrtm[j] * dukdx[j];
+      const double time = (k.gamma1 * rhoNp1Scs * ukNp1Scs + k.gamma2 * rhoNScs * ukNScs + k.gamma3 * rhoNm1Scs * ukNm1Scs) / k.dt;
+      const double residualPde = time + dFdxkAdv - dFdxkDiff + dpdx[kk] - contRes * ukNp1Scs * nonConservedForm;
+      const double residual = residualAlt * k.nso_alt_res_fac + residualPde * (1.0 - k.nso_alt_res_fac);
+      double gUpperMagGradQ = 0.0;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) gUpperMagGradQ += dukdx[i] * sym3(G, i, j) * dukdx[j];
+      const double nuResidual = sqrt((residual * residual) / (gUpperMagGradQ + small));
+      const double nu = fmin(Cupw * nuFirstOrder, nuResidual);
+      ws.ipd[ip][1 + kk] = -nu * gijFac; // residualNSO: rhs[L] -=, rhs[R] +=
+      ws.ipd[ip][4 + kk] = nu;
+    }
+  } else if (kind == NALU_K_MOMENTUM_ADV_DIFF) {
     // MomentumAdvDiffElemKernel.C:102-136 and the rhs part of :138-184
     const double (*g)[3] = (k.options & NALU_OPT_SHIFTED_GRAD_OP) ? ws.dndxs[ip] : ws.dndx[ip];
     double a1 = s1, a2 = s2, a3 = s3; // advection shape function location
@@ -457,6 +545,24 @@ __host__ __device__ inline void stage_lhs(int lane, ElemScratch<NDOF> &ws, const
         ws.lhs[(L * 3 + i) * R + lane] += v;
         ws.lhs[(Rn * 3 + i) * R + lane] -= v;
       }
+    }
+  } else if (kind == NALU_K_MOMENTUM_NSO) {
+    // MomentumNSOElemKernel.C:282-303: lhs(L k, ic k) += nu_k lhsfac, lhs(R k, ic k) -= nu_k lhsfac,
+    // lhsfac = -sum_ij g^ij dN_ic/dx_j A_i: no coupling between components
+    if (NDOF != 3 || lane >= 24) return;
+    const int ic = lane / 3, kk = lane % 3;
+    const bool sh = k.options & NALU_OPT_SHIFTED_GRAD_OP;
+    for (int ip = 0; ip < 12; ++ip) {
+      const int L = hex8::scs_left(ip), Rn = hex8::scs_right(ip);
+      const double *g = sh ? ws.dndxs[ip][ic] : ws.dndx[ip][ic];
+      const double *A = ws.areav[ip];
+      const double *G = gij_of(ws, ip);
+      double lhsfac = 0.0;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) lhsfac -= sym3(G, i, j) * g[j] * A[i];
+      const double v = ws.ipd[ip][4 + kk] * lhsfac;
+      ws.lhs[(L * 3 + kk) * R + lane] += v;
+      ws.lhs[(Rn * 3 + kk) * R + lane] -= v;
     }
   } else if (kind == NALU_K_CONTINUITY_ADV || kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF ||
              kind == NALU_K_SCALAR_UPW_ADV_DIFF) {
@@ -646,7 +752,7 @@ __host__ __device__ inline void stage_rhs(int lane, ElemScratch<NDOF> &ws, const
   const int kind = k.kind;
   if (lane >= R) return;
   int col;
-  if (kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_UPW_ADV_DIFF) col = 1 + lane % 3;
+  if (kind == NALU_K_MOMENTUM_ADV_DIFF || kind == NALU_K_MOMENTUM_UPW_ADV_DIFF || kind == NALU_K_MOMENTUM_NSO) col = 1 + lane % 3;
   else if (kind == NALU_K_CONTINUITY_ADV) col = 0;
   else if (kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF || kind == NALU_K_SCALAR_UPW_ADV_DIFF) col = 1;
   else return;

@@ -109,6 +109,44 @@ __host__ __device__ __forceinline__ double grad_op_ip(const CoordT &coords, doub
   return det;
 }
 
+// Metric tensors at a parametric point: HexSCS::gij (Hex8CVFEM.C:800-808) + generic_gij_3d
+// (MasterElementFunctions.h:171-236): g^ij = J J^T with J[i][k] = sum_n dN_n/dxi_k x_n,i, g_ij = its inverse.  Both are
+// symmetric: G[0..5] = upper 00 01 02 11 12 22, G[6..11] = lower in the same order.
+template <typename CoordT>
+__host__ __device__ __forceinline__ void gij_ip(const CoordT &coords, double s1, double s2, double s3, double *G)
+{
+  double jac[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    double d[3];
+    shape_deriv(n, s1, s2, s3, d);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) jac[i][j] += d[j] * coords[n][i];
+  }
+  const double u00 = jac[0][0] * jac[0][0] + jac[0][1] * jac[0][1] + jac[0][2] * jac[0][2];
+  const double u01 = jac[0][0] * jac[1][0] + jac[0][1] * jac[1][1] + jac[0][2] * jac[1][2];
+  const double u02 = jac[0][0] * jac[2][0] + jac[0][1] * jac[2][1] + jac[0][2] * jac[2][2];
+  const double u11 = jac[1][0] * jac[1][0] + jac[1][1] * jac[1][1] + jac[1][2] * jac[1][2];
+  const double u12 = jac[1][0] * jac[2][0] + jac[1][1] * jac[2][1] + jac[1][2] * jac[2][2];
+  const double u22 = jac[2][0] * jac[2][0] + jac[2][1] * jac[2][1] + jac[2][2] * jac[2][2];
+  const double inv = 1.0 / (u00 * (u11 * u22 - u12 * u12) - u01 * (u01 * u22 - u12 * u02) + u02 * (u01 * u12 - u11 * u02));
+  G[0] = u00; G[1] = u01; G[2] = u02; G[3] = u11; G[4] = u12; G[5] = u22;
+  G[6] = inv * (u11 * u22 - u12 * u12);
+  G[7] = inv * (u02 * u12 - u01 * u22);
+  G[8] = inv * (u01 * u12 - u02 * u11);
+  G[9] = inv * (u00 * u22 - u02 * u02);
+  G[10] = inv * (u02 * u01 - u00 * u12);
+  G[11] = inv * (u00 * u11 - u01 * u01);
+}
+// entry (i, j) of a symmetric 3x3 tensor stored as 00 01 02 11 12 22
+__host__ __device__ __forceinline__ double sym3(const double *g, int i, int j)
+{
+  const int a = i < j ? i : j, b = i < j ? j : i;
+  return g[a == 0 ? b : (a == 1 ? 2 + b : 5)];
+}
+
 // Physical position of the trilinear map at a parametric point (node averages when the
 // point is an edge / face / body midpoint)
 template <typename CoordT>

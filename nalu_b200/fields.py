@@ -31,6 +31,19 @@ def dpdx(coords):
     return g
 
 
+def dudx(coords):
+    """TrigFieldFunction::dudx (unit_tests/kernels/UnitTestKernelUtils.C:38-63): [n][3*i+j] = du_i/dx_j of `velocity`"""
+    x, y = coords[:, 0], coords[:, 1]
+    a_pi = A * PI
+    cosx, sinx, cosy, siny = np.cos(a_pi * x), np.sin(a_pi * x), np.cos(a_pi * y), np.sin(a_pi * y)
+    g = np.zeros((coords.shape[0], 9))
+    g[:, 0] = a_pi * sinx * siny
+    g[:, 1] = -a_pi * cosx * cosy
+    g[:, 3] = a_pi * cosx * cosy
+    g[:, 4] = -a_pi * sinx * siny
+    return g
+
+
 def density_trig(coords, rhonot=1.0):
     x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
     return rhonot * (np.cos(A * PI * x) * np.cos(A * PI * y) * np.cos(A * PI * z))

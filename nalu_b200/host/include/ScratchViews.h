@@ -143,6 +143,18 @@ public:
         break;
       case SCS_GRAD_OP: grad(dndx, det_j, 0.25, false, 12); break;
       case SCS_SHIFTED_GRAD_OP: grad(dndx_shifted, det_j, 0.5, false, 12); break;
+      case SCS_GIJ: // HexSCS::gij: always the unshifted points (src/master_element/Hex8CVFEM.C:800-808)
+        for (int ip = 0; ip < 12; ++ip) {
+          double s1, s2, s3, G[12];
+          h8::scs_intg_loc(ip, 0.25, s1, s2, s3);
+          h8::gij_ip(c, s1, s2, s3, G);
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+              gijUpper(ip, i, j) = h8::sym3(G, i, j);
+              gijLower(ip, i, j) = h8::sym3(G + 6, i, j);
+            }
+        }
+        break;
       case SCV_VOLUME:
         for (int ip = 0; ip < 8; ++ip) scv_volume(ip) = h8::scv_volume_ip(c, ip);
         break;

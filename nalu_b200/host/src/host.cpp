@@ -7,6 +7,7 @@
 #include "../include/kernel/SSTSrcElemKernels.h"
 #include "../include/kernel/ScalarAdvDiffElemKernel.h"
 #include "../include/kernel/UpwAdvDiffElemKernels.h"
+#include "../include/nso/MomentumNSOElemKernel.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -912,6 +913,78 @@ bool TurbKineticEnergyKsgsSrcElemKernel<AlgTraits>::device_descriptor(nalu_b200_
   return true;
 }
 
+// ---- src/nso/MomentumNSOElemKernel.C:27-125
+template <typename AlgTraits>
+MomentumNSOElemKernel<AlgTraits>::MomentumNSOElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                       VectorFieldType *velocity, GenericFieldType *Gju, ScalarFieldType *viscosity,
+                                                       const double fourthFac, const double altResFac, ElemDataRequests &dataPreReqs)
+    : Kernel(), viscosity_(viscosity), Gju_(Gju),
+      lrscv_(MasterElementRepo::get_surface_master_element(AlgTraits::topo_)->adjacentNodes()), fourthFac_(fourthFac),
+      altResFac_(altResFac), om_altResFac_(1.0 - altResFac), includeDivU_(solnOpts.includeDivU_),
+      shiftedGradOp_(solnOpts.get_shifted_grad_op(velocity->name()))
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  ScalarFieldType *density = metaData.get_field<double>(stk::topology::NODE_RANK, "density");
+  STK_ThrowRequireMsg(velocity && Gju && viscosity && density, "MomentumNSOElemKernel: field not registered");
+  pick_states(velocity, velocityNm1_, velocityN_, velocityNp1_);
+  pick_states(density, densityNm1_, densityN_, densityNp1_);
+  velocityRTM_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.does_mesh_move() ? "velocity_rtm" : "velocity");
+  pressure_ = metaData.get_field<double>(stk::topology::NODE_RANK, "pressure");
+  coordinates_ = metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name());
+  STK_ThrowRequireMsg(velocityRTM_ && pressure_ && coordinates_, "MomentumNSOElemKernel: velocity_rtm / pressure / coordinates not registered");
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(AlgTraits::topo_);
+  get_scs_shape_fn_data<AlgTraits>([&](double *ptr) { meSCS->shape_fcn(ptr); }, v_shape_function_);
+  dataPreReqs.add_cvfem_surface_me(meSCS);
+  dataPreReqs.add_gathered_nodal_field(*Gju_, AlgTraits::nDim_, AlgTraits::nDim_);
+  dataPreReqs.add_coordinates_field(*coordinates_, AlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*velocityNm1_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*velocityN_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*velocityNp1_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*velocityRTM_, AlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*densityNm1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityN_, 1);
+  dataPreReqs.add_gathered_nodal_field(*densityNp1_, 1);
+  dataPreReqs.add_gathered_nodal_field(*viscosity_, 1);
+  dataPreReqs.add_gathered_nodal_field(*pressure_, 1);
+  dataPreReqs.add_master_element_call(SCS_AREAV, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_GRAD_OP : SCS_GRAD_OP, CURRENT_COORDINATES);
+  dataPreReqs.add_master_element_call(SCS_GIJ, CURRENT_COORDINATES);
+}
+template <typename AlgTraits>
+void MomentumNSOElemKernel<AlgTraits>::setup(const TimeIntegrator &ti)
+{
+  dt_ = ti.get_time_step();
+  gamma1_ = ti.get_gamma1();
+  gamma2_ = ti.get_gamma2();
+  gamma3_ = ti.get_gamma3(); // gamma3 may be zero
+}
+template <typename AlgTraits>
+bool MomentumNSOElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel_desc &d)
+{
+  clear(d);
+  d.kind = NALU_K_MOMENTUM_NSO;
+  d.options = shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0;
+  d.include_divu = includeDivU_;
+  d.dt = dt_;
+  d.gamma1 = gamma1_;
+  d.gamma2 = gamma2_;
+  d.gamma3 = gamma3_;
+  d.nso_fourth_fac = fourthFac_;
+  d.nso_alt_res_fac = altResFac_;
+  bind(d, NALU_F_COORDINATES, coordinates_);
+  bind(d, NALU_F_GJU, Gju_);
+  bind(d, NALU_F_VELOCITY, velocityNp1_);
+  bind(d, NALU_F_VELOCITY_N, velocityN_);
+  bind(d, NALU_F_VELOCITY_NM1, velocityNm1_);
+  if (velocityRTM_ != velocityNp1_) bind(d, NALU_F_VELOCITY_RTM, velocityRTM_);
+  bind(d, NALU_F_DENSITY, densityNp1_);
+  bind(d, NALU_F_DENSITY_N, densityN_);
+  bind(d, NALU_F_DENSITY_NM1, densityNm1_);
+  bind(d, NALU_F_VISCOSITY, viscosity_);
+  bind(d, NALU_F_PRESSURE, pressure_);
+  return true;
+}
+
 // ---- upwind adv-diff kernels --------------------------------------------------------------------
 namespace {
 // EquationSystem::create_peclet_function (include/EquationSystem.h:306-325), captured as data
@@ -1072,6 +1145,7 @@ bool MomentumUpwAdvDiffElemKernel<AlgTraits>::device_descriptor(nalu_b200_kernel
 NALU_B200_DECLARE_KERNEL(TurbKineticEnergySSTSrcElemKernel)
 NALU_B200_DECLARE_KERNEL(TurbKineticEnergySSTDESSrcElemKernel)
 NALU_B200_DECLARE_KERNEL(TurbKineticEnergyKsgsSrcElemKernel)
+NALU_B200_DECLARE_KERNEL(MomentumNSOElemKernel)
 NALU_B200_DECLARE_KERNEL(ScalarUpwAdvDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumUpwAdvDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(SpecificDissipationRateSSTSrcElemKernel)

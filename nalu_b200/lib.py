@@ -19,7 +19,7 @@ ERR_NO_DEVICE = 3
 K = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3, continuity_mass=4,
          scalar_mass=5, scalar_diff=6, test_fixed_block=7, momentum_buoyancy_src=8,
          momentum_buoyancy_boussinesq_src=9, tke_sst_src=10, sdr_sst_src=11, scalar_upw_adv_diff=12,
-         momentum_upw_adv_diff=13, tke_sst_des_src=14, tke_ksgs_src=15)
+         momentum_upw_adv_diff=13, tke_sst_des_src=14, tke_ksgs_src=15, momentum_nso=16)
 OPT = dict(shifted_grad_op=1, skew_symmetric=2, lumped_mass=4, shift_mdot=8, shift_poisson=16, reduced_sens=32,
            use_limiter=64, peclet_tanh=128)
 F = dict(coordinates=0, velocity=1, velocity_n=2, velocity_nm1=3, viscosity=4, density=5, density_n=6,
@@ -36,7 +36,8 @@ class KernelDesc(C.Structure):
                 ("gamma1", C.c_double), ("gamma2", C.c_double), ("gamma3", C.c_double),
                 ("nodal", C.c_void_p * F_COUNT), ("mass_flow_rate", C.c_void_p), ("fixed_block", C.c_void_p),
                 ("gravity", C.c_double * 3), ("rho_ref", C.c_double), ("t_ref", C.c_double), ("beta", C.c_double),
-                ("turb", C.c_double * 10), ("upw", C.c_double * 8)]
+                ("turb", C.c_double * 10), ("upw", C.c_double * 8),
+                ("nso_fourth_fac", C.c_double), ("nso_alt_res_fac", C.c_double)]
 
 
 UPW = dict(alpha=0, alpha_upw=1, ho_upwind=2, hybrid_factor=3, tanh_trans=4, tanh_width=5)

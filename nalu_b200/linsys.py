@@ -200,6 +200,8 @@ class DeviceCsrLinearSystem:
         d.rho_ref = scalars.get("rho_ref", 0.0)
         d.t_ref = scalars.get("t_ref", 0.0)
         d.beta = scalars.get("beta", 0.0)
+        d.nso_fourth_fac = scalars.get("fourth_fac", 0.0)
+        d.nso_alt_res_fac = scalars.get("alt_res_fac", 0.0)
         for name, v in (scalars.get("turb") or {}).items():
             d.turb[_lib.TM[name]] = float(v)
         for name, v in (scalars.get("upw") or {}).items():

@@ -17,6 +17,7 @@ typedef struct {
   double deriv[12][8][3];
   double scv_volume[8];
   double dndx_scv[8][8][3]; /* dndx_scv or dndx_scv_shifted, whichever the SST kernels requested */
+  double gijUpper[12][3][3], gijLower[12][3][3];
   int have_areav, have_dndx, have_dndx_shifted, have_scv_volume;
 } me_views;
 
@@ -546,6 +547,128 @@ static void ksgs_src(const orc_kernel_desc *k, const int32_t *nodes, const me_vi
   }
 }
 
+/* ---- src/nso/MomentumNSOElemKernel.C:127-310 ---- */
+static void momentum_nso(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me, double *lhs, double *rhs)
+{
+  double v_Gju[8][3][3], v_uNm1[8][3], v_uN[8][3], v_uNp1[8][3], v_velocityRTM[8][3], v_rhoNm1[8], v_rhoN[8], v_rhoNp1[8],
+      v_viscosity[8], v_pressure[8];
+  gather(k->Gju, 9, nodes, &v_Gju[0][0][0]);
+  gather(k->velocityNm1, 3, nodes, &v_uNm1[0][0]);
+  gather(k->velocityN, 3, nodes, &v_uN[0][0]);
+  gather(k->velocity, 3, nodes, &v_uNp1[0][0]);
+  gather(k->velocityRTM ? k->velocityRTM : k->velocity, 3, nodes, &v_velocityRTM[0][0]);
+  gather(k->densityNm1, 1, nodes, v_rhoNm1);
+  gather(k->densityN, 1, nodes, v_rhoN);
+  gather(k->density, 1, nodes, v_rhoNp1);
+  gather(k->viscosity, 1, nodes, v_viscosity);
+  gather(k->pressure, 1, nodes, v_pressure);
+  const double (*v_dndx)[8][3] = k->shiftedGradOp ? me->dndx_shifted : me->dndx;
+  double v_shape_function_[12][8];
+  scs_shape(0, v_shape_function_);
+  const int *lrscv_ = orc_hex8_lrscv();
+  const double gamma1_ = k->gamma1, gamma2_ = k->gamma2, gamma3_ = k->gamma3, dt_ = k->dt;
+  const double fourthFac_ = k->fourthFac, altResFac_ = k->altResFac, om_altResFac_ = 1.0 - k->altResFac;
+  const double includeDivU_ = k->includeDivU, Cupw_ = 0.1, nonConservedForm_ = 0.0, small_ = 1.0e-16;
+  double w_dukdxScs[3], w_rhoVrtmScs[3], w_dpdxScs[3];
+
+  for (int ip = 0; ip < 12; ++ip) {
+    const int il = lrscv_[2 * ip];
+    const int ir = lrscv_[2 * ip + 1];
+    const int ilNdim = il * 3;
+    const int irNdim = ir * 3;
+
+    double rhoNm1Scs = 0.0, rhoNScs = 0.0, rhoNp1Scs = 0.0, dFdxCont = 0.0, divU = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      w_rhoVrtmScs[i] = 0.0;
+      w_dpdxScs[i] = 0.0;
+    }
+    for (int ic = 0; ic < 8; ++ic) {
+      const double r = v_shape_function_[ip][ic];
+      rhoNm1Scs += r * v_rhoNm1[ic];
+      rhoNScs += r * v_rhoN[ic];
+      rhoNp1Scs += r * v_rhoNp1[ic];
+      const double pIC = v_pressure[ic];
+      const double rhoIC = v_rhoNp1[ic];
+      for (int j = 0; j < 3; ++j) {
+        const double dnj = v_dndx[ip][ic][j];
+        const double vrtmj = v_velocityRTM[ic][j];
+        w_rhoVrtmScs[j] += r * rhoIC * vrtmj;
+        divU += r * v_Gju[ic][j][j];
+        dFdxCont += rhoIC * vrtmj * dnj;
+        w_dpdxScs[j] += pIC * dnj;
+      }
+    }
+    const double contRes = (gamma1_ * rhoNp1Scs + gamma2_ * rhoNScs + gamma3_ * rhoNm1Scs) / dt_ + dFdxCont;
+    const double twoThirds = 2.0 / 3.0;
+
+    for (int kk = 0; kk < 3; ++kk) {
+      const int indexL = ilNdim + kk;
+      const int indexR = irNdim + kk;
+      double dFdxkAdv = 0.0, dFdxkDiff = 0.0, ukNm1Scs = 0.0, ukNScs = 0.0, ukNp1Scs = 0.0;
+      for (int j = 0; j < 3; ++j) w_dukdxScs[j] = 0.0;
+
+      for (int ic = 0; ic < 8; ++ic) {
+        const double r = v_shape_function_[ip][ic];
+        const double ukNp1 = v_uNp1[ic][kk];
+        ukNm1Scs += r * v_uNm1[ic][kk];
+        ukNScs += r * v_uN[ic][kk];
+        ukNp1Scs += r * ukNp1;
+        const double rhoIC = v_rhoNp1[ic];
+        const double viscIC = v_viscosity[ic];
+        for (int j = 0; j < 3; ++j) {
+          const double dnj = v_dndx[ip][ic][j];
+          const double kd = (kk == j) ? 1.0 : 0.0;
+          w_dukdxScs[j] += ukNp1 * dnj;
+          dFdxkAdv += rhoIC * v_velocityRTM[ic][j] * ukNp1 * dnj;
+          dFdxkDiff += viscIC * (v_Gju[ic][kk][j] + v_Gju[ic][j][kk] - twoThirds * divU * kd * includeDivU_) * dnj;
+        }
+      }
+
+      double residualAlt = dFdxkAdv - ukNp1Scs * dFdxCont;
+      for (int j = 0; j < 3; ++j) residualAlt -= w_rhoVrtmScs[j] * w_dukdxScs[j];
+
+      const double time = (gamma1_ * rhoNp1Scs * ukNp1Scs + gamma2_ * rhoNScs * ukNScs + gamma3_ * rhoNm1Scs * ukNm1Scs) / dt_;
+      const double residualPde = time + dFdxkAdv - dFdxkDiff + w_dpdxScs[kk] - contRes * ukNp1Scs * nonConservedForm_;
+      const double residual = residualAlt * altResFac_ + residualPde * om_altResFac_;
+
+      double gUpperMagGradQ = 0.0, rhoVrtmiGLowerRhoVrtmj = 0.0;
+      for (int i = 0; i < 3; ++i) {
+        const double duidxScs = w_dukdxScs[i];
+        const double rhoVrtmi = w_rhoVrtmScs[i];
+        for (int j = 0; j < 3; ++j) {
+          gUpperMagGradQ += duidxScs * me->gijUpper[ip][i][j] * w_dukdxScs[j];
+          rhoVrtmiGLowerRhoVrtmj += rhoVrtmi * me->gijLower[ip][i][j] * w_rhoVrtmScs[j];
+        }
+      }
+      const double nuResidual = sqrt((residual * residual) / (gUpperMagGradQ + small_));
+      const double nuFirstOrder = sqrt(rhoVrtmiGLowerRhoVrtmj);
+      const double nu = fmin(Cupw_ * nuFirstOrder, nuResidual);
+
+      double gijFac = 0.0;
+      for (int ic = 0; ic < 8; ++ic) {
+        const double r = v_shape_function_[ip][ic];
+        const int icNdim = ic * 3;
+        const double ukNp1 = v_uNp1[ic][kk];
+        double lhsfac = 0.0;
+        for (int i = 0; i < 3; ++i) {
+          const double axi = me->scs_areav[ip][i];
+          for (int j = 0; j < 3; ++j) {
+            const double fac = me->gijUpper[ip][i][j] * v_dndx[ip][ic][j] * axi;
+            const double facGj = r * me->gijUpper[ip][i][j] * v_Gju[ic][kk][j] * axi;
+            gijFac = fma(fac, ukNp1, gijFac) - facGj * fourthFac_;
+            lhsfac -= fac;
+          }
+        }
+        lhs[indexL * 24 + icNdim + kk] = fma(nu, lhsfac, lhs[indexL * 24 + icNdim + kk]);
+        lhs[indexR * 24 + icNdim + kk] -= nu * lhsfac;
+      }
+      const double residualNSO = -nu * gijFac;
+      rhs[indexL] -= residualNSO;
+      rhs[indexR] += residualNSO;
+    }
+  }
+}
+
 /* ---- src/kernel/ScalarMassElemKernel.C:96-156 ---- */
 static void scalar_mass(const orc_kernel_desc *k, const int32_t *nodes, const me_views *me,
                         double *lhs, double *rhs)
@@ -870,6 +993,10 @@ static void me_needs(const orc_kernel_desc *k, int *areav, int *dndx, int *dndxs
     *areav = 1;
     if (k->shiftedGradOp) *dndxs = 1; else *dndx = 1;
     break;
+  case ORC_MOMENTUM_NSO: /* MomentumNSOElemKernel.C:98-104: SCS_AREAV, SCS_(SHIFTED_)GRAD_OP, SCS_GIJ */
+    *areav = 1;
+    if (k->shiftedGradOp) *dndxs = 1; else *dndx = 1;
+    break;
   case ORC_CONTINUITY_ADV: /* ContinuityAdvElemKernel.C:59-65 */
     *areav = 1;
     if (!k->shiftPoisson || !k->reducedSensitivities) *dndx = 1;
@@ -910,6 +1037,8 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     if (dndxs) orc_hex8_scs_grad_op(1, &me.coords[0][0], &me.dndx_shifted[0][0][0], &me.deriv[0][0][0]);
     if (scv) orc_hex8_scv_volume(&me.coords[0][0], me.scv_volume);
     for (int i = 0; i < nk; ++i)
+      if (kernels[i].kind == ORC_MOMENTUM_NSO) orc_hex8_scs_gij(&me.coords[0][0], &me.gijUpper[0][0][0], &me.gijLower[0][0][0]);
+    for (int i = 0; i < nk; ++i)
       if (kernels[i].kind == ORC_TKE_SST_SRC || kernels[i].kind == ORC_SDR_SST_SRC || kernels[i].kind == ORC_TKE_SST_DES_SRC) {
         /* SCV_GRAD_OP or SCV_SHIFTED_GRAD_OP (TurbKineticEnergySSTSrcElemKernel.C:84-89) */
         orc_hex8_scv_volume(&me.coords[0][0], me.scv_volume);
@@ -939,6 +1068,7 @@ void orc_element_lhs_rhs(const orc_kernel_desc *kernels, int nk, int numDof,
     case ORC_SDR_SST_SRC: sst_src(k, 1, elemNodes, &me, lhs, rhs); break;
     case ORC_TKE_SST_DES_SRC: sst_des_src(k, elemNodes, &me, lhs, rhs); break;
     case ORC_TKE_KSGS_SRC: ksgs_src(k, elemNodes, &me, lhs, rhs); break;
+    case ORC_MOMENTUM_NSO: momentum_nso(k, elemNodes, &me, lhs, rhs); break;
     case ORC_TEST_FIXED_BLOCK: /* unit_tests/UnitTestTpetra.C:125-139: lhs(i,j) = elemVals[i][j] */
       for (int q = 0; q < rhsSize * rhsSize; ++q) lhs[q] = k->fixedBlock[q];
       break;

@@ -346,6 +346,65 @@ int orc_hex8_scv_grad_op(int shifted, const double *coords, double *gradop, doub
   return orc_generic_grad_op(8, deriv, coords, gradop, NULL);
 }
 
+/* src/master_element/Hex8CVFEM.C:800-808 (HexSCS::gij, SharedMemView overload: always the unshifted integration
+ * points) + include/master_element/MasterElementFunctions.h:171-236 (generic_gij_3d): contravariant metric
+ * g^ij = J J^T with J[i][k] = sum_n dN_n/dxi_k x_n,i; covariant metric = its inverse (symmetric cofactor form) */
+void orc_hex8_scs_gij(const double *coords, double *gupper, double *glower)
+{
+  double loc[36];
+  double deriv[12 * 8 * 3];
+  orc_hex8_scs_intg_loc(0, loc);
+  orc_hex8_derivative(12, loc, deriv);
+#define GUP(ip, i, j) gupper[((ip)*3 + (i)) * 3 + (j)]
+#define GLO(ip, i, j) glower[((ip)*3 + (i)) * 3 + (j)]
+  for (int ip = 0; ip < 12; ++ip) {
+    double jac[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    for (int n = 0; n < 8; ++n) {
+      const double *d = &deriv[(ip * 8 + n) * 3];
+      jac[0][0] += d[0] * coords[n * 3 + 0];
+      jac[0][1] += d[1] * coords[n * 3 + 0];
+      jac[0][2] += d[2] * coords[n * 3 + 0];
+
+      jac[1][0] += d[0] * coords[n * 3 + 1];
+      jac[1][1] += d[1] * coords[n * 3 + 1];
+      jac[1][2] += d[2] * coords[n * 3 + 1];
+
+      jac[2][0] += d[0] * coords[n * 3 + 2];
+      jac[2][1] += d[1] * coords[n * 3 + 2];
+      jac[2][2] += d[2] * coords[n * 3 + 2];
+    }
+    GUP(ip, 0, 0) = jac[0][0] * jac[0][0] + jac[0][1] * jac[0][1] + jac[0][2] * jac[0][2];
+    GUP(ip, 0, 1) = jac[0][0] * jac[1][0] + jac[0][1] * jac[1][1] + jac[0][2] * jac[1][2];
+    GUP(ip, 0, 2) = jac[0][0] * jac[2][0] + jac[0][1] * jac[2][1] + jac[0][2] * jac[2][2];
+
+    GUP(ip, 1, 0) = GUP(ip, 0, 1);
+    GUP(ip, 1, 1) = jac[1][0] * jac[1][0] + jac[1][1] * jac[1][1] + jac[1][2] * jac[1][2];
+    GUP(ip, 1, 2) = jac[1][0] * jac[2][0] + jac[1][1] * jac[2][1] + jac[1][2] * jac[2][2];
+
+    GUP(ip, 2, 0) = GUP(ip, 0, 2);
+    GUP(ip, 2, 1) = GUP(ip, 1, 2);
+    GUP(ip, 2, 2) = jac[2][0] * jac[2][0] + jac[2][1] * jac[2][1] + jac[2][2] * jac[2][2];
+
+    const double inv_detj = 1.0 / (GUP(ip, 0, 0) * (GUP(ip, 1, 1) * GUP(ip, 2, 2) - GUP(ip, 1, 2) * GUP(ip, 1, 2)) -
+                                   GUP(ip, 0, 1) * (GUP(ip, 0, 1) * GUP(ip, 2, 2) - GUP(ip, 1, 2) * GUP(ip, 0, 2)) +
+                                   GUP(ip, 0, 2) * (GUP(ip, 0, 1) * GUP(ip, 1, 2) - GUP(ip, 1, 1) * GUP(ip, 0, 2)));
+
+    GLO(ip, 0, 0) = inv_detj * (GUP(ip, 1, 1) * GUP(ip, 2, 2) - GUP(ip, 1, 2) * GUP(ip, 1, 2));
+    GLO(ip, 0, 1) = inv_detj * (GUP(ip, 0, 2) * GUP(ip, 1, 2) - GUP(ip, 0, 1) * GUP(ip, 2, 2));
+    GLO(ip, 0, 2) = inv_detj * (GUP(ip, 0, 1) * GUP(ip, 1, 2) - GUP(ip, 0, 2) * GUP(ip, 1, 1));
+
+    GLO(ip, 1, 0) = GLO(ip, 0, 1);
+    GLO(ip, 1, 1) = inv_detj * (GUP(ip, 0, 0) * GUP(ip, 2, 2) - GUP(ip, 0, 2) * GUP(ip, 0, 2));
+    GLO(ip, 1, 2) = inv_detj * (GUP(ip, 0, 2) * GUP(ip, 0, 1) - GUP(ip, 0, 0) * GUP(ip, 1, 2));
+
+    GLO(ip, 2, 0) = GLO(ip, 0, 2);
+    GLO(ip, 2, 1) = GLO(ip, 1, 2);
+    GLO(ip, 2, 2) = inv_detj * (GUP(ip, 0, 0) * GUP(ip, 1, 1) - GUP(ip, 0, 1) * GUP(ip, 0, 1));
+  }
+#undef GUP
+#undef GLO
+}
+
 /* unit_tests/UnitTestUtils.C:41-54 (Lcg inside perturb_coord_hex_8) */
 double orc_lcg_next(uint32_t *state)
 {

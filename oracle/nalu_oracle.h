@@ -56,6 +56,7 @@ double orc_hex_volume_grandy(const double scvcoords[8][3]);
 /* HexSCS::grad_op / shifted_grad_op (Hex8CVFEM.C:523-542), HexSCV::grad_op / shifted (:182-190,:221-229) */
 int orc_hex8_scs_grad_op(int shifted, const double *coords, double *gradop, double *deriv);
 int orc_hex8_scv_grad_op(int shifted, const double *coords, double *gradop, double *deriv);
+void orc_hex8_scs_gij(const double *coords, double *gupper, double *glower); /* [12][3][3] each */
 
 /* ------------------------------------------------------------------ */
 /* Element kernels (src/kernel/ *.C)                                    */
@@ -76,7 +77,8 @@ enum orc_kernel_kind {
   ORC_SCALAR_UPW_ADV_DIFF = 12,             /* src/kernel/ScalarUpwAdvDiffElemKernel.C              */
   ORC_MOMENTUM_UPW_ADV_DIFF = 13,           /* src/kernel/MomentumUpwAdvDiffElemKernel.C            */
   ORC_TKE_SST_DES_SRC = 14,                 /* src/kernel/TurbKineticEnergySSTDESSrcElemKernel.C    */
-  ORC_TKE_KSGS_SRC = 15                     /* src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C      */
+  ORC_TKE_KSGS_SRC = 15,                    /* src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C      */
+  ORC_MOMENTUM_NSO = 16                     /* src/nso/MomentumNSOElemKernel.C                      */
 };
 
 /* what the kernel constructors/ setup() capture (options + time integrator) */
@@ -130,6 +132,8 @@ typedef struct orc_kernel_desc {
   const double *dsqrtkSq;       /* [1] dsqrtk_dx_sq (the viscosity field when lrksgsfac = 0) */
   const double *dualNodalVolume;/* [1] dual_nodal_volume                                     */
   double cDESke, cDESkw, lrksgsfac;
+  /* MomentumNSOElemKernel ctor arguments (src/nso/MomentumNSOElemKernel.C:28-36) */
+  double fourthFac, altResFac;
 } orc_kernel_desc;
 
 /* One element through the registered kernels, exactly as

@@ -11,7 +11,7 @@ _LIB = None
 KIND = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_mass=3,
             continuity_mass=4, scalar_mass=5, scalar_diff=6, test_fixed_block=7, momentum_buoyancy_src=8,
             momentum_buoyancy_boussinesq_src=9, tke_sst_src=10, sdr_sst_src=11, scalar_upw_adv_diff=12,
-            momentum_upw_adv_diff=13, tke_sst_des_src=14, tke_ksgs_src=15)
+            momentum_upw_adv_diff=13, tke_sst_des_src=14, tke_ksgs_src=15, momentum_nso=16)
 
 
 def build(force=False):
@@ -57,7 +57,7 @@ class KernelDesc(C.Structure):
                [("useLimiter", C.c_int), ("pecletTanh", C.c_int)] + \
                [(n, C.c_double) for n in ("hybridFactor", "tanhTrans", "tanhWidth")] + \
                [(n, C.c_void_p) for n in ("maxLengthScale", "cEps", "dsqrtkSq", "dualNodalVolume")] + \
-               [(n, C.c_double) for n in ("cDESke", "cDESkw", "lrksgsfac")]
+               [(n, C.c_double) for n in ("cDESke", "cDESkw", "lrksgsfac", "fourthFac", "altResFac")]
 
 
 _PTR_FIELDS = ("coordinates", "velocity", "velocityN", "velocityNm1", "viscosity", "density", "densityN",

@@ -164,6 +164,39 @@ int main()
       }
     }
 
+    // momentum NSO: shifted grad-op x divU, pde / linearized / blended residual, fourth-order term, BDF2 time term
+    for (int opt = 0; opt < 8; ++opt) {
+      static double gju[NN * 9], rtm[NN * 3];
+      for (int n = 0; n < NN * 9; ++n) gju[n] = frand();
+      for (int n = 0; n < NN * 3; ++n) rtm[n] = frand();
+      nalu_b200_kernel_desc k;
+      orc_kernel_desc o;
+      memset(&k, 0, sizeof(k));
+      memset(&o, 0, sizeof(o));
+      k.kind = NALU_K_MOMENTUM_NSO; o.kind = ORC_MOMENTUM_NSO;
+      if (opt & 1) { k.options |= NALU_OPT_SHIFTED_GRAD_OP; o.shiftedGradOp = 1; }
+      k.include_divu = o.includeDivU = (opt & 2) ? 1.0 : 0.0;
+      k.nso_alt_res_fac = o.altResFac = (opt & 4) ? 1.0 : 0.25 * (trial % 3);
+      k.nso_fourth_fac = o.fourthFac = (trial & 1) ? 1.0 : 0.0;
+      k.dt = o.dt = 0.05; k.gamma1 = o.gamma1 = 1.5; k.gamma2 = o.gamma2 = -2.0; k.gamma3 = o.gamma3 = 0.5;
+      k.nodal[NALU_F_COORDINATES] = o.coordinates = coords;
+      k.nodal[NALU_F_VELOCITY] = o.velocity = vel;
+      k.nodal[NALU_F_VELOCITY_N] = o.velocityN = velN;
+      k.nodal[NALU_F_VELOCITY_NM1] = o.velocityNm1 = velNm1;
+      if (opt & 2) k.nodal[NALU_F_VELOCITY_RTM] = o.velocityRTM = rtm;
+      k.nodal[NALU_F_DENSITY] = o.density = rho;
+      k.nodal[NALU_F_DENSITY_N] = o.densityN = rhoN;
+      k.nodal[NALU_F_DENSITY_NM1] = o.densityNm1 = rhoNm1;
+      k.nodal[NALU_F_VISCOSITY] = o.viscosity = visc;
+      k.nodal[NALU_F_PRESSURE] = o.pressure = p;
+      k.nodal[NALU_F_GJU] = o.Gju = gju;
+      std::vector<nalu_b200_kernel_desc> ks{k};
+      std::vector<orc_kernel_desc> os{o};
+      const double e = run_case<3>(ks, os, nodes, coords);
+      if (e > 1e-13) { printf("FAIL momentum NSO opt %d trial %d relerr %.3e\n", opt, trial, e); return 1; }
+      worst = fmax(worst, e);
+    }
+
     for (int kind = 0; kind < 7; ++kind) {
       for (int opt = 0; opt < 4; ++opt) {
         nalu_b200_kernel_desc k;

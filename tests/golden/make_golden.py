@@ -20,6 +20,7 @@ Sources (relative to /root/reference):
   unit_tests/UnitTestKokkosMEGold.h:13-79                   SCV grad-op tables (perturbed element)
   unit_tests/UnitTestTpetra.C:86-114                        2-element assembled matrix
   unit_tests/kernels/UnitTestSSTSrcElem.C:17-176            SST tke / tke-DES / sdr source lhs/rhs
+  unit_tests/kernels/UnitTestMomentumNSOElem.C:14-316       momentum NSO (2nd order; pde and linearized residual)
 """
 import json
 import os
@@ -110,6 +111,7 @@ def main():
         "kokkos_me_gold": "UnitTestKokkosMEGold.h",
         "tpetra_2elem": "UnitTestTpetra.C",
         "sst_src": "kernels/UnitTestSSTSrcElem.C",
+        "momentum_nso": "kernels/UnitTestMomentumNSOElem.C",
     }
     for key, rel in files.items():
         tabs = parse_tables(os.path.join(REF, rel))

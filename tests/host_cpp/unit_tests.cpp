@@ -18,6 +18,7 @@
 #include "kernel/SSTSrcElemKernels.h"
 #include "kernel/ScalarAdvDiffElemKernel.h"
 #include "kernel/UpwAdvDiffElemKernels.h"
+#include "nso/MomentumNSOElemKernel.h"
 
 #include <cmath>
 #include <cstdio>
@@ -475,6 +476,46 @@ static void test_momentum_mass(bool lumped)
   }
 }
 
+static void test_momentum_nso(bool alt)
+{
+  std::printf("MomentumKernelHex8Mesh.%s (unit_tests/kernels/UnitTestMomentumNSOElem.C:%s)\n", alt ? "nso_2nd_alt" : "nso_2nd",
+              alt ? "361-404" : "318-359");
+  LowMachKernelHex8Mesh fx;
+  fx.fill_mesh_and_init_fields();
+  // MomentumKernelHex8Mesh::fill_mesh_and_init_fields: dudx_test_function = TrigFieldFunction::dudx
+  // (unit_tests/kernels/UnitTestKernelUtils.h:343-351, UnitTestKernelUtils.C:38-63)
+  const double *x = fx.coordinates_->host_data();
+  for (size_t n = 0; n < fx.bulk_->num_nodes(); ++n) {
+    const double a_pi = unit_test_utils::a * unit_test_utils::pi, X = x[3 * n], Y = x[3 * n + 1];
+    double *g = fx.dudx_->host_data() + 9 * n;
+    for (int q = 0; q < 9; ++q) g[q] = 0.0;
+    g[0] = a_pi * std::sin(a_pi * X) * std::sin(a_pi * Y);
+    g[1] = -a_pi * std::cos(a_pi * X) * std::cos(a_pi * Y);
+    g[3] = a_pi * std::cos(a_pi * X) * std::cos(a_pi * Y);
+    g[4] = -a_pi * std::sin(a_pi * X) * std::sin(a_pi * Y);
+  }
+  fx.dudx_->modify_on_host();
+  fx.solnOpts_.meshMotion_ = false;
+  fx.solnOpts_.meshDeformation_ = false;
+  fx.solnOpts_.externalMeshDeformation_ = false;
+  fx.solnOpts_.includeDivU_ = 0.0;
+  HelperObjects helperObjs(fx.bulk_, stk::topology::HEX_8, 3, fx.partVec_[0]);
+  helperObjs.build_system();
+  std::unique_ptr<Kernel> kernel(new MomentumNSOElemKernel<AlgTraitsHex8>(*fx.bulk_, fx.solnOpts_, fx.velocity_, fx.dudx_, fx.viscosity_, 0.0,
+                                                                          alt ? 1.0 : 0.0,
+                                                                          helperObjs.assembleElemSolverAlg->dataNeededByKernels_));
+  helperObjs.assembleElemSolverAlg->activeKernels_.push_back(kernel.get());
+  TimeIntegrator &ti = *helperObjs.realm.timeIntegrator_;
+  ti.timeStepN_ = 0.1; ti.timeStepNm1_ = 0.1; ti.gamma1_ = 1.0; ti.gamma2_ = -1.0; ti.gamma3_ = 0.0;
+  helperObjs.assembleElemSolverAlg->execute();
+  std::vector<double> lhs, rhs;
+  helperObjs.element_lhs_rhs(lhs, rhs);
+  EXPECT_TRUE(rhs.size() == 24u && lhs.size() == 576u);
+  const std::string ns = alt ? "hex8_golds::nso_2nd_alt" : "hex8_golds::nso_2nd";
+  unit_test_utils::expect_all_near(rhs, gold("momentum_nso", ns + "::rhs"), 1e-15);
+  unit_test_utils::expect_all_near(lhs, gold("momentum_nso", ns + "::lhs"), 1e-15);
+}
+
 static void test_momentum_buoyancy(bool boussinesq)
 {
   std::printf("MomentumKernelHex8Mesh.%s (unit_tests/kernels/UnitTestMomentumBuoyancy%sSrcElem.C)\n",
@@ -820,6 +861,8 @@ int main(int argc, char **argv)
       test_momentum_mass(true);
       test_momentum_buoyancy(false);
       test_momentum_buoyancy(true);
+      test_momentum_nso(false);
+      test_momentum_nso(true);
       test_sst_src(0);
       test_sst_src(1);
       test_sst_src(2);

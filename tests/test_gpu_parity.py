@@ -307,6 +307,48 @@ def test_sst_des_src_golden():
         _compare_system(ls, orc)
 
 
+@pytest.mark.parametrize("ns,alt", [("nso_2nd", 0.0), ("nso_2nd_alt", 1.0)])
+def test_momentum_nso_golden(ns, alt):
+    """unit_tests/kernels/UnitTestMomentumNSOElem.C:318-404 through the CUDA path; then a perturbed box with the BDF2 time
+    term, the fourth-order term, a blended residual, divU, the shifted grad-op and a separate velocity_rtm against the oracle."""
+    from nalu_b200 import fields
+    g = load_golden("momentum_nso")
+    fx = LowMachFixture()
+    dev = _cuda()
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    ls = _linsys(fx.mesh, 3)
+    ls.zero_system()
+    f = dict(coordinates=tt(fx.coords), velocity=tt(fx.velocity), velocity_n=tt(fx.velocityN), velocity_nm1=tt(fx.velocityN),
+             density=tt(fx.density), density_n=tt(fx.densityN), density_nm1=tt(fx.densityN), viscosity=tt(fx.viscosity),
+             pressure=tt(fx.pressure), gju=tt(fields.dudx(fx.coords)))
+    ls.assemble_elem([ls.make_desc("momentum_nso", fields=f, fourth_fac=0.0, alt_res_fac=alt, dt=0.1, gamma1=1.0, gamma2=-1.0,
+                                   gamma3=0.0, include_divu=0.0)])
+    lhs, rhs = _one_element_lhs_rhs(ls, 3)
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=1e-15)
+
+    m = perturbed_box(6, 5, 4)
+    st = State(m)
+    d = st.to_device(dev)
+    rtm = st.velocity - 0.1 * np.cos(st.coordinates)
+    keep = []
+    sc = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    orc = oracle.LinSys([m], 3)
+    dd = oracle_desc(st, "momentum_nso", ("shifted_grad_op",), keep, include_divu=1.0, **sc)
+    dd.fourthFac, dd.altResFac = 1.0, 0.4
+    arr = np.ascontiguousarray(rtm)
+    keep.append(arr)
+    dd.velocityRTM = arr.ctypes.data
+    orc.assemble_elem(0, [dd])
+    ls = _linsys(m, 3)
+    ls.zero_system()
+    f = {k: v for k, v in d.items() if k != "mdot"}
+    f["velocity_rtm"] = tt(rtm)
+    assert ls.assemble_elem([ls.make_desc("momentum_nso", fields=f, options=("shifted_grad_op",), include_divu=1.0, fourth_fac=1.0,
+                                          alt_res_fac=0.4, **sc)]) == 1
+    _compare_system(ls, orc)
+
+
 @pytest.mark.parametrize("lrksgsfac", [0.0, 1.0])
 def test_ksgs_src_vs_oracle(lrksgsfac):
     """src/kernel/TurbKineticEnergyKsgsSrcElemKernel.C:78-128 (no reference unit test; the oracle restatement is

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from nalu_b200 import mesh
+from nalu_b200 import fields, mesh
 from golden_io import load_golden, tab
 from nalu_fixtures import LowMachFixture, MixtureFractionFixture, SSTFixture
 
@@ -169,6 +169,23 @@ def test_sst_des_src_gold():
     lhs, rhs = oracle.element_lhs_rhs([d], 1, fx.mesh.elem_nodes[0])
     np.testing.assert_allclose(rhs, tab(g, "hex8_golds::TurbKineticEnergySSTDESSrcElemKernel::rhs"), rtol=0, atol=TOL)
     np.testing.assert_allclose(lhs, tab(g, "hex8_golds::TurbKineticEnergySSTDESSrcElemKernel::lhs"), rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("ns,alt", [("nso_2nd", 0.0), ("nso_2nd_alt", 1.0)])
+def test_momentum_nso_gold(ns, alt):
+    # unit_tests/kernels/UnitTestMomentumNSOElem.C:318-404: MomentumKernelHex8Mesh (velocity / density with two states, only
+    # NP1 filled; dudx = the analytic gradient of the Taylor vortex), fourthFac = 0, altResFac = 0 / 1, dt = 0.1, BE
+    g = load_golden("momentum_nso")
+    fx = LowMachFixture()
+    keep = []
+    d = oracle.make_desc("momentum_nso", keep, coordinates=fx.coords, velocity=fx.velocity, velocityN=fx.velocityN,
+                         velocityNm1=fx.velocityN, density=fx.density, densityN=fx.densityN, densityNm1=fx.densityN,
+                         viscosity=fx.viscosity, pressure=fx.pressure, Gju=fields.dudx(fx.coords), fourthFac=0.0, altResFac=alt,
+                         dt=0.1, gamma1=1.0, gamma2=-1.0, gamma3=0.0, includeDivU=0.0)
+    lhs, rhs = oracle.element_lhs_rhs([d], 3, fx.mesh.elem_nodes[0])
+    # the gold tables are printed with 16 decimals
+    np.testing.assert_allclose(rhs, tab(g, f"hex8_golds::{ns}::rhs"), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(lhs, tab(g, f"hex8_golds::{ns}::lhs"), rtol=0, atol=1e-15)
 
 
 def test_ksgs_src_unit_cube_closed_form():
