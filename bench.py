@@ -365,7 +365,16 @@ def run_ours(args):
             with open(tf) as f:
                 t = json.load(f).get(kernel_name)
             if isinstance(t, dict):  # valid for the workload and per-rank element count it was captured on only
-                t = t["bytes"] if (t.get("workload") == workload_name and t.get("elements") == n_elems_rank) else None
+                ok = t.get("workload") == workload_name and t.get("elements") == n_elems_rank
+                if ok and "fp64" in t:
+                    # the co-limiting resource: FP64 work of one launch, counted once with ncu (static), over
+                    # the kernel time measured in this run
+                    f = t["fp64"]
+                    roofline["fp64"] = {"flops_per_launch": f["flops"], "flops_per_element": f["flops"] / n_elems_rank,
+                                        "achieved": f["flops"] / (asm_ms * 1e-3) / 1e12, "peak": f["peak_tflops"], "unit": "TFLOP/s",
+                                        "frac": f["flops"] / (asm_ms * 1e-3) / 1e12 / f["peak_tflops"],
+                                        "pipe_busy_pct_ncu": f["pipe_busy_pct"], "source": "static count: " + f["source"]}
+                t = t["bytes"] if ok else None
             if t is not None:
                 roofline["traffic"] = t
                 roofline["traffic_source"] = "static: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (profiles/traffic.json), not measured in this run"
