@@ -1093,3 +1093,58 @@ def test_decomposed_exodus_mesh_parity_after_load_complete(ndof, kind):
     orc.load_complete()
     for r, ls in enumerate(systems):
         _compare_system(ls, orc, rank=r)
+
+
+@pytest.mark.parametrize("eq", ["tke", "sdr"])
+def test_config4_sst_kernel_lists_on_abl_style_box(eq):
+    """BASELINE config 4 at test size: a box stretched in z like an atmospheric-boundary-layer mesh (cell heights growing
+    geometrically from the wall), SST trig fields, and the kernel lists of the turbulence equations
+    [ScalarMass(lumped), ScalarUpwAdvDiff, TurbKineticEnergySSTSrc | SpecificDissipationRateSSTSrc] on ONE algorithm
+    (src/TurbKineticEnergyEquationSystem.C / SpecificDissipationRateEquationSystem.C register them in this order)."""
+    from nalu_b200 import fields
+    m = perturbed_box(8, 6, 10, amp=0.05)
+    c = m.coords.copy()
+    c[:, 2] = 0.02 * (1.25 ** c[:, 2] - 1.0) / 0.25  # first cell 0.02 high, growth 1.25 per layer
+    c[:, 0] *= 0.4
+    c[:, 1] *= 0.4
+    m.coords = c
+    a = 0.3 * np.pi
+    x, y, z = c[:, 0], c[:, 1], c[:, 2]
+    vel = fields.velocity(c) + np.stack([np.log1p(20 * z), 0 * z, 0.02 * np.sin(a * x)], axis=1)
+    rho = 1.0 + 0.1 * np.cos(a * x) * np.cos(a * y)
+    tke = 2.0 + np.cos(a * x) * np.sin(a * y) * np.cos(a * z)
+    sdr = 2.0 + np.cos(a * x) * np.sin(a * y) * np.sin(a * z)
+    tvisc = 0.3 + 0.1 * np.sin(a * z)
+    f1 = 0.5 + 0.4 * np.sin(a * x) * np.cos(a * y)
+    q = tke if eq == "tke" else sdr
+    gjq = np.stack([np.cos(a * c[:, j] + 0.1 * j) * (0.2 + 0.05 * j) for j in range(3)], axis=1)
+    visc_eff = 1.8e-5 + tvisc * (0.85 if eq == "tke" else 0.5)
+    mdot = oracle.calc_mass_flow_rate_scs(m.elem_nodes, c, rho, vel)
+    bdf2 = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    upw = dict(alpha=0.0, alphaUpw=1.0, hoUpwind=1.0, hybridFactor=1.0)
+    turb = dict(betaStar=0.09, tkeProdLimitRatio=10.0, sigmaWTwo=0.856, betaOne=0.075, betaTwo=0.0828, gammaOne=5.0 / 9.0,
+                gammaTwo=0.44)
+    keep = []
+    src = "tke_sst_src" if eq == "tke" else "sdr_sst_src"
+    orc = oracle.LinSys([m], 1)
+    orc.assemble_elem(0, [
+        oracle.make_desc("scalar_mass", keep, coordinates=c, scalarQ=q, scalarQN=0.97 * q, scalarQNm1=0.93 * q, density=rho,
+                         densityN=0.98 * rho, densityNm1=0.95 * rho, lumpedMass=1, **bdf2),
+        oracle.make_desc("scalar_upw_adv_diff", keep, coordinates=c, velocity=vel, Gjq=gjq, scalarQ=q, density=rho,
+                         viscosity=visc_eff, massFlowRate=mdot, useLimiter=1, **upw),
+        oracle.make_desc(src, keep, coordinates=c, velocity=vel, density=rho, tke=tke, sdr=sdr, tvisc=tvisc, fOneBlend=f1, **turb)])
+    dev = _cuda()
+    tt = lambda v: torch.as_tensor(np.ascontiguousarray(v), device=dev)
+    ls = _linsys(m, 1)
+    ls.zero_system()
+    fl = dict(coordinates=tt(c), velocity=tt(vel), density=tt(rho), density_n=tt(0.98 * rho), density_nm1=tt(0.95 * rho),
+              scalarq=tt(q), scalarq_n=tt(0.97 * q), scalarq_nm1=tt(0.93 * q), viscosity=tt(visc_eff), gjq=tt(gjq), tke=tt(tke),
+              sdr=tt(sdr), tvisc=tt(tvisc), f_one_blend=tt(f1))
+    descs = [ls.make_desc("scalar_mass", fields=fl, options=("lumped_mass",), **bdf2),
+             ls.make_desc("scalar_upw_adv_diff", fields=fl, options=("use_limiter",), mass_flow_rate=tt(mdot),
+                          upw=dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, hybrid_factor=1.0)),
+             ls.make_desc(src, fields=fl, turb=dict(beta_star=0.09, tke_prod_limit_ratio=10.0, sigma_w_two=0.856, beta_one=0.075,
+                                                    beta_two=0.0828, gamma_one=5.0 / 9.0, gamma_two=0.44))]
+    assert ls.assemble_elem(descs, mode="auto") == 1
+    _compare_system(ls, orc)
+    assert ls.geometry_errors() == 0
