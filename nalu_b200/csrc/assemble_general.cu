@@ -34,8 +34,9 @@ struct GeneralParams {
 
 constexpr int kWarpsPerCta = 4;
 
-template <int NDOF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) assemble_general_kernel(const __grid_constant__ GeneralParams p)
+// MINB = CTAs per SM the register allocation is bounded for (2: 255 registers, 3: 168, 4: 128)
+template <int NDOF, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) assemble_general_kernel(const __grid_constant__ GeneralParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ElemScratch<NDOF> *all = reinterpret_cast<ElemScratch<NDOF> *>(smem_raw);
@@ -246,8 +247,12 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
     return NALU_B200_ERR_ARG;
   }
   const size_t smem = (g.ndof == 3 ? sizeof(ElemScratch<3>) : sizeof(ElemScratch<1>)) * kWarpsPerCta;
-  if (g.ndof == 3) NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else NALU_CUDA(cudaFuncSetAttribute(assemble_general_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int minb = tuning().general_minb;
+  void (*kern)(const GeneralParams) =
+      g.ndof == 3 ? (minb == 2 ? assemble_general_kernel<3, 2> : minb == 3 ? assemble_general_kernel<3, 3> : assemble_general_kernel<3, 4>)
+                  : (minb == 2 ? assemble_general_kernel<1, 2> : minb == 3 ? assemble_general_kernel<1, 3> : assemble_general_kernel<1, 4>);
+  NALU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NALU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   // one launch per (chunk, colour) group (same stream: the groups run in order), or a single atomic launch when there
   // is no colouring
   const long long ncolor = g.d_color_elems ? (long long)g.color_ptr.size() - 1 : 1;
@@ -257,8 +262,7 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
     if (p.n_elems == 0) continue;
     long long ctas = (p.n_elems + kWarpsPerCta - 1) / kWarpsPerCta;
     if (ctas > (long long)sms * 16) ctas = (long long)sms * 16;
-    if (g.ndof == 3) assemble_general_kernel<3><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
-    else assemble_general_kernel<1><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+    kern<<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
     count_launch();
   }
   NALU_CUDA(cudaGetLastError());

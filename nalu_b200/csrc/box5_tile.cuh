@@ -211,7 +211,7 @@ __host__ __device__ __forceinline__ void area_base(const Coef &C, double (&b)[3]
 // md = mass flow rate counted along +t.  Jacobian / cofactors / determinant as generic_grad_op
 // (MasterElementFunctions.h:51-108) in the coefficient basis; area vector = the reference's 27-point subdivision +
 // 4-triangle fan (Hex8GeometryFunctions.h:30-76,263-321) as the vector area of a closed polygon.
-template <int T>
+template <int T, int F = Cfg::FS>
 __host__ __device__ __forceinline__ void p1_point(const Coef &C, const double (&base)[3], double sgu, double sgv, double q, double md,
                                                   double *o, int *err)
 {
@@ -253,7 +253,6 @@ __host__ __device__ __forceinline__ void p1_point(const Coef &C, const double (&
   double B[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) B[k] = G[0][k] * A[0] + G[1][k] * A[1] + G[2][k] * A[2];
-  constexpr int F = Cfg::FS;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll

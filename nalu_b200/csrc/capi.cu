@@ -34,6 +34,7 @@ static Tuning &tuning_rw()
     if (const char *e = getenv("NALU_BOX_ZCHUNK")) v.box_zchunk = atoi(e) > 0 ? atoi(e) : 0;
     if (const char *e = getenv("NALU_SPLIT_LISTS")) v.split_lists = atoi(e) != 0;
     if (const char *e = getenv("NALU_CONT_BOX")) v.cont_tiled = atoi(e) != 0;
+    if (const char *e = getenv("NALU_GENERAL_MINB")) v.general_minb = atoi(e) < 2 ? 2 : (atoi(e) > 4 ? 4 : atoi(e));
     return v;
   }();
   return t;
@@ -172,6 +173,7 @@ int nalu_b200_tune(const char *name, int32_t value)
   else if (n == "box_zchunk") t.box_zchunk = value > 0 ? value : 0;
   else if (n == "split_lists") t.split_lists = value != 0;
   else if (n == "cont_tiled") t.cont_tiled = value != 0;
+  else if (n == "general_minb") t.general_minb = value < 2 ? 2 : (value > 4 ? 4 : value);
   else {
     set_error("tune: unknown knob " + n);
     return NALU_B200_ERR_ARG;

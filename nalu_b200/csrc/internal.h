@@ -74,6 +74,7 @@ struct Tuning {
   int box_zchunk = 0;
   bool split_lists = true;
   bool cont_tiled = true;
+  int general_minb = 4; // CTAs per SM the general kernel's registers are bounded for (2, 3 or 4)
 };
 const Tuning &tuning();
 
