@@ -420,6 +420,16 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   // takes its kernel first (it may overwrite), the others accumulate on top through the general kernel -- the sum the
   // reference forms in one scratch lhs/rhs (src/AssembleElemSolverAlgorithm.C:86-91), in another order.
   const bool split_lists = tuning().split_lists;
+  // scalar transport lists (config 4: lumped mass + upwind adv-diff + SST source) in one tiled write-once launch
+  if (mode != NALU_ASSEMBLE_GENERAL && tuning().cont_tiled && slist_box_supported(g, kernels, nk)) {
+    for (int i = 0; i < nk; ++i)
+      if (const char *missing = missing_field(kernels[i])) {
+        set_error(std::string("assemble_elem: field missing for kernel ") + std::to_string(i) + ": " + missing);
+        return NALU_B200_ERR_ARG;
+      }
+    set_last_mode(2);
+    return launch_assemble_slist_box(g, kernels, nk, d_values, d_rhs, overwrite, s);
+  }
   if (mode == NALU_ASSEMBLE_AUTO && nk > 1 && nk <= kMaxKernels && split_lists && !box_supported(g, kernels, nk)) {
     int t = -1;
     for (int i = 0; i < nk && t < 0; ++i)

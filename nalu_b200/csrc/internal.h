@@ -34,6 +34,10 @@ int launch_assemble_cont_box(const Graph &g, const nalu_b200_kernel_desc *k, int
 bool scalar_box_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
 int launch_assemble_scalar_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs,
                                int overwrite, cudaStream_t stream);
+// assemble_slist_box.cu: scalar kernel lists (lumped mass + (upwind) adv-diff + SST source) in one tiled launch
+bool slist_box_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
+int launch_assemble_slist_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs,
+                              int overwrite, cudaStream_t stream);
 bool scv_lumped_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
 int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs, cudaStream_t stream);
 int launch_nodal_grad(const Graph &g, const double *coords, const double *field, int ncomp, const double *dual_volume, int use_shifted,

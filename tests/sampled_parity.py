@@ -41,7 +41,7 @@ def subbox_origins(nx, ny, nz, size, n_random=16, seed=7, z_interfaces=()):
     return sorted(out)
 
 
-def make_subbox(nx, ny, nz, origin, size, amp):
+def make_subbox(nx, ny, nz, origin, size, amp, coord_map=None):
     """the sub-box [origin, origin + size) of the global generated box as a one-rank mesh with the id-keyed coordinate
     perturbation of the benchmark / test meshes; returns (mesh, global node ids, which nodes have all their elements in
     the sub-box)"""
@@ -56,6 +56,8 @@ def make_subbox(nx, ny, nz, origin, size, amp):
     true_gid, sub.node_gid = sub.node_gid, gid
     nmesh.perturb_coords_hash(sub, amp)
     sub.node_gid = true_gid  # the oracle's graph of the sub-box uses local ids; `gid` maps them back
+    if coord_map is not None:
+        sub.coords = coord_map(sub.coords)  # e.g. the stretched-z map of config 4 (lattice -> physical coordinates)
     complete = np.ones(sub.n_nodes, dtype=bool)
     for a, a0, s, ng in ((ii, i0, sx, nx), (jj, j0, sy, ny), (kk, k0, sz, nz)):
         complete &= ((a > 0) | (a0 == 0)) & ((a < s) | (a0 + s == ng))
@@ -63,7 +65,7 @@ def make_subbox(nx, ny, nz, origin, size, amp):
 
 
 def check_sampled_rows(ls, m, nz_global, field_fn, kernel_fn, ndof=3, size=5, n_random=16, row_floor=1e-2, amp=0.12, shift=True,
-                       sol_scale=1.0):
+                       sol_scale=1.0, coord_map=None):
     """ls: DeviceCsrLinearSystem holding the assembled (and, on several ranks, loadComplete'd) system of rank mesh `m`, a
     z-slab of the global nx x ny x nz_global generated box.  field_fn(coords) -> {name: nodal array} recreates the nodal
     fields of any set of nodes; kernel_fn(sub_mesh, fields) -> list of oracle descriptors (keeps its arrays alive).
@@ -87,7 +89,7 @@ def check_sampled_rows(ls, m, nz_global, field_fn, kernel_fn, ndof=3, size=5, n_
     nrows = nsub = 0
     NXl, NYl = nx + 1, ny + 1
     for origin in origins:
-        sub, gid, complete = make_subbox(nx, ny, nz_global, origin, size, amp)
+        sub, gid, complete = make_subbox(nx, ny, nz_global, origin, size, amp, coord_map)
         # global -> local node of this rank; rows this rank owns
         gi, gj, gk = (gid - 1) % NXl, ((gid - 1) // NXl) % NYl, (gid - 1) // (NXl * NYl)
         lk = gk - kz0

@@ -29,7 +29,8 @@ def _objs():
     return objs
 
 
-@pytest.mark.parametrize("name", ["hex8_host_check", "general_host_check", "box2_host_check", "box5_host_check", "cont_host_check", "scalar_host_check"])
+@pytest.mark.parametrize("name", ["hex8_host_check", "general_host_check", "box2_host_check", "box5_host_check", "cont_host_check", "scalar_host_check",
+                                  "slist_host_check"])
 def test_kernel_phases_on_cpu(name):
     exe = os.path.join(B, name)
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-fopenmp", os.path.join(H, name + ".cpp")] + _objs() +

@@ -1,0 +1,194 @@
+#!/usr/bin/env python3
+"""BASELINE config 4 per-GPU workload: an ABL-style (stretched-z) Hex8 box, n x n x (layers x world) elements in z-slabs (512 x
+512 x 64 per GPU = the 512^3 box on 8 GPUs), SST turbulence.  Times, per equation system, ONE assembly of the kernel list
+the reference registers on one AssembleElemSolverAlgorithm, device-resident inputs, CUDA events, max over ranks:
+  tke:      [ScalarMass(lumped), ScalarUpwAdvDiff, TurbKineticEnergySSTSrc]        (scalar-list tiled kernel, one launch)
+  sdr:      [ScalarMass(lumped), ScalarUpwAdvDiff, SpecificDissipationRateSSTSrc]  (same)
+  momentum: [MomentumMass(lumped), MomentumAdvDiff] with mu = mu_eff               (row-thread tiled kernel, one launch)
++ loadComplete on several ranks, and checks sampled rows of every system against the oracle on the timed mesh.
+usage: [torchrun ...] bench_config4.py [--n 512] [--layers 64] [--steps 10] [--no-momentum] [--mode auto|general]
+Prints one JSON line on rank 0."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402  (workload_fields / oracle_kernels of the momentum list)
+import config4_util as c4  # noqa: E402
+from nalu_b200 import dist as nd, lib, mesh  # noqa: E402
+from nalu_b200.linsys import DeviceCsrLinearSystem  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--layers", type=int, default=64, help="element layers per GPU")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mode", default="auto", choices=["auto", "general"])
+    ap.add_argument("--no-momentum", action="store_true")
+    ap.add_argument("--no-oracle-check", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    n, nzg = args.n, args.layers * world
+    amp, wave = 0.1, 40.0
+    # ABL-style column: first cell 0.05 high, 2 % growth per layer over the lowest 200 layers, uniform above
+    k_uni = 200.0
+    abl = lambda lat: c4.abl_coords(lat, h_xy=1.0, h0=0.05, growth=1.02, k_uniform=k_uni, h_top=0.05 * 1.02 ** k_uni)
+    m = mesh.generated_box_rank(n, n, nzg, rank, world)
+    mesh.perturb_coords_hash(m, amp)
+    m.coords = abl(m.coords)
+    L = lib.lib()
+    comm = nd.make_comm(rank, world) if world > 1 else None
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    out = {"workload": f"config4_abl_box_{n}x{n}x{nzg}_sst", "n_gpus": world, "elements_per_gpu": m.n_elems,
+           "elements_total": m.n_elems * world, "mode": args.mode, "partition": f"z-slabs x{world}",
+           "coordinates": "lattice + id-keyed perturbation (0.1 h) mapped to cell heights growing 2 %/layer from 0.05 (first 200 "
+                          "layers), uniform above; aspect ratio up to 20"}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(ls, descs, overwrite):
+        """-> (assembly ms, step ms incl. zeroSystem for accumulating kernels and loadComplete), max over ranks"""
+        def step(e0=None, e1=None):
+            if not overwrite:
+                ls.zero_system()
+            if e0 is not None:
+                e0.record()
+            ls.assemble_elem(descs, mode=args.mode, overwrite=overwrite)
+            if e1 is not None:
+                e1.record()
+            if comm is not None:
+                ls.load_complete(comm)
+        for _ in range(max(3, args.warmup)):
+            step()
+        barrier()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        for a, b, c, d in ev:
+            a.record()
+            step(b, c)
+            d.record()
+        barrier()
+        asm = float(np.mean([b.elapsed_time(c) for _, b, c, _ in ev]))
+        stp = float(np.mean([a.elapsed_time(d) for a, _, _, d in ev]))
+        if world > 1:
+            x = torch.tensor([asm, stp], dtype=torch.float64, device=dev)
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            asm, stp = float(x[0]), float(x[1])
+        return asm, stp
+
+    def sampled(ls, ndof, field_fn, kernel_fn, sol_scale=1.0):
+        import sampled_parity as sp
+        res = sp.check_sampled_rows(ls, m, nzg, field_fn, kernel_fn, ndof=ndof, size=4, n_random=6, amp=amp, coord_map=abl,
+                                    sol_scale=sol_scale)
+        agg = torch.tensor([res["max_rel_err_values"], res["max_rel_err_rhs"], float(res["rows"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = agg.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            res["max_rel_err_values"], res["max_rel_err_rhs"], res["rows"] = float(mx[0]), float(mx[1]), int(agg[2])
+        res["passed"] = bool(res["max_rel_err_values"] < 1e-12 and res["max_rel_err_rhs"] < 1e-12)
+        return res
+
+    peak = bench.load_peaks()[0]
+    nn = m.n_nodes
+
+    # ---- scalar systems: tke and sdr share one graph ------------------------------------------------------------------
+    t0 = time.perf_counter()
+    ls1 = DeviceCsrLinearSystem(m, 1, exchange=nd.make_exchange(rank, world) if world > 1 else None)
+    ls1.allocate(dev)
+    out["graph_build_s_ndof1"] = time.perf_counter() - t0
+    nnz1 = int(ls1.values.numel())
+    for eq in ("tke", "sdr"):
+        f = c4.state(m.coords, eq, wave=wave)
+        d = {k: t(v) for k, v in f.items()}
+        d[eq] = d["scalarq"]  # the dof field is turbulent_ke / specific_dissipation_rate itself
+        mdot = ls1.mdot_scs(d["coordinates"], d["density"], d["velocity"])
+        descs = c4.product_list(ls1, d, eq, mdot)
+        probe = ls1.assemble_elem(descs, mode=args.mode, overwrite=True)
+        overwrite = probe == 2
+        asm, stp = timed(ls1, descs, overwrite)
+        # doubles read per node: x3 q Gamma u3 rho Gjq3 other tvisc (+ f1) + q_n q_nm1 rho_n rho_nm1; mdot 12/elem; conn 32 B/elem
+        comps = 18 + (eq == "sdr")
+        bytes_alg = 8 * comps * nn + 96 * m.n_elems + 32 * m.n_elems + 8 * nnz1 + 8 * nn
+        r = {"kernels": ["ScalarMassElemKernel(lumped)", "ScalarUpwAdvDiffElemKernel(limiter)",
+                         ("TurbKineticEnergy" if eq == "tke" else "SpecificDissipationRate") + "SSTSrcElemKernel(lumped)"],
+             "assemble_mode": probe, "launch": "assemble_slist_box (one launch)" if probe == 2 else "assemble_general (coloured)",
+             "assemble_ms": asm, "step_ms": stp, "value": m.n_elems * world / stp / 1e3, "unit": "Melem/s",
+             "kernel_melem_s_per_gpu": m.n_elems / asm / 1e3, "bytes_per_element": bytes_alg / m.n_elems,
+             "roofline_frac": bytes_alg / (asm * 1e-3) / 1e9 / peak, "geometry_errors": ls1.geometry_errors()}
+        if not args.no_oracle_check:
+            keepers = []
+
+            def kernel_fn(sub, ff, eq=eq):
+                descs_o, keep = c4.oracle_list(sub, ff, eq)
+                keepers.append(keep)
+                return descs_o
+            r["sampled_rows_vs_oracle"] = sampled(ls1, 1, lambda c, eq=eq: c4.state(c, eq, wave=wave), kernel_fn, sol_scale=2.0)
+        out[eq] = r
+        del d, mdot, descs
+    del ls1
+    torch.cuda.empty_cache()
+
+    # ---- momentum with the effective viscosity ----------------------------------------------------------------------
+    if not args.no_momentum:
+        t0 = time.perf_counter()
+        ls3 = DeviceCsrLinearSystem(m, 3, exchange=nd.make_exchange(rank, world) if world > 1 else None)
+        ls3.allocate(dev)
+        out["graph_build_s_ndof3"] = time.perf_counter() - t0
+
+        def mom_fields(c):
+            f = bench.workload_fields(c)
+            f["viscosity"] = 1.8e-5 + 0.3 + 0.1 * np.sin(0.3 * np.pi / wave * c[:, 2])  # mu + mu_t
+            return f
+        h = mom_fields(m.coords)
+        d = {k: t(v) for k, v in h.items()}
+        mdot = ls3.mdot_scs(d["coordinates"], d["density"], d["velocity"])
+        descs = [ls3.make_desc("momentum_mass", fields={k: d[k] for k in ("coordinates", "velocity", "velocity_n", "velocity_nm1",
+                                                                          "density", "density_n", "density_nm1", "dpdx")},
+                               options=("lumped_mass",), **bench.MASS),
+                 ls3.make_desc("momentum_adv_diff", fields={k: d[k] for k in ("coordinates", "velocity", "viscosity")},
+                               mass_flow_rate=mdot, include_divu=1.0)]
+        probe = ls3.assemble_elem(descs, mode=args.mode, overwrite=True)
+        asm, stp = timed(ls3, descs, probe == 2)
+        bytes_alg = 8 * 19 * nn + 96 * m.n_elems + 32 * m.n_elems + 8 * int(ls3.values.numel()) + 24 * nn
+        r = {"kernels": ["MomentumMassElemKernel(lumped)", "MomentumAdvDiffElemKernel(includeDivU=1, mu_eff)"],
+             "assemble_mode": probe, "assemble_ms": asm, "step_ms": stp, "value": m.n_elems * world / stp / 1e3, "unit": "Melem/s",
+             "kernel_melem_s_per_gpu": m.n_elems / asm / 1e3, "bytes_per_element": bytes_alg / m.n_elems,
+             "roofline_frac": bytes_alg / (asm * 1e-3) / 1e9 / peak, "geometry_errors": ls3.geometry_errors()}
+        if not args.no_oracle_check:
+            r["sampled_rows_vs_oracle"] = sampled(ls3, 3, mom_fields, bench.oracle_kernels(["momentum_mass", "momentum_adv_diff"], 1.0))
+        out["momentum"] = r
+    if all(k in out for k in ("tke", "sdr", "momentum")):
+        tot = out["tke"]["step_ms"] + out["sdr"]["step_ms"] + out["momentum"]["step_ms"]
+        out["three_systems_ms"] = tot
+        out["three_systems_melem_s"] = m.n_elems * world / tot / 1e3
+    out["launch_count"] = int(L.nalu_b200_launch_count())
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
