@@ -201,6 +201,41 @@ void orc_linsys_load_complete(orc_linsys *ls);
 void orc_assemble_node_mass(orc_linsys *ls, int rank, const orc_kernel_desc *k,
                             const double *dualNodalVolume);
 
+/* ------------------------------------------------------------------ */
+/* Face/element boundary-condition path (oracle/face_kernels.c)         */
+/* ------------------------------------------------------------------ */
+enum orc_face_kernel_kind {
+  ORC_FK_MOMENTUM_SYMMETRY = 0,     /* src/kernel/MomentumSymmetryElemKernel.C     */
+  ORC_FK_SCALAR_OPEN_ADV = 1,       /* src/kernel/ScalarOpenAdvElemKernel.C        */
+  ORC_FK_CONTINUITY_OPEN = 2,       /* src/kernel/ContinuityOpenElemKernel.C       */
+  ORC_FK_MOMENTUM_OPEN_ADV_DIFF = 3 /* src/kernel/MomentumOpenAdvDiffElemKernel.C  */
+};
+/* what the face kernels' constructors / setup() capture; nodal fields [nNode][ncomp], face fields [nFaces][4 ips][ncomp] */
+typedef struct orc_face_kernel_desc {
+  int kind;
+  int shiftedGradOp, skewSymmetric, shiftMdot, reducedSensitivities, meshMoves;
+  int pecletTanh;
+  double includeDivU, dt, gamma1, alphaUpw, hoUpwind, hybridFactor, tanhTrans, tanhWidth;
+  const double *coordinates, *velocity, *velocityRTM, *meshVelocity, *viscosity, *density, *pressure, *pressureBc, *Gpdx;
+  const double *scalarQ, *bcScalarQ, *Gjq, *Gjui, *velocityBc;
+  const double *exposedAreaVec, *openMassFlowRate, *dynamicPressure; /* face fields: [.][4][3], [.][4], [.][4] */
+} orc_face_kernel_desc;
+
+const int *orc_hex8_side_node_ordinals(int ordinal); /* Hex8CVFEM.C:414-422,587-591 */
+const int *orc_hex8_face_ip_node_map(int ordinal);   /* Hex8CVFEM.C:381-393 */
+int orc_hex8_opposing_node(int ordinal, int ip);     /* Hex8CVFEM.C:288-300,853-858 */
+int orc_hex8_face_grad_op(int face_ordinal, int shifted, const double *coords /*[8][3]*/, double *gradop /*[4][8][3]*/);
+void orc_quad3d_scs_areav(const double *coords /*[4][3]*/, double *area /*[4][3]*/);
+void orc_quad3d_shape_fcn(int shifted, double shp[4][4]);
+/* src/ComputeGeometryBoundaryAlgorithm.C:62-123; a face = (element, face ordinal) */
+void orc_compute_exposed_area(int64_t nFaces, const int32_t *faceElem, const int32_t *faceOrdinal, const int32_t *elemNodes,
+                              const double *coords, double *areaVec);
+void orc_face_elem_lhs_rhs(const orc_face_kernel_desc *kernels, int nk, int numDof, const int32_t *elemNodes, int elemFaceOrdinal,
+                           int64_t faceIndex, double *lhs, double *rhs);
+/* AssembleFaceElemSolverAlgorithm::execute (src/AssembleFaceElemSolverAlgorithm.C:78-108) over the listed faces */
+void orc_assemble_face_elem(orc_linsys *ls, int rank, int numDof, const int32_t *elemNodes, const orc_face_kernel_desc *kernels,
+                            int nk, int64_t nFaces, const int32_t *faceElem, const int32_t *faceOrdinal);
+
 /* LocalGraphArrays test hooks (include/LinearSolver.h:62-120) */
 void *orc_graph_arrays_create(const size_t *rowLens, size_t n);
 void orc_graph_arrays_insert(void *h, size_t localRow, size_t numInds, const int32_t *inds, int numDof);

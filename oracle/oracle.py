@@ -16,7 +16,7 @@ KIND = dict(momentum_adv_diff=0, continuity_adv=1, scalar_adv_diff=2, momentum_m
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("hex8_me.c", "elem_kernels.c", "linsys.c", "nalu_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("hex8_me.c", "elem_kernels.c", "linsys.c", "face_kernels.c", "nalu_oracle.h")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
@@ -201,6 +201,89 @@ def compute_mdot_elem(elem_nodes, coords, density, velocity, pressure, Gpdx, pro
     return mdot
 
 
+# ---- face/element boundary-condition path (oracle/face_kernels.c) ---------------------------------------------------
+FACE_KIND = {"momentum_symmetry": 0, "scalar_open_adv": 1, "continuity_open": 2, "momentum_open_adv_diff": 3}
+_FACE_PTR_FIELDS = ("coordinates", "velocity", "velocityRTM", "meshVelocity", "viscosity", "density", "pressure", "pressureBc",
+                    "Gpdx", "scalarQ", "bcScalarQ", "Gjq", "Gjui", "velocityBc", "exposedAreaVec", "openMassFlowRate",
+                    "dynamicPressure")
+
+
+class FaceKernelDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("kind", "shiftedGradOp", "skewSymmetric", "shiftMdot", "reducedSensitivities", "meshMoves",
+                                       "pecletTanh")] + \
+               [(n, C.c_double) for n in ("includeDivU", "dt", "gamma1", "alphaUpw", "hoUpwind", "hybridFactor", "tanhTrans",
+                                          "tanhWidth")] + \
+               [(n, C.c_void_p) for n in _FACE_PTR_FIELDS]
+
+
+def make_face_desc(kind, keep, **kw):
+    """Build a FaceKernelDesc; numpy arrays given for pointer fields are kept alive in `keep`."""
+    d = FaceKernelDesc()
+    d.kind = FACE_KIND[kind] if isinstance(kind, str) else int(kind)
+    d.dt = 1.0
+    d.gamma1 = 1.0
+    for k, v in kw.items():
+        if k in _FACE_PTR_FIELDS:
+            if v is None:
+                continue
+            arr = _f64(v)
+            keep.append(arr)
+            setattr(d, k, arr.ctypes.data)
+        else:
+            setattr(d, k, v)
+    return d
+
+
+def quad3d_scs_areav(coords):
+    c = _f64(coords).reshape(4, 3)
+    out = np.zeros((4, 3))
+    lib().orc_quad3d_scs_areav(_p(c), _p(out))
+    return out
+
+
+def quad3d_shape_fcn(shifted=False):
+    out = np.zeros((4, 4))
+    lib().orc_quad3d_shape_fcn(int(shifted), _p(out))
+    return out
+
+
+def hex8_face_grad_op(face_ordinal, coords, shifted=False):
+    c = _f64(coords).reshape(8, 3)
+    out = np.zeros((4, 8, 3))
+    bad = lib().orc_hex8_face_grad_op(int(face_ordinal), int(shifted), _p(c), _p(out))
+    return out, bad
+
+
+def hex8_face_tables():
+    """(side_node_ordinals[6][4], face ipNodeMap[6][4], opposingNodes[6][4])"""
+    L = lib()
+    L.orc_hex8_side_node_ordinals.restype = C.POINTER(C.c_int)
+    L.orc_hex8_face_ip_node_map.restype = C.POINTER(C.c_int)
+    sno = np.array([[L.orc_hex8_side_node_ordinals(f)[k] for k in range(4)] for f in range(6)])
+    ipn = np.array([[L.orc_hex8_face_ip_node_map(f)[k] for k in range(4)] for f in range(6)])
+    opp = np.array([[L.orc_hex8_opposing_node(f, k) for k in range(4)] for f in range(6)])
+    return sno, ipn, opp
+
+
+def compute_exposed_area(face_elem, face_ordinal, elem_nodes, coords):
+    fe = np.ascontiguousarray(face_elem, dtype=np.int32)
+    fo = np.ascontiguousarray(face_ordinal, dtype=np.int32)
+    en = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+    c = _f64(coords)
+    out = np.zeros((fe.size, 4, 3))
+    lib().orc_compute_exposed_area(C.c_int64(fe.size), _p(fe), _p(fo), _p(en), _p(c), _p(out))
+    return out
+
+
+def face_elem_lhs_rhs(descs, num_dof, elem_nodes, face_ordinal, face_index=0):
+    arr = (FaceKernelDesc * len(descs))(*descs)
+    en = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+    n = 8 * num_dof
+    lhs, rhs = np.zeros((n, n)), np.zeros(n)
+    lib().orc_face_elem_lhs_rhs(arr, len(descs), int(num_dof), _p(en), int(face_ordinal), C.c_int64(face_index), _p(lhs), _p(rhs))
+    return lhs, rhs
+
+
 class LinSys:
     """All ranks of one simulated MPI job (orc_linsys)."""
 
@@ -275,6 +358,14 @@ class LinSys:
     def assemble_elem(self, r, descs):
         arr = (KernelDesc * len(descs))(*descs)
         self.L.orc_assemble_elem(self.h, r, arr, len(descs))
+
+    def assemble_face_elem(self, r, descs, face_elem, face_ordinal):
+        """AssembleFaceElemSolverAlgorithm::execute over the faces (element, ordinal) of rank r"""
+        arr = (FaceKernelDesc * len(descs))(*descs)
+        fe = np.ascontiguousarray(face_elem, dtype=np.int32)
+        fo = np.ascontiguousarray(face_ordinal, dtype=np.int32)
+        en = np.ascontiguousarray(self.meshes[r].elem_nodes, dtype=np.int32)
+        self.L.orc_assemble_face_elem(self.h, r, int(self.num_dof), _p(en), arr, len(descs), C.c_int64(fe.size), _p(fe), _p(fo))
 
     def assemble_node_mass(self, r, desc, dual_nodal_volume):
         dv = _f64(dual_nodal_volume)

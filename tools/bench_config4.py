@@ -6,7 +6,7 @@ the reference registers on one AssembleElemSolverAlgorithm, device-resident inpu
   sdr:      [ScalarMass(lumped), ScalarUpwAdvDiff, SpecificDissipationRateSSTSrc]  (same)
   momentum: [MomentumMass(lumped), MomentumAdvDiff] with mu = mu_eff               (row-thread tiled kernel, one launch)
 + loadComplete on several ranks, and checks sampled rows of every system against the oracle on the timed mesh.
-usage: [torchrun ...] bench_config4.py [--n 512] [--layers 64] [--steps 10] [--no-momentum] [--mode auto|general]
+usage: [torchrun ...] bench_config4.py [--nx 512] [--layers 64] [--steps 10] [--no-momentum] [--mode auto|general]
 Prints one JSON line on rank 0."""
 import argparse
 import json
@@ -28,7 +28,7 @@ from nalu_b200.linsys import DeviceCsrLinearSystem  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--nx", type=int, default=512)
     ap.add_argument("--layers", type=int, default=64, help="element layers per GPU")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -46,7 +46,7 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-    n, nzg = args.n, args.layers * world
+    n, nzg = args.nx, args.layers * world
     amp, wave = 0.1, 40.0
     # ABL-style column: first cell 0.05 high, 2 % growth per layer over the lowest 200 layers, uniform above
     k_uni = 200.0
