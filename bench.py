@@ -194,6 +194,47 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """CPU affinity of this rank on the NUMA node its GPU hangs off, set before any pinned host buffer exists, so that the
+    pinned buffers are first-touched in memory local to the GPU's PCIe root: N ranks streaming host->device copies no
+    longer share one socket's memory controllers and the inter-socket link (the e2e collapse of the previous round)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = None
+        if all(hasattr(p, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hnd = pynvml.nvmlDeviceGetHandleByIndex(i)
+                uuid = pynvml.nvmlDeviceGetUUID(hnd)
+                uuid = uuid.decode() if isinstance(uuid, bytes) else uuid
+                if str(getattr(p, "uuid", "")) in uuid:
+                    b = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+                    b = b.decode() if isinstance(b, bytes) else b
+                    bdf = b.lower()[-12:]
+        if bdf is None:
+            return {"bound": False, "why": "no PCI address"}
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return {"bound": False, "why": "numa_node = -1 (no NUMA information in this container)", "pci": bdf}
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"bound": False, "why": "no allowed CPU on the GPU's node", "numa_node": node, "pci": bdf}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "numa_node": node, "cpus": len(allowed), "pci": bdf}
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -208,6 +249,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the assembly path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -564,7 +606,7 @@ def run_ours(args):
                                     "nccl": "pack kernel -> torch.distributed send/recv -> unpack-add kernel",
                                     "pull": "owner kernel reads peer rows over NVLink (CUDA IPC), no pack/staging", "none": "none"}[halo],
                            "l2_policy": "working set (>=36 GB CSR per GPU at n=256) exceeds the 126 MB L2",
-                           "assemble_kernel": kernel_name, "graph_build_s": t_graph},
+                           "assemble_kernel": kernel_name, "graph_build_s": t_graph, "numa_binding": numa},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "wall_ms_per_step": wall_ms, "checks": props}
         print(json.dumps(line))

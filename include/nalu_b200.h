@@ -315,6 +315,73 @@ int nalu_b200_mdot_scs(const nalu_b200_graph *g, const double *d_coords, const d
                        const double *d_velocity, double *d_mdot, void *stream);
 
 /* ------------------------------------------------------------------------------------ */
+/* Face/element boundary-condition algorithms.                             */
+/* ------------------------------------------------------------------------------------ */
+/* Replaces AssembleFaceElemSolverAlgorithm::execute / run_face_elem_algorithm (src/AssembleFaceElemSolverAlgorithm.C:78-108,
+ * include/AssembleFaceElemSolverAlgorithm.h:45-133) for Quad4 faces of Hex8 elements (AlgTraitsQuad4Hex8): per exposed face
+ * the gather of the face's and the attached element's nodes, HexSCS::face_grad_op / shifted_face_grad_op
+ * (src/master_element/Hex8CVFEM.C:668-742), the registered face kernels and apply_coeff with the ELEMENT's connected nodes.
+ * A face is (local element, face ordinal); its nodes are the element's side_node_ordinals(ordinal) (Hex8CVFEM.C:414-422),
+ * the identity unit_tests/kernels/UnitTestFaceElemBasic.C:48-66 asserts.  Face fields are [n_faces][4 ips][ncomp] arrays in
+ * the order the faces were given to nalu_b200_face_set_create. */
+enum nalu_b200_face_kernel_kind {
+  NALU_FK_MOMENTUM_SYMMETRY = 0,      /* src/kernel/MomentumSymmetryElemKernel.C:68-163     */
+  NALU_FK_SCALAR_OPEN_ADV = 1,        /* src/kernel/ScalarOpenAdvElemKernel.C:90-195        */
+  NALU_FK_CONTINUITY_OPEN = 2,        /* src/kernel/ContinuityOpenElemKernel.C:80-199       */
+  NALU_FK_MOMENTUM_OPEN_ADV_DIFF = 3, /* src/kernel/MomentumOpenAdvDiffElemKernel.C:110-325 */
+  NALU_FK_COUNT = 4
+};
+/* nodal field slots of the face kernels */
+enum nalu_b200_face_nodal_slot {
+  NALU_FN_COORDINATES = 0,  /* 3 */
+  NALU_FN_VELOCITY = 1,     /* 3  velocity NP1 */
+  NALU_FN_VELOCITY_RTM = 2, /* 3  velocity_rtm (mesh motion); NULL: NALU_FN_VELOCITY */
+  NALU_FN_MESH_VELOCITY = 3,/* 3  mesh_velocity (mesh motion); NULL: NALU_FN_VELOCITY (MomentumOpenAdvDiffElemKernel.C:53-60) */
+  NALU_FN_VISCOSITY = 4,    /* 1  viscosity / diffFluxCoeff */
+  NALU_FN_DENSITY = 5,      /* 1 */
+  NALU_FN_PRESSURE = 6,     /* 1 */
+  NALU_FN_PRESSURE_BC = 7,  /* 1  pressure_bc */
+  NALU_FN_DPDX = 8,         /* 3 */
+  NALU_FN_SCALARQ = 9,      /* 1 */
+  NALU_FN_BC_SCALARQ = 10,  /* 1  the open bc's entrainment value */
+  NALU_FN_GJQ = 11,         /* 3 */
+  NALU_FN_GJUI = 12,        /* 9  dudx */
+  NALU_FN_VELOCITY_BC = 13, /* 3  open_velocity_bc */
+  NALU_FN_COUNT = 16
+};
+enum nalu_b200_face_field_slot {
+  NALU_FF_EXPOSED_AREA_VEC = 0,    /* [4][3] exposed_area_vector (nalu_b200_compute_exposed_area) */
+  NALU_FF_OPEN_MASS_FLOW_RATE = 1, /* [4]    open_mass_flow_rate */
+  NALU_FF_DYNAMIC_PRESSURE = 2,    /* [4]    dynamic_pressure */
+  NALU_FF_COUNT = 4
+};
+#define NALU_OPT_MESH_MOVES (1 << 8) /* solnOpts.does_mesh_move(): meshVelocityCorrection_ of the momentum open kernel */
+typedef struct nalu_b200_face_kernel_desc {
+  int32_t kind;    /* nalu_b200_face_kernel_kind */
+  int32_t options; /* NALU_OPT_SHIFTED_GRAD_OP, _SKEW_SYMMETRIC, _SHIFT_MDOT, _REDUCED_SENS, _PECLET_TANH, NALU_OPT_MESH_MOVES */
+  double include_divu;
+  double dt, gamma1; /* ContinuityOpenElemKernel::setup: projTimeScale = dt / gamma1 */
+  double upw[8];     /* NALU_UPW_ALPHA_UPW, _HO_UPWIND, _HYBRID_FACTOR, _TANH_TRANS, _TANH_WIDTH */
+  const double *nodal[NALU_FN_COUNT]; /* device pointers, NULL when unused */
+  const double *face[NALU_FF_COUNT];  /* device pointers */
+} nalu_b200_face_kernel_desc;
+
+/* The locally owned faces of a boundary part (host arrays, copied).  The set colours the faces (two faces of one colour
+ * share no node, so a colour is summed with plain read-modify-writes: deterministic, no atomics). */
+typedef struct nalu_b200_face_set nalu_b200_face_set;
+int nalu_b200_face_set_create(nalu_b200_face_set **out, const nalu_b200_graph *g, int64_t n_faces, const int32_t *face_elem,
+                              const int32_t *face_ordinal);
+void nalu_b200_face_set_destroy(nalu_b200_face_set *fs);
+int nalu_b200_face_set_num_colors(const nalu_b200_face_set *fs, int32_t *n_colors);
+/* ComputeGeometryBoundaryAlgorithm::execute (src/ComputeGeometryBoundaryAlgorithm.C:62-123): exposed_area_vector of every
+ * face of the set = Quad3DSCS::determinant (quad3d_scs_det, MasterElementWork.F:1467-1586); d_area_vec [n_faces][4][3] */
+int nalu_b200_compute_exposed_area(const nalu_b200_graph *g, const nalu_b200_face_set *fs, const double *d_coords,
+                                   double *d_area_vec, void *stream);
+/* AssembleFaceElemSolverAlgorithm::execute: every kernel of the list on every face, summed into the element's rows */
+int nalu_b200_assemble_face_elem(const nalu_b200_graph *g, const nalu_b200_face_set *fs, const nalu_b200_face_kernel_desc *k,
+                                 int32_t nk, double *d_values, double *d_rhs, void *stream);
+
+/* ------------------------------------------------------------------------------------ */
 /* loadComplete: shared-not-owned rows -> owners, ADD.                                   */
 /* ------------------------------------------------------------------------------------ */
 /* Per neighbour the exchange is a flat array of doubles: for each of my shared-not-owned

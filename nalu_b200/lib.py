@@ -45,6 +45,21 @@ TM = dict(beta_star=0, tke_prod_limit_ratio=1, sigma_w_two=2, beta_one=3, beta_t
           lrksgs_fac=9)
 
 
+# face/element boundary-condition kernels (nalu_b200_face_kernel_desc)
+FK = dict(momentum_symmetry=0, scalar_open_adv=1, continuity_open=2, momentum_open_adv_diff=3)
+FN = dict(coordinates=0, velocity=1, velocity_rtm=2, mesh_velocity=3, viscosity=4, density=5, pressure=6, pressure_bc=7, dpdx=8,
+          scalarq=9, bc_scalarq=10, gjq=11, gjui=12, velocity_bc=13)
+FN_COUNT = 16
+FF = dict(exposed_area_vector=0, open_mass_flow_rate=1, dynamic_pressure=2)
+FF_COUNT = 4
+OPT_MESH_MOVES = 1 << 8
+
+
+class FaceKernelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("options", C.c_int32), ("include_divu", C.c_double), ("dt", C.c_double),
+                ("gamma1", C.c_double), ("upw", C.c_double * 8), ("nodal", C.c_void_p * FN_COUNT), ("face", C.c_void_p * FF_COUNT)]
+
+
 class GraphInfo(C.Structure):
     _fields_ = [("num_dof", C.c_int32), ("n_owned_rows", C.c_int32), ("n_shared_rows", C.c_int32),
                 ("n_cols", C.c_int32), ("nnz_owned", C.c_int64), ("nnz_shared", C.c_int64),
@@ -66,6 +81,8 @@ SYMBOLS = [
     "nalu_b200_load_complete", "nalu_b200_ipc_get_handle", "nalu_b200_ipc_open_handle",
     "nalu_b200_ipc_close", "nalu_b200_malloc", "nalu_b200_free", "nalu_b200_memcpy_h2d",
     "nalu_b200_memcpy_d2h", "nalu_b200_stream_sync",
+    "nalu_b200_face_set_create", "nalu_b200_face_set_destroy", "nalu_b200_face_set_num_colors", "nalu_b200_compute_exposed_area",
+    "nalu_b200_assemble_face_elem",
 ]
 
 
@@ -83,6 +100,7 @@ def lib():
         L.nalu_b200_last_error.restype = C.c_char_p
         L.nalu_b200_launch_count.restype = C.c_int64
         L.nalu_b200_graph_destroy.restype = None
+        L.nalu_b200_face_set_destroy.restype = None
         L.nalu_b200_comm_destroy.restype = None
         _LIB = L
     return _LIB

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
-from .lib import F, K, MODE, OPT, GraphInfo, KernelDesc, check, ptr
+from .lib import F, FF, FK, FN, K, MODE, OPT, FaceKernelDesc, GraphInfo, KernelDesc, check, ptr
 
 
 def _exchange_single(send):
@@ -269,6 +269,40 @@ class DeviceCsrLinearSystem:
         check(self.L.nalu_b200_reset_rows(self.h, int(nodes.numel()), ptr(nodes), int(begin_pos), int(end_pos),
                                           ptr(self.values), ptr(self.rhs), self._stream()), "reset_rows")
 
+    # ---- face/element boundary-condition algorithms (AssembleFaceElemSolverAlgorithm) ---------------------------------
+    def face_set(self, face_elem, face_ordinal):
+        """The locally owned faces of a boundary part: (local element, Hex8 face ordinal) pairs (host arrays)."""
+        return FaceSet(self, face_elem, face_ordinal)
+
+    def make_face_desc(self, kind, fields=None, face_fields=None, options=(), **scalars):
+        """fields: {nodal slot name: device tensor}; face_fields: {face field name: device tensor [n_faces][4][..]}"""
+        d = FaceKernelDesc()
+        d.kind = FK[kind]
+        opt = 0
+        for o in options:
+            opt |= _lib.OPT_MESH_MOVES if o == "mesh_moves" else OPT[o]
+        d.options = opt
+        d.include_divu = scalars.get("include_divu", 0.0)
+        d.dt = scalars.get("dt", 1.0)
+        d.gamma1 = scalars.get("gamma1", 1.0)
+        for name, v in (scalars.get("upw") or {}).items():
+            d.upw[_lib.UPW[name]] = float(v)
+        for name, t in (fields or {}).items():
+            if t is None or name not in FN:
+                continue
+            self._keep.append(t)
+            d.nodal[FN[name]] = t.data_ptr()
+        for name, t in (face_fields or {}).items():
+            self._keep.append(t)
+            d.face[FF[name]] = t.data_ptr()
+        return d
+
+    def assemble_face_elem(self, face_set, descs):
+        """AssembleFaceElemSolverAlgorithm::execute: every kernel of the list on every face of the set."""
+        arr = (FaceKernelDesc * len(descs))(*descs)
+        check(self.L.nalu_b200_assemble_face_elem(self.h, face_set.h, arr, len(descs), ptr(self.values), ptr(self.rhs),
+                                                  self._stream()), "assemble_face_elem")
+
     def mdot_scs(self, coords, density, velocity, out=None):
         import torch
         if out is None:
@@ -346,3 +380,39 @@ class DeviceCsrLinearSystem:
         for i in range(len(recv)):
             self.halo_unpack_add(i, rbufs[i])
         self._keep_halo = (sbufs, rbufs)
+
+
+class FaceSet:
+    """nalu_b200_face_set: the faces of one boundary part, coloured for the atomic-free scatter."""
+
+    def __init__(self, ls, face_elem, face_ordinal):
+        self.ls = ls
+        self.L = ls.L
+        fe = np.ascontiguousarray(face_elem, dtype=np.int32)
+        fo = np.ascontiguousarray(face_ordinal, dtype=np.int32)
+        assert fe.shape == fo.shape
+        self.n_faces = int(fe.size)
+        self.h = C.c_void_p()
+        check(self.L.nalu_b200_face_set_create(C.byref(self.h), ls.h, C.c_int64(fe.size), ptr(fe), ptr(fo)), "face_set_create")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.nalu_b200_face_set_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+    def num_colors(self):
+        n = C.c_int32()
+        check(self.L.nalu_b200_face_set_num_colors(self.h, C.byref(n)), "face_set_num_colors")
+        return n.value
+
+    def exposed_area(self, coords, out=None):
+        """ComputeGeometryBoundaryAlgorithm::execute: exposed_area_vector [n_faces][4][3] on the device"""
+        import torch
+        if out is None:
+            out = torch.empty((self.n_faces, 4, 3), dtype=torch.float64, device=coords.device)
+        check(self.L.nalu_b200_compute_exposed_area(self.ls.h, self.h, ptr(coords), ptr(out), self.ls._stream()),
+              "compute_exposed_area")
+        return out

@@ -206,3 +206,35 @@ def perturb_coords_hash(mesh: HexMesh, amplitude=0.125):
         out[:, d] = (x >> np.uint64(11)).astype(np.float64) * (2.0 / float(1 << 53)) - 1.0
     mesh.coords += amplitude * out
     return mesh
+
+
+# ---- boundary faces (sidesets) ---------------------------------------------------------------------------------------
+# Hex8 side -> element-local node ordinals (src/master_element/Hex8CVFEM.C:414-422; the STK / Exodus HEX_8 side table)
+HEX8_SIDE_NODES = np.array([[0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [0, 4, 7, 3], [0, 3, 2, 1], [4, 5, 6, 7]], dtype=np.int32)
+
+
+def exposed_faces(mesh: HexMesh):
+    """(face_elem, face_ordinal) of every element side that no other element of this mesh shares: the skin of a one-rank
+    mesh (what `generated:...|sideset:xXyYzZ` or an Exodus side set lists), ordered by (element, ordinal)."""
+    en = mesh.elem_nodes
+    ne = en.shape[0]
+    gid = mesh.node_gid[en[:, HEX8_SIDE_NODES]]          # [ne, 6, 4]
+    key = np.sort(gid.reshape(ne * 6, 4), axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    single = np.nonzero(cnt[inv.reshape(-1)] == 1)[0]
+    return (single // 6).astype(np.int32), (single % 6).astype(np.int32)
+
+
+def box_side_faces(mesh: HexMesh, side: str):
+    """The faces of sideset `side` (one of x X y Y z Z: low / high end of an axis, Ioss `generated:` naming) of a generated
+    box or of this rank's z-slab of it; empty on a slab that does not touch the side."""
+    b = mesh.box
+    assert b is not None and side in "xXyYzZ"
+    nx, ny, lz = b.nx, b.ny, b.nz
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(lz), indexing="ij")
+    e = (i + nx * (j + ny * k)).astype(np.int32)
+    # ordinal of the side facing -x, +x, -y, +y, -z, +z
+    sel, ordinal = {"x": (i == 0, 3), "X": (i == nx - 1, 1), "y": (j == 0, 0), "Y": (j == ny - 1, 2),
+                    "z": ((k == 0) & (b.k0 == 0), 4), "Z": ((k == lz - 1) & (b.k0 + lz == b.nz_global), 5)}[side]
+    fe = np.sort(e[sel])
+    return fe, np.full(fe.size, ordinal, dtype=np.int32)
