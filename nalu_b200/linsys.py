@@ -311,6 +311,12 @@ class DeviceCsrLinearSystem:
               "mdot_scs")
         return out
 
+    def solve(self, tol=1e-10, max_iter=1000):
+        """LinearSystem::solve (src/TpetraLinearSystem.C:1841-1926) on the device-resident CSR, one rank: returns
+        (solution tensor, iterations, relative residual); see nalu_b200/solve.py"""
+        from . import solve as _solve
+        return _solve.solve(self, tol=tol, max_iter=max_iter)
+
     def geometry_errors(self):
         f = C.c_int32()
         check(self.L.nalu_b200_geometry_errors(self.h, C.byref(f)), "geometry_errors")

@@ -1176,3 +1176,29 @@ def test_config4_lists_tiled_many_tiles_and_ranks(eq, tune):
     orc.load_complete()
     for r, ls in enumerate(systems):
         _compare_system(ls, orc, rank=r, sol_scale=3.0)  # tke, sdr <= 3
+
+
+def test_solver_handoff_device_solution_equals_oracle_solution():
+    """SURVEY 8f-3, the consumer of the path: the device-assembled momentum system [MomentumMass(lumped), MomentumAdvDiff]
+    solved in place on the device (cuSPARSE products through torch.sparse_csr, Jacobi-BiCGStab), against a direct sparse
+    solve (scipy) of the ORACLE-assembled system: the solutions agree, so the CSR the kernels leave in HBM is the matrix."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from nalu_b200 import mesh as M
+    m = perturbed_box(10, 9, 8)
+    st = State(m)
+    dev = st.to_device(_cuda())
+    bdf2 = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    klist = [("momentum_mass", ("lumped_mass",), bdf2), ("momentum_adv_diff", (), dict(include_divu=1.0))]
+    keep = []
+    orc = oracle.LinSys([m], 3)
+    orc.assemble_elem(0, [oracle_desc(st, k, o, keep, **s) for k, o, s in klist])
+    ls = _linsys(m, 3)
+    assert ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], overwrite=True) == 2
+    x, iters, res = ls.solve(tol=1e-12, max_iter=400)
+    assert res < 1e-11 and 0 < iters < 400, (iters, res)
+    n = orc.n_owned_rows(0)
+    A = sp.csr_matrix((orc.values(0), orc.colidx(0), orc.rowptr(0).astype(np.int64)), shape=(n, n))
+    xo = spla.spsolve(A.tocsc(), orc.rhs(0))
+    err = np.abs(x.cpu().numpy() - xo).max() / np.abs(xo).max()
+    assert err < 1e-9, err
