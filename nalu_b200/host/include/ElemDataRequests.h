@@ -49,6 +49,7 @@ public:
   void add_gathered_nodal_field(const stk::mesh::FieldBase &field, unsigned scalarsPerNode);
   void add_gathered_nodal_field(const stk::mesh::FieldBase &field, unsigned tensorDim1, unsigned tensorDim2);
   void add_face_field(const stk::mesh::FieldBase &field, unsigned scalarsPerFace);
+  void add_face_field(const stk::mesh::FieldBase &field, unsigned tensorDim1, unsigned tensorDim2);
   void add_ip_field(const stk::mesh::FieldBase &field, unsigned scalarsPerElement);
   void add_element_field(const stk::mesh::FieldBase &field, unsigned scalarsPerElement);
   void add_ip_field(const stk::mesh::FieldBase &field, unsigned tensorDim1, unsigned tensorDim2);

@@ -88,7 +88,9 @@ public:
   void buildFaceToNodeGraph(const stk::mesh::PartVector &) override { unsupported("buildFaceToNodeGraph"); }
   void buildEdgeToNodeGraph(const stk::mesh::PartVector &) override { unsupported("buildEdgeToNodeGraph"); }
   void buildReducedElemToNodeGraph(const stk::mesh::PartVector &) override { unsupported("buildReducedElemToNodeGraph"); }
-  void buildFaceElemToNodeGraph(const stk::mesh::PartVector &) override { unsupported("buildFaceElemToNodeGraph"); }
+  // TpetraLinearSystem.C:487-521: the element attached to each face of the parts; all elements of the rank mesh are
+  // connected through the element graph already, so this adds nothing to it
+  void buildFaceElemToNodeGraph(const stk::mesh::PartVector &parts) override;
   void buildNonConformalNodeGraph(const stk::mesh::PartVector &) override { unsupported("buildNonConformalNodeGraph"); }
   void buildOversetNodeGraph(const stk::mesh::PartVector &) override { unsupported("buildOversetNodeGraph"); }
   void finalizeLinearSystem() override;                                     // TpetraLinearSystem.C:1257-1353
@@ -111,6 +113,8 @@ public:
   // ---- what the element algorithm and the parity tests use -----------------------------------
   /** batched device scatter: every active kernel of one AssembleElemSolverAlgorithm in one launch */
   void assembleElemDevice(const nalu_b200_kernel_desc *descs, int n, bool overwrite);
+  /** every active kernel of one AssembleFaceElemSolverAlgorithm over the faces of a face set */
+  void assembleFaceElemDevice(const nalu_b200_face_set *faces, const nalu_b200_face_kernel_desc *descs, int n);
   void setTransport(const HaloTransport &t) { transport_ = t; }
   const nalu_b200_graph *graph() const { return graph_; }
   int numOwnedRows() const { return info_.n_owned_rows; }

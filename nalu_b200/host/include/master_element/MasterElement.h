@@ -16,6 +16,8 @@ public:
   virtual ~MasterElement() {}
   virtual const int *adjacentNodes() { throw std::runtime_error("adjacentNodes not implemented"); }
   virtual const int *ipNodeMap(int /*ordinal*/ = 0) { throw std::runtime_error("ipNodeMap not implemented"); }
+  virtual const int *side_node_ordinals(int /*sideOrdinal*/) { throw std::runtime_error("side_node_ordinals not implemented"); }
+  virtual int opposingNodes(const int /*ordinal*/, const int /*node*/) { throw std::runtime_error("opposingNodes not implemented"); }
   virtual void shape_fcn(double *) { throw std::runtime_error("shape_fcn not implemented"); }
   virtual void shifted_shape_fcn(double *) { throw std::runtime_error("shifted_shape_fcn not implemented"); }
   virtual void determinant(const int, const double *, double *, double *)
@@ -33,10 +35,26 @@ class HexSCS : public MasterElement {
 public:
   HexSCS();
   const int *adjacentNodes() override { return lrscv_; }
+  // boundary tables (Hex8CVFEM.C:288-300,381-393,414-422): face ip -> nearest node, side -> node ordinals, opposing node
+  const int *ipNodeMap(int ordinal = 0) override { return &faceNodes_[ordinal * 4]; }
+  const int *side_node_ordinals(int ordinal) override { return &faceNodes_[ordinal * 4]; }
+  int opposingNodes(const int ordinal, const int node) override { return oppNode_[ordinal * 4 + node]; }
   void shape_fcn(double *shpfc) override;         // [12][8], intgLoc_
   void shifted_shape_fcn(double *shpfc) override; // [12][8], intgLocShift_
 private:
   int lrscv_[24];
+  int faceNodes_[24], oppNode_[24];
+};
+
+// Quad3DSCS (src/master_element/Quad43DCVFEM.C:20-148): the face master element of a Hex8 side
+class Quad3DSCS : public MasterElement {
+public:
+  Quad3DSCS();
+  const int *ipNodeMap(int = 0) override { return ipNodeMap_; }
+  void shape_fcn(double *shpfc) override;         // [4][4], intgLoc_ (+-1/4)
+  void shifted_shape_fcn(double *shpfc) override; // [4][4], the nodes
+private:
+  int ipNodeMap_[4];
 };
 
 class HexSCV : public MasterElement {

@@ -29,12 +29,25 @@ namespace stk {
 
 struct topology {
   enum rank_t { NODE_RANK = 0, EDGE_RANK = 1, FACE_RANK = 2, ELEM_RANK = 3, ELEMENT_RANK = 3, INVALID_RANK = 256 };
-  enum topology_t { INVALID_TOPOLOGY = 0, NODE, HEX_8, HEX_27, QUAD_4_2D };
+  enum topology_t { INVALID_TOPOLOGY = 0, NODE, HEX_8, HEX_27, QUAD_4_2D, QUAD_4, HEXAHEDRON_8 = HEX_8 };
   topology(topology_t t = INVALID_TOPOLOGY) : t_(t) {}
   operator topology_t() const { return t_; }
-  unsigned num_nodes() const { return t_ == HEX_8 ? 8 : (t_ == HEX_27 ? 27 : (t_ == QUAD_4_2D ? 4 : (t_ == NODE ? 1 : 0))); }
-  rank_t rank() const { return t_ == NODE ? NODE_RANK : ELEM_RANK; }
-  std::string name() const { return t_ == HEX_8 ? "HEXAHEDRON_8" : (t_ == HEX_27 ? "HEXAHEDRON_27" : "UNSUPPORTED"); }
+  unsigned num_nodes() const
+  {
+    return t_ == HEX_8 ? 8 : (t_ == HEX_27 ? 27 : ((t_ == QUAD_4_2D || t_ == QUAD_4) ? 4 : (t_ == NODE ? 1 : 0)));
+  }
+  rank_t rank() const { return t_ == NODE ? NODE_RANK : (t_ == QUAD_4 ? FACE_RANK : ELEM_RANK); }
+  std::string name() const
+  {
+    return t_ == HEX_8 ? "HEXAHEDRON_8" : (t_ == HEX_27 ? "HEXAHEDRON_27" : (t_ == QUAD_4 ? "QUADRILATERAL_4" : "UNSUPPORTED"));
+  }
+  // HEX_8 side table (the side_node_ordinals of HexSCS, src/master_element/Hex8CVFEM.C:414-422)
+  template <typename It>
+  void face_node_ordinals(unsigned face, It out) const
+  {
+    static const int t[6][4] = {{0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {0, 4, 7, 3}, {0, 3, 2, 1}, {4, 5, 6, 7}};
+    for (int i = 0; i < 4; ++i) *out++ = t[face][i];
+  }
   topology_t t_;
 };
 
@@ -66,10 +79,23 @@ public:
   }
   bool has_explicit_nodes() const { return explicit_nodes_; }
   const std::vector<int32_t> &nodes() const { return nodes_; }
+  // A side-set part: its locally owned faces as (local element, face ordinal) -- what bulk.begin_elements(face) /
+  // begin_element_ordinals(face) give in the reference (include/AssembleFaceElemSolverAlgorithm.h:91-103) -- numbered
+  // first_face() .. first_face() + n in the rank's face numbering (the index of a FACE_RANK field).
+  void set_faces(const std::vector<int32_t> &elems, const std::vector<int32_t> &ordinals, size_t first_face)
+  {
+    face_elem_ = elems;
+    face_ord_ = ordinals;
+    first_face_ = first_face;
+  }
+  const std::vector<int32_t> &face_elems() const { return face_elem_; }
+  const std::vector<int32_t> &face_ordinals() const { return face_ord_; }
+  size_t first_face() const { return first_face_; }
 private:
   std::string name_;
   stk::topology topo_;
-  std::vector<int32_t> nodes_;
+  std::vector<int32_t> nodes_, face_elem_, face_ord_;
+  size_t first_face_ = 0;
   bool explicit_nodes_ = false;
 };
 typedef std::vector<Part *> PartVector;
@@ -141,6 +167,13 @@ public:
     for (Part *p : parts_) delete p;
   }
   unsigned spatial_dimension() const { return dim_; }
+  EntityRank side_rank() const { return topology::FACE_RANK; }
+  Part *get_part(const std::string &name) const
+  {
+    for (Part *p : parts_)
+      if (p->name() == name) return p;
+    return nullptr;
+  }
   Part &declare_part_with_topology(const std::string &name, stk::topology t)
   {
     parts_.push_back(new Part(name, t));
@@ -198,6 +231,11 @@ public:
   // Ioss `generated:nx x ny x nz` piece of this rank under the z-slab decomposition
   // (unit_tests/UnitTestUtils.C:30-35): ids 1+i+(nx+1)j+(nx+1)(ny+1)k, unit spacing
   void fill_generated_mesh(int nx, int ny, int nz, Part &block, const std::string &coords_name = "coordinates");
+  // `|sideset:xXyYzZ` of the Ioss generated mesh: one QUAD_4 part "surface_<k>" per letter, in the order given (x / X: low /
+  // high x side, ...), holding this rank's faces of that side, plus "all_surfaces" = their union; sizes the FACE_RANK
+  // fields.  Call after fill_generated_mesh.
+  void create_generated_sidesets(const std::string &sides);
+  size_t num_faces() const { return num_faces_; }
   size_t num_nodes() const { return node_gid_.size(); }
   size_t num_elems() const { return conn_.size() / 8; }
   const std::vector<int64_t> &node_ids() const { return node_gid_; }    // naluGlobalId, 1-based
@@ -216,6 +254,8 @@ private:
   std::vector<int32_t> node_owner_, conn_;
   int64_t elem_gid0_ = 1;
   int box_[3] = {0, 0, 0};
+  int k0_ = 0, nz_global_ = 0;
+  size_t num_faces_ = 0;
   Part *block_ = nullptr;
 };
 

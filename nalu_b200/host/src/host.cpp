@@ -1,5 +1,6 @@
 // host.cpp -- host side of the drop-in boundary: the reference's registration API lowered onto the C ABI.
 #include "../include/AssembleElemSolverAlgorithm.h"
+#include "../include/AssembleFaceElemSolverAlgorithm.h"
 #include "../include/kernel/ContinuityAdvElemKernel.h"
 #include "../include/kernel/MassElemKernels.h"
 #include "../include/kernel/MomentumAdvDiffElemKernel.h"
@@ -82,9 +83,12 @@ void BulkData::fill_generated_mesh(int nx, int ny, int nzg, Part &block, const s
       }
   elem_gid0_ = 1 + int64_t(nx) * ny * k0;
   box_[0] = nx; box_[1] = ny; box_[2] = lz;
+  k0_ = k0;
+  nz_global_ = nzg;
   block_ = &block;
   for (FieldBase *f : meta_.fields_)
-    f->set_num_entities(f->entity_rank() == topology::NODE_RANK ? num_nodes() : num_elems());
+    f->set_num_entities(f->entity_rank() == topology::NODE_RANK ? num_nodes()
+                                                                 : (f->entity_rank() == topology::FACE_RANK ? num_faces_ : num_elems()));
   if (Field<double> *c = meta_.get_field<double>(topology::NODE_RANK, coords_name)) {
     STK_ThrowRequireMsg(c->max_size() == 3, "coordinates field must have 3 scalars per node");
     double *x = c->host_data();
@@ -98,6 +102,42 @@ void BulkData::fill_generated_mesh(int nx, int ny, int nzg, Part &block, const s
         }
     c->modify_on_host();
   }
+}
+
+void BulkData::create_generated_sidesets(const std::string &sides)
+{
+  STK_ThrowRequireMsg(box_[0] > 0, "create_generated_sidesets: fill_generated_mesh first");
+  const int nx = box_[0], ny = box_[1], lz = box_[2];
+  std::vector<int32_t> all_e, all_o;
+  int k = 0;
+  for (char c : sides) {
+    ++k;
+    std::vector<int32_t> fe, fo;
+    auto add = [&](int i, int j, int kk, int ord) {
+      fe.push_back(i + nx * (j + ny * kk));
+      fo.push_back(ord);
+    };
+    // element side facing -x: 3, +x: 1, -y: 0, +y: 2, -z: 4, +z: 5 (Hex8CVFEM.C:414-422)
+    for (int kk = 0; kk < lz; ++kk)
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+          if (c == 'x' && i == 0) add(i, j, kk, 3);
+          if (c == 'X' && i == nx - 1) add(i, j, kk, 1);
+          if (c == 'y' && j == 0) add(i, j, kk, 0);
+          if (c == 'Y' && j == ny - 1) add(i, j, kk, 2);
+          if (c == 'z' && kk == 0 && k0_ == 0) add(i, j, kk, 4);
+          if (c == 'Z' && kk == lz - 1 && k0_ + lz == nz_global_) add(i, j, kk, 5);
+        }
+    Part &p = meta_.declare_part_with_topology("surface_" + std::to_string(k), stk::topology::QUAD_4);
+    p.set_faces(fe, fo, all_e.size());
+    all_e.insert(all_e.end(), fe.begin(), fe.end());
+    all_o.insert(all_o.end(), fo.begin(), fo.end());
+  }
+  Part &all = meta_.declare_part_with_topology("all_surfaces", stk::topology::QUAD_4);
+  all.set_faces(all_e, all_o, 0);
+  num_faces_ = all_e.size();
+  for (FieldBase *f : meta_.fields_)
+    if (f->entity_rank() == topology::FACE_RANK) f->set_num_entities(num_faces_);
 }
 
 Entity BulkData::get_entity(EntityRank rank, int64_t id) const
@@ -174,6 +214,13 @@ void ElemDataRequests::add_face_field(const stk::mesh::FieldBase &field, unsigne
                                                                                  << field.entity_rank());
   add_ip_field(field, scalarsPerFace);
 }
+void ElemDataRequests::add_face_field(const stk::mesh::FieldBase &field, unsigned d1, unsigned d2)
+{
+  STK_ThrowRequireMsg(field.entity_rank() == stk::topology::FACE_RANK || field.entity_rank() == stk::topology::EDGE_RANK,
+                      "ElemDataRequests ERROR, add_face_field called with field " << field.name() << " which has entity-rank=="
+                                                                                 << field.entity_rank());
+  add_ip_field(field, d1, d2);
+}
 void ElemDataRequests::add_element_field(const stk::mesh::FieldBase &field, unsigned scalarsPerElement)
 {
   STK_ThrowRequireMsg(field.entity_rank() == stk::topology::ELEM_RANK,
@@ -243,7 +290,40 @@ HexSCS::HexSCS()
   nodesPerElement_ = 8;
   numIntPoints_ = 12;
   std::memcpy(lrscv_, kLrscv, sizeof(kLrscv));
+  static const int faceNodes[24] = {0, 1, 5, 4, 1, 2, 6, 5, 2, 3, 7, 6, 0, 4, 7, 3, 0, 3, 2, 1, 4, 5, 6, 7};
+  std::memcpy(faceNodes_, faceNodes, sizeof(faceNodes));
+  // the node across the element from face node k: the edge (opposing, nearest) is the one that leaves the face
+  for (int f = 0; f < 6; ++f)
+    for (int k = 0; k < 4; ++k) {
+      const int n = faceNodes[4 * f + k];
+      int opp = -1;
+      for (int e = 0; e < 12 && opp < 0; ++e) {
+        const int a = kLrscv[2 * e], b = kLrscv[2 * e + 1];
+        if (a != n && b != n) continue;
+        const int o = a == n ? b : a;
+        bool on_face = false;
+        for (int q = 0; q < 4; ++q) on_face = on_face || faceNodes[4 * f + q] == o;
+        if (!on_face) opp = o;
+      }
+      oppNode_[4 * f + k] = opp;
+    }
 }
+Quad3DSCS::Quad3DSCS()
+{
+  nodesPerElement_ = 4;
+  numIntPoints_ = 4;
+  for (int i = 0; i < 4; ++i) ipNodeMap_[i] = i;
+}
+namespace {
+void quad_shape(double q, double *shp)
+{
+  static const double sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
+  for (int p = 0; p < 4; ++p)
+    for (int n = 0; n < 4; ++n) shp[4 * p + n] = (0.5 + sx[n] * sx[p] * q) * (0.5 + sy[n] * sy[p] * q);
+}
+} // namespace
+void Quad3DSCS::shape_fcn(double *shpfc) { quad_shape(0.25, shpfc); }
+void Quad3DSCS::shifted_shape_fcn(double *shpfc) { quad_shape(0.5, shpfc); }
 void HexSCS::shape_fcn(double *shpfc)
 {
   double loc[36];
@@ -277,7 +357,9 @@ void HexSCV::shifted_shape_fcn(double *shpfc)
 MasterElement *MasterElementRepo::get_surface_master_element(const stk::topology &theTopo)
 {
   static HexSCS scs;
-  if (theTopo.t_ != stk::topology::HEX_8) throw std::runtime_error("only Hex8 master elements are on this path");
+  static Quad3DSCS quad;
+  if (theTopo.t_ == stk::topology::QUAD_4) return &quad;
+  if (theTopo.t_ != stk::topology::HEX_8) throw std::runtime_error("only Hex8 / Quad4-face master elements are on this path");
   return &scs;
 }
 MasterElement *MasterElementRepo::get_volume_master_element(const stk::topology &theTopo)
@@ -1159,6 +1241,307 @@ NALU_B200_DECLARE_KERNEL(MomentumMassElemKernel)
 NALU_B200_DECLARE_KERNEL(ContinuityMassElemKernel)
 NALU_B200_DECLARE_KERNEL(ScalarMassElemKernel)
 
+
+// ================================================================================================
+// Face/element boundary-condition kernels and AssembleFaceElemSolverAlgorithm
+// ================================================================================================
+void FaceElemKernel::clear(nalu_b200_face_kernel_desc &d) { std::memset(&d, 0, sizeof(d)); d.dt = 1.0; d.gamma1 = 1.0; }
+void FaceElemKernel::bind(nalu_b200_face_kernel_desc &d, int slot, stk::mesh::FieldBase *f)
+{
+  if (!f) throw std::runtime_error("face kernel field not found in MetaData");
+  d.nodal[slot] = f->device_data();
+}
+void FaceElemKernel::bind_face(nalu_b200_face_kernel_desc &d, int slot, stk::mesh::FieldBase *f, size_t first_face)
+{
+  if (!f) throw std::runtime_error("face kernel face field not found in MetaData");
+  d.face[slot] = f->device_data() + first_face * f->max_size();
+}
+namespace {
+void peclet_fill(nalu_b200_face_kernel_desc &d, const PecletFunctionSpec &p, double alphaUpw, double hoUpwind)
+{
+  d.upw[NALU_UPW_ALPHA_UPW] = alphaUpw;
+  d.upw[NALU_UPW_HO_UPWIND] = hoUpwind;
+  d.upw[NALU_UPW_HYBRID_FACTOR] = p.hybridFactor;
+  d.upw[NALU_UPW_TANH_TRANS] = p.c1;
+  d.upw[NALU_UPW_TANH_WIDTH] = p.c2;
+  if (p.tanh_form) d.options |= NALU_OPT_PECLET_TANH;
+}
+template <typename T>
+T *need(T *f, const char *kernel, const char *field)
+{
+  STK_ThrowRequireMsg(f, kernel << ": field " << field << " not registered");
+  return f;
+}
+} // namespace
+
+// ---- src/kernel/MomentumSymmetryElemKernel.C:23-63
+template <typename BcAlgTraits>
+MomentumSymmetryElemKernel<BcAlgTraits>::MomentumSymmetryElemKernel(const stk::mesh::MetaData &metaData, const SolutionOptions &solnOpts,
+                                                                   VectorFieldType *velocity, ScalarFieldType *viscosity,
+                                                                   ElemDataRequests &faceDataPreReqs, ElemDataRequests &elemDataPreReqs)
+    : viscosity_(viscosity), includeDivU_(solnOpts.includeDivU_), shiftedGradOp_(solnOpts.get_shifted_grad_op(velocity->name())),
+      meSCS_(MasterElementRepo::get_surface_master_element(BcAlgTraits::elemTopo_))
+{
+  velocityNp1_ = &(velocity->field_of_state(stk::mesh::StateNP1));
+  coordinates_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name()), name(), "coordinates");
+  exposedAreaVec_ = need(metaData.get_field<double>(metaData.side_rank(), "exposed_area_vector"), name(), "exposed_area_vector");
+  MasterElement *meFC = MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_);
+  faceDataPreReqs.add_cvfem_face_me(meFC);
+  elemDataPreReqs.add_cvfem_surface_me(meSCS_);
+  faceDataPreReqs.add_gathered_nodal_field(*viscosity_, 1);
+  faceDataPreReqs.add_face_field(*exposedAreaVec_, BcAlgTraits::numFaceIp_, BcAlgTraits::nDim_);
+  elemDataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  elemDataPreReqs.add_gathered_nodal_field(*velocityNp1_, BcAlgTraits::nDim_);
+  elemDataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_FACE_GRAD_OP : SCS_FACE_GRAD_OP, CURRENT_COORDINATES);
+  get_face_shape_fn_data<BcAlgTraits>([&](double *ptr) { meFC->shape_fcn(ptr); }, vf_shape_function_);
+}
+template <typename BcAlgTraits>
+bool MomentumSymmetryElemKernel<BcAlgTraits>::device_face_descriptor(nalu_b200_face_kernel_desc &d, size_t first_face)
+{
+  clear(d);
+  d.kind = NALU_FK_MOMENTUM_SYMMETRY;
+  d.options = shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0;
+  d.include_divu = includeDivU_;
+  bind(d, NALU_FN_COORDINATES, coordinates_);
+  bind(d, NALU_FN_VELOCITY, velocityNp1_);
+  bind(d, NALU_FN_VISCOSITY, viscosity_);
+  bind_face(d, NALU_FF_EXPOSED_AREA_VEC, exposedAreaVec_, first_face);
+  return true;
+}
+
+// ---- src/kernel/MomentumOpenAdvDiffElemKernel.C:26-100
+template <typename BcAlgTraits>
+MomentumOpenAdvDiffElemKernel<BcAlgTraits>::MomentumOpenAdvDiffElemKernel(const stk::mesh::MetaData &metaData, const SolutionOptions &solnOpts,
+                                                                         EquationSystem *eqSystem, VectorFieldType *velocity,
+                                                                         GenericFieldType *Gjui, ScalarFieldType *viscosity,
+                                                                         ElemDataRequests &faceDataPreReqs,
+                                                                         ElemDataRequests &elemDataPreReqs)
+    : viscosity_(viscosity), Gjui_(Gjui), alphaUpw_(solnOpts.get_alpha_upw_factor("velocity")), om_alphaUpw_(1.0 - alphaUpw_),
+      hoUpwind_(solnOpts.get_upw_factor("velocity")), includeDivU_(solnOpts.includeDivU_),
+      meshVelocityCorrection_(solnOpts.does_mesh_move() ? 1.0 : 0.0), shiftedGradOp_(solnOpts.get_shifted_grad_op(velocity->name())),
+      faceIpNodeMap_(MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_)->ipNodeMap()),
+      meSCS_(MasterElementRepo::get_surface_master_element(BcAlgTraits::elemTopo_)),
+      pecletFunction_(make_peclet_spec(eqSystem, velocity->name()))
+{
+  velocityNp1_ = &(velocity->field_of_state(stk::mesh::StateNP1));
+  if (solnOpts.does_mesh_move()) {
+    velocityRTM_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "velocity_rtm"), name(), "velocity_rtm");
+    meshVelocity_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "mesh_velocity"), name(), "mesh_velocity");
+  } else {
+    velocityRTM_ = velocityNp1_;
+    meshVelocity_ = velocityNp1_;
+  }
+  coordinates_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name()), name(), "coordinates");
+  density_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "density"), name(), "density");
+  exposedAreaVec_ = need(metaData.get_field<double>(metaData.side_rank(), "exposed_area_vector"), name(), "exposed_area_vector");
+  openMassFlowRate_ = need(metaData.get_field<double>(metaData.side_rank(), "open_mass_flow_rate"), name(), "open_mass_flow_rate");
+  velocityBc_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "open_velocity_bc"), name(), "open_velocity_bc");
+  MasterElement *meFC = MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_);
+  faceDataPreReqs.add_cvfem_face_me(meFC);
+  elemDataPreReqs.add_cvfem_surface_me(meSCS_);
+  faceDataPreReqs.add_gathered_nodal_field(*density_, 1);
+  faceDataPreReqs.add_gathered_nodal_field(*viscosity_, 1);
+  faceDataPreReqs.add_gathered_nodal_field(*velocityNp1_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_gathered_nodal_field(*meshVelocity_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_gathered_nodal_field(*velocityBc_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_gathered_nodal_field(*Gjui_, BcAlgTraits::nDim_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  faceDataPreReqs.add_face_field(*exposedAreaVec_, BcAlgTraits::numFaceIp_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_face_field(*openMassFlowRate_, BcAlgTraits::numFaceIp_);
+  elemDataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  elemDataPreReqs.add_gathered_nodal_field(*velocityNp1_, BcAlgTraits::nDim_);
+  elemDataPreReqs.add_gathered_nodal_field(*velocityRTM_, BcAlgTraits::nDim_);
+  elemDataPreReqs.add_gathered_nodal_field(*viscosity_, 1);
+  elemDataPreReqs.add_gathered_nodal_field(*density_, 1);
+  elemDataPreReqs.add_master_element_call(shiftedGradOp_ ? SCS_SHIFTED_FACE_GRAD_OP : SCS_FACE_GRAD_OP, CURRENT_COORDINATES);
+  get_face_shape_fn_data<BcAlgTraits>([&](double *ptr) { meFC->shape_fcn(ptr); }, vf_shape_function_);
+  skewSymmetric_ = solnOpts.get_skew_symmetric(velocity->name());
+  get_face_shape_fn_data<BcAlgTraits>([&](double *ptr) { skewSymmetric_ ? meFC->shifted_shape_fcn(ptr) : meFC->shape_fcn(ptr); },
+                                      vf_adv_shape_function_);
+}
+template <typename BcAlgTraits>
+bool MomentumOpenAdvDiffElemKernel<BcAlgTraits>::device_face_descriptor(nalu_b200_face_kernel_desc &d, size_t first_face)
+{
+  clear(d);
+  d.kind = NALU_FK_MOMENTUM_OPEN_ADV_DIFF;
+  d.options = (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0) | (skewSymmetric_ ? NALU_OPT_SKEW_SYMMETRIC : 0) |
+              (meshVelocityCorrection_ != 0.0 ? NALU_OPT_MESH_MOVES : 0);
+  d.include_divu = includeDivU_;
+  peclet_fill(d, pecletFunction_, alphaUpw_, hoUpwind_);
+  bind(d, NALU_FN_COORDINATES, coordinates_);
+  bind(d, NALU_FN_VELOCITY, velocityNp1_);
+  if (meshVelocityCorrection_ != 0.0) {
+    bind(d, NALU_FN_VELOCITY_RTM, velocityRTM_);
+    bind(d, NALU_FN_MESH_VELOCITY, meshVelocity_);
+  }
+  bind(d, NALU_FN_VISCOSITY, viscosity_);
+  bind(d, NALU_FN_DENSITY, density_);
+  bind(d, NALU_FN_GJUI, Gjui_);
+  bind(d, NALU_FN_VELOCITY_BC, velocityBc_);
+  bind_face(d, NALU_FF_EXPOSED_AREA_VEC, exposedAreaVec_, first_face);
+  bind_face(d, NALU_FF_OPEN_MASS_FLOW_RATE, openMassFlowRate_, first_face);
+  return true;
+}
+
+// ---- src/kernel/ScalarOpenAdvElemKernel.C:25-82
+template <typename BcAlgTraits>
+ScalarOpenAdvElemKernel<BcAlgTraits>::ScalarOpenAdvElemKernel(const stk::mesh::MetaData &metaData, const SolutionOptions &solnOpts,
+                                                             EquationSystem *eqSystem, ScalarFieldType *scalarQ,
+                                                             ScalarFieldType *bcScalarQ, VectorFieldType *Gjq,
+                                                             ScalarFieldType *diffFluxCoeff, ElemDataRequests &faceDataPreReqs,
+                                                             ElemDataRequests &elemDataPreReqs)
+    : scalarQ_(scalarQ), bcScalarQ_(bcScalarQ), Gjq_(Gjq), diffFluxCoeff_(diffFluxCoeff),
+      alphaUpw_(solnOpts.get_alpha_upw_factor(scalarQ->name())), om_alphaUpw_(1.0 - alphaUpw_),
+      hoUpwind_(solnOpts.get_upw_factor(scalarQ->name())),
+      faceIpNodeMap_(MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_)->ipNodeMap()),
+      meSCS_(MasterElementRepo::get_surface_master_element(BcAlgTraits::elemTopo_)),
+      pecletFunction_(make_peclet_spec(eqSystem, scalarQ->name()))
+{
+  velocityRTM_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.does_mesh_move() ? "velocity_rtm" : "velocity"),
+                      name(), "velocity");
+  coordinates_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name()), name(), "coordinates");
+  density_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "density"), name(), "density");
+  openMassFlowRate_ = need(metaData.get_field<double>(metaData.side_rank(), "open_mass_flow_rate"), name(), "open_mass_flow_rate");
+  MasterElement *meFC = MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_);
+  faceDataPreReqs.add_cvfem_face_me(meFC);
+  elemDataPreReqs.add_cvfem_surface_me(meSCS_);
+  faceDataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  faceDataPreReqs.add_gathered_nodal_field(*Gjq_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_gathered_nodal_field(*scalarQ_, 1);
+  faceDataPreReqs.add_gathered_nodal_field(*bcScalarQ_, 1);
+  faceDataPreReqs.add_face_field(*openMassFlowRate_, BcAlgTraits::numFaceIp_);
+  elemDataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  elemDataPreReqs.add_gathered_nodal_field(*velocityRTM_, BcAlgTraits::nDim_);
+  elemDataPreReqs.add_gathered_nodal_field(*diffFluxCoeff_, 1);
+  elemDataPreReqs.add_gathered_nodal_field(*density_, 1);
+  skewSymmetric_ = solnOpts.get_skew_symmetric(scalarQ_->name());
+  get_face_shape_fn_data<BcAlgTraits>([&](double *ptr) { skewSymmetric_ ? meFC->shifted_shape_fcn(ptr) : meFC->shape_fcn(ptr); },
+                                      vf_adv_shape_function_);
+}
+template <typename BcAlgTraits>
+bool ScalarOpenAdvElemKernel<BcAlgTraits>::device_face_descriptor(nalu_b200_face_kernel_desc &d, size_t first_face)
+{
+  clear(d);
+  d.kind = NALU_FK_SCALAR_OPEN_ADV;
+  d.options = skewSymmetric_ ? NALU_OPT_SKEW_SYMMETRIC : 0;
+  peclet_fill(d, pecletFunction_, alphaUpw_, hoUpwind_);
+  bind(d, NALU_FN_COORDINATES, coordinates_);
+  bind(d, NALU_FN_VELOCITY, velocityRTM_);
+  bind(d, NALU_FN_VISCOSITY, diffFluxCoeff_);
+  bind(d, NALU_FN_DENSITY, density_);
+  bind(d, NALU_FN_SCALARQ, scalarQ_);
+  bind(d, NALU_FN_BC_SCALARQ, bcScalarQ_);
+  bind(d, NALU_FN_GJQ, Gjq_);
+  bind_face(d, NALU_FF_OPEN_MASS_FLOW_RATE, openMassFlowRate_, first_face);
+  return true;
+}
+
+// ---- src/kernel/ContinuityOpenElemKernel.C:25-97
+template <typename BcAlgTraits>
+ContinuityOpenElemKernel<BcAlgTraits>::ContinuityOpenElemKernel(const stk::mesh::MetaData &metaData, const SolutionOptions &solnOpts,
+                                                               ElemDataRequests &faceDataPreReqs, ElemDataRequests &elemDataPreReqs)
+    : shiftedGradOp_(solnOpts.get_shifted_grad_op("pressure")), reducedSensitivities_(solnOpts.cvfemReducedSensPoisson_),
+      shiftMdot_(solnOpts.cvfemShiftMdot_), meSCS_(MasterElementRepo::get_surface_master_element(BcAlgTraits::elemTopo_))
+{
+  velocityRTM_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.does_mesh_move() ? "velocity_rtm" : "velocity"),
+                      name(), "velocity");
+  Gpdx_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "dpdx"), name(), "dpdx");
+  coordinates_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name()), name(), "coordinates");
+  pressure_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "pressure"), name(), "pressure");
+  pressureBc_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "pressure_bc"), name(), "pressure_bc");
+  density_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "density"), name(), "density");
+  exposedAreaVec_ = need(metaData.get_field<double>(metaData.side_rank(), "exposed_area_vector"), name(), "exposed_area_vector");
+  dynamicPressure_ = need(metaData.get_field<double>(metaData.side_rank(), "dynamic_pressure"), name(), "dynamic_pressure");
+  MasterElement *meFC = MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_);
+  faceDataPreReqs.add_cvfem_face_me(meFC);
+  elemDataPreReqs.add_cvfem_surface_me(meSCS_);
+  faceDataPreReqs.add_gathered_nodal_field(*pressure_, 1);
+  faceDataPreReqs.add_gathered_nodal_field(*pressureBc_, 1);
+  faceDataPreReqs.add_gathered_nodal_field(*density_, 1);
+  faceDataPreReqs.add_gathered_nodal_field(*velocityRTM_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_gathered_nodal_field(*Gpdx_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_face_field(*exposedAreaVec_, BcAlgTraits::numFaceIp_, BcAlgTraits::nDim_);
+  faceDataPreReqs.add_face_field(*dynamicPressure_, BcAlgTraits::numFaceIp_);
+  faceDataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  elemDataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  elemDataPreReqs.add_gathered_nodal_field(*pressure_, 1);
+  if (!shiftedGradOp_ || !reducedSensitivities_) elemDataPreReqs.add_master_element_call(SCS_FACE_GRAD_OP, CURRENT_COORDINATES);
+  if (shiftedGradOp_ || reducedSensitivities_) elemDataPreReqs.add_master_element_call(SCS_SHIFTED_FACE_GRAD_OP, CURRENT_COORDINATES);
+  get_face_shape_fn_data<BcAlgTraits>([&](double *ptr) { shiftMdot_ ? meFC->shifted_shape_fcn(ptr) : meFC->shape_fcn(ptr); },
+                                      vf_shape_function_);
+}
+template <typename BcAlgTraits>
+void ContinuityOpenElemKernel<BcAlgTraits>::setup(const TimeIntegrator &timeIntegrator)
+{
+  dt_ = timeIntegrator.get_time_step();
+  gamma1_ = timeIntegrator.get_gamma1();
+}
+template <typename BcAlgTraits>
+bool ContinuityOpenElemKernel<BcAlgTraits>::device_face_descriptor(nalu_b200_face_kernel_desc &d, size_t first_face)
+{
+  clear(d);
+  d.kind = NALU_FK_CONTINUITY_OPEN;
+  d.options = (shiftedGradOp_ ? NALU_OPT_SHIFTED_GRAD_OP : 0) | (reducedSensitivities_ ? NALU_OPT_REDUCED_SENS : 0) |
+              (shiftMdot_ ? NALU_OPT_SHIFT_MDOT : 0);
+  d.dt = dt_;
+  d.gamma1 = gamma1_;
+  bind(d, NALU_FN_COORDINATES, coordinates_);
+  bind(d, NALU_FN_VELOCITY, velocityRTM_);
+  bind(d, NALU_FN_DENSITY, density_);
+  bind(d, NALU_FN_PRESSURE, pressure_);
+  bind(d, NALU_FN_PRESSURE_BC, pressureBc_);
+  bind(d, NALU_FN_DPDX, Gpdx_);
+  bind_face(d, NALU_FF_EXPOSED_AREA_VEC, exposedAreaVec_, first_face);
+  bind_face(d, NALU_FF_DYNAMIC_PRESSURE, dynamicPressure_, first_face);
+  return true;
+}
+template class MomentumSymmetryElemKernel<AlgTraitsQuad4Hex8>;
+template class MomentumOpenAdvDiffElemKernel<AlgTraitsQuad4Hex8>;
+template class ScalarOpenAdvElemKernel<AlgTraitsQuad4Hex8>;
+template class ContinuityOpenElemKernel<AlgTraitsQuad4Hex8>;
+
+// ---- src/AssembleFaceElemSolverAlgorithm.C:48-108
+AssembleFaceElemSolverAlgorithm::AssembleFaceElemSolverAlgorithm(Realm &realm, stk::mesh::Part *part, EquationSystem *eqSystem,
+                                                                 unsigned nodesPerFace, unsigned nodesPerElem, bool interleaveMEViews)
+    : SolverAlgorithm(realm, part, eqSystem), numDof_(eqSystem->linsys_->numDof()), nodesPerFace_(nodesPerFace),
+      nodesPerElem_(nodesPerElem), rhsSize_(nodesPerFace * eqSystem->linsys_->numDof()), interleaveMEViews_(interleaveMEViews)
+{
+}
+AssembleFaceElemSolverAlgorithm::~AssembleFaceElemSolverAlgorithm()
+{
+  for (nalu_b200_face_set *fs : faceSets_) nalu_b200_face_set_destroy(fs);
+}
+void AssembleFaceElemSolverAlgorithm::initialize_connectivity() { eqSystem_->linsys_->buildFaceElemToNodeGraph(partVec_); }
+void AssembleFaceElemSolverAlgorithm::execute()
+{
+  for (Kernel *k : activeKernels_) k->setup(*realm_.timeIntegrator_);
+  DeviceCsrLinearSystem *ls = dynamic_cast<DeviceCsrLinearSystem *>(eqSystem_->linsys_);
+  if (!ls) throw std::runtime_error("AssembleFaceElemSolverAlgorithm: the device path needs a DeviceCsrLinearSystem");
+  STK_ThrowRequireMsg(nodesPerFace_ == 4 && nodesPerElem_ == 8,
+                      "AssembleFaceElemSolverAlgorithm expected nodesPerEntity_ = 4 (Quad4 faces of Hex8 elements), got " << nodesPerFace_);
+  if (activeKernels_.empty()) return;
+  if (faceSets_.empty()) {
+    STK_ThrowRequireMsg(ls->graph(), "AssembleFaceElemSolverAlgorithm::execute before finalizeLinearSystem");
+    for (stk::mesh::Part *part : partVec_) {
+      nalu_b200_face_set *fs = nullptr;
+      check(nalu_b200_face_set_create(&fs, ls->graph(), int64_t(part->face_elems().size()), part->face_elems().data(),
+                                      part->face_ordinals().data()),
+            "face_set_create");
+      faceSets_.push_back(fs);
+    }
+  }
+  for (size_t ip = 0; ip < partVec_.size(); ++ip) {
+    std::vector<nalu_b200_face_kernel_desc> descs(activeKernels_.size());
+    for (size_t i = 0; i < activeKernels_.size(); ++i) {
+      FaceElemKernel *fk = dynamic_cast<FaceElemKernel *>(activeKernels_[i]);
+      if (!fk || !fk->device_face_descriptor(descs[i], partVec_[ip]->first_face()))
+        throw std::runtime_error(std::string("kernel ") + activeKernels_[i]->name() +
+                                 " has no face/element device form; this path has no CPU fallback");
+    }
+    ls->assembleFaceElemDevice(faceSets_[ip], descs.data(), int(descs.size()));
+  }
+}
+
 // ================================================================================================
 // Algorithms
 // ================================================================================================
@@ -1277,6 +1660,17 @@ void DeviceCsrLinearSystem::buildElemToNodeGraph(const stk::mesh::PartVector &)
 {
   beginLinearSystemConstruction();
   elemGraphRequested_ = true;
+}
+void DeviceCsrLinearSystem::buildFaceElemToNodeGraph(const stk::mesh::PartVector &)
+{
+  // TpetraLinearSystem::buildFaceElemToNodeGraph (src/TpetraLinearSystem.C:487-521) connects the nodes of the element
+  // attached to each face: a subset of the element graph, which this system always holds
+  beginLinearSystemConstruction();
+  elemGraphRequested_ = true;
+}
+void DeviceCsrLinearSystem::assembleFaceElemDevice(const nalu_b200_face_set *faces, const nalu_b200_face_kernel_desc *descs, int n)
+{
+  check(nalu_b200_assemble_face_elem(graph_, faces, descs, n, d_values_, d_rhs_, nullptr), "assemble_face_elem");
 }
 void DeviceCsrLinearSystem::finalizeLinearSystem()
 {

@@ -9,6 +9,7 @@
 //   unit_tests <golden_dir> cpu     registration / error-convention tests, no device needed
 //   unit_tests <golden_dir> gpu     everything (runs the CUDA path through the C ABI)
 #include "AssembleElemSolverAlgorithm.h"
+#include "AssembleFaceElemSolverAlgorithm.h"
 #include "ScratchViews.h"
 #include "kernel/ContinuityAdvElemKernel.h"
 #include "kernel/KernelBuilder.h"
@@ -848,6 +849,249 @@ static void test_two_kernels_one_algorithm()
   EXPECT_TRUE(re <= 1e-12 * rs);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Face/element boundary-condition algorithm (unit_tests/kernels/UnitTestFaceElemBasic.C)
+// ---------------------------------------------------------------------------------------------------
+// Hex8ElementWithBCFields (unit_tests/UnitTestUtils.h:181-256): one reference element, every side in "all_surfaces",
+// the fields the BC kernels read, initialised to the fixture's constants (density is left zero-initialised there; 1 here
+// so that the entrainment velocity of the open kernel is finite and the results can be checked)
+struct Hex8ElementWithBCFields {
+  Hex8ElementWithBCFields(int n = 1) : meta_(3), bulk_(std::make_shared<stk::mesh::BulkData>(meta_))
+  {
+    block_ = &meta_.declare_part_with_topology("block_1", stk::topology::HEX_8);
+    auto node = [&](const char *name, unsigned scalars, double init) {
+      auto *f = &meta_.declare_field<double>(stk::topology::NODE_RANK, name);
+      stk::mesh::put_field_on_mesh(*f, *block_, scalars);
+      inits_.push_back({f, init});
+      return f;
+    };
+    coordinates_ = node("coordinates", 3, 0.0);
+    velocity_ = node("velocity", 3, 1.0);
+    density_ = node("density", 1, 1.0);
+    viscosity_ = node("viscosity", 1, 1.0);
+    bcVelocityOpen_ = node("open_velocity_bc", 3, 1.0);
+    Gjui_ = node("dudx", 9, 1.0);
+    scalarQ_ = node("scalar_q", 1, 1.0);
+    bcScalarQ_ = node("bc_scalar_q", 1, 1.0);
+    Gjq_ = node("Gjq", 3, 1.0);
+    pressure_ = node("pressure", 1, 0.0);
+    pressureBc_ = node("pressure_bc", 1, 0.0);
+    dpdx_ = node("dpdx", 3, 0.0);
+    exposedAreaVec_ = &meta_.declare_field<double>(meta_.side_rank(), "exposed_area_vector");
+    openMdot_ = &meta_.declare_field<double>(meta_.side_rank(), "open_mass_flow_rate");
+    dynamicP_ = &meta_.declare_field<double>(meta_.side_rank(), "dynamic_pressure");
+    stk::mesh::put_field_on_mesh(*exposedAreaVec_, *block_, 12);
+    stk::mesh::put_field_on_mesh(*openMdot_, *block_, 4);
+    stk::mesh::put_field_on_mesh(*dynamicP_, *block_, 4);
+    bulk_->fill_generated_mesh(n, n, n, *block_);
+    bulk_->create_generated_sidesets("xXyYzZ");
+    for (auto &fi : inits_) {
+      if (fi.first == coordinates_) continue;
+      std::fill(fi.first->host_data(), fi.first->host_data() + fi.first->num_entities() * fi.first->max_size(), fi.second);
+      fi.first->modify_on_host();
+    }
+    // oneVecFour = {1, 1, -1, -1}: two leaving and two entraining integration points per face (UnitTestUtils.h:188,227)
+    for (size_t f = 0; f < bulk_->num_faces(); ++f) {
+      double *m = openMdot_->host_data() + 4 * f;
+      m[0] = m[1] = 1.0;
+      m[2] = m[3] = -1.0;
+    }
+    openMdot_->modify_on_host();
+  }
+  stk::mesh::MetaData meta_;
+  std::shared_ptr<stk::mesh::BulkData> bulk_;
+  stk::mesh::Part *block_;
+  SolutionOptions solnOpts_;
+  VectorFieldType *coordinates_, *velocity_, *bcVelocityOpen_, *Gjq_, *dpdx_;
+  ScalarFieldType *density_, *viscosity_, *scalarQ_, *bcScalarQ_, *pressure_, *pressureBc_;
+  GenericFieldType *Gjui_, *exposedAreaVec_, *openMdot_, *dynamicP_;
+  std::vector<std::pair<stk::mesh::Field<double> *, double>> inits_;
+};
+
+// CPU: the connectivity the face/element algorithm hands to its kernels (UnitTestFaceElemBasic.C:83-125, TestFaceElemKernel)
+static void test_face_elem_basic()
+{
+  std::printf("Hex8Mesh.faceElemBasic\n");
+  Hex8ElementWithBCFields fx;
+  EXPECT_TRUE(fx.bulk_->num_faces() == 6); // verify_faces_exist
+  EXPECT_TRUE(fx.meta_.get_part("surface_1") && fx.meta_.get_part("surface_6") && !fx.meta_.get_part("surface_7"));
+  EXPECT_TRUE(fx.meta_.get_part("surface_1")->face_elems().size() == 1);
+  stk::topology faceTopo = stk::topology::QUAD_4, elemTopo = stk::topology::HEX_8;
+  EXPECT_TRUE(faceTopo.num_nodes() == 4 && faceTopo.rank() == stk::topology::FACE_RANK);
+  MasterElement *meFC = MasterElementRepo::get_surface_master_element(faceTopo);
+  MasterElement *meSCS = MasterElementRepo::get_surface_master_element(elemTopo);
+  MasterElement *meSCV = MasterElementRepo::get_volume_master_element(elemTopo);
+  EXPECT_TRUE(meFC->numIntPoints_ == 4 && meFC->nodesPerElement_ == 4);
+  Realm realm;
+  realm.bulkData_ = fx.bulk_;
+  EquationSystem eq(realm, "eq");
+  eq.linsys_ = LinearSystem::create(realm, 3, &eq, nullptr);
+  AssembleFaceElemSolverAlgorithm faceElemAlg(realm, fx.meta_.get_part("all_surfaces"), &eq, faceTopo.num_nodes(), elemTopo.num_nodes());
+  faceElemAlg.faceDataNeeded_.add_cvfem_face_me(meFC);
+  faceElemAlg.elemDataNeeded_.add_cvfem_surface_me(meSCS);
+  faceElemAlg.elemDataNeeded_.add_cvfem_volume_me(meSCV);
+  EXPECT_TRUE(faceElemAlg.faceDataNeeded_.get_cvfem_face_me() == meFC && faceElemAlg.rhsSize_ == 12 && faceElemAlg.numDof_ == 3);
+  unsigned numTimesExecuted = 0;
+  std::set<int> ordinals;
+  faceElemAlg.run_face_elem_algorithm(*fx.bulk_, [&](const FaceElemConnectivity &c) {
+    int faceNodeOrdinals[4];
+    elemTopo.face_node_ordinals(unsigned(c.elemFaceOrdinal), faceNodeOrdinals);
+    for (unsigned i = 0; i < faceTopo.num_nodes(); ++i) {
+      EXPECT_TRUE(c.faceNodes[i] == c.elemNodes[faceNodeOrdinals[i]]);
+      EXPECT_TRUE(faceNodeOrdinals[i] == meSCS->side_node_ordinals(c.elemFaceOrdinal)[i]);
+      EXPECT_TRUE(faceNodeOrdinals[i] == meSCS->ipNodeMap(c.elemFaceOrdinal)[i]);
+    }
+    ordinals.insert(c.elemFaceOrdinal);
+    ++numTimesExecuted;
+  });
+  EXPECT_TRUE(numTimesExecuted == 6 && ordinals.size() == 6);
+  // opposing nodes: across the element, never on the face (Hex8CVFEM.C:288-300)
+  const int opp0[4] = {3, 2, 6, 7}, opp5[4] = {0, 1, 2, 3};
+  for (int k = 0; k < 4; ++k) EXPECT_TRUE(meSCS->opposingNodes(0, k) == opp0[k] && meSCS->opposingNodes(5, k) == opp5[k]);
+  // Quad3DSCS shape functions: partition of unity; shifted = collocation
+  double shp[16], shs[16];
+  meFC->shape_fcn(shp);
+  meFC->shifted_shape_fcn(shs);
+  for (int p = 0; p < 4; ++p) {
+    EXPECT_NEAR(shp[4 * p] + shp[4 * p + 1] + shp[4 * p + 2] + shp[4 * p + 3], 1.0, 1e-15);
+    EXPECT_NEAR(shp[4 * p + p], 0.5625, 1e-15);
+    EXPECT_NEAR(shs[4 * p + p], 1.0, 0.0);
+  }
+  // a face field registered with (numFaceIp, nDim), as the BC kernels do
+  ElemDataRequests req;
+  req.add_face_field(*fx.exposedAreaVec_, 4, 3);
+  EXPECT_THROW(req.add_face_field(*fx.velocity_, 4, 3));
+}
+
+struct FaceHelper {
+  FaceHelper(Hex8ElementWithBCFields &fx, int numDof) : eq(realm, "eq")
+  {
+    realm.bulkData_ = fx.bulk_;
+    linsys = dynamic_cast<DeviceCsrLinearSystem *>(LinearSystem::create(realm, numDof, &eq, nullptr));
+    eq.linsys_ = linsys;
+    alg.reset(new AssembleFaceElemSolverAlgorithm(realm, fx.meta_.get_part("all_surfaces"), &eq, 4, 8));
+    alg->initialize_connectivity();
+    linsys->finalizeLinearSystem();
+    linsys->zeroSystem();
+    // ComputeGeometryBoundaryAlgorithm: exposed_area_vector on the device, adopted by the field
+    nalu_b200_face_set *fs = nullptr;
+    stk::mesh::Part *all = fx.meta_.get_part("all_surfaces");
+    if (nalu_b200_face_set_create(&fs, linsys->graph(), int64_t(all->face_elems().size()), all->face_elems().data(),
+                                  all->face_ordinals().data()) != 0)
+      throw std::runtime_error(nalu_b200_last_error());
+    void *d = nullptr;
+    nalu_b200_malloc(&d, fx.bulk_->num_faces() * 12 * 8);
+    if (nalu_b200_compute_exposed_area(linsys->graph(), fs, fx.coordinates_->device_data(), (double *)d, nullptr) != 0)
+      throw std::runtime_error(nalu_b200_last_error());
+    nalu_b200_memcpy_d2h(fx.exposedAreaVec_->host_data(), d, fx.bulk_->num_faces() * 12 * 8, nullptr);
+    nalu_b200_stream_sync(nullptr);
+    nalu_b200_free(d);
+    nalu_b200_face_set_destroy(fs);
+    fx.exposedAreaVec_->modify_on_host();
+  }
+  ~FaceHelper() { alg->activeKernels_.clear(); }
+  Realm realm;
+  EquationSystem eq;
+  DeviceCsrLinearSystem *linsys;
+  std::unique_ptr<AssembleFaceElemSolverAlgorithm> alg;
+};
+
+// GPU: UnitTestFaceElemBasic.C:148-229 (faceElemMomentumSymmetry, faceElemMomentumOpen, faceElemScalarOpen) -- the
+// reference only executes these; here the uniform fields of the fixture give closed forms
+static void test_face_elem_kernels()
+{
+  std::printf("Hex8ElementWithBCFields.faceElemMomentumSymmetry / faceElemMomentumOpen / faceElemScalarOpen / ContinuityOpen\n");
+  {
+    Hex8ElementWithBCFields fx;
+    FaceHelper h(fx, 3);
+    // the exposed area vectors of a unit cube: 1/4 per integration point, outward
+    double asum[3] = {0, 0, 0}, amag = 0;
+    for (size_t i = 0; i < fx.bulk_->num_faces() * 4; ++i) {
+      const double *a = fx.exposedAreaVec_->host_data() + 3 * i;
+      for (int j = 0; j < 3; ++j) asum[j] += a[j];
+      amag += std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    }
+    EXPECT_NEAR(amag, 6.0, 1e-14);
+    EXPECT_NEAR(std::fabs(asum[0]) + std::fabs(asum[1]) + std::fabs(asum[2]), 0.0, 1e-15);
+    MomentumSymmetryElemKernel<AlgTraitsQuad4Hex8> k(fx.meta_, fx.solnOpts_, fx.velocity_, fx.viscosity_, h.alg->faceDataNeeded_,
+                                                    h.alg->elemDataNeeded_);
+    h.alg->activeKernels_.push_back(&k);
+    h.alg->execute();
+    // uniform velocity: no strain, the residual vanishes and every lhs row annihilates a constant
+    const auto v = h.linsys->ownedValues();
+    const auto r = h.linsys->ownedRhs();
+    const auto rp = h.linsys->ownedRowPtr();
+    double vmax = 0, rmax = 0, rowsum = 0;
+    for (double x : v) vmax = std::fmax(vmax, std::fabs(x));
+    for (double x : r) rmax = std::fmax(rmax, std::fabs(x));
+    for (size_t row = 0; row + 1 < rp.size(); ++row) {
+      double s = 0;
+      for (uint64_t q = rp[row]; q < rp[row + 1]; ++q) s += v[q];
+      rowsum = std::fmax(rowsum, std::fabs(s));
+    }
+    EXPECT_TRUE(vmax > 0.1);
+    EXPECT_NEAR(rmax, 0.0, 1e-14);
+    EXPECT_NEAR(rowsum, 0.0, 1e-14);
+  }
+  {
+    Hex8ElementWithBCFields fx;
+    FaceHelper h(fx, 3);
+    MomentumOpenAdvDiffElemKernel<AlgTraitsQuad4Hex8> k(fx.meta_, fx.solnOpts_, &h.eq, fx.velocity_, fx.Gjui_, fx.viscosity_,
+                                                       h.alg->faceDataNeeded_, h.alg->elemDataNeeded_);
+    h.alg->activeKernels_.push_back(&k);
+    h.alg->execute();
+    // uniform u = (1,1,1): no viscous traction.  Leaving points (mdot = 1; alphaUpw = 1 but hybrid factor 0 -> pecfac = 0):
+    // rhs_i -= u_i and the lhs gets the advection shape functions: 6 faces x 2 points x 3 components -> sum lhs = 36,
+    // sum rhs = -36.  Entraining points (mdot = -1): rhs_i -= mdot (uEntrain n_i + uspec_i - (uspec . n) n_i) with
+    // uEntrain = mdot / (rho |A|) = -4 and uspec = (1,1,1): summed over i, -2 per point on a +side face and +6 on a -side
+    // face -> 3 x 2 x (-2) + 3 x 2 x 6 = +24.  Total -12.
+    const auto v = h.linsys->ownedValues();
+    const auto r = h.linsys->ownedRhs();
+    double vs = 0, rs = 0;
+    bool finite = true;
+    for (double x : v) { vs += x; finite = finite && std::isfinite(x); }
+    for (double x : r) { rs += x; finite = finite && std::isfinite(x); }
+    EXPECT_TRUE(finite);
+    EXPECT_NEAR(vs, 36.0, 1e-12);
+    EXPECT_NEAR(rs, -12.0, 1e-12);
+  }
+  {
+    Hex8ElementWithBCFields fx;
+    FaceHelper h(fx, 1);
+    ScalarOpenAdvElemKernel<AlgTraitsQuad4Hex8> k(fx.meta_, fx.solnOpts_, &h.eq, fx.scalarQ_, fx.bcScalarQ_, fx.Gjq_, fx.viscosity_,
+                                                 h.alg->faceDataNeeded_, h.alg->elemDataNeeded_);
+    h.alg->activeKernels_.push_back(&k);
+    h.alg->execute();
+    // q = q_bc = 1: every leaving point takes 1 out of its node, every entraining point brings 1 in
+    const auto v = h.linsys->ownedValues();
+    const auto r = h.linsys->ownedRhs();
+    double vs = 0, rs = 0, rabs = 0;
+    for (double x : v) vs += x;
+    for (double x : r) { rs += x; rabs += std::fabs(x); }
+    EXPECT_NEAR(vs, 12.0, 1e-13); // 6 faces x 2 leaving points x sum of the shape functions
+    EXPECT_NEAR(rs, 0.0, 1e-13);
+    EXPECT_TRUE(rabs <= 24.0 + 1e-12);
+  }
+  {
+    Hex8ElementWithBCFields fx;
+    FaceHelper h(fx, 1);
+    h.realm.timeIntegrator_->timeStepN_ = 0.5;
+    ContinuityOpenElemKernel<AlgTraitsQuad4Hex8> k(fx.meta_, fx.solnOpts_, h.alg->faceDataNeeded_, h.alg->elemDataNeeded_);
+    h.alg->activeKernels_.push_back(&k);
+    h.alg->execute();
+    // p = p_bc = 0, uniform rho u = (1,1,1): mdot = u . A; over the closed surface sum rhs = -sum mdot / tau = 0;
+    // every row's gradient columns cancel, leaving the penalty 2 |A| / L = 2 x 1/4 x 1 per point -> total 6 x 4 x 1/2
+    const auto v = h.linsys->ownedValues();
+    const auto r = h.linsys->ownedRhs();
+    double vs = 0, rs = 0, rabs = 0;
+    for (double x : v) vs += x;
+    for (double x : r) { rs += x; rabs += std::fabs(x); }
+    EXPECT_NEAR(vs, 12.0, 1e-12);
+    EXPECT_NEAR(rs, 0.0, 1e-12);
+    EXPECT_TRUE(rabs > 1.0);
+  }
+}
+
 int main(int argc, char **argv)
 {
   if (argc < 3) {
@@ -860,7 +1104,9 @@ int main(int argc, char **argv)
     test_elem_data_requests();
     test_kernel_registration();
     test_scratch_views();
+    test_face_elem_basic();
     if (gpu) {
+      test_face_elem_kernels();
       test_momentum_advection_diffusion();
       test_continuity_advection("advection_default");
       test_continuity_advection("advection_reduced_sens_cvfem_poisson");
