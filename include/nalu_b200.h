@@ -243,7 +243,7 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *g, const nalu_b200_kernel_des
 int nalu_b200_assemble_elem_zrange(const nalu_b200_graph *g, const nalu_b200_kernel_desc *kernels,
                                    int32_t n_kernels, double *d_values, double *d_rhs, int32_t overwrite,
                                    int32_t z_begin, int32_t z_end, void *stream);
-/* which kernel family the last nalu_b200_assemble_elem call used: 1 general (atomic scatter), 2 tiled write-once,
+/* which kernel family the last nalu_b200_assemble_elem call used: 1 general (coloured scatter), 2 tiled write-once,
  * 3 tiled write-once for one kernel of the list + general for the others */
 int nalu_b200_last_assemble_mode(void);
 /* Launch-configuration knobs for A/B measurements and tests; none changes what is computed.  name / value:
@@ -251,6 +251,9 @@ int nalu_b200_last_assemble_mode(void);
  *   "box_zchunk"  node planes per CTA of the tiled kernels, 0 = automatic
  *   "split_lists" 1 (default) a list with one tiled-capable kernel runs tiled + accumulate, 0 general kernel only
  *   "cont_tiled"  1 (default) one-dof lists on structured blocks use the tiled kernels
+ *   "general_minb"    CTAs per SM the general kernel's registers are bounded for: 2, 3 or 4 (default)
+ *   "general_scatter" coloured scatter of the general kernel: 1 (default) value-less reductions (red.global.add.f64), 0
+ *                     load / add / store; one element of a colour touches an address either way: same sums, bit for bit
  * The initial values come from the environment variables NALU_BOX_KERNEL, NALU_BOX_ZCHUNK, NALU_SPLIT_LISTS,
  * NALU_CONT_BOX, read once when the library is first used -- nothing on the launch path reads the environment.
  * Returns NALU_B200_ERR_ARG for an unknown name. */

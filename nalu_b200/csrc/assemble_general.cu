@@ -21,6 +21,7 @@ namespace nalu_b200 {
 struct GeneralParams {
   long long n_elems;          // elements this launch processes
   const int *elem_list;       // their ids (one colour), or null: 0 .. n_elems-1 with an atomic scatter
+  int red_scatter;            // coloured scatter by fire-and-forget reductions instead of load / add / store
   const int *elem_nodes;
   const int *node_row;
   const long long *browptr;
@@ -33,6 +34,9 @@ struct GeneralParams {
 };
 
 constexpr int kWarpsPerCta = 4;
+
+// value-less reduction: one add at the L2, nothing returned to the SM
+__device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
 // MINB = CTAs per SM the register allocation is bounded for (2: 255 registers, 3: 168, 4: 128)
 template <int NDOF, int MINB>
@@ -94,9 +98,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) assemble_general_kern
       const int ic = c / NDOF, j = c - ic * NDOF;
       return ws.rowbase[kn] + (long long)i * ws.rownb[kn] * NDOF + slots[kn * 8 + ic] * NDOF + j;
     };
-    if (p.elem_list) {
-      // no other element of this colour touches these rows: plain read-modify-write, the loads of a batch issued
-      // together (the entries of one element are distinct, so nothing aliases inside a batch)
+    if (p.elem_list && p.red_scatter) {
+      // No other element of this colour touches these rows and the entries of one element are distinct: every address
+      // receives exactly one add per launch, launches (colours) are stream-ordered -> the same sum in the same order as
+      // the read-modify-write below, bit for bit.  The reduction instruction does not return a value, so the warp does
+      // not wait a DRAM round trip per batch of entries (the RMW form's long-scoreboard stall: 32 % of its samples).
+      for (int q = lane; q < R * R; q += 32) {
+        const double v = ws.lhs[q];
+        if (v != 0.0) red_add(p.values + slot_of(q), v);
+      }
+    } else if (p.elem_list) {
+      // plain read-modify-write, the loads of a batch issued together (nothing aliases inside a batch)
       constexpr int NIT = (R * R + 31) / 32, B = NIT % 6 == 0 ? 6 : 2;
 #pragma unroll 1
       for (int it = 0; it < NIT; it += B) {
@@ -125,7 +137,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) assemble_general_kern
       const double v = ws.rhs[lane];
       double *r = p.rhs + (long long)ws.rownode[lane / NDOF] * NDOF + lane % NDOF;
       if (v != 0.0) {
-        if (p.elem_list) *r += v;
+        if (p.elem_list && p.red_scatter) red_add(r, v);
+        else if (p.elem_list) *r += v;
         else atomicAdd(r, v);
       }
     }
@@ -258,6 +271,7 @@ int launch_assemble_general(const Graph &g, const nalu_b200_kernel_desc *kernels
   const long long ncolor = g.d_color_elems ? (long long)g.color_ptr.size() - 1 : 1;
   for (long long c = 0; c < ncolor; ++c) {
     p.elem_list = g.d_color_elems ? g.d_color_elems + g.color_ptr[c] : nullptr;
+    p.red_scatter = tuning().general_scatter;
     p.n_elems = g.d_color_elems ? g.color_ptr[c + 1] - g.color_ptr[c] : g.n_elems;
     if (p.n_elems == 0) continue;
     long long ctas = (p.n_elems + kWarpsPerCta - 1) / kWarpsPerCta;

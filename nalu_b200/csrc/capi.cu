@@ -174,6 +174,7 @@ int nalu_b200_tune(const char *name, int32_t value)
   else if (n == "split_lists") t.split_lists = value != 0;
   else if (n == "cont_tiled") t.cont_tiled = value != 0;
   else if (n == "general_minb") t.general_minb = value < 2 ? 2 : (value > 4 ? 4 : value);
+  else if (n == "general_scatter") t.general_scatter = value != 0;
   else {
     set_error("tune: unknown knob " + n);
     return NALU_B200_ERR_ARG;

@@ -79,6 +79,9 @@ struct Tuning {
   bool split_lists = true;
   bool cont_tiled = true;
   int general_minb = 4; // CTAs per SM the general kernel's registers are bounded for (2, 3 or 4)
+  // coloured scatter of the general kernel: 0 = load / add / store, 1 = fire-and-forget reduction (red.global.add.f64).
+  // Either way exactly one element of a colour touches an address, so the result is the same sum in the same order.
+  int general_scatter = 1;
 };
 const Tuning &tuning();
 

@@ -14,6 +14,9 @@ from nalu_b200.linsys import DeviceCsrLinearSystem  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+if len(sys.argv) > 3:  # A/B of the general kernel's coloured scatter: 0 = load/add/store, 1 = red.global.add
+    from nalu_b200 import lib as _lib
+    _lib.tune(general_scatter=int(sys.argv[3]))
 dev = torch.device("cuda", 0)
 m = mesh.generated_box(n, n, n)
 mesh.perturb_coords_hash(m, 0.12)
