@@ -244,13 +244,15 @@ int nalu_b200_assemble_elem_zrange(const nalu_b200_graph *g, const nalu_b200_ker
                                    int32_t n_kernels, double *d_values, double *d_rhs, int32_t overwrite,
                                    int32_t z_begin, int32_t z_end, void *stream);
 /* which kernel family the last nalu_b200_assemble_elem call used: 1 general (coloured scatter), 2 tiled write-once,
- * 3 tiled write-once for one kernel of the list + general for the others */
+ * 3 tiled write-once for one kernel of the list + general for the others, 4 row-thread unstructured momentum kernel
+ * (any Hex8 connectivity with an element colouring, coloured value-less reductions) */
 int nalu_b200_last_assemble_mode(void);
 /* Launch-configuration knobs for A/B measurements and tests; none changes what is computed.  name / value:
  *   "box_kernel"  5 row-thread tiled momentum kernel (default), 2 column-pair kernel
  *   "box_zchunk"  node planes per CTA of the tiled kernels, 0 = automatic
  *   "split_lists" 1 (default) a list with one tiled-capable kernel runs tiled + accumulate, 0 general kernel only
  *   "cont_tiled"  1 (default) one-dof lists on structured blocks use the tiled kernels
+ *   "urow"            1 (default) momentum lists on non-lattice meshes use the row-thread unstructured kernel, 0 general kernel
  *   "general_minb"    CTAs per SM the general kernel's registers are bounded for: 2, 3 or 4 (default)
  *   "general_scatter" coloured scatter of the general kernel: 1 (default) value-less reductions (red.global.add.f64), 0
  *                     load / add / store; one element of a colour touches an address either way: same sums, bit for bit

@@ -1,0 +1,402 @@
+// assemble_urow.cu -- momentum assembly on ANY Hex8 connectivity (unstructured meshes, periodic aliasing, decomposed
+// pieces) without the warp-per-element scratch matrix of the general kernel:
+//   [MomentumMassElemKernel(lumped)]? + MomentumAdvDiffElemKernel  (src/LowMachEquationSystem.C:1304-1398, BASELINE config 3)
+// through AssembleElemSolverAlgorithm::execute (src/AssembleElemSolverAlgorithm.C:74-100) + sumInto
+// (src/TpetraLinearSystem.C:1457-1522).  Kernels followed: src/kernel/MomentumAdvDiffElemKernel.C:95-186,
+// src/kernel/MomentumMassElemKernel.C:98-171 (lumped).
+//
+// Decomposition: a thread owns (element, row node r): the 3 x 24 block of rows the element adds to node r.  Every sub-control
+// surface of the element that touches r is one of the three edges leaving r, so the thread needs the geometry of three
+// integration points only: area vector, G~ = -mu_ip adj(J) / det J, signed mass flow -- 16 doubles per point, after which
+// the coordinates are dead.  It then walks the 8 column nodes and finishes ONE 3 x 3 block at a time:
+//     h = G~ dN_c/dxi (9 FMAs), block += h (x) A (9), D_c += N_c mdot + h . A (4), divU_ip += u_c . h (3)
+// -- 10 accumulators live instead of the 72 a whole row block would take -- adds the block to the CSR through the element's
+// slot map and folds it into the residual (rhs = -(row . u) + 2/3 includeDivU sum_ip (mu divU)_ip A_ip, the form the tiled
+// kernel uses).  No shared memory, no warp barriers: the 6 350 warp instructions per element of the general kernel become
+// about 600.  Elements are processed colour by colour (graph.cpp): within a launch one element touches a row, so the
+// scatter is value-less reductions (red.global.add.f64), deterministic.
+#include "box5_tile.cuh"
+#include "hex8_dev.cuh"
+#include "internal.h"
+
+namespace nalu_b200 {
+namespace urow {
+
+struct UrowParams {
+  long long n_elems;       // elements of this colour
+  const int *elem_list;    // their ids
+  long long n_rows;        // row-owner kernel: row nodes, and the elements around each as (element << 3 | local node)
+  const long long *rowelem_ptr;
+  const int *rowelem;
+  const int *elem_nodes, *node_row;
+  const long long *browptr;
+  const unsigned char *elem_slot;
+  double *values, *rhs;
+  int *err;
+  // MomentumAdvDiffElemKernel
+  const double *coords, *vel, *visc, *mdot;
+  int options;
+  double include_divu;
+  // lumped MomentumMassElemKernel
+  int mass;
+  const double *vel_n, *vel_nm1, *rho, *rho_n, *rho_nm1, *dpdx;
+  double g1_dt, g2_dt, g3_dt, dens_fac, om_dens_fac;
+};
+
+// No "memory" clobber: the matrix and the residual never alias the fields the kernel reads, and the loads of the next column
+// must be free to move above the reductions of this one (the kernel is bound by gather latency, not by arithmetic).
+__device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v)); }
+
+struct IpGeom {
+  double As[3];    // area vector, signed so that it points OUT of node r's control volume
+  double Gt[3][3]; // Gt[i][a] = -mu_ip adj(J)[i][a] / det J: -mu dN/dx_i = sum_a Gt[i][a] dN/dxi_a
+  double tm;       // signed mass flow rate
+  double s[3];     // parametric location of the gradient operator
+};
+
+// geometry of the integration point on the edge leaving node r in direction DIR
+template <int DIR>
+__device__ __forceinline__ void ip_geometry(const UrowParams &P, const double (&x)[8][3], const int (&nodes)[8], long long e, int r,
+                                            IpGeom &g, double &mu_out)
+{
+  const int ip = box::ip_of(r, DIR);
+  const double sgn = hex8::scs_left(ip) == r ? 1.0 : -1.0;
+  double A[3];
+  hex8::scs_areav_ip(x, ip, A);
+  hex8::scs_intg_loc(ip, (P.options & NALU_OPT_SHIFTED_GRAD_OP) ? 0.5 : 0.25, g.s[0], g.s[1], g.s[2]);
+  double jact[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double u1, u2, u3, mu = 0.0;
+  hex8::scs_intg_loc(ip, 0.25, u1, u2, u3); // properties are never shifted
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    double d[3];
+    hex8::shape_deriv(n, g.s[0], g.s[1], g.s[2], d);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) jact[i][j] += d[j] * x[n][i];
+    mu += hex8::shape_fcn(n, u1, u2, u3) * P.visc[nodes[n]];
+  }
+  double adj[3][3];
+  adj[0][0] = jact[1][1] * jact[2][2] - jact[2][1] * jact[1][2];
+  adj[0][1] = jact[1][2] * jact[2][0] - jact[2][2] * jact[1][0];
+  adj[0][2] = jact[1][0] * jact[2][1] - jact[2][0] * jact[1][1];
+  adj[1][0] = jact[0][2] * jact[2][1] - jact[2][2] * jact[0][1];
+  adj[1][1] = jact[0][0] * jact[2][2] - jact[2][0] * jact[0][2];
+  adj[1][2] = jact[0][1] * jact[2][0] - jact[2][1] * jact[0][0];
+  adj[2][0] = jact[0][1] * jact[1][2] - jact[1][1] * jact[0][2];
+  adj[2][1] = jact[0][2] * jact[1][0] - jact[1][2] * jact[0][0];
+  adj[2][2] = jact[0][0] * jact[1][1] - jact[1][0] * jact[0][1];
+  const double det = jact[0][0] * adj[0][0] + jact[1][0] * adj[1][0] + jact[2][0] * adj[2][0];
+  if (!(det > 0.0)) *P.err = 1; // MasterElementFunctions.h:91-94
+  const double f = -mu / det;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    g.As[i] = sgn * A[i];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g.Gt[i][a] = f * adj[i][a];
+  }
+  g.tm = sgn * P.mdot[e * 12 + ip];
+  mu_out = mu;
+}
+
+// The rows element e adds to its node r.  OWNED: the calling thread is the only one that ever touches these rows (row-owner
+// kernel): plain adds, the residual is returned in res[].  Otherwise (element-colour kernel): value-less reductions.
+template <bool OWNED>
+__device__ __forceinline__ void row_contribution(const UrowParams &P, long long e, int r, double (&res)[3])
+{
+  int nodes[8];
+  double x[8][3];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) nodes[n] = P.elem_nodes[e * 8 + n];
+  {
+    // coordinates relative to the element's first node: the assembled system is translation invariant, the rounding of
+    // differences of absolute coordinates is not
+    const double o0 = P.coords[(size_t)nodes[0] * 3], o1 = P.coords[(size_t)nodes[0] * 3 + 1], o2 = P.coords[(size_t)nodes[0] * 3 + 2];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      x[n][0] = P.coords[(size_t)nodes[n] * 3] - o0;
+      x[n][1] = P.coords[(size_t)nodes[n] * 3 + 1] - o1;
+      x[n][2] = P.coords[(size_t)nodes[n] * 3 + 2] - o2;
+    }
+  }
+  // everything the tail of the kernel gathers is requested now, so that its latency hides behind the geometry
+  const int nd = nodes[r];
+  const int rn = P.node_row[nd];
+  const long long b0 = P.browptr[rn];
+  const int nb = (int)(P.browptr[rn + 1] - b0);
+  double m_rho = 0, m_rho_n = 0, m_rho_nm1 = 0, m_un[3] = {0, 0, 0}, m_unm1[3] = {0, 0, 0}, m_gp[3] = {0, 0, 0};
+  if (P.mass) {
+    m_rho = P.rho[nd];
+    m_rho_n = P.rho_n[nd];
+    m_rho_nm1 = P.rho_nm1[nd];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      m_un[i] = P.vel_n[(size_t)nd * 3 + i];
+      m_unm1[i] = P.vel_nm1[(size_t)nd * 3 + i];
+      m_gp[i] = P.dpdx[(size_t)nd * 3 + i];
+    }
+  }
+  // lumped mass: the sub-control volume of corner r (HexSCV::determinant, Hex8CVFEM.C:149-178, in the closed form of the
+  // tiled kernel: box5_tile.cuh) -- every quantity of the lumped kernel is the row node's own
+  double scV = 0.0;
+  if (P.mass) {
+    box5::Coef C;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) C.X[i][m] = x[box::node_of_bits(m & 1, (m >> 1) & 1, m >> 2)][i];
+      box::butterfly8(C.X[i]);
+    }
+    double vol[16];
+    box5::scv_volumes_part<0>(C, vol);
+    box5::scv_volumes_part<1>(C, vol);
+    scV = 0.0;
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n == r) scV = vol[n] + vol[8 + n];
+  }
+  IpGeom g[3];
+  double mu_ip[3];
+  ip_geometry<0>(P, x, nodes, e, r, g[0], mu_ip[0]);
+  ip_geometry<1>(P, x, nodes, e, r, g[1], mu_ip[1]);
+  ip_geometry<2>(P, x, nodes, e, r, g[2], mu_ip[2]);
+  const double qa = (P.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25;
+  double sa[3][3]; // advection shape-function location of the three points
+#pragma unroll
+  for (int k = 0; k < 3; ++k) hex8::scs_intg_loc(box::ip_of(r, k), qa, sa[k][0], sa[k][1], sa[k][2]);
+
+  double *const row0 = P.values + 9 * b0;
+  const unsigned char *slots = P.elem_slot + e * 64 + r * 8;
+  double divacc[3] = {0.0, 0.0, 0.0};
+
+  double un[3] = {P.vel[(size_t)nodes[0] * 3], P.vel[(size_t)nodes[0] * 3 + 1], P.vel[(size_t)nodes[0] * 3 + 2]};
+  // row-owner form: the current values of a 3 x 3 block are requested one column ahead, so that the read-modify-write of a
+  // block does not wait for its own load (the thread is the only writer of these rows; a block read ahead is stale only if
+  // the next column is the SAME column -- an element that reaches a node twice -- and is then re-read)
+  double old[3][3];
+  if (OWNED) {
+    const double *b = row0 + slots[0] * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) old[i][j] = b[(long long)i * nb * 3 + j];
+  }
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    double B[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, D = 0.0;
+    const double u[3] = {un[0], un[1], un[2]};
+    {
+      // the next column's velocity is requested before this column's arithmetic
+      const int nx = nodes[(c + 1) & 7];
+      un[0] = P.vel[(size_t)nx * 3];
+      un[1] = P.vel[(size_t)nx * 3 + 1];
+      un[2] = P.vel[(size_t)nx * 3 + 2];
+    }
+    double cur[3][3];
+    if (OWNED) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cur[i][j] = old[i][j];
+      if (c < 7) {
+        const double *b = row0 + slots[c + 1] * 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) old[i][j] = b[(long long)i * nb * 3 + j];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double d[3], h[3];
+      hex8::shape_deriv(c, g[k].s[0], g[k].s[1], g[k].s[2], d);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) h[i] = g[k].Gt[i][0] * d[0] + g[k].Gt[i][1] * d[1] + g[k].Gt[i][2] * d[2];
+      // MomentumAdvDiffElemKernel.C:138-176: lhsfacAdv + lhs_riC_i on the diagonal, lhsfacDiff_j = -mu dN/dx_i A_j
+      D += hex8::shape_fcn(c, sa[k][0], sa[k][1], sa[k][2]) * g[k].tm + h[0] * g[k].As[0] + h[1] * g[k].As[1] + h[2] * g[k].As[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) B[i][j] += h[i] * g[k].As[j];
+      divacc[k] += u[0] * h[0] + u[1] * h[1] + u[2] * h[2]; // = -mu_ip (u_c . grad N_c)
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) B[i][i] += D;
+    if (P.mass && c == r) {
+      // MomentumMassElemKernel.C:119-170 with the shifted (nodal) shape function
+      const double rp = m_rho, lhsfac = P.g1_dt * rp * scV, densFac = rp * P.dens_fac + P.om_dens_fac;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        B[i][i] += lhsfac;
+        // the residual below subtracts B . u: put back lhsfac u_i, then the kernel's own rhs
+        res[i] += lhsfac * u[i] -
+                  (P.g1_dt * rp * u[i] + P.g2_dt * m_rho_n * m_un[i] + P.g3_dt * m_rho_nm1 * m_unm1[i]) * scV - m_gp[i] * scV * densFac;
+      }
+    }
+    double *blk = row0 + slots[c] * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      res[i] -= B[i][0] * u[0] + B[i][1] * u[1] + B[i][2] * u[2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (OWNED) blk[(long long)i * nb * 3 + j] = cur[i][j] + B[i][j];
+        else red_add(blk + (long long)i * nb * 3 + j, B[i][j]);
+      }
+    }
+    if (OWNED && c < 7 && slots[c + 1] == slots[c]) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) old[i][j] = blk[(long long)i * nb * 3 + j];
+    }
+  }
+  // divUstress = 2/3 mu divU A_i includeDivU, rhs -= sgn divUstress (MomentumAdvDiffElemKernel.C:118-136); divacc = -mu divU
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    res[i] += (2.0 / 3.0) * P.include_divu * (divacc[0] * g[0].As[i] + divacc[1] * g[1].As[i] + divacc[2] * g[2].As[i]);
+  (void)mu_ip;
+}
+
+// one launch per element colour: thread = (element of the colour, row node)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_urow_kernel(const __grid_constant__ UrowParams P)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 3) >= P.n_elems) return;
+  const long long e = P.elem_list[t >> 3];
+  const int r = (int)(t & 7);
+  double res[3] = {0.0, 0.0, 0.0};
+  row_contribution<false>(P, e, r, res);
+  const int rn = P.node_row[P.elem_nodes[e * 8 + r]];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) red_add(P.rhs + (long long)rn * 3 + i, res[i]);
+}
+
+// ONE launch: thread = row node, walking the elements around it (rowelem: the transpose of the connectivity, built with
+// the graph).  The thread owns its three rows, so every add is a plain read-modify-write by one thread in a fixed order:
+// no atomics, no colouring, deterministic -- and an element that reaches a row through two of its nodes (a periodic box one
+// cell wide) is simply visited twice.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_urow_owner_kernel(const __grid_constant__ UrowParams P)
+{
+  const long long rn = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rn >= P.n_rows) return;
+  double res[3] = {0.0, 0.0, 0.0};
+  const long long q1 = P.rowelem_ptr[rn + 1];
+#pragma unroll 1
+  for (long long q = P.rowelem_ptr[rn]; q < q1; ++q) {
+    const int er = P.rowelem[q];
+    row_contribution<true>(P, er >> 3, er & 7, res);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) P.rhs[rn * 3 + i] += res[i];
+}
+
+
+} // namespace urow
+
+namespace {
+bool classify_urow(const nalu_b200_kernel_desc *k, int nk, int &ia, int &im)
+{
+  ia = im = -1;
+  for (int i = 0; i < nk; ++i) {
+    if (k[i].kind == NALU_K_MOMENTUM_ADV_DIFF) {
+      if (ia >= 0) return false;
+      ia = i;
+    } else if (k[i].kind == NALU_K_MOMENTUM_MASS) {
+      if (im >= 0 || !(k[i].options & NALU_OPT_LUMPED_MASS)) return false;
+      im = i;
+    } else {
+      return false;
+    }
+  }
+  return ia >= 0;
+}
+} // namespace
+
+bool urow_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+{
+  if (g.ndof != 3 || (!g.d_color_elems && !g.d_rowelem) || !g.d_elem_slot || nk < 1 || nk > 2) return false;
+  int ia, im;
+  if (!classify_urow(k, nk, ia, im)) return false;
+  const nalu_b200_kernel_desc &a = k[ia];
+  if (!a.nodal[NALU_F_COORDINATES] || !a.nodal[NALU_F_VELOCITY] || !a.nodal[NALU_F_VISCOSITY] || !a.mass_flow_rate) return false;
+  if (im >= 0) {
+    const nalu_b200_kernel_desc &m = k[im];
+    if (m.nodal[NALU_F_COORDINATES] != a.nodal[NALU_F_COORDINATES] || m.nodal[NALU_F_VELOCITY] != a.nodal[NALU_F_VELOCITY]) return false;
+    for (int f : {NALU_F_VELOCITY_N, NALU_F_VELOCITY_NM1, NALU_F_DENSITY, NALU_F_DENSITY_N, NALU_F_DENSITY_NM1, NALU_F_DPDX})
+      if (!m.nodal[f]) return false;
+  }
+  return true;
+}
+
+int launch_assemble_urow(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs, cudaStream_t stream)
+{
+  if (!urow_supported(g, k, nk)) {
+    set_error("assemble_urow: unsupported mesh / kernel list");
+    return NALU_B200_ERR_ARG;
+  }
+  if (g.n_elems == 0) return NALU_B200_OK;
+  int ia, im;
+  classify_urow(k, nk, ia, im);
+  const nalu_b200_kernel_desc &a = k[ia];
+  urow::UrowParams P = {};
+  P.elem_nodes = g.d_elem_nodes;
+  P.node_row = g.d_node_row;
+  P.browptr = (const long long *)g.d_browptr;
+  P.elem_slot = g.d_elem_slot;
+  P.values = d_values;
+  P.rhs = d_rhs;
+  P.err = g.d_err;
+  P.coords = a.nodal[NALU_F_COORDINATES];
+  P.vel = a.nodal[NALU_F_VELOCITY];
+  P.visc = a.nodal[NALU_F_VISCOSITY];
+  P.mdot = a.mass_flow_rate;
+  P.options = a.options & (NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC);
+  P.include_divu = a.include_divu;
+  if (im >= 0) {
+    const nalu_b200_kernel_desc &m = k[im];
+    P.mass = 1;
+    P.vel_n = m.nodal[NALU_F_VELOCITY_N];
+    P.vel_nm1 = m.nodal[NALU_F_VELOCITY_NM1];
+    P.rho = m.nodal[NALU_F_DENSITY];
+    P.rho_n = m.nodal[NALU_F_DENSITY_N];
+    P.rho_nm1 = m.nodal[NALU_F_DENSITY_NM1];
+    P.dpdx = m.nodal[NALU_F_DPDX];
+    P.g1_dt = m.gamma1 / m.dt;
+    P.g2_dt = m.gamma2 / m.dt;
+    P.g3_dt = m.gamma3 / m.dt;
+    P.dens_fac = m.dens_fac;
+    P.om_dens_fac = m.om_dens_fac;
+  }
+  const int minb = tuning().urow_minb;
+  if (g.d_rowelem && tuning().urow_owner) {
+    P.n_rows = g.n_row_nodes();
+    P.rowelem_ptr = (const long long *)g.d_rowelem_ptr;
+    P.rowelem = g.d_rowelem;
+    const unsigned grid = (unsigned)((P.n_rows + 127) / 128);
+    if (minb >= 4) urow::assemble_urow_owner_kernel<4><<<grid, 128, 0, stream>>>(P);
+    else if (minb == 3) urow::assemble_urow_owner_kernel<3><<<grid, 128, 0, stream>>>(P);
+    else urow::assemble_urow_owner_kernel<2><<<grid, 128, 0, stream>>>(P);
+    count_launch();
+    NALU_CUDA(cudaGetLastError());
+    return NALU_B200_OK;
+  }
+  const long long ncolor = (long long)g.color_ptr.size() - 1;
+  for (long long c = 0; c < ncolor; ++c) {
+    P.elem_list = g.d_color_elems + g.color_ptr[c];
+    P.n_elems = g.color_ptr[c + 1] - g.color_ptr[c];
+    if (P.n_elems == 0) continue;
+    const long long nt = 8 * P.n_elems;
+    const unsigned grid = (unsigned)((nt + 127) / 128);
+    if (minb >= 4) urow::assemble_urow_kernel<4><<<grid, 128, 0, stream>>>(P);
+    else if (minb == 3) urow::assemble_urow_kernel<3><<<grid, 128, 0, stream>>>(P);
+    else urow::assemble_urow_kernel<2><<<grid, 128, 0, stream>>>(P);
+    count_launch();
+  }
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+} // namespace nalu_b200

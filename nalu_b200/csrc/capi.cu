@@ -92,6 +92,7 @@ static void free_graph_device(Graph &g)
     p = nullptr;
   };
   F(g.d_elem_nodes); F(g.d_node_row); F(g.d_row_rep); F(g.d_color_elems); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_desc);
+  F(g.d_rowelem_ptr); F(g.d_rowelem);
   F(g.d_rowptr_owned); F(g.d_rowptr_shared); F(g.d_colidx_owned); F(g.d_colidx_shared); F(g.d_err);
   for (auto *peers : {&g.send_peers, &g.recv_peers})
     for (HaloPeer &p : *peers) {
@@ -113,6 +114,18 @@ static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const s
   if ((rc = upload(&g.d_node_slot27, node_slot27))) return rc;
   if ((rc = upload(&g.d_node_desc, g.node_desc))) return rc;
   std::vector<uint64_t>().swap(g.node_desc);
+  if (g.box[0] == 0 && g.ndof == 3 && g.n_elems > 0 && g.n_elems < (int64_t(1) << 28)) {
+    // row node -> (element, local node), elements in ascending order: a counting sort of the connectivity by row
+    const int nrow = g.n_row_nodes();
+    std::vector<int64_t> ptr(size_t(nrow) + 1, 0);
+    for (size_t q = 0; q < g.elem_nodes.size(); ++q) ++ptr[size_t(g.node_row[g.elem_nodes[q]]) + 1];
+    for (int r = 0; r < nrow; ++r) ptr[r + 1] += ptr[r];
+    std::vector<int32_t> re(g.elem_nodes.size());
+    std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+    for (size_t q = 0; q < g.elem_nodes.size(); ++q) re[size_t(pos[g.node_row[g.elem_nodes[q]]]++)] = int32_t(q); // q = e * 8 + local
+    if ((rc = upload(&g.d_rowelem_ptr, ptr))) return rc;
+    if ((rc = upload(&g.d_rowelem, re))) return rc;
+  }
   NALU_CUDA(cudaMalloc((void **)&g.d_err, sizeof(int)));
   NALU_CUDA(cudaMemset(g.d_err, 0, sizeof(int)));
   const int nown = g.n_owned_nodes, nrow = g.n_row_nodes(), ndof = g.ndof;
@@ -175,6 +188,10 @@ int nalu_b200_tune(const char *name, int32_t value)
   else if (n == "cont_tiled") t.cont_tiled = value != 0;
   else if (n == "general_minb") t.general_minb = value < 2 ? 2 : (value > 4 ? 4 : value);
   else if (n == "general_scatter") t.general_scatter = value != 0;
+  else if (n == "urow") t.urow = value != 0;
+  else if (n == "urow_owner") t.urow_owner = value != 0;
+  else if (n == "urow_minb") t.urow_minb = value < 2 ? 2 : (value > 4 ? 4 : value);
+  else if (n == "color_chunk") t.color_chunk = value > 0 ? value : 0;
   else {
     set_error("tune: unknown knob " + n);
     return NALU_B200_ERR_ARG;
@@ -196,6 +213,7 @@ int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, 
     h = new nalu_b200_graph();
     Graph &g = h->g;
     g.rank = rank; g.nranks = nranks; g.ndof = num_dof; g.n_nodes = n_nodes; g.n_elems = n_elems;
+    if (tuning().color_chunk > 0) g.color_chunk = tuning().color_chunk;
     g.box[0] = box_nx; g.box[1] = box_ny; g.box[2] = box_nz;
     if (!(box_nx > 0 && box_ny > 0 && box_nz > 0)) g.box[0] = g.box[1] = g.box[2] = 0;
     g.gid.assign(node_gid, node_gid + n_nodes);
@@ -479,6 +497,11 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   if (use_box) {
     set_last_mode(2);
     return launch_assemble_box(g, kernels, nk, d_values, d_rhs, overwrite, s);
+  }
+  // any Hex8 connectivity with an element colouring: the momentum list through the row-thread unstructured kernel
+  if (mode == NALU_ASSEMBLE_AUTO && tuning().urow && urow_supported(g, kernels, nk)) {
+    set_last_mode(4);
+    return launch_assemble_urow(g, kernels, nk, d_values, d_rhs, s);
   }
   set_last_mode(1);
   return launch_assemble_general(g, kernels, nk, d_values, d_rhs, s);

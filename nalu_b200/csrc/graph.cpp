@@ -161,14 +161,15 @@ int graph_number_and_adjacency(Graph &g, std::string &err)
     if (ok) {
       // sort key = (chunk of consecutive element ids, colour): the general kernel runs one launch per (chunk, colour) in
       // this order (graph.h, kColorChunk: one chunk today)
-      const int64_t nchunk = (ne + kColorChunk - 1) / kColorChunk;
+      const int64_t kChunk = g.color_chunk > 0 ? g.color_chunk : kColorChunk;
+      const int64_t nchunk = (ne + kChunk - 1) / kChunk;
       g.n_colors = ncolor;
       g.color_ptr.assign(size_t(nchunk * ncolor) + 1, 0);
-      for (int64_t e = 0; e < ne; ++e) ++g.color_ptr[(e / kColorChunk) * ncolor + color[e] + 1];
+      for (int64_t e = 0; e < ne; ++e) ++g.color_ptr[(e / kChunk) * ncolor + color[e] + 1];
       for (int64_t c = 0; c < nchunk * ncolor; ++c) g.color_ptr[c + 1] += g.color_ptr[c];
       g.color_elems.resize(size_t(ne));
       std::vector<int64_t> pos(g.color_ptr.begin(), g.color_ptr.end() - 1);
-      for (int64_t e = 0; e < ne; ++e) g.color_elems[pos[(e / kColorChunk) * ncolor + color[e]]++] = int32_t(e);
+      for (int64_t e = 0; e < ne; ++e) g.color_elems[pos[(e / kChunk) * ncolor + color[e]]++] = int32_t(e);
     }
   }
 

@@ -68,6 +68,7 @@ struct Graph {
   std::vector<int32_t> color_elems;
   std::vector<int64_t> color_ptr;
   int32_t n_colors = 0;
+  int64_t color_chunk = kColorChunk; // elements per chunk of the (chunk, colour) launch order; set before the numbering phase
   int32_t *d_color_elems = nullptr;
 
   // local adjacency (row node -> sorted unique row nodes), before the handshake
@@ -95,6 +96,10 @@ struct Graph {
   int64_t *d_browptr = nullptr;    // [n_row_nodes+1]
   int32_t *d_bcol = nullptr;
   uint8_t *d_elem_slot = nullptr;  // [n_elems][8][8]
+  // transpose of the connectivity for the row-owner kernel (assemble_urow.cu), non-lattice 3-dof graphs only: the elements
+  // around row node r are rowelem[rowelem_ptr[r] .. rowelem_ptr[r+1]), each packed as element << 3 | local node
+  int64_t *d_rowelem_ptr = nullptr;
+  int32_t *d_rowelem = nullptr;
   uint8_t *d_node_slot27 = nullptr; // box only: [n_nodes][27] slot of lattice neighbour (dz,dy,dx)
   // box only: [n_nodes][3] row descriptor of the tiled kernels: [0] first value of the node's rows (ndof^2 browptr[row]),
   // [1] row | blocks << 32 | natural << 40 (all 27 lattice neighbours present, in lattice order) | 1 << 41,

@@ -38,6 +38,9 @@ int launch_assemble_scalar_box(const Graph &g, const nalu_b200_kernel_desc *k, i
 bool slist_box_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
 int launch_assemble_slist_box(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs,
                               int overwrite, cudaStream_t stream);
+// assemble_urow.cu: [MomentumMass(lumped)]? + MomentumAdvDiff on any coloured Hex8 connectivity, thread = (element, row node)
+bool urow_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
+int launch_assemble_urow(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs, cudaStream_t stream);
 bool scv_lumped_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
 int launch_scv_lumped(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs, cudaStream_t stream);
 int launch_nodal_grad(const Graph &g, const double *coords, const double *field, int ncomp, const double *dual_volume, int use_shifted,
@@ -82,6 +85,10 @@ struct Tuning {
   // coloured scatter of the general kernel: 0 = load / add / store, 1 = fire-and-forget reduction (red.global.add.f64).
   // Either way exactly one element of a colour touches an address, so the result is the same sum in the same order.
   int general_scatter = 1;
+  int color_chunk = 0; // elements per (chunk, colour) launch group of graphs created from now on; 0 = one chunk
+  int urow_minb = 2;   // CTAs per SM the row-thread unstructured kernel's registers are bounded for
+  bool urow_owner = true; // row-owner form (one launch, thread = row node) when the graph carries the transposed connectivity
+  bool urow = true; // momentum lists on non-lattice meshes: row-thread unstructured kernel (assemble_urow.cu) instead of the general one
 };
 const Tuning &tuning();
 

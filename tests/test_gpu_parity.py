@@ -28,7 +28,7 @@ def tune():
     """nalu_b200_tune knobs, restored to their defaults after the test."""
     from nalu_b200 import lib
     yield lib.tune
-    lib.tune(box_kernel=5, box_zchunk=0, split_lists=1, cont_tiled=1)
+    lib.tune(box_kernel=5, box_zchunk=0, split_lists=1, cont_tiled=1, urow=1, urow_owner=1, general_scatter=1)
 
 
 def _cuda():
@@ -1038,11 +1038,12 @@ def test_assemble_nodal_grad_elem(ncomp, shifted):
 # ---------------------------------------------------------------------------------------------
 # real meshes of the reference's regression suite (tests/golden/meshes, read with nalu_b200.exodus)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["momentum_mass+advdiff", "continuity_mass+adv", "scalar_mass+upw_tanh", "momentum_upw",
-                                  "scalar_diff"])
+@pytest.mark.parametrize("case", ["momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu", "continuity_mass+adv",
+                                  "scalar_mass+upw_tanh", "momentum_upw", "scalar_diff"])
 def test_unstructured_exodus_mesh_parity(case):
-    """reg_tests/mesh/thex8_8.g (1 852 Hex8, 2 to 46 elements per node, rows of 12 to 141 node blocks): the coloured general
-    kernel against the oracle, every entry."""
+    """reg_tests/mesh/thex8_8.g (1 852 Hex8, 2 to 46 elements per node, rows of 12 to 141 node blocks): the row-thread
+    unstructured kernel (momentum lists, mode 4) and the coloured general kernel (everything else, mode 1) against the
+    oracle, every entry."""
     from nalu_b200 import exodus
     import os
     m = exodus.read_exodus_hex8(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "thex8_8.g"))
@@ -1055,7 +1056,8 @@ def test_unstructured_exodus_mesh_parity(case):
     ls = _linsys(m, ndof)
     assert ls.elem_colors()[0] >= 46
     ls.zero_system()
-    assert ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode="auto") == 1
+    urow = case in ("momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu")
+    assert ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode="auto") == (4 if urow else 1)
     _compare_system(ls, orc)
     assert ls.geometry_errors() == 0
     # deterministic: colour-by-colour plain read-modify-writes
@@ -1086,7 +1088,7 @@ def test_decomposed_exodus_mesh_parity_after_load_complete(ndof, kind):
         dev = st.to_device("cuda")
         orc.assemble_elem(r, [oracle_desc(st, kind, (), keep, **sc)])
         ls.zero_system()
-        assert ls.assemble_elem([product_desc(ls, dev, kind, **sc)]) == 1
+        assert ls.assemble_elem([product_desc(ls, dev, kind, **sc)]) == (4 if ndof == 3 else 1)
     torch.cuda.synchronize()
     for ls in systems:
         send, recv = ls.halo_peers()
@@ -1202,3 +1204,61 @@ def test_solver_handoff_device_solution_equals_oracle_solution():
     xo = spla.spsolve(A.tocsc(), orc.rhs(0))
     err = np.abs(x.cpu().numpy() - xo).max() / np.abs(xo).max()
     assert err < 1e-9, err
+
+
+@pytest.mark.parametrize("kind", ["shuffled", "periodic", "periodic_one_cell_wide"])
+@pytest.mark.parametrize("opts,divu,mass", [((), 1.0, True), (("shifted_grad_op", "skew_symmetric"), 0.0, True), ((), 1.0, False)])
+def test_row_thread_unstructured_momentum_kernel(kind, opts, divu, mass, tune):
+    """assemble_urow.cu: [MomentumMass(lumped)]? + MomentumAdvDiff on connectivity the tiled kernels do not take (shuffled
+    node ids, periodic aliasing) against the oracle: the row-owner form (ONE launch, thread = row node walking the elements
+    around it, plain adds) and the element-colour form (thread = (element, row node), value-less reductions); both bit
+    identical run to run."""
+    if kind == "periodic":
+        m, st = _periodic_state(9, 8, 7)
+    elif kind == "periodic_one_cell_wide":
+        # an element reaches a row through two of its nodes: no element colouring exists; the row-owner form visits the
+        # element twice and needs none
+        m, st = _periodic_state(1, 5, 4)
+    else:
+        m = perturbed_box(9, 8, 7)
+        m.node_gid = (np.random.default_rng(1).permutation(m.n_nodes) + 1).astype(np.int64)
+        m.box = None
+        st = State(m)
+    dev = st.to_device(_cuda())
+    bdf2 = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    klist = ([("momentum_mass", ("lumped_mass",), bdf2)] if mass else []) + [("momentum_adv_diff", opts, dict(include_divu=divu))]
+    orc = oracle.LinSys([m], 3)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, k, o, keep, **s) for k, o, s in klist])
+    ls = _linsys(m, 3)
+    descs = [product_desc(ls, dev, k, o, **s) for k, o, s in klist]
+    out = []
+    for _ in range(2):
+        launches0 = ls.L.nalu_b200_launch_count()
+        ls.zero_system()
+        assert ls.assemble_elem(descs, mode="auto") == 4
+        assert ls.L.nalu_b200_launch_count() - launches0 == 1
+        out.append((ls.values.clone(), ls.rhs.clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    _compare_system(ls, orc)
+    assert ls.geometry_errors() == 0
+    if ls.elem_colors()[0] == 0:
+        return
+    # the element-colour form of the same kernel (one launch per colour, value-less reductions)
+    tune(urow_owner=0)
+    launches0 = ls.L.nalu_b200_launch_count()
+    ls.zero_system()
+    assert ls.assemble_elem(descs, mode="auto") == 4
+    assert ls.L.nalu_b200_launch_count() - launches0 >= 8
+    _compare_system(ls, orc)
+    c0 = ls.values.clone()
+    ls.zero_system()
+    ls.assemble_elem(descs, mode="auto")
+    assert torch.equal(c0, ls.values)
+    tune(urow_owner=1)
+    # the knob takes the list back to the general kernel
+    tune(urow=0)
+    ls.zero_system()
+    assert ls.assemble_elem(descs, mode="auto") == 1
+    tune(urow=1)
+    _compare_system(ls, orc)

@@ -20,6 +20,18 @@ if len(sys.argv) > 3:  # A/B of the general kernel's coloured scatter: 0 = load/
 dev = torch.device("cuda", 0)
 m = mesh.generated_box(n, n, n)
 mesh.perturb_coords_hash(m, 0.12)
+if len(sys.argv) > 7:  # 1 row-owner form (one launch), 0 element-colour form of the unstructured kernel
+    from nalu_b200 import lib as _lib
+    _lib.tune(urow_owner=int(sys.argv[7]))
+if len(sys.argv) > 6:  # CTAs per SM the row-thread unstructured kernel is register-bounded for
+    from nalu_b200 import lib as _lib
+    _lib.tune(urow_minb=int(sys.argv[6]))
+if len(sys.argv) > 5:  # elements per (chunk, colour) launch group
+    from nalu_b200 import lib as _lib
+    _lib.tune(color_chunk=int(sys.argv[5]))
+if len(sys.argv) > 4 and sys.argv[4] == "nobox":
+    # the same elements declared as a general Hex8 mesh: "auto" is then the row-thread unstructured kernel (mode 4)
+    m.box = None
 c = m.coords
 t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
 vel, rho = fields.velocity(c), fields.smooth_density(c)
@@ -32,10 +44,12 @@ descs = [ls.make_desc("momentum_mass", fields=f, options=("lumped_mass",), dt=0.
 out = {"n": n, "elements": m.n_elems, "kernels": ["MomentumMassElemKernel(lumped)", "MomentumAdvDiffElemKernel(includeDivU=1)"]}
 ref = None
 for mode in ("general", "auto"):
-    def step():
-        if mode == "general":
+    fam = ls.assemble_elem(descs, mode=mode, overwrite=(mode == "auto"))
+
+    def step(fam=fam):
+        if fam != 2:  # only the tiled write-once kernels need no zeroSystem
             ls.zero_system()
-        return ls.assemble_elem(descs, mode=mode, overwrite=(mode == "auto"))
+        return ls.assemble_elem(descs, mode=mode, overwrite=(fam == 2))
     for _ in range(2):
         fam = step()
     torch.cuda.synchronize()
