@@ -33,8 +33,8 @@ struct UrowParams {
   const unsigned char *elem_slot;
   double *values, *rhs;
   int *err;
-  // MomentumAdvDiffElemKernel
-  const double *coords, *vel, *visc, *mdot;
+  // MomentumAdvDiffElemKernel (vel) / ScalarAdvDiffElemKernel, ScalarDiffElemKernel (q; visc = diffFluxCoeff; mdot may be null)
+  const double *coords, *vel, *visc, *mdot, *q;
   int options;
   double include_divu;
   // lumped MomentumMassElemKernel
@@ -96,7 +96,7 @@ __device__ __forceinline__ void ip_geometry(const UrowParams &P, const double (&
 #pragma unroll
     for (int a = 0; a < 3; ++a) g.Gt[i][a] = f * adj[i][a];
   }
-  g.tm = sgn * P.mdot[e * 12 + ip];
+  g.tm = P.mdot ? sgn * P.mdot[e * 12 + ip] : 0.0;
   mu_out = mu;
 }
 
@@ -294,6 +294,86 @@ __global__ void __launch_bounds__(128, MINB) assemble_urow_owner_kernel(const __
 }
 
 
+// ---- one dof per node: ScalarAdvDiffElemKernel / ScalarDiffElemKernel (src/kernel/ScalarAdvDiffElemKernel.C:69-127,
+// src/kernel/ScalarDiffElemKernel.C:64-110), row-owner form.  lhs(r, c) += sgn (N_c mdot - Gamma_ip grad N_c . A) over the three
+// points of node r, rhs_r -= sum_c lhs(r, c) q_c: per point only w_a = sum_i G~[i][a] A_i is needed (3 FMAs per column).
+__device__ __forceinline__ void row_contribution_scalar(const UrowParams &P, long long e, int r, double &res)
+{
+  int nodes[8];
+  double x[8][3];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) nodes[n] = P.elem_nodes[e * 8 + n];
+  {
+    const double o0 = P.coords[(size_t)nodes[0] * 3], o1 = P.coords[(size_t)nodes[0] * 3 + 1], o2 = P.coords[(size_t)nodes[0] * 3 + 2];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      x[n][0] = P.coords[(size_t)nodes[n] * 3] - o0;
+      x[n][1] = P.coords[(size_t)nodes[n] * 3 + 1] - o1;
+      x[n][2] = P.coords[(size_t)nodes[n] * 3 + 2] - o2;
+    }
+  }
+  const int rn = P.node_row[nodes[r]];
+  double *const row0 = P.values + P.browptr[rn];
+  const unsigned char *slots = P.elem_slot + e * 64 + r * 8;
+  // the row's current entries and the column values are requested before the geometry
+  double old[8], qc[8];
+  bool alias = false;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    old[c] = row0[slots[c]];
+    qc[c] = P.q[nodes[c]];
+#pragma unroll
+    for (int b = 0; b < c; ++b) alias = alias || slots[b] == slots[c];
+  }
+  double w[3][3], tm[3], s[3][3], sa[3][3], mu;
+  const double qa = (P.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25;
+  {
+    IpGeom g;
+    ip_geometry<0>(P, x, nodes, e, r, g, mu);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) w[0][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[0][a] = g.s[a];
+    tm[0] = g.tm;
+    ip_geometry<1>(P, x, nodes, e, r, g, mu);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) w[1][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[1][a] = g.s[a];
+    tm[1] = g.tm;
+    ip_geometry<2>(P, x, nodes, e, r, g, mu);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) w[2][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[2][a] = g.s[a];
+    tm[2] = g.tm;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) hex8::scs_intg_loc(box::ip_of(r, k), qa, sa[k][0], sa[k][1], sa[k][2]);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double d[3];
+      hex8::shape_deriv(c, s[k][0], s[k][1], s[k][2], d);
+      v += hex8::shape_fcn(c, sa[k][0], sa[k][1], sa[k][2]) * tm[k] + w[k][0] * d[0] + w[k][1] * d[1] + w[k][2] * d[2];
+    }
+    res -= v * qc[c];
+    if (alias) row0[slots[c]] += v; // an element that reaches a node twice: entries read ahead may be stale
+    else row0[slots[c]] = old[c] + v;
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_urow_owner_scalar_kernel(const __grid_constant__ UrowParams P)
+{
+  const long long rn = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rn >= P.n_rows) return;
+  double res = 0.0;
+  const long long q1 = P.rowelem_ptr[rn + 1];
+#pragma unroll 1
+  for (long long q = P.rowelem_ptr[rn]; q < q1; ++q) {
+    const int er = P.rowelem[q];
+    row_contribution_scalar(P, er >> 3, er & 7, res);
+  }
+  P.rhs[rn] += res;
+}
+
 } // namespace urow
 
 namespace {
@@ -315,8 +395,17 @@ bool classify_urow(const nalu_b200_kernel_desc *k, int nk, int &ia, int &im)
 }
 } // namespace
 
+static bool urow_scalar_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+{
+  if (g.ndof != 1 || !g.d_rowelem || !g.d_elem_slot || !tuning().urow_owner || nk != 1) return false;
+  if (k[0].kind != NALU_K_SCALAR_ADV_DIFF && k[0].kind != NALU_K_SCALAR_DIFF) return false;
+  if (!k[0].nodal[NALU_F_COORDINATES] || !k[0].nodal[NALU_F_SCALARQ] || !k[0].nodal[NALU_F_VISCOSITY]) return false;
+  return k[0].kind == NALU_K_SCALAR_DIFF || k[0].mass_flow_rate != nullptr;
+}
+
 bool urow_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
 {
+  if (urow_scalar_supported(g, k, nk)) return true;
   if (g.ndof != 3 || (!g.d_color_elems && !g.d_rowelem) || !g.d_elem_slot || nk < 1 || nk > 2) return false;
   int ia, im;
   if (!classify_urow(k, nk, ia, im)) return false;
@@ -338,6 +427,28 @@ int launch_assemble_urow(const Graph &g, const nalu_b200_kernel_desc *k, int nk,
     return NALU_B200_ERR_ARG;
   }
   if (g.n_elems == 0) return NALU_B200_OK;
+  if (urow_scalar_supported(g, k, nk)) {
+    urow::UrowParams P = {};
+    P.elem_nodes = g.d_elem_nodes;
+    P.node_row = g.d_node_row;
+    P.browptr = (const long long *)g.d_browptr;
+    P.elem_slot = g.d_elem_slot;
+    P.values = d_values;
+    P.rhs = d_rhs;
+    P.err = g.d_err;
+    P.coords = k[0].nodal[NALU_F_COORDINATES];
+    P.q = k[0].nodal[NALU_F_SCALARQ];
+    P.visc = k[0].nodal[NALU_F_VISCOSITY];
+    P.mdot = k[0].kind == NALU_K_SCALAR_DIFF ? nullptr : k[0].mass_flow_rate;
+    P.options = k[0].options & (NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC);
+    P.n_rows = g.n_row_nodes();
+    P.rowelem_ptr = (const long long *)g.d_rowelem_ptr;
+    P.rowelem = g.d_rowelem;
+    urow::assemble_urow_owner_scalar_kernel<2><<<(unsigned)((P.n_rows + 127) / 128), 128, 0, stream>>>(P);
+    count_launch();
+    NALU_CUDA(cudaGetLastError());
+    return NALU_B200_OK;
+  }
   int ia, im;
   classify_urow(k, nk, ia, im);
   const nalu_b200_kernel_desc &a = k[ia];

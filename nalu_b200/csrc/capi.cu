@@ -114,7 +114,7 @@ static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const s
   if ((rc = upload(&g.d_node_slot27, node_slot27))) return rc;
   if ((rc = upload(&g.d_node_desc, g.node_desc))) return rc;
   std::vector<uint64_t>().swap(g.node_desc);
-  if (g.box[0] == 0 && g.ndof == 3 && g.n_elems > 0 && g.n_elems < (int64_t(1) << 28)) {
+  if (g.box[0] == 0 && g.n_elems > 0 && g.n_elems < (int64_t(1) << 28)) {
     // row node -> (element, local node), elements in ascending order: a counting sort of the connectivity by row
     const int nrow = g.n_row_nodes();
     std::vector<int64_t> ptr(size_t(nrow) + 1, 0);

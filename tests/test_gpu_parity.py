@@ -1056,7 +1056,7 @@ def test_unstructured_exodus_mesh_parity(case):
     ls = _linsys(m, ndof)
     assert ls.elem_colors()[0] >= 46
     ls.zero_system()
-    urow = case in ("momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu")
+    urow = case in ("momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu", "scalar_diff")
     assert ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode="auto") == (4 if urow else 1)
     _compare_system(ls, orc)
     assert ls.geometry_errors() == 0
@@ -1217,7 +1217,10 @@ def test_row_thread_unstructured_momentum_kernel(kind, opts, divu, mass, tune):
         m, st = _periodic_state(9, 8, 7)
     elif kind == "periodic_one_cell_wide":
         # an element reaches a row through two of its nodes: no element colouring exists; the row-owner form visits the
-        # element twice and needs none
+        # element twice and needs none.  The reference itself is not defined here: sum_into_row_vec_3
+        # (src/TpetraLinearSystem.C:1386-1413) walks the row forward once per sorted column id, so the second of two equal
+        # ids is never found and it returns, dropping the rest of the element row -- the oracle restates that.  The check
+        # is against the general kernel (atomic fallback: every contribution summed).
         m, st = _periodic_state(1, 5, 4)
     else:
         m = perturbed_box(9, 8, 7)
@@ -1240,10 +1243,18 @@ def test_row_thread_unstructured_momentum_kernel(kind, opts, divu, mass, tune):
         assert ls.L.nalu_b200_launch_count() - launches0 == 1
         out.append((ls.values.clone(), ls.rhs.clone()))
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
-    _compare_system(ls, orc)
     assert ls.geometry_errors() == 0
-    if ls.elem_colors()[0] == 0:
+    if kind == "periodic_one_cell_wide":
+        assert ls.elem_colors()[0] == 0
+        tune(urow=0)
+        ls.zero_system()
+        assert ls.assemble_elem(descs, mode="auto") == 1
+        tune(urow=1)
+        gv, gr = ls.values, ls.rhs
+        assert float((gv - out[0][0]).abs().max() / gv.abs().max()) < 1e-13
+        assert float((gr - out[0][1]).abs().max() / gr.abs().max()) < 1e-12
         return
+    _compare_system(ls, orc)
     # the element-colour form of the same kernel (one launch per colour, value-less reductions)
     tune(urow_owner=0)
     launches0 = ls.L.nalu_b200_launch_count()
@@ -1262,3 +1273,44 @@ def test_row_thread_unstructured_momentum_kernel(kind, opts, divu, mass, tune):
     assert ls.assemble_elem(descs, mode="auto") == 1
     tune(urow=1)
     _compare_system(ls, orc)
+
+
+@pytest.mark.parametrize("kind", ["shuffled", "periodic", "periodic_one_cell_wide"])
+@pytest.mark.parametrize("kernel,opts", [("scalar_adv_diff", ()), ("scalar_adv_diff", ("shifted_grad_op", "skew_symmetric")),
+                                         ("scalar_diff", ("shifted_grad_op",))])
+def test_row_owner_unstructured_scalar_kernel(kind, kernel, opts, tune):
+    """assemble_urow.cu, one dof per node: ScalarAdvDiffElemKernel / ScalarDiffElemKernel on non-lattice connectivity (the
+    periodic box of BASELINE config 2) in ONE launch, thread = row node, no atomics; against the oracle, and against the
+    general kernel where the reference is not defined (see test_row_thread_unstructured_momentum_kernel)."""
+    if kind == "periodic":
+        m, st = _periodic_state(9, 8, 7)
+    elif kind == "periodic_one_cell_wide":
+        m, st = _periodic_state(1, 5, 4)
+    else:
+        m = perturbed_box(9, 8, 7)
+        m.node_gid = (np.random.default_rng(1).permutation(m.n_nodes) + 1).astype(np.int64)
+        m.box = None
+        st = State(m)
+    dev = st.to_device(_cuda())
+    orc = oracle.LinSys([m], 1)
+    keep = []
+    orc.assemble_elem(0, [oracle_desc(st, kernel, opts, keep)])
+    ls = _linsys(m, 1)
+    descs = [product_desc(ls, dev, kernel, opts)]
+    out = []
+    for _ in range(2):
+        launches0 = ls.L.nalu_b200_launch_count()
+        ls.zero_system()
+        assert ls.assemble_elem(descs, mode="auto") == 4
+        assert ls.L.nalu_b200_launch_count() - launches0 == 1
+        out.append((ls.values.clone(), ls.rhs.clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert ls.geometry_errors() == 0
+    if kind != "periodic_one_cell_wide":
+        _compare_system(ls, orc)
+    tune(urow=0)
+    ls.zero_system()
+    assert ls.assemble_elem(descs, mode="auto") == 1
+    tune(urow=1)
+    assert float((ls.values - out[0][0]).abs().max() / ls.values.abs().max()) < 1e-13
+    assert float((ls.rhs - out[0][1]).abs().max() / ls.rhs.abs().max()) < 1e-12
