@@ -35,6 +35,10 @@ struct UrowParams {
   int *err;
   // MomentumAdvDiffElemKernel (vel) / ScalarAdvDiffElemKernel, ScalarDiffElemKernel (q; visc = diffFluxCoeff; mdot may be null)
   const double *coords, *vel, *visc, *mdot, *q;
+  // ContinuityAdvElemKernel: vel (velocity_rtm), rho, pressure, dpdx; tau = dt / gamma1; NALU_OPT_SHIFT_MDOT / _SHIFT_POISSON /
+  // _REDUCED_SENS in options
+  const double *pressure;
+  double tau;
   int options;
   double include_divu;
   // lumped MomentumMassElemKernel
@@ -359,8 +363,114 @@ __device__ __forceinline__ void row_contribution_scalar(const UrowParams &P, lon
   }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) assemble_urow_owner_scalar_kernel(const __grid_constant__ UrowParams P)
+// ---- ContinuityAdvElemKernel (src/kernel/ContinuityAdvElemKernel.C:86-148), row-owner form.  Per point of node r:
+// lhs(r, c) += sgn (-grad N_c . A) with the (possibly shifted) lhs operator; rhs_r -= sgn mdot / tau,
+// mdot = (rho u - tau (grad p - Gp))_ip . A.  grad N_c . A = w . dN_c/dxi with w_a = sum_i adj(J)[i][a] A_i / det J.
+__device__ __forceinline__ void metric_dot_area(const double (&x)[8][3], int ip, double q, const double (&A)[3], double (&w)[3],
+                                                double (&s)[3], int *err)
+{
+  hex8::scs_intg_loc(ip, q, s[0], s[1], s[2]);
+  double jact[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    double d[3];
+    hex8::shape_deriv(n, s[0], s[1], s[2], d);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) jact[i][j] += d[j] * x[n][i];
+  }
+  double adj[3][3];
+  adj[0][0] = jact[1][1] * jact[2][2] - jact[2][1] * jact[1][2];
+  adj[0][1] = jact[1][2] * jact[2][0] - jact[2][2] * jact[1][0];
+  adj[0][2] = jact[1][0] * jact[2][1] - jact[2][0] * jact[1][1];
+  adj[1][0] = jact[0][2] * jact[2][1] - jact[2][2] * jact[0][1];
+  adj[1][1] = jact[0][0] * jact[2][2] - jact[2][0] * jact[0][2];
+  adj[1][2] = jact[0][1] * jact[2][0] - jact[2][1] * jact[0][0];
+  adj[2][0] = jact[0][1] * jact[1][2] - jact[1][1] * jact[0][2];
+  adj[2][1] = jact[0][2] * jact[1][0] - jact[1][2] * jact[0][0];
+  adj[2][2] = jact[0][0] * jact[1][1] - jact[1][0] * jact[0][1];
+  const double det = jact[0][0] * adj[0][0] + jact[1][0] * adj[1][0] + jact[2][0] * adj[2][0];
+  if (!(det > 0.0)) *err = 1;
+  const double inv = 1.0 / det;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) w[a] = (adj[0][a] * A[0] + adj[1][a] * A[1] + adj[2][a] * A[2]) * inv;
+}
+
+__device__ __forceinline__ void row_contribution_cont(const UrowParams &P, long long e, int r, double &res)
+{
+  int nodes[8];
+  double x[8][3];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) nodes[n] = P.elem_nodes[e * 8 + n];
+  {
+    const double o0 = P.coords[(size_t)nodes[0] * 3], o1 = P.coords[(size_t)nodes[0] * 3 + 1], o2 = P.coords[(size_t)nodes[0] * 3 + 2];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      x[n][0] = P.coords[(size_t)nodes[n] * 3] - o0;
+      x[n][1] = P.coords[(size_t)nodes[n] * 3 + 1] - o1;
+      x[n][2] = P.coords[(size_t)nodes[n] * 3 + 2] - o2;
+    }
+  }
+  const int rn = P.node_row[nodes[r]];
+  double *const row0 = P.values + P.browptr[rn];
+  const unsigned char *slots = P.elem_slot + e * 64 + r * 8;
+  double old[8];
+  bool alias = false;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    old[c] = row0[slots[c]];
+#pragma unroll
+    for (int b = 0; b < c; ++b) alias = alias || slots[b] == slots[c];
+  }
+  const bool shift_poisson = (P.options & NALU_OPT_SHIFT_POISSON) != 0;
+  const bool lhs_shifted = shift_poisson || (P.options & NALU_OPT_REDUCED_SENS) != 0;
+  const double qs = (P.options & NALU_OPT_SHIFT_MDOT) ? 0.5 : 0.25;
+  double As[3][3], wr[3][3], wl[3][3], sr[3][3], sl[3][3], ss[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int ip = box::ip_of(r, k);
+    const double sgn = hex8::scs_left(ip) == r ? 1.0 : -1.0;
+    double A[3];
+    hex8::scs_areav_ip(x, ip, A);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) As[k][j] = sgn * A[j];
+    metric_dot_area(x, ip, shift_poisson ? 0.5 : 0.25, As[k], wr[k], sr[k], P.err);
+    if (lhs_shifted != shift_poisson) {
+      metric_dot_area(x, ip, 0.5, As[k], wl[k], sl[k], P.err);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) wl[k][a] = wr[k][a], sl[k][a] = sr[k][a];
+    }
+    hex8::scs_intg_loc(ip, qs, ss[k][0], ss[k][1], ss[k][2]);
+  }
+  double mdot = 0.0; // sum over the three points of sgn mdot
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int nd = nodes[c];
+    const double p = P.pressure[nd], rho = P.rho[nd];
+    const double u[3] = {P.vel[(size_t)nd * 3], P.vel[(size_t)nd * 3 + 1], P.vel[(size_t)nd * 3 + 2]};
+    const double gp[3] = {P.dpdx[(size_t)nd * 3], P.dpdx[(size_t)nd * 3 + 1], P.dpdx[(size_t)nd * 3 + 2]};
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double d[3];
+      hex8::shape_deriv(c, sl[k][0], sl[k][1], sl[k][2], d);
+      v -= wl[k][0] * d[0] + wl[k][1] * d[1] + wl[k][2] * d[2];
+      hex8::shape_deriv(c, sr[k][0], sr[k][1], sr[k][2], d);
+      const double gpa = wr[k][0] * d[0] + wr[k][1] * d[1] + wr[k][2] * d[2]; // grad N_c . A
+      const double N = hex8::shape_fcn(c, ss[k][0], ss[k][1], ss[k][2]);
+      mdot += N * (rho * (u[0] * As[k][0] + u[1] * As[k][1] + u[2] * As[k][2]) + P.tau * (gp[0] * As[k][0] + gp[1] * As[k][1] + gp[2] * As[k][2])) -
+              P.tau * gpa * p;
+    }
+    if (alias) row0[slots[c]] += v;
+    else row0[slots[c]] = old[c] + v;
+  }
+  res -= mdot / P.tau;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128, 2) assemble_urow_owner_onedof_kernel(const __grid_constant__ UrowParams P)
 {
   const long long rn = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (rn >= P.n_rows) return;
@@ -369,7 +479,8 @@ __global__ void __launch_bounds__(128, MINB) assemble_urow_owner_scalar_kernel(c
 #pragma unroll 1
   for (long long q = P.rowelem_ptr[rn]; q < q1; ++q) {
     const int er = P.rowelem[q];
-    row_contribution_scalar(P, er >> 3, er & 7, res);
+    if (KIND == 0) row_contribution_scalar(P, er >> 3, er & 7, res);
+    else row_contribution_cont(P, er >> 3, er & 7, res);
   }
   P.rhs[rn] += res;
 }
@@ -398,6 +509,9 @@ bool classify_urow(const nalu_b200_kernel_desc *k, int nk, int &ia, int &im)
 static bool urow_scalar_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
 {
   if (g.ndof != 1 || !g.d_rowelem || !g.d_elem_slot || !tuning().urow_owner || nk != 1) return false;
+  if (k[0].kind == NALU_K_CONTINUITY_ADV)
+    return k[0].nodal[NALU_F_COORDINATES] && k[0].nodal[NALU_F_VELOCITY] && k[0].nodal[NALU_F_DENSITY] && k[0].nodal[NALU_F_PRESSURE] &&
+           k[0].nodal[NALU_F_DPDX];
   if (k[0].kind != NALU_K_SCALAR_ADV_DIFF && k[0].kind != NALU_K_SCALAR_DIFF) return false;
   if (!k[0].nodal[NALU_F_COORDINATES] || !k[0].nodal[NALU_F_SCALARQ] || !k[0].nodal[NALU_F_VISCOSITY]) return false;
   return k[0].kind == NALU_K_SCALAR_DIFF || k[0].mass_flow_rate != nullptr;
@@ -437,14 +551,25 @@ int launch_assemble_urow(const Graph &g, const nalu_b200_kernel_desc *k, int nk,
     P.rhs = d_rhs;
     P.err = g.d_err;
     P.coords = k[0].nodal[NALU_F_COORDINATES];
-    P.q = k[0].nodal[NALU_F_SCALARQ];
-    P.visc = k[0].nodal[NALU_F_VISCOSITY];
-    P.mdot = k[0].kind == NALU_K_SCALAR_DIFF ? nullptr : k[0].mass_flow_rate;
-    P.options = k[0].options & (NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC);
     P.n_rows = g.n_row_nodes();
     P.rowelem_ptr = (const long long *)g.d_rowelem_ptr;
     P.rowelem = g.d_rowelem;
-    urow::assemble_urow_owner_scalar_kernel<2><<<(unsigned)((P.n_rows + 127) / 128), 128, 0, stream>>>(P);
+    const unsigned grid = (unsigned)((P.n_rows + 127) / 128);
+    if (k[0].kind == NALU_K_CONTINUITY_ADV) {
+      P.vel = k[0].nodal[NALU_F_VELOCITY];
+      P.rho = k[0].nodal[NALU_F_DENSITY];
+      P.pressure = k[0].nodal[NALU_F_PRESSURE];
+      P.dpdx = k[0].nodal[NALU_F_DPDX];
+      P.tau = k[0].dt / k[0].gamma1;
+      P.options = k[0].options & (NALU_OPT_SHIFT_MDOT | NALU_OPT_SHIFT_POISSON | NALU_OPT_REDUCED_SENS);
+      urow::assemble_urow_owner_onedof_kernel<1><<<grid, 128, 0, stream>>>(P);
+    } else {
+      P.q = k[0].nodal[NALU_F_SCALARQ];
+      P.visc = k[0].nodal[NALU_F_VISCOSITY];
+      P.mdot = k[0].kind == NALU_K_SCALAR_DIFF ? nullptr : k[0].mass_flow_rate;
+      P.options = k[0].options & (NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC);
+      urow::assemble_urow_owner_onedof_kernel<0><<<grid, 128, 0, stream>>>(P);
+    }
     count_launch();
     NALU_CUDA(cudaGetLastError());
     return NALU_B200_OK;

@@ -1088,7 +1088,7 @@ def test_decomposed_exodus_mesh_parity_after_load_complete(ndof, kind):
         dev = st.to_device("cuda")
         orc.assemble_elem(r, [oracle_desc(st, kind, (), keep, **sc)])
         ls.zero_system()
-        assert ls.assemble_elem([product_desc(ls, dev, kind, **sc)]) == (4 if ndof == 3 else 1)
+        assert ls.assemble_elem([product_desc(ls, dev, kind, **sc)]) == 4  # row-owner kernels, momentum and continuity
     torch.cuda.synchronize()
     for ls in systems:
         send, recv = ls.halo_peers()
@@ -1277,11 +1277,13 @@ def test_row_thread_unstructured_momentum_kernel(kind, opts, divu, mass, tune):
 
 @pytest.mark.parametrize("kind", ["shuffled", "periodic", "periodic_one_cell_wide"])
 @pytest.mark.parametrize("kernel,opts", [("scalar_adv_diff", ()), ("scalar_adv_diff", ("shifted_grad_op", "skew_symmetric")),
-                                         ("scalar_diff", ("shifted_grad_op",))])
+                                         ("scalar_diff", ("shifted_grad_op",)), ("continuity_adv", ()),
+                                         ("continuity_adv", ("reduced_sens", "shift_mdot")), ("continuity_adv", ("shift_poisson",))])
 def test_row_owner_unstructured_scalar_kernel(kind, kernel, opts, tune):
-    """assemble_urow.cu, one dof per node: ScalarAdvDiffElemKernel / ScalarDiffElemKernel on non-lattice connectivity (the
-    periodic box of BASELINE config 2) in ONE launch, thread = row node, no atomics; against the oracle, and against the
-    general kernel where the reference is not defined (see test_row_thread_unstructured_momentum_kernel)."""
+    """assemble_urow.cu, one dof per node: ScalarAdvDiffElemKernel / ScalarDiffElemKernel / ContinuityAdvElemKernel on
+    non-lattice connectivity (the periodic box of BASELINE config 2) in ONE launch, thread = row node, no atomics; against
+    the oracle, and against the general kernel where the reference is not defined (see
+    test_row_thread_unstructured_momentum_kernel)."""
     if kind == "periodic":
         m, st = _periodic_state(9, 8, 7)
     elif kind == "periodic_one_cell_wide":
@@ -1292,11 +1294,12 @@ def test_row_owner_unstructured_scalar_kernel(kind, kernel, opts, tune):
         m.box = None
         st = State(m)
     dev = st.to_device(_cuda())
+    sc = dict(dt=0.05, gamma1=1.5) if kernel == "continuity_adv" else {}
     orc = oracle.LinSys([m], 1)
     keep = []
-    orc.assemble_elem(0, [oracle_desc(st, kernel, opts, keep)])
+    orc.assemble_elem(0, [oracle_desc(st, kernel, opts, keep, **sc)])
     ls = _linsys(m, 1)
-    descs = [product_desc(ls, dev, kernel, opts)]
+    descs = [product_desc(ls, dev, kernel, opts, **sc)]
     out = []
     for _ in range(2):
         launches0 = ls.L.nalu_b200_launch_count()

@@ -19,6 +19,8 @@ kind = sys.argv[3] if len(sys.argv) > 3 else "continuity_adv"
 dev = torch.device("cuda", 0)
 m = mesh.generated_box(n, n, n)
 mesh.perturb_coords_hash(m, 0.12)
+if len(sys.argv) > 4 and sys.argv[4] == "nobox":
+    m.box = None  # the same elements as a general Hex8 mesh: "auto" is the row-owner kernel (mode 4)
 c = m.coords
 t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
 f = dict(coordinates=t(c), velocity=t(fields.velocity(c)), density=t(fields.smooth_density(c)),
@@ -35,9 +37,9 @@ else:
 out = {"n": n, "elements": m.n_elems, "kind": kind}
 ref = None
 for mode in ("general", "auto"):
-    ow = mode == "auto"
+    ow = ls.assemble_elem([desc], mode=mode, overwrite=True) == 2  # only the tiled write-once kernels need no zeroSystem
 
-    def step():
+    def step(ow=ow):
         if not ow:
             ls.zero_system()
         return ls.assemble_elem([desc], mode=mode, overwrite=ow)
