@@ -59,11 +59,10 @@ struct IpGeom {
 };
 
 // geometry of the integration point on the edge leaving node r in direction DIR
-template <int DIR>
 __device__ __forceinline__ void ip_geometry(const UrowParams &P, const double (&x)[8][3], const int (&nodes)[8], long long e, int r,
-                                            IpGeom &g, double &mu_out)
+                                            int dir, IpGeom &g, double &mu_out)
 {
-  const int ip = box::ip_of(r, DIR);
+  const int ip = box::ip_of(r, dir);
   const double sgn = hex8::scs_left(ip) == r ? 1.0 : -1.0;
   double A[3];
   hex8::scs_areav_ip(x, ip, A);
@@ -162,9 +161,9 @@ __device__ __forceinline__ void row_contribution(const UrowParams &P, long long 
   }
   IpGeom g[3];
   double mu_ip[3];
-  ip_geometry<0>(P, x, nodes, e, r, g[0], mu_ip[0]);
-  ip_geometry<1>(P, x, nodes, e, r, g[1], mu_ip[1]);
-  ip_geometry<2>(P, x, nodes, e, r, g[2], mu_ip[2]);
+  ip_geometry(P, x, nodes, e, r, 0, g[0], mu_ip[0]);
+  ip_geometry(P, x, nodes, e, r, 1, g[1], mu_ip[1]);
+  ip_geometry(P, x, nodes, e, r, 2, g[2], mu_ip[2]);
   const double qa = (P.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25;
   double sa[3][3]; // advection shape-function location of the three points
 #pragma unroll
@@ -333,15 +332,15 @@ __device__ __forceinline__ void row_contribution_scalar(const UrowParams &P, lon
   const double qa = (P.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25;
   {
     IpGeom g;
-    ip_geometry<0>(P, x, nodes, e, r, g, mu);
+    ip_geometry(P, x, nodes, e, r, 0, g, mu);
 #pragma unroll
     for (int a = 0; a < 3; ++a) w[0][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[0][a] = g.s[a];
     tm[0] = g.tm;
-    ip_geometry<1>(P, x, nodes, e, r, g, mu);
+    ip_geometry(P, x, nodes, e, r, 1, g, mu);
 #pragma unroll
     for (int a = 0; a < 3; ++a) w[1][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[1][a] = g.s[a];
     tm[1] = g.tm;
-    ip_geometry<2>(P, x, nodes, e, r, g, mu);
+    ip_geometry(P, x, nodes, e, r, 2, g, mu);
 #pragma unroll
     for (int a = 0; a < 3; ++a) w[2][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[2][a] = g.s[a];
     tm[2] = g.tm;
