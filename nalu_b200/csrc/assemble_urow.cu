@@ -39,6 +39,17 @@ struct UrowParams {
   // _REDUCED_SENS in options
   const double *pressure;
   double tau;
+  // ScalarUpwAdvDiffElemKernel (upw = 1): Gjq, velocity_rtm in vel, density in rho; constants as in nalu_b200_kernel_desc::upw
+  int upw, upw_options;
+  const double *gjq;
+  double alpha, alpha_upw, ho_upwind, hybrid, tanh_trans, tanh_width;
+  // lumped ScalarMassElemKernel (mass = 1 with ndof 1): q_n, q_nm1 beside rho, rho_n, rho_nm1 and g*_dt
+  const double *q_n, *q_nm1;
+  // TurbKineticEnergySSTSrcElemKernel (src = 1) / SpecificDissipationRateSSTSrcElemKernel (src = 2): turbulent_ke,
+  // specific_dissipation_rate, turbulent_viscosity, sst_f_one_blending, velocity in src_vel, density in rho; NALU_TM_* constants
+  int src, src_lumped, src_shifted;
+  const double *tke, *sdr, *tvisc, *f1, *src_vel;
+  double turb[10];
   int options;
   double include_divu;
   // lumped MomentumMassElemKernel
@@ -297,9 +308,23 @@ __global__ void __launch_bounds__(128, MINB) assemble_urow_owner_kernel(const __
 }
 
 
-// ---- one dof per node: ScalarAdvDiffElemKernel / ScalarDiffElemKernel (src/kernel/ScalarAdvDiffElemKernel.C:69-127,
-// src/kernel/ScalarDiffElemKernel.C:64-110), row-owner form.  lhs(r, c) += sgn (N_c mdot - Gamma_ip grad N_c . A) over the three
-// points of node r, rhs_r -= sum_c lhs(r, c) q_c: per point only w_a = sum_i G~[i][a] A_i is needed (3 FMAs per column).
+// ---- one dof per node: [ScalarMassElemKernel(lumped)]? + ScalarAdvDiffElemKernel / ScalarDiffElemKernel /
+// ScalarUpwAdvDiffElemKernel (src/kernel/ScalarAdvDiffElemKernel.C:69-127, ScalarDiffElemKernel.C:64-110,
+// ScalarUpwAdvDiffElemKernel.C:110-256, ScalarMassElemKernel.C:117-154), row-owner form.  Over the three points of node r:
+// lhs(r, c) += sgn (N_c adv - Gamma_ip grad N_c . A) (+ the upwind factors on the two ends of the edge),
+// rhs_r -= sgn (advective flux + sum_c (-Gamma grad N_c . A) q_c); per point only w_a = sum_i G~[i][a] A_i is needed.
+__device__ __forceinline__ double urow_peclet(const UrowParams &P, double x)
+{
+  if (P.upw_options & NALU_OPT_PECLET_TANH) return 0.50 * (1.0 + tanh((x - P.tanh_trans) / P.tanh_width));
+  const double m = P.hybrid * x;
+  return m * m / (5.0 + m * m);
+}
+__device__ __forceinline__ double urow_van_leer(double dqm, double dqp)
+{
+  return (2.0 * (dqm * dqp + fabs(dqm * dqp))) / ((dqm + dqp) * (dqm + dqp) + 1.0e-16);
+}
+
+template <bool UPW, bool SRC>
 __device__ __forceinline__ void row_contribution_scalar(const UrowParams &P, long long e, int r, double &res)
 {
   int nodes[8];
@@ -329,36 +354,184 @@ __device__ __forceinline__ void row_contribution_scalar(const UrowParams &P, lon
     for (int b = 0; b < c; ++b) alias = alias || slots[b] == slots[c];
   }
   double w[3][3], tm[3], s[3][3], sa[3][3], mu;
+  double advc[3], aL[3] = {0, 0, 0}, aR[3] = {0, 0, 0}, pf[3] = {0, 0, 0}, qL[3] = {0, 0, 0}, qR[3] = {0, 0, 0}, sg[3];
+  int nbr[3]; // the other end of the edge leaving r in direction k
   const double qa = (P.options & NALU_OPT_SKEW_SYMMETRIC) ? 0.5 : 0.25;
-  {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
     IpGeom g;
-    ip_geometry(P, x, nodes, e, r, 0, g, mu);
+    ip_geometry(P, x, nodes, e, r, k, g, mu);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) w[0][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[0][a] = g.s[a];
-    tm[0] = g.tm;
-    ip_geometry(P, x, nodes, e, r, 1, g, mu);
+    for (int a = 0; a < 3; ++a) w[k][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[k][a] = g.s[a];
+    tm[k] = g.tm;
+    const int ip = box::ip_of(r, k);
+    hex8::scs_intg_loc(ip, qa, sa[k][0], sa[k][1], sa[k][2]);
+    const int il = hex8::scs_left(ip), ir = hex8::scs_right(ip);
+    sg[k] = il == r ? 1.0 : -1.0;
+    nbr[k] = il == r ? ir : il;
+    advc[k] = tm[k];
+    if (UPW) {
+      // ScalarUpwAdvDiffElemKernel.C:128-223: Peclet factor along the edge, limited extrapolation from both ends
+      const int nl = nodes[il], nr = nodes[ir];
+      const double tmdot = sg[k] * tm[k];
+      const double diffIp = 0.5 * (P.visc[nl] / P.rho[nl] + P.visc[nr] / P.rho[nr]);
+      double udotx = 0.0, dqL = 0.0, dqR = 0.0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) w[1][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[1][a] = g.s[a];
-    tm[1] = g.tm;
-    ip_geometry(P, x, nodes, e, r, 2, g, mu);
+      for (int j = 0; j < 3; ++j) {
+        double cip = 0.0; // adv-shape-function interpolation of the coordinates
 #pragma unroll
-    for (int a = 0; a < 3; ++a) w[2][a] = g.Gt[0][a] * g.As[0] + g.Gt[1][a] * g.As[1] + g.Gt[2][a] * g.As[2], s[2][a] = g.s[a];
-    tm[2] = g.tm;
+        for (int n = 0; n < 8; ++n) cip += hex8::shape_fcn(n, sa[k][0], sa[k][1], sa[k][2]) * x[n][j];
+        udotx += 0.5 * (P.vel[(size_t)nl * 3 + j] + P.vel[(size_t)nr * 3 + j]) * (x[ir][j] - x[il][j]);
+        dqL += (cip - x[il][j]) * P.gjq[(size_t)nl * 3 + j];
+        dqR += (x[ir][j] - cip) * P.gjq[(size_t)nr * 3 + j];
+      }
+      const double pecfac = urow_peclet(P, fabs(udotx) / (diffIp + 1.0e-16)), om_pecfac = 1.0 - pecfac;
+      double limitL = 1.0, limitR = 1.0;
+      if (P.upw_options & NALU_OPT_USE_LIMITER) {
+        const double dq = qc[ir] - qc[il];
+        limitL = urow_van_leer(2.0 * 2.0 * dqL - dq, dq);
+        limitR = urow_van_leer(2.0 * 2.0 * dqR - dq, dq);
+      }
+      qL[k] = qc[il] + dqL * P.ho_upwind * limitL;
+      qR[k] = qc[ir] - dqR * P.ho_upwind * limitR;
+      pf[k] = pecfac;
+      advc[k] = tm[k] * (pecfac * (1.0 - P.alpha_upw) + om_pecfac * (1.0 - P.alpha));
+      const double cds = 0.5 * P.alpha * om_pecfac * tmdot;
+      aL[k] = sg[k] * (0.5 * (tmdot + fabs(tmdot)) * pecfac * P.alpha_upw + cds);
+      aR[k] = sg[k] * (0.5 * (tmdot - fabs(tmdot)) * pecfac * P.alpha_upw + cds);
+    }
   }
+  // lumped ScalarMassElemKernel: every quantity is the row node's own, times the sub-control volume of corner r
+  double mdiag = 0.0;
+  if (P.mass) {
+    box5::Coef C;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) hex8::scs_intg_loc(box::ip_of(r, k), qa, sa[k][0], sa[k][1], sa[k][2]);
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) C.X[a][m] = x[box::node_of_bits(m & 1, (m >> 1) & 1, m >> 2)][a];
+      box::butterfly8(C.X[a]);
+    }
+    double vol[16], scV = 0.0;
+    box5::scv_volumes_part<0>(C, vol);
+    box5::scv_volumes_part<1>(C, vol);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n == r) scV = vol[n] + vol[8 + n];
+    const int nd = nodes[r];
+    const double rp = P.rho[nd];
+    mdiag = P.g1_dt * rp * scV;
+    res -= (P.g1_dt * rp * qc[r] + P.g2_dt * P.rho_n[nd] * P.q_n[nd] + P.g3_dt * P.rho_nm1[nd] * P.q_nm1[nd]) * scV;
+  }
+  // SST source of the sub-control volume of corner r (TurbKineticEnergySSTSrcElemKernel.C:95-174,
+  // SpecificDissipationRateSSTSrcElemKernel.C:100-204): its nearest node is r, so it belongs to this row
+  double sdiag[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (SRC) {
+    box5::Coef C;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) C.X[a][m] = x[box::node_of_bits(m & 1, (m >> 1) & 1, m >> 2)][a];
+      box::butterfly8(C.X[a]);
+    }
+    double vol[16], scV = 0.0;
+    box5::scv_volumes_part<0>(C, vol);
+    box5::scv_volumes_part<1>(C, vol);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n == r) scV = vol[n] + vol[8 + n];
+    // generic_grad_op at the SCV point of corner r
+    const double qg = P.src_shifted ? 0.5 : 0.25, qs = P.src_lumped ? 0.5 : 0.25;
+    const double g1 = hex8::sgn_x(r) * qg, g2 = hex8::sgn_y(r) * qg, g3 = hex8::sgn_z(r) * qg;
+    const double v1 = hex8::sgn_x(r) * qs, v2 = hex8::sgn_y(r) * qs, v3 = hex8::sgn_z(r) * qs;
+    double dndx[8][3];
+    const double det = hex8::grad_op_ip(x, g1, g2, g3, dndx);
+    if (!(det > 0.0)) *P.err = 1;
+    double dudx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, dk[3] = {0, 0, 0}, dw[3] = {0, 0, 0};
+    double rho = 0.0, tke = 0.0, sdr = 0.0, tvisc = 0.0, f1 = 0.0, N[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int nd = nodes[c];
+      N[c] = hex8::shape_fcn(c, v1, v2, v3);
+      const double kc = P.tke[nd], wc = P.sdr[nd];
+      rho += N[c] * P.rho[nd];
+      tke += N[c] * kc;
+      sdr += N[c] * wc;
+      tvisc += N[c] * P.tvisc[nd];
+      if (P.src == 2) f1 += N[c] * P.f1[nd];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double ui = P.src_vel[(size_t)nd * 3 + i];
+        dk[i] += dndx[c][i] * kc;
+        dw[i] += dndx[c][i] * wc;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dudx[i][j] += dndx[c][j] * ui;
+      }
+    }
+    double Pk = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Pk += dudx[i][j] * (dudx[i][j] + dudx[j][i]);
+    Pk *= tvisc;
+    const double betaStar = P.turb[NALU_TM_BETA_STAR], lim = P.turb[NALU_TM_TKE_PROD_LIMIT_RATIO];
+    double f, rs;
+    if (P.src == 1) {
+      const double tkeFac = betaStar * rho * sdr, Dk = tkeFac * tke;
+      Pk = fmin(Pk, lim * Dk);
+      rs = (Pk - Dk) * scV;
+      f = tkeFac * scV;
+    } else {
+      const double Dk = betaStar * rho * sdr * tke;
+      Pk = fmin(Pk, lim * Dk);
+      const double om = 1.0 - f1;
+      const double beta = f1 * P.turb[NALU_TM_BETA_ONE] + om * P.turb[NALU_TM_BETA_TWO];
+      const double gamma = f1 * P.turb[NALU_TM_GAMMA_ONE] + om * P.turb[NALU_TM_GAMMA_TWO];
+      const double sigmaD = 2.0 * om * P.turb[NALU_TM_SIGMA_W_TWO];
+      const double Pw = gamma * rho * Pk / fmax(tvisc, 1.0e-16);
+      const double Dw = beta * rho * sdr * sdr;
+      const double Sw = sigmaD * rho * (dk[0] * dw[0] + dk[1] * dw[1] + dk[2] * dw[2]) / sdr;
+      rs = (Pw - Dw + Sw) * scV;
+      f = (2.0 * beta * rho * sdr + fmax(Sw / sdr, 0.0)) * scV;
+    }
+    res += rs;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sdiag[c] = N[c] * f;
+  }
+  double qIp[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    double v = 0.0;
+    double v = SRC ? sdiag[c] : 0.0, vd = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       double d[3];
       hex8::shape_deriv(c, s[k][0], s[k][1], s[k][2], d);
-      v += hex8::shape_fcn(c, sa[k][0], sa[k][1], sa[k][2]) * tm[k] + w[k][0] * d[0] + w[k][1] * d[1] + w[k][2] * d[2];
+      const double N = hex8::shape_fcn(c, sa[k][0], sa[k][1], sa[k][2]);
+      qIp[k] += N * qc[c];
+      vd += w[k][0] * d[0] + w[k][1] * d[1] + w[k][2] * d[2];
+      v += N * advc[k];
+      if (UPW) {
+        // the upwind factors sit on the two ends of the edge: r itself and its neighbour in direction k
+        if (c == r) v += sg[k] > 0 ? aL[k] : aR[k];
+        if (c == nbr[k]) v += sg[k] > 0 ? aR[k] : aL[k];
+      }
     }
-    res -= v * qc[c];
+    res -= vd * qc[c];
+    v += vd;
+    if (c == r) v += mdiag;
     if (alias) row0[slots[c]] += v; // an element that reaches a node twice: entries read ahead may be stale
     else row0[slots[c]] = old[c] + v;
+  }
+  // advective flux of each point
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (UPW) {
+      const double tmdot = sg[k] * tm[k];
+      const double qUpwind = tmdot > 0 ? P.alpha_upw * qL[k] + (1.0 - P.alpha_upw) * qIp[k] : P.alpha_upw * qR[k] + (1.0 - P.alpha_upw) * qIp[k];
+      const double qHatL = P.alpha * qL[k] + (1.0 - P.alpha) * qIp[k], qHatR = P.alpha * qR[k] + (1.0 - P.alpha) * qIp[k];
+      res -= tm[k] * (pf[k] * qUpwind + (1.0 - pf[k]) * (0.5 * (qHatL + qHatR)));
+    } else {
+      res -= tm[k] * qIp[k];
+    }
   }
 }
 
@@ -478,7 +651,10 @@ __global__ void __launch_bounds__(128, 2) assemble_urow_owner_onedof_kernel(cons
 #pragma unroll 1
   for (long long q = P.rowelem_ptr[rn]; q < q1; ++q) {
     const int er = P.rowelem[q];
-    if (KIND == 0) row_contribution_scalar(P, er >> 3, er & 7, res);
+    if (KIND == 0) row_contribution_scalar<false, false>(P, er >> 3, er & 7, res);
+    else if (KIND == 2) row_contribution_scalar<true, false>(P, er >> 3, er & 7, res);
+    else if (KIND == 3) row_contribution_scalar<true, true>(P, er >> 3, er & 7, res);
+    else if (KIND == 4) row_contribution_scalar<false, true>(P, er >> 3, er & 7, res);
     else row_contribution_cont(P, er >> 3, er & 7, res);
   }
   P.rhs[rn] += res;
@@ -505,15 +681,65 @@ bool classify_urow(const nalu_b200_kernel_desc *k, int nk, int &ia, int &im)
 }
 } // namespace
 
+// one-dof lists of the row-owner kernel: ContinuityAdv alone, or [ScalarMass(lumped)]? + {ScalarAdvDiff, ScalarDiff, ScalarUpwAdvDiff}
+static bool classify_urow_scalar(const nalu_b200_kernel_desc *k, int nk, int &ia, int &im, int &is)
+{
+  ia = im = is = -1;
+  for (int i = 0; i < nk; ++i) {
+    const int kind = k[i].kind;
+    if (kind == NALU_K_TKE_SST_SRC || kind == NALU_K_SDR_SST_SRC) {
+      if (is >= 0) return false;
+      is = i;
+      continue;
+    }
+    if (kind == NALU_K_SCALAR_ADV_DIFF || kind == NALU_K_SCALAR_DIFF || kind == NALU_K_SCALAR_UPW_ADV_DIFF) {
+      if (ia >= 0) return false;
+      ia = i;
+    } else if (kind == NALU_K_SCALAR_MASS) {
+      if (im >= 0 || !(k[i].options & NALU_OPT_LUMPED_MASS)) return false;
+      im = i;
+    } else {
+      return false;
+    }
+  }
+  return ia >= 0;
+}
 static bool urow_scalar_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
 {
-  if (g.ndof != 1 || !g.d_rowelem || !g.d_elem_slot || !tuning().urow_owner || nk != 1) return false;
-  if (k[0].kind == NALU_K_CONTINUITY_ADV)
+  if (g.ndof != 1 || !g.d_rowelem || !g.d_elem_slot || !tuning().urow_owner || nk < 1 || nk > 3) return false;
+  if (nk == 1 && k[0].kind == NALU_K_CONTINUITY_ADV)
     return k[0].nodal[NALU_F_COORDINATES] && k[0].nodal[NALU_F_VELOCITY] && k[0].nodal[NALU_F_DENSITY] && k[0].nodal[NALU_F_PRESSURE] &&
            k[0].nodal[NALU_F_DPDX];
-  if (k[0].kind != NALU_K_SCALAR_ADV_DIFF && k[0].kind != NALU_K_SCALAR_DIFF) return false;
-  if (!k[0].nodal[NALU_F_COORDINATES] || !k[0].nodal[NALU_F_SCALARQ] || !k[0].nodal[NALU_F_VISCOSITY]) return false;
-  return k[0].kind == NALU_K_SCALAR_DIFF || k[0].mass_flow_rate != nullptr;
+  int ia, im, is;
+  if (!classify_urow_scalar(k, nk, ia, im, is)) return false;
+  const nalu_b200_kernel_desc &a = k[ia];
+  if (!a.nodal[NALU_F_COORDINATES] || !a.nodal[NALU_F_SCALARQ] || !a.nodal[NALU_F_VISCOSITY]) return false;
+  if (is >= 0) {
+    // the source's own scalar is the list's dof (one field, one pointer, as in Nalu)
+    const nalu_b200_kernel_desc &sk = k[is];
+    const bool tke = sk.kind == NALU_K_TKE_SST_SRC;
+    if (sk.nodal[NALU_F_COORDINATES] != a.nodal[NALU_F_COORDINATES] || sk.nodal[tke ? NALU_F_TKE : NALU_F_SDR] != a.nodal[NALU_F_SCALARQ])
+      return false;
+    if (!sk.nodal[tke ? NALU_F_SDR : NALU_F_TKE] || !sk.nodal[NALU_F_VELOCITY] || !sk.nodal[NALU_F_DENSITY] || !sk.nodal[NALU_F_TVISC])
+      return false;
+    if (!tke && !sk.nodal[NALU_F_FONE_BLEND]) return false;
+    if (a.kind == NALU_K_SCALAR_UPW_ADV_DIFF && sk.nodal[NALU_F_DENSITY] != a.nodal[NALU_F_DENSITY]) return false;
+    if (im >= 0 && k[im].nodal[NALU_F_DENSITY] != sk.nodal[NALU_F_DENSITY]) return false;
+  }
+  if (a.kind != NALU_K_SCALAR_DIFF && !a.mass_flow_rate) return false;
+  const double *rho = nullptr;
+  if (a.kind == NALU_K_SCALAR_UPW_ADV_DIFF) {
+    rho = a.nodal[NALU_F_DENSITY];
+    if (!rho || !a.nodal[NALU_F_GJQ] || !(a.nodal[NALU_F_VELOCITY_RTM] || a.nodal[NALU_F_VELOCITY])) return false;
+  }
+  if (im >= 0) {
+    const nalu_b200_kernel_desc &m = k[im];
+    if (m.nodal[NALU_F_COORDINATES] != a.nodal[NALU_F_COORDINATES] || m.nodal[NALU_F_SCALARQ] != a.nodal[NALU_F_SCALARQ]) return false;
+    for (int f : {NALU_F_SCALARQ_N, NALU_F_SCALARQ_NM1, NALU_F_DENSITY, NALU_F_DENSITY_N, NALU_F_DENSITY_NM1})
+      if (!m.nodal[f]) return false;
+    if (rho && m.nodal[NALU_F_DENSITY] != rho) return false;
+  }
+  return true;
 }
 
 bool urow_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
@@ -554,7 +780,7 @@ int launch_assemble_urow(const Graph &g, const nalu_b200_kernel_desc *k, int nk,
     P.rowelem_ptr = (const long long *)g.d_rowelem_ptr;
     P.rowelem = g.d_rowelem;
     const unsigned grid = (unsigned)((P.n_rows + 127) / 128);
-    if (k[0].kind == NALU_K_CONTINUITY_ADV) {
+    if (nk == 1 && k[0].kind == NALU_K_CONTINUITY_ADV) {
       P.vel = k[0].nodal[NALU_F_VELOCITY];
       P.rho = k[0].nodal[NALU_F_DENSITY];
       P.pressure = k[0].nodal[NALU_F_PRESSURE];
@@ -563,11 +789,55 @@ int launch_assemble_urow(const Graph &g, const nalu_b200_kernel_desc *k, int nk,
       P.options = k[0].options & (NALU_OPT_SHIFT_MDOT | NALU_OPT_SHIFT_POISSON | NALU_OPT_REDUCED_SENS);
       urow::assemble_urow_owner_onedof_kernel<1><<<grid, 128, 0, stream>>>(P);
     } else {
-      P.q = k[0].nodal[NALU_F_SCALARQ];
-      P.visc = k[0].nodal[NALU_F_VISCOSITY];
-      P.mdot = k[0].kind == NALU_K_SCALAR_DIFF ? nullptr : k[0].mass_flow_rate;
-      P.options = k[0].options & (NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC);
-      urow::assemble_urow_owner_onedof_kernel<0><<<grid, 128, 0, stream>>>(P);
+      int ia, im, is;
+      classify_urow_scalar(k, nk, ia, im, is);
+      const nalu_b200_kernel_desc &a = k[ia];
+      if (is >= 0) {
+        const nalu_b200_kernel_desc &sk = k[is];
+        P.src = sk.kind == NALU_K_TKE_SST_SRC ? 1 : 2;
+        P.src_lumped = (sk.options & NALU_OPT_LUMPED_MASS) != 0;
+        P.src_shifted = (sk.options & NALU_OPT_SHIFTED_GRAD_OP) != 0;
+        P.tke = sk.nodal[NALU_F_TKE];
+        P.sdr = sk.nodal[NALU_F_SDR];
+        P.tvisc = sk.nodal[NALU_F_TVISC];
+        P.f1 = sk.nodal[NALU_F_FONE_BLEND];
+        P.src_vel = sk.nodal[NALU_F_VELOCITY];
+        P.rho = sk.nodal[NALU_F_DENSITY];
+        for (int i = 0; i < 10; ++i) P.turb[i] = sk.turb[i];
+      }
+      P.q = a.nodal[NALU_F_SCALARQ];
+      P.visc = a.nodal[NALU_F_VISCOSITY];
+      P.mdot = a.kind == NALU_K_SCALAR_DIFF ? nullptr : a.mass_flow_rate;
+      P.options = a.options & (NALU_OPT_SHIFTED_GRAD_OP | NALU_OPT_SKEW_SYMMETRIC);
+      if (a.kind == NALU_K_SCALAR_UPW_ADV_DIFF) {
+        P.upw = 1;
+        P.upw_options = a.options & (NALU_OPT_USE_LIMITER | NALU_OPT_PECLET_TANH);
+        P.vel = a.nodal[NALU_F_VELOCITY_RTM] ? a.nodal[NALU_F_VELOCITY_RTM] : a.nodal[NALU_F_VELOCITY];
+        P.rho = a.nodal[NALU_F_DENSITY];
+        P.gjq = a.nodal[NALU_F_GJQ];
+        P.alpha = a.upw[NALU_UPW_ALPHA];
+        P.alpha_upw = a.upw[NALU_UPW_ALPHA_UPW];
+        P.ho_upwind = a.upw[NALU_UPW_HO_UPWIND];
+        P.hybrid = a.upw[NALU_UPW_HYBRID_FACTOR];
+        P.tanh_trans = a.upw[NALU_UPW_TANH_TRANS];
+        P.tanh_width = a.upw[NALU_UPW_TANH_WIDTH];
+      }
+      if (im >= 0) {
+        const nalu_b200_kernel_desc &m = k[im];
+        P.mass = 1;
+        P.rho = m.nodal[NALU_F_DENSITY];
+        P.rho_n = m.nodal[NALU_F_DENSITY_N];
+        P.rho_nm1 = m.nodal[NALU_F_DENSITY_NM1];
+        P.q_n = m.nodal[NALU_F_SCALARQ_N];
+        P.q_nm1 = m.nodal[NALU_F_SCALARQ_NM1];
+        P.g1_dt = m.gamma1 / m.dt;
+        P.g2_dt = m.gamma2 / m.dt;
+        P.g3_dt = m.gamma3 / m.dt;
+      }
+      if (P.upw && P.src) urow::assemble_urow_owner_onedof_kernel<3><<<grid, 128, 0, stream>>>(P);
+      else if (P.upw) urow::assemble_urow_owner_onedof_kernel<2><<<grid, 128, 0, stream>>>(P);
+      else if (P.src) urow::assemble_urow_owner_onedof_kernel<4><<<grid, 128, 0, stream>>>(P);
+      else urow::assemble_urow_owner_onedof_kernel<0><<<grid, 128, 0, stream>>>(P);
     }
     count_launch();
     NALU_CUDA(cudaGetLastError());

@@ -1056,7 +1056,7 @@ def test_unstructured_exodus_mesh_parity(case):
     ls = _linsys(m, ndof)
     assert ls.elem_colors()[0] >= 46
     ls.zero_system()
-    urow = case in ("momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu", "scalar_diff")
+    urow = case in ("momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu", "scalar_diff", "scalar_mass+upw_tanh")
     assert ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode="auto") == (4 if urow else 1)
     _compare_system(ls, orc)
     assert ls.geometry_errors() == 0
@@ -1275,14 +1275,28 @@ def test_row_thread_unstructured_momentum_kernel(kind, opts, divu, mass, tune):
     _compare_system(ls, orc)
 
 
+_ONEDOF_LISTS = {
+    "scalar_adv_diff": [("scalar_adv_diff", (), {})],
+    "scalar_adv_diff_shifted_skew": [("scalar_adv_diff", ("shifted_grad_op", "skew_symmetric"), {})],
+    "scalar_diff_shifted": [("scalar_diff", ("shifted_grad_op",), {})],
+    "continuity": [("continuity_adv", (), dict(dt=0.05, gamma1=1.5))],
+    "continuity_reduced_shiftmdot": [("continuity_adv", ("reduced_sens", "shift_mdot"), dict(dt=0.05, gamma1=1.5))],
+    "continuity_shift_poisson": [("continuity_adv", ("shift_poisson",), dict(dt=0.05, gamma1=1.5))],
+    "scalar_upw_limiter": [("scalar_upw_adv_diff", ("use_limiter",), dict(upw=dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, hybrid_factor=1.0)))],
+    "scalar_mass+upw_tanh": [("scalar_mass", ("lumped_mass",), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
+                             ("scalar_upw_adv_diff", ("peclet_tanh", "skew_symmetric", "shifted_grad_op"),
+                              dict(upw=dict(alpha=0.1, alpha_upw=0.75, ho_upwind=0.5, tanh_trans=2.0, tanh_width=4.0)))],
+    "scalar_mass+adv_diff": [("scalar_mass", ("lumped_mass",), dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)),
+                             ("scalar_adv_diff", (), {})],
+}
+
+
 @pytest.mark.parametrize("kind", ["shuffled", "periodic", "periodic_one_cell_wide"])
-@pytest.mark.parametrize("kernel,opts", [("scalar_adv_diff", ()), ("scalar_adv_diff", ("shifted_grad_op", "skew_symmetric")),
-                                         ("scalar_diff", ("shifted_grad_op",)), ("continuity_adv", ()),
-                                         ("continuity_adv", ("reduced_sens", "shift_mdot")), ("continuity_adv", ("shift_poisson",))])
-def test_row_owner_unstructured_scalar_kernel(kind, kernel, opts, tune):
-    """assemble_urow.cu, one dof per node: ScalarAdvDiffElemKernel / ScalarDiffElemKernel / ContinuityAdvElemKernel on
-    non-lattice connectivity (the periodic box of BASELINE config 2) in ONE launch, thread = row node, no atomics; against
-    the oracle, and against the general kernel where the reference is not defined (see
+@pytest.mark.parametrize("case", sorted(_ONEDOF_LISTS))
+def test_row_owner_unstructured_onedof_kernels(kind, case, tune):
+    """assemble_urow.cu, one dof per node: [ScalarMass(lumped)]? + ScalarAdvDiff / ScalarDiff / ScalarUpwAdvDiff, and
+    ContinuityAdv, on non-lattice connectivity (the periodic box of BASELINE config 2) in ONE launch, thread = row node, no
+    atomics; against the oracle, and against the general kernel where the reference is not defined (see
     test_row_thread_unstructured_momentum_kernel)."""
     if kind == "periodic":
         m, st = _periodic_state(9, 8, 7)
@@ -1294,12 +1308,12 @@ def test_row_owner_unstructured_scalar_kernel(kind, kernel, opts, tune):
         m.box = None
         st = State(m)
     dev = st.to_device(_cuda())
-    sc = dict(dt=0.05, gamma1=1.5) if kernel == "continuity_adv" else {}
+    klist = _ONEDOF_LISTS[case]
     orc = oracle.LinSys([m], 1)
     keep = []
-    orc.assemble_elem(0, [oracle_desc(st, kernel, opts, keep, **sc)])
+    orc.assemble_elem(0, [oracle_desc(st, k, o, keep, **sc) for k, o, sc in klist])
     ls = _linsys(m, 1)
-    descs = [product_desc(ls, dev, kernel, opts, **sc)]
+    descs = [product_desc(ls, dev, k, o, **sc) for k, o, sc in klist]
     out = []
     for _ in range(2):
         launches0 = ls.L.nalu_b200_launch_count()
@@ -1310,10 +1324,39 @@ def test_row_owner_unstructured_scalar_kernel(kind, kernel, opts, tune):
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
     assert ls.geometry_errors() == 0
     if kind != "periodic_one_cell_wide":
-        _compare_system(ls, orc)
+        _compare_system(ls, orc, sol_scale=1.0 if "upw" in case else None)
     tune(urow=0)
     ls.zero_system()
     assert ls.assemble_elem(descs, mode="auto") == 1
     tune(urow=1)
     assert float((ls.values - out[0][0]).abs().max() / ls.values.abs().max()) < 1e-13
     assert float((ls.rhs - out[0][1]).abs().max() / ls.rhs.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("eq", ["tke", "sdr"])
+@pytest.mark.parametrize("src_lumped", [True, False])
+def test_config4_lists_on_unstructured_connectivity(eq, src_lumped, tune):
+    """The turbulence lists of BASELINE config 4 [ScalarMass(lumped), ScalarUpwAdvDiff, SST source] on a mesh WITHOUT the
+    lattice numbering (shuffled node ids, stretched ABL-style coordinates): one launch of the row-owner kernel
+    (assemble_urow.cu, mode 4) against the oracle and against the general kernel."""
+    m = perturbed_box(8, 6, 10, amp=0.05)
+    f = _config4_state(m, eq)
+    m.node_gid = (np.random.default_rng(3).permutation(m.n_nodes) + 1).astype(np.int64)
+    m.box = None
+    orc = oracle.LinSys([m], 1)
+    _config4_oracle(orc, 0, m, f, eq, src_lumped)
+    ls = _linsys(m, 1)
+    descs = _config4_descs(ls, m, f, eq, src_lumped, True, _cuda())
+    launches0 = ls.L.nalu_b200_launch_count()
+    ls.zero_system()
+    assert ls.assemble_elem(descs, mode="auto") == 4
+    assert ls.L.nalu_b200_launch_count() - launches0 == 1
+    _compare_system(ls, orc, sol_scale=3.0)
+    assert ls.geometry_errors() == 0
+    v0, r0 = ls.values.clone(), ls.rhs.clone()
+    tune(urow=0)
+    ls.zero_system()
+    assert ls.assemble_elem(descs, mode="auto") == 1
+    tune(urow=1)
+    assert float((ls.values - v0).abs().max() / v0.abs().max()) < 1e-13
+    assert float((ls.rhs - r0).abs().max() / r0.abs().max()) < 1e-12

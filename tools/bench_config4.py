@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="auto", choices=["auto", "general"])
     ap.add_argument("--no-momentum", action="store_true")
+    ap.add_argument("--nobox", action="store_true", help="declare the slab as a general Hex8 mesh (row-owner / general kernels)")
     ap.add_argument("--no-oracle-check", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -54,6 +55,8 @@ def main():
     m = mesh.generated_box_rank(n, n, nzg, rank, world)
     mesh.perturb_coords_hash(m, amp)
     m.coords = abl(m.coords)
+    if args.nobox:
+        m.box = None
     L = lib.lib()
     comm = nd.make_comm(rank, world) if world > 1 else None
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
@@ -132,7 +135,7 @@ def main():
         bytes_alg = 8 * comps * nn + 96 * m.n_elems + 32 * m.n_elems + 8 * nnz1 + 8 * nn
         r = {"kernels": ["ScalarMassElemKernel(lumped)", "ScalarUpwAdvDiffElemKernel(limiter)",
                          ("TurbKineticEnergy" if eq == "tke" else "SpecificDissipationRate") + "SSTSrcElemKernel(lumped)"],
-             "assemble_mode": probe, "launch": "assemble_slist_box (one launch)" if probe == 2 else "assemble_general (coloured)",
+             "assemble_mode": probe, "launch": {2: "assemble_slist_box (one launch)", 4: "assemble_urow (row-owner, one launch)"}.get(probe, "assemble_general (coloured)"),
              "assemble_ms": asm, "step_ms": stp, "value": m.n_elems * world / stp / 1e3, "unit": "Melem/s",
              "kernel_melem_s_per_gpu": m.n_elems / asm / 1e3, "bytes_per_element": bytes_alg / m.n_elems,
              "roofline_frac": bytes_alg / (asm * 1e-3) / 1e9 / peak, "geometry_errors": ls1.geometry_errors()}
