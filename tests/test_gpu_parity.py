@@ -466,14 +466,16 @@ def test_system_parity_vs_oracle(case, mode):
     ls = _linsys(m, ndof)
     ls.zero_system()
     used = ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode=mode, overwrite=True)
-    assert used in (1, 2, 3)
+    assert used in (1, 2, 3, 4)
     tiled = {"momentum_adv_diff", "continuity_adv", "scalar_adv_diff", "scalar_diff"}
     if mode == "auto" and len(klist) > 1:
         # [lumped MomentumMass, MomentumAdvDiff]: one launch of the row-thread kernel (fused); another tiled-capable
         # kernel plus others: tiled + accumulate; otherwise the general kernel
         # ... and [lumped ScalarMass, ScalarUpwAdvDiff]: one launch of the scalar-list tiled kernel
         fused = case in ("momentum_mass+advdiff", "scalar_mass+upw_tanh")
-        assert used == (2 if fused else (3 if any(k in tiled for k, _, _ in klist) else 1))
+        # ... and the momentum upwind list, which no tiled kernel takes: the row-owner kernel, on the lattice too
+        rowowner = case == "momentum_mass+upw_tanh+buoyancy-free"
+        assert used == (2 if fused else (4 if rowowner else (3 if any(k in tiled for k, _, _ in klist) else 1)))
     _compare_system(ls, orc)
     assert ls.geometry_errors() == 0
 
@@ -1056,7 +1058,7 @@ def test_unstructured_exodus_mesh_parity(case):
     ls = _linsys(m, ndof)
     assert ls.elem_colors()[0] >= 46
     ls.zero_system()
-    urow = case in ("momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu", "scalar_diff", "scalar_mass+upw_tanh")
+    urow = case in ("momentum_mass+advdiff", "momentum_shifted_skew", "momentum_nodivu", "scalar_diff", "scalar_mass+upw_tanh", "momentum_upw")
     assert ls.assemble_elem([product_desc(ls, dev, k, o, **s) for k, o, s in klist], mode="auto") == (4 if urow else 1)
     _compare_system(ls, orc)
     assert ls.geometry_errors() == 0
@@ -1360,3 +1362,63 @@ def test_config4_lists_on_unstructured_connectivity(eq, src_lumped, tune):
     tune(urow=1)
     assert float((ls.values - v0).abs().max() / v0.abs().max()) < 1e-13
     assert float((ls.rhs - r0).abs().max() / r0.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["box", "shuffled", "periodic"])
+@pytest.mark.parametrize("variant", ["upw_limiter", "mass+upw_tanh+buoyancy", "mass+advdiff+boussinesq"])
+def test_row_owner_momentum_upwind_and_buoyancy_lists(kind, variant, tune):
+    """The momentum list of BASELINE config 1 in 3-D -- [MomentumMass(lumped), MomentumUpwAdvDiff, MomentumBuoyancySrc]
+    (reg_tests/test_files/heatedWaterChannelElem/heatedWaterChannelElem.i:152-155) -- and its relatives through the row-owner
+    kernel (mode 4) on a lattice (where no tiled kernel takes them), shuffled and periodic connectivity; against the oracle
+    and against the general kernel."""
+    if kind == "periodic":
+        m, st = _periodic_state(9, 8, 7)
+    else:
+        m = perturbed_box(9, 8, 7)
+        if kind == "shuffled":
+            m.node_gid = (np.random.default_rng(1).permutation(m.n_nodes) + 1).astype(np.int64)
+            m.box = None
+        st = State(m)
+    dev = st.to_device(_cuda())
+    bdf2 = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    g = (0.3, -1.7, -9.81)
+    temp = 300.0 * (1.0 + 0.01 * st.density)
+    klist, extra_o, extra_p = [], [], []
+    if variant == "upw_limiter":
+        klist = [("momentum_upw_adv_diff", ("use_limiter",), dict(include_divu=1.0, upw=dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, hybrid_factor=1.0)))]
+    elif variant == "mass+upw_tanh+buoyancy":
+        klist = [("momentum_mass", ("lumped_mass",), bdf2),
+                 ("momentum_upw_adv_diff", ("peclet_tanh", "shifted_grad_op", "skew_symmetric"),
+                  dict(include_divu=1.0, upw=dict(alpha=0.1, alpha_upw=0.75, ho_upwind=0.5, tanh_trans=2.0, tanh_width=4.0)))]
+        extra_o = [("momentum_buoyancy_src", dict(density=st.density, gravity=g, rhoRef=1.1))]
+        extra_p = [("momentum_buoyancy_src", dict(gravity=g, rho_ref=1.1), "density", st.density)]
+    else:
+        klist = [("momentum_mass", ("lumped_mass",), bdf2), ("momentum_adv_diff", (), dict(include_divu=0.0))]
+        extra_o = [("momentum_buoyancy_boussinesq_src", dict(temperature=temp, gravity=g, rhoRef=1.1, tRef=298.0, beta=3.4e-3))]
+        extra_p = [("momentum_buoyancy_boussinesq_src", dict(gravity=g, rho_ref=1.1, t_ref=298.0, beta=3.4e-3), "temperature", temp)]
+    keep = []
+    orc = oracle.LinSys([m], 3)
+    orc.assemble_elem(0, [oracle_desc(st, k, o, keep, **s) for k, o, s in klist] +
+                      [oracle.make_desc(k, keep, coordinates=st.coordinates, **kw) for k, kw in extra_o])
+    ls = _linsys(m, 3)
+    descs = [product_desc(ls, dev, k, o, **s) for k, o, s in klist]
+    for k, kw, fname, fval in extra_p:
+        descs.append(ls.make_desc(k, fields={"coordinates": dev["coordinates"], fname: torch.as_tensor(np.ascontiguousarray(fval), device="cuda")}, **kw))
+    # on a lattice a list with a tiled-capable member keeps the tiled write-once kernel for it (+ the others on top: mode 3)
+    want = 3 if (kind == "box" and variant == "mass+advdiff+boussinesq") else 4
+    out = []
+    for _ in range(2):
+        launches0 = ls.L.nalu_b200_launch_count()
+        ls.zero_system()
+        assert ls.assemble_elem(descs, mode="auto") == want
+        assert want == 3 or ls.L.nalu_b200_launch_count() - launches0 == 1
+        out.append((ls.values.clone(), ls.rhs.clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert ls.geometry_errors() == 0
+    _compare_system(ls, orc, sol_scale=1.0)
+    tune(urow=0)
+    ls.zero_system()
+    assert ls.assemble_elem(descs, mode="auto") in (1, 3)
+    tune(urow=1)
+    assert float((ls.values - out[0][0]).abs().max() / ls.values.abs().max()) < 1e-13
+    assert float((ls.rhs - out[0][1]).abs().max() / ls.rhs.abs().max()) < 1e-12
