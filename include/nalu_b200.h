@@ -169,6 +169,16 @@ int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, 
                            int32_t n_nodes, const int64_t *node_gid, const int32_t *node_owner,
                            int64_t n_elems, const int32_t *elem_nodes,
                            int32_t box_nx, int32_t box_ny, int32_t box_nz);
+/* Same, for a named element topology: nodes_per_elem = 8 (Hex8, AlgTraitsHex8) or 27 (Hex27, AlgTraitsHex27:
+ * include/AlgTraits.h:27-34; elem_nodes[n_elems][27] in STK's Hex27 node order, the one
+ * HexahedralP2Element::stkNodeMap_ maps to the tensor grid, src/master_element/Hex27CVFEM.C:36-47).  Numbering, graph,
+ * handshake, zeroSystem, loadComplete, Dirichlet / resetRows are topology independent and work as for Hex8.  On a Hex27
+ * graph nalu_b200_assemble_elem takes [MomentumAdvDiffElemKernel] (3 dof, default options; mass_flow_rate is
+ * [n_elems][216], the Hex27SCS point order of Hex27CVFEM.C:887-1050) and nalu_b200_mdot_scs produces that field; every
+ * other element-level entry point returns NALU_B200_ERR_STATE. */
+int nalu_b200_graph_create_topo(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof,
+                                int32_t nodes_per_elem, int32_t n_nodes, const int64_t *node_gid,
+                                const int32_t *node_owner, int64_t n_elems, const int32_t *elem_nodes);
 void nalu_b200_graph_destroy(nalu_b200_graph *g);
 
 /* Neighbour handshake (TpetraLinearSystem.C:678-738,924-952).  After create(), for every
@@ -245,7 +255,7 @@ int nalu_b200_assemble_elem_zrange(const nalu_b200_graph *g, const nalu_b200_ker
                                    int32_t z_begin, int32_t z_end, void *stream);
 /* which kernel family the last nalu_b200_assemble_elem call used: 1 general (coloured scatter), 2 tiled write-once,
  * 3 tiled write-once for one kernel of the list + general for the others, 4 row-thread unstructured momentum kernel
- * (any Hex8 connectivity with an element colouring, coloured value-less reductions) */
+ * (any Hex8 connectivity with an element colouring, coloured value-less reductions), 5 Hex27 kernel (CTA per element) */
 int nalu_b200_last_assemble_mode(void);
 /* Launch-configuration knobs for A/B measurements and tests; none changes what is computed.  name / value:
  *   "box_kernel"  5 row-thread tiled momentum kernel (default), 2 column-pair kernel
@@ -315,7 +325,7 @@ int nalu_b200_apply_dirichlet_bcs(const nalu_b200_graph *g, int32_t n_nodes, con
 int nalu_b200_reset_rows(const nalu_b200_graph *g, int32_t n_nodes, const int32_t *d_nodes, int32_t begin_pos,
                          int32_t end_pos, double *d_values, double *d_rhs, void *stream);
 
-/* calc_mass_flow_rate_scs: d_mdot[nElem][12] from coordinates, density, velocity */
+/* calc_mass_flow_rate_scs: d_mdot[nElem][12] (Hex27 graphs: [nElem][216]) from coordinates, density, velocity */
 int nalu_b200_mdot_scs(const nalu_b200_graph *g, const double *d_coords, const double *d_density,
                        const double *d_velocity, double *d_mdot, void *stream);
 

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnalu_b200.so")
-CU = ["capi.cu", "assemble_general.cu", "assemble_box.cu", "assemble_box2.cu", "assemble_box5.cu", "assemble_cont_box.cu", "assemble_scalar_box.cu", "assemble_slist_box.cu", "face_elem.cu", "assemble_urow.cu", "halo.cu"]
+CU = ["capi.cu", "assemble_general.cu", "assemble_box.cu", "assemble_box2.cu", "assemble_box5.cu", "assemble_cont_box.cu", "assemble_scalar_box.cu", "assemble_slist_box.cu", "face_elem.cu", "assemble_urow.cu", "assemble_hex27.cu", "halo.cu"]
 CPP = ["graph.cpp", "comm.cpp"]
 HDR = ["internal.h", "graph.h", "general_elem.cuh", "hex8_dev.cuh", "box_tile.cuh", "box2_tile.cuh", "box5_tile.cuh", "cont_tile.cuh", "scalar_tile.cuh", "slist_tile.cuh", "../../include/nalu_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

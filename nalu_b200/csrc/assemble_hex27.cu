@@ -1,0 +1,455 @@
+// assemble_hex27.cu -- MomentumAdvDiffElemKernel<AlgTraitsHex27> + sumInto on Hex27 (P2 CVFEM) meshes: BASELINE config 5,
+// the stress test of the per-element block size (27 nodes, 216 sub-control-surface points, an 81 x 81 element matrix).
+//
+// Reference path: src/kernel/MomentumAdvDiffElemKernel.C:95-186 instantiated with AlgTraitsHex27 (include/AlgTraits.h:27-34),
+// the master element src/master_element/Hex27CVFEM.C (HexahedralP2Element tables :25-75,192-262,355-632, Hex27SCS
+// :887-1050 integration points / lrscv / weights, :1428-1470 area vectors, generic_grad_op
+// include/master_element/MasterElementFunctions.h:52-108) and apply_coeff -> sumInto (src/TpetraLinearSystem.C:1457-1522).
+//
+// The reference fills a 52 KB scratch matrix per element (and 216 x 27 x 3 gradient weights) and then searches 81 CSR rows.
+// Here a CTA owns an element and the element matrix never exists:
+//   phase B  thread = integration point: J = sum_n x_n (x) dN_n/dxi and, with the same table pass, U' = sum_n u_n (x) dN_n/dxi;
+//            the area vector of a constant-xi_d surface is +-w cof(J)[:, d] (x_t x x_u etc. ARE cofactor columns), so one
+//            cofactor matrix gives the area vector, G = -mu_ip cof(J)/det J and div u = (cof/det) : U'.  16 doubles per point
+//            go to shared memory (G, A, mdot, the divU stress) -- 27 KB instead of the 52 KB matrix + 140 KB of dndx.
+//   phase C  thread = (row node r, three column nodes): walks the 12-24 points whose left or right sub-control volume is r's
+//            and accumulates its three 3 x 3 blocks in registers: h = G dN_c/dxi (= -mu dN_c/dx), block += h (x) A,
+//            diag += N_c mdot + h.A; the residual is -(row . u) - the divU stress (the reference's term-by-term sums
+//            regrouped: its advective flux mdot * u_ip IS sum_c (N_c mdot) u_c).
+//   scatter  elements are launched colour by colour (graph.cpp: elements of a colour share no row), every CSR entry receives
+//            exactly one value-less reduction (red.global.add.f64) per launch: deterministic, no atomics in the contended
+//            sense, no search (slot map built with the graph).
+// Reference-element tables (tensor products of the 1-D quadratic Lagrange basis at the Gauss points of each sub-surface
+// segment) are built on the host once, in two layouts: point-fastest for phase B, node-fastest for phase C.
+#include "internal.h"
+
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+namespace nalu_b200 {
+namespace hex27 {
+
+constexpr int NPE = 27, NIP = 216, NREC = 16;
+
+struct Tables {
+  double *dN_ipfast = nullptr;  // [27][3][216]
+  double *dN_nodefast = nullptr; // [216][27][3]
+  double *N_ipfast = nullptr;   // [27][216]
+  double *N_nodefast = nullptr; // [216][27]
+  double *wdir = nullptr;       // [216] signed weight: A = wdir * cof(J)[:, dir]
+  int *dir = nullptr;           // [216]
+  int *lr = nullptr;            // [216][2]
+  int *inc_ptr = nullptr;       // [28]
+  int *inc = nullptr;           // [432] ip << 1 | (1 if the node is the point's right node)
+};
+
+struct HostTables {
+  std::vector<double> dN, N, w; // [216][27][3], [216][27], [216]
+  std::vector<int> dir, lr;
+};
+
+// node (i, j, k) of the 3 x 3 x 3 tensor grid -> STK Hex27 ordinal (Hex27CVFEM.C:36-47)
+static const int kStkNodeMap[27] = {0, 8, 1, 11, 21, 9, 3, 10, 2, 12, 25, 13, 23, 20, 24, 15, 26, 14, 4, 16, 5, 19, 22, 17, 7, 18, 6};
+
+static void lagrange3(double x, double *l, double *d)
+{
+  l[0] = -0.5 * x * (1.0 - x); l[1] = (1.0 - x) * (1.0 + x); l[2] = 0.5 * x * (1.0 + x);
+  d[0] = x - 0.5; d[1] = -2.0 * x; d[2] = x + 0.5;
+}
+
+static HostTables build_host_tables()
+{
+  HostTables T;
+  T.dN.assign(size_t(NIP) * NPE * 3, 0.0);
+  T.N.assign(size_t(NIP) * NPE, 0.0);
+  T.w.assign(NIP, 0.0);
+  T.dir.assign(NIP, 0);
+  T.lr.assign(2 * NIP, 0);
+  const double scsDist = std::sqrt(3.0) / 3.0;
+  const double endLoc[4] = {-1.0, -scsDist, scsDist, 1.0};
+  const double gaussAbs[2] = {-std::sqrt(3.0) / 3.0, std::sqrt(3.0) / 3.0};
+  auto gp = [&](int node, int q) { // Gauss point q of the segment of 1-D node `node`
+    const double a = endLoc[node], b = endLoc[node + 1];
+    return gaussAbs[q] * (b - a) / 2.0 + (a + b) / 2.0;
+  };
+  auto seg = [&](int node) { return endLoc[node + 1] - endLoc[node]; };
+  const double scsLoc[2] = {-scsDist, scsDist};
+  const double orient[2] = {-1.0, 1.0};
+  // area vector = w * (x_s1 x x_s2) with (s1, s2) = (t, s), (s, u), (t, u) for the u-, t-, s-direction
+  // (Hex27CVFEM.C:1428-1470) = sign * cof(J)[:, d], sign = -1, -1, +1
+  const double cofsign[3] = {+1.0, -1.0, -1.0}; // indexed by direction s = 0, t = 1, u = 2
+  int ip = 0;
+  for (int pass = 0; pass < 3; ++pass) { // u, t, s surfaces in this order (Hex27CVFEM.C:912-1047)
+    const int d = 2 - pass;
+    for (int m = 0; m < 2; ++m)
+      for (int l = 0; l < 3; ++l)
+        for (int k = 0; k < 3; ++k) {
+          int lo[3], hi[3]; // tensor indices of the nodes on the two sides of surface m
+          if (d == 2) { lo[0] = k; lo[1] = l; lo[2] = m; }
+          else if (d == 1) { lo[0] = k; lo[1] = m; lo[2] = l; }
+          else { lo[0] = m; lo[1] = k; lo[2] = l; }
+          hi[0] = lo[0]; hi[1] = lo[1]; hi[2] = lo[2];
+          hi[d] += 1;
+          const int nlo = kStkNodeMap[lo[0] + 3 * (lo[1] + 3 * lo[2])], nhi = kStkNodeMap[hi[0] + 3 * (hi[1] + 3 * hi[2])];
+          for (int j = 0; j < 2; ++j)
+            for (int i = 0; i < 2; ++i, ++ip) {
+              T.lr[2 * ip] = m == 0 ? nlo : nhi;
+              T.lr[2 * ip + 1] = m == 0 ? nhi : nlo;
+              double x[3];
+              if (d == 2) { x[0] = gp(k, i); x[1] = gp(l, j); x[2] = scsLoc[m]; }
+              else if (d == 1) { x[0] = gp(k, i); x[1] = scsLoc[m]; x[2] = gp(l, j); }
+              else { x[0] = scsLoc[m]; x[1] = gp(k, i); x[2] = gp(l, j); }
+              const double w = seg(k) * seg(l) * 0.25 * (d == 0 ? -orient[m] : orient[m]);
+              T.w[ip] = w * cofsign[d];
+              T.dir[ip] = d;
+              double L[3][3], D[3][3];
+              for (int a = 0; a < 3; ++a) lagrange3(x[a], L[a], D[a]);
+              for (int c = 0; c < 3; ++c)
+                for (int b = 0; b < 3; ++b)
+                  for (int a = 0; a < 3; ++a) {
+                    const int n = kStkNodeMap[a + 3 * (b + 3 * c)];
+                    T.N[size_t(ip) * NPE + n] = L[0][a] * L[1][b] * L[2][c];
+                    T.dN[(size_t(ip) * NPE + n) * 3 + 0] = D[0][a] * L[1][b] * L[2][c];
+                    T.dN[(size_t(ip) * NPE + n) * 3 + 1] = L[0][a] * D[1][b] * L[2][c];
+                    T.dN[(size_t(ip) * NPE + n) * 3 + 2] = L[0][a] * L[1][b] * D[2][c];
+                  }
+            }
+        }
+  }
+  return T;
+}
+
+template <class V> static int to_device(V **d, const std::vector<V> &h)
+{
+  NALU_CUDA(cudaMalloc((void **)d, h.size() * sizeof(V)));
+  NALU_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice));
+  return NALU_B200_OK;
+}
+
+// one table set per device, built on first use (never freed: 0.4 MB)
+static int get_tables(const Tables **out)
+{
+  static std::mutex mu;
+  static Tables tab[64];
+  static bool have[64] = {false};
+  int dev = 0;
+  NALU_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) return NALU_B200_ERR_STATE;
+  if (!have[dev]) {
+    const HostTables H = build_host_tables();
+    std::vector<double> dNi(size_t(NPE) * 3 * NIP), Ni(size_t(NPE) * NIP);
+    for (int ip = 0; ip < NIP; ++ip)
+      for (int n = 0; n < NPE; ++n) {
+        Ni[size_t(n) * NIP + ip] = H.N[size_t(ip) * NPE + n];
+        for (int j = 0; j < 3; ++j) dNi[(size_t(n) * 3 + j) * NIP + ip] = H.dN[(size_t(ip) * NPE + n) * 3 + j];
+      }
+    std::vector<int> ptr(NPE + 1, 0), inc(2 * NIP);
+    for (int q = 0; q < 2 * NIP; ++q) ++ptr[H.lr[q] + 1];
+    for (int n = 0; n < NPE; ++n) ptr[n + 1] += ptr[n];
+    std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+    for (int q = 0; q < 2 * NIP; ++q) inc[pos[H.lr[q]]++] = q; // q = ip << 1 | side, ascending ip per node
+    Tables &t = tab[dev];
+    int rc;
+    if ((rc = to_device(&t.dN_ipfast, dNi)) || (rc = to_device(&t.dN_nodefast, H.dN)) || (rc = to_device(&t.N_ipfast, Ni)) ||
+        (rc = to_device(&t.N_nodefast, H.N)) || (rc = to_device(&t.wdir, H.w)) || (rc = to_device(&t.dir, H.dir)) ||
+        (rc = to_device(&t.lr, H.lr)) || (rc = to_device(&t.inc_ptr, ptr)) || (rc = to_device(&t.inc, inc)))
+      return rc;
+    have[dev] = true;
+  }
+  *out = &tab[dev];
+  return NALU_B200_OK;
+}
+
+__device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
+// cofactor matrix C of J (C[i][j] = d det / d J[i][j]) and det J
+__device__ __forceinline__ double cofactor(const double (&J)[3][3], double (&C)[3][3])
+{
+  C[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  C[0][1] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  C[0][2] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  C[1][0] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+  C[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+  C[1][2] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+  C[2][0] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+  C[2][1] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+  C[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  return J[0][0] * C[0][0] + J[1][0] * C[1][0] + J[2][0] * C[2][0];
+}
+
+struct Params {
+  Tables T;
+  const int *elem_list; // elements of this colour (null: all elements, atomic scatter)
+  long long n;
+  const int *elem_nodes;        // [nElem][27]
+  const unsigned char *elem_slot; // [nElem][27][27]
+  const int *node_row;
+  const long long *browptr;
+  const double *coords, *vel, *visc, *mdot; // mdot: [nElem][216]
+  double include_divu;
+  double *values, *rhs;
+  int *err;
+};
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __grid_constant__ Params P)
+{
+  __shared__ double s_x[NPE][3], s_u[NPE][3], s_mu[NPE];
+  __shared__ double s_rec[NREC][NIP];
+  __shared__ double s_part[NPE * 9][3];
+  __shared__ int s_row[NPE];
+
+  const int t = threadIdx.x;
+  const long long e = P.elem_list ? P.elem_list[blockIdx.x] : (long long)blockIdx.x;
+  const int *en = P.elem_nodes + e * NPE;
+  if (t < NPE) {
+    const int n = en[t];
+    s_row[t] = P.node_row[n];
+    s_mu[t] = P.visc[n];
+  }
+  if (t < 81) {
+    const int n = en[t / 3];
+    s_x[t / 3][t % 3] = P.coords[(size_t)n * 3 + t % 3];
+  } else if (t >= 96 && t < 96 + 81) {
+    const int q = t - 96, n = en[q / 3];
+    s_u[q / 3][q % 3] = P.vel[(size_t)n * 3 + q % 3];
+  }
+  __syncthreads();
+
+  // ---- phase B: thread = integration point ---------------------------------------------------------------------
+  if (t < NIP) {
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, U[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double mu = 0.0;
+    // coordinates relative to the element's first node: the Jacobian is translation invariant, its rounding error is not
+    const double x0 = s_x[0][0], y0 = s_x[0][1], z0 = s_x[0][2];
+#pragma unroll 3
+    for (int n = 0; n < NPE; ++n) {
+      const double d0 = P.T.dN_ipfast[(n * 3 + 0) * NIP + t], d1 = P.T.dN_ipfast[(n * 3 + 1) * NIP + t],
+                   d2 = P.T.dN_ipfast[(n * 3 + 2) * NIP + t];
+      const double xn[3] = {s_x[n][0] - x0, s_x[n][1] - y0, s_x[n][2] - z0};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        J[i][0] += d0 * xn[i]; J[i][1] += d1 * xn[i]; J[i][2] += d2 * xn[i];
+        U[i][0] += d0 * s_u[n][i]; U[i][1] += d1 * s_u[n][i]; U[i][2] += d2 * s_u[n][i];
+      }
+      mu += P.T.N_ipfast[n * NIP + t] * s_mu[n];
+    }
+    double C[3][3];
+    const double det = cofactor(J, C);
+    if (!(det > 0.0)) atomicExch(P.err, 1);
+    const double inv = 1.0 / det;
+    const int d = P.T.dir[t];
+    const double w = P.T.wdir[t];
+    double A[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) A[i] = w * (d == 0 ? C[i][0] : d == 1 ? C[i][1] : C[i][2]);
+    double divu = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) divu += C[i][j] * U[i][j];
+    divu *= inv;
+    const double f = -mu * inv;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s_rec[3 * i + j][t] = f * C[i][j];
+    const double ds = 2.0 / 3.0 * mu * divu * P.include_divu;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      s_rec[9 + i][t] = A[i];
+      s_rec[13 + i][t] = ds * A[i];
+    }
+    s_rec[12][t] = P.mdot[e * NIP + t];
+  }
+  __syncthreads();
+
+  // ---- phase C: thread = (row node, three column nodes) ----------------------------------------------------------
+  const int r = t / 9, g = t - 9 * r;
+  if (r < NPE) {
+    double blk[3][3][3], dg[3] = {0.0, 0.0, 0.0}, rs[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) blk[m][i][j] = 0.0;
+    const int q0 = P.T.inc_ptr[r], q1 = P.T.inc_ptr[r + 1];
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+      const int code = P.T.inc[q], ip = code >> 1;
+      const double sg = (code & 1) ? -1.0 : 1.0; // the left node gains what leaves through the point, the right node loses it
+      double G[3][3], A[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) G[i][j] = s_rec[3 * i + j][ip];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        A[i] = sg * s_rec[9 + i][ip];
+        rs[i] += sg * s_rec[13 + i][ip];
+      }
+      const double md = sg * s_rec[12][ip];
+      const double *dn = P.T.dN_nodefast + ((size_t)ip * NPE + 3 * g) * 3;
+      const double *sf = P.T.N_nodefast + (size_t)ip * NPE + 3 * g;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const double d0 = dn[3 * m], d1 = dn[3 * m + 1], d2 = dn[3 * m + 2];
+        double h[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) h[i] = G[i][0] * d0 + G[i][1] * d1 + G[i][2] * d2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) blk[m][i][j] += h[i] * A[j];
+        dg[m] += sf[m] * md + h[0] * A[0] + h[1] * A[1] + h[2] * A[2];
+      }
+    }
+    // residual part of this thread's three blocks, then the blocks leave
+    const int rn = s_row[r];
+    const long long b0 = P.browptr[rn];
+    const int nb = (int)(P.browptr[rn + 1] - b0);
+    double *rowv = P.values + 9 * b0;
+    const unsigned char *slots = P.elem_slot + (e * NPE + r) * NPE + 3 * g;
+    double pr[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const int c = 3 * g + m;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) blk[m][i][i] += dg[m];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pr[i] -= blk[m][i][j] * s_u[c][j];
+      double *dst = rowv + 3 * (int)slots[m];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (P.elem_list) red_add(dst + (long long)i * nb * 3 + j, blk[m][i][j]);
+          else atomicAdd(dst + (long long)i * nb * 3 + j, blk[m][i][j]);
+        }
+    }
+    if (g == 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pr[i] -= rs[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s_part[t][i] = pr[i];
+  }
+  __syncthreads();
+  if (t < 81) {
+    const int rr = t / 3, i = t - 3 * rr;
+    double v = 0.0;
+#pragma unroll
+    for (int gg = 0; gg < 9; ++gg) v += s_part[rr * 9 + gg][i];
+    double *dst = P.rhs + (long long)s_row[rr] * 3 + i;
+    if (P.elem_list) red_add(dst, v);
+    else atomicAdd(dst, v);
+  }
+}
+
+// mass_flow_rate_scs of a Hex27 element: mdot_ip = (sum_n N_n rho_n u_n) . A_ip (the unit tests' calc_mass_flow_rate_scs,
+// unit_tests/kernels/UnitTestKernelUtils.C:547-628, instantiated with AlgTraitsHex27); thread = (element, point)
+__global__ void __launch_bounds__(kThreads) mdot_hex27_kernel(Tables T, long long n_elems, const int *elem_nodes, const double *coords,
+                                                               const double *density, const double *vel, double *mdot)
+{
+  const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (tid >= n_elems * NIP) return;
+  const long long e = tid / NIP;
+  const int ip = (int)(tid - e * NIP);
+  const int *en = elem_nodes + e * NPE;
+  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, ru[3] = {0, 0, 0};
+  const int n0 = en[0];
+  const double x0[3] = {coords[(size_t)n0 * 3], coords[(size_t)n0 * 3 + 1], coords[(size_t)n0 * 3 + 2]};
+  for (int n = 0; n < NPE; ++n) {
+    const int nd = en[n];
+    const double sf = T.N_ipfast[n * NIP + ip] * density[nd];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double x = coords[(size_t)nd * 3 + i] - x0[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) J[i][j] += T.dN_ipfast[(n * 3 + j) * NIP + ip] * x;
+      ru[i] += sf * vel[(size_t)nd * 3 + i];
+    }
+  }
+  double C[3][3];
+  cofactor(J, C);
+  const int d = T.dir[ip];
+  const double w = T.wdir[ip];
+  double md = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) md += ru[i] * w * (d == 0 ? C[i][0] : d == 1 ? C[i][1] : C[i][2]);
+  mdot[tid] = md;
+}
+
+} // namespace hex27
+
+bool hex27_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+{
+  return g.npe == 27 && g.ndof == 3 && nk == 1 && k[0].kind == NALU_K_MOMENTUM_ADV_DIFF && k[0].options == 0 && g.d_elem_nodes27 &&
+         g.d_elem_slot27 && k[0].nodal[NALU_F_COORDINATES] && k[0].nodal[NALU_F_VELOCITY] && k[0].nodal[NALU_F_VISCOSITY] &&
+         k[0].mass_flow_rate;
+}
+
+int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double *d_values, double *d_rhs, cudaStream_t stream)
+{
+  using namespace hex27;
+  const Tables *T = nullptr;
+  int rc = get_tables(&T);
+  if (rc) return rc;
+  Params P;
+  P.T = *T;
+  P.elem_nodes = g.d_elem_nodes27;
+  P.elem_slot = g.d_elem_slot27;
+  P.node_row = g.d_node_row;
+  P.browptr = (const long long *)g.d_browptr;
+  P.coords = k.nodal[NALU_F_COORDINATES];
+  P.vel = k.nodal[NALU_F_VELOCITY];
+  P.visc = k.nodal[NALU_F_VISCOSITY];
+  P.mdot = k.mass_flow_rate;
+  P.include_divu = k.include_divu;
+  P.values = d_values;
+  P.rhs = d_rhs;
+  P.err = g.d_err;
+  if (g.d_color_elems && !g.color_ptr.empty()) {
+    const size_t ngroups = g.color_ptr.size() - 1;
+    for (size_t c = 0; c < ngroups; ++c) {
+      const long long n = g.color_ptr[c + 1] - g.color_ptr[c];
+      if (n <= 0) continue;
+      P.elem_list = g.d_color_elems + g.color_ptr[c];
+      P.n = n;
+      assemble_hex27_kernel<<<(unsigned)n, kThreads, 0, stream>>>(P);
+      count_launch();
+    }
+  } else if (g.n_elems > 0) { // an element that reaches one row through two of its nodes: contended atomics
+    P.elem_list = nullptr;
+    P.n = g.n_elems;
+    assemble_hex27_kernel<<<(unsigned)g.n_elems, kThreads, 0, stream>>>(P);
+    count_launch();
+  }
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+int launch_mdot_hex27(const Graph &g, const double *coords, const double *density, const double *velocity, double *mdot,
+                      cudaStream_t stream)
+{
+  using namespace hex27;
+  const Tables *T = nullptr;
+  int rc = get_tables(&T);
+  if (rc) return rc;
+  const long long nt = g.n_elems * NIP;
+  if (nt > 0) {
+    mdot_hex27_kernel<<<(unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, stream>>>(*T, g.n_elems, g.d_elem_nodes27, coords, density,
+                                                                                          velocity, mdot);
+    count_launch();
+  }
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
+
+} // namespace nalu_b200

@@ -92,7 +92,7 @@ static void free_graph_device(Graph &g)
     p = nullptr;
   };
   F(g.d_elem_nodes); F(g.d_node_row); F(g.d_row_rep); F(g.d_color_elems); F(g.d_browptr); F(g.d_bcol); F(g.d_elem_slot); F(g.d_node_slot27); F(g.d_node_desc);
-  F(g.d_rowelem_ptr); F(g.d_rowelem);
+  F(g.d_rowelem_ptr); F(g.d_rowelem); F(g.d_elem_nodes27); F(g.d_elem_slot27);
   F(g.d_rowptr_owned); F(g.d_rowptr_shared); F(g.d_colidx_owned); F(g.d_colidx_shared); F(g.d_err);
   for (auto *peers : {&g.send_peers, &g.recv_peers})
     for (HaloPeer &p : *peers) {
@@ -104,17 +104,17 @@ static void free_graph_device(Graph &g)
 static int upload_graph(Graph &g, const std::vector<uint8_t> &elem_slot, const std::vector<uint8_t> &node_slot27)
 {
   int rc;
-  if ((rc = upload(&g.d_elem_nodes, g.elem_nodes))) return rc;
+  if ((rc = upload(g.npe == 27 ? &g.d_elem_nodes27 : &g.d_elem_nodes, g.elem_nodes))) return rc;
   if ((rc = upload(&g.d_node_row, g.node_row))) return rc;
   if ((rc = upload(&g.d_row_rep, g.row_rep))) return rc;
   if ((rc = upload(&g.d_color_elems, g.color_elems))) return rc;
   if ((rc = upload(&g.d_browptr, g.browptr))) return rc;
   if ((rc = upload(&g.d_bcol, g.bcol))) return rc;
-  if ((rc = upload(&g.d_elem_slot, elem_slot))) return rc;
+  if ((rc = upload(g.npe == 27 ? &g.d_elem_slot27 : &g.d_elem_slot, elem_slot))) return rc;
   if ((rc = upload(&g.d_node_slot27, node_slot27))) return rc;
   if ((rc = upload(&g.d_node_desc, g.node_desc))) return rc;
   std::vector<uint64_t>().swap(g.node_desc);
-  if (g.box[0] == 0 && g.n_elems > 0 && g.n_elems < (int64_t(1) << 28)) {
+  if (g.npe == 8 && g.box[0] == 0 && g.n_elems > 0 && g.n_elems < (int64_t(1) << 28)) {
     // row node -> (element, local node), elements in ascending order: a counting sort of the connectivity by row
     const int nrow = g.n_row_nodes();
     std::vector<int64_t> ptr(size_t(nrow) + 1, 0);
@@ -199,9 +199,32 @@ int nalu_b200_tune(const char *name, int32_t value)
   return NALU_B200_OK;
 }
 
+static int graph_create_impl(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof, int32_t npe, int32_t n_nodes,
+                             const int64_t *node_gid, const int32_t *node_owner, int64_t n_elems, const int32_t *elem_nodes,
+                             int32_t box_nx, int32_t box_ny, int32_t box_nz);
+
 int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof, int32_t n_nodes,
                            const int64_t *node_gid, const int32_t *node_owner, int64_t n_elems,
                            const int32_t *elem_nodes, int32_t box_nx, int32_t box_ny, int32_t box_nz)
+{
+  return graph_create_impl(out, rank, nranks, num_dof, 8, n_nodes, node_gid, node_owner, n_elems, elem_nodes, box_nx, box_ny,
+                           box_nz);
+}
+
+int nalu_b200_graph_create_topo(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof, int32_t nodes_per_elem,
+                                int32_t n_nodes, const int64_t *node_gid, const int32_t *node_owner, int64_t n_elems,
+                                const int32_t *elem_nodes)
+{
+  if (nodes_per_elem != 8 && nodes_per_elem != 27) {
+    set_error("graph_create_topo: nodes_per_elem must be 8 (Hex8) or 27 (Hex27)");
+    return NALU_B200_ERR_ARG;
+  }
+  return graph_create_impl(out, rank, nranks, num_dof, nodes_per_elem, n_nodes, node_gid, node_owner, n_elems, elem_nodes, 0, 0, 0);
+}
+
+static int graph_create_impl(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof, int32_t npe, int32_t n_nodes,
+                             const int64_t *node_gid, const int32_t *node_owner, int64_t n_elems, const int32_t *elem_nodes,
+                             int32_t box_nx, int32_t box_ny, int32_t box_nz)
 {
   if (!out || nranks < 1 || rank < 0 || rank >= nranks || (num_dof != 1 && num_dof != 3) || n_nodes < 0 || n_elems < 0 ||
       (n_nodes && (!node_gid || !node_owner)) || (n_elems && !elem_nodes)) {
@@ -218,7 +241,8 @@ int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, 
     if (!(box_nx > 0 && box_ny > 0 && box_nz > 0)) g.box[0] = g.box[1] = g.box[2] = 0;
     g.gid.assign(node_gid, node_gid + n_nodes);
     g.owner.assign(node_owner, node_owner + n_nodes);
-    g.elem_nodes.assign(elem_nodes, elem_nodes + n_elems * 8);
+    g.npe = npe;
+    g.elem_nodes.assign(elem_nodes, elem_nodes + n_elems * npe);
     std::string err;
     if (graph_number_and_adjacency(g, err) || graph_build_send_messages(g, err)) {
       set_error("graph_create: " + err);
@@ -434,6 +458,18 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   }
   const Graph &g = h->g;
   cudaStream_t s = (cudaStream_t)stream;
+  if (g.npe == 27) { // Hex27 graphs (nalu_b200_graph_create_topo): one kernel, assemble_hex27.cu
+    if (!hex27_supported(g, kernels, nk)) {
+      set_error("assemble_elem: Hex27 graphs take [MomentumAdvDiffElemKernel] on a 3-dof system only");
+      return NALU_B200_ERR_ARG;
+    }
+    if (const char *missing = missing_field(kernels[0])) {
+      set_error(std::string("assemble_elem: field missing for kernel 0: ") + missing);
+      return NALU_B200_ERR_ARG;
+    }
+    set_last_mode(5);
+    return launch_assemble_hex27(g, kernels[0], d_values, d_rhs, s);
+  }
   // A list with one kernel the tiled write-once kernels know plus others (e.g. [MomentumMass(lumped), MomentumAdvDiff],
   // the momentum list of the low-Mach equation system, src/LowMachEquationSystem.C:1304-1398): the tiled kernel
   // takes its kernel first (it may overwrite), the others accumulate on top through the general kernel -- the sum the
@@ -575,6 +611,8 @@ int nalu_b200_reset_rows(const nalu_b200_graph *h, int32_t n_nodes, const int32_
 int nalu_b200_mdot_scs(const nalu_b200_graph *h, const double *d_coords, const double *d_density, const double *d_velocity,
                        double *d_mdot, void *stream)
 {
+  if (h && d_coords && d_density && d_velocity && d_mdot && h->g.npe == 27 && h->g.d_elem_nodes27)
+    return launch_mdot_hex27(h->g, d_coords, d_density, d_velocity, d_mdot, (cudaStream_t)stream);
   if (!h || !d_coords || !d_density || !d_velocity || !d_mdot || !h->g.d_elem_nodes) return NALU_B200_ERR_STATE;
   return launch_mdot(h->g, d_coords, d_density, d_velocity, d_mdot, (cudaStream_t)stream);
 }

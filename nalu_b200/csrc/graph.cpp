@@ -103,25 +103,26 @@ int graph_number_and_adjacency(Graph &g, std::string &err)
 
   // ---- element incidence per row node ------------------------------------------------
   const int64_t ne = g.n_elems;
-  std::vector<int32_t> erow(size_t(ne) * 8);
+  const int npe = g.npe; // 8 (Hex8) or 27 (Hex27)
+  std::vector<int32_t> erow(size_t(ne) * npe);
 #pragma omp parallel for schedule(static)
-  for (int64_t q = 0; q < ne * 8; ++q) {
+  for (int64_t q = 0; q < ne * npe; ++q) {
     const int32_t n = g.elem_nodes[q];
     erow[q] = (n >= 0 && n < nn) ? g.node_row[n] : -1;
   }
-  for (int64_t q = 0; q < ne * 8; ++q)
+  for (int64_t q = 0; q < ne * npe; ++q)
     if (erow[q] < 0) {
       err = "elem_nodes entry out of range";
       return 1;
     }
   std::vector<int64_t> inc_ptr(size_t(nrow) + 1, 0);
-  for (int64_t q = 0; q < ne * 8; ++q) ++inc_ptr[erow[q] + 1];
+  for (int64_t q = 0; q < ne * npe; ++q) ++inc_ptr[erow[q] + 1];
   for (int32_t r = 0; r < nrow; ++r) inc_ptr[r + 1] += inc_ptr[r];
-  std::vector<int64_t> inc(size_t(ne) * 8);
+  std::vector<int64_t> inc(size_t(ne) * npe);
   {
     std::vector<int64_t> pos(inc_ptr.begin(), inc_ptr.end() - 1);
     for (int64_t e = 0; e < ne; ++e)
-      for (int k = 0; k < 8; ++k) inc[pos[erow[e * 8 + k]]++] = e;
+      for (int k = 0; k < npe; ++k) inc[pos[erow[e * npe + k]]++] = e;
   }
 
   // ---- element colouring (greedy over the row-node incidence; parity of (i,j,k) on a generated box) ----------
@@ -134,10 +135,10 @@ int graph_number_and_adjacency(Graph &g, std::string &err)
     bool aliased = false; // an element that touches one row through two of its nodes races with itself
 #pragma omp parallel for schedule(static) reduction(|| : aliased)
     for (int64_t e = 0; e < ne; ++e)
-      for (int a = 0; a < 8; ++a)
-        for (int b = a + 1; b < 8; ++b) aliased = aliased || erow[e * 8 + a] == erow[e * 8 + b];
+      for (int a = 0; a < npe; ++a)
+        for (int b = a + 1; b < npe; ++b) aliased = aliased || erow[e * npe + a] == erow[e * npe + b];
     if (aliased) ok = false;
-    if (ok && g.box[0] > 0 && nrow == nn) {
+    if (ok && npe == 8 && g.box[0] > 0 && nrow == nn) {
       const int64_t nx = g.box[0], ny = g.box[1];
 #pragma omp parallel for schedule(static)
       for (int64_t e = 0; e < ne; ++e) color[e] = int8_t(((e % nx) & 1) | ((((e / nx) % ny) & 1) << 1) | (((e / (nx * ny)) & 1) << 2));
@@ -145,8 +146,8 @@ int graph_number_and_adjacency(Graph &g, std::string &err)
     } else if (ok) {
       for (int64_t e = 0; e < ne && ok; ++e) {
         uint64_t used = 0;
-        for (int k = 0; k < 8; ++k) {
-          const int32_t r = erow[e * 8 + k];
+        for (int k = 0; k < npe; ++k) {
+          const int32_t r = erow[e * npe + k];
           for (int64_t p = inc_ptr[r]; p < inc_ptr[r + 1]; ++p) {
             const int8_t c = color[inc[p]];
             if (c >= 0) used |= uint64_t(1) << c;
@@ -186,8 +187,8 @@ int graph_number_and_adjacency(Graph &g, std::string &err)
     for (int32_t r = r0; r < r1; ++r) {
       cand.clear();
       for (int64_t p = inc_ptr[r]; p < inc_ptr[r + 1]; ++p) {
-        const int32_t *en = &erow[inc[p] * 8];
-        cand.insert(cand.end(), en, en + 8);
+        const int32_t *en = &erow[inc[p] * npe];
+        cand.insert(cand.end(), en, en + npe);
       }
       std::sort(cand.begin(), cand.end());
       cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
@@ -360,17 +361,18 @@ int graph_finalize_host(Graph &g, std::vector<uint8_t> &elem_slot, std::vector<u
 
   // ---- element scatter map: slot of column node ic inside the row of node k -----------
   const int64_t ne = g.n_elems;
-  elem_slot.resize(size_t(ne) * 64);
+  const int npe = g.npe;
+  elem_slot.resize(size_t(ne) * npe * npe);
   int overflow = 0;
 #pragma omp parallel for schedule(static) reduction(+ : overflow)
   for (int64_t e = 0; e < ne; ++e) {
-    int32_t rn[8];
-    for (int k = 0; k < 8; ++k) rn[k] = g.node_row[g.elem_nodes[e * 8 + k]];
-    for (int k = 0; k < 8; ++k)
-      for (int ic = 0; ic < 8; ++ic) {
+    int32_t rn[27];
+    for (int k = 0; k < npe; ++k) rn[k] = g.node_row[g.elem_nodes[e * npe + k]];
+    for (int k = 0; k < npe; ++k)
+      for (int ic = 0; ic < npe; ++ic) {
         const int s = find_slot(rn[k], rn[ic]);
         if (s < 0 || s >= 255) ++overflow;
-        elem_slot[size_t(e) * 64 + k * 8 + ic] = uint8_t(s);
+        elem_slot[(size_t(e) * npe + k) * npe + ic] = uint8_t(s);
       }
   }
   if (overflow) { err = "row with more than 254 node blocks (or missing connection)"; return 1; }

@@ -48,6 +48,7 @@ struct Graph {
   int32_t rank = 0, nranks = 1, ndof = 1;
   int32_t n_nodes = 0;
   int64_t n_elems = 0;
+  int32_t npe = 8; // nodes per element: 8 (Hex8) or 27 (Hex27, nalu_b200_graph_create_topo; assemble_hex27.cu only)
   int32_t box[3] = {0, 0, 0};
   std::vector<int64_t> gid;
   std::vector<int32_t> owner;
@@ -90,7 +91,9 @@ struct Graph {
   int64_t nblk_owned = 0, nblk_shared = 0;
 
   // device
-  int32_t *d_elem_nodes = nullptr; // [n_elems][8]
+  int32_t *d_elem_nodes = nullptr; // [n_elems][8]; null on Hex27 graphs, so that every Hex8 entry point refuses them
+  int32_t *d_elem_nodes27 = nullptr; // Hex27 graphs: [n_elems][27] (STK node order)
+  uint8_t *d_elem_slot27 = nullptr;  // Hex27 graphs: [n_elems][27][27] slot of column node ic in the row of node k
   int32_t *d_node_row = nullptr;   // [n_nodes]
   int32_t *d_row_rep = nullptr;    // [n_row_nodes]
   int64_t *d_browptr = nullptr;    // [n_row_nodes+1]

@@ -64,6 +64,11 @@ namespace box { struct BoxParams; }
 int launch_assemble_box2(box::BoxParams &P, cudaStream_t stream);
 bool box5_supported(const box::BoxParams &P);
 int launch_assemble_box5(box::BoxParams &P, cudaStream_t stream);
+// assemble_hex27.cu: MomentumAdvDiffElemKernel<AlgTraitsHex27>, CTA = element, coloured value-less reductions
+bool hex27_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
+int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double *d_values, double *d_rhs, cudaStream_t stream);
+int launch_mdot_hex27(const Graph &g, const double *coords, const double *density, const double *velocity, double *mdot,
+                      cudaStream_t stream);
 // halo.cu
 int launch_halo_pack(const Graph &g, const HaloPeer &p, const double *d_values, const double *d_rhs,
                      double *d_buf, cudaStream_t stream);

@@ -32,8 +32,14 @@ class DeviceCsrLinearSystem:
         own = np.ascontiguousarray(mesh.node_owner, dtype=np.int32)
         en = np.ascontiguousarray(mesh.elem_nodes, dtype=np.int32)
         box = (mesh.box.nx, mesh.box.ny, mesh.box.nz) if (use_box and mesh.box is not None) else (0, 0, 0)
-        check(self.L.nalu_b200_graph_create(C.byref(self.h), mesh.rank, mesh.nranks, num_dof, gid.size, ptr(gid),
-                                            ptr(own), C.c_int64(en.shape[0]), ptr(en), *box), "graph_create")
+        self.nodes_per_elem = int(en.shape[1])
+        if self.nodes_per_elem == 8:
+            check(self.L.nalu_b200_graph_create(C.byref(self.h), mesh.rank, mesh.nranks, num_dof, gid.size, ptr(gid),
+                                                ptr(own), C.c_int64(en.shape[0]), ptr(en), *box), "graph_create")
+        else:  # Hex27 (mesh.hex27_box): AlgTraitsHex27
+            check(self.L.nalu_b200_graph_create_topo(C.byref(self.h), mesh.rank, mesh.nranks, num_dof, self.nodes_per_elem,
+                                                     gid.size, ptr(gid), ptr(own), C.c_int64(en.shape[0]), ptr(en)),
+                  "graph_create_topo")
         # --- handshake -------------------------------------------------------------------
         send = {}
         for p in range(mesh.nranks):
@@ -306,7 +312,7 @@ class DeviceCsrLinearSystem:
     def mdot_scs(self, coords, density, velocity, out=None):
         import torch
         if out is None:
-            out = torch.empty((self.mesh.n_elems, 12), dtype=torch.float64, device=coords.device)
+            out = torch.empty((self.mesh.n_elems, 12 if self.nodes_per_elem == 8 else 216), dtype=torch.float64, device=coords.device)
         check(self.L.nalu_b200_mdot_scs(self.h, ptr(coords), ptr(density), ptr(velocity), ptr(out), self._stream()),
               "mdot_scs")
         return out

@@ -238,3 +238,28 @@ def box_side_faces(mesh: HexMesh, side: str):
                     "z": ((k == 0) & (b.k0 == 0), 4), "Z": ((k == lz - 1) & (b.k0 + lz == b.nz_global), 5)}[side]
     fe = np.sort(e[sel])
     return fe, np.full(fe.size, ordinal, dtype=np.int32)
+
+
+# ---- Hex27 (P2 CVFEM) boxes: BASELINE config 5 ---------------------------------------------------------------------
+# tensor-grid node (i, j, k) of a Hex27 element -> STK Hex27 ordinal (HexahedralP2Element::stkNodeMap_,
+# src/master_element/Hex27CVFEM.C:36-47)
+HEX27_STK_NODE_MAP = np.array([0, 8, 1, 11, 21, 9, 3, 10, 2, 12, 25, 13, 23, 20, 24, 15, 26, 14, 4, 16, 5, 19, 22, 17,
+                               7, 18, 6], dtype=np.int32)
+
+
+def hex27_box(nx, ny, nz) -> HexMesh:
+    """nx*ny*nz Hex27 elements on the (2nx+1)(2ny+1)(2nz+1) node lattice of spacing 1/2 (what promoting a `generated:`
+    Hex8 box to P2 produces, up to the node numbering: here lexicographic, x fastest), elem_nodes[nElem, 27] in STK order."""
+    sx, sy, sz = 2 * nx + 1, 2 * ny + 1, 2 * nz + 1
+    zz, yy, xx = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    coords = 0.5 * np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1).astype(np.float64)
+    ek, ej, ei = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    n0 = (2 * ei + sx * (2 * ej + sy * 2 * ek)).ravel()
+    conn = np.empty((n0.size, 27), dtype=np.int32)
+    for c in range(3):
+        for b in range(3):
+            for a in range(3):
+                conn[:, HEX27_STK_NODE_MAP[a + 3 * (b + 3 * c)]] = n0 + a + sx * (b + sy * c)
+    n = sx * sy * sz
+    return HexMesh(coords=coords, node_gid=np.arange(1, n + 1, dtype=np.int64), node_owner=np.zeros(n, dtype=np.int32),
+                   elem_nodes=conn)

@@ -1,0 +1,284 @@
+"""Hex27 (P2 CVFEM, BASELINE config 5): oracle pinned by the reference's own Hex27 tests (they are property tests: the
+reference holds no Hex27 gold table), graph on Hex27 connectivity, and the CUDA kernel against the oracle.
+
+Restated reference tests:
+  unit_tests/UnitTestHexMasterElements.C:297-321  hex27_scs_interpolation / hex27_scv_interpolation / hex27_scs_derivatives
+  unit_tests/UnitTestMasterElements.C:185-229     volume_integration
+"""
+import numpy as np
+import pytest
+
+from nalu_b200 import mesh as M
+from oracle import hex27 as H
+
+# unit_tests/UnitTestUtils.C:218-233 create_one_reference_hex27_element
+REF_NODES = np.array([
+    [-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1],
+    [0, -1, -1], [1, 0, -1], [0, 1, -1], [-1, 0, -1], [-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0],
+    [0, -1, 1], [1, 0, 1], [0, 1, 1], [-1, 0, 1], [0, 0, 0], [0, 0, -1], [0, 0, 1], [-1, 0, 0], [1, 0, 0], [0, -1, 0],
+    [0, 1, 0]], dtype=np.float64)
+
+
+def _poly(rng, order=2):
+    return rng.uniform(-1.0, 1.0, size=(3, order + 1))
+
+
+def _poly_val(c, x):
+    x = np.atleast_2d(x)
+    out = np.ones(x.shape[0])
+    for d in range(3):
+        out = out * sum(c[d][j] * x[:, d] ** j for j in range(c.shape[1]))
+    return out
+
+
+def _poly_der(c, x, direction):
+    x = np.atleast_2d(x)
+    out = np.ones(x.shape[0])
+    for d in range(3):
+        if d == direction:
+            out = out * sum(j * c[d][j] * x[:, d] ** (j - 1) for j in range(1, c.shape[1]))
+        else:
+            out = out * sum(c[d][j] * x[:, d] ** j for j in range(c.shape[1]))
+    return out
+
+
+def _perturbed_box(n, amp=0.08, seed=3):
+    m = M.hex27_box(*n)
+    rng = np.random.default_rng(seed)
+    m.coords = m.coords + amp * rng.uniform(-1.0, 1.0, size=m.coords.shape)  # every node: curved (truly quadratic) elements
+    return m
+
+
+def _fields(m, seed=5):
+    rng = np.random.default_rng(seed)
+    x = m.coords
+    vel = np.stack([np.sin(0.9 * x[:, 1]) + 0.3 * x[:, 2], np.cos(0.7 * x[:, 0]) * x[:, 2], 0.2 * x[:, 0] * x[:, 1] - 0.5], axis=1)
+    vel += 0.05 * rng.uniform(-1, 1, size=vel.shape)
+    visc = 0.3 + 0.1 * np.cos(x[:, 0] + 2.0 * x[:, 1]) + 0.02 * rng.uniform(-1, 1, size=x.shape[0])
+    rho = 1.0 + 0.2 * np.sin(x[:, 2]) + 0.02 * rng.uniform(-1, 1, size=x.shape[0])
+    return vel, visc, rho
+
+
+# ---- oracle pinning (CPU) ------------------------------------------------------------------------------------------------
+
+def test_shape_functions_are_nodal_and_partition_unity():
+    f = H.hex27_shape_fcn(REF_NODES)
+    assert np.allclose(f, np.eye(27), atol=1e-15)  # the literal formulas are the Lagrange basis of REF_NODES in STK order
+    rng = np.random.default_rng(0)
+    p = rng.uniform(-1, 1, size=(50, 3))
+    assert np.allclose(H.hex27_shape_fcn(p).sum(axis=1), 1.0, atol=1e-14)
+    assert np.allclose(H.hex27_shape_deriv(p).sum(axis=1), 0.0, atol=1e-13)
+
+
+def test_shape_deriv_is_the_derivative_of_the_literal_shape_functions():
+    rng = np.random.default_rng(1)
+    p = rng.uniform(-1, 1, size=(40, 3))
+    d = H.hex27_shape_deriv(p)
+    h = 1e-6
+    for k in range(3):
+        e = np.zeros(3)
+        e[k] = h
+        fd = (H.hex27_shape_fcn(p + e) - H.hex27_shape_fcn(p - e)) / (2 * h)
+        assert np.abs(fd - d[:, :, k]).max() < 1e-9
+
+
+@pytest.mark.parametrize("me", ["scs", "scv"])
+def test_hex27_interpolation(me):
+    """hex27_scs_interpolation / hex27_scv_interpolation: a random quadratic (per direction) polynomial is interpolated
+    exactly to the integration points"""
+    m = H.Hex27SCS() if me == "scs" else H.Hex27SCV()
+    c = _poly(np.random.default_rng(0))
+    nodal = _poly_val(c, REF_NODES)
+    assert np.abs(m.shape_fcn @ nodal - _poly_val(c, m.intg_loc)).max() < 1e-12
+
+
+def test_hex27_scs_derivatives():
+    """hex27_scs_derivatives: grad_op on the reference element = shape derivatives, det = 1, polynomial derivative exact"""
+    m = H.Hex27SCS()
+    dndx, det = m.grad_op(REF_NODES[None])
+    assert np.abs(dndx[0] - m.shape_deriv).max() < 1e-12
+    assert np.abs(det - 1.0).max() < 1e-12
+    c = _poly(np.random.default_rng(0))
+    nodal = _poly_val(c, REF_NODES)
+    for d in range(3):
+        assert np.abs(dndx[0, :, :, d] @ nodal - _poly_der(c, m.intg_loc, d)).max() < 1e-12
+
+
+def test_hex27_volume_integration():
+    """volume_integration: SCV weights scale with det of a linear map; and they sum to the element volume"""
+    m = H.Hex27SCV()
+    rng = np.random.default_rng(0)
+    q, r = np.linalg.qr(rng.uniform(-1, 1, size=(3, 3)))
+    qr = q @ (np.eye(3) + 0.3 * np.triu(rng.uniform(-1, 1, size=(3, 3))))
+    if np.linalg.det(qr) < 0:
+        qr[:, 0] *= -1
+    v0 = m.volumes(REF_NODES[None])[0]
+    v1 = m.volumes((REF_NODES @ qr.T)[None])[0]
+    assert np.abs(np.linalg.det(qr) * v0 - v1).max() < 1e-13
+    assert abs(v0.sum() - 8.0) < 1e-13
+    # every node owns 8 points; 1-D dual lengths: 1 - 1/sqrt(3) (end nodes), 2/sqrt(3) (mid node)
+    per_node = np.bincount(m.ip_node_map, weights=v0, minlength=27)
+    l = np.array([1 - H.SCS_DIST, 2 * H.SCS_DIST, 1 - H.SCS_DIST])
+    expect = np.empty(27)
+    for cc in range(3):
+        for b in range(3):
+            for a in range(3):
+                expect[H.tensor_product_node_map(a, b, cc)] = l[a] * l[b] * l[cc]
+    assert np.abs(per_node - expect).max() < 1e-14
+
+
+def test_scs_area_vectors_closed_forms():
+    m = H.Hex27SCS()
+    a = m.area_vectors(REF_NODES[None])[0]
+    # a constant-u surface of the reference cube has area 4, normal +-z; the vector points from the left to the right node
+    for direction, axis in ((H.U_DIRECTION, 2), (H.T_DIRECTION, 1), (H.S_DIRECTION, 0)):
+        ips = np.nonzero(m.direction == direction)[0]
+        assert np.allclose(np.delete(a[ips], axis, axis=1), 0.0, atol=1e-15)
+        assert abs(np.abs(a[ips, axis]).sum() - 8.0) < 1e-13  # two surfaces of area 4
+        lr = REF_NODES[m.lrscv[ips, 1]] - REF_NODES[m.lrscv[ips, 0]]
+        assert np.all(np.sign(lr[:, axis]) == np.sign(a[ips, axis]))
+    # on a curved element every interior sub-control volume is closed: sum of outward area vectors of the centre node's
+    # control volume vanishes (all its faces are sub-control surfaces of this element)
+    rng = np.random.default_rng(2)
+    xc = REF_NODES + 0.1 * rng.uniform(-1, 1, size=REF_NODES.shape)
+    ac = m.area_vectors(xc[None])[0]
+    out = ac[m.lrscv[:, 0] == 20].sum(axis=0) - ac[m.lrscv[:, 1] == 20].sum(axis=0)
+    assert np.abs(out).max() < 1e-13
+
+
+def test_hex27_with_centred_mid_nodes_reproduces_trilinear_geometry():
+    """mid-edge / face / body nodes at the averages of a perturbed Hex8's corners: the quadratic map IS the trilinear one,
+    so Jacobians at the SCS points agree with the Hex8 shape derivatives evaluated there"""
+    rng = np.random.default_rng(4)
+    x = REF_NODES.copy()
+    x[:8] += 0.15 * rng.uniform(-1, 1, size=(8, 3))
+    corner_ref = REF_NODES[:8]
+    def tri(p):  # trilinear shape functions of the 8 corners at p
+        return np.prod(1.0 + corner_ref[None, :, :] * p[:, None, :], axis=2) / 8.0
+    x[8:] = tri(REF_NODES[8:]) @ x[:8]
+    m = H.Hex27SCS()
+    jact = np.einsum("pnj,ni->pij", m.shape_deriv, x)
+    h = 1e-6
+    for k in range(3):
+        e = np.zeros(3)
+        e[k] = h
+        fd = (tri(m.intg_loc + e) - tri(m.intg_loc - e)) @ x[:8] / (2 * h)
+        assert np.abs(fd - jact[:, :, k]).max() < 1e-9
+
+
+def test_momentum_adv_diff_identities():
+    """row sums of the diffusion + stress operator vanish (constants are in its null space), and a uniform velocity with
+    consistent mdot gives a residual = -(net advective flux) that sums to zero over an element"""
+    m = _perturbed_box((1, 1, 1))
+    vel, visc, rho = _fields(m)
+    mdot0 = np.zeros((1, 216))
+    lhs, rhs = H.momentum_adv_diff(m.elem_nodes, m.coords, vel, visc, mdot0, include_divu=1.0)
+    L = lhs.reshape(81, 27, 3)
+    assert np.abs(L.sum(axis=1)).max() < 1e-12 * np.abs(L).max() * 27
+    assert np.abs(rhs.reshape(27, 3).sum(axis=0)).max() < 1e-12  # fluxes telescope: every point adds to il what it takes from ir
+    # uniform velocity: no viscous force, no divergence
+    u0 = np.tile([0.3, -0.2, 0.7], (m.coords.shape[0], 1))
+    mdot = H.calc_mass_flow_rate_scs(m.elem_nodes, m.coords, np.ones(m.coords.shape[0]), u0)
+    lhs, rhs = H.momentum_adv_diff(m.elem_nodes, m.coords, u0, visc, mdot, include_divu=1.0)
+    # rhs(node, i) = -u0_i * (net mass flux out of the node's sub-control volume through interior surfaces)
+    me = H.scs()
+    net = np.zeros(27)
+    np.add.at(net, me.lrscv[:, 0], mdot[0])
+    np.add.at(net, me.lrscv[:, 1], -mdot[0])
+    assert np.abs(rhs.reshape(27, 3) + net[:, None] * u0[0][None, :]).max() < 1e-13
+
+
+def test_hex27_box_mesh():
+    m = M.hex27_box(2, 3, 2)
+    assert m.elem_nodes.shape == (12, 27) and m.coords.shape == (5 * 7 * 5, 3)
+    # element 0 in STK order = the reference element scaled by 1/2 and shifted
+    assert np.allclose(m.coords[m.elem_nodes[0]], 0.5 * (REF_NODES + 1.0))
+    v = H.Hex27SCV().volumes(m.coords[m.elem_nodes])
+    assert np.allclose(v.sum(axis=1), 1.0)
+
+
+def test_hex27_graph_host_only_matches_oracle_csr():
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    m = M.hex27_box(3, 2, 2)
+    ls = DeviceCsrLinearSystem(m, 3, host_only=True)
+    E = m.n_elems
+    rowptr, colidx, _, _ = H.assemble_csr(m.node_gid, m.elem_nodes, np.zeros((E, 81, 81)), np.zeros((E, 81)))
+    assert ls.n_owned_rows == 3 * m.n_nodes and ls.n_shared_rows == 0
+    assert np.array_equal(ls.rowptr().astype(np.int64), rowptr)
+    assert np.array_equal(ls.colidx().astype(np.int64), colidx)
+    nc, col = ls.elem_colors()
+    assert nc == 8
+    # elements of one colour share no node
+    for c in range(nc):
+        nodes = m.elem_nodes[col == c].ravel()
+        assert np.unique(nodes).size == nodes.size
+    # the widest row: a corner node shared by 8 elements couples to 5^3 nodes
+    assert int(np.diff(rowptr).max()) == 125 * 3
+
+
+def test_hex8_entry_points_refuse_hex27_graphs():
+    import ctypes as C
+    from nalu_b200 import lib as L
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    m = M.hex27_box(1, 1, 1)
+    ls = DeviceCsrLinearSystem(m, 3, host_only=True)
+    buf = np.zeros(8)
+    rc = ls.L.nalu_b200_compute_mdot_elem(ls.h, L.ptr(buf), L.ptr(buf), L.ptr(buf), L.ptr(buf), L.ptr(buf), C.c_double(0.0), 0,
+                                          L.ptr(buf), None)
+    assert rc != 0
+
+
+# ---- CUDA kernel vs oracle (GPU) -----------------------------------------------------------------------------------------
+
+def _device_assemble(m, vel, visc, rho, include_divu):
+    import torch
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    dev = torch.device("cuda:0")
+    ls = DeviceCsrLinearSystem(m, 3)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    coords, v, mu, r = t(m.coords), t(vel), t(visc), t(rho)
+    mdot = ls.mdot_scs(coords, r, v)
+    ls.allocate(dev)
+    ls.zero_system()
+    d = ls.make_desc("momentum_adv_diff", fields=dict(coordinates=coords, velocity=v, viscosity=mu), mass_flow_rate=mdot,
+                     include_divu=include_divu)
+    mode = ls.assemble_elem([d])
+    torch.cuda.synchronize()
+    return ls, mode, mdot.cpu().numpy()
+
+
+def _rel_err_rows(a, b, rowptr):
+    rowmax = np.maximum.reduceat(np.maximum(np.abs(a), np.abs(b)), rowptr[:-1])
+    floor = np.repeat(rowmax, np.diff(rowptr)) * 1e-2
+    return float((np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor + 1e-300)).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,include_divu", [((1, 1, 1), 1.0), ((3, 2, 2), 1.0), ((2, 3, 4), 0.0), ((4, 4, 3), 1.0)])
+def test_hex27_momentum_adv_diff_vs_oracle(shape, include_divu):
+    m = _perturbed_box(shape)
+    vel, visc, rho = _fields(m)
+    ls, mode, mdot_dev = _device_assemble(m, vel, visc, rho, include_divu)
+    assert mode == 5
+    assert ls.geometry_errors() == 0
+    mdot = H.calc_mass_flow_rate_scs(m.elem_nodes, m.coords, rho, vel)
+    assert np.abs(mdot_dev - mdot).max() <= 1e-12 * np.abs(mdot).max()
+    lhs, rhs = H.momentum_adv_diff(m.elem_nodes, m.coords, vel, visc, mdot, include_divu=include_divu)
+    rowptr, colidx, values, b = H.assemble_csr(m.node_gid, m.elem_nodes, lhs, rhs)
+    got_v = ls.owned_values().cpu().numpy()
+    got_b = ls.owned_rhs().cpu().numpy()
+    assert got_v.shape == values.shape
+    # tolerance: 1e-12 relative, floor 1 % of the largest entry of the same row
+    assert _rel_err_rows(got_v, values, rowptr) < 1e-12
+    scale = np.abs(values).max() * np.abs(vel).max()
+    assert np.abs(got_b - b).max() < 1e-12 * scale * 27
+
+
+@pytest.mark.gpu
+def test_hex27_assembly_is_deterministic_and_accumulates():
+    m = _perturbed_box((3, 3, 2))
+    vel, visc, rho = _fields(m)
+    ls1, _, _ = _device_assemble(m, vel, visc, rho, 1.0)
+    ls2, _, _ = _device_assemble(m, vel, visc, rho, 1.0)
+    import torch
+    assert torch.equal(ls1.owned_values(), ls2.owned_values()) and torch.equal(ls1.owned_rhs(), ls2.owned_rhs())
