@@ -42,10 +42,12 @@ struct Tables {
   int *lr = nullptr;            // [216][2]
   int *inc_ptr = nullptr;       // [28]
   int *inc = nullptr;           // [432] ip << 1 | (1 if the node is the point's right node)
+  double *pt = nullptr;         // [216][3] reference coordinates of the points
+  int *stk = nullptr;           // [27] tensor-grid node -> STK ordinal
 };
 
 struct HostTables {
-  std::vector<double> dN, N, w; // [216][27][3], [216][27], [216]
+  std::vector<double> dN, N, w, pt; // [216][27][3], [216][27], [216], [216][3]
   std::vector<int> dir, lr;
 };
 
@@ -64,6 +66,7 @@ static HostTables build_host_tables()
   T.dN.assign(size_t(NIP) * NPE * 3, 0.0);
   T.N.assign(size_t(NIP) * NPE, 0.0);
   T.w.assign(NIP, 0.0);
+  T.pt.assign(3 * NIP, 0.0);
   T.dir.assign(NIP, 0);
   T.lr.assign(2 * NIP, 0);
   const double scsDist = std::sqrt(3.0) / 3.0;
@@ -103,6 +106,7 @@ static HostTables build_host_tables()
               const double w = seg(k) * seg(l) * 0.25 * (d == 0 ? -orient[m] : orient[m]);
               T.w[ip] = w * cofsign[d];
               T.dir[ip] = d;
+              for (int a = 0; a < 3; ++a) T.pt[3 * ip + a] = x[a];
               double L[3][3], D[3][3];
               for (int a = 0; a < 3; ++a) lagrange3(x[a], L[a], D[a]);
               for (int c = 0; c < 3; ++c)
@@ -154,7 +158,8 @@ static int get_tables(const Tables **out)
     int rc;
     if ((rc = to_device(&t.dN_ipfast, dNi)) || (rc = to_device(&t.dN_nodefast, H.dN)) || (rc = to_device(&t.N_ipfast, Ni)) ||
         (rc = to_device(&t.N_nodefast, H.N)) || (rc = to_device(&t.wdir, H.w)) || (rc = to_device(&t.dir, H.dir)) ||
-        (rc = to_device(&t.lr, H.lr)) || (rc = to_device(&t.inc_ptr, ptr)) || (rc = to_device(&t.inc, inc)))
+        (rc = to_device(&t.lr, H.lr)) || (rc = to_device(&t.inc_ptr, ptr)) || (rc = to_device(&t.inc, inc)) ||
+        (rc = to_device(&t.pt, H.pt)) || (rc = to_device(&t.stk, std::vector<int>(kStkNodeMap, kStkNodeMap + 27))))
       return rc;
     have[dev] = true;
   }
@@ -195,48 +200,93 @@ struct Params {
 
 constexpr int kThreads = 256;
 
+// tensor-grid node (a, b, c) -> STK ordinal, usable as a compile-time constant in unrolled device loops
+__host__ __device__ constexpr int stk_of(int q)
+{
+  constexpr int m[27] = {0, 8, 1, 11, 21, 9, 3, 10, 2, 12, 25, 13, 23, 20, 24, 15, 26, 14, 4, 16, 5, 19, 22, 17, 7, 18, 6};
+  return m[q];
+}
+// row nodes in the order the threads of phase C take them: a node is the left or right node of 24 (body centre), 20 (face
+// centres), 16 (edge mids) or 12 (corners) points; a warp holds 3.5 rows, so heavy and light rows alternate
+// (face, corner, edge, edge: 64 points per 4 rows = the average) and every warp reaches the barrier at about the same time
+__constant__ int c_row_order[27] = {21, 0, 8, 9, 22, 1, 10, 11, 23, 2, 12, 13, 24, 3, 14, 15, 25, 4, 16, 17, 26, 5, 18, 19, 20, 6, 7};
+
+struct Smem {
+  double rec[NREC][NIP];  // per point: G (9), A (3), mdot, divU stress (3)
+  double oned[18][NIP];   // per point: l_a(xi_d) at [3 d + a], l_a'(xi_d) at [9 + 3 d + a]
+  double part[NPE * 9][3];
+  double x[NPE][3], u[NPE][3], mu[NPE];
+  int row[NPE], inc_ptr[NPE + 1], inc[2 * NIP];
+};
+
+__device__ __forceinline__ void lagrange3_dev(double x, double (&l)[3], double (&d)[3])
+{
+  l[0] = -0.5 * x * (1.0 - x); l[1] = (1.0 - x) * (1.0 + x); l[2] = 0.5 * x * (1.0 + x);
+  d[0] = x - 0.5; d[1] = -2.0 * x; d[2] = x + 0.5;
+}
+
+// The 27 shape functions are products of three 1-D quadratic Lagrange polynomials (the factorisation visible in
+// hex27_shape_fcn, Hex27CVFEM.C:355-421), so a point needs 18 numbers, not the 27 x 4 table entries the reference stores:
+// phase B keeps them in registers (its thread IS the point), phase C reads them from shared memory.
 __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __grid_constant__ Params P)
 {
-  __shared__ double s_x[NPE][3], s_u[NPE][3], s_mu[NPE];
-  __shared__ double s_rec[NREC][NIP];
-  __shared__ double s_part[NPE * 9][3];
-  __shared__ int s_row[NPE];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
 
   const int t = threadIdx.x;
   const long long e = P.elem_list ? P.elem_list[blockIdx.x] : (long long)blockIdx.x;
   const int *en = P.elem_nodes + e * NPE;
   if (t < NPE) {
     const int n = en[t];
-    s_row[t] = P.node_row[n];
-    s_mu[t] = P.visc[n];
+    S.row[t] = P.node_row[n];
+    S.mu[t] = P.visc[n];
   }
   if (t < 81) {
     const int n = en[t / 3];
-    s_x[t / 3][t % 3] = P.coords[(size_t)n * 3 + t % 3];
+    S.x[t / 3][t % 3] = P.coords[(size_t)n * 3 + t % 3];
   } else if (t >= 96 && t < 96 + 81) {
     const int q = t - 96, n = en[q / 3];
-    s_u[q / 3][q % 3] = P.vel[(size_t)n * 3 + q % 3];
+    S.u[q / 3][q % 3] = P.vel[(size_t)n * 3 + q % 3];
+  } else if (t >= 192 && t < 192 + NPE + 1) {
+    S.inc_ptr[t - 192] = P.T.inc_ptr[t - 192];
   }
+  for (int q = t; q < 2 * NIP; q += kThreads) S.inc[q] = P.T.inc[q];
   __syncthreads();
 
   // ---- phase B: thread = integration point ---------------------------------------------------------------------
   if (t < NIP) {
+    double L[3][3], D[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lagrange3_dev(P.T.pt[3 * t + d], L[d], D[d]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        S.oned[3 * d + a][t] = L[d][a];
+        S.oned[9 + 3 * d + a][t] = D[d][a];
+      }
+    }
     double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, U[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     double mu = 0.0;
     // coordinates relative to the element's first node: the Jacobian is translation invariant, its rounding error is not
-    const double x0 = s_x[0][0], y0 = s_x[0][1], z0 = s_x[0][2];
-#pragma unroll 3
-    for (int n = 0; n < NPE; ++n) {
-      const double d0 = P.T.dN_ipfast[(n * 3 + 0) * NIP + t], d1 = P.T.dN_ipfast[(n * 3 + 1) * NIP + t],
-                   d2 = P.T.dN_ipfast[(n * 3 + 2) * NIP + t];
-      const double xn[3] = {s_x[n][0] - x0, s_x[n][1] - y0, s_x[n][2] - z0};
+    const double x0 = S.x[0][0], y0 = S.x[0][1], z0 = S.x[0][2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        J[i][0] += d0 * xn[i]; J[i][1] += d1 * xn[i]; J[i][2] += d2 * xn[i];
-        U[i][0] += d0 * s_u[n][i]; U[i][1] += d1 * s_u[n][i]; U[i][2] += d2 * s_u[n][i];
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const double t1 = L[1][b] * L[2][c], t2 = D[1][b] * L[2][c], t3 = L[1][b] * D[2][c];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const int n = stk_of(a + 3 * (b + 3 * c));
+          const double d0 = D[0][a] * t1, d1 = L[0][a] * t2, d2 = L[0][a] * t3;
+          const double xn[3] = {S.x[n][0] - x0, S.x[n][1] - y0, S.x[n][2] - z0};
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            J[i][0] += d0 * xn[i]; J[i][1] += d1 * xn[i]; J[i][2] += d2 * xn[i];
+            U[i][0] += d0 * S.u[n][i]; U[i][1] += d1 * S.u[n][i]; U[i][2] += d2 * S.u[n][i];
+          }
+          mu += (L[0][a] * t1) * S.mu[n];
+        }
       }
-      mu += P.T.N_ipfast[n * NIP + t] * s_mu[n];
-    }
     double C[3][3];
     const double det = cofactor(J, C);
     if (!(det > 0.0)) atomicExch(P.err, 1);
@@ -256,20 +306,22 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) s_rec[3 * i + j][t] = f * C[i][j];
+      for (int j = 0; j < 3; ++j) S.rec[3 * i + j][t] = f * C[i][j];
     const double ds = 2.0 / 3.0 * mu * divu * P.include_divu;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      s_rec[9 + i][t] = A[i];
-      s_rec[13 + i][t] = ds * A[i];
+      S.rec[9 + i][t] = A[i];
+      S.rec[13 + i][t] = ds * A[i];
     }
-    s_rec[12][t] = P.mdot[e * NIP + t];
+    S.rec[12][t] = P.mdot[e * NIP + t];
   }
   __syncthreads();
 
-  // ---- phase C: thread = (row node, three column nodes) ----------------------------------------------------------
-  const int r = t / 9, g = t - 9 * r;
-  if (r < NPE) {
+  // ---- phase C: thread = (row node, the three column nodes (0..2, b, c) of one tensor line) -----------------------
+  const int rr = t / 9, g = t - 9 * rr;
+  if (rr < NPE) {
+    const int r = c_row_order[rr];
+    const int gb = g % 3, gc = g / 3;
     double blk[3][3][3], dg[3] = {0.0, 0.0, 0.0}, rs[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int m = 0; m < 3; ++m)
@@ -277,27 +329,28 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) blk[m][i][j] = 0.0;
-    const int q0 = P.T.inc_ptr[r], q1 = P.T.inc_ptr[r + 1];
+    const int q0 = S.inc_ptr[r], q1 = S.inc_ptr[r + 1];
 #pragma unroll 1
     for (int q = q0; q < q1; ++q) {
-      const int code = P.T.inc[q], ip = code >> 1;
+      const int code = S.inc[q], ip = code >> 1;
       const double sg = (code & 1) ? -1.0 : 1.0; // the left node gains what leaves through the point, the right node loses it
       double G[3][3], A[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) G[i][j] = s_rec[3 * i + j][ip];
+        for (int j = 0; j < 3; ++j) G[i][j] = S.rec[3 * i + j][ip];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        A[i] = sg * s_rec[9 + i][ip];
-        rs[i] += sg * s_rec[13 + i][ip];
+        A[i] = sg * S.rec[9 + i][ip];
+        rs[i] += sg * S.rec[13 + i][ip];
       }
-      const double md = sg * s_rec[12][ip];
-      const double *dn = P.T.dN_nodefast + ((size_t)ip * NPE + 3 * g) * 3;
-      const double *sf = P.T.N_nodefast + (size_t)ip * NPE + 3 * g;
+      const double md = sg * S.rec[12][ip];
+      const double l1 = S.oned[3 + gb][ip], d1b = S.oned[12 + gb][ip], l2 = S.oned[6 + gc][ip], d2c = S.oned[15 + gc][ip];
+      const double t1 = l1 * l2, t2 = d1b * l2, t3 = l1 * d2c;
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
-        const double d0 = dn[3 * m], d1 = dn[3 * m + 1], d2 = dn[3 * m + 2];
+        const double l0 = S.oned[m][ip], d0a = S.oned[9 + m][ip];
+        const double d0 = d0a * t1, d1 = l0 * t2, d2 = l0 * t3;
         double h[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) h[i] = G[i][0] * d0 + G[i][1] * d1 + G[i][2] * d2;
@@ -305,26 +358,26 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int j = 0; j < 3; ++j) blk[m][i][j] += h[i] * A[j];
-        dg[m] += sf[m] * md + h[0] * A[0] + h[1] * A[1] + h[2] * A[2];
+        dg[m] += (l0 * t1) * md + h[0] * A[0] + h[1] * A[1] + h[2] * A[2];
       }
     }
     // residual part of this thread's three blocks, then the blocks leave
-    const int rn = s_row[r];
+    const int rn = S.row[r];
     const long long b0 = P.browptr[rn];
     const int nb = (int)(P.browptr[rn + 1] - b0);
     double *rowv = P.values + 9 * b0;
-    const unsigned char *slots = P.elem_slot + (e * NPE + r) * NPE + 3 * g;
+    const unsigned char *slots = P.elem_slot + (e * NPE + r) * NPE;
     double pr[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
-      const int c = 3 * g + m;
+      const int c = P.T.stk[m + 3 * g];
 #pragma unroll
       for (int i = 0; i < 3; ++i) blk[m][i][i] += dg[m];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) pr[i] -= blk[m][i][j] * s_u[c][j];
-      double *dst = rowv + 3 * (int)slots[m];
+        for (int j = 0; j < 3; ++j) pr[i] -= blk[m][i][j] * S.u[c][j];
+      double *dst = rowv + 3 * (int)slots[c];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -338,15 +391,15 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
       for (int i = 0; i < 3; ++i) pr[i] -= rs[i];
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) s_part[t][i] = pr[i];
+    for (int i = 0; i < 3; ++i) S.part[t][i] = pr[i];
   }
   __syncthreads();
   if (t < 81) {
-    const int rr = t / 3, i = t - 3 * rr;
+    const int q = t / 3, i = t - 3 * q;
     double v = 0.0;
 #pragma unroll
-    for (int gg = 0; gg < 9; ++gg) v += s_part[rr * 9 + gg][i];
-    double *dst = P.rhs + (long long)s_row[rr] * 3 + i;
+    for (int gg = 0; gg < 9; ++gg) v += S.part[q * 9 + gg][i];
+    double *dst = P.rhs + (long long)S.row[c_row_order[q]] * 3 + i;
     if (P.elem_list) red_add(dst, v);
     else atomicAdd(dst, v);
   }
@@ -415,6 +468,7 @@ int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double
   P.values = d_values;
   P.rhs = d_rhs;
   P.err = g.d_err;
+  NALU_CUDA(cudaFuncSetAttribute(assemble_hex27_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   if (g.d_color_elems && !g.color_ptr.empty()) {
     const size_t ngroups = g.color_ptr.size() - 1;
     for (size_t c = 0; c < ngroups; ++c) {
@@ -422,13 +476,13 @@ int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double
       if (n <= 0) continue;
       P.elem_list = g.d_color_elems + g.color_ptr[c];
       P.n = n;
-      assemble_hex27_kernel<<<(unsigned)n, kThreads, 0, stream>>>(P);
+      assemble_hex27_kernel<<<(unsigned)n, kThreads, sizeof(Smem), stream>>>(P);
       count_launch();
     }
   } else if (g.n_elems > 0) { // an element that reaches one row through two of its nodes: contended atomics
     P.elem_list = nullptr;
     P.n = g.n_elems;
-    assemble_hex27_kernel<<<(unsigned)g.n_elems, kThreads, 0, stream>>>(P);
+    assemble_hex27_kernel<<<(unsigned)g.n_elems, kThreads, sizeof(Smem), stream>>>(P);
     count_launch();
   }
   NALU_CUDA(cudaGetLastError());

@@ -68,7 +68,7 @@ class GraphInfo(C.Structure):
 
 # every symbol include/nalu_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "nalu_b200_last_error", "nalu_b200_version", "nalu_b200_launch_count", "nalu_b200_graph_create",
+    "nalu_b200_last_error", "nalu_b200_version", "nalu_b200_launch_count", "nalu_b200_graph_create", "nalu_b200_graph_create_topo",
     "nalu_b200_graph_destroy", "nalu_b200_graph_send_size", "nalu_b200_graph_send_data",
     "nalu_b200_graph_recv_data", "nalu_b200_graph_finalize", "nalu_b200_graph_finalize_host_only",
     "nalu_b200_graph_get_info", "nalu_b200_graph_copy_rowptr", "nalu_b200_graph_copy_colidx",
