@@ -605,6 +605,20 @@ def run_ours(args):
         del ls1
         ls.assemble_elem(descs, mode=mode, overwrite=overwrite)  # leave the headline system in place
 
+    other = {}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # BASELINE config 5 (48^3 Hex27 box), a parity-and-stress case beside the headline: tools/bench_hex27.py, 2-3 s
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("bench_hex27", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_hex27.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            h = mod.run(48, 5, 3)
+            other["config5_hex27_48cubed"] = {"value": h["value"], "unit": h["unit"], "ms_per_step": h["ms_per_step"],
+                                              "roofline_frac": h["roofline"]["frac"], "checks": h["checks"],
+                                              "kernel_family": h["kernel_family"], "workload": h["config"]["workload"]}
+        except Exception as ex:  # never lose the headline line to a side case
+            other["config5_hex27_48cubed"] = {"error": repr(ex)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(2, 1, kernel_names(args), args.divu)
@@ -623,7 +637,7 @@ def run_ours(args):
                            "l2_policy": "working set (>=36 GB CSR per GPU at n=256) exceeds the 126 MB L2",
                            "assemble_kernel": kernel_name, "graph_build_s": t_graph, "numa_binding": numa},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "wall_ms_per_step": wall_ms, "checks": props}
+                "clocks": clocks, "wall_ms_per_step": wall_ms, "checks": props, "other_configs": other}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -67,13 +67,10 @@ def subbox_check(m, n, i0, vel, visc, rho, got_v, got_b, grp, gci):
     return nrows, worst_v, worst_b
 
 
-def main():
+def run(n=48, steps=10, warmup=3):
     import torch
     from nalu_b200 import mesh as M
     from nalu_b200.linsys import DeviceCsrLinearSystem
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-    warmup = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     dev = torch.device("cuda:0")
     m = M.hex27_box(n, n, n)
     rng = np.random.default_rng(7)
@@ -157,7 +154,14 @@ def main():
                          "sample": "%d elements through oracle/hex27.py (numpy)" % ns},
         "checks": checks,
     }
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    warmup = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    print(json.dumps(run(n, steps, warmup)))
 
 
 if __name__ == "__main__":
