@@ -128,12 +128,12 @@ def partition_slabs(mesh: HexMesh, nranks: int):
 
 
 def partition_elements(mesh: HexMesh, elem_rank: np.ndarray, nranks: int):
-    """General element partition of an arbitrary one-rank Hex8 mesh: rank r gets the elements
+    """General element partition of an arbitrary one-rank Hex8 or Hex27 mesh: rank r gets the elements
     with elem_rank==r and the closure of their nodes (ascending gid); a shared node is owned by
     the lowest rank that touches it."""
     ne = mesh.n_elems
     node_min_rank = np.full(mesh.n_nodes, nranks, dtype=np.int32)
-    np.minimum.at(node_min_rank, mesh.elem_nodes.ravel(), np.repeat(elem_rank.astype(np.int32), 8))
+    np.minimum.at(node_min_rank, mesh.elem_nodes.ravel(), np.repeat(elem_rank.astype(np.int32), mesh.elem_nodes.shape[1]))
     out = []
     for r in range(nranks):
         es = np.nonzero(elem_rank == r)[0]

@@ -228,6 +228,46 @@ def test_hex8_entry_points_refuse_hex27_graphs():
     assert rc != 0
 
 
+def _global_csr_lookup(m):
+    """sorted (row dof gid, col dof gid) keys of the one-rank Hex27 CSR, GID_ = 3 (id - 1) + i + 1"""
+    E = m.n_elems
+    rowptr, colidx, _, _ = H.assemble_csr(m.node_gid, m.elem_nodes, np.zeros((E, 81, 81)), np.zeros((E, 81)))
+    n = rowptr.size - 1
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    return (rows + 1) * (n + 1) + (colidx + 1), n
+
+
+def _rank_keys(ls, n, shared=False):
+    rp, ci = ls.rowptr(shared).astype(np.int64), ls.colidx(shared).astype(np.int64)
+    rg, cg = ls.row_gids(shared), ls.col_gids()
+    rows = np.repeat(rg, np.diff(rp))
+    return rows * (n + 1) + cg[ci]
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_hex27_graph_on_partitioned_mesh(nranks):
+    """owned rows of every rank = the rows of the one-rank graph (same columns, by global id); shared-not-owned rows hold
+    what the rank's own elements touch (src/TpetraLinearSystem.C:190-327, 678-738 on 27-node elements)"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_graph import build_product_systems
+    m = M.hex27_box(3, 2, 3)
+    rng = np.random.default_rng(11)
+    parts = M.partition_elements(m, rng.integers(0, nranks, size=m.n_elems), nranks)
+    systems = build_product_systems(parts, 3)
+    keys, n = _global_csr_lookup(m)
+    seen = []
+    for ls in systems:
+        k = _rank_keys(ls, n)
+        assert np.all(np.diff(k.reshape(-1)) != 0)
+        assert np.isin(k, keys).all()
+        seen.append(k)
+        ks = _rank_keys(ls, n, shared=True)
+        assert np.isin(ks, keys).all()
+    allk = np.sort(np.concatenate(seen))
+    assert np.array_equal(allk, keys)  # every row of the global graph is owned exactly once, with all its columns
+
+
 # ---- CUDA kernel vs oracle (GPU) -----------------------------------------------------------------------------------------
 
 def _device_assemble(m, vel, visc, rho, include_divu):
@@ -282,3 +322,61 @@ def test_hex27_assembly_is_deterministic_and_accumulates():
     ls2, _, _ = _device_assemble(m, vel, visc, rho, 1.0)
     import torch
     assert torch.equal(ls1.owned_values(), ls2.owned_values()) and torch.equal(ls1.owned_rhs(), ls2.owned_rhs())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_hex27_partitioned_assembly_after_load_complete(nranks):
+    """random element partition over simulated ranks on one GPU: assemble per rank, export-add the shared-not-owned rows
+    (loadComplete, src/TpetraLinearSystem.C:1757-1778), compare every owned entry with the one-rank oracle by global ids"""
+    import os, sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_graph import build_product_systems
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    m = _perturbed_box((3, 3, 2))
+    vel, visc, rho = _fields(m)
+    rng = np.random.default_rng(13)
+    elem_rank = rng.integers(0, nranks, size=m.n_elems)
+    parts = M.partition_elements(m, elem_rank, nranks)
+    host = build_product_systems(parts, 3)
+    sends = {p.mesh.rank: p.handshake_send for p in host}
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    systems = []
+    for pm in parts:
+        ex = lambda send, r=pm.rank: {src: sends[src][r] for src in sends if r in sends[src]}
+        ls = DeviceCsrLinearSystem(pm, 3, exchange=ex).allocate(dev)
+        # nodal fields of the rank's nodes: the partition keeps global ids, fields are functions of the global node
+        g = pm.node_gid - 1
+        coords, v, mu, r = t(m.coords[g]), t(vel[g]), t(visc[g]), t(rho[g])
+        mdot = ls.mdot_scs(coords, r, v)
+        ls.zero_system()
+        assert ls.assemble_elem([ls.make_desc("momentum_adv_diff", fields=dict(coordinates=coords, velocity=v, viscosity=mu),
+                                              mass_flow_rate=mdot, include_divu=1.0)]) == 5
+        systems.append(ls)
+    torch.cuda.synchronize()
+    for ls in systems:
+        send, recv = ls.halo_peers()
+        for i, (peer, n) in enumerate(recv):
+            src = systems[peer]
+            ssend, _ = src.halo_peers()
+            j = [q for q, (pr, _) in enumerate(ssend) if pr == ls.mesh.rank][0]
+            buf = torch.empty(ssend[j][1], dtype=torch.float64, device=dev)
+            src.halo_pack(j, buf)
+            ls.halo_unpack_add(i, buf)
+    torch.cuda.synchronize()
+    mdot = H.calc_mass_flow_rate_scs(m.elem_nodes, m.coords, rho, vel)
+    lhs, rhs = H.momentum_adv_diff(m.elem_nodes, m.coords, vel, visc, mdot, include_divu=1.0)
+    rowptr, colidx, values, b = H.assemble_csr(m.node_gid, m.elem_nodes, lhs, rhs)
+    n = rowptr.size - 1
+    keys = (np.repeat(np.arange(n), np.diff(rowptr)) + 1) * (n + 1) + (colidx + 1)
+    scale = np.abs(values).max()
+    for ls in systems:
+        k = _rank_keys(ls, n)
+        pos = np.searchsorted(keys, k)
+        assert np.array_equal(keys[pos], k)
+        got = ls.owned_values().cpu().numpy()
+        assert np.abs(got - values[pos]).max() < 1e-12 * scale
+        rg = ls.row_gids()
+        assert np.abs(ls.owned_rhs().cpu().numpy() - b[rg - 1]).max() < 1e-12 * scale * np.abs(vel).max() * 27
