@@ -263,3 +263,31 @@ def hex27_box(nx, ny, nz) -> HexMesh:
     n = sx * sy * sz
     return HexMesh(coords=coords, node_gid=np.arange(1, n + 1, dtype=np.int64), node_owner=np.zeros(n, dtype=np.int32),
                    elem_nodes=conn)
+
+
+def hex27_box_rank(nx, ny, nz, rank, nranks) -> HexMesh:
+    """Rank-local z-slab of the nx*ny*nz Hex27 box (`hex27_box` numbering: id = 1 + lexicographic index on the global
+    (2nx+1)(2ny+1)(2nz+1) lattice); the node plane shared with the lower rank is owned by the lower rank."""
+    k0, k1 = slab_ranges(nz, nranks)[rank]
+    lz = k1 - k0
+    assert lz > 0, "more ranks than element layers"
+    sx, sy = 2 * nx + 1, 2 * ny + 1
+    loc = hex27_box(nx, ny, lz)
+    loc.coords[:, 2] += k0
+    loc.node_gid = loc.node_gid + sx * sy * 2 * k0
+    owner = np.full(loc.n_nodes, rank, dtype=np.int32)
+    if rank > 0:
+        owner[:sx * sy] = rank - 1
+    loc.node_owner = owner
+    loc.rank, loc.nranks = rank, nranks
+    loc.elem_gid = np.arange(1, nx * ny * lz + 1, dtype=np.int64) + nx * ny * k0
+    return loc
+
+
+def perturb_coords_by_gid(mesh: HexMesh, amplitude):
+    """deterministic perturbation that depends on the node id only (every rank that holds a node moves it identically)"""
+    g = mesh.node_gid.astype(np.float64)
+    for d, (a, b) in enumerate(((12.9898, 43758.5453), (78.233, 24634.6345), (39.3468, 11938.1459))):
+        h = np.sin(g * a + d) * b
+        mesh.coords[:, d] += amplitude * (2.0 * (h - np.floor(h)) - 1.0)
+    return mesh
