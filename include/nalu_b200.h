@@ -173,9 +173,10 @@ int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, 
  * include/AlgTraits.h:27-34; elem_nodes[n_elems][27] in STK's Hex27 node order, the one
  * HexahedralP2Element::stkNodeMap_ maps to the tensor grid, src/master_element/Hex27CVFEM.C:36-47).  Numbering, graph,
  * handshake, zeroSystem, loadComplete, Dirichlet / resetRows are topology independent and work as for Hex8.  On a Hex27
- * graph nalu_b200_assemble_elem takes [MomentumAdvDiffElemKernel] (3 dof, default options; mass_flow_rate is
- * [n_elems][216], the Hex27SCS point order of Hex27CVFEM.C:887-1050) and nalu_b200_mdot_scs produces that field; every
- * other element-level entry point returns NALU_B200_ERR_STATE. */
+ * graph nalu_b200_assemble_elem takes [MomentumMassElemKernel(lumped)]? + MomentumAdvDiffElemKernel (3 dof, default options,
+ * either order, the mass fused into the same launches; mass_flow_rate is [n_elems][216], the Hex27SCS point order of
+ * Hex27CVFEM.C:887-1050) and nalu_b200_mdot_scs produces that field; other lists return NALU_B200_ERR_ARG and every other
+ * element-level entry point returns NALU_B200_ERR_STATE. */
 int nalu_b200_graph_create_topo(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof,
                                 int32_t nodes_per_elem, int32_t n_nodes, const int64_t *node_gid,
                                 const int32_t *node_owner, int64_t n_elems, const int32_t *elem_nodes);

@@ -44,11 +44,14 @@ struct Tables {
   int *inc = nullptr;           // [432] ip << 1 | (1 if the node is the point's right node)
   double *pt = nullptr;         // [216][3] reference coordinates of the points
   int *stk = nullptr;           // [27] tensor-grid node -> STK ordinal
+  double *scv_pt = nullptr;     // [216][3] Hex27SCV points, 8 per node, nodes in STK order (Hex27CVFEM.C:660-707 up to that order)
+  double *scv_w = nullptr;      // [216]
 };
 
 struct HostTables {
   std::vector<double> dN, N, w, pt; // [216][27][3], [216][27], [216], [216][3]
   std::vector<int> dir, lr;
+  std::vector<double> scv_pt, scv_w; // [216][3], [216]: point q of node n (STK ordinal) at index 8 n + q
 };
 
 // node (i, j, k) of the 3 x 3 x 3 tensor grid -> STK Hex27 ordinal (Hex27CVFEM.C:36-47)
@@ -121,6 +124,24 @@ static HostTables build_host_tables()
             }
         }
   }
+  // Hex27SCV::set_interior_info (Hex27CVFEM.C:660-707): 2 x 2 x 2 Gauss points in the sub-control volume of every node; stored
+  // node-major in STK order so that the 8 points of a node are 8 neighbouring threads
+  T.scv_pt.assign(3 * NIP, 0.0);
+  T.scv_w.assign(NIP, 0.0);
+  for (int c = 0; c < 3; ++c)
+    for (int b = 0; b < 3; ++b)
+      for (int a = 0; a < 3; ++a) {
+        const int n = kStkNodeMap[a + 3 * (b + 3 * c)];
+        for (int k = 0; k < 2; ++k)
+          for (int j = 0; j < 2; ++j)
+            for (int i = 0; i < 2; ++i) {
+              const int q = 8 * n + i + 2 * (j + 2 * k);
+              T.scv_pt[3 * q + 0] = gp(a, i);
+              T.scv_pt[3 * q + 1] = gp(b, j);
+              T.scv_pt[3 * q + 2] = gp(c, k);
+              T.scv_w[q] = seg(a) * seg(b) * seg(c) * 0.125;
+            }
+      }
   return T;
 }
 
@@ -159,7 +180,7 @@ static int get_tables(const Tables **out)
     if ((rc = to_device(&t.dN_ipfast, dNi)) || (rc = to_device(&t.dN_nodefast, H.dN)) || (rc = to_device(&t.N_ipfast, Ni)) ||
         (rc = to_device(&t.N_nodefast, H.N)) || (rc = to_device(&t.wdir, H.w)) || (rc = to_device(&t.dir, H.dir)) ||
         (rc = to_device(&t.lr, H.lr)) || (rc = to_device(&t.inc_ptr, ptr)) || (rc = to_device(&t.inc, inc)) ||
-        (rc = to_device(&t.pt, H.pt)) || (rc = to_device(&t.stk, std::vector<int>(kStkNodeMap, kStkNodeMap + 27))))
+        (rc = to_device(&t.pt, H.pt)) || (rc = to_device(&t.scv_pt, H.scv_pt)) || (rc = to_device(&t.scv_w, H.scv_w)) || (rc = to_device(&t.stk, std::vector<int>(kStkNodeMap, kStkNodeMap + 27))))
       return rc;
     have[dev] = true;
   }
@@ -194,6 +215,9 @@ struct Params {
   const long long *browptr;
   const double *coords, *vel, *visc, *mdot; // mdot: [nElem][216]
   double include_divu;
+  // fused lumped MomentumMassElemKernel (src/kernel/MomentumMassElemKernel.C:98-171 with the shifted SCV shape functions)
+  const double *vel_n, *vel_nm1, *rho, *rho_n, *rho_nm1, *gp;
+  double g1_dt, g2_dt, g3_dt, dens_fac, om_dens_fac;
   double *values, *rhs;
   int *err;
 };
@@ -216,6 +240,7 @@ struct Smem {
   double oned[18][NIP];   // per point: l_a(xi_d) at [3 d + a], l_a'(xi_d) at [9 + 3 d + a]
   double part[NPE * 9][3];
   double x[NPE][3], u[NPE][3], mu[NPE];
+  double vol[NPE]; // fused lumped mass: the part of each node's dual volume inside this element
   int row[NPE], inc_ptr[NPE + 1], inc[2 * NIP];
 };
 
@@ -225,9 +250,38 @@ __device__ __forceinline__ void lagrange3_dev(double x, double (&l)[3], double (
   d[0] = x - 0.5; d[1] = -2.0 * x; d[2] = x + 0.5;
 }
 
+// weight * det J at one Hex27SCV point (Hex27SCV::determinant, Hex27CVFEM.C:743-763, :809-845); its own function so that its
+// registers are not live together with phase B's
+__device__ __noinline__ double scv_point_volume(const double (*x)[3], const double *pt, double w)
+{
+  double Lv[3][3], Dv[3][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) lagrange3_dev(pt[d], Lv[d], Dv[d]);
+  double Jv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double t1 = Lv[1][b] * Lv[2][c], t2 = Dv[1][b] * Lv[2][c], t3 = Lv[1][b] * Dv[2][c];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int n = stk_of(a + 3 * (b + 3 * c));
+        const double d0 = Dv[0][a] * t1, d1 = Lv[0][a] * t2, d2 = Lv[0][a] * t3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double xn = x[n][i] - x[0][i];
+          Jv[i][0] += d0 * xn; Jv[i][1] += d1 * xn; Jv[i][2] += d2 * xn;
+        }
+      }
+    }
+  double Cv[3][3];
+  return w * cofactor(Jv, Cv);
+}
+
 // The 27 shape functions are products of three 1-D quadratic Lagrange polynomials (the factorisation visible in
 // hex27_shape_fcn, Hex27CVFEM.C:355-421), so a point needs 18 numbers, not the 27 x 4 table entries the reference stores:
 // phase B keeps them in registers (its thread IS the point), phase C reads them from shared memory.
+template <bool MASS>
 __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __grid_constant__ Params P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -253,6 +307,16 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
   for (int q = t; q < 2 * NIP; q += kThreads) S.inc[q] = P.T.inc[q];
   __syncthreads();
 
+  if (MASS && t < NIP) {
+    // fused lumped mass: thread = SCV point 8 n + q; the 8 points of a node are summed over 8 neighbouring lanes
+    double v = scv_point_volume(S.x, P.T.scv_pt + 3 * t, P.T.scv_w[t]);
+    if (!(v > 0.0)) atomicExch(P.err, 1);
+    const unsigned mask = t >= 192 ? 0x00FFFFFFu : 0xFFFFFFFFu; // the last active warp holds points 192..215
+    v += __shfl_xor_sync(mask, v, 1);
+    v += __shfl_xor_sync(mask, v, 2);
+    v += __shfl_xor_sync(mask, v, 4);
+    if ((t & 7) == 0) S.vol[t >> 3] = v;
+  }
   // ---- phase B: thread = integration point ---------------------------------------------------------------------
   if (t < NIP) {
     double L[3][3], D[3][3];
@@ -399,7 +463,23 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
     double v = 0.0;
 #pragma unroll
     for (int gg = 0; gg < 9; ++gg) v += S.part[q * 9 + gg][i];
-    double *dst = P.rhs + (long long)S.row[c_row_order[q]] * 3 + i;
+    const int r = c_row_order[q];
+    if (MASS) {
+      // shifted (nodal) SCV shape functions: every quantity is the row node's own
+      const int nd = en[r];
+      const double V = S.vol[r];
+      const double rp = P.rho[nd], ui = S.u[r][i];
+      v += -(P.g1_dt * rp * ui + P.g2_dt * P.rho_n[nd] * P.vel_n[(size_t)nd * 3 + i] + P.g3_dt * P.rho_nm1[nd] * P.vel_nm1[(size_t)nd * 3 + i]) * V -
+           P.gp[(size_t)nd * 3 + i] * V * (rp * P.dens_fac + P.om_dens_fac);
+      const int rn = S.row[r];
+      const long long b0 = P.browptr[rn];
+      const int nb = (int)(P.browptr[rn + 1] - b0);
+      double *dd = P.values + 9 * b0 + (long long)i * nb * 3 + 3 * (int)P.elem_slot[(e * NPE + r) * NPE + r] + i;
+      const double m = P.g1_dt * rp * V;
+      if (P.elem_list) red_add(dd, m);
+      else atomicAdd(dd, m);
+    }
+    double *dst = P.rhs + (long long)S.row[r] * 3 + i;
     if (P.elem_list) red_add(dst, v);
     else atomicAdd(dst, v);
   }
@@ -441,16 +521,41 @@ __global__ void __launch_bounds__(kThreads) mdot_hex27_kernel(Tables T, long lon
 
 } // namespace hex27
 
-bool hex27_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+// [MomentumAdvDiffElemKernel] or [MomentumMassElemKernel(lumped), MomentumAdvDiffElemKernel] in either order
+static bool classify_hex27(const nalu_b200_kernel_desc *k, int nk, int &ia, int &im)
 {
-  return g.npe == 27 && g.ndof == 3 && nk == 1 && k[0].kind == NALU_K_MOMENTUM_ADV_DIFF && k[0].options == 0 && g.d_elem_nodes27 &&
-         g.d_elem_slot27 && k[0].nodal[NALU_F_COORDINATES] && k[0].nodal[NALU_F_VELOCITY] && k[0].nodal[NALU_F_VISCOSITY] &&
-         k[0].mass_flow_rate;
+  ia = im = -1;
+  for (int i = 0; i < nk; ++i) {
+    if (k[i].kind == NALU_K_MOMENTUM_ADV_DIFF && k[i].options == 0 && ia < 0) ia = i;
+    else if (k[i].kind == NALU_K_MOMENTUM_MASS && k[i].options == NALU_OPT_LUMPED_MASS && im < 0) im = i;
+    else return false;
+  }
+  return ia >= 0;
 }
 
-int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double *d_values, double *d_rhs, cudaStream_t stream)
+bool hex27_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+{
+  int ia, im;
+  if (g.npe != 27 || g.ndof != 3 || nk < 1 || nk > 2 || !g.d_elem_nodes27 || !g.d_elem_slot27 || !classify_hex27(k, nk, ia, im)) return false;
+  const nalu_b200_kernel_desc &a = k[ia];
+  if (!a.nodal[NALU_F_COORDINATES] || !a.nodal[NALU_F_VELOCITY] || !a.nodal[NALU_F_VISCOSITY] || !a.mass_flow_rate) return false;
+  if (im >= 0) {
+    const nalu_b200_kernel_desc &m = k[im];
+    // one velocity / coordinates field for both kernels (velocity NP1 is the dof of both)
+    if (m.nodal[NALU_F_COORDINATES] != a.nodal[NALU_F_COORDINATES] || m.nodal[NALU_F_VELOCITY] != a.nodal[NALU_F_VELOCITY]) return false;
+    for (int f : {NALU_F_VELOCITY_N, NALU_F_VELOCITY_NM1, NALU_F_DENSITY, NALU_F_DENSITY_N, NALU_F_DENSITY_NM1, NALU_F_DPDX})
+      if (!m.nodal[f]) return false;
+  }
+  return true;
+}
+
+int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc *kernels, int nk, double *d_values, double *d_rhs,
+                          cudaStream_t stream)
 {
   using namespace hex27;
+  int ia, im;
+  if (!classify_hex27(kernels, nk, ia, im)) return NALU_B200_ERR_ARG;
+  const nalu_b200_kernel_desc &k = kernels[ia];
   const Tables *T = nullptr;
   int rc = get_tables(&T);
   if (rc) return rc;
@@ -468,7 +573,25 @@ int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double
   P.values = d_values;
   P.rhs = d_rhs;
   P.err = g.d_err;
-  NALU_CUDA(cudaFuncSetAttribute(assemble_hex27_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  const bool mass = im >= 0;
+  P.vel_n = P.vel_nm1 = P.rho = P.rho_n = P.rho_nm1 = P.gp = nullptr;
+  P.g1_dt = P.g2_dt = P.g3_dt = P.dens_fac = P.om_dens_fac = 0.0;
+  if (mass) {
+    const nalu_b200_kernel_desc &m = kernels[im];
+    P.vel_n = m.nodal[NALU_F_VELOCITY_N];
+    P.vel_nm1 = m.nodal[NALU_F_VELOCITY_NM1];
+    P.rho = m.nodal[NALU_F_DENSITY];
+    P.rho_n = m.nodal[NALU_F_DENSITY_N];
+    P.rho_nm1 = m.nodal[NALU_F_DENSITY_NM1];
+    P.gp = m.nodal[NALU_F_DPDX];
+    P.g1_dt = m.gamma1 / m.dt;
+    P.g2_dt = m.gamma2 / m.dt;
+    P.g3_dt = m.gamma3 / m.dt;
+    P.dens_fac = m.dens_fac;
+    P.om_dens_fac = m.om_dens_fac;
+  }
+  auto kern = mass ? assemble_hex27_kernel<true> : assemble_hex27_kernel<false>;
+  NALU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   if (g.d_color_elems && !g.color_ptr.empty()) {
     const size_t ngroups = g.color_ptr.size() - 1;
     for (size_t c = 0; c < ngroups; ++c) {
@@ -476,13 +599,13 @@ int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double
       if (n <= 0) continue;
       P.elem_list = g.d_color_elems + g.color_ptr[c];
       P.n = n;
-      assemble_hex27_kernel<<<(unsigned)n, kThreads, sizeof(Smem), stream>>>(P);
+      kern<<<(unsigned)n, kThreads, sizeof(Smem), stream>>>(P);
       count_launch();
     }
   } else if (g.n_elems > 0) { // an element that reaches one row through two of its nodes: contended atomics
     P.elem_list = nullptr;
     P.n = g.n_elems;
-    assemble_hex27_kernel<<<(unsigned)g.n_elems, kThreads, sizeof(Smem), stream>>>(P);
+    kern<<<(unsigned)g.n_elems, kThreads, sizeof(Smem), stream>>>(P);
     count_launch();
   }
   NALU_CUDA(cudaGetLastError());

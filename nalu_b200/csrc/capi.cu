@@ -460,15 +460,17 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   cudaStream_t s = (cudaStream_t)stream;
   if (g.npe == 27) { // Hex27 graphs (nalu_b200_graph_create_topo): one kernel, assemble_hex27.cu
     if (!hex27_supported(g, kernels, nk)) {
-      set_error("assemble_elem: Hex27 graphs take [MomentumAdvDiffElemKernel] on a 3-dof system only");
+      set_error("assemble_elem: Hex27 graphs take [MomentumMassElemKernel(lumped)]? + MomentumAdvDiffElemKernel (default options, "
+                "one velocity field) on a 3-dof system only");
       return NALU_B200_ERR_ARG;
     }
-    if (const char *missing = missing_field(kernels[0])) {
-      set_error(std::string("assemble_elem: field missing for kernel 0: ") + missing);
-      return NALU_B200_ERR_ARG;
-    }
+    for (int i = 0; i < nk; ++i)
+      if (const char *missing = missing_field(kernels[i])) {
+        set_error(std::string("assemble_elem: field missing for kernel ") + std::to_string(i) + ": " + missing);
+        return NALU_B200_ERR_ARG;
+      }
     set_last_mode(5);
-    return launch_assemble_hex27(g, kernels[0], d_values, d_rhs, s);
+    return launch_assemble_hex27(g, kernels, nk, d_values, d_rhs, s);
   }
   // A list with one kernel the tiled write-once kernels know plus others (e.g. [MomentumMass(lumped), MomentumAdvDiff],
   // the momentum list of the low-Mach equation system, src/LowMachEquationSystem.C:1304-1398): the tiled kernel

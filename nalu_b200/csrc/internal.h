@@ -66,7 +66,7 @@ bool box5_supported(const box::BoxParams &P);
 int launch_assemble_box5(box::BoxParams &P, cudaStream_t stream);
 // assemble_hex27.cu: MomentumAdvDiffElemKernel<AlgTraitsHex27>, CTA = element, coloured value-less reductions
 bool hex27_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk);
-int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc &k, double *d_values, double *d_rhs, cudaStream_t stream);
+int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc *k, int nk, double *d_values, double *d_rhs, cudaStream_t stream);
 int launch_mdot_hex27(const Graph &g, const double *coords, const double *density, const double *velocity, double *mdot,
                       cudaStream_t stream);
 // halo.cu

@@ -247,6 +247,19 @@ class Hex27SCV:
                                 idx += 1
         self.shape_fcn = hex27_shape_fcn(self.intg_loc)
         self.shape_deriv = hex27_shape_deriv(self.intg_loc)
+        # shifted points (Hex27CVFEM.C:214-222,688-690): gaussAbscissaeShift_ = {-1,-1,0,0,+1,+1}[2 node + ip], i.e. the node itself
+        shift = np.array([-1.0, -1.0, 0.0, 0.0, 1.0, 1.0])
+        self.intg_loc_shift = np.zeros((NIP, 3))
+        idx = 0
+        for n in range(3):
+            for m in range(3):
+                for l in range(3):
+                    for k in range(2):
+                        for j in range(2):
+                            for i in range(2):
+                                self.intg_loc_shift[idx] = (shift[2 * l + i], shift[2 * m + j], shift[2 * n + k])
+                                idx += 1
+        self.shape_fcn_shift = hex27_shape_fcn(self.intg_loc_shift)
 
     def volumes(self, coords):
         _, det = generic_grad_op(self.shape_deriv, coords)
@@ -319,6 +332,45 @@ def momentum_adv_diff(elem_nodes, coords, velocity, viscosity, mdot, include_div
         rhs[:, il] -= r
         rhs[:, ir] += r
     del ar
+    return lhs.reshape(E, 81, 81), rhs.reshape(E, 81)
+
+
+_SCV = None
+
+
+def scv():
+    global _SCV
+    if _SCV is None:
+        _SCV = Hex27SCV()
+    return _SCV
+
+
+def momentum_mass(elem_nodes, coords, vel_np1, vel_n, vel_nm1, rho_np1, rho_n, rho_nm1, gpdx, dt, gamma1, gamma2, gamma3,
+                  lumped=True, dens_fac=0.0, om_dens_fac=1.0):
+    """MomentumMassElemKernel<AlgTraitsHex27>::execute (src/kernel/MomentumMassElemKernel.C:98-171): lhs [E,81,81], rhs [E,81];
+    lumped = the shifted SCV shape functions (:60-63)"""
+    me = scv()
+    E = elem_nodes.shape[0]
+    sf = me.shape_fcn_shift if lumped else me.shape_fcn       # v_shape_function_ [216,27]
+    c = np.asarray(coords)[elem_nodes]
+    scv_vol = me.volumes(c)                                   # v_scv_volume [E,216]
+    g = lambda a: np.asarray(a)[elem_nodes]
+    rho_m_ip, rho_n_ip, rho_p_ip = g(rho_nm1) @ sf.T, g(rho_n) @ sf.T, g(rho_np1) @ sf.T            # [E,216]
+    u_m = np.einsum("pn,enj->epj", sf, g(vel_nm1))
+    u_n = np.einsum("pn,enj->epj", sf, g(vel_n))
+    u_p = np.einsum("pn,enj->epj", sf, g(vel_np1))
+    gjp = np.einsum("pn,enj->epj", sf, g(gpdx))
+    lhs = np.zeros((E, 27, 3, 27, 3))
+    rhs = np.zeros((E, 27, 3))
+    for ip in range(NIP):
+        nn = me.ip_node_map[ip]
+        v = scv_vol[:, ip]
+        fac = rho_p_ip[:, ip] * dens_fac + om_dens_fac
+        rhs[:, nn] += -(gamma1 * rho_p_ip[:, ip, None] * u_p[:, ip] + gamma2 * rho_n_ip[:, ip, None] * u_n[:, ip]
+                        + gamma3 * rho_m_ip[:, ip, None] * u_m[:, ip]) * (v / dt)[:, None] - gjp[:, ip] * (v * fac)[:, None]
+        lhsfac = sf[ip][None, :] * (gamma1 * rho_p_ip[:, ip] * v / dt)[:, None]                      # [E,ic]
+        for j in range(3):
+            lhs[:, nn, j, :, j] += lhsfac
     return lhs.reshape(E, 81, 81), rhs.reshape(E, 81)
 
 

@@ -188,6 +188,23 @@ def test_momentum_adv_diff_identities():
     assert np.abs(rhs.reshape(27, 3) + net[:, None] * u0[0][None, :]).max() < 1e-13
 
 
+def test_scv_shifted_points_are_nodal_and_lumped_mass_closed_form():
+    """scv_shifted_ips_are_nodal (unit_tests/UnitTestMasterElements.C:161-183, run by the reference for P1 elements only; the
+    Hex27 tables have the same property) and the lumped mass of a unit-density box: diagonal = gamma1 * dual volume / dt"""
+    me = H.scv()
+    assert np.array_equal(me.shape_fcn_shift, np.eye(27)[me.ip_node_map])
+    m = M.hex27_box(1, 1, 1)
+    n = m.n_nodes
+    one, zero3 = np.ones(n), np.zeros((n, 3))
+    u = np.tile([1.0, 2.0, 3.0], (n, 1))
+    lhs, rhs = H.momentum_mass(m.elem_nodes, m.coords, u, u, u, one, one, one, zero3, dt=0.5, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    vol = np.bincount(me.ip_node_map, weights=me.volumes(m.coords[m.elem_nodes])[0], minlength=27)
+    assert abs(vol.sum() - 1.0) < 1e-14
+    assert np.allclose(np.diag(lhs[0]), np.repeat(1.5 * vol / 0.5, 3), rtol=0, atol=1e-15)
+    assert np.abs(lhs[0] - np.diag(np.diag(lhs[0]))).max() == 0.0
+    assert np.abs(rhs).max() < 1e-14  # gamma1 + gamma2 + gamma3 = 0 on a steady state
+
+
 def test_hex27_box_mesh():
     m = M.hex27_box(2, 3, 2)
     assert m.elem_nodes.shape == (12, 27) and m.coords.shape == (5 * 7 * 5, 3)
@@ -312,6 +329,47 @@ def test_hex27_momentum_adv_diff_vs_oracle(shape, include_divu):
     assert _rel_err_rows(got_v, values, rowptr) < 1e-12
     scale = np.abs(values).max() * np.abs(vel).max()
     assert np.abs(got_b - b).max() < 1e-12 * scale * 27
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["mass_first", "advdiff_first"])
+def test_hex27_momentum_list_with_fused_lumped_mass_vs_oracle(order):
+    """[MomentumMassElemKernel(lumped), MomentumAdvDiffElemKernel] (the low-Mach momentum list, src/LowMachEquationSystem.C:1304-1398)
+    on Hex27 in one launch family"""
+    import torch
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    m = _perturbed_box((3, 2, 3))
+    vel, visc, rho = _fields(m)
+    rng = np.random.default_rng(9)
+    vn, vm = 0.9 * vel + 0.01, 0.8 * vel - 0.02
+    rn, rm = 0.98 * rho, 0.95 * rho
+    gp = 0.3 * rng.uniform(-1, 1, size=vel.shape)
+    bdf2 = dict(dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    ls = DeviceCsrLinearSystem(m, 3).allocate(dev)
+    f = dict(coordinates=t(m.coords), velocity=t(vel), velocity_n=t(vn), velocity_nm1=t(vm), viscosity=t(visc), density=t(rho),
+             density_n=t(rn), density_nm1=t(rm), dpdx=t(gp))
+    mdot_dev = ls.mdot_scs(f["coordinates"], f["density"], f["velocity"])
+    descs = [ls.make_desc("momentum_mass", fields=f, options=("lumped_mass",), **bdf2),
+             ls.make_desc("momentum_adv_diff", fields=f, mass_flow_rate=mdot_dev, include_divu=1.0)]
+    if order == "advdiff_first":
+        descs = descs[::-1]
+    ls.zero_system()
+    assert ls.assemble_elem(descs) == 5
+    torch.cuda.synchronize()
+    assert ls.geometry_errors() == 0
+    mdot = H.calc_mass_flow_rate_scs(m.elem_nodes, m.coords, rho, vel)
+    l1, r1 = H.momentum_adv_diff(m.elem_nodes, m.coords, vel, visc, mdot, include_divu=1.0)
+    l2, r2 = H.momentum_mass(m.elem_nodes, m.coords, vel, vn, vm, rho, rn, rm, gp, lumped=True, **bdf2)
+    rowptr, colidx, values, b = H.assemble_csr(m.node_gid, m.elem_nodes, l1 + l2, r1 + r2)
+    got_v, got_b = ls.owned_values().cpu().numpy(), ls.owned_rhs().cpu().numpy()
+    assert _rel_err_rows(got_v, values, rowptr) < 1e-12
+    assert np.abs(got_b - b).max() < 1e-12 * max(np.abs(b).max(), np.abs(values).max() * np.abs(vel).max())
+    # a consistent-mass list is refused, not silently mis-assembled
+    bad = [ls.make_desc("momentum_mass", fields=f, **bdf2), descs[0] if order == "advdiff_first" else descs[1]]
+    with pytest.raises(Exception):
+        ls.assemble_elem(bad)
 
 
 @pytest.mark.gpu

@@ -194,6 +194,26 @@ def run(n=48, steps=10, warmup=3):
                                          "tolerance": 1e-12, "passed": bool(worst[0] > 0 and worst[1] < 1e-12 and worst[2] < 1e-12),
                                          "across_rank_interfaces": world > 1},
               "finite": finite, "geometry_errors": geom}
+    mlist = None
+    if world == 1:
+        # the low-Mach momentum list [MomentumMass(lumped), MomentumAdvDiff] with the mass fused into the same launches
+        f = dict(coordinates=coords, velocity=v, velocity_n=t(0.9 * vel + 0.01), velocity_nm1=t(0.8 * vel - 0.02), viscosity=mu,
+                 density=r, density_n=t(0.98 * rho), density_nm1=t(0.95 * rho), dpdx=t(0.1 * vel))
+        dl = [ls.make_desc("momentum_mass", fields=f, options=("lumped_mass",), dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5), d]
+        for _ in range(2):
+            ls.zero_system()
+            ls.assemble_elem(dl)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(steps):
+            ls.zero_system()
+            ls.assemble_elem(dl)
+        b1.record()
+        torch.cuda.synchronize()
+        lms = b0.elapsed_time(b1) / steps
+        mlist = {"kernels": ["MomentumMassElemKernel(lumped)", "MomentumAdvDiffElemKernel(includeDivU=1)"], "value": ne / lms / 1e3,
+                 "unit": "Melem/s", "ms_per_step": lms, "finite": bool(torch.isfinite(ls.values).all())}
     cpu = None
     if world == 1:
         # cpu baseline: the oracle on a bounded sample
@@ -222,7 +242,7 @@ def run(n=48, steps=10, warmup=3):
                      "algorithmic_bytes_per_elem": alg_bytes / ne,
                      "fp64": {"flop_per_elem_static": 2 * (216 * (27 * 23 + 60) + 243 * 16 * 81),
                               "note": "FMA = 2 flop, static count of phase B + C"}},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "momentum_list": mlist,
         "checks": checks,
     }
     if own_group:
