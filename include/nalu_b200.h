@@ -345,7 +345,11 @@ enum nalu_b200_face_kernel_kind {
   NALU_FK_SCALAR_OPEN_ADV = 1,        /* src/kernel/ScalarOpenAdvElemKernel.C:90-195        */
   NALU_FK_CONTINUITY_OPEN = 2,        /* src/kernel/ContinuityOpenElemKernel.C:80-199       */
   NALU_FK_MOMENTUM_OPEN_ADV_DIFF = 3, /* src/kernel/MomentumOpenAdvDiffElemKernel.C:110-325 */
-  NALU_FK_COUNT = 4
+  /* src/kernel/MomentumWallFunctionElemKernel.C:73-155.  The reference runs it on an AssembleElemSolverAlgorithm over the wall
+   * part's FACES (a 12 x 12 matrix on the face's nodes); here it is one more kernel of the face set, adding the same values to
+   * the same CSR entries through the attached element's slot map. */
+  NALU_FK_MOMENTUM_WALL_FUNCTION = 4,
+  NALU_FK_COUNT = 5
 };
 /* nodal field slots of the face kernels */
 enum nalu_b200_face_nodal_slot {
@@ -363,13 +367,16 @@ enum nalu_b200_face_nodal_slot {
   NALU_FN_GJQ = 11,         /* 3 */
   NALU_FN_GJUI = 12,        /* 9  dudx */
   NALU_FN_VELOCITY_BC = 13, /* 3  open_velocity_bc */
+  NALU_FN_WALL_VELOCITY_BC = 14, /* 3  wall_velocity_bc */
   NALU_FN_COUNT = 16
 };
 enum nalu_b200_face_field_slot {
   NALU_FF_EXPOSED_AREA_VEC = 0,    /* [4][3] exposed_area_vector (nalu_b200_compute_exposed_area) */
   NALU_FF_OPEN_MASS_FLOW_RATE = 1, /* [4]    open_mass_flow_rate */
   NALU_FF_DYNAMIC_PRESSURE = 2,    /* [4]    dynamic_pressure */
-  NALU_FF_COUNT = 4
+  NALU_FF_WALL_FRICTION_VELOCITY_BIP = 3, /* [4] wall_friction_velocity_bip */
+  NALU_FF_WALL_NORMAL_DISTANCE_BIP = 4,   /* [4] wall_normal_distance_bip */
+  NALU_FF_COUNT = 6
 };
 #define NALU_OPT_MESH_MOVES (1 << 8) /* solnOpts.does_mesh_move(): meshVelocityCorrection_ of the momentum open kernel */
 typedef struct nalu_b200_face_kernel_desc {
@@ -380,7 +387,9 @@ typedef struct nalu_b200_face_kernel_desc {
   double upw[8];     /* NALU_UPW_ALPHA_UPW, _HO_UPWIND, _HYBRID_FACTOR, _TANH_TRANS, _TANH_WIDTH */
   const double *nodal[NALU_FN_COUNT]; /* device pointers, NULL when unused */
   const double *face[NALU_FF_COUNT];  /* device pointers */
+  double wall[4]; /* wall function: NALU_WALL_ELOG, _KAPPA, _YPLUS_CRIT = get_turb_model_constant(TM_elog / TM_kappa / TM_yplus_crit) */
 } nalu_b200_face_kernel_desc;
+enum { NALU_WALL_ELOG = 0, NALU_WALL_KAPPA = 1, NALU_WALL_YPLUS_CRIT = 2 };
 
 /* The locally owned faces of a boundary part (host arrays, copied).  The set colours the faces (two faces of one colour
  * share no node, so a colour is summed with plain read-modify-writes: deterministic, no atomics). */

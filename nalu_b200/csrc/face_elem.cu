@@ -328,6 +328,47 @@ struct FaceParams {
   nalu_b200_face_kernel_desc k[kMaxFaceKernels];
 };
 
+// ---- MomentumWallFunctionElemKernel (src/kernel/MomentumWallFunctionElemKernel.C:73-155) ------------------------------------
+// lambda (I - n n^T) acting on the wall-parallel part of (u - u_wall) at the face point, lambda = rho kappa u_tau / ln(E y+) |A|
+// in the log layer, mu / y_p |A| below y+_crit; columns = the face's four nodes only
+__device__ void momentum_wall_function(const nalu_b200_face_kernel_desc &k, const FaceCtx &F, RowBlock<3> &B)
+{
+  const double *A = k.face[NALU_FF_EXPOSED_AREA_VEC] + 12 * F.face + 3 * F.ip;
+  const double amag = sqrt(A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
+  const double nx[3] = {A[0] / amag, A[1] / amag, A[2] / amag};
+  double rho = 0.0, mu = 0.0, u[3] = {0.0, 0.0, 0.0}, ub[3] = {0.0, 0.0, 0.0}, sf[4];
+#pragma unroll
+  for (int ic = 0; ic < 4; ++ic) {
+    const int nd = F.nodes[F.fn[ic]];
+    sf[ic] = quad_shape(F.ip, ic, false);
+    rho += sf[ic] * k.nodal[NALU_FN_DENSITY][nd];
+    mu += sf[ic] * k.nodal[NALU_FN_VISCOSITY][nd];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      u[j] += sf[ic] * k.nodal[NALU_FN_VELOCITY][(size_t)nd * 3 + j];
+      ub[j] += sf[ic] * k.nodal[NALU_FN_WALL_VELOCITY_BC][(size_t)nd * 3 + j];
+    }
+  }
+  const double yp = k.face[NALU_FF_WALL_NORMAL_DISTANCE_BIP][4 * F.face + F.ip];
+  const double utau = k.face[NALU_FF_WALL_FRICTION_VELOCITY_BIP][4 * F.face + F.ip];
+  const double yplus = rho * yp * utau / mu;
+  const double lambda = yplus > k.wall[NALU_WALL_YPLUS_CRIT] ? rho * k.wall[NALU_WALL_KAPPA] * utau / log(k.wall[NALU_WALL_ELOG] * yplus) * amag
+                                                             : mu / yp * amag;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double utan = 0.0, ubtan = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double pij = (i == j ? 1.0 : 0.0) - nx[i] * nx[j];
+      utan += pij * u[j];
+      ubtan += pij * ub[j];
+#pragma unroll
+      for (int ic = 0; ic < 4; ++ic) B.a[i][F.fn[ic] * 3 + j] += lambda * pij * sf[ic];
+    }
+    B.r[i] -= lambda * (utan - ubtan);
+  }
+}
+
 template <int NDOF>
 __global__ void __launch_bounds__(128) assemble_face_elem_kernel(const __grid_constant__ FaceParams p)
 {
@@ -361,6 +402,7 @@ __global__ void __launch_bounds__(128) assemble_face_elem_kernel(const __grid_co
     const nalu_b200_face_kernel_desc &k = p.k[i];
     if constexpr (NDOF == 3) {
       if (k.kind == NALU_FK_MOMENTUM_SYMMETRY) momentum_symmetry(k, F, B);
+      else if (k.kind == NALU_FK_MOMENTUM_WALL_FUNCTION) momentum_wall_function(k, F, B);
       else momentum_open_adv_diff(k, F, B);
     } else {
       if (k.kind == NALU_FK_SCALAR_OPEN_ADV) scalar_open_adv(k, F, B);
@@ -450,6 +492,14 @@ const char *missing_face_field(const nalu_b200_face_kernel_desc &k)
         (m = need_f(NALU_FF_OPEN_MASS_FLOW_RATE, "open_mass_flow_rate")))
       return m;
     if (moves && ((m = need_n(NALU_FN_VELOCITY_RTM, "velocity_rtm")) || (m = need_n(NALU_FN_MESH_VELOCITY, "mesh_velocity")))) return m;
+    break;
+  case NALU_FK_MOMENTUM_WALL_FUNCTION:
+    if ((m = need_n(NALU_FN_VELOCITY, "velocity")) || (m = need_n(NALU_FN_WALL_VELOCITY_BC, "wall_velocity_bc")) ||
+        (m = need_n(NALU_FN_DENSITY, "density")) || (m = need_n(NALU_FN_VISCOSITY, "viscosity")) ||
+        (m = need_f(NALU_FF_EXPOSED_AREA_VEC, "exposed_area_vector")) ||
+        (m = need_f(NALU_FF_WALL_FRICTION_VELOCITY_BIP, "wall_friction_velocity_bip")) ||
+        (m = need_f(NALU_FF_WALL_NORMAL_DISTANCE_BIP, "wall_normal_distance_bip")))
+      return m;
     break;
   default: return "kind";
   }
@@ -566,7 +616,8 @@ int nalu_b200_assemble_face_elem(const nalu_b200_graph *h, const nalu_b200_face_
       set_error("assemble_face_elem: unknown kernel kind");
       return NALU_B200_ERR_ARG;
     }
-    const bool vec = k[i].kind == NALU_FK_MOMENTUM_SYMMETRY || k[i].kind == NALU_FK_MOMENTUM_OPEN_ADV_DIFF;
+    const bool vec = k[i].kind == NALU_FK_MOMENTUM_SYMMETRY || k[i].kind == NALU_FK_MOMENTUM_OPEN_ADV_DIFF ||
+                     k[i].kind == NALU_FK_MOMENTUM_WALL_FUNCTION;
     if ((vec && g.ndof != 3) || (!vec && g.ndof != 1)) {
       set_error("assemble_face_elem: kernel kind does not match the linear system's numDof");
       return NALU_B200_ERR_ARG;

@@ -46,18 +46,21 @@ TM = dict(beta_star=0, tke_prod_limit_ratio=1, sigma_w_two=2, beta_one=3, beta_t
 
 
 # face/element boundary-condition kernels (nalu_b200_face_kernel_desc)
-FK = dict(momentum_symmetry=0, scalar_open_adv=1, continuity_open=2, momentum_open_adv_diff=3)
+FK = dict(momentum_symmetry=0, scalar_open_adv=1, continuity_open=2, momentum_open_adv_diff=3, momentum_wall_function=4)
 FN = dict(coordinates=0, velocity=1, velocity_rtm=2, mesh_velocity=3, viscosity=4, density=5, pressure=6, pressure_bc=7, dpdx=8,
-          scalarq=9, bc_scalarq=10, gjq=11, gjui=12, velocity_bc=13)
+          scalarq=9, bc_scalarq=10, gjq=11, gjui=12, velocity_bc=13, wall_velocity_bc=14)
 FN_COUNT = 16
-FF = dict(exposed_area_vector=0, open_mass_flow_rate=1, dynamic_pressure=2)
-FF_COUNT = 4
+FF = dict(exposed_area_vector=0, open_mass_flow_rate=1, dynamic_pressure=2, wall_friction_velocity_bip=3,
+          wall_normal_distance_bip=4)
+FF_COUNT = 6
+WALL = dict(elog=0, kappa=1, yplus_crit=2)
 OPT_MESH_MOVES = 1 << 8
 
 
 class FaceKernelDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("options", C.c_int32), ("include_divu", C.c_double), ("dt", C.c_double),
-                ("gamma1", C.c_double), ("upw", C.c_double * 8), ("nodal", C.c_void_p * FN_COUNT), ("face", C.c_void_p * FF_COUNT)]
+                ("gamma1", C.c_double), ("upw", C.c_double * 8), ("nodal", C.c_void_p * FN_COUNT), ("face", C.c_void_p * FF_COUNT),
+                ("wall", C.c_double * 4)]
 
 
 class GraphInfo(C.Structure):

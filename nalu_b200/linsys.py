@@ -293,6 +293,8 @@ class DeviceCsrLinearSystem:
         d.gamma1 = scalars.get("gamma1", 1.0)
         for name, v in (scalars.get("upw") or {}).items():
             d.upw[_lib.UPW[name]] = float(v)
+        for name, v in (scalars.get("wall") or {}).items():
+            d.wall[_lib.WALL[name]] = float(v)
         for name, t in (fields or {}).items():
             if t is None or name not in FN:
                 continue

@@ -480,6 +480,75 @@ static void momentum_open_adv_diff(const orc_face_kernel_desc *k, const int32_t 
 
 /* one face through the registered kernels: zero, run every kernel in order (AssembleFaceElemSolverAlgorithm.C:90-97);
  * lhs is [rhsSize][rhsSize] with rhsSize = 8 * numDof (the ELEMENT's nodes, include/AssembleFaceElemSolverAlgorithm.h:67) */
+/* ---- src/kernel/MomentumWallFunctionElemKernel.C:73-155 ----
+ * The reference registers this kernel on an AssembleElemSolverAlgorithm over the FACES of the wall part (lhs is 12 x 12 on the
+ * face's 4 nodes).  Here it is written into the (8 nodes x 3)^2 matrix of the element the face belongs to, at the rows / columns
+ * of the face's nodes (side_node_ordinals): the same CSR entries receive the same values. */
+static void momentum_wall_function(const orc_face_kernel_desc *k, const int32_t *nodes, int elemFaceOrdinal, int64_t face,
+                                   double *lhs, double *rhs)
+{
+  const int n = 24;
+  const int *ord = orc_hex8_side_node_ordinals(elemFaceOrdinal);
+  double v_uNp1[4][3], v_bcVelocity[4][3], v_density[4], v_viscosity[4], vf_shape_function_[4][4];
+  double w_uNp1Bip[3], w_uBcBip[3], w_unitNormal[3];
+  const double *vf_exposedAreaVec = k->exposedAreaVec + 12 * face;
+  const double *vf_utau = k->wallFrictionVelocityBip + 4 * face;
+  const double *vf_yp = k->wallNormalDistanceBip + 4 * face;
+  gather_face(k->velocity, 3, nodes, ord, &v_uNp1[0][0]);
+  gather_face(k->wallVelocityBc, 3, nodes, ord, &v_bcVelocity[0][0]);
+  gather_face(k->density, 1, nodes, ord, v_density);
+  gather_face(k->viscosity, 1, nodes, ord, v_viscosity);
+  orc_quad3d_shape_fcn(0, vf_shape_function_);
+  const double elog_ = k->elog, kappa_ = k->kappa, yplusCrit_ = k->yplusCrit;
+
+  for (int ip = 0; ip < 4; ++ip) {
+    /* Quad3DSCS::ipNodeMap is the identity (face-local); the face's node ip is element node ord[ip] */
+    const int nearestNode = ord[ip];
+    double aMag = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      w_uNp1Bip[j] = 0.0;
+      w_uBcBip[j] = 0.0;
+      const double axj = vf_exposedAreaVec[3 * ip + j];
+      aMag += axj * axj;
+    }
+    aMag = sqrt(aMag);
+    double rhoBip = 0.0, muBip = 0.0;
+    for (int ic = 0; ic < 4; ++ic) {
+      const double r = vf_shape_function_[ip][ic];
+      rhoBip += r * v_density[ic];
+      muBip += r * v_viscosity[ic];
+      for (int j = 0; j < 3; ++j) {
+        w_uNp1Bip[j] += r * v_uNp1[ic][j];
+        w_uBcBip[j] += r * v_bcVelocity[ic][j];
+      }
+    }
+    for (int j = 0; j < 3; ++j) w_unitNormal[j] = vf_exposedAreaVec[3 * ip + j] / aMag;
+    const double yp = vf_yp[ip];
+    const double utau = vf_utau[ip];
+    const double yplus = rhoBip * yp * utau / muBip;
+    const double lambda = yplus > yplusCrit_ ? rhoBip * kappa_ * utau / log(elog_ * yplus) * aMag : muBip / yp * aMag;
+
+    for (int i = 0; i < 3; ++i) {
+      const int indexR = nearestNode * 3 + i;
+      double uiTan = 0.0, uiBcTan = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        const double ninj = w_unitNormal[i] * w_unitNormal[j];
+        if (i == j) {
+          const double om_nini = 1.0 - ninj;
+          uiTan += om_nini * w_uNp1Bip[j];
+          uiBcTan += om_nini * w_uBcBip[j];
+          for (int ic = 0; ic < 4; ++ic) lhs[indexR * n + ord[ic] * 3 + i] += lambda * om_nini * vf_shape_function_[ip][ic];
+        } else {
+          uiTan -= ninj * w_uNp1Bip[j];
+          uiBcTan -= ninj * w_uBcBip[j];
+          for (int ic = 0; ic < 4; ++ic) lhs[indexR * n + ord[ic] * 3 + j] -= lambda * ninj * vf_shape_function_[ip][ic];
+        }
+      }
+      rhs[indexR] -= lambda * (uiTan - uiBcTan);
+    }
+  }
+}
+
 void orc_face_elem_lhs_rhs(const orc_face_kernel_desc *kernels, int nk, int numDof, const int32_t *elemNodes, int elemFaceOrdinal,
                            int64_t faceIndex, double *lhs, double *rhs)
 {
@@ -493,6 +562,7 @@ void orc_face_elem_lhs_rhs(const orc_face_kernel_desc *kernels, int nk, int numD
     case ORC_FK_SCALAR_OPEN_ADV: scalar_open_adv(k, elemNodes, elemFaceOrdinal, faceIndex, lhs, rhs); break;
     case ORC_FK_CONTINUITY_OPEN: continuity_open(k, elemNodes, elemFaceOrdinal, faceIndex, lhs, rhs); break;
     case ORC_FK_MOMENTUM_OPEN_ADV_DIFF: momentum_open_adv_diff(k, elemNodes, elemFaceOrdinal, faceIndex, lhs, rhs); break;
+    case ORC_FK_MOMENTUM_WALL_FUNCTION: momentum_wall_function(k, elemNodes, elemFaceOrdinal, faceIndex, lhs, rhs); break;
     default: abort();
     }
   }

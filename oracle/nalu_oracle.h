@@ -208,7 +208,8 @@ enum orc_face_kernel_kind {
   ORC_FK_MOMENTUM_SYMMETRY = 0,     /* src/kernel/MomentumSymmetryElemKernel.C     */
   ORC_FK_SCALAR_OPEN_ADV = 1,       /* src/kernel/ScalarOpenAdvElemKernel.C        */
   ORC_FK_CONTINUITY_OPEN = 2,       /* src/kernel/ContinuityOpenElemKernel.C       */
-  ORC_FK_MOMENTUM_OPEN_ADV_DIFF = 3 /* src/kernel/MomentumOpenAdvDiffElemKernel.C  */
+  ORC_FK_MOMENTUM_OPEN_ADV_DIFF = 3,/* src/kernel/MomentumOpenAdvDiffElemKernel.C  */
+  ORC_FK_MOMENTUM_WALL_FUNCTION = 4 /* src/kernel/MomentumWallFunctionElemKernel.C */
 };
 /* what the face kernels' constructors / setup() capture; nodal fields [nNode][ncomp], face fields [nFaces][4 ips][ncomp] */
 typedef struct orc_face_kernel_desc {
@@ -219,6 +220,10 @@ typedef struct orc_face_kernel_desc {
   const double *coordinates, *velocity, *velocityRTM, *meshVelocity, *viscosity, *density, *pressure, *pressureBc, *Gpdx;
   const double *scalarQ, *bcScalarQ, *Gjq, *Gjui, *velocityBc;
   const double *exposedAreaVec, *openMassFlowRate, *dynamicPressure; /* face fields: [.][4][3], [.][4], [.][4] */
+  /* MomentumWallFunctionElemKernel: wall_velocity_bc (nodal), wall_friction_velocity_bip / wall_normal_distance_bip ([.][4]),
+   * TM_elog / TM_kappa / TM_yplus_crit (src/SolutionOptions.C) */
+  const double *wallVelocityBc, *wallFrictionVelocityBip, *wallNormalDistanceBip;
+  double elog, kappa, yplusCrit;
 } orc_face_kernel_desc;
 
 const int *orc_hex8_side_node_ordinals(int ordinal); /* Hex8CVFEM.C:414-422,587-591 */

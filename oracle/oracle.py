@@ -202,10 +202,12 @@ def compute_mdot_elem(elem_nodes, coords, density, velocity, pressure, Gpdx, pro
 
 
 # ---- face/element boundary-condition path (oracle/face_kernels.c) ---------------------------------------------------
-FACE_KIND = {"momentum_symmetry": 0, "scalar_open_adv": 1, "continuity_open": 2, "momentum_open_adv_diff": 3}
+FACE_KIND = {"momentum_symmetry": 0, "scalar_open_adv": 1, "continuity_open": 2, "momentum_open_adv_diff": 3,
+             "momentum_wall_function": 4}
 _FACE_PTR_FIELDS = ("coordinates", "velocity", "velocityRTM", "meshVelocity", "viscosity", "density", "pressure", "pressureBc",
                     "Gpdx", "scalarQ", "bcScalarQ", "Gjq", "Gjui", "velocityBc", "exposedAreaVec", "openMassFlowRate",
                     "dynamicPressure")
+_FACE_WALL_PTR_FIELDS = ("wallVelocityBc", "wallFrictionVelocityBip", "wallNormalDistanceBip")
 
 
 class FaceKernelDesc(C.Structure):
@@ -213,7 +215,8 @@ class FaceKernelDesc(C.Structure):
                                        "pecletTanh")] + \
                [(n, C.c_double) for n in ("includeDivU", "dt", "gamma1", "alphaUpw", "hoUpwind", "hybridFactor", "tanhTrans",
                                           "tanhWidth")] + \
-               [(n, C.c_void_p) for n in _FACE_PTR_FIELDS]
+               [(n, C.c_void_p) for n in _FACE_PTR_FIELDS] + \
+               [(n, C.c_void_p) for n in _FACE_WALL_PTR_FIELDS] + [(n, C.c_double) for n in ("elog", "kappa", "yplusCrit")]
 
 
 def make_face_desc(kind, keep, **kw):
@@ -223,7 +226,7 @@ def make_face_desc(kind, keep, **kw):
     d.dt = 1.0
     d.gamma1 = 1.0
     for k, v in kw.items():
-        if k in _FACE_PTR_FIELDS:
+        if k in _FACE_PTR_FIELDS or k in _FACE_WALL_PTR_FIELDS:
             if v is None:
                 continue
             arr = _f64(v)

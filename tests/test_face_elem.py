@@ -160,6 +160,42 @@ def test_momentum_symmetry_plus_open_diffusion_is_the_full_traction():
             np.testing.assert_allclose(rhs[rows], -ref @ u.ravel(), atol=1e-14)
 
 
+def test_momentum_wall_function_closed_form():
+    """flat wall (bottom face of the unit cube), uniform velocity U with a wall-normal part, wall at rest: every face point
+    pulls its nearest node with -lambda (I - n n^T) U, lambda = mu / y_p |A| below y+_crit and rho kappa u_tau / ln(E y+) |A|
+    above; the lhs rows are lambda (I - n n^T) times the face shape functions, on the face's nodes only
+    (src/kernel/MomentumWallFunctionElemKernel.C:73-155)"""
+    c = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=np.float64)
+    sno, ipn, _ = oracle.hex8_face_tables()
+    f = 4  # ordinal 4: nodes 0 3 2 1, outward normal -z
+    area = oracle.quad3d_scs_areav(c[sno[f]])[None]
+    assert np.allclose(area[0], [[0, 0, -0.25]] * 4)
+    U = np.array([0.3, -0.2, 0.5])
+    rho, mu, kappa, elog, ycrit = 1.2, 0.1, 0.41, 9.8, 11.63
+    shp = oracle.quad3d_shape_fcn()
+    for utau, yp in ((0.2, 0.05), (4.0, 0.5)):
+        keep = []
+        fld = _one_elem_fields(c)
+        d = oracle.make_face_desc("momentum_wall_function", keep, exposedAreaVec=area, wallVelocityBc=np.zeros((8, 3)),
+                                  wallFrictionVelocityBip=np.full((1, 4), utau), wallNormalDistanceBip=np.full((1, 4), yp),
+                                  elog=elog, kappa=kappa, yplusCrit=ycrit, **fld)
+        lhs, rhs = oracle.face_elem_lhs_rhs([d], 3, np.arange(8), f)
+        yplus = rho * yp * utau / mu
+        lam = (rho * kappa * utau / np.log(elog * yplus) if yplus > ycrit else mu / yp) * 0.25
+        assert (yplus > ycrit) == (utau > 1.0)
+        P = np.diag([1.0, 1.0, 0.0])  # I - n n^T for n = -z
+        L = lhs.reshape(8, 3, 8, 3)
+        for k in range(4):
+            node = sno[f][k]
+            assert np.allclose(rhs.reshape(8, 3)[node], -lam * P @ U, rtol=0, atol=1e-15)
+            for ic in range(4):
+                assert np.allclose(L[node, :, sno[f][ic], :], lam * P * shp[k][ic], rtol=0, atol=1e-15)
+        others = np.setdiff1d(np.arange(8), sno[f])
+        assert not L[others].any() and not L[:, :, others, :].any()
+        # total wall force = -lambda_total (tangential velocity): the four points cover the whole face
+        assert np.allclose(rhs.reshape(8, 3).sum(axis=0), -4 * lam * P @ U)
+
+
 def test_exposed_faces_of_a_box():
     m = M.generated_box(4, 3, 2)
     fe, fo = M.exposed_faces(m)
@@ -192,18 +228,23 @@ def _face_state(m, fe, fo, seed=2):
     fld = dict(coordinates=c, velocity=st.velocity, velocityRTM=st.velocity - 0.1 * np.cos(c), meshVelocity=0.1 * np.cos(c),
                viscosity=st.viscosity, density=st.density, pressure=st.pressure, pressureBc=0.9 * st.pressure + 0.05,
                Gpdx=st.dpdx, scalarQ=st.scalarq, bcScalarQ=0.5 + 0.2 * np.sin(a * c[:, 1]), Gjq=st.gjq, Gjui=st.gju,
-               velocityBc=0.5 * st.velocity + 0.02)
+               velocityBc=0.5 * st.velocity + 0.02, wallVelocityBc=0.1 * st.velocity - 0.03)
     # open mass flow of both signs on every side; a dynamic pressure
     mf = (area * (st.density[:, None] * st.velocity)[m.elem_nodes[fe][np.arange(nf)[:, None], M.HEX8_SIDE_NODES[fo]]]).sum(2)
     mf += 0.05 * rng.uniform(-1, 1, mf.shape) * np.abs(mf).max()
-    ff = dict(exposedAreaVec=area, openMassFlowRate=mf, dynamicPressure=0.01 * rng.uniform(0, 1, (nf, 4)))
+    # wall distances / friction velocities that put face points on both sides of y+_crit
+    ff = dict(exposedAreaVec=area, openMassFlowRate=mf, dynamicPressure=0.01 * rng.uniform(0, 1, (nf, 4)),
+              wallFrictionVelocityBip=rng.uniform(0.05, 2.0, (nf, 4)), wallNormalDistanceBip=rng.uniform(0.02, 0.3, (nf, 4)))
     return fld, ff
 
 
 _PN = dict(coordinates="coordinates", velocity="velocity", velocityRTM="velocity_rtm", meshVelocity="mesh_velocity",
            viscosity="viscosity", density="density", pressure="pressure", pressureBc="pressure_bc", Gpdx="dpdx", scalarQ="scalarq",
-           bcScalarQ="bc_scalarq", Gjq="gjq", Gjui="gjui", velocityBc="velocity_bc")
-_PF = dict(exposedAreaVec="exposed_area_vector", openMassFlowRate="open_mass_flow_rate", dynamicPressure="dynamic_pressure")
+           bcScalarQ="bc_scalarq", Gjq="gjq", Gjui="gjui", velocityBc="velocity_bc", wallVelocityBc="wall_velocity_bc")
+_PF = dict(exposedAreaVec="exposed_area_vector", openMassFlowRate="open_mass_flow_rate", dynamicPressure="dynamic_pressure",
+           wallFrictionVelocityBip="wall_friction_velocity_bip", wallNormalDistanceBip="wall_normal_distance_bip")
+_WALL = dict(elog=9.8, kappa=0.41, yplusCrit=11.63)   # SolutionOptions defaults of TM_elog, TM_kappa, TM_yplus_crit
+_WALL_ABI = dict(elog=9.8, kappa=0.41, yplus_crit=11.63)
 _UPW = dict(alphaUpw=0.75, hoUpwind=0.9, hybridFactor=1.0, tanhTrans=2.0, tanhWidth=4.0)
 _UPW_ABI = dict(alpha_upw=0.75, ho_upwind=0.9, hybrid_factor=1.0, tanh_trans=2.0, tanh_width=4.0)
 
@@ -216,6 +257,9 @@ FACE_CASES = {
                                        ("mesh_moves", "peclet_tanh", "skew_symmetric", "shifted_grad_op"))]),
     "momentum_symmetry+open": (3, [("momentum_symmetry", dict(includeDivU=1.0), ()),
                                    ("momentum_open_adv_diff", dict(includeDivU=1.0, **_UPW), ())]),
+    "momentum_wall_function": (3, [("momentum_wall_function", dict(**_WALL), ())]),
+    "momentum_symmetry+wall_function": (3, [("momentum_symmetry", dict(includeDivU=1.0), ()),
+                                            ("momentum_wall_function", dict(**_WALL), ())]),
     "scalar_open": (1, [("scalar_open_adv", dict(**_UPW), ())]),
     "scalar_open_skew_tanh": (1, [("scalar_open_adv", dict(skewSymmetric=1, pecletTanh=1, **_UPW), ("skew_symmetric", "peclet_tanh"))]),
     "continuity_open": (1, [("continuity_open", dict(dt=0.05, gamma1=1.5), ())]),
@@ -236,7 +280,7 @@ def _product_face_descs(ls, klist, fld, ff, dev):
         else:
             f = dn
         out.append(ls.make_face_desc(kind, fields=f, face_fields=df, options=opts, include_divu=sc.get("includeDivU", 0.0),
-                                     dt=sc.get("dt", 1.0), gamma1=sc.get("gamma1", 1.0), upw=_UPW_ABI))
+                                     dt=sc.get("dt", 1.0), gamma1=sc.get("gamma1", 1.0), upw=_UPW_ABI, wall=_WALL_ABI))
     return out
 
 
