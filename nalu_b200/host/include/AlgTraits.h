@@ -1,4 +1,4 @@
-// AlgTraits.h -- include/AlgTraits.h:18-25 (only the Hex8 traits are on this path)
+// AlgTraits.h -- include/AlgTraits.h:18-34 (the Hex8 traits, and Hex27 for the momentum kernels)
 #pragma once
 #include "stk_shim.h"
 namespace sierra {
@@ -10,6 +10,15 @@ struct AlgTraitsHex8 {
   static constexpr int numScvIp_ = 8;
   static constexpr int numGp_ = 8;
   static constexpr stk::topology::topology_t topo_ = stk::topology::HEX_8;
+};
+// include/AlgTraits.h:27-34: BASELINE config 5; MomentumAdvDiffElemKernel and MomentumMassElemKernel are instantiated for it
+struct AlgTraitsHex27 {
+  static constexpr int nDim_ = 3;
+  static constexpr int nodesPerElement_ = 27;
+  static constexpr int numScsIp_ = 216;
+  static constexpr int numScvIp_ = 216;
+  static constexpr int numGp_ = 27;
+  static constexpr stk::topology::topology_t topo_ = stk::topology::HEX_27;
 };
 // include/AlgTraits.h:81-88 (AlgTraitsQuad4), :157-176 (AlgTraitsFaceElem), :199
 struct AlgTraitsQuad4 {

@@ -7,6 +7,7 @@
 // (device_descriptor) and evaluates the whole registered list in ONE fused CUDA launch through the C
 // ABI (nalu_b200_assemble_elem).  There is no CPU execute(): the product path has no CPU fallback.
 #pragma once
+#include <type_traits>
 #include "../../../../include/nalu_b200.h"
 #include "../AlgTraits.h"
 #include "../ElemDataRequests.h"
@@ -30,6 +31,10 @@ void get_scv_shape_fn_data(LambdaFunction lambdaFunction, double (&view)[AlgTrai
 {
   lambdaFunction(&view[0][0]);
 }
+
+// kernels that are also instantiated for AlgTraitsHex27 (build_topo_kernel dispatches HEX_27 parts to them)
+template <template <typename> class T>
+struct has_hex27_instantiation : std::false_type {};
 
 class Kernel {
 public:

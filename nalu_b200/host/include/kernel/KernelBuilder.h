@@ -28,8 +28,11 @@ Kernel *build_topo_kernel(stk::topology topo, Args &&...args)
   switch (topo.t_) {
   case stk::topology::HEX_8:
     return new T<AlgTraitsHex8>(std::forward<Args>(args)...);
+  case stk::topology::HEX_27:
+    if constexpr (has_hex27_instantiation<T>::value) return new T<AlgTraitsHex27>(std::forward<Args>(args)...);
+    else throw std::runtime_error("build_topo_kernel: this kernel is not instantiated for HEXAHEDRON_27 (the momentum list is)");
   default:
-    throw std::runtime_error("build_topo_kernel: only Hex8 is on this path (topology " + topo.name() + ")");
+    throw std::runtime_error("build_topo_kernel: only Hex8 (and Hex27 for the momentum list) is on this path (topology " + topo.name() + ")");
   }
 }
 

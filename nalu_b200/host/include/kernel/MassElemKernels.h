@@ -63,5 +63,8 @@ private:
   const int *ipNodeMap_;
 };
 
+template <>
+struct has_hex27_instantiation<MomentumMassElemKernel> : std::true_type {};
+
 } // namespace nalu
 } // namespace sierra

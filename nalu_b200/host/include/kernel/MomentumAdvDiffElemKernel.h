@@ -26,5 +26,7 @@ private:
   const bool shiftedGradOp_;
   bool skewSymmetric_;
 };
+template <>
+struct has_hex27_instantiation<MomentumAdvDiffElemKernel> : std::true_type {};
 } // namespace nalu
 } // namespace sierra

@@ -7,6 +7,7 @@
 #pragma once
 #include "../stk_shim.h"
 #include <stdexcept>
+#include <vector>
 
 namespace sierra {
 namespace nalu {
@@ -65,6 +66,41 @@ public:
   void shifted_shape_fcn(double *shpfc) override; // identity: lumping
 private:
   int ipNodeMap_[8];
+};
+
+// HexahedralP2Element tables (src/master_element/Hex27CVFEM.C:25-75,192-262,355-421): STK node map, sub-control-surface end
+// locations, the 2-point rule per segment
+class HexahedralP2Element : public MasterElement {
+public:
+  HexahedralP2Element();
+  int tensor_product_node_map(int i, int j, int k) const { return stkNodeMap_[i + 3 * (j + 3 * k)]; }
+  double gauss_point_location(int nodeOrdinal, int gaussPointOrdinal) const;
+  double shifted_gauss_point_location(int nodeOrdinal, int gaussPointOrdinal) const;
+  void hex27_shape_fcn(int numIntPoints, const double *intgLoc, double *shpfc) const;
+protected:
+  int stkNodeMap_[27];
+  double scsDist_, scsEndLoc_[4], gaussAbscissae_[2], gaussAbscissaeShift_[6];
+  std::vector<double> intgLoc_, intgLocShift_;
+};
+// Hex27SCS (Hex27CVFEM.C:851-1050): 216 points, lrscv
+class Hex27SCS : public HexahedralP2Element {
+public:
+  Hex27SCS();
+  const int *adjacentNodes() override { return lrscv_.data(); }
+  void shape_fcn(double *shpfc) override { hex27_shape_fcn(numIntPoints_, intgLoc_.data(), shpfc); }                 // [216][27]
+  void shifted_shape_fcn(double *shpfc) override { hex27_shape_fcn(numIntPoints_, intgLocShift_.data(), shpfc); }
+private:
+  std::vector<int> lrscv_;
+};
+// Hex27SCV (Hex27CVFEM.C:634-722): 216 points, 8 per node
+class Hex27SCV : public HexahedralP2Element {
+public:
+  Hex27SCV();
+  const int *ipNodeMap(int = 0) override { return ipNodeMap_.data(); }
+  void shape_fcn(double *shpfc) override { hex27_shape_fcn(numIntPoints_, intgLoc_.data(), shpfc); }
+  void shifted_shape_fcn(double *shpfc) override { hex27_shape_fcn(numIntPoints_, intgLocShift_.data(), shpfc); }   // nodal: lumping
+private:
+  std::vector<int> ipNodeMap_;
 };
 
 struct MasterElementRepo {

@@ -235,13 +235,17 @@ public:
   // high x side, ...), holding this rank's faces of that side, plus "all_surfaces" = their union; sizes the FACE_RANK
   // fields.  Call after fill_generated_mesh.
   void create_generated_sidesets(const std::string &sides);
+  // nx x ny x nz HEX_27 elements on the (2nx+1)(2ny+1)(2nz+1) lattice of spacing 1/2 (one rank): ids 1 + lexicographic
+  // index, connectivity in STK's Hex27 node order (what promoting the generated Hex8 box to P2 produces, up to the numbering)
+  void fill_generated_hex27_mesh(int nx, int ny, int nz, Part &block, const std::string &coords_name = "coordinates");
+  int nodes_per_elem() const { return npe_; }
   size_t num_faces() const { return num_faces_; }
   size_t num_nodes() const { return node_gid_.size(); }
-  size_t num_elems() const { return conn_.size() / 8; }
+  size_t num_elems() const { return conn_.size() / size_t(npe_); }
   const std::vector<int64_t> &node_ids() const { return node_gid_; }    // naluGlobalId, 1-based
   const std::vector<int32_t> &node_owners() const { return node_owner_; }
-  const std::vector<int32_t> &connectivity() const { return conn_; }   // [nElem][8], local node indices
-  const int32_t *begin_nodes(Entity elem) const { return &conn_[size_t(elem.index) * 8]; }
+  const std::vector<int32_t> &connectivity() const { return conn_; }   // [nElem][8] (Hex27 meshes: [nElem][27]), local node indices
+  const int32_t *begin_nodes(Entity elem) const { return &conn_[size_t(elem.index) * size_t(npe_)]; }
   int64_t identifier(Entity e) const { return e.rank == topology::NODE_RANK ? node_gid_[size_t(e.index)] : elem_gid0_ + e.index; }
   Entity get_entity(EntityRank rank, int64_t id) const;
   const int *box() const { return box_; } // local element counts when the mesh is a generated box
@@ -253,6 +257,7 @@ private:
   std::vector<int64_t> node_gid_;
   std::vector<int32_t> node_owner_, conn_;
   int64_t elem_gid0_ = 1;
+  int npe_ = 8;
   int box_[3] = {0, 0, 0};
   int k0_ = 0, nz_global_ = 0;
   size_t num_faces_ = 0;

@@ -11,6 +11,7 @@
 #include "../include/nso/MomentumNSOElemKernel.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -99,6 +100,50 @@ void BulkData::fill_generated_mesh(int nx, int ny, int nzg, Part &block, const s
           x[3 * n + 0] = xx;
           x[3 * n + 1] = y;
           x[3 * n + 2] = z + k0;
+        }
+    c->modify_on_host();
+  }
+}
+
+void BulkData::fill_generated_hex27_mesh(int nx, int ny, int nz, Part &block, const std::string &coords_name)
+{
+  STK_ThrowRequireMsg(nranks_ == 1, "fill_generated_hex27_mesh: one rank (partitioned Hex27 meshes come through the C ABI)");
+  // tensor-grid node (i, j, k) of an element -> STK Hex27 ordinal (HexahedralP2Element::stkNodeMap_, Hex27CVFEM.C:36-47)
+  static const int stk27[27] = {0, 8, 1, 11, 21, 9, 3, 10, 2, 12, 25, 13, 23, 20, 24, 15, 26, 14, 4, 16, 5, 19, 22, 17, 7, 18, 6};
+  const int NX = 2 * nx + 1, NY = 2 * ny + 1, NZ = 2 * nz + 1;
+  node_gid_.clear(); node_owner_.clear(); conn_.clear();
+  for (int64_t n = 0; n < int64_t(NX) * NY * NZ; ++n) {
+    node_gid_.push_back(n + 1);
+    node_owner_.push_back(0);
+  }
+  npe_ = 27;
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) {
+        int32_t c[27];
+        for (int cz = 0; cz < 3; ++cz)
+          for (int b = 0; b < 3; ++b)
+            for (int a = 0; a < 3; ++a) c[stk27[a + 3 * (b + 3 * cz)]] = (2 * i + a) + NX * ((2 * j + b) + NY * (2 * k + cz));
+        conn_.insert(conn_.end(), c, c + 27);
+      }
+  elem_gid0_ = 1;
+  box_[0] = box_[1] = box_[2] = 0;
+  k0_ = 0;
+  nz_global_ = nz;
+  block_ = &block;
+  for (FieldBase *f : meta_.fields_)
+    f->set_num_entities(f->entity_rank() == topology::NODE_RANK ? num_nodes()
+                                                                 : (f->entity_rank() == topology::FACE_RANK ? num_faces_ : num_elems()));
+  if (Field<double> *c = meta_.get_field<double>(topology::NODE_RANK, coords_name)) {
+    STK_ThrowRequireMsg(c->max_size() == 3, "coordinates field must have 3 scalars per node");
+    double *x = c->host_data();
+    size_t n = 0;
+    for (int z = 0; z < NZ; ++z)
+      for (int y = 0; y < NY; ++y)
+        for (int xx = 0; xx < NX; ++xx, ++n) {
+          x[3 * n + 0] = 0.5 * xx;
+          x[3 * n + 1] = 0.5 * y;
+          x[3 * n + 2] = 0.5 * z;
         }
     c->modify_on_host();
   }
@@ -354,8 +399,95 @@ void HexSCV::shifted_shape_fcn(double *shpfc)
   scv_loc(0.5, loc);
   hex_shape(loc, 8, shpfc);
 }
+// ---- Hex27 (src/master_element/Hex27CVFEM.C) ---------------------------------------------------------------------------
+HexahedralP2Element::HexahedralP2Element()
+{
+  static const int m[27] = {0, 8, 1, 11, 21, 9, 3, 10, 2, 12, 25, 13, 23, 20, 24, 15, 26, 14, 4, 16, 5, 19, 22, 17, 7, 18, 6};
+  for (int q = 0; q < 27; ++q) stkNodeMap_[q] = m[q];
+  nodesPerElement_ = 27;
+  scsDist_ = std::sqrt(3.0) / 3.0;
+  scsEndLoc_[0] = -1.0; scsEndLoc_[1] = -scsDist_; scsEndLoc_[2] = scsDist_; scsEndLoc_[3] = 1.0;
+  gaussAbscissae_[0] = -std::sqrt(3.0) / 3.0; gaussAbscissae_[1] = std::sqrt(3.0) / 3.0;
+  const double sh[6] = {-1.0, -1.0, 0.0, 0.0, +1.0, +1.0};
+  for (int q = 0; q < 6; ++q) gaussAbscissaeShift_[q] = sh[q];
+}
+double HexahedralP2Element::gauss_point_location(int nodeOrdinal, int gaussPointOrdinal) const
+{
+  const double b = scsEndLoc_[nodeOrdinal + 1], a = scsEndLoc_[nodeOrdinal]; // isoparametric_mapping(b, a, xi)
+  return gaussAbscissae_[gaussPointOrdinal] * (b - a) / 2.0 + (a + b) / 2.0;
+}
+double HexahedralP2Element::shifted_gauss_point_location(int nodeOrdinal, int gaussPointOrdinal) const
+{
+  return gaussAbscissaeShift_[nodeOrdinal * 2 + gaussPointOrdinal];
+}
+// the 27 formulas of Hex27CVFEM.C:355-421 are the products l_a(s) l_b(t) l_c(u) of the 1-D quadratic Lagrange basis on
+// {-1, 0, 1}, stored at the STK ordinal of tensor node (a, b, c)
+void HexahedralP2Element::hex27_shape_fcn(int numIntPoints, const double *intgLoc, double *shpfc) const
+{
+  for (int ip = 0; ip < numIntPoints; ++ip) {
+    double l[3][3];
+    for (int d = 0; d < 3; ++d) {
+      const double x = intgLoc[3 * ip + d];
+      l[d][0] = -0.5 * x * (1.0 - x); l[d][1] = (1.0 - x) * (1.0 + x); l[d][2] = 0.5 * x * (1.0 + x);
+    }
+    for (int c = 0; c < 3; ++c)
+      for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) shpfc[27 * ip + tensor_product_node_map(a, b, c)] = l[0][a] * l[1][b] * l[2][c];
+  }
+}
+Hex27SCS::Hex27SCS()
+{
+  numIntPoints_ = 216;
+  const double scsLoc[2] = {-scsDist_, scsDist_};
+  // u, t, s surfaces in this order; per surface 3 x 3 node segments x 2 x 2 Gauss points (Hex27CVFEM.C:912-1047)
+  for (int dir = 2; dir >= 0; --dir)
+    for (int m = 0; m < 2; ++m)
+      for (int l = 0; l < 3; ++l)
+        for (int k = 0; k < 3; ++k) {
+          int lo[3], hi[3];
+          if (dir == 2) { lo[0] = k; lo[1] = l; lo[2] = m; }
+          else if (dir == 1) { lo[0] = k; lo[1] = m; lo[2] = l; }
+          else { lo[0] = m; lo[1] = k; lo[2] = l; }
+          hi[0] = lo[0]; hi[1] = lo[1]; hi[2] = lo[2];
+          hi[dir] += 1;
+          const int nlo = tensor_product_node_map(lo[0], lo[1], lo[2]), nhi = tensor_product_node_map(hi[0], hi[1], hi[2]);
+          for (int j = 0; j < 2; ++j)
+            for (int i = 0; i < 2; ++i) {
+              lrscv_.push_back(m == 0 ? nlo : nhi);
+              lrscv_.push_back(m == 0 ? nhi : nlo);
+              double x[3], xs[3];
+              const double g1 = gauss_point_location(k, i), g2 = gauss_point_location(l, j);
+              const double s1 = shifted_gauss_point_location(k, i), s2 = shifted_gauss_point_location(l, j);
+              if (dir == 2) { x[0] = g1; x[1] = g2; x[2] = scsLoc[m]; xs[0] = s1; xs[1] = s2; xs[2] = scsLoc[m]; }
+              else if (dir == 1) { x[0] = g1; x[1] = scsLoc[m]; x[2] = g2; xs[0] = s1; xs[1] = scsLoc[m]; xs[2] = s2; }
+              else { x[0] = scsLoc[m]; x[1] = g1; x[2] = g2; xs[0] = scsLoc[m]; xs[1] = s1; xs[2] = s2; }
+              intgLoc_.insert(intgLoc_.end(), x, x + 3);
+              intgLocShift_.insert(intgLocShift_.end(), xs, xs + 3);
+            }
+        }
+}
+Hex27SCV::Hex27SCV()
+{
+  numIntPoints_ = 216;
+  for (int n = 0; n < 3; ++n)
+    for (int m = 0; m < 3; ++m)
+      for (int l = 0; l < 3; ++l)
+        for (int k = 0; k < 2; ++k)
+          for (int j = 0; j < 2; ++j)
+            for (int i = 0; i < 2; ++i) {
+              const double x[3] = {gauss_point_location(l, i), gauss_point_location(m, j), gauss_point_location(n, k)};
+              const double xs[3] = {shifted_gauss_point_location(l, i), shifted_gauss_point_location(m, j),
+                                    shifted_gauss_point_location(n, k)};
+              intgLoc_.insert(intgLoc_.end(), x, x + 3);
+              intgLocShift_.insert(intgLocShift_.end(), xs, xs + 3);
+              ipNodeMap_.push_back(tensor_product_node_map(l, m, n));
+            }
+}
+
 MasterElement *MasterElementRepo::get_surface_master_element(const stk::topology &theTopo)
 {
+  static Hex27SCS scs27;
+  if (theTopo.t_ == stk::topology::HEX_27) return &scs27;
   static HexSCS scs;
   static Quad3DSCS quad;
   if (theTopo.t_ == stk::topology::QUAD_4) return &quad;
@@ -365,6 +497,8 @@ MasterElement *MasterElementRepo::get_surface_master_element(const stk::topology
 MasterElement *MasterElementRepo::get_volume_master_element(const stk::topology &theTopo)
 {
   static HexSCV scv;
+  static Hex27SCV scv27;
+  if (theTopo.t_ == stk::topology::HEX_27) return &scv27;
   if (theTopo.t_ != stk::topology::HEX_8) throw std::runtime_error("only Hex8 master elements are on this path");
   return &scv;
 }
@@ -1240,6 +1374,9 @@ NALU_B200_DECLARE_KERNEL(ScalarDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumMassElemKernel)
 NALU_B200_DECLARE_KERNEL(ContinuityMassElemKernel)
 NALU_B200_DECLARE_KERNEL(ScalarMassElemKernel)
+// Hex27 (BASELINE config 5): the momentum list
+template class MomentumAdvDiffElemKernel<AlgTraitsHex27>;
+template class MomentumMassElemKernel<AlgTraitsHex27>;
 
 
 // ================================================================================================
@@ -1566,8 +1703,9 @@ void AssembleElemSolverAlgorithm::execute()
   for (Kernel *k : activeKernels_) k->setup(*realm_.timeIntegrator_);
   DeviceCsrLinearSystem *ls = dynamic_cast<DeviceCsrLinearSystem *>(eqSystem_->linsys_);
   if (!ls) throw std::runtime_error("AssembleElemSolverAlgorithm: the device path needs a DeviceCsrLinearSystem");
-  STK_ThrowRequireMsg(nodesPerEntity_ == 8 && entityRank_ == stk::topology::ELEM_RANK,
-                      "AssembleElemSolverAlgorithm expected nodesPerEntity_ = 8 (Hex8), got " << nodesPerEntity_);
+  STK_ThrowRequireMsg((nodesPerEntity_ == 8 || nodesPerEntity_ == 27) && entityRank_ == stk::topology::ELEM_RANK &&
+                          nodesPerEntity_ == unsigned(realm_.bulk_data().nodes_per_elem()),
+                      "AssembleElemSolverAlgorithm expected nodesPerEntity_ = 8 (Hex8) or 27 (Hex27) matching the mesh, got " << nodesPerEntity_);
   std::vector<nalu_b200_kernel_desc> descs(activeKernels_.size());
   for (size_t i = 0; i < activeKernels_.size(); ++i)
     if (!activeKernels_[i]->device_descriptor(descs[i]))
@@ -1680,10 +1818,16 @@ void DeviceCsrLinearSystem::finalizeLinearSystem()
   inConstruction_ = false;
   stk::mesh::BulkData &bulk = realm_.bulk_data();
   const int *box = bulk.box();
-  check(nalu_b200_graph_create(&graph_, bulk.parallel_rank(), bulk.parallel_size(), int(numDof_), int(bulk.num_nodes()),
-                               bulk.node_ids().data(), bulk.node_owners().data(), int64_t(bulk.num_elems()),
-                               bulk.connectivity().data(), box[0], box[1], box[2]),
-        "graph_create");
+  if (bulk.nodes_per_elem() == 8)
+    check(nalu_b200_graph_create(&graph_, bulk.parallel_rank(), bulk.parallel_size(), int(numDof_), int(bulk.num_nodes()),
+                                 bulk.node_ids().data(), bulk.node_owners().data(), int64_t(bulk.num_elems()),
+                                 bulk.connectivity().data(), box[0], box[1], box[2]),
+          "graph_create");
+  else // HEX_27 parts
+    check(nalu_b200_graph_create_topo(&graph_, bulk.parallel_rank(), bulk.parallel_size(), int(numDof_), bulk.nodes_per_elem(),
+                                      int(bulk.num_nodes()), bulk.node_ids().data(), bulk.node_owners().data(),
+                                      int64_t(bulk.num_elems()), bulk.connectivity().data()),
+          "graph_create_topo");
   if (bulk.parallel_size() > 1) {
     STK_ThrowRequireMsg(bool(transport_.exchange_graph), "multi-rank DeviceCsrLinearSystem needs a HaloTransport (setTransport)");
     std::map<int, std::vector<int64_t>> send;

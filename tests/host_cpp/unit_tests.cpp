@@ -850,6 +850,156 @@ static void test_two_kernels_one_algorithm()
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Hex27 (BASELINE config 5): master-element tables on the host, the momentum list through the registration API
+// ---------------------------------------------------------------------------------------------------
+static void test_hex27_master_elements()
+{
+  std::printf("MasterElementHexSerial.hex27_* (unit_tests/UnitTestHexMasterElements.C:297-321) on the host tables\n");
+  MasterElement *scs = MasterElementRepo::get_surface_master_element(stk::topology::HEX_27);
+  MasterElement *scv = MasterElementRepo::get_volume_master_element(stk::topology::HEX_27);
+  EXPECT_TRUE(scs->numIntPoints_ == AlgTraitsHex27::numScsIp_ && scv->numIntPoints_ == AlgTraitsHex27::numScvIp_);
+  EXPECT_TRUE(scs->nodesPerElement_ == 27 && scv->nodesPerElement_ == 27);
+  std::vector<double> sf(216 * 27), sfs(216 * 27);
+  scs->shape_fcn(sf.data());
+  const int *lr = scs->adjacentNodes();
+  // reference element (unit_tests/UnitTestUtils.C:218-233): node coordinate along x = its position in the tensor line; a
+  // linear field is reproduced at every point, and every point separates two different nodes
+  static const double X[27] = {-1, 1, 1, -1, -1, 1, 1, -1, 0, 1, 0, -1, -1, 1, 1, -1, 0, 1, 0, -1, 0, 0, 0, -1, 1, 0, 0};
+  for (int ip = 0; ip < 216; ++ip) {
+    double sum = 0.0, x = 0.0;
+    for (int n = 0; n < 27; ++n) { sum += sf[ip * 27 + n]; x += sf[ip * 27 + n] * X[n]; }
+    EXPECT_NEAR(sum, 1.0, 1e-14);
+    EXPECT_TRUE(std::fabs(x) <= 1.0);
+    EXPECT_TRUE(lr[2 * ip] != lr[2 * ip + 1] && lr[2 * ip] >= 0 && lr[2 * ip] < 27 && lr[2 * ip + 1] >= 0 && lr[2 * ip + 1] < 27);
+  }
+  // s-direction points (the last 72) sit at x = -+1/sqrt(3) and point from the low-x to the high-x node
+  for (int ip = 144; ip < 216; ++ip) {
+    double x = 0.0;
+    for (int n = 0; n < 27; ++n) x += sf[ip * 27 + n] * X[n];
+    EXPECT_NEAR(std::fabs(x), 1.0 / std::sqrt(3.0), 1e-14);
+    EXPECT_TRUE(x < 0 ? X[lr[2 * ip]] < X[lr[2 * ip + 1]] : X[lr[2 * ip]] > X[lr[2 * ip + 1]]); // left node on the outer side
+  }
+  scv->shifted_shape_fcn(sfs.data());
+  const int *nn = scv->ipNodeMap();
+  int count[27] = {0};
+  for (int ip = 0; ip < 216; ++ip) {
+    ++count[nn[ip]];
+    for (int n = 0; n < 27; ++n) EXPECT_NEAR(sfs[ip * 27 + n], n == nn[ip] ? 1.0 : 0.0, 1e-15); // lumping: nodal
+  }
+  for (int n = 0; n < 27; ++n) EXPECT_TRUE(count[n] == 8);
+  // topology dispatch of the kernel builder: the momentum list exists for HEX_27, other kernels say so
+  stk::mesh::MetaData meta(3);
+  bool threw = false;
+  try {
+    std::vector<Kernel *> v;
+    ElemDataRequests req;
+    std::shared_ptr<stk::mesh::BulkData> bulk = std::make_shared<stk::mesh::BulkData>(meta);
+    SolutionOptions so;
+    build_topo_kernel<ContinuityAdvElemKernel>(stk::topology::HEX_27, *bulk, so, req);
+  } catch (const std::exception &e) {
+    threw = std::string(e.what()).find("HEXAHEDRON_27") != std::string::npos;
+  }
+  EXPECT_TRUE(threw);
+}
+
+static void test_hex27_momentum_list()
+{
+  std::printf("Hex27 element: [MomentumMass(lumped), MomentumAdvDiff] through build_topo_kernel / AssembleElemSolverAlgorithm "
+              "(gold: tests/golden/make_hex27_host_gold.py)\n");
+  stk::mesh::MetaData meta(3);
+  auto bulk = std::make_shared<stk::mesh::BulkData>(meta);
+  stk::mesh::Part *part = &meta.declare_part_with_topology("block_1", stk::topology::HEX_27);
+  VectorFieldType *coords = &meta.declare_field<double>(stk::topology::NODE_RANK, "coordinates");
+  VectorFieldType *velocity = &meta.declare_field<double>(stk::topology::NODE_RANK, "velocity", 3);
+  VectorFieldType *dpdx = &meta.declare_field<double>(stk::topology::NODE_RANK, "dpdx");
+  ScalarFieldType *density = &meta.declare_field<double>(stk::topology::NODE_RANK, "density", 3);
+  ScalarFieldType *viscosity = &meta.declare_field<double>(stk::topology::NODE_RANK, "viscosity");
+  GenericFieldType *mdot = &meta.declare_field<double>(stk::topology::ELEM_RANK, "mass_flow_rate_scs");
+  stk::mesh::put_field_on_mesh(*coords, *part, 3);
+  stk::mesh::put_field_on_mesh(*velocity, *part, 3);
+  stk::mesh::put_field_on_mesh(*dpdx, *part, 3);
+  stk::mesh::put_field_on_mesh(*density, *part, 1);
+  stk::mesh::put_field_on_mesh(*viscosity, *part, 1);
+  stk::mesh::put_field_on_mesh(*mdot, *part, AlgTraitsHex27::numScsIp_);
+  bulk->fill_generated_hex27_mesh(1, 1, 1, *part);
+  EXPECT_TRUE(bulk->num_nodes() == 27u && bulk->num_elems() == 1u && bulk->nodes_per_elem() == 27);
+  // closed-form mesh and fields of the gold script
+  auto &uN = velocity->field_of_state(stk::mesh::StateN), &uNm1 = velocity->field_of_state(stk::mesh::StateNM1);
+  auto &rN = density->field_of_state(stk::mesh::StateN), &rNm1 = density->field_of_state(stk::mesh::StateNM1);
+  for (size_t n = 0; n < bulk->num_nodes(); ++n) {
+    double *x = coords->host_data() + 3 * n;
+    const double X0 = x[0], Y0 = x[1], Z0 = x[2];
+    x[0] = X0 + 0.04 * std::sin(3.1 * Y0 + 1.7 * Z0 + 0.3);
+    x[1] = Y0 + 0.04 * std::cos(2.3 * X0 - 1.1 * Z0);
+    x[2] = Z0 + 0.04 * std::sin(1.9 * X0 + 2.9 * Y0 + 0.5);
+    const double X = x[0], Y = x[1], Z = x[2];
+    const double u[3] = {std::sin(0.9 * Y) + 0.3 * Z, std::cos(0.7 * X) * Z, 0.2 * X * Y - 0.5};
+    for (int j = 0; j < 3; ++j) {
+      velocity->host_data()[3 * n + j] = u[j];
+      uN.host_data()[3 * n + j] = 0.9 * u[j] + 0.01;
+      uNm1.host_data()[3 * n + j] = 0.8 * u[j] - 0.02;
+    }
+    viscosity->host_data()[n] = 0.3 + 0.1 * std::cos(X + 2.0 * Y);
+    const double rho = 1.0 + 0.2 * std::sin(Z);
+    density->host_data()[n] = rho;
+    rN.host_data()[n] = 0.98 * rho;
+    rNm1.host_data()[n] = 0.95 * rho;
+    dpdx->host_data()[3 * n + 0] = 0.1 * X;
+    dpdx->host_data()[3 * n + 1] = -0.2 * Y;
+    dpdx->host_data()[3 * n + 2] = 0.05 * Z;
+  }
+  for (stk::mesh::FieldBase *f : std::initializer_list<stk::mesh::FieldBase *>{coords, velocity, &uN, &uNm1, viscosity, density, &rN, &rNm1, dpdx})
+    f->modify_on_host();
+  SolutionOptions solnOpts;
+  solnOpts.includeDivU_ = 1.0;
+  HelperObjects h(bulk, stk::topology::HEX_27, 3, part);
+  h.build_system();
+  TimeIntegrator &ti = *h.realm.timeIntegrator_;
+  ti.timeStepN_ = 0.05; ti.timeStepNm1_ = 0.05; ti.gamma1_ = 1.5; ti.gamma2_ = -2.0; ti.gamma3_ = 0.5;
+  // mass_flow_rate_scs on the device (216 per element), checked against the gold before it is used
+  {
+    void *d = nullptr;
+    const size_t n = bulk->num_elems() * 216;
+    if (nalu_b200_malloc(&d, n * 8) != 0) throw std::runtime_error("malloc");
+    if (nalu_b200_mdot_scs(h.linsys->graph(), coords->device_data(), density->device_data(), velocity->device_data(), (double *)d, nullptr) != 0)
+      throw std::runtime_error(nalu_b200_last_error());
+    nalu_b200_memcpy_d2h(mdot->host_data(), d, n * 8, nullptr);
+    nalu_b200_stream_sync(nullptr);
+    nalu_b200_free(d);
+    mdot->modify_on_host();
+    const Table g = gold("hex27_host", "mdot");
+    for (int ip = 0; ip < 216; ++ip) EXPECT_NEAR(mdot->host_data()[ip], g.v[ip], 1e-14);
+  }
+  auto &req = h.assembleElemSolverAlg->dataNeededByKernels_;
+  std::unique_ptr<Kernel> mass(build_topo_kernel<MomentumMassElemKernel>(stk::topology::HEX_27, *bulk, solnOpts, req, true));
+  std::unique_ptr<Kernel> advdiff(build_topo_kernel<MomentumAdvDiffElemKernel>(stk::topology::HEX_27, *bulk, solnOpts, velocity, viscosity, req));
+  h.assembleElemSolverAlg->activeKernels_.push_back(mass.get());
+  h.assembleElemSolverAlg->activeKernels_.push_back(advdiff.get());
+  h.assembleElemSolverAlg->execute();
+  EXPECT_TRUE(h.linsys->lastAssembleKernelFamily() == 5);
+  // element lhs / rhs in (STK node, dof) order from the one-element CSR
+  const int n = 81;
+  const auto rp = h.linsys->ownedRowPtr();
+  const auto ci = h.linsys->ownedColIdx();
+  const auto v = h.linsys->ownedValues();
+  const auto r = h.linsys->ownedRhs();
+  const int32_t *en = bulk->begin_nodes(stk::mesh::Entity{stk::topology::ELEM_RANK, 0});
+  std::vector<int> rows;
+  for (int k = 0; k < 27; ++k)
+    for (int d = 0; d < 3; ++d) rows.push_back(h.linsys->entityToLID(stk::mesh::Entity{stk::topology::NODE_RANK, en[k]}) + d);
+  std::vector<int> pos(n, -1);
+  for (int j = 0; j < n; ++j) pos[rows[j]] = j;
+  std::vector<double> lhs(size_t(n) * n, 0.0), rhs(n);
+  for (int i = 0; i < n; ++i) {
+    rhs[i] = r[rows[i]];
+    EXPECT_TRUE(rp[rows[i] + 1] - rp[rows[i]] == uint64_t(n));
+    for (uint64_t q = rp[rows[i]]; q < rp[rows[i] + 1]; ++q) lhs[size_t(i) * n + pos[ci[q]]] = v[q];
+  }
+  unit_test_utils::expect_all_near(lhs, gold("hex27_host", "momentum_list::lhs"), 2e-13);
+  unit_test_utils::expect_all_near(rhs, gold("hex27_host", "momentum_list::rhs"), 2e-13);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Face/element boundary-condition algorithm (unit_tests/kernels/UnitTestFaceElemBasic.C)
 // ---------------------------------------------------------------------------------------------------
 // Hex8ElementWithBCFields (unit_tests/UnitTestUtils.h:181-256): one reference element, every side in "all_surfaces",
@@ -1105,7 +1255,9 @@ int main(int argc, char **argv)
     test_kernel_registration();
     test_scratch_views();
     test_face_elem_basic();
+    test_hex27_master_elements();
     if (gpu) {
+      test_hex27_momentum_list();
       test_face_elem_kernels();
       test_momentum_advection_diffusion();
       test_continuity_advection("advection_default");
