@@ -13,7 +13,7 @@ enum TurbulenceModel { LAMINAR = 0, KSGS = 1, SMAGORINSKY = 2, WALE = 3, SST = 4
 enum TurbulenceModelConstant {
   TM_cMu = 0, TM_kappa = 1, TM_cDESke = 2, TM_cDESkw = 3, TM_tkeProdLimitRatio = 4, TM_cmuEps = 5, TM_cEps = 6,
   TM_betaStar = 7, TM_aOne = 8, TM_betaOne = 9, TM_betaTwo = 10, TM_gammaOne = 11, TM_gammaTwo = 12,
-  TM_sigmaKOne = 13, TM_sigmaKTwo = 14, TM_sigmaWOne = 15, TM_sigmaWTwo = 16, TM_END = 27
+  TM_sigmaKOne = 13, TM_sigmaKTwo = 14, TM_sigmaWOne = 15, TM_sigmaWTwo = 16, TM_elog = 23, TM_yplus_crit = 24, TM_END = 27
 };
 class SolutionOptions {
 public:
@@ -45,6 +45,8 @@ public:
     turbModelConstantMap_[TM_sigmaKTwo] = 1.0;
     turbModelConstantMap_[TM_sigmaWOne] = 0.50;
     turbModelConstantMap_[TM_sigmaWTwo] = 0.856;
+    turbModelConstantMap_[TM_elog] = 9.8;         // src/SolutionOptions.C:769-770
+    turbModelConstantMap_[TM_yplus_crit] = 11.63;
   }
   double get_turb_model_constant(TurbulenceModelConstant turbModelEnum) const
   {

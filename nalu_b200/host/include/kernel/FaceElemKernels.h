@@ -125,5 +125,26 @@ private:
   MasterElement *meSCS_{nullptr};
 };
 
+// include/kernel/MomentumWallFunctionElemKernel.h:26-70.  The reference registers it on an AssembleElemSolverAlgorithm over the
+// wall part's faces (BcAlgTraits = AlgTraitsQuad4, one ElemDataRequests); here it is a kernel of the face/element algorithm of
+// that part (the face set already knows the element attached to each face, whose slot map carries the scatter), so BcAlgTraits =
+// AlgTraitsQuad4Hex8 and the face requirements go to faceDataNeeded_.
+template <typename BcAlgTraits>
+class MomentumWallFunctionElemKernel : public FaceElemKernel {
+public:
+  MomentumWallFunctionElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts, ElemDataRequests &dataPreReqs);
+  virtual ~MomentumWallFunctionElemKernel() {}
+  bool device_face_descriptor(nalu_b200_face_kernel_desc &, size_t first_face) override;
+  const char *name() const override { return "MomentumWallFunctionElemKernel"; }
+  double vf_shape_function_[BcAlgTraits::numFaceIp_][BcAlgTraits::nodesPerFace_];
+private:
+  MomentumWallFunctionElemKernel() = delete;
+  const double elog_, kappa_, yplusCrit_;
+  const int *ipNodeMap_;
+  VectorFieldType *velocityNp1_{nullptr}, *bcVelocity_{nullptr}, *coordinates_{nullptr};
+  ScalarFieldType *density_{nullptr}, *viscosity_{nullptr};
+  GenericFieldType *exposedAreaVec_{nullptr}, *wallFrictionVelocityBip_{nullptr}, *wallNormalDistanceBip_{nullptr};
+};
+
 } // namespace nalu
 } // namespace sierra

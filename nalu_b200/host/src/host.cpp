@@ -1632,6 +1632,57 @@ bool ContinuityOpenElemKernel<BcAlgTraits>::device_face_descriptor(nalu_b200_fac
   bind_face(d, NALU_FF_DYNAMIC_PRESSURE, dynamicPressure_, first_face);
   return true;
 }
+// ---- src/kernel/MomentumWallFunctionElemKernel.C:26-66
+template <typename BcAlgTraits>
+MomentumWallFunctionElemKernel<BcAlgTraits>::MomentumWallFunctionElemKernel(const stk::mesh::BulkData &bulkData, const SolutionOptions &solnOpts,
+                                                                           ElemDataRequests &dataPreReqs)
+    : elog_(solnOpts.get_turb_model_constant(TM_elog)), kappa_(solnOpts.get_turb_model_constant(TM_kappa)),
+      yplusCrit_(solnOpts.get_turb_model_constant(TM_yplus_crit)),
+      ipNodeMap_(MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_)->ipNodeMap())
+{
+  const stk::mesh::MetaData &metaData = bulkData.mesh_meta_data();
+  VectorFieldType *velocity = need(metaData.get_field<double>(stk::topology::NODE_RANK, "velocity"), name(), "velocity");
+  velocityNp1_ = &(velocity->field_of_state(stk::mesh::StateNP1));
+  bcVelocity_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "wall_velocity_bc"), name(), "wall_velocity_bc");
+  density_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "density"), name(), "density");
+  viscosity_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, "viscosity"), name(), "viscosity");
+  exposedAreaVec_ = need(metaData.get_field<double>(metaData.side_rank(), "exposed_area_vector"), name(), "exposed_area_vector");
+  wallFrictionVelocityBip_ =
+      need(metaData.get_field<double>(metaData.side_rank(), "wall_friction_velocity_bip"), name(), "wall_friction_velocity_bip");
+  wallNormalDistanceBip_ =
+      need(metaData.get_field<double>(metaData.side_rank(), "wall_normal_distance_bip"), name(), "wall_normal_distance_bip");
+  coordinates_ = need(metaData.get_field<double>(stk::topology::NODE_RANK, solnOpts.get_coordinates_name()), name(), "coordinates");
+  MasterElement *meFC = MasterElementRepo::get_surface_master_element(BcAlgTraits::faceTopo_);
+  get_face_shape_fn_data<BcAlgTraits>([&](double *ptr) { meFC->shape_fcn(ptr); }, vf_shape_function_);
+  dataPreReqs.add_cvfem_face_me(meFC);
+  dataPreReqs.add_coordinates_field(*coordinates_, BcAlgTraits::nDim_, CURRENT_COORDINATES);
+  dataPreReqs.add_gathered_nodal_field(*velocityNp1_, BcAlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*bcVelocity_, BcAlgTraits::nDim_);
+  dataPreReqs.add_gathered_nodal_field(*density_, 1);
+  dataPreReqs.add_gathered_nodal_field(*viscosity_, 1);
+  dataPreReqs.add_face_field(*exposedAreaVec_, BcAlgTraits::numFaceIp_, BcAlgTraits::nDim_);
+  dataPreReqs.add_face_field(*wallFrictionVelocityBip_, BcAlgTraits::numFaceIp_);
+  dataPreReqs.add_face_field(*wallNormalDistanceBip_, BcAlgTraits::numFaceIp_);
+}
+template <typename BcAlgTraits>
+bool MomentumWallFunctionElemKernel<BcAlgTraits>::device_face_descriptor(nalu_b200_face_kernel_desc &d, size_t first_face)
+{
+  clear(d);
+  d.kind = NALU_FK_MOMENTUM_WALL_FUNCTION;
+  d.wall[NALU_WALL_ELOG] = elog_;
+  d.wall[NALU_WALL_KAPPA] = kappa_;
+  d.wall[NALU_WALL_YPLUS_CRIT] = yplusCrit_;
+  bind(d, NALU_FN_COORDINATES, coordinates_);
+  bind(d, NALU_FN_VELOCITY, velocityNp1_);
+  bind(d, NALU_FN_WALL_VELOCITY_BC, bcVelocity_);
+  bind(d, NALU_FN_DENSITY, density_);
+  bind(d, NALU_FN_VISCOSITY, viscosity_);
+  bind_face(d, NALU_FF_EXPOSED_AREA_VEC, exposedAreaVec_, first_face);
+  bind_face(d, NALU_FF_WALL_FRICTION_VELOCITY_BIP, wallFrictionVelocityBip_, first_face);
+  bind_face(d, NALU_FF_WALL_NORMAL_DISTANCE_BIP, wallNormalDistanceBip_, first_face);
+  return true;
+}
+template class MomentumWallFunctionElemKernel<AlgTraitsQuad4Hex8>;
 template class MomentumSymmetryElemKernel<AlgTraitsQuad4Hex8>;
 template class MomentumOpenAdvDiffElemKernel<AlgTraitsQuad4Hex8>;
 template class ScalarOpenAdvElemKernel<AlgTraitsQuad4Hex8>;

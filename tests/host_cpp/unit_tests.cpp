@@ -1020,6 +1020,7 @@ struct Hex8ElementWithBCFields {
     density_ = node("density", 1, 1.0);
     viscosity_ = node("viscosity", 1, 1.0);
     bcVelocityOpen_ = node("open_velocity_bc", 3, 1.0);
+    bcVelocityWall_ = node("wall_velocity_bc", 3, 0.0);
     Gjui_ = node("dudx", 9, 1.0);
     scalarQ_ = node("scalar_q", 1, 1.0);
     bcScalarQ_ = node("bc_scalar_q", 1, 1.0);
@@ -1033,6 +1034,10 @@ struct Hex8ElementWithBCFields {
     stk::mesh::put_field_on_mesh(*exposedAreaVec_, *block_, 12);
     stk::mesh::put_field_on_mesh(*openMdot_, *block_, 4);
     stk::mesh::put_field_on_mesh(*dynamicP_, *block_, 4);
+    wallUtau_ = &meta_.declare_field<double>(meta_.side_rank(), "wall_friction_velocity_bip");
+    wallYp_ = &meta_.declare_field<double>(meta_.side_rank(), "wall_normal_distance_bip");
+    stk::mesh::put_field_on_mesh(*wallUtau_, *block_, 4);
+    stk::mesh::put_field_on_mesh(*wallYp_, *block_, 4);
     bulk_->fill_generated_mesh(n, n, n, *block_);
     bulk_->create_generated_sidesets("xXyYzZ");
     for (auto &fi : inits_) {
@@ -1052,9 +1057,9 @@ struct Hex8ElementWithBCFields {
   std::shared_ptr<stk::mesh::BulkData> bulk_;
   stk::mesh::Part *block_;
   SolutionOptions solnOpts_;
-  VectorFieldType *coordinates_, *velocity_, *bcVelocityOpen_, *Gjq_, *dpdx_;
+  VectorFieldType *coordinates_, *velocity_, *bcVelocityOpen_, *bcVelocityWall_, *Gjq_, *dpdx_;
   ScalarFieldType *density_, *viscosity_, *scalarQ_, *bcScalarQ_, *pressure_, *pressureBc_;
-  GenericFieldType *Gjui_, *exposedAreaVec_, *openMdot_, *dynamicP_;
+  GenericFieldType *Gjui_, *exposedAreaVec_, *openMdot_, *dynamicP_, *wallUtau_, *wallYp_;
   std::vector<std::pair<stk::mesh::Field<double> *, double>> inits_;
 };
 
@@ -1182,6 +1187,36 @@ static void test_face_elem_kernels()
     EXPECT_TRUE(vmax > 0.1);
     EXPECT_NEAR(rmax, 0.0, 1e-14);
     EXPECT_NEAR(rowsum, 0.0, 1e-14);
+  }
+  {
+    // MomentumWallFunctionElemKernel on every side of the unit cube, u = (1,1,1), wall at rest, rho = mu = 1: a point below
+    // y+_crit (y_p = 0.5, u_tau = 1: y+ = 0.5) pulls with lambda = mu / y_p |A| = 0.5, one in the log layer (y_p = 0.5,
+    // u_tau = 40: y+ = 20) with rho kappa u_tau / ln(E y+) |A|.  Per point the residual is -lambda (I - n n^T) u: the two
+    // wall-parallel components, -lambda each
+    Hex8ElementWithBCFields fx;
+    FaceHelper h(fx, 3);
+    const double utau[2] = {1.0, 40.0};
+    for (size_t f = 0; f < fx.bulk_->num_faces(); ++f)
+      for (int ip = 0; ip < 4; ++ip) {
+        fx.wallUtau_->host_data()[4 * f + ip] = utau[ip & 1];
+        fx.wallYp_->host_data()[4 * f + ip] = 0.5;
+      }
+    fx.wallUtau_->modify_on_host();
+    fx.wallYp_->modify_on_host();
+    fx.solnOpts_.initialize_turbulence_constants(); // TM_elog, TM_kappa, TM_yplus_crit (src/SolutionOptions.C:742-770)
+    MomentumWallFunctionElemKernel<AlgTraitsQuad4Hex8> k(*fx.bulk_, fx.solnOpts_, h.alg->faceDataNeeded_);
+    h.alg->activeKernels_.push_back(&k);
+    h.alg->execute();
+    const double lam[2] = {1.0 / 0.5 * 0.25, 0.41 * 40.0 / std::log(9.8 * 20.0) * 0.25};
+    const auto r = h.linsys->ownedRhs();
+    const auto v = h.linsys->ownedValues();
+    double rs = 0, vs = 0;
+    for (double x : r) rs += x;
+    for (double x : v) vs += x;
+    // 6 faces x 4 points, two of each kind per face, two tangential components each
+    EXPECT_NEAR(rs, -6.0 * 2.0 * 2.0 * (lam[0] + lam[1]), 1e-12);
+    // lhs: lambda (I - n n^T) x shape functions (summing to 1): trace 2 per point, the off-diagonal n_i n_j vanish on a cube
+    EXPECT_NEAR(vs, 6.0 * 2.0 * 2.0 * (lam[0] + lam[1]), 1e-12);
   }
   {
     Hex8ElementWithBCFields fx;
