@@ -260,6 +260,9 @@ def run_ours(args):
     nzg = n if strong else n * world   # element layers of the global box
     L = lib.lib()
     lib.tune(box_kernel=args.box_kernel)
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1: give the host graph builder this rank's share of the cores back
+        lib.tune(host_threads=max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world))))
 
     # ---- mesh, graph (once per mesh; outside the timed region) ------------------------------
     t0 = time.perf_counter()

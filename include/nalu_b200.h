@@ -267,6 +267,8 @@ int nalu_b200_last_assemble_mode(void);
  *   "general_minb"    CTAs per SM the general kernel's registers are bounded for: 2, 3 or 4 (default)
  *   "general_scatter" coloured scatter of the general kernel: 1 (default) value-less reductions (red.global.add.f64), 0
  *                     load / add / store; one element of a colour touches an address either way: same sums, bit for bit
+ *   "host_threads"    OpenMP threads of the host graph builder (graph_create / graph_finalize) for the calling thread; launchers
+ *                     such as torchrun export OMP_NUM_THREADS=1, which makes a 17 M-node graph take 27 s instead of 9
  * The initial values come from the environment variables NALU_BOX_KERNEL, NALU_BOX_ZCHUNK, NALU_SPLIT_LISTS,
  * NALU_CONT_BOX, read once when the library is first used -- nothing on the launch path reads the environment.
  * Returns NALU_B200_ERR_ARG for an unknown name. */

@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" boundary declared in include/nalu_b200.h.
 #include "internal.h"
+#include <omp.h>
 #include <cstdlib>
 
 #include <atomic>
@@ -192,6 +193,10 @@ int nalu_b200_tune(const char *name, int32_t value)
   else if (n == "urow_owner") t.urow_owner = value != 0;
   else if (n == "urow_minb") t.urow_minb = value < 2 ? 2 : (value > 4 ? 4 : value);
   else if (n == "color_chunk") t.color_chunk = value > 0 ? value : 0;
+  else if (n == "host_threads") {
+    // OpenMP threads of the host graph builder for the calling thread (launchers such as torchrun export OMP_NUM_THREADS=1)
+    if (value > 0) omp_set_num_threads(value);
+  }
   else {
     set_error("tune: unknown knob " + n);
     return NALU_B200_ERR_ARG;

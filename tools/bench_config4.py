@@ -115,6 +115,9 @@ def main():
     peak = bench.load_peaks()[0]
     nn = m.n_nodes
 
+    if world > 1:
+        from nalu_b200 import lib as _l
+        _l.tune(host_threads=max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     # ---- scalar systems: tke and sdr share one graph ------------------------------------------------------------------
     t0 = time.perf_counter()
     ls1 = DeviceCsrLinearSystem(m, 1, exchange=nd.make_exchange(rank, world) if world > 1 else None)

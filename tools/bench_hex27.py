@@ -100,6 +100,9 @@ def run(n=48, steps=10, warmup=3):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
             own_group = True
     dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
+    if world > 1:
+        from nalu_b200 import lib as _l
+        _l.tune(host_threads=max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     nzg = n * world
     m = M.hex27_box_rank(n, n, nzg, rank, world)
     M.perturb_coords_by_gid(m, AMPLITUDE)
