@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "row_owner or row_thread or exodus or config4" 2>&1 | tail -5
+python tools/bench_config1_list.py 128 5 > gpurun_out/s3x_config1_list_128.json 2> gpurun_out/s3x_err.txt
+python -c "import json; d=json.loads(open('gpurun_out/s3x_config1_list_128.json').read().strip().splitlines()[-1]); print('config1 list: general', round(d['general']['Melem_per_s'],1), 'row-owner', d['auto']['kernel_family'], round(d['auto']['Melem_per_s'],1), d['auto_vs_general_values_relerr'], d['auto_vs_general_rhs_relerr'])"
+timeout 600 python tools/bench_config4.py --nx 128 --layers 128 --steps 3 --nobox --no-momentum --no-oracle-check > gpurun_out/s3x_config4_nobox_128.json 2>> gpurun_out/s3x_err.txt
+python -c "import json; d=json.loads(open('gpurun_out/s3x_config4_nobox_128.json').read().strip().splitlines()[-1]); print('config4 nobox: tke', d['tke']['assemble_mode'], round(d['tke']['kernel_melem_s_per_gpu'],1), 'sdr', round(d['sdr']['kernel_melem_s_per_gpu'],1), 'Melem/s')"
+python tools/bench_momentum_list.py 128 5 1 nobox > gpurun_out/s3x_urow_128.json 2>> gpurun_out/s3x_err.txt
+python -c "import json; d=json.loads(open('gpurun_out/s3x_urow_128.json').read().strip().splitlines()[-1]); print('momentum list nobox: row-owner', round(d['auto']['Melem_per_s'],1))"
+tail -3 gpurun_out/s3x_err.txt
