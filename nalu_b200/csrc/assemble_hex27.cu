@@ -411,13 +411,19 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
       const double md = sg * S.rec[12][ip];
       const double l1 = S.oned[3 + gb][ip], d1b = S.oned[12 + gb][ip], l2 = S.oned[6 + gc][ip], d2c = S.oned[15 + gc][ip];
       const double t1 = l1 * l2, t2 = d1b * l2, t3 = l1 * d2c;
+      // h = G grad_xi N_c with grad_xi N_c = (l0' t1, l0 t2, l0 t3): the parts common to the three columns of the line first
+      double ga[3], gb[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        ga[i] = G[i][0] * t1;
+        gb[i] = G[i][1] * t2 + G[i][2] * t3;
+      }
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         const double l0 = S.oned[m][ip], d0a = S.oned[9 + m][ip];
-        const double d0 = d0a * t1, d1 = l0 * t2, d2 = l0 * t3;
         double h[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) h[i] = G[i][0] * d0 + G[i][1] * d1 + G[i][2] * d2;
+        for (int i = 0; i < 3; ++i) h[i] = ga[i] * d0a + gb[i] * l0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
