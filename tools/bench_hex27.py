@@ -166,6 +166,13 @@ def run(n=48, steps=10, warmup=3):
         peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")))["assemble_hex27"]
+        if tj["elements"] == ne:
+            traffic = {"bytes": tj["bytes"], "source": "static: " + tj["source"]}
+    except Exception:
+        pass
     got_v = ls.owned_values().cpu().numpy()
     got_b = ls.owned_rhs().cpu().numpy()
     rp, ci = ls.rowptr().astype(np.int64), ls.colidx().astype(np.int64)
@@ -241,7 +248,7 @@ def run(n=48, steps=10, warmup=3):
         "kernel_family": mode, "gpu_launches": int(l1 - l0) // max(warmup, 1),
         "nodes_per_s_M": n_owned_nodes * world / tot_ms / 1e3,
         "roofline": {"bound": "hbm", "achieved": alg_bytes / tot_ms / 1e6, "peak": peak, "unit": "GB/s",
-                     "frac": alg_bytes / tot_ms / 1e6 / peak, "traffic": None,
+                     "frac": alg_bytes / tot_ms / 1e6 / peak, "traffic": traffic,
                      "algorithmic_bytes_per_elem": alg_bytes / ne,
                      "fp64": {"flop_per_elem_static": 2 * (216 * (27 * 23 + 60) + 243 * 16 * 81),
                               "note": "FMA = 2 flop, static count of phase B + C"}},
