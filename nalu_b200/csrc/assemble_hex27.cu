@@ -491,6 +491,172 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_kernel(const __gri
   }
 }
 
+// ---- one-dof systems on Hex27: ContinuityAdvElemKernel (src/kernel/ContinuityAdvElemKernel.C:95-175) and ScalarAdvDiffElemKernel
+// (src/kernel/ScalarAdvDiffElemKernel.C:69-127) with AlgTraitsHex27, default options ------------------------------------------
+// Both add, per point, (b . grad_xi N_c + a N_c) to the left node's row and subtract it from the right node's:
+//   continuity  b = -cof(J)^T A / det J (so that b . grad_xi N_c = -dN_c/dx . A), a = 0, flux f = mdot / tau with
+//               mdot = (rho u)_ip . A - tau (grad p . A - (Gp)_ip . A) and grad p . A = -b . sum_c p_c grad_xi N_c
+//   scalar      b = -Gamma_ip cof(J)^T A / det J, a = mdot_ip, residual = -(row . q)
+// Same phases as the momentum kernel with a 5-double record per point.
+struct OneDofParams {
+  Tables T;
+  const int *elem_list;
+  const int *elem_nodes;
+  const unsigned char *elem_slot;
+  const int *node_row;
+  const long long *browptr;
+  const double *coords;
+  const double *f0, *f1, *f2, *f3; // continuity: pressure, density, velocity, Gpdx; scalar: scalarQ, diffFluxCoeff
+  const double *mdot;              // scalar: [nElem][216]
+  double tau;                      // continuity: projTimeScale = dt / gamma1
+  double *values, *rhs;
+  int *err;
+};
+struct SmemOneDof {
+  double rec[5][NIP];    // b (3), a, f
+  double oned[18][NIP];
+  double part[NPE * 9];
+  double x[NPE][3], u[NPE][3], gp[NPE][3], p[NPE], rho[NPE];
+  int row[NPE], inc_ptr[NPE + 1], inc[2 * NIP];
+};
+
+template <int KIND> // 0 continuity, 1 scalar adv-diff
+__global__ void __launch_bounds__(kThreads, 2) assemble_hex27_onedof_kernel(const __grid_constant__ OneDofParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemOneDof &S = *reinterpret_cast<SmemOneDof *>(smem_raw);
+  const int t = threadIdx.x;
+  const long long e = P.elem_list ? P.elem_list[blockIdx.x] : (long long)blockIdx.x;
+  const int *en = P.elem_nodes + e * NPE;
+  if (t < NPE) {
+    const int n = en[t];
+    S.row[t] = P.node_row[n];
+    S.p[t] = P.f0[n];   // pressure | scalarQ
+    S.rho[t] = P.f1[n]; // density | diffFluxCoeff
+  }
+  if (t < 81) {
+    const int n = en[t / 3];
+    S.x[t / 3][t % 3] = P.coords[(size_t)n * 3 + t % 3];
+  } else if (KIND == 0 && t >= 96 && t < 96 + 81) {
+    const int q = t - 96, n = en[q / 3];
+    S.u[q / 3][q % 3] = P.f2[(size_t)n * 3 + q % 3];
+    S.gp[q / 3][q % 3] = P.f3[(size_t)n * 3 + q % 3];
+  } else if (t >= 192 && t < 192 + NPE + 1) {
+    S.inc_ptr[t - 192] = P.T.inc_ptr[t - 192];
+  }
+  for (int q = t; q < 2 * NIP; q += kThreads) S.inc[q] = P.T.inc[q];
+  __syncthreads();
+
+  if (t < NIP) {
+    double L[3][3], D[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lagrange3_dev(P.T.pt[3 * t + d], L[d], D[d]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        S.oned[3 * d + a][t] = L[d][a];
+        S.oned[9 + 3 * d + a][t] = D[d][a];
+      }
+    }
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double pg[3] = {0, 0, 0}, ru[3] = {0, 0, 0}, gpi[3] = {0, 0, 0}, gam = 0.0;
+    const double x0 = S.x[0][0], y0 = S.x[0][1], z0 = S.x[0][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const double t1 = L[1][b] * L[2][c], t2 = D[1][b] * L[2][c], t3 = L[1][b] * D[2][c];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const int n = stk_of(a + 3 * (b + 3 * c));
+          const double d0 = D[0][a] * t1, d1 = L[0][a] * t2, d2 = L[0][a] * t3, sf = L[0][a] * t1;
+          const double xn[3] = {S.x[n][0] - x0, S.x[n][1] - y0, S.x[n][2] - z0};
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            J[i][0] += d0 * xn[i]; J[i][1] += d1 * xn[i]; J[i][2] += d2 * xn[i];
+          }
+          if (KIND == 0) {
+            pg[0] += d0 * S.p[n]; pg[1] += d1 * S.p[n]; pg[2] += d2 * S.p[n];
+            const double sr = sf * S.rho[n];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              ru[i] += sr * S.u[n][i];
+              gpi[i] += sf * S.gp[n][i];
+            }
+          } else {
+            gam += sf * S.rho[n];
+          }
+        }
+      }
+    double C[3][3];
+    const double det = cofactor(J, C);
+    if (!(det > 0.0)) atomicExch(P.err, 1);
+    const double inv = 1.0 / det;
+    const int d = P.T.dir[t];
+    const double w = P.T.wdir[t];
+    double A[3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) A[i] = w * (d == 0 ? C[i][0] : d == 1 ? C[i][1] : C[i][2]);
+    const double scale = KIND == 0 ? -inv : -gam * inv;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) b[k] = scale * (C[0][k] * A[0] + C[1][k] * A[1] + C[2][k] * A[2]);
+    S.rec[0][t] = b[0]; S.rec[1][t] = b[1]; S.rec[2][t] = b[2];
+    if (KIND == 0) {
+      const double dpdxA = -(b[0] * pg[0] + b[1] * pg[1] + b[2] * pg[2]);
+      const double mdot = (ru[0] * A[0] + ru[1] * A[1] + ru[2] * A[2]) -
+                          P.tau * (dpdxA - (gpi[0] * A[0] + gpi[1] * A[1] + gpi[2] * A[2]));
+      S.rec[3][t] = 0.0;
+      S.rec[4][t] = mdot / P.tau;
+    } else {
+      S.rec[3][t] = P.mdot[e * NIP + t];
+      S.rec[4][t] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  const int rr = t / 9, g = t - 9 * rr;
+  if (rr < NPE) {
+    const int r = c_row_order[rr];
+    const int gb = g % 3, gc = g / 3;
+    double acc[3] = {0.0, 0.0, 0.0}, rs = 0.0;
+    const int q0 = S.inc_ptr[r], q1 = S.inc_ptr[r + 1];
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+      const int code = S.inc[q], ip = code >> 1;
+      const double sg = (code & 1) ? -1.0 : 1.0;
+      const double l1 = S.oned[3 + gb][ip], d1b = S.oned[12 + gb][ip], l2 = S.oned[6 + gc][ip], d2c = S.oned[15 + gc][ip];
+      const double t1 = l1 * l2, t2 = d1b * l2, t3 = l1 * d2c;
+      const double ba = sg * S.rec[0][ip] * t1;
+      const double bb = sg * (S.rec[1][ip] * t2 + S.rec[2][ip] * t3 + S.rec[3][ip] * t1);
+      rs += sg * S.rec[4][ip];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) acc[m] += ba * S.oned[9 + m][ip] + bb * S.oned[m][ip];
+    }
+    const int rn = S.row[r];
+    double *rowv = P.values + P.browptr[rn];
+    const unsigned char *slots = P.elem_slot + (e * NPE + r) * NPE;
+    double pr = 0.0;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const int c = P.T.stk[m + 3 * g];
+      if (KIND == 1) pr -= acc[m] * S.p[c];
+      if (P.elem_list) red_add(rowv + (int)slots[c], acc[m]);
+      else atomicAdd(rowv + (int)slots[c], acc[m]);
+    }
+    if (KIND == 0 && g == 0) pr -= rs;
+    S.part[t] = pr;
+  }
+  __syncthreads();
+  if (t < NPE) {
+    double v = 0.0;
+#pragma unroll
+    for (int gg = 0; gg < 9; ++gg) v += S.part[t * 9 + gg];
+    double *dst = P.rhs + S.row[c_row_order[t]];
+    if (P.elem_list) red_add(dst, v);
+    else atomicAdd(dst, v);
+  }
+}
+
 // mass_flow_rate_scs of a Hex27 element: mdot_ip = (sum_n N_n rho_n u_n) . A_ip (the unit tests' calc_mass_flow_rate_scs,
 // unit_tests/kernels/UnitTestKernelUtils.C:547-628, instantiated with AlgTraitsHex27); thread = (element, point)
 __global__ void __launch_bounds__(kThreads) mdot_hex27_kernel(Tables T, long long n_elems, const int *elem_nodes, const double *coords,
@@ -539,8 +705,19 @@ static bool classify_hex27(const nalu_b200_kernel_desc *k, int nk, int &ia, int 
   return ia >= 0;
 }
 
+static bool hex27_onedof_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
+{
+  if (g.npe != 27 || g.ndof != 1 || nk != 1 || !g.d_elem_nodes27 || !g.d_elem_slot27 || k[0].options != 0 || !k[0].nodal[NALU_F_COORDINATES])
+    return false;
+  if (k[0].kind == NALU_K_CONTINUITY_ADV)
+    return k[0].nodal[NALU_F_VELOCITY] && k[0].nodal[NALU_F_DENSITY] && k[0].nodal[NALU_F_PRESSURE] && k[0].nodal[NALU_F_DPDX];
+  if (k[0].kind == NALU_K_SCALAR_ADV_DIFF) return k[0].nodal[NALU_F_SCALARQ] && k[0].nodal[NALU_F_VISCOSITY] && k[0].mass_flow_rate;
+  return false;
+}
+
 bool hex27_supported(const Graph &g, const nalu_b200_kernel_desc *k, int nk)
 {
+  if (hex27_onedof_supported(g, k, nk)) return true;
   int ia, im;
   if (g.npe != 27 || g.ndof != 3 || nk < 1 || nk > 2 || !g.d_elem_nodes27 || !g.d_elem_slot27 || !classify_hex27(k, nk, ia, im)) return false;
   const nalu_b200_kernel_desc &a = k[ia];
@@ -559,6 +736,46 @@ int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc *kernels, 
                           cudaStream_t stream)
 {
   using namespace hex27;
+  if (hex27_onedof_supported(g, kernels, nk)) {
+    const nalu_b200_kernel_desc &k = kernels[0];
+    const Tables *T = nullptr;
+    int rc = get_tables(&T);
+    if (rc) return rc;
+    OneDofParams P;
+    P.T = *T;
+    P.elem_nodes = g.d_elem_nodes27;
+    P.elem_slot = g.d_elem_slot27;
+    P.node_row = g.d_node_row;
+    P.browptr = (const long long *)g.d_browptr;
+    P.coords = k.nodal[NALU_F_COORDINATES];
+    const bool cont = k.kind == NALU_K_CONTINUITY_ADV;
+    P.f0 = cont ? k.nodal[NALU_F_PRESSURE] : k.nodal[NALU_F_SCALARQ];
+    P.f1 = cont ? k.nodal[NALU_F_DENSITY] : k.nodal[NALU_F_VISCOSITY];
+    P.f2 = cont ? k.nodal[NALU_F_VELOCITY] : nullptr;
+    P.f3 = cont ? k.nodal[NALU_F_DPDX] : nullptr;
+    P.mdot = k.mass_flow_rate;
+    P.tau = k.dt / k.gamma1;
+    P.values = d_values;
+    P.rhs = d_rhs;
+    P.err = g.d_err;
+    auto kern = cont ? assemble_hex27_onedof_kernel<0> : assemble_hex27_onedof_kernel<1>;
+    NALU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemOneDof)));
+    if (g.d_color_elems && !g.color_ptr.empty()) {
+      for (size_t c = 0; c + 1 < g.color_ptr.size(); ++c) {
+        const long long n = g.color_ptr[c + 1] - g.color_ptr[c];
+        if (n <= 0) continue;
+        P.elem_list = g.d_color_elems + g.color_ptr[c];
+        kern<<<(unsigned)n, kThreads, sizeof(SmemOneDof), stream>>>(P);
+        count_launch();
+      }
+    } else if (g.n_elems > 0) {
+      P.elem_list = nullptr;
+      kern<<<(unsigned)g.n_elems, kThreads, sizeof(SmemOneDof), stream>>>(P);
+      count_launch();
+    }
+    NALU_CUDA(cudaGetLastError());
+    return NALU_B200_OK;
+  }
   int ia, im;
   if (!classify_hex27(kernels, nk, ia, im)) return NALU_B200_ERR_ARG;
   const nalu_b200_kernel_desc &k = kernels[ia];

@@ -466,7 +466,8 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   if (g.npe == 27) { // Hex27 graphs (nalu_b200_graph_create_topo): one kernel, assemble_hex27.cu
     if (!hex27_supported(g, kernels, nk)) {
       set_error("assemble_elem: Hex27 graphs take [MomentumMassElemKernel(lumped)]? + MomentumAdvDiffElemKernel (default options, "
-                "one velocity field) on a 3-dof system only");
+                "one velocity field) on a 3-dof system, [ContinuityAdvElemKernel] or [ScalarAdvDiffElemKernel] (default options) "
+                "on a 1-dof system");
       return NALU_B200_ERR_ARG;
     }
     for (int i = 0; i < nk; ++i)

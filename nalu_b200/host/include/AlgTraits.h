@@ -11,7 +11,7 @@ struct AlgTraitsHex8 {
   static constexpr int numGp_ = 8;
   static constexpr stk::topology::topology_t topo_ = stk::topology::HEX_8;
 };
-// include/AlgTraits.h:27-34: BASELINE config 5; MomentumAdvDiffElemKernel and MomentumMassElemKernel are instantiated for it
+// include/AlgTraits.h:27-34: BASELINE config 5; MomentumAdvDiff, MomentumMass, ContinuityAdv and ScalarAdvDiff are instantiated for it
 struct AlgTraitsHex27 {
   static constexpr int nDim_ = 3;
   static constexpr int nodesPerElement_ = 27;

@@ -24,5 +24,7 @@ private:
   const bool meshMotion_, shiftMdot_, shiftPoisson_, reducedSensitivities_;
   const int *lrscv_;
 };
+template <>
+struct has_hex27_instantiation<ContinuityAdvElemKernel> : std::true_type {};
 } // namespace nalu
 } // namespace sierra

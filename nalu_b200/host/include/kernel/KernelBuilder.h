@@ -30,9 +30,9 @@ Kernel *build_topo_kernel(stk::topology topo, Args &&...args)
     return new T<AlgTraitsHex8>(std::forward<Args>(args)...);
   case stk::topology::HEX_27:
     if constexpr (has_hex27_instantiation<T>::value) return new T<AlgTraitsHex27>(std::forward<Args>(args)...);
-    else throw std::runtime_error("build_topo_kernel: this kernel is not instantiated for HEXAHEDRON_27 (the momentum list is)");
+    else throw std::runtime_error("build_topo_kernel: this kernel is not instantiated for HEXAHEDRON_27 (the momentum list, ContinuityAdv and ScalarAdvDiff are)");
   default:
-    throw std::runtime_error("build_topo_kernel: only Hex8 (and Hex27 for the momentum list) is on this path (topology " + topo.name() + ")");
+    throw std::runtime_error("build_topo_kernel: only Hex8 (and Hex27 for four kernels) is on this path (topology " + topo.name() + ")");
   }
 }
 

@@ -42,5 +42,7 @@ private:
   const int *lrscv_;
   const bool shiftedGradOp_;
 };
+template <>
+struct has_hex27_instantiation<ScalarAdvDiffElemKernel> : std::true_type {};
 } // namespace nalu
 } // namespace sierra

@@ -1374,9 +1374,11 @@ NALU_B200_DECLARE_KERNEL(ScalarDiffElemKernel)
 NALU_B200_DECLARE_KERNEL(MomentumMassElemKernel)
 NALU_B200_DECLARE_KERNEL(ContinuityMassElemKernel)
 NALU_B200_DECLARE_KERNEL(ScalarMassElemKernel)
-// Hex27 (BASELINE config 5): the momentum list
+// Hex27 (BASELINE config 5): the momentum list and the one-dof kernels assemble_hex27.cu serves
 template class MomentumAdvDiffElemKernel<AlgTraitsHex27>;
 template class MomentumMassElemKernel<AlgTraitsHex27>;
+template class ContinuityAdvElemKernel<AlgTraitsHex27>;
+template class ScalarAdvDiffElemKernel<AlgTraitsHex27>;
 
 
 // ================================================================================================

@@ -335,6 +335,65 @@ def momentum_adv_diff(elem_nodes, coords, velocity, viscosity, mdot, include_div
     return lhs.reshape(E, 81, 81), rhs.reshape(E, 81)
 
 
+def continuity_adv(elem_nodes, coords, velocity, density, pressure, gpdx, dt, gamma1):
+    """ContinuityAdvElemKernel<AlgTraitsHex27>::execute (src/kernel/ContinuityAdvElemKernel.C:95-175), default options (no
+    shifted mdot / Poisson operator, full sensitivities): lhs [E,27,27], rhs [E,27]"""
+    me = scs()
+    E = elem_nodes.shape[0]
+    proj_time_scale = dt / gamma1
+    c = np.asarray(coords)[elem_nodes]
+    u = np.asarray(velocity)[elem_nodes]
+    rho = np.asarray(density)[elem_nodes]
+    p = np.asarray(pressure)[elem_nodes]
+    gp = np.asarray(gpdx)[elem_nodes]
+    areav = me.area_vectors(c)
+    dndx, _ = me.grad_op(c)
+    sf = me.shape_fcn
+    lhs = np.zeros((E, 27, 27))
+    rhs = np.zeros((E, 27))
+    for ip in range(NIP):
+        il, ir = me.lrscv[ip]
+        a = areav[:, ip]
+        w_gpdx_ip = np.einsum("n,enj->ej", sf[ip], gp)
+        w_rho_u_ip = np.einsum("n,en,enj->ej", sf[ip], rho, u)
+        w_dpdx_ip = np.einsum("enj,en->ej", dndx[:, ip], p)
+        lhsfac = -np.einsum("enj,ej->en", dndx[:, ip], a)
+        lhs[:, il] += lhsfac
+        lhs[:, ir] -= lhsfac
+        mdot = np.einsum("ej,ej->e", w_rho_u_ip - proj_time_scale * (w_dpdx_ip - w_gpdx_ip), a)
+        rhs[:, il] -= mdot / proj_time_scale
+        rhs[:, ir] += mdot / proj_time_scale
+    return lhs, rhs
+
+
+def scalar_adv_diff(elem_nodes, coords, scalar_q, diff_flux_coeff, mdot):
+    """ScalarAdvDiffElemKernel<AlgTraitsHex27>::execute (src/kernel/ScalarAdvDiffElemKernel.C:69-127), default options:
+    lhs [E,27,27], rhs [E,27]"""
+    me = scs()
+    E = elem_nodes.shape[0]
+    c = np.asarray(coords)[elem_nodes]
+    q = np.asarray(scalar_q)[elem_nodes]
+    gam = np.asarray(diff_flux_coeff)[elem_nodes]
+    areav = me.area_vectors(c)
+    dndx, _ = me.grad_op(c)
+    sf = me.shape_fcn
+    lhs = np.zeros((E, 27, 27))
+    rhs = np.zeros((E, 27))
+    for ip in range(NIP):
+        il, ir = me.lrscv[ip]
+        tmdot = mdot[:, ip]
+        gam_ip = gam @ sf[ip]
+        lhsfac_adv = sf[ip][None, :] * tmdot[:, None]
+        lhsfac_diff = -gam_ip[:, None] * np.einsum("enj,ej->en", dndx[:, ip], areav[:, ip])
+        tot = lhsfac_adv + lhsfac_diff
+        lhs[:, il] += tot
+        lhs[:, ir] -= tot
+        flux = np.einsum("en,en->e", tot, q)   # qAdv + qDiff
+        rhs[:, il] -= flux
+        rhs[:, ir] += flux
+    return lhs, rhs
+
+
 _SCV = None
 
 

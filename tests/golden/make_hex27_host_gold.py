@@ -33,10 +33,15 @@ def main():
     l2, r2 = H.momentum_mass(m.elem_nodes, c, u, un, um, rho, rn, rm, gp, dt=0.05, gamma1=1.5, gamma2=-2.0, gamma3=0.5, lumped=True)
     # element ordering of the gold = (STK node ordinal, dof)
     lhs, rhs = (l1 + l2)[0], (r1 + r2)[0]
+    X, Y, Z = c[:, 0], c[:, 1], c[:, 2]
+    pr = 0.5 * np.cos(0.8 * X) * np.sin(0.6 * Y) + 0.1 * Z
+    lc, rc = H.continuity_adv(m.elem_nodes, c, u, rho, pr, gp, dt=0.05, gamma1=1.5)
     out = {"source": "oracle/hex27.py via tests/golden/make_hex27_host_gold.py (no reference gold exists for Hex27 kernels)",
            "tables": {"momentum_list::lhs": {"dims": [81, 81], "values": [float(x) for x in lhs.ravel()]},
                       "momentum_list::rhs": {"dims": [81], "values": [float(x) for x in rhs]},
-                      "mdot": {"dims": [216], "values": [float(x) for x in mdot[0]]}}}
+                      "mdot": {"dims": [216], "values": [float(x) for x in mdot[0]]},
+                      "continuity::lhs": {"dims": [27, 27], "values": [float(x) for x in lc[0].ravel()]},
+                      "continuity::rhs": {"dims": [27], "values": [float(x) for x in rc[0]]}}}
     with open(os.path.join(ROOT, "tests", "golden", "hex27_host.json"), "w") as fh:
         json.dump(out, fh)
     print("wrote hex27_host.json", np.abs(lhs).max(), np.abs(rhs).max())

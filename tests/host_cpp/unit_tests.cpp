@@ -895,7 +895,7 @@ static void test_hex27_master_elements()
     ElemDataRequests req;
     std::shared_ptr<stk::mesh::BulkData> bulk = std::make_shared<stk::mesh::BulkData>(meta);
     SolutionOptions so;
-    build_topo_kernel<ContinuityAdvElemKernel>(stk::topology::HEX_27, *bulk, so, req);
+    build_topo_kernel<MomentumBuoyancySrcElemKernel>(stk::topology::HEX_27, *bulk, so, req);
   } catch (const std::exception &e) {
     threw = std::string(e.what()).find("HEXAHEDRON_27") != std::string::npos;
   }
@@ -997,6 +997,67 @@ static void test_hex27_momentum_list()
   }
   unit_test_utils::expect_all_near(lhs, gold("hex27_host", "momentum_list::lhs"), 2e-13);
   unit_test_utils::expect_all_near(rhs, gold("hex27_host", "momentum_list::rhs"), 2e-13);
+}
+
+static void test_hex27_continuity()
+{
+  std::printf("Hex27 element: ContinuityAdvElemKernel through build_topo_kernel / AssembleElemSolverAlgorithm (oracle gold)\n");
+  stk::mesh::MetaData meta(3);
+  auto bulk = std::make_shared<stk::mesh::BulkData>(meta);
+  stk::mesh::Part *part = &meta.declare_part_with_topology("block_1", stk::topology::HEX_27);
+  VectorFieldType *coords = &meta.declare_field<double>(stk::topology::NODE_RANK, "coordinates");
+  VectorFieldType *velocity = &meta.declare_field<double>(stk::topology::NODE_RANK, "velocity", 2);
+  VectorFieldType *dpdx = &meta.declare_field<double>(stk::topology::NODE_RANK, "dpdx");
+  ScalarFieldType *density = &meta.declare_field<double>(stk::topology::NODE_RANK, "density", 2);
+  ScalarFieldType *pressure = &meta.declare_field<double>(stk::topology::NODE_RANK, "pressure");
+  stk::mesh::put_field_on_mesh(*coords, *part, 3);
+  stk::mesh::put_field_on_mesh(*velocity, *part, 3);
+  stk::mesh::put_field_on_mesh(*dpdx, *part, 3);
+  stk::mesh::put_field_on_mesh(*density, *part, 1);
+  stk::mesh::put_field_on_mesh(*pressure, *part, 1);
+  bulk->fill_generated_hex27_mesh(1, 1, 1, *part);
+  for (size_t n = 0; n < bulk->num_nodes(); ++n) {
+    double *x = coords->host_data() + 3 * n;
+    const double X0 = x[0], Y0 = x[1], Z0 = x[2];
+    x[0] = X0 + 0.04 * std::sin(3.1 * Y0 + 1.7 * Z0 + 0.3);
+    x[1] = Y0 + 0.04 * std::cos(2.3 * X0 - 1.1 * Z0);
+    x[2] = Z0 + 0.04 * std::sin(1.9 * X0 + 2.9 * Y0 + 0.5);
+    const double X = x[0], Y = x[1], Z = x[2];
+    velocity->host_data()[3 * n + 0] = std::sin(0.9 * Y) + 0.3 * Z;
+    velocity->host_data()[3 * n + 1] = std::cos(0.7 * X) * Z;
+    velocity->host_data()[3 * n + 2] = 0.2 * X * Y - 0.5;
+    density->host_data()[n] = 1.0 + 0.2 * std::sin(Z);
+    pressure->host_data()[n] = 0.5 * std::cos(0.8 * X) * std::sin(0.6 * Y) + 0.1 * Z;
+    dpdx->host_data()[3 * n + 0] = 0.1 * X;
+    dpdx->host_data()[3 * n + 1] = -0.2 * Y;
+    dpdx->host_data()[3 * n + 2] = 0.05 * Z;
+  }
+  for (stk::mesh::FieldBase *f : std::initializer_list<stk::mesh::FieldBase *>{coords, velocity, density, pressure, dpdx}) f->modify_on_host();
+  SolutionOptions solnOpts;
+  HelperObjects h(bulk, stk::topology::HEX_27, 1, part);
+  h.build_system();
+  TimeIntegrator &ti = *h.realm.timeIntegrator_;
+  ti.timeStepN_ = 0.05; ti.timeStepNm1_ = 0.05; ti.gamma1_ = 1.5; ti.gamma2_ = -2.0; ti.gamma3_ = 0.5;
+  std::unique_ptr<Kernel> k(build_topo_kernel<ContinuityAdvElemKernel>(stk::topology::HEX_27, *bulk, solnOpts,
+                                                                         h.assembleElemSolverAlg->dataNeededByKernels_));
+  h.assembleElemSolverAlg->activeKernels_.push_back(k.get());
+  h.assembleElemSolverAlg->execute();
+  EXPECT_TRUE(h.linsys->lastAssembleKernelFamily() == 5);
+  const auto rp = h.linsys->ownedRowPtr();
+  const auto ci = h.linsys->ownedColIdx();
+  const auto v = h.linsys->ownedValues();
+  const auto r = h.linsys->ownedRhs();
+  const int32_t *en = bulk->begin_nodes(stk::mesh::Entity{stk::topology::ELEM_RANK, 0});
+  std::vector<int> rows(27), pos(27, -1);
+  for (int kk = 0; kk < 27; ++kk) rows[kk] = h.linsys->entityToLID(stk::mesh::Entity{stk::topology::NODE_RANK, en[kk]});
+  for (int j = 0; j < 27; ++j) pos[rows[j]] = j;
+  std::vector<double> lhs(27 * 27, 0.0), rhs(27);
+  for (int i = 0; i < 27; ++i) {
+    rhs[i] = r[rows[i]];
+    for (uint64_t q = rp[rows[i]]; q < rp[rows[i] + 1]; ++q) lhs[size_t(i) * 27 + pos[ci[q]]] = v[q];
+  }
+  unit_test_utils::expect_all_near(lhs, gold("hex27_host", "continuity::lhs"), 1e-13);
+  unit_test_utils::expect_all_near(rhs, gold("hex27_host", "continuity::rhs"), 2e-12); // entries ~ mdot / tau = 30 mdot
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1293,6 +1354,7 @@ int main(int argc, char **argv)
     test_hex27_master_elements();
     if (gpu) {
       test_hex27_momentum_list();
+      test_hex27_continuity();
       test_face_elem_kernels();
       test_momentum_advection_diffusion();
       test_continuity_advection("advection_default");

@@ -372,6 +372,67 @@ def test_hex27_momentum_list_with_fused_lumped_mass_vs_oracle(order):
         ls.assemble_elem(bad)
 
 
+def test_one_dof_oracle_identities():
+    """continuity: the Laplacian-like operator annihilates constants and, with p = 0 and Gp = 0 on a uniform rho u, the
+    residual is -(net mass flux of the sub-control volume)/tau; scalar: a constant q has no diffusive flux"""
+    m = _perturbed_box((1, 1, 1))
+    n = m.n_nodes
+    u0 = np.tile([0.3, -0.2, 0.7], (n, 1))
+    lhs, rhs = H.continuity_adv(m.elem_nodes, m.coords, u0, np.ones(n), np.zeros(n), np.zeros((n, 3)), dt=0.05, gamma1=1.5)
+    assert np.abs(lhs[0].sum(axis=1)).max() < 1e-12 * np.abs(lhs).max() * 27
+    mdot = H.calc_mass_flow_rate_scs(m.elem_nodes, m.coords, np.ones(n), u0)
+    me = H.scs()
+    net = np.zeros(27)
+    np.add.at(net, me.lrscv[:, 0], mdot[0])
+    np.add.at(net, me.lrscv[:, 1], -mdot[0])
+    assert np.abs(rhs[0] + net / (0.05 / 1.5)).max() < 1e-12
+    # a linear pressure with its exact gradient as Gp: the two pressure terms cancel
+    g = np.array([0.4, -0.3, 0.2])
+    lhs2, rhs2 = H.continuity_adv(m.elem_nodes, m.coords, u0, np.ones(n), m.coords @ g, np.tile(g, (n, 1)), dt=0.05, gamma1=1.5)
+    assert np.abs(rhs2 - rhs).max() < 1e-11
+    l3, r3 = H.scalar_adv_diff(m.elem_nodes, m.coords, np.full(n, 2.5), np.full(n, 0.1), mdot)
+    assert np.abs(r3[0] + 2.5 * net).max() < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["continuity_adv", "scalar_adv_diff"])
+def test_hex27_one_dof_kernels_vs_oracle(kind):
+    import torch
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    m = _perturbed_box((3, 2, 3))
+    vel, visc, rho = _fields(m)
+    x = m.coords
+    p = 0.5 * np.cos(0.8 * x[:, 0]) * np.sin(0.6 * x[:, 1]) + 0.1 * x[:, 2]
+    gp = np.stack([-0.4 * np.sin(0.8 * x[:, 0]), 0.3 * np.cos(0.6 * x[:, 1]), 0.1 + 0.05 * x[:, 2]], axis=1)
+    q = 1.0 + 0.5 * np.sin(x[:, 0] + 0.5 * x[:, 1]) * np.cos(0.7 * x[:, 2])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    ls = DeviceCsrLinearSystem(m, 1).allocate(dev)
+    ls.zero_system()
+    mdot = H.calc_mass_flow_rate_scs(m.elem_nodes, m.coords, rho, vel)
+    if kind == "continuity_adv":
+        d = ls.make_desc("continuity_adv", fields=dict(coordinates=t(x), velocity=t(vel), density=t(rho), pressure=t(p), dpdx=t(gp)),
+                         dt=0.05, gamma1=1.5)
+        lhs, rhs = H.continuity_adv(m.elem_nodes, x, vel, rho, p, gp, dt=0.05, gamma1=1.5)
+    else:
+        d = ls.make_desc("scalar_adv_diff", fields=dict(coordinates=t(x), scalarq=t(q), viscosity=t(visc)), mass_flow_rate=t(mdot))
+        lhs, rhs = H.scalar_adv_diff(m.elem_nodes, x, q, visc, mdot)
+    assert ls.assemble_elem([d]) == 5
+    torch.cuda.synchronize()
+    assert ls.geometry_errors() == 0
+    rowptr, colidx, values, b = H.assemble_csr(m.node_gid, m.elem_nodes, lhs, rhs, num_dof=1)
+    assert np.array_equal(ls.rowptr().astype(np.int64), rowptr) and np.array_equal(ls.colidx().astype(np.int64), colidx)
+    got_v, got_b = ls.owned_values().cpu().numpy(), ls.owned_rhs().cpu().numpy()
+    assert _rel_err_rows(got_v, values, rowptr) < 1e-12
+    rowsum = np.add.reduceat(np.abs(values), rowptr[:-1])
+    assert np.abs(got_b - b).max() < 1e-12 * max(np.abs(b).max(), rowsum.max() * np.abs(q).max())
+    # deterministic
+    v0, r0 = ls.owned_values().clone(), ls.owned_rhs().clone()
+    ls.zero_system()
+    ls.assemble_elem([d])
+    assert torch.equal(v0, ls.owned_values()) and torch.equal(r0, ls.owned_rhs())
+
+
 @pytest.mark.gpu
 def test_hex27_assembly_is_deterministic_and_accumulates():
     m = _perturbed_box((3, 3, 2))

@@ -224,6 +224,35 @@ def run(n=48, steps=10, warmup=3):
         lms = b0.elapsed_time(b1) / steps
         mlist = {"kernels": ["MomentumMassElemKernel(lumped)", "MomentumAdvDiffElemKernel(includeDivU=1)"], "value": ne / lms / 1e3,
                  "unit": "Melem/s", "ms_per_step": lms, "finite": bool(torch.isfinite(ls.values).all())}
+    onedof = None
+    if world == 1:
+        # the one-dof Hex27 kernels on the same mesh: ContinuityAdvElemKernel and ScalarAdvDiffElemKernel (their own 1-dof graph)
+        ls1 = DeviceCsrLinearSystem(m, 1)
+        ls1.allocate(dev)
+        x = m.coords
+        pr = t(0.5 * np.cos(0.8 * x[:, 0]) * np.sin(0.6 * x[:, 1]) + 0.1 * x[:, 2])
+        gpx = t(0.1 * vel)
+        qq = t(1.0 + 0.5 * np.sin(x[:, 0] + 0.5 * x[:, 1]) * np.cos(0.7 * x[:, 2]))
+        dk = {"continuity_adv": ls1.make_desc("continuity_adv", fields=dict(coordinates=coords, velocity=v, density=r, pressure=pr, dpdx=gpx),
+                                              dt=0.05, gamma1=1.5),
+              "scalar_adv_diff": ls1.make_desc("scalar_adv_diff", fields=dict(coordinates=coords, scalarq=qq, viscosity=mu), mass_flow_rate=mdot)}
+        onedof = {}
+        for name, dd in dk.items():
+            for _ in range(2):
+                ls1.zero_system()
+                ls1.assemble_elem([dd])
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(steps):
+                ls1.zero_system()
+                ls1.assemble_elem([dd])
+            c1.record()
+            torch.cuda.synchronize()
+            oms = c0.elapsed_time(c1) / steps
+            onedof[name] = {"value": ne / oms / 1e3, "unit": "Melem/s", "ms_per_step": oms, "finite": bool(torch.isfinite(ls1.values).all()),
+                            "nnz": int(ls1.nnz_owned)}
+        del ls1
     cpu = None
     if world == 1:
         # cpu baseline: the oracle on a bounded sample
@@ -252,7 +281,7 @@ def run(n=48, steps=10, warmup=3):
                      "algorithmic_bytes_per_elem": alg_bytes / ne,
                      "fp64": {"flop_per_elem_static": 2 * (216 * (27 * 23 + 60) + 243 * 16 * 81),
                               "note": "FMA = 2 flop, static count of phase B + C"}},
-        "cpu_baseline": cpu, "momentum_list": mlist,
+        "cpu_baseline": cpu, "momentum_list": mlist, "one_dof_kernels": onedof,
         "checks": checks,
     }
     if own_group:
