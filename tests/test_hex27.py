@@ -434,6 +434,32 @@ def test_hex27_one_dof_kernels_vs_oracle(kind):
 
 
 @pytest.mark.gpu
+def test_hex27_periodic_aliasing_takes_the_atomic_path():
+    """a box one element wide and periodic in x (the subject plane adopts the monarch's ids, src/PeriodicManager.C:698-724): every
+    element reaches rows through two of its nodes, no colouring exists, the kernel sums with atomics -- every contribution is
+    kept (the reference's sum_into_row drops part of a row with repeated column ids, as for Hex8: DESIGN 1.2)"""
+    import torch
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    m = _perturbed_box((1, 2, 2))
+    sx = 3
+    ix = np.arange(m.n_nodes) % sx
+    m.node_gid = np.where(ix == 2, m.node_gid - 2, m.node_gid)   # x = 1 plane -> ids of the x = 0 plane
+    vel, visc, rho = _fields(m)
+    # periodic fields: the aliased nodes carry the monarch's values (coordinates stay their own)
+    mon = np.where(ix == 2, np.arange(m.n_nodes) - 2, np.arange(m.n_nodes))
+    vel, visc, rho = vel[mon], visc[mon], rho[mon]
+    ls, mode, _ = _device_assemble(m, vel, visc, rho, 1.0)
+    assert mode == 5 and ls.elem_colors()[0] == 0
+    mdot = H.calc_mass_flow_rate_scs(m.elem_nodes, m.coords, rho, vel)
+    lhs, rhs = H.momentum_adv_diff(m.elem_nodes, m.coords, vel, visc, mdot, include_divu=1.0)
+    rowptr, colidx, values, b = H.assemble_csr(m.node_gid, m.elem_nodes, lhs, rhs)
+    assert np.array_equal(ls.rowptr().astype(np.int64), rowptr) and np.array_equal(ls.colidx().astype(np.int64), colidx)
+    got_v, got_b = ls.owned_values().cpu().numpy(), ls.owned_rhs().cpu().numpy()
+    assert np.abs(got_v - values).max() < 1e-12 * np.abs(values).max()
+    assert np.abs(got_b - b).max() < 1e-12 * np.abs(values).max() * np.abs(vel).max() * 27
+
+
+@pytest.mark.gpu
 def test_hex27_assembly_is_deterministic_and_accumulates():
     m = _perturbed_box((3, 3, 2))
     vel, visc, rho = _fields(m)
