@@ -453,7 +453,8 @@ int nalu_b200_zero_system(const nalu_b200_graph *h, double *d_values, double *d_
 int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_desc *kernels, int32_t nk, double *d_values,
                             double *d_rhs, int32_t mode, int32_t overwrite, void *stream)
 {
-  if (!h || !kernels || !d_values || !d_rhs) {
+  // an empty part (no elements, hence no matrix entries) may come with null arrays: nothing is dereferenced
+  if (!h || !kernels || (!d_values && h->g.nnz_owned() + h->g.nnz_shared() > 0) || (!d_rhs && h->g.n_row_nodes() > 0)) {
     set_error("assemble_elem: null argument");
     return NALU_B200_ERR_ARG;
   }
@@ -463,6 +464,10 @@ int nalu_b200_assemble_elem(const nalu_b200_graph *h, const nalu_b200_kernel_des
   }
   const Graph &g = h->g;
   cudaStream_t s = (cudaStream_t)stream;
+  if (g.n_elems == 0) { // AssembleElemSolverAlgorithm::execute over empty buckets (src/AssembleElemSolverAlgorithm.C:74-100)
+    set_last_mode(0);
+    return NALU_B200_OK;
+  }
   if (g.npe == 27) { // Hex27 graphs (nalu_b200_graph_create_topo): one kernel, assemble_hex27.cu
     if (!hex27_supported(g, kernels, nk)) {
       set_error("assemble_elem: Hex27 graphs take [MomentumMassElemKernel(lumped)]? + MomentumAdvDiffElemKernel (default options, "
