@@ -241,7 +241,8 @@ enum {
 /* AssembleElemSolverAlgorithm::execute for all locally-owned elements.
  * `overwrite` != 0 tells the tiled kernel that the system holds no earlier contributions,
  * so it may store instead of add (zero_system is then unnecessary for the matrix values and
- * RHS rows it covers).  The general kernel always adds.   A graph without elements (an empty part / rank) is a no-op and may be given null value / rhs arrays. */
+ * RHS rows it covers).  The general kernel always adds.  A graph without elements (an empty
+ * part / rank) is a no-op and may be given null value / rhs arrays. */
 int nalu_b200_assemble_elem(const nalu_b200_graph *g, const nalu_b200_kernel_desc *kernels,
                             int32_t n_kernels, double *d_values, double *d_rhs, int32_t mode,
                             int32_t overwrite, void *stream);
