@@ -659,15 +659,18 @@ __global__ void __launch_bounds__(kThreads, 2) assemble_hex27_onedof_kernel(cons
 
 // mass_flow_rate_scs of a Hex27 element: mdot_ip = (sum_n N_n rho_n u_n) . A_ip (the unit tests' calc_mass_flow_rate_scs,
 // unit_tests/kernels/UnitTestKernelUtils.C:547-628, instantiated with AlgTraitsHex27); thread = (element, point)
-__global__ void __launch_bounds__(kThreads) mdot_hex27_kernel(Tables T, long long n_elems, const int *elem_nodes, const double *coords,
-                                                               const double *density, const double *vel, double *mdot)
+// with `pressure` non-null: ComputeMdotElemAlgorithm (src/ComputeMdotElemAlgorithm.C:85-254, default options) on AlgTraitsHex27,
+// mdot_ip = (rho u_ip - tau (grad p_ip - (Gp)_ip)) . A_ip -- the flux ContinuityAdvElemKernel forms for its residual
+__global__ void __launch_bounds__(kThreads) mdot_hex27_kernel(Tables T, long long e0, long long n_elems, const int *elem_nodes, const double *coords,
+                                                               const double *density, const double *vel, const double *pressure,
+                                                               const double *gpdx, double tau, double *mdot)
 {
   const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (tid >= n_elems * NIP) return;
-  const long long e = tid / NIP;
-  const int ip = (int)(tid - e * NIP);
+  const long long e = e0 + tid / NIP;
+  const int ip = (int)(tid % NIP);
   const int *en = elem_nodes + e * NPE;
-  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, ru[3] = {0, 0, 0};
+  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, ru[3] = {0, 0, 0}, pg[3] = {0, 0, 0}, gp[3] = {0, 0, 0};
   const int n0 = en[0];
   const double x0[3] = {coords[(size_t)n0 * 3], coords[(size_t)n0 * 3 + 1], coords[(size_t)n0 * 3 + 2]};
   for (int n = 0; n < NPE; ++n) {
@@ -680,15 +683,34 @@ __global__ void __launch_bounds__(kThreads) mdot_hex27_kernel(Tables T, long lon
       for (int j = 0; j < 3; ++j) J[i][j] += T.dN_ipfast[(n * 3 + j) * NIP + ip] * x;
       ru[i] += sf * vel[(size_t)nd * 3 + i];
     }
+    if (pressure) {
+      const double p = pressure[nd], sn = T.N_ipfast[n * NIP + ip];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        pg[j] += T.dN_ipfast[(n * 3 + j) * NIP + ip] * p;
+        gp[j] += sn * gpdx[(size_t)nd * 3 + j];
+      }
+    }
   }
   double C[3][3];
-  cofactor(J, C);
+  const double det = cofactor(J, C);
   const int d = T.dir[ip];
   const double w = T.wdir[ip];
-  double md = 0.0;
+  double A[3], md = 0.0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) md += ru[i] * w * (d == 0 ? C[i][0] : d == 1 ? C[i][1] : C[i][2]);
-  mdot[tid] = md;
+  for (int i = 0; i < 3; ++i) {
+    A[i] = w * (d == 0 ? C[i][0] : d == 1 ? C[i][1] : C[i][2]);
+    md += ru[i] * A[i];
+  }
+  if (pressure) {
+    // grad p . A = sum_k (cof(J)^T A)_k / det * (sum_c p_c dN_c/dxi_k)
+    double dpdxA = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dpdxA += (C[0][k] * A[0] + C[1][k] * A[1] + C[2][k] * A[2]) * pg[k];
+    dpdxA /= det;
+    md -= tau * (dpdxA - (gp[0] * A[0] + gp[1] * A[1] + gp[2] * A[2]));
+  }
+  mdot[e * NIP + ip] = md;
 }
 
 } // namespace hex27
@@ -836,16 +858,18 @@ int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc *kernels, 
 }
 
 int launch_mdot_hex27(const Graph &g, const double *coords, const double *density, const double *velocity, double *mdot,
-                      cudaStream_t stream)
+                      cudaStream_t stream, const double *pressure, const double *gpdx, double tau, long long e0, long long e1)
 {
   using namespace hex27;
   const Tables *T = nullptr;
   int rc = get_tables(&T);
   if (rc) return rc;
-  const long long nt = g.n_elems * NIP;
+  if (e1 < 0 || e1 > g.n_elems) e1 = g.n_elems;
+  if (e0 < 0) e0 = 0;
+  const long long ne = e1 - e0, nt = ne * NIP;
   if (nt > 0) {
-    mdot_hex27_kernel<<<(unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, stream>>>(*T, g.n_elems, g.d_elem_nodes27, coords, density,
-                                                                                          velocity, mdot);
+    mdot_hex27_kernel<<<(unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, stream>>>(*T, e0, ne, g.d_elem_nodes27, coords, density, velocity,
+                                                                                          pressure, gpdx, tau, mdot);
     count_launch();
   }
   NALU_CUDA(cudaGetLastError());

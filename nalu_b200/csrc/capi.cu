@@ -641,6 +641,13 @@ int nalu_b200_compute_mdot_elem(const nalu_b200_graph *h, const double *d_coords
                                 const double *d_pressure, const double *d_gpdx, double proj_time_scale, int32_t options,
                                 double *d_mdot, void *stream)
 {
+  if (h && d_coords && d_density && d_velocity && d_pressure && d_gpdx && d_mdot && h->g.npe == 27 && h->g.d_elem_nodes27) {
+    if (options != 0) {
+      set_error("compute_mdot_elem: Hex27 graphs take the default options only");
+      return NALU_B200_ERR_ARG;
+    }
+    return launch_mdot_hex27(h->g, d_coords, d_density, d_velocity, d_mdot, (cudaStream_t)stream, d_pressure, d_gpdx, proj_time_scale);
+  }
   if (!h || !d_coords || !d_density || !d_velocity || !d_pressure || !d_gpdx || !d_mdot || !h->g.d_elem_nodes) return NALU_B200_ERR_STATE;
   return launch_compute_mdot(h->g, d_coords, d_density, d_velocity, d_pressure, d_gpdx, proj_time_scale, options, d_mdot,
                              (cudaStream_t)stream);
@@ -650,6 +657,14 @@ int nalu_b200_compute_mdot_elem_range(const nalu_b200_graph *h, const double *d_
                                       const double *d_velocity, const double *d_pressure, const double *d_gpdx, double proj_time_scale,
                                       int32_t options, int64_t e_begin, int64_t e_end, double *d_mdot, void *stream)
 {
+  if (h && d_coords && d_density && d_velocity && d_pressure && d_gpdx && d_mdot && h->g.npe == 27 && h->g.d_elem_nodes27) {
+    if (options != 0) {
+      set_error("compute_mdot_elem_range: Hex27 graphs take the default options only");
+      return NALU_B200_ERR_ARG;
+    }
+    return launch_mdot_hex27(h->g, d_coords, d_density, d_velocity, d_mdot, (cudaStream_t)stream, d_pressure, d_gpdx, proj_time_scale, e_begin,
+                             e_end);
+  }
   if (!h || !d_coords || !d_density || !d_velocity || !d_pressure || !d_gpdx || !d_mdot || !h->g.d_elem_nodes) return NALU_B200_ERR_STATE;
   return launch_compute_mdot(h->g, d_coords, d_density, d_velocity, d_pressure, d_gpdx, proj_time_scale, options, d_mdot,
                              (cudaStream_t)stream, e_begin, e_end);

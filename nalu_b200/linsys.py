@@ -254,7 +254,7 @@ class DeviceCsrLinearSystem:
         """ComputeMdotElemAlgorithm::execute: mass_flow_rate_scs of every locally-owned element (or of elements e_range)."""
         import torch
         if out is None:
-            out = torch.empty((self.mesh.n_elems, 12), dtype=torch.float64, device=coords.device)
+            out = torch.empty((self.mesh.n_elems, 12 if self.nodes_per_elem == 8 else 216), dtype=torch.float64, device=coords.device)
         opt = 0
         for o in options:
             opt |= OPT[o]

@@ -366,6 +366,24 @@ def continuity_adv(elem_nodes, coords, velocity, density, pressure, gpdx, dt, ga
     return lhs, rhs
 
 
+def compute_mdot_elem(elem_nodes, coords, density, velocity, pressure, gpdx, proj_time_scale):
+    """ComputeMdotElemAlgorithm::execute (src/ComputeMdotElemAlgorithm.C:85-254) with the Hex27 master element, default options:
+    mdot[E,216] = (rho u_ip - projTimeScale (dpdx_ip - Gpdx_ip)) . areav_ip"""
+    me = scs()
+    c = np.asarray(coords)[elem_nodes]
+    u = np.asarray(velocity)[elem_nodes]
+    rho = np.asarray(density)[elem_nodes]
+    p = np.asarray(pressure)[elem_nodes]
+    gp = np.asarray(gpdx)[elem_nodes]
+    areav = me.area_vectors(c)
+    dndx, _ = me.grad_op(c)
+    sf = me.shape_fcn
+    rho_u_ip = np.einsum("pn,en,enj->epj", sf, rho, u)
+    gp_ip = np.einsum("pn,enj->epj", sf, gp)
+    dpdx_ip = np.einsum("epnj,en->epj", dndx, p)
+    return np.einsum("epj,epj->ep", rho_u_ip - proj_time_scale * (dpdx_ip - gp_ip), areav)
+
+
 def scalar_adv_diff(elem_nodes, coords, scalar_q, diff_flux_coeff, mdot):
     """ScalarAdvDiffElemKernel<AlgTraitsHex27>::execute (src/kernel/ScalarAdvDiffElemKernel.C:69-127), default options:
     lhs [E,27,27], rhs [E,27]"""

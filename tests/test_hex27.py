@@ -240,8 +240,8 @@ def test_hex8_entry_points_refuse_hex27_graphs():
     m = M.hex27_box(1, 1, 1)
     ls = DeviceCsrLinearSystem(m, 3, host_only=True)
     buf = np.zeros(8)
-    rc = ls.L.nalu_b200_compute_mdot_elem(ls.h, L.ptr(buf), L.ptr(buf), L.ptr(buf), L.ptr(buf), L.ptr(buf), C.c_double(0.0), 0,
-                                          L.ptr(buf), None)
+    # AssembleNodalGradElemAlgorithm exists for Hex8 only
+    rc = ls.L.nalu_b200_assemble_nodal_grad_elem(ls.h, L.ptr(buf), L.ptr(buf), 1, L.ptr(buf), 0, L.ptr(buf), None)
     assert rc != 0
 
 
@@ -431,6 +431,41 @@ def test_hex27_one_dof_kernels_vs_oracle(kind):
     ls.zero_system()
     ls.assemble_elem([d])
     assert torch.equal(v0, ls.owned_values()) and torch.equal(r0, ls.owned_rhs())
+
+
+@pytest.mark.gpu
+def test_hex27_compute_mdot_elem_vs_oracle():
+    """ComputeMdotElemAlgorithm on Hex27: the pressure-stabilised mass flow rate, whole mesh and an element range; it is the flux
+    whose divergence the continuity kernel puts in its residual"""
+    import torch
+    from nalu_b200.linsys import DeviceCsrLinearSystem
+    m = _perturbed_box((3, 2, 2))
+    vel, visc, rho = _fields(m)
+    x = m.coords
+    p = 0.5 * np.cos(0.8 * x[:, 0]) * np.sin(0.6 * x[:, 1]) + 0.1 * x[:, 2]
+    gp = np.stack([-0.4 * np.sin(0.8 * x[:, 0]), 0.3 * np.cos(0.6 * x[:, 1]), 0.1 + 0.05 * x[:, 2]], axis=1)
+    tau = 0.05 / 1.5
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    ls = DeviceCsrLinearSystem(m, 1)
+    ref = H.compute_mdot_elem(m.elem_nodes, x, rho, vel, p, gp, tau)
+    got = ls.compute_mdot_elem(t(x), t(rho), t(vel), t(p), t(gp), tau)
+    assert got.shape == (m.n_elems, 216)
+    assert np.abs(got.cpu().numpy() - ref).max() < 1e-12 * np.abs(ref).max()
+    part = torch.full((m.n_elems, 216), np.nan, dtype=torch.float64, device=dev)
+    ls.compute_mdot_elem(t(x), t(rho), t(vel), t(p), t(gp), tau, out=part, e_range=(4, 9))
+    pn = part.cpu().numpy()
+    assert np.isnan(pn[:4]).all() and np.isnan(pn[9:]).all() and np.abs(pn[4:9] - ref[4:9]).max() < 1e-12 * np.abs(ref).max()
+    # consistency with the continuity kernel: rhs = -(net flux of every sub-control volume) / tau
+    lhs, rhs = H.continuity_adv(m.elem_nodes, x, vel, rho, p, gp, dt=0.05, gamma1=1.5)
+    me = H.scs()
+    net = np.zeros((m.n_elems, 27))
+    for e in range(m.n_elems):
+        np.add.at(net[e], me.lrscv[:, 0], ref[e])
+        np.add.at(net[e], me.lrscv[:, 1], -ref[e])
+    assert np.abs(rhs + net / tau).max() < 1e-11 * np.abs(rhs).max()
+    with pytest.raises(Exception):
+        ls.compute_mdot_elem(t(x), t(rho), t(vel), t(p), t(gp), tau, options=("shift_mdot",))
 
 
 @pytest.mark.gpu
