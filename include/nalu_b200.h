@@ -176,8 +176,8 @@ int nalu_b200_graph_create(nalu_b200_graph **out, int32_t rank, int32_t nranks, 
  * graph nalu_b200_assemble_elem takes [MomentumMassElemKernel(lumped)]? + MomentumAdvDiffElemKernel (3 dof, default options,
  * either order, the mass fused into the same launches; mass_flow_rate is [n_elems][216], the Hex27SCS point order of
  * Hex27CVFEM.C:887-1050) and nalu_b200_mdot_scs produces that field; on a 1-dof Hex27 graph it takes [ContinuityAdvElemKernel]
- * or [ScalarAdvDiffElemKernel] (default options); nalu_b200_compute_mdot_elem(_range) is ComputeMdotElemAlgorithm on Hex27
- * (default options).  Other lists return NALU_B200_ERR_ARG and every other element-level entry point returns
+ * or [ScalarAdvDiffElemKernel] (default options); nalu_b200_compute_mdot_elem(_range) is ComputeMdotElemAlgorithm and
+ * nalu_b200_assemble_nodal_grad_elem is AssembleNodalGrad(U)ElemAlgorithm on Hex27 (default options).  Other lists return NALU_B200_ERR_ARG and every other element-level entry point returns
  * NALU_B200_ERR_STATE. */
 int nalu_b200_graph_create_topo(nalu_b200_graph **out, int32_t rank, int32_t nranks, int32_t num_dof,
                                 int32_t nodes_per_elem, int32_t n_nodes, const int64_t *node_gid,

@@ -713,6 +713,53 @@ __global__ void __launch_bounds__(kThreads) mdot_hex27_kernel(Tables T, long lon
   mdot[e * NIP + ip] = md;
 }
 
+// AssembleNodalGradElemAlgorithm / AssembleNodalGradUElemAlgorithm (src/AssembleNodalGradElemAlgorithm.C:64-150,
+// src/AssembleNodalGradUElemAlgorithm.C:120-195) on Hex27: Green-Gauss contributions q_ip A_ip / V to the left node and minus that
+// to the right node of every point; thread = (element, point), atomics as for Hex8
+template <int NCOMP>
+__global__ void __launch_bounds__(kThreads) nodal_grad_hex27_kernel(Tables T, long long n_elems, const int *elem_nodes, const double *coords,
+                                                                     const double *field, const double *dual_volume, double *grad)
+{
+  const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (tid >= n_elems * NIP) return;
+  const long long e = tid / NIP;
+  const int ip = (int)(tid - e * NIP);
+  const int *en = elem_nodes + e * NPE;
+  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, q[NCOMP];
+#pragma unroll
+  for (int i = 0; i < NCOMP; ++i) q[i] = 0.0;
+  const int n0 = en[0];
+  const double x0[3] = {coords[(size_t)n0 * 3], coords[(size_t)n0 * 3 + 1], coords[(size_t)n0 * 3 + 2]};
+  for (int n = 0; n < NPE; ++n) {
+    const int nd = en[n];
+    const double sf = T.N_ipfast[n * NIP + ip];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double x = coords[(size_t)nd * 3 + i] - x0[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) J[i][j] += T.dN_ipfast[(n * 3 + j) * NIP + ip] * x;
+    }
+#pragma unroll
+    for (int i = 0; i < NCOMP; ++i) q[i] += sf * field[(size_t)nd * NCOMP + i];
+  }
+  double C[3][3];
+  cofactor(J, C);
+  const int d = T.dir[ip];
+  const double w = T.wdir[ip];
+  const int nl = en[T.lr[2 * ip]], nr = en[T.lr[2 * ip + 1]];
+  const double ivl = 1.0 / dual_volume[nl], ivr = 1.0 / dual_volume[nr];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double a = w * (d == 0 ? C[j][0] : d == 1 ? C[j][1] : C[j][2]);
+#pragma unroll
+    for (int i = 0; i < NCOMP; ++i) {
+      const double fac = q[i] * a;
+      atomicAdd(grad + (size_t)nl * NCOMP * 3 + i * 3 + j, fac * ivl);
+      atomicAdd(grad + (size_t)nr * NCOMP * 3 + i * 3 + j, -fac * ivr);
+    }
+  }
+}
+
 } // namespace hex27
 
 // [MomentumAdvDiffElemKernel] or [MomentumMassElemKernel(lumped), MomentumAdvDiffElemKernel] in either order
@@ -876,4 +923,28 @@ int launch_mdot_hex27(const Graph &g, const double *coords, const double *densit
   return NALU_B200_OK;
 }
 
+} // namespace nalu_b200
+
+namespace nalu_b200 {
+int launch_nodal_grad_hex27(const Graph &g, const double *coords, const double *field, int ncomp, const double *dual_volume, double *grad,
+                            cudaStream_t stream)
+{
+  using namespace hex27;
+  if (ncomp != 1 && ncomp != 3) {
+    set_error("assemble_nodal_grad_elem: ncomp must be 1 (scalar) or 3 (vector)");
+    return NALU_B200_ERR_ARG;
+  }
+  const Tables *T = nullptr;
+  int rc = get_tables(&T);
+  if (rc) return rc;
+  const long long nt = g.n_elems * NIP;
+  if (nt > 0) {
+    const unsigned nb = (unsigned)((nt + kThreads - 1) / kThreads);
+    if (ncomp == 1) nodal_grad_hex27_kernel<1><<<nb, kThreads, 0, stream>>>(*T, g.n_elems, g.d_elem_nodes27, coords, field, dual_volume, grad);
+    else nodal_grad_hex27_kernel<3><<<nb, kThreads, 0, stream>>>(*T, g.n_elems, g.d_elem_nodes27, coords, field, dual_volume, grad);
+    count_launch();
+  }
+  NALU_CUDA(cudaGetLastError());
+  return NALU_B200_OK;
+}
 } // namespace nalu_b200

@@ -633,6 +633,13 @@ int nalu_b200_mdot_scs(const nalu_b200_graph *h, const double *d_coords, const d
 int nalu_b200_assemble_nodal_grad_elem(const nalu_b200_graph *h, const double *d_coords, const double *d_field, int32_t ncomp,
                                        const double *d_dual_volume, int32_t use_shifted, double *d_grad, void *stream)
 {
+  if (h && d_coords && d_field && d_dual_volume && d_grad && h->g.npe == 27 && h->g.d_elem_nodes27) {
+    if (use_shifted) {
+      set_error("assemble_nodal_grad_elem: Hex27 graphs take the unshifted shape functions only");
+      return NALU_B200_ERR_ARG;
+    }
+    return launch_nodal_grad_hex27(h->g, d_coords, d_field, ncomp, d_dual_volume, d_grad, (cudaStream_t)stream);
+  }
   if (!h || !d_coords || !d_field || !d_dual_volume || !d_grad || !h->g.d_elem_nodes) return NALU_B200_ERR_STATE;
   return launch_nodal_grad(h->g, d_coords, d_field, ncomp, d_dual_volume, use_shifted, d_grad, (cudaStream_t)stream);
 }

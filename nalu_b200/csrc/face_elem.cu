@@ -519,6 +519,10 @@ int nalu_b200_face_set_create(nalu_b200_face_set **out, const nalu_b200_graph *h
   if (!out || !h || n_faces < 0 || (n_faces > 0 && (!face_elem || !face_ordinal))) return NALU_B200_ERR_ARG;
   const Graph &g = h->g;
   if (!g.finalized) return NALU_B200_ERR_STATE;
+  if (g.npe != 8) {
+    set_error("face_set_create: Quad4 faces of Hex8 elements only (the graph holds 27-node elements)");
+    return NALU_B200_ERR_STATE;
+  }
   // greedy colouring over the ROWS the faces add to: a face touches the rows of its four nodes (aliases of one row on
   // periodic meshes count as one), lowest colour not yet used at any of them
   std::vector<uint64_t> used((size_t)g.n_row_nodes(), 0);

@@ -70,6 +70,8 @@ int launch_assemble_hex27(const Graph &g, const nalu_b200_kernel_desc *k, int nk
 int launch_mdot_hex27(const Graph &g, const double *coords, const double *density, const double *velocity, double *mdot,
                       cudaStream_t stream, const double *pressure = nullptr, const double *gpdx = nullptr, double tau = 0.0,
                       long long e0 = 0, long long e1 = -1);
+int launch_nodal_grad_hex27(const Graph &g, const double *coords, const double *field, int ncomp, const double *dual_volume, double *grad,
+                            cudaStream_t stream);
 // halo.cu
 int launch_halo_pack(const Graph &g, const HaloPeer &p, const double *d_values, const double *d_rhs,
                      double *d_buf, cudaStream_t stream);

@@ -384,6 +384,34 @@ def compute_mdot_elem(elem_nodes, coords, density, velocity, pressure, gpdx, pro
     return np.einsum("epj,epj->ep", rho_u_ip - proj_time_scale * (dpdx_ip - gp_ip), areav)
 
 
+def dual_nodal_volume(elem_nodes, coords, n_nodes):
+    """dual_nodal_volume: the SCV volumes of every element summed into their nodes (src/ComputeGeometryInteriorAlgorithm.C:72-150)"""
+    me = scv()
+    vol = me.volumes(np.asarray(coords)[elem_nodes])                        # [E,216]
+    out = np.zeros(n_nodes)
+    np.add.at(out, elem_nodes[:, me.ip_node_map], vol)
+    return out
+
+
+def assemble_nodal_grad_elem(elem_nodes, coords, field, dual_volume):
+    """AssembleNodalGradElemAlgorithm / AssembleNodalGradUElemAlgorithm::execute (src/AssembleNodalGradElemAlgorithm.C:64-150,
+    src/AssembleNodalGradUElemAlgorithm.C:120-195) with the Hex27 master element: grad[n, i, j] += q_i,ip A_j / V_n at the left
+    node, minus at the right node; field [nNodes] or [nNodes, ncomp]"""
+    me = scs()
+    f = np.asarray(field, dtype=np.float64)
+    f2 = f[:, None] if f.ndim == 1 else f
+    c = np.asarray(coords)[elem_nodes]
+    areav = me.area_vectors(c)                                               # [E,216,3]
+    q_ip = np.einsum("pn,eni->epi", me.shape_fcn, f2[elem_nodes])            # [E,216,ncomp]
+    fac = q_ip[:, :, :, None] * areav[:, :, None, :]                          # [E,216,ncomp,3]
+    grad = np.zeros((f2.shape[0], f2.shape[1], 3))
+    nl, nr = elem_nodes[:, me.lrscv[:, 0]], elem_nodes[:, me.lrscv[:, 1]]
+    dv = np.asarray(dual_volume)
+    np.add.at(grad, nl, fac / dv[nl][:, :, None, None])
+    np.add.at(grad, nr, -fac / dv[nr][:, :, None, None])
+    return grad[:, 0, :] if f.ndim == 1 else grad
+
+
 def scalar_adv_diff(elem_nodes, coords, scalar_q, diff_flux_coeff, mdot):
     """ScalarAdvDiffElemKernel<AlgTraitsHex27>::execute (src/kernel/ScalarAdvDiffElemKernel.C:69-127), default options:
     lhs [E,27,27], rhs [E,27]"""
